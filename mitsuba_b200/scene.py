@@ -1,0 +1,325 @@
+"""Host-side scene description mirroring the Mitsuba 0.6 plugin/property vocabulary.
+
+Plain-data mirror of what the reference's scene graph holds for the `path` hot path: BSDF plugins
+(`diffuse`, `roughconductor`, `roughdielectric`, `coating`; property names as in
+src/bsdfs/*.cpp), triangle meshes with an optional `area` emitter child (src/emitters/area.cpp),
+a `perspective` sensor (src/sensors/perspective.cpp:126-179), and the integrator / sampler / film /
+rfilter properties (src/librender/integrator.cpp:190-225, src/samplers/sobol.cpp:86-102,
+src/librender/film.cpp:24-95).  A SceneDesc is what the C-ABI (include/b2mts.h) consumes; the XML
+loader (mitsuba_b200/host) produces the same structure from a Mitsuba scene file.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+# named IORs, src/bsdfs/ior.h:39-66
+NAMED_IOR = {
+    "vacuum": 1.0, "helium": 1.000036, "hydrogen": 1.000132, "air": 1.000277, "carbon dioxide": 1.00045,
+    "water": 1.3330, "acetone": 1.36, "ethanol": 1.361, "carbon tetrachloride": 1.461, "glycerol": 1.4729,
+    "benzene": 1.501, "silicone oil": 1.52045, "bromine": 1.661, "water ice": 1.31, "fused quartz": 1.458,
+    "pyrex": 1.470, "acrylic glass": 1.49, "polypropylene": 1.49, "bk7": 1.5046, "sodium chloride": 1.544,
+    "amber": 1.55, "pet": 1.5750, "diamond": 2.419,
+}
+
+BSDF_TYPES = {"diffuse": 0, "roughconductor": 1, "roughdielectric": 2, "coating": 3}
+DISTRIBUTIONS = {"beckmann": 0, "ggx": 1, "phong": 2, "as": 2}
+
+
+def lookup_ior(value, default: str) -> float:
+    """src/bsdfs/ior.h:68-100 lookupIOR: a float wins over a name."""
+    if value is None:
+        value = default
+    if isinstance(value, str):
+        return float(NAMED_IOR[value.lower()])
+    return float(value)
+
+
+@dataclass
+class Bsdf:
+    """One BSDF plugin instance; property names and defaults follow the reference constructors."""
+    type: str = "diffuse"
+    reflectance: Sequence[float] = (0.5, 0.5, 0.5)            # diffuse.cpp:75-77
+    specular_reflectance: Sequence[float] = (1.0, 1.0, 1.0)   # roughconductor.cpp:171-172 etc.
+    specular_transmittance: Sequence[float] = (1.0, 1.0, 1.0)  # roughdielectric.cpp:186-187
+    distribution: str = "beckmann"                             # microfacet.h:99-100
+    alpha_u: float = 0.1
+    alpha_v: float = 0.1
+    sample_visible: bool = True                                # microfacet.h:138
+    eta: Sequence[float] = (0.0, 0.0, 0.0)                     # roughconductor eta (RGB), material="none"
+    k: Sequence[float] = (1.0, 1.0, 1.0)
+    ext_eta: object = "air"                                    # roughconductor.cpp:187
+    int_ior: object = "bk7"                                    # roughdielectric.cpp:190 / coating.cpp:112
+    ext_ior: object = "air"
+    thickness: float = 1.0                                     # coating.cpp:126
+    sigma_a: Sequence[float] = (0.0, 0.0, 0.0)                 # coating.cpp:129-130
+    nested: Optional["Bsdf"] = None                            # coating child BSDF
+
+    def flat(self) -> dict:
+        t = BSDF_TYPES[self.type]
+        distr = DISTRIBUTIONS[self.distribution.lower()]
+        sv = bool(self.sample_visible) and distr != 2           # microfacet.h:145-148
+        d = dict(type=t, distr=distr, sampleVisible=int(sv), nested=-1,
+                 alphaU=float(self.alpha_u), alphaV=float(self.alpha_v), eta=1.0,
+                 thickness=float(self.thickness), reflectance=(0.0, 0.0, 0.0),
+                 transmittance=tuple(float(x) for x in self.specular_transmittance),
+                 etaC=(0.0, 0.0, 0.0), kC=(1.0, 1.0, 1.0), sigmaA=tuple(float(x) for x in self.sigma_a))
+        if t == 0:
+            d["reflectance"] = tuple(float(x) for x in self.reflectance)
+        else:
+            d["reflectance"] = tuple(float(x) for x in self.specular_reflectance)
+        if t == 1:
+            ext = np.float32(lookup_ior(self.ext_eta, "air"))
+            d["etaC"] = tuple(float(np.float32(x) / ext) for x in self.eta)  # roughconductor.cpp:189-190
+            d["kC"] = tuple(float(np.float32(x) / ext) for x in self.k)
+        if t in (2, 3):
+            d["eta"] = float(np.float32(lookup_ior(self.int_ior, "bk7")) / np.float32(lookup_ior(self.ext_ior, "air")))
+        return d
+
+
+@dataclass
+class Mesh:
+    """A TriMesh after TriMesh::configure (normals already generated or absent = face normals)."""
+    P: np.ndarray                       # (nV,3) f32
+    idx: np.ndarray                     # (nT,3) u32
+    N: Optional[np.ndarray] = None      # (nV,3) f32 or None
+    UV: Optional[np.ndarray] = None     # (nV,2) f32 or None
+    bsdf: Optional[Bsdf] = None         # None -> shape.cpp:48-72 default
+    radiance: Optional[Sequence[float]] = None   # `area` emitter child (area.cpp:64-70)
+    sampling_weight: float = 1.0        # emitter.cpp:103
+    name: str = ""
+
+
+@dataclass
+class Camera:
+    to_world: np.ndarray                # 4x4 camera-to-world (row major)
+    fov: float = 39.3077                # degrees along `fov_axis`
+    fov_axis: str = "x"
+    near: float = 1e-2                  # sensor.cpp:158
+    far: float = 1e4                    # sensor.cpp:160
+    width: int = 768                    # film.cpp:30-33
+    height: int = 576
+
+    def xfov(self) -> float:
+        """src/librender/sensor.cpp:243-263,293-316."""
+        aspect = self.width / self.height
+        ax = self.fov_axis.lower()
+        if ax == "smaller":
+            ax = "y" if aspect > 1 else "x"
+        elif ax == "larger":
+            ax = "x" if aspect > 1 else "y"
+        if ax == "x":
+            return self.fov
+        if ax == "y":
+            return math.degrees(2 * math.atan(math.tan(0.5 * math.radians(self.fov)) * aspect))
+        if ax == "diagonal":
+            diagonal = 2 * math.tan(0.5 * math.radians(self.fov))
+            width = diagonal / math.sqrt(1.0 + 1.0 / (aspect * aspect))
+            return math.degrees(2 * math.atan(width * 0.5))
+        raise ValueError("fovAxis must be one of smaller, larger, diagonal, x, y")
+
+    def sample_to_camera(self) -> np.ndarray:
+        """Inverse of m_cameraToSample, src/sensors/perspective.cpp:146-153 (no crop window)."""
+        aspect = self.width / self.height
+        recip = 1.0 / (self.far - self.near)
+        cot = 1.0 / math.tan(math.radians(self.xfov() / 2.0))
+        persp = np.array([[cot, 0, 0, 0], [0, cot, 0, 0],
+                          [0, 0, self.far * recip, -self.near * self.far * recip], [0, 0, 1, 0]], dtype=np.float64)
+        tr = np.eye(4); tr[0, 3] = -1.0; tr[1, 3] = -1.0 / aspect
+        sc = np.diag([-0.5, -0.5 * aspect, 1.0, 1.0])
+        cam_to_sample = sc @ tr @ persp
+        return np.linalg.inv(cam_to_sample).astype(np.float32)
+
+
+@dataclass
+class RenderParams:
+    """Integrator / sampler / film properties on the path (reference defaults)."""
+    spp: int = 4                        # sobol.cpp:88 sampleCount
+    sampler: str = "sobol"              # "sobol" | "independent"
+    seed: int = 0                       # sobol `scramble`; independent stream seed
+    max_depth: int = -1                 # integrator.cpp:199
+    rr_depth: int = 5                   # integrator.cpp:193
+    strict_normals: bool = False
+    hide_emitters: bool = False
+    rfilter: str = "gaussian"           # film.cpp:89-95 default
+    rfilter_param: float = 0.5          # box: radius; gaussian: stddev
+    sample_lo: int = 0                  # shard: sample indices [lo,hi) of every pixel
+    sample_hi: int = 0                  # 0 -> spp
+
+
+@dataclass
+class SceneDesc:
+    meshes: List[Mesh] = field(default_factory=list)
+    camera: Optional[Camera] = None
+
+    def flat_bsdfs(self):
+        """Flatten the BSDF tree to an array (nested referenced by index); returns (list, per-mesh id)."""
+        out, ids, memo = [], [], {}
+
+        def add(b: Bsdf) -> int:
+            if id(b) in memo:
+                return memo[id(b)]
+            d = b.flat()
+            if b.type == "coating":
+                if b.nested is None:
+                    raise ValueError("coating: A child BSDF instance is required")  # coating.cpp:157-158
+                d["nested"] = add(b.nested)
+            out.append(d)
+            memo[id(b)] = len(out) - 1
+            return memo[id(b)]
+
+        for m in self.meshes:
+            b = m.bsdf
+            if b is None:  # shape.cpp:48-72
+                b = Bsdf("diffuse", reflectance=(0.0,) * 3 if m.radiance is not None else (0.5,) * 3)
+                m.bsdf = b
+            ids.append(add(b))
+        return out, ids
+
+    def n_triangles(self) -> int:
+        return int(sum(len(m.idx) for m in self.meshes))
+
+
+def look_at(origin, target, up) -> np.ndarray:
+    """src/libcore/transform.cpp:191-214 Transform::lookAt (camera-to-world)."""
+    p = np.asarray(origin, np.float64); t = np.asarray(target, np.float64); u = np.asarray(up, np.float64)
+    d = t - p; d /= np.linalg.norm(d)
+    left = np.cross(u, d); left /= np.linalg.norm(left)
+    new_up = np.cross(d, left)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = left, new_up, d, p
+    return m.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic scenes.  cbox.xml is not in the reference tree; S1 is authored
+# from the classic Cornell measurements.
+# ------------------------------------------------------------------------------------------------
+
+def _quad(verts, facing=None):
+    """Two triangles (0,1,2),(0,2,3); flip winding so the face normal has positive dot with `facing`."""
+    P = np.asarray(verts, np.float32)
+    idx = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    if facing is not None:
+        n = np.cross(P[1] - P[0], P[2] - P[0])
+        if np.dot(n, np.asarray(facing, np.float32)) < 0:
+            idx = idx[:, ::-1].copy()
+    return P, idx
+
+
+def _merge(parts):
+    Ps, Is, off = [], [], 0
+    for P, I in parts:
+        Ps.append(P); Is.append(I + off); off += len(P)
+    return np.concatenate(Ps).astype(np.float32), np.concatenate(Is).astype(np.uint32)
+
+
+def cornell_box(width=1024, height=1024) -> SceneDesc:
+    """S1: 5 walls + short box + tall box + ceiling light = 32 triangles in the 556-unit Cornell cube."""
+    white = Bsdf("diffuse", reflectance=(0.73, 0.73, 0.73))
+    red = Bsdf("diffuse", reflectance=(0.63, 0.065, 0.05))
+    green = Bsdf("diffuse", reflectance=(0.14, 0.45, 0.091))
+    light_bsdf = Bsdf("diffuse", reflectance=(0.78, 0.78, 0.78))
+    meshes = []
+    floor = _quad([(552.8, 0, 0), (0, 0, 0), (0, 0, 559.2), (549.6, 0, 559.2)], (0, 1, 0))
+    ceil = _quad([(556, 548.8, 0), (556, 548.8, 559.2), (0, 548.8, 559.2), (0, 548.8, 0)], (0, -1, 0))
+    back = _quad([(549.6, 0, 559.2), (0, 0, 559.2), (0, 548.8, 559.2), (556, 548.8, 559.2)], (0, 0, -1))
+    P, I = _merge([floor, ceil, back])
+    meshes.append(Mesh(P, I, bsdf=white, name="walls"))
+    P, I = _quad([(0, 0, 559.2), (0, 0, 0), (0, 548.8, 0), (0, 548.8, 559.2)], (1, 0, 0))
+    meshes.append(Mesh(P, I, bsdf=green, name="right"))
+    P, I = _quad([(552.8, 0, 0), (549.6, 0, 559.2), (556, 548.8, 559.2), (556, 548.8, 0)], (-1, 0, 0))
+    meshes.append(Mesh(P, I, bsdf=red, name="left"))
+
+    def block(top, h):
+        top = [np.array(v, np.float32) for v in top]
+        c = np.mean(top, axis=0); c[1] = h / 2
+        parts = [_quad(top, (0, 1, 0))]
+        for i in range(4):
+            a, b = top[i], top[(i + 1) % 4]
+            q = [(a[0], 0, a[2]), (a[0], h, a[2]), (b[0], h, b[2]), (b[0], 0, b[2])]
+            mid = (np.array(q[0]) + np.array(q[2])) / 2
+            parts.append(_quad(q, mid - c))
+        return _merge(parts)
+
+    P, I = block([(130, 165, 65), (82, 165, 225), (240, 165, 272), (290, 165, 114)], 165)
+    meshes.append(Mesh(P, I, bsdf=white, name="short"))
+    P, I = block([(423, 330, 247), (265, 330, 296), (314, 330, 456), (472, 330, 406)], 330)
+    meshes.append(Mesh(P, I, bsdf=white, name="tall"))
+    # light strictly below the ceiling (no coplanar overlap, SURVEY Appendix A tie-breaking)
+    P, I = _quad([(343, 548.3, 227), (343, 548.3, 332), (213, 548.3, 332), (213, 548.3, 227)], (0, -1, 0))
+    meshes.append(Mesh(P, I, bsdf=light_bsdf, radiance=(17.0, 12.0, 4.0), name="light"))
+    cam = Camera(look_at((278, 273, -800), (278, 273, 0), (0, 1, 0)), fov=39.3077, near=10.0, far=2800.0,
+                 width=width, height=height)
+    return SceneDesc(meshes, cam)
+
+
+def uv_sphere(center, radius, n_theta=64, n_phi=128, smooth=True, with_uv=False):
+    """Latitude/longitude sphere; returns (P, N, UV, idx) with outward winding."""
+    c = np.asarray(center, np.float64)
+    th = np.linspace(0, math.pi, n_theta + 1)
+    ph = np.linspace(0, 2 * math.pi, n_phi + 1)
+    T, Ph = np.meshgrid(th, ph, indexing="ij")
+    D = np.stack([np.sin(T) * np.cos(Ph), np.cos(T), np.sin(T) * np.sin(Ph)], -1).reshape(-1, 3)
+    P = (c + radius * D).astype(np.float32)
+    N = D.astype(np.float32) if smooth else None
+    UV = np.stack([Ph / (2 * math.pi), T / math.pi], -1).reshape(-1, 2).astype(np.float32) if with_uv else None
+    idx = []
+    W = n_phi + 1
+    for i in range(n_theta):
+        for j in range(n_phi):
+            a, b, c2, d = i * W + j, i * W + j + 1, (i + 1) * W + j + 1, (i + 1) * W + j
+            if i != 0:
+                idx.append((a, b, c2))
+            if i != n_theta - 1:
+                idx.append((a, c2, d))
+    idx = np.array(idx, np.uint32)
+    # make winding outward
+    n = np.cross(P[idx[:, 1]] - P[idx[:, 0]], P[idx[:, 2]] - P[idx[:, 0]])
+    cen = P[idx].mean(1) - c.astype(np.float32)
+    flip = (n * cen).sum(1) < 0
+    idx[flip] = idx[flip][:, ::-1]
+    return P, N, UV, idx
+
+
+def material_ball(bsdf: Bsdf, width=1024, height=1024, n_theta=200, n_phi=200) -> SceneDesc:
+    """S2: UV sphere (~80k triangles at 200x200) on a diffuse ground quad under one area light."""
+    ground = Bsdf("diffuse", reflectance=(0.5, 0.5, 0.5))
+    P, I = _quad([(-8, 0, -8), (-8, 0, 8), (8, 0, 8), (8, 0, -8)], (0, 1, 0))
+    meshes = [Mesh(P, I, bsdf=ground, name="ground")]
+    P, N, UV, I = uv_sphere((0, 1.0, 0), 1.0, n_theta, n_phi, smooth=True)
+    meshes.append(Mesh(P, I, N=N, bsdf=bsdf, name="ball"))
+    P, I = _quad([(-1.5, 4.0, -1.5), (-1.5, 4.0, 1.5), (1.5, 4.0, 1.5), (1.5, 4.0, -1.5)], (0, -1, 0))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(20.0, 20.0, 20.0), name="light"))
+    P, I = _quad([(-8, 0, 8), (-8, 8, 8), (8, 8, 8), (8, 0, 8)], (0, 0, -1))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0.4, 0.45, 0.6)), name="backdrop"))
+    cam = Camera(look_at((0, 2.2, -5.0), (0, 0.9, 0), (0, 1, 0)), fov=35.0, near=0.1, far=100.0,
+                 width=width, height=height)
+    return SceneDesc(meshes, cam)
+
+
+def stress_scene(n_instances=100, n_theta=224, n_phi=224, width=2048, height=2048, seed=7) -> SceneDesc:
+    """S3: one ~100k-triangle bumpy sphere instanced on a jittered grid, flattened (config 5 class)."""
+    rng = np.random.default_rng(seed)
+    P0, N0, _, I0 = uv_sphere((0, 0, 0), 1.0, n_theta, n_phi, smooth=True)
+    bump = 1.0 + 0.08 * np.sin(9 * P0[:, 0]) * np.sin(7 * P0[:, 1]) * np.sin(11 * P0[:, 2])
+    P0 = (P0 * bump[:, None]).astype(np.float32)
+    g = int(math.ceil(math.sqrt(n_instances)))
+    mats = [Bsdf("diffuse", reflectance=tuple(rng.uniform(0.2, 0.8, 3))) for _ in range(8)]
+    meshes = []
+    for k in range(n_instances):
+        gx, gz = k % g, k // g
+        s = rng.uniform(0.7, 1.1)
+        t = np.array([(gx - g / 2 + 0.5) * 2.6 + rng.uniform(-0.3, 0.3), s * 1.0, (gz - g / 2 + 0.5) * 2.6 + rng.uniform(-0.3, 0.3)])
+        meshes.append(Mesh((P0 * s + t).astype(np.float32), I0.copy(), N=N0, bsdf=mats[k % 8], name=f"inst{k}"))
+    e = g * 1.6 + 2
+    P, I = _quad([(-e, 0, -e), (-e, 0, e), (e, 0, e), (e, 0, -e)], (0, 1, 0))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0.6, 0.6, 0.6)), name="ground"))
+    P, I = _quad([(-e / 2, 9.0, -e / 2), (-e / 2, 9.0, e / 2), (e / 2, 9.0, e / 2), (e / 2, 9.0, -e / 2)], (0, -1, 0))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(6.0, 6.0, 6.0), name="light"))
+    cam = Camera(look_at((0, e * 0.9, -e * 1.5), (0, 0.5, 0), (0, 1, 0)), fov=45.0, near=0.1, far=1000.0,
+                 width=width, height=height)
+    return SceneDesc(meshes, cam)

@@ -1,0 +1,725 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.h header; parity status: image level "unpinned").
+ *
+ * CPU restatement of the Mitsuba 0.6 `path` integrator hot path:
+ *   a1  MIPathTracer::Li                    src/integrators/path/path.cpp:119-300
+ *   a2  SamplingIntegrator::renderBlock     src/librender/integrator.cpp:140-188
+ *   a3-a5 ray queries                       orc_accel.h
+ *   a6  fillIntersectionRecord<true>        include/mitsuba/render/skdtree.h:343-428
+ *   a7-a8 BSDFs / microfacet                orc_bsdf.h
+ *   a9  Scene::sampleEmitterDirect          src/librender/scene.cpp:828-852,949-952
+ *   a10 AreaLight / Shape / TriMesh / Triangle sampling
+ *                                           src/emitters/area.cpp:104-183, src/librender/shape.cpp:102-126,
+ *                                           src/librender/trimesh.cpp:358-424, src/libcore/triangle.cpp:24-62
+ *   a11 samplers                            orc_sampler.h
+ *   a12 perspective sensor                  src/sensors/perspective.cpp:271-298
+ *   a13 ImageBlock::put + filter table      include/mitsuba/render/imageblock.h:124-204, src/libcore/rfilter.cpp:37-57
+ *   a14 film merge / develop                include/mitsuba/render/imageblock.h:103-107, src/libcore/fmtconv.cpp:955-990
+ * Exposed as a flat C API for ctypes (oracle/oracle_api.py).                                            */
+#include "orc_math.h"
+#include "orc_sampler.h"
+#include "orc_accel.h"
+#include "orc_bsdf.h"
+#include <thread>
+#include <atomic>
+#include <mutex>
+#include <memory>
+#include <cstdio>
+
+using namespace orc;
+
+extern "C" {
+typedef struct OrcRenderParams {
+    int32_t spp;
+    int32_t sampler;        /* 0 sobol, 1 independent (SFMT, thread-order dependent), 2 counter-based TEA */
+    uint64_t seed;          /* sobol: `scramble` property; others: seed */
+    int32_t maxDepth, rrDepth, strictNormals, hideEmitters; /* integrator.cpp:190-225 */
+    int32_t rfilter;        /* 0 box, 1 gaussian */
+    float rfilterParam;     /* box: radius property (0.5); gaussian: stddev (0.5) */
+    int32_t sampleLo, sampleHi; /* render sample indices [lo,hi) of every pixel (multi-GPU sharding mirror); hi<=0 -> spp */
+    int32_t threads;        /* 0 -> hardware_concurrency */
+    int32_t blockSize;      /* scene.cpp:24 default 32 */
+} OrcRenderParams;
+typedef struct OrcStats {
+    uint64_t samples, rays, shadowRays, pathLengthSum, nodeVisits, primTests, badSamples, dimOverflow;
+} OrcStats;
+}
+
+namespace {
+
+struct Mesh {
+    std::vector<V3> P, N; std::vector<float> UV; /* UV: 2 per vertex */
+    std::vector<uint32_t> idx; /* 3 per triangle */
+    std::vector<V3> dpdu;      /* per triangle, only if UVs exist (trimesh.cpp:683-735) */
+    std::vector<uint8_t> hasTangent;
+    int bsdf = -1; int emitter = -1;
+    uint32_t primOffset = 0;
+    /* area sampling: trimesh.cpp:388-403 + pmf.h */
+    std::vector<float> cdf; float surfaceArea = -1, invSurfaceArea = 0;
+    uint32_t nTri() const { return (uint32_t) (idx.size() / 3); }
+};
+
+/* include/mitsuba/core/pmf.h:60-187 */
+struct Discrete {
+    std::vector<float> cdf{0.0f}; float sum = 0, normalization = 0;
+    void append(float v) { cdf.push_back(cdf.back() + v); }
+    float normalize() {
+        sum = cdf.back();
+        if (sum > 0) {
+            normalization = 1.0f / sum;
+            for (size_t i = 1; i < cdf.size(); ++i) cdf[i] *= normalization;
+            cdf.back() = 1.0f;
+        } else normalization = 0.0f;
+        return sum;
+    }
+    float operator[](size_t i) const { return cdf[i + 1] - cdf[i]; }
+    size_t sample(float v) const {
+        auto entry = std::lower_bound(cdf.begin(), cdf.end(), v);
+        size_t index = std::min(cdf.size() - 2, (size_t) std::max((ptrdiff_t) 0, (ptrdiff_t) (entry - cdf.begin()) - 1));
+        while ((*this)[index] == 0 && index < cdf.size() - 1) ++index;
+        return index;
+    }
+    size_t sampleReuse(float &v) const {
+        size_t index = sample(v);
+        v = (v - cdf[index]) / (cdf[index + 1] - cdf[index]);
+        return index;
+    }
+    size_t sampleReuse(float &v, float &pdf) const {
+        size_t index = sample(v);
+        pdf = (*this)[index];
+        v = (v - cdf[index]) / (cdf[index + 1] - cdf[index]);
+        return index;
+    }
+};
+
+struct Emitter { V3 radiance; float samplingWeight; int mesh; };
+
+struct Intersection { /* include/mitsuba/render/shape.h:131-171 (fields `path` reads) */
+    float t = kInf; V3 p; Frame geoFrame, shFrame; V3 wi; V3 dpdu; int mesh = -1; uint32_t prim = 0;
+    bool isValid() const { return t != kInf; }
+};
+
+struct DRec { /* include/mitsuba/render/common.h:85-123,241-255 */
+    V3 p, n, ref, refN, d; float pdf = 0, dist = 0; int emitter = -1; bool solidAngle = true;
+};
+
+struct Scene {
+    std::vector<OrcBsdf> bsdfs;
+    std::vector<Mesh> meshes;
+    std::vector<Emitter> emitters;
+    std::vector<uint32_t> primMesh; /* prim -> mesh (m_shapeMap) */
+    Accel accel;
+    Discrete emitterPDF;
+    SobolTables sobol;
+    /* camera */
+    float camToWorld[16], sampleToCamera[16]; float nearClip = 1e-2f, farClip = 1e4f; int W = 0, H = 0;
+    V3 camOrigin;
+
+    void commit(bool tree) {
+        accel.tri.clear(); accel.triBox.clear(); primMesh.clear();
+        for (size_t mi = 0; mi < meshes.size(); ++mi) {
+            Mesh &m = meshes[mi];
+            m.primOffset = (uint32_t) accel.tri.size();
+            for (uint32_t j = 0; j < m.nTri(); ++j) {
+                const V3 &v0 = m.P[m.idx[3 * j]], &v1 = m.P[m.idx[3 * j + 1]], &v2 = m.P[m.idx[3 * j + 2]];
+                TriAccel ta; memset(&ta, 0, sizeof(ta));
+                ta.load(v0, v1, v2);                 /* skdtree.cpp:88-94 */
+                ta.shapeIndex = (uint32_t) mi; ta.primIndex = j;
+                accel.tri.push_back(ta);
+                AABB b; b.expandBy(v0); b.expandBy(v1); b.expandBy(v2);
+                accel.triBox.push_back(b);
+                primMesh.push_back((uint32_t) mi);
+            }
+            /* trimesh.cpp:683-735 computeUVTangents (called unconditionally at :385) */
+            m.dpdu.clear(); m.hasTangent.clear();
+            if (!m.UV.empty()) {
+                m.dpdu.resize(m.nTri()); m.hasTangent.assign(m.nTri(), 1);
+                for (uint32_t j = 0; j < m.nTri(); ++j) {
+                    uint32_t i0 = m.idx[3 * j], i1 = m.idx[3 * j + 1], i2 = m.idx[3 * j + 2];
+                    V3 dP1 = m.P[i1] - m.P[i0], dP2 = m.P[i2] - m.P[i0];
+                    float du1 = m.UV[2 * i1] - m.UV[2 * i0], dv1 = m.UV[2 * i1 + 1] - m.UV[2 * i0 + 1];
+                    float du2 = m.UV[2 * i2] - m.UV[2 * i0], dv2 = m.UV[2 * i2 + 1] - m.UV[2 * i0 + 1];
+                    V3 n = cross(dP1, dP2);
+                    float length = n.length();
+                    if (length == 0) { m.dpdu[j] = V3(0.0f); continue; } /* memset-zero tangent, :695 */
+                    float determinant = du1 * dv2 - dv1 * du2;
+                    if (determinant == 0) {
+                        V3 a, b; coordinateSystem(n / length, a, b); m.dpdu[j] = a;
+                    } else {
+                        float invDet = 1.0f / determinant;
+                        m.dpdu[j] = (dv2 * dP1 - dv1 * dP2) * invDet;
+                    }
+                }
+            }
+            /* trimesh.cpp:388-403 prepareSamplingTable (only emitters need it) */
+            if (m.emitter >= 0) {
+                Discrete dd;
+                for (uint32_t j = 0; j < m.nTri(); ++j) {
+                    V3 sideA = m.P[m.idx[3 * j + 1]] - m.P[m.idx[3 * j]], sideB = m.P[m.idx[3 * j + 2]] - m.P[m.idx[3 * j]];
+                    dd.append(0.5f * cross(sideA, sideB).length()); /* triangle.cpp:64-70 */
+                }
+                m.surfaceArea = dd.normalize();
+                m.invSurfaceArea = 1.0f / m.surfaceArea;
+                m.cdf = dd.cdf;
+            }
+        }
+        accel.build(tree);
+        /* scene.cpp:375-380 */
+        emitterPDF = Discrete();
+        for (auto &e : emitters) emitterPDF.append(e.samplingWeight);
+        if (!emitters.empty()) emitterPDF.normalize();
+        camOrigin = V3(camToWorld[3], camToWorld[7], camToWorld[11]); /* trafo.transformAffine(Point(0)) */
+    }
+
+    /* skdtree.h:343-428 fillIntersectionRecord<true> for triangle meshes */
+    void fill(const Ray &ray, const Hit &h, Intersection &its) const {
+        const uint32_t mi = accel.tri[h.prim].shapeIndex, pi = accel.tri[h.prim].primIndex;
+        const Mesh &m = meshes[mi];
+        const V3 b(1 - h.u - h.v, h.u, h.v);
+        const uint32_t i0 = m.idx[3 * pi], i1 = m.idx[3 * pi + 1], i2 = m.idx[3 * pi + 2];
+        const V3 &p0 = m.P[i0], &p1 = m.P[i1], &p2 = m.P[i2];
+        its.t = h.t;
+        its.p = p0 * b.x + p1 * b.y + p2 * b.z;
+        V3 side1(p1 - p0), side2(p2 - p0);
+        V3 faceNormal(cross(side1, side2));
+        float length = faceNormal.length();
+        if (!faceNormal.isZero()) faceNormal /= length;
+        if (!m.dpdu.empty()) its.dpdu = m.dpdu[pi]; else its.dpdu = side1;
+        if (!m.N.empty()) {
+            const V3 &n0 = m.N[i0], &n1 = m.N[i1], &n2 = m.N[i2];
+            its.shFrame.n = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
+            if (dot(faceNormal, its.shFrame.n) < 0) faceNormal = -faceNormal;
+        } else its.shFrame.n = faceNormal;
+        its.geoFrame = Frame(faceNormal);
+        its.mesh = (int) mi; its.prim = pi;
+        computeShadingFrame(its.shFrame.n, its.dpdu, its.shFrame);
+        its.wi = its.shFrame.toLocal(-ray.d);
+    }
+
+    /* area.cpp:104-109 */
+    Spectrum emitterEval(int e, const Intersection &its, const V3 &d) const {
+        if (dot(its.shFrame.n, d) <= 0) return Spectrum(0.0f);
+        return emitters[e].radiance;
+    }
+    /* scene.cpp:828-852 with testVisibility=true; returns value, fills dRec; `occl` counts shadow rays */
+    Spectrum sampleEmitterDirect(DRec &dRec, float sx, float sy, OrcStats &st) const {
+        float emPdf;
+        size_t index = emitterPDF.sampleReuse(sx, emPdf);
+        const Emitter &em = emitters[index];
+        const Mesh &m = meshes[em.mesh];
+        /* area.cpp:158-173 -> shape.cpp:102-115 -> trimesh.cpp:412-424 -> triangle.cpp:24-62 */
+        {
+            Discrete dd; dd.cdf = m.cdf;
+            size_t ti = dd.sampleReuse(sy);
+            const V3 &p0 = m.P[m.idx[3 * ti]], &p1 = m.P[m.idx[3 * ti + 1]], &p2 = m.P[m.idx[3 * ti + 2]];
+            float bx, by;
+            squareToUniformTriangle(sx, sy, bx, by);
+            V3 sideA = p1 - p0, sideB = p2 - p0;
+            dRec.p = p0 + (sideA * bx) + (sideB * by);
+            if (!m.N.empty()) {
+                const V3 &n0 = m.N[m.idx[3 * ti]], &n1 = m.N[m.idx[3 * ti + 1]], &n2 = m.N[m.idx[3 * ti + 2]];
+                dRec.n = normalize(n0 * (1.0f - bx - by) + n1 * bx + n2 * by);
+            } else dRec.n = normalize(cross(sideA, sideB));
+            dRec.pdf = m.invSurfaceArea;
+        }
+        dRec.d = dRec.p - dRec.ref;
+        float distSquared = dRec.d.lengthSquared();
+        dRec.dist = std::sqrt(distSquared);
+        dRec.d /= dRec.dist;
+        float dp = absDot(dRec.d, dRec.n);
+        dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0f;
+        dRec.solidAngle = true;
+        Spectrum value;
+        if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = em.radiance / dRec.pdf;
+        else { dRec.pdf = 0.0f; value = Spectrum(0.0f); }
+        if (dRec.pdf != 0) {
+            Ray ray(dRec.ref, dRec.d, kEpsilon, dRec.dist * (1 - kShadowEpsilon));
+            ++st.shadowRays;
+            if (accel.rayOccluded(ray, &st.nodeVisits, &st.primTests)) return Spectrum(0.0f);
+            dRec.emitter = (int) index;
+            dRec.pdf *= emPdf;
+            value /= emPdf;
+            return value;
+        }
+        return Spectrum(0.0f);
+    }
+    /* scene.cpp:949-952; scene.h:848-850; area.cpp:175-183; shape.cpp:117-126; trimesh.cpp:358-360 */
+    float pdfEmitterDirect(const DRec &dRec) const {
+        const Emitter &em = emitters[dRec.emitter];
+        float pdfDirect = 0.0f;
+        if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
+            float pdfPos = meshes[em.mesh].invSurfaceArea;
+            pdfDirect = pdfPos * (dRec.dist * dRec.dist) / absDot(dRec.d, dRec.n);
+        }
+        return pdfDirect * (em.samplingWeight * emitterPDF.normalization);
+    }
+
+    static float miWeight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); }
+
+    bool rayIntersect(const Ray &ray, Intersection &its, OrcStats &st) const {
+        Hit h; ++st.rays;
+        its.t = kInf;
+        if (accel.rayIntersect(ray, h, &st.nodeVisits, &st.primTests)) { fill(ray, h, its); return true; }
+        return false;
+    }
+
+    /* path.cpp:119-294.  `alpha` mirrors RadianceQueryRecord::rayIntersect (records.inl:117-144). */
+    Spectrum Li(const Ray &r, Sampler *sampler, const OrcRenderParams &rp, float &alpha, OrcStats &st) const {
+        BsdfSet bs{bsdfs.data(), (int) bsdfs.size()};
+        Intersection its;
+        Ray ray(r);
+        Spectrum Li(0.0f);
+        bool scattered = false;
+        int depth = 1;                          /* newQuery: depth = 1 (integrator.h:221-227) */
+        bool emittedRadiance = true;            /* ERadiance has EEmittedRadiance until path.cpp:274 */
+        rayIntersect(ray, its, st);
+        alpha = its.isValid() ? 1.0f : 0.0f;
+        ray.mint = kEpsilon;
+        Spectrum throughput(1.0f);
+        float eta = 1.0f;
+        const int maxDepth = rp.maxDepth, rrDepth = rp.rrDepth;
+        while (depth <= maxDepth || maxDepth < 0) {
+            if (!its.isValid()) break;          /* no environment emitter in scope */
+            const Mesh &mesh = meshes[its.mesh];
+            const int bsdf = mesh.bsdf;
+            if (mesh.emitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered))
+                Li += throughput * emitterEval(mesh.emitter, its, -ray.d);
+            if ((depth >= maxDepth && maxDepth > 0) ||
+                (rp.strictNormals && dot(ray.d, its.geoFrame.n) * Frame::cosTheta(its.wi) >= 0))
+                break;
+            const uint32_t btype = bs.type(bsdf);
+            /* DirectSamplingRecord(its): records.inl:156-164 */
+            DRec dRec;
+            dRec.ref = its.p; dRec.refN = V3(0.0f);
+            if ((btype & (ETransmission | EBackSide)) == 0) dRec.refN = its.shFrame.n;
+            if (!emitters.empty() && (btype & ESmooth)) {
+                float sx, sy; sampler->next2D(sx, sy);
+                Spectrum value = sampleEmitterDirect(dRec, sx, sy, st);
+                if (!value.isZero()) {
+                    BRec bRec; bRec.wi = its.wi; bRec.wo = its.shFrame.toLocal(dRec.d); bRec.sampler = sampler;
+                    const Spectrum bsdfVal = bs.eval(bsdf, bRec);
+                    if (!bsdfVal.isZero() && (!rp.strictNormals || dot(its.geoFrame.n, dRec.d) * Frame::cosTheta(bRec.wo) > 0)) {
+                        float bsdfPdf = bs.pdf(bsdf, bRec); /* area emitter: onSurface && solid angle */
+                        float weight = miWeight(dRec.pdf, bsdfPdf);
+                        Li += throughput * value * bsdfVal * weight;
+                    }
+                }
+            } else if (emitters.empty() && (btype & ESmooth)) {
+                /* scene without emitters: reference would still draw the 2D sample; sampleReuse on an
+                   empty PMF is undefined there -- not a supported configuration */
+            }
+            float bsdfPdf;
+            BRec bRec; bRec.wi = its.wi; bRec.sampler = sampler;
+            float sx, sy; sampler->next2D(sx, sy);
+            Spectrum bsdfWeight = bs.sample(bsdf, bRec, bsdfPdf, sx, sy);
+            if (bsdfWeight.isZero()) break;
+            scattered |= bRec.sampledType != ENull;
+            const V3 wo = its.shFrame.toWorld(bRec.wo);
+            float woDotGeoN = dot(its.geoFrame.n, wo);
+            if (rp.strictNormals && woDotGeoN * Frame::cosTheta(bRec.wo) <= 0) break;
+            bool hitEmitter = false;
+            Spectrum value;
+            ray = Ray(its.p, wo);
+            if (rayIntersect(ray, its, st)) {
+                const Mesh &m2 = meshes[its.mesh];
+                if (m2.emitter >= 0) {
+                    value = emitterEval(m2.emitter, its, -ray.d);
+                    /* dRec.setQuery(ray, its): records.inl:171-179 */
+                    dRec.p = its.p; dRec.n = its.shFrame.n; dRec.solidAngle = true; dRec.emitter = m2.emitter;
+                    dRec.d = ray.d; dRec.dist = its.t;
+                    hitEmitter = true;
+                }
+            } else break; /* no environment */
+            throughput *= bsdfWeight;
+            eta *= bRec.eta;
+            if (hitEmitter) {
+                const float lumPdf = (!(bRec.sampledType & EDelta)) ? pdfEmitterDirect(dRec) : 0;
+                Li += throughput * value * miWeight(bsdfPdf, lumPdf);
+            }
+            if (!its.isValid()) break;
+            emittedRadiance = false;            /* rRec.type = ERadianceNoEmission */
+            if (depth++ >= rrDepth) {
+                float q = std::min(throughput.max() * eta * eta, 0.95f);
+                if (sampler->next1D() >= q) break;
+                throughput /= q;
+            }
+        }
+        st.pathLengthSum += (uint64_t) depth;
+        return Li;
+    }
+
+    /* perspective.cpp:271-298 (ray part only; differentials unused by constant textures) */
+    Ray sampleRay(float sxp, float syp) const {
+        const float *M = sampleToCamera;
+        float px = sxp * (1.0f / (float) W), py = syp * (1.0f / (float) H), pz = 0.0f; /* m_invResolution, sensor.cpp:104-107 */
+        float x = M[0] * px + M[1] * py + M[2] * pz + M[3];
+        float y = M[4] * px + M[5] * py + M[6] * pz + M[7];
+        float z = M[8] * px + M[9] * py + M[10] * pz + M[11];
+        float w = M[12] * px + M[13] * py + M[14] * pz + M[15];
+        V3 nearP(x, y, z);
+        if (w != 1.0f) nearP = nearP / w;       /* transform.h:108-125 */
+        V3 d = normalize(nearP);
+        float invZ = 1.0f / d.z;
+        const float *T = camToWorld;
+        V3 dw(T[0] * d.x + T[1] * d.y + T[2] * d.z, T[4] * d.x + T[5] * d.y + T[6] * d.z, T[8] * d.x + T[9] * d.y + T[10] * d.z);
+        return Ray(camOrigin, dw, nearClip * invZ, farClip * invZ);
+    }
+};
+
+/* src/libcore/rfilter.cpp:37-57 + rfilters/{box,gaussian}.cpp */
+struct RFilter {
+    float radius, values[32], scaleFactor; int borderSize;
+    RFilter(int kind, float param) {
+        float stddev = param;
+        if (kind == 0) radius = param + 1e-5f;          /* box.cpp:41 */
+        else radius = 4 * stddev;                        /* gaussian.cpp:38 */
+        float sum = 0.0f;
+        for (int i = 0; i < 31; ++i) {
+            float x = (radius * i) / 31, value;
+            if (kind == 0) value = std::abs(x) <= radius ? 1.0f : 0.0f;
+            else {
+                float alpha = -1.0f / (2.0f * stddev * stddev);
+                value = std::max(0.0f, fastexp(alpha * x * x) - fastexp(alpha * radius * radius));
+            }
+            values[i] = value; sum += value;
+        }
+        values[31] = 0.0f;
+        scaleFactor = 31 / radius;
+        borderSize = (int) std::ceil(radius - 0.5f);
+        sum *= 2 * radius / 31;
+        float normalization = 1.0f / sum;
+        for (int i = 0; i < 31; ++i) values[i] *= normalization;
+    }
+    float evalDiscretized(float x) const { return values[std::min((int) std::abs(x * scaleFactor), 31)]; }
+};
+
+/* imageblock.h: a block of (size + 2*border)^2 x 5 floats */
+struct ImageBlock {
+    int ox, oy, sx, sy, border; std::vector<float> data; const RFilter *f;
+    int bw() const { return sx + 2 * border; }
+    int bh() const { return sy + 2 * border; }
+    ImageBlock(int ox_, int oy_, int sx_, int sy_, const RFilter *f_) : ox(ox_), oy(oy_), sx(sx_), sy(sy_), border(f_->borderSize), f(f_) {
+        data.assign((size_t) bw() * bh() * 5, 0.0f);
+    }
+    /* imageblock.h:124-204 */
+    bool put(float px, float py, const Spectrum &spec, float alpha) {
+        float value[5] = {spec.x, spec.y, spec.z, alpha, 1.0f};
+        for (int i = 0; i < 5; ++i)
+            if (!std::isfinite(value[i]) || value[i] < 0) return false;
+        const float filterRadius = f->radius;
+        const int sizeX = bw(), sizeY = bh();
+        const float posx = px - 0.5f - (ox - border), posy = py - 0.5f - (oy - border);
+        const int minx = std::max((int) std::ceil(posx - filterRadius), 0), miny = std::max((int) std::ceil(posy - filterRadius), 0),
+                  maxx = std::min((int) std::floor(posx + filterRadius), sizeX - 1), maxy = std::min((int) std::floor(posy + filterRadius), sizeY - 1);
+        float wX[64], wY[64]; /* m_weightsX/Y: 2*ceil(radius)+1 entries; radius <= 31 here */
+        for (int x = minx, i = 0; x <= maxx; ++x) wX[i++] = f->evalDiscretized(x - posx);
+        for (int y = miny, i = 0; y <= maxy; ++y) wY[i++] = f->evalDiscretized(y - posy);
+        for (int y = miny, yr = 0; y <= maxy; ++y, ++yr) {
+            const float weightY = wY[yr];
+            float *dest = data.data() + ((size_t) y * sizeX + minx) * 5;
+            for (int x = minx, xr = 0; x <= maxx; ++x, ++xr) {
+                const float weight = wX[xr] * weightY;
+                for (int k = 0; k < 5; ++k) *dest++ += weight * value[k];
+            }
+        }
+        return true;
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+void *orc_scene_new() { return new Scene(); }
+void orc_scene_free(void *s) { delete (Scene *) s; }
+void orc_set_sobol_tables(void *s, const uint32_t *m32, const uint64_t *vdc, const uint64_t *inv) {
+    Scene *sc = (Scene *) s; sc->sobol.m32 = m32; sc->sobol.vdc = vdc; sc->sobol.inv = inv;
+}
+int orc_add_bsdf(void *s, const OrcBsdf *b) { Scene *sc = (Scene *) s; sc->bsdfs.push_back(*b); return (int) sc->bsdfs.size() - 1; }
+int orc_add_mesh(void *s, const float *P, const float *N, const float *UV, uint32_t nV, const uint32_t *idx, uint32_t nT,
+                 int bsdf, const float *radiance, float samplingWeight) {
+    Scene *sc = (Scene *) s;
+    Mesh m;
+    m.P.resize(nV);
+    for (uint32_t i = 0; i < nV; ++i) m.P[i] = V3(P[3 * i], P[3 * i + 1], P[3 * i + 2]);
+    if (N) { m.N.resize(nV); for (uint32_t i = 0; i < nV; ++i) m.N[i] = V3(N[3 * i], N[3 * i + 1], N[3 * i + 2]); }
+    if (UV) m.UV.assign(UV, UV + 2 * nV);
+    m.idx.assign(idx, idx + 3 * nT);
+    m.bsdf = bsdf;
+    if (radiance) {
+        Emitter e; e.radiance = V3(radiance[0], radiance[1], radiance[2]); e.samplingWeight = samplingWeight;
+        e.mesh = (int) sc->meshes.size();
+        m.emitter = (int) sc->emitters.size();
+        sc->emitters.push_back(e);
+    }
+    sc->meshes.push_back(std::move(m));
+    return (int) sc->meshes.size() - 1;
+}
+void orc_set_camera(void *s, const float *camToWorld, const float *sampleToCamera, float nearClip, float farClip, int W, int H) {
+    Scene *sc = (Scene *) s;
+    memcpy(sc->camToWorld, camToWorld, 64); memcpy(sc->sampleToCamera, sampleToCamera, 64);
+    sc->nearClip = nearClip; sc->farClip = farClip; sc->W = W; sc->H = H;
+}
+void orc_commit(void *s, int useTree) { ((Scene *) s)->commit(useTree != 0); }
+void orc_accel_info(void *s, uint64_t *out /* nTri, nNodes, nIndices, nLeaves, maxDepth */, float *aabb6) {
+    Scene *sc = (Scene *) s;
+    out[0] = sc->accel.tri.size(); out[1] = sc->accel.nodes.size(); out[2] = sc->accel.indices.size();
+    out[3] = sc->accel.nLeaves; out[4] = (uint64_t) sc->accel.maxDepth;
+    for (int i = 0; i < 3; ++i) { aabb6[i] = sc->accel.aabb.min[i]; aabb6[3 + i] = sc->accel.aabb.max[i]; }
+}
+void orc_get_triaccel(void *s, void *out48) { Scene *sc = (Scene *) s; memcpy(out48, sc->accel.tri.data(), sc->accel.tri.size() * sizeof(TriAccel)); }
+
+/* rays: n x 8 floats (o.xyz, mint, d.xyz, maxt).  mode 0 closest (out t,u,v,prim), 1 occlusion (prim = 0/1).
+ * accelMode: -1 scene default, 0 brute force, 1 tree */
+void orc_trace(void *s, uint64_t n, const float *rays, int mode, int accelMode, float *t, float *u, float *v, uint32_t *prim) {
+    Scene *sc = (Scene *) s;
+    Accel &A = sc->accel;
+    bool saved = A.useTree;
+    if (accelMode >= 0) A.useTree = accelMode != 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *r = rays + 8 * i;
+        Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7]);
+        if (mode == 0) {
+            Hit h; h.t = kInf; h.u = h.v = 0; h.prim = 0xFFFFFFFFu;
+            bool ok = A.rayIntersect(ray, h);
+            t[i] = ok ? h.t : kInf; u[i] = ok ? h.u : 0; v[i] = ok ? h.v : 0; prim[i] = ok ? h.prim : 0xFFFFFFFFu;
+        } else prim[i] = A.rayOccluded(ray) ? 1u : 0u;
+    }
+    A.useTree = saved;
+}
+
+/* primary rays for pixel-sample positions (n x 2) -> n x 8 */
+void orc_camera_rays(void *s, uint64_t n, const float *pos, float *rays) {
+    Scene *sc = (Scene *) s;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r = sc->sampleRay(pos[2 * i], pos[2 * i + 1]);
+        float *o = rays + 8 * i;
+        o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.mint; o[4] = r.d.x; o[5] = r.d.y; o[6] = r.d.z; o[7] = r.maxt;
+    }
+}
+
+/* full intersection records for given rays: out 24 floats: p(3) geoN(3) shN(3) s(3) t(3) wi(3) t(1) mesh(1) prim(1) valid(1) pad(2) */
+void orc_intersect_full(void *s, uint64_t n, const float *rays, float *out) {
+    Scene *sc = (Scene *) s; OrcStats st{};
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *r = rays + 8 * i;
+        Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7]);
+        Intersection its; float *o = out + 24 * i; memset(o, 0, 96);
+        if (sc->rayIntersect(ray, its, st)) {
+            V3 vs[6] = {its.p, its.geoFrame.n, its.shFrame.n, its.shFrame.s, its.shFrame.t, its.wi};
+            for (int k = 0; k < 6; ++k) { o[3 * k] = vs[k].x; o[3 * k + 1] = vs[k].y; o[3 * k + 2] = vs[k].z; }
+            o[18] = its.t; o[19] = (float) its.mesh; o[20] = (float) its.prim; o[21] = 1.0f;
+        }
+    }
+}
+
+/* ---- render ---- */
+static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcStats *stats,
+                        float *perSample /* optional: W*H*(hi-lo)*4 floats Li.rgb, alpha */) {
+    const int W = sc->W, H = sc->H;
+    RFilter filter(rp->rfilter, rp->rfilterParam);
+    const int bs = rp->blockSize > 0 ? rp->blockSize : 32;
+    const int nbx = (W + bs - 1) / bs, nby = (H + bs - 1) / bs, nBlocks = nbx * nby;
+    const int lo = rp->sampleLo, hi = rp->sampleHi > 0 ? rp->sampleHi : rp->spp;
+    int nThreads = rp->threads > 0 ? rp->threads : (int) std::thread::hardware_concurrency();
+    if (nThreads < 1) nThreads = 1;
+    std::vector<std::unique_ptr<ImageBlock>> blocks(nBlocks);
+    std::atomic<int> next(0);
+    std::vector<OrcStats> tstats(nThreads);
+    auto worker = [&](int tid) {
+        OrcStats st{};
+        std::unique_ptr<Sampler> sampler;
+        if (rp->sampler == 0) sampler.reset(new SobolSampler(&sc->sobol, rp->seed, W, H));
+        else if (rp->sampler == 1) sampler.reset(new IndependentSampler(rp->seed + (uint64_t) tid));
+        else sampler.reset(new CounterSampler(W, (uint32_t) rp->spp, rp->seed));
+        for (;;) {
+            int b = next.fetch_add(1);
+            if (b >= nBlocks) break;
+            int bx = b % nbx, by = b / nbx;
+            int ox = bx * bs, oy = by * bs, sx = std::min(bs, W - ox), sy = std::min(bs, H - oy);
+            std::unique_ptr<ImageBlock> blk(new ImageBlock(ox, oy, sx, sy, &filter));
+            /* integrator.cpp:162-187; pixel order inside the block is scanline here (the reference
+               uses a Hilbert curve, renderproc.cpp:79-81 -- affects float summation order only) */
+            for (int y = oy; y < oy + sy; ++y)
+                for (int x = ox; x < ox + sx; ++x) {
+                    sampler->generate(x, y);
+                    for (int j = 0; j < lo; ++j) sampler->advance(); /* skip to the shard start (sobol/counter: exact) */
+                    for (int j = lo; j < hi; ++j) {
+                        float ax, ay; sampler->next2D(ax, ay);
+                        float spx = (float) x + ax, spy = (float) y + ay;
+                        Ray ray = sc->sampleRay(spx, spy);
+                        float alpha;
+                        Spectrum spec = sc->Li(ray, sampler.get(), *rp, alpha, st); /* sensor weight = 1 */
+                        if (!blk->put(spx, spy, spec, alpha)) ++st.badSamples;
+                        if (perSample) {
+                            float *o = perSample + (((size_t) y * W + x) * (size_t) (hi - lo) + (size_t) (j - lo)) * 4;
+                            o[0] = spec.x; o[1] = spec.y; o[2] = spec.z; o[3] = alpha;
+                        }
+                        ++st.samples;
+                        sampler->advance();
+                    }
+                }
+            if (rp->sampler == 0 && ((SobolSampler *) sampler.get())->dimOverflow) st.dimOverflow = 1;
+            blocks[b] = std::move(blk);
+        }
+        tstats[tid] = st;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nThreads; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : th) t.join();
+    /* film->put(block): imageblock.h:103-107 -> Bitmap::accumulate, clipped to the film; merged in
+       block order so the oracle is deterministic (the reference merges in completion order) */
+    memset(film, 0, (size_t) W * H * 5 * sizeof(float));
+    for (int b = 0; b < nBlocks; ++b) {
+        ImageBlock &blk = *blocks[b];
+        for (int y = 0; y < blk.bh(); ++y) {
+            int fy = blk.oy - blk.border + y;
+            if (fy < 0 || fy >= H) continue;
+            for (int x = 0; x < blk.bw(); ++x) {
+                int fx = blk.ox - blk.border + x;
+                if (fx < 0 || fx >= W) continue;
+                const float *src = blk.data.data() + ((size_t) y * blk.bw() + x) * 5;
+                float *dst = film + ((size_t) fy * W + fx) * 5;
+                for (int k = 0; k < 5; ++k) dst[k] += src[k];
+            }
+        }
+    }
+    if (stats) {
+        OrcStats tot{};
+        for (auto &s : tstats) {
+            tot.samples += s.samples; tot.rays += s.rays; tot.shadowRays += s.shadowRays; tot.pathLengthSum += s.pathLengthSum;
+            tot.nodeVisits += s.nodeVisits; tot.primTests += s.primTests; tot.badSamples += s.badSamples; tot.dimOverflow |= s.dimOverflow;
+        }
+        *stats = tot;
+    }
+}
+void orc_render(void *s, const OrcRenderParams *rp, float *film, OrcStats *stats) { render_impl((Scene *) s, rp, film, stats, nullptr); }
+void orc_render_samples(void *s, const OrcRenderParams *rp, float *film, OrcStats *stats, float *perSample) {
+    render_impl((Scene *) s, rp, film, stats, perSample);
+}
+/* fmtconv.cpp:979-990: rgb = spec * (weight != 0 ? 1/weight : weight) */
+void orc_develop(const float *film, int W, int H, float *rgb) {
+    for (size_t i = 0; i < (size_t) W * H; ++i) {
+        float weight = film[5 * i + 4], invWeight = (weight != 0) ? 1 / weight : weight;
+        for (int k = 0; k < 3; ++k) rgb[3 * i + k] = film[5 * i + k] * invWeight;
+    }
+}
+void orc_filter_table(int kind, float param, float *values32, float *radius, int *border) {
+    RFilter f(kind, param); memcpy(values32, f.values, 128); *radius = f.radius; *border = f.borderSize;
+}
+/* splat n samples (pos 2, value 4: rgb+alpha) into a W x H film through 32x32 ImageBlocks */
+void orc_splat(int W, int H, int kind, float param, uint64_t n, const float *pos, const float *val, float *film) {
+    RFilter filter(kind, param);
+    const int bs = 32, nbx = (W + bs - 1) / bs, nby = (H + bs - 1) / bs;
+    std::vector<std::unique_ptr<ImageBlock>> blocks((size_t) nbx * nby);
+    for (int b = 0; b < nbx * nby; ++b) {
+        int ox = (b % nbx) * bs, oy = (b / nbx) * bs;
+        blocks[b].reset(new ImageBlock(ox, oy, std::min(bs, W - ox), std::min(bs, H - oy), &filter));
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        int px = (int) std::floor(pos[2 * i]), py = (int) std::floor(pos[2 * i + 1]);
+        if (px < 0 || py < 0 || px >= W || py >= H) continue;
+        blocks[(size_t) (py / bs) * nbx + px / bs]->put(pos[2 * i], pos[2 * i + 1], V3(val[4 * i], val[4 * i + 1], val[4 * i + 2]), val[4 * i + 3]);
+    }
+    memset(film, 0, (size_t) W * H * 5 * sizeof(float));
+    for (auto &bp : blocks) {
+        ImageBlock &blk = *bp;
+        for (int y = 0; y < blk.bh(); ++y) {
+            int fy = blk.oy - blk.border + y; if (fy < 0 || fy >= H) continue;
+            for (int x = 0; x < blk.bw(); ++x) {
+                int fx = blk.ox - blk.border + x; if (fx < 0 || fx >= W) continue;
+                for (int k = 0; k < 5; ++k) film[((size_t) fy * W + fx) * 5 + k] += blk.data[((size_t) y * blk.bw() + x) * 5 + k];
+            }
+        }
+    }
+}
+
+/* ---- component entry points for fixtures / parity tests ---- */
+void orc_sfmt_words(uint64_t seed, uint64_t n, uint64_t *out) { SFMT r; r.seed(seed); for (uint64_t i = 0; i < n; ++i) out[i] = r.nextULong(); }
+void orc_sfmt_floats(uint64_t seed, uint64_t n, float *out) { SFMT r; r.seed(seed); for (uint64_t i = 0; i < n; ++i) out[i] = r.nextFloat(); }
+uint64_t orc_tea(uint32_t v0, uint32_t v1, int rounds) { return sampleTEA(v0, v1, rounds); }
+void orc_sobol_sample(const uint32_t *m32, uint64_t n, const uint64_t *index, const uint32_t *dim, uint32_t scramble, float *out) {
+    SobolTables T; T.m32 = m32;
+    for (uint64_t i = 0; i < n; ++i) out[i] = sobolSample(T, index[i], dim[i], scramble);
+}
+void orc_sobol_lookup(const uint64_t *vdc, const uint64_t *inv, uint32_t m, uint64_t n, const uint32_t *frame, const uint32_t *px,
+                      const uint32_t *py, uint64_t scramble, uint64_t *out) {
+    SobolTables T; T.vdc = vdc; T.inv = inv;
+    for (uint64_t i = 0; i < n; ++i) out[i] = sobolLookUp(T, m, frame[i], px[i], py[i], scramble);
+}
+/* the first `ndim` sampler outputs of (pixel, sample) exactly as renderBlock + Li would draw them
+ * (dims 0,1 through next2D's pixel rescale); sampler kinds as in OrcRenderParams */
+void orc_sampler_stream(void *s, int kind, uint64_t seed, int W, int H, int spp, int px, int py, int sampleIdx, int ndim, float *out) {
+    Scene *sc = (Scene *) s;
+    std::unique_ptr<Sampler> sm;
+    if (kind == 0) sm.reset(new SobolSampler(&sc->sobol, seed, W, H));
+    else if (kind == 1) sm.reset(new IndependentSampler(seed));
+    else sm.reset(new CounterSampler(W, (uint32_t) spp, seed));
+    sm->generate(px, py);
+    for (int j = 0; j < sampleIdx; ++j) sm->advance();
+    int i = 0;
+    if (ndim >= 2) { sm->next2D(out[0], out[1]); i = 2; }
+    for (; i < ndim; ++i) out[i] = sm->next1D();
+}
+
+struct ReplaySampler : Sampler { /* test_chisquare.cpp:58-92 FakeSampler analogue */
+    float v; explicit ReplaySampler(float x) : v(x) {}
+    void generate(int, int) override {} void advance() override {}
+    float next1D() override { return v; }
+    void next2D(float &a, float &b) override { a = b = v; }
+};
+/* BSDF component calls on local-frame directions. bsdfs: array of nB descs, id = which to query.
+ * wi/wo: n x 3; samples: n x 3 (2D sample + the extra 1D a rough dielectric draws).
+ * out_sample: n x 10: wo(3) weight(3) pdf(1) sampledType(1) eta(1) pad */
+void orc_bsdf_eval(const OrcBsdf *b, int nB, int id, uint64_t n, const float *wi, const float *wo, float *outRgb, float *outPdf) {
+    BsdfSet bs{b, nB};
+    for (uint64_t i = 0; i < n; ++i) {
+        BRec r; r.wi = V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]); r.wo = V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        Spectrum f = bs.eval(id, r); outRgb[3 * i] = f.x; outRgb[3 * i + 1] = f.y; outRgb[3 * i + 2] = f.z;
+        outPdf[i] = bs.pdf(id, r);
+    }
+}
+void orc_bsdf_sample(const OrcBsdf *b, int nB, int id, uint64_t n, const float *wi, const float *samples, float *out) {
+    BsdfSet bs{b, nB};
+    for (uint64_t i = 0; i < n; ++i) {
+        ReplaySampler rs(samples[3 * i + 2]);
+        BRec r; r.wi = V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]); r.sampler = &rs;
+        float pdf = 0;
+        Spectrum w = bs.sample(id, r, pdf, samples[3 * i], samples[3 * i + 1]);
+        float *o = out + 10 * i;
+        o[0] = r.wo.x; o[1] = r.wo.y; o[2] = r.wo.z; o[3] = w.x; o[4] = w.y; o[5] = w.z;
+        o[6] = w.isZero() ? 0.0f : pdf; o[7] = (float) r.sampledType; o[8] = r.eta; o[9] = 0;
+    }
+}
+uint32_t orc_bsdf_type(const OrcBsdf *b, int nB, int id) { BsdfSet bs{b, nB}; return bs.type(id); }
+/* microfacet protocol of src/tests/test_microfacet.cpp:50-131.  out: n x 6: m(3), pdf from sample(), pdf(wi,m), eval(m) */
+void orc_microfacet_sample(int type, float alphaU, float alphaV, int sampleVisible, uint64_t n, const float *wi, const float *samples, float *out) {
+    Microfacet d(type, alphaU, alphaV, sampleVisible != 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 w(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        float pdf; V3 m = d.sample(w, samples[2 * i], samples[2 * i + 1], pdf);
+        float *o = out + 6 * i; o[0] = m.x; o[1] = m.y; o[2] = m.z; o[3] = pdf; o[4] = d.pdf(w, m); o[5] = d.eval(m);
+    }
+}
+void orc_microfacet_eval(int type, float alphaU, float alphaV, int sampleVisible, uint64_t n, const float *wi, const float *m, float *out /* n x 3: D, pdf, G1(wi,m) */) {
+    Microfacet d(type, alphaU, alphaV, sampleVisible != 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 w(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), mm(m[3 * i], m[3 * i + 1], m[3 * i + 2]);
+        out[3 * i] = d.eval(mm); out[3 * i + 1] = d.pdf(w, mm); out[3 * i + 2] = d.smithG1(w, mm);
+    }
+}
+/* emitter direct sampling from reference points (n x 6: ref, refN) with 2D samples -> n x 12:
+ * d(3) dist pdf value(3) visible p(3) */
+void orc_sample_emitter_direct(void *s, uint64_t n, const float *ref, const float *samples, float *out) {
+    Scene *sc = (Scene *) s; OrcStats st{};
+    for (uint64_t i = 0; i < n; ++i) {
+        DRec d; d.ref = V3(ref[6 * i], ref[6 * i + 1], ref[6 * i + 2]); d.refN = V3(ref[6 * i + 3], ref[6 * i + 4], ref[6 * i + 5]);
+        Spectrum v = sc->sampleEmitterDirect(d, samples[2 * i], samples[2 * i + 1], st);
+        float *o = out + 12 * i;
+        o[0] = d.d.x; o[1] = d.d.y; o[2] = d.d.z; o[3] = d.dist; o[4] = v.isZero() ? 0.0f : d.pdf; o[5] = v.x; o[6] = v.y; o[7] = v.z;
+        o[8] = v.isZero() ? 0.0f : 1.0f; o[9] = d.p.x; o[10] = d.p.y; o[11] = d.p.z;
+    }
+}
+int orc_hardware_threads() { return (int) std::thread::hardware_concurrency(); }
+
+} // extern "C"
