@@ -1,0 +1,163 @@
+/* b2mts.h -- C-ABI of the B200-native wavefront path tracer that stands in for Mitsuba 0.6's
+ * `path` integrator hot path.  Plain C: opaque handles, pointers and sizes; no C++ or torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the Mitsuba 0.6
+ * tree).  A Mitsuba-side `Integrator` plugin shim marshals its Scene into these
+ * calls from Integrator::render() (include/mitsuba/render/integrator.h:61-118), exactly like the
+ * `vpl` integrator replaces block rendering wholesale (src/integrators/vpl/vpl.cpp:143-237).
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (b2_last_error() gives the
+ * text; nothing throws across the boundary -- the reference's Log(EError) throws,
+ * src/libcore/logger.cpp:100-147, the shim converts).  All input buffers are copied; the caller
+ * keeps ownership.  Output buffers are caller-allocated.  There is NO CPU fallback: every compute
+ * entry point fails with B2_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef B2MTS_H
+#define B2MTS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_INVALID 1
+#define B2_ERR_NO_DEVICE 2
+#define B2_ERR_CUDA 3
+#define B2_ERR_IO 4
+#define B2_ERR_CANCELLED 5
+
+typedef struct b2_ctx b2_ctx;
+typedef struct b2_scene b2_scene;
+
+/* BSDF plugins on the path.  Field meaning = the reference constructors' properties after their
+ * host-side preprocessing (IOR lookup, /extEta), see src/bsdfs/{diffuse,roughconductor,
+ * roughdielectric,coating}.cpp and src/bsdfs/microfacet.h:99-148. */
+enum { B2_BSDF_DIFFUSE = 0, B2_BSDF_ROUGHCONDUCTOR = 1, B2_BSDF_ROUGHDIELECTRIC = 2, B2_BSDF_COATING = 3 };
+enum { B2_DISTR_BECKMANN = 0, B2_DISTR_GGX = 1, B2_DISTR_PHONG = 2 };
+typedef struct b2_material_desc {
+    int32_t type;            /* B2_BSDF_* */
+    int32_t distr;           /* B2_DISTR_*            microfacet.h:48-57 */
+    int32_t sample_visible;  /* microfacet.h:138 (must be 0 for phong, :145-148) */
+    int32_t nested;          /* coating: material id of the nested BSDF (coating.cpp:190-199); else -1 */
+    float alpha_u, alpha_v;  /* roughness before the 1e-4 clamp (microfacet.h:70-71) */
+    float eta;               /* roughdielectric / coating: intIOR/extIOR */
+    float thickness;         /* coating.cpp:126 */
+    float reflectance[3];    /* diffuse: reflectance; others: specularReflectance */
+    float transmittance[3];  /* roughdielectric: specularTransmittance */
+    float eta_c[3], k_c[3];  /* roughconductor eta, k divided by extEta (roughconductor.cpp:189-190) */
+    float sigma_a[3];        /* coating.cpp:129-130 */
+} b2_material_desc;
+
+/* Integrator + Sampler + Film/ReconstructionFilter properties that parameterise one render:
+ * MonteCarloIntegrator (src/librender/integrator.cpp:190-225), SobolSampler / IndependentSampler
+ * (src/samplers/sobol.cpp:86-102, independent.cpp:52-58), rfilters (src/rfilters/{box,gaussian}.cpp). */
+enum { B2_SAMPLER_SOBOL = 0, B2_SAMPLER_INDEPENDENT = 2 };
+enum { B2_RFILTER_BOX = 0, B2_RFILTER_GAUSSIAN = 1 };
+typedef struct b2_render_params {
+    int32_t spp;             /* sampleCount */
+    int32_t sampler;         /* B2_SAMPLER_* (independent = counter-based stream) */
+    uint64_t seed;           /* sobol: `scramble`; independent: stream seed */
+    int32_t max_depth;       /* -1 = unbounded */
+    int32_t rr_depth;        /* 5 */
+    int32_t strict_normals, hide_emitters;
+    int32_t rfilter;         /* B2_RFILTER_* */
+    float rfilter_param;     /* box: radius (0.5); gaussian: stddev (0.5) */
+    int32_t sample_lo, sample_hi; /* this call renders sample indices [lo,hi) of every pixel; hi<=0 -> spp.
+                                     Shards the work across GPUs (replaces BlockedImageProcess work units,
+                                     src/librender/imageproc.cpp:43-78) */
+    int32_t parity_mode;     /* 1: kernels compiled with -fmad=false (tight float parity); 0: FMA contraction on */
+    int32_t pool_size;       /* in-flight paths (0 = default) */
+    int32_t film_on_device;  /* 1: `film` of b2_render is a device pointer on the context's device */
+    int32_t flags;           /* bit0: material-sorted shading on; bit1: force unsorted */
+} b2_render_params;
+
+/* Counters with the meaning of the reference's statistics (path.cpp:24,290-291; skdtree.cpp:46-47) plus
+ * per-stage device times of the last b2_render. */
+typedef struct b2_stats {
+    uint64_t samples, rays, shadow_rays, path_length_sum, bad_samples, dim_overflow;
+    uint64_t node_visits, prim_tests;       /* only counted when built with B2_COUNT_TRAVERSAL */
+    uint64_t iterations, kernel_launches;
+    float ms_total, ms_generate, ms_extend, ms_shade, ms_occluded, ms_film;
+    uint64_t n_triangles, n_bvh_nodes;
+} b2_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int b2_context_create(int device, b2_ctx **out);          /* one context per GPU / per rank */
+void b2_context_destroy(b2_ctx *);
+const char *b2_last_error(b2_ctx *);                       /* NULL ctx -> last global error */
+int b2_scene_create(b2_ctx *, b2_scene **out);            /* replaces Scene (src/librender/scene.cpp) for the path */
+void b2_scene_destroy(b2_scene *);
+
+/* ---- scene description (what the shim reads through Scene::getMeshes/getEmitters/getSensor,
+ *      include/mitsuba/render/scene.h:992-1094, trimesh.h:122-153) ------------------------------- */
+/* PerspectiveCameraImpl::configure (src/sensors/perspective.cpp:126-179): camera-to-world matrix (row
+ * major), x field of view in degrees, clip planes, film size.  m_sampleToCamera is derived inside. */
+int b2_scene_set_camera(b2_scene *, const float to_world[16], float xfov_deg, float near_clip, float far_clip,
+                        int width, int height);
+int b2_scene_get_sample_to_camera(b2_scene *, float out[16]);
+/* BSDF plugin instance -> id (>=0) or -1 */
+int b2_scene_add_material(b2_scene *, const b2_material_desc *);
+/* AreaLight (src/emitters/area.cpp:64-70): radiance, samplingWeight -> id (>=0) or -1 */
+int b2_scene_add_area_emitter(b2_scene *, const float radiance[3], float sampling_weight);
+/* TriMesh after configure(): positions, optional normals / texcoords (NULL = none -> face normals,
+ * skdtree.h:383-399), triangles, material and emitter ids (-1 = no emitter).  An emitter id may be
+ * attached to exactly one mesh (area.cpp:185-199).  Returns mesh id or -1. */
+int b2_scene_add_mesh(b2_scene *, const float *P, const float *N, const float *UV, uint32_t n_vertices,
+                      const uint32_t *idx, uint32_t n_triangles, int material_id, int emitter_id);
+/* Scene::initialize (src/librender/scene.cpp:322-384): TriAccel precompute (skdtree.cpp:74-109),
+ * acceleration structure build (BVH; replaces GenericKDTree::buildInternal, gkdtree.h:958-1263),
+ * emitter / triangle-area CDFs (scene.cpp:375-380, trimesh.cpp:388-403), upload to HBM. */
+int b2_scene_commit(b2_scene *);
+
+/* ---- the hot path: SamplingIntegrator::render + renderBlock + MIPathTracer::Li
+ *      (src/librender/integrator.cpp:95-188, src/integrators/path/path.cpp:119-294) ------------- */
+/* film: H*W*5 floats (R,G,B,alpha,weight) = the HDRFilm storage format ESpectrumAlphaWeight
+ * (src/films/hdrfilm.cpp:351-356), overwritten.  Host pointer unless params->film_on_device. */
+int b2_render(b2_scene *, const b2_render_params *, float *film);
+/* Integrator::cancel (integrator.h:90-93): callable from another thread */
+int b2_cancel(b2_scene *);
+/* Film::develop normalisation (src/libcore/fmtconv.cpp:979-990): rgb = spec * (w != 0 ? 1/w : w). host buffers */
+int b2_film_develop(const float *film, int width, int height, float *rgb);
+int b2_get_stats(b2_scene *, b2_stats *);
+
+/* ---- component entry points (the reference exposes the same pieces through its Python bindings
+ *      and test plugins: ShapeKDTree::rayIntersect src/libpython/render.cpp:352-369, BSDF
+ *      sample/eval/pdf src/tests/test_chisquare.cpp:94-200, kdbench src/utils/kdbench.cpp) ------- */
+/* rays: n x 8 floats (o.xyz, mint, d.xyz, maxt); mode 0 closest hit -> t,u,v,prim (prim = 0xFFFFFFFF on miss,
+ * t = +inf); mode 1 occlusion -> prim = 0/1.  Host buffers.  ShapeKDTree::rayIntersect, skdtree.cpp:112-226. */
+int b2_trace(b2_scene *, uint64_t n, const float *rays, int mode, int parity_mode, float *t, float *u, float *v,
+             uint32_t *prim, float *ms_kernel);
+/* Same, all buffers resident on the device (traversal benchmark) */
+int b2_trace_device(b2_scene *, uint64_t n, const float *d_rays, int mode, int parity_mode, float *d_tuvp, float *ms_kernel);
+/* BSDF::eval + pdf for local-frame (wi, wo) pairs: out_rgb n x 3, out_pdf n */
+int b2_bsdf_eval(b2_scene *, int material_id, uint64_t n, const float *wi, const float *wo, int parity_mode,
+                 float *out_rgb, float *out_pdf);
+/* BSDF::sample(bRec, pdf, sample): samples n x 3 (2-D sample + the extra 1-D a rough dielectric draws);
+ * out n x 10: wo(3) weight(3) pdf sampledType eta pad */
+int b2_bsdf_sample(b2_scene *, int material_id, uint64_t n, const float *wi, const float *samples, int parity_mode, float *out);
+/* Scene::sampleEmitterDirect without the visibility test folded into `visible`:
+ * ref n x 6 (ref, refN), samples n x 2 -> out n x 12: d(3) dist pdf value(3) visible p(3) */
+int b2_sample_emitter_direct(b2_scene *, uint64_t n, const float *ref, const float *samples, int parity_mode, float *out);
+/* The first ndim sampler outputs of (pixel, sample) as renderBlock + Li draw them */
+int b2_sampler_stream(b2_scene *, int sampler, uint64_t seed, int spp, int px, int py, int sample_idx, int ndim, float *out);
+/* primary rays (PerspectiveCameraImpl::sampleRayDifferential, perspective.cpp:271-298): pos n x 2 -> rays n x 8 */
+int b2_camera_rays(b2_scene *, uint64_t n, const float *pos, int parity_mode, float *rays);
+/* ImageBlock::put (imageblock.h:124-204) for n samples: pos n x 2, val n x 4 (rgb, alpha) -> film H*W*5 */
+int b2_splat(b2_ctx *, int width, int height, int rfilter, float rfilter_param, uint64_t n, const float *pos,
+             const float *val, float *film);
+/* TriAccel records (n_triangles x 12 words) as uploaded, in prim order */
+int b2_get_triaccel(b2_scene *, float *out);
+
+/* ---- scene files: the SceneHandler subset (src/librender/scenehandler.cpp:70-106) --------------- */
+/* defines: "key=value" strings ($key substitution, src/mitsuba/mitsuba.cpp:154).  Fills *params from the
+ * <integrator>/<sampler>/<film>/<rfilter> elements. */
+int b2_load_xml(b2_ctx *, const char *path, const char *const *defines, int n_defines, b2_scene **out,
+                b2_render_params *params);
+
+const char *b2_version(void);
+int b2_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

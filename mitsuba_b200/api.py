@@ -1,0 +1,294 @@
+"""ctypes binding of the C-ABI (include/b2mts.h) -- the Python host side used by tests, bench.py and
+the multi-GPU driver.  Everything here calls libb2mts.so; there is no Python or CPU compute fallback:
+when the library (or a GPU) is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .scene import RenderParams, SceneDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libb2mts.so")
+_LIB = None
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+class b2_material_desc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("distr", C.c_int32), ("sample_visible", C.c_int32), ("nested", C.c_int32),
+                ("alpha_u", C.c_float), ("alpha_v", C.c_float), ("eta", C.c_float), ("thickness", C.c_float),
+                ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3), ("eta_c", C.c_float * 3),
+                ("k_c", C.c_float * 3), ("sigma_a", C.c_float * 3)]
+
+
+class b2_render_params(C.Structure):
+    _fields_ = [("spp", C.c_int32), ("sampler", C.c_int32), ("seed", C.c_uint64), ("max_depth", C.c_int32),
+                ("rr_depth", C.c_int32), ("strict_normals", C.c_int32), ("hide_emitters", C.c_int32),
+                ("rfilter", C.c_int32), ("rfilter_param", C.c_float), ("sample_lo", C.c_int32), ("sample_hi", C.c_int32),
+                ("parity_mode", C.c_int32), ("pool_size", C.c_int32), ("film_on_device", C.c_int32), ("flags", C.c_int32)]
+
+
+class b2_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("samples", "rays", "shadow_rays", "path_length_sum", "bad_samples", "dim_overflow",
+                                          "node_visits", "prim_tests", "iterations", "kernel_launches")] + \
+               [(n, C.c_float) for n in ("ms_total", "ms_generate", "ms_extend", "ms_shade", "ms_occluded", "ms_film")] + \
+               [("n_triangles", C.c_uint64), ("n_bvh_nodes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
+           "b2_scene_set_camera", "b2_scene_get_sample_to_camera", "b2_scene_add_material", "b2_scene_add_area_emitter",
+           "b2_scene_add_mesh", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
+           "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
+           "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
+
+
+def lib():
+    """Load libb2mts.so (built in-tree by mitsuba_b200.build).  Raises if it is missing: no fallback."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIBPATH):
+            raise B2Error(f"{_LIBPATH} not built: run `python -m mitsuba_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(_LIBPATH)
+        L.b2_last_error.restype = C.c_char_p
+        L.b2_last_error.argtypes = [C.c_void_p]
+        L.b2_version.restype = C.c_char_p
+        for name in ("b2_scene_add_material", "b2_scene_add_area_emitter", "b2_scene_add_mesh"):
+            getattr(L, name).restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a, t=C.c_float):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+SAMPLERS = {"sobol": 0, "independent": 2}
+RFILTERS = {"box": 0, "gaussian": 1}
+
+
+def make_params(rp: RenderParams, parity=False, pool_size=0, film_on_device=False, flags=0) -> b2_render_params:
+    p = b2_render_params()
+    p.spp, p.sampler, p.seed = rp.spp, SAMPLERS[rp.sampler], rp.seed
+    p.max_depth, p.rr_depth = rp.max_depth, rp.rr_depth
+    p.strict_normals, p.hide_emitters = int(rp.strict_normals), int(rp.hide_emitters)
+    p.rfilter, p.rfilter_param = RFILTERS[rp.rfilter], rp.rfilter_param
+    p.sample_lo, p.sample_hi = rp.sample_lo, rp.sample_hi
+    p.parity_mode, p.pool_size, p.film_on_device, p.flags = int(parity), pool_size, int(film_on_device), flags
+    return p
+
+
+def params_to_render_params(p: b2_render_params) -> RenderParams:
+    inv_s = {v: k for k, v in SAMPLERS.items()}
+    inv_f = {v: k for k, v in RFILTERS.items()}
+    return RenderParams(spp=p.spp, sampler=inv_s[p.sampler], seed=p.seed, max_depth=p.max_depth, rr_depth=p.rr_depth,
+                        strict_normals=bool(p.strict_normals), hide_emitters=bool(p.hide_emitters), rfilter=inv_f[p.rfilter],
+                        rfilter_param=p.rfilter_param, sample_lo=p.sample_lo, sample_hi=p.sample_hi)
+
+
+class Context:
+    """One per GPU / rank (b2_context_create)."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        rc = self.L.b2_context_create(C.c_int(device), C.byref(self.h))
+        if rc:
+            raise B2Error(f"b2_context_create({device}) failed [{rc}]: {self.L.b2_last_error(None).decode()}")
+        self.device = device
+
+    def err(self):
+        return self.L.b2_last_error(self.h).decode()
+
+    def close(self):
+        if self.h:
+            self.L.b2_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def splat(self, W, H, kind, param, pos, val):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 2)
+        val = np.ascontiguousarray(val, np.float32).reshape(-1, 4)
+        film = np.zeros((H, W, 5), np.float32)
+        rc = self.L.b2_splat(self.h, C.c_int(W), C.c_int(H), C.c_int(RFILTERS[kind]), C.c_float(param), C.c_uint64(len(pos)),
+                             _p(pos), _p(val), _p(film))
+        if rc:
+            raise B2Error(self.err())
+        return film
+
+    def load_xml(self, path, defines=()):
+        hs = C.c_void_p()
+        p = b2_render_params()
+        arr = (C.c_char_p * max(1, len(defines)))(*[d.encode() for d in defines])
+        rc = self.L.b2_load_xml(self.h, path.encode(), arr, C.c_int(len(defines)), C.byref(hs), C.byref(p))
+        if rc:
+            raise B2Error(f"b2_load_xml failed [{rc}]: {self.err()}")
+        sc = Scene.__new__(Scene)
+        sc.ctx, sc.L, sc.h = self, self.L, hs
+        W = C.c_int(); H = C.c_int()
+        s2c = np.zeros(16, np.float32)
+        self.L.b2_scene_get_sample_to_camera(hs, _p(s2c))
+        sc.material_ids = None
+        sc._size_from_stats()
+        return sc, params_to_render_params(p)
+
+
+class Scene:
+    """Device scene built from a SceneDesc through the C-ABI."""
+
+    def __init__(self, ctx: Context, desc: SceneDesc):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        self._ck(self.L.b2_scene_create(ctx.h, C.byref(self.h)))
+        cam = desc.camera
+        self.W, self.H = cam.width, cam.height
+        c2w = np.ascontiguousarray(cam.to_world, np.float32)
+        self._ck(self.L.b2_scene_set_camera(self.h, _p(c2w), C.c_float(cam.xfov()), C.c_float(cam.near), C.c_float(cam.far),
+                                            C.c_int(cam.width), C.c_int(cam.height)))
+        flat, ids = desc.flat_bsdfs()
+        self.flat_bsdfs = flat
+        self.material_ids = ids
+        for d in flat:
+            m = b2_material_desc()
+            m.type, m.distr, m.sample_visible, m.nested = d["type"], d["distr"], d["sampleVisible"], d["nested"]
+            m.alpha_u, m.alpha_v, m.eta, m.thickness = d["alphaU"], d["alphaV"], d["eta"], d["thickness"]
+            for k, src in (("reflectance", "reflectance"), ("transmittance", "transmittance"), ("eta_c", "etaC"), ("k_c", "kC"), ("sigma_a", "sigmaA")):
+                for j in range(3):
+                    getattr(m, k)[j] = d[src][j]
+            if self.L.b2_scene_add_material(self.h, C.byref(m)) < 0:
+                raise B2Error(ctx.err())
+        for mesh, bid in zip(desc.meshes, ids):
+            eid = -1
+            if mesh.radiance is not None:
+                rad = np.asarray(mesh.radiance, np.float32)
+                eid = self.L.b2_scene_add_area_emitter(self.h, _p(rad), C.c_float(mesh.sampling_weight))
+                if eid < 0:
+                    raise B2Error(ctx.err())
+            P = np.ascontiguousarray(mesh.P, np.float32)
+            N = np.ascontiguousarray(mesh.N, np.float32) if mesh.N is not None else None
+            UV = np.ascontiguousarray(mesh.UV, np.float32) if mesh.UV is not None else None
+            I = np.ascontiguousarray(mesh.idx, np.uint32)
+            if self.L.b2_scene_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
+                                        C.c_int(bid), C.c_int(eid)) < 0:
+                raise B2Error(ctx.err())
+        self._ck(self.L.b2_scene_commit(self.h))
+
+    def _ck(self, rc):
+        if rc:
+            raise B2Error(f"[{rc}] {self.ctx.err()}")
+
+    def _size_from_stats(self):
+        self.W = self.H = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b2_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sample_to_camera(self):
+        out = np.zeros(16, np.float32)
+        self._ck(self.L.b2_scene_get_sample_to_camera(self.h, _p(out)))
+        return out.reshape(4, 4)
+
+    def stats(self):
+        st = b2_stats()
+        self.L.b2_get_stats(self.h, C.byref(st))
+        return st.as_dict()
+
+    def triaccel(self):
+        n = self.stats()["n_triangles"]
+        out = np.zeros((n, 12), np.float32)
+        self._ck(self.L.b2_get_triaccel(self.h, _p(out)))
+        return out
+
+    def render(self, rp: RenderParams, parity=False, pool_size=0, flags=0, film=None, width=None, height=None):
+        """Returns (film H x W x 5 float32 host array, stats).  `film`: optional torch CUDA tensor (H,W,5) to fill in place."""
+        W, H = width or self.W, height or self.H
+        if film is not None:
+            p = make_params(rp, parity, pool_size, True, flags)
+            assert film.is_cuda and film.is_contiguous() and film.numel() == W * H * 5
+            self._ck(self.L.b2_render(self.h, C.byref(p), C.c_void_p(film.data_ptr())))
+            return film, self.stats()
+        p = make_params(rp, parity, pool_size, False, flags)
+        out = np.zeros((H, W, 5), np.float32)
+        self._ck(self.L.b2_render(self.h, C.byref(p), _p(out)))
+        return out, self.stats()
+
+    def trace(self, rays, mode=0, parity=True):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = len(rays)
+        t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32); prim = np.zeros(n, np.uint32)
+        ms = C.c_float()
+        self._ck(self.L.b2_trace(self.h, C.c_uint64(n), _p(rays), C.c_int(mode), C.c_int(int(parity)), _p(t), _p(u), _p(v),
+                                 _p(prim, C.c_uint32), C.byref(ms)))
+        return t, u, v, prim
+
+    def trace_device(self, d_rays, d_out, n, mode=0, parity=False):
+        """d_rays / d_out: torch CUDA float32 tensors (n*8, n*4).  Returns kernel ms."""
+        ms = C.c_float()
+        self._ck(self.L.b2_trace_device(self.h, C.c_uint64(n), C.c_void_p(d_rays.data_ptr()), C.c_int(mode), C.c_int(int(parity)),
+                                        C.c_void_p(d_out.data_ptr()), C.byref(ms)))
+        return ms.value
+
+    def camera_rays(self, pos, parity=True):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 2)
+        rays = np.zeros((len(pos), 8), np.float32)
+        self._ck(self.L.b2_camera_rays(self.h, C.c_uint64(len(pos)), _p(pos), C.c_int(int(parity)), _p(rays)))
+        return rays
+
+    def bsdf_eval(self, mat, wi, wo, parity=True):
+        wi = np.ascontiguousarray(wi, np.float32).reshape(-1, 3); wo = np.ascontiguousarray(wo, np.float32).reshape(-1, 3)
+        rgb = np.zeros((len(wi), 3), np.float32); pdf = np.zeros(len(wi), np.float32)
+        self._ck(self.L.b2_bsdf_eval(self.h, C.c_int(mat), C.c_uint64(len(wi)), _p(wi), _p(wo), C.c_int(int(parity)), _p(rgb), _p(pdf)))
+        return rgb, pdf
+
+    def bsdf_sample(self, mat, wi, samples, parity=True):
+        wi = np.ascontiguousarray(wi, np.float32).reshape(-1, 3); samples = np.ascontiguousarray(samples, np.float32).reshape(-1, 3)
+        out = np.zeros((len(wi), 10), np.float32)
+        self._ck(self.L.b2_bsdf_sample(self.h, C.c_int(mat), C.c_uint64(len(wi)), _p(wi), _p(samples), C.c_int(int(parity)), _p(out)))
+        return dict(wo=out[:, 0:3], weight=out[:, 3:6], pdf=out[:, 6], type=out[:, 7].astype(np.uint32), eta=out[:, 8])
+
+    def sample_emitter_direct(self, ref, samples, parity=True):
+        ref = np.ascontiguousarray(ref, np.float32).reshape(-1, 6); samples = np.ascontiguousarray(samples, np.float32).reshape(-1, 2)
+        out = np.zeros((len(ref), 12), np.float32)
+        self._ck(self.L.b2_sample_emitter_direct(self.h, C.c_uint64(len(ref)), _p(ref), _p(samples), C.c_int(int(parity)), _p(out)))
+        return out
+
+    def sampler_stream(self, kind, seed, spp, px, py, sample_idx, ndim):
+        out = np.zeros(ndim, np.float32)
+        self._ck(self.L.b2_sampler_stream(self.h, C.c_int(SAMPLERS[kind]), C.c_uint64(seed), C.c_int(spp), C.c_int(px), C.c_int(py),
+                                          C.c_int(sample_idx), C.c_int(ndim), _p(out)))
+        return out
+
+
+def develop(film):
+    film = np.ascontiguousarray(film, np.float32)
+    H, W = film.shape[:2]
+    rgb = np.zeros((H, W, 3), np.float32)
+    rc = lib().b2_film_develop(_p(film), C.c_int(W), C.c_int(H), _p(rgb))
+    if rc:
+        raise B2Error("b2_film_develop failed")
+    return rgb
+
+
+def device_count() -> int:
+    return int(lib().b2_device_count())

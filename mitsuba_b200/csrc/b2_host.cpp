@@ -1,0 +1,987 @@
+// C-ABI implementation (include/b2mts.h): scene commit (TriAccel precompute, BVH, CDFs, upload to HBM),
+// the wavefront render loop, film handling and the component entry points.
+#include "../../include/b2mts.h"
+#include "b2_types.h"
+#include "b2_launch.h"
+#include "bvh_builder.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace b2;
+
+namespace {
+std::string g_lastError;
+std::mutex g_errMutex;
+}
+
+struct b2_ctx {
+    int device = 0;
+    int numSMs = 0;
+    cudaStream_t stream = nullptr;
+    std::string lastError;
+    // Sobol tables on the device
+    uint32_t *dM32 = nullptr;
+    uint64_t *dVdc = nullptr, *dInv = nullptr;
+    bool tablesLoaded = false;
+};
+
+static int fail(b2_ctx *ctx, int code, const std::string &msg) {
+    {
+        std::lock_guard<std::mutex> g(g_errMutex);
+        g_lastError = msg;
+    }
+    if (ctx) ctx->lastError = msg;
+    return code;
+}
+#define CK(ctx, call)                                                                                          \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess)                                                                                 \
+            return fail(ctx, B2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+struct HostMesh {
+    std::vector<float> P, N, UV;
+    std::vector<uint32_t> idx;
+    int material = -1, emitter = -1;
+    uint32_t primOffset = 0;
+};
+struct HostEmitter {
+    float radiance[3];
+    float samplingWeight;
+    int mesh = -1;
+};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        if (count == n && p) return cudaSuccess;
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **) &p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &v) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+struct b2_scene {
+    b2_ctx *ctx = nullptr;
+    std::vector<b2_material_desc> materials;
+    std::vector<HostEmitter> emitters;
+    std::vector<HostMesh> meshes;
+    // camera
+    float camToWorld[16];
+    float sampleToCamera[16];
+    float xfov = 0, nearClip = 1e-2f, farClip = 1e4f;
+    int W = 0, H = 0;
+    bool hasCamera = false, committed = false;
+    // device scene
+    DScene ds{};
+    DevBuf<float4> dTriAccel, dVerts, dNorms;
+    DevBuf<BVHNode> dNodes;
+    DevBuf<DMaterial> dMaterials;
+    DevBuf<DEmitter> dEmitters;
+    DevBuf<float> dEmitterCdf, dTriCdf;
+    std::vector<float4> hTriAccelPrimOrder; // for b2_get_triaccel
+    LaunchCfg cfgParity, cfgFast;
+    bool classPresent[4] = {false, false, false, false};
+    // pool
+    DPool pool{};
+    DevBuf<float4> pRayO, pRayD, pHit, pThr, pLi, pShD, pShC;
+    DevBuf<uint4> pSmp;
+    DevBuf<uint2> pMeta;
+    DevBuf<uint32_t> pMatQueue;
+    DevBuf<unsigned long long> dCounters;
+    DevBuf<float4> dFilmRGBA;
+    DevBuf<float> dFilmW, dFilmOut;
+    unsigned long long *hPinned = nullptr; // ring of {active, next} pairs
+    std::vector<cudaEvent_t> ringEvents;
+    std::atomic<int> cancel{0};
+    b2_stats stats{};
+    uint32_t nPrims = 0;
+    int bvhDepth = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *b2_version(void) { return "b2mts 0.1 (sm_100a wavefront path tracer)"; }
+extern "C" int b2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" const char *b2_last_error(b2_ctx *ctx) {
+    if (ctx) return ctx->lastError.c_str();
+    return g_lastError.c_str();
+}
+
+static std::string dataDir() {
+    const char *env = getenv("B2MTS_DATA");
+    if (env) return env;
+    // <dir>/libb2mts.so -> <dir>/data
+    Dl_info info;
+    if (dladdr((const void *) &b2_version, &info) && info.dli_fname) {
+        std::string p(info.dli_fname);
+        size_t k = p.find_last_of('/');
+        return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/data";
+    }
+    return "data";
+}
+template <typename T> static bool readFile(const std::string &path, std::vector<T> &out, size_t expect) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    out.resize(expect);
+    f.read((char *) out.data(), (std::streamsize) (expect * sizeof(T)));
+    return (size_t) f.gcount() == expect * sizeof(T);
+}
+
+extern "C" int b2_context_create(int device, b2_ctx **out) {
+    if (!out) return fail(nullptr, B2_ERR_INVALID, "b2_context_create: null out pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail(nullptr, B2_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, B2_ERR_INVALID, "device index out of range");
+    b2_ctx *ctx = new b2_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return fail(nullptr, B2_ERR_CUDA, "cudaSetDevice failed"); }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->numSMs = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(nullptr, B2_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, B2_ERR_CUDA, "stream create failed"); }
+    // Sobol tables
+    std::vector<uint32_t> m32;
+    std::vector<uint64_t> vdc, inv;
+    std::string dir = dataDir();
+    if (!readFile(dir + "/sobol_matrices32.bin", m32, 1024 * 52) || !readFile(dir + "/sobol_vdc.bin", vdc, 25 * 52) ||
+        !readFile(dir + "/sobol_vdc_inv.bin", inv, 26 * 52)) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(nullptr, B2_ERR_IO, "cannot read Sobol tables from " + dir + " (set B2MTS_DATA)");
+    }
+    vdc.resize(26 * 52, 0);
+    cudaMalloc((void **) &ctx->dM32, m32.size() * 4);
+    cudaMalloc((void **) &ctx->dVdc, vdc.size() * 8);
+    cudaMalloc((void **) &ctx->dInv, inv.size() * 8);
+    cudaMemcpy(ctx->dM32, m32.data(), m32.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->dVdc, vdc.data(), vdc.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->dInv, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice);
+    ctx->tablesLoaded = true;
+    *out = ctx;
+    return B2_OK;
+}
+extern "C" void b2_context_destroy(b2_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->dM32) cudaFree(ctx->dM32);
+    if (ctx->dVdc) cudaFree(ctx->dVdc);
+    if (ctx->dInv) cudaFree(ctx->dInv);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" int b2_scene_create(b2_ctx *ctx, b2_scene **out) {
+    if (!ctx || !out) return fail(ctx, B2_ERR_INVALID, "b2_scene_create: null argument");
+    b2_scene *s = new b2_scene();
+    s->ctx = ctx;
+    *out = s;
+    return B2_OK;
+}
+extern "C" void b2_scene_destroy(b2_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    if (s->hPinned) cudaFreeHost(s->hPinned);
+    for (auto e : s->ringEvents) cudaEventDestroy(e);
+    delete s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene description
+// ------------------------------------------------------------------------------------------------
+static void mat4mul(const double *a, const double *b, double *c) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            c[i * 4 + j] = s;
+        }
+}
+static bool mat4inv(const double *m, double *inv) {
+    double a[4][8];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) { a[i][j] = m[i * 4 + j]; a[i][4 + j] = i == j ? 1.0 : 0.0; }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r)
+            if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+        if (std::fabs(a[piv][c]) < 1e-300) return false;
+        if (piv != c)
+            for (int j = 0; j < 8; ++j) std::swap(a[piv][j], a[c][j]);
+        double d = a[c][c];
+        for (int j = 0; j < 8; ++j) a[c][j] /= d;
+        for (int r = 0; r < 4; ++r)
+            if (r != c) {
+                double f = a[r][c];
+                if (f != 0)
+                    for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+            }
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) inv[i * 4 + j] = a[i][4 + j];
+    return true;
+}
+
+extern "C" int b2_scene_set_camera(b2_scene *s, const float to_world[16], float xfov_deg, float near_clip, float far_clip, int width,
+                                   int height) {
+    if (!s || !to_world) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_set_camera: null argument");
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535) return fail(s->ctx, B2_ERR_INVALID, "film size must be in [1, 65535]");
+    if (near_clip <= 0) return fail(s->ctx, B2_ERR_INVALID, "The 'nearClip' parameter must be greater than zero!");   // sensor.cpp:164-165
+    if (near_clip >= far_clip) return fail(s->ctx, B2_ERR_INVALID, "The 'nearClip' parameter must be smaller than 'farClip'."); // :166-167
+    memcpy(s->camToWorld, to_world, 64);
+    s->xfov = xfov_deg; s->nearClip = near_clip; s->farClip = far_clip; s->W = width; s->H = height;
+    // perspective.cpp:146-153 (no crop window) evaluated in double, rounded once
+    const double aspect = (double) width / (double) height;
+    const double recip = 1.0 / ((double) far_clip - (double) near_clip);
+    const double cot = 1.0 / std::tan(((double) xfov_deg / 2.0) * (M_PI / 180.0));
+    double persp[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, far_clip * recip, -(double) near_clip * far_clip * recip, 0, 0, 1, 0};
+    double tr[16] = {1, 0, 0, -1, 0, 1, 0, -1.0 / aspect, 0, 0, 1, 0, 0, 0, 0, 1};
+    double sc[16] = {-0.5, 0, 0, 0, 0, -0.5 * aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double t1[16], c2s[16], s2c[16];
+    mat4mul(tr, persp, t1);
+    mat4mul(sc, t1, c2s);
+    if (!mat4inv(c2s, s2c)) return fail(s->ctx, B2_ERR_INVALID, "singular camera matrix");
+    for (int i = 0; i < 16; ++i) s->sampleToCamera[i] = (float) s2c[i];
+    s->hasCamera = true;
+    s->committed = false;
+    return B2_OK;
+}
+extern "C" int b2_scene_get_sample_to_camera(b2_scene *s, float out[16]) {
+    if (!s || !s->hasCamera) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "camera not set");
+    memcpy(out, s->sampleToCamera, 64);
+    return B2_OK;
+}
+extern "C" int b2_scene_add_material(b2_scene *s, const b2_material_desc *m) {
+    if (!s || !m) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_material: null argument"); return -1; }
+    if (m->type < 0 || m->type > 3) { fail(s->ctx, B2_ERR_INVALID, "unknown BSDF type"); return -1; }
+    if (m->type == B2_BSDF_COATING) {
+        if (m->nested < 0 || m->nested >= (int) s->materials.size()) { fail(s->ctx, B2_ERR_INVALID, "coating: A child BSDF instance is required"); return -1; }
+        if (s->materials[m->nested].type == B2_BSDF_COATING) { fail(s->ctx, B2_ERR_INVALID, "coating over coating is not supported on the device"); return -1; }
+    }
+    if ((m->type == B2_BSDF_ROUGHDIELECTRIC || m->type == B2_BSDF_COATING) && (m->eta <= 0 || m->eta == 1.0f)) {
+        fail(s->ctx, B2_ERR_INVALID, "The interior and exterior indices of refraction must be positive and differ!"); // roughdielectric.cpp:196-198
+        return -1;
+    }
+    s->materials.push_back(*m);
+    s->committed = false;
+    return (int) s->materials.size() - 1;
+}
+extern "C" int b2_scene_add_area_emitter(b2_scene *s, const float radiance[3], float sampling_weight) {
+    if (!s || !radiance) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_area_emitter: null argument"); return -1; }
+    HostEmitter e;
+    memcpy(e.radiance, radiance, 12);
+    e.samplingWeight = sampling_weight;
+    s->emitters.push_back(e);
+    s->committed = false;
+    return (int) s->emitters.size() - 1;
+}
+extern "C" int b2_scene_add_mesh(b2_scene *s, const float *P, const float *N, const float *UV, uint32_t nV, const uint32_t *idx, uint32_t nT,
+                                 int material_id, int emitter_id) {
+    if (!s || !P || !idx) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_mesh: null argument"); return -1; }
+    if (nT == 0) { fail(s->ctx, B2_ERR_INVALID, "Encountered an empty triangle mesh!"); return -1; } // trimesh.cpp:389-392
+    if (material_id < 0 || material_id >= (int) s->materials.size()) { fail(s->ctx, B2_ERR_INVALID, "invalid material id"); return -1; }
+    if (emitter_id >= (int) s->emitters.size()) { fail(s->ctx, B2_ERR_INVALID, "invalid emitter id"); return -1; }
+    if (emitter_id >= 0 && s->emitters[emitter_id].mesh >= 0) { fail(s->ctx, B2_ERR_INVALID, "An area light cannot be parent of multiple shapes"); return -1; } // area.cpp:190-192
+    for (uint32_t i = 0; i < 3 * nT; ++i)
+        if (idx[i] >= nV) { fail(s->ctx, B2_ERR_INVALID, "triangle index out of range"); return -1; }
+    HostMesh m;
+    m.P.assign(P, P + 3 * (size_t) nV);
+    if (N) m.N.assign(N, N + 3 * (size_t) nV);
+    if (UV) m.UV.assign(UV, UV + 2 * (size_t) nV);
+    m.idx.assign(idx, idx + 3 * (size_t) nT);
+    m.material = material_id;
+    m.emitter = emitter_id;
+    if (emitter_id >= 0) s->emitters[emitter_id].mesh = (int) s->meshes.size();
+    s->meshes.push_back(std::move(m));
+    s->committed = false;
+    return (int) s->meshes.size() - 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// commit
+// ------------------------------------------------------------------------------------------------
+struct H3 {
+    float x, y, z;
+};
+static inline H3 sub3(const float *a, const float *b) { return {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
+static inline H3 cross3(const H3 &a, const H3 &b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+static inline float comp3(const H3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// TriAccel::load, include/mitsuba/render/triaccel.h:61-94
+static void triAccelLoad(const float *A, const float *B, const float *C, uint32_t words[12]) {
+    static const int waldModulo[4] = {1, 2, 0, 1};
+    memset(words, 0, 48);
+    H3 b = sub3(C, A), c = sub3(B, A), N = cross3(c, b);
+    uint32_t k = 0;
+    for (int j = 0; j < 3; j++)
+        if (std::fabs(comp3(N, j)) > std::fabs(comp3(N, k))) k = j;
+    uint32_t u = waldModulo[k], v = waldModulo[k + 1];
+    const float n_k = comp3(N, k), denom = comp3(b, u) * comp3(c, v) - comp3(b, v) * comp3(c, u);
+    float f[12];
+    memset(f, 0, sizeof(f));
+    if (denom == 0) {
+        k = 3;
+    } else {
+        f[1] = comp3(N, u) / n_k;
+        f[2] = comp3(N, v) / n_k;
+        f[3] = (A[0] * N.x + A[1] * N.y + A[2] * N.z) / n_k;
+        f[6] = comp3(b, u) / denom;
+        f[7] = -comp3(b, v) / denom;
+        f[4] = A[u];
+        f[5] = A[v];
+        f[8] = comp3(c, v) / denom;
+        f[9] = -comp3(c, u) / denom;
+    }
+    memcpy(words, f, 48);
+    words[0] = k;
+}
+
+static uint32_t materialFlags(const std::vector<b2_material_desc> &mats, int id) {
+    // combined BSDF type as BSDF::configure ORs the components
+    const b2_material_desc &d = mats[id];
+    const uint32_t EDiffuseReflection = 0x2, EGlossyReflection = 0x8, EGlossyTransmission = 0x10, EDeltaReflection = 0x20, EAnisotropic = 0x1000,
+                   ENonSymmetric = 0x4000, EFrontSide = 0x8000, EBackSide = 0x10000, EUsesSampler = 0x20000;
+    switch (d.type) {
+        case 0: return (std::max(std::max(d.reflectance[0], d.reflectance[1]), d.reflectance[2]) > 0) ? (EDiffuseReflection | EFrontSide) : 0; // diffuse.cpp:98-103
+        case 1: return EGlossyReflection | EFrontSide | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
+        case 2: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide | EUsesSampler | ENonSymmetric | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
+        default: return materialFlags(mats, d.nested) | EDeltaReflection | EFrontSide | EBackSide;
+    }
+}
+
+extern "C" int b2_scene_commit(b2_scene *s) {
+    if (!s) return fail(nullptr, B2_ERR_INVALID, "b2_scene_commit: null scene");
+    b2_ctx *ctx = s->ctx;
+    if (!s->hasCamera) return fail(ctx, B2_ERR_INVALID, "scene has no sensor");
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (size_t e = 0; e < s->emitters.size(); ++e)
+        if (s->emitters[e].mesh < 0) return fail(ctx, B2_ERR_INVALID, "area emitter without a parent shape");
+    // ---- flatten meshes: prim order = mesh order, triangle order (skdtree.cpp:68-72 m_shapeMap) ----
+    size_t nPrims = 0;
+    for (auto &m : s->meshes) { m.primOffset = (uint32_t) nPrims; nPrims += m.idx.size() / 3; }
+    if (nPrims >= (1u << 28)) return fail(ctx, B2_ERR_INVALID, "too many triangles (limit 2^28)");
+    s->nPrims = (uint32_t) nPrims;
+    bool anyNorm = false;
+    for (auto &m : s->meshes) anyNorm |= !m.N.empty() || !m.UV.empty();
+    std::vector<float4> verts(3 * nPrims), norms(anyNorm ? 3 * nPrims : 0), triAccel(3 * nPrims);
+    std::vector<PrimBox> boxes;
+    std::vector<uint32_t> ids;
+    boxes.reserve(nPrims); ids.reserve(nPrims);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t mi = 0; mi < s->meshes.size(); ++mi) {
+        const HostMesh &m = s->meshes[mi];
+        const size_t nT = m.idx.size() / 3;
+        for (size_t j = 0; j < nT; ++j) {
+            const size_t p = m.primOffset + j;
+            const uint32_t i0 = m.idx[3 * j], i1 = m.idx[3 * j + 1], i2 = m.idx[3 * j + 2];
+            const float *p0 = &m.P[3 * i0], *p1 = &m.P[3 * i1], *p2 = &m.P[3 * i2];
+            uint32_t tflags = (m.N.empty() ? 0u : 1u) | (m.UV.empty() ? 0u : 2u);
+            int matBits = m.material, emBits = m.emitter;
+            float w0, w1, w2;
+            memcpy(&w0, &matBits, 4); memcpy(&w1, &emBits, 4); memcpy(&w2, &tflags, 4);
+            verts[3 * p] = make_float4(p0[0], p0[1], p0[2], w0);
+            verts[3 * p + 1] = make_float4(p1[0], p1[1], p1[2], w1);
+            verts[3 * p + 2] = make_float4(p2[0], p2[1], p2[2], w2);
+            if (anyNorm) {
+                float n[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, dpdu[3] = {0, 0, 0};
+                if (!m.N.empty()) {
+                    memcpy(n[0], &m.N[3 * i0], 12); memcpy(n[1], &m.N[3 * i1], 12); memcpy(n[2], &m.N[3 * i2], 12);
+                }
+                if (!m.UV.empty()) { // TriMesh::computeUVTangents, trimesh.cpp:683-735
+                    H3 dP1 = sub3(p1, p0), dP2 = sub3(p2, p0);
+                    float du1 = m.UV[2 * i1] - m.UV[2 * i0], dv1 = m.UV[2 * i1 + 1] - m.UV[2 * i0 + 1];
+                    float du2 = m.UV[2 * i2] - m.UV[2 * i0], dv2 = m.UV[2 * i2 + 1] - m.UV[2 * i0 + 1];
+                    H3 nn = cross3(dP1, dP2);
+                    float length = std::sqrt(nn.x * nn.x + nn.y * nn.y + nn.z * nn.z);
+                    if (length != 0) {
+                        float determinant = du1 * dv2 - dv1 * du2;
+                        if (determinant == 0) {
+                            // coordinateSystem(n/length, dpdu, dpdv): util.cpp:592-601 -- dpdu is the `b` output
+                            float r = 1.0f / length;
+                            H3 a = {nn.x * r, nn.y * r, nn.z * r}, c;
+                            if (std::fabs(a.x) > std::fabs(a.y)) {
+                                float invLen = 1.0f / std::sqrt(a.x * a.x + a.z * a.z);
+                                c = {a.z * invLen, 0.0f, -a.x * invLen};
+                            } else {
+                                float invLen = 1.0f / std::sqrt(a.y * a.y + a.z * a.z);
+                                c = {0.0f, a.z * invLen, -a.y * invLen};
+                            }
+                            H3 b = cross3(c, a);
+                            dpdu[0] = b.x; dpdu[1] = b.y; dpdu[2] = b.z;
+                        } else {
+                            float invDet = 1.0f / determinant;
+                            dpdu[0] = (dv2 * dP1.x - dv1 * dP2.x) * invDet;
+                            dpdu[1] = (dv2 * dP1.y - dv1 * dP2.y) * invDet;
+                            dpdu[2] = (dv2 * dP1.z - dv1 * dP2.z) * invDet;
+                        }
+                    }
+                }
+                norms[3 * p] = make_float4(n[0][0], n[0][1], n[0][2], dpdu[0]);
+                norms[3 * p + 1] = make_float4(n[1][0], n[1][1], n[1][2], dpdu[1]);
+                norms[3 * p + 2] = make_float4(n[2][0], n[2][1], n[2][2], dpdu[2]);
+            }
+            uint32_t wds[12];
+            triAccelLoad(p0, p1, p2, wds);
+            wds[10] = (uint32_t) p;       // global prim id (reference: shapeIndex)
+            wds[11] = (uint32_t) j;       // primIndex within the mesh
+            memcpy(&triAccel[3 * p], wds, 48);
+            PrimBox pb;
+            for (int a = 0; a < 3; ++a) {
+                pb.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
+                pb.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
+                lo[a] = std::min(lo[a], pb.lo[a]);
+                hi[a] = std::max(hi[a], pb.hi[a]);
+            }
+            if (wds[0] != 3) { boxes.push_back(pb); ids.push_back((uint32_t) p); } // k == 3: degenerate, never hit (triaccel.h:75-78)
+        }
+    }
+    s->hTriAccelPrimOrder = triAccel;
+    // ---- BVH ----
+    BVHResult bvh;
+    int threads = (int) std::thread::hardware_concurrency();
+    buildBVH(boxes, ids, 4, B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh);
+    s->bvhDepth = bvh.depth;
+    std::vector<float4> leafTri(3 * bvh.leafPrims.size());
+    for (size_t i = 0; i < bvh.leafPrims.size(); ++i) memcpy(&leafTri[3 * i], &triAccel[3 * (size_t) bvh.leafPrims[i]], 48);
+    // ---- materials ----
+    std::vector<DMaterial> dm(s->materials.size());
+    for (int c = 0; c < 4; ++c) s->classPresent[c] = false;
+    for (size_t i = 0; i < s->materials.size(); ++i) {
+        const b2_material_desc &m = s->materials[i];
+        DMaterial &d = dm[i];
+        memset(&d, 0, sizeof(d));
+        d.type = m.type; d.distr = m.distr; d.sampleVisible = (m.distr == B2_DISTR_PHONG) ? 0 : m.sample_visible; d.nested = m.nested;
+        d.alphaU = m.alpha_u; d.alphaV = m.alpha_v; d.eta = m.eta; d.thickness = m.thickness;
+        memcpy(d.reflectance, m.reflectance, 12); memcpy(d.transmittance, m.transmittance, 12);
+        memcpy(d.etaC, m.eta_c, 12); memcpy(d.kC, m.k_c, 12); memcpy(d.sigmaA, m.sigma_a, 12);
+        d.flags = materialFlags(s->materials, (int) i);
+        if (m.type == B2_BSDF_COATING) { // coating.cpp:177-181
+            float acc = 0.0f;
+            for (int k = 0; k < 3; ++k) acc += (float) std::exp((double) (m.sigma_a[k] * (-2 * m.thickness)));
+            float avgAbsorption = acc * (1.0f / 3.0f);
+            d.specSamplingWeight = 1.0f / (avgAbsorption + 1.0f);
+        }
+    }
+    for (auto &m : s->meshes) s->classPresent[s->materials[m.material].type] = true;
+    // ---- emitters: scene.cpp:375-380, trimesh.cpp:388-403, pmf.h ----
+    std::vector<DEmitter> de(s->emitters.size());
+    std::vector<float> emCdf(1, 0.0f), triCdf;
+    float emNorm = 0.0f;
+    for (size_t e = 0; e < s->emitters.size(); ++e) {
+        const HostEmitter &he = s->emitters[e];
+        const HostMesh &m = s->meshes[he.mesh];
+        DEmitter &d = de[e];
+        memcpy(d.radiance, he.radiance, 12);
+        d.samplingWeight = he.samplingWeight;
+        d.cdfOffset = (uint32_t) triCdf.size();
+        d.nTri = (uint32_t) (m.idx.size() / 3);
+        d.primOffset = m.primOffset;
+        size_t base = triCdf.size();
+        triCdf.push_back(0.0f);
+        for (uint32_t j = 0; j < d.nTri; ++j) {
+            const float *p0 = &m.P[3 * m.idx[3 * j]], *p1 = &m.P[3 * m.idx[3 * j + 1]], *p2 = &m.P[3 * m.idx[3 * j + 2]];
+            H3 n = cross3(sub3(p1, p0), sub3(p2, p0));
+            float area = 0.5f * std::sqrt(n.x * n.x + n.y * n.y + n.z * n.z); // triangle.cpp:64-70
+            triCdf.push_back(triCdf.back() + area);
+        }
+        float sum = triCdf.back();
+        if (sum > 0) {
+            float normalization = 1.0f / sum;
+            for (size_t k = base + 1; k < triCdf.size(); ++k) triCdf[k] *= normalization;
+            triCdf.back() = 1.0f;
+        }
+        d.invSurfaceArea = 1.0f / sum;
+        emCdf.push_back(emCdf.back() + he.samplingWeight);
+    }
+    if (!s->emitters.empty()) {
+        float sum = emCdf.back();
+        if (sum > 0) {
+            emNorm = 1.0f / sum;
+            for (size_t k = 1; k < emCdf.size(); ++k) emCdf[k] *= emNorm;
+            emCdf.back() = 1.0f;
+        }
+    }
+    // ---- upload ----
+    CK(ctx, s->dTriAccel.upload(leafTri));
+    CK(ctx, s->dVerts.upload(verts));
+    CK(ctx, s->dNorms.upload(norms));
+    CK(ctx, s->dNodes.upload(bvh.nodes));
+    CK(ctx, s->dMaterials.upload(dm));
+    CK(ctx, s->dEmitters.upload(de));
+    CK(ctx, s->dEmitterCdf.upload(emCdf));
+    CK(ctx, s->dTriCdf.upload(triCdf));
+    DScene &ds = s->ds;
+    memset(&ds, 0, sizeof(ds));
+    ds.triAccel = s->dTriAccel.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
+    ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef;
+    // gkdtree.h:1213-1220: enlarged scene box (the max side uses the already-moved min, as in the reference)
+    if (nPrims == 0) { for (int a = 0; a < 3; ++a) { lo[a] = 0; hi[a] = 0; } }
+    const float eps = 1e-3f;
+    for (int a = 0; a < 3; ++a) {
+        float mn = lo[a] - ((hi[a] - lo[a]) * eps + eps);
+        float mx = hi[a] + ((hi[a] - mn) * eps + eps);
+        ds.aabbMin[a] = mn; ds.aabbMax[a] = mx;
+    }
+    ds.verts = s->dVerts.p; ds.norms = s->dNorms.p; ds.nPrims = (uint32_t) nPrims;
+    ds.materials = s->dMaterials.p; ds.nMaterials = (uint32_t) dm.size();
+    ds.emitters = s->dEmitters.p; ds.nEmitters = (uint32_t) de.size();
+    ds.emitterCdf = s->dEmitterCdf.p; ds.emitterNormalization = emNorm; ds.triCdf = s->dTriCdf.p;
+    memcpy(ds.cam.camToWorld, s->camToWorld, 64);
+    memcpy(ds.cam.sampleToCamera, s->sampleToCamera, 64);
+    ds.cam.nearClip = s->nearClip; ds.cam.farClip = s->farClip;
+    ds.cam.invResX = 1.0f / (float) s->W; ds.cam.invResY = 1.0f / (float) s->H; // sensor.cpp:104-107
+    ds.cam.origin[0] = s->camToWorld[3]; ds.cam.origin[1] = s->camToWorld[7]; ds.cam.origin[2] = s->camToWorld[11];
+    ds.cam.W = s->W; ds.cam.H = s->H;
+    ds.sobolM32 = ctx->dM32; ds.sobolVdc = ctx->dVdc; ds.sobolInv = ctx->dInv;
+    // shared-memory staging budget: up to 256 nodes (16 KB) and 256 triangles (12 KB) per CTA
+    ds.stageNodes = std::min<uint32_t>(ds.nNodes, 256u);
+    ds.stageTris = std::min<uint32_t>(ds.nLeafTris, 256u);
+    parity::KernelSet_init(s->cfgParity, ds, ctx->numSMs);
+    fast::KernelSet_init(s->cfgFast, ds, ctx->numSMs);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, s->dCounters.alloc(CTR_COUNT));
+    memset(&s->stats, 0, sizeof(s->stats));
+    s->stats.n_triangles = nPrims;
+    s->stats.n_bvh_nodes = bvh.nodes.size();
+    s->committed = true;
+    return B2_OK;
+}
+
+extern "C" int b2_get_triaccel(b2_scene *s, float *out) {
+    if (!s || !s->committed || !out) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "scene not committed");
+    memcpy(out, s->hTriAccelPrimOrder.data(), s->hTriAccelPrimOrder.size() * sizeof(float4));
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter table: rfilter.cpp:37-57, box.cpp:41-45, gaussian.cpp:35-57
+// ------------------------------------------------------------------------------------------------
+static int makeFilter(b2_ctx *ctx, int kind, float param, DFilter &f) {
+    if (kind != B2_RFILTER_BOX && kind != B2_RFILTER_GAUSSIAN) return fail(ctx, B2_ERR_INVALID, "unknown reconstruction filter");
+    float radius = kind == B2_RFILTER_BOX ? param + 1e-5f : 4 * param;
+    if (!(radius > 0) || radius > 30) return fail(ctx, B2_ERR_INVALID, "reconstruction filter radius out of range");
+    float sum = 0.0f;
+    for (int i = 0; i < 31; ++i) {
+        float x = (radius * i) / 31, value;
+        if (kind == B2_RFILTER_BOX) value = std::fabs(x) <= radius ? 1.0f : 0.0f;
+        else {
+            float alpha = -1.0f / (2.0f * param * param);
+            value = std::max(0.0f, (float) std::exp((double) (alpha * x * x)) - (float) std::exp((double) (alpha * radius * radius)));
+        }
+        f.values[i] = value;
+        sum += value;
+    }
+    f.values[31] = 0.0f;
+    f.scaleFactor = 31 / radius;
+    f.borderSize = (int) std::ceil(radius - 0.5f);
+    sum *= 2 * radius / 31;
+    float normalization = 1.0f / sum;
+    for (int i = 0; i < 31; ++i) f.values[i] *= normalization;
+    f.radius = radius;
+    f.kind = kind;
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// render
+// ------------------------------------------------------------------------------------------------
+static uint64_t teaHost(uint32_t v0, uint32_t v1, int rounds = 4) { // qmc.h:146-156
+    uint32_t sum = 0;
+    for (int i = 0; i < rounds; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xA341316Cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xC8013EA4u);
+        v1 += ((v0 << 4) + 0xAD90777Du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7E95761Eu);
+    }
+    return ((uint64_t) v1 << 32) + v0;
+}
+static uint32_t roundToPowerOfTwo(uint32_t i) {
+    i--; i |= i >> 1; i |= i >> 2; i |= i >> 4; i |= i >> 8; i |= i >> 16;
+    return i + 1;
+}
+
+static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
+    b2_ctx *ctx = s->ctx;
+    if (p->spp <= 0) return fail(ctx, B2_ERR_INVALID, "sampleCount must be positive");
+    if (p->rr_depth <= 0) return fail(ctx, B2_ERR_INVALID, "'rrDepth' must be set to a value greater than zero!"); // integrator.cpp:218-219
+    if (p->max_depth <= 0 && p->max_depth != -1)
+        return fail(ctx, B2_ERR_INVALID, "'maxDepth' must be set to -1 (infinite) or a value greater than zero!"); // :221-222
+    if (p->sampler != B2_SAMPLER_SOBOL && p->sampler != B2_SAMPLER_INDEPENDENT) return fail(ctx, B2_ERR_INVALID, "unknown sampler");
+    memset(&r, 0, sizeof(r));
+    r.spp = p->spp; r.sampler = p->sampler;
+    r.maxDepth = p->max_depth; r.rrDepth = p->rr_depth; r.strictNormals = p->strict_normals; r.hideEmitters = p->hide_emitters;
+    r.sampleLo = p->sample_lo; r.sampleHi = p->sample_hi > 0 ? p->sample_hi : p->spp;
+    if (r.sampleLo < 0 || r.sampleHi > p->spp || r.sampleLo >= r.sampleHi) return fail(ctx, B2_ERR_INVALID, "invalid sample range");
+    if (p->sampler == B2_SAMPLER_SOBOL) {
+        r.scramble = p->seed ? teaHost((uint32_t) p->seed, (uint32_t) (p->seed >> 32)) : 0; // sobol.cpp:96-102
+        uint32_t res = roundToPowerOfTwo((uint32_t) std::max(s->W, s->H));                  // sobol.cpp:147-158
+        r.resolution = (float) res;
+        uint32_t lg = 0;
+        while ((1u << lg) < res) ++lg;
+        r.logRes = lg;
+    } else {
+        r.scramble = p->seed;
+    }
+    r.tilesX = (uint32_t) (s->W + 7) / 8; r.tilesY = (uint32_t) (s->H + 7) / 8;
+    r.totalWork = (uint64_t) r.tilesX * r.tilesY * 64ull * (uint64_t) (r.sampleHi - r.sampleLo);
+    return B2_OK;
+}
+
+static int ensurePool(b2_scene *s, uint32_t Q) {
+    b2_ctx *ctx = s->ctx;
+    if (s->pool.capacity == Q) return B2_OK;
+    CK(ctx, s->pRayO.alloc(Q)); CK(ctx, s->pRayD.alloc(Q)); CK(ctx, s->pHit.alloc(Q)); CK(ctx, s->pThr.alloc(Q));
+    CK(ctx, s->pLi.alloc(Q)); CK(ctx, s->pShD.alloc(Q)); CK(ctx, s->pShC.alloc(Q)); CK(ctx, s->pSmp.alloc(Q));
+    CK(ctx, s->pMeta.alloc(Q)); CK(ctx, s->pMatQueue.alloc((size_t) 4 * Q));
+    DPool &p = s->pool;
+    p.capacity = Q;
+    p.rayO = s->pRayO.p; p.rayD = s->pRayD.p; p.hit = s->pHit.p; p.thr = s->pThr.p; p.li = s->pLi.p;
+    p.smp = s->pSmp.p; p.meta = s->pMeta.p; p.shD = s->pShD.p; p.shC = s->pShC.p; p.matQueue = s->pMatQueue.p;
+    p.counters = s->dCounters.p;
+    return B2_OK;
+}
+
+static const int kRing = 32;
+
+extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
+    if (!s || !p || !film) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_render: null argument");
+    b2_ctx *ctx = s->ctx;
+    if (!s->committed) return fail(ctx, B2_ERR_INVALID, "b2_render: scene not committed");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DRender r;
+    int rc = fillRender(s, p, r);
+    if (rc) return rc;
+    DFilter filt;
+    rc = makeFilter(ctx, p->rfilter, p->rfilter_param, filt);
+    if (rc) return rc;
+    const bool parityMode = p->parity_mode != 0;
+    const LaunchCfg &cfg = parityMode ? s->cfgParity : s->cfgFast;
+    uint32_t Q = p->pool_size > 0 ? (uint32_t) p->pool_size : (1u << 20);
+    Q = std::max<uint32_t>(Q, 1024u);
+    Q = (uint32_t) std::min<uint64_t>(Q, std::max<uint64_t>(1024u, r.totalWork));
+    Q = (Q + 255u) & ~255u;
+    rc = ensurePool(s, Q);
+    if (rc) return rc;
+    const size_t nPix = (size_t) s->W * s->H;
+    CK(ctx, s->dFilmRGBA.alloc(nPix));
+    CK(ctx, s->dFilmW.alloc(nPix));
+    r.filmRGBA = s->dFilmRGBA.p; r.filmW = s->dFilmW.p;
+    if (!s->hPinned) {
+        CK(ctx, cudaMallocHost((void **) &s->hPinned, sizeof(unsigned long long) * 2 * kRing));
+        s->ringEvents.resize(kRing);
+        for (auto &e : s->ringEvents) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    CK(ctx, cudaMemsetAsync(s->dFilmRGBA.p, 0, nPix * sizeof(float4), st));
+    CK(ctx, cudaMemsetAsync(s->dFilmW.p, 0, nPix * sizeof(float), st));
+    CK(ctx, cudaMemsetAsync(s->dCounters.p, 0, CTR_COUNT * sizeof(unsigned long long), st));
+    CK(ctx, cudaMemsetAsync(s->pMeta.p, 0, (size_t) Q * sizeof(uint2), st));
+    int nClasses = 0, onlyClass = -1;
+    for (int c = 0; c < 4; ++c)
+        if (s->classPresent[c]) { ++nClasses; onlyClass = c; }
+    bool sorted = nClasses > 1;
+    if (p->flags & 2) sorted = false;
+    s->cancel.store(0);
+    cudaEvent_t evStart, evStop;
+    CK(ctx, cudaEventCreate(&evStart));
+    CK(ctx, cudaEventCreate(&evStop));
+    CK(ctx, cudaEventRecord(evStart, st));
+    uint64_t iter = 0, checked = 0, launches = 0;
+    bool finished = false;
+    int status = B2_OK;
+#define LAUNCH(ns)                                                                                              \
+    do {                                                                                                        \
+        ns::launch_generate(cfg, s->ds, s->pool, r, filt, st);                                                  \
+        cudaMemcpyAsync(s->hPinned + 2 * (iter % kRing), s->dCounters.p + CTR_ACTIVE, 8, cudaMemcpyDeviceToHost, st); \
+        cudaMemcpyAsync(s->hPinned + 2 * (iter % kRing) + 1, s->dCounters.p + CTR_NEXT, 8, cudaMemcpyDeviceToHost, st); \
+        cudaEventRecord(s->ringEvents[iter % kRing], st);                                                       \
+        ns::launch_extend(cfg, s->ds, s->pool, sorted, st);                                                     \
+        if (sorted) {                                                                                           \
+            for (int c = 0; c < 4; ++c)                                                                         \
+                if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, st); ++launches; }  \
+        } else {                                                                                                \
+            ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);                \
+            ++launches;                                                                                         \
+        }                                                                                                       \
+        ns::launch_occluded(cfg, s->ds, s->pool, st);                                                           \
+        launches += 3;                                                                                          \
+    } while (0)
+    while (!finished) {
+        if (s->cancel.load()) { status = B2_ERR_CANCELLED; break; }
+        // the ring slot we are about to reuse must have been consumed
+        if (iter >= (uint64_t) kRing && checked + kRing <= iter) {
+            cudaEventSynchronize(s->ringEvents[checked % kRing]);
+        }
+        while (checked < iter) {
+            cudaError_t q = cudaEventQuery(s->ringEvents[checked % kRing]);
+            if (q == cudaErrorNotReady) break;
+            if (q != cudaSuccess) { status = fail(ctx, B2_ERR_CUDA, std::string("render loop: ") + cudaGetErrorString(q)); finished = true; break; }
+            unsigned long long active = s->hPinned[2 * (checked % kRing)], next = s->hPinned[2 * (checked % kRing) + 1];
+            ++checked;
+            if (active == 0 && next >= r.totalWork) { finished = true; break; }
+        }
+        if (finished) break;
+        CK(ctx, cudaMemsetAsync(s->dCounters.p + CTR_SHADOW, 0, 6 * sizeof(unsigned long long), st));
+        if (parityMode) LAUNCH(parity);
+        else LAUNCH(fast);
+        ++iter;
+        if (iter > 100000000ull) { status = fail(ctx, B2_ERR_CUDA, "render loop did not terminate"); break; }
+    }
+#undef LAUNCH
+    // pack + copy out
+    CK(ctx, cudaEventRecord(evStop, st));
+    if (status == B2_OK) {
+        float *dOut = film;
+        if (!p->film_on_device) {
+            CK(ctx, s->dFilmOut.alloc(nPix * 5));
+            dOut = s->dFilmOut.p;
+        }
+        if (parityMode) parity::launch_film_pack(cfg, s->dFilmRGBA.p, s->dFilmW.p, dOut, nPix, st);
+        else fast::launch_film_pack(cfg, s->dFilmRGBA.p, s->dFilmW.p, dOut, nPix, st);
+        if (!p->film_on_device) CK(ctx, cudaMemcpyAsync(film, dOut, nPix * 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, cudaGetLastError());
+    std::vector<unsigned long long> ctr(CTR_COUNT);
+    CK(ctx, cudaMemcpy(ctr.data(), s->dCounters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, evStart, evStop);
+    cudaEventDestroy(evStart);
+    cudaEventDestroy(evStop);
+    b2_stats &t = s->stats;
+    t.samples = ctr[CTR_SAMPLES]; t.rays = ctr[CTR_RAYS]; t.shadow_rays = ctr[CTR_SHADOWRAYS]; t.path_length_sum = ctr[CTR_PATHLEN];
+    t.bad_samples = ctr[CTR_BAD]; t.dim_overflow = ctr[CTR_DIMOVF]; t.iterations = iter; t.kernel_launches = launches + 1;
+    t.ms_total = ms;
+    return status;
+}
+
+extern "C" int b2_cancel(b2_scene *s) {
+    if (!s) return B2_ERR_INVALID;
+    s->cancel.store(1);
+    return B2_OK;
+}
+extern "C" int b2_get_stats(b2_scene *s, b2_stats *out) {
+    if (!s || !out) return B2_ERR_INVALID;
+    *out = s->stats;
+    return B2_OK;
+}
+extern "C" int b2_film_develop(const float *film, int W, int H, float *rgb) { // fmtconv.cpp:979-990
+    if (!film || !rgb || W <= 0 || H <= 0) return fail(nullptr, B2_ERR_INVALID, "b2_film_develop: invalid argument");
+    for (size_t i = 0; i < (size_t) W * H; ++i) {
+        float weight = film[5 * i + 4], invWeight = (weight != 0) ? 1 / weight : weight;
+        for (int k = 0; k < 3; ++k) rgb[3 * i + k] = film[5 * i + k] * invWeight;
+    }
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// component entry points
+// ------------------------------------------------------------------------------------------------
+struct TmpDev {
+    std::vector<void *> ptrs;
+    ~TmpDev() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> T *alloc(size_t n) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (T *) p;
+    }
+    template <typename T> T *upload(const T *h, size_t n) {
+        T *d = alloc<T>(n);
+        if (d && n) cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice);
+        return d;
+    }
+};
+#define NEED_COMMIT(s) if (!(s) || !(s)->committed) return fail((s) ? (s)->ctx : nullptr, B2_ERR_INVALID, "scene not committed")
+
+extern "C" int b2_trace_device(b2_scene *s, uint64_t n, const float *d_rays, int mode, int parity_mode, float *d_tuvp, float *ms_kernel) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    const bool count = (mode & 2) != 0;
+    const bool shadow = (mode & 1) != 0;
+    if (count) cudaMemsetAsync(s->dCounters.p + CTR_NODEVIS, 0, 16, st);
+    cudaEventRecord(a, st);
+    if (parity_mode) parity::launch_trace(s->cfgParity, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, st);
+    else fast::launch_trace(s->cfgFast, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, st);
+    cudaEventRecord(b, st);
+    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (ms_kernel) *ms_kernel = ms;
+    if (count) {
+        unsigned long long c[2];
+        cudaMemcpy(c, s->dCounters.p + CTR_NODEVIS, 16, cudaMemcpyDeviceToHost);
+        s->stats.node_visits = c[0]; s->stats.prim_tests = c[1];
+    }
+    return B2_OK;
+}
+extern "C" int b2_trace(b2_scene *s, uint64_t n, const float *rays, int mode, int parity_mode, float *t, float *u, float *v, uint32_t *prim,
+                        float *ms_kernel) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dR = tmp.upload(rays, 8 * n);
+    float *dO = tmp.alloc<float>(4 * n);
+    if (!dR || !dO) return fail(ctx, B2_ERR_CUDA, "b2_trace: device allocation failed");
+    int rc = b2_trace_device(s, n, dR, mode, parity_mode, dO, ms_kernel);
+    if (rc) return rc;
+    std::vector<float> h(4 * n);
+    CK(ctx, cudaMemcpy(h.data(), dO, 4 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n; ++i) {
+        if (t) t[i] = h[4 * i];
+        if (u) u[i] = h[4 * i + 1];
+        if (v) v[i] = h[4 * i + 2];
+        if (prim) memcpy(&prim[i], &h[4 * i + 3], 4);
+    }
+    return B2_OK;
+}
+extern "C" int b2_bsdf_eval(b2_scene *s, int mat, uint64_t n, const float *wi, const float *wo, int parity_mode, float *out_rgb, float *out_pdf) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (mat < 0 || mat >= (int) s->materials.size()) return fail(ctx, B2_ERR_INVALID, "invalid material id");
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dWi = tmp.upload(wi, 3 * n), *dWo = tmp.upload(wo, 3 * n), *dRgb = tmp.alloc<float>(3 * n), *dPdf = tmp.alloc<float>(n);
+    if (parity_mode) parity::launch_bsdf_eval(s->cfgParity, s->ds, mat, n, dWi, dWo, dRgb, dPdf, ctx->stream);
+    else fast::launch_bsdf_eval(s->cfgFast, s->ds, mat, n, dWi, dWo, dRgb, dPdf, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out_rgb, dRgb, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(ctx, cudaMemcpy(out_pdf, dPdf, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+extern "C" int b2_bsdf_sample(b2_scene *s, int mat, uint64_t n, const float *wi, const float *samples, int parity_mode, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (mat < 0 || mat >= (int) s->materials.size()) return fail(ctx, B2_ERR_INVALID, "invalid material id");
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dWi = tmp.upload(wi, 3 * n), *dS = tmp.upload(samples, 3 * n), *dO = tmp.alloc<float>(10 * n);
+    if (parity_mode) parity::launch_bsdf_sample(s->cfgParity, s->ds, mat, n, dWi, dS, dO, ctx->stream);
+    else fast::launch_bsdf_sample(s->cfgFast, s->ds, mat, n, dWi, dS, dO, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, dO, 10 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+extern "C" int b2_sample_emitter_direct(b2_scene *s, uint64_t n, const float *ref, const float *samples, int parity_mode, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (s->emitters.empty()) return fail(ctx, B2_ERR_INVALID, "scene has no emitters");
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dR = tmp.upload(ref, 6 * n), *dS = tmp.upload(samples, 2 * n), *dO = tmp.alloc<float>(12 * n);
+    if (parity_mode) parity::launch_emitter_direct(s->cfgParity, s->ds, n, dR, dS, dO, ctx->stream);
+    else fast::launch_emitter_direct(s->cfgFast, s->ds, n, dR, dS, dO, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    std::vector<float> h(12 * n);
+    CK(ctx, cudaMemcpy(h.data(), dO, 12 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    // fold the visibility test (scene.cpp:838-843) into `visible` with the occlusion kernel
+    std::vector<float> rays(8 * n);
+    for (uint64_t i = 0; i < n; ++i) {
+        float *r = &rays[8 * i];
+        r[0] = ref[6 * i]; r[1] = ref[6 * i + 1]; r[2] = ref[6 * i + 2]; r[3] = 1e-4f;
+        r[4] = h[12 * i]; r[5] = h[12 * i + 1]; r[6] = h[12 * i + 2]; r[7] = h[12 * i + 3] * (1 - 1e-3f);
+    }
+    std::vector<uint32_t> occ(n);
+    int rc = b2_trace(s, n, rays.data(), 1, parity_mode, nullptr, nullptr, nullptr, occ.data(), nullptr);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (h[12 * i + 8] != 0 && occ[i]) { h[12 * i + 8] = 0; h[12 * i + 4] = 0; h[12 * i + 5] = h[12 * i + 6] = h[12 * i + 7] = 0; }
+        else if (h[12 * i + 8] == 0) { h[12 * i + 4] = 0; }
+    }
+    memcpy(out, h.data(), 12 * n * sizeof(float));
+    return B2_OK;
+}
+extern "C" int b2_camera_rays(b2_scene *s, uint64_t n, const float *pos, int parity_mode, float *rays) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dP = tmp.upload(pos, 2 * n), *dR = tmp.alloc<float>(8 * n);
+    if (parity_mode) parity::launch_camera_rays(s->cfgParity, s->ds, n, dP, dR, ctx->stream);
+    else fast::launch_camera_rays(s->cfgFast, s->ds, n, dP, dR, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(rays, dR, 8 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+extern "C" int b2_sampler_stream(b2_scene *s, int sampler, uint64_t seed, int spp, int px, int py, int sample_idx, int ndim, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    b2_render_params p;
+    memset(&p, 0, sizeof(p));
+    p.spp = spp; p.sampler = sampler; p.seed = seed; p.max_depth = -1; p.rr_depth = 5;
+    DRender r;
+    int rc = fillRender(s, &p, r);
+    if (rc) return rc;
+    TmpDev tmp;
+    float *dO = tmp.alloc<float>(ndim);
+    parity::launch_sampler_stream(s->ds, r, px, py, sample_idx, ndim, dO, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, dO, ndim * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+extern "C" int b2_splat(b2_ctx *ctx, int W, int H, int rfilter, float param, uint64_t n, const float *pos, const float *val, float *film) {
+    if (!ctx || !pos || !val || !film || W <= 0 || H <= 0) return fail(ctx, B2_ERR_INVALID, "b2_splat: invalid argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    DFilter f;
+    int rc = makeFilter(ctx, rfilter, param, f);
+    if (rc) return rc;
+    TmpDev tmp;
+    const size_t nPix = (size_t) W * H;
+    float *dP = tmp.upload(pos, 2 * n), *dV = tmp.upload(val, 4 * n);
+    float4 *dRGBA = tmp.alloc<float4>(nPix);
+    float *dW = tmp.alloc<float>(nPix), *dOut = tmp.alloc<float>(5 * nPix);
+    cudaMemsetAsync(dRGBA, 0, nPix * sizeof(float4), ctx->stream);
+    cudaMemsetAsync(dW, 0, nPix * sizeof(float), ctx->stream);
+    LaunchCfg cfg;
+    cfg.numSMs = ctx->numSMs;
+    parity::launch_splat(cfg, f, W, H, n, dP, dV, dRGBA, dW, ctx->stream);
+    parity::launch_film_pack(cfg, dRGBA, dW, dOut, nPix, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(film, dOut, 5 * nPix * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}

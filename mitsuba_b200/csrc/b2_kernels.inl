@@ -1,0 +1,803 @@
+// Wavefront kernels.  This file is compiled twice: kernels_parity.cu (-fmad=false, namespace
+// b2::parity) and kernels_fast.cu (FMA contraction on, namespace b2::fast).  B2_KNS names the namespace.
+//
+// One iteration of the host loop = one bounce stage for every in-flight path:
+//   k_generate : splat finished paths into the film (ImageBlock::put, imageblock.h:124-204) and refill
+//                their slots with new (pixel, sample) work: sampler->generate/advance, camera ray
+//                (integrator.cpp:162-187, perspective.cpp:271-298)
+//   k_extend   : closest-hit query of every live path (skdtree.cpp:112-142) [+ material-class binning]
+//   k_shade<C> : the body of MIPathTracer::Li's loop (path.cpp:135-287) for one material class:
+//                emitter-hit MIS + Russian roulette of the previous bounce, then emission, NEE sampling
+//                (emits a shadow ray into the compacted shadow queue) and BSDF sampling (next ray)
+//   k_occluded : any-hit query of the shadow queue (skdtree.cpp:207-226); unoccluded -> Li += contribution
+#include "b2_math.cuh"
+#include "b2_types.h"
+#include "b2_sampler.cuh"
+#include "b2_bsdf.cuh"
+#include "b2_trace.cuh"
+#include "b2_launch.h"
+
+namespace b2 {
+namespace B2_KNS {
+
+// ------------------------------------------------------------------------------------------------
+// TMA staging of the head of the node / triangle arrays into shared memory (cp.async.bulk + mbarrier)
+// ------------------------------------------------------------------------------------------------
+B2_DEV uint32_t smemAddr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t *bar) {
+    const uint32_t nb = sc.stageNodes * 64u, tb = sc.stageTris * 48u;
+    const uint32_t barA = smemAddr(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barA), "r"(nb + tb) : "memory");
+        if (nb)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(sNodes)),
+                         "l"(sc.nodes), "r"(nb), "r"(barA)
+                         : "memory");
+        if (tb)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(sTris)),
+                         "l"(sc.triAccel), "r"(tb), "r"(barA)
+                         : "memory");
+    }
+    // every thread waits for phase 0
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(barA)
+            : "memory");
+    }
+}
+
+// dynamic shared memory carve-up for the traversal kernels
+B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem) {
+    uint32_t *stack = (uint32_t *) smem;
+    size_t off = (size_t) B2_STACK_DEPTH * blockDim.x * sizeof(uint32_t);
+    off = (off + 127) & ~(size_t) 127;
+    float4 *sNodes = (float4 *) (smem + off);
+    off += (size_t) sc.stageNodes * 64;
+    float4 *sTris = (float4 *) (smem + off);
+    off += (size_t) sc.stageTris * 48;
+    off = (off + 15) & ~(size_t) 15;
+    uint64_t *bar = (uint64_t *) (smem + off);
+    stageScene(sc, sNodes, sTris, bar);
+    TraceMem tm;
+    tm.gNodes = (const float4 *) sc.nodes;
+    tm.gTris = sc.triAccel;
+    tm.sNodes = sNodes;
+    tm.sTris = sTris;
+    tm.stageNodes = sc.stageNodes;
+    tm.stageTris = sc.stageTris;
+    tm.stack = stack + threadIdx.x;
+    tm.stride = blockDim.x;
+    return tm;
+}
+
+B2_DEV uint32_t warpSum(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// warp-ballot stream compaction: lanes with `want` get consecutive indices from *counter (one atomic per warp)
+B2_DEV unsigned long long warpAppend64(bool want, unsigned long long *counter) {
+    const unsigned active = __activemask();
+    const unsigned mask = __ballot_sync(active, want);
+    if (!want) return ~0ull;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long) __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (unsigned long long) __popc(mask & ((1u << lane) - 1u));
+}
+B2_DEV uint32_t warpAppend(bool want, unsigned long long *counter) { return (uint32_t) warpAppend64(want, counter); }
+
+// ------------------------------------------------------------------------------------------------
+// film: ImageBlock::put(pos, spec, alpha) with global atomics (imageblock.h:124-204, full-frame form)
+// ------------------------------------------------------------------------------------------------
+B2_DEV float evalDiscretized(const DFilter &f, float x) { // rfilter.h:76-77
+    int i = (int) fabsf(x * f.scaleFactor);
+    return f.values[i < 31 ? i : 31];
+}
+B2_DEV void redAddV4(float4 *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+B2_DEV bool filmPut(const DFilter &f, float4 *filmRGBA, float *filmW, int W, int H, float posX, float posY, const V3 &spec, float alpha) {
+    const float value[5] = {spec.x, spec.y, spec.z, alpha, 1.0f};
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        if (!isfinite(value[i]) || value[i] < 0) return false;
+    const float px = posX - 0.5f, py = posY - 0.5f;
+    const int minx = max((int) ceilf(px - f.radius), 0), miny = max((int) ceilf(py - f.radius), 0);
+    const int maxx = min((int) floorf(px + f.radius), W - 1), maxy = min((int) floorf(py + f.radius), H - 1);
+    for (int y = miny; y <= maxy; ++y) {
+        const float wy = evalDiscretized(f, (float) y - py);
+        for (int x = minx; x <= maxx; ++x) {
+            const float w = evalDiscretized(f, (float) x - px) * wy;
+            const size_t o = (size_t) y * W + x;
+            redAddV4(filmRGBA + o, w * value[0], w * value[1], w * value[2], w * value[3]);
+            atomicAdd(filmW + o, w * value[4]);
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// camera: perspective.cpp:271-298
+// ------------------------------------------------------------------------------------------------
+B2_DEV void cameraRay(const DCamera &cam, float sx, float sy, V3 &o, V3 &d, float &mint, float &maxt) {
+    const float *M = cam.sampleToCamera;
+    float px = sx * cam.invResX, py = sy * cam.invResY;
+    float x = M[0] * px + M[1] * py + M[2] * 0.0f + M[3];
+    float y = M[4] * px + M[5] * py + M[6] * 0.0f + M[7];
+    float z = M[8] * px + M[9] * py + M[10] * 0.0f + M[11];
+    float w = M[12] * px + M[13] * py + M[14] * 0.0f + M[15];
+    V3 nearP(x, y, z);
+    if (w != 1.0f) nearP = nearP / w;
+    V3 dl = normalize(nearP);
+    float invZ = 1.0f / dl.z;
+    const float *T = cam.camToWorld;
+    d = V3(T[0] * dl.x + T[1] * dl.y + T[2] * dl.z, T[4] * dl.x + T[5] * dl.y + T[6] * dl.z, T[8] * dl.x + T[9] * dl.y + T[10] * dl.z);
+    o = V3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    mint = cam.nearClip * invZ;
+    maxt = cam.farClip * invZ;
+}
+
+// sampler set-up for (pixel, sample): sobol.cpp:204-216 / counter stream
+B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uint32_t s, PathSampler &smp, float &ax, float &ay) {
+    smp.kind = rp.sampler;
+    smp.m32 = sc.sobolM32;
+    smp.overflow = false;
+    smp.dim = 0;
+    if (rp.sampler == 0) {
+        smp.scramble32 = (uint32_t) rp.scramble;
+        uint64_t idx = s;
+        if (rp.logRes > 1) idx = sobolLookUp(sc.sobolVdc, sc.sobolInv, rp.logRes, s, (uint32_t) px, (uint32_t) py, rp.scramble);
+        smp.index = idx;
+        if (idx != (uint64_t) s) { // sobol.cpp:241-243
+            ax = smp.next1D() * rp.resolution - (float) px;
+            ay = smp.next1D() * rp.resolution - (float) py;
+        } else {
+            ax = smp.next1D();
+            ay = smp.next1D();
+        }
+    } else {
+        smp.scramble32 = (uint32_t) (rp.scramble >> 32);
+        smp.index = ((((uint32_t) py * (uint32_t) sc.cam.W + (uint32_t) px) * (uint32_t) rp.spp + s) ^ (uint32_t) rp.scramble);
+        ax = smp.next1D();
+        ay = smp.next1D();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_generate
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
+    const uint32_t Q = pool.capacity;
+    uint32_t nSamples = 0, nBad = 0, nDimOvf = 0;
+    unsigned long long pathLen = 0;
+    uint32_t nActive = 0;
+    const uint32_t nS = (uint32_t) (rp.sampleHi - rp.sampleLo);
+    const uint32_t perTile = 64u * nS;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool inRange = i < Q;
+        uint2 meta = inRange ? pool.meta[i] : make_uint2(0, 0);
+        uint32_t flags = meta.y & 0xFFu;
+        if (inRange && (flags & PF_DONE)) {
+            const float4 li = pool.li[i];
+            const uint4 sm = pool.smp[i];
+            const float alpha = (flags & PF_ALPHA) ? 1.0f : 0.0f;
+            if (!filmPut(filt, rp.filmRGBA, rp.filmW, sc.cam.W, sc.cam.H, __uint_as_float(sm.z), __uint_as_float(sm.w), V3(li.x, li.y, li.z), alpha))
+                ++nBad;
+            ++nSamples;
+            pathLen += (meta.y >> 8) & 0xFFFu;
+            flags = 0;
+        }
+        bool want = inRange && !(flags & PF_ALIVE);
+        // claim work: one atomic per warp
+        const unsigned long long w = warpAppend64(want, pool.counters + CTR_NEXT);
+        if (want) {
+            bool valid = w < rp.totalWork;
+            int px = 0, py = 0;
+            uint32_t s = 0;
+            if (valid) {
+                const uint32_t tile = (uint32_t) (w / perTile), r = (uint32_t) (w % perTile);
+                s = (uint32_t) rp.sampleLo + r / 64u;
+                const uint32_t p = r & 63u;
+                px = (int) ((tile % rp.tilesX) * 8u + (p & 7u));
+                py = (int) ((tile / rp.tilesX) * 8u + (p >> 3));
+                valid = px < sc.cam.W && py < sc.cam.H;
+            }
+            if (valid) {
+                PathSampler smp;
+                float ax, ay;
+                samplerInit(sc, rp, px, py, s, smp, ax, ay);
+                const float spx = (float) px + ax, spy = (float) py + ay;
+                V3 o, d;
+                float mint, maxt;
+                cameraRay(sc.cam, spx, spy, o, d, mint, maxt);
+                pool.rayO[i] = make_float4(o.x, o.y, o.z, mint);
+                pool.rayD[i] = make_float4(d.x, d.y, d.z, maxt);
+                pool.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                pool.li[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                pool.smp[i] = make_uint4((uint32_t) smp.index, (uint32_t) (smp.index >> 32), __float_as_uint(spx), __float_as_uint(spy));
+                flags = PF_ALIVE | PF_FRESH;
+                meta.x = ((uint32_t) py << 16) | (uint32_t) px;
+                meta.y = flags | (1u << 8) | (smp.dim << 20); // depth = 1 (integrator.h:221-227)
+            } else {
+                meta.y = 0;
+            }
+            pool.meta[i] = meta;
+        }
+        if (inRange && (meta.y & PF_ALIVE)) ++nActive;
+    }
+    nActive = warpSum(nActive);
+    nSamples = warpSum(nSamples);
+    nBad = warpSum(nBad);
+    nDimOvf = warpSum(nDimOvf);
+    uint32_t plLo = warpSum((uint32_t) pathLen);
+    if ((threadIdx.x & 31) == 0) {
+        if (nActive) atomicAdd(pool.counters + CTR_ACTIVE, (unsigned long long) nActive);
+        if (nSamples) atomicAdd(pool.counters + CTR_SAMPLES, (unsigned long long) nSamples);
+        if (nBad) atomicAdd(pool.counters + CTR_BAD, (unsigned long long) nBad);
+        if (plLo) atomicAdd(pool.counters + CTR_PATHLEN, (unsigned long long) plLo);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_extend: closest hit for every live slot (+ optional material-class binning)
+// ------------------------------------------------------------------------------------------------
+template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(DScene sc, DPool pool) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TraceMem tm = setupTraceMem(sc, smem);
+    const uint32_t Q = pool.capacity;
+    uint32_t nRays = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool live = i < Q && (pool.meta[i].y & PF_ALIVE);
+        int cls = -1;
+        if (live) {
+            const float4 ro = pool.rayO[i], rd = pool.rayD[i];
+            const V3 o(ro.x, ro.y, ro.z), d(rd.x, rd.y, rd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // ray.h:83-84
+            HitRec h;
+            h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
+            float mint, maxt;
+            uint32_t nv = 0, pt = 0;
+            if (clipRay<false>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt)) {
+                if (!traverse<false, false>(sc, tm, o, d, mint, maxt, h, nv, pt)) { h.t = B2_INF; h.prim = 0xFFFFFFFFu; }
+            }
+            pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            ++nRays;
+            if (SORT) {
+                cls = 0;
+                if (h.prim != 0xFFFFFFFFu) {
+                    const int mat = __float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w));
+                    cls = sc.materials[mat].type;
+                }
+            }
+        }
+        if (SORT) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t at = warpAppend(cls == c, pool.counters + CTR_CLASS0 + c);
+                if (cls == c) pool.matQueue[(size_t) c * Q + at] = i;
+            }
+        }
+    }
+    nRays = warpSum(nRays);
+    if ((threadIdx.x & 31) == 0 && nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
+}
+
+// ------------------------------------------------------------------------------------------------
+// intersection record: skdtree.h:343-428 fillIntersectionRecord<true>
+// ------------------------------------------------------------------------------------------------
+struct Isect {
+    V3 p;
+    V3 geoN;
+    Frame sh;
+    V3 wi;
+    int material, emitter;
+};
+B2_DEV void fillIntersection(const DScene &sc, const V3 &rayD, uint32_t prim, float u, float v, Isect &its) {
+    const float4 a0 = __ldg(&sc.verts[3 * (size_t) prim]), a1 = __ldg(&sc.verts[3 * (size_t) prim + 1]), a2 = __ldg(&sc.verts[3 * (size_t) prim + 2]);
+    const V3 p0(a0.x, a0.y, a0.z), p1(a1.x, a1.y, a1.z), p2(a2.x, a2.y, a2.z);
+    its.material = __float_as_int(a0.w);
+    its.emitter = __float_as_int(a1.w);
+    const uint32_t tflags = __float_as_uint(a2.w);
+    const V3 b(1 - u - v, u, v);
+    its.p = p0 * b.x + p1 * b.y + p2 * b.z;
+    const V3 side1 = p1 - p0, side2 = p2 - p0;
+    V3 faceNormal = cross(side1, side2);
+    const float len = length(faceNormal);
+    if (!isZero(faceNormal)) faceNormal = faceNormal / len;
+    V3 dpdu = side1;
+    V3 shN;
+    if (tflags & 3u) {
+        const float4 n0 = __ldg(&sc.norms[3 * (size_t) prim]), n1 = __ldg(&sc.norms[3 * (size_t) prim + 1]), n2 = __ldg(&sc.norms[3 * (size_t) prim + 2]);
+        if (tflags & 2u) dpdu = V3(n0.w, n1.w, n2.w);
+        if (tflags & 1u) {
+            shN = normalize(V3(n0.x, n0.y, n0.z) * b.x + V3(n1.x, n1.y, n1.z) * b.y + V3(n2.x, n2.y, n2.z) * b.z);
+            if (dot(faceNormal, shN) < 0) faceNormal = -faceNormal;
+        } else shN = faceNormal;
+    } else shN = faceNormal;
+    its.geoN = faceNormal;
+    computeShadingFrame(shN, dpdu, its.sh);
+    its.wi = its.sh.toLocal(-rayD);
+}
+
+B2_DEV float miWeight(float pdfA, float pdfB) { // path.cpp:296-300
+    pdfA *= pdfA;
+    pdfB *= pdfB;
+    return pdfA / (pdfA + pdfB);
+}
+
+// DiscreteDistribution::sample (pmf.h:128-141): lower_bound on the cdf, index clamp, zero-probability skip
+B2_DEV uint32_t cdfSample(const float *__restrict__ cdf, uint32_t n /* entries, cdf has n+1 */, float v) {
+    uint32_t lo = 0, cnt = n + 1; // lower_bound over cdf[0..n]
+    while (cnt > 0) {
+        uint32_t step = cnt >> 1, it = lo + step;
+        if (__ldg(cdf + it) < v) { lo = it + 1; cnt -= step + 1; }
+        else cnt = step;
+    }
+    int idx = (int) lo - 1;
+    if (idx < 0) idx = 0;
+    if ((uint32_t) idx > n - 1) idx = (int) n - 1;
+    while ((__ldg(cdf + idx + 1) - __ldg(cdf + idx)) == 0 && (uint32_t) idx < n) ++idx;
+    return (uint32_t) idx;
+}
+
+struct DirectSample {
+    V3 d, p, n;
+    float dist, pdf;
+    Spectrum value;
+    int emitter;
+};
+// Scene::sampleEmitterDirect (scene.cpp:828-852) up to, not including, the visibility ray:
+// emitter pick (pmf.h sampleReuse), AreaLight::sampleDirect (area.cpp:158-173), Shape::sampleDirect
+// (shape.cpp:102-115), TriMesh::samplePosition (trimesh.cpp:412-424), Triangle::sample (triangle.cpp:24-62)
+B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN, float sx, float sy, DirectSample &ds) {
+    const uint32_t ei = cdfSample(sc.emitterCdf, sc.nEmitters, sx);
+    const float c0 = __ldg(sc.emitterCdf + ei), c1 = __ldg(sc.emitterCdf + ei + 1);
+    const float emPdf = c1 - c0;
+    sx = (sx - c0) / (c1 - c0);
+    const DEmitter &em = sc.emitters[ei];
+    const float *tcdf = sc.triCdf + em.cdfOffset;
+    const uint32_t ti = cdfSample(tcdf, em.nTri, sy);
+    const float t0 = __ldg(tcdf + ti), t1 = __ldg(tcdf + ti + 1);
+    sy = (sy - t0) / (t1 - t0);
+    const size_t prim = (size_t) em.primOffset + ti;
+    const float4 a0 = __ldg(&sc.verts[3 * prim]), a1 = __ldg(&sc.verts[3 * prim + 1]), a2 = __ldg(&sc.verts[3 * prim + 2]);
+    const V3 p0(a0.x, a0.y, a0.z), p1(a1.x, a1.y, a1.z), p2(a2.x, a2.y, a2.z);
+    float bx, by;
+    squareToUniformTriangle(sx, sy, bx, by);
+    const V3 sideA = p1 - p0, sideB = p2 - p0;
+    ds.p = p0 + (sideA * bx) + (sideB * by);
+    if (__float_as_uint(a2.w) & 1u) {
+        const float4 n0 = __ldg(&sc.norms[3 * prim]), n1 = __ldg(&sc.norms[3 * prim + 1]), n2 = __ldg(&sc.norms[3 * prim + 2]);
+        ds.n = normalize(V3(n0.x, n0.y, n0.z) * (1.0f - bx - by) + V3(n1.x, n1.y, n1.z) * bx + V3(n2.x, n2.y, n2.z) * by);
+    } else ds.n = normalize(cross(sideA, sideB));
+    float pdf = em.invSurfaceArea;
+    ds.d = ds.p - ref;
+    const float distSquared = lengthSquared(ds.d);
+    ds.dist = sqrtf(distSquared);
+    ds.d = ds.d / ds.dist;
+    const float dp = absDot(ds.d, ds.n);
+    pdf *= dp != 0 ? (distSquared / dp) : 0.0f;
+    ds.emitter = (int) ei;
+    if (dot(ds.d, refN) >= 0 && dot(ds.d, ds.n) < 0 && pdf != 0) {
+        ds.value = V3(em.radiance[0], em.radiance[1], em.radiance[2]) / pdf;
+        ds.pdf = pdf * emPdf;
+        ds.value = ds.value / emPdf;
+        return true;
+    }
+    ds.pdf = 0.0f;
+    ds.value = Spectrum(0.0f);
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_shade
+// ------------------------------------------------------------------------------------------------
+template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
+                                                                             const unsigned long long *queueCount) {
+    const uint32_t Q = pool.capacity;
+    const uint32_t n = queue ? (uint32_t) *queueCount : Q;
+    uint32_t nDimOvf = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        uint32_t i = 0;
+        bool live = j < n;
+        if (live) i = queue ? queue[j] : j;
+        uint2 meta = live ? pool.meta[i] : make_uint2(0, 0);
+        uint32_t flags = meta.y & 0xFFu;
+        if (!queue) live = live && (flags & PF_ALIVE);
+        // shadow-ray output of this lane
+        bool emitShadow = false;
+        V3 shD(0.0f);
+        float shMaxt = 0;
+        Spectrum shC(0.0f);
+        if (live) {
+            int depth = (int) ((meta.y >> 8) & 0xFFFu);
+            const float4 hit = pool.hit[i];
+            const float4 rd4 = pool.rayD[i];
+            const V3 rayD(rd4.x, rd4.y, rd4.z);
+            float4 thr4 = pool.thr[i];
+            float4 li4 = pool.li[i];
+            const uint4 sm4 = pool.smp[i];
+            Spectrum T(thr4.x, thr4.y, thr4.z), Li(li4.x, li4.y, li4.z);
+            float eta = thr4.w;
+            const float bsdfPdfPrev = li4.w;
+            PathSampler smp;
+            smp.kind = rp.sampler;
+            smp.m32 = sc.sobolM32;
+            smp.overflow = false;
+            smp.index = ((uint64_t) sm4.y << 32) | sm4.x;
+            smp.dim = meta.y >> 20;
+            smp.scramble32 = rp.sampler == 0 ? (uint32_t) rp.scramble : (uint32_t) (rp.scramble >> 32);
+            const uint32_t prim = __float_as_uint(hit.w);
+            const bool valid = prim != 0xFFFFFFFFu;
+            bool done = false;
+            Isect its;
+            if (valid) fillIntersection(sc, rayD, prim, hit.y, hit.z, its);
+            const bool fresh = (flags & PF_FRESH) != 0;
+            if (fresh) {
+                if (valid) flags |= PF_ALPHA; // records.inl:117-144 (EOpacity)
+            } else {
+                // ---- tail of the previous loop iteration: path.cpp:226-286 ----
+                if (!valid) done = true; // no environment emitter: `break` at :246
+                else {
+                    if (its.emitter >= 0) {
+                        const DEmitter &em = sc.emitters[its.emitter];
+                        // its.Le(-ray.d): area.cpp:104-109
+                        Spectrum value = dot(its.sh.n, -rayD) <= 0 ? Spectrum(0.0f) : V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                        // pdfEmitterDirect: scene.cpp:949-952, area.cpp:175-183, shape.cpp:117-126
+                        float lumPdf = 0.0f;
+                        if (!(flags & PF_DELTA)) {
+                            float pdfDirect = 0.0f;
+                            if ((flags & PF_REFN_OK) && dot(rayD, its.sh.n) < 0)
+                                pdfDirect = em.invSurfaceArea * (hit.x * hit.x) / absDot(rayD, its.sh.n);
+                            lumPdf = pdfDirect * (em.samplingWeight * sc.emitterNormalization);
+                        }
+                        Li = Li + T * value * miWeight(bsdfPdfPrev, lumPdf);
+                    }
+                    // rRec.type = ERadianceNoEmission; Russian roulette :276-286
+                    if (depth++ >= rp.rrDepth) {
+                        float q = fminf(maxComp(T) * eta * eta, 0.95f);
+                        if (smp.next1D() >= q) done = true;
+                        else T = T / q;
+                    }
+                }
+            }
+            // ---- head of the loop: path.cpp:135-222 ----
+            if (!done && !(depth <= rp.maxDepth || rp.maxDepth < 0)) done = true;
+            if (!done && !valid) done = true; // camera ray missed (:136-143)
+            if (!done) {
+                const DMaterial *mats = sc.materials;
+                const int mat = its.material;
+                const uint32_t btype = mats[mat].flags;
+                if (its.emitter >= 0 && fresh && (!rp.hideEmitters || (flags & PF_SCATTERED))) {
+                    const DEmitter &em = sc.emitters[its.emitter];
+                    Spectrum le = dot(its.sh.n, -rayD) <= 0 ? Spectrum(0.0f) : V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                    Li = Li + T * le;
+                }
+                if ((depth >= rp.maxDepth && rp.maxDepth > 0) || (rp.strictNormals && dot(rayD, its.geoN) * cosTheta(its.wi) >= 0)) done = true;
+                if (!done) {
+                    V3 refN(0.0f);
+                    if ((btype & (ETransmission | EBackSide)) == 0) refN = its.sh.n; // records.inl:160-164
+                    // ---- direct illumination: path.cpp:172-200 ----
+                    if (btype & ESmooth) {
+                        float sx, sy;
+                        smp.next2D(sx, sy);
+                        DirectSample ds;
+                        if (sc.nEmitters > 0 && sampleEmitterDirect(sc, its.p, refN, sx, sy, ds)) {
+                            BRec bRec;
+                            bRec.wi = its.wi;
+                            bRec.wo = its.sh.toLocal(ds.d);
+                            const Spectrum bsdfVal = bsdfEval<CLS>(mats, mat, bRec);
+                            if (!isZero(bsdfVal) && (!rp.strictNormals || dot(its.geoN, ds.d) * cosTheta(bRec.wo) > 0)) {
+                                const float bp = bsdfPdf<CLS>(mats, mat, bRec);
+                                const float weight = miWeight(ds.pdf, bp);
+                                shC = T * ds.value * bsdfVal * weight;
+                                shD = ds.d;
+                                shMaxt = ds.dist * (1 - B2_SHADOW_EPSILON);
+                                emitShadow = true;
+                            }
+                        }
+                    }
+                    // ---- BSDF sampling: path.cpp:206-226 ----
+                    float bsdfPdfNew;
+                    BRec bRec;
+                    bRec.wi = its.wi;
+                    float sx, sy;
+                    smp.next2D(sx, sy);
+                    const Spectrum bsdfWeight = bsdfSample<CLS>(mats, mat, bRec, bsdfPdfNew, sx, sy, smp);
+                    if (isZero(bsdfWeight)) done = true;
+                    else {
+                        flags &= ~(PF_DELTA | PF_REFN_OK | PF_FRESH);
+                        if (bRec.sampledType != ENull) flags |= PF_SCATTERED;
+                        const V3 wo = its.sh.toWorld(bRec.wo);
+                        const float woDotGeoN = dot(its.geoN, wo);
+                        if (rp.strictNormals && woDotGeoN * cosTheta(bRec.wo) <= 0) done = true;
+                        else {
+                            if (bRec.sampledType & EDelta) flags |= PF_DELTA;
+                            if (dot(wo, refN) >= 0) flags |= PF_REFN_OK;
+                            pool.rayO[i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
+                            pool.rayD[i] = make_float4(wo.x, wo.y, wo.z, B2_INF);
+                            T = T * bsdfWeight; // :252-253 (applied early: only read again if the next ray hits)
+                            eta *= bRec.eta;
+                            li4.w = bsdfPdfNew;
+                        }
+                    }
+                    if (done && emitShadow) {
+                        // the path ends here but its shadow ray still has to be resolved: k_occluded reads the origin from rayO
+                        pool.rayO[i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
+                    }
+                }
+            }
+            if (smp.overflow) ++nDimOvf;
+            flags &= ~PF_FRESH;
+            if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
+            pool.thr[i] = make_float4(T.x, T.y, T.z, eta);
+            pool.li[i] = make_float4(Li.x, Li.y, Li.z, li4.w);
+            meta.y = flags | ((uint32_t) depth << 8) | (smp.dim << 20);
+            pool.meta[i] = meta;
+        }
+        // shadow-ray compaction (warp ballot, one atomic per warp)
+        const uint32_t at = warpAppend(emitShadow, pool.counters + CTR_SHADOW);
+        if (emitShadow) {
+            pool.shD[at] = make_float4(shD.x, shD.y, shD.z, shMaxt);
+            pool.shC[at] = make_float4(shC.x, shC.y, shC.z, __uint_as_float(i));
+        }
+    }
+    nDimOvf = warpSum(nDimOvf);
+    if ((threadIdx.x & 31) == 0 && nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_occluded
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool pool) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TraceMem tm = setupTraceMem(sc, smem);
+    const uint32_t n = (uint32_t) pool.counters[CTR_SHADOW];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        if (j < n) {
+            const float4 sd = pool.shD[j], scn = pool.shC[j];
+            const uint32_t slot = __float_as_uint(scn.w);
+            const float4 ro = pool.rayO[slot];
+            const V3 o(ro.x, ro.y, ro.z), d(sd.x, sd.y, sd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            float mint, maxt;
+            bool occluded = false;
+            HitRec h;
+            uint32_t nv = 0, pt = 0;
+            if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt)) occluded = traverse<true, false>(sc, tm, o, d, mint, maxt, h, nv, pt);
+            if (!occluded) {
+                float4 li = pool.li[slot];
+                li.x += scn.x; li.y += scn.y; li.z += scn.z;
+                pool.li[slot] = li;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(pool.counters + CTR_SHADOWRAYS, (unsigned long long) n);
+}
+
+// film pack: (float4 rgba, float w) planes -> interleaved H*W*5 (hdrfilm.cpp:351-356 ESpectrumAlphaWeight)
+__global__ void k_film_pack(const float4 *rgba, const float *w, float *out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const float4 v = rgba[i];
+        float *o = out + 5 * i;
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; o[4] = w[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// component kernels (b2_trace / b2_bsdf_* / b2_sample_emitter_direct / b2_camera_rays / b2_sampler_stream / b2_splat)
+// ------------------------------------------------------------------------------------------------
+template <bool SHADOW, bool COUNT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_trace_rays(DScene sc, const float4 *rays, float4 *out, uint64_t n,
+                                                                                                   unsigned long long *counters) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TraceMem tm = setupTraceMem(sc, smem);
+    uint32_t nv = 0, pt = 0;
+    for (uint64_t base = blockIdx.x * (uint64_t) blockDim.x; base < n; base += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        if (i < n) {
+            const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+            const V3 o(ro.x, ro.y, ro.z), d(rd.x, rd.y, rd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            HitRec h;
+            h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
+            float mint, maxt;
+            bool found = false;
+            if (clipRay<SHADOW>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt)) found = traverse<SHADOW, COUNT>(sc, tm, o, d, mint, maxt, h, nv, pt);
+            if (SHADOW) out[i] = make_float4(0, 0, 0, __uint_as_float(found ? 1u : 0u));
+            else {
+                if (!found) { h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu; }
+                out[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            }
+        }
+    }
+    if (COUNT) {
+        nv = warpSum(nv); pt = warpSum(pt);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(counters + CTR_NODEVIS, (unsigned long long) nv);
+            atomicAdd(counters + CTR_PRIMTESTS, (unsigned long long) pt);
+        }
+    }
+}
+
+__global__ void k_bsdf_eval(DScene sc, int mat, uint64_t n, const float *wi, const float *wo, float *rgb, float *pdf) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        BRec r;
+        r.wi = V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        r.wo = V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        const Spectrum f = bsdfEval<-1>(sc.materials, mat, r);
+        rgb[3 * i] = f.x; rgb[3 * i + 1] = f.y; rgb[3 * i + 2] = f.z;
+        pdf[i] = bsdfPdf<-1>(sc.materials, mat, r);
+    }
+}
+__global__ void k_bsdf_sample(DScene sc, int mat, uint64_t n, const float *wi, const float *samples, float *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        // replay sampler (kind 3): next1D() returns the third sample component (test_chisquare.cpp:58-92 FakeSampler)
+        PathSampler smp;
+        smp.kind = 3; smp.m32 = nullptr; smp.overflow = false; smp.dim = 0; smp.index = 0;
+        smp.scramble32 = __float_as_uint(samples[3 * i + 2]);
+        BRec r;
+        r.wi = V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        r.wo = V3(0.0f); r.eta = 1.0f; r.sampledType = 0;
+        float pdf = 0;
+        const Spectrum w = bsdfSample<-1>(sc.materials, mat, r, pdf, samples[3 * i], samples[3 * i + 1], smp);
+        float *o = out + 10 * i;
+        o[0] = r.wo.x; o[1] = r.wo.y; o[2] = r.wo.z; o[3] = w.x; o[4] = w.y; o[5] = w.z;
+        o[6] = isZero(w) ? 0.0f : pdf; o[7] = (float) r.sampledType; o[8] = r.eta; o[9] = 0;
+    }
+}
+__global__ void k_emitter_direct(DScene sc, uint64_t n, const float *ref, const float *samples, float *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        DirectSample ds;
+        const V3 r(ref[6 * i], ref[6 * i + 1], ref[6 * i + 2]), rn(ref[6 * i + 3], ref[6 * i + 4], ref[6 * i + 5]);
+        const bool ok = sampleEmitterDirect(sc, r, rn, samples[2 * i], samples[2 * i + 1], ds);
+        float *o = out + 12 * i;
+        o[0] = ds.d.x; o[1] = ds.d.y; o[2] = ds.d.z; o[3] = ds.dist; o[4] = ok ? ds.pdf : 0.0f;
+        o[5] = ds.value.x; o[6] = ds.value.y; o[7] = ds.value.z; o[8] = ok ? 1.0f : 0.0f; o[9] = ds.p.x; o[10] = ds.p.y; o[11] = ds.p.z;
+    }
+}
+__global__ void k_camera_rays(DScene sc, uint64_t n, const float *pos, float *rays) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        V3 o, d;
+        float mint, maxt;
+        cameraRay(sc.cam, pos[2 * i], pos[2 * i + 1], o, d, mint, maxt);
+        float *r = rays + 8 * i;
+        r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = mint; r[4] = d.x; r[5] = d.y; r[6] = d.z; r[7] = maxt;
+    }
+}
+__global__ void k_sampler_stream(DScene sc, DRender rp, int px, int py, int sampleIdx, int ndim, float *out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        PathSampler smp;
+        float ax, ay;
+        samplerInit(sc, rp, px, py, (uint32_t) sampleIdx, smp, ax, ay);
+        if (ndim > 0) out[0] = ax;
+        if (ndim > 1) out[1] = ay;
+        for (int i = 2; i < ndim; ++i) out[i] = smp.next1D();
+    }
+}
+__global__ void k_splat(DFilter f, int W, int H, uint64_t n, const float *pos, const float *val, float4 *rgba, float *wgt) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const int px = (int) floorf(pos[2 * i]), py = (int) floorf(pos[2 * i + 1]);
+        if (px < 0 || py < 0 || px >= W || py >= H) continue;
+        filmPut(f, rgba, wgt, W, H, pos[2 * i], pos[2 * i + 1], V3(val[4 * i], val[4 * i + 1], val[4 * i + 2]), val[4 * i + 3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers (host side of this translation unit)
+// ------------------------------------------------------------------------------------------------
+static size_t traceSmemBytes(const DScene &sc, int block) {
+    size_t off = (size_t) B2_STACK_DEPTH * block * sizeof(uint32_t);
+    off = (off + 127) & ~(size_t) 127;
+    off += (size_t) sc.stageNodes * 64 + (size_t) sc.stageTris * 48;
+    off = (off + 15) & ~(size_t) 15;
+    return off + 16;
+}
+
+template <typename K> static int occupancyGrid(K kernel, int block, size_t smem, int numSMs) {
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, smem);
+    if (perSM < 1) perSM = 1;
+    return perSM * numSMs; // a multiple of the SM count: every SM holds the same number of resident CTAs
+}
+
+static void setSmemAttr(const void *fn, size_t smem) {
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+}
+
+void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
+    cfg.numSMs = numSMs;
+    cfg.traceSmem = traceSmemBytes(sc, B2_TRACE_BLOCK);
+    setSmemAttr((const void *) k_extend<false>, cfg.traceSmem);
+    setSmemAttr((const void *) k_extend<true>, cfg.traceSmem);
+    setSmemAttr((const void *) k_occluded, cfg.traceSmem);
+    setSmemAttr((const void *) k_trace_rays<false, false>, cfg.traceSmem);
+    setSmemAttr((const void *) k_trace_rays<true, false>, cfg.traceSmem);
+    setSmemAttr((const void *) k_trace_rays<false, true>, cfg.traceSmem);
+    setSmemAttr((const void *) k_trace_rays<true, true>, cfg.traceSmem);
+    cfg.gridExtend = occupancyGrid(k_extend<false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
+    cfg.gridExtendSort = occupancyGrid(k_extend<true>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
+    cfg.gridOccluded = occupancyGrid(k_occluded, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
+    cfg.gridTrace = occupancyGrid(k_trace_rays<false, false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
+    cfg.gridGenerate = occupancyGrid(k_generate, 256, 0, numSMs);
+    cfg.gridShade[0] = occupancyGrid(k_shade<0>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[1] = occupancyGrid(k_shade<1>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[2] = occupancyGrid(k_shade<2>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[3] = occupancyGrid(k_shade<3>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[4] = occupancyGrid(k_shade<-1>, B2_SHADE_BLOCK, 0, numSMs);
+}
+
+void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, cudaStream_t st) {
+    k_generate<<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
+}
+void launch_extend(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, bool sort, cudaStream_t st) {
+    if (sort) k_extend<true><<<cfg.gridExtendSort, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool);
+    else k_extend<false><<<cfg.gridExtend, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool);
+}
+void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, int cls, bool queued, cudaStream_t st) {
+    const uint32_t *q = queued ? pool.matQueue + (size_t) cls * pool.capacity : nullptr;
+    const unsigned long long *qc = queued ? pool.counters + CTR_CLASS0 + cls : nullptr;
+    switch (cls) {
+        case 0: k_shade<0><<<cfg.gridShade[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 1: k_shade<1><<<cfg.gridShade[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 2: k_shade<2><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 3: k_shade<3><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        default: k_shade<-1><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr); break;
+    }
+}
+void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, cudaStream_t st) {
+    k_occluded<<<cfg.gridOccluded, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool);
+}
+void launch_film_pack(const LaunchCfg &cfg, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t st) {
+    k_film_pack<<<cfg.numSMs * 4, 256, 0, st>>>(rgba, w, out, n);
+}
+void launch_trace(const LaunchCfg &cfg, const DScene &sc, const float4 *rays, float4 *out, uint64_t n, bool shadow, bool count,
+                  unsigned long long *counters, cudaStream_t st) {
+    const int g = cfg.gridTrace;
+    if (shadow) {
+        if (count) k_trace_rays<true, true><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
+        else k_trace_rays<true, false><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
+    } else {
+        if (count) k_trace_rays<false, true><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
+        else k_trace_rays<false, false><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
+    }
+}
+void launch_bsdf_eval(const LaunchCfg &cfg, const DScene &sc, int mat, uint64_t n, const float *wi, const float *wo, float *rgb, float *pdf, cudaStream_t st) {
+    k_bsdf_eval<<<cfg.numSMs * 2, 128, 0, st>>>(sc, mat, n, wi, wo, rgb, pdf);
+}
+void launch_bsdf_sample(const LaunchCfg &cfg, const DScene &sc, int mat, uint64_t n, const float *wi, const float *samples, float *out, cudaStream_t st) {
+    k_bsdf_sample<<<cfg.numSMs * 2, 128, 0, st>>>(sc, mat, n, wi, samples, out);
+}
+void launch_emitter_direct(const LaunchCfg &cfg, const DScene &sc, uint64_t n, const float *ref, const float *samples, float *out, cudaStream_t st) {
+    k_emitter_direct<<<cfg.numSMs * 2, 128, 0, st>>>(sc, n, ref, samples, out);
+}
+void launch_camera_rays(const LaunchCfg &cfg, const DScene &sc, uint64_t n, const float *pos, float *rays, cudaStream_t st) {
+    k_camera_rays<<<cfg.numSMs * 2, 128, 0, st>>>(sc, n, pos, rays);
+}
+void launch_sampler_stream(const DScene &sc, const DRender &rp, int px, int py, int sampleIdx, int ndim, float *out, cudaStream_t st) {
+    k_sampler_stream<<<1, 32, 0, st>>>(sc, rp, px, py, sampleIdx, ndim, out);
+}
+void launch_splat(const LaunchCfg &cfg, const DFilter &f, int W, int H, uint64_t n, const float *pos, const float *val, float4 *rgba, float *wgt, cudaStream_t st) {
+    k_splat<<<cfg.numSMs * 2, 128, 0, st>>>(f, W, H, n, pos, val, rgba, wgt);
+}
+
+} // namespace B2_KNS
+} // namespace b2

@@ -1,0 +1,44 @@
+// Host-callable launchers of the wavefront kernels.  The kernel translation unit is compiled twice
+// (b2::parity with -fmad=false, b2::fast with FMA contraction); both export the same functions.
+#pragma once
+#include "b2_types.h"
+
+#define B2_TRACE_BLOCK 256
+#define B2_SHADE_BLOCK 128
+
+namespace b2 {
+
+struct LaunchCfg {
+    int numSMs = 0;
+    size_t traceSmem = 0;
+    int gridExtend = 0, gridExtendSort = 0, gridOccluded = 0, gridTrace = 0, gridGenerate = 0;
+    int gridShade[5] = {0, 0, 0, 0, 0};
+};
+
+#define B2_DECLARE_LAUNCHERS(NS)                                                                                               \
+    namespace NS {                                                                                                             \
+    void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs);                                                         \
+    void launch_generate(const LaunchCfg &, const DScene &, const DPool &, const DRender &, const DFilter &, cudaStream_t);    \
+    void launch_extend(const LaunchCfg &, const DScene &, const DPool &, bool sort, cudaStream_t);                             \
+    void launch_shade(const LaunchCfg &, const DScene &, const DPool &, const DRender &, int cls, bool queued, cudaStream_t);  \
+    void launch_occluded(const LaunchCfg &, const DScene &, const DPool &, cudaStream_t);                                      \
+    void launch_film_pack(const LaunchCfg &, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t);          \
+    void launch_trace(const LaunchCfg &, const DScene &, const float4 *rays, float4 *out, uint64_t n, bool shadow, bool count, \
+                      unsigned long long *counters, cudaStream_t);                                                             \
+    void launch_bsdf_eval(const LaunchCfg &, const DScene &, int mat, uint64_t n, const float *wi, const float *wo,            \
+                          float *rgb, float *pdf, cudaStream_t);                                                               \
+    void launch_bsdf_sample(const LaunchCfg &, const DScene &, int mat, uint64_t n, const float *wi, const float *samples,     \
+                            float *out, cudaStream_t);                                                                         \
+    void launch_emitter_direct(const LaunchCfg &, const DScene &, uint64_t n, const float *ref, const float *samples,          \
+                               float *out, cudaStream_t);                                                                      \
+    void launch_camera_rays(const LaunchCfg &, const DScene &, uint64_t n, const float *pos, float *rays, cudaStream_t);       \
+    void launch_sampler_stream(const DScene &, const DRender &, int px, int py, int sampleIdx, int ndim, float *out,           \
+                               cudaStream_t);                                                                                  \
+    void launch_splat(const LaunchCfg &, const DFilter &, int W, int H, uint64_t n, const float *pos, const float *val,        \
+                      float4 *rgba, float *wgt, cudaStream_t);                                                                 \
+    }
+
+B2_DECLARE_LAUNCHERS(parity)
+B2_DECLARE_LAUNCHERS(fast)
+
+} // namespace b2

@@ -1,0 +1,89 @@
+// Sampler state in registers: Sobol' (src/samplers/sobol.cpp:204-252 + sobolseq.h:45-133) and the
+// counter-based `independent` stream (TEA, include/mitsuba/core/qmc.h:146-156).
+#pragma once
+#include "b2_math.cuh"
+#include "b2_types.h"
+
+namespace b2 {
+
+B2_HD uint64_t sampleTEA(uint32_t v0, uint32_t v1, int rounds = 4) {
+    uint32_t sum = 0;
+    for (int i = 0; i < rounds; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xA341316Cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xC8013EA4u);
+        v1 += ((v0 << 4) + 0xAD90777Du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7E95761Eu);
+    }
+    return ((uint64_t) v1 << 32) + v0;
+}
+
+// sobolseq.h:45-60: XOR of the matrix columns selected by the set bits of `index`.  XOR is
+// associative, so visiting only the set bits (ffs) gives the identical word.
+B2_DEV float sobolSample(const uint32_t *__restrict__ m32, uint64_t index, uint32_t dimension, uint32_t scramble) {
+    uint32_t result = scramble;
+    const uint32_t *col = m32 + dimension * 52u;
+    uint32_t lo = (uint32_t) index, hi = (uint32_t) (index >> 32);
+    while (lo) {
+        int b = __ffs(lo) - 1;
+        result ^= __ldg(col + b);
+        lo &= lo - 1;
+    }
+    while (hi) {
+        int b = __ffs(hi) - 1;
+        result ^= __ldg(col + 32 + b);
+        hi &= hi - 1;
+    }
+    return fminf(result * (1.0f / 4294967296.0f), B2_ONE_MINUS_EPS);
+}
+
+// sobolseq.h:104-133 look_up (SINGLE_PRECISION scramble branch)
+B2_DEV uint64_t sobolLookUp(const uint64_t *__restrict__ vdc, const uint64_t *__restrict__ inv, uint32_t m, uint32_t frame,
+                            uint32_t px, uint32_t py, uint64_t scramble) {
+    const uint32_t m2 = m << 1;
+    uint64_t index = (uint64_t) frame << m2;
+    uint64_t delta = 0;
+    const uint64_t *vrow = vdc + (m - 1) * 52u;
+    while (frame) {
+        int c = __ffs(frame) - 1;
+        delta ^= __ldg(vrow + c);
+        frame &= frame - 1;
+    }
+    scramble = (scramble & 0xFFFFFFFFull) >> (32 - m);
+    uint64_t b = (((uint64_t) (px ^ scramble) << m) | (py ^ scramble)) ^ delta;
+    const uint64_t *irow = inv + (m - 1) * 52u;
+    while (b) {
+        int c = __ffsll((long long) b) - 1;
+        index ^= __ldg(irow + c);
+        b &= b - 1;
+    }
+    return index;
+}
+
+// The per-path sampler: 12 bytes of state (u64 index/key, u32 dimension), lives in registers inside
+// a kernel and in DPool::smp / meta between kernels.
+struct PathSampler {
+    uint64_t index;      // sobol: m_sobolSampleIndex; independent: stream key
+    uint32_t dim;
+    int kind;            // 0 sobol, 2 counter
+    uint32_t scramble32; // sobol scramble (low 32 bits) / seed hi for the counter stream
+    const uint32_t *m32;
+    bool overflow;
+
+    B2_DEV float next1D() {
+        if (kind == 3) return __uint_as_float(scramble32); // replay (component tests)
+        if (kind == 0) {
+            if (dim >= 1024u) { overflow = true; dim = 1023u; } // sobol.cpp:223-225 raises an error here
+            return sobolSample(m32, index, dim++, scramble32);
+        } else {
+            uint64_t r = sampleTEA((uint32_t) index, (dim++) ^ scramble32);
+            uint32_t u = ((uint32_t) (r & 0xFFFFFFFFull) >> 9) | 0x3f800000u; // random.cpp:630-640
+            return __uint_as_float(u) - 1.0f;
+        }
+    }
+    B2_DEV void next2D(float &a, float &b) {
+        if (kind == 0 && dim + 1 >= 1024u) { overflow = true; dim = 1022u; }
+        a = next1D();
+        b = next1D();
+    }
+};
+
+} // namespace b2

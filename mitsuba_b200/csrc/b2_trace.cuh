@@ -1,0 +1,162 @@
+// Ray queries on the device: ShapeKDTree::rayIntersect semantics (src/librender/skdtree.cpp:112-226:
+// scene-box clip, adaptive epsilon, closest / any hit) over a BVH2 instead of the SAH kd-tree, with the
+// reference's TriAccel test (include/mitsuba/render/triaccel.h:96-158) as the only arithmetic that
+// decides a hit.  The returned (t,u,v,prim) is argmin_t over TriAccel tests -- identical to what the
+// Havran kd-tree traversal (sahkdtree3.h:178-308) returns, except for exact-t ties.
+//
+// Per-lane traversal stack lives in shared memory (interleaved: entry k of thread i at
+// stack[k * blockDim + i], conflict free); the leading part of the node / triangle arrays is staged
+// into shared memory by a TMA bulk copy (see b2_kernels.inl: stageScene).
+#pragma once
+#include "b2_math.cuh"
+#include "b2_types.h"
+
+namespace b2 {
+
+
+struct TraceMem {
+    const float4 *gNodes;   // global: 4 x float4 per node
+    const float4 *gTris;    // global: 3 x float4 per leaf-ordered triangle
+    const float4 *sNodes;   // shared copies of the first stageNodes / stageTris records
+    const float4 *sTris;
+    uint32_t stageNodes, stageTris;
+    uint32_t *stack;        // this thread's column of the shared stack
+    uint32_t stride;        // blockDim.x
+};
+
+struct HitRec {
+    float t, u, v;
+    uint32_t prim;
+};
+
+// triaccel.h:96-158
+B2_DEV bool triAccelIntersect(const float4 &q0, const float4 &q1, const float4 &q2, const V3 &o, const V3 &d, float mint,
+                              float maxt, float &u, float &v, float &t) {
+    const uint32_t k = __float_as_uint(q0.x);
+    float o_u, o_v, o_k, d_u, d_v, d_k;
+    if (k == 0) { o_u = o.y; o_v = o.z; o_k = o.x; d_u = d.y; d_v = d.z; d_k = d.x; }
+    else if (k == 1) { o_u = o.z; o_v = o.x; o_k = o.y; d_u = d.z; d_v = d.x; d_k = d.y; }
+    else if (k == 2) { o_u = o.x; o_v = o.y; o_k = o.z; d_u = d.x; d_v = d.y; d_k = d.z; }
+    else return false;
+    const float n_u = q0.y, n_v = q0.z, n_d = q0.w;
+    t = (n_d - o_u * n_u - o_v * n_v - o_k) / (d_u * n_u + d_v * n_v + d_k);
+    if (t < mint || t > maxt) return false;
+    const float hu = o_u + t * d_u - q1.x;
+    const float hv = o_v + t * d_v - q1.y;
+    u = hv * q1.z + hu * q1.w;
+    v = hu * q2.x + hv * q2.y;
+    return u >= 0 && v >= 0 && u + v <= 1.0f;
+}
+
+// include/mitsuba/core/aabb.h:308-338
+B2_DEV bool sceneBoxIntersect(const DScene &sc, const V3 &o, const V3 &d, const V3 &dRcp, float &nearT, float &farT) {
+    nearT = -B2_INF; farT = B2_INF;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float origin = comp(o, i), minVal = sc.aabbMin[i], maxVal = sc.aabbMax[i];
+        const float di = comp(d, i);
+        if (di == 0) {
+            if (origin < minVal || origin > maxVal) return false;
+        } else {
+            float t1 = (minVal - origin) * comp(dRcp, i);
+            float t2 = (maxVal - origin) * comp(dRcp, i);
+            if (t1 > t2) { float tmp = t1; t1 = t2; t2 = tmp; }
+            nearT = fmaxf(t1, nearT);
+            farT = fminf(t2, farT);
+            if (!(nearT <= farT)) return false;
+        }
+    }
+    return true;
+}
+
+// skdtree.cpp:124-133 (closest) / :211-218 (occlusion): clip to the scene box and apply the adaptive epsilon
+template <bool SHADOW> B2_DEV bool clipRay(const DScene &sc, const V3 &o, const V3 &d, const V3 &dRcp, float rayMint, float rayMaxt,
+                                            float &mint, float &maxt) {
+    if (!sceneBoxIntersect(sc, o, d, dRcp, mint, maxt)) return false;
+    float rayMinT = rayMint;
+    if (rayMinT == B2_EPSILON) {
+        float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+        if (!SHADOW) m = fmaxf(m, B2_EPSILON);
+        rayMinT *= m;
+    }
+    if (rayMinT > mint) mint = rayMinT;
+    if (rayMaxt < maxt) maxt = rayMaxt;
+    return maxt > mint;
+}
+
+// slab test against one child box; conservative (boxes are padded at build time, far side scaled by 1+2ulp)
+B2_DEV bool boxHit(float bx0, float by0, float bz0, float bx1, float by1, float bz1, const V3 &o, const V3 &idir, float mint, float maxt,
+                   float &tEntry) {
+    float tx0 = (bx0 - o.x) * idir.x, tx1 = (bx1 - o.x) * idir.x;
+    float ty0 = (by0 - o.y) * idir.y, ty1 = (by1 - o.y) * idir.y;
+    float tz0 = (bz0 - o.z) * idir.z, tz1 = (bz1 - o.z) * idir.z;
+    float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), mint));
+    float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), maxt));
+    tEntry = tmin;
+    return tmin <= tmax * 1.0000003f;
+}
+
+// Returns true if something was hit.  Closest: fills `hit`; SHADOW: returns at the first hit.
+template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
+                                                         HitRec &hit, uint32_t &nodeVisits, uint32_t &primTests) {
+    // safe reciprocal for the slab test only (0 -> huge, keeps NaN out of min/max chains)
+    V3 idir(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    bool found = false;
+    int sp = 0;
+    int ref = sc.rootRef;
+    const uint32_t stride = tm.stride;
+    while (true) {
+        if (ref >= 0) {
+            float4 a, b, c, e;
+            if ((uint32_t) ref < tm.stageNodes) {
+                const float4 *p = tm.sNodes + 4 * ref;
+                a = p[0]; b = p[1]; c = p[2]; e = p[3];
+            } else {
+                const float4 *p = tm.gNodes + 4 * (size_t) ref;
+                a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); e = __ldg(p + 3);
+            }
+            if (COUNT) ++nodeVisits;
+            float tL, tR;
+            bool hL = boxHit(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, mint, maxt, tL);
+            bool hR = boxHit(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, mint, maxt, tR);
+            int lref = __float_as_int(e.x), rref = __float_as_int(e.y);
+            if (hL && hR) {
+                int nearRef = lref, farRef = rref;
+                if (tR < tL) { nearRef = rref; farRef = lref; }
+                tm.stack[sp * stride] = (uint32_t) farRef;
+                ++sp;
+                ref = nearRef;
+                continue;
+            } else if (hL) { ref = lref; continue; }
+            else if (hR) { ref = rref; continue; }
+        } else {
+            uint32_t bits = ~(uint32_t) ref;
+            uint32_t start = bits & 0x0FFFFFFFu, count = bits >> 28;
+            for (uint32_t i = 0; i < count; ++i) {
+                uint32_t ti = start + i;
+                float4 q0, q1, q2;
+                if (ti < tm.stageTris) {
+                    const float4 *p = tm.sTris + 3 * ti;
+                    q0 = p[0]; q1 = p[1]; q2 = p[2];
+                } else {
+                    const float4 *p = tm.gTris + 3 * (size_t) ti;
+                    q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2);
+                }
+                if (COUNT) ++primTests;
+                float tu, tv, tt;
+                if (triAccelIntersect(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
+                    if (SHADOW) return true;
+                    hit.t = tt; hit.u = tu; hit.v = tv; hit.prim = __float_as_uint(q2.z);
+                    maxt = tt;
+                    found = true;
+                }
+            }
+        }
+        if (sp == 0) break;
+        --sp;
+        ref = (int) tm.stack[sp * stride];
+    }
+    return found;
+}
+
+} // namespace b2

@@ -1,0 +1,132 @@
+// Plain data shared by the host side (scene commit, render loop) and the kernels: the layout of the
+// scene in HBM and of the wavefront path pool.  DESIGN.md "data layout" documents every array.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+// per-lane traversal stack entries in shared memory; the BVH builder caps the tree depth below this
+#define B2_STACK_DEPTH 40
+
+namespace b2 {
+
+// One BSDF node, device copy of b2_material_desc plus values precomputed once on the host
+struct DMaterial {
+    int32_t type, distr, sampleVisible, nested;
+    float alphaU, alphaV, eta, thickness;
+    float reflectance[3], transmittance[3], etaC[3], kC[3], sigmaA[3];
+    uint32_t flags;        // BSDF type flags (bsdf.h:224-285) incl. nested, as BSDF::configure ORs them
+    float specSamplingWeight; // coating.cpp:177-181
+    float pad[2];
+};
+
+// Area emitter + its mesh's area distribution (area.cpp, trimesh.cpp:388-403)
+struct DEmitter {
+    float radiance[3];
+    float samplingWeight;
+    float invSurfaceArea;
+    uint32_t cdfOffset;    // into triCdf (nTri + 1 floats, cdf[0] = 0)
+    uint32_t nTri;
+    uint32_t primOffset;   // global prim index of the mesh's first triangle
+};
+
+// 64-byte BVH2 node: both children's boxes + child references.
+// ref >= 0: inner node index; ref < 0: leaf, bits = ~ref, start = bits & 0x0FFFFFFF (into the
+// leaf-ordered TriAccel array), count = bits >> 28.
+struct BVHNode {
+    float lmin[3], lmax[3], rmin[3], rmax[3];
+    int32_t left, right, pad0, pad1;
+};
+static_assert(sizeof(BVHNode) == 64, "BVHNode must be 64 bytes");
+
+struct DCamera {
+    float camToWorld[16];
+    float sampleToCamera[16];
+    float nearClip, farClip;
+    float invResX, invResY;
+    float origin[3];
+    int32_t W, H;
+};
+
+// Scene resident in HBM
+struct DScene {
+    // leaf-ordered TriAccel records, 3 x float4 each (triaccel.h:37-59; word 10 = global prim id)
+    const float4 *triAccel;
+    uint32_t nLeafTris;
+    const BVHNode *nodes;
+    uint32_t nNodes;
+    int32_t rootRef;           // root child reference (leaf-only scenes: a leaf ref)
+    float aabbMin[3], aabbMax[3]; // enlarged scene box (gkdtree.h:1213-1220)
+    // per-prim shading data in prim order: verts[3*p+k] = (position k, w = {material id, emitter id, flags} as int bits)
+    const float4 *verts;
+    // optional: norms[3*p+k] = (vertex normal k, w = dpdu component k); flags bit0 = has normals, bit1 = has dpdu
+    const float4 *norms;
+    uint32_t nPrims;
+    const DMaterial *materials;
+    uint32_t nMaterials;
+    const DEmitter *emitters;
+    uint32_t nEmitters;
+    const float *emitterCdf;   // nEmitters + 1
+    float emitterNormalization; // DiscreteDistribution::getNormalization (pmf.h)
+    const float *triCdf;
+    DCamera cam;
+    // Sobol tables (sobolseq.h:31-38)
+    const uint32_t *sobolM32;  // [1024][52]
+    const uint64_t *sobolVdc;  // [25][52]
+    const uint64_t *sobolInv;  // [26][52]
+    // staging limits for shared memory (number of leading BVH nodes / TriAccel records copied by TMA)
+    uint32_t stageNodes, stageTris;
+};
+
+struct DFilter {
+    float values[32];
+    float radius, scaleFactor;
+    int32_t borderSize, kind;
+};
+
+// Path flags
+enum : uint32_t {
+    PF_ALIVE = 1u << 0,       // slot holds a path that still needs work
+    PF_DONE = 1u << 1,        // path finished: Li must be splatted, slot can be regenerated
+    PF_FRESH = 1u << 2,       // ray is the camera ray (EEmittedRadiance still set, depth == 1)
+    PF_SCATTERED = 1u << 3,
+    PF_DELTA = 1u << 4,       // last sampled lobe was EDelta (path.cpp:261)
+    PF_REFN_OK = 1u << 5,     // dot(wo, refN) >= 0 for the pending emitter-hit MIS test (area.cpp:178)
+    PF_ALPHA = 1u << 6,       // camera ray hit something
+};
+
+// Wavefront pool: structure of arrays, one entry per in-flight path ("slot"), 16-byte records
+struct DPool {
+    uint32_t capacity;
+    float4 *rayO;      // o.xyz, mint
+    float4 *rayD;      // d.xyz, maxt
+    float4 *hit;       // t, u, v, prim (bits)
+    float4 *thr;       // throughput rgb, eta
+    float4 *li;        // Li rgb, bsdfPdf of the pending BSDF sample
+    uint4 *smp;        // sampler state: {index lo, index hi, samplePos.x bits, samplePos.y bits}
+    uint2 *meta;       // {pixel (y << 16 | x), flags | depth << 8 | dimension << 20}
+    // shadow queue (compacted by warp ballot)
+    float4 *shD;       // d.xyz, maxt
+    float4 *shC;       // contribution rgb, slot (bits)
+    // material-class queues
+    uint32_t *matQueue;   // [nClasses][capacity]
+    // counters (device): [0] next work item (u64 split), [2] shadow count, [3] active count, [4..7] class counts, [8..] stats
+    unsigned long long *counters;
+};
+
+enum { CTR_NEXT = 0, CTR_SHADOW = 1, CTR_ACTIVE = 2, CTR_CLASS0 = 3, /* 3..6 */ CTR_RAYS = 8, CTR_SHADOWRAYS = 9,
+       CTR_PATHLEN = 10, CTR_SAMPLES = 11, CTR_BAD = 12, CTR_DIMOVF = 13, CTR_NODEVIS = 14, CTR_PRIMTESTS = 15, CTR_COUNT = 16 };
+
+struct DRender {
+    int32_t spp, sampler;
+    uint64_t scramble;       // sobol: after the TEA step (sobol.cpp:96-102); independent: seed
+    int32_t maxDepth, rrDepth, strictNormals, hideEmitters;
+    int32_t sampleLo, sampleHi;
+    uint32_t logRes;         // sobol m_logResolution
+    float resolution;        // sobol m_resolution
+    uint64_t totalWork;      // W*H*(hi-lo)
+    uint32_t tilesX, tilesY;
+    float4 *filmRGBA;        // H*W float4 (r,g,b,alpha) accumulators
+    float *filmW;            // H*W weight accumulators
+};
+
+} // namespace b2
