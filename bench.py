@@ -1,0 +1,295 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): Msamples/s of the Cornell-box-class scene,
+1024 x 1024 @ 1024 spp per GPU, `path` integrator, sobol sampler, box reconstruction filter.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the CPU restatement of the reference on the host cores
+
+One "step" = one complete render of the workload (all pixels x all samples of this rank's shard) + the film reduce.
+N > 1: weak scaling -- every rank renders its own 1024 sample indices of every pixel (rank r: [r*1024, (r+1)*1024) of a
+1024*N-spp image), one torch.distributed reduce(SUM) of the (H, W, 5) film over NCCL at the end of every step.
+`value` = samples rendered by all ranks / max-over-ranks device time.  `e2e` = the same metric through the C-ABI with HOST
+buffers: scene description -> b2_scene_commit (BVH build + H2D upload) -> b2_render into a host film (D2H) inside the timed
+region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(scene="cornell_box S1 (32 triangles, diffuse + area light)", width=1024, height=1024, spp_per_gpu=1024,
+                integrator="path maxDepth=-1 rrDepth=5", sampler="sobol scramble=0", rfilter="box")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sample_spp=None, threads=0):
+    """The CPU restatement of the reference (oracle, kind "port") on the host cores: a bounded sample of the SAME workload
+    (the first `sample_spp` sample indices of every pixel of the 1024 x 1024 image)."""
+    from mitsuba_b200.scene import RenderParams, cornell_box
+    from oracle import oracle_api as O
+    cores = threads or O.hardware_threads()
+    d = cornell_box(WORKLOAD["width"], WORKLOAD["height"])
+    sc = O.OracleScene(d)
+    if sample_spp is None:
+        # calibrate so one step is ~4-10 s of wall time
+        rp = RenderParams(spp=WORKLOAD["spp_per_gpu"], sampler="sobol", rfilter="box", sample_lo=0, sample_hi=1)
+        t = time.time(); sc.render(rp, threads=cores); dt = time.time() - t
+        sample_spp = int(min(16, max(1, round(5.0 / max(dt, 1e-3)))))
+    rp = RenderParams(spp=WORKLOAD["spp_per_gpu"], sampler="sobol", rfilter="box", sample_lo=0, sample_hi=sample_spp)
+    for _ in range(warmup):
+        sc.render(rp, threads=cores)
+    t0 = time.time()
+    st = None
+    for _ in range(steps):
+        _, st = sc.render(rp, threads=cores)
+    dt = (time.time() - t0) / max(steps, 1)
+    n = WORKLOAD["width"] * WORKLOAD["height"] * sample_spp
+    return dict(value=n / dt / 1e6, unit="Msamples/s", cores=cores, kind="port",
+                sample=f"sample indices [0,{sample_spp}) of every pixel of the 1024x1024 @1024spp workload ({n / 1e6:.1f} Msamples per step)",
+                ms_per_step=dt * 1e3, mean_path_length=st["pathLengthSum"] / st["samples"])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": "Msamples/sec Cornell box 1024spp", "value": r["value"], "unit": "Msamples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Cornell box (S1) 1024x1024, path/sobol/box, bounded sample on the host cores", **WORKLOAD},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "Mitsuba-0.6-equivalent CPU restatement (oracle/), not the Mitsuba binary: the reference cannot be built offline (DESIGN.md)"}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--spp", type=int, default=WORKLOAD["spp_per_gpu"], help="samples per pixel per GPU (headline: 1024)")
+    ap.add_argument("--res", type=int, default=WORKLOAD["width"])
+    ap.add_argument("--pool", type=int, default=0)
+    ap.add_argument("--parity", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from mitsuba_b200 import api
+    from mitsuba_b200.distributed import shard_range
+    from mitsuba_b200.scene import RenderParams, cornell_box
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this implementation has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = api.Context(local)
+    W = H = args.res
+    desc = cornell_box(W, H)
+    scene = api.Scene(ctx, desc)
+    total_spp = args.spp * world
+    lo, hi = shard_range(total_spp, rank, world)
+    rp = RenderParams(spp=total_spp, sampler="sobol", rfilter="box", sample_lo=lo, sample_hi=hi)
+    film = torch.zeros((H, W, 5), dtype=torch.float32, device=f"cuda:{local}")
+
+    def step(flags=4):
+        scene.render(rp, parity=bool(args.parity), pool_size=args.pool, flags=flags, film=film)
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)   # the one collective of the path: film merge over NVLink
+        return scene.stats()
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    agg = dict(ms_generate=0.0, ms_extend=0.0, ms_shade=0.0, ms_occluded=0.0, n_generate=0, n_extend=0, n_shade=0, n_occluded=0,
+               launches=0, rays=0, shadow_rays=0, path_length_sum=0, samples=0, ms_render=0.0)
+    t_wall = time.time()
+    for _ in range(args.steps):
+        st = step()
+        for k in ("ms_generate", "ms_extend", "ms_shade", "ms_occluded", "n_generate", "n_extend", "n_shade", "n_occluded", "rays", "shadow_rays",
+                  "path_length_sum", "samples"):
+            agg[k] += st[k]
+        agg["launches"] += st["kernel_launches"] + (1 if world > 1 else 0)
+        agg["ms_render"] += st["ms_total"]
+    ev1.record()
+    sync()
+    wall = time.time() - t_wall
+    # b2_render times itself with CUDA events on ITS stream (torch's events only see torch's stream); each b2_render call
+    # synchronises its stream before returning, so the per-step device time = render ms (+ reduce, measured by torch events)
+    ms_torch = ev0.elapsed_time(ev1)
+    ms_total = max(ms_torch, agg["ms_render"])
+    t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clock_info = clocks.stop() if clocks else None
+    samples_per_step = W * H * args.spp * world
+    value = samples_per_step * args.steps / (ms_total / 1e3) / 1e6
+    pool = scene.stats()["pool_size"]
+
+    # ---- e2e: through the C-ABI with host buffers (scene commit + render into a host film), same metric ----
+    e2e = None
+    if rank == 0 or world > 1:
+        host_film = np.zeros((H, W, 5), np.float32)
+        import ctypes as C
+        p = api.make_params(rp, bool(args.parity), args.pool, False, 0)
+
+        def e2e_step():
+            sc2 = api.Scene(ctx, desc)                                  # b2_scene_create .. b2_scene_commit (H2D upload)
+            rc = ctx.L.b2_render(sc2.h, C.byref(p), host_film.ctypes.data_as(C.POINTER(C.c_float)))  # D2H film inside
+            if rc:
+                raise RuntimeError(ctx.err())
+            up = sc2.stats()["bytes_uploaded"]
+            sc2.close()
+            return up
+        e2e_step()
+        sync()
+        t0 = time.time()
+        n_e2e = max(1, min(args.steps, 2))
+        up = 0
+        for _ in range(n_e2e):
+            up = e2e_step()
+        sync()
+        dt = time.time() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": samples_per_step * n_e2e / float(tt.item()) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(up) + 64,
+               "d2h_bytes_per_step": int(H * W * 5 * 4), "steps": n_e2e}
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        # dominant kernel by summed device time inside the timed region
+        shares = {k: agg["ms_" + k] for k in ("generate", "extend", "shade", "occluded")}
+        dom = max(shares, key=shares.get)
+        n_dom = max(1, agg["n_" + dom])
+        avg_ms = shares[dom] / n_dom
+        # algorithmic bytes per launch (DESIGN.md "roofline model"): per live path / shadow ray and launch
+        per_item = {"extend": 32 + 16 + 8, "occluded": 32 + 16 + 16 + 16, "shade": 16 + 16 + 16 + 16 + 16 + 8 + 32 + 16 + 16 + 8 + 32,
+                    "generate": 8 + 8}[dom]
+        items = {"extend": agg["rays"], "occluded": agg["shadow_rays"], "shade": agg["rays"], "generate": pool * n_dom}[dom] / n_dom
+        achieved = per_item * items / (avg_ms / 1e3) / 1e9 if avg_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("k_" + dom)
+            except Exception:
+                pass
+        line = {
+            "metric": "Msamples/sec Cornell box 1024spp", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Cornell box (S1) {W}x{H} @ {args.spp} spp per GPU, path/sobol/box (BASELINE configs[1])", **WORKLOAD,
+                       "spp_per_gpu": args.spp, "width": W, "height": H, "parallelism": f"sample-index sharding x{world}, 1 film reduce",
+                       "pool_size": int(pool), "l2": "path pool + film (%.0f MB) exceed the 126 MB L2; every step re-streams them" % ((pool * 136 + W * H * 20) / 1e6),
+                       "fp": "parity (-fmad=false)" if args.parity else "fast (FMA contraction)"},
+            "e2e": e2e,
+            "gpu_launches": int(agg["launches"]),
+            "clocks": clock_info,
+            "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                         "frac": achieved / peaks.get("hbm_gbs", 1.0), "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                         "avg_launch_ms": avg_ms, "share_of_step": shares[dom] / max(1e-9, sum(shares.values())),
+                         "kernel_ms": shares,
+                         "note": "Cornell scene (3.5 KB) is shared-memory resident: traversal is issue/latency bound, HBM traffic is queue traffic only"},
+            "stats": {"mean_path_length": agg["path_length_sum"] / max(1, agg["samples"]), "rays_per_sample": agg["rays"] / max(1, agg["samples"]),
+                      "shadow_rays_per_sample": agg["shadow_rays"] / max(1, agg["samples"]), "wall_s": wall},
+        }
+        if not args.no_cpu_baseline:
+            cb = cpu_reference_run(1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

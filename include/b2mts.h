@@ -68,7 +68,8 @@ typedef struct b2_render_params {
     int32_t parity_mode;     /* 1: kernels compiled with -fmad=false (tight float parity); 0: FMA contraction on */
     int32_t pool_size;       /* in-flight paths (0 = default) */
     int32_t film_on_device;  /* 1: `film` of b2_render is a device pointer on the context's device */
-    int32_t flags;           /* bit0: material-sorted shading on; bit1: force unsorted */
+    int32_t flags;           /* bit1: force unsorted shading (default: material-sorted when > 1 BSDF class);
+                                bit2: time every kernel launch with CUDA events (fills b2_stats.ms_*) */
 } b2_render_params;
 
 /* Counters with the meaning of the reference's statistics (path.cpp:24,290-291; skdtree.cpp:46-47) plus
@@ -79,6 +80,9 @@ typedef struct b2_stats {
     uint64_t iterations, kernel_launches;
     float ms_total, ms_generate, ms_extend, ms_shade, ms_occluded, ms_film;
     uint64_t n_triangles, n_bvh_nodes;
+    uint64_t n_generate, n_extend, n_shade, n_occluded; /* launches behind the ms_* sums (flags bit2) */
+    uint64_t bytes_uploaded;                /* host->device bytes of the last b2_scene_commit */
+    uint64_t pool_size;                     /* in-flight paths of the last b2_render */
 } b2_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

@@ -38,7 +38,8 @@ class b2_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "rays", "shadow_rays", "path_length_sum", "bad_samples", "dim_overflow",
                                           "node_visits", "prim_tests", "iterations", "kernel_launches")] + \
                [(n, C.c_float) for n in ("ms_total", "ms_generate", "ms_extend", "ms_shade", "ms_occluded", "ms_film")] + \
-               [("n_triangles", C.c_uint64), ("n_bvh_nodes", C.c_uint64)]
+               [(n, C.c_uint64) for n in ("n_triangles", "n_bvh_nodes", "n_generate", "n_extend", "n_shade", "n_occluded",
+                                          "bytes_uploaded", "pool_size")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -32,8 +32,9 @@ struct b2_ctx {
     cudaStream_t stream = nullptr;
     std::string lastError;
     // Sobol tables on the device
-    uint32_t *dM32 = nullptr;
+    uint32_t *dM32 = nullptr, *dNib = nullptr;
     uint64_t *dVdc = nullptr, *dInv = nullptr;
+    std::vector<uint64_t> hVdc, hInv; // host copies: per-render look_up nibble tables are derived from them
     bool tablesLoaded = false;
 };
 
@@ -45,6 +46,7 @@ static int fail(b2_ctx *ctx, int code, const std::string &msg) {
     if (ctx) ctx->lastError = msg;
     return code;
 }
+extern "C" int b2_set_error_(b2_ctx *ctx, int code, const char *msg) { return fail(ctx, code, msg ? msg : ""); }
 #define CK(ctx, call)                                                                                          \
     do {                                                                                                       \
         cudaError_t e_ = (call);                                                                               \
@@ -109,12 +111,14 @@ struct b2_scene {
     DevBuf<float4> pRayO, pRayD, pHit, pThr, pLi, pShD, pShC;
     DevBuf<uint4> pSmp;
     DevBuf<uint2> pMeta;
-    DevBuf<uint32_t> pMatQueue;
+    DevBuf<uint32_t> pMatQueue, pDoneQueue;
+    DevBuf<uint64_t> dLookupNib;
     DevBuf<unsigned long long> dCounters;
     DevBuf<float4> dFilmRGBA;
     DevBuf<float> dFilmW, dFilmOut;
     unsigned long long *hPinned = nullptr; // ring of {active, next} pairs
     std::vector<cudaEvent_t> ringEvents;
+    std::vector<cudaEvent_t> timingEvents; // pool for per-launch timing (flags bit2)
     std::atomic<int> cancel{0};
     b2_stats stats{};
     uint32_t nPrims = 0;
@@ -184,6 +188,20 @@ extern "C" int b2_context_create(int device, b2_ctx **out) {
         return fail(nullptr, B2_ERR_IO, "cannot read Sobol tables from " + dir + " (set B2MTS_DATA)");
     }
     vdc.resize(26 * 52, 0);
+    ctx->hVdc = vdc; ctx->hInv = inv;
+    {   // nibble-sliced direction matrices: nib[d][p][v] = XOR_{k in bits(v)} m32[d][4p + k]  (b2_sampler.cuh: sobolSampleNib)
+        std::vector<uint32_t> nib((size_t) 1024 * 13 * 16, 0u);
+        for (int d = 0; d < 1024; ++d)
+            for (int p = 0; p < 13; ++p)
+                for (int v = 0; v < 16; ++v) {
+                    uint32_t x = 0;
+                    for (int k = 0; k < 4; ++k)
+                        if ((v >> k) & 1) x ^= m32[(size_t) d * 52 + 4 * p + k];
+                    nib[((size_t) d * 13 + p) * 16 + v] = x;
+                }
+        cudaMalloc((void **) &ctx->dNib, nib.size() * 4);
+        cudaMemcpy(ctx->dNib, nib.data(), nib.size() * 4, cudaMemcpyHostToDevice);
+    }
     cudaMalloc((void **) &ctx->dM32, m32.size() * 4);
     cudaMalloc((void **) &ctx->dVdc, vdc.size() * 8);
     cudaMalloc((void **) &ctx->dInv, inv.size() * 8);
@@ -198,6 +216,7 @@ extern "C" void b2_context_destroy(b2_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->dM32) cudaFree(ctx->dM32);
+    if (ctx->dNib) cudaFree(ctx->dNib);
     if (ctx->dVdc) cudaFree(ctx->dVdc);
     if (ctx->dInv) cudaFree(ctx->dInv);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -215,6 +234,7 @@ extern "C" void b2_scene_destroy(b2_scene *s) {
     cudaSetDevice(s->ctx->device);
     if (s->hPinned) cudaFreeHost(s->hPinned);
     for (auto e : s->ringEvents) cudaEventDestroy(e);
+    for (auto e : s->timingEvents) cudaEventDestroy(e);
     delete s;
 }
 
@@ -471,7 +491,19 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     // ---- BVH ----
     BVHResult bvh;
     int threads = (int) std::thread::hardware_concurrency();
-    buildBVH(boxes, ids, 4, B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh);
+    // Tiny scenes skip the tree: the whole triangle list is one leaf, staged in shared memory and tested by all lanes
+    // in lockstep (no divergence).  Break-even against the BVH2 walk measured on the Cornell scene, see DESIGN.md.
+    uint32_t flatLimit = 64;
+    if (const char *e = getenv("B2_FLAT_LIMIT")) flatLimit = (uint32_t) atoi(e);
+    uint32_t rootCount = 0;
+    if (!ids.empty() && ids.size() <= flatLimit) {
+        bvh.leafPrims = ids;
+        bvh.rootRef = -1; // ~0: leaf starting at triangle 0
+        bvh.depth = 1;
+        rootCount = (uint32_t) ids.size();
+    } else {
+        buildBVH(boxes, ids, 4, B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh);
+    }
     s->bvhDepth = bvh.depth;
     std::vector<float4> leafTri(3 * bvh.leafPrims.size());
     for (size_t i = 0; i < bvh.leafPrims.size(); ++i) memcpy(&leafTri[3 * i], &triAccel[3 * (size_t) bvh.leafPrims[i]], 48);
@@ -545,7 +577,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     DScene &ds = s->ds;
     memset(&ds, 0, sizeof(ds));
     ds.triAccel = s->dTriAccel.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
-    ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef;
+    ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef; ds.rootCount = rootCount;
     // gkdtree.h:1213-1220: enlarged scene box (the max side uses the already-moved min, as in the reference)
     if (nPrims == 0) { for (int a = 0; a < 3; ++a) { lo[a] = 0; hi[a] = 0; } }
     const float eps = 1e-3f;
@@ -564,7 +596,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.cam.invResX = 1.0f / (float) s->W; ds.cam.invResY = 1.0f / (float) s->H; // sensor.cpp:104-107
     ds.cam.origin[0] = s->camToWorld[3]; ds.cam.origin[1] = s->camToWorld[7]; ds.cam.origin[2] = s->camToWorld[11];
     ds.cam.W = s->W; ds.cam.H = s->H;
-    ds.sobolM32 = ctx->dM32; ds.sobolVdc = ctx->dVdc; ds.sobolInv = ctx->dInv;
+    ds.sobolM32 = ctx->dM32; ds.sobolVdc = ctx->dVdc; ds.sobolInv = ctx->dInv; ds.sobolNib = ctx->dNib;
     // shared-memory staging budget: up to 256 nodes (16 KB) and 256 triangles (12 KB) per CTA
     ds.stageNodes = std::min<uint32_t>(ds.nNodes, 256u);
     ds.stageTris = std::min<uint32_t>(ds.nLeafTris, 256u);
@@ -575,6 +607,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     memset(&s->stats, 0, sizeof(s->stats));
     s->stats.n_triangles = nPrims;
     s->stats.n_bvh_nodes = bvh.nodes.size();
+    s->stats.bytes_uploaded = leafTri.size() * 16 + verts.size() * 16 + norms.size() * 16 + bvh.nodes.size() * sizeof(BVHNode) +
+                              dm.size() * sizeof(DMaterial) + de.size() * sizeof(DEmitter) + (emCdf.size() + triCdf.size()) * 4;
     s->committed = true;
     return B2_OK;
 }
@@ -655,6 +689,30 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     }
     r.tilesX = (uint32_t) (s->W + 7) / 8; r.tilesY = (uint32_t) (s->H + 7) / 8;
     r.totalWork = (uint64_t) r.tilesX * r.tilesY * 64ull * (uint64_t) (r.sampleHi - r.sampleLo);
+    // nibble tables of sobol::look_up for this m (sobolseq.h:104-133) and the nibble counts that cover the indices
+    auto bitsOf = [](uint64_t v) { uint32_t b = 0; while (v) { ++b; v >>= 1; } return b; };
+    const uint32_t frameBits = std::max(1u, bitsOf((uint64_t) r.sampleHi - 1));
+    r.frameNibbles = (frameBits + 3) / 4;
+    r.bNibbles = (2 * r.logRes + 3) / 4;
+    const uint32_t indexBits = (p->sampler == B2_SAMPLER_SOBOL && r.logRes > 1) ? frameBits + 2 * r.logRes : frameBits;
+    if (indexBits > 52) return fail(ctx, B2_ERR_INVALID, "sample index exceeds the 52-bit range of the Sobol' tables");
+    r.indexNibbles = std::max(8u, (indexBits + 3) / 4);
+    if (p->sampler == B2_SAMPLER_SOBOL && r.logRes > 1) {
+        if (r.logRes > 25) return fail(ctx, B2_ERR_INVALID, "film resolution too large for the Sobol' look_up tables");
+        std::vector<uint64_t> lut((size_t) 2 * 13 * 16, 0ull);
+        const uint64_t *vrow = ctx->hVdc.data() + (size_t) (r.logRes - 1) * 52, *irow = ctx->hInv.data() + (size_t) (r.logRes - 1) * 52;
+        for (int q = 0; q < 13; ++q)
+            for (int v = 0; v < 16; ++v) {
+                uint64_t a = 0, b = 0;
+                for (int k = 0; k < 4; ++k)
+                    if ((v >> k) & 1) { a ^= vrow[4 * q + k]; b ^= irow[4 * q + k]; }
+                lut[(size_t) q * 16 + v] = a;
+                lut[(size_t) (13 + q) * 16 + v] = b;
+            }
+        if (s->dLookupNib.alloc(lut.size()) != cudaSuccess) return fail(ctx, B2_ERR_CUDA, "cudaMalloc(lookup tables) failed");
+        if (cudaMemcpy(s->dLookupNib.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return fail(ctx, B2_ERR_CUDA, "upload of lookup tables failed");
+        r.lookupNib = s->dLookupNib.p;
+    }
     return B2_OK;
 }
 
@@ -663,11 +721,12 @@ static int ensurePool(b2_scene *s, uint32_t Q) {
     if (s->pool.capacity == Q) return B2_OK;
     CK(ctx, s->pRayO.alloc(Q)); CK(ctx, s->pRayD.alloc(Q)); CK(ctx, s->pHit.alloc(Q)); CK(ctx, s->pThr.alloc(Q));
     CK(ctx, s->pLi.alloc(Q)); CK(ctx, s->pShD.alloc(Q)); CK(ctx, s->pShC.alloc(Q)); CK(ctx, s->pSmp.alloc(Q));
-    CK(ctx, s->pMeta.alloc(Q)); CK(ctx, s->pMatQueue.alloc((size_t) 4 * Q));
+    CK(ctx, s->pMeta.alloc(Q)); CK(ctx, s->pMatQueue.alloc((size_t) 4 * Q)); CK(ctx, s->pDoneQueue.alloc((size_t) 2 * Q));
     DPool &p = s->pool;
     p.capacity = Q;
     p.rayO = s->pRayO.p; p.rayD = s->pRayD.p; p.hit = s->pHit.p; p.thr = s->pThr.p; p.li = s->pLi.p;
     p.smp = s->pSmp.p; p.meta = s->pMeta.p; p.shD = s->pShD.p; p.shC = s->pShC.p; p.matQueue = s->pMatQueue.p;
+    p.doneQueue = s->pDoneQueue.p;
     p.counters = s->dCounters.p;
     return B2_OK;
 }
@@ -720,13 +779,28 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     uint64_t iter = 0, checked = 0, launches = 0;
     bool finished = false;
     int status = B2_OK;
+    const bool timing = (p->flags & 4) != 0;
+    std::vector<std::pair<int, size_t>> timed; // (stage, index of the start event)
+    size_t evUsed = 0;
+    auto tick = [&](int stage) { // record a start or stop event for `stage`
+        if (!timing) return;
+        if (evUsed == s->timingEvents.size()) { cudaEvent_t e; cudaEventCreate(&e); s->timingEvents.push_back(e); }
+        cudaEventRecord(s->timingEvents[evUsed], st);
+        if (stage >= 0) timed.emplace_back(stage, evUsed);
+        ++evUsed;
+    };
 #define LAUNCH(ns)                                                                                              \
     do {                                                                                                        \
+        tick(0);                                                                                                \
         ns::launch_generate(cfg, s->ds, s->pool, r, filt, st);                                                  \
+        tick(-1);                                                                                               \
         cudaMemcpyAsync(s->hPinned + 2 * (iter % kRing), s->dCounters.p + CTR_ACTIVE, 8, cudaMemcpyDeviceToHost, st); \
         cudaMemcpyAsync(s->hPinned + 2 * (iter % kRing) + 1, s->dCounters.p + CTR_NEXT, 8, cudaMemcpyDeviceToHost, st); \
         cudaEventRecord(s->ringEvents[iter % kRing], st);                                                       \
+        tick(1);                                                                                                \
         ns::launch_extend(cfg, s->ds, s->pool, sorted, st);                                                     \
+        tick(-1);                                                                                               \
+        tick(2);                                                                                                \
         if (sorted) {                                                                                           \
             for (int c = 0; c < 4; ++c)                                                                         \
                 if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, st); ++launches; }  \
@@ -734,7 +808,10 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
             ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);                \
             ++launches;                                                                                         \
         }                                                                                                       \
+        tick(-1);                                                                                               \
+        tick(3);                                                                                                \
         ns::launch_occluded(cfg, s->ds, s->pool, st);                                                           \
+        tick(-1);                                                                                               \
         launches += 3;                                                                                          \
     } while (0)
     while (!finished) {
@@ -752,7 +829,9 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
             if (active == 0 && next >= r.totalWork) { finished = true; break; }
         }
         if (finished) break;
-        CK(ctx, cudaMemsetAsync(s->dCounters.p + CTR_SHADOW, 0, 6 * sizeof(unsigned long long), st));
+        // zero {shadow, class, done[iter & 1]} counters: a 48-byte window that slides with the iteration parity
+        CK(ctx, cudaMemsetAsync(s->dCounters.p + ((iter & 1ull) ? CTR_SHADOW : CTR_DONE0), 0, 6 * sizeof(unsigned long long), st));
+        r.iteration = (uint32_t) iter;
         if (parityMode) LAUNCH(parity);
         else LAUNCH(fast);
         ++iter;
@@ -780,6 +859,19 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     cudaEventDestroy(evStart);
     cudaEventDestroy(evStop);
     b2_stats &t = s->stats;
+    t.ms_generate = t.ms_extend = t.ms_shade = t.ms_occluded = 0;
+    t.n_generate = t.n_extend = t.n_shade = t.n_occluded = 0;
+    for (auto &te : timed) {
+        float e = 0;
+        cudaEventElapsedTime(&e, s->timingEvents[te.second], s->timingEvents[te.second + 1]);
+        switch (te.first) {
+            case 0: t.ms_generate += e; ++t.n_generate; break;
+            case 1: t.ms_extend += e; ++t.n_extend; break;
+            case 2: t.ms_shade += e; ++t.n_shade; break;
+            default: t.ms_occluded += e; ++t.n_occluded; break;
+        }
+    }
+    t.pool_size = Q;
     t.samples = ctr[CTR_SAMPLES]; t.rays = ctr[CTR_RAYS]; t.shadow_rays = ctr[CTR_SHADOWRAYS]; t.path_length_sum = ctr[CTR_PATHLEN];
     t.bad_samples = ctr[CTR_BAD]; t.dim_overflow = ctr[CTR_DIMOVF]; t.iterations = iter; t.kernel_launches = launches + 1;
     t.ms_total = ms;

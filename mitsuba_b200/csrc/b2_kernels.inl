@@ -111,19 +111,31 @@ B2_DEV float evalDiscretized(const DFilter &f, float x) { // rfilter.h:76-77
 B2_DEV void redAddV4(float4 *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-B2_DEV bool filmPut(const DFilter &f, float4 *filmRGBA, float *filmW, int W, int H, float posX, float posY, const V3 &spec, float alpha) {
+// The footprint arithmetic is relative to the 32x32 render block (scene.cpp:24) that owns the generating pixel,
+// exactly like ImageBlock::put: pos = _pos - 0.5 - (offset - border).  (Full-frame arithmetic would round
+// differently and occasionally pick a neighbouring filter bin.)  Block + border pixels outside the film are
+// dropped, as Bitmap::accumulate clips them when the block is merged (imageblock.h:103-107).
+B2_DEV bool filmPut(const DFilter &f, float4 *filmRGBA, float *filmW, int W, int H, float posX, float posY, int pixX, int pixY,
+                    const V3 &spec, float alpha) {
     const float value[5] = {spec.x, spec.y, spec.z, alpha, 1.0f};
 #pragma unroll
     for (int i = 0; i < 5; ++i)
         if (!isfinite(value[i]) || value[i] < 0) return false;
-    const float px = posX - 0.5f, py = posY - 0.5f;
+    const int border = f.borderSize;
+    const int ox = (pixX >> 5) << 5, oy = (pixY >> 5) << 5;
+    const int sizeX = min(32, W - ox) + 2 * border, sizeY = min(32, H - oy) + 2 * border;
+    const float px = posX - 0.5f - (float) (ox - border), py = posY - 0.5f - (float) (oy - border);
     const int minx = max((int) ceilf(px - f.radius), 0), miny = max((int) ceilf(py - f.radius), 0);
-    const int maxx = min((int) floorf(px + f.radius), W - 1), maxy = min((int) floorf(py + f.radius), H - 1);
+    const int maxx = min((int) floorf(px + f.radius), sizeX - 1), maxy = min((int) floorf(py + f.radius), sizeY - 1);
     for (int y = miny; y <= maxy; ++y) {
+        const int fy = oy - border + y;
+        if (fy < 0 || fy >= H) continue;
         const float wy = evalDiscretized(f, (float) y - py);
         for (int x = minx; x <= maxx; ++x) {
+            const int fx = ox - border + x;
+            if (fx < 0 || fx >= W) continue;
             const float w = evalDiscretized(f, (float) x - px) * wy;
-            const size_t o = (size_t) y * W + x;
+            const size_t o = (size_t) fy * W + fx;
             redAddV4(filmRGBA + o, w * value[0], w * value[1], w * value[2], w * value[3]);
             atomicAdd(filmW + o, w * value[4]);
         }
@@ -155,13 +167,14 @@ B2_DEV void cameraRay(const DCamera &cam, float sx, float sy, V3 &o, V3 &d, floa
 // sampler set-up for (pixel, sample): sobol.cpp:204-216 / counter stream
 B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uint32_t s, PathSampler &smp, float &ax, float &ay) {
     smp.kind = rp.sampler;
-    smp.m32 = sc.sobolM32;
+    smp.m32 = sc.sobolNib;
+    smp.nNib = rp.indexNibbles;
     smp.overflow = false;
     smp.dim = 0;
     if (rp.sampler == 0) {
         smp.scramble32 = (uint32_t) rp.scramble;
         uint64_t idx = s;
-        if (rp.logRes > 1) idx = sobolLookUp(sc.sobolVdc, sc.sobolInv, rp.logRes, s, (uint32_t) px, (uint32_t) py, rp.scramble);
+        if (rp.logRes > 1) idx = sobolLookUpNib(rp.lookupNib, rp.logRes, s, (uint32_t) px, (uint32_t) py, rp.scramble, rp.frameNibbles, rp.bNibbles);
         smp.index = idx;
         if (idx != (uint64_t) s) { // sobol.cpp:241-243
             ax = smp.next1D() * rp.resolution - (float) px;
@@ -179,34 +192,37 @@ B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uin
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_generate
+// k_generate: drains the finished-path queue of the previous iteration with full warps: splat (ImageBlock::put),
+// then refill the slot with the next (pixel, sample) work item.  FIRST: every slot is empty, no queue yet.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
+template <bool FIRST> __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
     const uint32_t Q = pool.capacity;
-    uint32_t nSamples = 0, nBad = 0, nDimOvf = 0;
-    unsigned long long pathLen = 0;
-    uint32_t nActive = 0;
+    const uint32_t *queue = pool.doneQueue + (size_t) ((rp.iteration + 1u) & 1u) * Q; // written by k_shade of iteration - 1
+    const uint32_t n = FIRST ? Q : (uint32_t) pool.counters[((rp.iteration + 1u) & 1u) ? CTR_DONE1 : CTR_DONE0];
+    uint32_t nSamples = 0, nBad = 0, nNew = 0;
+    uint32_t pathLen = 0;
     const uint32_t nS = (uint32_t) (rp.sampleHi - rp.sampleLo);
     const uint32_t perTile = 64u * nS;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const bool inRange = i < Q;
-        uint2 meta = inRange ? pool.meta[i] : make_uint2(0, 0);
-        uint32_t flags = meta.y & 0xFFu;
-        if (inRange && (flags & PF_DONE)) {
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t j = base + threadIdx.x;
+        const bool inRange = j < n;
+        const uint32_t i = inRange ? (FIRST ? j : queue[j]) : 0u;
+        uint2 meta = make_uint2(0, 0);
+        if (inRange && !FIRST) {
+            meta = pool.meta[i];
+            const uint32_t flags = meta.y & 0xFFu;
             const float4 li = pool.li[i];
             const uint4 sm = pool.smp[i];
             const float alpha = (flags & PF_ALPHA) ? 1.0f : 0.0f;
-            if (!filmPut(filt, rp.filmRGBA, rp.filmW, sc.cam.W, sc.cam.H, __uint_as_float(sm.z), __uint_as_float(sm.w), V3(li.x, li.y, li.z), alpha))
+            if (!filmPut(filt, rp.filmRGBA, rp.filmW, sc.cam.W, sc.cam.H, __uint_as_float(sm.z), __uint_as_float(sm.w), (int) (meta.x & 0xFFFFu),
+                         (int) (meta.x >> 16), V3(li.x, li.y, li.z), alpha))
                 ++nBad;
             ++nSamples;
             pathLen += (meta.y >> 8) & 0xFFFu;
-            flags = 0;
         }
-        bool want = inRange && !(flags & PF_ALIVE);
         // claim work: one atomic per warp
-        const unsigned long long w = warpAppend64(want, pool.counters + CTR_NEXT);
-        if (want) {
+        const unsigned long long w = warpAppend64(inRange, pool.counters + CTR_NEXT);
+        if (inRange) {
             bool valid = w < rp.totalWork;
             int px = 0, py = 0;
             uint32_t s = 0;
@@ -231,26 +247,24 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender
                 pool.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
                 pool.li[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 pool.smp[i] = make_uint4((uint32_t) smp.index, (uint32_t) (smp.index >> 32), __float_as_uint(spx), __float_as_uint(spy));
-                flags = PF_ALIVE | PF_FRESH;
                 meta.x = ((uint32_t) py << 16) | (uint32_t) px;
-                meta.y = flags | (1u << 8) | (smp.dim << 20); // depth = 1 (integrator.h:221-227)
+                meta.y = (PF_ALIVE | PF_FRESH) | (1u << 8) | (smp.dim << 20); // depth = 1 (integrator.h:221-227)
+                ++nNew;
             } else {
                 meta.y = 0;
             }
             pool.meta[i] = meta;
         }
-        if (inRange && (meta.y & PF_ALIVE)) ++nActive;
     }
-    nActive = warpSum(nActive);
+    nNew = warpSum(nNew);
     nSamples = warpSum(nSamples);
     nBad = warpSum(nBad);
-    nDimOvf = warpSum(nDimOvf);
-    uint32_t plLo = warpSum((uint32_t) pathLen);
+    pathLen = warpSum(pathLen);
     if ((threadIdx.x & 31) == 0) {
-        if (nActive) atomicAdd(pool.counters + CTR_ACTIVE, (unsigned long long) nActive);
+        if (nNew) atomicAdd(pool.counters + CTR_ACTIVE, (unsigned long long) nNew);
         if (nSamples) atomicAdd(pool.counters + CTR_SAMPLES, (unsigned long long) nSamples);
         if (nBad) atomicAdd(pool.counters + CTR_BAD, (unsigned long long) nBad);
-        if (plLo) atomicAdd(pool.counters + CTR_PATHLEN, (unsigned long long) plLo);
+        if (pathLen) atomicAdd(pool.counters + CTR_PATHLEN, (unsigned long long) pathLen);
     }
 }
 
@@ -413,7 +427,7 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
                                                                              const unsigned long long *queueCount) {
     const uint32_t Q = pool.capacity;
     const uint32_t n = queue ? (uint32_t) *queueCount : Q;
-    uint32_t nDimOvf = 0;
+    uint32_t nDimOvf = 0, nShadowRef = 0, nDone = 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
         uint32_t i = 0;
@@ -440,7 +454,8 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
             const float bsdfPdfPrev = li4.w;
             PathSampler smp;
             smp.kind = rp.sampler;
-            smp.m32 = sc.sobolM32;
+            smp.m32 = sc.sobolNib;
+            smp.nNib = rp.indexNibbles;
             smp.overflow = false;
             smp.index = ((uint64_t) sm4.y << 32) | sm4.x;
             smp.dim = meta.y >> 20;
@@ -501,6 +516,7 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
                         smp.next2D(sx, sy);
                         DirectSample ds;
                         if (sc.nEmitters > 0 && sampleEmitterDirect(sc, its.p, refN, sx, sy, ds)) {
+                            ++nShadowRef; // the reference traces (and counts, skdtree.cpp:210) the shadow ray before BSDF::eval
                             BRec bRec;
                             bRec.wi = its.wi;
                             bRec.wo = its.sh.toLocal(ds.d);
@@ -553,6 +569,15 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
             meta.y = flags | ((uint32_t) depth << 8) | (smp.dim << 20);
             pool.meta[i] = meta;
         }
+        // finished paths: queue the slot for the next k_generate (splat + refill), one atomic per warp
+        {
+            const bool fin = live && (meta.y & PF_DONE);
+            const uint32_t dq = warpAppend(fin, pool.counters + ((rp.iteration & 1u) ? CTR_DONE1 : CTR_DONE0));
+            if (fin) {
+                pool.doneQueue[(size_t) (rp.iteration & 1u) * Q + dq] = i;
+                ++nDone;
+            }
+        }
         // shadow-ray compaction (warp ballot, one atomic per warp)
         const uint32_t at = warpAppend(emitShadow, pool.counters + CTR_SHADOW);
         if (emitShadow) {
@@ -561,7 +586,13 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
         }
     }
     nDimOvf = warpSum(nDimOvf);
-    if ((threadIdx.x & 31) == 0 && nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
+    nShadowRef = warpSum(nShadowRef);
+    nDone = warpSum(nDone);
+    if ((threadIdx.x & 31) == 0) {
+        if (nDone) atomicAdd(pool.counters + CTR_ACTIVE, ~(unsigned long long) nDone + 1ull); // -= nDone
+        if (nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
+        if (nShadowRef) atomicAdd(pool.counters + CTR_SHADOWRAYS, (unsigned long long) nShadowRef);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -591,7 +622,6 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(pool.counters + CTR_SHADOWRAYS, (unsigned long long) n);
 }
 
 // film pack: (float4 rgba, float w) planes -> interleaved H*W*5 (hdrfilm.cpp:351-356 ESpectrumAlphaWeight)
@@ -652,7 +682,7 @@ __global__ void k_bsdf_sample(DScene sc, int mat, uint64_t n, const float *wi, c
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         // replay sampler (kind 3): next1D() returns the third sample component (test_chisquare.cpp:58-92 FakeSampler)
         PathSampler smp;
-        smp.kind = 3; smp.m32 = nullptr; smp.overflow = false; smp.dim = 0; smp.index = 0;
+        smp.kind = 3; smp.m32 = nullptr; smp.nNib = 8; smp.overflow = false; smp.dim = 0; smp.index = 0;
         smp.scramble32 = __float_as_uint(samples[3 * i + 2]);
         BRec r;
         r.wi = V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
@@ -697,7 +727,7 @@ __global__ void k_splat(DFilter f, int W, int H, uint64_t n, const float *pos, c
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const int px = (int) floorf(pos[2 * i]), py = (int) floorf(pos[2 * i + 1]);
         if (px < 0 || py < 0 || px >= W || py >= H) continue;
-        filmPut(f, rgba, wgt, W, H, pos[2 * i], pos[2 * i + 1], V3(val[4 * i], val[4 * i + 1], val[4 * i + 2]), val[4 * i + 3]);
+        filmPut(f, rgba, wgt, W, H, pos[2 * i], pos[2 * i + 1], px, py, V3(val[4 * i], val[4 * i + 1], val[4 * i + 2]), val[4 * i + 3]);
     }
 }
 
@@ -737,7 +767,7 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridExtendSort = occupancyGrid(k_extend<true>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridOccluded = occupancyGrid(k_occluded, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridTrace = occupancyGrid(k_trace_rays<false, false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
-    cfg.gridGenerate = occupancyGrid(k_generate, 256, 0, numSMs);
+    cfg.gridGenerate = occupancyGrid(k_generate<false>, 256, 0, numSMs);
     cfg.gridShade[0] = occupancyGrid(k_shade<0>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShade[1] = occupancyGrid(k_shade<1>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShade[2] = occupancyGrid(k_shade<2>, B2_SHADE_BLOCK, 0, numSMs);
@@ -746,7 +776,8 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
 }
 
 void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, cudaStream_t st) {
-    k_generate<<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
+    if (rp.iteration == 0) k_generate<true><<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
+    else k_generate<false><<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
 }
 void launch_extend(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, bool sort, cudaStream_t st) {
     if (sort) k_extend<true><<<cfg.gridExtendSort, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool);

@@ -35,6 +35,37 @@ B2_DEV float sobolSample(const uint32_t *__restrict__ m32, uint64_t index, uint3
     return fminf(result * (1.0f / 4294967296.0f), B2_ONE_MINUS_EPS);
 }
 
+// Same word through nibble-sliced tables: nib[dim][p][v] = XOR of columns 4p..4p+3 of `dim` selected by the bits of v.
+// XOR is associative/commutative, so the result is bit-identical to the column loop; 8 independent loads cover a
+// 32-bit index (no data-dependent trip count, no divergence), `extra` more nibbles cover longer indices.
+B2_DEV float sobolSampleNib(const uint32_t *__restrict__ nib, uint64_t index, uint32_t dimension, uint32_t scramble, uint32_t nNib) {
+    const uint32_t *t = nib + dimension * (13u * 16u);
+    const uint32_t lo = (uint32_t) index;
+    uint32_t r0 = __ldg(t + 0 * 16 + (lo & 15u)), r1 = __ldg(t + 1 * 16 + ((lo >> 4) & 15u)), r2 = __ldg(t + 2 * 16 + ((lo >> 8) & 15u)),
+             r3 = __ldg(t + 3 * 16 + ((lo >> 12) & 15u)), r4 = __ldg(t + 4 * 16 + ((lo >> 16) & 15u)), r5 = __ldg(t + 5 * 16 + ((lo >> 20) & 15u)),
+             r6 = __ldg(t + 6 * 16 + ((lo >> 24) & 15u)), r7 = __ldg(t + 7 * 16 + (lo >> 28));
+    uint32_t result = scramble ^ r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
+    if (nNib > 8u) { // uniform across the launch
+        uint32_t hi = (uint32_t) (index >> 32);
+        for (uint32_t p = 8; p < nNib; ++p, hi >>= 4) result ^= __ldg(t + p * 16 + (hi & 15u));
+    }
+    return fminf(result * (1.0f / 4294967296.0f), B2_ONE_MINUS_EPS);
+}
+
+// sobolseq.h:104-133 look_up through nibble tables built on the host for this render's m (see DRender::lookupNib)
+B2_DEV uint64_t sobolLookUpNib(const uint64_t *__restrict__ lut, uint32_t m, uint32_t frame, uint32_t px, uint32_t py, uint64_t scramble,
+                               uint32_t frameNib, uint32_t bNib) {
+    const uint32_t m2 = m << 1;
+    uint64_t index = (uint64_t) frame << m2;
+    uint64_t delta = 0;
+    for (uint32_t p = 0; p < frameNib; ++p) delta ^= __ldg(lut + p * 16 + ((frame >> (4 * p)) & 15u));
+    scramble = (scramble & 0xFFFFFFFFull) >> (32 - m);
+    uint64_t b = (((uint64_t) (px ^ scramble) << m) | (py ^ scramble)) ^ delta;
+    const uint64_t *inv = lut + 13 * 16;
+    for (uint32_t p = 0; p < bNib; ++p) index ^= __ldg(inv + p * 16 + (uint32_t) ((b >> (4 * p)) & 15ull));
+    return index;
+}
+
 // sobolseq.h:104-133 look_up (SINGLE_PRECISION scramble branch)
 B2_DEV uint64_t sobolLookUp(const uint64_t *__restrict__ vdc, const uint64_t *__restrict__ inv, uint32_t m, uint32_t frame,
                             uint32_t px, uint32_t py, uint64_t scramble) {
@@ -65,14 +96,15 @@ struct PathSampler {
     uint32_t dim;
     int kind;            // 0 sobol, 2 counter
     uint32_t scramble32; // sobol scramble (low 32 bits) / seed hi for the counter stream
-    const uint32_t *m32;
+    const uint32_t *m32;   // nibble-sliced tables (DScene::sobolNib)
+    uint32_t nNib;
     bool overflow;
 
     B2_DEV float next1D() {
         if (kind == 3) return __uint_as_float(scramble32); // replay (component tests)
         if (kind == 0) {
             if (dim >= 1024u) { overflow = true; dim = 1023u; } // sobol.cpp:223-225 raises an error here
-            return sobolSample(m32, index, dim++, scramble32);
+            return sobolSampleNib(m32, index, dim++, scramble32, nNib);
         } else {
             uint64_t r = sampleTEA((uint32_t) index, (dim++) ^ scramble32);
             uint32_t u = ((uint32_t) (r & 0xFFFFFFFFull) >> 9) | 0x3f800000u; // random.cpp:630-640

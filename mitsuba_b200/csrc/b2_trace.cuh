@@ -131,7 +131,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
             else if (hR) { ref = rref; continue; }
         } else {
             uint32_t bits = ~(uint32_t) ref;
-            uint32_t start = bits & 0x0FFFFFFFu, count = bits >> 28;
+            uint32_t start = bits & 0x0FFFFFFFu, count = sc.rootCount ? sc.rootCount : (bits >> 28);
             for (uint32_t i = 0; i < count; ++i) {
                 uint32_t ti = start + i;
                 float4 q0, q1, q2;

@@ -55,6 +55,7 @@ struct DScene {
     const BVHNode *nodes;
     uint32_t nNodes;
     int32_t rootRef;           // root child reference (leaf-only scenes: a leaf ref)
+    uint32_t rootCount;        // > 0: the whole scene is one flat leaf of rootCount triangles (tiny scenes, tested in lockstep)
     float aabbMin[3], aabbMax[3]; // enlarged scene box (gkdtree.h:1213-1220)
     // per-prim shading data in prim order: verts[3*p+k] = (position k, w = {material id, emitter id, flags} as int bits)
     const float4 *verts;
@@ -73,6 +74,7 @@ struct DScene {
     const uint32_t *sobolM32;  // [1024][52]
     const uint64_t *sobolVdc;  // [25][52]
     const uint64_t *sobolInv;  // [26][52]
+    const uint32_t *sobolNib;  // [1024][13][16]: XOR of the 4 columns of nibble p selected by v (b2_host.cpp: buildSobolNibbles)
     // staging limits for shared memory (number of leading BVH nodes / TriAccel records copied by TMA)
     uint32_t stageNodes, stageTris;
 };
@@ -109,12 +111,17 @@ struct DPool {
     float4 *shC;       // contribution rgb, slot (bits)
     // material-class queues
     uint32_t *matQueue;   // [nClasses][capacity]
-    // counters (device): [0] next work item (u64 split), [2] shadow count, [3] active count, [4..7] class counts, [8..] stats
+    // finished-path queues, double buffered: k_shade of iteration k appends to doneQueue[k & 1], k_generate of
+    // iteration k + 1 drains it (splat + refill) with full warps
+    uint32_t *doneQueue;  // [2][capacity]
+    // counters (device, u64): see CTR_*
     unsigned long long *counters;
 };
 
-enum { CTR_NEXT = 0, CTR_SHADOW = 1, CTR_ACTIVE = 2, CTR_CLASS0 = 3, /* 3..6 */ CTR_RAYS = 8, CTR_SHADOWRAYS = 9,
-       CTR_PATHLEN = 10, CTR_SAMPLES = 11, CTR_BAD = 12, CTR_DIMOVF = 13, CTR_NODEVIS = 14, CTR_PRIMTESTS = 15, CTR_COUNT = 16 };
+// [CTR_DONE0, CTR_SHADOW, CTR_CLASS0..3, CTR_DONE1] is zeroed per iteration as one 48-byte window that slides by one
+// entry with the iteration parity (even: DONE0..CLASS3, odd: SHADOW..DONE1)
+enum { CTR_DONE0 = 0, CTR_SHADOW = 1, CTR_CLASS0 = 2, /* 2..5 */ CTR_DONE1 = 6, CTR_NEXT = 7, CTR_ACTIVE = 8, CTR_RAYS = 9, CTR_SHADOWRAYS = 10,
+       CTR_PATHLEN = 11, CTR_SAMPLES = 12, CTR_BAD = 13, CTR_DIMOVF = 14, CTR_NODEVIS = 15, CTR_PRIMTESTS = 16, CTR_COUNT = 18 };
 
 struct DRender {
     int32_t spp, sampler;
@@ -127,6 +134,10 @@ struct DRender {
     uint32_t tilesX, tilesY;
     float4 *filmRGBA;        // H*W float4 (r,g,b,alpha) accumulators
     float *filmW;            // H*W weight accumulators
+    const uint64_t *lookupNib; // [2][13][16] nibble tables of sobol look_up for this render's m: [0] vdc (delta), [1] inv
+    uint32_t indexNibbles;   // nibbles needed to cover the largest Sobol' index of this render (<= 13)
+    uint32_t frameNibbles, bNibbles; // nibbles of the sample index / of the 2m-bit pixel code in look_up
+    uint32_t iteration;      // host loop iteration (parity selects the done queue)
 };
 
 } // namespace b2

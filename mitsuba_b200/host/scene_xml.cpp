@@ -1,0 +1,696 @@
+// Scene-file front end: the subset of Mitsuba 0.6's SceneHandler (src/librender/scenehandler.cpp:70-106,
+// 300-700) that describes the `path` hot path, parsed with expat and lowered onto the C-ABI (b2mts.h).
+//
+// Supported elements: scene, integrator(path), sensor(perspective) with transform/sampler/film/rfilter,
+// bsdf(diffuse | roughconductor | roughdielectric | coating) incl. id/ref, shape(obj | rectangle | cube) with
+// toWorld transform, bsdf child / ref and emitter(area) child; property tags integer, float, boolean, string,
+// rgb, srgb, spectrum (1 or 3 values), point, vector, transform{translate, rotate, scale, lookat, matrix},
+// default, and $name substitution from `defines` (src/mitsuba/mitsuba.cpp:154 -D).
+// Anything else is rejected with an error naming the element -- nothing is silently ignored.
+#include "../../include/b2mts.h"
+#include <expat.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct M4 {
+    double m[16];
+    M4() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+    M4 operator*(const M4 &o) const {
+        M4 r;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double s = 0;
+                for (int k = 0; k < 4; ++k) s += m[i * 4 + k] * o.m[k * 4 + j];
+                r.m[i * 4 + j] = s;
+            }
+        return r;
+    }
+    void point(const double *p, double *o) const {
+        for (int i = 0; i < 3; ++i) o[i] = m[i * 4] * p[0] + m[i * 4 + 1] * p[1] + m[i * 4 + 2] * p[2] + m[i * 4 + 3];
+    }
+    bool inverse(M4 &out) const {
+        double a[4][8];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) { a[i][j] = m[i * 4 + j]; a[i][4 + j] = i == j; }
+        for (int c = 0; c < 4; ++c) {
+            int piv = c;
+            for (int r = c + 1; r < 4; ++r) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+            if (std::fabs(a[piv][c]) < 1e-300) return false;
+            for (int j = 0; j < 8; ++j) std::swap(a[piv][j], a[c][j]);
+            double d = a[c][c];
+            for (int j = 0; j < 8; ++j) a[c][j] /= d;
+            for (int r = 0; r < 4; ++r) if (r != c) { double f = a[r][c]; for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j]; }
+        }
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out.m[i * 4 + j] = a[i][4 + j];
+        return true;
+    }
+    // normals: inverse transpose (transform.h operator()(Normal))
+    void normal(const M4 &inv, const double *n, double *o) const {
+        for (int i = 0; i < 3; ++i) o[i] = inv.m[0 * 4 + i] * n[0] + inv.m[1 * 4 + i] * n[1] + inv.m[2 * 4 + i] * n[2];
+    }
+};
+
+struct Value {
+    enum Kind { Int, Float, Bool, String, Spectrum, Vec, Transform } kind = Float;
+    double f = 0; long long i = 0; bool b = false; std::string s; double v[3] = {0, 0, 0}; M4 t;
+};
+
+struct Node {
+    std::string tag, type, id, name;
+    std::map<std::string, Value> props;
+    std::vector<std::unique_ptr<Node>> children;
+    Node *parent = nullptr;
+    M4 xform;          // while parsing a <transform>
+    bool queried(const std::string &) { return true; }
+};
+
+struct Err : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct Parser {
+    std::map<std::string, std::string> defines;
+    std::unique_ptr<Node> root;
+    Node *cur = nullptr;
+    std::string baseDir;
+    XML_Parser xp = nullptr;
+
+    std::string subst(const std::string &s) { // scenehandler.cpp:214-236: $key replacement
+        if (s.find('$') == std::string::npos) return s;
+        std::string out = s;
+        // longest keys first
+        std::vector<std::pair<std::string, std::string>> kv(defines.begin(), defines.end());
+        std::sort(kv.begin(), kv.end(), [](auto &a, auto &b) { return a.first.size() > b.first.size(); });
+        for (auto &p : kv) {
+            std::string key = "$" + p.first;
+            size_t pos;
+            while ((pos = out.find(key)) != std::string::npos) out.replace(pos, key.size(), p.second);
+        }
+        if (out.find('$') != std::string::npos) throw Err("The scene referenced an undefined parameter: \"" + out + "\"");
+        return out;
+    }
+    static double toF(const std::string &s, const char *what) {
+        char *end = nullptr;
+        double v = strtod(s.c_str(), &end);
+        if (end == s.c_str() || *end != '\0') throw Err(std::string("Could not parse floating point value \"") + s + "\" (" + what + ")");
+        return v;
+    }
+    static std::vector<std::string> tokenize(const std::string &s, const char *delim = ", ") {
+        std::vector<std::string> out;
+        size_t i = 0;
+        while (i < s.size()) {
+            size_t j = s.find_first_of(delim, i);
+            if (j == std::string::npos) j = s.size();
+            if (j > i) out.push_back(s.substr(i, j - i));
+            i = j + 1;
+        }
+        return out;
+    }
+    static void srgbToLinear(double *v) { // Spectrum::fromSRGB
+        for (int i = 0; i < 3; ++i) v[i] = v[i] <= 0.04045 ? v[i] / 12.92 : std::pow((v[i] + 0.055) / 1.055, 2.4);
+    }
+
+    void start(const char *tagC, const char **atts) {
+        std::string tag = tagC;
+        std::map<std::string, std::string> a;
+        for (int i = 0; atts[i]; i += 2) a[atts[i]] = subst(atts[i + 1]);
+        auto need = [&](const char *k) -> const std::string & {
+            auto it = a.find(k);
+            if (it == a.end()) throw Err("<" + tag + ">: missing attribute '" + k + "'");
+            return it->second;
+        };
+        auto opt = [&](const char *k, double dflt) { auto it = a.find(k); return it == a.end() || it->second.empty() ? dflt : toF(it->second, k); };
+        if (tag == "default") { // scenehandler.cpp:646-652
+            if (!defines.count(need("name"))) defines[need("name")] = need("value");
+            return;
+        }
+        static const char *objects[] = {"scene", "integrator", "sensor", "sampler", "film", "rfilter", "bsdf", "shape", "emitter", "ref", "transform"};
+        bool isObject = std::find_if(std::begin(objects), std::end(objects), [&](const char *o) { return tag == o; }) != std::end(objects);
+        if (isObject) {
+            auto n = std::make_unique<Node>();
+            n->tag = tag; n->type = a.count("type") ? a["type"] : ""; n->id = a.count("id") ? a["id"] : ""; n->name = a.count("name") ? a["name"] : "";
+            n->parent = cur;
+            Node *raw = n.get();
+            if (!cur) { if (tag != "scene") throw Err("root element must be <scene>"); root = std::move(n); }
+            else cur->children.push_back(std::move(n));
+            cur = raw;
+            return;
+        }
+        if (!cur) throw Err("unexpected <" + tag + "> outside <scene>");
+        // transform operations (scenehandler.cpp:348-441): each one is applied on the left
+        if (cur->tag == "transform") {
+            M4 op;
+            if (tag == "translate") { op.m[3] = opt("x", 0); op.m[7] = opt("y", 0); op.m[11] = opt("z", 0); }
+            else if (tag == "scale") {
+                bool hasV = a.count("value") && !a["value"].empty();
+                double x = hasV ? toF(a["value"], "scale") : opt("x", 1), y = hasV ? x : opt("y", 1), z = hasV ? x : opt("z", 1);
+                op.m[0] = x; op.m[5] = y; op.m[10] = z;
+            } else if (tag == "rotate") { // transform.cpp:65-98
+                double ax[3] = {opt("x", 0), opt("y", 0), opt("z", 0)}, ang = toF(need("angle"), "angle") * M_PI / 180.0;
+                double l = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+                if (l == 0) throw Err("<rotate>: zero axis");
+                for (double &c : ax) c /= l;
+                double s = std::sin(ang), c = std::cos(ang);
+                op.m[0] = ax[0] * ax[0] + (1 - ax[0] * ax[0]) * c; op.m[1] = ax[0] * ax[1] * (1 - c) - ax[2] * s; op.m[2] = ax[0] * ax[2] * (1 - c) + ax[1] * s;
+                op.m[4] = ax[0] * ax[1] * (1 - c) + ax[2] * s; op.m[5] = ax[1] * ax[1] + (1 - ax[1] * ax[1]) * c; op.m[6] = ax[1] * ax[2] * (1 - c) - ax[0] * s;
+                op.m[8] = ax[0] * ax[2] * (1 - c) - ax[1] * s; op.m[9] = ax[1] * ax[2] * (1 - c) + ax[0] * s; op.m[10] = ax[2] * ax[2] + (1 - ax[2] * ax[2]) * c;
+            } else if (tag == "lookat") { // transform.cpp:191-214
+                auto v3 = [&](const char *k, double *o, bool required) {
+                    auto it = a.find(k);
+                    if (it == a.end() || it->second.empty()) { if (required) throw Err(std::string("<lookat>: invalid '") + k + "' argument"); return false; }
+                    auto t = tokenize(it->second);
+                    if (t.size() != 3) throw Err(std::string("<lookat>: invalid '") + k + "' argument");
+                    for (int i = 0; i < 3; ++i) o[i] = toF(t[i], k);
+                    return true;
+                };
+                double o[3], t[3], u[3] = {0, 0, 0};
+                v3("origin", o, true); v3("target", t, true); v3("up", u, false);
+                double d[3] = {t[0] - o[0], t[1] - o[1], t[2] - o[2]};
+                double l = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                if (l == 0) throw Err("lookAt(): 'origin' and 'target' coincide!");
+                for (double &c : d) c /= l;
+                if (u[0] == 0 && u[1] == 0 && u[2] == 0) { // arbitrary axis (scenehandler.cpp:392-396)
+                    double c3[3];
+                    if (std::fabs(d[0]) > std::fabs(d[1])) { double il = 1 / std::sqrt(d[0] * d[0] + d[2] * d[2]); c3[0] = d[2] * il; c3[1] = 0; c3[2] = -d[0] * il; }
+                    else { double il = 1 / std::sqrt(d[1] * d[1] + d[2] * d[2]); c3[0] = 0; c3[1] = d[2] * il; c3[2] = -d[1] * il; }
+                    u[0] = c3[1] * d[2] - c3[2] * d[1]; u[1] = c3[2] * d[0] - c3[0] * d[2]; u[2] = c3[0] * d[1] - c3[1] * d[0];
+                }
+                double left[3] = {u[1] * d[2] - u[2] * d[1], u[2] * d[0] - u[0] * d[2], u[0] * d[1] - u[1] * d[0]};
+                l = std::sqrt(left[0] * left[0] + left[1] * left[1] + left[2] * left[2]);
+                if (l == 0) throw Err("lookAt(): the forward and upward direction must be linearly independent!");
+                for (double &c : left) c /= l;
+                double nu[3] = {d[1] * left[2] - d[2] * left[1], d[2] * left[0] - d[0] * left[2], d[0] * left[1] - d[1] * left[0]};
+                for (int i = 0; i < 3; ++i) { op.m[i * 4] = left[i]; op.m[i * 4 + 1] = nu[i]; op.m[i * 4 + 2] = d[i]; op.m[i * 4 + 3] = o[i]; }
+            } else if (tag == "matrix") {
+                auto t = tokenize(need("value"));
+                if (t.size() != 16) throw Err("Invalid matrix specified");
+                for (int i = 0; i < 16; ++i) op.m[i] = toF(t[i], "matrix");
+            } else throw Err("unsupported transform operation <" + tag + ">");
+            cur->xform = op * cur->xform;
+            return;
+        }
+        // plain properties
+        Value v;
+        const std::string &pname = need("name");
+        if (tag == "integer") { v.kind = Value::Int; v.i = (long long) toF(need("value"), "integer"); v.f = (double) v.i; }
+        else if (tag == "float") { v.kind = Value::Float; v.f = toF(need("value"), "float"); }
+        else if (tag == "boolean") {
+            std::string b = need("value");
+            std::transform(b.begin(), b.end(), b.begin(), ::tolower);
+            if (b != "true" && b != "false") throw Err("Could not parse boolean value \"" + b + "\"");
+            v.kind = Value::Bool; v.b = b == "true";
+        } else if (tag == "string") { v.kind = Value::String; v.s = need("value"); }
+        else if (tag == "rgb" || tag == "srgb" || tag == "spectrum") {
+            v.kind = Value::Spectrum;
+            if (tag == "spectrum" && a.count("filename")) throw Err("<spectrum filename=...>: .spd spectra are not supported (use RGB values)");
+            auto t = tokenize(need("value"));
+            if (t.size() == 1 && t[0].size() == 7 && t[0][0] == '#' && tag != "spectrum") {
+                long enc = strtol(t[0].c_str() + 1, nullptr, 16);
+                v.v[0] = ((enc >> 16) & 0xFF) / 255.0; v.v[1] = ((enc >> 8) & 0xFF) / 255.0; v.v[2] = (enc & 0xFF) / 255.0;
+            } else if (t.size() == 1) {
+                if (t[0].find(':') != std::string::npos) throw Err("<spectrum>: wavelength:value lists are not supported (use RGB values)");
+                v.v[0] = v.v[1] = v.v[2] = toF(t[0], "spectrum"); // reflectance: flat; illuminant: D65 == white in the RGB build
+            } else if (t.size() == 3) { for (int i = 0; i < 3; ++i) v.v[i] = toF(t[i], "spectrum"); }
+            else throw Err("Invalid spectrum value specified (length does not match the current spectral discretization!)");
+            if (tag == "srgb") srgbToLinear(v.v);
+        } else if (tag == "point" || tag == "vector") {
+            v.kind = Value::Vec; v.v[0] = opt("x", 0); v.v[1] = opt("y", 0); v.v[2] = opt("z", 0);
+        } else throw Err("unsupported element <" + tag + ">");
+        cur->props[pname] = v;
+    }
+    void end(const char *tagC) {
+        std::string tag = tagC;
+        if (!cur || cur->tag != tag) return; // property / transform-op tags
+        Node *n = cur;
+        cur = n->parent;
+        if (tag == "transform" && cur) {
+            Value v; v.kind = Value::Transform; v.t = n->xform;
+            cur->props[n->name.empty() ? "toWorld" : n->name] = v;
+        }
+    }
+};
+
+// exceptions must not unwind through expat's C frames: record the first error and stop the parser
+std::string g_parseError;
+void XMLCALL onStart(void *u, const char *t, const char **a) {
+    Parser *P = (Parser *) u;
+    try { P->start(t, a); } catch (const std::exception &e) { if (g_parseError.empty()) g_parseError = e.what(); XML_StopParser(P->xp, XML_FALSE); }
+}
+void XMLCALL onEnd(void *u, const char *t) {
+    Parser *P = (Parser *) u;
+    try { P->end(t); } catch (const std::exception &e) { if (g_parseError.empty()) g_parseError = e.what(); XML_StopParser(P->xp, XML_FALSE); }
+}
+
+// ---- property access with the reference's defaults and "unqueried property" discipline ----
+struct Props {
+    Node *n;
+    std::map<std::string, bool> used;
+    explicit Props(Node *n_) : n(n_) {}
+    bool has(const std::string &k) const { return n->props.count(k) != 0; }
+    double f(const std::string &k, double d) { used[k] = true; auto it = n->props.find(k); if (it == n->props.end()) return d; if (it->second.kind != Value::Float && it->second.kind != Value::Int) throw Err("property '" + k + "' has the wrong type"); return it->second.f; }
+    long long i(const std::string &k, long long d) { used[k] = true; auto it = n->props.find(k); if (it == n->props.end()) return d; if (it->second.kind != Value::Int) throw Err("property '" + k + "' must be an integer"); return it->second.i; }
+    bool b(const std::string &k, bool d) { used[k] = true; auto it = n->props.find(k); if (it == n->props.end()) return d; if (it->second.kind != Value::Bool) throw Err("property '" + k + "' must be a boolean"); return it->second.b; }
+    std::string s(const std::string &k, const std::string &d) { used[k] = true; auto it = n->props.find(k); if (it == n->props.end()) return d; if (it->second.kind != Value::String) throw Err("property '" + k + "' must be a string"); return it->second.s; }
+    void spec(const std::string &k, const double *d, float *out) { used[k] = true; auto it = n->props.find(k); const double *v = d; if (it != n->props.end()) { if (it->second.kind != Value::Spectrum) throw Err("property '" + k + "' must be a spectrum"); v = it->second.v; } for (int c = 0; c < 3; ++c) out[c] = (float) v[c]; }
+    M4 xf(const std::string &k) { used[k] = true; auto it = n->props.find(k); return it == n->props.end() ? M4() : it->second.t; }
+    void checkAllUsed() { // Properties "unqueried" check (src/libcore/plugin.cpp:185-196)
+        for (auto &p : n->props) if (!used.count(p.first)) throw Err("<" + n->tag + " type=\"" + n->type + "\">: unreferenced property \"" + p.first + "\"");
+    }
+};
+
+static double namedIOR(Props &p, const std::string &key, const char *dflt) { // src/bsdfs/ior.h:39-100
+    static const std::map<std::string, double> table = {
+        {"vacuum", 1.0}, {"helium", 1.000036}, {"hydrogen", 1.000132}, {"air", 1.000277}, {"carbon dioxide", 1.00045}, {"water", 1.3330},
+        {"acetone", 1.36}, {"ethanol", 1.361}, {"carbon tetrachloride", 1.461}, {"glycerol", 1.4729}, {"benzene", 1.501}, {"silicone oil", 1.52045},
+        {"bromine", 1.661}, {"water ice", 1.31}, {"fused quartz", 1.458}, {"pyrex", 1.470}, {"acrylic glass", 1.49}, {"polypropylene", 1.49},
+        {"bk7", 1.5046}, {"sodium chloride", 1.544}, {"amber", 1.55}, {"pet", 1.5750}, {"diamond", 2.419}};
+    p.used[key] = true;
+    auto it = p.n->props.find(key);
+    std::string name = dflt;
+    if (it != p.n->props.end()) {
+        if (it->second.kind == Value::Float || it->second.kind == Value::Int) return it->second.f;
+        if (it->second.kind != Value::String) throw Err("property '" + key + "' must be a float or a material name");
+        name = it->second.s;
+    }
+    std::transform(name.begin(), name.end(), name.begin(), ::tolower);
+    auto t = table.find(name);
+    if (t == table.end()) throw Err("Unable to find an IOR value for \"" + name + "\"");
+    return t->second;
+}
+
+struct Loader {
+    b2_scene *scene = nullptr;
+    std::map<std::string, int> bsdfIds; // id -> material id
+    std::string baseDir;
+
+    static void microfacet(Props &p, b2_material_desc &m) { // microfacet.h:95-148
+        m.distr = B2_DISTR_BECKMANN; m.alpha_u = m.alpha_v = 0.1f;
+        if (p.has("distribution")) {
+            std::string d = p.s("distribution", "beckmann");
+            std::transform(d.begin(), d.end(), d.begin(), ::tolower);
+            if (d == "beckmann") m.distr = B2_DISTR_BECKMANN; else if (d == "ggx") m.distr = B2_DISTR_GGX; else if (d == "phong" || d == "as") m.distr = B2_DISTR_PHONG;
+            else throw Err("Specified an invalid distribution \"" + d + "\", must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
+        }
+        if (p.has("alpha")) {
+            if (p.has("alphaU") || p.has("alphaV")) throw Err("Microfacet model: please specify either 'alpha' or 'alphaU'/'alphaV'.");
+            m.alpha_u = m.alpha_v = (float) p.f("alpha", 0.1);
+        } else if (p.has("alphaU") || p.has("alphaV")) {
+            if (!p.has("alphaU") || !p.has("alphaV")) throw Err("Microfacet model: both 'alphaU' and 'alphaV' must be specified.");
+            m.alpha_u = (float) p.f("alphaU", 0.1); m.alpha_v = (float) p.f("alphaV", 0.1);
+        }
+        m.sample_visible = p.b("sampleVisible", true) ? 1 : 0;
+        if (m.distr == B2_DISTR_PHONG) m.sample_visible = 0;
+    }
+
+    int addBsdf(Node *n) {
+        Props p(n);
+        b2_material_desc m;
+        memset(&m, 0, sizeof(m));
+        m.nested = -1; m.eta = 1.0f; m.thickness = 1.0f; m.sample_visible = 1; m.alpha_u = m.alpha_v = 0.1f;
+        const double one[3] = {1, 1, 1}, zero[3] = {0, 0, 0}, half[3] = {0.5, 0.5, 0.5};
+        for (int c = 0; c < 3; ++c) { m.transmittance[c] = 1; m.k_c[c] = 1; }
+        if (n->type == "diffuse") {
+            m.type = B2_BSDF_DIFFUSE;
+            p.spec(p.has("reflectance") ? "reflectance" : "diffuseReflectance", half, m.reflectance); // diffuse.cpp:75-77
+        } else if (n->type == "roughconductor") {
+            m.type = B2_BSDF_ROUGHCONDUCTOR;
+            p.spec("specularReflectance", one, m.reflectance);
+            std::string material = p.s("material", "Cu");
+            std::string lower = material;
+            std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
+            double eta[3] = {0, 0, 0}, k[3] = {1, 1, 1};
+            if (lower != "none" && !(p.has("eta") && p.has("k")))
+                throw Err("roughconductor: material=\"" + material + "\" needs the data/ior .spd tables (not supported); pass RGB 'eta' and 'k'");
+            float fe[3], fk[3];
+            p.spec("eta", eta, fe); p.spec("k", k, fk);
+            float ext = (float) namedIOR(p, "extEta", "air");
+            for (int c = 0; c < 3; ++c) { m.eta_c[c] = fe[c] / ext; m.k_c[c] = fk[c] / ext; } // roughconductor.cpp:189-190
+            microfacet(p, m);
+        } else if (n->type == "roughdielectric") {
+            m.type = B2_BSDF_ROUGHDIELECTRIC;
+            p.spec("specularReflectance", one, m.reflectance); p.spec("specularTransmittance", one, m.transmittance);
+            float intI = (float) namedIOR(p, "intIOR", "bk7"), extI = (float) namedIOR(p, "extIOR", "air");
+            if (intI < 0 || extI < 0 || intI == extI) throw Err("The interior and exterior indices of refraction must be positive and differ!");
+            m.eta = intI / extI;
+            microfacet(p, m);
+        } else if (n->type == "coating") {
+            m.type = B2_BSDF_COATING;
+            float intI = (float) namedIOR(p, "intIOR", "bk7"), extI = (float) namedIOR(p, "extIOR", "air");
+            if (intI < 0 || extI < 0 || intI == extI) throw Err("The interior and exterior indices of refraction must be positive and differ!");
+            m.eta = intI / extI;
+            m.thickness = (float) p.f("thickness", 1);
+            p.spec("sigmaA", zero, m.sigma_a); p.spec("specularReflectance", one, m.reflectance);
+            int nested = -1;
+            for (auto &c : n->children) {
+                if (c->tag == "bsdf") { if (nested >= 0) throw Err("Only a single nested BRDF can be added!"); nested = addBsdf(c.get()); }
+                else if (c->tag == "ref") { if (nested >= 0) throw Err("Only a single nested BRDF can be added!"); nested = resolveRef(c.get()); }
+            }
+            if (nested < 0) throw Err("coating: A child BSDF instance is required");
+            m.nested = nested;
+        } else throw Err("unsupported BSDF plugin \"" + n->type + "\" (hot path: diffuse, roughconductor, roughdielectric, coating)");
+        p.checkAllUsed();
+        int id = b2_scene_add_material(scene, &m);
+        if (id < 0) throw Err(b2_last_error(nullptr));
+        if (!n->id.empty()) bsdfIds[n->id] = id;
+        return id;
+    }
+    int resolveRef(Node *r) {
+        auto it = bsdfIds.find(r->id);
+        if (it == bsdfIds.end()) throw Err("Referenced object \"" + r->id + "\" not found (only BSDF references are supported)");
+        return it->second;
+    }
+
+    struct MeshData { std::vector<float> P, N, UV; std::vector<uint32_t> idx; };
+
+    void loadObj(const std::string &path, MeshData &md) {
+        std::ifstream f(path);
+        if (!f) throw Err("OBJ file \"" + path + "\" could not be found!");
+        std::vector<double> v, vn, vt;
+        std::map<std::tuple<int, int, int>, uint32_t> uniq;
+        bool anyN = false, anyT = false, allN = true, allT = true;
+        struct Corner { int v, t, n; };
+        std::vector<std::vector<Corner>> faces;
+        std::string line;
+        while (std::getline(f, line)) {
+            std::istringstream ss(line);
+            std::string k;
+            if (!(ss >> k)) continue;
+            if (k == "v") { double x, y, z; ss >> x >> y >> z; v.insert(v.end(), {x, y, z}); }
+            else if (k == "vn") { double x, y, z; ss >> x >> y >> z; vn.insert(vn.end(), {x, y, z}); }
+            else if (k == "vt") { double x = 0, y = 0; ss >> x >> y; vt.insert(vt.end(), {x, y}); }
+            else if (k == "f") {
+                std::vector<Corner> face;
+                std::string tok;
+                while (ss >> tok) {
+                    Corner c{0, 0, 0};
+                    int part = 0; size_t i = 0;
+                    while (i <= tok.size()) {
+                        size_t j = tok.find('/', i);
+                        if (j == std::string::npos) j = tok.size();
+                        std::string s = tok.substr(i, j - i);
+                        int val = s.empty() ? 0 : atoi(s.c_str());
+                        if (part == 0) c.v = val; else if (part == 1) c.t = val; else c.n = val;
+                        ++part; i = j + 1;
+                    }
+                    auto fix = [](int idx, size_t count) { return idx < 0 ? (int) count + idx + 1 : idx; };
+                    c.v = fix(c.v, v.size() / 3); c.t = fix(c.t, vt.size() / 2); c.n = fix(c.n, vn.size() / 3);
+                    if (c.v <= 0 || (size_t) c.v > v.size() / 3) throw Err("OBJ: vertex index out of range in \"" + path + "\"");
+                    face.push_back(c);
+                }
+                if (face.size() < 3) continue;
+                faces.push_back(face);
+                for (auto &c : face) { anyN |= c.n > 0; anyT |= c.t > 0; allN &= c.n > 0; allT &= c.t > 0; }
+            }
+        }
+        bool useN = anyN && allN, useT = anyT && allT;
+        for (auto &face : faces)
+            for (size_t k = 1; k + 1 < face.size(); ++k) { // fan triangulation
+                const Corner cs[3] = {face[0], face[k], face[k + 1]};
+                for (auto &c : cs) {
+                    auto key = std::make_tuple(c.v, useT ? c.t : 0, useN ? c.n : 0);
+                    auto it = uniq.find(key);
+                    uint32_t id;
+                    if (it == uniq.end()) {
+                        id = (uint32_t) (md.P.size() / 3);
+                        uniq[key] = id;
+                        for (int d = 0; d < 3; ++d) md.P.push_back((float) v[3 * (c.v - 1) + d]);
+                        if (useN) for (int d = 0; d < 3; ++d) md.N.push_back((float) vn[3 * (c.n - 1) + d]);
+                        if (useT) for (int d = 0; d < 2; ++d) md.UV.push_back((float) vt[2 * (c.t - 1) + d]);
+                    } else id = it->second;
+                    md.idx.push_back(id);
+                }
+            }
+        if (md.idx.empty()) throw Err("OBJ file \"" + path + "\" contains no faces");
+    }
+
+    // TriMesh::computeNormals (trimesh.cpp:608-681): face-normal mode or angle-weighted smooth normals
+    static void computeNormals(MeshData &md, bool faceNormals, bool flipNormals) {
+        const size_t nV = md.P.size() / 3, nT = md.idx.size() / 3;
+        if (faceNormals) {
+            md.N.clear();
+            if (flipNormals) for (size_t t = 0; t < nT; ++t) std::swap(md.idx[3 * t], md.idx[3 * t + 1]);
+            return;
+        }
+        if (!md.N.empty()) { if (flipNormals) for (float &x : md.N) x = -x; return; }
+        std::vector<double> acc(3 * nV, 0.0);
+        auto sub = [&](uint32_t a, uint32_t b, float *o) { for (int d = 0; d < 3; ++d) o[d] = md.P[3 * a + d] - md.P[3 * b + d]; };
+        for (size_t t = 0; t < nT; ++t) {
+            float n[3] = {0, 0, 0};
+            for (int i = 0; i < 3; ++i) {
+                uint32_t i0 = md.idx[3 * t + i], i1 = md.idx[3 * t + (i + 1) % 3], i2 = md.idx[3 * t + (i + 2) % 3];
+                float sa[3], sb[3];
+                sub(i1, i0, sa); sub(i2, i0, sb);
+                if (i == 0) {
+                    n[0] = sa[1] * sb[2] - sa[2] * sb[1]; n[1] = sa[2] * sb[0] - sa[0] * sb[2]; n[2] = sa[0] * sb[1] - sa[1] * sb[0];
+                    float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                    if (len == 0) break;
+                    for (float &c : n) c /= len;
+                }
+                float la = std::sqrt(sa[0] * sa[0] + sa[1] * sa[1] + sa[2] * sa[2]), lb = std::sqrt(sb[0] * sb[0] + sb[1] * sb[1] + sb[2] * sb[2]);
+                float ua[3] = {sa[0] / la, sa[1] / la, sa[2] / la}, ub[3] = {sb[0] / lb, sb[1] / lb, sb[2] / lb};
+                // unitAngle (vector.h): numerically robust angle between unit vectors
+                float dp = ua[0] * ub[0] + ua[1] * ub[1] + ua[2] * ub[2], angle;
+                if (dp < 0) { float s[3] = {ub[0] + ua[0], ub[1] + ua[1], ub[2] + ua[2]}; angle = (float) M_PI - 2 * std::asin(0.5f * std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2])); }
+                else { float s[3] = {ub[0] - ua[0], ub[1] - ua[1], ub[2] - ua[2]}; angle = 2 * std::asin(0.5f * std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2])); }
+                for (int d = 0; d < 3; ++d) acc[3 * i0 + d] += n[d] * angle;
+            }
+        }
+        md.N.resize(3 * nV);
+        for (size_t i = 0; i < nV; ++i) {
+            double len = std::sqrt(acc[3 * i] * acc[3 * i] + acc[3 * i + 1] * acc[3 * i + 1] + acc[3 * i + 2] * acc[3 * i + 2]);
+            if (flipNormals) len = -len;
+            if (len != 0) for (int d = 0; d < 3; ++d) md.N[3 * i + d] = (float) (acc[3 * i + d] / len);
+            else { md.N[3 * i] = 1; md.N[3 * i + 1] = 0; md.N[3 * i + 2] = 0; }
+        }
+    }
+
+    void addShape(Node *n) {
+        Props p(n);
+        MeshData md;
+        M4 toWorld = p.xf("toWorld"), inv;
+        if (!toWorld.inverse(inv)) throw Err("shape: singular toWorld transform");
+        bool flip = p.b("flipNormals", false);
+        if (n->type == "obj") {
+            std::string fn = p.s("filename", "");
+            if (fn.empty()) throw Err("obj: missing 'filename'");
+            if (fn[0] != '/') fn = baseDir + "/" + fn;
+            loadObj(fn, md);
+            bool faceN = p.b("faceNormals", false);
+            p.f("maxSmoothAngle", 0.0); p.b("flipTexCoords", true); p.b("collapse", false);
+            // object -> world
+            for (size_t i = 0; i < md.P.size() / 3; ++i) {
+                double q[3] = {md.P[3 * i], md.P[3 * i + 1], md.P[3 * i + 2]}, o[3];
+                toWorld.point(q, o);
+                for (int d = 0; d < 3; ++d) md.P[3 * i + d] = (float) o[d];
+                if (!md.N.empty()) {
+                    double nn[3] = {md.N[3 * i], md.N[3 * i + 1], md.N[3 * i + 2]}, on[3];
+                    toWorld.normal(inv, nn, on);
+                    double l = std::sqrt(on[0] * on[0] + on[1] * on[1] + on[2] * on[2]);
+                    for (int d = 0; d < 3; ++d) md.N[3 * i + d] = (float) (l > 0 ? on[d] / l : on[d]);
+                }
+            }
+            computeNormals(md, faceN, flip);
+        } else if (n->type == "rectangle") { // rectangle.cpp:170-205 createTriMesh
+            const double v[4][3] = {{-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0}}, uv[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
+            double nz[3] = {0, 0, flip ? -1.0 : 1.0}, nw[3];
+            toWorld.normal(inv, nz, nw);
+            double l = std::sqrt(nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2]);
+            for (int i = 0; i < 4; ++i) {
+                double o[3];
+                toWorld.point(v[i], o);
+                for (int d = 0; d < 3; ++d) { md.P.push_back((float) o[d]); md.N.push_back((float) (nw[d] / l)); }
+                md.UV.push_back((float) uv[i][0]); md.UV.push_back((float) uv[i][1]);
+            }
+            md.idx = {0, 1, 2, 2, 3, 0};
+        } else if (n->type == "cube") { // cube.cpp:73-106: 24 unshared vertices, per-face normals and UVs
+            const double fn[6][3] = {{0, 0, -1}, {0, 0, 1}, {0, -1, 0}, {0, 1, 0}, {-1, 0, 0}, {1, 0, 0}};
+            for (int f = 0; f < 6; ++f) {
+                const double *nn = fn[f];
+                double a[3], b[3];
+                int ax = nn[0] != 0 ? 0 : (nn[1] != 0 ? 1 : 2);
+                double s = nn[ax];
+                for (int d = 0; d < 3; ++d) { a[d] = 0; b[d] = 0; }
+                a[(ax + 1) % 3] = 1; b[(ax + 2) % 3] = s; // right-handed: a x b = n
+                const double c[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+                double nw[3];
+                double nflip[3] = {flip ? -nn[0] : nn[0], flip ? -nn[1] : nn[1], flip ? -nn[2] : nn[2]};
+                toWorld.normal(inv, nflip, nw);
+                double l = std::sqrt(nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2]);
+                uint32_t base = (uint32_t) (md.P.size() / 3);
+                for (int i = 0; i < 4; ++i) {
+                    double q[3], o[3];
+                    for (int d = 0; d < 3; ++d) q[d] = nn[d] + c[i][0] * a[d] + c[i][1] * b[d];
+                    toWorld.point(q, o);
+                    for (int d = 0; d < 3; ++d) { md.P.push_back((float) o[d]); md.N.push_back((float) (nw[d] / l)); }
+                    md.UV.push_back((float) (0.5 * (c[i][0] + 1))); md.UV.push_back((float) (0.5 * (c[i][1] + 1)));
+                }
+                md.idx.insert(md.idx.end(), {base, base + 1, base + 2, base + 3, base, base + 2});
+            }
+        } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, rectangle, cube)");
+        // children: bsdf / ref / emitter
+        int mat = -1, em = -1;
+        bool isEmitter = false;
+        for (auto &c : n->children) {
+            if (c->tag == "bsdf") mat = addBsdf(c.get());
+            else if (c->tag == "ref") mat = resolveRef(c.get());
+            else if (c->tag == "emitter") {
+                if (c->type != "area") throw Err("unsupported emitter plugin \"" + c->type + "\" (hot path: area)");
+                Props ep(c.get());
+                const double one[3] = {1, 1, 1};
+                float rad[3];
+                ep.spec("radiance", one, rad);
+                float w = (float) ep.f("samplingWeight", 1.0);
+                ep.checkAllUsed();
+                em = b2_scene_add_area_emitter(scene, rad, w);
+                if (em < 0) throw Err(b2_last_error(nullptr));
+                isEmitter = true;
+            } else if (c->tag != "transform") throw Err("unsupported child <" + c->tag + "> of <shape>");
+        }
+        if (mat < 0) { // shape.cpp:48-72
+            b2_material_desc m;
+            memset(&m, 0, sizeof(m));
+            m.type = B2_BSDF_DIFFUSE; m.nested = -1; m.eta = 1; m.thickness = 1; m.sample_visible = 1; m.alpha_u = m.alpha_v = 0.1f;
+            for (int c = 0; c < 3; ++c) { m.reflectance[c] = isEmitter ? 0.0f : 0.5f; m.transmittance[c] = 1; m.k_c[c] = 1; }
+            mat = b2_scene_add_material(scene, &m);
+        }
+        p.checkAllUsed();
+        int id = b2_scene_add_mesh(scene, md.P.data(), md.N.empty() ? nullptr : md.N.data(), md.UV.empty() ? nullptr : md.UV.data(),
+                                   (uint32_t) (md.P.size() / 3), md.idx.data(), (uint32_t) (md.idx.size() / 3), mat, em);
+        if (id < 0) throw Err(b2_last_error(nullptr));
+    }
+
+    void run(Node *root, b2_render_params *rp) {
+        memset(rp, 0, sizeof(*rp));
+        rp->spp = 4; rp->sampler = B2_SAMPLER_INDEPENDENT; rp->max_depth = -1; rp->rr_depth = 5; // independent is Mitsuba's default sampler
+        rp->rfilter = B2_RFILTER_GAUSSIAN; rp->rfilter_param = 0.5f;
+        bool haveSensor = false;
+        for (auto &c : root->children) if (c->tag == "bsdf") addBsdf(c.get());
+        for (auto &cu : root->children) {
+            Node *c = cu.get();
+            if (c->tag == "bsdf") continue;
+            if (c->tag == "integrator") {
+                if (c->type != "path") throw Err("unsupported integrator \"" + c->type + "\": this library implements the `path` plugin");
+                Props p(c);
+                rp->max_depth = (int) p.i("maxDepth", -1); rp->rr_depth = (int) p.i("rrDepth", 5);
+                rp->strict_normals = p.b("strictNormals", false); rp->hide_emitters = p.b("hideEmitters", false);
+                p.checkAllUsed();
+            } else if (c->tag == "sensor") {
+                if (c->type != "perspective") throw Err("unsupported sensor \"" + c->type + "\" (hot path: perspective)");
+                Props p(c);
+                int W = 768, H = 576; // film.cpp:30-33
+                for (auto &ch : c->children) {
+                    if (ch->tag == "film") {
+                        Props fp(ch.get());
+                        W = (int) fp.i("width", 768); H = (int) fp.i("height", 576);
+                        fp.s("pixelFormat", "rgb"); fp.s("fileFormat", "openexr"); fp.s("componentFormat", "float16"); fp.b("banner", true);
+                        fp.b("attachLog", true); fp.b("highQualityEdges", false);
+                        fp.checkAllUsed();
+                        for (auto &rf : ch->children) {
+                            if (rf->tag != "rfilter") throw Err("unsupported child <" + rf->tag + "> of <film>");
+                            Props rfp(rf.get());
+                            if (rf->type == "box") { rp->rfilter = B2_RFILTER_BOX; rp->rfilter_param = (float) rfp.f("radius", 0.5); }
+                            else if (rf->type == "gaussian") { rp->rfilter = B2_RFILTER_GAUSSIAN; rp->rfilter_param = (float) rfp.f("stddev", 0.5); }
+                            else throw Err("unsupported reconstruction filter \"" + rf->type + "\" (supported: box, gaussian)");
+                            rfp.checkAllUsed();
+                        }
+                    } else if (ch->tag == "sampler") {
+                        Props sp(ch.get());
+                        rp->spp = (int) sp.i("sampleCount", 4);
+                        if (ch->type == "sobol") { rp->sampler = B2_SAMPLER_SOBOL; rp->seed = (uint64_t) sp.i("scramble", 0); }
+                        else if (ch->type == "independent") { rp->sampler = B2_SAMPLER_INDEPENDENT; rp->seed = (uint64_t) sp.i("seed", 0); }
+                        else throw Err("unsupported sampler \"" + ch->type + "\" (hot path: sobol, independent)");
+                        sp.checkAllUsed();
+                    } else if (ch->tag != "transform") throw Err("unsupported child <" + ch->tag + "> of <sensor>");
+                }
+                // fov handling: sensor.cpp:221-275,293-316
+                double aspect = (double) W / H, fov = p.f("fov", 0);
+                if (!p.has("fov")) {
+                    std::string fl = p.s("focalLength", "50mm");
+                    if (fl.size() > 2 && fl.substr(fl.size() - 2) == "mm") fl = fl.substr(0, fl.size() - 2);
+                    double value = Parser::toF(fl, "focalLength");
+                    double diag = 2 * 180 / M_PI * std::atan(std::sqrt(36.0 * 36 + 24 * 24) / (2 * value));
+                    double dl = 2 * std::tan(0.5 * diag * M_PI / 180), width = dl / std::sqrt(1.0 + 1.0 / (aspect * aspect));
+                    fov = 2 * std::atan(width * 0.5) * 180 / M_PI;
+                    p.s("fovAxis", "x");
+                } else {
+                    std::string ax = p.s("fovAxis", "x");
+                    std::transform(ax.begin(), ax.end(), ax.begin(), ::tolower);
+                    if (ax == "smaller") ax = aspect > 1 ? "y" : "x"; else if (ax == "larger") ax = aspect > 1 ? "x" : "y";
+                    if (ax == "y") fov = 2 * std::atan(std::tan(0.5 * fov * M_PI / 180) * aspect) * 180 / M_PI;
+                    else if (ax == "diagonal") { double dl = 2 * std::tan(0.5 * fov * M_PI / 180), width = dl / std::sqrt(1.0 + 1.0 / (aspect * aspect)); fov = 2 * std::atan(width * 0.5) * 180 / M_PI; }
+                    else if (ax != "x") throw Err("The 'fovAxis' parameter must be set to one of 'smaller', 'larger', 'diagonal', 'x', or 'y'!");
+                }
+                M4 tw = p.xf("toWorld");
+                float twf[16];
+                for (int i = 0; i < 16; ++i) twf[i] = (float) tw.m[i];
+                float nearC = (float) p.f("nearClip", 1e-2), farC = (float) p.f("farClip", 1e4);
+                p.f("focusDistance", 0); p.f("shutterOpen", 0); p.f("shutterClose", 0);
+                p.checkAllUsed();
+                if (b2_scene_set_camera(scene, twf, (float) fov, nearC, farC, W, H)) throw Err(b2_last_error(nullptr));
+                haveSensor = true;
+            } else if (c->tag == "shape") addShape(c);
+            else if (c->tag == "emitter") throw Err("unsupported top-level emitter \"" + c->type + "\" (hot path: area emitters attached to shapes)");
+            else throw Err("unsupported top-level element <" + c->tag + ">");
+        }
+        if (!haveSensor) throw Err("scene has no <sensor>");
+    }
+};
+
+} // namespace
+
+extern "C" int b2_set_error_(b2_ctx *, int, const char *);
+
+extern "C" int b2_load_xml(b2_ctx *ctx, const char *path, const char *const *defines, int n_defines, b2_scene **out, b2_render_params *params) {
+    if (!ctx || !path || !out || !params) return b2_set_error_(ctx, B2_ERR_INVALID, "b2_load_xml: null argument");
+    *out = nullptr;
+    Parser P;
+    for (int i = 0; i < n_defines; ++i) {
+        std::string d = defines[i];
+        size_t eq = d.find('=');
+        if (eq == std::string::npos) return b2_set_error_(ctx, B2_ERR_INVALID, "b2_load_xml: defines must look like key=value");
+        P.defines[d.substr(0, eq)] = d.substr(eq + 1);
+    }
+    std::string p = path;
+    size_t slash = p.find_last_of('/');
+    std::string baseDir = slash == std::string::npos ? "." : p.substr(0, slash);
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return b2_set_error_(ctx, B2_ERR_IO, (std::string("cannot open scene file ") + path).c_str());
+    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    b2_scene *scene = nullptr;
+    XML_Parser xp = XML_ParserCreate(nullptr);
+    try {
+        XML_SetUserData(xp, &P);
+        XML_SetElementHandler(xp, onStart, onEnd);
+        P.xp = xp;
+        g_parseError.clear();
+        if (XML_Parse(xp, text.data(), (int) text.size(), 1) == XML_STATUS_ERROR) {
+            std::ostringstream oss;
+            oss << path << ":" << XML_GetCurrentLineNumber(xp) << ": " << (g_parseError.empty() ? XML_ErrorString(XML_GetErrorCode(xp)) : g_parseError.c_str());
+            throw Err(oss.str());
+        }
+        if (!P.root) throw Err("empty scene file");
+        if (b2_scene_create(ctx, &scene)) throw Err(b2_last_error(ctx));
+        Loader L;
+        L.scene = scene;
+        L.baseDir = baseDir;
+        L.run(P.root.get(), params);
+        if (b2_scene_commit(scene)) throw Err(b2_last_error(ctx));
+    } catch (const std::exception &e) {
+        XML_ParserFree(xp);
+        if (scene) b2_scene_destroy(scene);
+        return b2_set_error_(ctx, B2_ERR_INVALID, e.what());
+    }
+    XML_ParserFree(xp);
+    *out = scene;
+    return B2_OK;
+}

@@ -110,7 +110,7 @@ def make_params(rp, threads=0, sampler=None):
 class OracleScene:
     """Oracle-side scene built from a mitsuba_b200.scene.SceneDesc (plain data only)."""
 
-    def __init__(self, desc, use_tree=True):
+    def __init__(self, desc, use_tree=True, sample_to_camera=None):
         L = lib()
         self.L = L
         self.h = C.c_void_p(L.orc_scene_new())
@@ -133,7 +133,9 @@ class OracleScene:
         cam = desc.camera
         self.W, self.H = cam.width, cam.height
         c2w = np.ascontiguousarray(cam.to_world, np.float32)
-        s2c = np.ascontiguousarray(cam.sample_to_camera(), np.float32)
+        # the camera matrix may be handed over from the implementation under test so both sides start from
+        # identical float32 inputs (its derivation is host-side set-up, perspective.cpp:146-153, not the hot path)
+        s2c = np.ascontiguousarray(cam.sample_to_camera() if sample_to_camera is None else sample_to_camera, np.float32)
         L.orc_set_camera(self.h, _p(c2w), _p(s2c), C.c_float(cam.near), C.c_float(cam.far), C.c_int(cam.width), C.c_int(cam.height))
         L.orc_commit(self.h, C.c_int(1 if use_tree else 0))
 

@@ -1,0 +1,70 @@
+"""The C-ABI library builds, loads and exports every symbol include/b2mts.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b2mts.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for must in ("b2_context_create", "b2_scene_add_mesh", "b2_scene_commit", "b2_render", "b2_trace", "b2_load_xml", "b2_film_develop"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from mitsuba_b200 import api
+    L = api.lib()
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(api.EXPORTS) <= set(declared_symbols())
+    assert b"sm_100a" in L.b2_version()
+
+
+def test_struct_layouts_match_header():
+    from mitsuba_b200 import api
+    assert ctypes.sizeof(api.b2_material_desc) == 4 * 4 + 4 * 4 + 15 * 4
+    assert ctypes.sizeof(api.b2_render_params) == 64
+    assert api.b2_render_params.seed.offset == 8 and api.b2_render_params.flags.offset == 60
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a GPU every compute entry point must fail loudly (B2_ERR_NO_DEVICE), never fall back."""
+    from mitsuba_b200 import api
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.B2Error) as e:
+        api.Context(0)
+    assert "no CUDA device" in str(e.value) or "[2]" in str(e.value)
+
+
+def test_film_develop_host_math():
+    """fmtconv.cpp:979-990: rgb = spec * (w != 0 ? 1/w : w)."""
+    import numpy as np
+    from mitsuba_b200 import api
+    film = np.zeros((2, 2, 5), np.float32)
+    film[0, 0] = [2, 4, 6, 1, 2]; film[0, 1] = [1, 1, 1, 0, 0]; film[1, 0] = [3, 0, 0, 3, 3]
+    rgb = api.develop(film)
+    assert np.allclose(rgb[0, 0], [1, 2, 3]) and np.allclose(rgb[0, 1], 0) and np.allclose(rgb[1, 0], [1, 0, 0])
+
+
+def test_product_does_not_import_the_oracle():
+    """Nothing under mitsuba_b200/ may reference oracle/ (the oracle is the checker, not a backend)."""
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "mitsuba_b200")):
+        if "_obj" in d:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".inl")):
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"oracle/|oracle_api|libmtsoracle|import oracle|from oracle|\borc_", txt):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
