@@ -243,6 +243,11 @@ def main():
         e2e = {"value": samples_per_step * n_e2e / float(tt.item()) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(up) + 64,
                "d2h_bytes_per_step": int(H * W * 5 * 4), "steps": n_e2e}
 
+    # cross-check of the in-kernel %globaltimer stamps: one extra, untimed step with plain launches bracketed by CUDA events
+    ev_check = None
+    if rank == 0:
+        stc = step(flags=4 | 8)
+        ev_check = {k: stc["ms_" + k] / max(1, stc["n_" + k]) for k in ("generate", "extend", "shade", "occluded")}
     if rank == 0:
         peaks, which = measured_peaks()
         # dominant kernel by summed device time inside the timed region
@@ -275,7 +280,9 @@ def main():
             "clocks": clock_info,
             "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                          "frac": achieved / peaks.get("hbm_gbs", 1.0), "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "avg_launch_ms": avg_ms, "share_of_step": shares[dom] / max(1e-9, sum(shares.values())),
+                         "avg_launch_ms": avg_ms, "avg_launch_ms_cuda_events": ev_check["" + dom] if ev_check else None,
+                         "timer": "%globaltimer stamps inside the kernels (max CTA end - min CTA start per launch), timed region runs as one CUDA graph per iteration; cross-checked by an untimed step with CUDA events around plain launches",
+                         "share_of_step": shares[dom] / max(1e-9, sum(shares.values())),
                          "kernel_ms": shares,
                          "note": "Cornell scene (3.5 KB) is shared-memory resident: traversal is issue/latency bound, HBM traffic is queue traffic only"},
             "stats": {"mean_path_length": agg["path_length_sum"] / max(1, agg["samples"]), "rays_per_sample": agg["rays"] / max(1, agg["samples"]),

@@ -98,7 +98,8 @@ struct b2_scene {
     bool hasCamera = false, committed = false;
     // device scene
     DScene ds{};
-    DevBuf<float4> dTriAccel, dVerts, dNorms;
+    DevBuf<float4> dTriAccel, dTriPlane, dVerts, dNorms;
+    DevBuf<uint32_t> dLeafPrim;
     DevBuf<BVHNode> dNodes;
     DevBuf<DMaterial> dMaterials;
     DevBuf<DEmitter> dEmitters;
@@ -116,9 +117,9 @@ struct b2_scene {
     DevBuf<unsigned long long> dCounters;
     DevBuf<float4> dFilmRGBA;
     DevBuf<float> dFilmW, dFilmOut;
-    unsigned long long *hPinned = nullptr; // ring of {active, next} pairs
-    std::vector<cudaEvent_t> ringEvents;
-    std::vector<cudaEvent_t> timingEvents; // pool for per-launch timing (flags bit2)
+    unsigned long long *hRing = nullptr, *dRing = nullptr; // mapped pinned progress ring written by k_publish
+    DevBuf<unsigned long long> dStampStart, dStampEnd;      // per-launch %globaltimer stamps (flags bit2)
+    std::vector<cudaEvent_t> timingEvents;                  // per-launch CUDA events (flags bit3)
     std::atomic<int> cancel{0};
     b2_stats stats{};
     uint32_t nPrims = 0;
@@ -232,8 +233,7 @@ extern "C" int b2_scene_create(b2_ctx *ctx, b2_scene **out) {
 extern "C" void b2_scene_destroy(b2_scene *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    if (s->hPinned) cudaFreeHost(s->hPinned);
-    for (auto e : s->ringEvents) cudaEventDestroy(e);
+    if (s->hRing) cudaFreeHost(s->hRing);
     for (auto e : s->timingEvents) cudaEventDestroy(e);
     delete s;
 }
@@ -505,8 +505,25 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         buildBVH(boxes, ids, 4, B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh);
     }
     s->bvhDepth = bvh.depth;
-    std::vector<float4> leafTri(3 * bvh.leafPrims.size());
-    for (size_t i = 0; i < bvh.leafPrims.size(); ++i) memcpy(&leafTri[3 * i], &triAccel[3 * (size_t) bvh.leafPrims[i]], 48);
+    std::vector<float4> leafTri(3 * bvh.leafPrims.size()), leafPlane(3 * bvh.leafPrims.size());
+    for (size_t i = 0; i < bvh.leafPrims.size(); ++i) {
+        const size_t p = bvh.leafPrims[i];
+        memcpy(&leafTri[3 * i], &triAccel[3 * p], 48);
+        // plane form, evaluated in double: N = e1 x e2, U = (e2 x N)/|N|^2, V = (N x e1)/|N|^2
+        const float4 &a = verts[3 * p], &b = verts[3 * p + 1], &c = verts[3 * p + 2];
+        const double p0[3] = {a.x, a.y, a.z}, e1[3] = {(double) b.x - a.x, (double) b.y - a.y, (double) b.z - a.z},
+                     e2[3] = {(double) c.x - a.x, (double) c.y - a.y, (double) c.z - a.z};
+        const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+        const double U[3] = {(e2[1] * N[2] - e2[2] * N[1]) / nn, (e2[2] * N[0] - e2[0] * N[2]) / nn, (e2[0] * N[1] - e2[1] * N[0]) / nn};
+        const double V[3] = {(N[1] * e1[2] - N[2] * e1[1]) / nn, (N[2] * e1[0] - N[0] * e1[2]) / nn, (N[0] * e1[1] - N[1] * e1[0]) / nn};
+        // scale the t-plane so that |N| ~ 1 (keeps num/den well inside float range)
+        const double inv = 1.0 / std::sqrt(nn);
+        leafPlane[3 * i] = make_float4((float) (N[0] * inv), (float) (N[1] * inv), (float) (N[2] * inv),
+                                       (float) ((N[0] * p0[0] + N[1] * p0[1] + N[2] * p0[2]) * inv));
+        leafPlane[3 * i + 1] = make_float4((float) U[0], (float) U[1], (float) U[2], (float) -(U[0] * p0[0] + U[1] * p0[1] + U[2] * p0[2]));
+        leafPlane[3 * i + 2] = make_float4((float) V[0], (float) V[1], (float) V[2], (float) -(V[0] * p0[0] + V[1] * p0[1] + V[2] * p0[2]));
+    }
     // ---- materials ----
     std::vector<DMaterial> dm(s->materials.size());
     for (int c = 0; c < 4; ++c) s->classPresent[c] = false;
@@ -567,6 +584,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     }
     // ---- upload ----
     CK(ctx, s->dTriAccel.upload(leafTri));
+    CK(ctx, s->dTriPlane.upload(leafPlane));
+    CK(ctx, s->dLeafPrim.upload(bvh.leafPrims));
     CK(ctx, s->dVerts.upload(verts));
     CK(ctx, s->dNorms.upload(norms));
     CK(ctx, s->dNodes.upload(bvh.nodes));
@@ -576,7 +595,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     CK(ctx, s->dTriCdf.upload(triCdf));
     DScene &ds = s->ds;
     memset(&ds, 0, sizeof(ds));
-    ds.triAccel = s->dTriAccel.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
+    ds.triAccel = s->dTriAccel.p; ds.triPlane = s->dTriPlane.p; ds.leafPrim = s->dLeafPrim.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
     ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef; ds.rootCount = rootCount;
     // gkdtree.h:1213-1220: enlarged scene box (the max side uses the already-moved min, as in the reference)
     if (nPrims == 0) { for (int a = 0; a < 3; ++a) { lo[a] = 0; hi[a] = 0; } }
@@ -607,7 +626,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     memset(&s->stats, 0, sizeof(s->stats));
     s->stats.n_triangles = nPrims;
     s->stats.n_bvh_nodes = bvh.nodes.size();
-    s->stats.bytes_uploaded = leafTri.size() * 16 + verts.size() * 16 + norms.size() * 16 + bvh.nodes.size() * sizeof(BVHNode) +
+    s->stats.bytes_uploaded = leafTri.size() * 16 + leafPlane.size() * 16 + bvh.leafPrims.size() * 4 + verts.size() * 16 + norms.size() * 16 + bvh.nodes.size() * sizeof(BVHNode) +
                               dm.size() * sizeof(DMaterial) + de.size() * sizeof(DEmitter) + (emCdf.size() + triCdf.size()) * 4;
     s->committed = true;
     return B2_OK;
@@ -731,8 +750,6 @@ static int ensurePool(b2_scene *s, uint32_t Q) {
     return B2_OK;
 }
 
-static const int kRing = 32;
-
 extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     if (!s || !p || !film) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_render: null argument");
     b2_ctx *ctx = s->ctx;
@@ -747,7 +764,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     if (rc) return rc;
     const bool parityMode = p->parity_mode != 0;
     const LaunchCfg &cfg = parityMode ? s->cfgParity : s->cfgFast;
-    uint32_t Q = p->pool_size > 0 ? (uint32_t) p->pool_size : (1u << 20);
+    uint32_t Q = p->pool_size > 0 ? (uint32_t) p->pool_size : (1u << 22); // 4M paths: measured sweet spot on B200
     Q = std::max<uint32_t>(Q, 1024u);
     Q = (uint32_t) std::min<uint64_t>(Q, std::max<uint64_t>(1024u, r.totalWork));
     Q = (Q + 255u) & ~255u;
@@ -757,10 +774,20 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     CK(ctx, s->dFilmRGBA.alloc(nPix));
     CK(ctx, s->dFilmW.alloc(nPix));
     r.filmRGBA = s->dFilmRGBA.p; r.filmW = s->dFilmW.p;
-    if (!s->hPinned) {
-        CK(ctx, cudaMallocHost((void **) &s->hPinned, sizeof(unsigned long long) * 2 * kRing));
-        s->ringEvents.resize(kRing);
-        for (auto &e : s->ringEvents) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!s->hRing) {
+        CK(ctx, cudaHostAlloc((void **) &s->hRing, sizeof(unsigned long long) * 4 * B2_RING, cudaHostAllocMapped));
+        CK(ctx, cudaHostGetDevicePointer((void **) &s->dRing, s->hRing, 0));
+    }
+    memset(s->hRing, 0, sizeof(unsigned long long) * 4 * B2_RING);
+    r.ring = s->dRing;
+    const bool timing = (p->flags & 4) != 0;      // per-launch device time stamps (%globaltimer inside the kernels)
+    const bool useEvents = (p->flags & 8) != 0;   // no graph: plain launches bracketed by CUDA events (cross-check path)
+    if (timing) {
+        CK(ctx, s->dStampStart.alloc((size_t) B2_MAX_STAMPS * 4));
+        CK(ctx, s->dStampEnd.alloc((size_t) B2_MAX_STAMPS * 4));
+        CK(ctx, cudaMemsetAsync(s->dStampStart.p, 0xFF, (size_t) B2_MAX_STAMPS * 4 * 8, st));
+        CK(ctx, cudaMemsetAsync(s->dStampEnd.p, 0, (size_t) B2_MAX_STAMPS * 4 * 8, st));
+        r.stampStart = s->dStampStart.p; r.stampEnd = s->dStampEnd.p;
     }
     CK(ctx, cudaMemsetAsync(s->dFilmRGBA.p, 0, nPix * sizeof(float4), st));
     CK(ctx, cudaMemsetAsync(s->dFilmW.p, 0, nPix * sizeof(float), st));
@@ -779,65 +806,77 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     uint64_t iter = 0, checked = 0, launches = 0;
     bool finished = false;
     int status = B2_OK;
-    const bool timing = (p->flags & 4) != 0;
-    std::vector<std::pair<int, size_t>> timed; // (stage, index of the start event)
+    std::vector<std::pair<int, size_t>> timed; // (stage, index of the start event) -- events path only
     size_t evUsed = 0;
-    auto tick = [&](int stage) { // record a start or stop event for `stage`
-        if (!timing) return;
+    auto tick = [&](int stage) {
+        if (!useEvents) return;
         if (evUsed == s->timingEvents.size()) { cudaEvent_t e; cudaEventCreate(&e); s->timingEvents.push_back(e); }
         cudaEventRecord(s->timingEvents[evUsed], st);
         if (stage >= 0) timed.emplace_back(stage, evUsed);
         ++evUsed;
     };
-#define LAUNCH(ns)                                                                                              \
-    do {                                                                                                        \
-        tick(0);                                                                                                \
-        ns::launch_generate(cfg, s->ds, s->pool, r, filt, st);                                                  \
-        tick(-1);                                                                                               \
-        cudaMemcpyAsync(s->hPinned + 2 * (iter % kRing), s->dCounters.p + CTR_ACTIVE, 8, cudaMemcpyDeviceToHost, st); \
-        cudaMemcpyAsync(s->hPinned + 2 * (iter % kRing) + 1, s->dCounters.p + CTR_NEXT, 8, cudaMemcpyDeviceToHost, st); \
-        cudaEventRecord(s->ringEvents[iter % kRing], st);                                                       \
-        tick(1);                                                                                                \
-        ns::launch_extend(cfg, s->ds, s->pool, sorted, st);                                                     \
-        tick(-1);                                                                                               \
-        tick(2);                                                                                                \
-        if (sorted) {                                                                                           \
-            for (int c = 0; c < 4; ++c)                                                                         \
-                if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, st); ++launches; }  \
-        } else {                                                                                                \
-            ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);                \
-            ++launches;                                                                                         \
-        }                                                                                                       \
-        tick(-1);                                                                                               \
-        tick(3);                                                                                                \
-        ns::launch_occluded(cfg, s->ds, s->pool, st);                                                           \
-        tick(-1);                                                                                               \
-        launches += 3;                                                                                          \
-    } while (0)
+    int launchesPerIter = 0;
+    // one iteration = generate (+publish) -> extend -> shade (per material class) -> occluded
+    auto enqueueIteration = [&]() {
+        launchesPerIter = 0;
+#define ITER(ns)                                                                                               \
+        do {                                                                                                   \
+            tick(0); ns::launch_generate(cfg, s->ds, s->pool, r, filt, st); tick(-1);                          \
+            tick(1); ns::launch_extend(cfg, s->ds, s->pool, r, sorted, st); tick(-1);                          \
+            tick(2);                                                                                           \
+            if (sorted) {                                                                                      \
+                for (int c = 0; c < 4; ++c)                                                                    \
+                    if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, st); ++launchesPerIter; } \
+            } else {                                                                                           \
+                ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);           \
+                ++launchesPerIter;                                                                             \
+            }                                                                                                  \
+            tick(-1);                                                                                          \
+            tick(3); ns::launch_occluded(cfg, s->ds, s->pool, r, st); tick(-1);                                \
+            launchesPerIter += 4;                                                                              \
+        } while (0)
+        if (parityMode) ITER(parity);
+        else ITER(fast);
+#undef ITER
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+    if (!useEvents) {
+        // the iteration index lives on the device (CTR_ITER, advanced by k_publish): one captured graph replays for every iteration
+        CK(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        enqueueIteration();
+        CK(ctx, cudaStreamEndCapture(st, &graph));
+        CK(ctx, cudaGraphInstantiate(&graphExec, graph, 0));
+    }
+    volatile unsigned long long *ring = s->hRing;
     while (!finished) {
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; break; }
-        // the ring slot we are about to reuse must have been consumed
-        if (iter >= (uint64_t) kRing && checked + kRing <= iter) {
-            cudaEventSynchronize(s->ringEvents[checked % kRing]);
-        }
-        while (checked < iter) {
-            cudaError_t q = cudaEventQuery(s->ringEvents[checked % kRing]);
-            if (q == cudaErrorNotReady) break;
-            if (q != cudaSuccess) { status = fail(ctx, B2_ERR_CUDA, std::string("render loop: ") + cudaGetErrorString(q)); finished = true; break; }
-            unsigned long long active = s->hPinned[2 * (checked % kRing)], next = s->hPinned[2 * (checked % kRing) + 1];
-            ++checked;
-            if (active == 0 && next >= r.totalWork) { finished = true; break; }
+        // consume published progress; never run more than B2_RING - 1 iterations ahead of the device
+        for (;;) {
+            while (checked < iter && ring[(checked % B2_RING) * 4] == checked + 1) {
+                const unsigned long long active = ring[(checked % B2_RING) * 4 + 1], next = ring[(checked % B2_RING) * 4 + 2];
+                ++checked;
+                if (active == 0 && next >= r.totalWork) { finished = true; break; }
+            }
+            if (finished || iter - checked < (uint64_t) B2_RING - 1) break;
+            if (cudaStreamQuery(st) != cudaErrorNotReady && ring[(checked % B2_RING) * 4] != checked + 1) {
+                cudaError_t e = cudaStreamSynchronize(st);
+                if (ring[(checked % B2_RING) * 4] != checked + 1) {
+                    status = fail(ctx, B2_ERR_CUDA, std::string("render loop: device made no progress: ") + cudaGetErrorString(e == cudaSuccess ? cudaGetLastError() : e));
+                    finished = true;
+                    break;
+                }
+            }
         }
         if (finished) break;
-        // zero {shadow, class, done[iter & 1]} counters: a 48-byte window that slides with the iteration parity
-        CK(ctx, cudaMemsetAsync(s->dCounters.p + ((iter & 1ull) ? CTR_SHADOW : CTR_DONE0), 0, 6 * sizeof(unsigned long long), st));
-        r.iteration = (uint32_t) iter;
-        if (parityMode) LAUNCH(parity);
-        else LAUNCH(fast);
+        if (useEvents) enqueueIteration();
+        else if (cudaGraphLaunch(graphExec, st) != cudaSuccess) { status = fail(ctx, B2_ERR_CUDA, "cudaGraphLaunch failed"); break; }
+        launches += launchesPerIter;
         ++iter;
         if (iter > 100000000ull) { status = fail(ctx, B2_ERR_CUDA, "render loop did not terminate"); break; }
     }
-#undef LAUNCH
+    if (graphExec) cudaGraphExecDestroy(graphExec);
+    if (graph) cudaGraphDestroy(graph);
     // pack + copy out
     CK(ctx, cudaEventRecord(evStop, st));
     if (status == B2_OK) {
@@ -870,6 +909,21 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
             case 2: t.ms_shade += e; ++t.n_shade; break;
             default: t.ms_occluded += e; ++t.n_occluded; break;
         }
+    }
+    if (timing && !useEvents) {
+        const size_t nIt = (size_t) std::min<uint64_t>(iter, B2_MAX_STAMPS);
+        std::vector<unsigned long long> a(nIt * 4), b(nIt * 4);
+        if (nIt) {
+            CK(ctx, cudaMemcpy(a.data(), s->dStampStart.p, nIt * 4 * 8, cudaMemcpyDeviceToHost));
+            CK(ctx, cudaMemcpy(b.data(), s->dStampEnd.p, nIt * 4 * 8, cudaMemcpyDeviceToHost));
+        }
+        float *ms[4] = {&t.ms_generate, &t.ms_extend, &t.ms_shade, &t.ms_occluded};
+        uint64_t *cnt[4] = {&t.n_generate, &t.n_extend, &t.n_shade, &t.n_occluded};
+        double acc[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i < nIt; ++i)
+            for (int k = 0; k < 4; ++k)
+                if (b[i * 4 + k] > a[i * 4 + k] && a[i * 4 + k] != ~0ull) { acc[k] += (double) (b[i * 4 + k] - a[i * 4 + k]) * 1e-6; ++*cnt[k]; }
+        for (int k = 0; k < 4; ++k) *ms[k] = (float) acc[k];
     }
     t.pool_size = Q;
     t.samples = ctr[CTR_SAMPLES]; t.rays = ctr[CTR_RAYS]; t.shadow_rays = ctr[CTR_SHADOWRAYS]; t.path_length_sum = ctr[CTR_PATHLEN];

@@ -28,6 +28,11 @@ B2_DEV uint32_t smemAddr(const void *p) { return (uint32_t) __cvta_generic_to_sh
 B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t *bar) {
     const uint32_t nb = sc.stageNodes * 64u, tb = sc.stageTris * 48u;
     const uint32_t barA = smemAddr(bar);
+#ifdef B2_FAST_TRI
+    const float4 *triSrc = sc.triPlane;
+#else
+    const float4 *triSrc = sc.triAccel;
+#endif
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -41,7 +46,7 @@ B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t
                          : "memory");
         if (tb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(sTris)),
-                         "l"(sc.triAccel), "r"(tb), "r"(barA)
+                         "l"(triSrc), "r"(tb), "r"(barA)
                          : "memory");
     }
     // every thread waits for phase 0
@@ -71,7 +76,11 @@ B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem) {
     stageScene(sc, sNodes, sTris, bar);
     TraceMem tm;
     tm.gNodes = (const float4 *) sc.nodes;
+#ifdef B2_FAST_TRI
+    tm.gTris = sc.triPlane;
+#else
     tm.gTris = sc.triAccel;
+#endif
     tm.sNodes = sNodes;
     tm.sTris = sTris;
     tm.stageNodes = sc.stageNodes;
@@ -79,6 +88,19 @@ B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem) {
     tm.stack = stack + threadIdx.x;
     tm.stride = blockDim.x;
     return tm;
+}
+
+B2_DEV unsigned long long globalTimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// per-launch duration = max over CTAs of the end stamp - min over CTAs of the start stamp
+B2_DEV void stampBegin(const DRender &rp, uint32_t it, int stage) {
+    if (rp.stampStart && threadIdx.x == 0 && it < B2_MAX_STAMPS) atomicMin(rp.stampStart + (size_t) it * 4 + stage, globalTimer());
+}
+B2_DEV void stampEnd(const DRender &rp, uint32_t it, int stage) {
+    if (rp.stampEnd && threadIdx.x == 0 && it < B2_MAX_STAMPS) atomicMax(rp.stampEnd + (size_t) it * 4 + stage, globalTimer());
 }
 
 B2_DEV uint32_t warpSum(uint32_t v) {
@@ -195,10 +217,13 @@ B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uin
 // k_generate: drains the finished-path queue of the previous iteration with full warps: splat (ImageBlock::put),
 // then refill the slot with the next (pixel, sample) work item.  FIRST: every slot is empty, no queue yet.
 // ------------------------------------------------------------------------------------------------
-template <bool FIRST> __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
+__global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
     const uint32_t Q = pool.capacity;
-    const uint32_t *queue = pool.doneQueue + (size_t) ((rp.iteration + 1u) & 1u) * Q; // written by k_shade of iteration - 1
-    const uint32_t n = FIRST ? Q : (uint32_t) pool.counters[((rp.iteration + 1u) & 1u) ? CTR_DONE1 : CTR_DONE0];
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER];
+    const bool FIRST = it == 0;
+    stampBegin(rp, it, STAGE_GENERATE);
+    const uint32_t *queue = pool.doneQueue + (size_t) ((it + 1u) & 1u) * Q; // written by k_shade of iteration it - 1
+    const uint32_t n = FIRST ? Q : (uint32_t) pool.counters[((it + 1u) & 1u) ? CTR_DONE1 : CTR_DONE0];
     uint32_t nSamples = 0, nBad = 0, nNew = 0;
     uint32_t pathLen = 0;
     const uint32_t nS = (uint32_t) (rp.sampleHi - rp.sampleLo);
@@ -266,13 +291,33 @@ template <bool FIRST> __global__ void __launch_bounds__(256) k_generate(DScene s
         if (nBad) atomicAdd(pool.counters + CTR_BAD, (unsigned long long) nBad);
         if (pathLen) atomicAdd(pool.counters + CTR_PATHLEN, (unsigned long long) pathLen);
     }
+    stampEnd(rp, it, STAGE_GENERATE);
+}
+
+// One thread, between k_generate and k_extend: publishes progress to the host ring, clears the per-iteration queue
+// counters and advances the iteration.  Keeping the iteration on the device lets ONE CUDA graph serve every iteration.
+__global__ void k_publish(DPool pool, DRender rp) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned long long *c = pool.counters;
+    const unsigned long long it = c[CTR_ITER];
+    volatile unsigned long long *slot = rp.ring + (it % B2_RING) * 4;
+    slot[1] = c[CTR_ACTIVE];
+    slot[2] = c[CTR_NEXT];
+    __threadfence_system();
+    slot[0] = it + 1;
+    c[CTR_SHADOW] = 0;
+    c[CTR_CLASS0] = 0; c[CTR_CLASS0 + 1] = 0; c[CTR_CLASS0 + 2] = 0; c[CTR_CLASS0 + 3] = 0;
+    c[((it + 1) & 1) ? CTR_DONE1 : CTR_DONE0] = 0; // drained by this iteration's k_generate, refilled by k_shade of it + 1
+    c[CTR_ITER] = it + 1;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_extend: closest hit for every live slot (+ optional material-class binning)
 // ------------------------------------------------------------------------------------------------
-template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(DScene sc, DPool pool) {
+template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(DScene sc, DPool pool, DRender rp) {
     extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u; // k_publish already advanced the counter
+    stampBegin(rp, it, STAGE_EXTEND);
     const TraceMem tm = setupTraceMem(sc, smem);
     const uint32_t Q = pool.capacity;
     uint32_t nRays = 0;
@@ -311,6 +356,7 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
     }
     nRays = warpSum(nRays);
     if ((threadIdx.x & 31) == 0 && nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
+    stampEnd(rp, it, STAGE_EXTEND);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -427,6 +473,8 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
                                                                              const unsigned long long *queueCount) {
     const uint32_t Q = pool.capacity;
     const uint32_t n = queue ? (uint32_t) *queueCount : Q;
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
+    stampBegin(rp, it, STAGE_SHADE);
     uint32_t nDimOvf = 0, nShadowRef = 0, nDone = 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
@@ -572,9 +620,9 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
         // finished paths: queue the slot for the next k_generate (splat + refill), one atomic per warp
         {
             const bool fin = live && (meta.y & PF_DONE);
-            const uint32_t dq = warpAppend(fin, pool.counters + ((rp.iteration & 1u) ? CTR_DONE1 : CTR_DONE0));
+            const uint32_t dq = warpAppend(fin, pool.counters + ((it & 1u) ? CTR_DONE1 : CTR_DONE0));
             if (fin) {
-                pool.doneQueue[(size_t) (rp.iteration & 1u) * Q + dq] = i;
+                pool.doneQueue[(size_t) (it & 1u) * Q + dq] = i;
                 ++nDone;
             }
         }
@@ -593,13 +641,16 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
         if (nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
         if (nShadowRef) atomicAdd(pool.counters + CTR_SHADOWRAYS, (unsigned long long) nShadowRef);
     }
+    stampEnd(rp, it, STAGE_SHADE);
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_occluded
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool pool) {
+__global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool pool, DRender rp) {
     extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
+    stampBegin(rp, it, STAGE_OCCLUDED);
     const TraceMem tm = setupTraceMem(sc, smem);
     const uint32_t n = (uint32_t) pool.counters[CTR_SHADOW];
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -622,6 +673,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
             }
         }
     }
+    stampEnd(rp, it, STAGE_OCCLUDED);
 }
 
 // film pack: (float4 rgba, float w) planes -> interleaved H*W*5 (hdrfilm.cpp:351-356 ESpectrumAlphaWeight)
@@ -767,7 +819,7 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridExtendSort = occupancyGrid(k_extend<true>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridOccluded = occupancyGrid(k_occluded, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridTrace = occupancyGrid(k_trace_rays<false, false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
-    cfg.gridGenerate = occupancyGrid(k_generate<false>, 256, 0, numSMs);
+    cfg.gridGenerate = occupancyGrid(k_generate, 256, 0, numSMs);
     cfg.gridShade[0] = occupancyGrid(k_shade<0>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShade[1] = occupancyGrid(k_shade<1>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShade[2] = occupancyGrid(k_shade<2>, B2_SHADE_BLOCK, 0, numSMs);
@@ -776,12 +828,12 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
 }
 
 void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, cudaStream_t st) {
-    if (rp.iteration == 0) k_generate<true><<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
-    else k_generate<false><<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
+    k_generate<<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
+    k_publish<<<1, 32, 0, st>>>(pool, rp);
 }
-void launch_extend(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, bool sort, cudaStream_t st) {
-    if (sort) k_extend<true><<<cfg.gridExtendSort, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool);
-    else k_extend<false><<<cfg.gridExtend, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool);
+void launch_extend(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, bool sort, cudaStream_t st) {
+    if (sort) k_extend<true><<<cfg.gridExtendSort, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
+    else k_extend<false><<<cfg.gridExtend, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
 void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, int cls, bool queued, cudaStream_t st) {
     const uint32_t *q = queued ? pool.matQueue + (size_t) cls * pool.capacity : nullptr;
@@ -794,8 +846,8 @@ void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, con
         default: k_shade<-1><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr); break;
     }
 }
-void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, cudaStream_t st) {
-    k_occluded<<<cfg.gridOccluded, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool);
+void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {
+    k_occluded<<<cfg.gridOccluded, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
 void launch_film_pack(const LaunchCfg &cfg, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t st) {
     k_film_pack<<<cfg.numSMs * 4, 256, 0, st>>>(rgba, w, out, n);

@@ -19,9 +19,9 @@ struct LaunchCfg {
     namespace NS {                                                                                                             \
     void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs);                                                         \
     void launch_generate(const LaunchCfg &, const DScene &, const DPool &, const DRender &, const DFilter &, cudaStream_t);    \
-    void launch_extend(const LaunchCfg &, const DScene &, const DPool &, bool sort, cudaStream_t);                             \
+    void launch_extend(const LaunchCfg &, const DScene &, const DPool &, const DRender &, bool sort, cudaStream_t);            \
     void launch_shade(const LaunchCfg &, const DScene &, const DPool &, const DRender &, int cls, bool queued, cudaStream_t);  \
-    void launch_occluded(const LaunchCfg &, const DScene &, const DPool &, cudaStream_t);                                      \
+    void launch_occluded(const LaunchCfg &, const DScene &, const DPool &, const DRender &, cudaStream_t);                     \
     void launch_film_pack(const LaunchCfg &, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t);          \
     void launch_trace(const LaunchCfg &, const DScene &, const float4 *rays, float4 *out, uint64_t n, bool shadow, bool count, \
                       unsigned long long *counters, cudaStream_t);                                                             \

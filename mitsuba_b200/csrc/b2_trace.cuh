@@ -48,6 +48,25 @@ B2_DEV bool triAccelIntersect(const float4 &q0, const float4 &q1, const float4 &
     return u >= 0 && v >= 0 && u + v <= 1.0f;
 }
 
+// Throughput build: the same triangle as three planes; branch free, no component permutation, reciprocal instead of an
+// IEEE division.  t, u, v agree with the TriAccel arithmetic to a few ulp (DESIGN.md "fast build").
+B2_DEV bool triPlaneIntersect(const float4 &q0, const float4 &q1, const float4 &q2, const V3 &o, const V3 &d, float mint, float maxt,
+                              float &u, float &v, float &t) {
+    const float den = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+    const float num = q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z);
+    t = __fdividef(num, den);
+    const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
+    u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+    v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+    return (t >= mint) & (t <= maxt) & (u >= 0.0f) & (v >= 0.0f) & (u + v <= 1.0f);
+}
+
+#ifdef B2_FAST_TRI
+#define B2_TRI_TEST triPlaneIntersect
+#else
+#define B2_TRI_TEST triAccelIntersect
+#endif
+
 // include/mitsuba/core/aabb.h:308-338
 B2_DEV bool sceneBoxIntersect(const DScene &sc, const V3 &o, const V3 &d, const V3 &dRcp, float &nearT, float &farT) {
     nearT = -B2_INF; farT = B2_INF;
@@ -96,12 +115,37 @@ B2_DEV bool boxHit(float bx0, float by0, float bz0, float bx1, float by1, float 
     return tmin <= tmax * 1.0000003f;
 }
 
+// Tiny scenes (DScene::rootCount > 0): every lane tests the whole shared-memory resident triangle list in lockstep.
+template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
+                                                             HitRec &hit, uint32_t &primTests) {
+    const uint32_t n = sc.rootCount;
+    bool found = false;
+    uint32_t best = 0;
+    const float4 *p = tm.sTris;
+#pragma unroll 4
+    for (uint32_t i = 0; i < n; ++i, p += 3) {
+        const float4 q0 = p[0], q1 = p[1], q2 = p[2];
+        float tu, tv, tt;
+        if (B2_TRI_TEST(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
+            if (SHADOW) return true;
+            hit.t = tt; hit.u = tu; hit.v = tv; best = i;
+            maxt = tt;
+            found = true;
+        }
+    }
+    if (COUNT) primTests += n;
+    if (found) hit.prim = __ldg(sc.leafPrim + best);
+    return found;
+}
+
 // Returns true if something was hit.  Closest: fills `hit`; SHADOW: returns at the first hit.
 template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
                                                          HitRec &hit, uint32_t &nodeVisits, uint32_t &primTests) {
+    if (sc.rootCount) return traverseFlat<SHADOW, COUNT>(sc, tm, o, d, mint, maxt, hit, primTests);
     // safe reciprocal for the slab test only (0 -> huge, keeps NaN out of min/max chains)
     V3 idir(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     bool found = false;
+    uint32_t best = 0xFFFFFFFFu;
     int sp = 0;
     int ref = sc.rootRef;
     const uint32_t stride = tm.stride;
@@ -131,7 +175,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
             else if (hR) { ref = rref; continue; }
         } else {
             uint32_t bits = ~(uint32_t) ref;
-            uint32_t start = bits & 0x0FFFFFFFu, count = sc.rootCount ? sc.rootCount : (bits >> 28);
+            uint32_t start = bits & 0x0FFFFFFFu, count = bits >> 28;
             for (uint32_t i = 0; i < count; ++i) {
                 uint32_t ti = start + i;
                 float4 q0, q1, q2;
@@ -144,9 +188,9 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
                 }
                 if (COUNT) ++primTests;
                 float tu, tv, tt;
-                if (triAccelIntersect(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
+                if (B2_TRI_TEST(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
                     if (SHADOW) return true;
-                    hit.t = tt; hit.u = tu; hit.v = tv; hit.prim = __float_as_uint(q2.z);
+                    hit.t = tt; hit.u = tu; hit.v = tv; best = ti;
                     maxt = tt;
                     found = true;
                 }
@@ -156,6 +200,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
         --sp;
         ref = (int) tm.stack[sp * stride];
     }
+    if (found) hit.prim = __ldg(sc.leafPrim + best);
     return found;
 }
 

@@ -51,6 +51,10 @@ struct DCamera {
 struct DScene {
     // leaf-ordered TriAccel records, 3 x float4 each (triaccel.h:37-59; word 10 = global prim id)
     const float4 *triAccel;
+    // same triangles as three planes (N, d0), (U, -U.p0), (V, -V.p0): branch-free test used by the throughput build
+    // (t = (d0 - N.o) / N.d, u = U.P + du, v = V.P + dv); leafPrim maps the leaf-ordered index to the prim id
+    const float4 *triPlane;
+    const uint32_t *leafPrim;
     uint32_t nLeafTris;
     const BVHNode *nodes;
     uint32_t nNodes;
@@ -121,7 +125,15 @@ struct DPool {
 // [CTR_DONE0, CTR_SHADOW, CTR_CLASS0..3, CTR_DONE1] is zeroed per iteration as one 48-byte window that slides by one
 // entry with the iteration parity (even: DONE0..CLASS3, odd: SHADOW..DONE1)
 enum { CTR_DONE0 = 0, CTR_SHADOW = 1, CTR_CLASS0 = 2, /* 2..5 */ CTR_DONE1 = 6, CTR_NEXT = 7, CTR_ACTIVE = 8, CTR_RAYS = 9, CTR_SHADOWRAYS = 10,
-       CTR_PATHLEN = 11, CTR_SAMPLES = 12, CTR_BAD = 13, CTR_DIMOVF = 14, CTR_NODEVIS = 15, CTR_PRIMTESTS = 16, CTR_COUNT = 18 };
+       CTR_PATHLEN = 11, CTR_SAMPLES = 12, CTR_BAD = 13, CTR_DIMOVF = 14, CTR_NODEVIS = 15, CTR_PRIMTESTS = 16,
+       CTR_ITER = 17,   // host-loop iteration, advanced on the device by k_publish (one graph serves every iteration)
+       CTR_COUNT = 18 };
+
+// progress ring in mapped pinned host memory, written by k_publish: {sequence = iteration + 1, live paths, next work item, -}
+#define B2_RING 64
+// per-launch device time stamps (%globaltimer): [iteration][stage]{min start, max end}
+#define B2_MAX_STAMPS (1u << 17)
+enum { STAGE_GENERATE = 0, STAGE_EXTEND = 1, STAGE_SHADE = 2, STAGE_OCCLUDED = 3 };
 
 struct DRender {
     int32_t spp, sampler;
@@ -137,7 +149,9 @@ struct DRender {
     const uint64_t *lookupNib; // [2][13][16] nibble tables of sobol look_up for this render's m: [0] vdc (delta), [1] inv
     uint32_t indexNibbles;   // nibbles needed to cover the largest Sobol' index of this render (<= 13)
     uint32_t frameNibbles, bNibbles; // nibbles of the sample index / of the 2m-bit pixel code in look_up
-    uint32_t iteration;      // host loop iteration (parity selects the done queue)
+    unsigned long long *ring;       // device pointer of the mapped host progress ring (B2_RING x 4 words)
+    unsigned long long *stampStart; // null unless per-launch timing was requested (b2_render_params.flags bit2)
+    unsigned long long *stampEnd;
 };
 
 } // namespace b2
