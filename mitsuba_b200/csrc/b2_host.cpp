@@ -109,9 +109,10 @@ struct b2_scene {
     bool classPresent[4] = {false, false, false, false};
     // pool
     DPool pool{};
-    DevBuf<float4> pRayO, pRayD, pHit, pThr, pLi, pShD, pShC;
-    DevBuf<uint4> pSmp;
-    DevBuf<uint2> pMeta;
+    DevBuf<float4> pRay, pSt, pHit, pShD, pShC;
+    DevBuf<uint2> pSmp;
+    DevBuf<float2> pPos;
+    DevBuf<uint32_t> pPix, pFlags;
     DevBuf<uint32_t> pMatQueue, pDoneQueue;
     DevBuf<uint64_t> dLookupNib;
     DevBuf<unsigned long long> dCounters;
@@ -738,13 +739,14 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
 static int ensurePool(b2_scene *s, uint32_t Q) {
     b2_ctx *ctx = s->ctx;
     if (s->pool.capacity == Q) return B2_OK;
-    CK(ctx, s->pRayO.alloc(Q)); CK(ctx, s->pRayD.alloc(Q)); CK(ctx, s->pHit.alloc(Q)); CK(ctx, s->pThr.alloc(Q));
-    CK(ctx, s->pLi.alloc(Q)); CK(ctx, s->pShD.alloc(Q)); CK(ctx, s->pShC.alloc(Q)); CK(ctx, s->pSmp.alloc(Q));
-    CK(ctx, s->pMeta.alloc(Q)); CK(ctx, s->pMatQueue.alloc((size_t) 4 * Q)); CK(ctx, s->pDoneQueue.alloc((size_t) 2 * Q));
+    CK(ctx, s->pRay.alloc((size_t) 2 * Q)); CK(ctx, s->pSt.alloc((size_t) 2 * Q)); CK(ctx, s->pHit.alloc(Q));
+    CK(ctx, s->pShD.alloc(Q)); CK(ctx, s->pShC.alloc(Q)); CK(ctx, s->pSmp.alloc(Q)); CK(ctx, s->pPos.alloc(Q));
+    CK(ctx, s->pPix.alloc(Q)); CK(ctx, s->pFlags.alloc(Q));
+    CK(ctx, s->pMatQueue.alloc((size_t) 4 * Q)); CK(ctx, s->pDoneQueue.alloc((size_t) 2 * Q));
     DPool &p = s->pool;
     p.capacity = Q;
-    p.rayO = s->pRayO.p; p.rayD = s->pRayD.p; p.hit = s->pHit.p; p.thr = s->pThr.p; p.li = s->pLi.p;
-    p.smp = s->pSmp.p; p.meta = s->pMeta.p; p.shD = s->pShD.p; p.shC = s->pShC.p; p.matQueue = s->pMatQueue.p;
+    p.ray = s->pRay.p; p.st = s->pSt.p; p.hit = s->pHit.p; p.smp = s->pSmp.p; p.pos = s->pPos.p; p.pix = s->pPix.p; p.flags = s->pFlags.p;
+    p.shD = s->pShD.p; p.shC = s->pShC.p; p.matQueue = s->pMatQueue.p;
     p.doneQueue = s->pDoneQueue.p;
     p.counters = s->dCounters.p;
     return B2_OK;
@@ -792,7 +794,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     CK(ctx, cudaMemsetAsync(s->dFilmRGBA.p, 0, nPix * sizeof(float4), st));
     CK(ctx, cudaMemsetAsync(s->dFilmW.p, 0, nPix * sizeof(float), st));
     CK(ctx, cudaMemsetAsync(s->dCounters.p, 0, CTR_COUNT * sizeof(unsigned long long), st));
-    CK(ctx, cudaMemsetAsync(s->pMeta.p, 0, (size_t) Q * sizeof(uint2), st));
+    CK(ctx, cudaMemsetAsync(s->pFlags.p, 0, (size_t) Q * sizeof(uint32_t), st));
     int nClasses = 0, onlyClass = -1;
     for (int c = 0; c < 4; ++c)
         if (s->classPresent[c]) { ++nClasses; onlyClass = c; }

@@ -122,6 +122,20 @@ B2_DEV unsigned long long warpAppend64(bool want, unsigned long long *counter) {
     return base + (unsigned long long) __popc(mask & ((1u << lane) - 1u));
 }
 B2_DEV uint32_t warpAppend(bool want, unsigned long long *counter) { return (uint32_t) warpAppend64(want, counter); }
+// two independent appends whose atomics are issued back to back (their latencies overlap); all 32 lanes must call
+B2_DEV void warpAppend2(bool wantA, unsigned long long *ctrA, bool wantB, unsigned long long *ctrB, uint32_t &idxA, uint32_t &idxB) {
+    const unsigned mA = __ballot_sync(0xffffffffu, wantA), mB = __ballot_sync(0xffffffffu, wantB);
+    const int lane = threadIdx.x & 31;
+    unsigned long long bA = 0, bB = 0;
+    if (lane == 0) {
+        if (mA) bA = atomicAdd(ctrA, (unsigned long long) __popc(mA));
+        if (mB) bB = atomicAdd(ctrB, (unsigned long long) __popc(mB));
+    }
+    bA = __shfl_sync(0xffffffffu, bA, 0);
+    bB = __shfl_sync(0xffffffffu, bB, 0);
+    idxA = (uint32_t) bA + __popc(mA & ((1u << lane) - 1u));
+    idxB = (uint32_t) bB + __popc(mB & ((1u << lane) - 1u));
+}
 
 // ------------------------------------------------------------------------------------------------
 // film: ImageBlock::put(pos, spec, alpha) with global atomics (imageblock.h:124-204, full-frame form)
@@ -226,27 +240,26 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender
     const uint32_t n = FIRST ? Q : (uint32_t) pool.counters[((it + 1u) & 1u) ? CTR_DONE1 : CTR_DONE0];
     uint32_t nSamples = 0, nBad = 0, nNew = 0;
     uint32_t pathLen = 0;
+    // work items are handed out without atomics: entry j of the drained queue takes item base + j; k_publish advances
+    // CTR_NEXT by the queue length after this kernel
+    const unsigned long long workBase = pool.counters[CTR_NEXT];
     const uint32_t nS = (uint32_t) (rp.sampleHi - rp.sampleLo);
     const uint32_t perTile = 64u * nS;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
         const bool inRange = j < n;
         const uint32_t i = inRange ? (FIRST ? j : queue[j]) : 0u;
-        uint2 meta = make_uint2(0, 0);
         if (inRange && !FIRST) {
-            meta = pool.meta[i];
-            const uint32_t flags = meta.y & 0xFFu;
-            const float4 li = pool.li[i];
-            const uint4 sm = pool.smp[i];
-            const float alpha = (flags & PF_ALPHA) ? 1.0f : 0.0f;
-            if (!filmPut(filt, rp.filmRGBA, rp.filmW, sc.cam.W, sc.cam.H, __uint_as_float(sm.z), __uint_as_float(sm.w), (int) (meta.x & 0xFFFFu),
-                         (int) (meta.x >> 16), V3(li.x, li.y, li.z), alpha))
+            const uint32_t fl = pool.flags[i], pixel = pool.pix[i];
+            const float4 li = pool.st[2 * (size_t) i + 1];
+            const float2 sp = pool.pos[i];
+            const float alpha = (fl & PF_ALPHA) ? 1.0f : 0.0f;
+            if (!filmPut(filt, rp.filmRGBA, rp.filmW, sc.cam.W, sc.cam.H, sp.x, sp.y, (int) (pixel & 0xFFFFu), (int) (pixel >> 16), V3(li.x, li.y, li.z), alpha))
                 ++nBad;
             ++nSamples;
-            pathLen += (meta.y >> 8) & 0xFFFu;
+            pathLen += (fl >> 8) & 0xFFFu;
         }
-        // claim work: one atomic per warp
-        const unsigned long long w = warpAppend64(inRange, pool.counters + CTR_NEXT);
+        const unsigned long long w = workBase + j;
         if (inRange) {
             bool valid = w < rp.totalWork;
             int px = 0, py = 0;
@@ -267,18 +280,18 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender
                 V3 o, d;
                 float mint, maxt;
                 cameraRay(sc.cam, spx, spy, o, d, mint, maxt);
-                pool.rayO[i] = make_float4(o.x, o.y, o.z, mint);
-                pool.rayD[i] = make_float4(d.x, d.y, d.z, maxt);
-                pool.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-                pool.li[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                pool.smp[i] = make_uint4((uint32_t) smp.index, (uint32_t) (smp.index >> 32), __float_as_uint(spx), __float_as_uint(spy));
-                meta.x = ((uint32_t) py << 16) | (uint32_t) px;
-                meta.y = (PF_ALIVE | PF_FRESH) | (1u << 8) | (smp.dim << 20); // depth = 1 (integrator.h:221-227)
+                pool.ray[2 * (size_t) i] = make_float4(o.x, o.y, o.z, mint);
+                pool.ray[2 * (size_t) i + 1] = make_float4(d.x, d.y, d.z, maxt);
+                pool.st[2 * (size_t) i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                pool.st[2 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                pool.smp[i] = make_uint2((uint32_t) smp.index, (uint32_t) (smp.index >> 32));
+                pool.pos[i] = make_float2(spx, spy);
+                pool.pix[i] = ((uint32_t) py << 16) | (uint32_t) px;
+                pool.flags[i] = (PF_ALIVE | PF_FRESH) | (1u << 8) | (smp.dim << 20); // depth = 1 (integrator.h:221-227)
                 ++nNew;
             } else {
-                meta.y = 0;
+                pool.flags[i] = 0;
             }
-            pool.meta[i] = meta;
         }
     }
     nNew = warpSum(nNew);
@@ -302,12 +315,14 @@ __global__ void k_publish(DPool pool, DRender rp) {
     const unsigned long long it = c[CTR_ITER];
     volatile unsigned long long *slot = rp.ring + (it % B2_RING) * 4;
     slot[1] = c[CTR_ACTIVE];
-    slot[2] = c[CTR_NEXT];
+    slot[2] = c[CTR_NEXT] + (it == 0 ? (unsigned long long) pool.capacity : c[((it + 1) & 1) ? CTR_DONE1 : CTR_DONE0]);
     __threadfence_system();
     slot[0] = it + 1;
     c[CTR_SHADOW] = 0;
     c[CTR_CLASS0] = 0; c[CTR_CLASS0 + 1] = 0; c[CTR_CLASS0 + 2] = 0; c[CTR_CLASS0 + 3] = 0;
-    c[((it + 1) & 1) ? CTR_DONE1 : CTR_DONE0] = 0; // drained by this iteration's k_generate, refilled by k_shade of it + 1
+    const int dq = ((it + 1) & 1) ? CTR_DONE1 : CTR_DONE0;
+    c[CTR_NEXT] += it == 0 ? (unsigned long long) pool.capacity : c[dq]; // work items k_generate just handed out
+    c[dq] = 0; // drained by this iteration's k_generate, refilled by k_shade of it + 1
     c[CTR_ITER] = it + 1;
 }
 
@@ -323,10 +338,13 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
     uint32_t nRays = 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
-        const bool live = i < Q && (pool.meta[i].y & PF_ALIVE);
+        const uint32_t fl = i < Q ? pool.flags[i] : 0u;
+        const bool live = (fl & PF_ALIVE) != 0;
         int cls = -1;
         if (live) {
-            const float4 ro = pool.rayO[i], rd = pool.rayD[i];
+            const float4 ro = pool.ray[2 * (size_t) i];
+            float4 rd = pool.ray[2 * (size_t) i + 1];
+            if (!(fl & PF_FRESH)) rd.w = B2_INF; // w carries the pending BSDF pdf for non-camera rays; their maxt is +inf (ray.h:66-68)
             const V3 o(ro.x, ro.y, ro.z), d(rd.x, rd.y, rd.z);
             const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // ray.h:83-84
             HitRec h;
@@ -481,8 +499,18 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
         uint32_t i = 0;
         bool live = j < n;
         if (live) i = queue ? queue[j] : j;
-        uint2 meta = live ? pool.meta[i] : make_uint2(0, 0);
-        uint32_t flags = meta.y & 0xFFu;
+        // all loads of the slot are issued together (memory-level parallelism); Li is fetched only when it changes
+        uint32_t state = 0;
+        float4 hit = make_float4(0, 0, 0, 0), rd4 = hit, thr4 = hit;
+        uint2 sm2 = make_uint2(0, 0);
+        if (live) {
+            state = pool.flags[i];
+            hit = pool.hit[i];
+            rd4 = pool.ray[2 * (size_t) i + 1];
+            thr4 = pool.st[2 * (size_t) i];
+            sm2 = pool.smp[i];
+        }
+        uint32_t flags = state & 0xFFu;
         if (!queue) live = live && (flags & PF_ALIVE);
         // shadow-ray output of this lane
         bool emitShadow = false;
@@ -490,23 +518,20 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
         float shMaxt = 0;
         Spectrum shC(0.0f);
         if (live) {
-            int depth = (int) ((meta.y >> 8) & 0xFFFu);
-            const float4 hit = pool.hit[i];
-            const float4 rd4 = pool.rayD[i];
+            int depth = (int) ((state >> 8) & 0xFFFu);
             const V3 rayD(rd4.x, rd4.y, rd4.z);
-            float4 thr4 = pool.thr[i];
-            float4 li4 = pool.li[i];
-            const uint4 sm4 = pool.smp[i];
-            Spectrum T(thr4.x, thr4.y, thr4.z), Li(li4.x, li4.y, li4.z);
+            Spectrum T(thr4.x, thr4.y, thr4.z), LiAdd(0.0f); // LiAdd: radiance added by this invocation (emitter hits)
+            bool liTouched = false;
             float eta = thr4.w;
-            const float bsdfPdfPrev = li4.w;
+            const float bsdfPdfPrev = rd4.w;
+            float bsdfPdfOut = 0.0f;
             PathSampler smp;
             smp.kind = rp.sampler;
             smp.m32 = sc.sobolNib;
             smp.nNib = rp.indexNibbles;
             smp.overflow = false;
-            smp.index = ((uint64_t) sm4.y << 32) | sm4.x;
-            smp.dim = meta.y >> 20;
+            smp.index = ((uint64_t) sm2.y << 32) | sm2.x;
+            smp.dim = state >> 20;
             smp.scramble32 = rp.sampler == 0 ? (uint32_t) rp.scramble : (uint32_t) (rp.scramble >> 32);
             const uint32_t prim = __float_as_uint(hit.w);
             const bool valid = prim != 0xFFFFFFFFu;
@@ -532,7 +557,8 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
                                 pdfDirect = em.invSurfaceArea * (hit.x * hit.x) / absDot(rayD, its.sh.n);
                             lumPdf = pdfDirect * (em.samplingWeight * sc.emitterNormalization);
                         }
-                        Li = Li + T * value * miWeight(bsdfPdfPrev, lumPdf);
+                        LiAdd = T * value * miWeight(bsdfPdfPrev, lumPdf);
+                        liTouched = true;
                     }
                     // rRec.type = ERadianceNoEmission; Russian roulette :276-286
                     if (depth++ >= rp.rrDepth) {
@@ -552,7 +578,8 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
                 if (its.emitter >= 0 && fresh && (!rp.hideEmitters || (flags & PF_SCATTERED))) {
                     const DEmitter &em = sc.emitters[its.emitter];
                     Spectrum le = dot(its.sh.n, -rayD) <= 0 ? Spectrum(0.0f) : V3(em.radiance[0], em.radiance[1], em.radiance[2]);
-                    Li = Li + T * le;
+                    LiAdd = T * le; // camera ray only (fresh): the MIS term above cannot have fired
+                    liTouched = true;
                 }
                 if ((depth >= rp.maxDepth && rp.maxDepth > 0) || (rp.strictNormals && dot(rayD, its.geoN) * cosTheta(its.wi) >= 0)) done = true;
                 if (!done) {
@@ -596,38 +623,41 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DSc
                         else {
                             if (bRec.sampledType & EDelta) flags |= PF_DELTA;
                             if (dot(wo, refN) >= 0) flags |= PF_REFN_OK;
-                            pool.rayO[i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
-                            pool.rayD[i] = make_float4(wo.x, wo.y, wo.z, B2_INF);
+                            pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
+                            pool.ray[2 * (size_t) i + 1] = make_float4(wo.x, wo.y, wo.z, bsdfPdfNew); // w: pdf of this sample (maxt = inf)
                             T = T * bsdfWeight; // :252-253 (applied early: only read again if the next ray hits)
                             eta *= bRec.eta;
-                            li4.w = bsdfPdfNew;
+                            bsdfPdfOut = bsdfPdfNew;
                         }
                     }
                     if (done && emitShadow) {
                         // the path ends here but its shadow ray still has to be resolved: k_occluded reads the origin from rayO
-                        pool.rayO[i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
+                        pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
                     }
                 }
             }
             if (smp.overflow) ++nDimOvf;
             flags &= ~PF_FRESH;
             if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
-            pool.thr[i] = make_float4(T.x, T.y, T.z, eta);
-            pool.li[i] = make_float4(Li.x, Li.y, Li.z, li4.w);
-            meta.y = flags | ((uint32_t) depth << 8) | (smp.dim << 20);
-            pool.meta[i] = meta;
-        }
-        // finished paths: queue the slot for the next k_generate (splat + refill), one atomic per warp
-        {
-            const bool fin = live && (meta.y & PF_DONE);
-            const uint32_t dq = warpAppend(fin, pool.counters + ((it & 1u) ? CTR_DONE1 : CTR_DONE0));
-            if (fin) {
-                pool.doneQueue[(size_t) (it & 1u) * Q + dq] = i;
-                ++nDone;
+            (void) bsdfPdfOut;
+            pool.st[2 * (size_t) i] = make_float4(T.x, T.y, T.z, eta);
+            if (liTouched) { // Li += ... (path.cpp:150,263): read-modify-write only on emitter hits
+                float4 li4 = pool.st[2 * (size_t) i + 1];
+                li4.x += LiAdd.x; li4.y += LiAdd.y; li4.z += LiAdd.z;
+                pool.st[2 * (size_t) i + 1] = li4;
             }
+            state = flags | ((uint32_t) depth << 8) | (smp.dim << 20);
+            pool.flags[i] = state;
         }
-        // shadow-ray compaction (warp ballot, one atomic per warp)
-        const uint32_t at = warpAppend(emitShadow, pool.counters + CTR_SHADOW);
+        // finished paths: queue the slot for the next k_generate (splat + refill); shadow-ray compaction.
+        // Warp ballot, one atomic per warp and queue, both in flight together.
+        const bool fin = live && (state & PF_DONE);
+        uint32_t dq, at;
+        warpAppend2(fin, pool.counters + ((it & 1u) ? CTR_DONE1 : CTR_DONE0), emitShadow, pool.counters + CTR_SHADOW, dq, at);
+        if (fin) {
+            pool.doneQueue[(size_t) (it & 1u) * Q + dq] = i;
+            ++nDone;
+        }
         if (emitShadow) {
             pool.shD[at] = make_float4(shD.x, shD.y, shD.z, shMaxt);
             pool.shC[at] = make_float4(shC.x, shC.y, shC.z, __uint_as_float(i));
@@ -658,7 +688,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
         if (j < n) {
             const float4 sd = pool.shD[j], scn = pool.shC[j];
             const uint32_t slot = __float_as_uint(scn.w);
-            const float4 ro = pool.rayO[slot];
+            const float4 ro = pool.ray[2 * (size_t) slot];
             const V3 o(ro.x, ro.y, ro.z), d(sd.x, sd.y, sd.z);
             const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             float mint, maxt;
@@ -667,9 +697,9 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
             uint32_t nv = 0, pt = 0;
             if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt)) occluded = traverse<true, false>(sc, tm, o, d, mint, maxt, h, nv, pt);
             if (!occluded) {
-                float4 li = pool.li[slot];
+                float4 li = pool.st[2 * (size_t) slot + 1];
                 li.x += scn.x; li.y += scn.y; li.z += scn.z;
-                pool.li[slot] = li;
+                pool.st[2 * (size_t) slot + 1] = li;
             }
         }
     }

@@ -103,13 +103,14 @@ enum : uint32_t {
 // Wavefront pool: structure of arrays, one entry per in-flight path ("slot"), 16-byte records
 struct DPool {
     uint32_t capacity;
-    float4 *rayO;      // o.xyz, mint
-    float4 *rayD;      // d.xyz, maxt
+    // 32-byte records (one full DRAM sector each, also when slots are written in scattered order by k_generate):
+    float4 *ray;       // [2i] = o.xyz, mint ; [2i+1] = d.xyz, w  (w = maxt for the camera ray, else the pdf of the pending BSDF sample; maxt = inf)
+    float4 *st;        // [2i] = throughput rgb, eta ; [2i+1] = Li rgb, -
     float4 *hit;       // t, u, v, prim (bits)
-    float4 *thr;       // throughput rgb, eta
-    float4 *li;        // Li rgb, bsdfPdf of the pending BSDF sample
-    uint4 *smp;        // sampler state: {index lo, index hi, samplePos.x bits, samplePos.y bits}
-    uint2 *meta;       // {pixel (y << 16 | x), flags | depth << 8 | dimension << 20}
+    uint2 *smp;        // sampler state: Sobol' index / stream key (lo, hi)
+    float2 *pos;       // samplePos (film coordinates of the sample; read again only when the path is splatted)
+    uint32_t *pix;     // pixel (y << 16 | x)
+    uint32_t *flags;   // PF_* | depth << 8 | sampler dimension << 20
     // shadow queue (compacted by warp ballot)
     float4 *shD;       // d.xyz, maxt
     float4 *shC;       // contribution rgb, slot (bits)
