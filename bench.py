@@ -188,13 +188,14 @@ def main():
     sync()
     ev0.record()
     agg = dict(ms_generate=0.0, ms_extend=0.0, ms_shade=0.0, ms_occluded=0.0, n_generate=0, n_extend=0, n_shade=0, n_occluded=0,
-               launches=0, rays=0, shadow_rays=0, path_length_sum=0, samples=0, ms_render=0.0)
+               launches=0, rays=0, shadow_rays=0, path_length_sum=0, samples=0, ms_render=0.0, unoccluded=0)
     t_wall = time.time()
     for _ in range(args.steps):
         st = step()
         for k in ("ms_generate", "ms_extend", "ms_shade", "ms_occluded", "n_generate", "n_extend", "n_shade", "n_occluded", "rays", "shadow_rays",
                   "path_length_sum", "samples"):
             agg[k] += st[k]
+        agg["unoccluded"] += st["unoccluded_shadow_rays"]
         agg["launches"] += st["kernel_launches"] + (1 if world > 1 else 0)
         agg["ms_render"] += st["ms_total"]
     ev1.record()
@@ -256,9 +257,13 @@ def main():
         n_dom = max(1, agg["n_" + dom])
         avg_ms = shares[dom] / n_dom
         # algorithmic bytes per launch (DESIGN.md "roofline model"): per live path / shadow ray and launch
-        per_item = {"extend": 32 + 16 + 8, "occluded": 32 + 16 + 16 + 16, "shade": 16 + 16 + 16 + 16 + 16 + 8 + 32 + 16 + 16 + 8 + 32,
-                    "generate": 8 + 8}[dom]
-        items = {"extend": agg["rays"], "occluded": agg["shadow_rays"], "shade": agg["rays"], "generate": pool * n_dom}[dom] / n_dom
+        # algorithmic bytes per item of each stage ("roofline model"; 32-byte pool records)
+        rays, shadow, smp = max(1, agg["rays"]), max(1, agg["shadow_rays"]), max(1, agg["samples"])
+        per_item = {"extend": 4 + 32 + 16,
+                    "occluded": 16 + 16 + 16 + 32 * agg["unoccluded"] / shadow,
+                    "shade": (4 + 16 + 16 + 16 + 8) + (32 + 16 + 4) + 32 * shadow / rays + 4 * smp / rays,
+                    "generate": (4 + 4 + 4 + 16 + 8) + 2 * 20 + (32 + 32 + 8 + 8 + 4 + 4)}[dom]
+        items = {"extend": rays, "occluded": shadow, "shade": rays, "generate": smp}[dom] / n_dom
         achieved = per_item * items / (avg_ms / 1e3) / 1e9 if avg_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -273,7 +278,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"Cornell box (S1) {W}x{H} @ {args.spp} spp per GPU, path/sobol/box (BASELINE configs[1])", **WORKLOAD,
                        "spp_per_gpu": args.spp, "width": W, "height": H, "parallelism": f"sample-index sharding x{world}, 1 film reduce",
-                       "pool_size": int(pool), "l2": "path pool + film (%.0f MB) exceed the 126 MB L2; every step re-streams them" % ((pool * 136 + W * H * 20) / 1e6),
+                       "pool_size": int(pool), "l2": "path pool + film (%.0f MB) exceed the 126 MB L2; every iteration re-streams them" % ((pool * (64 + 16 + 8 + 8 + 8 + 32 + 8) + W * H * 20) / 1e6),
                        "fp": "parity (-fmad=false)" if args.parity else "fast (FMA contraction)"},
             "e2e": e2e,
             "gpu_launches": int(agg["launches"]),

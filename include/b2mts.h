@@ -83,6 +83,7 @@ typedef struct b2_stats {
     uint64_t n_generate, n_extend, n_shade, n_occluded; /* launches behind the ms_* sums (flags bit2) */
     uint64_t bytes_uploaded;                /* host->device bytes of the last b2_scene_commit */
     uint64_t pool_size;                     /* in-flight paths of the last b2_render */
+    uint64_t unoccluded_shadow_rays;        /* shadow rays that reached the emitter (their contribution was added) */
 } b2_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -99,6 +100,7 @@ void b2_scene_destroy(b2_scene *);
 int b2_scene_set_camera(b2_scene *, const float to_world[16], float xfov_deg, float near_clip, float far_clip,
                         int width, int height);
 int b2_scene_get_sample_to_camera(b2_scene *, float out[16]);
+int b2_scene_film_size(b2_scene *, int *width, int *height);   /* Film::getSize (include/mitsuba/render/film.h) */
 /* BSDF plugin instance -> id (>=0) or -1 */
 int b2_scene_add_material(b2_scene *, const b2_material_desc *);
 /* AreaLight (src/emitters/area.cpp:64-70): radiance, samplingWeight -> id (>=0) or -1 */

@@ -39,14 +39,14 @@ class b2_stats(C.Structure):
                                           "node_visits", "prim_tests", "iterations", "kernel_launches")] + \
                [(n, C.c_float) for n in ("ms_total", "ms_generate", "ms_extend", "ms_shade", "ms_occluded", "ms_film")] + \
                [(n, C.c_uint64) for n in ("n_triangles", "n_bvh_nodes", "n_generate", "n_extend", "n_shade", "n_occluded",
-                                          "bytes_uploaded", "pool_size")]
+                                          "bytes_uploaded", "pool_size", "unoccluded_shadow_rays")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
-           "b2_scene_set_camera", "b2_scene_get_sample_to_camera", "b2_scene_add_material", "b2_scene_add_area_emitter",
+           "b2_scene_set_camera", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
            "b2_scene_add_mesh", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
@@ -140,10 +140,9 @@ class Context:
         sc = Scene.__new__(Scene)
         sc.ctx, sc.L, sc.h = self, self.L, hs
         W = C.c_int(); H = C.c_int()
-        s2c = np.zeros(16, np.float32)
-        self.L.b2_scene_get_sample_to_camera(hs, _p(s2c))
+        self.L.b2_scene_film_size(hs, C.byref(W), C.byref(H))
+        sc.W, sc.H = W.value, H.value
         sc.material_ids = None
-        sc._size_from_stats()
         return sc, params_to_render_params(p)
 
 
@@ -190,9 +189,6 @@ class Scene:
     def _ck(self, rc):
         if rc:
             raise B2Error(f"[{rc}] {self.ctx.err()}")
-
-    def _size_from_stats(self):
-        self.W = self.H = None
 
     def close(self):
         if getattr(self, "h", None):

@@ -69,6 +69,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    # stand-alone CLI driver over the C-ABI (mirrors `mitsuba -o out -D k=v scene.xml`)
+    exe = os.path.join(HERE, "mtsb200")
+    main_src = os.path.join(HOST, "mtsb200_main.cpp")
+    if os.path.exists(main_src) and (force or _newer(exe, [main_src, LIB])):
+        cmd = ["g++", "-O2", "-std=c++17", "-o", exe, main_src, "-L", HERE, "-lb2mts", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("mtsb200 link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

@@ -304,6 +304,11 @@ extern "C" int b2_scene_get_sample_to_camera(b2_scene *s, float out[16]) {
     memcpy(out, s->sampleToCamera, 64);
     return B2_OK;
 }
+extern "C" int b2_scene_film_size(b2_scene *s, int *width, int *height) {
+    if (!s || !s->hasCamera || !width || !height) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "camera not set");
+    *width = s->W; *height = s->H;
+    return B2_OK;
+}
 extern "C" int b2_scene_add_material(b2_scene *s, const b2_material_desc *m) {
     if (!s || !m) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_material: null argument"); return -1; }
     if (m->type < 0 || m->type > 3) { fail(s->ctx, B2_ERR_INVALID, "unknown BSDF type"); return -1; }
@@ -928,6 +933,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         for (int k = 0; k < 4; ++k) *ms[k] = (float) acc[k];
     }
     t.pool_size = Q;
+    t.unoccluded_shadow_rays = ctr[CTR_UNOCCLUDED];
     t.samples = ctr[CTR_SAMPLES]; t.rays = ctr[CTR_RAYS]; t.shadow_rays = ctr[CTR_SHADOWRAYS]; t.path_length_sum = ctr[CTR_PATHLEN];
     t.bad_samples = ctr[CTR_BAD]; t.dim_overflow = ctr[CTR_DIMOVF]; t.iterations = iter; t.kernel_launches = launches + 1;
     t.ms_total = ms;

@@ -683,6 +683,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
     stampBegin(rp, it, STAGE_OCCLUDED);
     const TraceMem tm = setupTraceMem(sc, smem);
     const uint32_t n = (uint32_t) pool.counters[CTR_SHADOW];
+    uint32_t nClear = 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
         if (j < n) {
@@ -700,9 +701,12 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
                 float4 li = pool.st[2 * (size_t) slot + 1];
                 li.x += scn.x; li.y += scn.y; li.z += scn.z;
                 pool.st[2 * (size_t) slot + 1] = li;
+                ++nClear;
             }
         }
     }
+    nClear = warpSum(nClear);
+    if ((threadIdx.x & 31) == 0 && nClear) atomicAdd(pool.counters + CTR_UNOCCLUDED, (unsigned long long) nClear);
     stampEnd(rp, it, STAGE_OCCLUDED);
 }
 

@@ -128,7 +128,7 @@ struct DPool {
 enum { CTR_DONE0 = 0, CTR_SHADOW = 1, CTR_CLASS0 = 2, /* 2..5 */ CTR_DONE1 = 6, CTR_NEXT = 7, CTR_ACTIVE = 8, CTR_RAYS = 9, CTR_SHADOWRAYS = 10,
        CTR_PATHLEN = 11, CTR_SAMPLES = 12, CTR_BAD = 13, CTR_DIMOVF = 14, CTR_NODEVIS = 15, CTR_PRIMTESTS = 16,
        CTR_ITER = 17,   // host-loop iteration, advanced on the device by k_publish (one graph serves every iteration)
-       CTR_COUNT = 18 };
+       CTR_UNOCCLUDED = 18, CTR_COUNT = 20 };
 
 // progress ring in mapped pinned host memory, written by k_publish: {sequence = iteration + 1, live paths, next work item, -}
 #define B2_RING 64
