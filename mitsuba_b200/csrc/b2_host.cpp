@@ -624,7 +624,9 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.sobolM32 = ctx->dM32; ds.sobolVdc = ctx->dVdc; ds.sobolInv = ctx->dInv; ds.sobolNib = ctx->dNib;
     // shared-memory staging budget: up to 256 nodes (16 KB) and 256 triangles (12 KB) per CTA
     ds.stageNodes = std::min<uint32_t>(ds.nNodes, 256u);
-    ds.stageTris = std::min<uint32_t>(ds.nLeafTris, 256u);
+    ds.stageTris = rootCount ? rootCount : 0u; // a BVH's leaf-ordered head is arbitrary: only the flat leaf is worth staging
+    ds.refill = 16; // measured sweep 8..32 on the material-ball and 1M-triangle scenes
+    if (const char *e = getenv("B2_REFILL")) ds.refill = (uint32_t) std::max(1, std::min(32, atoi(e)));
     parity::KernelSet_init(s->cfgParity, ds, ctx->numSMs);
     fast::KernelSet_init(s->cfgFast, ds, ctx->numSMs);
     CK(ctx, cudaGetLastError());
@@ -988,7 +990,9 @@ extern "C" int b2_trace_device(b2_scene *s, uint64_t n, const float *d_rays, int
     cudaEventCreate(&a); cudaEventCreate(&b);
     const bool count = (mode & 2) != 0;
     const bool shadow = (mode & 1) != 0;
+    if (n > 0xFFFFFFFFull) return fail(ctx, B2_ERR_INVALID, "b2_trace: at most 2^32-1 rays per call");
     if (count) cudaMemsetAsync(s->dCounters.p + CTR_NODEVIS, 0, 16, st);
+    cudaMemsetAsync(s->dCounters.p + CTR_TICKET_EXT, 0, 8, st);
     cudaEventRecord(a, st);
     if (parity_mode) parity::launch_trace(s->cfgParity, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, st);
     else fast::launch_trace(s->cfgFast, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, st);

@@ -318,6 +318,7 @@ __global__ void k_publish(DPool pool, DRender rp) {
     slot[2] = c[CTR_NEXT] + (it == 0 ? (unsigned long long) pool.capacity : c[((it + 1) & 1) ? CTR_DONE1 : CTR_DONE0]);
     __threadfence_system();
     slot[0] = it + 1;
+    c[CTR_TICKET_EXT] = 0; c[CTR_TICKET_OCC] = 0;
     c[CTR_SHADOW] = 0;
     c[CTR_CLASS0] = 0; c[CTR_CLASS0 + 1] = 0; c[CTR_CLASS0 + 2] = 0; c[CTR_CLASS0 + 3] = 0;
     const int dq = ((it + 1) & 1) ? CTR_DONE1 : CTR_DONE0;
@@ -336,6 +337,34 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
     const TraceMem tm = setupTraceMem(sc, smem);
     const uint32_t Q = pool.capacity;
     uint32_t nRays = 0;
+    if (!sc.rootCount) {
+        // BVH scenes: persistent loop with per-lane ray replacement (b2_trace.cuh: traverseQueue)
+        uint32_t nv = 0, pt = 0;
+        auto fetch = [&](uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) -> int {
+            const uint32_t fl = pool.flags[i];
+            if (!(fl & PF_ALIVE)) return 0;
+            const float4 ro = pool.ray[2 * (size_t) i];
+            float4 rd = pool.ray[2 * (size_t) i + 1];
+            if (!(fl & PF_FRESH)) rd.w = B2_INF;
+            o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            ++nRays;
+            return clipRay<false>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt) ? 2 : 1;
+        };
+        auto commit = [&](uint32_t i, bool found, const HitRec &h) {
+            pool.hit[i] = found ? make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)) : make_float4(B2_INF, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+            if (SORT) {
+                int cls = 0;
+                if (found) cls = sc.materials[__float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w))].type;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t at = warpAppend(cls == c, pool.counters + CTR_CLASS0 + c);
+                    if (cls == c) pool.matQueue[(size_t) c * Q + at] = i;
+                }
+            }
+        };
+        traverseQueue<false, false>(sc, tm, Q, pool.counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
+    } else
     for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         const uint32_t fl = i < Q ? pool.flags[i] : 0u;
@@ -684,6 +713,28 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
     const TraceMem tm = setupTraceMem(sc, smem);
     const uint32_t n = (uint32_t) pool.counters[CTR_SHADOW];
     uint32_t nClear = 0;
+    if (!sc.rootCount) {
+        uint32_t nv = 0, pt = 0;
+        float4 cur = make_float4(0, 0, 0, 0); // contribution + slot of the ray this lane is tracing
+        auto fetch = [&](uint32_t j, V3 &o, V3 &d, float &mint, float &maxt) -> int {
+            const float4 sd = pool.shD[j];
+            cur = pool.shC[j];
+            const float4 ro = pool.ray[2 * (size_t) __float_as_uint(cur.w)];
+            o = V3(ro.x, ro.y, ro.z); d = V3(sd.x, sd.y, sd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            return clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt) ? 2 : 1;
+        };
+        auto commit = [&](uint32_t, bool found, const HitRec &) {
+            if (!found) {
+                const uint32_t slot = __float_as_uint(cur.w);
+                float4 li = pool.st[2 * (size_t) slot + 1];
+                li.x += cur.x; li.y += cur.y; li.z += cur.z;
+                pool.st[2 * (size_t) slot + 1] = li;
+                ++nClear;
+            }
+        };
+        traverseQueue<true, false>(sc, tm, n, pool.counters + CTR_TICKET_OCC, fetch, commit, nv, pt);
+    } else
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
         if (j < n) {
@@ -727,6 +778,19 @@ template <bool SHADOW, bool COUNT> __global__ void __launch_bounds__(B2_TRACE_BL
     extern __shared__ __align__(128) unsigned char smem[];
     const TraceMem tm = setupTraceMem(sc, smem);
     uint32_t nv = 0, pt = 0;
+    if (!sc.rootCount) {
+        auto fetch = [&](uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) -> int {
+            const float4 ro = rays[2 * (size_t) i], rd = rays[2 * (size_t) i + 1];
+            o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            return clipRay<SHADOW>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt) ? 2 : 1;
+        };
+        auto commit = [&](uint32_t i, bool found, const HitRec &h) {
+            if (SHADOW) out[i] = make_float4(0, 0, 0, __uint_as_float(found ? 1u : 0u));
+            else out[i] = found ? make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)) : make_float4(B2_INF, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+        };
+        traverseQueue<SHADOW, COUNT>(sc, tm, (uint32_t) n, counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
+    } else
     for (uint64_t base = blockIdx.x * (uint64_t) blockDim.x; base < n; base += (uint64_t) gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
         if (i < n) {

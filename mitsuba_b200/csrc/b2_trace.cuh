@@ -103,12 +103,21 @@ template <bool SHADOW> B2_DEV bool clipRay(const DScene &sc, const V3 &o, const 
     return maxt > mint;
 }
 
+B2_DEV void slabSetup(const V3 &o, const V3 &d, V3 &idir, V3 &ood) {
+    const float tiny = 1e-20f;
+    const float dx = fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x), dy = fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y),
+                dz = fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z);
+    idir = V3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+    ood = V3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+}
+
 // slab test against one child box; conservative (boxes are padded at build time, far side scaled by 1+2ulp)
-B2_DEV bool boxHit(float bx0, float by0, float bz0, float bx1, float by1, float bz1, const V3 &o, const V3 &idir, float mint, float maxt,
+B2_DEV bool boxHit(float bx0, float by0, float bz0, float bx1, float by1, float bz1, const V3 &ood, const V3 &idir, float mint, float maxt,
                    float &tEntry) {
-    float tx0 = (bx0 - o.x) * idir.x, tx1 = (bx1 - o.x) * idir.x;
-    float ty0 = (by0 - o.y) * idir.y, ty1 = (by1 - o.y) * idir.y;
-    float tz0 = (bz0 - o.z) * idir.z, tz1 = (bz1 - o.z) * idir.z;
+    // (b - o) * idir evaluated as b * idir - o * idir: one FMA per plane (boxes are padded, the test stays conservative)
+    float tx0 = fmaf(bx0, idir.x, -ood.x), tx1 = fmaf(bx1, idir.x, -ood.x);
+    float ty0 = fmaf(by0, idir.y, -ood.y), ty1 = fmaf(by1, idir.y, -ood.y);
+    float tz0 = fmaf(bz0, idir.z, -ood.z), tz1 = fmaf(bz1, idir.z, -ood.z);
     float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), mint));
     float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), maxt));
     tEntry = tmin;
@@ -142,8 +151,9 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, co
 template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
                                                          HitRec &hit, uint32_t &nodeVisits, uint32_t &primTests) {
     if (sc.rootCount) return traverseFlat<SHADOW, COUNT>(sc, tm, o, d, mint, maxt, hit, primTests);
-    // safe reciprocal for the slab test only (0 -> huge, keeps NaN out of min/max chains)
-    V3 idir(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    // reciprocal for the slab test only; |d| below 1e-20 is clamped so o * idir stays finite (conservative: boxes are padded)
+    V3 idir, ood;
+    slabSetup(o, d, idir, ood);
     bool found = false;
     uint32_t best = 0xFFFFFFFFu;
     int sp = 0;
@@ -161,8 +171,8 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
             }
             if (COUNT) ++nodeVisits;
             float tL, tR;
-            bool hL = boxHit(a.x, a.y, a.z, a.w, b.x, b.y, o, idir, mint, maxt, tL);
-            bool hR = boxHit(b.z, b.w, c.x, c.y, c.z, c.w, o, idir, mint, maxt, tR);
+            bool hL = boxHit(a.x, a.y, a.z, a.w, b.x, b.y, ood, idir, mint, maxt, tL);
+            bool hR = boxHit(b.z, b.w, c.x, c.y, c.z, c.w, ood, idir, mint, maxt, tR);
             int lref = __float_as_int(e.x), rref = __float_as_int(e.y);
             if (hL && hR) {
                 int nearRef = lref, farRef = rref;
@@ -202,6 +212,128 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
     }
     if (found) hit.prim = __ldg(sc.leafPrim + best);
     return found;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent traversal with per-lane ray replacement: a warp keeps walking while its lanes finish at different times;
+// when REFILL or more lanes are idle they commit their results and pull the next rays from a global ticket counter
+// (one atomic per refill), so lanes do not idle until the slowest ray of a 32-ray batch is done.
+//   fetch(idx, o, d, mint, maxt) -> 0: nothing to do for this item, 1: ray misses the scene box (commit a miss), 2: traverse
+//   commit(idx, found, hit)
+// ------------------------------------------------------------------------------------------------------------
+template <bool SHADOW, bool COUNT, typename Fetch, typename Commit>
+B2_DEV void traverseQueue(const DScene &sc, const TraceMem &tm, uint32_t n, unsigned long long *ticket, Fetch fetch, Commit commit,
+                          uint32_t &nodeVisits, uint32_t &primTests) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = tm.stride;
+    bool active = false, pending = false, exhausted = false, found = false;
+    uint32_t idx = 0, best = 0;
+    V3 o(0.0f), d(0.0f), idir(0.0f), ood(0.0f);
+    float mint = 0, maxt = 0;
+    HitRec hit;
+    hit.t = B2_INF; hit.u = 0; hit.v = 0; hit.prim = 0xFFFFFFFFu;
+    int sp = 0, ref = 0;
+    const int refill = (int) sc.refill;
+    // tickets a warp reserves per atomic: 128 for big launches, down to 32 so that small launches still spread over the grid
+    const unsigned warpsInGrid = gridDim.x * (blockDim.x >> 5);
+    const unsigned long long CHUNK = (unsigned long long) min(128u, max(32u, (n / (4u * warpsInGrid)) & ~31u));
+    unsigned long long chunkNext = 0, chunkEnd = 0; // warp-uniform: locally reserved ticket range
+    while (true) {
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle == FULL || (!exhausted && __popc(idle) >= refill)) {
+            if (pending) {
+                if (found) hit.prim = __ldg(sc.leafPrim + best);
+                commit(idx, found, hit);
+                pending = false;
+            }
+            if (!exhausted) {
+                const unsigned need = (unsigned) __popc(idle);
+                const unsigned rank = (unsigned) __popc(idle & ((1u << lane) - 1u));
+                // tickets come from a warp-local reservation; a new chunk is reserved (one atomic) when it runs dry
+                const unsigned long long have = chunkEnd - chunkNext;
+                unsigned long long base2 = 0;
+                if (have < need) {
+                    if (lane == 0) base2 = atomicAdd(ticket, (unsigned long long) CHUNK);
+                    base2 = __shfl_sync(FULL, base2, 0);
+                }
+                unsigned long long my;
+                if (rank < have) my = chunkNext + rank;
+                else my = base2 + (rank - have);
+                if (have < need) { chunkNext = base2 + (need - have); chunkEnd = base2 + CHUNK; }
+                else chunkNext += need;
+                const unsigned long long base = chunkNext - need; // only used for the exhaustion test below
+                if (!active) {
+                    if (my < n) {
+                        idx = (uint32_t) my;
+                        found = false;
+                        hit.t = B2_INF; hit.u = 0; hit.v = 0; hit.prim = 0xFFFFFFFFu;
+                        const int r = fetch(idx, o, d, mint, maxt);
+                        if (r == 2) {
+                            active = true;
+                            sp = 0;
+                            ref = sc.rootRef;
+                            slabSetup(o, d, idir, ood);
+                        } else if (r == 1) pending = true;
+                    }
+                }
+                (void) base;
+                if (chunkNext >= n) exhausted = true; // every later ticket of this warp is out of range
+            }
+            if (__ballot_sync(FULL, active) == 0) {
+                if (exhausted) {
+                    if (pending) { commit(idx, found, hit); pending = false; }
+                    break;
+                }
+                continue;
+            }
+        }
+        if (active) {
+            if (ref >= 0) {
+                float4 a, b, c, e;
+                if ((uint32_t) ref < tm.stageNodes) {
+                    const float4 *p = tm.sNodes + 4 * ref;
+                    a = p[0]; b = p[1]; c = p[2]; e = p[3];
+                } else {
+                    const float4 *p = tm.gNodes + 4 * (size_t) ref;
+                    a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); e = __ldg(p + 3);
+                }
+                if (COUNT) ++nodeVisits;
+                float tL, tR;
+                const bool hL = boxHit(a.x, a.y, a.z, a.w, b.x, b.y, ood, idir, mint, maxt, tL);
+                const bool hR = boxHit(b.z, b.w, c.x, c.y, c.z, c.w, ood, idir, mint, maxt, tR);
+                const int lref = __float_as_int(e.x), rref = __float_as_int(e.y);
+                if (hL && hR) {
+                    int nearRef = lref, farRef = rref;
+                    if (tR < tL) { nearRef = rref; farRef = lref; }
+                    tm.stack[sp * stride] = (uint32_t) farRef;
+                    ++sp;
+                    ref = nearRef;
+                    continue;
+                } else if (hL) { ref = lref; continue; }
+                else if (hR) { ref = rref; continue; }
+            } else {
+                const uint32_t bits = ~(uint32_t) ref;
+                const uint32_t start = bits & 0x0FFFFFFFu, count = bits >> 28;
+                for (uint32_t i = 0; i < count; ++i) {
+                    const uint32_t ti = start + i;
+                    const float4 *p = tm.gTris + 3 * (size_t) ti;
+                    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                    if (COUNT) ++primTests;
+                    float tu, tv, tt;
+                    if (B2_TRI_TEST(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
+                        found = true;
+                        if (SHADOW) break;
+                        hit.t = tt; hit.u = tu; hit.v = tv; best = ti;
+                        maxt = tt;
+                    }
+                }
+                if (SHADOW && found) { active = false; pending = true; continue; }
+            }
+            if (sp == 0) { active = false; pending = true; }
+            else { --sp; ref = (int) tm.stack[sp * stride]; }
+        }
+    }
 }
 
 } // namespace b2

@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 
 // per-lane traversal stack entries in shared memory; the BVH builder caps the tree depth below this
-#define B2_STACK_DEPTH 40
+#define B2_STACK_DEPTH 32
 
 namespace b2 {
 
@@ -81,6 +81,7 @@ struct DScene {
     const uint32_t *sobolNib;  // [1024][13][16]: XOR of the 4 columns of nibble p selected by v (b2_host.cpp: buildSobolNibbles)
     // staging limits for shared memory (number of leading BVH nodes / TriAccel records copied by TMA)
     uint32_t stageNodes, stageTris;
+    uint32_t refill;           // persistent traversal: refill a warp when at least this many lanes are idle (B2_REFILL, default 16)
 };
 
 struct DFilter {
@@ -128,7 +129,9 @@ struct DPool {
 enum { CTR_DONE0 = 0, CTR_SHADOW = 1, CTR_CLASS0 = 2, /* 2..5 */ CTR_DONE1 = 6, CTR_NEXT = 7, CTR_ACTIVE = 8, CTR_RAYS = 9, CTR_SHADOWRAYS = 10,
        CTR_PATHLEN = 11, CTR_SAMPLES = 12, CTR_BAD = 13, CTR_DIMOVF = 14, CTR_NODEVIS = 15, CTR_PRIMTESTS = 16,
        CTR_ITER = 17,   // host-loop iteration, advanced on the device by k_publish (one graph serves every iteration)
-       CTR_UNOCCLUDED = 18, CTR_COUNT = 20 };
+       CTR_UNOCCLUDED = 18,
+       CTR_TICKET_EXT = 19, CTR_TICKET_OCC = 20, // work tickets of the persistent traversal loops (zeroed by k_publish)
+       CTR_COUNT = 22 };
 
 // progress ring in mapped pinned host memory, written by k_publish: {sequence = iteration + 1, live paths, next work item, -}
 #define B2_RING 64

@@ -280,3 +280,19 @@ def test_error_behaviour(b2ctx):
     d.meshes[0].bsdf = Bsdf("roughdielectric", int_ior=1.5, ext_ior=1.5)
     with pytest.raises(api.B2Error, match="indices of refraction"):
         api.Scene(b2ctx, d)
+
+
+def test_traversal_counters(b2ctx):
+    """b2_trace_device in counting mode reports node visits / triangle tests (the E_trav, E_prim of the roofline model)."""
+    import torch
+    P, N, _, I = uv_sphere((0, 0, 0), 1.0, 64, 64)
+    d = SceneDesc([Mesh(P, I, N=N, bsdf=Bsdf("diffuse"))], Camera(look_at((0, 0, -4), (0, 0, 0), (0, 1, 0)), width=16, height=16))
+    g = api.Scene(b2ctx, d)
+    n = 1 << 16
+    rays = torch.tensor(random_rays(np.random.default_rng(11), n, -0.3, 0.3), device="cuda").contiguous()
+    out = torch.zeros((n, 4), device="cuda")
+    g.trace_device(rays, out, n, mode=0 | 2)
+    st = g.stats()
+    assert st["node_visits"] > 4 * n and st["prim_tests"] > n            # every ray starts inside the sphere and must hit it
+    prim = out[:, 3].view(torch.int32)
+    assert int((prim >= 0).sum()) == n
