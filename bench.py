@@ -247,7 +247,8 @@ def main():
     # cross-check of the in-kernel %globaltimer stamps: one extra, untimed step with plain launches bracketed by CUDA events
     ev_check = None
     if rank == 0:
-        stc = step(flags=4 | 8)
+        # (render only -- no collective here: the other ranks do not take part)
+        _, stc = scene.render(rp, parity=bool(args.parity), pool_size=args.pool, flags=4 | 8, film=film)
         ev_check = {k: stc["ms_" + k] / max(1, stc["n_" + k]) for k in ("generate", "extend", "shade", "occluded")}
     if rank == 0:
         peaks, which = measured_peaks()
