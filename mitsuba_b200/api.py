@@ -12,7 +12,7 @@ import numpy as np
 from .scene import RenderParams, SceneDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libb2mts.so")
+_LIBPATH = os.environ.get("B2MTS_LIB", os.path.join(_HERE, "libb2mts.so"))  # B2MTS_LIB: A/B builds of the same ABI
 _LIB = None
 
 

@@ -24,7 +24,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 UNITS = [
     # (source, extra flags)
     (os.path.join(CSRC, "kernels_parity.cu"), ["-fmad=false"]),
-    (os.path.join(CSRC, "kernels_fast.cu"), []),
+    # throughput build: FMA contraction + fast intrinsics (approximate div/sqrt/sincos/exp, flush-to-zero); the image
+    # parity tests hold it to the same 1e-3 relative-L2 tolerance as the parity build
+    (os.path.join(CSRC, "kernels_fast.cu"), ["--use_fast_math"]),
     (os.path.join(CSRC, "b2_host.cpp"), ["-x", "cu"]),
     (os.path.join(CSRC, "bvh_builder.cpp"), []),
     (os.path.join(HOST, "scene_xml.cpp"), []),
@@ -39,6 +41,30 @@ def _newer(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(name: str, fast_flags, defines=()) -> str:
+    """A/B helper: same sources, different flags for the throughput translation unit -> mitsuba_b200/libb2mts_<name>.so"""
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    for src, extra in UNITS:
+        if not os.path.exists(src):
+            continue
+        base = os.path.basename(src)
+        if base == "kernels_fast.cu":
+            obj = os.path.join(OBJ, f"{base}.{name}.o")
+            cmd = [NVCC] + ARCH + COMMON + list(fast_flags) + [f"-D{d}" for d in defines] + ["-c", src, "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(r.stdout + r.stderr)
+        else:
+            obj = os.path.join(OBJ, base + ".o")
+        objs.append(obj)
+    lib = os.path.join(HERE, f"libb2mts_{name}.so")
+    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-lexpat", "-ldl", "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout + r.stderr)
+    return lib
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

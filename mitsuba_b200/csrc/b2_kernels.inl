@@ -516,7 +516,11 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
 // ------------------------------------------------------------------------------------------------
 // k_shade
 // ------------------------------------------------------------------------------------------------
-template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
+// resident CTAs per SM the register allocator must leave room for (6 x 128 threads -> <= 85 registers; measured best)
+#ifndef B2_SHADE_MINBLOCKS
+#define B2_SHADE_MINBLOCKS 6
+#endif
+template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MINBLOCKS) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
                                                                              const unsigned long long *queueCount) {
     const uint32_t Q = pool.capacity;
     const uint32_t n = queue ? (uint32_t) *queueCount : Q;
