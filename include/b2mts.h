@@ -69,7 +69,8 @@ typedef struct b2_render_params {
     int32_t pool_size;       /* in-flight paths (0 = default) */
     int32_t film_on_device;  /* 1: `film` of b2_render is a device pointer on the context's device */
     int32_t flags;           /* bit1: force unsorted shading (default: material-sorted when > 1 BSDF class);
-                                bit2: time every kernel launch with CUDA events (fills b2_stats.ms_*) */
+                                bit2: per-launch device time stamps (fills b2_stats.ms_*); bit3: plain launches + CUDA events
+                                instead of the CUDA graph; bit4: fuse the ray casts into generate/shade for tiny scenes (experiment, slower) */
 } b2_render_params;
 
 /* Counters with the meaning of the reference's statistics (path.cpp:24,290-291; skdtree.cpp:46-47) plus

@@ -807,6 +807,12 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         if (s->classPresent[c]) { ++nClasses; onlyClass = c; }
     bool sorted = nClasses > 1;
     if (p->flags & 2) sorted = false;
+    // Optional (flags bit4) for shared-memory resident scenes: rays cast inline by k_generate / k_shade (no k_extend /
+    // k_occluded launches, no ray / shadow records through HBM).  Measured on Cornell it is ~4 % SLOWER than the separate
+    // stages (1407 vs 1463 Msamples/s): the triangle tests then run inside the divergent, low-occupancy shade kernel
+    // instead of the lockstep traversal kernels, so the default keeps the stages separate.
+    const bool fused = s->ds.rootCount > 0 && (p->flags & 16);
+    if (fused) sorted = false;
     s->cancel.store(0);
     cudaEvent_t evStart, evStop;
     CK(ctx, cudaEventCreate(&evStart));
@@ -830,19 +836,19 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         launchesPerIter = 0;
 #define ITER(ns)                                                                                               \
         do {                                                                                                   \
-            tick(0); ns::launch_generate(cfg, s->ds, s->pool, r, filt, st); tick(-1);                          \
-            tick(1); ns::launch_extend(cfg, s->ds, s->pool, r, sorted, st); tick(-1);                          \
+            tick(0); ns::launch_generate(cfg, s->ds, s->pool, r, filt, fused, st); tick(-1);                   \
+            if (!fused) { tick(1); ns::launch_extend(cfg, s->ds, s->pool, r, sorted, st); tick(-1); ++launchesPerIter; } \
             tick(2);                                                                                           \
             if (sorted) {                                                                                      \
                 for (int c = 0; c < 4; ++c)                                                                    \
-                    if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, st); ++launchesPerIter; } \
+                    if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, fused, st); ++launchesPerIter; } \
             } else {                                                                                           \
-                ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);           \
+                ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, fused, st);    \
                 ++launchesPerIter;                                                                             \
             }                                                                                                  \
             tick(-1);                                                                                          \
-            tick(3); ns::launch_occluded(cfg, s->ds, s->pool, r, st); tick(-1);                                \
-            launchesPerIter += 4;                                                                              \
+            if (!fused) { tick(3); ns::launch_occluded(cfg, s->ds, s->pool, r, st); tick(-1); ++launchesPerIter; } \
+            launchesPerIter += 2;                                                                              \
         } while (0)
         if (parityMode) ITER(parity);
         else ITER(fast);

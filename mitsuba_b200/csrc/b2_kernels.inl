@@ -90,6 +90,41 @@ B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem) {
     return tm;
 }
 
+// Tiny scenes: only the triangle list is staged (no node array, no traversal stack); used by the kernels that cast their
+// rays inline (k_generate<true>, k_shade<CLS, true>)
+B2_DEV TraceMem setupFlatMem(const DScene &sc, unsigned char *smem) {
+    float4 *sTris = (float4 *) smem;
+    size_t off = ((size_t) sc.stageTris * 48 + 15) & ~(size_t) 15;
+    uint64_t *bar = (uint64_t *) (smem + off);
+    stageScene(sc, sTris, sTris, bar);
+    TraceMem tm;
+    tm.gNodes = nullptr; tm.sNodes = nullptr; tm.stageNodes = 0;
+    tm.sTris = sTris; tm.stageTris = sc.stageTris; tm.stack = nullptr; tm.stride = 0;
+#ifdef B2_FAST_TRI
+    tm.gTris = sc.triPlane;
+#else
+    tm.gTris = sc.triAccel;
+#endif
+    return tm;
+}
+// closest hit / occlusion of one ray against the staged flat leaf, with the reference's clip + adaptive epsilon
+B2_DEV void castClosestFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float rayMint, float rayMaxt, HitRec &h) {
+    h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
+    const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float mint, maxt;
+    uint32_t pt = 0;
+    if (clipRay<false>(sc, o, d, dRcp, rayMint, rayMaxt, mint, maxt))
+        if (!traverseFlat<false, false>(sc, tm, o, d, mint, maxt, h, pt)) { h.t = B2_INF; h.prim = 0xFFFFFFFFu; }
+}
+B2_DEV bool castOccludedFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float rayMaxt) {
+    const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float mint, maxt;
+    uint32_t pt = 0;
+    HitRec h;
+    if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, rayMaxt, mint, maxt)) return traverseFlat<true, false>(sc, tm, o, d, mint, maxt, h, pt);
+    return false;
+}
+
 B2_DEV unsigned long long globalTimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -231,11 +266,17 @@ B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uin
 // k_generate: drains the finished-path queue of the previous iteration with full warps: splat (ImageBlock::put),
 // then refill the slot with the next (pixel, sample) work item.  FIRST: every slot is empty, no queue yet.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
+// FLAT (tiny scenes, DScene::rootCount > 0): the camera ray is cast inline against the shared-memory resident triangle
+// list -- the kernel is memory-latency bound, the extra arithmetic hides behind it and the k_extend launch disappears.
+template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t Q = pool.capacity;
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER];
     const bool FIRST = it == 0;
     stampBegin(rp, it, STAGE_GENERATE);
+    TraceMem tm;
+    if (FLAT) tm = setupFlatMem(sc, smem);
+    uint32_t nRays = 0;
     const uint32_t *queue = pool.doneQueue + (size_t) ((it + 1u) & 1u) * Q; // written by k_shade of iteration it - 1
     const uint32_t n = FIRST ? Q : (uint32_t) pool.counters[((it + 1u) & 1u) ? CTR_DONE1 : CTR_DONE0];
     uint32_t nSamples = 0, nBad = 0, nNew = 0;
@@ -280,7 +321,14 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender
                 V3 o, d;
                 float mint, maxt;
                 cameraRay(sc.cam, spx, spy, o, d, mint, maxt);
-                pool.ray[2 * (size_t) i] = make_float4(o.x, o.y, o.z, mint);
+                if (FLAT) {
+                    HitRec h;
+                    castClosestFlat(sc, tm, o, d, mint, maxt, h);
+                    pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                    ++nRays;
+                } else {
+                    pool.ray[2 * (size_t) i] = make_float4(o.x, o.y, o.z, mint);
+                }
                 pool.ray[2 * (size_t) i + 1] = make_float4(d.x, d.y, d.z, maxt);
                 pool.st[2 * (size_t) i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
                 pool.st[2 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -303,6 +351,10 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender
         if (nSamples) atomicAdd(pool.counters + CTR_SAMPLES, (unsigned long long) nSamples);
         if (nBad) atomicAdd(pool.counters + CTR_BAD, (unsigned long long) nBad);
         if (pathLen) atomicAdd(pool.counters + CTR_PATHLEN, (unsigned long long) pathLen);
+    }
+    if (FLAT) {
+        nRays = warpSum(nRays);
+        if ((threadIdx.x & 31) == 0 && nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
     }
     stampEnd(rp, it, STAGE_GENERATE);
 }
@@ -520,8 +572,14 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
 #ifndef B2_SHADE_MINBLOCKS
 #define B2_SHADE_MINBLOCKS 6
 #endif
-template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MINBLOCKS) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
+// FLAT: the shadow ray and the next ray are cast inline against the shared-memory resident triangle list (tiny scenes):
+// no shadow queue, no k_extend / k_occluded launches, no ray / shadow records through HBM.
+template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MINBLOCKS) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
                                                                              const unsigned long long *queueCount) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    TraceMem tm;
+    if (FLAT) tm = setupFlatMem(sc, smem);
+    uint32_t nRays = 0, nClear = 0;
     const uint32_t Q = pool.capacity;
     const uint32_t n = queue ? (uint32_t) *queueCount : Q;
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
@@ -553,8 +611,8 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MI
         if (live) {
             int depth = (int) ((state >> 8) & 0xFFFu);
             const V3 rayD(rd4.x, rd4.y, rd4.z);
-            Spectrum T(thr4.x, thr4.y, thr4.z), LiAdd(0.0f); // LiAdd: radiance added by this invocation (emitter hits)
-            bool liTouched = false;
+            Spectrum T(thr4.x, thr4.y, thr4.z), LiAdd(0.0f), LiNee(0.0f); // radiance added by this invocation: emitter hit, then (FLAT) NEE
+            bool liTouched = false, neeTouched = false;
             float eta = thr4.w;
             const float bsdfPdfPrev = rd4.w;
             float bsdfPdfOut = 0.0f;
@@ -635,7 +693,9 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MI
                                 shC = T * ds.value * bsdfVal * weight;
                                 shD = ds.d;
                                 shMaxt = ds.dist * (1 - B2_SHADOW_EPSILON);
-                                emitShadow = true;
+                                if (FLAT) { // visibility test of Scene::sampleEmitterDirect (scene.cpp:838-843), inline
+                                    if (!castOccludedFlat(sc, tm, its.p, shD, shMaxt)) { LiNee = shC; neeTouched = true; ++nClear; }
+                                } else emitShadow = true;
                             }
                         }
                     }
@@ -656,7 +716,14 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MI
                         else {
                             if (bRec.sampledType & EDelta) flags |= PF_DELTA;
                             if (dot(wo, refN) >= 0) flags |= PF_REFN_OK;
-                            pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
+                            if (FLAT) { // scene->rayIntersect(ray, its) of path.cpp:226, inline
+                                HitRec h;
+                                castClosestFlat(sc, tm, its.p, wo, B2_EPSILON, B2_INF, h);
+                                pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+                                ++nRays;
+                            } else {
+                                pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
+                            }
                             pool.ray[2 * (size_t) i + 1] = make_float4(wo.x, wo.y, wo.z, bsdfPdfNew); // w: pdf of this sample (maxt = inf)
                             T = T * bsdfWeight; // :252-253 (applied early: only read again if the next ray hits)
                             eta *= bRec.eta;
@@ -674,9 +741,10 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MI
             if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
             (void) bsdfPdfOut;
             pool.st[2 * (size_t) i] = make_float4(T.x, T.y, T.z, eta);
-            if (liTouched) { // Li += ... (path.cpp:150,263): read-modify-write only on emitter hits
+            if (liTouched || neeTouched) { // Li += ... (path.cpp:150,197,263), same order as the reference
                 float4 li4 = pool.st[2 * (size_t) i + 1];
-                li4.x += LiAdd.x; li4.y += LiAdd.y; li4.z += LiAdd.z;
+                if (liTouched) { li4.x += LiAdd.x; li4.y += LiAdd.y; li4.z += LiAdd.z; }
+                if (neeTouched) { li4.x += LiNee.x; li4.y += LiNee.y; li4.z += LiNee.z; }
                 pool.st[2 * (size_t) i + 1] = li4;
             }
             state = flags | ((uint32_t) depth << 8) | (smp.dim << 20);
@@ -699,6 +767,14 @@ template <int CLS> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MI
     nDimOvf = warpSum(nDimOvf);
     nShadowRef = warpSum(nShadowRef);
     nDone = warpSum(nDone);
+    if (FLAT) {
+        nRays = warpSum(nRays);
+        nClear = warpSum(nClear);
+        if ((threadIdx.x & 31) == 0) {
+            if (nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
+            if (nClear) atomicAdd(pool.counters + CTR_UNOCCLUDED, (unsigned long long) nClear);
+        }
+    }
     if ((threadIdx.x & 31) == 0) {
         if (nDone) atomicAdd(pool.counters + CTR_ACTIVE, ~(unsigned long long) nDone + 1ull); // -= nDone
         if (nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
@@ -921,31 +997,52 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridExtendSort = occupancyGrid(k_extend<true>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridOccluded = occupancyGrid(k_occluded, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridTrace = occupancyGrid(k_trace_rays<false, false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
-    cfg.gridGenerate = occupancyGrid(k_generate, 256, 0, numSMs);
-    cfg.gridShade[0] = occupancyGrid(k_shade<0>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[1] = occupancyGrid(k_shade<1>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[2] = occupancyGrid(k_shade<2>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[3] = occupancyGrid(k_shade<3>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[4] = occupancyGrid(k_shade<-1>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.flatSmem = (((size_t) sc.stageTris * 48 + 15) & ~(size_t) 15) + 16;
+    cfg.gridGenerate = occupancyGrid(k_generate<false>, 256, 0, numSMs);
+    cfg.gridShade[0] = occupancyGrid(k_shade<0, false>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[1] = occupancyGrid(k_shade<1, false>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[2] = occupancyGrid(k_shade<2, false>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[3] = occupancyGrid(k_shade<3, false>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[4] = occupancyGrid(k_shade<-1, false>, B2_SHADE_BLOCK, 0, numSMs);
+    if (sc.rootCount) { // fused variants for shared-memory resident scenes
+        cfg.gridGenerateFlat = occupancyGrid(k_generate<true>, 256, cfg.flatSmem, numSMs);
+        cfg.gridShadeFlat[0] = occupancyGrid(k_shade<0, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
+        cfg.gridShadeFlat[1] = occupancyGrid(k_shade<1, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
+        cfg.gridShadeFlat[2] = occupancyGrid(k_shade<2, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
+        cfg.gridShadeFlat[3] = occupancyGrid(k_shade<3, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
+        cfg.gridShadeFlat[4] = occupancyGrid(k_shade<-1, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
+    }
 }
 
-void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, cudaStream_t st) {
-    k_generate<<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
+void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, bool flat, cudaStream_t st) {
+    if (flat) k_generate<true><<<cfg.gridGenerateFlat, 256, cfg.flatSmem, st>>>(sc, pool, rp, f);
+    else k_generate<false><<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
     k_publish<<<1, 32, 0, st>>>(pool, rp);
 }
 void launch_extend(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, bool sort, cudaStream_t st) {
     if (sort) k_extend<true><<<cfg.gridExtendSort, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
     else k_extend<false><<<cfg.gridExtend, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
-void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, int cls, bool queued, cudaStream_t st) {
+void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, int cls, bool queued, bool flat, cudaStream_t st) {
     const uint32_t *q = queued ? pool.matQueue + (size_t) cls * pool.capacity : nullptr;
     const unsigned long long *qc = queued ? pool.counters + CTR_CLASS0 + cls : nullptr;
+    if (flat) {
+        const size_t sm = cfg.flatSmem;
+        switch (cls) {
+            case 0: k_shade<0, true><<<cfg.gridShadeFlat[0], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
+            case 1: k_shade<1, true><<<cfg.gridShadeFlat[1], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
+            case 2: k_shade<2, true><<<cfg.gridShadeFlat[2], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
+            case 3: k_shade<3, true><<<cfg.gridShadeFlat[3], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
+            default: k_shade<-1, true><<<cfg.gridShadeFlat[4], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, nullptr, nullptr); break;
+        }
+        return;
+    }
     switch (cls) {
-        case 0: k_shade<0><<<cfg.gridShade[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        case 1: k_shade<1><<<cfg.gridShade[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        case 2: k_shade<2><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        case 3: k_shade<3><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        default: k_shade<-1><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr); break;
+        case 0: k_shade<0, false><<<cfg.gridShade[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 1: k_shade<1, false><<<cfg.gridShade[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 2: k_shade<2, false><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 3: k_shade<3, false><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        default: k_shade<-1, false><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr); break;
     }
 }
 void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {

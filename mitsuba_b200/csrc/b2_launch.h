@@ -13,14 +13,20 @@ struct LaunchCfg {
     size_t traceSmem = 0;
     int gridExtend = 0, gridExtendSort = 0, gridOccluded = 0, gridTrace = 0, gridGenerate = 0;
     int gridShade[5] = {0, 0, 0, 0, 0};
+    // fused variants for shared-memory resident scenes (rays cast inline by k_generate / k_shade)
+    size_t flatSmem = 0;
+    int gridGenerateFlat = 0;
+    int gridShadeFlat[5] = {0, 0, 0, 0, 0};
 };
 
 #define B2_DECLARE_LAUNCHERS(NS)                                                                                               \
     namespace NS {                                                                                                             \
     void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs);                                                         \
-    void launch_generate(const LaunchCfg &, const DScene &, const DPool &, const DRender &, const DFilter &, cudaStream_t);    \
+    void launch_generate(const LaunchCfg &, const DScene &, const DPool &, const DRender &, const DFilter &, bool flat,        \
+                         cudaStream_t);                                                                                        \
     void launch_extend(const LaunchCfg &, const DScene &, const DPool &, const DRender &, bool sort, cudaStream_t);            \
-    void launch_shade(const LaunchCfg &, const DScene &, const DPool &, const DRender &, int cls, bool queued, cudaStream_t);  \
+    void launch_shade(const LaunchCfg &, const DScene &, const DPool &, const DRender &, int cls, bool queued, bool flat,      \
+                      cudaStream_t);                                                                                           \
     void launch_occluded(const LaunchCfg &, const DScene &, const DPool &, const DRender &, cudaStream_t);                     \
     void launch_film_pack(const LaunchCfg &, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t);          \
     void launch_trace(const LaunchCfg &, const DScene &, const float4 *rays, float4 *out, uint64_t n, bool shadow, bool count, \

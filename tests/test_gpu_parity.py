@@ -296,3 +296,16 @@ def test_traversal_counters(b2ctx):
     assert st["node_visits"] > 4 * n and st["prim_tests"] > n            # every ray starts inside the sphere and must hit it
     prim = out[:, 3].view(torch.int32)
     assert int((prim >= 0).sum()) == n
+
+
+def test_fused_and_unfused_pipelines_agree(cbox):
+    """flags bit4 casts the rays of tiny scenes inline (k_generate / k_shade) instead of the separate k_extend / k_occluded
+    stages.  Same arithmetic, so the films agree up to atomic summation order and the counters exactly."""
+    _, g, _ = cbox
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="gaussian")
+    for parity in (True, False):
+        a, sa = g.render(rp, parity=parity)
+        b, sb = g.render(rp, parity=parity, flags=16)
+        assert np.allclose(a, b, rtol=2e-5, atol=2e-5)
+        for k in ("samples", "rays", "shadow_rays", "path_length_sum", "unoccluded_shadow_rays"):
+            assert sa[k] == sb[k], k
