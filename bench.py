@@ -109,6 +109,46 @@ def cpu_reference_run(steps, warmup, sample_spp=None, threads=0):
                 ms_per_step=dt * 1e3, mean_path_length=st["pathLengthSum"] / st["samples"])
 
 
+def traversal_metric(ctx, hbm_gbs, n_inst=10, n_rays=1 << 22):
+    """Second half of BASELINE's metric ("traversal HBM GB/s vs peak"): k_trace_rays (the traversal loop of k_extend) on an
+    S3-class scene that is NOT cache resident -- 1 M triangles (10 x 100 k instanced, flattened) -- with incoherent rays from
+    the bounding sphere (kdbench-style origins, src/utils/kdbench.cpp:222-229) aimed at random mesh vertices.  Algorithmic bytes per ray = 48 (ray in, hit out) + 64 B per
+    node visit + 48 B per triangle test, visits/tests counted by the kernel itself."""
+    import torch
+    from mitsuba_b200 import api
+    from mitsuba_b200.scene import stress_scene
+    d = stress_scene(n_inst, width=64, height=64)
+    sc = api.Scene(ctx, d)
+    P = np.concatenate([m.P for m in d.meshes]); lo, hi = P.min(0), P.max(0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    def sph():
+        v = torch.randn((n_rays, 3), device="cuda", generator=g)
+        return v / v.norm(dim=1, keepdim=True)
+    c = torch.tensor((lo + hi) / 2, device="cuda", dtype=torch.float32); r = float(np.linalg.norm(hi - lo) / 2)
+    # origin: uniform on the bounding sphere (kdbench); target: a random mesh vertex of the instanced geometry, so that every ray
+    # descends to the leaves instead of ending on the two ground triangles
+    Pg = torch.tensor(np.concatenate([m.P for m in d.meshes[:-2]]), device="cuda")
+    a = c + r * sph()
+    b = Pg[torch.randint(0, len(Pg), (n_rays,), device="cuda", generator=g)]
+    dd = b - a; L = dd.norm(dim=1, keepdim=True)
+    rays = torch.cat([a, torch.zeros((n_rays, 1), device="cuda"), dd / L, 2 * L], 1).contiguous().float()
+    out = torch.zeros((n_rays, 4), device="cuda")
+    sc.trace_device(rays, out, n_rays, mode=2)
+    st = sc.stats()
+    nv, pt = st["node_visits"] / n_rays, st["prim_tests"] / n_rays
+    for _ in range(3):
+        sc.trace_device(rays, out, n_rays, mode=0)
+    ms = min(sc.trace_device(rays, out, n_rays, mode=0) for _ in range(5))
+    alg = (48 + 64 * nv + 48 * pt) * n_rays
+    res = {"scene": f"stress {n_inst}x100k = {d.n_triangles()} triangles, BVH2 {st['n_bvh_nodes']} nodes", "rays": n_rays, "kernel": "k_trace_rays (closest hit)",
+           "mrays_s": n_rays / ms / 1e3, "ms": ms, "node_visits_per_ray": nv, "tri_tests_per_ray": pt, "achieved": alg / ms / 1e6, "unit": "GB/s",
+           "peak": hbm_gbs, "frac": alg / ms / 1e6 / hbm_gbs,
+           "note": "algorithmic bytes; the top of the tree is served from shared memory / L1 / L2, so DRAM traffic is far lower (profiles/)"}
+    sc.close()
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,6 +176,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--parity", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traversal", action="store_true", help="skip the isolated BVH-traversal measurement (S3-class scene)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -294,6 +335,8 @@ def main():
             "stats": {"mean_path_length": agg["path_length_sum"] / max(1, agg["samples"]), "rays_per_sample": agg["rays"] / max(1, agg["samples"]),
                       "shadow_rays_per_sample": agg["shadow_rays"] / max(1, agg["samples"]), "wall_s": wall},
         }
+        if not args.no_traversal:
+            line["traversal"] = traversal_metric(ctx, peaks.get("hbm_gbs", 6650.0))
         if not args.no_cpu_baseline:
             cb = cpu_reference_run(1, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -309,3 +309,63 @@ def test_fused_and_unfused_pipelines_agree(cbox):
         assert np.allclose(a, b, rtol=2e-5, atol=2e-5)
         for k in ("samples", "rays", "shadow_rays", "path_length_sum", "unoccluded_shadow_rays"):
             assert sa[k] == sb[k], k
+
+
+def test_ragged_film_and_non_square(b2ctx):
+    """Film sizes that are not multiples of the 8x8 work tiles / 32x32 render blocks, W != H (edge handling of the splat)."""
+    d = cornell_box(70, 45)
+    g, o = pair(b2ctx, d)
+    for rf in ("box", "gaussian"):
+        rp = RenderParams(spp=8, sampler="sobol", rfilter=rf)
+        fo, so = o.render(rp); fg, sg = g.render(rp, parity=True)
+        assert sg["samples"] == 70 * 45 * 8 == so["samples"]
+        assert np.allclose(fg[..., 4], fo[..., 4], rtol=1e-5, atol=1e-5)
+        assert rel_l2(api.develop(fg), O.develop(fo)) < 5e-4
+    d1 = cornell_box(1, 1)
+    g1, o1 = pair(b2ctx, d1)
+    rp = RenderParams(spp=64, sampler="sobol", rfilter="box")
+    f1, _ = g1.render(rp, parity=True); f0, _ = o1.render(rp)
+    assert np.allclose(f1, f0, rtol=1e-3, atol=1e-4)
+
+
+def test_sobol_indices_beyond_32_bits(b2ctx):
+    """Config-5 class index range: 2048^2 film, sample indices >= 1024 -> 33-bit Sobol' indices (nibble tables past word 0)."""
+    d = cornell_box(2048, 2048)
+    g, o = pair(b2ctx, d)
+    for (px, py, s) in [(0, 0, 2047), (2047, 2047, 2047), (1234, 77, 1500), (5, 2000, 1024)]:
+        a, b = g.sampler_stream("sobol", 0, 2048, px, py, s, 16), o.sampler_stream("sobol", 0, 2048, px, py, s, 16)
+        assert np.array_equal(a, b)
+    idx = O.sobol_lookup(11, np.array([2047], np.uint32), 2047, 2047)[0]
+    assert int(idx) >= 1 << 32
+
+
+def test_degenerate_and_emitterless_scenes(b2ctx):
+    """k = 3 TriAccel records (zero-area triangles, triaccel.h:75-78) are never hit; a scene without emitters renders black."""
+    d = cornell_box(32, 32)
+    m = d.meshes[0]
+    m.P = np.concatenate([m.P, np.array([[100, 100, 100], [100, 100, 100], [200, 200, 200]], np.float32)])
+    m.idx = np.concatenate([m.idx, np.array([[12, 13, 14]], np.uint32)])
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=8, sampler="sobol", rfilter="box")
+    fo, _ = o.render(rp); fg, st = g.render(rp, parity=True)
+    assert st["n_triangles"] == 33 and rel_l2(api.develop(fg), O.develop(fo)) < 5e-4
+    d2 = cornell_box(32, 32)
+    d2.meshes[-1].radiance = None
+    g2 = api.Scene(b2ctx, d2)
+    f2, s2 = g2.render(rp, parity=True)
+    assert not f2[..., :3].any() and s2["samples"] == 32 * 32 * 8 and s2["shadow_rays"] == 0
+
+
+def test_cancel_returns_status(b2ctx):
+    """Integrator::cancel (integrator.h:90-93): a cancel issued from another thread stops the host loop with B2_ERR_CANCELLED."""
+    import threading, time, ctypes as C
+    d = cornell_box(512, 512)
+    g = api.Scene(b2ctx, d)
+    p = api.make_params(RenderParams(spp=4096, sampler="sobol", rfilter="box"), False, 0, False, 0)
+    film = np.zeros((512, 512, 5), np.float32)
+    rc = {}
+    t = threading.Thread(target=lambda: rc.setdefault("rc", g.L.b2_render(g.h, C.byref(p), film.ctypes.data_as(C.POINTER(C.c_float)))))
+    t.start(); time.sleep(0.05); g.L.b2_cancel(g.h); t.join(timeout=60)
+    assert not t.is_alive() and rc["rc"] == 5
+    f, s = g.render(RenderParams(spp=2, sampler="sobol", rfilter="box"))       # the scene stays usable
+    assert s["samples"] == 512 * 512 * 2
