@@ -99,7 +99,8 @@ struct b2_scene {
     // device scene
     DScene ds{};
     DevBuf<float4> dTriAccel, dTriPlane, dVerts, dNorms;
-    DevBuf<uint32_t> dLeafPrim;
+    DevBuf<uint32_t> dLeafPrim, dFlatIdx;
+    DevBuf<float4> dFlatRec;
     DevBuf<BVHNode> dNodes;
     DevBuf<DMaterial> dMaterials;
     DevBuf<DEmitter> dEmitters;
@@ -512,11 +513,9 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     }
     s->bvhDepth = bvh.depth;
     std::vector<float4> leafTri(3 * bvh.leafPrims.size()), leafPlane(3 * bvh.leafPrims.size());
-    for (size_t i = 0; i < bvh.leafPrims.size(); ++i) {
-        const size_t p = bvh.leafPrims[i];
-        memcpy(&leafTri[3 * i], &triAccel[3 * p], 48);
-        // plane form, evaluated in double: N = e1 x e2, U = (e2 x N)/|N|^2, V = (N x e1)/|N|^2
-        const float4 &a = verts[3 * p], &b = verts[3 * p + 1], &c = verts[3 * p + 2];
+    // plane form of triangle (a, b, c), evaluated in double: N = e1 x e2, U = (e2 x N)/|N|^2, V = (N x e1)/|N|^2;
+    // u(p) = U.p + du and v(p) = V.p + dv are the barycentrics of b and c
+    auto planeRows = [](const float4 &a, const float4 &b, const float4 &c, float4 *out) {
         const double p0[3] = {a.x, a.y, a.z}, e1[3] = {(double) b.x - a.x, (double) b.y - a.y, (double) b.z - a.z},
                      e2[3] = {(double) c.x - a.x, (double) c.y - a.y, (double) c.z - a.z};
         const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
@@ -525,11 +524,86 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         const double V[3] = {(N[1] * e1[2] - N[2] * e1[1]) / nn, (N[2] * e1[0] - N[0] * e1[2]) / nn, (N[0] * e1[1] - N[1] * e1[0]) / nn};
         // scale the t-plane so that |N| ~ 1 (keeps num/den well inside float range)
         const double inv = 1.0 / std::sqrt(nn);
-        leafPlane[3 * i] = make_float4((float) (N[0] * inv), (float) (N[1] * inv), (float) (N[2] * inv),
-                                       (float) ((N[0] * p0[0] + N[1] * p0[1] + N[2] * p0[2]) * inv));
-        leafPlane[3 * i + 1] = make_float4((float) U[0], (float) U[1], (float) U[2], (float) -(U[0] * p0[0] + U[1] * p0[1] + U[2] * p0[2]));
-        leafPlane[3 * i + 2] = make_float4((float) V[0], (float) V[1], (float) V[2], (float) -(V[0] * p0[0] + V[1] * p0[1] + V[2] * p0[2]));
+        out[0] = make_float4((float) (N[0] * inv), (float) (N[1] * inv), (float) (N[2] * inv), (float) ((N[0] * p0[0] + N[1] * p0[1] + N[2] * p0[2]) * inv));
+        out[1] = make_float4((float) U[0], (float) U[1], (float) U[2], (float) -(U[0] * p0[0] + U[1] * p0[1] + U[2] * p0[2]));
+        out[2] = make_float4((float) V[0], (float) V[1], (float) V[2], (float) -(V[0] * p0[0] + V[1] * p0[1] + V[2] * p0[2]));
+    };
+    for (size_t i = 0; i < bvh.leafPrims.size(); ++i) {
+        const size_t p = bvh.leafPrims[i];
+        memcpy(&leafTri[3 * i], &triAccel[3 * p], 48);
+        planeRows(verts[3 * p], verts[3 * p + 1], verts[3 * p + 2], &leafPlane[3 * i]);
     }
+    // ---- flat leaf of the throughput build: coplanar triangle pairs share the plane test ----
+    // Two triangles with a common edge that lie in one plane are stored as ONE record: a parallelogram (3 rows: the
+    // lockstep test is 0 <= u,v <= 1 in the frame of the unshared corner) or a general coplanar pair (5 rows: one t and
+    // hit point, two (u,v) evaluations).  Everything else stays a single triangle.  Order: parallelograms, pairs, singles.
+    std::vector<float4> flatRec;
+    std::vector<uint32_t> flatIdx; // 2 per record: leaf index of the first / second triangle
+    uint32_t flatP = 0, flatC = 0, flatS = 0;
+    if (rootCount) {
+        const uint32_t n = rootCount;
+        const double diag = std::sqrt((double) (hi[0] - lo[0]) * (hi[0] - lo[0]) + (double) (hi[1] - lo[1]) * (hi[1] - lo[1]) + (double) (hi[2] - lo[2]) * (hi[2] - lo[2]));
+        const double tol = 1e-6 * std::max(diag, 1e-30);
+        std::vector<int> mate(n, -1), kind(n, 0), cornerA(n, 0);
+        auto V = [&](uint32_t leaf, int k) -> const float4 & { return verts[3 * (size_t) bvh.leafPrims[leaf] + k]; };
+        auto same = [](const float4 &a, const float4 &b) { return a.x == b.x && a.y == b.y && a.z == b.z; };
+        if (!getenv("B2_NO_QUADS"))
+        for (uint32_t i = 0; i < n; ++i) {
+            if (mate[i] >= 0) continue;
+            for (uint32_t j = i + 1; j < n && mate[i] < 0; ++j) {
+                if (mate[j] >= 0) continue;
+                int sharedA[3] = {0, 0, 0}, sharedB[3] = {0, 0, 0}, ns = 0;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        if (!sharedA[a] && !sharedB[b] && same(V(i, a), V(j, b))) { sharedA[a] = sharedB[b] = 1; ++ns; }
+                if (ns != 2) continue;
+                int ka = !sharedA[0] ? 0 : (!sharedA[1] ? 1 : 2), kb = !sharedB[0] ? 0 : (!sharedB[1] ? 1 : 2);
+                const float4 &pa = V(i, ka), &s0 = V(i, (ka + 1) % 3), &s1 = V(i, (ka + 2) % 3), &pb = V(j, kb);
+                const double e[3] = {(double) s1.x - s0.x, (double) s1.y - s0.y, (double) s1.z - s0.z};
+                const double fa[3] = {(double) pa.x - s0.x, (double) pa.y - s0.y, (double) pa.z - s0.z};
+                const double fb[3] = {(double) pb.x - s0.x, (double) pb.y - s0.y, (double) pb.z - s0.z};
+                const double na[3] = {e[1] * fa[2] - e[2] * fa[1], e[2] * fa[0] - e[0] * fa[2], e[0] * fa[1] - e[1] * fa[0]};
+                const double nb[3] = {e[1] * fb[2] - e[2] * fb[1], e[2] * fb[0] - e[0] * fb[2], e[0] * fb[1] - e[1] * fb[0]};
+                const double la = std::sqrt(na[0] * na[0] + na[1] * na[1] + na[2] * na[2]), lb = std::sqrt(nb[0] * nb[0] + nb[1] * nb[1] + nb[2] * nb[2]);
+                if (!(la > 0) || !(lb > 0)) continue;
+                if (na[0] * nb[0] + na[1] * nb[1] + na[2] * nb[2] >= 0) continue; // both on the same side of the common edge: overlap
+                const double dist = (na[0] * fb[0] + na[1] * fb[1] + na[2] * fb[2]) / la; // distance of the 4th corner from the plane
+                if (std::fabs(dist) > tol) continue;
+                mate[i] = (int) j; mate[j] = (int) i;
+                cornerA[i] = ka;
+                const double q[3] = {(double) s0.x + s1.x - pa.x, (double) s0.y + s1.y - pa.y, (double) s0.z + s1.z - pa.z};
+                const bool para = std::fabs(q[0] - pb.x) <= tol && std::fabs(q[1] - pb.y) <= tol && std::fabs(q[2] - pb.z) <= tol;
+                kind[i] = para ? 1 : 2;
+            }
+        }
+        for (int pass = 1; pass <= 3; ++pass)
+            for (uint32_t i = 0; i < n; ++i) {
+                if (pass < 3) {
+                    if (mate[i] < (int) i || kind[i] != pass) continue; // each pair once, from its lower index
+                    const uint32_t j = (uint32_t) mate[i];
+                    float4 rows[3];
+                    if (pass == 1) {
+                        const int ka = cornerA[i];
+                        planeRows(V(i, ka), V(i, (ka + 1) % 3), V(i, (ka + 2) % 3), rows);
+                        flatRec.insert(flatRec.end(), rows, rows + 3);
+                        ++flatP;
+                    } else {
+                        flatRec.insert(flatRec.end(), &leafPlane[3 * i], &leafPlane[3 * i] + 3);
+                        flatRec.insert(flatRec.end(), &leafPlane[3 * j + 1], &leafPlane[3 * j + 1] + 2);
+                        ++flatC;
+                    }
+                    flatIdx.push_back(i); flatIdx.push_back(j);
+                } else {
+                    if (mate[i] >= 0) continue;
+                    flatRec.insert(flatRec.end(), &leafPlane[3 * i], &leafPlane[3 * i] + 3);
+                    flatIdx.push_back(i); flatIdx.push_back(i);
+                    ++flatS;
+                }
+            }
+    }
+    if (getenv("B2_VERBOSE"))
+        fprintf(stderr, "[b2mts] commit: %zu triangles, flat leaf %u (parallelograms %u, coplanar pairs %u, singles %u), bvh nodes %zu depth %d\n", nPrims, rootCount,
+                flatP, flatC, flatS, bvh.nodes.size(), bvh.depth);
     // ---- materials ----
     std::vector<DMaterial> dm(s->materials.size());
     for (int c = 0; c < 4; ++c) s->classPresent[c] = false;
@@ -592,6 +666,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     CK(ctx, s->dTriAccel.upload(leafTri));
     CK(ctx, s->dTriPlane.upload(leafPlane));
     CK(ctx, s->dLeafPrim.upload(bvh.leafPrims));
+    CK(ctx, s->dFlatRec.upload(flatRec));
+    CK(ctx, s->dFlatIdx.upload(flatIdx));
     CK(ctx, s->dVerts.upload(verts));
     CK(ctx, s->dNorms.upload(norms));
     CK(ctx, s->dNodes.upload(bvh.nodes));
@@ -603,6 +679,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     memset(&ds, 0, sizeof(ds));
     ds.triAccel = s->dTriAccel.p; ds.triPlane = s->dTriPlane.p; ds.leafPrim = s->dLeafPrim.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
     ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef; ds.rootCount = rootCount;
+    ds.flatRec = s->dFlatRec.p; ds.flatIdx = (const uint2 *) s->dFlatIdx.p; ds.flatP = flatP; ds.flatC = flatC; ds.flatS = flatS;
+    ds.flatBytes = (uint32_t) (flatRec.size() * 16);
     // gkdtree.h:1213-1220: enlarged scene box (the max side uses the already-moved min, as in the reference)
     if (nPrims == 0) { for (int a = 0; a < 3; ++a) { lo[a] = 0; hi[a] = 0; } }
     const float eps = 1e-3f;
@@ -627,6 +705,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.stageTris = rootCount ? rootCount : 0u; // a BVH's leaf-ordered head is arbitrary: only the flat leaf is worth staging
     ds.refill = 16; // measured sweep 8..32 on the material-ball and 1M-triangle scenes
     if (const char *e = getenv("B2_REFILL")) ds.refill = (uint32_t) std::max(1, std::min(32, atoi(e)));
+    ds.leafVote = 8;
+    if (const char *e = getenv("B2_LEAFVOTE")) ds.leafVote = (uint32_t) std::max(1, std::min(32, atoi(e)));
     parity::KernelSet_init(s->cfgParity, ds, ctx->numSMs);
     fast::KernelSet_init(s->cfgFast, ds, ctx->numSMs);
     CK(ctx, cudaGetLastError());

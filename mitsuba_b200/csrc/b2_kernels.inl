@@ -26,12 +26,15 @@ namespace B2_KNS {
 B2_DEV uint32_t smemAddr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
 B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t *bar) {
-    const uint32_t nb = sc.stageNodes * 64u, tb = sc.stageTris * 48u;
+    const uint32_t nb = sc.stageNodes * 64u;
     const uint32_t barA = smemAddr(bar);
 #ifdef B2_FAST_TRI
-    const float4 *triSrc = sc.triPlane;
+    // flat leaf: the paired records (never larger than the triangle list they replace); BVH: head of the plane array
+    const float4 *triSrc = sc.rootCount ? sc.flatRec : sc.triPlane;
+    const uint32_t tb = sc.rootCount ? sc.flatBytes : sc.stageTris * 48u;
 #else
     const float4 *triSrc = sc.triAccel;
+    const uint32_t tb = sc.stageTris * 48u;
 #endif
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));

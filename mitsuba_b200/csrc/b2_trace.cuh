@@ -125,6 +125,76 @@ B2_DEV bool boxHit(float bx0, float by0, float bz0, float bx1, float by1, float 
 }
 
 // Tiny scenes (DScene::rootCount > 0): every lane tests the whole shared-memory resident triangle list in lockstep.
+#ifdef B2_FAST_TRI
+// Throughput build: the list holds paired records (b2_host.cpp "flat leaf of the throughput build"): a coplanar pair of
+// triangles costs one plane test + one hit point; a parallelogram additionally shares (u, v).
+template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
+                                                             HitRec &hit, uint32_t &primTests) {
+    const uint32_t nP = sc.flatP, nC = sc.flatC, nS = sc.flatS;
+    int best = -1;
+    bool second = false;
+    const float4 *p = tm.sTris;
+#pragma unroll 4
+    for (uint32_t i = 0; i < nP; ++i, p += 3) {
+        const float4 q0 = p[0], q1 = p[1], q2 = p[2];
+        const float den = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+        const float num = q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z);
+        const float t = __fdividef(num, den);
+        const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
+        const float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+        const float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+        if ((t >= mint) & (t <= maxt) & (u >= 0.0f) & (v >= 0.0f) & (u <= 1.0f) & (v <= 1.0f)) {
+            if (SHADOW) return true;
+            hit.t = t; hit.u = u; hit.v = v; best = (int) i;
+            maxt = t;
+        }
+    }
+#pragma unroll 2
+    for (uint32_t i = 0; i < nC; ++i, p += 5) {
+        const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4];
+        const float den = q0.x * d.x + q0.y * d.y + q0.z * d.z;
+        const float num = q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z);
+        const float t = __fdividef(num, den);
+        const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
+        const float uA = q1.x * px + q1.y * py + q1.z * pz + q1.w;
+        const float vA = q2.x * px + q2.y * py + q2.z * pz + q2.w;
+        const float uB = q3.x * px + q3.y * py + q3.z * pz + q3.w;
+        const float vB = q4.x * px + q4.y * py + q4.z * pz + q4.w;
+        const bool hA = (uA >= 0.0f) & (vA >= 0.0f) & (uA + vA <= 1.0f);
+        const bool hB = (uB >= 0.0f) & (vB >= 0.0f) & (uB + vB <= 1.0f);
+        if ((t >= mint) & (t <= maxt) & (hA | hB)) {
+            if (SHADOW) return true;
+            hit.t = t; hit.u = hB ? uB : uA; hit.v = hB ? vB : vA; best = (int) (nP + i); second = hB;
+            maxt = t;
+        }
+    }
+#pragma unroll 2
+    for (uint32_t i = 0; i < nS; ++i, p += 3) {
+        const float4 q0 = p[0], q1 = p[1], q2 = p[2];
+        float tu, tv, tt;
+        if (triPlaneIntersect(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
+            if (SHADOW) return true;
+            hit.t = tt; hit.u = tu; hit.v = tv; best = (int) (nP + nC + i); second = false;
+            maxt = tt;
+        }
+    }
+    if (COUNT) primTests += sc.rootCount;
+    if (best < 0) return false;
+    const uint2 id = __ldg(sc.flatIdx + best);
+    uint32_t leaf = id.x;
+    if ((uint32_t) best < nP) {
+        // the record's frame starts at the unshared corner of the first triangle: pick the half, then evaluate that
+        // triangle's own barycentrics at the hit point
+        if (hit.u + hit.v > 1.0f) leaf = id.y;
+        const float4 r1 = __ldg(sc.triPlane + 3 * leaf + 1), r2 = __ldg(sc.triPlane + 3 * leaf + 2);
+        const float px = o.x + hit.t * d.x, py = o.y + hit.t * d.y, pz = o.z + hit.t * d.z;
+        hit.u = r1.x * px + r1.y * py + r1.z * pz + r1.w;
+        hit.v = r2.x * px + r2.y * py + r2.z * pz + r2.w;
+    } else if (second) leaf = id.y;
+    hit.prim = __ldg(sc.leafPrim + leaf);
+    return true;
+}
+#else
 template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
                                                              HitRec &hit, uint32_t &primTests) {
     const uint32_t n = sc.rootCount;
@@ -146,6 +216,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, co
     if (found) hit.prim = __ldg(sc.leafPrim + best);
     return found;
 }
+#endif
 
 // Returns true if something was hit.  Closest: fills `hit`; SHADOW: returns at the first hit.
 template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
@@ -235,6 +306,7 @@ B2_DEV void traverseQueue(const DScene &sc, const TraceMem &tm, uint32_t n, unsi
     hit.t = B2_INF; hit.u = 0; hit.v = 0; hit.prim = 0xFFFFFFFFu;
     int sp = 0, ref = 0;
     const int refill = (int) sc.refill;
+    const int leafVote = (int) sc.leafVote;
     // tickets a warp reserves per atomic: 128 for big launches, down to 32 so that small launches still spread over the grid
     const unsigned warpsInGrid = gridDim.x * (blockDim.x >> 5);
     const unsigned long long CHUNK = (unsigned long long) min(128u, max(32u, (n / (4u * warpsInGrid)) & ~31u));
@@ -288,8 +360,17 @@ B2_DEV void traverseQueue(const DScene &sc, const TraceMem &tm, uint32_t n, unsi
                 continue;
             }
         }
-        if (active) {
-            if (ref >= 0) {
+        // ---- node phase ("while-while" with a vote): lanes standing on an inner node keep descending; lanes that reached
+        // a leaf wait, so that the leaf code below runs with many lanes instead of 2-3.  The phase ends when enough lanes
+        // wait at a leaf, nobody is on a node any more, or enough lanes went idle to make a refill worthwhile.
+        while (true) {
+            const bool atNode = active && ref >= 0;
+            const unsigned nm = __ballot_sync(FULL, atNode);
+            if (nm == 0) break;
+            const unsigned lm = __ballot_sync(FULL, active && ref < 0);
+            if (__popc(lm) >= leafVote) break;
+            if (!exhausted && __popc(~(nm | lm)) >= refill) break;
+            if (atNode) {
                 float4 a, b, c, e;
                 if ((uint32_t) ref < tm.stageNodes) {
                     const float4 *p = tm.sNodes + 4 * ref;
@@ -309,28 +390,30 @@ B2_DEV void traverseQueue(const DScene &sc, const TraceMem &tm, uint32_t n, unsi
                     tm.stack[sp * stride] = (uint32_t) farRef;
                     ++sp;
                     ref = nearRef;
-                    continue;
-                } else if (hL) { ref = lref; continue; }
-                else if (hR) { ref = rref; continue; }
-            } else {
-                const uint32_t bits = ~(uint32_t) ref;
-                const uint32_t start = bits & 0x0FFFFFFFu, count = bits >> 28;
-                for (uint32_t i = 0; i < count; ++i) {
-                    const uint32_t ti = start + i;
-                    const float4 *p = tm.gTris + 3 * (size_t) ti;
-                    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-                    if (COUNT) ++primTests;
-                    float tu, tv, tt;
-                    if (B2_TRI_TEST(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
-                        found = true;
-                        if (SHADOW) break;
-                        hit.t = tt; hit.u = tu; hit.v = tv; best = ti;
-                        maxt = tt;
-                    }
-                }
-                if (SHADOW && found) { active = false; pending = true; continue; }
+                } else if (hL) ref = lref;
+                else if (hR) ref = rref;
+                else if (sp == 0) { active = false; pending = true; }
+                else { --sp; ref = (int) tm.stack[sp * stride]; }
             }
-            if (sp == 0) { active = false; pending = true; }
+        }
+        // ---- leaf phase
+        if (active && ref < 0) {
+            const uint32_t bits = ~(uint32_t) ref;
+            const uint32_t start = bits & 0x0FFFFFFFu, count = bits >> 28;
+            for (uint32_t i = 0; i < count; ++i) {
+                const uint32_t ti = start + i;
+                const float4 *p = tm.gTris + 3 * (size_t) ti;
+                const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                if (COUNT) ++primTests;
+                float tu, tv, tt;
+                if (B2_TRI_TEST(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
+                    found = true;
+                    if (SHADOW) break;
+                    hit.t = tt; hit.u = tu; hit.v = tv; best = ti;
+                    maxt = tt;
+                }
+            }
+            if ((SHADOW && found) || sp == 0) { active = false; pending = true; }
             else { --sp; ref = (int) tm.stack[sp * stride]; }
         }
     }

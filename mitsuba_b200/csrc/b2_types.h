@@ -55,6 +55,11 @@ struct DScene {
     // (t = (d0 - N.o) / N.d, u = U.P + du, v = V.P + dv); leafPrim maps the leaf-ordered index to the prim id
     const float4 *triPlane;
     const uint32_t *leafPrim;
+    // throughput build, flat leaf only: flatP parallelogram records (3 rows), flatC coplanar pairs (5 rows), flatS single
+    // triangles (3 rows), in this order; flatIdx[r] = leaf indices of the record's first / second triangle
+    const float4 *flatRec;
+    const uint2 *flatIdx;
+    uint32_t flatP, flatC, flatS, flatBytes;
     uint32_t nLeafTris;
     const BVHNode *nodes;
     uint32_t nNodes;
@@ -81,6 +86,7 @@ struct DScene {
     const uint32_t *sobolNib;  // [1024][13][16]: XOR of the 4 columns of nibble p selected by v (b2_host.cpp: buildSobolNibbles)
     // staging limits for shared memory (number of leading BVH nodes / TriAccel records copied by TMA)
     uint32_t stageNodes, stageTris;
+    uint32_t leafVote;         // persistent traversal: run the leaf code once this many lanes wait at a leaf (B2_LEAFVOTE, default 8)
     uint32_t refill;           // persistent traversal: refill a warp when at least this many lanes are idle (B2_REFILL, default 16)
 };
 
