@@ -106,7 +106,7 @@ struct PathSampler {
             if (dim >= 1024u) { overflow = true; dim = 1023u; } // sobol.cpp:223-225 raises an error here
             return sobolSampleNib(m32, index, dim++, scramble32, nNib);
         } else {
-            uint64_t r = sampleTEA((uint32_t) index, (dim++) ^ scramble32);
+            uint64_t r = sampleTEA((uint32_t) index, (dim++) ^ scramble32, 8); // 8 rounds: 4 leave consecutive keys correlated (tests/test_oracle_volpath.py)
             uint32_t u = ((uint32_t) (r & 0xFFFFFFFFull) >> 9) | 0x3f800000u; // random.cpp:630-640
             return __uint_as_float(u) - 1.0f;
         }

@@ -25,7 +25,7 @@ NAMED_IOR = {
     "amber": 1.55, "pet": 1.5750, "diamond": 2.419,
 }
 
-BSDF_TYPES = {"diffuse": 0, "roughconductor": 1, "roughdielectric": 2, "coating": 3}
+BSDF_TYPES = {"diffuse": 0, "roughconductor": 1, "roughdielectric": 2, "coating": 3, "null": 4}
 DISTRIBUTIONS = {"beckmann": 0, "ggx": 1, "phong": 2, "as": 2}
 
 
@@ -81,6 +81,79 @@ class Bsdf:
 
 
 @dataclass
+class Medium:
+    """A participating medium plugin instance + its phase function.
+
+    `homogeneous` (src/medium/homogeneous.cpp:156-222): sigma_a / sigma_s RGB, strategy balance|single|manual.
+    `heterogeneous` (src/medium/heterogeneous.cpp:182-260, method woodcock): a float32 `gridvolume` density in [0, 1]
+    (src/volume/gridvolume.cpp), a constant albedo (`constvolume`), `scale`.  Phase: `isotropic` or `hg` (g).
+    """
+    type: str = "heterogeneous"
+    sigma_a: Sequence[float] = (0.0, 0.0, 0.0)
+    sigma_s: Sequence[float] = (0.0, 0.0, 0.0)
+    strategy: str = "balance"
+    sampling_density: float = 0.0          # strategy manual
+    channel: Optional[int] = None          # strategy single
+    medium_sampling_weight: float = -1.0
+    scale: float = 1.0
+    albedo: Sequence[float] = (0.75, 0.75, 0.75)
+    density: Optional[np.ndarray] = None   # (nz, ny, nx) float32 in [0, 1]
+    aabb_min: Sequence[float] = (0.0, 0.0, 0.0)   # data box of the .vol header (gridvolume.cpp:285-292)
+    aabb_max: Sequence[float] = (1.0, 1.0, 1.0)
+    to_world: Optional[np.ndarray] = None  # gridvolume `toWorld`
+    phase: str = "isotropic"
+    g: float = 0.8                         # hg.cpp:49
+
+    def flat(self) -> dict:
+        d = dict(type={"homogeneous": 0, "heterogeneous": 1}[self.type], phase={"isotropic": 0, "hg": 1}[self.phase], g=float(self.g),
+                 sigmaA=tuple(float(x) for x in self.sigma_a), sigmaS=tuple(float(x) for x in self.sigma_s), strategy=0,
+                 samplingDensity=0.0, mediumSamplingWeight=0.0, scale=float(self.scale), albedo=tuple(float(x) for x in self.albedo),
+                 res=(0, 0, 0), worldToGrid=(0.0,) * 12, aabbMin=(0.0,) * 3, aabbMax=(0.0,) * 3, density=None)
+        if self.type == "homogeneous":
+            sa, ss = np.float32(self.sigma_a), np.float32(self.sigma_s)
+            st = sa + ss
+            w = np.float32(self.medium_sampling_weight)
+            if w == -1:  # homogeneous.cpp:168-184
+                for i in range(3):
+                    if st[i] != 0:
+                        alb = ss[i] / st[i]
+                        if alb > w:
+                            w = alb
+                if w > 0:
+                    w = max(w, np.float32(0.5))
+            d["mediumSamplingWeight"] = float(w)
+            strat = self.strategy.lower()
+            if strat == "balance":
+                d["strategy"] = 0
+            elif strat == "single":  # homogeneous.cpp:188-203: the channel with the smallest sigma_t
+                d["strategy"] = 1
+                ch = int(np.argmin(st)) if self.channel is None else int(self.channel)
+                d["samplingDensity"] = float(st[ch])
+            elif strat == "manual":
+                d["strategy"] = 2
+                d["samplingDensity"] = float(self.sampling_density)
+            else:
+                raise ValueError("Specified an unknown sampling strategy")  # `maximum` is not on the path
+        else:
+            if self.density is None:
+                raise ValueError("No density specified!")  # heterogeneous.cpp:230
+            dens = np.ascontiguousarray(self.density, np.float32)
+            nz, ny, nx = dens.shape
+            lo, hi = np.float64(self.aabb_min), np.float64(self.aabb_max)
+            v2w = np.eye(4) if self.to_world is None else np.float64(self.to_world)
+            w2v = np.linalg.inv(v2w)
+            ext = hi - lo
+            S = np.diag([(nx - 1) / ext[0], (ny - 1) / ext[1], (nz - 1) / ext[2], 1.0])
+            T = np.eye(4); T[:3, 3] = -lo
+            w2g = (S @ T @ w2v).astype(np.float32)  # gridvolume.cpp:186-193
+            corners = np.array([[x, y, z, 1.0] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+            wc = (corners @ v2w.T)[:, :3].astype(np.float32)
+            d.update(res=(nx, ny, nz), worldToGrid=tuple(float(x) for x in w2g[:3].reshape(-1)), aabbMin=tuple(float(x) for x in wc.min(0)),
+                     aabbMax=tuple(float(x) for x in wc.max(0)), density=dens)
+        return d
+
+
+@dataclass
 class Mesh:
     """A TriMesh after TriMesh::configure (normals already generated or absent = face normals)."""
     P: np.ndarray                       # (nV,3) f32
@@ -91,6 +164,8 @@ class Mesh:
     radiance: Optional[Sequence[float]] = None   # `area` emitter child (area.cpp:64-70)
     sampling_weight: float = 1.0        # emitter.cpp:103
     name: str = ""
+    interior: Optional[Medium] = None   # <ref name="interior"> (shape.cpp:160-176); with bsdf None -> `null` BSDF
+    exterior: Optional[Medium] = None
 
 
 @dataclass
@@ -146,6 +221,7 @@ class RenderParams:
     hide_emitters: bool = False
     rfilter: str = "gaussian"           # film.cpp:89-95 default
     rfilter_param: float = 0.5          # box: radius; gaussian: stddev
+    integrator: str = "path"            # "path" (path.cpp) | "volpath" (volpath.cpp)
     sample_lo: int = 0                  # shard: sample indices [lo,hi) of every pixel
     sample_hi: int = 0                  # 0 -> spp
 
@@ -174,9 +250,27 @@ class SceneDesc:
         for m in self.meshes:
             b = m.bsdf
             if b is None:  # shape.cpp:48-72
-                b = Bsdf("diffuse", reflectance=(0.0,) * 3 if m.radiance is not None else (0.5,) * 3)
+                if m.radiance is None and (m.interior is not None or m.exterior is not None):
+                    b = Bsdf("null")
+                else:
+                    b = Bsdf("diffuse", reflectance=(0.0,) * 3 if m.radiance is not None else (0.5,) * 3)
                 m.bsdf = b
             ids.append(add(b))
+        return out, ids
+
+    def flat_media(self):
+        """Unique media in first-use order; returns (list of Medium, per-mesh (interior id, exterior id))."""
+        out, memo, ids = [], {}, []
+
+        def add(md):
+            if md is None:
+                return -1
+            if id(md) not in memo:
+                memo[id(md)] = len(out); out.append(md)
+            return memo[id(md)]
+
+        for m in self.meshes:
+            ids.append((add(m.interior), add(m.exterior)))
         return out, ids
 
     def n_triangles(self) -> int:
@@ -323,3 +417,55 @@ def stress_scene(n_instances=100, n_theta=224, n_phi=224, width=2048, height=204
     cam = Camera(look_at((0, e * 0.9, -e * 1.5), (0, 0.5, 0), (0, 1, 0)), fov=45.0, near=0.1, far=1000.0,
                  width=width, height=height)
     return SceneDesc(meshes, cam)
+
+
+def cube_mesh(lo, hi):
+    """Axis-aligned box with outward-facing triangles (12 triangles, 8 shared vertices)."""
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    P = np.array([[x, y, z] for z in (lo[2], hi[2]) for y in (lo[1], hi[1]) for x in (lo[0], hi[0])], np.float32)
+    quads = [(0, 2, 3, 1), (4, 5, 7, 6), (0, 1, 5, 4), (2, 6, 7, 3), (0, 4, 6, 2), (1, 3, 7, 5)]
+    idx = []
+    c = (lo + hi) / 2
+    for q in quads:
+        for tri in ((q[0], q[1], q[2]), (q[0], q[2], q[3])):
+            n = np.cross(P[tri[1]] - P[tri[0]], P[tri[2]] - P[tri[0]])
+            if np.dot(n, P[list(tri)].mean(0) - c) < 0:
+                tri = tri[::-1]
+            idx.append(tri)
+    return P, np.array(idx, np.uint32)
+
+
+def smoke_density(res=128, seed=3) -> np.ndarray:
+    """Procedural smoke in [0, 1]: a soft blob modulated by a few sinusoidal octaves ((nz, ny, nx) float32)."""
+    rng = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(*(np.linspace(0, 1, res, dtype=np.float32),) * 3, indexing="ij")
+    r2 = (x - 0.5) ** 2 + (y - 0.45) ** 2 * 0.8 + (z - 0.5) ** 2
+    d = np.exp(-r2 / 0.045).astype(np.float32)
+    for k in range(1, 5):
+        f = rng.uniform(2.0, 5.0, 3) * k
+        ph = rng.uniform(0, 2 * math.pi, 3)
+        d *= (1.0 + 0.45 / k * np.sin(f[0] * x * 2 * math.pi + ph[0]) * np.sin(f[1] * y * 2 * math.pi + ph[1]) * np.sin(f[2] * z * 2 * math.pi + ph[2])).astype(np.float32)
+    d = np.clip(d / d.max(), 0.0, 1.0)
+    d[d < 0.02] = 0.0
+    return np.ascontiguousarray(d, np.float32)
+
+
+def smoke_scene(width=512, height=512, res=128, scale=24.0, albedo=(0.9, 0.9, 0.9), phase="isotropic", g=0.0, density=None) -> SceneDesc:
+    """S4 (config 4): a res^3 density grid in the unit cube, `heterogeneous` Woodcock medium behind an index-matched
+    (BSDF-less) cube, on a diffuse floor under one area light."""
+    dens = smoke_density(res) if density is None else density
+    med = Medium("heterogeneous", scale=scale, albedo=albedo, density=dens, aabb_min=(0, 0, 0), aabb_max=(1, 1, 1), phase=phase, g=g)
+    meshes = []
+    P, I = _quad([(-3, 0, -3), (-3, 0, 4), (4, 0, 4), (4, 0, -3)], (0, 1, 0))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0.45, 0.45, 0.45)), name="floor"))
+    P, I = _quad([(-3, 0, 4), (-3, 5, 4), (4, 5, 4), (4, 0, 4)], (0, 0, -1))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0.3, 0.35, 0.5)), name="backdrop"))
+    P, I = cube_mesh((0, 0.001, 0), (1, 1.001, 1))
+    meshes.append(Mesh(P, I, bsdf=None, interior=med, name="smoke-bounds"))
+    P, I = _quad([(-0.4, 2.6, -0.2), (-0.4, 2.6, 0.9), (0.9, 2.6, 0.9), (0.9, 2.6, -0.2)], (0, -1, 0))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(30.0, 28.0, 24.0), name="light"))
+    cam = Camera(look_at((0.5, 1.1, -2.6), (0.5, 0.5, 0.5), (0, 1, 0)), fov=36.0, near=0.05, far=100.0, width=width, height=height)
+    sd = SceneDesc(meshes, cam)
+    # the grid sits in the cube that bounds it: data box = the cube (offset by the 1 mm lift)
+    med.aabb_min, med.aabb_max = (0.0, 0.001, 0.0), (1.0, 1.001, 1.0)
+    return sd

@@ -19,6 +19,7 @@
 #include "orc_sampler.h"
 #include "orc_accel.h"
 #include "orc_bsdf.h"
+#include "orc_medium.h"
 #include <thread>
 #include <atomic>
 #include <mutex>
@@ -38,6 +39,7 @@ typedef struct OrcRenderParams {
     int32_t sampleLo, sampleHi; /* render sample indices [lo,hi) of every pixel (multi-GPU sharding mirror); hi<=0 -> spp */
     int32_t threads;        /* 0 -> hardware_concurrency */
     int32_t blockSize;      /* scene.cpp:24 default 32 */
+    int32_t integrator;     /* 0 path (path.cpp), 1 volpath (volpath.cpp) */
 } OrcRenderParams;
 typedef struct OrcStats {
     uint64_t samples, rays, shadowRays, pathLengthSum, nodeVisits, primTests, badSamples, dimOverflow;
@@ -52,6 +54,8 @@ struct Mesh {
     std::vector<V3> dpdu;      /* per triangle, only if UVs exist (trimesh.cpp:683-735) */
     std::vector<uint8_t> hasTangent;
     int bsdf = -1; int emitter = -1;
+    int interior = -1, exterior = -1; /* shape.h:427-435 media ids (-1 = vacuum) */
+    bool isMediumTransition() const { return interior >= 0 || exterior >= 0; }
     uint32_t primOffset = 0;
     /* area sampling: trimesh.cpp:388-403 + pmf.h */
     std::vector<float> cdf; float surfaceArea = -1, invSurfaceArea = 0;
@@ -106,6 +110,8 @@ struct Scene {
     std::vector<OrcBsdf> bsdfs;
     std::vector<Mesh> meshes;
     std::vector<Emitter> emitters;
+    std::vector<OrcMedium> media;
+    std::vector<std::vector<float>> mediaData; /* owned copies of the density grids */
     std::vector<uint32_t> primMesh; /* prim -> mesh (m_shapeMap) */
     Accel accel;
     Discrete emitterPDF;
@@ -201,7 +207,7 @@ struct Scene {
         return emitters[e].radiance;
     }
     /* scene.cpp:828-852 with testVisibility=true; returns value, fills dRec; `occl` counts shadow rays */
-    Spectrum sampleEmitterDirect(DRec &dRec, float sx, float sy, OrcStats &st) const {
+    Spectrum sampleEmitterDirect(DRec &dRec, float sx, float sy, OrcStats &st, bool testVisibility = true, float *emPdfOut = nullptr) const {
         float emPdf;
         size_t index = emitterPDF.sampleReuse(sx, emPdf);
         const Emitter &em = emitters[index];
@@ -231,6 +237,11 @@ struct Scene {
         Spectrum value;
         if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) value = em.radiance / dRec.pdf;
         else { dRec.pdf = 0.0f; value = Spectrum(0.0f); }
+        if (!testVisibility) { /* sampleAttenuatedEmitterDirect (scene.cpp:854-898): the caller applies transmittance / emPdf */
+            dRec.emitter = (int) index;
+            if (emPdfOut) *emPdfOut = emPdf;
+            return value;
+        }
         if (dRec.pdf != 0) {
             Ray ray(dRec.ref, dRec.d, kEpsilon, dRec.dist * (1 - kShadowEpsilon));
             ++st.shadowRays;
@@ -347,6 +358,230 @@ struct Scene {
         return Li;
     }
 
+
+    /* ---------------------------------------------------------------------------------------------------------
+     * volpath: src/integrators/path/volpath.cpp:84-366 (Li), :368-426 (rayIntersectAndLookForEmitter),
+     * Scene::evalTransmittance scene.cpp:619-679, Scene::sampleAttenuatedEmitterDirect scene.cpp:854-898
+     * --------------------------------------------------------------------------------------------------------- */
+    int targetMedium(const Mesh &m, const V3 &geoN, const V3 &d) const { /* records.inl:81-86 */
+        return dot(d, geoN) > 0 ? m.exterior : m.interior;
+    }
+    /* ShapeKDTree::rayIntersect(ray, t, shape, n, uv), skdtree.cpp:144-204: closest hit, epsilon scale without the
+       inner max, unflipped face normal */
+    bool rayIntersectNormal(const Ray &ray, float &t, int &mesh, V3 &n, OrcStats &st) const {
+        float mint, maxt;
+        t = kInf;
+        ++st.shadowRays;
+        if (accel.aabb.rayIntersect(ray, mint, maxt)) {
+            float rayMinT = ray.mint;
+            if (rayMinT == kEpsilon) rayMinT *= std::max(std::max(std::abs(ray.o.x), std::abs(ray.o.y)), std::abs(ray.o.z));
+            if (rayMinT > mint) mint = rayMinT;
+            if (ray.maxt < maxt) maxt = ray.maxt;
+            if (maxt > mint) {
+                Hit h;
+                if (accel.query<false>(ray, mint, maxt, h, &st.nodeVisits, &st.primTests)) {
+                    t = h.t;
+                    const uint32_t mi = accel.tri[h.prim].shapeIndex, pi = accel.tri[h.prim].primIndex;
+                    const Mesh &m = meshes[mi];
+                    const V3 &p0 = m.P[m.idx[3 * pi]], &p1 = m.P[m.idx[3 * pi + 1]], &p2 = m.P[m.idx[3 * pi + 2]];
+                    n = normalize(cross(p1 - p0, p2 - p0));
+                    mesh = (int) mi;
+                    return true;
+                }
+            }
+        }
+        return false;
+    }
+    Spectrum evalTransmittance(const V3 &p1, bool p1OnSurface, const V3 &p2, bool p2OnSurface, int medium, int &interactions,
+                               Sampler *sampler, OrcStats &st) const {
+        BsdfSet bs{bsdfs.data(), (int) bsdfs.size()};
+        V3 d = p2 - p1;
+        float remaining = d.length();
+        d /= remaining;
+        float lengthFactor = p2OnSurface ? (1 - kShadowEpsilon) : 1;
+        Ray ray(p1, d, p1OnSurface ? kEpsilon : 0, remaining * lengthFactor);
+        Spectrum transmittance(1.0f);
+        int maxInteractions = interactions;
+        interactions = 0;
+        while (remaining > 0) {
+            float t; int mesh = -1; V3 n;
+            bool surface = rayIntersectNormal(ray, t, mesh, n, st);
+            if (surface && (interactions == maxInteractions || !(bs.type(meshes[mesh].bsdf) & ENull))) return Spectrum(0.0f);
+            if (medium >= 0)
+                transmittance *= MediumEval(media[medium]).evalTransmittance(Ray(ray.o, ray.d, 0, std::min(t, remaining)), sampler);
+            if (!surface || transmittance.isZero()) break;
+            /* null BSDF: eval(bRec, EDiscrete) with typeMask = ENull is 1 (null.cpp:45-47) */
+            const Mesh &m = meshes[mesh];
+            if (m.isMediumTransition()) {
+                if (medium != targetMedium(m, n, -d)) return Spectrum(0.0f); /* mediumInconsistencies */
+                medium = targetMedium(m, n, d);
+            }
+            if (++interactions > 100) break;
+            ray.o = ray(t);
+            remaining -= t;
+            ray.maxt = remaining * lengthFactor;
+            ray.mint = kEpsilon;
+        }
+        return transmittance;
+    }
+    void rayIntersectAndLookForEmitter(Sampler *sampler, int medium, int maxInteractions, Ray ray, Intersection &_its, DRec &dRec,
+                                       Spectrum &value, OrcStats &st) const {
+        BsdfSet bs{bsdfs.data(), (int) bsdfs.size()};
+        Intersection its2, *its = &_its;
+        Spectrum transmittance(1.0f);
+        bool surface = false;
+        int interactions = 0;
+        while (true) {
+            surface = rayIntersect(ray, *its, st);
+            if (medium >= 0)
+                transmittance *= MediumEval(media[medium]).evalTransmittance(Ray(ray.o, ray.d, 0, its->t), sampler);
+            if (surface && (interactions == maxInteractions || !(bs.type(meshes[its->mesh].bsdf) & ENull) || meshes[its->mesh].emitter >= 0)) break;
+            if (!surface) break;
+            if (transmittance.isZero()) return;
+            const Mesh &m = meshes[its->mesh];
+            if (m.isMediumTransition()) medium = targetMedium(m, its->geoFrame.n, ray.d);
+            /* transmittance *= bsdf->eval(bRec, EDiscrete) = 1 for the null BSDF */
+            ray.o = ray(its->t);
+            ray.mint = kEpsilon;
+            its = &its2;
+            if (++interactions > 100) return;
+        }
+        if (surface) {
+            const Mesh &m = meshes[its->mesh];
+            if (m.emitter >= 0) {
+                /* dRec.setQuery(ray, its): records.inl:171-179 */
+                dRec.p = its->p; dRec.n = its->shFrame.n; dRec.solidAngle = true; dRec.emitter = m.emitter;
+                dRec.d = ray.d; dRec.dist = its->t;
+                value = transmittance * emitterEval(m.emitter, *its, -ray.d);
+            }
+        }
+    }
+    Spectrum LiVol(const Ray &r, Sampler *sampler, const OrcRenderParams &rp, float &alpha, OrcStats &st) const {
+        BsdfSet bs{bsdfs.data(), (int) bsdfs.size()};
+        Intersection its;
+        Ray ray(r);
+        Spectrum Li(0.0f);
+        float eta = 1.0f;
+        int depth = 1;
+        int medium = -1;                        /* sensor medium: vacuum (a camera inside a medium is not in scope) */
+        bool emittedRadiance = true;            /* EEmittedRadiance bit of rRec.type */
+        rayIntersect(ray, its, st);
+        alpha = its.isValid() ? 1.0f : 0.0f;    /* Simpson-integrated opacity of index-matched boundaries not restated */
+        Spectrum throughput(1.0f);
+        bool scattered = false;
+        const int maxDepth = rp.maxDepth, rrDepth = rp.rrDepth;
+        while (depth <= maxDepth || maxDepth < 0) {
+            MediumSamplingRecord mRec;
+            if (medium >= 0 && MediumEval(media[medium]).sampleDistance(Ray(ray.o, ray.d, 0, its.t), mRec, sampler)) {
+                MediumEval me(media[medium]);
+                if (depth >= maxDepth && maxDepth != -1) break;
+                throughput *= mRec.sigmaS * mRec.transmittance / mRec.pdfSuccess;
+                /* luminaire sampling */
+                DRec dRec; dRec.ref = mRec.p; dRec.refN = V3(0.0f);
+                if (!emitters.empty()) {
+                    int interactions = maxDepth - depth - 1;
+                    float sx, sy; sampler->next2D(sx, sy);
+                    float emPdf = 1;
+                    Spectrum value = sampleEmitterDirect(dRec, sx, sy, st, false, &emPdf);
+                    if (dRec.pdf != 0) {
+                        value *= evalTransmittance(dRec.ref, false, dRec.p, true, medium, interactions, sampler, st) / emPdf;
+                        dRec.pdf *= emPdf;
+                    } else value = Spectrum(0.0f);
+                    if (!value.isZero()) {
+                        float phaseVal = me.phaseEval(-ray.d, dRec.d);
+                        if (phaseVal != 0) {
+                            float phasePdf = phaseVal; /* PhaseFunction::pdf = eval (phase.cpp:21-23); area emitter: on surface, solid angle */
+                            const float weight = miWeight(dRec.pdf, phasePdf);
+                            Li += throughput * value * phaseVal * weight;
+                        }
+                    }
+                }
+                /* phase function sampling */
+                float phasePdf; V3 wo;
+                float phaseVal = me.phaseSample(-ray.d, wo, phasePdf, sampler);
+                if (phaseVal == 0) break;
+                throughput *= phaseVal;
+                ray = Ray(mRec.p, wo, 0, kInf);
+                Spectrum value(0.0f);
+                rayIntersectAndLookForEmitter(sampler, medium, maxDepth - depth - 1, ray, its, dRec, value, st);
+                if (!value.isZero()) {
+                    const float emitterPdf = pdfEmitterDirect(dRec);
+                    Li += throughput * value * miWeight(phasePdf, emitterPdf);
+                }
+                emittedRadiance = false;
+            } else {
+                if (medium >= 0) throughput *= mRec.transmittance / mRec.pdfFailure;
+                if (!its.isValid()) break; /* no environment emitter */
+                const Mesh &mesh = meshes[its.mesh];
+                const int bsdf = mesh.bsdf;
+                if (mesh.emitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered))
+                    Li += throughput * emitterEval(mesh.emitter, its, -ray.d);
+                if (depth >= maxDepth && maxDepth != -1) break;
+                float wiDotGeoN = -dot(its.geoFrame.n, ray.d), wiDotShN = Frame::cosTheta(its.wi);
+                if (wiDotGeoN * wiDotShN < 0 && rp.strictNormals) break;
+                const uint32_t btype = bs.type(bsdf);
+                DRec dRec; dRec.ref = its.p; dRec.refN = V3(0.0f);
+                if ((btype & (ETransmission | EBackSide)) == 0) dRec.refN = its.shFrame.n;
+                if (!emitters.empty() && (btype & ESmooth)) {
+                    int interactions = maxDepth - depth - 1;
+                    float sx, sy; sampler->next2D(sx, sy);
+                    float emPdf = 1;
+                    Spectrum value = sampleEmitterDirect(dRec, sx, sy, st, false, &emPdf);
+                    if (dRec.pdf != 0) {
+                        int med = medium;
+                        if (mesh.isMediumTransition()) med = targetMedium(mesh, its.geoFrame.n, dRec.d);
+                        value *= evalTransmittance(its.p, true, dRec.p, true, med, interactions, sampler, st) / emPdf;
+                        dRec.pdf *= emPdf;
+                    } else value = Spectrum(0.0f);
+                    if (!value.isZero()) {
+                        BRec bRec; bRec.wi = its.wi; bRec.wo = its.shFrame.toLocal(dRec.d); bRec.sampler = sampler;
+                        const Spectrum bsdfVal = bs.eval(bsdf, bRec);
+                        float woDotGeoN = dot(its.geoFrame.n, dRec.d);
+                        if (!bsdfVal.isZero() && (!rp.strictNormals || woDotGeoN * Frame::cosTheta(bRec.wo) > 0)) {
+                            float bsdfPdf = bs.pdf(bsdf, bRec);
+                            const float weight = miWeight(dRec.pdf, bsdfPdf);
+                            Li += throughput * value * bsdfVal * weight;
+                        }
+                    }
+                }
+                /* BSDF sampling */
+                BRec bRec; bRec.wi = its.wi; bRec.sampler = sampler;
+                float bsdfPdf;
+                float sx, sy; sampler->next2D(sx, sy);
+                Spectrum bsdfWeight = bs.sample(bsdf, bRec, bsdfPdf, sx, sy);
+                if (bsdfWeight.isZero()) break;
+                const V3 wo = its.shFrame.toWorld(bRec.wo);
+                float woDotGeoN = dot(its.geoFrame.n, wo);
+                if (woDotGeoN * Frame::cosTheta(bRec.wo) <= 0 && rp.strictNormals) break;
+                ray = Ray(its.p, wo);
+                throughput *= bsdfWeight;
+                eta *= bRec.eta;
+                if (mesh.isMediumTransition()) medium = targetMedium(mesh, its.geoFrame.n, ray.d);
+                if (bRec.sampledType == ENull) {
+                    emittedRadiance = !scattered; /* rRec.type = scattered ? ERadianceNoEmission : ERadiance */
+                    rayIntersect(ray, its, st);
+                    depth++;
+                    continue;
+                }
+                Spectrum value(0.0f);
+                rayIntersectAndLookForEmitter(sampler, medium, maxDepth - depth - 1, ray, its, dRec, value, st);
+                if (!value.isZero()) {
+                    const float emitterPdf = (!(bRec.sampledType & EDelta)) ? pdfEmitterDirect(dRec) : 0;
+                    Li += throughput * value * miWeight(bsdfPdf, emitterPdf);
+                }
+                emittedRadiance = false;
+            }
+            if (depth++ >= rrDepth) {
+                float q = std::min(throughput.max() * eta * eta, 0.95f);
+                if (sampler->next1D() >= q) break;
+                throughput /= q;
+            }
+            scattered = true;
+        }
+        st.pathLengthSum += (uint64_t) depth;
+        return Li;
+    }
+
     /* perspective.cpp:271-298 (ray part only; differentials unused by constant textures) */
     Ray sampleRay(float sxp, float syp) const {
         const float *M = sampleToCamera;
@@ -454,6 +689,64 @@ int orc_add_mesh(void *s, const float *P, const float *N, const float *UV, uint3
     sc->meshes.push_back(std::move(m));
     return (int) sc->meshes.size() - 1;
 }
+/* Medium plugin instance (homogeneous / heterogeneous + phase function); the density grid is copied */
+int orc_add_medium(void *s, const OrcMedium *m) {
+    Scene *sc = (Scene *) s;
+    OrcMedium mm = *m;
+    sc->mediaData.emplace_back();
+    if (m->type == 1 && m->density) {
+        size_t n = (size_t) m->res[0] * m->res[1] * m->res[2];
+        sc->mediaData.back().assign(m->density, m->density + n);
+    }
+    sc->media.push_back(mm);
+    for (size_t i = 0; i < sc->media.size(); ++i) sc->media[i].density = sc->mediaData[i].empty() ? nullptr : sc->mediaData[i].data();
+    return (int) sc->media.size() - 1;
+}
+/* <ref name="interior"/"exterior"> of a shape (shape.cpp:160-176) */
+void orc_set_mesh_media(void *s, int mesh, int interior, int exterior) {
+    Scene *sc = (Scene *) s; sc->meshes[mesh].interior = interior; sc->meshes[mesh].exterior = exterior;
+}
+/* component probes for the medium tests: n x (o, d, mint, maxt) rays */
+void orc_medium_transmittance(void *s, int medium, uint64_t n, const float *rays, uint64_t seed, float *out) {
+    Scene *sc = (Scene *) s;
+    CounterSampler smp(1 << 16, 1, seed);
+    for (uint64_t i = 0; i < n; ++i) {
+        smp.generate((int) (i & 0xFFFF), (int) (i >> 16));
+        const float *r = rays + 8 * i;
+        Spectrum t = MediumEval(sc->media[medium]).evalTransmittance(Ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7]), &smp);
+        out[3 * i] = t.x; out[3 * i + 1] = t.y; out[3 * i + 2] = t.z;
+    }
+}
+void orc_medium_sample_distance(void *s, int medium, uint64_t n, const float *rays, uint64_t seed, float *out /* n x 12: ok, t, sigmaS rgb, transmittance rgb, pdfSuccess, pdfFailure, sigmaA.r, pad */) {
+    Scene *sc = (Scene *) s;
+    CounterSampler smp(1 << 16, 1, seed);
+    for (uint64_t i = 0; i < n; ++i) {
+        smp.generate((int) (i & 0xFFFF), (int) (i >> 16));
+        const float *r = rays + 8 * i;
+        MediumSamplingRecord mRec;
+        bool ok = MediumEval(sc->media[medium]).sampleDistance(Ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7]), mRec, &smp);
+        float *o = out + 12 * i;
+        o[0] = ok ? 1.0f : 0.0f; o[1] = mRec.t; o[2] = mRec.sigmaS.x; o[3] = mRec.sigmaS.y; o[4] = mRec.sigmaS.z;
+        o[5] = mRec.transmittance.x; o[6] = mRec.transmittance.y; o[7] = mRec.transmittance.z; o[8] = mRec.pdfSuccess; o[9] = mRec.pdfFailure;
+        o[10] = mRec.sigmaA.x; o[11] = 0;
+    }
+}
+void orc_medium_density(void *s, int medium, uint64_t n, const float *p, float *out) {
+    Scene *sc = (Scene *) s;
+    for (uint64_t i = 0; i < n; ++i) out[i] = MediumEval(sc->media[medium]).lookupDensity(V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+}
+void orc_phase(void *s, int medium, uint64_t n, const float *wi, const float *samples, float *out /* n x 5: wo xyz, pdf, eval(wi, wo) */) {
+    Scene *sc = (Scene *) s;
+    for (uint64_t i = 0; i < n; ++i) {
+        struct Two : Sampler { float a, b; int k = 0; void generate(int, int) override {} void advance() override {}
+            float next1D() override { return (k++ & 1) ? b : a; } void next2D(float &x, float &y) override { x = a; y = b; } } two;
+        two.a = samples[2 * i]; two.b = samples[2 * i + 1];
+        MediumEval me(sc->media[medium]);
+        V3 w(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), wo; float pdf;
+        me.phaseSample(w, wo, pdf, &two);
+        float *o = out + 5 * i; o[0] = wo.x; o[1] = wo.y; o[2] = wo.z; o[3] = pdf; o[4] = me.phaseEval(w, wo);
+    }
+}
 void orc_set_camera(void *s, const float *camToWorld, const float *sampleToCamera, float nearClip, float farClip, int W, int H) {
     Scene *sc = (Scene *) s;
     memcpy(sc->camToWorld, camToWorld, 64); memcpy(sc->sampleToCamera, sampleToCamera, 64);
@@ -548,7 +841,7 @@ static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcSt
                         float spx = (float) x + ax, spy = (float) y + ay;
                         Ray ray = sc->sampleRay(spx, spy);
                         float alpha;
-                        Spectrum spec = sc->Li(ray, sampler.get(), *rp, alpha, st); /* sensor weight = 1 */
+                        Spectrum spec = rp->integrator == 1 ? sc->LiVol(ray, sampler.get(), *rp, alpha, st) : sc->Li(ray, sampler.get(), *rp, alpha, st); /* sensor weight = 1 */
                         if (!blk->put(spx, spy, spec, alpha)) ++st.badSamples;
                         if (perSample) {
                             float *o = perSample + (((size_t) y * W + x) * (size_t) (hi - lo) + (size_t) (j - lo)) * 4;

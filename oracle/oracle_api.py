@@ -28,7 +28,14 @@ class OrcRenderParams(C.Structure):
     _fields_ = [("spp", C.c_int32), ("sampler", C.c_int32), ("seed", C.c_uint64), ("maxDepth", C.c_int32),
                 ("rrDepth", C.c_int32), ("strictNormals", C.c_int32), ("hideEmitters", C.c_int32),
                 ("rfilter", C.c_int32), ("rfilterParam", C.c_float), ("sampleLo", C.c_int32), ("sampleHi", C.c_int32),
-                ("threads", C.c_int32), ("blockSize", C.c_int32)]
+                ("threads", C.c_int32), ("blockSize", C.c_int32), ("integrator", C.c_int32)]
+
+
+class OrcMedium(C.Structure):
+    _fields_ = [("type", C.c_int32), ("phase", C.c_int32), ("g", C.c_float), ("sigmaA", C.c_float * 3), ("sigmaS", C.c_float * 3),
+                ("strategy", C.c_int32), ("samplingDensity", C.c_float), ("mediumSamplingWeight", C.c_float), ("scale", C.c_float),
+                ("albedo", C.c_float * 3), ("res", C.c_int32 * 3), ("worldToGrid", C.c_float * 12), ("aabbMin", C.c_float * 3),
+                ("aabbMax", C.c_float * 3), ("density", C.POINTER(C.c_float))]
 
 
 class OrcStats(C.Structure):
@@ -41,7 +48,7 @@ class OrcStats(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "_build", "libmtsoracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("mts_oracle.cpp", "orc_math.h", "orc_sampler.h", "orc_accel.h", "orc_bsdf.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("mts_oracle.cpp", "orc_math.h", "orc_sampler.h", "orc_accel.h", "orc_bsdf.h", "orc_medium.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
     return so
@@ -55,6 +62,7 @@ def lib():
         L.orc_scene_new.restype = C.c_void_p
         L.orc_add_bsdf.restype = C.c_int
         L.orc_add_mesh.restype = C.c_int
+        L.orc_add_medium.restype = C.c_int
         L.orc_tea.restype = C.c_uint64
         L.orc_bsdf_type.restype = C.c_uint32
         L.orc_hardware_threads.restype = C.c_int
@@ -90,6 +98,21 @@ def make_bsdf_array(flat_list):
     return arr
 
 
+def make_medium(d):
+    m = OrcMedium()
+    m.type, m.phase, m.g, m.strategy = d["type"], d["phase"], d["g"], d["strategy"]
+    m.samplingDensity, m.mediumSamplingWeight, m.scale = d["samplingDensity"], d["mediumSamplingWeight"], d["scale"]
+    for k in ("sigmaA", "sigmaS", "albedo", "aabbMin", "aabbMax"):
+        for j in range(3):
+            getattr(m, k)[j] = d[k][j]
+    for j in range(3):
+        m.res[j] = d["res"][j]
+    for j in range(12):
+        m.worldToGrid[j] = d["worldToGrid"][j]
+    m.density = d["density"].ctypes.data_as(C.POINTER(C.c_float)) if d["density"] is not None else None
+    return m
+
+
 SAMPLERS = {"sobol": 0, "independent_sfmt": 1, "independent": 2}
 RFILTERS = {"box": 0, "gaussian": 1}
 
@@ -104,6 +127,7 @@ def make_params(rp, threads=0, sampler=None):
     p.rfilter, p.rfilterParam = RFILTERS[rp.rfilter], rp.rfilter_param
     p.sampleLo, p.sampleHi = rp.sample_lo, rp.sample_hi
     p.threads, p.blockSize = threads, 32
+    p.integrator = {"path": 0, "volpath": 1}[getattr(rp, "integrator", "path")]
     return p
 
 
@@ -130,6 +154,13 @@ class OracleScene:
             rad = np.asarray(m.radiance, np.float32) if m.radiance is not None else None
             L.orc_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
                            C.c_int(bid), _p(rad), C.c_float(m.sampling_weight))
+        media, mids = desc.flat_media()
+        self.flat_media = [md.flat() for md in media]
+        for d in self.flat_media:
+            L.orc_add_medium(self.h, C.byref(make_medium(d)))
+        for i, (mi, me) in enumerate(mids):
+            if mi >= 0 or me >= 0:
+                L.orc_set_mesh_media(self.h, C.c_int(i), C.c_int(mi), C.c_int(me))
         cam = desc.camera
         self.W, self.H = cam.width, cam.height
         c2w = np.ascontiguousarray(cam.to_world, np.float32)
@@ -187,6 +218,32 @@ class OracleScene:
         out = np.zeros(ndim, np.float32)
         self.L.orc_sampler_stream(self.h, C.c_int(SAMPLERS[kind]), C.c_uint64(seed), C.c_int(self.W), C.c_int(self.H),
                                   C.c_int(spp), C.c_int(px), C.c_int(py), C.c_int(sample_idx), C.c_int(ndim), _p(out))
+        return out
+
+    # ---- medium component probes (tests/test_oracle_volpath.py, tests/test_gpu_volpath.py) ----
+    def medium_transmittance(self, medium, rays, seed=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        out = np.zeros((len(rays), 3), np.float32)
+        self.L.orc_medium_transmittance(self.h, C.c_int(medium), C.c_uint64(len(rays)), _p(rays), C.c_uint64(seed), _p(out))
+        return out
+
+    def medium_sample_distance(self, medium, rays, seed=0):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        out = np.zeros((len(rays), 12), np.float32)
+        self.L.orc_medium_sample_distance(self.h, C.c_int(medium), C.c_uint64(len(rays)), _p(rays), C.c_uint64(seed), _p(out))
+        return out
+
+    def medium_density(self, medium, p):
+        p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)
+        out = np.zeros(len(p), np.float32)
+        self.L.orc_medium_density(self.h, C.c_int(medium), C.c_uint64(len(p)), _p(p), _p(out))
+        return out
+
+    def phase(self, medium, wi, samples):
+        wi = np.ascontiguousarray(wi, np.float32).reshape(-1, 3)
+        samples = np.ascontiguousarray(samples, np.float32).reshape(-1, 2)
+        out = np.zeros((len(wi), 5), np.float32)
+        self.L.orc_phase(self.h, C.c_int(medium), C.c_uint64(len(wi)), _p(wi), _p(samples), _p(out))
         return out
 
     def render(self, rp, threads=0, sampler=None, per_sample=False):

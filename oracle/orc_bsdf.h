@@ -11,7 +11,7 @@
 extern "C" {
 /* plain-C description of one BSDF node; `nested` indexes the same array (coating only) */
 typedef struct OrcBsdf {
-    int32_t type;          /* 0 diffuse, 1 roughconductor, 2 roughdielectric, 3 coating */
+    int32_t type;          /* 0 diffuse, 1 roughconductor, 2 roughdielectric, 3 coating, 4 null (index-matched boundary, src/bsdfs/null.cpp) */
     int32_t distr;         /* 0 beckmann, 1 ggx, 2 phong/as   (microfacet.h:48-57) */
     int32_t sampleVisible; /* microfacet.h:138 default true; forced false for phong :145-148 */
     int32_t nested;        /* coating: index of the nested BSDF; else -1 */
@@ -241,6 +241,7 @@ struct BsdfSet {
             case 0: return (std::max(std::max(d.reflectance[0], d.reflectance[1]), d.reflectance[2]) > 0) ? (EDiffuseReflection | EFrontSide) : 0; /* diffuse.cpp:98-103 */
             case 1: return EGlossyReflection | EFrontSide | (d.alphaU != d.alphaV ? EAnisotropic : 0);                  /* roughconductor.cpp:229-238 */
             case 2: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide | EUsesSampler | ENonSymmetric | (d.alphaU != d.alphaV ? EAnisotropic : 0); /* roughdielectric.cpp:240-255 */
+            case 4: return ENull | EFrontSide | EBackSide;                                                              /* null.cpp:38-43 */
             default: return type(d.nested) | EDeltaReflection | EFrontSide | EBackSide;                                  /* coating.cpp:160-171 */
         }
     }
@@ -288,6 +289,7 @@ struct BsdfSet {
                 return V3(d.transmittance[0], d.transmittance[1], d.transmittance[2]) * std::abs(value * factor * factor);
             }
         }
+        case 4: return Spectrum(discrete ? 1.0f : 0.0f); /* null.cpp:45-47 (typeMask contains ENull) */
         default: { /* coating.cpp:208-248 */
             const float m_eta = d.eta, m_invEta = 1 / d.eta;
             bool sampleNested = (type(d.nested) & EAll) != 0;
@@ -364,6 +366,7 @@ struct BsdfSet {
             prob *= reflect ? F : (1 - F);
             return std::abs(prob * dwh_dwo);
         }
+        case 4: return discrete ? 1.0f : 0.0f; /* null.cpp:49-51 */
         default: { /* coating.cpp:250-286 */
             const float m_invEta = 1 / d.eta;
             bool sampleNested = (type(d.nested) & EAll) != 0;
@@ -452,6 +455,10 @@ struct BsdfSet {
             else weight *= std::abs(ds.eval(m) * ds.G(r.wi, r.wo, m) * dot(r.wi, m) / (microfacetPDF * Frame::cosTheta(r.wi)));
             pdfOut *= std::abs(dwh_dwo);
             return weight;
+        }
+        case 4: { /* null.cpp:65-76 */
+            r.wo = -r.wi; r.sampledType = ENull; r.eta = 1.0f; pdfOut = 1;
+            return Spectrum(1.0f);
         }
         default: { /* coating.cpp:288-371 */
             const float m_invEta = 1 / d.eta;
