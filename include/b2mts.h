@@ -32,7 +32,8 @@ typedef struct b2_scene b2_scene;
 /* BSDF plugins on the path.  Field meaning = the reference constructors' properties after their
  * host-side preprocessing (IOR lookup, /extEta), see src/bsdfs/{diffuse,roughconductor,
  * roughdielectric,coating}.cpp and src/bsdfs/microfacet.h:99-148. */
-enum { B2_BSDF_DIFFUSE = 0, B2_BSDF_ROUGHCONDUCTOR = 1, B2_BSDF_ROUGHDIELECTRIC = 2, B2_BSDF_COATING = 3 };
+enum { B2_BSDF_DIFFUSE = 0, B2_BSDF_ROUGHCONDUCTOR = 1, B2_BSDF_ROUGHDIELECTRIC = 2, B2_BSDF_COATING = 3,
+       B2_BSDF_NULL = 4 /* index-matched boundary, src/bsdfs/null.cpp (what Shape::configure assigns to a BSDF-less medium transition, shape.cpp:64-68) */ };
 enum { B2_DISTR_BECKMANN = 0, B2_DISTR_GGX = 1, B2_DISTR_PHONG = 2 };
 typedef struct b2_material_desc {
     int32_t type;            /* B2_BSDF_* */
@@ -48,11 +49,33 @@ typedef struct b2_material_desc {
     float sigma_a[3];        /* coating.cpp:129-130 */
 } b2_material_desc;
 
+/* Participating medium + phase function: `homogeneous` (src/medium/homogeneous.cpp:156-222, strategies
+ * balance / single / manual) or `heterogeneous` with method woodcock (src/medium/heterogeneous.cpp:182-260) over a float32
+ * `gridvolume` density in [0,1] (src/volume/gridvolume.cpp) and a constant albedo (`constvolume`); phase `isotropic` or `hg`. */
+enum { B2_MEDIUM_HOMOGENEOUS = 0, B2_MEDIUM_HETEROGENEOUS = 1 };
+enum { B2_PHASE_ISOTROPIC = 0, B2_PHASE_HG = 1 };
+typedef struct b2_medium_desc {
+    int32_t type;               /* B2_MEDIUM_* */
+    int32_t phase;              /* B2_PHASE_* */
+    float g;                    /* hg.cpp:49 */
+    float sigma_a[3], sigma_s[3]; /* homogeneous (medium.cpp:30-36) */
+    int32_t strategy;           /* homogeneous.cpp:186-222: 0 balance, 1 single, 2 manual */
+    float sampling_density;     /* single: sigma_t[channel]; manual: `samplingDensity` */
+    float medium_sampling_weight; /* homogeneous.cpp:160-183, after its max(., 0.5) clamp */
+    float scale;                /* heterogeneous.cpp:185 */
+    float albedo[3];            /* heterogeneous: constant `albedo` volume */
+    int32_t res[3];             /* grid resolution x, y, z */
+    float world_to_grid[12];    /* rows of m_worldToGrid, gridvolume.cpp:186-193 */
+    float aabb_min[3], aabb_max[3]; /* world box of the transformed data box, gridvolume.cpp:197-199 */
+    const float *density;       /* res[0]*res[1]*res[2] float32, x fastest; copied */
+} b2_medium_desc;
+
 /* Integrator + Sampler + Film/ReconstructionFilter properties that parameterise one render:
  * MonteCarloIntegrator (src/librender/integrator.cpp:190-225), SobolSampler / IndependentSampler
  * (src/samplers/sobol.cpp:86-102, independent.cpp:52-58), rfilters (src/rfilters/{box,gaussian}.cpp). */
 enum { B2_SAMPLER_SOBOL = 0, B2_SAMPLER_INDEPENDENT = 2 };
 enum { B2_RFILTER_BOX = 0, B2_RFILTER_GAUSSIAN = 1 };
+enum { B2_INTEGRATOR_PATH = 0 /* src/integrators/path/path.cpp */, B2_INTEGRATOR_VOLPATH = 1 /* src/integrators/path/volpath.cpp */ };
 typedef struct b2_render_params {
     int32_t spp;             /* sampleCount */
     int32_t sampler;         /* B2_SAMPLER_* (independent = counter-based stream) */
@@ -71,6 +94,8 @@ typedef struct b2_render_params {
     int32_t flags;           /* bit1: force unsorted shading (default: material-sorted when > 1 BSDF class);
                                 bit2: per-launch device time stamps (fills b2_stats.ms_*); bit3: plain launches + CUDA events
                                 instead of the CUDA graph; bit4: fuse the ray casts into generate/shade for tiny scenes (experiment, slower) */
+    int32_t integrator;      /* B2_INTEGRATOR_* (<integrator type="path"|"volpath">) */
+    int32_t reserved;        /* must be 0 */
 } b2_render_params;
 
 /* Counters with the meaning of the reference's statistics (path.cpp:24,290-291; skdtree.cpp:46-47) plus
@@ -111,6 +136,10 @@ int b2_scene_add_area_emitter(b2_scene *, const float radiance[3], float samplin
  * attached to exactly one mesh (area.cpp:185-199).  Returns mesh id or -1. */
 int b2_scene_add_mesh(b2_scene *, const float *P, const float *N, const float *UV, uint32_t n_vertices,
                       const uint32_t *idx, uint32_t n_triangles, int material_id, int emitter_id);
+/* Medium plugin instance -> id (>=0) or -1; <ref name="interior"/"exterior"> of a shape (shape.cpp:160-176; -1 = none).
+ * A mesh whose material is B2_BSDF_NULL is an index-matched boundary. */
+int b2_scene_add_medium(b2_scene *, const b2_medium_desc *);
+int b2_scene_set_mesh_media(b2_scene *, int mesh_id, int interior_medium, int exterior_medium);
 /* Scene::initialize (src/librender/scene.cpp:322-384): TriAccel precompute (skdtree.cpp:74-109),
  * acceleration structure build (BVH; replaces GenericKDTree::buildInternal, gkdtree.h:958-1263),
  * emitter / triangle-area CDFs (scene.cpp:375-380, trimesh.cpp:388-403), upload to HBM. */
@@ -145,6 +174,10 @@ int b2_bsdf_sample(b2_scene *, int material_id, uint64_t n, const float *wi, con
 /* Scene::sampleEmitterDirect without the visibility test folded into `visible`:
  * ref n x 6 (ref, refN), samples n x 2 -> out n x 12: d(3) dist pdf value(3) visible p(3) */
 int b2_sample_emitter_direct(b2_scene *, uint64_t n, const float *ref, const float *samples, int parity_mode, float *out);
+/* Medium components: what = 0 Medium::evalTransmittance (in n x 8 rays (o, mint, d, maxt) -> out n x 3), 1 Medium::sampleDistance
+ * (-> n x 12: ok t sigmaS(3) transmittance(3) pdfSuccess pdfFailure - -), 2 GridDataSource::lookupFloat (in n x 3 -> n),
+ * 3 PhaseFunction::sample + eval (in n x 5: wi, two uniforms -> n x 5: wo pdf eval); random numbers: counter stream `seed` */
+int b2_medium_probe(b2_scene *, int medium_id, int what, uint64_t n, const float *in, uint64_t seed, int parity_mode, float *out);
 /* The first ndim sampler outputs of (pixel, sample) as renderBlock + Li draw them */
 int b2_sampler_stream(b2_scene *, int sampler, uint64_t seed, int spp, int px, int py, int sample_idx, int ndim, float *out);
 /* primary rays (PerspectiveCameraImpl::sampleRayDifferential, perspective.cpp:271-298): pos n x 2 -> rays n x 8 */

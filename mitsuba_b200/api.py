@@ -31,7 +31,18 @@ class b2_render_params(C.Structure):
     _fields_ = [("spp", C.c_int32), ("sampler", C.c_int32), ("seed", C.c_uint64), ("max_depth", C.c_int32),
                 ("rr_depth", C.c_int32), ("strict_normals", C.c_int32), ("hide_emitters", C.c_int32),
                 ("rfilter", C.c_int32), ("rfilter_param", C.c_float), ("sample_lo", C.c_int32), ("sample_hi", C.c_int32),
-                ("parity_mode", C.c_int32), ("pool_size", C.c_int32), ("film_on_device", C.c_int32), ("flags", C.c_int32)]
+                ("parity_mode", C.c_int32), ("pool_size", C.c_int32), ("film_on_device", C.c_int32), ("flags", C.c_int32),
+                ("integrator", C.c_int32), ("reserved", C.c_int32)]
+
+
+class b2_medium_desc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("phase", C.c_int32), ("g", C.c_float), ("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3),
+                ("strategy", C.c_int32), ("sampling_density", C.c_float), ("medium_sampling_weight", C.c_float), ("scale", C.c_float),
+                ("albedo", C.c_float * 3), ("res", C.c_int32 * 3), ("world_to_grid", C.c_float * 12), ("aabb_min", C.c_float * 3),
+                ("aabb_max", C.c_float * 3), ("density", C.POINTER(C.c_float))]
+
+
+INTEGRATORS = {"path": 0, "volpath": 1}
 
 
 class b2_stats(C.Structure):
@@ -47,7 +58,7 @@ class b2_stats(C.Structure):
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
            "b2_scene_set_camera", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
+           "b2_scene_add_mesh", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -62,7 +73,7 @@ def lib():
         L.b2_last_error.restype = C.c_char_p
         L.b2_last_error.argtypes = [C.c_void_p]
         L.b2_version.restype = C.c_char_p
-        for name in ("b2_scene_add_material", "b2_scene_add_area_emitter", "b2_scene_add_mesh"):
+        for name in ("b2_scene_add_material", "b2_scene_add_area_emitter", "b2_scene_add_mesh", "b2_scene_add_medium"):
             getattr(L, name).restype = C.c_int
         _LIB = L
     return _LIB
@@ -84,6 +95,7 @@ def make_params(rp: RenderParams, parity=False, pool_size=0, film_on_device=Fals
     p.rfilter, p.rfilter_param = RFILTERS[rp.rfilter], rp.rfilter_param
     p.sample_lo, p.sample_hi = rp.sample_lo, rp.sample_hi
     p.parity_mode, p.pool_size, p.film_on_device, p.flags = int(parity), pool_size, int(film_on_device), flags
+    p.integrator = INTEGRATORS[getattr(rp, "integrator", "path")]
     return p
 
 
@@ -92,7 +104,8 @@ def params_to_render_params(p: b2_render_params) -> RenderParams:
     inv_f = {v: k for k, v in RFILTERS.items()}
     return RenderParams(spp=p.spp, sampler=inv_s[p.sampler], seed=p.seed, max_depth=p.max_depth, rr_depth=p.rr_depth,
                         strict_normals=bool(p.strict_normals), hide_emitters=bool(p.hide_emitters), rfilter=inv_f[p.rfilter],
-                        rfilter_param=p.rfilter_param, sample_lo=p.sample_lo, sample_hi=p.sample_hi)
+                        rfilter_param=p.rfilter_param, sample_lo=p.sample_lo, sample_hi=p.sample_hi,
+                        integrator={v: k for k, v in INTEGRATORS.items()}[p.integrator])
 
 
 class Context:
@@ -170,6 +183,22 @@ class Scene:
                     getattr(m, k)[j] = d[src][j]
             if self.L.b2_scene_add_material(self.h, C.byref(m)) < 0:
                 raise B2Error(ctx.err())
+        media, media_ids = desc.flat_media()
+        self.flat_media = [md.flat() for md in media]
+        for d in self.flat_media:
+            m = b2_medium_desc()
+            m.type, m.phase, m.g, m.strategy = d["type"], d["phase"], d["g"], d["strategy"]
+            m.sampling_density, m.medium_sampling_weight, m.scale = d["samplingDensity"], d["mediumSamplingWeight"], d["scale"]
+            for k, src in (("sigma_a", "sigmaA"), ("sigma_s", "sigmaS"), ("albedo", "albedo"), ("aabb_min", "aabbMin"), ("aabb_max", "aabbMax")):
+                for j in range(3):
+                    getattr(m, k)[j] = d[src][j]
+            for j in range(3):
+                m.res[j] = d["res"][j]
+            for j in range(12):
+                m.world_to_grid[j] = d["worldToGrid"][j]
+            m.density = d["density"].ctypes.data_as(C.POINTER(C.c_float)) if d["density"] is not None else None
+            if self.L.b2_scene_add_medium(self.h, C.byref(m)) < 0:
+                raise B2Error(ctx.err())
         for mesh, bid in zip(desc.meshes, ids):
             eid = -1
             if mesh.radiance is not None:
@@ -184,6 +213,9 @@ class Scene:
             if self.L.b2_scene_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
                                         C.c_int(bid), C.c_int(eid)) < 0:
                 raise B2Error(ctx.err())
+        for i, (mi, me) in enumerate(media_ids):
+            if mi >= 0 or me >= 0:
+                self._ck(self.L.b2_scene_set_mesh_media(self.h, C.c_int(i), C.c_int(mi), C.c_int(me)))
         self._ck(self.L.b2_scene_commit(self.h))
 
     def _ck(self, rc):
@@ -269,6 +301,15 @@ class Scene:
         out = np.zeros((len(ref), 12), np.float32)
         self._ck(self.L.b2_sample_emitter_direct(self.h, C.c_uint64(len(ref)), _p(ref), _p(samples), C.c_int(int(parity)), _p(out)))
         return out
+
+    def medium_probe(self, medium, what, data, seed=0, parity=True):
+        """what: 'transmittance' | 'sample_distance' | 'density' | 'phase' (b2_medium_probe)."""
+        w = {"transmittance": (0, 8, 3), "sample_distance": (1, 8, 12), "density": (2, 3, 1), "phase": (3, 5, 5)}[what]
+        data = np.ascontiguousarray(data, np.float32).reshape(-1, w[1])
+        out = np.zeros((len(data), w[2]), np.float32)
+        self._ck(self.L.b2_medium_probe(self.h, C.c_int(medium), C.c_int(w[0]), C.c_uint64(len(data)), _p(data), C.c_uint64(seed),
+                                        C.c_int(int(parity)), _p(out)))
+        return out[:, 0] if w[2] == 1 else out
 
     def sampler_stream(self, kind, seed, spp, px, py, sample_idx, ndim):
         out = np.zeros(ndim, np.float32)

@@ -230,6 +230,7 @@ B2_DEV V3 ld3(const float *p) { return V3(p[0], p[1], p[2]); }
 template <int HINT> B2_DEV Spectrum leafEval(const DMaterial &d, const BRec &r, bool discrete) {
     const V3 R = ld3(d.reflectance);
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
+    if (type == 4) return Spectrum(discrete ? 1.0f : 0.0f); // null.cpp:45-47 (index-matched boundary)
     if (type == 0) { // diffuse.cpp:110-118
         if (discrete || d.flags == 0 || cosTheta(r.wi) <= 0 || cosTheta(r.wo) <= 0) return Spectrum(0.0f);
         return R * (B2_INV_PI * cosTheta(r.wo));
@@ -271,6 +272,7 @@ template <int HINT> B2_DEV Spectrum leafEval(const DMaterial &d, const BRec &r, 
 
 template <int HINT> B2_DEV float leafPdf(const DMaterial &d, const BRec &r, bool discrete) {
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
+    if (type == 4) return discrete ? 1.0f : 0.0f; // null.cpp:49-51
     if (type == 0) { // diffuse.cpp:120-128
         if (discrete || d.flags == 0 || cosTheta(r.wi) <= 0 || cosTheta(r.wo) <= 0) return 0.0f;
         return squareToCosineHemispherePdf(r.wo);
@@ -308,6 +310,10 @@ template <int HINT> B2_DEV float leafPdf(const DMaterial &d, const BRec &r, bool
 template <int HINT> B2_DEV Spectrum leafSample(const DMaterial &d, BRec &r, float &pdfOut, float sx, float sy, PathSampler &smp) {
     const V3 R = ld3(d.reflectance);
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
+    if (type == 4) { // null.cpp:65-76
+        r.wo = -r.wi; r.sampledType = ENull; r.eta = 1.0f; pdfOut = 1.0f;
+        return Spectrum(1.0f);
+    }
     if (type == 0) { // diffuse.cpp:141-150
         if (d.flags == 0 || cosTheta(r.wi) <= 0) return Spectrum(0.0f);
         r.wo = squareToCosineHemisphere(sx, sy);

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -58,6 +59,7 @@ struct HostMesh {
     std::vector<float> P, N, UV;
     std::vector<uint32_t> idx;
     int material = -1, emitter = -1;
+    int interior = -1, exterior = -1; // media ids (shape.h:427-435), -1 = vacuum
     uint32_t primOffset = 0;
 };
 struct HostEmitter {
@@ -90,6 +92,8 @@ struct b2_scene {
     std::vector<b2_material_desc> materials;
     std::vector<HostEmitter> emitters;
     std::vector<HostMesh> meshes;
+    struct HostMedium { b2_medium_desc desc; std::vector<float> density; };
+    std::vector<HostMedium> media;
     // camera
     float camToWorld[16];
     float sampleToCamera[16];
@@ -105,13 +109,17 @@ struct b2_scene {
     DevBuf<DMaterial> dMaterials;
     DevBuf<DEmitter> dEmitters;
     DevBuf<float> dEmitterCdf, dTriCdf;
+    DevBuf<DMedium> dMedia;
+    DevBuf<int2> dPrimMedia;
+    std::vector<std::unique_ptr<DevBuf<float>>> dDensity;
+    bool hasNullBsdf = false;
     std::vector<float4> hTriAccelPrimOrder; // for b2_get_triaccel
     LaunchCfg cfgParity, cfgFast;
     bool classPresent[4] = {false, false, false, false};
     // pool
     DPool pool{};
     DevBuf<float4> pRay, pSt, pHit, pShD, pShC;
-    DevBuf<uint2> pSmp;
+    DevBuf<uint2> pSmp, pVol;
     DevBuf<float2> pPos;
     DevBuf<uint32_t> pPix, pFlags;
     DevBuf<uint32_t> pMatQueue, pDoneQueue;
@@ -312,7 +320,7 @@ extern "C" int b2_scene_film_size(b2_scene *s, int *width, int *height) {
 }
 extern "C" int b2_scene_add_material(b2_scene *s, const b2_material_desc *m) {
     if (!s || !m) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_material: null argument"); return -1; }
-    if (m->type < 0 || m->type > 3) { fail(s->ctx, B2_ERR_INVALID, "unknown BSDF type"); return -1; }
+    if (m->type < 0 || m->type > B2_BSDF_NULL) { fail(s->ctx, B2_ERR_INVALID, "unknown BSDF type"); return -1; }
     if (m->type == B2_BSDF_COATING) {
         if (m->nested < 0 || m->nested >= (int) s->materials.size()) { fail(s->ctx, B2_ERR_INVALID, "coating: A child BSDF instance is required"); return -1; }
         if (s->materials[m->nested].type == B2_BSDF_COATING) { fail(s->ctx, B2_ERR_INVALID, "coating over coating is not supported on the device"); return -1; }
@@ -354,6 +362,38 @@ extern "C" int b2_scene_add_mesh(b2_scene *s, const float *P, const float *N, co
     s->meshes.push_back(std::move(m));
     s->committed = false;
     return (int) s->meshes.size() - 1;
+}
+
+// Medium plugin instance + phase function (src/medium/{homogeneous,heterogeneous}.cpp, src/phase/{isotropic,hg}.cpp)
+extern "C" int b2_scene_add_medium(b2_scene *s, const b2_medium_desc *m) {
+    if (!s || !m) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_medium: null argument"); return -1; }
+    if (m->type != B2_MEDIUM_HOMOGENEOUS && m->type != B2_MEDIUM_HETEROGENEOUS) { fail(s->ctx, B2_ERR_INVALID, "unknown medium type"); return -1; }
+    if (m->phase != B2_PHASE_ISOTROPIC && m->phase != B2_PHASE_HG) { fail(s->ctx, B2_ERR_INVALID, "unknown phase function"); return -1; }
+    b2_scene::HostMedium hm;
+    hm.desc = *m;
+    if (m->type == B2_MEDIUM_HETEROGENEOUS) {
+        if (!m->density) { fail(s->ctx, B2_ERR_INVALID, "No density specified!"); return -1; } // heterogeneous.cpp:230
+        if (m->res[0] < 2 || m->res[1] < 2 || m->res[2] < 2) { fail(s->ctx, B2_ERR_INVALID, "density grid needs at least 2 samples per axis"); return -1; }
+        if (!(m->scale > 0)) { fail(s->ctx, B2_ERR_INVALID, "heterogeneous medium: 'scale' must be positive"); return -1; }
+        const size_t n = (size_t) m->res[0] * m->res[1] * m->res[2];
+        hm.density.assign(m->density, m->density + n);
+    } else {
+        if (m->strategy < 0 || m->strategy > 2) { fail(s->ctx, B2_ERR_INVALID, "Specified an unknown sampling strategy"); return -1; } // homogeneous.cpp:220
+    }
+    hm.desc.density = nullptr;
+    s->media.push_back(std::move(hm));
+    s->committed = false;
+    return (int) s->media.size() - 1;
+}
+// <ref name="interior"/"exterior"> children of a shape (shape.cpp:160-176)
+extern "C" int b2_scene_set_mesh_media(b2_scene *s, int mesh, int interior, int exterior) {
+    if (!s) return fail(nullptr, B2_ERR_INVALID, "b2_scene_set_mesh_media: null scene");
+    if (mesh < 0 || mesh >= (int) s->meshes.size()) return fail(s->ctx, B2_ERR_INVALID, "invalid mesh id");
+    if (interior >= (int) s->media.size() || exterior >= (int) s->media.size()) return fail(s->ctx, B2_ERR_INVALID, "invalid medium id");
+    s->meshes[mesh].interior = interior < 0 ? -1 : interior;
+    s->meshes[mesh].exterior = exterior < 0 ? -1 : exterior;
+    s->committed = false;
+    return B2_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,6 +444,7 @@ static uint32_t materialFlags(const std::vector<b2_material_desc> &mats, int id)
         case 0: return (std::max(std::max(d.reflectance[0], d.reflectance[1]), d.reflectance[2]) > 0) ? (EDiffuseReflection | EFrontSide) : 0; // diffuse.cpp:98-103
         case 1: return EGlossyReflection | EFrontSide | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
         case 2: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide | EUsesSampler | ENonSymmetric | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
+        case 4: return 0x1u /* ENull */ | EFrontSide | EBackSide; // null.cpp:38-43
         default: return materialFlags(mats, d.nested) | EDeltaReflection | EFrontSide | EBackSide;
     }
 }
@@ -623,7 +664,39 @@ extern "C" int b2_scene_commit(b2_scene *s) {
             d.specSamplingWeight = 1.0f / (avgAbsorption + 1.0f);
         }
     }
-    for (auto &m : s->meshes) s->classPresent[s->materials[m.material].type] = true;
+    s->hasNullBsdf = false;
+    for (auto &m : s->meshes) {
+        const int t = s->materials[m.material].type;
+        if (t == B2_BSDF_NULL) {
+            s->hasNullBsdf = true; // shaded by the generic kernel (no per-class queue)
+            if (m.emitter >= 0) return fail(ctx, B2_ERR_INVALID, "Shape has an index-matched BSDF and an emitter attachment. This is not allowed!"); // shape.cpp:76-78
+        } else s->classPresent[t] = true;
+    }
+    // ---- media (volpath) ----
+    std::vector<DMedium> dmed(s->media.size());
+    s->dDensity.clear();
+    for (size_t i = 0; i < s->media.size(); ++i) {
+        const b2_medium_desc &m = s->media[i].desc;
+        DMedium &d = dmed[i];
+        memset(&d, 0, sizeof(d));
+        d.type = m.type; d.phase = m.phase; d.g = m.g; d.strategy = m.strategy;
+        memcpy(d.sigmaA, m.sigma_a, 12); memcpy(d.sigmaS, m.sigma_s, 12);
+        d.samplingDensity = m.sampling_density; d.mediumSamplingWeight = m.medium_sampling_weight;
+        d.scale = m.scale; d.invMaxDensity = 1.0f / (m.scale * 1.0f); // heterogeneous.cpp:239-243, gridvolume.cpp:583-585
+        memcpy(d.albedo, m.albedo, 12); memcpy(d.res, m.res, 12); memcpy(d.worldToGrid, m.world_to_grid, 48);
+        memcpy(d.aabbMin, m.aabb_min, 12); memcpy(d.aabbMax, m.aabb_max, 12);
+        s->dDensity.emplace_back(new DevBuf<float>());
+        CK(ctx, s->dDensity.back()->upload(s->media[i].density));
+        d.density = s->dDensity.back()->p;
+    }
+    std::vector<int2> primMedia;
+    bool anyMedia = false;
+    for (auto &m : s->meshes) anyMedia |= m.interior >= 0 || m.exterior >= 0;
+    if (anyMedia) {
+        primMedia.resize(nPrims);
+        for (auto &m : s->meshes)
+            for (size_t j = 0; j < m.idx.size() / 3; ++j) primMedia[m.primOffset + j] = make_int2(m.interior, m.exterior);
+    }
     // ---- emitters: scene.cpp:375-380, trimesh.cpp:388-403, pmf.h ----
     std::vector<DEmitter> de(s->emitters.size());
     std::vector<float> emCdf(1, 0.0f), triCdf;
@@ -675,9 +748,12 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     CK(ctx, s->dEmitters.upload(de));
     CK(ctx, s->dEmitterCdf.upload(emCdf));
     CK(ctx, s->dTriCdf.upload(triCdf));
+    CK(ctx, s->dMedia.upload(dmed));
+    CK(ctx, s->dPrimMedia.upload(primMedia));
     DScene &ds = s->ds;
     memset(&ds, 0, sizeof(ds));
     ds.triAccel = s->dTriAccel.p; ds.triPlane = s->dTriPlane.p; ds.leafPrim = s->dLeafPrim.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
+    ds.media = s->dMedia.p; ds.primMedia = anyMedia ? s->dPrimMedia.p : nullptr; ds.nMedia = (uint32_t) dmed.size();
     ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef; ds.rootCount = rootCount;
     ds.flatRec = s->dFlatRec.p; ds.flatIdx = (const uint2 *) s->dFlatIdx.p; ds.flatP = flatP; ds.flatC = flatC; ds.flatS = flatS;
     ds.flatBytes = (uint32_t) (flatRec.size() * 16);
@@ -783,6 +859,8 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     r.spp = p->spp; r.sampler = p->sampler;
     r.maxDepth = p->max_depth; r.rrDepth = p->rr_depth; r.strictNormals = p->strict_normals; r.hideEmitters = p->hide_emitters;
     r.sampleLo = p->sample_lo; r.sampleHi = p->sample_hi > 0 ? p->sample_hi : p->spp;
+    if (p->integrator != B2_INTEGRATOR_PATH && p->integrator != B2_INTEGRATOR_VOLPATH) return fail(ctx, B2_ERR_INVALID, "unknown integrator");
+    r.integrator = p->integrator;
     if (r.sampleLo < 0 || r.sampleHi > p->spp || r.sampleLo >= r.sampleHi) return fail(ctx, B2_ERR_INVALID, "invalid sample range");
     if (p->sampler == B2_SAMPLER_SOBOL) {
         r.scramble = p->seed ? teaHost((uint32_t) p->seed, (uint32_t) (p->seed >> 32)) : 0; // sobol.cpp:96-102
@@ -823,8 +901,9 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     return B2_OK;
 }
 
-static int ensurePool(b2_scene *s, uint32_t Q) {
+static int ensurePool(b2_scene *s, uint32_t Q, bool vol) {
     b2_ctx *ctx = s->ctx;
+    if (vol && s->pVol.n != Q) { CK(ctx, s->pVol.alloc(Q)); s->pool.vol = s->pVol.p; }
     if (s->pool.capacity == Q) return B2_OK;
     CK(ctx, s->pRay.alloc((size_t) 2 * Q)); CK(ctx, s->pSt.alloc((size_t) 2 * Q)); CK(ctx, s->pHit.alloc(Q));
     CK(ctx, s->pShD.alloc(Q)); CK(ctx, s->pShC.alloc(Q)); CK(ctx, s->pSmp.alloc(Q)); CK(ctx, s->pPos.alloc(Q));
@@ -836,6 +915,7 @@ static int ensurePool(b2_scene *s, uint32_t Q) {
     p.shD = s->pShD.p; p.shC = s->pShC.p; p.matQueue = s->pMatQueue.p;
     p.doneQueue = s->pDoneQueue.p;
     p.counters = s->dCounters.p;
+    p.vol = s->pVol.p;
     return B2_OK;
 }
 
@@ -857,7 +937,8 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     Q = std::max<uint32_t>(Q, 1024u);
     Q = (uint32_t) std::min<uint64_t>(Q, std::max<uint64_t>(1024u, r.totalWork));
     Q = (Q + 255u) & ~255u;
-    rc = ensurePool(s, Q);
+    const bool volpath = p->integrator == B2_INTEGRATOR_VOLPATH;
+    rc = ensurePool(s, Q, volpath);
     if (rc) return rc;
     const size_t nPix = (size_t) s->W * s->H;
     CK(ctx, s->dFilmRGBA.alloc(nPix));
@@ -887,11 +968,12 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         if (s->classPresent[c]) { ++nClasses; onlyClass = c; }
     bool sorted = nClasses > 1;
     if (p->flags & 2) sorted = false;
+    if (s->hasNullBsdf) { sorted = false; nClasses = 2; } // index-matched boundaries: generic shading kernel
     // Optional (flags bit4) for shared-memory resident scenes: rays cast inline by k_generate / k_shade (no k_extend /
     // k_occluded launches, no ray / shadow records through HBM).  Measured on Cornell it is ~4 % SLOWER than the separate
     // stages (1407 vs 1463 Msamples/s): the triangle tests then run inside the divergent, low-occupancy shade kernel
     // instead of the lockstep traversal kernels, so the default keeps the stages separate.
-    const bool fused = s->ds.rootCount > 0 && (p->flags & 16);
+    const bool fused = s->ds.rootCount > 0 && (p->flags & 16) && !volpath;
     if (fused) sorted = false;
     s->cancel.store(0);
     cudaEvent_t evStart, evStop;
@@ -917,6 +999,11 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
 #define ITER(ns)                                                                                               \
         do {                                                                                                   \
             tick(0); ns::launch_generate(cfg, s->ds, s->pool, r, filt, fused, st); tick(-1);                   \
+            if (volpath) { /* volpath: every ray of an iteration is cast inline by k_volstep */                 \
+                tick(2); ns::launch_volstep(cfg, s->ds, s->pool, r, st); tick(-1);                             \
+                launchesPerIter = 3;                                                                           \
+                break;                                                                                         \
+            }                                                                                                  \
             if (!fused) { tick(1); ns::launch_extend(cfg, s->ds, s->pool, r, sorted, st); tick(-1); ++launchesPerIter; } \
             tick(2);                                                                                           \
             if (sorted) {                                                                                      \
@@ -937,9 +1024,27 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graphExec = nullptr;
     if (!useEvents) {
+        if (volpath) {
+            // k_volstep has a deep local-memory frame: its first launch may have to grow the context's local-memory pool, which
+            // is not allowed inside a stream capture.  The first iteration therefore runs as plain launches.
+            enqueueIteration();
+            launches += launchesPerIter;
+            ++iter;
+        }
         // the iteration index lives on the device (CTR_ITER, advanced by k_publish): one captured graph replays for every iteration
         CK(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         enqueueIteration();
+        {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cs);
+            const cudaError_t le = cudaPeekAtLastError();
+            if (cs != cudaStreamCaptureStatusActive || le != cudaSuccess) {
+                cudaStreamEndCapture(st, &graph);
+                cudaGetLastError();
+                return fail(ctx, B2_ERR_CUDA, std::string("graph capture of the iteration failed: ") + cudaGetErrorString(le) +
+                                              (volpath ? " (volpath)" : " (path)") + ", grid " + std::to_string(cfg.gridVolstep) + ", smem " + std::to_string(cfg.traceSmem));
+            }
+        }
         CK(ctx, cudaStreamEndCapture(st, &graph));
         CK(ctx, cudaGraphInstantiate(&graphExec, graph, 0));
     }
@@ -1174,6 +1279,24 @@ extern "C" int b2_sample_emitter_direct(b2_scene *s, uint64_t n, const float *re
         else if (h[12 * i + 8] == 0) { h[12 * i + 4] = 0; }
     }
     memcpy(out, h.data(), 12 * n * sizeof(float));
+    return B2_OK;
+}
+// Medium component probe (parity tests): what = 0 evalTransmittance (in: n x 8 ray floats, out n x 3), 1 sampleDistance (out n x 12),
+// 2 density lookup (in n x 3, out n), 3 phase sample (in n x 5: wi, two uniforms; out n x 5: wo, pdf, eval)
+extern "C" int b2_medium_probe(b2_scene *s, int medium, int what, uint64_t n, const float *in, uint64_t seed, int parity_mode, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (medium < 0 || medium >= (int) s->media.size()) return fail(ctx, B2_ERR_INVALID, "invalid medium id");
+    if (what < 0 || what > 3 || !in || !out) return fail(ctx, B2_ERR_INVALID, "b2_medium_probe: invalid argument");
+    static const int inW[4] = {8, 8, 3, 5}, outW[4] = {3, 12, 1, 5};
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dI = tmp.upload(in, (size_t) inW[what] * n), *dO = tmp.alloc<float>((size_t) outW[what] * n);
+    if (parity_mode) parity::launch_medium_probe(s->cfgParity, s->ds, medium, what, n, dI, seed, dO, ctx->stream);
+    else fast::launch_medium_probe(s->cfgFast, s->ds, medium, what, n, dI, seed, dO, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, dO, (size_t) outW[what] * n * sizeof(float), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 extern "C" int b2_camera_rays(b2_scene *s, uint64_t n, const float *pos, int parity_mode, float *rays) {

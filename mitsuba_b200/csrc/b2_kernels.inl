@@ -15,6 +15,7 @@
 #include "b2_sampler.cuh"
 #include "b2_bsdf.cuh"
 #include "b2_trace.cuh"
+#include "b2_medium.cuh"
 #include "b2_launch.h"
 
 namespace b2 {
@@ -528,7 +529,7 @@ struct DirectSample {
 // Scene::sampleEmitterDirect (scene.cpp:828-852) up to, not including, the visibility ray:
 // emitter pick (pmf.h sampleReuse), AreaLight::sampleDirect (area.cpp:158-173), Shape::sampleDirect
 // (shape.cpp:102-115), TriMesh::samplePosition (trimesh.cpp:412-424), Triangle::sample (triangle.cpp:24-62)
-B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN, float sx, float sy, DirectSample &ds) {
+B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN, float sx, float sy, DirectSample &ds, float *emPdfOut = nullptr) {
     const uint32_t ei = cdfSample(sc.emitterCdf, sc.nEmitters, sx);
     const float c0 = __ldg(sc.emitterCdf + ei), c1 = __ldg(sc.emitterCdf + ei + 1);
     const float emPdf = c1 - c0;
@@ -559,6 +560,11 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
     ds.emitter = (int) ei;
     if (dot(ds.d, refN) >= 0 && dot(ds.d, ds.n) < 0 && pdf != 0) {
         ds.value = V3(em.radiance[0], em.radiance[1], em.radiance[2]) / pdf;
+        if (emPdfOut) { // sampleAttenuatedEmitterDirect (scene.cpp:854-898): the caller multiplies by transmittance / emPdf
+            ds.pdf = pdf;
+            *emPdfOut = emPdf;
+            return true;
+        }
         ds.pdf = pdf * emPdf;
         ds.value = ds.value / emPdf;
         return true;
@@ -844,6 +850,371 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
     stampEnd(rp, it, STAGE_OCCLUDED);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// volpath: src/integrators/path/volpath.cpp:84-366.  One launch advances every live path by one loop
+// iteration (plus any chain of index-matched boundary crossings, which the reference handles with `continue`).  The
+// medium work is sequential per path and data dependent (Woodcock walks draw a variable number of random numbers
+// BEFORE the direction is sampled), so the rays of an iteration are cast inline by the thread that owns the path.
+// ------------------------------------------------------------------------------------------------
+struct VolEnv {
+    const DScene &sc;
+    const TraceMem &tm;
+    uint32_t nRays, nShadow;
+    B2_DEV VolEnv(const DScene &s, const TraceMem &t) : sc(s), tm(t), nRays(0), nShadow(0) {}
+    // Scene::rayIntersect(ray, its): skdtree.cpp:112-142
+    B2_DEV bool closest(const V3 &o, const V3 &d, float rayMint, float rayMaxt, HitRec &h) {
+        h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
+        const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        float mint, maxt;
+        uint32_t nv = 0, pt = 0;
+        ++nRays;
+        if (clipRay<false>(sc, o, d, dRcp, rayMint, rayMaxt, mint, maxt) && traverse<false, false>(sc, tm, o, d, mint, maxt, h, nv, pt)) return true;
+        h.t = B2_INF; h.prim = 0xFFFFFFFFu;
+        return false;
+    }
+    // ShapeKDTree::rayIntersect(ray, t, shape, n, uv): skdtree.cpp:144-204 -- closest hit, epsilon scale without the inner
+    // max, unflipped face normal
+    B2_DEV bool closestNormal(const V3 &o, const V3 &d, float rayMint, float rayMaxt, float &t, uint32_t &prim, V3 &n) {
+        HitRec h;
+        h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
+        const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        float mint, maxt;
+        uint32_t nv = 0, pt = 0;
+        ++nShadow;
+        t = B2_INF;
+        if (clipRay<true>(sc, o, d, dRcp, rayMint, rayMaxt, mint, maxt) && traverse<false, false>(sc, tm, o, d, mint, maxt, h, nv, pt)) {
+            t = h.t; prim = h.prim;
+            const float4 a0 = __ldg(&sc.verts[3 * (size_t) prim]), a1 = __ldg(&sc.verts[3 * (size_t) prim + 1]), a2 = __ldg(&sc.verts[3 * (size_t) prim + 2]);
+            const V3 p0(a0.x, a0.y, a0.z), p1(a1.x, a1.y, a1.z), p2(a2.x, a2.y, a2.z);
+            n = normalize(cross(p1 - p0, p2 - p0));
+            return true;
+        }
+        return false;
+    }
+    B2_DEV int2 mediaOf(uint32_t prim) const { return sc.primMedia ? __ldg(sc.primMedia + prim) : make_int2(-1, -1); }
+    B2_DEV int materialOf(uint32_t prim) const { return __float_as_int(__ldg(&sc.verts[3 * (size_t) prim].w)); }
+    B2_DEV int emitterOf(uint32_t prim) const { return __float_as_int(__ldg(&sc.verts[3 * (size_t) prim + 1].w)); }
+};
+B2_DEV int targetMedium(const int2 &media, const V3 &geoN, const V3 &d) { return dot(d, geoN) > 0 ? media.y : media.x; } // records.inl:81-86
+
+// Scene::evalTransmittance: scene.cpp:619-679
+B2_DEV Spectrum volEvalTransmittance(VolEnv &env, const V3 &p1, bool p1OnSurface, const V3 &p2, bool p2OnSurface, int medium, int maxInteractions,
+                                     PathSampler &smp) {
+    const DScene &sc = env.sc;
+    V3 d = p2 - p1;
+    float remaining = length(d);
+    d = d / remaining;
+    const float lengthFactor = p2OnSurface ? (1 - B2_SHADOW_EPSILON) : 1;
+    V3 o = p1;
+    float rayMint = p1OnSurface ? B2_EPSILON : 0.0f, rayMaxt = remaining * lengthFactor;
+    Spectrum transmittance(1.0f);
+    int interactions = 0;
+    while (remaining > 0) {
+        float t;
+        uint32_t prim = 0;
+        V3 n;
+        const bool surface = env.closestNormal(o, d, rayMint, rayMaxt, t, prim, n);
+        if (surface && (interactions == maxInteractions || !(sc.materials[env.materialOf(prim)].flags & ENull))) return Spectrum(0.0f);
+        if (medium >= 0) transmittance = transmittance * mediumTransmittance(sc.media[medium], o, d, 0.0f, fminf(t, remaining), smp);
+        if (!surface || isZero(transmittance)) break;
+        const int2 media = env.mediaOf(prim); // null BSDF: eval(bRec, EDiscrete) with typeMask = ENull is 1
+        if (media.x >= 0 || media.y >= 0) {
+            if (medium != targetMedium(media, n, -d)) return Spectrum(0.0f); // mediumInconsistencies
+            medium = targetMedium(media, n, d);
+        }
+        if (++interactions > 100) break;
+        o = o + d * t;
+        remaining -= t;
+        rayMaxt = remaining * lengthFactor;
+        rayMint = B2_EPSILON;
+    }
+    return transmittance;
+}
+
+struct EmitterQuery { // DirectSamplingRecord fields pdfEmitterDirect reads (records.inl:171-179)
+    V3 d, n;
+    float dist;
+    int emitter;
+};
+// volpath.cpp:368-426: first intersection into `hit` (and `rayD`-relative), attenuated emitter radiance in `value`
+B2_DEV void volIntersectAndLookForEmitter(VolEnv &env, PathSampler &smp, int medium, int maxInteractions, V3 o, const V3 &d, float rayMint, HitRec &hit,
+                                          EmitterQuery &eq, Spectrum &value) {
+    const DScene &sc = env.sc;
+    HitRec h2;
+    HitRec *cur = &hit;
+    Spectrum transmittance(1.0f);
+    bool surface = false;
+    int interactions = 0;
+    while (true) {
+        surface = env.closest(o, d, rayMint, B2_INF, *cur);
+        if (medium >= 0) transmittance = transmittance * mediumTransmittance(sc.media[medium], o, d, 0.0f, cur->t, smp);
+        if (surface) {
+            const uint32_t prim = cur->prim;
+            if (interactions == maxInteractions || !(sc.materials[env.materialOf(prim)].flags & ENull) || env.emitterOf(prim) >= 0) break;
+        } else break;
+        if (isZero(transmittance)) return;
+        const int2 media = env.mediaOf(cur->prim);
+        if (media.x >= 0 || media.y >= 0) {
+            Isect its; // its->geoFrame.n of the full record (flipped towards the shading normal)
+            fillIntersection(sc, d, cur->prim, cur->u, cur->v, its);
+            medium = targetMedium(media, its.geoN, d);
+        }
+        o = o + d * cur->t;
+        rayMint = B2_EPSILON;
+        cur = &h2;
+        if (++interactions > 100) return;
+    }
+    if (surface) {
+        const int em = env.emitterOf(cur->prim);
+        if (em >= 0) {
+            Isect its;
+            fillIntersection(sc, d, cur->prim, cur->u, cur->v, its);
+            eq.n = its.sh.n; eq.d = d; eq.dist = cur->t; eq.emitter = em;
+            const DEmitter &e = sc.emitters[em];
+            const Spectrum le = dot(its.sh.n, -d) <= 0 ? Spectrum(0.0f) : V3(e.radiance[0], e.radiance[1], e.radiance[2]); // area.cpp:104-109
+            value = transmittance * le;
+        }
+    }
+}
+// scene.cpp:949-952; area.cpp:175-183; shape.cpp:117-126
+B2_DEV float volPdfEmitterDirect(const DScene &sc, const EmitterQuery &eq, const V3 &refN) {
+    const DEmitter &em = sc.emitters[eq.emitter];
+    float pdfDirect = 0.0f;
+    if (dot(eq.d, refN) >= 0 && dot(eq.d, eq.n) < 0) pdfDirect = em.invSurfaceArea * (eq.dist * eq.dist) / absDot(eq.d, eq.n);
+    return pdfDirect * (em.samplingWeight * sc.emitterNormalization);
+}
+
+__global__ void __launch_bounds__(B2_TRACE_BLOCK) k_volstep(DScene sc, DPool pool, DRender rp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
+    stampBegin(rp, it, STAGE_SHADE);
+    const TraceMem tm = setupTraceMem(sc, smem);
+    const uint32_t Q = pool.capacity;
+    VolEnv env(sc, tm);
+    uint32_t nDimOvf = 0, nDone = 0;
+    const DMaterial *mats = sc.materials;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t state = i < Q ? pool.flags[i] : 0u;
+        const bool live = (state & PF_ALIVE) != 0;
+        if (live) {
+            uint32_t flags = state & 0xFFu;
+            int depth = (int) ((state >> 8) & 0xFFFu);
+            const float4 ro4 = pool.ray[2 * (size_t) i], rd4 = pool.ray[2 * (size_t) i + 1], thr4 = pool.st[2 * (size_t) i];
+            float4 li4 = pool.st[2 * (size_t) i + 1];
+            const uint2 sm2 = pool.smp[i];
+            V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
+            Spectrum T(thr4.x, thr4.y, thr4.z), Li(li4.x, li4.y, li4.z);
+            float eta = thr4.w;
+            PathSampler smp;
+            smp.kind = rp.sampler; smp.m32 = sc.sobolNib; smp.nNib = rp.indexNibbles; smp.overflow = false;
+            smp.index = ((uint64_t) sm2.y << 32) | sm2.x;
+            smp.scramble32 = rp.sampler == 0 ? (uint32_t) rp.scramble : (uint32_t) (rp.scramble >> 32);
+            int medium;
+            HitRec hit;
+            if (flags & PF_FRESH) {
+                smp.dim = state >> 20;
+                medium = -1; // sensor medium: vacuum (a camera inside a medium is out of scope)
+                env.closest(rayO, rayD, ro4.w, rd4.w, hit); // rRec.rayIntersect(ray), volpath.cpp:97
+                if (hit.prim != 0xFFFFFFFFu) flags |= PF_ALPHA;
+                flags &= ~PF_FRESH;
+            } else {
+                const uint2 v = pool.vol[i];
+                medium = (int) v.x; smp.dim = v.y;
+                const float4 h4 = pool.hit[i];
+                hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+            }
+            bool done = false;
+            while (true) { // one loop iteration of volpath.cpp:104-357; repeats only after an index-matched boundary (`continue`)
+                if (!(depth <= rp.maxDepth || rp.maxDepth < 0)) { done = true; break; }
+                const bool scattered = (flags & PF_SCATTERED) != 0;
+                MediumRec mRec;
+                mRec.transmittance = Spectrum(1.0f); mRec.pdfFailure = 1.0f; mRec.pdfSuccess = 1.0f;
+                if (medium >= 0 && mediumSampleDistance(sc.media[medium], rayO, rayD, 0.0f, hit.t, mRec, smp)) {
+                    const DMedium &med = sc.media[medium];
+                    if (depth >= rp.maxDepth && rp.maxDepth != -1) { done = true; break; }
+                    T = T * (mRec.sigmaS * mRec.transmittance / mRec.pdfSuccess);
+                    // ---- luminaire sampling (volpath.cpp:122-151) ----
+                    if (sc.nEmitters > 0) {
+                        const int interactions = rp.maxDepth - depth - 1;
+                        float sx, sy;
+                        smp.next2D(sx, sy);
+                        DirectSample ds;
+                        float emPdf = 1.0f;
+                        if (sampleEmitterDirect(sc, mRec.p, V3(0.0f), sx, sy, ds, &emPdf)) {
+                            Spectrum value = ds.value * (volEvalTransmittance(env, mRec.p, false, ds.p, true, medium, interactions, smp) / emPdf);
+                            ds.pdf *= emPdf;
+                            if (!isZero(value)) {
+                                const float phaseVal = phaseEval(med, -rayD, ds.d);
+                                if (phaseVal != 0) Li = Li + T * value * phaseVal * miWeight(ds.pdf, phaseVal);
+                            }
+                        }
+                    }
+                    // ---- phase function sampling (volpath.cpp:153-180) ----
+                    float phasePdf;
+                    V3 wo;
+                    const float phaseVal = phaseSample(med, -rayD, wo, phasePdf, smp);
+                    if (phaseVal == 0) { done = true; break; }
+                    T = T * phaseVal;
+                    rayO = mRec.p; rayD = wo;
+                    Spectrum value(0.0f);
+                    EmitterQuery eq;
+                    volIntersectAndLookForEmitter(env, smp, medium, rp.maxDepth - depth - 1, rayO, rayD, 0.0f, hit, eq, value);
+                    if (!isZero(value)) Li = Li + T * value * miWeight(phasePdf, volPdfEmitterDirect(sc, eq, V3(0.0f)));
+                } else {
+                    if (medium >= 0) T = T * (mRec.transmittance / mRec.pdfFailure);
+                    if (hit.prim == 0xFFFFFFFFu) { done = true; break; } // no environment emitter
+                    Isect its;
+                    fillIntersection(sc, rayD, hit.prim, hit.u, hit.v, its);
+                    const int mat = its.material;
+                    const uint32_t btype = mats[mat].flags;
+                    if (its.emitter >= 0 && !scattered /* EEmittedRadiance <=> !scattered */ && (!rp.hideEmitters || scattered)) {
+                        const DEmitter &em = sc.emitters[its.emitter];
+                        const Spectrum le = dot(its.sh.n, -rayD) <= 0 ? Spectrum(0.0f) : V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                        Li = Li + T * le;
+                    }
+                    if (depth >= rp.maxDepth && rp.maxDepth != -1) { done = true; break; }
+                    if ((-dot(its.geoN, rayD)) * cosTheta(its.wi) < 0 && rp.strictNormals) { done = true; break; }
+                    V3 refN(0.0f);
+                    if ((btype & (ETransmission | EBackSide)) == 0) refN = its.sh.n; // records.inl:160-164
+                    const int2 media = env.mediaOf(hit.prim);
+                    const bool transition = media.x >= 0 || media.y >= 0;
+                    // ---- luminaire sampling (volpath.cpp:238-272) ----
+                    if (sc.nEmitters > 0 && (btype & ESmooth)) {
+                        const int interactions = rp.maxDepth - depth - 1;
+                        float sx, sy;
+                        smp.next2D(sx, sy);
+                        DirectSample ds;
+                        float emPdf = 1.0f;
+                        if (sampleEmitterDirect(sc, its.p, refN, sx, sy, ds, &emPdf)) {
+                            int med = medium;
+                            if (transition) med = targetMedium(media, its.geoN, ds.d);
+                            Spectrum value = ds.value * (volEvalTransmittance(env, its.p, true, ds.p, true, med, interactions, smp) / emPdf);
+                            ds.pdf *= emPdf;
+                            if (!isZero(value)) {
+                                BRec bRec;
+                                bRec.wi = its.wi;
+                                bRec.wo = its.sh.toLocal(ds.d);
+                                const Spectrum bsdfVal = bsdfEval<-1>(mats, mat, bRec);
+                                if (!isZero(bsdfVal) && (!rp.strictNormals || dot(its.geoN, ds.d) * cosTheta(bRec.wo) > 0)) {
+                                    const float bp = bsdfPdf<-1>(mats, mat, bRec);
+                                    Li = Li + T * value * bsdfVal * miWeight(ds.pdf, bp);
+                                }
+                            }
+                        }
+                    }
+                    // ---- BSDF sampling (volpath.cpp:279-300) ----
+                    BRec bRec;
+                    bRec.wi = its.wi;
+                    float bsdfPdfNew;
+                    float sx, sy;
+                    smp.next2D(sx, sy);
+                    const Spectrum bsdfWeight = bsdfSample<-1>(mats, mat, bRec, bsdfPdfNew, sx, sy, smp);
+                    if (isZero(bsdfWeight)) { done = true; break; }
+                    const V3 wo = its.sh.toWorld(bRec.wo);
+                    if (dot(its.geoN, wo) * cosTheta(bRec.wo) <= 0 && rp.strictNormals) { done = true; break; }
+                    rayO = its.p; rayD = wo;
+                    T = T * bsdfWeight;
+                    eta *= bRec.eta;
+                    if (transition) medium = targetMedium(media, its.geoN, rayD);
+                    if (bRec.sampledType == ENull) { // index-matched boundary: volpath.cpp:302-311
+                        env.closest(rayO, rayD, B2_EPSILON, B2_INF, hit);
+                        depth++;
+                        continue;
+                    }
+                    Spectrum value(0.0f);
+                    EmitterQuery eq;
+                    volIntersectAndLookForEmitter(env, smp, medium, rp.maxDepth - depth - 1, rayO, rayD, B2_EPSILON, hit, eq, value);
+                    if (!isZero(value)) {
+                        const float emitterPdf = !(bRec.sampledType & EDelta) ? volPdfEmitterDirect(sc, eq, refN) : 0.0f;
+                        Li = Li + T * value * miWeight(bsdfPdfNew, emitterPdf);
+                    }
+                }
+                if (depth++ >= rp.rrDepth) { // volpath.cpp:345-354
+                    const float q = fminf(maxComp(T) * eta * eta, 0.95f);
+                    if (smp.next1D() >= q) { done = true; break; }
+                    T = T / q;
+                }
+                flags |= PF_SCATTERED;
+                // not in the reference (it aborts the render, sobol.cpp:223-225): a path that ran past the Sobol' table ends here
+                if (smp.overflow) done = true;
+                break;
+            }
+            if (smp.overflow) ++nDimOvf;
+            if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
+            else {
+                pool.ray[2 * (size_t) i] = make_float4(rayO.x, rayO.y, rayO.z, 0.0f);
+                pool.ray[2 * (size_t) i + 1] = make_float4(rayD.x, rayD.y, rayD.z, 0.0f);
+                pool.hit[i] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+                pool.st[2 * (size_t) i] = make_float4(T.x, T.y, T.z, eta);
+                pool.vol[i] = make_uint2((uint32_t) medium, smp.dim);
+            }
+            pool.st[2 * (size_t) i + 1] = make_float4(Li.x, Li.y, Li.z, 0.0f);
+            state = flags | ((uint32_t) min(depth, 0xFFF) << 8);
+            pool.flags[i] = state;
+        }
+        const bool fin = live && (state & PF_DONE);
+        const uint32_t dq = warpAppend(fin, pool.counters + ((it & 1u) ? CTR_DONE1 : CTR_DONE0));
+        if (fin) {
+            pool.doneQueue[(size_t) (it & 1u) * Q + dq] = i;
+            ++nDone;
+        }
+    }
+    nDimOvf = warpSum(nDimOvf);
+    nDone = warpSum(nDone);
+    const uint32_t nRays = warpSum(env.nRays), nShadow = warpSum(env.nShadow);
+    if ((threadIdx.x & 31) == 0) {
+        if (nDone) atomicAdd(pool.counters + CTR_ACTIVE, ~(unsigned long long) nDone + 1ull);
+        if (nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
+        if (nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
+        if (nShadow) atomicAdd(pool.counters + CTR_SHADOWRAYS, (unsigned long long) nShadow);
+    }
+    stampEnd(rp, it, STAGE_SHADE);
+}
+
+
+// medium component probes (b2_medium_probe): what = 0 transmittance (in: 8 floats/ray -> 3), 1 sampleDistance (-> 12),
+// 2 density lookup (in: 3 floats -> 1), 3 phase sample (in: wi xyz + 2 samples -> 5); counter stream keyed like the oracle probe
+__global__ void k_medium_probe(DScene sc, int medium, int what, uint64_t n, const float *in, uint64_t seed, float *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const DMedium &m = sc.media[medium];
+        PathSampler smp;
+        smp.kind = 2; smp.m32 = nullptr; smp.nNib = 0; smp.overflow = false; smp.dim = 0;
+        smp.scramble32 = (uint32_t) (seed >> 32);
+        const uint32_t px = (uint32_t) (i & 0xFFFF), py = (uint32_t) (i >> 16);
+        smp.index = ((py * 65536u + px) * 1u + 0u) ^ (uint32_t) seed;
+        if (what == 0 || what == 1) {
+            const float *r = in + 8 * i;
+            const V3 o(r[0], r[1], r[2]), d(r[4], r[5], r[6]);
+            if (what == 0) {
+                const Spectrum t = mediumTransmittance(m, o, d, r[3], r[7], smp);
+                out[3 * i] = t.x; out[3 * i + 1] = t.y; out[3 * i + 2] = t.z;
+            } else {
+                MediumRec mRec;
+                mRec.t = 0; mRec.p = V3(0.0f); mRec.sigmaS = Spectrum(0.0f); mRec.transmittance = Spectrum(1.0f); mRec.pdfFailure = 1; mRec.pdfSuccess = 1;
+                const bool ok = mediumSampleDistance(m, o, d, r[3], r[7], mRec, smp);
+                float *q = out + 12 * i;
+                q[0] = ok ? 1.0f : 0.0f; q[1] = mRec.t; q[2] = mRec.sigmaS.x; q[3] = mRec.sigmaS.y; q[4] = mRec.sigmaS.z;
+                q[5] = mRec.transmittance.x; q[6] = mRec.transmittance.y; q[7] = mRec.transmittance.z; q[8] = mRec.pdfSuccess; q[9] = mRec.pdfFailure;
+                q[10] = 0; q[11] = 0;
+            }
+        } else if (what == 2) {
+            out[i] = lookupDensity(m, V3(in[3 * i], in[3 * i + 1], in[3 * i + 2]));
+        } else {
+            const float *r = in + 5 * i;
+            smp.kind = 4; // two-value replay
+            smp.replayA = r[3]; smp.replayB = r[4];
+            V3 wo;
+            float pdf;
+            const V3 wi(r[0], r[1], r[2]);
+            phaseSample(m, wi, wo, pdf, smp);
+            float *q = out + 5 * i;
+            q[0] = wo.x; q[1] = wo.y; q[2] = wo.z; q[3] = pdf; q[4] = phaseEval(m, wi, wo);
+        }
+    }
+}
+
 // film pack: (float4 rgba, float w) planes -> interleaved H*W*5 (hdrfilm.cpp:351-356 ESpectrumAlphaWeight)
 __global__ void k_film_pack(const float4 *rgba, const float *w, float *out, size_t n) {
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
@@ -982,8 +1353,12 @@ template <typename K> static int occupancyGrid(K kernel, int block, size_t smem,
     return perSM * numSMs; // a multiple of the SM count: every SM holds the same number of resident CTAs
 }
 
+// The opt-in limit is a per-function, process-wide attribute: it is set to one generous bound (never lowered), because
+// several committed scenes with different staging sizes share the kernels (a scene committed later must not shrink the
+// limit of one committed earlier).  The bound covers the stack (32 KB) + 256 staged nodes + 64 staged triangles.
 static void setSmemAttr(const void *fn, size_t smem) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    const size_t bound = 96 * 1024;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (smem > bound ? smem : bound));
 }
 
 void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
@@ -1000,6 +1375,8 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridExtendSort = occupancyGrid(k_extend<true>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridOccluded = occupancyGrid(k_occluded, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridTrace = occupancyGrid(k_trace_rays<false, false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
+    setSmemAttr((const void *) k_volstep, cfg.traceSmem);
+    cfg.gridVolstep = occupancyGrid(k_volstep, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.flatSmem = (((size_t) sc.stageTris * 48 + 15) & ~(size_t) 15) + 16;
     cfg.gridGenerate = occupancyGrid(k_generate<false>, 256, 0, numSMs);
     cfg.gridShade[0] = occupancyGrid(k_shade<0, false>, B2_SHADE_BLOCK, 0, numSMs);
@@ -1050,6 +1427,13 @@ void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, con
 }
 void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {
     k_occluded<<<cfg.gridOccluded, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
+}
+void launch_volstep(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {
+    k_volstep<<<cfg.gridVolstep, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
+}
+void launch_medium_probe(const LaunchCfg &cfg, const DScene &sc, int medium, int what, uint64_t n, const float *in, uint64_t seed, float *out,
+                         cudaStream_t st) {
+    k_medium_probe<<<cfg.numSMs * 4, 128, 0, st>>>(sc, medium, what, n, in, seed, out);
 }
 void launch_film_pack(const LaunchCfg &cfg, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t st) {
     k_film_pack<<<cfg.numSMs * 4, 256, 0, st>>>(rgba, w, out, n);

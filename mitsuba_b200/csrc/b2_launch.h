@@ -11,7 +11,7 @@ namespace b2 {
 struct LaunchCfg {
     int numSMs = 0;
     size_t traceSmem = 0;
-    int gridExtend = 0, gridExtendSort = 0, gridOccluded = 0, gridTrace = 0, gridGenerate = 0;
+    int gridExtend = 0, gridExtendSort = 0, gridOccluded = 0, gridTrace = 0, gridGenerate = 0, gridVolstep = 0;
     int gridShade[5] = {0, 0, 0, 0, 0};
     // fused variants for shared-memory resident scenes (rays cast inline by k_generate / k_shade)
     size_t flatSmem = 0;
@@ -28,6 +28,9 @@ struct LaunchCfg {
     void launch_shade(const LaunchCfg &, const DScene &, const DPool &, const DRender &, int cls, bool queued, bool flat,      \
                       cudaStream_t);                                                                                           \
     void launch_occluded(const LaunchCfg &, const DScene &, const DPool &, const DRender &, cudaStream_t);                     \
+    void launch_volstep(const LaunchCfg &, const DScene &, const DPool &, const DRender &, cudaStream_t);                      \
+    void launch_medium_probe(const LaunchCfg &, const DScene &, int medium, int what, uint64_t n, const float *in,             \
+                             uint64_t seed, float *out, cudaStream_t);                                                         \
     void launch_film_pack(const LaunchCfg &, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t);          \
     void launch_trace(const LaunchCfg &, const DScene &, const float4 *rays, float4 *out, uint64_t n, bool shadow, bool count, \
                       unsigned long long *counters, cudaStream_t);                                                             \

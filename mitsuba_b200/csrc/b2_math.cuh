@@ -51,8 +51,19 @@ typedef V3 Spectrum;
 
 // include/mitsuba/core/math.h:185-237: on Linux/x86_64 the reference evaluates exp/log in double and
 // rounds; expf/logf differ from that by <= 1 ulp, inside the stated tolerance.
+// math.h:174-200: on Linux/x86-64 the reference evaluates exp/log in double and rounds once; the parity build does the same,
+// the throughput build uses the single-precision intrinsics
+#ifdef B2_FAST_TRI
 B2_DEV float fastexp(float v) { return expf(v); }
 B2_DEV float fastlog(float v) { return logf(v); }
+// log(1 - u) of the free-path sampling: under --use_fast_math logf is __logf, whose absolute error (2^-21) is a relative error
+// of 1e-4..1e-3 for the small steps u << 1; log1pf keeps full relative accuracy
+B2_DEV float logOneMinus(float u) { return log1pf(-u); }
+#else
+B2_DEV float fastexp(float v) { return (float) exp((double) v); }
+B2_DEV float fastlog(float v) { return (float) log((double) v); }
+B2_DEV float logOneMinus(float u) { return fastlog(1 - u); }
+#endif
 B2_DEV float safe_sqrt(float v) { return sqrtf(fmaxf(0.0f, v)); }
 B2_DEV float signum(float v) { return copysignf(1.0f, v); }
 B2_DEV V3 expSpec(const V3 &v) { return V3(fastexp(v.x), fastexp(v.y), fastexp(v.z)); }

@@ -99,9 +99,11 @@ struct PathSampler {
     const uint32_t *m32;   // nibble-sliced tables (DScene::sobolNib)
     uint32_t nNib;
     bool overflow;
+    float replayA, replayB; // kind 4 (component tests): next1D alternates A, B
 
     B2_DEV float next1D() {
         if (kind == 3) return __uint_as_float(scramble32); // replay (component tests)
+        if (kind == 4) return (dim++ & 1u) ? replayB : replayA;
         if (kind == 0) {
             if (dim >= 1024u) { overflow = true; dim = 1023u; } // sobol.cpp:223-225 raises an error here
             return sobolSampleNib(m32, index, dim++, scramble32, nNib);

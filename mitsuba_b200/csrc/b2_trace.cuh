@@ -68,11 +68,11 @@ B2_DEV bool triPlaneIntersect(const float4 &q0, const float4 &q1, const float4 &
 #endif
 
 // include/mitsuba/core/aabb.h:308-338
-B2_DEV bool sceneBoxIntersect(const DScene &sc, const V3 &o, const V3 &d, const V3 &dRcp, float &nearT, float &farT) {
+B2_DEV bool aabbRayIntersect(const float *bmin, const float *bmax, const V3 &o, const V3 &d, const V3 &dRcp, float &nearT, float &farT) {
     nearT = -B2_INF; farT = B2_INF;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const float origin = comp(o, i), minVal = sc.aabbMin[i], maxVal = sc.aabbMax[i];
+        const float origin = comp(o, i), minVal = bmin[i], maxVal = bmax[i];
         const float di = comp(d, i);
         if (di == 0) {
             if (origin < minVal || origin > maxVal) return false;
@@ -86,6 +86,10 @@ B2_DEV bool sceneBoxIntersect(const DScene &sc, const V3 &o, const V3 &d, const 
         }
     }
     return true;
+}
+
+B2_DEV bool sceneBoxIntersect(const DScene &sc, const V3 &o, const V3 &d, const V3 &dRcp, float &nearT, float &farT) {
+    return aabbRayIntersect(sc.aabbMin, sc.aabbMax, o, d, dRcp, nearT, farT);
 }
 
 // skdtree.cpp:124-133 (closest) / :211-218 (occlusion): clip to the scene box and apply the adaptive epsilon

@@ -19,6 +19,21 @@ struct DMaterial {
     float pad[2];
 };
 
+// One participating medium + its phase function (device copy of b2_medium_desc)
+struct DMedium {
+    int32_t type, phase;      // 0 homogeneous / 1 heterogeneous (Woodcock); 0 isotropic / 1 hg
+    float g;
+    int32_t strategy;         // homogeneous.cpp:186-222: 0 balance, 1 single, 2 manual
+    float sigmaA[3], sigmaS[3];
+    float samplingDensity, mediumSamplingWeight;
+    float scale, invMaxDensity; // heterogeneous.cpp:185,239-243 (gridvolume maximum value 1)
+    float albedo[3];
+    int32_t res[3];
+    float worldToGrid[12];    // gridvolume.cpp:186-193
+    float aabbMin[3], aabbMax[3]; // world box of the density grid (gridvolume.cpp:197-199)
+    const float *density;     // res.x * res.y * res.z, x fastest
+};
+
 // Area emitter + its mesh's area distribution (area.cpp, trimesh.cpp:388-403)
 struct DEmitter {
     float radiance[3];
@@ -61,6 +76,10 @@ struct DScene {
     const uint2 *flatIdx;
     uint32_t flatP, flatC, flatS, flatBytes;
     uint32_t nLeafTris;
+    // participating media (volpath): media table and per-prim (interior, exterior) ids, -1 = vacuum; null without media
+    const DMedium *media;
+    const int2 *primMedia;
+    uint32_t nMedia;
     const BVHNode *nodes;
     uint32_t nNodes;
     int32_t rootRef;           // root child reference (leaf-only scenes: a leaf ref)
@@ -118,6 +137,7 @@ struct DPool {
     float2 *pos;       // samplePos (film coordinates of the sample; read again only when the path is splatted)
     uint32_t *pix;     // pixel (y << 16 | x)
     uint32_t *flags;   // PF_* | depth << 8 | sampler dimension << 20
+    uint2 *vol;        // volpath only: (current medium id or -1, sampler dimension); null for `path`
     // shadow queue (compacted by warp ballot)
     float4 *shD;       // d.xyz, maxt
     float4 *shC;       // contribution rgb, slot (bits)
@@ -150,6 +170,7 @@ struct DRender {
     uint64_t scramble;       // sobol: after the TEA step (sobol.cpp:96-102); independent: seed
     int32_t maxDepth, rrDepth, strictNormals, hideEmitters;
     int32_t sampleLo, sampleHi;
+    int32_t integrator;      // 0 path, 1 volpath
     uint32_t logRes;         // sobol m_logResolution
     float resolution;        // sobol m_resolution
     uint64_t totalWork;      // W*H*(hi-lo)

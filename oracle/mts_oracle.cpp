@@ -577,6 +577,8 @@ struct Scene {
                 throughput /= q;
             }
             scattered = true;
+            /* not in the reference (it raises an error, sobol.cpp:223-225): a path that ran past the Sobol' table ends here */
+            if (sampler->exhausted()) break;
         }
         st.pathLengthSum += (uint64_t) depth;
         return Li;

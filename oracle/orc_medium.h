@@ -122,6 +122,7 @@ struct MediumEval {
         const float invMaxDensity = 1.0f / (m.scale * 1.0f); /* gridvolume.cpp:583-585: maximum value 1 */
         const int nSamples = 2;
         float result = 0;
+        uint32_t steps = 0; /* not in the reference: both restatement and CUDA code stop a stuck random stream after 2^20 steps */
         for (int i = 0; i < nSamples; ++i) {
             float t = mint;
             while (true) {
@@ -130,6 +131,7 @@ struct MediumEval {
                 V3 p = ray(t);
                 float density = lookupDensity(p) * m.scale;
                 if (density * invMaxDensity > sampler->next1D()) break;
+                if (++steps > (1u << 20)) break;
             }
         }
         return Spectrum(result / nSamples);
@@ -183,6 +185,7 @@ struct MediumEval {
         const float invMaxDensity = 1.0f / (m.scale * 1.0f);
         float t = mint, densityAtT = 0;
         bool success = false;
+        uint32_t steps = 0;
         while (true) {
             t -= fastlog(1 - sampler->next1D()) * invMaxDensity;
             if (t >= maxt) break;
@@ -198,6 +201,7 @@ struct MediumEval {
                 success = true;
                 break;
             }
+            if (++steps > (1u << 20)) break;
         }
         return success && mRec.pdfSuccess > 0;
     }

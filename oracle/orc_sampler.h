@@ -141,6 +141,9 @@ struct Sampler {
     virtual void advance() = 0;                          /* next sample of the pixel */
     virtual float next1D() = 0;
     virtual void next2D(float &a, float &b) = 0;
+    /* true once the current sample ran past the sampler's dimension table (Sobol': the reference aborts the render,
+       sobol.cpp:223-225; volpath here ends the path instead) */
+    virtual bool exhausted() const { return false; }
 };
 
 /* src/samplers/sobol.cpp:147-158,167-216,218-252.  No sample arrays are requested by `path`,
@@ -153,7 +156,7 @@ struct SobolSampler : Sampler {
     int px = 0, py = 0;
     uint64_t sampleIndex = 0, sobolIndex = 0;
     uint32_t dimension = 0;
-    bool dimOverflow = false;
+    bool dimOverflow = false, sampleOverflow = false;
     SobolSampler(const SobolTables *t, uint64_t scrambleProp, int filmW, int filmH) : T(t) {
         if (scrambleProp) scramble = sampleTEA((uint32_t) scrambleProp, (uint32_t) (scrambleProp >> 32));
         /* setFilmResolution(res, bucketed=true) -- integrator.cpp:38-42 */
@@ -161,8 +164,9 @@ struct SobolSampler : Sampler {
         resolution = (float) res;
         logResolution = log2i(res);
     }
+    bool exhausted() const override { return sampleOverflow; }
     void setSampleIndex(uint64_t i) {
-        dimension = 0;
+        dimension = 0; sampleOverflow = false;
         sampleIndex = i;
         if (logResolution > 1 && px >= 0)
             sobolIndex = sobolLookUp(*T, logResolution, (uint32_t) sampleIndex, (uint32_t) px, (uint32_t) py, scramble);
@@ -172,11 +176,11 @@ struct SobolSampler : Sampler {
     void generate(int x, int y) override { px = x; py = y; setSampleIndex(0); }
     void advance() override { setSampleIndex(sampleIndex + 1); }
     float next1D() override {
-        if (dimension >= kSobolDims) { dimOverflow = true; dimension = kSobolDims - 1; } /* reference: Log(EError) */
+        if (dimension >= kSobolDims) { dimOverflow = sampleOverflow = true; dimension = kSobolDims - 1; } /* reference: Log(EError) */
         return sobolSample(*T, sobolIndex, dimension++, (uint32_t) scramble);
     }
     void next2D(float &a, float &b) override {
-        if (dimension + 1 >= kSobolDims) { dimOverflow = true; dimension = kSobolDims - 2; }
+        if (dimension + 1 >= kSobolDims) { dimOverflow = sampleOverflow = true; dimension = kSobolDims - 2; }
         if (dimension == 0 && sobolIndex != sampleIndex) {
             a = sobolSample(*T, sobolIndex, dimension++, (uint32_t) scramble) * resolution - px;
             b = sobolSample(*T, sobolIndex, dimension++, (uint32_t) scramble) * resolution - py;

@@ -4,7 +4,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from mitsuba_b200 import api
-from mitsuba_b200.scene import Bsdf, RenderParams, cornell_box, material_ball, stress_scene
+from mitsuba_b200.scene import Bsdf, RenderParams, cornell_box, material_ball, stress_scene, smoke_scene
 
 ctx = api.Context(0)
 HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
@@ -77,3 +77,9 @@ if "stress" in which:
     d = stress_scene(ninst, width=1024, height=1024)
     sc = render_rate(f"stress_{ninst}x100k", d, RenderParams(spp=16, rfilter="box"))
     trace_bench(f"stress_{ninst}x100k", sc, d)
+if "smoke" in which:
+    # config 4: 128^3 heterogeneous medium (Woodcock), isotropic phase, volpath, 512x512
+    d = smoke_scene(512, 512, res=128)
+    for smp in ("independent", "sobol"):
+        render_rate("smoke_128/" + smp, d, RenderParams(spp=64, rfilter="gaussian", sampler=smp, integrator="volpath"), pool_size=1 << 20)
+    render_rate("smoke_128/pool4M", d, RenderParams(spp=64, rfilter="gaussian", sampler="independent", integrator="volpath"))

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --timeout 180 > gpurun_out/vol_tests.log 2>&1; tail -8 gpurun_out/vol_tests.log

@@ -32,8 +32,10 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from mitsuba_b200 import api
     assert ctypes.sizeof(api.b2_material_desc) == 4 * 4 + 4 * 4 + 15 * 4
-    assert ctypes.sizeof(api.b2_render_params) == 64
-    assert api.b2_render_params.seed.offset == 8 and api.b2_render_params.flags.offset == 60
+    assert ctypes.sizeof(api.b2_render_params) == 72
+    assert api.b2_render_params.seed.offset == 8 and api.b2_render_params.flags.offset == 60 and api.b2_render_params.integrator.offset == 64
+    # b2_medium_desc: 37 four-byte fields (148 B), padding, one pointer
+    assert api.b2_medium_desc.aabb_max.offset == 136 and api.b2_medium_desc.density.offset == 152 and ctypes.sizeof(api.b2_medium_desc) == 160
 
 
 def test_no_cpu_fallback_without_a_device():

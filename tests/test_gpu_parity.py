@@ -365,7 +365,11 @@ def test_cancel_returns_status(b2ctx):
     film = np.zeros((512, 512, 5), np.float32)
     rc = {}
     t = threading.Thread(target=lambda: rc.setdefault("rc", g.L.b2_render(g.h, C.byref(p), film.ctypes.data_as(C.POINTER(C.c_float)))))
-    t.start(); time.sleep(0.05); g.L.b2_cancel(g.h); t.join(timeout=60)
+    t.start(); time.sleep(0.05)
+    t0 = time.time()
+    while t.is_alive() and time.time() - t0 < 60:   # b2_render clears the flag when it starts: keep asking until it lands
+        g.L.b2_cancel(g.h); time.sleep(0.005)
+    t.join(timeout=60)
     assert not t.is_alive() and rc["rc"] == 5
     f, s = g.render(RenderParams(spp=2, sampler="sobol", rfilter="box"))       # the scene stays usable
     assert s["samples"] == 512 * 512 * 2

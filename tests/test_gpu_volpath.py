@@ -1,0 +1,189 @@
+"""GPU parity for the `volpath` row: media components and volumetric renders through the C-ABI against the
+oracle on the same seeded inputs.  Images: per-pixel relative L2 <= 1e-3 (BASELINE.json); index work exact."""
+import dataclasses
+import math
+
+import numpy as np
+import pytest
+
+from mitsuba_b200 import api
+from mitsuba_b200.scene import Bsdf, Camera, Medium, Mesh, RenderParams, SceneDesc, cornell_box, cube_mesh, look_at, smoke_scene
+from oracle import oracle_api as O
+from test_oracle_volpath import box_scene, const_medium, rays_through
+
+pytestmark = pytest.mark.gpu
+REL_L2_TOL = 1e-3
+
+
+def rel_l2(a, b):
+    return float(np.sqrt(((a.astype(np.float64) - b) ** 2).sum() / (b.astype(np.float64) ** 2).sum()))
+
+
+def pair(ctx, d):
+    g = api.Scene(ctx, d)
+    return g, O.OracleScene(d, sample_to_camera=g.sample_to_camera())
+
+
+@pytest.fixture(scope="module")
+def smoke(b2ctx):
+    d = smoke_scene(64, 64, res=32)
+    g, o = pair(b2ctx, d)
+    return d, g, o
+
+
+def test_density_lookup_bit_exact(b2ctx):
+    rng = np.random.default_rng(1)
+    dens = rng.uniform(0, 1, (9, 6, 7)).astype(np.float32)
+    to_world = np.eye(4); to_world[:3, :3] = np.diag([2.0, 1.5, 0.5]); to_world[:3, 3] = (0.3, -0.2, 1.0)
+    med = Medium("heterogeneous", density=dens, aabb_min=(-1, 0, 0), aabb_max=(1, 1, 2), to_world=to_world)
+    g, o = pair(b2ctx, box_scene(med))
+    p = (rng.uniform(-0.2, 1.2, (20000, 3)) * (4.0, 1.5, 1.0) + (0.3 - 2.0, -0.2, 1.0)).astype(np.float32)
+    assert np.array_equal(g.medium_probe(0, "density", p, parity=True), o.medium_density(0, p))
+    assert np.allclose(g.medium_probe(0, "density", p, parity=False), o.medium_density(0, p), rtol=1e-5, atol=1e-6)
+
+
+def test_woodcock_components_match_the_oracle(smoke):
+    """Same counter stream, same walk: the transmittance estimates and sampled distances agree sample by sample (a 1-ulp
+    difference of logf may flip a rare decision)."""
+    _, g, o = smoke
+    rng = np.random.default_rng(2)
+    n = 20000
+    orig = rng.uniform(-0.5, 1.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([orig, np.zeros((n, 1), np.float32), d, rng.uniform(0.2, 3.0, (n, 1)).astype(np.float32)], 1)
+    a = g.medium_probe(0, "transmittance", rays, seed=7, parity=True)
+    b = o.medium_transmittance(0, rays, seed=7)
+    assert (a != b).any(1).mean() < 2e-4
+    assert 0.05 < b[:, 0].mean() < 0.999
+    t_ref = b[:, 0].mean()
+    a = g.medium_probe(0, "sample_distance", rays, seed=9, parity=True)
+    b = o.medium_sample_distance(0, rays, seed=9)
+    same = a[:, 0] == b[:, 0]
+    assert (~same).mean() < 2e-4
+    ok = same & (b[:, 0] > 0)
+    assert ok.sum() > 500
+    np.testing.assert_allclose(a[ok, 1:10], b[ok, 1:10], rtol=2e-5, atol=1e-7)
+    # throughput build: statistically the same
+    c = g.medium_probe(0, "transmittance", rays, seed=7, parity=False)
+    assert abs(c[:, 0].mean() - t_ref) < 0.01
+
+
+def test_homogeneous_components(b2ctx):
+    med = Medium("homogeneous", sigma_a=(0.2, 0.3, 0.1), sigma_s=(1.8, 0.7, 0.4), strategy="balance")
+    g, o = pair(b2ctx, box_scene(med))
+    r = rays_through(5000, np.random.default_rng(3)); r[:, 3] = 1.0; r[:, 7] = np.random.default_rng(4).uniform(1.05, 2.5, 5000)
+    np.testing.assert_allclose(g.medium_probe(0, "transmittance", r, parity=True), o.medium_transmittance(0, r), rtol=1e-6)
+    a = g.medium_probe(0, "sample_distance", r, seed=5, parity=True); b = o.medium_sample_distance(0, r, seed=5)
+    assert np.array_equal(a[:, 0], b[:, 0])
+    np.testing.assert_allclose(a[:, 1:10], b[:, 1:10], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("g_hg", [0.0, 0.6, -0.85])
+def test_phase_functions(b2ctx, g_hg):
+    med = Medium("homogeneous", sigma_s=(1, 1, 1), phase="hg" if g_hg else "isotropic", g=g_hg)
+    g, o = pair(b2ctx, box_scene(med))
+    rng = np.random.default_rng(6)
+    n = 20000
+    wi = rng.normal(size=(n, 3)).astype(np.float32); wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+    s = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    a = g.medium_probe(0, "phase", np.concatenate([wi, s], 1), parity=True)
+    b = o.phase(0, wi, s)
+    np.testing.assert_allclose(a[:, :3], b[:, :3], atol=3e-6)
+    np.testing.assert_allclose(a[:, 3:], b[:, 3:], rtol=3e-5)
+
+
+@pytest.mark.parametrize("sampler", ["independent", "sobol"])
+def test_smoke_render_matches_oracle(smoke, sampler):
+    _, g, o = smoke
+    # parity build: same decisions sample by sample.  Throughput build: a path whose Woodcock walk takes a different
+    # turn (fast-math sincos / division, plane-form triangles) changes one sample by O(1); its weight in the image falls
+    # as 1/spp, so that build is compared at 64 spp (the contract's 1e-3 is quoted at 256 spp, BASELINE.json configs[3]).
+    for parity, spp, tol in ((True, 16, 3e-4), (False, 64, REL_L2_TOL)):
+        rp = RenderParams(spp=spp, rfilter="box", sampler=sampler, integrator="volpath")
+        ref, so = o.render(rp)
+        film, st = g.render(rp, parity=parity, pool_size=1 << 14)
+        e = rel_l2(api.develop(film), api.develop(ref))
+        assert e < tol, (sampler, parity, e)
+        assert np.array_equal(film[..., 4], ref[..., 4])  # weights: exact
+        assert st["samples"] == so["samples"] and st["bad_samples"] == 0
+        # reference statistics: rays (skdtree.cpp:122), shadow rays (:152), avgPathLength (volpath.cpp:359-360)
+        lim = 2e-4 if parity else 2e-3
+        assert abs(st["rays"] - so["rays"]) <= lim * so["rays"]
+        assert abs(st["shadow_rays"] - so["shadowRays"]) <= lim * so["shadowRays"]
+        assert abs(st["path_length_sum"] - so["pathLengthSum"]) <= lim * so["pathLengthSum"]
+
+
+def test_smoke_render_gaussian_hg_and_depth_limits(b2ctx):
+    d = smoke_scene(48, 48, res=24, phase="hg", g=0.6, scale=16.0, albedo=(0.9, 0.7, 0.5))
+    g, o = pair(b2ctx, d)
+    for kw in (dict(), dict(max_depth=3), dict(max_depth=2), dict(rr_depth=2), dict(strict_normals=True)):
+        rp = RenderParams(spp=8, rfilter="gaussian", sampler="independent", integrator="volpath", **kw)
+        ref, _ = o.render(rp)
+        film, _ = g.render(rp, parity=True)
+        assert rel_l2(api.develop(film), api.develop(ref)) < 3e-4, kw
+
+
+def test_homogeneous_medium_render(b2ctx):
+    med = Medium("homogeneous", sigma_a=(0.3, 0.4, 0.6), sigma_s=(2.0, 1.5, 1.0), phase="hg", g=0.3)
+    d = smoke_scene(48, 48, res=4)
+    for m in d.meshes:
+        if m.interior is not None:
+            m.interior = med
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=16, rfilter="box", sampler="independent", integrator="volpath")
+    ref, so = o.render(rp)
+    film, st = g.render(rp, parity=True)
+    assert rel_l2(api.develop(film), api.develop(ref)) < 3e-4
+    film, _ = g.render(rp, parity=False)
+    assert rel_l2(api.develop(film), api.develop(ref)) < REL_L2_TOL
+
+
+def test_volpath_without_media_equals_path(b2ctx):
+    d = cornell_box(64, 64)
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=8, rfilter="box", sampler="sobol")
+    a, _ = g.render(rp, parity=True)
+    b, _ = g.render(dataclasses.replace(rp, integrator="volpath"), parity=True)
+    assert rel_l2(api.develop(b), api.develop(a)) < 1e-5
+    ref, _ = o.render(dataclasses.replace(rp, integrator="volpath"))
+    assert rel_l2(api.develop(b), api.develop(ref)) < 2e-4
+
+
+def test_path_integrator_passes_through_index_matched_boundaries(smoke):
+    """`path` ignores media but must cross BSDF-less boundaries (null BSDF, path.cpp:232)."""
+    _, g, o = smoke
+    rp = RenderParams(spp=8, rfilter="box", sampler="sobol", integrator="path")
+    ref, _ = o.render(rp)
+    for parity in (True, False):
+        film, _ = g.render(rp, parity=parity)
+        assert rel_l2(api.develop(film), api.develop(ref)) < (3e-4 if parity else REL_L2_TOL)
+
+
+def test_sharding_and_pool_independence(smoke):
+    _, g, _ = smoke
+    rp = RenderParams(spp=8, rfilter="box", sampler="independent", integrator="volpath")
+    full, _ = g.render(rp, parity=True, pool_size=1 << 12)
+    other, _ = g.render(rp, parity=True, pool_size=1 << 16)
+    assert rel_l2(api.develop(other), api.develop(full)) < 1e-6
+    lo, _ = g.render(dataclasses.replace(rp, sample_lo=0, sample_hi=5), parity=True)
+    hi, _ = g.render(dataclasses.replace(rp, sample_lo=5, sample_hi=8), parity=True)
+    np.testing.assert_allclose(lo + hi, full, rtol=1e-4, atol=1e-5)
+
+
+def test_furnace_on_the_gpu(b2ctx):
+    med = const_medium(4.0, albedo=1.0)
+    d = box_scene(med, emit_box=((-60, -60, -60), (61, 61, 61)), cam_from=(0.5, 0.5, -3.0), res=16)
+    g = api.Scene(b2ctx, d)
+    film, st = g.render(RenderParams(spp=1024, rfilter="box", sampler="independent", integrator="volpath", rr_depth=40), parity=False)
+    assert abs(api.develop(film).mean() - 1.0) < 0.02
+    assert st["path_length_sum"] / st["samples"] > 2.0
+
+
+def test_invalid_media_are_rejected(b2ctx):
+    d = smoke_scene(16, 16, res=8)
+    for m in d.meshes:
+        if m.interior is not None:
+            m.radiance = (1.0, 1.0, 1.0)  # index-matched boundary + emitter: shape.cpp:76-78
+            m.bsdf = Bsdf("null")
+    with pytest.raises(api.B2Error, match="index-matched"):
+        api.Scene(b2ctx, d)
