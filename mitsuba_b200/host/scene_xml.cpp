@@ -134,7 +134,8 @@ struct Parser {
             if (!defines.count(need("name"))) defines[need("name")] = need("value");
             return;
         }
-        static const char *objects[] = {"scene", "integrator", "sensor", "sampler", "film", "rfilter", "bsdf", "shape", "emitter", "ref", "transform"};
+        static const char *objects[] = {"scene", "integrator", "sensor", "sampler", "film", "rfilter", "bsdf", "shape", "emitter", "ref", "transform",
+                                        "medium", "volume", "phase"};
         bool isObject = std::find_if(std::begin(objects), std::end(objects), [&](const char *o) { return tag == o; }) != std::end(objects);
         if (isObject) {
             auto n = std::make_unique<Node>();
@@ -262,6 +263,7 @@ struct Props {
     bool b(const std::string &k, bool d) { used[k] = true; auto it = n->props.find(k); if (it == n->props.end()) return d; if (it->second.kind != Value::Bool) throw Err("property '" + k + "' must be a boolean"); return it->second.b; }
     std::string s(const std::string &k, const std::string &d) { used[k] = true; auto it = n->props.find(k); if (it == n->props.end()) return d; if (it->second.kind != Value::String) throw Err("property '" + k + "' must be a string"); return it->second.s; }
     void spec(const std::string &k, const double *d, float *out) { used[k] = true; auto it = n->props.find(k); const double *v = d; if (it != n->props.end()) { if (it->second.kind != Value::Spectrum) throw Err("property '" + k + "' must be a spectrum"); v = it->second.v; } for (int c = 0; c < 3; ++c) out[c] = (float) v[c]; }
+    bool vec(const std::string &k, double *out) { used[k] = true; auto it = n->props.find(k); if (it == n->props.end()) return false; if (it->second.kind != Value::Vec) throw Err("property '" + k + "' must be a point"); for (int c = 0; c < 3; ++c) out[c] = it->second.v[c]; return true; }
     M4 xf(const std::string &k) { used[k] = true; auto it = n->props.find(k); return it == n->props.end() ? M4() : it->second.t; }
     void checkAllUsed() { // Properties "unqueried" check (src/libcore/plugin.cpp:185-196)
         for (auto &p : n->props) if (!used.count(p.first)) throw Err("<" + n->tag + " type=\"" + n->type + "\">: unreferenced property \"" + p.first + "\"");
@@ -366,8 +368,157 @@ struct Loader {
     }
     int resolveRef(Node *r) {
         auto it = bsdfIds.find(r->id);
-        if (it == bsdfIds.end()) throw Err("Referenced object \"" + r->id + "\" not found (only BSDF references are supported)");
+        if (it == bsdfIds.end()) throw Err("Referenced object \"" + r->id + "\" not found (BSDF and medium references are supported)");
         return it->second;
+    }
+
+    // ---- participating media ----
+    std::map<std::string, int> mediumIds;
+    // GridDataSource::loadFromFile, gridvolume.cpp:225-296: "VOL" 3, type (1 = float32), res x/y/z, channels, data box, data
+    static void loadVol(const std::string &path, int res[3], double lo[3], double hi[3], std::vector<float> &data) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Err("gridvolume: cannot open \"" + path + "\"");
+        char hdr[4];
+        f.read(hdr, 4);
+        if (!f || hdr[0] != 'V' || hdr[1] != 'O' || hdr[2] != 'L') throw Err("Encountered an invalid volume data file (incorrect header identifier)");
+        if (hdr[3] != 3) throw Err("Encountered an invalid volume data file (incorrect file version)");
+        int32_t h[5];
+        f.read((char *) h, 20);
+        if (h[0] != 1 || h[4] != 1) throw Err("gridvolume: only single-channel float32 density grids are supported (type " + std::to_string(h[0]) + ", channels " + std::to_string(h[4]) + ")");
+        res[0] = h[1]; res[1] = h[2]; res[2] = h[3];
+        float bb[6];
+        f.read((char *) bb, 24);
+        for (int i = 0; i < 3; ++i) { lo[i] = bb[i]; hi[i] = bb[3 + i]; }
+        const size_t n = (size_t) res[0] * res[1] * res[2];
+        if (!f || res[0] < 2 || res[1] < 2 || res[2] < 2) throw Err("gridvolume: invalid resolution");
+        data.resize(n);
+        f.read((char *) data.data(), (std::streamsize) (n * 4));
+        if (!f) throw Err("gridvolume: file is truncated");
+    }
+    int addMedium(Node *n) {
+        if (!n->id.empty() && mediumIds.count(n->id)) return mediumIds[n->id];
+        Props p(n);
+        b2_medium_desc m;
+        memset(&m, 0, sizeof(m));
+        m.scale = 1;
+        for (int c = 0; c < 3; ++c) m.albedo[c] = 0;
+        std::vector<float> density;
+        double g = 0;
+        // phase function child (medium.cpp:57-65: isotropic when absent)
+        m.phase = B2_PHASE_ISOTROPIC;
+        for (auto &c : n->children) {
+            if (c->tag == "phase") {
+                Props pp(c.get());
+                if (c->type == "isotropic") m.phase = B2_PHASE_ISOTROPIC;
+                else if (c->type == "hg") {
+                    m.phase = B2_PHASE_HG;
+                    m.g = (float) pp.f("g", 0.8); // hg.cpp:49
+                    if (m.g >= 1 || m.g <= -1) throw Err("The asymmetry parameter must lie in the interval (-1, 1)!"); // hg.cpp:50-51
+                } else throw Err("unsupported phase function \"" + c->type + "\" (supported: isotropic, hg)");
+                pp.checkAllUsed();
+            }
+        }
+        if (n->type == "homogeneous") { // medium.cpp:27-37 + materials.h:90-190 (no preset table) + homogeneous.cpp:156-222
+            m.type = B2_MEDIUM_HOMOGENEOUS;
+            if (p.has("material")) throw Err("homogeneous: material presets are not supported, give sigmaS/sigmaA or sigmaT/albedo");
+            const bool hasAS = p.has("sigmaS") || p.has("sigmaA"), hasTA = p.has("sigmaT") || p.has("albedo");
+            if (hasAS && hasTA) throw Err("You can either specify sigmaS & sigmaA *or* sigmaT & albedo, but no other combinations!");
+            if (!hasAS && !hasTA) throw Err("homogeneous: give sigmaS/sigmaA or sigmaT/albedo (material presets are not supported)");
+            const double zero[3] = {0, 0, 0};
+            float sS[3], sA[3];
+            if (hasAS) { p.spec("sigmaS", zero, sS); p.spec("sigmaA", zero, sA); }
+            else {
+                float sT[3], al[3];
+                if (!p.has("sigmaT") || !p.has("albedo")) throw Err("homogeneous: sigmaT and albedo must be given together");
+                p.spec("sigmaT", zero, sT); p.spec("albedo", zero, al);
+                for (int c = 0; c < 3; ++c) { sS[c] = al[c] * sT[c]; sA[c] = sT[c] - sS[c]; }
+            }
+            if (p.has("g")) g = p.f("g", 0);
+            if (g <= -1 || g >= 1) throw Err("The anisotropy parameter 'g' must be in the range (-1, 1)!");
+            const float scale = (float) p.f("scale", 1.0);
+            for (int c = 0; c < 3; ++c) { m.sigma_s[c] = sS[c] * scale * (1.0f - (float) g); m.sigma_a[c] = sA[c] * scale; }
+            float sT[3] = {m.sigma_a[0] + m.sigma_s[0], m.sigma_a[1] + m.sigma_s[1], m.sigma_a[2] + m.sigma_s[2]};
+            float w = (float) p.f("mediumSamplingWeight", -1);
+            if (w == -1) { // homogeneous.cpp:168-184
+                for (int c = 0; c < 3; ++c) { float alb = m.sigma_s[c] / sT[c]; if (alb > w && sT[c] != 0) w = alb; }
+                if (w > 0) w = std::max(w, 0.5f);
+            }
+            m.medium_sampling_weight = w;
+            std::string strategy = p.s("strategy", "balance");
+            if (strategy == "balance") m.strategy = 0;
+            else if (strategy == "single") {
+                m.strategy = 1;
+                int channel = 0;
+                float smallest = INFINITY;
+                for (int c = 0; c < 3; ++c) if (sT[c] < smallest) { smallest = sT[c]; channel = c; }
+                channel = (int) p.i("channel", channel);
+                if (channel < 0 || channel > 2) throw Err("homogeneous: 'channel' out of range");
+                m.sampling_density = sT[channel];
+                if (p.b("monochromatic", false)) throw Err("homogeneous: 'monochromatic' is not supported");
+            } else if (strategy == "manual") { m.strategy = 2; m.sampling_density = (float) p.f("samplingDensity", 0); }
+            else throw Err("Specified an unknown sampling strategy"); // `maximum` is not on the path
+        } else if (n->type == "heterogeneous") { // heterogeneous.cpp:182-260
+            m.type = B2_MEDIUM_HETEROGENEOUS;
+            if (p.has("sigmaS") || p.has("sigmaA"))
+                throw Err("The 'sigmaS' and 'sigmaA' properties are only supported by homogeneous media. Please use nested volume instances to supply these parameters");
+            std::string method = p.s("method", "woodcock");
+            std::transform(method.begin(), method.end(), method.begin(), ::tolower);
+            if (method != "woodcock") throw Err("Unsupported integration method \"" + method + "\"! (this library implements woodcock)");
+            m.scale = (float) p.f("scale", 1.0);
+            p.f("stepSize", 0);
+            bool haveDensity = false, haveAlbedo = false;
+            for (auto &c : n->children) {
+                if (c->tag != "volume") continue;
+                Props vp(c.get());
+                if (c->name == "density") {
+                    if (c->type != "gridvolume") throw Err("heterogeneous: the density must be a `gridvolume` (got \"" + c->type + "\")");
+                    std::string fn = vp.s("filename", "");
+                    if (fn.empty()) throw Err("gridvolume: missing 'filename'");
+                    if (fn[0] != '/') fn = baseDir + "/" + fn;
+                    double lo[3], hi[3];
+                    loadVol(fn, m.res, lo, hi, density);
+                    double pmin[3], pmax[3];
+                    const bool hasMin = vp.vec("min", pmin), hasMax = vp.vec("max", pmax);
+                    if (hasMin && hasMax) for (int i = 0; i < 3; ++i) { lo[i] = pmin[i]; hi[i] = pmax[i]; } // gridvolume.cpp:112-117
+                    vp.b("sendData", false);
+                    M4 v2w = vp.xf("toWorld"), w2v;
+                    if (!v2w.inverse(w2v)) throw Err("gridvolume: singular toWorld transform");
+                    // m_worldToGrid = scale((res - 1) / extents) * translate(-min) * worldToVolume (gridvolume.cpp:186-193)
+                    M4 S, T;
+                    for (int i = 0; i < 3; ++i) { S.m[i * 5] = (m.res[i] - 1) / (hi[i] - lo[i]); T.m[i * 4 + 3] = -lo[i]; }
+                    M4 w2g = S * (T * w2v);
+                    for (int i = 0; i < 12; ++i) m.world_to_grid[i] = (float) w2g.m[i];
+                    for (int i = 0; i < 3; ++i) { m.aabb_min[i] = INFINITY; m.aabb_max[i] = -INFINITY; }
+                    for (int k = 0; k < 8; ++k) { // gridvolume.cpp:197-199
+                        const double q[3] = {(k & 4) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 1) ? hi[2] : lo[2]};
+                        double o[3];
+                        v2w.point(q, o);
+                        for (int i = 0; i < 3; ++i) { m.aabb_min[i] = std::min(m.aabb_min[i], (float) o[i]); m.aabb_max[i] = std::max(m.aabb_max[i], (float) o[i]); }
+                    }
+                    haveDensity = true;
+                } else if (c->name == "albedo") {
+                    if (c->type != "constvolume") throw Err("heterogeneous: the albedo must be a `constvolume` (got \"" + c->type + "\")");
+                    auto it = c->props.find("value");
+                    if (it == c->props.end()) throw Err("constvolume: missing 'value'");
+                    vp.used["value"] = true;
+                    if (it->second.kind == Value::Spectrum) for (int k = 0; k < 3; ++k) m.albedo[k] = (float) it->second.v[k];
+                    else if (it->second.kind == Value::Float || it->second.kind == Value::Int) for (int k = 0; k < 3; ++k) m.albedo[k] = (float) it->second.f;
+                    else throw Err("constvolume: 'value' must be a spectrum or a float");
+                    haveAlbedo = true;
+                } else throw Err("heterogeneous: unsupported volume \"" + c->name + "\" (supported: density, albedo)");
+                vp.checkAllUsed();
+            }
+            if (!haveDensity) throw Err("No density specified!");
+            if (!haveAlbedo) throw Err("No albedo specified!");
+            m.density = density.data();
+        } else throw Err("unsupported medium \"" + n->type + "\" (supported: homogeneous, heterogeneous)");
+        for (auto &c : n->children)
+            if (c->tag != "phase" && c->tag != "volume" && c->tag != "transform") throw Err("unsupported child <" + c->tag + "> of <medium>");
+        p.checkAllUsed();
+        const int id = b2_scene_add_medium(scene, &m);
+        if (id < 0) throw Err(b2_last_error(nullptr));
+        if (!n->id.empty()) mediumIds[n->id] = id;
+        return id;
     }
 
     struct MeshData { std::vector<float> P, N, UV; std::vector<uint32_t> idx; };
@@ -538,10 +689,22 @@ struct Loader {
             }
         } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, rectangle, cube)");
         // children: bsdf / ref / emitter
-        int mat = -1, em = -1;
+        int mat = -1, em = -1, interior = -1, exterior = -1;
         bool isEmitter = false;
         for (auto &c : n->children) {
             if (c->tag == "bsdf") mat = addBsdf(c.get());
+            else if (c->tag == "medium" || (c->tag == "ref" && (c->name == "interior" || c->name == "exterior"))) { // shape.cpp:160-176
+                int mid;
+                if (c->tag == "medium") mid = addMedium(c.get());
+                else {
+                    auto it = mediumIds.find(c->id);
+                    if (it == mediumIds.end()) throw Err("Referenced object \"" + c->id + "\" not found");
+                    mid = it->second;
+                }
+                if (c->name == "interior") interior = mid;
+                else if (c->name == "exterior") exterior = mid;
+                else throw Err("Shape: Invalid medium child (must be named 'interior' or 'exterior')!");
+            }
             else if (c->tag == "ref") mat = resolveRef(c.get());
             else if (c->tag == "emitter") {
                 if (c->type != "area") throw Err("unsupported emitter plugin \"" + c->type + "\" (hot path: area)");
@@ -556,10 +719,12 @@ struct Loader {
                 isEmitter = true;
             } else if (c->tag != "transform") throw Err("unsupported child <" + c->tag + "> of <shape>");
         }
-        if (mat < 0) { // shape.cpp:48-72
+        if (mat < 0) { // shape.cpp:48-72: emitter -> black diffuse; medium transition -> null; else 0.5 diffuse
             b2_material_desc m;
             memset(&m, 0, sizeof(m));
-            m.type = B2_BSDF_DIFFUSE; m.nested = -1; m.eta = 1; m.thickness = 1; m.sample_visible = 1; m.alpha_u = m.alpha_v = 0.1f;
+            const bool transition = interior >= 0 || exterior >= 0;
+            m.type = (!isEmitter && transition) ? B2_BSDF_NULL : B2_BSDF_DIFFUSE;
+            m.nested = -1; m.eta = 1; m.thickness = 1; m.sample_visible = 1; m.alpha_u = m.alpha_v = 0.1f;
             for (int c = 0; c < 3; ++c) { m.reflectance[c] = isEmitter ? 0.0f : 0.5f; m.transmittance[c] = 1; m.k_c[c] = 1; }
             mat = b2_scene_add_material(scene, &m);
         }
@@ -567,6 +732,7 @@ struct Loader {
         int id = b2_scene_add_mesh(scene, md.P.data(), md.N.empty() ? nullptr : md.N.data(), md.UV.empty() ? nullptr : md.UV.data(),
                                    (uint32_t) (md.P.size() / 3), md.idx.data(), (uint32_t) (md.idx.size() / 3), mat, em);
         if (id < 0) throw Err(b2_last_error(nullptr));
+        if ((interior >= 0 || exterior >= 0) && b2_scene_set_mesh_media(scene, id, interior, exterior)) throw Err(b2_last_error(nullptr));
     }
 
     void run(Node *root, b2_render_params *rp) {
@@ -575,11 +741,13 @@ struct Loader {
         rp->rfilter = B2_RFILTER_GAUSSIAN; rp->rfilter_param = 0.5f;
         bool haveSensor = false;
         for (auto &c : root->children) if (c->tag == "bsdf") addBsdf(c.get());
+        for (auto &c : root->children) if (c->tag == "medium") addMedium(c.get());
         for (auto &cu : root->children) {
             Node *c = cu.get();
-            if (c->tag == "bsdf") continue;
+            if (c->tag == "bsdf" || c->tag == "medium") continue;
             if (c->tag == "integrator") {
-                if (c->type != "path") throw Err("unsupported integrator \"" + c->type + "\": this library implements the `path` plugin");
+                if (c->type == "volpath") rp->integrator = B2_INTEGRATOR_VOLPATH;
+                else if (c->type != "path") throw Err("unsupported integrator \"" + c->type + "\": this library implements the `path` and `volpath` plugins");
                 Props p(c);
                 rp->max_depth = (int) p.i("maxDepth", -1); rp->rr_depth = (int) p.i("rrDepth", 5);
                 rp->strict_normals = p.b("strictNormals", false); rp->hide_emitters = p.b("hideEmitters", false);
