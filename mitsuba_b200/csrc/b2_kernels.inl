@@ -244,7 +244,7 @@ B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uin
     smp.kind = rp.sampler;
     smp.m32 = sc.sobolNib;
     smp.nNib = rp.indexNibbles;
-    smp.overflow = false;
+    smp.overflow = false; smp.cacheDim = 0xFFFFFFFFu;
     smp.dim = 0;
     if (rp.sampler == 0) {
         smp.scramble32 = (uint32_t) rp.scramble;
@@ -629,7 +629,7 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
             smp.kind = rp.sampler;
             smp.m32 = sc.sobolNib;
             smp.nNib = rp.indexNibbles;
-            smp.overflow = false;
+            smp.overflow = false; smp.cacheDim = 0xFFFFFFFFu;
             smp.index = ((uint64_t) sm2.y << 32) | sm2.x;
             smp.dim = state >> 20;
             smp.scramble32 = rp.sampler == 0 ? (uint32_t) rp.scramble : (uint32_t) (rp.scramble >> 32);
@@ -863,7 +863,8 @@ struct VolEnv {
     uint32_t nRays, nShadow;
     B2_DEV VolEnv(const DScene &s, const TraceMem &t) : sc(s), tm(t), nRays(0), nShadow(0) {}
     // Scene::rayIntersect(ray, its): skdtree.cpp:112-142
-    B2_DEV bool closest(const V3 &o, const V3 &d, float rayMint, float rayMaxt, HitRec &h) {
+    // not inlined: one copy of the traversal for the six call sites (see woodcockWalk)
+    __device__ __noinline__ bool closest(const V3 &o, const V3 &d, float rayMint, float rayMaxt, HitRec &h) {
         h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
         const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         float mint, maxt;
@@ -875,7 +876,7 @@ struct VolEnv {
     }
     // ShapeKDTree::rayIntersect(ray, t, shape, n, uv): skdtree.cpp:144-204 -- closest hit, epsilon scale without the inner
     // max, unflipped face normal
-    B2_DEV bool closestNormal(const V3 &o, const V3 &d, float rayMint, float rayMaxt, float &t, uint32_t &prim, V3 &n) {
+    __device__ __noinline__ bool closestNormal(const V3 &o, const V3 &d, float rayMint, float rayMaxt, float &t, uint32_t &prim, V3 &n) {
         HitRec h;
         h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
         const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -985,7 +986,10 @@ B2_DEV float volPdfEmitterDirect(const DScene &sc, const EmitterQuery &eq, const
     return pdfDirect * (em.samplingWeight * sc.emitterNormalization);
 }
 
-__global__ void __launch_bounds__(B2_TRACE_BLOCK) k_volstep(DScene sc, DPool pool, DRender rp) {
+#ifndef B2_VOL_MINBLOCKS
+#define B2_VOL_MINBLOCKS 5 // 256 x 5 threads per SM, <= 51 registers: measured best (the kernel is latency bound; sweep 2..8 in DESIGN.md)
+#endif
+__global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DScene sc, DPool pool, DRender rp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
     stampBegin(rp, it, STAGE_SHADE);
@@ -994,8 +998,17 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_volstep(DScene sc, DPool poo
     VolEnv env(sc, tm);
     uint32_t nDimOvf = 0, nDone = 0;
     const DMaterial *mats = sc.materials;
+#ifndef B2_VOL_STATIC
+    // Slots are handed out per lane from a ticket counter (zeroed by k_publish): a lane that finishes its path vertex early
+    // takes the next slot instead of idling until the slowest Woodcock walk of its warp is done; lanes that sit in the same
+    // inner loop for different slots still issue together.
+    for (;;) {
+        const uint32_t i = (uint32_t) atomicAdd(pool.counters + CTR_TICKET_EXT, 1ull);
+        if (i >= Q) break;
+#else
     for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
+#endif
         uint32_t state = i < Q ? pool.flags[i] : 0u;
         const bool live = (state & PF_ALIVE) != 0;
         if (live) {
@@ -1008,7 +1021,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_volstep(DScene sc, DPool poo
             Spectrum T(thr4.x, thr4.y, thr4.z), Li(li4.x, li4.y, li4.z);
             float eta = thr4.w;
             PathSampler smp;
-            smp.kind = rp.sampler; smp.m32 = sc.sobolNib; smp.nNib = rp.indexNibbles; smp.overflow = false;
+            smp.kind = rp.sampler; smp.m32 = sc.sobolNib; smp.nNib = rp.indexNibbles; smp.overflow = false; smp.cacheDim = 0xFFFFFFFFu;
             smp.index = ((uint64_t) sm2.y << 32) | sm2.x;
             smp.scramble32 = rp.sampler == 0 ? (uint32_t) rp.scramble : (uint32_t) (rp.scramble >> 32);
             int medium;
@@ -1180,7 +1193,7 @@ __global__ void k_medium_probe(DScene sc, int medium, int what, uint64_t n, cons
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const DMedium &m = sc.media[medium];
         PathSampler smp;
-        smp.kind = 2; smp.m32 = nullptr; smp.nNib = 0; smp.overflow = false; smp.dim = 0;
+        smp.kind = 2; smp.m32 = nullptr; smp.nNib = 0; smp.overflow = false; smp.cacheDim = 0xFFFFFFFFu; smp.dim = 0;
         smp.scramble32 = (uint32_t) (seed >> 32);
         const uint32_t px = (uint32_t) (i & 0xFFFF), py = (uint32_t) (i >> 16);
         smp.index = ((py * 65536u + px) * 1u + 0u) ^ (uint32_t) seed;
@@ -1286,7 +1299,7 @@ __global__ void k_bsdf_sample(DScene sc, int mat, uint64_t n, const float *wi, c
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         // replay sampler (kind 3): next1D() returns the third sample component (test_chisquare.cpp:58-92 FakeSampler)
         PathSampler smp;
-        smp.kind = 3; smp.m32 = nullptr; smp.nNib = 8; smp.overflow = false; smp.dim = 0; smp.index = 0;
+        smp.kind = 3; smp.m32 = nullptr; smp.nNib = 8; smp.overflow = false; smp.cacheDim = 0xFFFFFFFFu; smp.dim = 0; smp.index = 0;
         smp.scramble32 = __float_as_uint(samples[3 * i + 2]);
         BRec r;
         r.wi = V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);

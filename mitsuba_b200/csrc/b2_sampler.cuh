@@ -100,6 +100,7 @@ struct PathSampler {
     uint32_t nNib;
     bool overflow;
     float replayA, replayB; // kind 4 (component tests): next1D alternates A, B
+    uint32_t cacheWord, cacheDim; // counter stream: the high word of the last TEA block and the (odd) dimension it serves
 
     B2_DEV float next1D() {
         if (kind == 3) return __uint_as_float(scramble32); // replay (component tests)
@@ -108,8 +109,23 @@ struct PathSampler {
             if (dim >= 1024u) { overflow = true; dim = 1023u; } // sobol.cpp:223-225 raises an error here
             return sobolSampleNib(m32, index, dim++, scramble32, nNib);
         } else {
-            uint64_t r = sampleTEA((uint32_t) index, (dim++) ^ scramble32, 8); // 8 rounds: 4 leave consecutive keys correlated (tests/test_oracle_volpath.py)
-            uint32_t u = ((uint32_t) (r & 0xFFFFFFFFull) >> 9) | 0x3f800000u; // random.cpp:630-640
+            // one 8-round TEA block (4 rounds leave consecutive keys correlated) serves two dimensions: 2k -> low word, 2k+1 -> high word
+            const uint32_t d = dim++;
+            uint32_t w;
+#ifdef B2_TEA_CACHE
+            if ((d & 1u) && cacheDim == d) w = cacheWord;
+            else {
+                const uint64_t r = sampleTEA((uint32_t) index, (d >> 1) ^ scramble32, 8);
+                w = (d & 1u) ? (uint32_t) (r >> 32) : (uint32_t) r;
+                cacheWord = (uint32_t) (r >> 32); cacheDim = d | 1u;
+            }
+#else
+            {
+                const uint64_t r = sampleTEA((uint32_t) index, (d >> 1) ^ scramble32, 8);
+                w = (d & 1u) ? (uint32_t) (r >> 32) : (uint32_t) r;
+            }
+#endif
+            uint32_t u = (w >> 9) | 0x3f800000u; // random.cpp:630-640
             return __uint_as_float(u) - 1.0f;
         }
     }

@@ -204,7 +204,7 @@ struct IndependentSampler : Sampler {
 
 /* Counter-based stream keyed by (pixel linear index, sample index, dimension): the GPU's
  * `independent` (DESIGN.md "samplers"); restated here so the GPU path can be checked sample for
- * sample.  u = TEA(v0 = pixel*spp + sample (mod 2^32) ^ seed_lo, v1 = dim ^ seed_hi) -> low 32 bits ->
+ * sample.  (lo, hi) = TEA8(v0 = pixel*spp + sample (mod 2^32) ^ seed_lo, v1 = (dim >> 1) ^ seed_hi); even dim -> lo, odd dim -> hi;
  * float via the MTGP trick of random.cpp:630-640. */
 struct CounterSampler : Sampler {
     uint32_t W, spp, seedLo, seedHi, key = 0, dim = 0, s = 0;
@@ -214,9 +214,13 @@ struct CounterSampler : Sampler {
     void generate(int x, int y) override { px = x; py = y; s = 0; rekey(); }
     void advance() override { ++s; rekey(); }
     float next1D() override {
-        uint64_t r = sampleTEA(key, (dim++) ^ seedHi, 8); /* 8 rounds: with 4, consecutive keys give correlated low words (chi^2 fails) */
+        /* one 8-round TEA block (with 4 rounds consecutive keys give correlated words: chi^2 fails) serves two dimensions:
+           2k -> low word, 2k+1 -> high word */
+        uint32_t d = dim++;
+        uint64_t r = sampleTEA(key, (d >> 1) ^ seedHi, 8);
+        uint32_t w = (d & 1u) ? (uint32_t) (r >> 32) : (uint32_t) r;
         union { uint32_t u; float f; } x;
-        x.u = ((uint32_t) (r & 0xFFFFFFFF) >> 9) | 0x3f800000UL;
+        x.u = (w >> 9) | 0x3f800000UL;
         return x.f - 1.0f;
     }
     void next2D(float &a, float &b) override { a = next1D(); b = next1D(); }

@@ -82,4 +82,12 @@ if "smoke" in which:
     d = smoke_scene(512, 512, res=128)
     for smp in ("independent", "sobol"):
         render_rate("smoke_128/" + smp, d, RenderParams(spp=64, rfilter="gaussian", sampler=smp, integrator="volpath"), pool_size=1 << 20)
-    render_rate("smoke_128/pool4M", d, RenderParams(spp=64, rfilter="gaussian", sampler="independent", integrator="volpath"))
+    render_rate("smoke_128/pool4M", d, RenderParams(spp=256, rfilter="gaussian", sampler="independent", integrator="volpath"))
+    render_rate("smoke_128/parity_build", d, RenderParams(spp=16, rfilter="gaussian", sampler="independent", integrator="volpath"), parity=True)
+    if os.environ.get("SMOKE_ORACLE", "1") == "1":  # CPU restatement on the host cores, bounded sample
+        from oracle import oracle_api as O
+        d2 = smoke_scene(256, 256, res=128)
+        o = O.OracleScene(d2)
+        rp = RenderParams(spp=16, rfilter="gaussian", sampler="independent", integrator="volpath")
+        t = time.time(); _, so = o.render(rp); dt = time.time() - t
+        print(json.dumps(dict(scene="smoke_128/cpu_oracle", res=256, spp=16, threads=os.cpu_count(), msamples_s=round(so["samples"] / dt / 1e6, 2), seconds=round(dt, 2))), flush=True)
