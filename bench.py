@@ -149,6 +149,36 @@ def traversal_metric(ctx, hbm_gbs, n_inst=10, n_rays=1 << 22):
     return res
 
 
+def volpath_metric(ctx, with_cpu=True):
+    """BASELINE configs[3], reported next to the headline: the S4 smoke scene -- a 128^3 density grid in the unit cube,
+    `heterogeneous` Woodcock medium, isotropic phase, `volpath`, 512x512 @ 256 spp -- on this rank's GPU, plus the oracle's rate for
+    the same scene on the host cores (bounded sample)."""
+    from mitsuba_b200 import api
+    from mitsuba_b200.scene import RenderParams, smoke_scene
+    d = smoke_scene(512, 512, res=128)
+    sc = api.Scene(ctx, d)
+    rp = RenderParams(spp=256, rfilter="gaussian", sampler="independent", integrator="volpath")
+    sc.render(RenderParams(spp=16, rfilter="gaussian", sampler="independent", integrator="volpath"))
+    best = None
+    for _ in range(2):
+        _, st = sc.render(rp, flags=4)
+        if best is None or st["ms_total"] < best["ms_total"]:
+            best = st
+    n = 512 * 512 * 256
+    res = {"workload": "S4 smoke: 128^3 gridvolume, heterogeneous (woodcock), isotropic, volpath, independent sampler, gaussian filter, 512x512 @ 256 spp, 1 GPU",
+           "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"], "kernel": "k_volstep", "kernel_ms": best["ms_shade"],
+           "mean_path_length": best["path_length_sum"] / best["samples"], "rays_per_sample": (best["rays"] + best["shadow_rays"]) / best["samples"]}
+    sc.close()
+    if with_cpu:
+        from oracle import oracle_api as O
+        o = O.OracleScene(smoke_scene(512, 512, res=128))
+        rp2 = RenderParams(spp=8, rfilter="gaussian", sampler="independent", integrator="volpath")
+        t0 = time.time(); _, so = o.render(rp2); dt = time.time() - t0
+        res["cpu_baseline"] = {"value": so["samples"] / dt / 1e6, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "sample indices [0,8) of every pixel of the same scene"}
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -176,6 +206,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--parity", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-volpath", action="store_true", help="skip the volpath (BASELINE configs[3]) side measurement")
     ap.add_argument("--no-traversal", action="store_true", help="skip the isolated BVH-traversal measurement (S3-class scene)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -337,6 +368,8 @@ def main():
         }
         if not args.no_traversal:
             line["traversal"] = traversal_metric(ctx, peaks.get("hbm_gbs", 6650.0))
+        if not args.no_volpath:
+            line["volpath"] = volpath_metric(ctx, with_cpu=not args.no_cpu_baseline)
         if not args.no_cpu_baseline:
             cb = cpu_reference_run(1, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
