@@ -33,20 +33,26 @@ typedef struct b2_scene b2_scene;
  * host-side preprocessing (IOR lookup, /extEta), see src/bsdfs/{diffuse,roughconductor,
  * roughdielectric,coating}.cpp and src/bsdfs/microfacet.h:99-148. */
 enum { B2_BSDF_DIFFUSE = 0, B2_BSDF_ROUGHCONDUCTOR = 1, B2_BSDF_ROUGHDIELECTRIC = 2, B2_BSDF_COATING = 3,
-       B2_BSDF_NULL = 4 /* index-matched boundary, src/bsdfs/null.cpp (what Shape::configure assigns to a BSDF-less medium transition, shape.cpp:64-68) */ };
+       B2_BSDF_NULL = 4 /* index-matched boundary, src/bsdfs/null.cpp (what Shape::configure assigns to a BSDF-less medium transition, shape.cpp:64-68) */,
+       B2_BSDF_TWOSIDED = 5, B2_BSDF_DIELECTRIC = 6, B2_BSDF_CONDUCTOR = 7, B2_BSDF_PLASTIC = 8 /* src/bsdfs/{twosided,dielectric,conductor,plastic}.cpp */ };
 enum { B2_DISTR_BECKMANN = 0, B2_DISTR_GGX = 1, B2_DISTR_PHONG = 2 };
 typedef struct b2_material_desc {
     int32_t type;            /* B2_BSDF_* */
     int32_t distr;           /* B2_DISTR_*            microfacet.h:48-57 */
     int32_t sample_visible;  /* microfacet.h:138 (must be 0 for phong, :145-148) */
-    int32_t nested;          /* coating: material id of the nested BSDF (coating.cpp:190-199); else -1 */
+    int32_t nested;          /* coating / twosided: material id of the nested BSDF (coating.cpp:190-199, twosided.cpp:186-197); else -1 */
     float alpha_u, alpha_v;  /* roughness before the 1e-4 clamp (microfacet.h:70-71) */
     float eta;               /* roughdielectric / coating: intIOR/extIOR */
     float thickness;         /* coating.cpp:126 */
     float reflectance[3];    /* diffuse: reflectance; others: specularReflectance */
-    float transmittance[3];  /* roughdielectric: specularTransmittance */
-    float eta_c[3], k_c[3];  /* roughconductor eta, k divided by extEta (roughconductor.cpp:189-190) */
+    float transmittance[3];  /* roughdielectric / dielectric: specularTransmittance */
+    float eta_c[3], k_c[3];  /* roughconductor / conductor eta, k divided by extEta (roughconductor.cpp:189-190, conductor.cpp:174-175) */
     float sigma_a[3];        /* coating.cpp:129-130 */
+    int32_t nested2;         /* twosided: material id of the back-side BSDF (= nested when one child was given, twosided.cpp:89-90) */
+    float diffuse_reflectance[3]; /* plastic.cpp:158-159 */
+    float fdr_int, fdr_ext;  /* plastic.cpp:194-195: fresnelDiffuseReflectance(1/eta), (eta) */
+    float spec_sampling_weight; /* plastic.cpp:199-202 */
+    int32_t nonlinear;       /* plastic.cpp:161 */
 } b2_material_desc;
 
 /* Participating medium + phase function: `homogeneous` (src/medium/homogeneous.cpp:156-222, strategies

@@ -24,7 +24,8 @@ class b2_material_desc(C.Structure):
     _fields_ = [("type", C.c_int32), ("distr", C.c_int32), ("sample_visible", C.c_int32), ("nested", C.c_int32),
                 ("alpha_u", C.c_float), ("alpha_v", C.c_float), ("eta", C.c_float), ("thickness", C.c_float),
                 ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3), ("eta_c", C.c_float * 3),
-                ("k_c", C.c_float * 3), ("sigma_a", C.c_float * 3)]
+                ("k_c", C.c_float * 3), ("sigma_a", C.c_float * 3), ("nested2", C.c_int32), ("diffuse_reflectance", C.c_float * 3),
+                ("fdr_int", C.c_float), ("fdr_ext", C.c_float), ("spec_sampling_weight", C.c_float), ("nonlinear", C.c_int32)]
 
 
 class b2_render_params(C.Structure):
@@ -178,9 +179,11 @@ class Scene:
             m = b2_material_desc()
             m.type, m.distr, m.sample_visible, m.nested = d["type"], d["distr"], d["sampleVisible"], d["nested"]
             m.alpha_u, m.alpha_v, m.eta, m.thickness = d["alphaU"], d["alphaV"], d["eta"], d["thickness"]
-            for k, src in (("reflectance", "reflectance"), ("transmittance", "transmittance"), ("eta_c", "etaC"), ("k_c", "kC"), ("sigma_a", "sigmaA")):
+            for k, src in (("reflectance", "reflectance"), ("transmittance", "transmittance"), ("eta_c", "etaC"), ("k_c", "kC"), ("sigma_a", "sigmaA"),
+                           ("diffuse_reflectance", "diffuseReflectance")):
                 for j in range(3):
                     getattr(m, k)[j] = d[src][j]
+            m.nested2, m.fdr_int, m.fdr_ext, m.spec_sampling_weight, m.nonlinear = d["nested2"], d["fdrInt"], d["fdrExt"], d["specSamplingWeight"], d["nonlinear"]
             if self.L.b2_scene_add_material(self.h, C.byref(m)) < 0:
                 raise B2Error(ctx.err())
         media, media_ids = desc.flat_media()

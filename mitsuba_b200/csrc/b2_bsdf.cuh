@@ -231,6 +231,37 @@ template <int HINT> B2_DEV Spectrum leafEval(const DMaterial &d, const BRec &r, 
     const V3 R = ld3(d.reflectance);
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
     if (type == 4) return Spectrum(discrete ? 1.0f : 0.0f); // null.cpp:45-47 (index-matched boundary)
+    if (type == 6) { // dielectric.cpp:229-255
+        float cosThetaT;
+        const float F = fresnelDielectricExt(cosTheta(r.wi), cosThetaT, d.eta);
+        const float invEta = 1 / d.eta;
+        if (cosTheta(r.wi) * cosTheta(r.wo) >= 0) {
+            if (!discrete || fabsf(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > B2_DELTA_EPSILON) return Spectrum(0.0f);
+            return R * F;
+        }
+        const float scale = -(cosThetaT < 0 ? invEta : d.eta);
+        if (!discrete || fabsf(dot(V3(scale * r.wi.x, scale * r.wi.y, cosThetaT), r.wo) - 1) > B2_DELTA_EPSILON) return Spectrum(0.0f);
+        const float factor = cosThetaT < 0 ? invEta : d.eta;
+        return ld3(d.transmittance) * factor * factor * (1 - F);
+    }
+    if (type == 7) { // conductor.cpp:221-235
+        if (!discrete || cosTheta(r.wi) <= 0 || cosTheta(r.wo) <= 0 || fabsf(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > B2_DELTA_EPSILON) return Spectrum(0.0f);
+        return R * fresnelConductorExact(cosTheta(r.wi), ld3(d.etaC), ld3(d.kC));
+    }
+    if (type == 8) { // plastic.cpp:243-279
+        if (cosTheta(r.wo) <= 0 || cosTheta(r.wi) <= 0) return Spectrum(0.0f);
+        const float Fi = fresnelDielectricExt(cosTheta(r.wi), d.eta);
+        if (discrete) {
+            if (fabsf(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) < B2_DELTA_EPSILON) return R * Fi;
+            return Spectrum(0.0f);
+        }
+        const float Fo = fresnelDielectricExt(cosTheta(r.wo), d.eta);
+        Spectrum diff = ld3(d.diffuseReflectance);
+        if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
+        else diff = diff / (1 - d.fdrInt);
+        const float invEta2 = 1 / (d.eta * d.eta);
+        return diff * (squareToCosineHemispherePdf(r.wo) * invEta2 * (1 - Fi) * (1 - Fo));
+    }
     if (type == 0) { // diffuse.cpp:110-118
         if (discrete || d.flags == 0 || cosTheta(r.wi) <= 0 || cosTheta(r.wo) <= 0) return Spectrum(0.0f);
         return R * (B2_INV_PI * cosTheta(r.wo));
@@ -273,6 +304,30 @@ template <int HINT> B2_DEV Spectrum leafEval(const DMaterial &d, const BRec &r, 
 template <int HINT> B2_DEV float leafPdf(const DMaterial &d, const BRec &r, bool discrete) {
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
     if (type == 4) return discrete ? 1.0f : 0.0f; // null.cpp:49-51
+    if (type == 6) { // dielectric.cpp:257-279
+        float cosThetaT;
+        const float F = fresnelDielectricExt(cosTheta(r.wi), cosThetaT, d.eta);
+        const float invEta = 1 / d.eta;
+        if (cosTheta(r.wi) * cosTheta(r.wo) >= 0) {
+            if (!discrete || fabsf(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > B2_DELTA_EPSILON) return 0.0f;
+            return F;
+        }
+        const float scale = -(cosThetaT < 0 ? invEta : d.eta);
+        if (!discrete || fabsf(dot(V3(scale * r.wi.x, scale * r.wi.y, cosThetaT), r.wo) - 1) > B2_DELTA_EPSILON) return 0.0f;
+        return 1 - F;
+    }
+    if (type == 7) { // conductor.cpp:237-250
+        if (!discrete || cosTheta(r.wi) <= 0 || cosTheta(r.wo) <= 0 || fabsf(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > B2_DELTA_EPSILON) return 0.0f;
+        return 1.0f;
+    }
+    if (type == 8) { // plastic.cpp:281-309
+        if (cosTheta(r.wo) <= 0 || cosTheta(r.wi) <= 0) return 0.0f;
+        const float Fi = fresnelDielectricExt(cosTheta(r.wi), d.eta);
+        const float w = d.specSamplingWeight;
+        const float probSpecular = (Fi * w) / (Fi * w + (1 - Fi) * (1 - w));
+        if (discrete) return fabsf(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) < B2_DELTA_EPSILON ? probSpecular : 0.0f;
+        return squareToCosineHemispherePdf(r.wo) * (1 - probSpecular);
+    }
     if (type == 0) { // diffuse.cpp:120-128
         if (discrete || d.flags == 0 || cosTheta(r.wi) <= 0 || cosTheta(r.wo) <= 0) return 0.0f;
         return squareToCosineHemispherePdf(r.wo);
@@ -313,6 +368,55 @@ template <int HINT> B2_DEV Spectrum leafSample(const DMaterial &d, BRec &r, floa
     if (type == 4) { // null.cpp:65-76
         r.wo = -r.wi; r.sampledType = ENull; r.eta = 1.0f; pdfOut = 1.0f;
         return Spectrum(1.0f);
+    }
+    if (type == 6) { // dielectric.cpp:281-310 (both components enabled)
+        float cosThetaT;
+        const float F = fresnelDielectricExt(cosTheta(r.wi), cosThetaT, d.eta);
+        const float invEta = 1 / d.eta;
+        if (sx <= F) {
+            r.sampledType = EDeltaReflection;
+            r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z);
+            r.eta = 1.0f;
+            pdfOut = F;
+            return R;
+        }
+        r.sampledType = EDeltaTransmission;
+        const float scale = -(cosThetaT < 0 ? invEta : d.eta);
+        r.wo = V3(scale * r.wi.x, scale * r.wi.y, cosThetaT);
+        r.eta = cosThetaT < 0 ? d.eta : invEta;
+        pdfOut = 1 - F;
+        const float factor = cosThetaT < 0 ? invEta : d.eta;
+        return ld3(d.transmittance) * (factor * factor);
+    }
+    if (type == 7) { // conductor.cpp:268-283
+        if (cosTheta(r.wi) <= 0) return Spectrum(0.0f);
+        r.sampledType = EDeltaReflection;
+        r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z);
+        r.eta = 1.0f;
+        pdfOut = 1.0f;
+        return R * fresnelConductorExact(cosTheta(r.wi), ld3(d.etaC), ld3(d.kC));
+    }
+    if (type == 8) { // plastic.cpp:377-424 (both components enabled)
+        if (cosTheta(r.wi) <= 0) return Spectrum(0.0f);
+        const float Fi = fresnelDielectricExt(cosTheta(r.wi), d.eta);
+        r.eta = 1.0f;
+        const float w = d.specSamplingWeight;
+        const float probSpecular = (Fi * w) / (Fi * w + (1 - Fi) * (1 - w));
+        if (sx < probSpecular) {
+            r.sampledType = EDeltaReflection;
+            r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z);
+            pdfOut = probSpecular;
+            return R * Fi / probSpecular;
+        }
+        r.sampledType = EDiffuseReflection;
+        r.wo = squareToCosineHemisphere((sx - probSpecular) / (1 - probSpecular), sy);
+        const float Fo = fresnelDielectricExt(cosTheta(r.wo), d.eta);
+        Spectrum diff = ld3(d.diffuseReflectance);
+        if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
+        else diff = diff / (1 - d.fdrInt);
+        pdfOut = (1 - probSpecular) * squareToCosineHemispherePdf(r.wo);
+        const float invEta2 = 1 / (d.eta * d.eta);
+        return diff * (invEta2 * (1 - Fi) * (1 - Fo) / (1 - probSpecular));
     }
     if (type == 0) { // diffuse.cpp:141-150
         if (d.flags == 0 || cosTheta(r.wi) <= 0) return Spectrum(0.0f);
@@ -388,7 +492,7 @@ B2_DEV V3 coatRefractOut(const DMaterial &d, const V3 &wi, float &R) { // coatin
     return V3(d.eta * wi.x, d.eta * wi.y, -signum(cosTheta(wi)) * cosThetaT);
 }
 
-template <int HINT> B2_DEV Spectrum bsdfEval(const DMaterial *mats, int id, const BRec &r) {
+template <int HINT> B2_DEV Spectrum bsdfEval1(const DMaterial *mats, int id, const BRec &r) {
     const DMaterial &d = mats[id];
     if (HINT >= 0 && HINT < 3) return leafEval<HINT>(d, r, false);
     if (HINT != 3 && d.type != 3) return leafEval<-1>(d, r, false);
@@ -408,7 +512,7 @@ template <int HINT> B2_DEV Spectrum bsdfEval(const DMaterial *mats, int id, cons
     return result;
 }
 
-template <int HINT> B2_DEV float bsdfPdf(const DMaterial *mats, int id, const BRec &r) {
+template <int HINT> B2_DEV float bsdfPdf1(const DMaterial *mats, int id, const BRec &r) {
     const DMaterial &d = mats[id];
     if (HINT >= 0 && HINT < 3) return leafPdf<HINT>(d, r, false);
     if (HINT != 3 && d.type != 3) return leafPdf<-1>(d, r, false);
@@ -430,7 +534,7 @@ template <int HINT> B2_DEV float bsdfPdf(const DMaterial *mats, int id, const BR
     return p * (1 - probSpecular);
 }
 
-template <int HINT> B2_DEV Spectrum bsdfSample(const DMaterial *mats, int id, BRec &r, float &pdfOut, float sx, float sy, PathSampler &smp) {
+template <int HINT> B2_DEV Spectrum bsdfSample1(const DMaterial *mats, int id, BRec &r, float &pdfOut, float sx, float sy, PathSampler &smp) {
     const DMaterial &d = mats[id];
     if (HINT >= 0 && HINT < 3) return leafSample<HINT>(d, r, pdfOut, sx, sy, smp);
     if (HINT != 3 && d.type != 3) return leafSample<-1>(d, r, pdfOut, sx, sy, smp);
@@ -471,6 +575,42 @@ template <int HINT> B2_DEV Spectrum bsdfSample(const DMaterial *mats, int id, BR
     result = result * ((1 - R12) * (1 - R21));
     if (!(r.sampledType & EDelta)) pdfOut *= m_invEta * m_invEta * cosTheta(r.wo) / cosTheta(woPrime);
     return result;
+}
+
+// ---------------------------------------------------------------------------------------------
+// top level: the twosided adapter (twosided.cpp:109-184) around everything else; only the generic instantiation (HINT < 0)
+// can meet it -- the class-specialised kernels are launched for scenes whose materials are all of types 0..3
+// ---------------------------------------------------------------------------------------------
+template <int HINT> B2_DEV Spectrum bsdfEval(const DMaterial *mats, int id, const BRec &r) {
+    if (HINT < 0 && mats[id].type == 5) {
+        if (cosTheta(r.wi) > 0) return bsdfEval1<-1>(mats, mats[id].nested, r);
+        BRec b = r;
+        b.wi.z *= -1; b.wo.z *= -1;
+        return bsdfEval1<-1>(mats, mats[id].nested2, b);
+    }
+    return bsdfEval1<HINT>(mats, id, r);
+}
+template <int HINT> B2_DEV float bsdfPdf(const DMaterial *mats, int id, const BRec &r) {
+    if (HINT < 0 && mats[id].type == 5) {
+        if (r.wi.z > 0) return bsdfPdf1<-1>(mats, mats[id].nested, r);
+        BRec b = r;
+        b.wi.z *= -1; b.wo.z *= -1;
+        return bsdfPdf1<-1>(mats, mats[id].nested2, b);
+    }
+    return bsdfPdf1<HINT>(mats, id, r);
+}
+template <int HINT> B2_DEV Spectrum bsdfSample(const DMaterial *mats, int id, BRec &r, float &pdfOut, float sx, float sy, PathSampler &smp) {
+    if (HINT < 0 && mats[id].type == 5) {
+        bool flipped = false;
+        if (cosTheta(r.wi) < 0) { r.wi.z *= -1; flipped = true; }
+        const Spectrum result = bsdfSample1<-1>(mats, flipped ? mats[id].nested2 : mats[id].nested, r, pdfOut, sx, sy, smp);
+        if (flipped) {
+            r.wi.z *= -1;
+            if (!isZero(result) && pdfOut != 0) r.wo.z *= -1;
+        }
+        return result;
+    }
+    return bsdfSample1<HINT>(mats, id, r, pdfOut, sx, sy, smp);
 }
 
 } // namespace b2

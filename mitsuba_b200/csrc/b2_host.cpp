@@ -318,13 +318,26 @@ extern "C" int b2_scene_film_size(b2_scene *s, int *width, int *height) {
     *width = s->W; *height = s->H;
     return B2_OK;
 }
+static uint32_t materialFlags(const std::vector<b2_material_desc> &mats, int id);
 extern "C" int b2_scene_add_material(b2_scene *s, const b2_material_desc *m) {
     if (!s || !m) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_material: null argument"); return -1; }
-    if (m->type < 0 || m->type > B2_BSDF_NULL) { fail(s->ctx, B2_ERR_INVALID, "unknown BSDF type"); return -1; }
+    if (m->type < 0 || m->type > B2_BSDF_PLASTIC) { fail(s->ctx, B2_ERR_INVALID, "unknown BSDF type"); return -1; }
     if (m->type == B2_BSDF_COATING) {
         if (m->nested < 0 || m->nested >= (int) s->materials.size()) { fail(s->ctx, B2_ERR_INVALID, "coating: A child BSDF instance is required"); return -1; }
         if (s->materials[m->nested].type == B2_BSDF_COATING) { fail(s->ctx, B2_ERR_INVALID, "coating over coating is not supported on the device"); return -1; }
     }
+    if (m->type == B2_BSDF_TWOSIDED) { // twosided.cpp:87-107
+        const int n0 = m->nested, n1 = m->nested2;
+        if (n0 < 0 || n0 >= (int) s->materials.size()) { fail(s->ctx, B2_ERR_INVALID, "A nested one-sided material is required!"); return -1; }
+        if (n1 < 0 || n1 >= (int) s->materials.size()) { fail(s->ctx, B2_ERR_INVALID, "twosided: invalid back-side material id"); return -1; }
+        for (int n : {n0, n1}) {
+            const int t = s->materials[n].type;
+            if (t == B2_BSDF_TWOSIDED) { fail(s->ctx, B2_ERR_INVALID, "twosided inside twosided is not supported on the device"); return -1; }
+            if (materialFlags(s->materials, n) & 0x55u /* ETransmission */) { fail(s->ctx, B2_ERR_INVALID, "Only materials without a transmission component can be nested!"); return -1; }
+        }
+    }
+    if (m->type == B2_BSDF_COATING && s->materials[m->nested].type == B2_BSDF_TWOSIDED) { fail(s->ctx, B2_ERR_INVALID, "coating over twosided is not supported on the device"); return -1; }
+    if ((m->type == B2_BSDF_DIELECTRIC || m->type == B2_BSDF_PLASTIC) && m->eta <= 0) { fail(s->ctx, B2_ERR_INVALID, "The interior and exterior indices of refraction must be positive!"); return -1; }
     if ((m->type == B2_BSDF_ROUGHDIELECTRIC || m->type == B2_BSDF_COATING) && (m->eta <= 0 || m->eta == 1.0f)) {
         fail(s->ctx, B2_ERR_INVALID, "The interior and exterior indices of refraction must be positive and differ!"); // roughdielectric.cpp:196-198
         return -1;
@@ -445,6 +458,10 @@ static uint32_t materialFlags(const std::vector<b2_material_desc> &mats, int id)
         case 1: return EGlossyReflection | EFrontSide | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
         case 2: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide | EUsesSampler | ENonSymmetric | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
         case 4: return 0x1u /* ENull */ | EFrontSide | EBackSide; // null.cpp:38-43
+        case 5: return ((materialFlags(mats, d.nested) & ~EBackSide) | EFrontSide) | ((materialFlags(mats, d.nested2) & ~EFrontSide) | EBackSide); // twosided.cpp:96-102
+        case 6: return EDeltaReflection | 0x40u /* EDeltaTransmission */ | EFrontSide | EBackSide | ENonSymmetric; // dielectric.cpp:190-194
+        case 7: return EDeltaReflection | EFrontSide;                                                            // conductor.cpp:181-183
+        case 8: return EDeltaReflection | EDiffuseReflection | EFrontSide;                                       // plastic.cpp:211-215
         default: return materialFlags(mats, d.nested) | EDeltaReflection | EFrontSide | EBackSide;
     }
 }
@@ -657,6 +674,9 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         memcpy(d.reflectance, m.reflectance, 12); memcpy(d.transmittance, m.transmittance, 12);
         memcpy(d.etaC, m.eta_c, 12); memcpy(d.kC, m.k_c, 12); memcpy(d.sigmaA, m.sigma_a, 12);
         d.flags = materialFlags(s->materials, (int) i);
+        d.nested2 = m.nested2; d.nonlinear = m.nonlinear; d.fdrInt = m.fdr_int;
+        memcpy(d.diffuseReflectance, m.diffuse_reflectance, 12);
+        if (m.type == B2_BSDF_PLASTIC) d.specSamplingWeight = m.spec_sampling_weight;
         if (m.type == B2_BSDF_COATING) { // coating.cpp:177-181
             float acc = 0.0f;
             for (int k = 0; k < 3; ++k) acc += (float) std::exp((double) (m.sigma_a[k] * (-2 * m.thickness)));
@@ -667,9 +687,10 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     s->hasNullBsdf = false;
     for (auto &m : s->meshes) {
         const int t = s->materials[m.material].type;
-        if (t == B2_BSDF_NULL) {
-            s->hasNullBsdf = true; // shaded by the generic kernel (no per-class queue)
-            if (m.emitter >= 0) return fail(ctx, B2_ERR_INVALID, "Shape has an index-matched BSDF and an emitter attachment. This is not allowed!"); // shape.cpp:76-78
+        if (t >= B2_BSDF_NULL) {
+            s->hasNullBsdf = true; // types without a specialised kernel are shaded by the generic one (no per-class queue)
+            if (t == B2_BSDF_NULL && m.emitter >= 0)
+                return fail(ctx, B2_ERR_INVALID, "Shape has an index-matched BSDF and an emitter attachment. This is not allowed!"); // shape.cpp:76-78
         } else s->classPresent[t] = true;
     }
     // ---- media (volpath) ----

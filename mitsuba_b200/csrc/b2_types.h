@@ -15,8 +15,11 @@ struct DMaterial {
     float alphaU, alphaV, eta, thickness;
     float reflectance[3], transmittance[3], etaC[3], kC[3], sigmaA[3];
     uint32_t flags;        // BSDF type flags (bsdf.h:224-285) incl. nested, as BSDF::configure ORs them
-    float specSamplingWeight; // coating.cpp:177-181
-    float pad[2];
+    float specSamplingWeight; // coating.cpp:177-181; plastic.cpp:199-202
+    int32_t nested2;       // twosided: back-side BSDF
+    int32_t nonlinear;     // plastic.cpp:161
+    float diffuseReflectance[3]; // plastic
+    float fdrInt;          // plastic.cpp:194 (fdrExt is only used by getDiffuseReflectance)
 };
 
 // One participating medium + its phase function (device copy of b2_medium_desc)

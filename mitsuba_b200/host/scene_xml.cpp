@@ -290,6 +290,21 @@ static double namedIOR(Props &p, const std::string &key, const char *dflt) { // 
     return t->second;
 }
 
+// util.cpp:807-859 fresnelDiffuseReflectance(eta, fast = false): integral over xi in [0,1] of F(sqrt(xi), eta), composite Simpson
+static double fresnelDiffuseReflectance(double eta) {
+    auto F = [eta](double cosI) { // util.cpp:651-681 for cosI >= 0
+        if (eta == 1) return 0.0;
+        const double scale = 1 / eta, ct2 = 1 - (1 - cosI * cosI) * scale * scale;
+        if (ct2 <= 0) return 1.0;
+        const double ct = std::sqrt(ct2), rs = (cosI - eta * ct) / (cosI + eta * ct), rp = (eta * cosI - ct) / (eta * cosI + ct);
+        return 0.5 * (rs * rs + rp * rp);
+    };
+    const int n = 1 << 14;
+    double acc = F(0.0) + F(1.0);
+    for (int i = 1; i < n; ++i) acc += ((i & 1) ? 4.0 : 2.0) * F(std::sqrt((double) i / n));
+    return acc / (3.0 * n);
+}
+
 struct Loader {
     b2_scene *scene = nullptr;
     std::map<std::string, int> bsdfIds; // id -> material id
@@ -318,7 +333,7 @@ struct Loader {
         Props p(n);
         b2_material_desc m;
         memset(&m, 0, sizeof(m));
-        m.nested = -1; m.eta = 1.0f; m.thickness = 1.0f; m.sample_visible = 1; m.alpha_u = m.alpha_v = 0.1f;
+        m.nested = -1; m.nested2 = -1; m.eta = 1.0f; m.thickness = 1.0f; m.sample_visible = 1; m.alpha_u = m.alpha_v = 0.1f;
         const double one[3] = {1, 1, 1}, zero[3] = {0, 0, 0}, half[3] = {0.5, 0.5, 0.5};
         for (int c = 0; c < 3; ++c) { m.transmittance[c] = 1; m.k_c[c] = 1; }
         if (n->type == "diffuse") {
@@ -359,7 +374,47 @@ struct Loader {
             }
             if (nested < 0) throw Err("coating: A child BSDF instance is required");
             m.nested = nested;
-        } else throw Err("unsupported BSDF plugin \"" + n->type + "\" (hot path: diffuse, roughconductor, roughdielectric, coating)");
+        } else if (n->type == "twosided") { // twosided.cpp:186-197
+            m.type = B2_BSDF_TWOSIDED;
+            int kids[2] = {-1, -1}, nk = 0;
+            for (auto &c : n->children) {
+                if (c->tag != "bsdf" && c->tag != "ref") continue;
+                if (nk == 2) throw Err("No more than two nested BRDFs can be added!");
+                kids[nk++] = c->tag == "bsdf" ? addBsdf(c.get()) : resolveRef(c.get());
+            }
+            if (nk == 0) throw Err("A nested one-sided material is required!");
+            m.nested = kids[0]; m.nested2 = nk == 2 ? kids[1] : kids[0];
+        } else if (n->type == "dielectric") { // dielectric.cpp:145-162
+            m.type = B2_BSDF_DIELECTRIC;
+            p.spec("specularReflectance", one, m.reflectance); p.spec("specularTransmittance", one, m.transmittance);
+            float intI = (float) namedIOR(p, "intIOR", "bk7"), extI = (float) namedIOR(p, "extIOR", "air");
+            if (intI < 0 || extI < 0) throw Err("The interior and exterior indices of refraction must be positive!");
+            m.eta = intI / extI;
+        } else if (n->type == "conductor") { // conductor.cpp:153-176
+            m.type = B2_BSDF_CONDUCTOR;
+            p.spec("specularReflectance", one, m.reflectance);
+            std::string material = p.s("material", "Cu");
+            std::string lower = material;
+            std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
+            double eta[3] = {0, 0, 0}, k[3] = {1, 1, 1};
+            if (lower != "none" && !(p.has("eta") && p.has("k")))
+                throw Err("conductor: material=\"" + material + "\" needs the data/ior .spd tables (not supported); pass RGB 'eta' and 'k'");
+            float fe[3], fk[3];
+            p.spec("eta", eta, fe); p.spec("k", k, fk);
+            float ext = (float) namedIOR(p, "extEta", "air");
+            for (int c = 0; c < 3; ++c) { m.eta_c[c] = fe[c] / ext; m.k_c[c] = fk[c] / ext; }
+        } else if (n->type == "plastic") { // plastic.cpp:145-204
+            m.type = B2_BSDF_PLASTIC;
+            float intI = (float) namedIOR(p, "intIOR", "polypropylene"), extI = (float) namedIOR(p, "extIOR", "air");
+            if (intI < 0 || extI < 0) throw Err("The interior and exterior indices of refraction must be positive!");
+            m.eta = intI / extI;
+            p.spec("specularReflectance", one, m.reflectance); p.spec("diffuseReflectance", half, m.diffuse_reflectance);
+            m.nonlinear = p.b("nonlinear", false) ? 1 : 0;
+            m.fdr_int = (float) fresnelDiffuseReflectance(1.0 / m.eta); m.fdr_ext = (float) fresnelDiffuseReflectance(m.eta);
+            auto lum = [](const float *c) { return c[0] * 0.212671f + c[1] * 0.715160f + c[2] * 0.072169f; }; // spectrum.h:725-727
+            const float dAvg = lum(m.diffuse_reflectance), sAvg = lum(m.reflectance);
+            m.spec_sampling_weight = sAvg / (dAvg + sAvg);
+        } else throw Err("unsupported BSDF plugin \"" + n->type + "\" (supported: diffuse, roughconductor, roughdielectric, coating, twosided, dielectric, conductor, plastic)");
         p.checkAllUsed();
         int id = b2_scene_add_material(scene, &m);
         if (id < 0) throw Err(b2_last_error(nullptr));

@@ -25,7 +25,8 @@ NAMED_IOR = {
     "amber": 1.55, "pet": 1.5750, "diamond": 2.419,
 }
 
-BSDF_TYPES = {"diffuse": 0, "roughconductor": 1, "roughdielectric": 2, "coating": 3, "null": 4}
+BSDF_TYPES = {"diffuse": 0, "roughconductor": 1, "roughdielectric": 2, "coating": 3, "null": 4, "twosided": 5, "dielectric": 6,
+              "conductor": 7, "plastic": 8}
 DISTRIBUTIONS = {"beckmann": 0, "ggx": 1, "phong": 2, "as": 2}
 
 
@@ -36,6 +37,31 @@ def lookup_ior(value, default: str) -> float:
     if isinstance(value, str):
         return float(NAMED_IOR[value.lower()])
     return float(value)
+
+
+def _fresnel_dielectric_ext(cos_i, eta):
+    """util.cpp:651-681 fresnelDielectricExt in float64 (vectorised), used only for the host-side integral below."""
+    cos_i = np.asarray(cos_i, np.float64)
+    scale = np.where(cos_i > 0, 1.0 / eta, eta)
+    cos_t2 = 1 - (1 - cos_i * cos_i) * scale * scale
+    tir = cos_t2 <= 0
+    ci = np.abs(cos_i)
+    ct = np.sqrt(np.maximum(cos_t2, 0))
+    e = np.where(cos_i > 0, eta, 1.0 / eta)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rs = (ci - e * ct) / (ci + e * ct)
+        rp = (e * ci - ct) / (e * ci + ct)
+    return np.where(tir, 1.0, 0.5 * (rs * rs + rp * rp))
+
+
+def fresnel_diffuse_reflectance(eta: float) -> float:
+    """util.cpp:807-859 fresnelDiffuseReflectance(eta, fast=false): integral of F(sqrt(xi), eta) over xi in [0, 1]
+    (composite Simpson in float64 instead of the reference's adaptive Gauss-Lobatto with 1e-5 tolerance)."""
+    n = 1 << 14
+    xi = np.linspace(0.0, 1.0, n + 1)
+    f = _fresnel_dielectric_ext(np.sqrt(xi), eta)
+    w = np.ones(n + 1); w[1:-1:2] = 4; w[2:-1:2] = 2
+    return float(np.float32((w * f).sum() / (3 * n)))
 
 
 @dataclass
@@ -56,7 +82,10 @@ class Bsdf:
     ext_ior: object = "air"
     thickness: float = 1.0                                     # coating.cpp:126
     sigma_a: Sequence[float] = (0.0, 0.0, 0.0)                 # coating.cpp:129-130
-    nested: Optional["Bsdf"] = None                            # coating child BSDF
+    nested: Optional["Bsdf"] = None                            # coating / twosided child BSDF
+    nested_back: Optional["Bsdf"] = None                       # twosided: optional second child (twosided.cpp:89-90)
+    diffuse_reflectance: Sequence[float] = (0.5, 0.5, 0.5)     # plastic.cpp:158-159
+    nonlinear: bool = False                                    # plastic.cpp:161
 
     def flat(self) -> dict:
         t = BSDF_TYPES[self.type]
@@ -66,17 +95,28 @@ class Bsdf:
                  alphaU=float(self.alpha_u), alphaV=float(self.alpha_v), eta=1.0,
                  thickness=float(self.thickness), reflectance=(0.0, 0.0, 0.0),
                  transmittance=tuple(float(x) for x in self.specular_transmittance),
-                 etaC=(0.0, 0.0, 0.0), kC=(1.0, 1.0, 1.0), sigmaA=tuple(float(x) for x in self.sigma_a))
+                 etaC=(0.0, 0.0, 0.0), kC=(1.0, 1.0, 1.0), sigmaA=tuple(float(x) for x in self.sigma_a),
+                 nested2=-1, diffuseReflectance=tuple(float(x) for x in self.diffuse_reflectance), fdrInt=0.0, fdrExt=0.0,
+                 specSamplingWeight=0.0, nonlinear=int(self.nonlinear))
         if t == 0:
             d["reflectance"] = tuple(float(x) for x in self.reflectance)
         else:
             d["reflectance"] = tuple(float(x) for x in self.specular_reflectance)
-        if t == 1:
+        if t in (1, 7):  # roughconductor.cpp:187-190, conductor.cpp:172-175
             ext = np.float32(lookup_ior(self.ext_eta, "air"))
             d["etaC"] = tuple(float(np.float32(x) / ext) for x in self.eta)  # roughconductor.cpp:189-190
             d["kC"] = tuple(float(np.float32(x) / ext) for x in self.k)
-        if t in (2, 3):
+        if t in (2, 3, 6):
             d["eta"] = float(np.float32(lookup_ior(self.int_ior, "bk7")) / np.float32(lookup_ior(self.ext_ior, "air")))
+        if t == 8:  # plastic.cpp:145-161,186-204
+            int_ior = self.int_ior if self.int_ior != "bk7" else "polypropylene"
+            eta = np.float32(lookup_ior(int_ior, "polypropylene")) / np.float32(lookup_ior(self.ext_ior, "air"))
+            d["eta"] = float(eta)
+            d["fdrInt"] = fresnel_diffuse_reflectance(1.0 / float(eta))
+            d["fdrExt"] = fresnel_diffuse_reflectance(float(eta))
+            lum = lambda c: float(c[0]) * 0.212671 + float(c[1]) * 0.715160 + float(c[2]) * 0.072169  # spectrum.h:725-727
+            d_avg, s_avg = lum(self.diffuse_reflectance), lum(self.specular_reflectance)
+            d["specSamplingWeight"] = float(np.float32(s_avg / (d_avg + s_avg)))
         return d
 
 
@@ -243,6 +283,11 @@ class SceneDesc:
                 if b.nested is None:
                     raise ValueError("coating: A child BSDF instance is required")  # coating.cpp:157-158
                 d["nested"] = add(b.nested)
+            if b.type == "twosided":
+                if b.nested is None:
+                    raise ValueError("A nested one-sided material is required!")  # twosided.cpp:87-88
+                d["nested"] = add(b.nested)
+                d["nested2"] = d["nested"] if b.nested_back is None else add(b.nested_back)
             out.append(d)
             memo[id(b)] = len(out) - 1
             return memo[id(b)]

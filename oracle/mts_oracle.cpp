@@ -974,6 +974,15 @@ void orc_bsdf_eval(const OrcBsdf *b, int nB, int id, uint64_t n, const float *wi
         outPdf[i] = bs.pdf(id, r);
     }
 }
+/* measure == EDiscrete: the delta components (test_chisquare.cpp:131-160 checks them the same way) */
+void orc_bsdf_eval_discrete(const OrcBsdf *b, int nB, int id, uint64_t n, const float *wi, const float *wo, float *outRgb, float *outPdf) {
+    BsdfSet bs{b, nB};
+    for (uint64_t i = 0; i < n; ++i) {
+        BRec r; r.wi = V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]); r.wo = V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        Spectrum f = bs.eval(id, r, true); outRgb[3 * i] = f.x; outRgb[3 * i + 1] = f.y; outRgb[3 * i + 2] = f.z;
+        outPdf[i] = bs.pdf(id, r, true);
+    }
+}
 void orc_bsdf_sample(const OrcBsdf *b, int nB, int id, uint64_t n, const float *wi, const float *samples, float *out) {
     BsdfSet bs{b, nB};
     for (uint64_t i = 0; i < n; ++i) {

@@ -21,7 +21,8 @@ class OrcBsdf(C.Structure):
     _fields_ = [("type", C.c_int32), ("distr", C.c_int32), ("sampleVisible", C.c_int32), ("nested", C.c_int32),
                 ("alphaU", C.c_float), ("alphaV", C.c_float), ("eta", C.c_float), ("thickness", C.c_float),
                 ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3), ("etaC", C.c_float * 3),
-                ("kC", C.c_float * 3), ("sigmaA", C.c_float * 3)]
+                ("kC", C.c_float * 3), ("sigmaA", C.c_float * 3), ("nested2", C.c_int32), ("diffuseReflectance", C.c_float * 3),
+                ("fdrInt", C.c_float), ("fdrExt", C.c_float), ("specSamplingWeight", C.c_float), ("nonlinear", C.c_int32)]
 
 
 class OrcRenderParams(C.Structure):
@@ -92,9 +93,10 @@ def make_bsdf_array(flat_list):
         b = arr[i]
         b.type, b.distr, b.sampleVisible, b.nested = d["type"], d["distr"], d["sampleVisible"], d["nested"]
         b.alphaU, b.alphaV, b.eta, b.thickness = d["alphaU"], d["alphaV"], d["eta"], d["thickness"]
-        for k in ("reflectance", "transmittance", "etaC", "kC", "sigmaA"):
+        for k in ("reflectance", "transmittance", "etaC", "kC", "sigmaA", "diffuseReflectance"):
             for j in range(3):
                 getattr(b, k)[j] = d[k][j]
+        b.nested2, b.fdrInt, b.fdrExt, b.specSamplingWeight, b.nonlinear = d["nested2"], d["fdrInt"], d["fdrExt"], d["specSamplingWeight"], d["nonlinear"]
     return arr
 
 
@@ -316,11 +318,11 @@ def sobol_lookup(m, frame, px, py, scramble=0):
     return out
 
 
-def bsdf_eval(flat_list, bid, wi, wo):
+def bsdf_eval(flat_list, bid, wi, wo, discrete=False):
     arr = make_bsdf_array(flat_list)
     wi = np.ascontiguousarray(wi, np.float32).reshape(-1, 3); wo = np.ascontiguousarray(wo, np.float32).reshape(-1, 3)
     rgb = np.zeros((len(wi), 3), np.float32); pdf = np.zeros(len(wi), np.float32)
-    lib().orc_bsdf_eval(arr, C.c_int(len(flat_list)), C.c_int(bid), C.c_uint64(len(wi)), _p(wi), _p(wo), _p(rgb), _p(pdf))
+    (lib().orc_bsdf_eval_discrete if discrete else lib().orc_bsdf_eval)(arr, C.c_int(len(flat_list)), C.c_int(bid), C.c_uint64(len(wi)), _p(wi), _p(wo), _p(rgb), _p(pdf))
     return rgb, pdf
 
 

@@ -11,7 +11,8 @@
 extern "C" {
 /* plain-C description of one BSDF node; `nested` indexes the same array (coating only) */
 typedef struct OrcBsdf {
-    int32_t type;          /* 0 diffuse, 1 roughconductor, 2 roughdielectric, 3 coating, 4 null (index-matched boundary, src/bsdfs/null.cpp) */
+    int32_t type;          /* 0 diffuse, 1 roughconductor, 2 roughdielectric, 3 coating, 4 null (src/bsdfs/null.cpp), 5 twosided,
+                              6 dielectric, 7 conductor, 8 plastic (src/bsdfs/{twosided,dielectric,conductor,plastic}.cpp) */
     int32_t distr;         /* 0 beckmann, 1 ggx, 2 phong/as   (microfacet.h:48-57) */
     int32_t sampleVisible; /* microfacet.h:138 default true; forced false for phong :145-148 */
     int32_t nested;        /* coating: index of the nested BSDF; else -1 */
@@ -22,6 +23,11 @@ typedef struct OrcBsdf {
     float transmittance[3];/* roughdielectric specularTransmittance */
     float etaC[3], kC[3];  /* roughconductor eta, k (already divided by extEta, roughconductor.cpp:189-190) */
     float sigmaA[3];       /* coating.cpp:129-130 */
+    int32_t nested2;       /* twosided: BSDF of the back side (= nested when only one child was given, twosided.cpp:89-90) */
+    float diffuseReflectance[3]; /* plastic.cpp:158-159 */
+    float fdrInt, fdrExt;  /* plastic.cpp:194-195 fresnelDiffuseReflectance(1/eta), (eta), integrated on the host */
+    float specSamplingWeight;    /* plastic.cpp:199-202 */
+    int32_t nonlinear;     /* plastic.cpp:161 */
 } OrcBsdf;
 }
 
@@ -242,6 +248,10 @@ struct BsdfSet {
             case 1: return EGlossyReflection | EFrontSide | (d.alphaU != d.alphaV ? EAnisotropic : 0);                  /* roughconductor.cpp:229-238 */
             case 2: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide | EUsesSampler | ENonSymmetric | (d.alphaU != d.alphaV ? EAnisotropic : 0); /* roughdielectric.cpp:240-255 */
             case 4: return ENull | EFrontSide | EBackSide;                                                              /* null.cpp:38-43 */
+            case 5: return ((type(d.nested) & ~EBackSide) | EFrontSide) | ((type(d.nested2) & ~EFrontSide) | EBackSide);  /* twosided.cpp:96-102 */
+            case 6: return EDeltaReflection | EDeltaTransmission | EFrontSide | EBackSide | ENonSymmetric;               /* dielectric.cpp:190-194 */
+            case 7: return EDeltaReflection | EFrontSide;                                                               /* conductor.cpp:181-183 */
+            case 8: return EDeltaReflection | EDiffuseReflection | EFrontSide;                                          /* plastic.cpp:211-215 */
             default: return type(d.nested) | EDeltaReflection | EFrontSide | EBackSide;                                  /* coating.cpp:160-171 */
         }
     }
@@ -290,6 +300,44 @@ struct BsdfSet {
             }
         }
         case 4: return Spectrum(discrete ? 1.0f : 0.0f); /* null.cpp:45-47 (typeMask contains ENull) */
+        case 5: { /* twosided.cpp:109-121 */
+            if (Frame::cosTheta(r.wi) > 0) return eval(d.nested, r, discrete);
+            BRec b = r; b.wi.z *= -1; b.wo.z *= -1;
+            return eval(d.nested2, b, discrete);
+        }
+        case 6: { /* dielectric.cpp:229-255 */
+            float cosThetaT;
+            float F = fresnelDielectricExt(Frame::cosTheta(r.wi), cosThetaT, d.eta);
+            const float invEta = 1 / d.eta;
+            if (Frame::cosTheta(r.wi) * Frame::cosTheta(r.wo) >= 0) {
+                if (!discrete || std::abs(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > kDeltaEpsilon) return Spectrum(0.0f);
+                return R * F;
+            } else {
+                float scale = -(cosThetaT < 0 ? invEta : d.eta);
+                if (!discrete || std::abs(dot(V3(scale * r.wi.x, scale * r.wi.y, cosThetaT), r.wo) - 1) > kDeltaEpsilon) return Spectrum(0.0f);
+                float factor = cosThetaT < 0 ? invEta : d.eta; /* ERadiance */
+                return V3(d.transmittance[0], d.transmittance[1], d.transmittance[2]) * factor * factor * (1 - F);
+            }
+        }
+        case 7: { /* conductor.cpp:221-235 */
+            if (!discrete || Frame::cosTheta(r.wi) <= 0 || Frame::cosTheta(r.wo) <= 0 ||
+                std::abs(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > kDeltaEpsilon) return Spectrum(0.0f);
+            return R * fresnelConductorExact(Frame::cosTheta(r.wi), V3(d.etaC[0], d.etaC[1], d.etaC[2]), V3(d.kC[0], d.kC[1], d.kC[2]));
+        }
+        case 8: { /* plastic.cpp:243-279 */
+            if (Frame::cosTheta(r.wo) <= 0 || Frame::cosTheta(r.wi) <= 0) return Spectrum(0.0f);
+            float Fi = fresnelDielectricExt(Frame::cosTheta(r.wi), d.eta);
+            if (discrete) {
+                if (std::abs(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) < kDeltaEpsilon) return R * Fi;
+                return Spectrum(0.0f);
+            }
+            float Fo = fresnelDielectricExt(Frame::cosTheta(r.wo), d.eta);
+            Spectrum diff(d.diffuseReflectance[0], d.diffuseReflectance[1], d.diffuseReflectance[2]);
+            if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
+            else diff /= 1 - d.fdrInt;
+            const float invEta2 = 1 / (d.eta * d.eta);
+            return diff * (squareToCosineHemispherePdf(r.wo) * invEta2 * (1 - Fi) * (1 - Fo));
+        }
         default: { /* coating.cpp:208-248 */
             const float m_eta = d.eta, m_invEta = 1 / d.eta;
             bool sampleNested = (type(d.nested) & EAll) != 0;
@@ -367,6 +415,39 @@ struct BsdfSet {
             return std::abs(prob * dwh_dwo);
         }
         case 4: return discrete ? 1.0f : 0.0f; /* null.cpp:49-51 */
+        case 5: { /* twosided.cpp:123-135 */
+            if (r.wi.z > 0) return pdf(d.nested, r, discrete);
+            BRec b = r; b.wi.z *= -1; b.wo.z *= -1;
+            return pdf(d.nested2, b, discrete);
+        }
+        case 6: { /* dielectric.cpp:257-279 */
+            float cosThetaT;
+            float F = fresnelDielectricExt(Frame::cosTheta(r.wi), cosThetaT, d.eta);
+            const float invEta = 1 / d.eta;
+            if (Frame::cosTheta(r.wi) * Frame::cosTheta(r.wo) >= 0) {
+                if (!discrete || std::abs(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > kDeltaEpsilon) return 0.0f;
+                return F;
+            } else {
+                float scale = -(cosThetaT < 0 ? invEta : d.eta);
+                if (!discrete || std::abs(dot(V3(scale * r.wi.x, scale * r.wi.y, cosThetaT), r.wo) - 1) > kDeltaEpsilon) return 0.0f;
+                return 1 - F;
+            }
+        }
+        case 7: /* conductor.cpp:237-250 */
+            if (!discrete || Frame::cosTheta(r.wi) <= 0 || Frame::cosTheta(r.wo) <= 0 ||
+                std::abs(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) > kDeltaEpsilon) return 0.0f;
+            return 1.0f;
+        case 8: { /* plastic.cpp:281-309 */
+            if (Frame::cosTheta(r.wo) <= 0 || Frame::cosTheta(r.wi) <= 0) return 0.0f;
+            float Fi = fresnelDielectricExt(Frame::cosTheta(r.wi), d.eta);
+            float w = d.specSamplingWeight;
+            float probSpecular = (Fi * w) / (Fi * w + (1 - Fi) * (1 - w));
+            if (discrete) {
+                if (std::abs(dot(V3(-r.wi.x, -r.wi.y, r.wi.z), r.wo) - 1) < kDeltaEpsilon) return probSpecular;
+                return 0.0f;
+            }
+            return squareToCosineHemispherePdf(r.wo) * (1 - probSpecular);
+        }
         default: { /* coating.cpp:250-286 */
             const float m_invEta = 1 / d.eta;
             bool sampleNested = (type(d.nested) & EAll) != 0;
@@ -459,6 +540,67 @@ struct BsdfSet {
         case 4: { /* null.cpp:65-76 */
             r.wo = -r.wi; r.sampledType = ENull; r.eta = 1.0f; pdfOut = 1;
             return Spectrum(1.0f);
+        }
+        case 5: { /* twosided.cpp:162-184 */
+            bool flipped = false;
+            if (Frame::cosTheta(r.wi) < 0) { r.wi.z *= -1; flipped = true; }
+            Spectrum result = sample(flipped ? d.nested2 : d.nested, r, pdfOut, sx, sy);
+            if (flipped) {
+                r.wi.z *= -1;
+                if (!result.isZero() && pdfOut != 0) r.wo.z *= -1;
+            }
+            return result;
+        }
+        case 6: { /* dielectric.cpp:281-310 (both components enabled) */
+            float cosThetaT;
+            float F = fresnelDielectricExt(Frame::cosTheta(r.wi), cosThetaT, d.eta);
+            const float invEta = 1 / d.eta;
+            if (sx <= F) {
+                r.sampledType = EDeltaReflection;
+                r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z);
+                r.eta = 1.0f;
+                pdfOut = F;
+                return R;
+            } else {
+                r.sampledType = EDeltaTransmission;
+                float scale = -(cosThetaT < 0 ? invEta : d.eta);
+                r.wo = V3(scale * r.wi.x, scale * r.wi.y, cosThetaT);
+                r.eta = cosThetaT < 0 ? d.eta : invEta;
+                pdfOut = 1 - F;
+                float factor = cosThetaT < 0 ? invEta : d.eta;
+                return V3(d.transmittance[0], d.transmittance[1], d.transmittance[2]) * (factor * factor);
+            }
+        }
+        case 7: { /* conductor.cpp:268-283 */
+            if (Frame::cosTheta(r.wi) <= 0) return Spectrum(0.0f);
+            r.sampledType = EDeltaReflection;
+            r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z);
+            r.eta = 1.0f;
+            pdfOut = 1;
+            return R * fresnelConductorExact(Frame::cosTheta(r.wi), V3(d.etaC[0], d.etaC[1], d.etaC[2]), V3(d.kC[0], d.kC[1], d.kC[2]));
+        }
+        case 8: { /* plastic.cpp:377-424 (both components enabled) */
+            if (Frame::cosTheta(r.wi) <= 0) return Spectrum(0.0f);
+            float Fi = fresnelDielectricExt(Frame::cosTheta(r.wi), d.eta);
+            r.eta = 1.0f;
+            float w = d.specSamplingWeight;
+            float probSpecular = (Fi * w) / (Fi * w + (1 - Fi) * (1 - w));
+            if (sx < probSpecular) {
+                r.sampledType = EDeltaReflection;
+                r.wo = V3(-r.wi.x, -r.wi.y, r.wi.z);
+                pdfOut = probSpecular;
+                return R * Fi / probSpecular;
+            } else {
+                r.sampledType = EDiffuseReflection;
+                r.wo = squareToCosineHemisphere((sx - probSpecular) / (1 - probSpecular), sy);
+                float Fo = fresnelDielectricExt(Frame::cosTheta(r.wo), d.eta);
+                Spectrum diff(d.diffuseReflectance[0], d.diffuseReflectance[1], d.diffuseReflectance[2]);
+                if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
+                else diff /= 1 - d.fdrInt;
+                pdfOut = (1 - probSpecular) * squareToCosineHemispherePdf(r.wo);
+                const float invEta2 = 1 / (d.eta * d.eta);
+                return diff * (invEta2 * (1 - Fi) * (1 - Fo) / (1 - probSpecular));
+            }
         }
         default: { /* coating.cpp:288-371 */
             const float m_invEta = 1 / d.eta;

@@ -20,6 +20,15 @@ def configs():
     c["roughconductor_ggx_all"] = Bsdf("roughconductor", distribution="ggx", alpha_u=0.2, alpha_v=0.2, sample_visible=False, **CU)
     c["coating_diffuse"] = Bsdf("coating", int_ior=1.5, ext_ior=1.0, sigma_a=(0.1, 0.2, 0.3), thickness=2.0, nested=Bsdf("diffuse"))
     c["coating_roughconductor"] = Bsdf("coating", int_ior=1.5, ext_ior=1.0, nested=Bsdf("roughconductor", **CU))
+    # f-3 plugins, parameters of data/tests/test_bsdf.xml where it has them (dielectric intIOR 1.5/extIOR 1.0, plastic defaults)
+    c["dielectric"] = Bsdf("dielectric", int_ior=1.5, ext_ior=1.0)
+    c["conductor"] = Bsdf("conductor", **CU)
+    c["plastic"] = Bsdf("plastic", int_ior=1.5, ext_ior=1.0, diffuse_reflectance=(0.4, 0.5, 0.2))
+    c["plastic_nonlinear"] = Bsdf("plastic", nonlinear=True, diffuse_reflectance=(0.7, 0.3, 0.2), specular_reflectance=(0.8, 0.8, 0.8))
+    c["twosided_diffuse"] = Bsdf("twosided", nested=Bsdf("diffuse", reflectance=(0.6, 0.4, 0.3)))
+    c["twosided_two"] = Bsdf("twosided", nested=Bsdf("roughconductor", distribution="ggx", alpha_u=0.2, alpha_v=0.2, **CU),
+                             nested_back=Bsdf("plastic", diffuse_reflectance=(0.2, 0.3, 0.6)))
+    c["twosided_coating"] = Bsdf("twosided", nested=Bsdf("coating", int_ior=1.5, ext_ior=1.0, nested=Bsdf("diffuse")))
     return c
 
 

@@ -212,6 +212,58 @@ def test_material_ball_image_parity(b2ctx, name, sorted_shading):
     assert rel_l2(api.develop(fg2), O.develop(fo)) <= REL_L2_TOL
 
 
+MATERIALS_F3 = {   # SURVEY.md 8f-3 plugins (generic shading kernel)
+    "dielectric": Bsdf("dielectric", int_ior="bk7", ext_ior="air"),
+    "conductor": Bsdf("conductor", eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421)),
+    "plastic": Bsdf("plastic", diffuse_reflectance=(0.1, 0.27, 0.36)),
+    "plastic_nonlinear": Bsdf("plastic", diffuse_reflectance=(0.6, 0.3, 0.2), nonlinear=True, int_ior=1.9),
+    "twosided_plastic": Bsdf("twosided", nested=Bsdf("plastic", diffuse_reflectance=(0.5, 0.2, 0.2)), nested_back=Bsdf("diffuse", reflectance=(0.1, 0.6, 0.1))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MATERIALS_F3))
+def test_f3_material_ball_image_parity(b2ctx, name):
+    d = material_ball(MATERIALS_F3[name], 64, 64, 48, 96)
+    # the ground becomes a two-sided diffuse sheet seen from below by part of the light transport
+    d.meshes[0].bsdf = Bsdf("twosided", nested=Bsdf("diffuse", reflectance=(0.5, 0.5, 0.5)))
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=32, sampler="sobol", rfilter="gaussian")
+    fo, so = o.render(rp)
+    fg, sg = g.render(rp, parity=True)
+    e = rel_l2(api.develop(fg), O.develop(fo))
+    assert e <= REL_L2_TOL, (name, e)
+    assert abs(sg["path_length_sum"] - so["pathLengthSum"]) <= 1e-3 * so["pathLengthSum"]
+    fg2, _ = g.render(rp, parity=False)
+    assert rel_l2(api.develop(fg2), O.develop(fo)) <= REL_L2_TOL
+
+
+def test_twosided_sheet_is_lit_from_both_sides(b2ctx):
+    """A one-sided diffuse sheet is black from behind (diffuse.cpp:112-113); wrapped in `twosided` it is not."""
+    from mitsuba_b200.scene import _quad
+    def scene(bsdf):
+        P, I = _quad([(-1, 0, -1), (-1, 0, 1), (1, 0, 1), (1, 0, -1)], (0, 1, 0))
+        sheet = Mesh(P, I, bsdf=bsdf)
+        P, I = _quad([(-0.5, -2, -0.5), (-0.5, -2, 0.5), (0.5, -2, 0.5), (0.5, -2, -0.5)], (0, 1, 0))
+        light = Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(10, 10, 10))
+        return SceneDesc([sheet, light], Camera(look_at((0, -1.5, -3), (0, 0, 0), (0, 1, 0)), fov=40, width=32, height=32))
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="box")
+    one, _ = api.Scene(b2ctx, scene(Bsdf("diffuse"))).render(rp, parity=True)
+    two_d = scene(Bsdf("twosided", nested=Bsdf("diffuse")))
+    g, o = pair(b2ctx, two_d)
+    two, _ = g.render(rp, parity=True)
+    fo, _ = o.render(rp)
+    centre = (slice(12, 20), slice(12, 20))
+    assert api.develop(one)[centre].max() == 0 and api.develop(two)[centre].mean() > 0.05
+    assert rel_l2(api.develop(two), O.develop(fo)) < 2e-4
+
+
+def test_invalid_nesting_is_rejected(b2ctx):
+    d = cornell_box(16, 16)
+    d.meshes[0].bsdf = Bsdf("twosided", nested=Bsdf("dielectric"))
+    with pytest.raises(api.B2Error, match="without a transmission component"):   # twosided.cpp:105-107
+        api.Scene(b2ctx, d)
+
+
 def test_uv_tangent_frames_parity(b2ctx):
     """Meshes with texcoords take the UV-tangent shading frame (trimesh.cpp:683-735, skdtree.h:373-380): anisotropic BSDF."""
     P, N, UV, I = uv_sphere((0, 1, 0), 1.0, 32, 64, with_uv=True)

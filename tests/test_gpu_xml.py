@@ -67,3 +67,31 @@ def test_medium_xml_errors(b2ctx, tmp_path):
     p.write_text(head + '<shape type="cube"><ref name="interior" id="nope"/></shape></scene>')
     with pytest.raises(api.B2Error, match="not found"):
         b2ctx.load_xml(str(p))
+
+
+def test_f3_bsdf_plugins_through_xml(b2ctx, tmp_path):
+    """twosided / dielectric / conductor / plastic in a scene file vs the same scene built in Python."""
+    import shutil
+    from mitsuba_b200.scene import Bsdf
+    shutil.copytree(os.path.join(ROOT, "scenes", "meshes"), tmp_path / "meshes")
+    xml = open(os.path.join(ROOT, "scenes", "cbox.xml")).read()
+    repl = {"cbox_walls": '<bsdf type="twosided"><bsdf type="diffuse"><rgb name="reflectance" value="0.73 0.73 0.73"/></bsdf></bsdf>',
+            "cbox_short": '<bsdf type="plastic"><rgb name="diffuseReflectance" value="0.1 0.27 0.36"/><float name="intIOR" value="1.9"/></bsdf>',
+            "cbox_tall": '<bsdf type="conductor"><string name="material" value="none"/><rgb name="eta" value="0.2 0.92 1.1"/><rgb name="k" value="3.9 2.45 2.14"/></bsdf>',
+            "cbox_right": '<bsdf type="dielectric"><string name="intIOR" value="water"/></bsdf>'}
+    import re
+    for key, b in repl.items():
+        xml = re.sub(r'(<string name="filename" value="meshes/%s.obj"/>\s*<boolean name="faceNormals" value="true"/>\s*)<bsdf type="diffuse">.*?</bsdf>' % key,
+                     lambda m: m.group(1) + b, xml, count=1, flags=re.S)
+    p = tmp_path / "zoo.xml"
+    p.write_text(xml)
+    sc, rp = b2ctx.load_xml(str(p), ["spp=16", "res=48"])
+    film, st = sc.render(rp, parity=True, width=48, height=48)
+    d = cornell_box(48, 48)
+    by = {m.name: m for m in d.meshes}
+    by["walls"].bsdf = Bsdf("twosided", nested=Bsdf("diffuse", reflectance=(0.73, 0.73, 0.73)))
+    by["short"].bsdf = Bsdf("plastic", diffuse_reflectance=(0.1, 0.27, 0.36), int_ior=1.9)
+    by["tall"].bsdf = Bsdf("conductor", eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14))
+    by["right"].bsdf = Bsdf("dielectric", int_ior="water")
+    fo, so = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert rel_l2(api.develop(film), O.develop(fo)) < 5e-4

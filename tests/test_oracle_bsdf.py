@@ -2,6 +2,8 @@
 own tests: src/tests/test_chisquare.cpp:30-37,94-200,391-440 (chi^2 of sample() vs integrated pdf(),
 10 x 20 bins, significance 0.0025; three-way agreement sample/eval/pdf to 1e-2 relative) and
 src/tests/test_microfacet.cpp:50-131 (unit-length normals, pdf agreement 1e-4 ... here 1e-3 in f32)."""
+import math
+
 import numpy as np
 import pytest
 from scipy import stats
@@ -64,7 +66,10 @@ def chi2_one(flat, bid, wi, rng, n_samples=120000, sub=32):
     return 1 - stats.chi2.cdf(chi, dof), obs.sum(), exp.sum()
 
 
-@pytest.mark.parametrize("name", sorted(CFG))
+DELTA_ONLY = {"dielectric", "conductor"}   # no continuous component: nothing for the chi^2 histogram
+
+
+@pytest.mark.parametrize("name", sorted(set(CFG) - DELTA_ONLY))
 def test_chi_square(name):
     flat, bid = flatten(CFG[name])
     rng = np.random.default_rng(hash(name) % 2 ** 31)
@@ -80,7 +85,7 @@ def test_chi_square(name):
         assert p > alpha, (name, wi, p)
 
 
-@pytest.mark.parametrize("name", sorted(CFG))
+@pytest.mark.parametrize("name", sorted(set(CFG) - DELTA_ONLY))
 def test_three_way_agreement(name):
     """sample(bRec, pdf, s) vs eval()/pdf(): weight * pdf == eval and pdf == pdf(), 1e-2 relative (test_chisquare.cpp:35)."""
     flat, bid = flatten(CFG[name])
@@ -96,6 +101,70 @@ def test_three_way_agreement(name):
     lhs = r["weight"][ok] * r["pdf"][ok][:, None]
     assert np.allclose(lhs[big], f[big], rtol=1e-2, atol=1e-4), name
     assert ok.sum() > n // 4
+
+
+@pytest.mark.parametrize("name", ["dielectric", "conductor", "plastic", "plastic_nonlinear", "coating_diffuse", "twosided_two", "twosided_coating"])
+def test_delta_components_three_way(name):
+    """Discrete lobes, as test_chisquare.cpp checks them: weight * pdf == eval(EDiscrete) and pdf == pdf(EDiscrete)."""
+    flat, bid = flatten(CFG[name])
+    rng = np.random.default_rng(5 + hash(name) % 2 ** 31)
+    n = 4000
+    both = name in ("dielectric", "twosided_two")
+    wi = sph(np.arccos(rng.uniform(0.05, 0.98, n)), rng.uniform(0, 2 * np.pi, n))
+    if both:
+        wi[n // 2:, 2] *= -1
+    s = rng.uniform(size=(n, 3)).astype(np.float32)
+    r = O.bsdf_sample(flat, bid, wi, s)
+    delta = (np.abs(r["weight"]).sum(1) > 0) & ((r["type"] & 0x60) != 0)
+    assert delta.sum() > (n // 20)
+    f, pdf = O.bsdf_eval(flat, bid, wi[delta], r["wo"][delta], discrete=True)
+    assert np.allclose(pdf, r["pdf"][delta], rtol=1e-4, atol=1e-6), name
+    assert np.allclose(r["weight"][delta] * r["pdf"][delta][:, None], f, rtol=1e-3, atol=1e-6), name
+    # the continuous measure sees nothing of a delta lobe
+    f2, pdf2 = O.bsdf_eval(flat, bid, wi[delta], r["wo"][delta])
+    if name in DELTA_ONLY:
+        assert not f2.any() and not pdf2.any()
+
+
+def test_dielectric_closed_form():
+    """dielectric.cpp:281-310: reflect with probability F, refract along Snell's direction, radiance scaled by (eta_i/eta_t)^2."""
+    flat, bid = flatten(CFG["dielectric"])
+    eta = flat[bid]["eta"]
+    rng = np.random.default_rng(3)
+    n = 20000
+    for side in (1.0, -1.0):
+        wi = sph(np.full(n, np.arccos(0.6)), rng.uniform(0, 2 * np.pi, n)); wi[:, 2] *= side
+        r = O.bsdf_sample(flat, bid, wi, rng.uniform(size=(n, 3)).astype(np.float32))
+        refl = (r["type"] & 0x20) != 0
+        e = eta if side > 0 else 1 / eta
+        sin_t = math.sqrt(1 - 0.36) / e
+        if sin_t >= 1:
+            assert refl.all(); continue
+        cos_t = math.sqrt(1 - sin_t * sin_t)
+        rs = (0.6 - e * cos_t) / (0.6 + e * cos_t); rp = (e * 0.6 - cos_t) / (e * 0.6 + cos_t)
+        F = 0.5 * (rs * rs + rp * rp)
+        assert abs(refl.mean() - F) < 4.5 * math.sqrt(F * (1 - F) / n)
+        assert np.allclose(r["wo"][refl], wi[refl] * [-1, -1, 1], atol=1e-6)
+        t = ~refl
+        assert np.allclose(r["wo"][t][:, 2], -side * cos_t, atol=1e-5) and np.allclose(np.linalg.norm(r["wo"][t], axis=1), 1, atol=1e-5)
+        assert np.allclose(r["weight"][t], (1 / e) ** 2, rtol=1e-5) and np.allclose(r["eta"][t], e, rtol=1e-6)
+    assert O.bsdf_type(flat, bid) == (0x20 | 0x40 | 0x8000 | 0x10000 | 0x4000)
+
+
+def test_twosided_mirrors_the_front_side():
+    """twosided.cpp:109-184: from behind, the nested BRDF is evaluated with both directions mirrored."""
+    flat, bid = flatten(CFG["twosided_diffuse"])
+    fl1, b1 = flatten(CFG["twosided_diffuse"].nested)
+    rng = np.random.default_rng(4)
+    wi = sph(np.arccos(rng.uniform(0.1, 1, 500)), rng.uniform(0, 2 * np.pi, 500))
+    wo = sph(np.arccos(rng.uniform(0.1, 1, 500)), rng.uniform(0, 2 * np.pi, 500))
+    f0, p0 = O.bsdf_eval(fl1, b1, wi, wo)
+    for sgn in (1, -1):
+        f, p = O.bsdf_eval(flat, bid, wi * [1, 1, sgn], wo * [1, 1, sgn])
+        assert np.array_equal(f, f0) and np.array_equal(p, p0)
+    f, p = O.bsdf_eval(flat, bid, wi, wo * [1, 1, -1])
+    assert not f.any() and not p.any()
+    assert O.bsdf_type(flat, bid) == (0x2 | 0x8000 | 0x10000)
 
 
 def test_diffuse_closed_form():
