@@ -137,6 +137,9 @@ int b2_scene_film_size(b2_scene *, int *width, int *height);   /* Film::getSize 
 int b2_scene_add_material(b2_scene *, const b2_material_desc *);
 /* AreaLight (src/emitters/area.cpp:64-70): radiance, samplingWeight -> id (>=0) or -1 */
 int b2_scene_add_area_emitter(b2_scene *, const float radiance[3], float sampling_weight);
+/* ConstantBackgroundEmitter (src/emitters/constant.cpp:47-52): radiance, samplingWeight -> emitter id (>=0) or -1.  At most one
+ * environment emitter per scene (scene.cpp:510-514); `path` only. */
+int b2_scene_add_constant_emitter(b2_scene *, const float radiance[3], float sampling_weight);
 /* TriMesh after configure(): positions, optional normals / texcoords (NULL = none -> face normals,
  * skdtree.h:383-399), triangles, material and emitter ids (-1 = no emitter).  An emitter id may be
  * attached to exactly one mesh (area.cpp:185-199).  Returns mesh id or -1. */

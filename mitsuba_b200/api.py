@@ -59,7 +59,7 @@ class b2_stats(C.Structure):
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
            "b2_scene_set_camera", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
+           "b2_scene_add_mesh", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -74,7 +74,7 @@ def lib():
         L.b2_last_error.restype = C.c_char_p
         L.b2_last_error.argtypes = [C.c_void_p]
         L.b2_version.restype = C.c_char_p
-        for name in ("b2_scene_add_material", "b2_scene_add_area_emitter", "b2_scene_add_mesh", "b2_scene_add_medium"):
+        for name in ("b2_scene_add_material", "b2_scene_add_area_emitter", "b2_scene_add_mesh", "b2_scene_add_medium", "b2_scene_add_constant_emitter"):
             getattr(L, name).restype = C.c_int
         _LIB = L
     return _LIB
@@ -215,6 +215,10 @@ class Scene:
             I = np.ascontiguousarray(mesh.idx, np.uint32)
             if self.L.b2_scene_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
                                         C.c_int(bid), C.c_int(eid)) < 0:
+                raise B2Error(ctx.err())
+        if getattr(desc, "env_radiance", None) is not None:
+            rad = np.asarray(desc.env_radiance, np.float32)
+            if self.L.b2_scene_add_constant_emitter(self.h, _p(rad), C.c_float(desc.env_sampling_weight)) < 0:
                 raise B2Error(ctx.err())
         for i, (mi, me) in enumerate(media_ids):
             if mi >= 0 or me >= 0:

@@ -66,6 +66,7 @@ struct HostEmitter {
     float radiance[3];
     float samplingWeight;
     int mesh = -1;
+    bool env = false; // `constant` environment emitter (no parent shape)
 };
 
 template <typename T> struct DevBuf {
@@ -355,12 +356,26 @@ extern "C" int b2_scene_add_area_emitter(b2_scene *s, const float radiance[3], f
     s->committed = false;
     return (int) s->emitters.size() - 1;
 }
+// <emitter type="constant"> (src/emitters/constant.cpp:47-52); one environment emitter per scene (scene.cpp:510-514)
+extern "C" int b2_scene_add_constant_emitter(b2_scene *s, const float radiance[3], float sampling_weight) {
+    if (!s || !radiance) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_constant_emitter: null argument"); return -1; }
+    for (auto &e : s->emitters)
+        if (e.env) { fail(s->ctx, B2_ERR_INVALID, "The scene may only contain one environment emitter"); return -1; }
+    HostEmitter e;
+    memcpy(e.radiance, radiance, 12);
+    e.samplingWeight = sampling_weight;
+    e.env = true;
+    s->emitters.push_back(e);
+    s->committed = false;
+    return (int) s->emitters.size() - 1;
+}
 extern "C" int b2_scene_add_mesh(b2_scene *s, const float *P, const float *N, const float *UV, uint32_t nV, const uint32_t *idx, uint32_t nT,
                                  int material_id, int emitter_id) {
     if (!s || !P || !idx) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_mesh: null argument"); return -1; }
     if (nT == 0) { fail(s->ctx, B2_ERR_INVALID, "Encountered an empty triangle mesh!"); return -1; } // trimesh.cpp:389-392
     if (material_id < 0 || material_id >= (int) s->materials.size()) { fail(s->ctx, B2_ERR_INVALID, "invalid material id"); return -1; }
     if (emitter_id >= (int) s->emitters.size()) { fail(s->ctx, B2_ERR_INVALID, "invalid emitter id"); return -1; }
+    if (emitter_id >= 0 && s->emitters[emitter_id].env) { fail(s->ctx, B2_ERR_INVALID, "an environment emitter cannot be attached to a shape"); return -1; }
     if (emitter_id >= 0 && s->emitters[emitter_id].mesh >= 0) { fail(s->ctx, B2_ERR_INVALID, "An area light cannot be parent of multiple shapes"); return -1; } // area.cpp:190-192
     for (uint32_t i = 0; i < 3 * nT; ++i)
         if (idx[i] >= nV) { fail(s->ctx, B2_ERR_INVALID, "triangle index out of range"); return -1; }
@@ -472,7 +487,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     if (!s->hasCamera) return fail(ctx, B2_ERR_INVALID, "scene has no sensor");
     CK(ctx, cudaSetDevice(ctx->device));
     for (size_t e = 0; e < s->emitters.size(); ++e)
-        if (s->emitters[e].mesh < 0) return fail(ctx, B2_ERR_INVALID, "area emitter without a parent shape");
+        if (s->emitters[e].mesh < 0 && !s->emitters[e].env) return fail(ctx, B2_ERR_INVALID, "area emitter without a parent shape");
     // ---- flatten meshes: prim order = mesh order, triangle order (skdtree.cpp:68-72 m_shapeMap) ----
     size_t nPrims = 0;
     for (auto &m : s->meshes) { m.primOffset = (uint32_t) nPrims; nPrims += m.idx.size() / 3; }
@@ -724,10 +739,15 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     float emNorm = 0.0f;
     for (size_t e = 0; e < s->emitters.size(); ++e) {
         const HostEmitter &he = s->emitters[e];
-        const HostMesh &m = s->meshes[he.mesh];
         DEmitter &d = de[e];
         memcpy(d.radiance, he.radiance, 12);
         d.samplingWeight = he.samplingWeight;
+        if (he.env) { // constant.cpp: no mesh, no area distribution
+            d.cdfOffset = 0; d.nTri = 0; d.primOffset = 0; d.invSurfaceArea = 0;
+            emCdf.push_back(emCdf.back() + he.samplingWeight);
+            continue;
+        }
+        const HostMesh &m = s->meshes[he.mesh];
         d.cdfOffset = (uint32_t) triCdf.size();
         d.nTri = (uint32_t) (m.idx.size() / 3);
         d.primOffset = m.primOffset;
@@ -774,6 +794,24 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     DScene &ds = s->ds;
     memset(&ds, 0, sizeof(ds));
     ds.triAccel = s->dTriAccel.p; ds.triPlane = s->dTriPlane.p; ds.leafPrim = s->dLeafPrim.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
+    // environment emitter: index + constant.cpp:67-70 bounding sphere of (acceleration-structure box U sensor position) (scene.cpp:386-399)
+    ds.envEmitter = -1;
+    for (size_t e = 0; e < s->emitters.size(); ++e) if (s->emitters[e].env) ds.envEmitter = (int) e;
+    {
+        float bl[3], bh[3];
+        for (int a = 0; a < 3; ++a) {
+            const float eps = 1e-3f;
+            float l = nPrims ? lo[a] : 0.0f, h = nPrims ? hi[a] : 0.0f;
+            float mn = l - ((h - l) * eps + eps), mx = h + ((h - mn) * eps + eps); // gkdtree.h:1213-1220 (as ds.aabbMin/Max below)
+            const float camP = s->camToWorld[4 * a + 3];
+            bl[a] = std::min(mn, camP); bh[a] = std::max(mx, camP);
+        }
+        float c[3], r2 = 0;
+        for (int a = 0; a < 3; ++a) { c[a] = (bh[a] + bl[a]) * 0.5f; ds.bsCenter[a] = c[a]; }
+        const float dx = c[0] - bh[0], dy = c[1] - bh[1], dz = c[2] - bh[2];
+        r2 = dx * dx + dy * dy + dz * dz;
+        ds.bsRadius = std::max(1e-4f, std::sqrt(r2) * 1.5f);
+    }
     ds.media = s->dMedia.p; ds.primMedia = anyMedia ? s->dPrimMedia.p : nullptr; ds.nMedia = (uint32_t) dmed.size();
     ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef; ds.rootCount = rootCount;
     ds.flatRec = s->dFlatRec.p; ds.flatIdx = (const uint2 *) s->dFlatIdx.p; ds.flatP = flatP; ds.flatC = flatC; ds.flatS = flatS;
@@ -881,6 +919,7 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     r.maxDepth = p->max_depth; r.rrDepth = p->rr_depth; r.strictNormals = p->strict_normals; r.hideEmitters = p->hide_emitters;
     r.sampleLo = p->sample_lo; r.sampleHi = p->sample_hi > 0 ? p->sample_hi : p->spp;
     if (p->integrator != B2_INTEGRATOR_PATH && p->integrator != B2_INTEGRATOR_VOLPATH) return fail(ctx, B2_ERR_INVALID, "unknown integrator");
+    if (p->integrator == B2_INTEGRATOR_VOLPATH && s->ds.envEmitter >= 0) return fail(ctx, B2_ERR_INVALID, "volpath with an environment emitter is not supported");
     r.integrator = p->integrator;
     if (r.sampleLo < 0 || r.sampleHi > p->spp || r.sampleLo >= r.sampleHi) return fail(ctx, B2_ERR_INVALID, "invalid sample range");
     if (p->sampler == B2_SAMPLER_SOBOL) {

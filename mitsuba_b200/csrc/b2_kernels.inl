@@ -405,7 +405,8 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
             o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z);
             const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             ++nRays;
-            return clipRay<false>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt) ? 2 : 1;
+            // non-camera rays: mint = Epsilon (ray.h:66-68); their ray[2i].w carries dot(wo, refN) for the environment MIS term
+            return clipRay<false>(sc, o, d, dRcp, (fl & PF_FRESH) ? ro.w : B2_EPSILON, rd.w, mint, maxt) ? 2 : 1;
         };
         auto commit = [&](uint32_t i, bool found, const HitRec &h) {
             pool.hit[i] = found ? make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)) : make_float4(B2_INF, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
@@ -436,7 +437,7 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
             h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
             float mint, maxt;
             uint32_t nv = 0, pt = 0;
-            if (clipRay<false>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt)) {
+            if (clipRay<false>(sc, o, d, dRcp, (fl & PF_FRESH) ? ro.w : B2_EPSILON, rd.w, mint, maxt)) {
                 if (!traverse<false, false>(sc, tm, o, d, mint, maxt, h, nv, pt)) { h.t = B2_INF; h.prim = 0xFFFFFFFFu; }
             }
             pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
@@ -535,6 +536,44 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
     const float emPdf = c1 - c0;
     sx = (sx - c0) / (c1 - c0);
     const DEmitter &em = sc.emitters[ei];
+    if (em.nTri == 0) { // `constant` environment emitter: constant.cpp:171-208
+        V3 d;
+        float pdf;
+        if (!isZero(refN)) {
+            d = squareToCosineHemisphere(sx, sy);
+            pdf = squareToCosineHemispherePdf(d);
+            Frame f;
+            f.n = refN;
+            coordinateSystem(f.n, f.s, f.t);
+            d = f.toWorld(d);
+        } else {
+            const float z = 1.0f - 2.0f * sy, r = safe_sqrt(1.0f - z * z); // warp.cpp:25-31
+            float sinPhi, cosPhi;
+            sincosf(2.0f * B2_PI * sx, &sinPhi, &cosPhi);
+            d = V3(r * cosPhi, r * sinPhi, z);
+            pdf = 0.07957747154594766788f;
+        }
+        ds.pdf = 0.0f; ds.value = Spectrum(0.0f); ds.emitter = (int) ei;
+        // bsphere.h:88-95 + util.cpp:447-485
+        const V3 c(sc.bsCenter[0], sc.bsCenter[1], sc.bsCenter[2]);
+        const V3 o = ref - c;
+        const float A = lengthSquared(d), B = 2 * dot(o, d), C = lengthSquared(o) - sc.bsRadius * sc.bsRadius;
+        const float discrim = B * B - 4.0f * A * C;
+        if (A == 0 || discrim < 0) return false;
+        const float sq = sqrtf(discrim), temp = B < 0 ? -0.5f * (B - sq) : -0.5f * (B + sq);
+        float x0 = temp / A, x1 = C / temp;
+        if (x0 > x1) { const float t = x0; x0 = x1; x1 = t; }
+        if (!(x0 < 0 && x1 > 0)) return false;
+        ds.p = ref + d * x1;
+        ds.n = normalize(c - ds.p);
+        ds.d = d; ds.dist = x1;
+        if (!isZero(refN) && dot(d, refN) <= 0) return false; // roundoff moved the sample to the back side: value 0
+        ds.value = V3(em.radiance[0], em.radiance[1], em.radiance[2]) / pdf;
+        if (emPdfOut) { ds.pdf = pdf; *emPdfOut = emPdf; return true; }
+        ds.pdf = pdf * emPdf;
+        ds.value = ds.value / emPdf;
+        return true;
+    }
     const float *tcdf = sc.triCdf + em.cdfOffset;
     const uint32_t ti = cdfSample(tcdf, em.nTri, sy);
     const float t0 = __ldg(tcdf + ti), t1 = __ldg(tcdf + ti + 1);
@@ -643,8 +682,20 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
                 if (valid) flags |= PF_ALPHA; // records.inl:117-144 (EOpacity)
             } else {
                 // ---- tail of the previous loop iteration: path.cpp:226-286 ----
-                if (!valid) done = true; // no environment emitter: `break` at :246
-                else {
+                if (!valid) { // :239-252: the BSDF sample left the scene
+                    if (sc.envEmitter >= 0 && !(rp.hideEmitters && !(flags & PF_SCATTERED))) {
+                        const DEmitter &em = sc.emitters[sc.envEmitter];
+                        float lumPdf = 0.0f;
+                        if (!(flags & PF_DELTA)) { // constant.cpp:210-224 (ESolidAngle) x emitter pick probability
+                            const float c = pool.ray[2 * (size_t) i].w; // dot(wo, refN) of the vertex that sampled this ray; 2 = refN is zero
+                            const float pdfSA = c == 2.0f ? 0.07957747154594766788f : B2_INV_PI * fmaxf(0.0f, c);
+                            lumPdf = pdfSA * (em.samplingWeight * sc.emitterNormalization);
+                        }
+                        LiAdd = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]) * miWeight(bsdfPdfPrev, lumPdf);
+                        liTouched = true;
+                    }
+                    done = true;
+                } else {
                     if (its.emitter >= 0) {
                         const DEmitter &em = sc.emitters[its.emitter];
                         // its.Le(-ray.d): area.cpp:104-109
@@ -670,7 +721,14 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
             }
             // ---- head of the loop: path.cpp:135-222 ----
             if (!done && !(depth <= rp.maxDepth || rp.maxDepth < 0)) done = true;
-            if (!done && !valid) done = true; // camera ray missed (:136-143)
+            if (!done && !valid) { // camera ray missed (:136-143): environment radiance unless hidden
+                if (sc.envEmitter >= 0 && !rp.hideEmitters) {
+                    const DEmitter &em = sc.emitters[sc.envEmitter];
+                    LiAdd = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                    liTouched = true;
+                }
+                done = true;
+            }
             if (!done) {
                 const DMaterial *mats = sc.materials;
                 const int mat = its.material;
@@ -731,7 +789,7 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
                                 pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
                                 ++nRays;
                             } else {
-                                pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
+                                pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, isZero(refN) ? 2.0f : dot(wo, refN));
                             }
                             pool.ray[2 * (size_t) i + 1] = make_float4(wo.x, wo.y, wo.z, bsdfPdfNew); // w: pdf of this sample (maxt = inf)
                             T = T * bsdfWeight; // :252-253 (applied early: only read again if the next ray hits)

@@ -43,7 +43,7 @@ struct DEmitter {
     float samplingWeight;
     float invSurfaceArea;
     uint32_t cdfOffset;    // into triCdf (nTri + 1 floats, cdf[0] = 0)
-    uint32_t nTri;
+    uint32_t nTri;         // 0: `constant` environment emitter (src/emitters/constant.cpp), no mesh
     uint32_t primOffset;   // global prim index of the mesh's first triangle
 };
 
@@ -79,6 +79,8 @@ struct DScene {
     const uint2 *flatIdx;
     uint32_t flatP, flatC, flatS, flatBytes;
     uint32_t nLeafTris;
+    int32_t envEmitter;        // index of the environment emitter or -1 (Scene::getEnvironmentEmitter)
+    float bsCenter[3], bsRadius; // constant.cpp:67-70 m_sceneBSphere: sphere of the scene box (incl. the sensor position), radius x 1.5
     // participating media (volpath): media table and per-prim (interior, exterior) ids, -1 = vacuum; null without media
     const DMedium *media;
     const int2 *primMedia;

@@ -270,6 +270,8 @@ class RenderParams:
 class SceneDesc:
     meshes: List[Mesh] = field(default_factory=list)
     camera: Optional[Camera] = None
+    env_radiance: Optional[Sequence[float]] = None   # <emitter type="constant"> (src/emitters/constant.cpp:47-52), after all area emitters
+    env_sampling_weight: float = 1.0
 
     def flat_bsdfs(self):
         """Flatten the BSDF tree to an array (nested referenced by index); returns (list, per-mesh id)."""

@@ -95,7 +95,7 @@ struct Discrete {
     }
 };
 
-struct Emitter { V3 radiance; float samplingWeight; int mesh; };
+struct Emitter { V3 radiance; float samplingWeight; int mesh; /* -1: `constant` environment emitter (src/emitters/constant.cpp) */ };
 
 struct Intersection { /* include/mitsuba/render/shape.h:131-171 (fields `path` reads) */
     float t = kInf; V3 p; Frame geoFrame, shFrame; V3 wi; V3 dpdu; int mesh = -1; uint32_t prim = 0;
@@ -111,6 +111,8 @@ struct Scene {
     std::vector<Mesh> meshes;
     std::vector<Emitter> emitters;
     std::vector<OrcMedium> media;
+    int envEmitter = -1;                 /* Scene::getEnvironmentEmitter */
+    V3 bsCenter; float bsRadius = 0;     /* constant.cpp:67-70 m_sceneBSphere */
     std::vector<std::vector<float>> mediaData; /* owned copies of the density grids */
     std::vector<uint32_t> primMesh; /* prim -> mesh (m_shapeMap) */
     Accel accel;
@@ -174,6 +176,17 @@ struct Scene {
         for (auto &e : emitters) emitterPDF.append(e.samplingWeight);
         if (!emitters.empty()) emitterPDF.normalize();
         camOrigin = V3(camToWorld[3], camToWorld[7], camToWorld[11]); /* trafo.transformAffine(Point(0)) */
+        /* scene.cpp:386-399: m_aabb = kd-tree box expanded by the sensor position; constant.cpp:67-70: its bounding sphere
+           (aabb.cpp:44-47), radius * 1.5 */
+        envEmitter = -1;
+        for (size_t e = 0; e < emitters.size(); ++e) if (emitters[e].mesh < 0) envEmitter = (int) e;
+        {
+            AABB b = accel.aabb;
+            if (accel.tri.empty()) { b.min = V3(0.0f); b.max = V3(0.0f); }
+            b.expandBy(camOrigin);
+            bsCenter = (b.max + b.min) * 0.5f;
+            bsRadius = std::max(kEpsilon, (bsCenter - b.max).length() * 1.5f);
+        }
     }
 
     /* skdtree.h:343-428 fillIntersectionRecord<true> for triangle meshes */
@@ -211,6 +224,34 @@ struct Scene {
         float emPdf;
         size_t index = emitterPDF.sampleReuse(sx, emPdf);
         const Emitter &em = emitters[index];
+        if (em.mesh < 0) { /* constant.cpp:171-208 sampleDirect */
+            V3 d; float pdf;
+            if (!dRec.refN.isZero()) {
+                d = squareToCosineHemisphere(sx, sy);
+                pdf = squareToCosineHemispherePdf(d);
+                d = Frame(dRec.refN).toWorld(d);
+            } else {
+                d = squareToUniformSphere(sx, sy);
+                pdf = kInvFourPi;
+            }
+            dRec.pdf = 0.0f;
+            float nearT, farT;
+            if (!bsphereIntersect(dRec.ref, d, nearT, farT)) return Spectrum(0.0f);
+            if (!(nearT < 0 && farT > 0)) return Spectrum(0.0f);
+            dRec.p = dRec.ref + d * farT;
+            dRec.n = normalize(bsCenter - dRec.p);
+            dRec.solidAngle = true; dRec.d = d; dRec.dist = farT; dRec.pdf = pdf;
+            Spectrum value = em.radiance / pdf;
+            if (!dRec.refN.isZero() && dot(dRec.d, dRec.refN) <= 0) value = Spectrum(0.0f); /* roundoff moved it to the back side; pdf stays != 0 */
+            if (!testVisibility) { dRec.emitter = (int) index; if (emPdfOut) *emPdfOut = emPdf; return value; }
+            Ray ray(dRec.ref, dRec.d, kEpsilon, dRec.dist * (1 - kShadowEpsilon)); /* scene.cpp:838-843: not on a surface, but the same ray */
+            ++st.shadowRays;
+            if (accel.rayOccluded(ray, &st.nodeVisits, &st.primTests)) return Spectrum(0.0f);
+            dRec.emitter = (int) index;
+            dRec.pdf *= emPdf;
+            value /= emPdf;
+            return value;
+        }
         const Mesh &m = meshes[em.mesh];
         /* area.cpp:158-173 -> shape.cpp:102-115 -> trimesh.cpp:412-424 -> triangle.cpp:24-62 */
         {
@@ -254,8 +295,25 @@ struct Scene {
         return Spectrum(0.0f);
     }
     /* scene.cpp:949-952; scene.h:848-850; area.cpp:175-183; shape.cpp:117-126; trimesh.cpp:358-360 */
+    /* bsphere.h:88-95 + util.cpp:447-485 */
+    bool bsphereIntersect(const V3 &ro, const V3 &rd, float &x0, float &x1) const {
+        V3 o = ro - bsCenter;
+        float a = rd.lengthSquared(), b = 2 * dot(o, rd), c = o.lengthSquared() - bsRadius * bsRadius;
+        if (a == 0) { if (b != 0) { x0 = x1 = -c / b; return true; } return false; }
+        float discrim = b * b - 4.0f * a * c;
+        if (discrim < 0) return false;
+        float temp, sqrtDiscrim = std::sqrt(discrim);
+        if (b < 0) temp = -0.5f * (b - sqrtDiscrim); else temp = -0.5f * (b + sqrtDiscrim);
+        x0 = temp / a; x1 = c / temp;
+        if (x0 > x1) std::swap(x0, x1);
+        return true;
+    }
     float pdfEmitterDirect(const DRec &dRec) const {
         const Emitter &em = emitters[dRec.emitter];
+        if (em.mesh < 0) { /* constant.cpp:210-224, measure == ESolidAngle */
+            float pdfSA = !dRec.refN.isZero() ? kInvPi * std::max(0.0f, dot(dRec.d, dRec.refN)) : kInvFourPi;
+            return pdfSA * (em.samplingWeight * emitterPDF.normalization);
+        }
         float pdfDirect = 0.0f;
         if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) {
             float pdfPos = meshes[em.mesh].invSurfaceArea;
@@ -289,7 +347,10 @@ struct Scene {
         float eta = 1.0f;
         const int maxDepth = rp.maxDepth, rrDepth = rp.rrDepth;
         while (depth <= maxDepth || maxDepth < 0) {
-            if (!its.isValid()) break;          /* no environment emitter in scope */
+            if (!its.isValid()) { /* path.cpp:136-143 */
+                if (envEmitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered)) Li += throughput * emitters[envEmitter].radiance;
+                break;
+            }
             const Mesh &mesh = meshes[its.mesh];
             const int bsdf = mesh.bsdf;
             if (mesh.emitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered))
@@ -339,7 +400,17 @@ struct Scene {
                     dRec.d = ray.d; dRec.dist = its.t;
                     hitEmitter = true;
                 }
-            } else break; /* no environment */
+            } else { /* path.cpp:239-252 */
+                if (envEmitter < 0) break;
+                if (rp.hideEmitters && !scattered) break;
+                value = emitters[envEmitter].radiance;
+                /* fillDirectSamplingRecord (constant.cpp:239-253): the ray starts inside the bounding sphere */
+                float nearT, farT;
+                if (!bsphereIntersect(ray.o, ray.d, nearT, farT) || nearT > 0 || farT < 0) break;
+                dRec.p = ray(farT); dRec.n = normalize(bsCenter - dRec.p); dRec.solidAngle = true; dRec.emitter = envEmitter;
+                dRec.d = ray.d; dRec.dist = farT;
+                hitEmitter = true;
+            }
             throughput *= bsdfWeight;
             eta *= bRec.eta;
             if (hitEmitter) {
@@ -748,6 +819,13 @@ void orc_phase(void *s, int medium, uint64_t n, const float *wi, const float *sa
         me.phaseSample(w, wo, pdf, &two);
         float *o = out + 5 * i; o[0] = wo.x; o[1] = wo.y; o[2] = wo.z; o[3] = pdf; o[4] = me.phaseEval(w, wo);
     }
+}
+/* <emitter type="constant">: radiance, samplingWeight (constant.cpp:47-52); at most one environment emitter (scene.cpp:510-514) */
+int orc_add_constant_emitter(void *s, const float *radiance, float samplingWeight) {
+    Scene *sc = (Scene *) s;
+    Emitter e; e.radiance = V3(radiance[0], radiance[1], radiance[2]); e.samplingWeight = samplingWeight; e.mesh = -1;
+    sc->emitters.push_back(e);
+    return (int) sc->emitters.size() - 1;
 }
 void orc_set_camera(void *s, const float *camToWorld, const float *sampleToCamera, float nearClip, float farClip, int W, int H) {
     Scene *sc = (Scene *) s;

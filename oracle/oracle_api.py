@@ -156,6 +156,9 @@ class OracleScene:
             rad = np.asarray(m.radiance, np.float32) if m.radiance is not None else None
             L.orc_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
                            C.c_int(bid), _p(rad), C.c_float(m.sampling_weight))
+        if getattr(desc, "env_radiance", None) is not None:
+            rad = np.asarray(desc.env_radiance, np.float32)
+            L.orc_add_constant_emitter(self.h, _p(rad), C.c_float(desc.env_sampling_weight))
         media, mids = desc.flat_media()
         self.flat_media = [md.flat() for md in media]
         for d in self.flat_media:

@@ -264,6 +264,41 @@ def test_invalid_nesting_is_rejected(b2ctx):
         api.Scene(b2ctx, d)
 
 
+@pytest.mark.parametrize("mat", ["diffuse", "roughdielectric", "plastic"])
+def test_constant_environment_emitter_parity(b2ctx, mat):
+    """`constant` emitter (src/emitters/constant.cpp): environment hit by BSDF sampling (MIS with the cosine / uniform-sphere
+    direct-sampling density), direct sampling through the scene bounding sphere, hideEmitters, together with an area light."""
+    b = {"diffuse": Bsdf("diffuse", reflectance=(0.6, 0.5, 0.4)), "roughdielectric": MATERIALS["roughdielectric_ggx"], "plastic": MATERIALS_F3["plastic"]}[mat]
+    d = material_ball(b, 64, 64, 32, 64)
+    d.meshes = [m for m in d.meshes if m.name != "backdrop"]
+    d.env_radiance = (0.4, 0.6, 1.0); d.env_sampling_weight = 2.0
+    g, o = pair(b2ctx, d)
+    for kw in (dict(), dict(hide_emitters=True), dict(max_depth=2)):
+        rp = RenderParams(spp=32, sampler="sobol", rfilter="box", **kw)
+        fo, so = o.render(rp)
+        fg, sg = g.render(rp, parity=True)
+        assert rel_l2(api.develop(fg), O.develop(fo)) <= 3e-4, (mat, kw)
+        assert abs(sg["path_length_sum"] - so["pathLengthSum"]) <= 1e-3 * so["pathLengthSum"]
+    fg2, _ = g.render(RenderParams(spp=32, sampler="sobol", rfilter="box"), parity=False)
+    fo, _ = o.render(RenderParams(spp=32, sampler="sobol", rfilter="box"))
+    assert rel_l2(api.develop(fg2), O.develop(fo)) <= REL_L2_TOL
+
+
+def test_environment_only_scene_and_errors(b2ctx):
+    P, N, _, I = uv_sphere((0, 0, 0), 1.0, 24, 48)
+    d = SceneDesc([Mesh(P, I, N=N, bsdf=Bsdf("diffuse", reflectance=(1, 1, 1)))], Camera(look_at((0, 0, -4), (0, 0, 0), (0, 1, 0)), fov=40, width=32, height=32),
+                  env_radiance=(0.7, 0.8, 0.9))
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=64, sampler="independent", rfilter="box", rr_depth=50)
+    fg, _ = g.render(rp, parity=False)
+    assert np.allclose(api.develop(fg).reshape(-1, 3).mean(0), (0.7, 0.8, 0.9), rtol=3e-3)   # white furnace
+    fo, _ = o.render(rp)
+    fg, _ = g.render(rp, parity=True)
+    assert rel_l2(api.develop(fg), O.develop(fo)) <= 3e-4
+    with pytest.raises(api.B2Error, match="environment emitter"):
+        g.render(dataclasses.replace(rp, integrator="volpath"))
+
+
 def test_uv_tangent_frames_parity(b2ctx):
     """Meshes with texcoords take the UV-tangent shading frame (trimesh.cpp:683-735, skdtree.h:373-380): anisotropic BSDF."""
     P, N, UV, I = uv_sphere((0, 1, 0), 1.0, 32, 64, with_uv=True)

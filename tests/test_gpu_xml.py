@@ -95,3 +95,17 @@ def test_f3_bsdf_plugins_through_xml(b2ctx, tmp_path):
     by["right"].bsdf = Bsdf("dielectric", int_ior="water")
     fo, so = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
     assert rel_l2(api.develop(film), O.develop(fo)) < 5e-4
+
+
+def test_constant_emitter_through_xml(b2ctx, tmp_path):
+    import shutil
+    shutil.copytree(os.path.join(ROOT, "scenes", "meshes"), tmp_path / "meshes")
+    xml = open(os.path.join(ROOT, "scenes", "cbox.xml")).read().replace("</scene>", '\t<emitter type="constant"><rgb name="radiance" value="0.2 0.3 0.5"/><float name="samplingWeight" value="0.5"/></emitter>\n</scene>')
+    p = tmp_path / "sky.xml"
+    p.write_text(xml)
+    sc, rp = b2ctx.load_xml(str(p), ["spp=16", "res=48"])
+    film, _ = sc.render(rp, parity=True, width=48, height=48)
+    d = cornell_box(48, 48)
+    d.env_radiance = (0.2, 0.3, 0.5); d.env_sampling_weight = 0.5
+    fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert rel_l2(api.develop(film), O.develop(fo)) < 3e-4

@@ -211,3 +211,23 @@ def test_splat_matches_block_put():
                     if 0 <= fx < W and 0 <= fy < H:
                         ref[fy, fx] += f32(wx * wy) * np.array([v[0], v[1], v[2], v[3], 1.0])
         assert np.allclose(film, ref, rtol=2e-4, atol=1e-5), kind   # f32 accumulation order vs f64
+
+
+def test_constant_environment_white_furnace():
+    """`constant` emitter (constant.cpp): a white diffuse sphere under a uniform sky shows exactly the sky radiance."""
+    P, N, _, I = uv_sphere((0, 0, 0), 1.0, 32, 64)
+    d = SceneDesc([Mesh(P, I, N=N, bsdf=Bsdf("diffuse", reflectance=(1, 1, 1)))], Camera(look_at((0, 0, -4), (0, 0, 0), (0, 1, 0)), fov=40, width=24, height=24),
+                  env_radiance=(0.7, 0.8, 0.9))
+    sc = O.OracleScene(d)
+    film, st = sc.render(RenderParams(spp=128, sampler="independent", rfilter="box", rr_depth=50))
+    rgb = O.develop(film)
+    assert np.allclose(rgb.reshape(-1, 3).mean(0), (0.7, 0.8, 0.9), rtol=2e-3)
+    assert rgb.reshape(-1, 3).std(0).max() < 5e-3
+    # hideEmitters hides the directly visible sky only
+    film, _ = sc.render(RenderParams(spp=16, sampler="independent", rfilter="box", hide_emitters=True))
+    rgb = O.develop(film)
+    assert rgb[0, 0].max() == 0 and rgb[12, 12].min() > 0.3
+    # grey sphere: radiance = L * rho / (1 - 0) first bounce only sees sky -> rho * L at the centre... the full series: L * rho (no interreflection on a convex body)
+    d.meshes[0].bsdf = Bsdf("diffuse", reflectance=(0.5, 0.5, 0.5))
+    film, _ = O.OracleScene(d).render(RenderParams(spp=256, sampler="independent", rfilter="box"))
+    assert np.allclose(O.develop(film)[12, 12], np.float32([0.7, 0.8, 0.9]) * 0.5, rtol=0.02)
