@@ -682,19 +682,111 @@ struct Loader {
         }
     }
 
+    // Stanford PLY (src/shapes/ply.cpp): ascii and binary (either byte order); vertex x y z [nx ny nz] [u|s|texture_u v|t|texture_v],
+    // other vertex properties are skipped; faces with 3 or 4 vertices, a quad (f0 f1 f2 f3) becomes (f0 f1 f2)(f3 f0 f2) (ply.cpp:276-287)
+    void loadPly(const std::string &path, MeshData &md) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Err("PLY file \"" + path + "\" could not be found!");
+        std::string line;
+        std::getline(f, line);
+        if (line.substr(0, 3) != "ply") throw Err("\"" + path + "\" is not a PLY file");
+        enum Fmt { Ascii, LE, BE } fmt = Ascii;
+        struct Prop { std::string name, type, countType; bool list = false; };
+        struct Elem { std::string name; size_t count = 0; std::vector<Prop> props; };
+        std::vector<Elem> elems;
+        while (std::getline(f, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            std::istringstream ls(line);
+            std::string k;
+            ls >> k;
+            if (k == "format") { std::string v; ls >> v; fmt = v == "ascii" ? Ascii : (v == "binary_little_endian" ? LE : BE); }
+            else if (k == "element") { Elem e; ls >> e.name >> e.count; elems.push_back(e); }
+            else if (k == "property") {
+                if (elems.empty()) throw Err("PLY: property before element");
+                Prop pr; std::string t; ls >> t;
+                if (t == "list") { pr.list = true; ls >> pr.countType >> pr.type >> pr.name; } else { pr.type = t; ls >> pr.name; }
+                elems.back().props.push_back(pr);
+            } else if (k == "end_header") break;
+        }
+        auto typeSize = [](const std::string &t) -> int {
+            if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+            if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+            if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+            if (t == "double" || t == "float64") return 8;
+            throw Err("PLY: unknown property type \"" + t + "\"");
+        };
+        auto readNum = [&](const std::string &t) -> double {
+            if (fmt == Ascii) { double v; if (!(f >> v)) throw Err("PLY: unexpected end of file"); return v; }
+            unsigned char b[8];
+            const int n = typeSize(t);
+            f.read((char *) b, n);
+            if (!f) throw Err("PLY: unexpected end of file");
+            if (fmt == BE) std::reverse(b, b + n);
+            if (t == "float" || t == "float32") { float v; memcpy(&v, b, 4); return v; }
+            if (t == "double" || t == "float64") { double v; memcpy(&v, b, 8); return v; }
+            if (t == "char" || t == "int8") return (double) (int8_t) b[0];
+            if (t == "uchar" || t == "uint8") return (double) b[0];
+            if (t == "short" || t == "int16") { int16_t v; memcpy(&v, b, 2); return v; }
+            if (t == "ushort" || t == "uint16") { uint16_t v; memcpy(&v, b, 2); return v; }
+            if (t == "int" || t == "int32") { int32_t v; memcpy(&v, b, 4); return v; }
+            uint32_t v; memcpy(&v, b, 4); return v;
+        };
+        bool hasN = false, hasUV = false;
+        for (auto &e : elems) {
+            if (e.name == "vertex") {
+                for (auto &pr : e.props) { hasN |= pr.name == "nx"; hasUV |= pr.name == "u" || pr.name == "s" || pr.name == "texture_u"; }
+                md.P.resize(3 * e.count);
+                if (hasN) md.N.resize(3 * e.count);
+                if (hasUV) md.UV.resize(2 * e.count);
+                for (size_t i = 0; i < e.count; ++i)
+                    for (auto &pr : e.props) {
+                        if (pr.list) { const int n = (int) readNum(pr.countType); for (int k = 0; k < n; ++k) readNum(pr.type); continue; }
+                        const double v = readNum(pr.type);
+                        if (pr.name == "x") md.P[3 * i] = (float) v; else if (pr.name == "y") md.P[3 * i + 1] = (float) v; else if (pr.name == "z") md.P[3 * i + 2] = (float) v;
+                        else if (pr.name == "nx") md.N[3 * i] = (float) v; else if (pr.name == "ny") md.N[3 * i + 1] = (float) v; else if (pr.name == "nz") md.N[3 * i + 2] = (float) v;
+                        else if (pr.name == "u" || pr.name == "s" || pr.name == "texture_u") md.UV[2 * i] = (float) v;
+                        else if (pr.name == "v" || pr.name == "t" || pr.name == "texture_v") md.UV[2 * i + 1] = (float) v;
+                    }
+            } else if (e.name == "face") {
+                for (size_t i = 0; i < e.count; ++i)
+                    for (auto &pr : e.props) {
+                        if (!pr.list) { readNum(pr.type); continue; }
+                        const int n = (int) readNum(pr.countType);
+                        if (pr.name != "vertex_indices" && pr.name != "vertex_index") { for (int k = 0; k < n; ++k) readNum(pr.type); continue; }
+                        if (n != 3 && n != 4) throw Err("Only triangle and quad-based PLY meshes are supported for now."); // ply.cpp:252-254
+                        uint32_t face[4];
+                        for (int k = 0; k < n; ++k) {
+                            const double v = readNum(pr.type);
+                            if (v < 0 || (size_t) v >= md.P.size() / 3) throw Err("PLY: vertex index out of range");
+                            face[k] = (uint32_t) v;
+                        }
+                        md.idx.insert(md.idx.end(), {face[0], face[1], face[2]});
+                        if (n == 4) md.idx.insert(md.idx.end(), {face[3], face[0], face[2]});
+                    }
+            } else { // skip unknown elements
+                for (size_t i = 0; i < e.count; ++i)
+                    for (auto &pr : e.props) {
+                        if (pr.list) { const int n = (int) readNum(pr.countType); for (int k = 0; k < n; ++k) readNum(pr.type); } else readNum(pr.type);
+                    }
+            }
+        }
+        if (md.idx.empty() || md.P.empty()) throw Err("Unable to load \"" + path + "\" (no triangles or vertices found)!");
+    }
+
     void addShape(Node *n) {
         Props p(n);
         MeshData md;
         M4 toWorld = p.xf("toWorld"), inv;
         if (!toWorld.inverse(inv)) throw Err("shape: singular toWorld transform");
         bool flip = p.b("flipNormals", false);
-        if (n->type == "obj") {
+        if (n->type == "obj" || n->type == "ply") {
             std::string fn = p.s("filename", "");
-            if (fn.empty()) throw Err("obj: missing 'filename'");
+            if (fn.empty()) throw Err(n->type + ": missing 'filename'");
             if (fn[0] != '/') fn = baseDir + "/" + fn;
-            loadObj(fn, md);
+            if (n->type == "obj") { loadObj(fn, md); p.b("flipTexCoords", true); p.b("collapse", false); }
+            else { loadPly(fn, md); p.b("srgb", true); }
             bool faceN = p.b("faceNormals", false);
-            p.f("maxSmoothAngle", 0.0); p.b("flipTexCoords", true); p.b("collapse", false);
+            p.f("maxSmoothAngle", 0.0);
             // object -> world
             for (size_t i = 0; i < md.P.size() / 3; ++i) {
                 double q[3] = {md.P[3 * i], md.P[3 * i + 1], md.P[3 * i + 2]}, o[3];
@@ -744,7 +836,7 @@ struct Loader {
                 }
                 md.idx.insert(md.idx.end(), {base, base + 1, base + 2, base + 3, base, base + 2});
             }
-        } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, rectangle, cube)");
+        } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, ply, rectangle, cube)");
         // children: bsdf / ref / emitter
         int mat = -1, em = -1, interior = -1, exterior = -1;
         bool isEmitter = false;

@@ -109,3 +109,58 @@ def test_constant_emitter_through_xml(b2ctx, tmp_path):
     d.env_radiance = (0.2, 0.3, 0.5); d.env_sampling_weight = 0.5
     fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
     assert rel_l2(api.develop(film), O.develop(fo)) < 3e-4
+
+
+def _write_ply(path, P, N, idx, fmt):
+    import struct
+    n, m = len(P), len(idx)
+    hdr = f"ply\nformat {fmt} 1.0\ncomment generated by tests/test_gpu_xml.py\nelement vertex {n}\nproperty float x\nproperty float y\nproperty float z\n"
+    if N is not None:
+        hdr += "property float nx\nproperty float ny\nproperty float nz\n"
+    hdr += f"property uchar red\nelement face {m}\nproperty list uchar int vertex_indices\nend_header\n"
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        if fmt == "ascii":
+            for i in range(n):
+                row = list(P[i]) + (list(N[i]) if N is not None else []) + [255]
+                f.write((" ".join(repr(float(x)) if k < len(row) - 1 else str(int(x)) for k, x in enumerate(row)) + "\n").encode())
+            for t in idx:
+                f.write((f"{len(t)} " + " ".join(str(int(i)) for i in t) + "\n").encode())
+        else:
+            e = "<" if fmt == "binary_little_endian" else ">"
+            for i in range(n):
+                f.write(struct.pack(e + "3f", *P[i]))
+                if N is not None:
+                    f.write(struct.pack(e + "3f", *N[i]))
+                f.write(struct.pack("B", 255))
+            for t in idx:
+                f.write(struct.pack("B", len(t)) + struct.pack(e + f"{len(t)}i", *[int(i) for i in t]))
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+def test_ply_shape_through_xml(b2ctx, tmp_path, fmt):
+    """<shape type="ply"> (src/shapes/ply.cpp): ascii / binary, vertex normals, an extra vertex property, a quad face."""
+    from mitsuba_b200.scene import Bsdf, Camera, Mesh, SceneDesc, look_at, uv_sphere, _quad
+    P, N, _, I = uv_sphere((0, 1, 0), 1.0, 16, 32)
+    _write_ply(tmp_path / "ball.ply", P, N, [tuple(t) for t in I], fmt)
+    Pq = np.float32([(-4, 0, -4), (-4, 0, 4), (4, 0, 4), (4, 0, -4)])
+    _write_ply(tmp_path / "ground.ply", Pq, None, [(0, 1, 2, 3)], fmt)
+    Pl, Il = _quad([(-1, 4, -1), (-1, 4, 1), (1, 4, 1), (1, 4, -1)], (0, -1, 0))
+    _write_ply(tmp_path / "light.ply", Pl, None, [tuple(t) for t in Il], fmt)
+    (tmp_path / "s.xml").write_text('''<scene version="0.5.0"><integrator type="path"/>
+      <sensor type="perspective"><float name="fov" value="35"/><transform name="toWorld"><lookat origin="0,2.2,-5" target="0,0.9,0" up="0,1,0"/></transform>
+        <sampler type="sobol"><integer name="sampleCount" value="16"/></sampler>
+        <film type="hdrfilm"><integer name="width" value="40"/><integer name="height" value="40"/><rfilter type="box"/></film></sensor>
+      <shape type="ply"><string name="filename" value="ball.ply"/><bsdf type="diffuse"><rgb name="reflectance" value="0.7 0.4 0.3"/></bsdf></shape>
+      <shape type="ply"><string name="filename" value="ground.ply"/><boolean name="faceNormals" value="true"/><bsdf type="diffuse"/></shape>
+      <shape type="ply"><string name="filename" value="light.ply"/><boolean name="faceNormals" value="true"/><emitter type="area"><rgb name="radiance" value="20 20 20"/></emitter></shape>
+    </scene>''')
+    sc, rp = b2ctx.load_xml(str(tmp_path / "s.xml"))
+    film, st = sc.render(rp, parity=True, width=40, height=40)
+    ground_idx = np.uint32([(0, 1, 2), (3, 0, 2)])  # ply.cpp:276-287
+    d = SceneDesc([Mesh(P, I, N=N, bsdf=Bsdf("diffuse", reflectance=(0.7, 0.4, 0.3))), Mesh(Pq, ground_idx, bsdf=Bsdf("diffuse")),
+                   Mesh(Pl, Il, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(20, 20, 20))],
+                  Camera(look_at((0, 2.2, -5), (0, 0.9, 0), (0, 1, 0)), fov=35, near=1e-2, far=1e4, width=40, height=40))
+    fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert st["n_triangles"] == d.n_triangles()
+    assert rel_l2(api.develop(film), O.develop(fo)) < 3e-4
