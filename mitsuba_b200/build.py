@@ -61,7 +61,7 @@ def build_variant(name: str, fast_flags, defines=()) -> str:
             obj = os.path.join(OBJ, base + ".o")
         objs.append(obj)
     lib = os.path.join(HERE, f"libb2mts_{name}.so")
-    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-lexpat", "-ldl", "-lpthread"], capture_output=True, text=True)
+    r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-lexpat", "-lz", "-ldl", "-lpthread"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(r.stdout + r.stderr)
     return lib
@@ -91,7 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print("\n".join(outs))
     if force or jobs or _newer(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lexpat", "-ldl", "-lpthread"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lexpat", "-lz", "-ldl", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

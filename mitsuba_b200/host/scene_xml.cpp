@@ -9,6 +9,7 @@
 // Anything else is rejected with an error naming the element -- nothing is silently ignored.
 #include "../../include/b2mts.h"
 #include <expat.h>
+#include <zlib.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -773,19 +774,86 @@ struct Loader {
         if (md.idx.empty() || md.P.empty()) throw Err("Unable to load \"" + path + "\" (no triangles or vertices found)!");
     }
 
+    // Mitsuba's compressed triangle-mesh format (src/librender/trimesh.cpp:147-300, src/shapes/serialized.cpp): u16 0x041C, u16 version
+    // (3 | 4), zlib stream {u32 flags, [v4: name\0], u64 nV, u64 nT, positions, [normals], [texcoords], [colors], u32 indices}; several
+    // shapes per file are addressed through the offset dictionary at the end (u32 offsets in v3, u64 in v4, then u32 count)
+    void loadSerialized(const std::string &path, int shapeIndex, MeshData &md, bool &fileFaceNormals) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Err("serialized: cannot open \"" + path + "\"");
+        std::vector<unsigned char> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        auto rd16 = [&](size_t o) { if (o + 2 > file.size()) throw Err("serialized: truncated file"); return (uint16_t) (file[o] | (file[o + 1] << 8)); };
+        auto rd32 = [&](size_t o) { if (o + 4 > file.size()) throw Err("serialized: truncated file"); uint32_t v; memcpy(&v, &file[o], 4); return v; };
+        auto rd64 = [&](size_t o) { if (o + 8 > file.size()) throw Err("serialized: truncated file"); uint64_t v; memcpy(&v, &file[o], 8); return v; };
+        auto header = [&](size_t o) -> int {
+            const uint16_t format = rd16(o), version = rd16(o + 2);
+            if (format != 0x041C) throw Err("Encountered an invalid file format!");
+            if (version != 3 && version != 4) throw Err("Encountered an incompatible file version!");
+            return version;
+        };
+        const int version = header(0);
+        size_t offset = 0;
+        if (shapeIndex != 0) { // trimesh.cpp:273-292 readOffset
+            const uint32_t count = rd32(file.size() - 4);
+            if (shapeIndex < 0 || shapeIndex >= (int) count) throw Err("Unable to unserialize mesh, shape index is out of range!");
+            offset = version == 4 ? (size_t) rd64(file.size() - 8 * (size_t) (count - shapeIndex) - 4) : (size_t) rd32(file.size() - 4 * (size_t) (count - shapeIndex + 1));
+            header(offset);
+        }
+        // inflate everything from offset + 4 (the stream ends at Z_STREAM_END)
+        std::vector<unsigned char> data;
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit(&zs) != Z_OK) throw Err("serialized: inflateInit failed");
+        zs.next_in = file.data() + offset + 4;
+        zs.avail_in = (uInt) std::min<size_t>(file.size() - offset - 4, 0xFFFFFFFFu);
+        unsigned char buf[1 << 16];
+        int rc;
+        do {
+            zs.next_out = buf; zs.avail_out = sizeof(buf);
+            rc = inflate(&zs, Z_NO_FLUSH);
+            if (rc != Z_OK && rc != Z_STREAM_END) { inflateEnd(&zs); throw Err("serialized: corrupt zlib stream"); }
+            data.insert(data.end(), buf, buf + (sizeof(buf) - zs.avail_out));
+        } while (rc != Z_STREAM_END);
+        inflateEnd(&zs);
+        size_t pos = 0;
+        auto need = [&](size_t n) { if (pos + n > data.size()) throw Err("serialized: truncated mesh record"); };
+        need(4);
+        uint32_t flags; memcpy(&flags, &data[pos], 4); pos += 4;
+        if (version == 4) { while (true) { need(1); if (data[pos++] == 0) break; } }
+        need(16);
+        uint64_t nV, nT; memcpy(&nV, &data[pos], 8); memcpy(&nT, &data[pos + 8], 8); pos += 16;
+        const bool dbl = (flags & 0x2000) != 0;
+        fileFaceNormals = (flags & 0x0010) != 0;
+        auto readFloats = [&](std::vector<float> &out, size_t n) {
+            out.resize(n);
+            if (dbl) { need(8 * n); for (size_t i = 0; i < n; ++i) { double v; memcpy(&v, &data[pos + 8 * i], 8); out[i] = (float) v; } pos += 8 * n; }
+            else { need(4 * n); memcpy(out.data(), &data[pos], 4 * n); pos += 4 * n; }
+        };
+        readFloats(md.P, 3 * (size_t) nV);
+        if (flags & 0x0001) readFloats(md.N, 3 * (size_t) nV);
+        if (flags & 0x0002) readFloats(md.UV, 2 * (size_t) nV);
+        if (flags & 0x0008) { std::vector<float> colors; readFloats(colors, 3 * (size_t) nV); }
+        need(12 * (size_t) nT);
+        md.idx.resize(3 * (size_t) nT);
+        memcpy(md.idx.data(), &data[pos], 12 * (size_t) nT);
+        for (uint32_t i : md.idx) if (i >= nV) throw Err("serialized: vertex index out of range");
+        if (nT == 0 || nV == 0) throw Err("Encountered an empty triangle mesh!");
+    }
+
     void addShape(Node *n) {
         Props p(n);
         MeshData md;
         M4 toWorld = p.xf("toWorld"), inv;
         if (!toWorld.inverse(inv)) throw Err("shape: singular toWorld transform");
         bool flip = p.b("flipNormals", false);
-        if (n->type == "obj" || n->type == "ply") {
+        if (n->type == "obj" || n->type == "ply" || n->type == "serialized") {
             std::string fn = p.s("filename", "");
             if (fn.empty()) throw Err(n->type + ": missing 'filename'");
             if (fn[0] != '/') fn = baseDir + "/" + fn;
+            bool fileFaceNormals = false;
             if (n->type == "obj") { loadObj(fn, md); p.b("flipTexCoords", true); p.b("collapse", false); }
-            else { loadPly(fn, md); p.b("srgb", true); }
-            bool faceN = p.b("faceNormals", false);
+            else if (n->type == "ply") { loadPly(fn, md); p.b("srgb", true); }
+            else loadSerialized(fn, (int) p.i("shapeIndex", 0), md, fileFaceNormals);
+            bool faceN = p.b("faceNormals", false) || fileFaceNormals;
             p.f("maxSmoothAngle", 0.0);
             // object -> world
             for (size_t i = 0; i < md.P.size() / 3; ++i) {
@@ -836,7 +904,7 @@ struct Loader {
                 }
                 md.idx.insert(md.idx.end(), {base, base + 1, base + 2, base + 3, base, base + 2});
             }
-        } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, ply, rectangle, cube)");
+        } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, ply, serialized, rectangle, cube)");
         // children: bsdf / ref / emitter
         int mat = -1, em = -1, interior = -1, exterior = -1;
         bool isEmitter = false;

@@ -164,3 +164,52 @@ def test_ply_shape_through_xml(b2ctx, tmp_path, fmt):
     fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
     assert st["n_triangles"] == d.n_triangles()
     assert rel_l2(api.develop(film), O.develop(fo)) < 3e-4
+
+
+def _serialized_blob(version, P, N, idx, double=False, face_normals=False, name=b"mesh"):
+    """One mesh record of src/librender/trimesh.cpp:175-250 (header + zlib stream)."""
+    import struct, zlib
+    flags = (0x2000 if double else 0x1000) | (0x0001 if N is not None else 0) | (0x0010 if face_normals else 0)
+    ft = "<f8" if double else "<f4"
+    body = struct.pack("<I", flags) + ((name + b"\0") if version == 4 else b"") + struct.pack("<QQ", len(P), len(idx))
+    body += np.ascontiguousarray(P, ft).tobytes()
+    if N is not None:
+        body += np.ascontiguousarray(N, ft).tobytes()
+    body += np.ascontiguousarray(idx, "<u4").tobytes()
+    return struct.pack("<HH", 0x041C, version) + zlib.compress(body)
+
+
+def test_serialized_shape_through_xml(b2ctx, tmp_path):
+    """<shape type="serialized"> (src/shapes/serialized.cpp): v4 multi-shape file with the offset dictionary, v3 single shape,
+    double precision, the face-normal flag, shapeIndex."""
+    import struct
+    from mitsuba_b200.scene import Bsdf, Camera, Mesh, SceneDesc, look_at, uv_sphere, _quad
+    P, N, _, I = uv_sphere((0, 1, 0), 1.0, 16, 32)
+    Pq, Iq = _quad([(-4, 0, -4), (-4, 0, 4), (4, 0, 4), (4, 0, -4)], (0, 1, 0))
+    Pl, Il = _quad([(-1, 4, -1), (-1, 4, 1), (1, 4, 1), (1, 4, -1)], (0, -1, 0))
+    blobs = [_serialized_blob(4, P, N, I, double=True), _serialized_blob(4, Pq, None, Iq, face_normals=True)]
+    offs, data = [], b""
+    for b in blobs:
+        offs.append(len(data)); data += b
+    data += b"".join(struct.pack("<Q", o) for o in offs) + struct.pack("<I", len(blobs))
+    (tmp_path / "scene.serialized").write_bytes(data)
+    (tmp_path / "light.serialized").write_bytes(_serialized_blob(3, Pl, None, Il) + struct.pack("<II", 0, 1))
+    (tmp_path / "s.xml").write_text('''<scene version="0.5.0"><integrator type="path"/>
+      <sensor type="perspective"><float name="fov" value="35"/><transform name="toWorld"><lookat origin="0,2.2,-5" target="0,0.9,0" up="0,1,0"/></transform>
+        <sampler type="sobol"><integer name="sampleCount" value="16"/></sampler>
+        <film type="hdrfilm"><integer name="width" value="40"/><integer name="height" value="40"/><rfilter type="box"/></film></sensor>
+      <shape type="serialized"><string name="filename" value="scene.serialized"/><bsdf type="diffuse"><rgb name="reflectance" value="0.7 0.4 0.3"/></bsdf></shape>
+      <shape type="serialized"><string name="filename" value="scene.serialized"/><integer name="shapeIndex" value="1"/><bsdf type="diffuse"/></shape>
+      <shape type="serialized"><string name="filename" value="light.serialized"/><boolean name="faceNormals" value="true"/><emitter type="area"><rgb name="radiance" value="20 20 20"/></emitter></shape>
+    </scene>''')
+    sc, rp = b2ctx.load_xml(str(tmp_path / "s.xml"))
+    film, st = sc.render(rp, parity=True, width=40, height=40)
+    d = SceneDesc([Mesh(P, I, N=N, bsdf=Bsdf("diffuse", reflectance=(0.7, 0.4, 0.3))), Mesh(Pq, Iq, bsdf=Bsdf("diffuse")),
+                   Mesh(Pl, Il, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(20, 20, 20))],
+                  Camera(look_at((0, 2.2, -5), (0, 0.9, 0), (0, 1, 0)), fov=35, near=1e-2, far=1e4, width=40, height=40))
+    fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert st["n_triangles"] == d.n_triangles()
+    assert rel_l2(api.develop(film), O.develop(fo)) < 3e-4
+    (tmp_path / "bad.xml").write_text((tmp_path / "s.xml").read_text().replace('name="shapeIndex" value="1"', 'name="shapeIndex" value="7"'))
+    with pytest.raises(api.B2Error, match="out of range"):
+        b2ctx.load_xml(str(tmp_path / "bad.xml"))
