@@ -149,6 +149,12 @@ int b2_scene_add_mesh(b2_scene *, const float *P, const float *N, const float *U
  * A mesh whose material is B2_BSDF_NULL is an index-matched boundary. */
 int b2_scene_add_medium(b2_scene *, const b2_medium_desc *);
 int b2_scene_set_mesh_media(b2_scene *, int mesh_id, int interior_medium, int exterior_medium);
+/* Instancing (src/shapes/{shapegroup,instance}.cpp): meshes assigned to a shapegroup live in its object space and are only
+ * visible through instances; `to_world` / `to_object` are the affine instance transform and its inverse (row major).
+ * Emitters cannot be instanced (shapegroup.cpp:115-116); `path` only. */
+int b2_scene_add_shapegroup(b2_scene *);                                   /* -> group id */
+int b2_scene_set_mesh_group(b2_scene *, int mesh_id, int group_id);
+int b2_scene_add_instance(b2_scene *, int group_id, const float to_world[16], const float to_object[16]);
 /* Scene::initialize (src/librender/scene.cpp:322-384): TriAccel precompute (skdtree.cpp:74-109),
  * acceleration structure build (BVH; replaces GenericKDTree::buildInternal, gkdtree.h:958-1263),
  * emitter / triangle-area CDFs (scene.cpp:375-380, trimesh.cpp:388-403), upload to HBM. */

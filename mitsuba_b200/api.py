@@ -59,7 +59,7 @@ class b2_stats(C.Structure):
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
            "b2_scene_set_camera", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
+           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -202,6 +202,8 @@ class Scene:
             m.density = d["density"].ctypes.data_as(C.POINTER(C.c_float)) if d["density"] is not None else None
             if self.L.b2_scene_add_medium(self.h, C.byref(m)) < 0:
                 raise B2Error(ctx.err())
+        for _ in range(desc.n_groups()):
+            self.L.b2_scene_add_shapegroup(self.h)
         for mesh, bid in zip(desc.meshes, ids):
             eid = -1
             if mesh.radiance is not None:
@@ -213,8 +215,16 @@ class Scene:
             N = np.ascontiguousarray(mesh.N, np.float32) if mesh.N is not None else None
             UV = np.ascontiguousarray(mesh.UV, np.float32) if mesh.UV is not None else None
             I = np.ascontiguousarray(mesh.idx, np.uint32)
-            if self.L.b2_scene_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
-                                        C.c_int(bid), C.c_int(eid)) < 0:
+            mid = self.L.b2_scene_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
+                                           C.c_int(bid), C.c_int(eid))
+            if mid < 0:
+                raise B2Error(ctx.err())
+            if mesh.group >= 0:
+                self._ck(self.L.b2_scene_set_mesh_group(self.h, C.c_int(mid), C.c_int(mesh.group)))
+        for inst in desc.instances:
+            M64 = np.asarray(inst.to_world, np.float64)
+            M, Minv = np.ascontiguousarray(M64, np.float32), np.ascontiguousarray(np.linalg.inv(M64), np.float32)
+            if self.L.b2_scene_add_instance(self.h, C.c_int(inst.group), _p(M), _p(Minv)) < 0:
                 raise B2Error(ctx.err())
         if getattr(desc, "env_radiance", None) is not None:
             rad = np.asarray(desc.env_radiance, np.float32)

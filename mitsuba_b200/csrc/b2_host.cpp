@@ -60,6 +60,7 @@ struct HostMesh {
     std::vector<uint32_t> idx;
     int material = -1, emitter = -1;
     int interior = -1, exterior = -1; // media ids (shape.h:427-435), -1 = vacuum
+    int group = -1;                   // >= 0: member of that shapegroup (object space), src/shapes/shapegroup.cpp
     uint32_t primOffset = 0;
 };
 struct HostEmitter {
@@ -94,6 +95,9 @@ struct b2_scene {
     std::vector<HostEmitter> emitters;
     std::vector<HostMesh> meshes;
     struct HostMedium { b2_medium_desc desc; std::vector<float> density; };
+    struct HostInstance { int group; float M[16], Minv[16]; };
+    std::vector<HostInstance> instances;
+    int nGroups = 0;
     std::vector<HostMedium> media;
     // camera
     float camToWorld[16];
@@ -111,6 +115,7 @@ struct b2_scene {
     DevBuf<DEmitter> dEmitters;
     DevBuf<float> dEmitterCdf, dTriCdf;
     DevBuf<DMedium> dMedia;
+    DevBuf<DInstance> dInstances;
     DevBuf<int2> dPrimMedia;
     std::vector<std::unique_ptr<DevBuf<float>>> dDensity;
     bool hasNullBsdf = false;
@@ -121,6 +126,7 @@ struct b2_scene {
     DPool pool{};
     DevBuf<float4> pRay, pSt, pHit, pShD, pShC;
     DevBuf<uint2> pSmp, pVol;
+    DevBuf<uint32_t> pInst;
     DevBuf<float2> pPos;
     DevBuf<uint32_t> pPix, pFlags;
     DevBuf<uint32_t> pMatQueue, pDoneQueue;
@@ -424,6 +430,31 @@ extern "C" int b2_scene_set_mesh_media(b2_scene *s, int mesh, int interior, int 
     return B2_OK;
 }
 
+// <shape type="shapegroup"> / <shape type="instance"> (src/shapes/{shapegroup,instance}.cpp)
+extern "C" int b2_scene_add_shapegroup(b2_scene *s) {
+    if (!s) { fail(nullptr, B2_ERR_INVALID, "b2_scene_add_shapegroup: null scene"); return -1; }
+    s->committed = false;
+    return s->nGroups++;
+}
+extern "C" int b2_scene_set_mesh_group(b2_scene *s, int mesh, int group) {
+    if (!s) return fail(nullptr, B2_ERR_INVALID, "b2_scene_set_mesh_group: null scene");
+    if (mesh < 0 || mesh >= (int) s->meshes.size() || group < 0 || group >= s->nGroups) return fail(s->ctx, B2_ERR_INVALID, "invalid mesh or shapegroup id");
+    if (s->meshes[mesh].emitter >= 0) return fail(s->ctx, B2_ERR_INVALID, "Instancing of emitters is not supported"); // shapegroup.cpp:115-116
+    s->meshes[mesh].group = group;
+    s->committed = false;
+    return B2_OK;
+}
+extern "C" int b2_scene_add_instance(b2_scene *s, int group, const float to_world[16], const float to_object[16]) {
+    if (!s || !to_world || !to_object) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_instance: null argument"); return -1; }
+    if (group < 0 || group >= s->nGroups) { fail(s->ctx, B2_ERR_INVALID, "A reference to a 'shapegroup' must be specified!"); return -1; } // instance.cpp:75-78
+    b2_scene::HostInstance in;
+    in.group = group;
+    memcpy(in.M, to_world, 64); memcpy(in.Minv, to_object, 64);
+    s->instances.push_back(in);
+    s->committed = false;
+    return (int) s->instances.size() - 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // commit
 // ------------------------------------------------------------------------------------------------
@@ -496,8 +527,12 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     bool anyNorm = false;
     for (auto &m : s->meshes) anyNorm |= !m.N.empty() || !m.UV.empty();
     std::vector<float4> verts(3 * nPrims), norms(anyNorm ? 3 * nPrims : 0), triAccel(3 * nPrims);
-    std::vector<PrimBox> boxes;
-    std::vector<uint32_t> ids;
+    // candidate primitives per acceleration structure: bucket 0 = world, bucket g + 1 = shapegroup g
+    const bool instanced = !s->instances.empty();
+    std::vector<std::vector<PrimBox>> bBoxes(1 + (size_t) s->nGroups);
+    std::vector<std::vector<uint32_t>> bIds(1 + (size_t) s->nGroups);
+    std::vector<PrimBox> &boxes = bBoxes[0];
+    std::vector<uint32_t> &ids = bIds[0];
     boxes.reserve(nPrims); ids.reserve(nPrims);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (size_t mi = 0; mi < s->meshes.size(); ++mi) {
@@ -561,10 +596,9 @@ extern "C" int b2_scene_commit(b2_scene *s) {
             for (int a = 0; a < 3; ++a) {
                 pb.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
                 pb.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
-                lo[a] = std::min(lo[a], pb.lo[a]);
-                hi[a] = std::max(hi[a], pb.hi[a]);
+                if (m.group < 0) { lo[a] = std::min(lo[a], pb.lo[a]); hi[a] = std::max(hi[a], pb.hi[a]); }
             }
-            if (wds[0] != 3) { boxes.push_back(pb); ids.push_back((uint32_t) p); } // k == 3: degenerate, never hit (triaccel.h:75-78)
+            if (wds[0] != 3) { bBoxes[m.group + 1].push_back(pb); bIds[m.group + 1].push_back((uint32_t) p); } // k == 3: degenerate, never hit (triaccel.h:75-78)
         }
     }
     s->hTriAccelPrimOrder = triAccel;
@@ -576,13 +610,90 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     uint32_t flatLimit = 64;
     if (const char *e = getenv("B2_FLAT_LIMIT")) flatLimit = (uint32_t) atoi(e);
     uint32_t rootCount = 0;
-    if (!ids.empty() && ids.size() <= flatLimit) {
+    if (!instanced && !ids.empty() && ids.size() <= flatLimit) {
         bvh.leafPrims = ids;
         bvh.rootRef = -1; // ~0: leaf starting at triangle 0
         bvh.depth = 1;
         rootCount = (uint32_t) ids.size();
     } else {
-        buildBVH(boxes, ids, 4, B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh);
+        buildBVH(boxes, ids, 4, instanced ? 19 : B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh);
+    }
+    // ---- instancing: one BVH per shapegroup appended to the node / leaf arrays, then a top-level BVH over the items
+    //      (item 0 = the world triangles, item k = instance k - 1); stack budget: 9 (top) + 3 (leaf items) + 19 (bottom) < 32 ----
+    std::vector<DInstance> items;
+    int tlasRoot = -1;
+    float topLo[3] = {lo[0], lo[1], lo[2]}, topHi[3] = {hi[0], hi[1], hi[2]};
+    if (instanced) {
+        struct GroupInfo { int rootRef = -1; float lo[3], hi[3]; bool empty = true; };
+        std::vector<GroupInfo> gi((size_t) s->nGroups);
+        auto appendTree = [&](BVHResult &g) -> int { // returns the root reference inside the merged arrays
+            const uint32_t nodeBase = (uint32_t) bvh.nodes.size(), leafBase = (uint32_t) bvh.leafPrims.size();
+            auto fix = [&](int32_t r) -> int32_t {
+                if (r >= 0) return r + (int32_t) nodeBase;
+                const uint32_t bits = ~(uint32_t) r;
+                return (int32_t) ~(((bits & 0x0FFFFFFFu) + leafBase) | (bits & 0xF0000000u));
+            };
+            for (auto nd : g.nodes) { nd.left = fix(nd.left); nd.right = fix(nd.right); bvh.nodes.push_back(nd); }
+            bvh.leafPrims.insert(bvh.leafPrims.end(), g.leafPrims.begin(), g.leafPrims.end());
+            return fix(g.rootRef);
+        };
+        for (int g = 0; g < s->nGroups; ++g) {
+            if (bIds[g + 1].empty()) continue;
+            BVHResult r;
+            buildBVH(bBoxes[g + 1], bIds[g + 1], 4, 19, threads > 0 ? threads : 1, r);
+            gi[g].rootRef = appendTree(r);
+            gi[g].empty = false;
+            float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (auto &b : bBoxes[g + 1]) for (int a = 0; a < 3; ++a) { l[a] = std::min(l[a], b.lo[a]); h[a] = std::max(h[a], b.hi[a]); }
+            const float eps = 1e-3f; // the group's kd-tree box, enlarged (gkdtree.h:1213-1220)
+            for (int a = 0; a < 3; ++a) { gi[g].lo[a] = l[a] - ((h[a] - l[a]) * eps + eps); gi[g].hi[a] = h[a] + ((h[a] - gi[g].lo[a]) * eps + eps); }
+            bvh.depth = std::max(bvh.depth, r.depth);
+        }
+        if (bvh.leafPrims.size() >= (1u << 28)) return fail(ctx, B2_ERR_INVALID, "too many triangles (limit 2^28)");
+        std::vector<PrimBox> itemBoxes;
+        std::vector<uint32_t> itemIds;
+        if (!ids.empty()) { // item: the world triangles, identity transform, no clipping
+            DInstance it; memset(&it, 0, sizeof(it));
+            it.identity = 1; it.rootRef = bvh.rootRef;
+            PrimBox pb; for (int a = 0; a < 3; ++a) { pb.lo[a] = lo[a]; pb.hi[a] = hi[a]; }
+            itemBoxes.push_back(pb); itemIds.push_back((uint32_t) items.size()); items.push_back(it);
+        }
+        for (size_t k = 0; k < s->instances.size(); ++k) {
+            const auto &hi_ = s->instances[k];
+            const GroupInfo &g = gi[hi_.group];
+            if (g.empty) continue;
+            DInstance it; memset(&it, 0, sizeof(it));
+            for (int r = 0; r < 12; ++r) { it.M[r] = hi_.M[r]; it.Minv[r] = hi_.Minv[r]; }
+            it.rootRef = g.rootRef; it.instance = (int32_t) k;
+            memcpy(it.aabbMin, g.lo, 12); memcpy(it.aabbMax, g.hi, 12);
+            PrimBox pb; for (int a = 0; a < 3; ++a) { pb.lo[a] = INFINITY; pb.hi[a] = -INFINITY; }
+            for (int c = 0; c < 8; ++c) { // Instance::getAABB, instance.cpp:80-96
+                const float q[3] = {(c & 1) ? g.hi[0] : g.lo[0], (c & 2) ? g.hi[1] : g.lo[1], (c & 4) ? g.hi[2] : g.lo[2]};
+                for (int a = 0; a < 3; ++a) {
+                    const float w = hi_.M[4 * a] * q[0] + hi_.M[4 * a + 1] * q[1] + hi_.M[4 * a + 2] * q[2] + hi_.M[4 * a + 3];
+                    pb.lo[a] = std::min(pb.lo[a], w); pb.hi[a] = std::max(pb.hi[a], w);
+                }
+            }
+            for (int a = 0; a < 3; ++a) { topLo[a] = std::min(topLo[a], pb.lo[a]); topHi[a] = std::max(topHi[a], pb.hi[a]); }
+            itemBoxes.push_back(pb); itemIds.push_back((uint32_t) items.size()); items.push_back(it);
+        }
+        if (items.size() >= (1u << 20)) return fail(ctx, B2_ERR_INVALID, "too many instances (limit 2^20)");
+        BVHResult top;
+        buildBVH(itemBoxes, itemIds, 4, 9, 1, top);
+        if (top.depth > 10) return fail(ctx, B2_ERR_INVALID, "instance hierarchy too deep for the traversal stack");
+        // top-level leaves reference items, not triangles: keep their refs apart from the triangle leaf array
+        const uint32_t nodeBase = (uint32_t) bvh.nodes.size();
+        std::vector<uint32_t> order = top.leafPrims; // item order of the top-level leaves
+        std::vector<DInstance> sorted(items.size());
+        for (size_t k = 0; k < order.size(); ++k) sorted[k] = items[order[k]];
+        items.swap(sorted);
+        for (auto nd : top.nodes) {
+            if (nd.left >= 0) nd.left += (int32_t) nodeBase;
+            if (nd.right >= 0) nd.right += (int32_t) nodeBase;
+            bvh.nodes.push_back(nd);
+        }
+        tlasRoot = top.rootRef >= 0 ? top.rootRef + (int32_t) nodeBase : top.rootRef;
+        lo[0] = topLo[0]; lo[1] = topLo[1]; lo[2] = topLo[2]; hi[0] = topHi[0]; hi[1] = topHi[1]; hi[2] = topHi[2];
     }
     s->bvhDepth = bvh.depth;
     std::vector<float4> leafTri(3 * bvh.leafPrims.size()), leafPlane(3 * bvh.leafPrims.size());
@@ -790,6 +901,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     CK(ctx, s->dEmitterCdf.upload(emCdf));
     CK(ctx, s->dTriCdf.upload(triCdf));
     CK(ctx, s->dMedia.upload(dmed));
+    CK(ctx, s->dInstances.upload(items));
     CK(ctx, s->dPrimMedia.upload(primMedia));
     DScene &ds = s->ds;
     memset(&ds, 0, sizeof(ds));
@@ -812,12 +924,13 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         r2 = dx * dx + dy * dy + dz * dz;
         ds.bsRadius = std::max(1e-4f, std::sqrt(r2) * 1.5f);
     }
+    ds.items = s->dInstances.p; ds.nItems = (uint32_t) items.size(); ds.tlasRoot = tlasRoot;
     ds.media = s->dMedia.p; ds.primMedia = anyMedia ? s->dPrimMedia.p : nullptr; ds.nMedia = (uint32_t) dmed.size();
     ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef; ds.rootCount = rootCount;
     ds.flatRec = s->dFlatRec.p; ds.flatIdx = (const uint2 *) s->dFlatIdx.p; ds.flatP = flatP; ds.flatC = flatC; ds.flatS = flatS;
     ds.flatBytes = (uint32_t) (flatRec.size() * 16);
     // gkdtree.h:1213-1220: enlarged scene box (the max side uses the already-moved min, as in the reference)
-    if (nPrims == 0) { for (int a = 0; a < 3; ++a) { lo[a] = 0; hi[a] = 0; } }
+    if (nPrims == 0 || !(lo[0] <= hi[0])) { for (int a = 0; a < 3; ++a) { lo[a] = 0; hi[a] = 0; } }
     const float eps = 1e-3f;
     for (int a = 0; a < 3; ++a) {
         float mn = lo[a] - ((hi[a] - lo[a]) * eps + eps);
@@ -919,6 +1032,7 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     r.maxDepth = p->max_depth; r.rrDepth = p->rr_depth; r.strictNormals = p->strict_normals; r.hideEmitters = p->hide_emitters;
     r.sampleLo = p->sample_lo; r.sampleHi = p->sample_hi > 0 ? p->sample_hi : p->spp;
     if (p->integrator != B2_INTEGRATOR_PATH && p->integrator != B2_INTEGRATOR_VOLPATH) return fail(ctx, B2_ERR_INVALID, "unknown integrator");
+    if (p->integrator == B2_INTEGRATOR_VOLPATH && s->ds.nItems) return fail(ctx, B2_ERR_INVALID, "volpath with instanced geometry is not supported");
     if (p->integrator == B2_INTEGRATOR_VOLPATH && s->ds.envEmitter >= 0) return fail(ctx, B2_ERR_INVALID, "volpath with an environment emitter is not supported");
     r.integrator = p->integrator;
     if (r.sampleLo < 0 || r.sampleHi > p->spp || r.sampleLo >= r.sampleHi) return fail(ctx, B2_ERR_INVALID, "invalid sample range");
@@ -964,6 +1078,7 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
 static int ensurePool(b2_scene *s, uint32_t Q, bool vol) {
     b2_ctx *ctx = s->ctx;
     if (vol && s->pVol.n != Q) { CK(ctx, s->pVol.alloc(Q)); s->pool.vol = s->pVol.p; }
+    if (s->ds.nItems && s->pInst.n != Q) { CK(ctx, s->pInst.alloc(Q)); s->pool.inst = s->pInst.p; }
     if (s->pool.capacity == Q) return B2_OK;
     CK(ctx, s->pRay.alloc((size_t) 2 * Q)); CK(ctx, s->pSt.alloc((size_t) 2 * Q)); CK(ctx, s->pHit.alloc(Q));
     CK(ctx, s->pShD.alloc(Q)); CK(ctx, s->pShC.alloc(Q)); CK(ctx, s->pSmp.alloc(Q)); CK(ctx, s->pPos.alloc(Q));
@@ -976,6 +1091,7 @@ static int ensurePool(b2_scene *s, uint32_t Q, bool vol) {
     p.doneQueue = s->pDoneQueue.p;
     p.counters = s->dCounters.p;
     p.vol = s->pVol.p;
+    p.inst = s->pInst.p;
     return B2_OK;
 }
 

@@ -393,7 +393,7 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
     const TraceMem tm = setupTraceMem(sc, smem);
     const uint32_t Q = pool.capacity;
     uint32_t nRays = 0;
-    if (!sc.rootCount) {
+    if (!sc.rootCount && !sc.nItems) {
         // BVH scenes: persistent loop with per-lane ray replacement (b2_trace.cuh: traverseQueue)
         uint32_t nv = 0, pt = 0;
         auto fetch = [&](uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) -> int {
@@ -437,9 +437,12 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
             h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
             float mint, maxt;
             uint32_t nv = 0, pt = 0;
+            uint32_t item = 0xFFFFFFFFu;
             if (clipRay<false>(sc, o, d, dRcp, (fl & PF_FRESH) ? ro.w : B2_EPSILON, rd.w, mint, maxt)) {
-                if (!traverse<false, false>(sc, tm, o, d, mint, maxt, h, nv, pt)) { h.t = B2_INF; h.prim = 0xFFFFFFFFu; }
+                const bool found = sc.nItems ? traverseTop<false, false>(sc, tm, o, d, mint, maxt, h, item, nv, pt) : traverse<false, false>(sc, tm, o, d, mint, maxt, h, nv, pt);
+                if (!found) { h.t = B2_INF; h.prim = 0xFFFFFFFFu; }
             }
+            if (sc.nItems) pool.inst[i] = item;
             pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
             ++nRays;
             if (SORT) {
@@ -497,6 +500,37 @@ B2_DEV void fillIntersection(const DScene &sc, const V3 &rayD, uint32_t prim, fl
     } else shN = faceNormal;
     its.geoN = faceNormal;
     computeShadingFrame(shN, dpdu, its.sh);
+    its.wi = its.sh.toLocal(-rayD);
+}
+
+// Instance::fillIntersectionRecord (instance.cpp:149-162): the nested record is filled in object space with p = ray'(t)
+// (skdtree.h fillIntersectionRecord<false>), then normals (inverse transpose), dpdu and p go to world space and the shading
+// frame is rebuilt from the transformed quantities (skdtree.h:424-427)
+B2_DEV void fillIntersectionInst(const DScene &sc, const V3 &rayO, const V3 &rayD, float t, uint32_t prim, float u, float v, const DInstance &in, Isect &its) {
+    const V3 oo = xfPoint(in.Minv, rayO), od = xfVector(in.Minv, rayD);
+    const float4 a0 = __ldg(&sc.verts[3 * (size_t) prim]), a1 = __ldg(&sc.verts[3 * (size_t) prim + 1]), a2 = __ldg(&sc.verts[3 * (size_t) prim + 2]);
+    const V3 p0(a0.x, a0.y, a0.z), p1(a1.x, a1.y, a1.z), p2(a2.x, a2.y, a2.z);
+    its.material = __float_as_int(a0.w);
+    its.emitter = __float_as_int(a1.w);
+    const uint32_t tflags = __float_as_uint(a2.w);
+    const V3 b(1 - u - v, u, v);
+    const V3 side1 = p1 - p0, side2 = p2 - p0;
+    V3 faceNormal = cross(side1, side2);
+    const float len = length(faceNormal);
+    if (!isZero(faceNormal)) faceNormal = faceNormal / len;
+    V3 dpdu = side1;
+    V3 shN;
+    if (tflags & 3u) {
+        const float4 n0 = __ldg(&sc.norms[3 * (size_t) prim]), n1 = __ldg(&sc.norms[3 * (size_t) prim + 1]), n2 = __ldg(&sc.norms[3 * (size_t) prim + 2]);
+        if (tflags & 2u) dpdu = V3(n0.w, n1.w, n2.w);
+        if (tflags & 1u) {
+            shN = normalize(V3(n0.x, n0.y, n0.z) * b.x + V3(n1.x, n1.y, n1.z) * b.y + V3(n2.x, n2.y, n2.z) * b.z);
+            if (dot(faceNormal, shN) < 0) faceNormal = -faceNormal;
+        } else shN = faceNormal;
+    } else shN = faceNormal;
+    its.p = xfPoint(in.M, oo + od * t);
+    its.geoN = normalize(xfNormal(in.Minv, faceNormal));
+    computeShadingFrame(normalize(xfNormal(in.Minv, shN)), xfVector(in.M, dpdu), its.sh);
     its.wi = its.sh.toLocal(-rayD);
 }
 
@@ -676,7 +710,13 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
             const bool valid = prim != 0xFFFFFFFFu;
             bool done = false;
             Isect its;
-            if (valid) fillIntersection(sc, rayD, prim, hit.y, hit.z, its);
+            if (valid) {
+                const uint32_t item = sc.nItems ? pool.inst[i] : 0xFFFFFFFFu;
+                if (item != 0xFFFFFFFFu && !sc.items[item].identity) {
+                    const float4 ro4 = pool.ray[2 * (size_t) i];
+                    fillIntersectionInst(sc, V3(ro4.x, ro4.y, ro4.z), rayD, hit.x, prim, hit.y, hit.z, sc.items[item], its);
+                } else fillIntersection(sc, rayD, prim, hit.y, hit.z, its);
+            }
             const bool fresh = (flags & PF_FRESH) != 0;
             if (fresh) {
                 if (valid) flags |= PF_ALPHA; // records.inl:117-144 (EOpacity)
@@ -860,7 +900,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
     const TraceMem tm = setupTraceMem(sc, smem);
     const uint32_t n = (uint32_t) pool.counters[CTR_SHADOW];
     uint32_t nClear = 0;
-    if (!sc.rootCount) {
+    if (!sc.rootCount && !sc.nItems) {
         uint32_t nv = 0, pt = 0;
         float4 cur = make_float4(0, 0, 0, 0); // contribution + slot of the ray this lane is tracing
         auto fetch = [&](uint32_t j, V3 &o, V3 &d, float &mint, float &maxt) -> int {
@@ -894,7 +934,9 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
             bool occluded = false;
             HitRec h;
             uint32_t nv = 0, pt = 0;
-            if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt)) occluded = traverse<true, false>(sc, tm, o, d, mint, maxt, h, nv, pt);
+            uint32_t item = 0;
+            if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt))
+                occluded = sc.nItems ? traverseTop<true, false>(sc, tm, o, d, mint, maxt, h, item, nv, pt) : traverse<true, false>(sc, tm, o, d, mint, maxt, h, nv, pt);
             if (!occluded) {
                 float4 li = pool.st[2 * (size_t) slot + 1];
                 li.x += scn.x; li.y += scn.y; li.z += scn.z;
@@ -1303,7 +1345,7 @@ template <bool SHADOW, bool COUNT> __global__ void __launch_bounds__(B2_TRACE_BL
     extern __shared__ __align__(128) unsigned char smem[];
     const TraceMem tm = setupTraceMem(sc, smem);
     uint32_t nv = 0, pt = 0;
-    if (!sc.rootCount) {
+    if (!sc.rootCount && !sc.nItems) {
         auto fetch = [&](uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) -> int {
             const float4 ro = rays[2 * (size_t) i], rd = rays[2 * (size_t) i + 1];
             o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z);
@@ -1326,7 +1368,9 @@ template <bool SHADOW, bool COUNT> __global__ void __launch_bounds__(B2_TRACE_BL
             h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
             float mint, maxt;
             bool found = false;
-            if (clipRay<SHADOW>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt)) found = traverse<SHADOW, COUNT>(sc, tm, o, d, mint, maxt, h, nv, pt);
+            uint32_t item = 0;
+            if (clipRay<SHADOW>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt))
+                found = sc.nItems ? traverseTop<SHADOW, COUNT>(sc, tm, o, d, mint, maxt, h, item, nv, pt) : traverse<SHADOW, COUNT>(sc, tm, o, d, mint, maxt, h, nv, pt);
             if (SHADOW) out[i] = make_float4(0, 0, 0, __uint_as_float(found ? 1u : 0u));
             else {
                 if (!found) { h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu; }

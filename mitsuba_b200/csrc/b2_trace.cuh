@@ -290,6 +290,104 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Instanced scenes (src/shapes/{shapegroup,instance}.cpp): a top-level BVH over items (the world triangles, each `instance`),
+// below it the shapegroup's own BVH in object space.  Entering an item transforms the ray with the instance's inverse
+// (transform.h:262-278: o and d, t keeps its meaning), clips [mint, maxt] against the group's box like the nested query of
+// skdtree.h:430-458, and remembers the stack height; when the stack falls back to that height the world ray is restored.
+// ------------------------------------------------------------------------------------------------------------
+B2_DEV V3 xfPoint(const float *M, const V3 &p) { return V3(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]); }
+B2_DEV V3 xfVector(const float *M, const V3 &v) { return V3(M[0] * v.x + M[1] * v.y + M[2] * v.z, M[4] * v.x + M[5] * v.y + M[6] * v.z, M[8] * v.x + M[9] * v.y + M[10] * v.z); }
+B2_DEV V3 xfNormal(const float *Minv, const V3 &n) { return V3(Minv[0] * n.x + Minv[4] * n.y + Minv[8] * n.z, Minv[1] * n.x + Minv[5] * n.y + Minv[9] * n.z, Minv[2] * n.x + Minv[6] * n.y + Minv[10] * n.z); }
+
+template <bool SHADOW, bool COUNT> B2_DEV bool traverseTop(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt, HitRec &hit,
+                                                            uint32_t &item, uint32_t &nodeVisits, uint32_t &primTests) {
+    V3 co = o, cd = d, idir, ood;
+    slabSetup(co, cd, idir, ood);
+    bool found = false;
+    uint32_t best = 0xFFFFFFFFu;
+    int sp = 0, ref = sc.tlasRoot;
+    int blasBase = -1;        // stack height at which the current item was entered; -1: in the top-level tree
+    uint32_t curItem = 0;
+    float lo = mint, hiClip = B2_INF; // [lo, min(maxt, hiClip)]: valid range inside the current item
+    const uint32_t stride = tm.stride;
+    while (true) {
+        bool pop = true;
+        if (ref >= 0) {
+            const float4 *p = tm.gNodes + 4 * (size_t) ref;
+            const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), e = __ldg(p + 3);
+            if (COUNT) ++nodeVisits;
+            float tL, tR;
+            const float hi = fminf(maxt, hiClip);
+            const bool hL = boxHit(a.x, a.y, a.z, a.w, b.x, b.y, ood, idir, lo, hi, tL);
+            const bool hR = boxHit(b.z, b.w, c.x, c.y, c.z, c.w, ood, idir, lo, hi, tR);
+            const int lref = __float_as_int(e.x), rref = __float_as_int(e.y);
+            if (hL && hR) {
+                int nearRef = lref, farRef = rref;
+                if (tR < tL) { nearRef = rref; farRef = lref; }
+                tm.stack[sp * stride] = (uint32_t) farRef;
+                ++sp;
+                ref = nearRef; pop = false;
+            } else if (hL) { ref = lref; pop = false; }
+            else if (hR) { ref = rref; pop = false; }
+        } else {
+            const uint32_t bits = ~(uint32_t) ref;
+            const uint32_t start = bits & 0x0FFFFFFFu, count = bits >> 28;
+            if (blasBase < 0) { // top-level leaf: items; all but the first go back on the stack as single-item leaves
+                if (count > 0) {
+                    for (uint32_t k = 1; k < count; ++k) { tm.stack[sp * stride] = ~((start + k) | (1u << 28)); ++sp; }
+                    const DInstance &in = sc.items[start];
+                    bool enter = true;
+                    if (in.identity) { co = o; cd = d; lo = mint; hiClip = B2_INF; }
+                    else {
+                        co = xfPoint(in.Minv, o); cd = xfVector(in.Minv, d);
+                        const V3 dRcp(1.0f / cd.x, 1.0f / cd.y, 1.0f / cd.z);
+                        float m0, m1;
+                        enter = aabbRayIntersect(in.aabbMin, in.aabbMax, co, cd, dRcp, m0, m1);
+                        if (enter) {
+                            if (mint > m0) m0 = mint;
+                            if (maxt < m1) m1 = maxt;
+                            enter = m1 > m0;
+                            lo = m0; hiClip = m1;
+                        }
+                    }
+                    if (enter) {
+                        slabSetup(co, cd, idir, ood);
+                        blasBase = sp; curItem = start;
+                        ref = in.rootRef; pop = false;
+                    } else { co = o; cd = d; lo = mint; hiClip = B2_INF; slabSetup(co, cd, idir, ood); }
+                }
+            } else {
+                const float hi = fminf(maxt, hiClip);
+                for (uint32_t i = 0; i < count; ++i) {
+                    const uint32_t ti = start + i;
+                    const float4 *p = tm.gTris + 3 * (size_t) ti;
+                    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                    if (COUNT) ++primTests;
+                    float tu, tv, tt;
+                    if (B2_TRI_TEST(q0, q1, q2, co, cd, lo, fminf(maxt, hi), tu, tv, tt)) {
+                        if (SHADOW) return true;
+                        hit.t = tt; hit.u = tu; hit.v = tv; best = ti; item = curItem;
+                        maxt = tt;
+                        found = true;
+                    }
+                }
+            }
+        }
+        if (!pop) continue;
+        if (blasBase >= 0 && sp == blasBase) { // the item is exhausted: back to the world ray
+            blasBase = -1;
+            co = o; cd = d; lo = mint; hiClip = B2_INF;
+            slabSetup(co, cd, idir, ood);
+        }
+        if (sp == 0) break;
+        --sp;
+        ref = (int) tm.stack[sp * stride];
+    }
+    if (found) hit.prim = __ldg(sc.leafPrim + best);
+    return found;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Persistent traversal with per-lane ray replacement: a warp keeps walking while its lanes finish at different times;
 // when REFILL or more lanes are idle they commit their results and pull the next rays from a global ticket counter
 // (one atomic per refill), so lanes do not idle until the slowest ray of a 32-ray batch is done.

@@ -37,6 +37,18 @@ struct DMedium {
     const float *density;     // res.x * res.y * res.z, x fastest
 };
 
+// One item of the top-level BVH of an instanced scene: the world triangles (identity) or one `instance` shape
+// (src/shapes/instance.cpp): affine object-to-world rows, its inverse, the root of the shapegroup's BVH and the group's box
+struct DInstance {
+    float M[12], Minv[12];
+    int32_t rootRef;
+    int32_t identity;      // 1: world triangles, no transform, no clipping
+    int32_t instance;      // index of the instance (statistics / debugging)
+    int32_t pad;
+    float aabbMin[3], aabbMax[3]; // the group's enlarged kd-tree box in object space (skdtree.h:430-458 clips against it)
+    float pad2[2];
+};
+
 // Area emitter + its mesh's area distribution (area.cpp, trimesh.cpp:388-403)
 struct DEmitter {
     float radiance[3];
@@ -79,6 +91,9 @@ struct DScene {
     const uint2 *flatIdx;
     uint32_t flatP, flatC, flatS, flatBytes;
     uint32_t nLeafTris;
+    const DInstance *items;    // instanced scenes only (nItems > 0): top-level items in the order of the top-level leaves
+    uint32_t nItems;
+    int32_t tlasRoot;          // root reference of the top-level BVH (leaf refs there index `items`)
     int32_t envEmitter;        // index of the environment emitter or -1 (Scene::getEnvironmentEmitter)
     float bsCenter[3], bsRadius; // constant.cpp:67-70 m_sceneBSphere: sphere of the scene box (incl. the sensor position), radius x 1.5
     // participating media (volpath): media table and per-prim (interior, exterior) ids, -1 = vacuum; null without media
@@ -142,6 +157,7 @@ struct DPool {
     float2 *pos;       // samplePos (film coordinates of the sample; read again only when the path is splatted)
     uint32_t *pix;     // pixel (y << 16 | x)
     uint32_t *flags;   // PF_* | depth << 8 | sampler dimension << 20
+    uint32_t *inst;    // instanced scenes only: item index of the hit (0xFFFFFFFF = none)
     uint2 *vol;        // volpath only: (current medium id or -1, sampler dimension); null for `path`
     // shadow queue (compacted by warp ballot)
     float4 *shD;       // d.xyz, maxt

@@ -839,7 +839,36 @@ struct Loader {
         if (nT == 0 || nV == 0) throw Err("Encountered an empty triangle mesh!");
     }
 
-    void addShape(Node *n) {
+    std::map<std::string, int> groupIds;
+    void addShape(Node *n, int group = -1) {
+        if (n->type == "shapegroup") { // shapegroup.cpp:107-135: children live in the group's object space
+            if (group >= 0) throw Err("Nested instancing is not permitted");
+            const int gid = b2_scene_add_shapegroup(scene);
+            for (auto &c : n->children) {
+                if (c->tag != "shape") throw Err("unsupported child <" + c->tag + "> of <shape type=\"shapegroup\">");
+                if (c->type == "shapegroup" || c->type == "instance") throw Err("Nested instancing is not permitted");
+                addShape(c.get(), gid);
+            }
+            if (!n->id.empty()) groupIds[n->id] = gid;
+            return;
+        }
+        if (n->type == "instance") { // instance.cpp:49-78
+            if (group >= 0) throw Err("Nested instancing is not permitted");
+            Props ip(n);
+            int gid = -1;
+            for (auto &c : n->children) {
+                if (c->tag == "ref") { auto it = groupIds.find(c->id); if (it == groupIds.end()) throw Err("Referenced object \"" + c->id + "\" not found"); gid = it->second; }
+                else if (c->tag != "transform") throw Err("unsupported child <" + c->tag + "> of <shape type=\"instance\">");
+            }
+            if (gid < 0) throw Err("A reference to a 'shapegroup' must be specified!");
+            M4 tw = ip.xf("toWorld"), inv;
+            if (!tw.inverse(inv)) throw Err("instance: singular toWorld transform");
+            ip.checkAllUsed();
+            float a[16], b[16];
+            for (int i = 0; i < 16; ++i) { a[i] = (float) tw.m[i]; b[i] = (float) inv.m[i]; }
+            if (b2_scene_add_instance(scene, gid, a, b) < 0) throw Err(b2_last_error(nullptr));
+            return;
+        }
         Props p(n);
         MeshData md;
         M4 toWorld = p.xf("toWorld"), inv;
@@ -904,7 +933,7 @@ struct Loader {
                 }
                 md.idx.insert(md.idx.end(), {base, base + 1, base + 2, base + 3, base, base + 2});
             }
-        } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, ply, serialized, rectangle, cube)");
+        } else throw Err("unsupported shape plugin \"" + n->type + "\" (supported: obj, ply, serialized, rectangle, cube, shapegroup, instance)");
         // children: bsdf / ref / emitter
         int mat = -1, em = -1, interior = -1, exterior = -1;
         bool isEmitter = false;
@@ -950,6 +979,7 @@ struct Loader {
                                    (uint32_t) (md.P.size() / 3), md.idx.data(), (uint32_t) (md.idx.size() / 3), mat, em);
         if (id < 0) throw Err(b2_last_error(nullptr));
         if ((interior >= 0 || exterior >= 0) && b2_scene_set_mesh_media(scene, id, interior, exterior)) throw Err(b2_last_error(nullptr));
+        if (group >= 0 && b2_scene_set_mesh_group(scene, id, group)) throw Err(b2_last_error(nullptr));
     }
 
     void run(Node *root, b2_render_params *rp) {

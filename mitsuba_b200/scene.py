@@ -206,6 +206,14 @@ class Mesh:
     name: str = ""
     interior: Optional[Medium] = None   # <ref name="interior"> (shape.cpp:160-176); with bsdf None -> `null` BSDF
     exterior: Optional[Medium] = None
+    group: int = -1                     # >= 0: member of that `shapegroup` (src/shapes/shapegroup.cpp), vertices in object space
+
+
+@dataclass
+class Instance:
+    """<shape type="instance"> (src/shapes/instance.cpp): a shapegroup placed with `toWorld`."""
+    group: int
+    to_world: np.ndarray                # 4x4 object-to-world (affine)
 
 
 @dataclass
@@ -270,6 +278,7 @@ class RenderParams:
 class SceneDesc:
     meshes: List[Mesh] = field(default_factory=list)
     camera: Optional[Camera] = None
+    instances: List["Instance"] = field(default_factory=list)
     env_radiance: Optional[Sequence[float]] = None   # <emitter type="constant"> (src/emitters/constant.cpp:47-52), after all area emitters
     env_sampling_weight: float = 1.0
 
@@ -321,7 +330,11 @@ class SceneDesc:
         return out, ids
 
     def n_triangles(self) -> int:
+        """Unique triangles (instanced geometry counts once)."""
         return int(sum(len(m.idx) for m in self.meshes))
+
+    def n_groups(self) -> int:
+        return 1 + max([m.group for m in self.meshes] + [i.group for i in self.instances] + [-1])
 
 
 def look_at(origin, target, up) -> np.ndarray:
@@ -442,20 +455,27 @@ def material_ball(bsdf: Bsdf, width=1024, height=1024, n_theta=200, n_phi=200) -
     return SceneDesc(meshes, cam)
 
 
-def stress_scene(n_instances=100, n_theta=224, n_phi=224, width=2048, height=2048, seed=7) -> SceneDesc:
-    """S3: one ~100k-triangle bumpy sphere instanced on a jittered grid, flattened (config 5 class)."""
+def stress_scene(n_instances=100, n_theta=224, n_phi=224, width=2048, height=2048, seed=7, instanced=False) -> SceneDesc:
+    """S3: one ~100k-triangle bumpy sphere instanced on a jittered grid (config 5 class): flattened into world-space meshes, or
+    (`instanced=True`) one shapegroup + `instance` shapes with scale/translate transforms and one material."""
     rng = np.random.default_rng(seed)
     P0, N0, _, I0 = uv_sphere((0, 0, 0), 1.0, n_theta, n_phi, smooth=True)
     bump = 1.0 + 0.08 * np.sin(9 * P0[:, 0]) * np.sin(7 * P0[:, 1]) * np.sin(11 * P0[:, 2])
     P0 = (P0 * bump[:, None]).astype(np.float32)
     g = int(math.ceil(math.sqrt(n_instances)))
     mats = [Bsdf("diffuse", reflectance=tuple(rng.uniform(0.2, 0.8, 3))) for _ in range(8)]
-    meshes = []
+    meshes, instances = [], []
+    if instanced:
+        meshes.append(Mesh(P0, I0.copy(), N=N0, bsdf=mats[0], name="proto", group=0))
     for k in range(n_instances):
         gx, gz = k % g, k // g
         s = rng.uniform(0.7, 1.1)
         t = np.array([(gx - g / 2 + 0.5) * 2.6 + rng.uniform(-0.3, 0.3), s * 1.0, (gz - g / 2 + 0.5) * 2.6 + rng.uniform(-0.3, 0.3)])
-        meshes.append(Mesh((P0 * s + t).astype(np.float32), I0.copy(), N=N0, bsdf=mats[k % 8], name=f"inst{k}"))
+        if instanced:
+            M = np.eye(4); M[:3, :3] *= s; M[:3, 3] = t
+            instances.append(Instance(0, M.astype(np.float32)))
+        else:
+            meshes.append(Mesh((P0 * s + t).astype(np.float32), I0.copy(), N=N0, bsdf=mats[k % 8], name=f"inst{k}"))
     e = g * 1.6 + 2
     P, I = _quad([(-e, 0, -e), (-e, 0, e), (e, 0, e), (e, 0, -e)], (0, 1, 0))
     meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0.6, 0.6, 0.6)), name="ground"))
@@ -463,7 +483,7 @@ def stress_scene(n_instances=100, n_theta=224, n_phi=224, width=2048, height=204
     meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(6.0, 6.0, 6.0), name="light"))
     cam = Camera(look_at((0, e * 0.9, -e * 1.5), (0, 0.5, 0), (0, 1, 0)), fov=45.0, near=0.1, far=1000.0,
                  width=width, height=height)
-    return SceneDesc(meshes, cam)
+    return SceneDesc(meshes, cam, instances=instances)
 
 
 def cube_mesh(lo, hi):

@@ -55,6 +55,7 @@ struct Mesh {
     std::vector<uint8_t> hasTangent;
     int bsdf = -1; int emitter = -1;
     int interior = -1, exterior = -1; /* shape.h:427-435 media ids (-1 = vacuum) */
+    int group = -1;                   /* >= 0: member of that ShapeGroup (src/shapes/shapegroup.cpp), in object space */
     bool isMediumTransition() const { return interior >= 0 || exterior >= 0; }
     uint32_t primOffset = 0;
     /* area sampling: trimesh.cpp:388-403 + pmf.h */
@@ -98,7 +99,7 @@ struct Discrete {
 struct Emitter { V3 radiance; float samplingWeight; int mesh; /* -1: `constant` environment emitter (src/emitters/constant.cpp) */ };
 
 struct Intersection { /* include/mitsuba/render/shape.h:131-171 (fields `path` reads) */
-    float t = kInf; V3 p; Frame geoFrame, shFrame; V3 wi; V3 dpdu; int mesh = -1; uint32_t prim = 0;
+    float t = kInf; V3 p; Frame geoFrame, shFrame; V3 wi; V3 dpdu; int mesh = -1; uint32_t prim = 0; int instance = -1;
     bool isValid() const { return t != kInf; }
 };
 
@@ -111,6 +112,11 @@ struct Scene {
     std::vector<Mesh> meshes;
     std::vector<Emitter> emitters;
     std::vector<OrcMedium> media;
+    /* instancing: src/shapes/{shapegroup,instance}.cpp */
+    struct Instance { int group; float M[16], Minv[16]; };
+    std::vector<Accel> groups;          /* one kd-tree per ShapeGroup (object space) */
+    std::vector<Instance> instances;
+    AABB topAABB;                       /* top-level kd-tree box: world triangles + instance boxes, enlarged */
     int envEmitter = -1;                 /* Scene::getEnvironmentEmitter */
     V3 bsCenter; float bsRadius = 0;     /* constant.cpp:67-70 m_sceneBSphere */
     std::vector<std::vector<float>> mediaData; /* owned copies of the density grids */
@@ -124,8 +130,10 @@ struct Scene {
 
     void commit(bool tree) {
         accel.tri.clear(); accel.triBox.clear(); primMesh.clear();
+        for (auto &g : groups) { g.tri.clear(); g.triBox.clear(); }
         for (size_t mi = 0; mi < meshes.size(); ++mi) {
             Mesh &m = meshes[mi];
+            Accel &accel = m.group >= 0 ? groups[m.group] : this->accel;
             m.primOffset = (uint32_t) accel.tri.size();
             for (uint32_t j = 0; j < m.nTri(); ++j) {
                 const V3 &v0 = m.P[m.idx[3 * j]], &v1 = m.P[m.idx[3 * j + 1]], &v2 = m.P[m.idx[3 * j + 2]];
@@ -135,7 +143,7 @@ struct Scene {
                 accel.tri.push_back(ta);
                 AABB b; b.expandBy(v0); b.expandBy(v1); b.expandBy(v2);
                 accel.triBox.push_back(b);
-                primMesh.push_back((uint32_t) mi);
+                if (m.group < 0) primMesh.push_back((uint32_t) mi);
             }
             /* trimesh.cpp:683-735 computeUVTangents (called unconditionally at :385) */
             m.dpdu.clear(); m.hasTangent.clear();
@@ -171,6 +179,25 @@ struct Scene {
             }
         }
         accel.build(tree);
+        for (auto &g : groups) g.build(tree);
+        /* top-level box: the kd-tree over world triangles and Instance::getAABB boxes (instance.cpp:80-96), enlarged like every tree */
+        topAABB = accel.aabb;
+        if (!instances.empty()) {
+            AABB b;
+            for (auto &tb : accel.triBox) { b.expandBy(tb.min); b.expandBy(tb.max); }
+            for (auto &in : instances) {
+                const AABB &ga = groups[in.group].aabb;
+                if (groups[in.group].tri.empty()) continue;
+                for (int c = 0; c < 8; ++c) {
+                    V3 corner((c & 1) ? ga.max.x : ga.min.x, (c & 2) ? ga.max.y : ga.min.y, (c & 4) ? ga.max.z : ga.min.z);
+                    b.expandBy(xfPoint(in.M, corner));
+                }
+            }
+            const float eps = 1e-3f;
+            b.min = b.min - ((b.max - b.min) * eps + V3(eps));
+            b.max = b.max + ((b.max - b.min) * eps + V3(eps));
+            topAABB = b;
+        }
         /* scene.cpp:375-380 */
         emitterPDF = Discrete();
         for (auto &e : emitters) emitterPDF.append(e.samplingWeight);
@@ -181,8 +208,8 @@ struct Scene {
         envEmitter = -1;
         for (size_t e = 0; e < emitters.size(); ++e) if (emitters[e].mesh < 0) envEmitter = (int) e;
         {
-            AABB b = accel.aabb;
-            if (accel.tri.empty()) { b.min = V3(0.0f); b.max = V3(0.0f); }
+            AABB b = topAABB;
+            if (accel.tri.empty() && instances.empty()) { b.min = V3(0.0f); b.max = V3(0.0f); }
             b.expandBy(camOrigin);
             bsCenter = (b.max + b.min) * 0.5f;
             bsRadius = std::max(kEpsilon, (bsCenter - b.max).length() * 1.5f);
@@ -190,7 +217,22 @@ struct Scene {
     }
 
     /* skdtree.h:343-428 fillIntersectionRecord<true> for triangle meshes */
-    void fill(const Ray &ray, const Hit &h, Intersection &its) const {
+    /* transform.h:108-124 (affine: w == 1), :175-183, :203-211 */
+    static V3 xfPoint(const float *M, const V3 &p) {
+        return V3(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]);
+    }
+    static V3 xfVector(const float *M, const V3 &v) {
+        return V3(M[0] * v.x + M[1] * v.y + M[2] * v.z, M[4] * v.x + M[5] * v.y + M[6] * v.z, M[8] * v.x + M[9] * v.y + M[10] * v.z);
+    }
+    static V3 xfNormal(const float *Minv, const V3 &n) { /* inverse transpose */
+        return V3(Minv[0] * n.x + Minv[4] * n.y + Minv[8] * n.z, Minv[1] * n.x + Minv[5] * n.y + Minv[9] * n.z, Minv[2] * n.x + Minv[6] * n.y + Minv[10] * n.z);
+    }
+    static Ray xfRay(const float *Minv, const Ray &r) { /* transform.h:262-278 */
+        return Ray(xfPoint(Minv, r.o), xfVector(Minv, r.d), r.mint, r.maxt);
+    }
+    void fill(const Ray &wray, const Hit &h, Intersection &its, int inst = -1) const {
+        const Accel &accel = inst >= 0 ? groups[instances[inst].group] : this->accel;
+        const Ray ray = inst >= 0 ? xfRay(instances[inst].Minv, wray) : wray;
         const uint32_t mi = accel.tri[h.prim].shapeIndex, pi = accel.tri[h.prim].primIndex;
         const Mesh &m = meshes[mi];
         const V3 b(1 - h.u - h.v, h.u, h.v);
@@ -209,9 +251,67 @@ struct Scene {
             if (dot(faceNormal, its.shFrame.n) < 0) faceNormal = -faceNormal;
         } else its.shFrame.n = faceNormal;
         its.geoFrame = Frame(faceNormal);
-        its.mesh = (int) mi; its.prim = pi;
+        its.mesh = (int) mi; its.prim = pi; its.instance = inst;
+        if (inst >= 0) { /* Instance::fillIntersectionRecord, instance.cpp:149-162 (nested record: skdtree.h fillIntersectionRecord<false>) */
+            const Instance &in = instances[inst];
+            its.p = ray(its.t);
+            its.shFrame.n = normalize(xfNormal(in.Minv, its.shFrame.n));
+            its.geoFrame = Frame(normalize(xfNormal(in.Minv, its.geoFrame.n)));
+            its.dpdu = xfVector(in.M, its.dpdu);
+            its.p = xfPoint(in.M, its.p);
+        }
         computeShadingFrame(its.shFrame.n, its.dpdu, its.shFrame);
-        its.wi = its.shFrame.toLocal(-ray.d);
+        its.wi = its.shFrame.toLocal(-wray.d);
+    }
+    /* top-level queries with instances: skdtree.cpp:112-142 / :207-226 over world triangles and Instance::rayIntersect
+       (instance.cpp:115-133 -> the nested tree's plain query, skdtree.h:430-458) */
+    bool topClosest(const Ray &ray, Hit &best, int &inst, OrcStats &st) const {
+        float mint, maxt;
+        best.t = kInf; inst = -1;
+        if (!topAABB.rayIntersect(ray, mint, maxt)) return false;
+        float rayMinT = ray.mint;
+        if (rayMinT == kEpsilon) rayMinT *= std::max(std::max(std::max(std::abs(ray.o.x), std::abs(ray.o.y)), std::abs(ray.o.z)), kEpsilon);
+        if (rayMinT > mint) mint = rayMinT;
+        if (ray.maxt < maxt) maxt = ray.maxt;
+        if (!(maxt > mint)) return false;
+        bool found = false;
+        Hit h;
+        if (!accel.tri.empty() && accel.query<false>(ray, mint, maxt, h, &st.nodeVisits, &st.primTests)) { best = h; maxt = h.t; found = true; }
+        for (size_t i = 0; i < instances.size(); ++i) {
+            const Accel &g = groups[instances[i].group];
+            if (g.tri.empty()) continue;
+            const Ray r2 = xfRay(instances[i].Minv, ray);
+            float m0, m1;
+            if (!g.aabb.rayIntersect(r2, m0, m1)) continue;
+            if (mint > m0) m0 = mint;
+            if (maxt < m1) m1 = maxt;
+            if (!(m1 > m0)) continue;
+            if (g.query<false>(r2, m0, m1, h, &st.nodeVisits, &st.primTests)) { best = h; maxt = h.t; inst = (int) i; found = true; }
+        }
+        return found;
+    }
+    bool topOccluded(const Ray &ray, OrcStats &st) const {
+        float mint, maxt;
+        if (!topAABB.rayIntersect(ray, mint, maxt)) return false;
+        float rayMinT = ray.mint;
+        if (rayMinT == kEpsilon) rayMinT *= std::max(std::max(std::abs(ray.o.x), std::abs(ray.o.y)), std::abs(ray.o.z));
+        if (rayMinT > mint) mint = rayMinT;
+        if (ray.maxt < maxt) maxt = ray.maxt;
+        if (!(maxt > mint)) return false;
+        Hit h;
+        if (!accel.tri.empty() && accel.query<true>(ray, mint, maxt, h, &st.nodeVisits, &st.primTests)) return true;
+        for (size_t i = 0; i < instances.size(); ++i) {
+            const Accel &g = groups[instances[i].group];
+            if (g.tri.empty()) continue;
+            const Ray r2 = xfRay(instances[i].Minv, ray);
+            float m0, m1;
+            if (!g.aabb.rayIntersect(r2, m0, m1)) continue;
+            if (mint > m0) m0 = mint;
+            if (maxt < m1) m1 = maxt;
+            if (!(m1 > m0)) continue;
+            if (g.query<true>(r2, m0, m1, h, &st.nodeVisits, &st.primTests)) return true;
+        }
+        return false;
     }
 
     /* area.cpp:104-109 */
@@ -246,7 +346,7 @@ struct Scene {
             if (!testVisibility) { dRec.emitter = (int) index; if (emPdfOut) *emPdfOut = emPdf; return value; }
             Ray ray(dRec.ref, dRec.d, kEpsilon, dRec.dist * (1 - kShadowEpsilon)); /* scene.cpp:838-843: not on a surface, but the same ray */
             ++st.shadowRays;
-            if (accel.rayOccluded(ray, &st.nodeVisits, &st.primTests)) return Spectrum(0.0f);
+            if (instances.empty() ? accel.rayOccluded(ray, &st.nodeVisits, &st.primTests) : topOccluded(ray, st)) return Spectrum(0.0f);
             dRec.emitter = (int) index;
             dRec.pdf *= emPdf;
             value /= emPdf;
@@ -286,7 +386,7 @@ struct Scene {
         if (dRec.pdf != 0) {
             Ray ray(dRec.ref, dRec.d, kEpsilon, dRec.dist * (1 - kShadowEpsilon));
             ++st.shadowRays;
-            if (accel.rayOccluded(ray, &st.nodeVisits, &st.primTests)) return Spectrum(0.0f);
+            if (instances.empty() ? accel.rayOccluded(ray, &st.nodeVisits, &st.primTests) : topOccluded(ray, st)) return Spectrum(0.0f);
             dRec.emitter = (int) index;
             dRec.pdf *= emPdf;
             value /= emPdf;
@@ -327,6 +427,11 @@ struct Scene {
     bool rayIntersect(const Ray &ray, Intersection &its, OrcStats &st) const {
         Hit h; ++st.rays;
         its.t = kInf;
+        if (!instances.empty()) {
+            int inst;
+            if (topClosest(ray, h, inst, st)) { fill(ray, h, its, inst); return true; }
+            return false;
+        }
         if (accel.rayIntersect(ray, h, &st.nodeVisits, &st.primTests)) { fill(ray, h, its); return true; }
         return false;
     }
@@ -826,6 +931,15 @@ int orc_add_constant_emitter(void *s, const float *radiance, float samplingWeigh
     Emitter e; e.radiance = V3(radiance[0], radiance[1], radiance[2]); e.samplingWeight = samplingWeight; e.mesh = -1;
     sc->emitters.push_back(e);
     return (int) sc->emitters.size() - 1;
+}
+/* <shape type="shapegroup"> / <shape type="instance">: meshes added with orc_set_mesh_group live in the group's object space */
+int orc_add_shapegroup(void *s) { Scene *sc = (Scene *) s; sc->groups.emplace_back(); return (int) sc->groups.size() - 1; }
+void orc_set_mesh_group(void *s, int mesh, int group) { ((Scene *) s)->meshes[mesh].group = group; }
+int orc_add_instance(void *s, int group, const float *M, const float *Minv) {
+    Scene *sc = (Scene *) s;
+    Scene::Instance in; in.group = group; memcpy(in.M, M, 64); memcpy(in.Minv, Minv, 64);
+    sc->instances.push_back(in);
+    return (int) sc->instances.size() - 1;
 }
 void orc_set_camera(void *s, const float *camToWorld, const float *sampleToCamera, float nearClip, float farClip, int W, int H) {
     Scene *sc = (Scene *) s;

@@ -100,6 +100,12 @@ def make_bsdf_array(flat_list):
     return arr
 
 
+def instance_matrices(to_world):
+    """float32 (M, M^-1) of an instance transform; the inverse is taken in float64 once so that both sides use the same numbers."""
+    M64 = np.asarray(to_world, np.float64)
+    return np.ascontiguousarray(M64, np.float32), np.ascontiguousarray(np.linalg.inv(M64), np.float32)
+
+
 def make_medium(d):
     m = OrcMedium()
     m.type, m.phase, m.g, m.strategy = d["type"], d["phase"], d["g"], d["strategy"]
@@ -148,14 +154,23 @@ class OracleScene:
         arr = make_bsdf_array(flat)
         for i in range(len(flat)):
             L.orc_add_bsdf(self.h, C.byref(arr[i]))
+        for _ in range(desc.n_groups() if hasattr(desc, "n_groups") else 0):
+            L.orc_add_shapegroup(self.h)
         for m, bid in zip(desc.meshes, ids):
             P = np.ascontiguousarray(m.P, np.float32)
             N = np.ascontiguousarray(m.N, np.float32) if m.N is not None else None
             UV = np.ascontiguousarray(m.UV, np.float32) if m.UV is not None else None
             I = np.ascontiguousarray(m.idx, np.uint32)
             rad = np.asarray(m.radiance, np.float32) if m.radiance is not None else None
-            L.orc_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
-                           C.c_int(bid), _p(rad), C.c_float(m.sampling_weight))
+            mid = L.orc_add_mesh(self.h, _p(P), _p(N), _p(UV), C.c_uint32(len(P)), _p(I, C.c_uint32), C.c_uint32(len(I)),
+                                 C.c_int(bid), _p(rad), C.c_float(m.sampling_weight))
+            if getattr(m, "group", -1) >= 0:
+                if m.radiance is not None:
+                    raise ValueError("Instancing of emitters is not supported")  # shapegroup.cpp:115-116
+                L.orc_set_mesh_group(self.h, C.c_int(mid), C.c_int(m.group))
+        for inst in getattr(desc, "instances", []):
+            M, Minv = instance_matrices(inst.to_world)
+            L.orc_add_instance(self.h, C.c_int(inst.group), _p(M), _p(Minv))
         if getattr(desc, "env_radiance", None) is not None:
             rad = np.asarray(desc.env_radiance, np.float32)
             L.orc_add_constant_emitter(self.h, _p(rad), C.c_float(desc.env_sampling_weight))

@@ -460,3 +460,67 @@ def test_cancel_returns_status(b2ctx):
     assert not t.is_alive() and rc["rc"] == 5
     f, s = g.render(RenderParams(spp=2, sampler="sobol", rfilter="box"))       # the scene stays usable
     assert s["samples"] == 512 * 512 * 2
+
+
+# ---- instancing: src/shapes/{shapegroup,instance}.cpp ----
+def _instanced_scene(n=5, res=48):
+    from mitsuba_b200.scene import Instance, stress_scene
+    d = stress_scene(n, 20, 20, res, res, instanced=True)
+    # a second group with two meshes (one with UVs -> tangent frames through the instance transform), rotated + sheared instances
+    P, N, UV, I = uv_sphere((0, 0, 0), 0.6, 12, 24, with_uv=True)
+    d.meshes.append(Mesh(P, I, N=N, UV=UV, bsdf=MATERIALS["roughconductor_beckmann_aniso"], group=1))
+    from mitsuba_b200.scene import cube_mesh
+    Pc, Ic = cube_mesh((-0.4, -0.9, -0.4), (0.4, -0.6, 0.4))
+    d.meshes.append(Mesh(Pc, Ic, bsdf=Bsdf("diffuse", reflectance=(0.2, 0.6, 0.3)), group=1))
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    M = np.eye(4); M[:3, :3] = np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]]) @ np.diag([1.3, 0.8, 1.0]); M[0, 1] = 0.2; M[:3, 3] = (0.5, 2.6, -1.0)
+    d.instances.append(Instance(1, M.astype(np.float32)))
+    M2 = np.eye(4); M2[:3, :3] *= 0.7; M2[:3, 3] = (-2.0, 2.2, 0.5)
+    d.instances.append(Instance(1, M2.astype(np.float32)))
+    return d
+
+
+def test_instanced_scene_image_parity(b2ctx):
+    d = _instanced_scene()
+    g, o = pair(b2ctx, d)
+    st0 = g.stats()
+    assert st0["n_triangles"] == d.n_triangles()
+    for rp in (RenderParams(spp=16, sampler="sobol", rfilter="box"), RenderParams(spp=8, sampler="independent", rfilter="gaussian", max_depth=3)):
+        fo, so = o.render(rp)
+        fg, sg = g.render(rp, parity=True)
+        assert rel_l2(api.develop(fg), O.develop(fo)) <= 3e-4
+        assert abs(sg["rays"] - so["rays"]) <= 1e-3 * so["rays"] and abs(sg["path_length_sum"] - so["pathLengthSum"]) <= 1e-3 * so["pathLengthSum"]
+    # throughput build (plane-form triangles, fast math): a ray that lands on the other side of an edge changes a whole path, whose
+    # weight in the image falls with the sample count -- compared at 64 spp
+    rp = RenderParams(spp=64, sampler="sobol", rfilter="box")
+    fo, _ = o.render(rp)
+    fg2, _ = g.render(rp, parity=False)
+    assert rel_l2(api.develop(fg2), O.develop(fo)) <= REL_L2_TOL
+
+
+def test_instancing_matches_flattened_geometry(b2ctx):
+    """The same geometry once as instances, once flattened into world space: images agree to float rounding of the transforms."""
+    from mitsuba_b200.scene import stress_scene
+    a = stress_scene(6, 24, 24, 64, 64, instanced=True)
+    b = stress_scene(6, 24, 24, 64, 64, instanced=False)
+    for m in b.meshes:
+        if m.name.startswith("inst"):
+            m.bsdf = a.meshes[0].bsdf
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="box")
+    fa, sa = api.Scene(b2ctx, a).render(rp, parity=True)
+    fb, sb = api.Scene(b2ctx, b).render(rp, parity=True)
+    assert rel_l2(api.develop(fa), api.develop(fb)) < 5e-3
+    assert abs(sa["path_length_sum"] - sb["path_length_sum"]) <= 2e-3 * sb["path_length_sum"]
+    assert sa["n_triangles"] * 5 < sb["n_triangles"]
+
+
+def test_instancing_errors(b2ctx):
+    from mitsuba_b200.scene import stress_scene
+    d = stress_scene(2, 8, 8, 16, 16, instanced=True)
+    d.meshes[0].radiance = (1.0, 1.0, 1.0)
+    with pytest.raises(api.B2Error, match="Instancing of emitters"):
+        api.Scene(b2ctx, d)
+    d = stress_scene(2, 8, 8, 16, 16, instanced=True)
+    g = api.Scene(b2ctx, d)
+    with pytest.raises(api.B2Error, match="instanced geometry"):
+        g.render(RenderParams(spp=1, integrator="volpath"))
