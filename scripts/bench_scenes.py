@@ -77,6 +77,15 @@ if "stress" in which:
     d = stress_scene(ninst, width=1024, height=1024)
     sc = render_rate(f"stress_{ninst}x100k", d, RenderParams(spp=16, rfilter="box"))
     trace_bench(f"stress_{ninst}x100k", sc, d)
+if "inst" in which:
+    ninst = int(os.environ.get("STRESS_INSTANCES", "100"))
+    for inst in (True, False):
+        d = stress_scene(ninst, width=1024, height=1024, instanced=inst)
+        if not inst:
+            for m in d.meshes:
+                if m.name.startswith("inst"):
+                    m.bsdf = d.meshes[0].bsdf
+        render_rate(f"stress_{ninst}x100k/" + ("instanced" if inst else "flattened"), d, RenderParams(spp=16, rfilter="box"))
 if "smoke" in which:
     # config 4: 128^3 heterogeneous medium (Woodcock), isotropic phase, volpath, 512x512
     d = smoke_scene(512, 512, res=128)

@@ -468,7 +468,10 @@ def _instanced_scene(n=5, res=48):
     d = stress_scene(n, 20, 20, res, res, instanced=True)
     # a second group with two meshes (one with UVs -> tangent frames through the instance transform), rotated + sheared instances
     P, N, UV, I = uv_sphere((0, 0, 0), 0.6, 12, 24, with_uv=True)
-    d.meshes.append(Mesh(P, I, N=N, UV=UV, bsdf=MATERIALS["roughconductor_beckmann_aniso"], group=1))
+    # anisotropic, so the UV tangent frame matters, but not mirror-like: a near-specular lobe on a coarse sphere turns single
+    # fast-math perturbations into isolated bright pixels that dominate the L2 of a 48x48 image
+    aniso = Bsdf("roughconductor", distribution="beckmann", alpha_u=0.15, alpha_v=0.4, eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421))
+    d.meshes.append(Mesh(P, I, N=N, UV=UV, bsdf=aniso, group=1))
     from mitsuba_b200.scene import cube_mesh
     Pc, Ic = cube_mesh((-0.4, -0.9, -0.4), (0.4, -0.6, 0.4))
     d.meshes.append(Mesh(Pc, Ic, bsdf=Bsdf("diffuse", reflectance=(0.2, 0.6, 0.3)), group=1))
