@@ -289,13 +289,13 @@ def main():
     # ---- e2e: through the C-ABI with host buffers (scene commit + render into a host film), same metric ----
     e2e = None
     if rank == 0 or world > 1:
-        host_film = np.zeros((H, W, 5), np.float32)
+        host_film = torch.zeros((H, W, 5), dtype=torch.float32).pin_memory()   # the step's result is read back into pinned host memory
         import ctypes as C
         p = api.make_params(rp, bool(args.parity), args.pool, False, 0)
 
         def e2e_step():
             sc2 = api.Scene(ctx, desc)                                  # b2_scene_create .. b2_scene_commit (H2D upload)
-            rc = ctx.L.b2_render(sc2.h, C.byref(p), host_film.ctypes.data_as(C.POINTER(C.c_float)))  # D2H film inside
+            rc = ctx.L.b2_render(sc2.h, C.byref(p), C.cast(host_film.data_ptr(), C.POINTER(C.c_float)))  # D2H film inside
             if rc:
                 raise RuntimeError(ctx.err())
             up = sc2.stats()["bytes_uploaded"]

@@ -27,7 +27,9 @@ std::string g_lastError;
 std::mutex g_errMutex;
 }
 
+struct RenderStore;
 struct b2_ctx {
+    RenderStore *store = nullptr; // render-time buffers (path pool, film accumulators, progress ring) shared by the scenes of this context
     int device = 0;
     int numSMs = 0;
     cudaStream_t stream = nullptr;
@@ -89,6 +91,25 @@ template <typename T> struct DevBuf {
     }
 };
 
+// Render-time buffers live in the context, not in the scene: a 4 Mi-path pool is ~0.6 GB, and allocating / freeing it around every
+// scene costs tens to hundreds of milliseconds (cudaFree synchronises) -- more than committing a small scene.  One render at a
+// time per context (renderMutex); scenes refresh their DPool pointers from here at the start of every b2_render.
+struct RenderStore {
+    std::mutex renderMutex;
+    uint32_t capacity = 0;
+    DevBuf<float4> pRay, pSt, pHit, pShD, pShC;
+    DevBuf<uint2> pSmp, pVol;
+    DevBuf<uint32_t> pInst;
+    DevBuf<float2> pPos;
+    DevBuf<uint32_t> pPix, pFlags;
+    DevBuf<uint32_t> pMatQueue, pDoneQueue;
+    DevBuf<float4> dFilmRGBA;
+    DevBuf<float> dFilmW, dFilmOut;
+    unsigned long long *hRing = nullptr, *dRing = nullptr; // mapped pinned progress ring written by k_publish
+    DevBuf<unsigned long long> dStampStart, dStampEnd;      // per-launch %globaltimer stamps (flags bit2)
+    ~RenderStore() { if (hRing) cudaFreeHost(hRing); }
+};
+
 struct b2_scene {
     b2_ctx *ctx = nullptr;
     std::vector<b2_material_desc> materials;
@@ -124,18 +145,8 @@ struct b2_scene {
     bool classPresent[4] = {false, false, false, false};
     // pool
     DPool pool{};
-    DevBuf<float4> pRay, pSt, pHit, pShD, pShC;
-    DevBuf<uint2> pSmp, pVol;
-    DevBuf<uint32_t> pInst;
-    DevBuf<float2> pPos;
-    DevBuf<uint32_t> pPix, pFlags;
-    DevBuf<uint32_t> pMatQueue, pDoneQueue;
     DevBuf<uint64_t> dLookupNib;
     DevBuf<unsigned long long> dCounters;
-    DevBuf<float4> dFilmRGBA;
-    DevBuf<float> dFilmW, dFilmOut;
-    unsigned long long *hRing = nullptr, *dRing = nullptr; // mapped pinned progress ring written by k_publish
-    DevBuf<unsigned long long> dStampStart, dStampEnd;      // per-launch %globaltimer stamps (flags bit2)
     std::vector<cudaEvent_t> timingEvents;                  // per-launch CUDA events (flags bit3)
     std::atomic<int> cancel{0};
     b2_stats stats{};
@@ -185,16 +196,17 @@ extern "C" int b2_context_create(int device, b2_ctx **out) {
         return fail(nullptr, B2_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= n) return fail(nullptr, B2_ERR_INVALID, "device index out of range");
     b2_ctx *ctx = new b2_ctx();
+    ctx->store = new RenderStore();
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return fail(nullptr, B2_ERR_CUDA, "cudaSetDevice failed"); }
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx->store; delete ctx; return fail(nullptr, B2_ERR_CUDA, "cudaSetDevice failed"); }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->numSMs = prop.multiProcessorCount;
     if (prop.major < 10) {
-        delete ctx;
+        delete ctx->store; delete ctx;
         return fail(nullptr, B2_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
     }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, B2_ERR_CUDA, "stream create failed"); }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx->store; delete ctx; return fail(nullptr, B2_ERR_CUDA, "stream create failed"); }
     // Sobol tables
     std::vector<uint32_t> m32;
     std::vector<uint64_t> vdc, inv;
@@ -202,7 +214,7 @@ extern "C" int b2_context_create(int device, b2_ctx **out) {
     if (!readFile(dir + "/sobol_matrices32.bin", m32, 1024 * 52) || !readFile(dir + "/sobol_vdc.bin", vdc, 25 * 52) ||
         !readFile(dir + "/sobol_vdc_inv.bin", inv, 26 * 52)) {
         cudaStreamDestroy(ctx->stream);
-        delete ctx;
+        delete ctx->store; delete ctx;
         return fail(nullptr, B2_ERR_IO, "cannot read Sobol tables from " + dir + " (set B2MTS_DATA)");
     }
     vdc.resize(26 * 52, 0);
@@ -237,6 +249,7 @@ extern "C" void b2_context_destroy(b2_ctx *ctx) {
     if (ctx->dNib) cudaFree(ctx->dNib);
     if (ctx->dVdc) cudaFree(ctx->dVdc);
     if (ctx->dInv) cudaFree(ctx->dInv);
+    delete ctx->store;
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -250,7 +263,6 @@ extern "C" int b2_scene_create(b2_ctx *ctx, b2_scene **out) {
 extern "C" void b2_scene_destroy(b2_scene *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    if (s->hRing) cudaFreeHost(s->hRing);
     for (auto e : s->timingEvents) cudaEventDestroy(e);
     delete s;
 }
@@ -1077,21 +1089,25 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
 
 static int ensurePool(b2_scene *s, uint32_t Q, bool vol) {
     b2_ctx *ctx = s->ctx;
-    if (vol && s->pVol.n != Q) { CK(ctx, s->pVol.alloc(Q)); s->pool.vol = s->pVol.p; }
-    if (s->ds.nItems && s->pInst.n != Q) { CK(ctx, s->pInst.alloc(Q)); s->pool.inst = s->pInst.p; }
-    if (s->pool.capacity == Q) return B2_OK;
-    CK(ctx, s->pRay.alloc((size_t) 2 * Q)); CK(ctx, s->pSt.alloc((size_t) 2 * Q)); CK(ctx, s->pHit.alloc(Q));
-    CK(ctx, s->pShD.alloc(Q)); CK(ctx, s->pShC.alloc(Q)); CK(ctx, s->pSmp.alloc(Q)); CK(ctx, s->pPos.alloc(Q));
-    CK(ctx, s->pPix.alloc(Q)); CK(ctx, s->pFlags.alloc(Q));
-    CK(ctx, s->pMatQueue.alloc((size_t) 4 * Q)); CK(ctx, s->pDoneQueue.alloc((size_t) 2 * Q));
+    RenderStore &R = *ctx->store;
+    if (R.capacity != Q) {
+        CK(ctx, R.pRay.alloc((size_t) 2 * Q)); CK(ctx, R.pSt.alloc((size_t) 2 * Q)); CK(ctx, R.pHit.alloc(Q));
+        CK(ctx, R.pShD.alloc(Q)); CK(ctx, R.pShC.alloc(Q)); CK(ctx, R.pSmp.alloc(Q)); CK(ctx, R.pPos.alloc(Q));
+        CK(ctx, R.pPix.alloc(Q)); CK(ctx, R.pFlags.alloc(Q));
+        CK(ctx, R.pMatQueue.alloc((size_t) 4 * Q)); CK(ctx, R.pDoneQueue.alloc((size_t) 2 * Q));
+        R.pVol.release(); R.pInst.release();
+        R.capacity = Q;
+    }
+    if (vol && R.pVol.n != Q) CK(ctx, R.pVol.alloc(Q));
+    if (s->ds.nItems && R.pInst.n != Q) CK(ctx, R.pInst.alloc(Q));
     DPool &p = s->pool;
     p.capacity = Q;
-    p.ray = s->pRay.p; p.st = s->pSt.p; p.hit = s->pHit.p; p.smp = s->pSmp.p; p.pos = s->pPos.p; p.pix = s->pPix.p; p.flags = s->pFlags.p;
-    p.shD = s->pShD.p; p.shC = s->pShC.p; p.matQueue = s->pMatQueue.p;
-    p.doneQueue = s->pDoneQueue.p;
+    p.ray = R.pRay.p; p.st = R.pSt.p; p.hit = R.pHit.p; p.smp = R.pSmp.p; p.pos = R.pPos.p; p.pix = R.pPix.p; p.flags = R.pFlags.p;
+    p.shD = R.pShD.p; p.shC = R.pShC.p; p.matQueue = R.pMatQueue.p;
+    p.doneQueue = R.pDoneQueue.p;
     p.counters = s->dCounters.p;
-    p.vol = s->pVol.p;
-    p.inst = s->pInst.p;
+    p.vol = R.pVol.p;
+    p.inst = R.pInst.p;
     return B2_OK;
 }
 
@@ -1100,6 +1116,8 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     b2_ctx *ctx = s->ctx;
     if (!s->committed) return fail(ctx, B2_ERR_INVALID, "b2_render: scene not committed");
     CK(ctx, cudaSetDevice(ctx->device));
+    RenderStore &R = *ctx->store;
+    std::lock_guard<std::mutex> renderLock(R.renderMutex);
     cudaStream_t st = ctx->stream;
     DRender r;
     int rc = fillRender(s, p, r);
@@ -1117,28 +1135,28 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     rc = ensurePool(s, Q, volpath);
     if (rc) return rc;
     const size_t nPix = (size_t) s->W * s->H;
-    CK(ctx, s->dFilmRGBA.alloc(nPix));
-    CK(ctx, s->dFilmW.alloc(nPix));
-    r.filmRGBA = s->dFilmRGBA.p; r.filmW = s->dFilmW.p;
-    if (!s->hRing) {
-        CK(ctx, cudaHostAlloc((void **) &s->hRing, sizeof(unsigned long long) * 4 * B2_RING, cudaHostAllocMapped));
-        CK(ctx, cudaHostGetDevicePointer((void **) &s->dRing, s->hRing, 0));
+    CK(ctx, R.dFilmRGBA.alloc(nPix));
+    CK(ctx, R.dFilmW.alloc(nPix));
+    r.filmRGBA = R.dFilmRGBA.p; r.filmW = R.dFilmW.p;
+    if (!R.hRing) {
+        CK(ctx, cudaHostAlloc((void **) &R.hRing, sizeof(unsigned long long) * 4 * B2_RING, cudaHostAllocMapped));
+        CK(ctx, cudaHostGetDevicePointer((void **) &R.dRing, R.hRing, 0));
     }
-    memset(s->hRing, 0, sizeof(unsigned long long) * 4 * B2_RING);
-    r.ring = s->dRing;
+    memset(R.hRing, 0, sizeof(unsigned long long) * 4 * B2_RING);
+    r.ring = R.dRing;
     const bool timing = (p->flags & 4) != 0;      // per-launch device time stamps (%globaltimer inside the kernels)
     const bool useEvents = (p->flags & 8) != 0;   // no graph: plain launches bracketed by CUDA events (cross-check path)
     if (timing) {
-        CK(ctx, s->dStampStart.alloc((size_t) B2_MAX_STAMPS * 4));
-        CK(ctx, s->dStampEnd.alloc((size_t) B2_MAX_STAMPS * 4));
-        CK(ctx, cudaMemsetAsync(s->dStampStart.p, 0xFF, (size_t) B2_MAX_STAMPS * 4 * 8, st));
-        CK(ctx, cudaMemsetAsync(s->dStampEnd.p, 0, (size_t) B2_MAX_STAMPS * 4 * 8, st));
-        r.stampStart = s->dStampStart.p; r.stampEnd = s->dStampEnd.p;
+        CK(ctx, R.dStampStart.alloc((size_t) B2_MAX_STAMPS * 4));
+        CK(ctx, R.dStampEnd.alloc((size_t) B2_MAX_STAMPS * 4));
+        CK(ctx, cudaMemsetAsync(R.dStampStart.p, 0xFF, (size_t) B2_MAX_STAMPS * 4 * 8, st));
+        CK(ctx, cudaMemsetAsync(R.dStampEnd.p, 0, (size_t) B2_MAX_STAMPS * 4 * 8, st));
+        r.stampStart = R.dStampStart.p; r.stampEnd = R.dStampEnd.p;
     }
-    CK(ctx, cudaMemsetAsync(s->dFilmRGBA.p, 0, nPix * sizeof(float4), st));
-    CK(ctx, cudaMemsetAsync(s->dFilmW.p, 0, nPix * sizeof(float), st));
+    CK(ctx, cudaMemsetAsync(R.dFilmRGBA.p, 0, nPix * sizeof(float4), st));
+    CK(ctx, cudaMemsetAsync(R.dFilmW.p, 0, nPix * sizeof(float), st));
     CK(ctx, cudaMemsetAsync(s->dCounters.p, 0, CTR_COUNT * sizeof(unsigned long long), st));
-    CK(ctx, cudaMemsetAsync(s->pFlags.p, 0, (size_t) Q * sizeof(uint32_t), st));
+    CK(ctx, cudaMemsetAsync(R.pFlags.p, 0, (size_t) Q * sizeof(uint32_t), st));
     int nClasses = 0, onlyClass = -1;
     for (int c = 0; c < 4; ++c)
         if (s->classPresent[c]) { ++nClasses; onlyClass = c; }
@@ -1224,7 +1242,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         CK(ctx, cudaStreamEndCapture(st, &graph));
         CK(ctx, cudaGraphInstantiate(&graphExec, graph, 0));
     }
-    volatile unsigned long long *ring = s->hRing;
+    volatile unsigned long long *ring = R.hRing;
     while (!finished) {
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; break; }
         // consume published progress; never run more than B2_RING - 1 iterations ahead of the device
@@ -1258,11 +1276,11 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     if (status == B2_OK) {
         float *dOut = film;
         if (!p->film_on_device) {
-            CK(ctx, s->dFilmOut.alloc(nPix * 5));
-            dOut = s->dFilmOut.p;
+            CK(ctx, R.dFilmOut.alloc(nPix * 5));
+            dOut = R.dFilmOut.p;
         }
-        if (parityMode) parity::launch_film_pack(cfg, s->dFilmRGBA.p, s->dFilmW.p, dOut, nPix, st);
-        else fast::launch_film_pack(cfg, s->dFilmRGBA.p, s->dFilmW.p, dOut, nPix, st);
+        if (parityMode) parity::launch_film_pack(cfg, R.dFilmRGBA.p, R.dFilmW.p, dOut, nPix, st);
+        else fast::launch_film_pack(cfg, R.dFilmRGBA.p, R.dFilmW.p, dOut, nPix, st);
         if (!p->film_on_device) CK(ctx, cudaMemcpyAsync(film, dOut, nPix * 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CK(ctx, cudaStreamSynchronize(st));
@@ -1290,8 +1308,8 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         const size_t nIt = (size_t) std::min<uint64_t>(iter, B2_MAX_STAMPS);
         std::vector<unsigned long long> a(nIt * 4), b(nIt * 4);
         if (nIt) {
-            CK(ctx, cudaMemcpy(a.data(), s->dStampStart.p, nIt * 4 * 8, cudaMemcpyDeviceToHost));
-            CK(ctx, cudaMemcpy(b.data(), s->dStampEnd.p, nIt * 4 * 8, cudaMemcpyDeviceToHost));
+            CK(ctx, cudaMemcpy(a.data(), R.dStampStart.p, nIt * 4 * 8, cudaMemcpyDeviceToHost));
+            CK(ctx, cudaMemcpy(b.data(), R.dStampEnd.p, nIt * 4 * 8, cudaMemcpyDeviceToHost));
         }
         float *ms[4] = {&t.ms_generate, &t.ms_extend, &t.ms_shade, &t.ms_occluded};
         uint64_t *cnt[4] = {&t.n_generate, &t.n_extend, &t.n_shade, &t.n_occluded};
