@@ -430,8 +430,6 @@ struct Loader {
 
     // ---- participating media ----
     std::map<std::string, int> mediumIds;
-    bool pendingEnv = false;
-    float envRadiance[3] = {0, 0, 0}, envWeight = 1;
     // GridDataSource::loadFromFile, gridvolume.cpp:225-296: "VOL" 3, type (1 = float32), res x/y/z, channels, data box, data
     static void loadVol(const std::string &path, int res[3], double lo[3], double hi[3], std::vector<float> &data) {
         std::ifstream f(path, std::ios::binary);
@@ -1062,12 +1060,11 @@ struct Loader {
                 ep.spec("radiance", one, rad); // constant.cpp:47-50
                 const float w = (float) ep.f("samplingWeight", 1.0);
                 ep.checkAllUsed();
-                pendingEnv = true; envRadiance[0] = rad[0]; envRadiance[1] = rad[1]; envRadiance[2] = rad[2]; envWeight = w;
+                // emitters keep their document order (it is the order of Scene::m_emitters and therefore of the emitter-selection CDF)
+                if (b2_scene_add_constant_emitter(scene, rad, w) < 0) throw Err(b2_last_error(nullptr));
             }
             else throw Err("unsupported top-level element <" + c->tag + ">");
         }
-        // the environment emitter goes last, like the Python scene description does it (emitter order = sampling-CDF order)
-        if (pendingEnv && b2_scene_add_constant_emitter(scene, envRadiance, envWeight) < 0) throw Err(b2_last_error(nullptr));
         if (!haveSensor) throw Err("scene has no <sensor>");
     }
 };
