@@ -131,6 +131,9 @@ void b2_scene_destroy(b2_scene *);
  * major), x field of view in degrees, clip planes, film size.  m_sampleToCamera is derived inside. */
 int b2_scene_set_camera(b2_scene *, const float to_world[16], float xfov_deg, float near_clip, float far_clip,
                         int width, int height);
+/* ThinLens (src/sensors/thinlens.cpp:132-142,327-350): aperture radius and focus distance of the camera set before; 0 = pinhole.
+ * The aperture sample takes Sobol' dimensions 2 and 3 (integrator.cpp:173-174). */
+int b2_scene_set_thinlens(b2_scene *, float aperture_radius, float focus_distance);
 int b2_scene_get_sample_to_camera(b2_scene *, float out[16]);
 int b2_scene_film_size(b2_scene *, int *width, int *height);   /* Film::getSize (include/mitsuba/render/film.h) */
 /* BSDF plugin instance -> id (>=0) or -1 */

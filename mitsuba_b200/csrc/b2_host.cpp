@@ -124,6 +124,7 @@ struct b2_scene {
     float camToWorld[16];
     float sampleToCamera[16];
     float xfov = 0, nearClip = 1e-2f, farClip = 1e4f;
+    float apertureRadius = 0, focusDistance = 0;
     int W = 0, H = 0;
     bool hasCamera = false, committed = false;
     // device scene
@@ -324,6 +325,17 @@ extern "C" int b2_scene_set_camera(b2_scene *s, const float to_world[16], float 
     if (!mat4inv(c2s, s2c)) return fail(s->ctx, B2_ERR_INVALID, "singular camera matrix");
     for (int i = 0; i < 16; ++i) s->sampleToCamera[i] = (float) s2c[i];
     s->hasCamera = true;
+    s->committed = false;
+    return B2_OK;
+}
+// <sensor type="thinlens">: apertureRadius (required there, thinlens.cpp:132-142) and focusDistance (sensor.cpp:162, default farClip);
+// call after b2_scene_set_camera.  aperture_radius = 0 returns to the pinhole camera.
+extern "C" int b2_scene_set_thinlens(b2_scene *s, float aperture_radius, float focus_distance) {
+    if (!s) return fail(nullptr, B2_ERR_INVALID, "b2_scene_set_thinlens: null scene");
+    if (!s->hasCamera) return fail(s->ctx, B2_ERR_INVALID, "b2_scene_set_thinlens: set the camera first");
+    if (aperture_radius < 0) return fail(s->ctx, B2_ERR_INVALID, "thinlens: 'apertureRadius' must be non-negative");
+    if (aperture_radius > 0 && !(focus_distance > 0)) return fail(s->ctx, B2_ERR_INVALID, "thinlens: 'focusDistance' must be positive");
+    s->apertureRadius = aperture_radius; s->focusDistance = focus_distance;
     s->committed = false;
     return B2_OK;
 }
@@ -959,6 +971,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.cam.invResX = 1.0f / (float) s->W; ds.cam.invResY = 1.0f / (float) s->H; // sensor.cpp:104-107
     ds.cam.origin[0] = s->camToWorld[3]; ds.cam.origin[1] = s->camToWorld[7]; ds.cam.origin[2] = s->camToWorld[11];
     ds.cam.W = s->W; ds.cam.H = s->H;
+    ds.cam.apertureRadius = s->apertureRadius; ds.cam.focusDistance = s->focusDistance;
     ds.sobolM32 = ctx->dM32; ds.sobolVdc = ctx->dVdc; ds.sobolInv = ctx->dInv; ds.sobolNib = ctx->dNib;
     // shared-memory staging budget: up to 256 nodes (16 KB) and 256 triangles (12 KB) per CTA
     ds.stageNodes = std::min<uint32_t>(ds.nNodes, 256u);

@@ -221,7 +221,7 @@ B2_DEV bool filmPut(const DFilter &f, float4 *filmRGBA, float *filmW, int W, int
 // ------------------------------------------------------------------------------------------------
 // camera: perspective.cpp:271-298
 // ------------------------------------------------------------------------------------------------
-B2_DEV void cameraRay(const DCamera &cam, float sx, float sy, V3 &o, V3 &d, float &mint, float &maxt) {
+B2_DEV void cameraRay(const DCamera &cam, float sx, float sy, V3 &o, V3 &d, float &mint, float &maxt, float apx = 0.5f, float apy = 0.5f) {
     const float *M = cam.sampleToCamera;
     float px = sx * cam.invResX, py = sy * cam.invResY;
     float x = M[0] * px + M[1] * py + M[2] * 0.0f + M[3];
@@ -230,6 +230,21 @@ B2_DEV void cameraRay(const DCamera &cam, float sx, float sy, V3 &o, V3 &d, floa
     float w = M[12] * px + M[13] * py + M[14] * 0.0f + M[15];
     V3 nearP(x, y, z);
     if (w != 1.0f) nearP = nearP / w;
+    if (cam.apertureRadius > 0) { // thinlens.cpp:327-350: aperture point on the lens disk, direction through the point in focus
+        float tx, ty;
+        squareToUniformDiskConcentric(apx, apy, tx, ty);
+        tx *= cam.apertureRadius; ty *= cam.apertureRadius;
+        const V3 apertureP(tx, ty, 0.0f);
+        const V3 focusP = nearP * (cam.focusDistance / nearP.z);
+        const V3 dl = normalize(focusP - apertureP);
+        const float invZ = 1.0f / dl.z;
+        const float *T = cam.camToWorld;
+        o = V3(T[0] * tx + T[1] * ty + T[2] * 0.0f + T[3], T[4] * tx + T[5] * ty + T[6] * 0.0f + T[7], T[8] * tx + T[9] * ty + T[10] * 0.0f + T[11]);
+        d = V3(T[0] * dl.x + T[1] * dl.y + T[2] * dl.z, T[4] * dl.x + T[5] * dl.y + T[6] * dl.z, T[8] * dl.x + T[9] * dl.y + T[10] * dl.z);
+        mint = cam.nearClip * invZ;
+        maxt = cam.farClip * invZ;
+        return;
+    }
     V3 dl = normalize(nearP);
     float invZ = 1.0f / dl.z;
     const float *T = cam.camToWorld;
@@ -324,7 +339,9 @@ template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc
                 const float spx = (float) px + ax, spy = (float) py + ay;
                 V3 o, d;
                 float mint, maxt;
-                cameraRay(sc.cam, spx, spy, o, d, mint, maxt);
+                float apx = 0.5f, apy = 0.5f;
+                if (sc.cam.apertureRadius > 0) smp.next2D(apx, apy); // needsApertureSample, integrator.cpp:173-174
+                cameraRay(sc.cam, spx, spy, o, d, mint, maxt, apx, apy);
                 if (FLAT) {
                     HitRec h;
                     castClosestFlat(sc, tm, o, d, mint, maxt, h);

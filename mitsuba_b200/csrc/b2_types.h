@@ -75,6 +75,7 @@ struct DCamera {
     float invResX, invResY;
     float origin[3];
     int32_t W, H;
+    float apertureRadius, focusDistance; // > 0: `thinlens` sensor (src/sensors/thinlens.cpp); 0: pinhole
 };
 
 // Scene resident in HBM

@@ -998,7 +998,7 @@ struct Loader {
                 rp->strict_normals = p.b("strictNormals", false); rp->hide_emitters = p.b("hideEmitters", false);
                 p.checkAllUsed();
             } else if (c->tag == "sensor") {
-                if (c->type != "perspective") throw Err("unsupported sensor \"" + c->type + "\" (hot path: perspective)");
+                if (c->type != "perspective" && c->type != "thinlens") throw Err("unsupported sensor \"" + c->type + "\" (supported: perspective, thinlens)");
                 Props p(c);
                 int W = 768, H = 576; // film.cpp:30-33
                 for (auto &ch : c->children) {
@@ -1047,9 +1047,17 @@ struct Loader {
                 float twf[16];
                 for (int i = 0; i < 16; ++i) twf[i] = (float) tw.m[i];
                 float nearC = (float) p.f("nearClip", 1e-2), farC = (float) p.f("farClip", 1e4);
-                p.f("focusDistance", 0); p.f("shutterOpen", 0); p.f("shutterClose", 0);
+                const float focusD = (float) p.f("focusDistance", farC); // sensor.cpp:162
+                p.f("shutterOpen", 0); p.f("shutterClose", 0);
+                float aperture = 0;
+                if (c->type == "thinlens") {
+                    if (!p.has("apertureRadius")) throw Err("thinlens: missing required property 'apertureRadius'"); // thinlens.cpp:133
+                    aperture = (float) p.f("apertureRadius", 0);
+                    if (aperture == 0) aperture = 1e-4f; // thinlens.cpp:134-138: a zero radius becomes Epsilon
+                }
                 p.checkAllUsed();
                 if (b2_scene_set_camera(scene, twf, (float) fov, nearC, farC, W, H)) throw Err(b2_last_error(nullptr));
+                if (aperture > 0 && b2_scene_set_thinlens(scene, aperture, focusD)) throw Err(b2_last_error(nullptr));
                 haveSensor = true;
             } else if (c->tag == "shape") addShape(c);
             else if (c->tag == "emitter") {

@@ -225,6 +225,8 @@ class Camera:
     far: float = 1e4                    # sensor.cpp:160
     width: int = 768                    # film.cpp:30-33
     height: int = 576
+    aperture_radius: float = 0.0        # > 0: `thinlens` sensor (src/sensors/thinlens.cpp:132-142)
+    focus_distance: float = 0.0         # sensor.cpp:162 (default: farClip)
 
     def xfov(self) -> float:
         """src/librender/sensor.cpp:243-263,293-316."""

@@ -126,6 +126,7 @@ struct Scene {
     SobolTables sobol;
     /* camera */
     float camToWorld[16], sampleToCamera[16]; float nearClip = 1e-2f, farClip = 1e4f; int W = 0, H = 0;
+    float apertureRadius = 0, focusDistance = 0; /* > 0: `thinlens` sensor (src/sensors/thinlens.cpp) */
     V3 camOrigin;
 
     void commit(bool tree) {
@@ -761,7 +762,7 @@ struct Scene {
     }
 
     /* perspective.cpp:271-298 (ray part only; differentials unused by constant textures) */
-    Ray sampleRay(float sxp, float syp) const {
+    Ray sampleRay(float sxp, float syp, float apx = 0.5f, float apy = 0.5f) const {
         const float *M = sampleToCamera;
         float px = sxp * (1.0f / (float) W), py = syp * (1.0f / (float) H), pz = 0.0f; /* m_invResolution, sensor.cpp:104-107 */
         float x = M[0] * px + M[1] * py + M[2] * pz + M[3];
@@ -770,6 +771,19 @@ struct Scene {
         float w = M[12] * px + M[13] * py + M[14] * pz + M[15];
         V3 nearP(x, y, z);
         if (w != 1.0f) nearP = nearP / w;       /* transform.h:108-125 */
+        if (apertureRadius > 0) { /* thinlens.cpp:327-350 */
+            float tx, ty;
+            squareToUniformDiskConcentric(apx, apy, tx, ty);
+            tx *= apertureRadius; ty *= apertureRadius;
+            V3 apertureP(tx, ty, 0.0f);
+            V3 focusP = nearP * (focusDistance / nearP.z);
+            V3 d = normalize(focusP - apertureP);
+            float invZ = 1.0f / d.z;
+            const float *T = camToWorld;
+            V3 ow(T[0] * tx + T[1] * ty + T[2] * 0.0f + T[3], T[4] * tx + T[5] * ty + T[6] * 0.0f + T[7], T[8] * tx + T[9] * ty + T[10] * 0.0f + T[11]);
+            V3 dw(T[0] * d.x + T[1] * d.y + T[2] * d.z, T[4] * d.x + T[5] * d.y + T[6] * d.z, T[8] * d.x + T[9] * d.y + T[10] * d.z);
+            return Ray(ow, dw, nearClip * invZ, farClip * invZ);
+        }
         V3 d = normalize(nearP);
         float invZ = 1.0f / d.z;
         const float *T = camToWorld;
@@ -946,6 +960,8 @@ void orc_set_camera(void *s, const float *camToWorld, const float *sampleToCamer
     memcpy(sc->camToWorld, camToWorld, 64); memcpy(sc->sampleToCamera, sampleToCamera, 64);
     sc->nearClip = nearClip; sc->farClip = farClip; sc->W = W; sc->H = H;
 }
+/* <sensor type="thinlens">: apertureRadius, focusDistance (thinlens.cpp:132-142, sensor.cpp:162) */
+void orc_set_thinlens(void *s, float apertureRadius, float focusDistance) { Scene *sc = (Scene *) s; sc->apertureRadius = apertureRadius; sc->focusDistance = focusDistance; }
 void orc_commit(void *s, int useTree) { ((Scene *) s)->commit(useTree != 0); }
 void orc_accel_info(void *s, uint64_t *out /* nTri, nNodes, nIndices, nLeaves, maxDepth */, float *aabb6) {
     Scene *sc = (Scene *) s;
@@ -1033,7 +1049,9 @@ static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcSt
                     for (int j = lo; j < hi; ++j) {
                         float ax, ay; sampler->next2D(ax, ay);
                         float spx = (float) x + ax, spy = (float) y + ay;
-                        Ray ray = sc->sampleRay(spx, spy);
+                        float apx = 0.5f, apy = 0.5f;
+                        if (sc->apertureRadius > 0) sampler->next2D(apx, apy); /* needsApertureSample, integrator.cpp:173-174 */
+                        Ray ray = sc->sampleRay(spx, spy, apx, apy);
                         float alpha;
                         Spectrum spec = rp->integrator == 1 ? sc->LiVol(ray, sampler.get(), *rp, alpha, st) : sc->Li(ray, sampler.get(), *rp, alpha, st); /* sensor weight = 1 */
                         if (!blk->put(spx, spy, spec, alpha)) ++st.badSamples;

@@ -188,6 +188,8 @@ class OracleScene:
         # identical float32 inputs (its derivation is host-side set-up, perspective.cpp:146-153, not the hot path)
         s2c = np.ascontiguousarray(cam.sample_to_camera() if sample_to_camera is None else sample_to_camera, np.float32)
         L.orc_set_camera(self.h, _p(c2w), _p(s2c), C.c_float(cam.near), C.c_float(cam.far), C.c_int(cam.width), C.c_int(cam.height))
+        if getattr(cam, "aperture_radius", 0.0) > 0:
+            L.orc_set_thinlens(self.h, C.c_float(cam.aperture_radius), C.c_float(cam.focus_distance if cam.focus_distance > 0 else cam.far))
         L.orc_commit(self.h, C.c_int(1 if use_tree else 0))
 
     def __del__(self):

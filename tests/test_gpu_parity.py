@@ -527,3 +527,23 @@ def test_instancing_errors(b2ctx):
     g = api.Scene(b2ctx, d)
     with pytest.raises(api.B2Error, match="instanced geometry"):
         g.render(RenderParams(spp=1, integrator="volpath"))
+
+
+def test_thinlens_sensor_parity(b2ctx):
+    """<sensor type="thinlens"> (src/sensors/thinlens.cpp:327-350): aperture sample on Sobol' dimensions 2, 3; rays start on the lens."""
+    d = cornell_box(64, 64)
+    d.camera = dataclasses.replace(d.camera, aperture_radius=25.0, focus_distance=1100.0)
+    g, o = pair(b2ctx, d)
+    for smp in ("sobol", "independent"):
+        rp = RenderParams(spp=16, sampler=smp, rfilter="box")
+        fo, so = o.render(rp)
+        fg, sg = g.render(rp, parity=True)
+        assert rel_l2(api.develop(fg), O.develop(fo)) <= 3e-4
+        assert abs(sg["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+    fg2, _ = g.render(RenderParams(spp=16, sampler="sobol", rfilter="box"), parity=False)
+    fo, _ = o.render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert rel_l2(api.develop(fg2), O.develop(fo)) <= REL_L2_TOL
+    # and it differs from the pinhole image
+    gp = api.Scene(b2ctx, cornell_box(64, 64))
+    fp, _ = gp.render(RenderParams(spp=16, sampler="sobol", rfilter="box"), parity=True)
+    assert rel_l2(api.develop(fg), api.develop(fp)) > 0.02

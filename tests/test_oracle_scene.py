@@ -252,3 +252,29 @@ def test_instancing_equals_flattened_geometry():
     fc, _ = O.OracleScene(b, use_tree=False).render(rp)
     assert np.array_equal(fb, fc)
     assert b.n_triangles() * 3 < a.n_triangles()
+
+
+def test_thinlens_sensor_focus_and_blur():
+    """thinlens.cpp:327-350: a small emitter in the focal plane images sharply for any aperture; out of focus its image spreads into
+    a disc of the predicted diameter; a tiny aperture reproduces the pinhole image."""
+    import dataclasses
+    from mitsuba_b200.scene import _quad
+    P, I = _quad([(-0.05, -0.05, 5), (-0.05, 0.05, 5), (0.05, 0.05, 5), (0.05, -0.05, 5)], (0, 0, -1))
+    light = Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(1, 1, 1))
+    cam = Camera(look_at((0, 0, 0), (0, 0, 1), (0, 1, 0)), fov=20.0, near=0.1, far=100.0, width=64, height=64)
+    rp = RenderParams(spp=64, sampler="independent", rfilter="box", max_depth=1)
+
+    def lit_pixels(c):
+        film, _ = O.OracleScene(SceneDesc([light], c)).render(rp)
+        return int((O.develop(film).sum(2) > 0.02).sum()), float(O.develop(film).sum())
+    n_pin, e_pin = lit_pixels(cam)
+    n_focus, e_focus = lit_pixels(dataclasses.replace(cam, aperture_radius=0.2, focus_distance=5.0))
+    n_blur, e_blur = lit_pixels(dataclasses.replace(cam, aperture_radius=0.2, focus_distance=2.5))
+    n_tiny, e_tiny = lit_pixels(dataclasses.replace(cam, aperture_radius=1e-5, focus_distance=2.5))
+    # quad: 0.1 wide at z = 5 -> 0.1 / (2 * 5 * tan(10 deg)) * 64 = 3.6 pixels across
+    assert 9 <= n_pin <= 25 and abs(n_focus - n_pin) <= 6 and abs(n_tiny - n_pin) <= 2
+    # defocus: circle of confusion at the focal plane z = 2.5 has radius 0.2 * (5 - 2.5) / 5 = 0.1 -> 0.2 / (2 * 2.5 * tan(10 deg)) * 64 = 14.5 px
+    # across (plus the quad): > 100 lit pixels
+    assert n_blur > 100
+    # the lens collects the same flux in all cases (energy spreads, it is not lost)
+    assert abs(e_focus - e_pin) < 0.1 * e_pin and abs(e_blur - e_pin) < 0.1 * e_pin
