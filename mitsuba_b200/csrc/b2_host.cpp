@@ -1058,7 +1058,6 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     r.sampleLo = p->sample_lo; r.sampleHi = p->sample_hi > 0 ? p->sample_hi : p->spp;
     if (p->integrator != B2_INTEGRATOR_PATH && p->integrator != B2_INTEGRATOR_VOLPATH) return fail(ctx, B2_ERR_INVALID, "unknown integrator");
     if (p->integrator == B2_INTEGRATOR_VOLPATH && s->ds.nItems) return fail(ctx, B2_ERR_INVALID, "volpath with instanced geometry is not supported");
-    if (p->integrator == B2_INTEGRATOR_VOLPATH && s->ds.envEmitter >= 0) return fail(ctx, B2_ERR_INVALID, "volpath with an environment emitter is not supported");
     r.integrator = p->integrator;
     if (r.sampleLo < 0 || r.sampleHi > p->spp || r.sampleLo >= r.sampleHi) return fail(ctx, B2_ERR_INVALID, "invalid sample range");
     if (p->sampler == B2_SAMPLER_SOBOL) {

@@ -1093,11 +1093,19 @@ B2_DEV void volIntersectAndLookForEmitter(VolEnv &env, PathSampler &smp, int med
             const Spectrum le = dot(its.sh.n, -d) <= 0 ? Spectrum(0.0f) : V3(e.radiance[0], e.radiance[1], e.radiance[2]); // area.cpp:104-109
             value = transmittance * le;
         }
+    } else if (sc.envEmitter >= 0) { // volpath.cpp:418-424: the ray left the scene -> environment emitter (constant.cpp:239-253)
+        const DEmitter &e = sc.emitters[sc.envEmitter];
+        eq.d = d; eq.n = V3(0.0f); eq.dist = 0.0f; eq.emitter = sc.envEmitter; // the solid-angle density needs d only
+        value = transmittance * V3(e.radiance[0], e.radiance[1], e.radiance[2]);
     }
 }
-// scene.cpp:949-952; area.cpp:175-183; shape.cpp:117-126
+// scene.cpp:949-952; area.cpp:175-183; shape.cpp:117-126; constant.cpp:210-224
 B2_DEV float volPdfEmitterDirect(const DScene &sc, const EmitterQuery &eq, const V3 &refN) {
     const DEmitter &em = sc.emitters[eq.emitter];
+    if (em.nTri == 0) {
+        const float pdfSA = !isZero(refN) ? B2_INV_PI * fmaxf(0.0f, dot(eq.d, refN)) : 0.07957747154594766788f;
+        return pdfSA * (em.samplingWeight * sc.emitterNormalization);
+    }
     float pdfDirect = 0.0f;
     if (dot(eq.d, refN) >= 0 && dot(eq.d, eq.n) < 0) pdfDirect = em.invSurfaceArea * (eq.dist * eq.dist) / absDot(eq.d, eq.n);
     return pdfDirect * (em.samplingWeight * sc.emitterNormalization);
@@ -1143,7 +1151,9 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
             smp.scramble32 = rp.sampler == 0 ? (uint32_t) rp.scramble : (uint32_t) (rp.scramble >> 32);
             int medium;
             HitRec hit;
+            float rayMintCur = ro4.w, rayMaxtCur = B2_INF; // ray.mint / ray.maxt of the current path segment
             if (flags & PF_FRESH) {
+                rayMaxtCur = rd4.w;
                 smp.dim = state >> 20;
                 medium = -1; // sensor medium: vacuum (a camera inside a medium is out of scope)
                 env.closest(rayO, rayD, ro4.w, rd4.w, hit); // rRec.rayIntersect(ray), volpath.cpp:97
@@ -1187,14 +1197,22 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
                     const float phaseVal = phaseSample(med, -rayD, wo, phasePdf, smp);
                     if (phaseVal == 0) { done = true; break; }
                     T = T * phaseVal;
-                    rayO = mRec.p; rayD = wo;
+                    rayO = mRec.p; rayD = wo; rayMintCur = 0.0f; rayMaxtCur = B2_INF;
                     Spectrum value(0.0f);
                     EmitterQuery eq;
                     volIntersectAndLookForEmitter(env, smp, medium, rp.maxDepth - depth - 1, rayO, rayD, 0.0f, hit, eq, value);
                     if (!isZero(value)) Li = Li + T * value * miWeight(phasePdf, volPdfEmitterDirect(sc, eq, V3(0.0f)));
                 } else {
                     if (medium >= 0) T = T * (mRec.transmittance / mRec.pdfFailure);
-                    if (hit.prim == 0xFFFFFFFFu) { done = true; break; } // no environment emitter
+                    if (hit.prim == 0xFFFFFFFFu) { // volpath.cpp:190-202
+                        if (sc.envEmitter >= 0 && !scattered && !rp.hideEmitters) {
+                            const DEmitter &em = sc.emitters[sc.envEmitter];
+                            Spectrum value = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                            if (medium >= 0) value = value * mediumTransmittance(sc.media[medium], rayO, rayD, rayMintCur, rayMaxtCur, smp);
+                            Li = Li + value;
+                        }
+                        done = true; break;
+                    }
                     Isect its;
                     fillIntersection(sc, rayD, hit.prim, hit.u, hit.v, its);
                     const int mat = its.material;
@@ -1244,7 +1262,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
                     if (isZero(bsdfWeight)) { done = true; break; }
                     const V3 wo = its.sh.toWorld(bRec.wo);
                     if (dot(its.geoN, wo) * cosTheta(bRec.wo) <= 0 && rp.strictNormals) { done = true; break; }
-                    rayO = its.p; rayD = wo;
+                    rayO = its.p; rayD = wo; rayMintCur = B2_EPSILON; rayMaxtCur = B2_INF;
                     T = T * bsdfWeight;
                     eta *= bRec.eta;
                     if (transition) medium = targetMedium(media, its.geoN, rayD);
@@ -1274,7 +1292,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
             if (smp.overflow) ++nDimOvf;
             if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
             else {
-                pool.ray[2 * (size_t) i] = make_float4(rayO.x, rayO.y, rayO.z, 0.0f);
+                pool.ray[2 * (size_t) i] = make_float4(rayO.x, rayO.y, rayO.z, rayMintCur);
                 pool.ray[2 * (size_t) i + 1] = make_float4(rayD.x, rayD.y, rayD.z, 0.0f);
                 pool.hit[i] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
                 pool.st[2 * (size_t) i] = make_float4(T.x, T.y, T.z, eta);

@@ -631,6 +631,13 @@ struct Scene {
                 dRec.d = ray.d; dRec.dist = its->t;
                 value = transmittance * emitterEval(m.emitter, *its, -ray.d);
             }
+        } else if (envEmitter >= 0) { /* volpath.cpp:418-424: env->fillDirectSamplingRecord(dRec, ray) && evalEnvironment */
+            float nearT, farT;
+            if (bsphereIntersect(ray.o, ray.d, nearT, farT) && !(nearT > 0) && !(farT < 0)) {
+                dRec.p = ray(farT); dRec.n = normalize(bsCenter - dRec.p); dRec.solidAngle = true; dRec.emitter = envEmitter;
+                dRec.d = ray.d; dRec.dist = farT;
+                value = transmittance * emitters[envEmitter].radiance;
+            }
         }
     }
     Spectrum LiVol(const Ray &r, Sampler *sampler, const OrcRenderParams &rp, float &alpha, OrcStats &st) const {
@@ -688,7 +695,14 @@ struct Scene {
                 emittedRadiance = false;
             } else {
                 if (medium >= 0) throughput *= mRec.transmittance / mRec.pdfFailure;
-                if (!its.isValid()) break; /* no environment emitter */
+                if (!its.isValid()) { /* volpath.cpp:190-202 */
+                    if (envEmitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered)) {
+                        Spectrum value = throughput * emitters[envEmitter].radiance;
+                        if (medium >= 0) value *= MediumEval(media[medium]).evalTransmittance(ray, sampler);
+                        Li += value;
+                    }
+                    break;
+                }
                 const Mesh &mesh = meshes[its.mesh];
                 const int bsdf = mesh.bsdf;
                 if (mesh.emitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered))

@@ -187,3 +187,20 @@ def test_invalid_media_are_rejected(b2ctx):
             m.bsdf = Bsdf("null")
     with pytest.raises(api.B2Error, match="index-matched"):
         api.Scene(b2ctx, d)
+
+
+def test_smoke_under_a_constant_sky(b2ctx):
+    """volpath + `constant` environment emitter (volpath.cpp:190-202,418-424): attenuated environment seen through the medium,
+    environment found by the emitter look-up after scattering, MIS against its uniform-sphere / cosine density."""
+    d = smoke_scene(48, 48, res=24, scale=12.0)
+    d.env_radiance = (0.3, 0.4, 0.6)
+    g, o = pair(b2ctx, d)
+    for kw in (dict(), dict(hide_emitters=True)):
+        rp = RenderParams(spp=16, rfilter="box", sampler="independent", integrator="volpath", **kw)
+        ref, so = o.render(rp)
+        film, st = g.render(rp, parity=True)
+        assert rel_l2(api.develop(film), api.develop(ref)) < 3e-4, kw
+        assert abs(st["rays"] - so["rays"]) <= 2e-4 * so["rays"]
+    film, _ = g.render(RenderParams(spp=64, rfilter="box", sampler="independent", integrator="volpath"), parity=False)
+    ref, _ = o.render(RenderParams(spp=64, rfilter="box", sampler="independent", integrator="volpath"))
+    assert rel_l2(api.develop(film), api.develop(ref)) < REL_L2_TOL
