@@ -1322,6 +1322,244 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// k_volstep_lockstep: the same loop iteration as k_volstep, arranged so that the 32 paths of a warp walk through it TOGETHER.
+// The medium-scattering and the surface branch of volpath.cpp:108-343 only differ in how they evaluate the scattering function;
+// their three expensive parts -- the distance-sampling walk, the attenuated shadow connection (scene.cpp:619-679) and the emitter
+// look-up after sampling a direction (volpath.cpp:368-426) -- are hoisted out of the branches into ONE call site each, and slots are
+// assigned statically, so every lane of a warp enters the same Woodcock loop at the same time (ncu: k_volstep ran 2.3 of 32 lanes per
+// instruction).  Same draws in the same order per path as k_volstep and the oracle.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(B2_TRACE_BLOCK, 4) k_volstep_lockstep(DScene sc, DPool pool, DRender rp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
+    stampBegin(rp, it, STAGE_SHADE);
+    const TraceMem tm = setupTraceMem(sc, smem);
+    const uint32_t Q = pool.capacity;
+    VolEnv env(sc, tm);
+    uint32_t nDimOvf = 0, nDone = 0;
+    const DMaterial *mats = sc.materials;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t state = i < Q ? pool.flags[i] : 0u;
+        const bool live = (state & PF_ALIVE) != 0;
+        uint32_t flags = state & 0xFFu;
+        int depth = (int) ((state >> 8) & 0xFFFu);
+        V3 rayO(0.0f), rayD(0.0f, 0.0f, 1.0f);
+        Spectrum T(0.0f), Li(0.0f);
+        float eta = 1.0f;
+        PathSampler smp;
+        smp.kind = rp.sampler; smp.m32 = sc.sobolNib; smp.nNib = rp.indexNibbles; smp.overflow = false; smp.cacheDim = 0xFFFFFFFFu;
+        smp.index = 0; smp.dim = 0;
+        smp.scramble32 = rp.sampler == 0 ? (uint32_t) rp.scramble : (uint32_t) (rp.scramble >> 32);
+        int medium = -1;
+        HitRec hit;
+        hit.t = B2_INF; hit.u = 0; hit.v = 0; hit.prim = 0xFFFFFFFFu;
+        float rayMintCur = 0.0f, rayMaxtCur = B2_INF;
+        bool fresh = false;
+        if (live) {
+            const float4 ro4 = pool.ray[2 * (size_t) i], rd4 = pool.ray[2 * (size_t) i + 1], thr4 = pool.st[2 * (size_t) i], li4 = pool.st[2 * (size_t) i + 1];
+            const uint2 sm2 = pool.smp[i];
+            rayO = V3(ro4.x, ro4.y, ro4.z); rayD = V3(rd4.x, rd4.y, rd4.z);
+            T = Spectrum(thr4.x, thr4.y, thr4.z); Li = Spectrum(li4.x, li4.y, li4.z);
+            eta = thr4.w;
+            smp.index = ((uint64_t) sm2.y << 32) | sm2.x;
+            rayMintCur = ro4.w;
+            fresh = (flags & PF_FRESH) != 0;
+            if (fresh) { rayMaxtCur = rd4.w; smp.dim = state >> 20; }
+            else {
+                const uint2 v = pool.vol[i];
+                medium = (int) v.x; smp.dim = v.y;
+                const float4 h4 = pool.hit[i];
+                hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+            }
+        }
+        // rRec.rayIntersect(ray) of the camera ray (volpath.cpp:97): one call site for the warp
+        if (fresh) {
+            env.closest(rayO, rayD, rayMintCur, rayMaxtCur, hit);
+            if (hit.prim != 0xFFFFFFFFu) flags |= PF_ALPHA;
+            flags &= ~PF_FRESH;
+        }
+        bool done = false, busy = live; // busy: this lane still has a loop iteration to run (an index-matched boundary repeats it)
+        while (__any_sync(__activemask(), busy)) {
+            // ---- A: loop condition + distance sampling (one walk for the whole warp) ----
+            bool run = busy;
+            if (run && !(depth <= rp.maxDepth || rp.maxDepth < 0)) { done = true; busy = false; run = false; }
+            const bool scattered = (flags & PF_SCATTERED) != 0;
+            MediumRec mRec;
+            mRec.t = 0; mRec.p = V3(0.0f); mRec.sigmaS = Spectrum(0.0f); mRec.transmittance = Spectrum(1.0f); mRec.pdfFailure = 1.0f; mRec.pdfSuccess = 1.0f;
+            bool mediumEvent = false;
+            if (run && medium >= 0) mediumEvent = mediumSampleDistance(sc.media[medium], rayO, rayD, 0.0f, hit.t, mRec, smp);
+            // ---- B: branch-specific preparation of the direct-illumination query ----
+            Isect its;
+            its.material = 0; its.emitter = -1;
+            V3 neeRef(0.0f), refN(0.0f);
+            bool doNee = false, neeOnSurface = false;
+            int2 media = make_int2(-1, -1);
+            uint32_t btype = 0;
+            if (run) {
+                if (mediumEvent) {
+                    if (depth >= rp.maxDepth && rp.maxDepth != -1) { done = true; busy = false; run = false; }
+                    else {
+                        T = T * (mRec.sigmaS * mRec.transmittance / mRec.pdfSuccess);
+                        neeRef = mRec.p; doNee = sc.nEmitters > 0;
+                    }
+                } else {
+                    if (medium >= 0) T = T * (mRec.transmittance / mRec.pdfFailure);
+                    if (hit.prim == 0xFFFFFFFFu) { // volpath.cpp:190-202
+                        if (sc.envEmitter >= 0 && !scattered && !rp.hideEmitters) {
+                            const DEmitter &em = sc.emitters[sc.envEmitter];
+                            Spectrum value = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                            if (medium >= 0) value = value * mediumTransmittance(sc.media[medium], rayO, rayD, rayMintCur, rayMaxtCur, smp);
+                            Li = Li + value;
+                        }
+                        done = true; busy = false; run = false;
+                    } else {
+                        fillIntersection(sc, rayD, hit.prim, hit.u, hit.v, its);
+                        btype = mats[its.material].flags;
+                        if (its.emitter >= 0 && !scattered && (!rp.hideEmitters || scattered)) {
+                            const DEmitter &em = sc.emitters[its.emitter];
+                            const Spectrum le = dot(its.sh.n, -rayD) <= 0 ? Spectrum(0.0f) : V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                            Li = Li + T * le;
+                        }
+                        if ((depth >= rp.maxDepth && rp.maxDepth != -1) || ((-dot(its.geoN, rayD)) * cosTheta(its.wi) < 0 && rp.strictNormals)) { done = true; busy = false; run = false; }
+                        else {
+                            if ((btype & (ETransmission | EBackSide)) == 0) refN = its.sh.n; // records.inl:160-164
+                            media = env.mediaOf(hit.prim);
+                            neeRef = its.p; neeOnSurface = true;
+                            doNee = sc.nEmitters > 0 && (btype & ESmooth);
+                        }
+                    }
+                }
+            }
+            const bool transition = media.x >= 0 || media.y >= 0;
+            // ---- C: luminaire sampling, shared by both branches (volpath.cpp:122-151, 238-272) ----
+            {
+                DirectSample ds;
+                float emPdf = 1.0f;
+                bool ok = false;
+                if (run && doNee) {
+                    float sx, sy;
+                    smp.next2D(sx, sy);
+                    ok = sampleEmitterDirect(sc, neeRef, refN, sx, sy, ds, &emPdf);
+                }
+                int med = medium;
+                if (ok && neeOnSurface && transition) med = targetMedium(media, its.geoN, ds.d);
+                Spectrum tr(0.0f);
+                if (ok) tr = volEvalTransmittance(env, neeRef, neeOnSurface, ds.p, true, med, rp.maxDepth - depth - 1, smp);
+                if (ok) {
+                    const Spectrum value = ds.value * (tr / emPdf);
+                    ds.pdf *= emPdf;
+                    if (!isZero(value)) {
+                        if (mediumEvent) {
+                            const float phaseVal = phaseEval(sc.media[medium], -rayD, ds.d);
+                            if (phaseVal != 0) Li = Li + T * value * phaseVal * miWeight(ds.pdf, phaseVal);
+                        } else {
+                            BRec bRec;
+                            bRec.wi = its.wi;
+                            bRec.wo = its.sh.toLocal(ds.d);
+                            const Spectrum bsdfVal = bsdfEval<-1>(mats, its.material, bRec);
+                            if (!isZero(bsdfVal) && (!rp.strictNormals || dot(its.geoN, ds.d) * cosTheta(bRec.wo) > 0))
+                                Li = Li + T * value * bsdfVal * miWeight(ds.pdf, bsdfPdf<-1>(mats, its.material, bRec));
+                        }
+                    }
+                }
+            }
+            // ---- D: sample the next direction (phase function or BSDF) ----
+            float scatterPdf = 0.0f;
+            bool isNull = false, isDelta = false;
+            float lookMint = 0.0f;
+            if (run) {
+                if (mediumEvent) {
+                    V3 wo;
+                    const float phaseVal = phaseSample(sc.media[medium], -rayD, wo, scatterPdf, smp);
+                    if (phaseVal == 0) { done = true; busy = false; run = false; }
+                    else {
+                        T = T * phaseVal;
+                        rayO = mRec.p; rayD = wo; rayMintCur = 0.0f; rayMaxtCur = B2_INF;
+                        refN = V3(0.0f);
+                    }
+                } else {
+                    BRec bRec;
+                    bRec.wi = its.wi;
+                    float sx, sy;
+                    smp.next2D(sx, sy);
+                    const Spectrum bsdfWeight = bsdfSample<-1>(mats, its.material, bRec, scatterPdf, sx, sy, smp);
+                    const V3 wo = its.sh.toWorld(bRec.wo);
+                    if (isZero(bsdfWeight) || (dot(its.geoN, wo) * cosTheta(bRec.wo) <= 0 && rp.strictNormals)) { done = true; busy = false; run = false; }
+                    else {
+                        rayO = its.p; rayD = wo; rayMintCur = B2_EPSILON; rayMaxtCur = B2_INF;
+                        T = T * bsdfWeight;
+                        eta *= bRec.eta;
+                        if (transition) medium = targetMedium(media, its.geoN, rayD);
+                        isNull = bRec.sampledType == ENull;
+                        isDelta = (bRec.sampledType & EDelta) != 0;
+                        lookMint = B2_EPSILON;
+                    }
+                }
+            }
+            // ---- E: index-matched boundary (volpath.cpp:302-311): plain intersection, no Russian roulette, repeat the iteration ----
+            if (run && isNull) {
+                env.closest(rayO, rayD, B2_EPSILON, B2_INF, hit);
+                depth++;
+                run = false; // busy stays set: this lane takes another turn of the while loop
+            }
+            // ---- F: first intersection along the new ray + attenuated emitter behind index-matched boundaries (one call site) ----
+            Spectrum value(0.0f);
+            EmitterQuery eq;
+            eq.emitter = -1;
+            if (run) volIntersectAndLookForEmitter(env, smp, medium, rp.maxDepth - depth - 1, rayO, rayD, lookMint, hit, eq, value);
+            // ---- G: MIS with the emitter's density, Russian roulette ----
+            if (run) {
+                if (!isZero(value)) {
+                    const float emitterPdf = isDelta ? 0.0f : volPdfEmitterDirect(sc, eq, refN);
+                    Li = Li + T * value * miWeight(scatterPdf, emitterPdf);
+                }
+                if (depth++ >= rp.rrDepth) { // volpath.cpp:345-354
+                    const float q = fminf(maxComp(T) * eta * eta, 0.95f);
+                    if (smp.next1D() >= q) done = true;
+                    else T = T / q;
+                }
+                if (!done) {
+                    flags |= PF_SCATTERED;
+                    if (smp.overflow) done = true; // a path that ran past the Sobol' table ends here (see k_volstep)
+                }
+                busy = false;
+            }
+        }
+        if (live) {
+            if (smp.overflow) ++nDimOvf;
+            if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
+            else {
+                pool.ray[2 * (size_t) i] = make_float4(rayO.x, rayO.y, rayO.z, rayMintCur);
+                pool.ray[2 * (size_t) i + 1] = make_float4(rayD.x, rayD.y, rayD.z, 0.0f);
+                pool.hit[i] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+                pool.st[2 * (size_t) i] = make_float4(T.x, T.y, T.z, eta);
+                pool.vol[i] = make_uint2((uint32_t) medium, smp.dim);
+            }
+            pool.st[2 * (size_t) i + 1] = make_float4(Li.x, Li.y, Li.z, 0.0f);
+            state = flags | ((uint32_t) min(depth, 0xFFF) << 8);
+            pool.flags[i] = state;
+        }
+        const bool fin = live && (state & PF_DONE);
+        const uint32_t dq = warpAppend(fin, pool.counters + ((it & 1u) ? CTR_DONE1 : CTR_DONE0));
+        if (fin) {
+            pool.doneQueue[(size_t) (it & 1u) * Q + dq] = i;
+            ++nDone;
+        }
+    }
+    nDimOvf = warpSum(nDimOvf);
+    nDone = warpSum(nDone);
+    const uint32_t nRays = warpSum(env.nRays), nShadow = warpSum(env.nShadow);
+    if ((threadIdx.x & 31) == 0) {
+        if (nDone) atomicAdd(pool.counters + CTR_ACTIVE, ~(unsigned long long) nDone + 1ull);
+        if (nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
+        if (nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
+        if (nShadow) atomicAdd(pool.counters + CTR_SHADOWRAYS, (unsigned long long) nShadow);
+    }
+    stampEnd(rp, it, STAGE_SHADE);
+}
+
 // medium component probes (b2_medium_probe): what = 0 transmittance (in: 8 floats/ray -> 3), 1 sampleDistance (-> 12),
 // 2 density lookup (in: 3 floats -> 1), 3 phase sample (in: wi xyz + 2 samples -> 5); counter stream keyed like the oracle probe
 __global__ void k_medium_probe(DScene sc, int medium, int what, uint64_t n, const float *in, uint64_t seed, float *out) {
@@ -1527,6 +1765,9 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridTrace = occupancyGrid(k_trace_rays<false, false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     setSmemAttr((const void *) k_volstep, cfg.traceSmem);
     cfg.gridVolstep = occupancyGrid(k_volstep, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
+    setSmemAttr((const void *) k_volstep_lockstep, cfg.traceSmem);
+    cfg.gridVolLockstep = occupancyGrid(k_volstep_lockstep, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
+    cfg.volLockstep = getenv("B2_VOL_LOCKSTEP") ? atoi(getenv("B2_VOL_LOCKSTEP")) : 0;
     cfg.flatSmem = (((size_t) sc.stageTris * 48 + 15) & ~(size_t) 15) + 16;
     cfg.gridGenerate = occupancyGrid(k_generate<false>, 256, 0, numSMs);
     cfg.gridShade[0] = occupancyGrid(k_shade<0, false>, B2_SHADE_BLOCK, 0, numSMs);
@@ -1579,7 +1820,8 @@ void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, 
     k_occluded<<<cfg.gridOccluded, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
 void launch_volstep(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {
-    k_volstep<<<cfg.gridVolstep, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
+    if (cfg.volLockstep) k_volstep_lockstep<<<cfg.gridVolLockstep, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
+    else k_volstep<<<cfg.gridVolstep, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
 void launch_medium_probe(const LaunchCfg &cfg, const DScene &sc, int medium, int what, uint64_t n, const float *in, uint64_t seed, float *out,
                          cudaStream_t st) {
