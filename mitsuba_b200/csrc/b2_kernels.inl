@@ -1380,8 +1380,10 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, 4) k_volstep_lockstep(DScene s
             if (hit.prim != 0xFFFFFFFFu) flags |= PF_ALPHA;
             flags &= ~PF_FRESH;
         }
-        bool done = false, busy = live; // busy: this lane still has a loop iteration to run (an index-matched boundary repeats it)
-        while (__any_sync(__activemask(), busy)) {
+        // One pass per launch: a lane that crosses an index-matched boundary (the reference `continue`s, volpath.cpp:302-311) keeps its
+        // state and takes the repeated loop iteration in the NEXT launch -- repeating it here would leave the rest of the warp waiting.
+        bool done = false, busy = live;
+        {
             // ---- A: loop condition + distance sampling (one walk for the whole warp) ----
             bool run = busy;
             if (run && !(depth <= rp.maxDepth || rp.maxDepth < 0)) { done = true; busy = false; run = false; }
@@ -1502,7 +1504,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, 4) k_volstep_lockstep(DScene s
             if (run && isNull) {
                 env.closest(rayO, rayD, B2_EPSILON, B2_INF, hit);
                 depth++;
-                run = false; // busy stays set: this lane takes another turn of the while loop
+                run = false; busy = false; // the next loop iteration of this path runs in the next launch
             }
             // ---- F: first intersection along the new ray + attenuated emitter behind index-matched boundaries (one call site) ----
             Spectrum value(0.0f);
@@ -1767,7 +1769,7 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridVolstep = occupancyGrid(k_volstep, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     setSmemAttr((const void *) k_volstep_lockstep, cfg.traceSmem);
     cfg.gridVolLockstep = occupancyGrid(k_volstep_lockstep, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
-    cfg.volLockstep = getenv("B2_VOL_LOCKSTEP") ? atoi(getenv("B2_VOL_LOCKSTEP")) : 0;
+    cfg.volLockstep = getenv("B2_VOL_LOCKSTEP") ? atoi(getenv("B2_VOL_LOCKSTEP")) : 1; // measured: 105 vs 95 Msamples/s (smoke 128^3, 512^2 @ 256 spp)
     cfg.flatSmem = (((size_t) sc.stageTris * 48 + 15) & ~(size_t) 15) + 16;
     cfg.gridGenerate = occupancyGrid(k_generate<false>, 256, 0, numSMs);
     cfg.gridShade[0] = occupancyGrid(k_shade<0, false>, B2_SHADE_BLOCK, 0, numSMs);

@@ -12,7 +12,7 @@ struct LaunchCfg {
     int numSMs = 0;
     size_t traceSmem = 0;
     int gridExtend = 0, gridExtendSort = 0, gridOccluded = 0, gridTrace = 0, gridGenerate = 0, gridVolstep = 0, gridVolLockstep = 0;
-    int volLockstep = 0; // B2_VOL_LOCKSTEP: k_volstep_lockstep instead of k_volstep
+    int volLockstep = 1; // B2_VOL_LOCKSTEP=0: the ticketed k_volstep instead of k_volstep_lockstep
     int gridShade[5] = {0, 0, 0, 0, 0};
     // fused variants for shared-memory resident scenes (rays cast inline by k_generate / k_shade)
     size_t flatSmem = 0;
