@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from mitsuba_b200.distributed import render_sharded, shard_range, torch_reduce_sum
-from mitsuba_b200.scene import RenderParams, cornell_box
+from mitsuba_b200.scene import RenderParams, cornell_box, smoke_scene
 
 
 def test_shard_ranges_tile_the_sample_range():
@@ -30,14 +30,20 @@ def test_shard_ranges_tile_the_sample_range():
         shard_range(8, 2, 2)
 
 
-def _worker(rank, world, port, out_path):
+def _case(kind):
+    if kind == "volpath":   # the medium does not change the partitioning (independent (pixel, sample) units)
+        return smoke_scene(24, 24, res=12), RenderParams(spp=6, rfilter="gaussian", sampler="independent", integrator="volpath")
+    return cornell_box(32, 32), RenderParams(spp=6, rfilter="gaussian")
+
+
+def _worker(rank, world, port, out_path, kind="path"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import oracle_api as O
-    sc = O.OracleScene(cornell_box(32, 32))
-    rp = RenderParams(spp=6, rfilter="gaussian")
+    desc, rp = _case(kind)
+    sc = O.OracleScene(desc)
 
     def render_fn(shard):
         film, _ = sc.render(shard, threads=1)
@@ -52,12 +58,14 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_reduce_equals_single_process(tmp_path):
+@pytest.mark.parametrize("kind", ["path", "volpath"])
+def test_two_rank_gloo_reduce_equals_single_process(tmp_path, kind):
     out = str(tmp_path / "film.npy")
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29500 + (os.getpid() + (7 if kind == "volpath" else 0)) % 2000
+    mp.spawn(_worker, args=(2, port, out, kind), nprocs=2, join=True)
     film2 = np.load(out)
     from oracle import oracle_api as O
-    full, _ = O.OracleScene(cornell_box(32, 32)).render(RenderParams(spp=6, rfilter="gaussian"), threads=1)
+    desc, rp = _case(kind)
+    full, _ = O.OracleScene(desc).render(rp, threads=1)
     assert np.allclose(film2, full, rtol=1e-5, atol=1e-6)
     assert np.allclose(film2[..., 4], full[..., 4], rtol=1e-6)
