@@ -213,3 +213,15 @@ def test_serialized_shape_through_xml(b2ctx, tmp_path):
     (tmp_path / "bad.xml").write_text((tmp_path / "s.xml").read_text().replace('name="shapeIndex" value="1"', 'name="shapeIndex" value="7"'))
     with pytest.raises(api.B2Error, match="out of range"):
         b2ctx.load_xml(str(tmp_path / "bad.xml"))
+
+
+def test_instances_xml_matches_python_scene(b2ctx):
+    """shapegroup + instance (<ref id>, toWorld matrix) through b2_load_xml (scenes/instances.xml, tools/make_instances_scene.py)."""
+    from mitsuba_b200.scene import stress_scene
+    sc, rp = b2ctx.load_xml(os.path.join(ROOT, "scenes", "instances.xml"), ["spp=16", "res=64"])
+    film, st = sc.render(rp, parity=True)
+    ref = api.Scene(b2ctx, stress_scene(9, 32, 32, 64, 64, instanced=True))
+    f2, s2 = ref.render(RenderParams(spp=16, sampler="sobol", rfilter="box"), parity=True)
+    assert st["n_triangles"] == s2["n_triangles"]
+    assert rel_l2(api.develop(film), api.develop(f2)) < 1e-3
+    assert abs(st["rays"] - s2["rays"]) <= 1e-3 * s2["rays"]
