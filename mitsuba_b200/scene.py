@@ -64,11 +64,44 @@ def fresnel_diffuse_reflectance(eta: float) -> float:
     return float(np.float32((w * f).sum() / (3 * n)))
 
 
+TEX_FILTERS = {"nearest": 0, "bilinear": 1, "trilinear": 2, "ewa": 3}           # bitmap.cpp:213-230
+TEX_WRAP = {"repeat": 0, "clamp": 1, "mirror": 2, "zero": 3, "black": 3, "one": 4, "white": 4}  # bitmap.cpp:324-338
+
+
+@dataclass
+class Texture:
+    """`bitmap` texture plugin instance (src/textures/bitmap.cpp).
+
+    `pixels`: linear float32 image, shape (H, W) (luminance) or (H, W, 3) (RGB), row 0 = top row of the file --
+    what Bitmap::convert(.., EFloat, gamma 1) hands to the MIP map (mipmap.h:225-229); file decoding is the loader's job.
+    """
+    pixels: np.ndarray = None
+    filter_type: str = "ewa"
+    wrap_u: str = "repeat"
+    wrap_v: str = "repeat"
+    max_anisotropy: float = 20.0
+    uoffset: float = 0.0                   # texture.cpp:82-95
+    voffset: float = 0.0
+    uscale: float = 1.0
+    vscale: float = 1.0
+
+    def flat(self) -> dict:
+        px = np.ascontiguousarray(self.pixels, np.float32)
+        if px.ndim == 3 and px.shape[2] == 1:
+            px = px[:, :, 0]
+        if px.ndim not in (2, 3) or (px.ndim == 3 and px.shape[2] != 3):
+            raise ValueError("The input image has an unsupported pixel format!")  # bitmap.cpp:276-278
+        return dict(width=int(px.shape[1]), height=int(px.shape[0]), channels=1 if px.ndim == 2 else 3,
+                    filterType=TEX_FILTERS[self.filter_type.lower()], wrapU=TEX_WRAP[self.wrap_u], wrapV=TEX_WRAP[self.wrap_v],
+                    maxAnisotropy=float(self.max_anisotropy), uoffset=float(self.uoffset), voffset=float(self.voffset),
+                    uscale=float(self.uscale), vscale=float(self.vscale), pixels=np.ascontiguousarray(px))
+
+
 @dataclass
 class Bsdf:
     """One BSDF plugin instance; property names and defaults follow the reference constructors."""
     type: str = "diffuse"
-    reflectance: Sequence[float] = (0.5, 0.5, 0.5)            # diffuse.cpp:75-77
+    reflectance: object = (0.5, 0.5, 0.5)                      # diffuse.cpp:75-77; an RGB triple or a Texture (diffuse only)
     specular_reflectance: Sequence[float] = (1.0, 1.0, 1.0)   # roughconductor.cpp:171-172 etc.
     specular_transmittance: Sequence[float] = (1.0, 1.0, 1.0)  # roughdielectric.cpp:186-187
     distribution: str = "beckmann"                             # microfacet.h:99-100
@@ -97,8 +130,11 @@ class Bsdf:
                  transmittance=tuple(float(x) for x in self.specular_transmittance),
                  etaC=(0.0, 0.0, 0.0), kC=(1.0, 1.0, 1.0), sigmaA=tuple(float(x) for x in self.sigma_a),
                  nested2=-1, diffuseReflectance=tuple(float(x) for x in self.diffuse_reflectance), fdrInt=0.0, fdrExt=0.0,
-                 specSamplingWeight=0.0, nonlinear=int(self.nonlinear))
-        if t == 0:
+                 specSamplingWeight=0.0, nonlinear=int(self.nonlinear), texture=-1)
+        if t == 0 and isinstance(self.reflectance, Texture):
+            d["texture_obj"] = self.reflectance   # resolved to an index by SceneDesc.flat_bsdfs()
+            d["reflectance"] = (0.5, 0.5, 0.5)
+        elif t == 0:
             d["reflectance"] = tuple(float(x) for x in self.reflectance)
         else:
             d["reflectance"] = tuple(float(x) for x in self.specular_reflectance)
@@ -287,11 +323,17 @@ class SceneDesc:
     def flat_bsdfs(self):
         """Flatten the BSDF tree to an array (nested referenced by index); returns (list, per-mesh id)."""
         out, ids, memo = [], [], {}
+        self._textures, tmemo = [], {}
 
         def add(b: Bsdf) -> int:
             if id(b) in memo:
                 return memo[id(b)]
             d = b.flat()
+            tex = d.pop("texture_obj", None)
+            if tex is not None:
+                if id(tex) not in tmemo:
+                    tmemo[id(tex)] = len(self._textures); self._textures.append(tex)
+                d["texture"] = tmemo[id(tex)]
             if b.type == "coating":
                 if b.nested is None:
                     raise ValueError("coating: A child BSDF instance is required")  # coating.cpp:157-158
@@ -315,6 +357,11 @@ class SceneDesc:
                 m.bsdf = b
             ids.append(add(b))
         return out, ids
+
+    def flat_textures(self):
+        """Unique bitmap textures in first-use order (the indices stored in flat_bsdfs()[0][i]["texture"])."""
+        self.flat_bsdfs()
+        return [t.flat() for t in self._textures]
 
     def flat_media(self):
         """Unique media in first-use order; returns (list of Medium, per-mesh (interior id, exterior id))."""
@@ -454,6 +501,40 @@ def material_ball(bsdf: Bsdf, width=1024, height=1024, n_theta=200, n_phi=200) -
     meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0.4, 0.45, 0.6)), name="backdrop"))
     cam = Camera(look_at((0, 2.2, -5.0), (0, 0.9, 0), (0, 1, 0)), fov=35.0, near=0.1, far=100.0,
                  width=width, height=height)
+    return SceneDesc(meshes, cam)
+
+
+def checker_image(w=256, h=256, cells=8, seed=5, rgb=True) -> np.ndarray:
+    """Procedural test image: coloured checkerboard + fine noise (so that filtering matters), linear float32 in [0, 1]."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    chk = (((x * cells) // w + (y * cells) // h) % 2).astype(np.float32)
+    noise = rng.random((h, w)).astype(np.float32)
+    lum = np.clip(0.15 + 0.6 * chk + 0.25 * noise, 0.0, 1.0).astype(np.float32)
+    if not rgb:
+        return lum
+    tint = np.stack([0.5 + 0.5 * x / max(w - 1, 1), 0.5 + 0.5 * y / max(h - 1, 1), np.full((h, w), 0.8)], -1).astype(np.float32)
+    return (lum[:, :, None] * tint).astype(np.float32)
+
+
+def textured_scene(width=512, height=512, filter_type="ewa", tex_res=256, wrap="repeat", n_theta=64, n_phi=128, two_sided=False) -> SceneDesc:
+    """S2 with bitmap textures: a ground quad whose uv run 0..4 (wrap mode visible, grazing angles ->
+    anisotropic EWA footprints), an RGB-textured sphere, a luminance-textured backdrop, one area light."""
+    ground_tex = Texture(checker_image(tex_res, tex_res, 8, 5), filter_type=filter_type, wrap_u=wrap, wrap_v=wrap)
+    ball_tex = Texture(checker_image(tex_res, tex_res // 2, 16, 6), filter_type=filter_type, uscale=2.0, voffset=0.25)
+    back_tex = Texture(checker_image(tex_res // 2 + 3, tex_res // 4 + 1, 4, 7, rgb=False), filter_type=filter_type, wrap_u="mirror", wrap_v="clamp")
+    P, I = _quad([(-8, 0, -8), (-8, 0, 8), (8, 0, 8), (8, 0, -8)], (0, 1, 0))
+    UV = np.array([(0, 0), (0, 4), (4, 4), (4, 0)], np.float32)
+    gb = Bsdf("diffuse", reflectance=ground_tex)
+    meshes = [Mesh(P, I, UV=UV, bsdf=Bsdf("twosided", nested=gb) if two_sided else gb, name="ground")]
+    P, N, UV, I = uv_sphere((0, 1.0, 0), 1.0, n_theta, n_phi, smooth=True, with_uv=True)
+    meshes.append(Mesh(P, I, N=N, UV=UV, bsdf=Bsdf("diffuse", reflectance=ball_tex), name="ball"))
+    P, I = _quad([(-1.5, 4.0, -1.5), (-1.5, 4.0, 1.5), (1.5, 4.0, 1.5), (1.5, 4.0, -1.5)], (0, -1, 0))
+    meshes.append(Mesh(P, I, bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(20.0, 20.0, 20.0), name="light"))
+    P, I = _quad([(-8, 0, 8), (-8, 8, 8), (8, 8, 8), (8, 0, 8)], (0, 0, -1))
+    UV = np.array([(-0.5, 1.5), (-0.5, -0.5), (1.5, -0.5), (1.5, 1.5)], np.float32)[[0, 1, 2, 3]]
+    meshes.append(Mesh(P, I, UV=UV, bsdf=Bsdf("diffuse", reflectance=back_tex), name="backdrop"))
+    cam = Camera(look_at((0, 2.2, -5.0), (0, 0.9, 0), (0, 1, 0)), fov=35.0, near=0.1, far=100.0, width=width, height=height)
     return SceneDesc(meshes, cam)
 
 

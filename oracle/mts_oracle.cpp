@@ -51,7 +51,7 @@ namespace {
 struct Mesh {
     std::vector<V3> P, N; std::vector<float> UV; /* UV: 2 per vertex */
     std::vector<uint32_t> idx; /* 3 per triangle */
-    std::vector<V3> dpdu;      /* per triangle, only if UVs exist (trimesh.cpp:683-735) */
+    std::vector<V3> dpdu, dpdv; /* per triangle, only if UVs exist (trimesh.cpp:683-735) */
     std::vector<uint8_t> hasTangent;
     int bsdf = -1; int emitter = -1;
     int interior = -1, exterior = -1; /* shape.h:427-435 media ids (-1 = vacuum) */
@@ -99,9 +99,11 @@ struct Discrete {
 struct Emitter { V3 radiance; float samplingWeight; int mesh; /* -1: `constant` environment emitter (src/emitters/constant.cpp) */ };
 
 struct Intersection { /* include/mitsuba/render/shape.h:131-171 (fields `path` reads) */
-    float t = kInf; V3 p; Frame geoFrame, shFrame; V3 wi; V3 dpdu; int mesh = -1; uint32_t prim = 0; int instance = -1;
+    float t = kInf; V3 p; Frame geoFrame, shFrame; V3 wi; V3 dpdu, dpdv; int mesh = -1; uint32_t prim = 0; int instance = -1;
+    TexCtx tex; /* uv, hasUVPartials, dudx.. (shape.h:147-165) in the form the BSDFs' texture look-up takes them */
     bool isValid() const { return t != kInf; }
 };
+struct RayDiff { bool has = false; V3 rxO, ryO, rxD, ryD; }; /* include/mitsuba/core/ray.h:120-176 */
 
 struct DRec { /* include/mitsuba/render/common.h:85-123,241-255 */
     V3 p, n, ref, refN, d; float pdf = 0, dist = 0; int emitter = -1; bool solidAngle = true;
@@ -109,6 +111,7 @@ struct DRec { /* include/mitsuba/render/common.h:85-123,241-255 */
 
 struct Scene {
     std::vector<OrcBsdf> bsdfs;
+    std::vector<Texture> textures; /* `bitmap` textures (orc_texture.h) referenced by OrcBsdf::texture */
     std::vector<Mesh> meshes;
     std::vector<Emitter> emitters;
     std::vector<OrcMedium> media;
@@ -147,9 +150,9 @@ struct Scene {
                 if (m.group < 0) primMesh.push_back((uint32_t) mi);
             }
             /* trimesh.cpp:683-735 computeUVTangents (called unconditionally at :385) */
-            m.dpdu.clear(); m.hasTangent.clear();
+            m.dpdu.clear(); m.dpdv.clear(); m.hasTangent.clear();
             if (!m.UV.empty()) {
-                m.dpdu.resize(m.nTri()); m.hasTangent.assign(m.nTri(), 1);
+                m.dpdu.resize(m.nTri()); m.dpdv.resize(m.nTri()); m.hasTangent.assign(m.nTri(), 1);
                 for (uint32_t j = 0; j < m.nTri(); ++j) {
                     uint32_t i0 = m.idx[3 * j], i1 = m.idx[3 * j + 1], i2 = m.idx[3 * j + 2];
                     V3 dP1 = m.P[i1] - m.P[i0], dP2 = m.P[i2] - m.P[i0];
@@ -157,13 +160,14 @@ struct Scene {
                     float du2 = m.UV[2 * i2] - m.UV[2 * i0], dv2 = m.UV[2 * i2 + 1] - m.UV[2 * i0 + 1];
                     V3 n = cross(dP1, dP2);
                     float length = n.length();
-                    if (length == 0) { m.dpdu[j] = V3(0.0f); continue; } /* memset-zero tangent, :695 */
+                    if (length == 0) { m.dpdu[j] = V3(0.0f); m.dpdv[j] = V3(0.0f); continue; } /* memset-zero tangent, :695 */
                     float determinant = du1 * dv2 - dv1 * du2;
                     if (determinant == 0) {
-                        V3 a, b; coordinateSystem(n / length, a, b); m.dpdu[j] = a;
+                        V3 a, b; coordinateSystem(n / length, a, b); m.dpdu[j] = a; m.dpdv[j] = b;
                     } else {
                         float invDet = 1.0f / determinant;
                         m.dpdu[j] = (dv2 * dP1 - dv1 * dP2) * invDet;
+                        m.dpdv[j] = (-du2 * dP1 + du1 * dP2) * invDet;
                     }
                 }
             }
@@ -245,7 +249,13 @@ struct Scene {
         V3 faceNormal(cross(side1, side2));
         float length = faceNormal.length();
         if (!faceNormal.isZero()) faceNormal /= length;
-        if (!m.dpdu.empty()) its.dpdu = m.dpdu[pi]; else its.dpdu = side1;
+        if (!m.dpdu.empty()) { its.dpdu = m.dpdu[pi]; its.dpdv = m.dpdv[pi]; } else { its.dpdu = side1; its.dpdv = side2; }
+        its.tex = TexCtx();
+        its.tex.textures = textures.data();
+        if (!m.UV.empty()) { /* skdtree.h:398-405 */
+            its.tex.u = m.UV[2 * i0] * b.x + m.UV[2 * i1] * b.y + m.UV[2 * i2] * b.z;
+            its.tex.v = m.UV[2 * i0 + 1] * b.x + m.UV[2 * i1 + 1] * b.y + m.UV[2 * i2 + 1] * b.z;
+        } else { its.tex.u = b.y; its.tex.v = b.z; }
         if (!m.N.empty()) {
             const V3 &n0 = m.N[i0], &n1 = m.N[i1], &n2 = m.N[i2];
             its.shFrame.n = normalize(n0 * b.x + n1 * b.y + n2 * b.z);
@@ -259,6 +269,7 @@ struct Scene {
             its.shFrame.n = normalize(xfNormal(in.Minv, its.shFrame.n));
             its.geoFrame = Frame(normalize(xfNormal(in.Minv, its.geoFrame.n)));
             its.dpdu = xfVector(in.M, its.dpdu);
+            its.dpdv = xfVector(in.M, its.dpdv);
             its.p = xfPoint(in.M, its.p);
         }
         computeShadingFrame(its.shFrame.n, its.dpdu, its.shFrame);
@@ -423,6 +434,40 @@ struct Scene {
         return pdfDirect * (em.samplingWeight * emitterPDF.normalization);
     }
 
+    /* Intersection::computePartials, src/librender/intersection.cpp:23-85; called through Intersection::getBSDF(ray)
+       (records.inl:69-75) when the BSDF uses ray differentials */
+    static void computePartials(Intersection &its, const Ray &ray, const RayDiff &rd) {
+        TexCtx &t = its.tex;
+        if (t.hasUVPartials || !rd.has) return;
+        t.hasUVPartials = true;
+        if (its.dpdu.isZero() && its.dpdv.isZero()) { t.dudx = t.dvdx = t.dudy = t.dvdy = 0.0f; return; }
+        const V3 &n = its.geoFrame.n;
+        const float pp = dot(n, its.p), pox = dot(n, rd.rxO), poy = dot(n, rd.ryO), prx = dot(n, rd.rxD), pry = dot(n, rd.ryD);
+        if (prx == 0 || pry == 0) { t.dudx = t.dvdx = t.dudy = t.dvdy = 0.0f; return; }
+        const float tx = (pp - pox) / prx, ty = (pp - poy) / pry;
+        const float absX = std::abs(n.x), absY = std::abs(n.y), absZ = std::abs(n.z);
+        int axes[2];
+        if (absX > absY && absX > absZ) { axes[0] = 1; axes[1] = 2; }
+        else if (absY > absZ) { axes[0] = 0; axes[1] = 2; }
+        else { axes[0] = 0; axes[1] = 1; }
+        float A[2][2], Bx[2], By[2], x[2];
+        A[0][0] = its.dpdu[axes[0]]; A[0][1] = its.dpdv[axes[0]];
+        A[1][0] = its.dpdu[axes[1]]; A[1][1] = its.dpdv[axes[1]];
+        const V3 px = rd.rxO + rd.rxD * tx, py = rd.ryO + rd.ryD * ty;
+        Bx[0] = px[axes[0]] - its.p[axes[0]]; Bx[1] = px[axes[1]] - its.p[axes[1]];
+        By[0] = py[axes[0]] - its.p[axes[0]]; By[1] = py[axes[1]] - its.p[axes[1]];
+        if (solveLinearSystem2x2(A, Bx, x)) { t.dudx = x[0]; t.dvdx = x[1]; } else { t.dudx = 1; t.dvdx = 0; }
+        if (solveLinearSystem2x2(A, By, x)) { t.dudy = x[0]; t.dvdy = x[1]; } else { t.dudy = 1; /* sic: `dudy = 0; dudy = 1;`, dvdy stays as it was (0 here) */ }
+    }
+    static bool solveLinearSystem2x2(const float a[2][2], const float b[2], float x[2]) { /* src/libcore/util.cpp:527-539 */
+        const float det = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+        if (std::abs(det) <= 2.93873587705571876e-39f) return false; /* RCPOVERFLOW_FLT */
+        const float inverse = 1.0f / det;
+        x[0] = (a[1][1] * b[0] - a[0][1] * b[1]) * inverse;
+        x[1] = (a[0][0] * b[1] - a[1][0] * b[0]) * inverse;
+        return true;
+    }
+
     static float miWeight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); }
 
     bool rayIntersect(const Ray &ray, Intersection &its, OrcStats &st) const {
@@ -438,10 +483,12 @@ struct Scene {
     }
 
     /* path.cpp:119-294.  `alpha` mirrors RadianceQueryRecord::rayIntersect (records.inl:117-144). */
-    Spectrum Li(const Ray &r, Sampler *sampler, const OrcRenderParams &rp, float &alpha, OrcStats &st) const {
+    Spectrum Li(const Ray &r, Sampler *sampler, const OrcRenderParams &rp, float &alpha, OrcStats &st, const RayDiff *sensorDiff = nullptr) const {
         BsdfSet bs{bsdfs.data(), (int) bsdfs.size()};
         Intersection its;
         Ray ray(r);
+        RayDiff rayDiff; /* RayDifferential ray(r), path.cpp:122; plain Rays assigned later carry no differentials (ray.h:150-157) */
+        if (sensorDiff) rayDiff = *sensorDiff;
         Spectrum Li(0.0f);
         bool scattered = false;
         int depth = 1;                          /* newQuery: depth = 1 (integrator.h:221-227) */
@@ -465,6 +512,7 @@ struct Scene {
                 (rp.strictNormals && dot(ray.d, its.geoFrame.n) * Frame::cosTheta(its.wi) >= 0))
                 break;
             const uint32_t btype = bs.type(bsdf);
+            if (bs.usesRayDifferentials(bsdf)) computePartials(its, ray, rayDiff); /* its.getBSDF(ray), path.cpp:162 */
             /* DirectSamplingRecord(its): records.inl:156-164 */
             DRec dRec;
             dRec.ref = its.p; dRec.refN = V3(0.0f);
@@ -473,7 +521,7 @@ struct Scene {
                 float sx, sy; sampler->next2D(sx, sy);
                 Spectrum value = sampleEmitterDirect(dRec, sx, sy, st);
                 if (!value.isZero()) {
-                    BRec bRec; bRec.wi = its.wi; bRec.wo = its.shFrame.toLocal(dRec.d); bRec.sampler = sampler;
+                    BRec bRec; bRec.wi = its.wi; bRec.wo = its.shFrame.toLocal(dRec.d); bRec.sampler = sampler; bRec.its = &its.tex;
                     const Spectrum bsdfVal = bs.eval(bsdf, bRec);
                     if (!bsdfVal.isZero() && (!rp.strictNormals || dot(its.geoFrame.n, dRec.d) * Frame::cosTheta(bRec.wo) > 0)) {
                         float bsdfPdf = bs.pdf(bsdf, bRec); /* area emitter: onSurface && solid angle */
@@ -486,7 +534,7 @@ struct Scene {
                    empty PMF is undefined there -- not a supported configuration */
             }
             float bsdfPdf;
-            BRec bRec; bRec.wi = its.wi; bRec.sampler = sampler;
+            BRec bRec; bRec.wi = its.wi; bRec.sampler = sampler; bRec.its = &its.tex;
             float sx, sy; sampler->next2D(sx, sy);
             Spectrum bsdfWeight = bs.sample(bsdf, bRec, bsdfPdf, sx, sy);
             if (bsdfWeight.isZero()) break;
@@ -497,6 +545,7 @@ struct Scene {
             bool hitEmitter = false;
             Spectrum value;
             ray = Ray(its.p, wo);
+            rayDiff.has = false;
             if (rayIntersect(ray, its, st)) {
                 const Mesh &m2 = meshes[its.mesh];
                 if (m2.emitter >= 0) {
@@ -775,16 +824,38 @@ struct Scene {
         return Li;
     }
 
-    /* perspective.cpp:271-298 (ray part only; differentials unused by constant textures) */
-    Ray sampleRay(float sxp, float syp, float apx = 0.5f, float apy = 0.5f) const {
+    V3 sampleToCameraPoint(float px, float py, float pz) const { /* Transform::operator()(Point), transform.h:108-125 */
         const float *M = sampleToCamera;
-        float px = sxp * (1.0f / (float) W), py = syp * (1.0f / (float) H), pz = 0.0f; /* m_invResolution, sensor.cpp:104-107 */
         float x = M[0] * px + M[1] * py + M[2] * pz + M[3];
         float y = M[4] * px + M[5] * py + M[6] * pz + M[7];
         float z = M[8] * px + M[9] * py + M[10] * pz + M[11];
         float w = M[12] * px + M[13] * py + M[14] * pz + M[15];
-        V3 nearP(x, y, z);
-        if (w != 1.0f) nearP = nearP / w;       /* transform.h:108-125 */
+        V3 r(x, y, z);
+        if (w != 1.0f) r = r / w;
+        return r;
+    }
+    V3 camVectorToWorld(const V3 &d) const {
+        const float *T = camToWorld;
+        return V3(T[0] * d.x + T[1] * d.y + T[2] * d.z, T[4] * d.x + T[5] * d.y + T[6] * d.z, T[8] * d.x + T[9] * d.y + T[10] * d.z);
+    }
+    /* perspective.cpp:271-298 / thinlens.cpp:324-361 sampleRayDifferential; `diff` (optional) receives the offset rays, already
+       scaled by diffScale = 1/sqrt(sampleCount) as SamplingIntegrator::renderBlock does (integrator.cpp:144-145,181; ray.h:163-168) */
+    Ray sampleRay(float sxp, float syp, float apx = 0.5f, float apy = 0.5f, RayDiff *diff = nullptr, float diffScale = 1.0f) const {
+        const float invResX = 1.0f / (float) W, invResY = 1.0f / (float) H; /* m_invResolution, sensor.cpp:104-107 */
+        const V3 nearP = sampleToCameraPoint(sxp * invResX, syp * invResY, 0.0f);
+        V3 dx, dy; /* m_dx, m_dy: perspective.cpp:160-163 */
+        if (diff) {
+            const V3 zero = sampleToCameraPoint(0.0f, 0.0f, 0.0f);
+            dx = sampleToCameraPoint(invResX, 0.0f, 0.0f) - zero;
+            dy = sampleToCameraPoint(0.0f, invResY, 0.0f) - zero;
+        }
+        auto finish = [&](const V3 &o, const V3 &d, const V3 &rxd, const V3 &ryd) {
+            if (!diff) return;
+            diff->has = true;
+            diff->rxO = o; diff->ryO = o; /* rxOrigin = ryOrigin = ray.o */
+            diff->rxD = d + (rxd - d) * diffScale;
+            diff->ryD = d + (ryd - d) * diffScale;
+        };
         if (apertureRadius > 0) { /* thinlens.cpp:327-350 */
             float tx, ty;
             squareToUniformDiskConcentric(apx, apy, tx, ty);
@@ -796,12 +867,17 @@ struct Scene {
             const float *T = camToWorld;
             V3 ow(T[0] * tx + T[1] * ty + T[2] * 0.0f + T[3], T[4] * tx + T[5] * ty + T[6] * 0.0f + T[7], T[8] * tx + T[9] * ty + T[10] * 0.0f + T[11]);
             V3 dw(T[0] * d.x + T[1] * d.y + T[2] * d.z, T[4] * d.x + T[5] * d.y + T[6] * d.z, T[8] * d.x + T[9] * d.y + T[10] * d.z);
+            if (diff) { /* thinlens.cpp:341-357 */
+                const float fDist = focusDistance / nearP.z;
+                const V3 focusPx = (nearP + dx) * fDist, focusPy = (nearP + dy) * fDist;
+                finish(ow, dw, camVectorToWorld(normalize(focusPx - apertureP)), camVectorToWorld(normalize(focusPy - apertureP)));
+            }
             return Ray(ow, dw, nearClip * invZ, farClip * invZ);
         }
         V3 d = normalize(nearP);
         float invZ = 1.0f / d.z;
-        const float *T = camToWorld;
-        V3 dw(T[0] * d.x + T[1] * d.y + T[2] * d.z, T[4] * d.x + T[5] * d.y + T[6] * d.z, T[8] * d.x + T[9] * d.y + T[10] * d.z);
+        const V3 dw = camVectorToWorld(d);
+        if (diff) finish(camOrigin, dw, camVectorToWorld(normalize(nearP + dx)), camVectorToWorld(normalize(nearP + dy))); /* perspective.cpp:291-295 */
         return Ray(camOrigin, dw, nearClip * invZ, farClip * invZ);
     }
 };
@@ -1029,6 +1105,49 @@ void orc_intersect_full(void *s, uint64_t n, const float *rays, float *out) {
     }
 }
 
+/* ---- bitmap textures (orc_texture.h) ---- */
+int orc_add_texture(void *s, const OrcTextureDesc *d, const float *pixels) {
+    Scene *sc = (Scene *) s;
+    sc->textures.emplace_back();
+    sc->textures.back().build(*d, pixels);
+    return (int) sc->textures.size() - 1;
+}
+/* out: levels, then (w, h) per level */
+void orc_texture_info(void *s, int tex, int32_t *out, float *maximum, float *bsdfScale) {
+    const Texture &t = ((Scene *) s)->textures[tex];
+    out[0] = t.levels;
+    for (int l = 0; l < t.levels; ++l) { out[1 + 2 * l] = t.lw[l]; out[2 + 2 * l] = t.lh[l]; }
+    *maximum = t.maximum; *bsdfScale = t.bsdfScale;
+}
+void orc_texture_level(void *s, int tex, int level, float *out) {
+    const Texture &t = ((Scene *) s)->textures[tex];
+    memcpy(out, t.pyramid[level].data(), t.pyramid[level].size() * sizeof(float));
+}
+/* Texture2D::eval for n look-ups: uv (2n), partials (4n: dudx dudy dvdx dvdy) or NULL for the unfiltered path; out rgb (3n) */
+void orc_texture_eval(void *s, int tex, uint64_t n, const float *uv, const float *partials, float *out) {
+    const Texture &t = ((Scene *) s)->textures[tex];
+    for (uint64_t i = 0; i < n; ++i) {
+        const V3 r = partials ? t.eval(uv[2 * i], uv[2 * i + 1], true, partials[4 * i], partials[4 * i + 1], partials[4 * i + 2], partials[4 * i + 3])
+                              : t.eval(uv[2 * i], uv[2 * i + 1], false, 0, 0, 0, 0);
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    }
+}
+/* primary-ray intersections with uv partials (sampleRayDifferential + scaleDifferential + computePartials):
+   pos (2n) -> out 8n: valid, u, v, dudx, dudy, dvdx, dvdy, mesh */
+void orc_primary_partials(void *s, uint64_t n, const float *pos, int spp, float *out) {
+    Scene *sc = (Scene *) s; OrcStats st{};
+    const float scale = 1.0f / std::sqrt((float) spp);
+    for (uint64_t i = 0; i < n; ++i) {
+        RayDiff rd;
+        Ray r = sc->sampleRay(pos[2 * i], pos[2 * i + 1], 0.5f, 0.5f, &rd, scale);
+        Intersection its; float *o = out + 8 * i; memset(o, 0, 32);
+        if (sc->rayIntersect(r, its, st)) {
+            Scene::computePartials(its, r, rd);
+            o[0] = 1; o[1] = its.tex.u; o[2] = its.tex.v; o[3] = its.tex.dudx; o[4] = its.tex.dudy; o[5] = its.tex.dvdx; o[6] = its.tex.dvdy; o[7] = (float) its.mesh;
+        }
+    }
+}
+
 /* ---- render ---- */
 static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcStats *stats,
                         float *perSample /* optional: W*H*(hi-lo)*4 floats Li.rgb, alpha */) {
@@ -1042,6 +1161,8 @@ static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcSt
     std::vector<std::unique_ptr<ImageBlock>> blocks(nBlocks);
     std::atomic<int> next(0);
     std::vector<OrcStats> tstats(nThreads);
+    const bool useDiff = !sc->textures.empty();
+    const float diffScaleFactor = 1.0f / std::sqrt((float) rp->spp); /* integrator.cpp:144-145 */
     auto worker = [&](int tid) {
         OrcStats st{};
         std::unique_ptr<Sampler> sampler;
@@ -1065,9 +1186,10 @@ static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcSt
                         float spx = (float) x + ax, spy = (float) y + ay;
                         float apx = 0.5f, apy = 0.5f;
                         if (sc->apertureRadius > 0) sampler->next2D(apx, apy); /* needsApertureSample, integrator.cpp:173-174 */
-                        Ray ray = sc->sampleRay(spx, spy, apx, apy);
+                        RayDiff rd;
+                        Ray ray = sc->sampleRay(spx, spy, apx, apy, useDiff ? &rd : nullptr, diffScaleFactor);
                         float alpha;
-                        Spectrum spec = rp->integrator == 1 ? sc->LiVol(ray, sampler.get(), *rp, alpha, st) : sc->Li(ray, sampler.get(), *rp, alpha, st); /* sensor weight = 1 */
+                        Spectrum spec = rp->integrator == 1 ? sc->LiVol(ray, sampler.get(), *rp, alpha, st) : sc->Li(ray, sampler.get(), *rp, alpha, st, useDiff ? &rd : nullptr); /* sensor weight = 1 */
                         if (!blk->put(spx, spy, spec, alpha)) ++st.badSamples;
                         if (perSample) {
                             float *o = perSample + (((size_t) y * W + x) * (size_t) (hi - lo) + (size_t) (j - lo)) * 4;

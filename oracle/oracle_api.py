@@ -22,7 +22,14 @@ class OrcBsdf(C.Structure):
                 ("alphaU", C.c_float), ("alphaV", C.c_float), ("eta", C.c_float), ("thickness", C.c_float),
                 ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3), ("etaC", C.c_float * 3),
                 ("kC", C.c_float * 3), ("sigmaA", C.c_float * 3), ("nested2", C.c_int32), ("diffuseReflectance", C.c_float * 3),
-                ("fdrInt", C.c_float), ("fdrExt", C.c_float), ("specSamplingWeight", C.c_float), ("nonlinear", C.c_int32)]
+                ("fdrInt", C.c_float), ("fdrExt", C.c_float), ("specSamplingWeight", C.c_float), ("nonlinear", C.c_int32),
+                ("texture", C.c_int32)]
+
+
+class OrcTextureDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32), ("filterType", C.c_int32),
+                ("wrapU", C.c_int32), ("wrapV", C.c_int32), ("maxAnisotropy", C.c_float), ("uoffset", C.c_float),
+                ("voffset", C.c_float), ("uscale", C.c_float), ("vscale", C.c_float)]
 
 
 class OrcRenderParams(C.Structure):
@@ -64,6 +71,7 @@ def lib():
         L.orc_add_bsdf.restype = C.c_int
         L.orc_add_mesh.restype = C.c_int
         L.orc_add_medium.restype = C.c_int
+        L.orc_add_texture.restype = C.c_int
         L.orc_tea.restype = C.c_uint64
         L.orc_bsdf_type.restype = C.c_uint32
         L.orc_hardware_threads.restype = C.c_int
@@ -97,7 +105,15 @@ def make_bsdf_array(flat_list):
             for j in range(3):
                 getattr(b, k)[j] = d[k][j]
         b.nested2, b.fdrInt, b.fdrExt, b.specSamplingWeight, b.nonlinear = d["nested2"], d["fdrInt"], d["fdrExt"], d["specSamplingWeight"], d["nonlinear"]
+        b.texture = d.get("texture", -1)
     return arr
+
+
+def make_texture_desc(d):
+    t = OrcTextureDesc()
+    for k, _ in OrcTextureDesc._fields_:
+        setattr(t, k, d[k])
+    return t
 
 
 def instance_matrices(to_world):
@@ -154,6 +170,9 @@ class OracleScene:
         arr = make_bsdf_array(flat)
         for i in range(len(flat)):
             L.orc_add_bsdf(self.h, C.byref(arr[i]))
+        self.flat_textures = desc.flat_textures() if hasattr(desc, "flat_textures") else []
+        for d in self.flat_textures:
+            L.orc_add_texture(self.h, C.byref(make_texture_desc(d)), _p(d["pixels"]))
         for _ in range(desc.n_groups() if hasattr(desc, "n_groups") else 0):
             L.orc_add_shapegroup(self.h)
         for m, bid in zip(desc.meshes, ids):
@@ -227,6 +246,37 @@ class OracleScene:
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         out = np.zeros((len(rays), 24), np.float32)
         self.L.orc_intersect_full(self.h, C.c_uint64(len(rays)), _p(rays), _p(out))
+        return out
+
+    # ---- bitmap textures (orc_texture.h) ----
+    def texture_info(self, tex):
+        out = np.zeros(1 + 2 * 32, np.int32)
+        mx, sc = C.c_float(), C.c_float()
+        self.L.orc_texture_info(self.h, C.c_int(tex), _p(out, C.c_int32), C.byref(mx), C.byref(sc))
+        n = int(out[0])
+        return dict(levels=n, sizes=[(int(out[1 + 2 * l]), int(out[2 + 2 * l])) for l in range(n)], maximum=mx.value, bsdf_scale=sc.value)
+
+    def texture_level(self, tex, level):
+        info = self.texture_info(tex)
+        w, h = info["sizes"][level]
+        ch = self.flat_textures[tex]["channels"]
+        out = np.zeros((h, w, ch), np.float32)
+        self.L.orc_texture_level(self.h, C.c_int(tex), C.c_int(level), _p(out))
+        return out
+
+    def texture_eval(self, tex, uv, partials=None):
+        """Texture2D::eval: uv (n,2); partials (n,4) = dudx, dudy, dvdx, dvdy for the filtered look-up or None."""
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        pt = np.ascontiguousarray(partials, np.float32).reshape(-1, 4) if partials is not None else None
+        out = np.zeros((len(uv), 3), np.float32)
+        self.L.orc_texture_eval(self.h, C.c_int(tex), C.c_uint64(len(uv)), _p(uv), _p(pt), _p(out))
+        return out
+
+    def primary_partials(self, pos, spp):
+        """(n,8): valid, u, v, dudx, dudy, dvdx, dvdy, mesh for camera rays through film positions `pos`."""
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 2)
+        out = np.zeros((len(pos), 8), np.float32)
+        self.L.orc_primary_partials(self.h, C.c_uint64(len(pos)), _p(pos), C.c_int(spp), _p(out))
         return out
 
     def sample_emitter_direct(self, ref, samples):

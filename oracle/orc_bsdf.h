@@ -7,6 +7,7 @@
 #pragma once
 #include "orc_math.h"
 #include "orc_sampler.h"
+#include "orc_texture.h"
 
 extern "C" {
 /* plain-C description of one BSDF node; `nested` indexes the same array (coating only) */
@@ -28,6 +29,7 @@ typedef struct OrcBsdf {
     float fdrInt, fdrExt;  /* plastic.cpp:194-195 fresnelDiffuseReflectance(1/eta), (eta), integrated on the host */
     float specSamplingWeight;    /* plastic.cpp:199-202 */
     int32_t nonlinear;     /* plastic.cpp:161 */
+    int32_t texture;       /* diffuse: index of a `bitmap` texture that replaces `reflectance` (src/textures/bitmap.cpp), -1 = constant */
 } OrcBsdf;
 }
 
@@ -232,8 +234,12 @@ struct Microfacet {
 
 /* BSDFSamplingRecord (include/mitsuba/render/bsdf.h:123-192) restricted to what `path` sets:
  * typeMask = EAll, component = -1, mode = ERadiance. */
+struct TexCtx { /* what `m_reflectance->eval(bRec.its)` reads of the intersection: uv and, once computePartials() ran, the uv partials */
+    const Texture *textures = nullptr;
+    float u = 0, v = 0; bool hasUVPartials = false; float dudx = 0, dudy = 0, dvdx = 0, dvdy = 0;
+};
 struct BRec {
-    V3 wi, wo; float eta = 1; uint32_t sampledType = 0; Sampler *sampler = nullptr;
+    V3 wi, wo; float eta = 1; uint32_t sampledType = 0; Sampler *sampler = nullptr; const TexCtx *its = nullptr;
 };
 
 struct BsdfSet {
@@ -244,7 +250,8 @@ struct BsdfSet {
     uint32_t type(int id) const {
         const OrcBsdf &d = b[id];
         switch (d.type) {
-            case 0: return (std::max(std::max(d.reflectance[0], d.reflectance[1]), d.reflectance[2]) > 0) ? (EDiffuseReflection | EFrontSide) : 0; /* diffuse.cpp:98-103 */
+            case 0: if (d.texture >= 0) return EDiffuseReflection | EFrontSide | ESpatiallyVarying; /* a texture that is not all black */
+                    return (std::max(std::max(d.reflectance[0], d.reflectance[1]), d.reflectance[2]) > 0) ? (EDiffuseReflection | EFrontSide) : 0; /* diffuse.cpp:98-103 */
             case 1: return EGlossyReflection | EFrontSide | (d.alphaU != d.alphaV ? EAnisotropic : 0);                  /* roughconductor.cpp:229-238 */
             case 2: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide | EUsesSampler | ENonSymmetric | (d.alphaU != d.alphaV ? EAnisotropic : 0); /* roughdielectric.cpp:240-255 */
             case 4: return ENull | EFrontSide | EBackSide;                                                              /* null.cpp:38-43 */
@@ -256,9 +263,26 @@ struct BsdfSet {
         }
     }
 
+    /* m_reflectance->eval(bRec.its): constant, or the bitmap texture at the intersection (diffuse.cpp:115,148) */
+    static V3 reflectance(const OrcBsdf &d, const BRec &r) {
+        if (d.type == 0 && d.texture >= 0 && r.its) {
+            const TexCtx &t = *r.its;
+            return t.textures[d.texture].eval(t.u, t.v, t.hasUVPartials, t.dudx, t.dudy, t.dvdx, t.dvdy);
+        }
+        return V3(d.reflectance[0], d.reflectance[1], d.reflectance[2]);
+    }
+    /* BSDF::usesRayDifferentials(): diffuse.cpp:101, twosided.cpp:91-92; the other plugins take constants here */
+    bool usesRayDifferentials(int id) const {
+        const OrcBsdf &d = b[id];
+        if (d.type == 0) return d.texture >= 0;
+        if (d.type == 5) return usesRayDifferentials(d.nested) || usesRayDifferentials(d.nested2);
+        if (d.type == 3) return usesRayDifferentials(d.nested); /* coating.cpp:172-174 */
+        return false;
+    }
+
     Spectrum eval(int id, const BRec &r, bool discrete = false) const {
         const OrcBsdf &d = b[id];
-        const V3 R(d.reflectance[0], d.reflectance[1], d.reflectance[2]);
+        const V3 R = reflectance(d, r);
         switch (d.type) {
         case 0: { /* diffuse.cpp:110-118 */
             if (discrete || type(id) == 0 || Frame::cosTheta(r.wi) <= 0 || Frame::cosTheta(r.wo) <= 0) return Spectrum(0.0f);
@@ -475,7 +499,7 @@ struct BsdfSet {
     /* sample(bRec, pdf, sample): returns weight = f*cos/pdf; r.wo, r.eta, r.sampledType set */
     Spectrum sample(int id, BRec &r, float &pdfOut, float sx, float sy) const {
         const OrcBsdf &d = b[id];
-        const V3 R(d.reflectance[0], d.reflectance[1], d.reflectance[2]);
+        const V3 R = reflectance(d, r);
         switch (d.type) {
         case 0: { /* diffuse.cpp:141-150 */
             if (type(id) == 0 || Frame::cosTheta(r.wi) <= 0) return Spectrum(0.0f);
