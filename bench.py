@@ -179,6 +179,35 @@ def volpath_metric(ctx, with_cpu=True):
     return res
 
 
+def textured_metric(ctx, with_cpu=True):
+    """SURVEY.md 8f-4, reported next to the headline: the textured material-ball scene (three `bitmap` textures of 1024^2 texels, EWA
+    filtering through ray differentials on camera hits, bilinear on the bounces), `path`, 1024x1024 @ 64 spp on this rank's GPU, plus
+    the oracle's rate for the same scene on the host cores (bounded sample)."""
+    from mitsuba_b200 import api
+    from mitsuba_b200.scene import RenderParams, textured_scene
+    mk = lambda: textured_scene(1024, 1024, filter_type="ewa", tex_res=1024, n_theta=200, n_phi=200)
+    sc = api.Scene(ctx, mk())
+    rp = RenderParams(spp=64, rfilter="gaussian", sampler="sobol")
+    sc.render(RenderParams(spp=4, rfilter="gaussian", sampler="sobol"))
+    best = None
+    for _ in range(2):
+        _, st = sc.render(rp, flags=4)
+        if best is None or st["ms_total"] < best["ms_total"]:
+            best = st
+    n = 1024 * 1024 * 64
+    res = {"workload": "S2 material ball, 3 bitmap textures (1024^2, ewa, maxAnisotropy 20), ~80k triangles, path, sobol, gaussian filter, 1024x1024 @ 64 spp, 1 GPU",
+           "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"], "kernel": "k_shade<-1, false, TEX>", "kernel_ms": best["ms_shade"],
+           "mean_path_length": best["path_length_sum"] / best["samples"]}
+    sc.close()
+    if with_cpu:
+        from oracle import oracle_api as O
+        o = O.OracleScene(mk())
+        t0 = time.time(); _, so = o.render(RenderParams(spp=4, rfilter="gaussian", sampler="sobol")); dt = time.time() - t0
+        res["cpu_baseline"] = {"value": so["samples"] / dt / 1e6, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "sample indices [0,4) of every pixel of the same scene"}
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -370,6 +399,10 @@ def main():
             line["traversal"] = traversal_metric(ctx, peaks.get("hbm_gbs", 6650.0))
         if not args.no_volpath:
             line["volpath"] = volpath_metric(ctx, with_cpu=not args.no_cpu_baseline)
+            try:
+                line["textured"] = textured_metric(ctx, with_cpu=not args.no_cpu_baseline)
+            except Exception as e:  # a side measurement must not take the headline line down with it
+                line["textured"] = {"error": str(e)}
         if not args.no_cpu_baseline:
             cb = cpu_reference_run(1, 0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

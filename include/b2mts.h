@@ -53,7 +53,24 @@ typedef struct b2_material_desc {
     float fdr_int, fdr_ext;  /* plastic.cpp:194-195: fresnelDiffuseReflectance(1/eta), (eta) */
     float spec_sampling_weight; /* plastic.cpp:199-202 */
     int32_t nonlinear;       /* plastic.cpp:161 */
+    int32_t reflectance_texture; /* diffuse only: 0 = `reflectance` is the constant above; k > 0 = the bitmap texture with id k - 1
+                                    (b2_scene_add_texture) is bound to `reflectance` (diffuse.cpp:75-77,115,148) */
 } b2_material_desc;
+
+/* `bitmap` texture plugin (src/textures/bitmap.cpp): the decoded image as linear float (what
+ * Bitmap::convert(.., EFloat, gamma 1) hands to the MIP map, mipmap.h:225-229), 1 (luminance) or 3 (RGB) channels, row-major,
+ * first row = top of the file.  The MIP pyramid (Lanczos-2, mipmap.h:155-303) is built by b2_scene_commit. */
+enum { B2_TEX_NEAREST = 0, B2_TEX_BILINEAR = 1, B2_TEX_TRILINEAR = 2, B2_TEX_EWA = 3 };                     /* bitmap.cpp:213-230 */
+enum { B2_WRAP_REPEAT = 0, B2_WRAP_CLAMP = 1, B2_WRAP_MIRROR = 2, B2_WRAP_ZERO = 3, B2_WRAP_ONE = 4 };        /* bitmap.cpp:324-338 */
+typedef struct b2_texture_desc {
+    int32_t width, height, channels;
+    int32_t filter_type;       /* B2_TEX_*, plugin default ewa */
+    int32_t wrap_u, wrap_v;    /* B2_WRAP_*, plugin default repeat */
+    float max_anisotropy;      /* bitmap.cpp:232-235 (plugin default 20; ignored unless ewa) */
+    float uoffset, voffset, uscale, vscale; /* texture.cpp:82-95 (plugin defaults 0, 0, 1, 1) */
+    uint32_t reserved;
+    const float *pixels;       /* width * height * channels float32; copied */
+} b2_texture_desc;
 
 /* Participating medium + phase function: `homogeneous` (src/medium/homogeneous.cpp:156-222, strategies
  * balance / single / manual) or `heterogeneous` with method woodcock (src/medium/heterogeneous.cpp:182-260) over a float32
@@ -151,6 +168,9 @@ int b2_scene_add_mesh(b2_scene *, const float *P, const float *N, const float *U
 /* Medium plugin instance -> id (>=0) or -1; <ref name="interior"/"exterior"> of a shape (shape.cpp:160-176; -1 = none).
  * A mesh whose material is B2_BSDF_NULL is an index-matched boundary. */
 int b2_scene_add_medium(b2_scene *, const b2_medium_desc *);
+/* Texture plugin instance -> id (>=0) or -1; bind it with b2_material_desc::reflectance_texture = id + 1 (materials added afterwards).
+ * `path` only. */
+int b2_scene_add_texture(b2_scene *, const b2_texture_desc *);
 int b2_scene_set_mesh_media(b2_scene *, int mesh_id, int interior_medium, int exterior_medium);
 /* Instancing (src/shapes/{shapegroup,instance}.cpp): meshes assigned to a shapegroup live in its object space and are only
  * visible through instances; `to_world` / `to_object` are the affine instance transform and its inverse (row major).
@@ -196,6 +216,16 @@ int b2_sample_emitter_direct(b2_scene *, uint64_t n, const float *ref, const flo
  * (-> n x 12: ok t sigmaS(3) transmittance(3) pdfSuccess pdfFailure - -), 2 GridDataSource::lookupFloat (in n x 3 -> n),
  * 3 PhaseFunction::sample + eval (in n x 5: wi, two uniforms -> n x 5: wo pdf eval); random numbers: counter stream `seed` */
 int b2_medium_probe(b2_scene *, int medium_id, int what, uint64_t n, const float *in, uint64_t seed, int parity_mode, float *out);
+/* Texture components: Texture2D::eval (texture.cpp:124-133) of n look-ups, uv n x 2, partials n x 4 (dudx dudy dvdx dvdy; NULL = the
+ * unfiltered look-up of a ray without differentials) -> out n x 3 */
+int b2_texture_eval(b2_scene *, int texture_id, uint64_t n, const float *uv, const float *partials, int parity_mode, float *out);
+/* uv and uv partials of camera-ray hits (sampleRayDifferential + scaleDifferential(1/sqrt(spp)) + Intersection::computePartials):
+ * pos_hit n x 6 = film position (2), then t, u, v, prim as b2_trace returns them -> out n x 6: u v dudx dudy dvdx dvdy */
+int b2_texture_partials(b2_scene *, uint64_t n, const float *pos_hit, int spp, int parity_mode, float *out);
+/* One level of the MIP pyramid built at commit (TMIPMap constructor, mipmap.h:155-303); out may be NULL to query the size */
+int b2_texture_level(b2_scene *, int texture_id, int level, int *levels, int *width, int *height, float *out);
+/* The same without a scene or a device: host-side pyramid construction for the given description */
+int b2_mipmap_level(const b2_texture_desc *, int level, int *levels, int *width, int *height, float *out);
 /* The first ndim sampler outputs of (pixel, sample) as renderBlock + Li draw them */
 int b2_sampler_stream(b2_scene *, int sampler, uint64_t seed, int spp, int px, int py, int sample_idx, int ndim, float *out);
 /* primary rays (PerspectiveCameraImpl::sampleRayDifferential, perspective.cpp:271-298): pos n x 2 -> rays n x 8 */

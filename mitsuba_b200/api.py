@@ -25,7 +25,15 @@ class b2_material_desc(C.Structure):
                 ("alpha_u", C.c_float), ("alpha_v", C.c_float), ("eta", C.c_float), ("thickness", C.c_float),
                 ("reflectance", C.c_float * 3), ("transmittance", C.c_float * 3), ("eta_c", C.c_float * 3),
                 ("k_c", C.c_float * 3), ("sigma_a", C.c_float * 3), ("nested2", C.c_int32), ("diffuse_reflectance", C.c_float * 3),
-                ("fdr_int", C.c_float), ("fdr_ext", C.c_float), ("spec_sampling_weight", C.c_float), ("nonlinear", C.c_int32)]
+                ("fdr_int", C.c_float), ("fdr_ext", C.c_float), ("spec_sampling_weight", C.c_float), ("nonlinear", C.c_int32),
+                ("reflectance_texture", C.c_int32)]
+
+
+class b2_texture_desc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32), ("filter_type", C.c_int32),
+                ("wrap_u", C.c_int32), ("wrap_v", C.c_int32), ("max_anisotropy", C.c_float), ("uoffset", C.c_float),
+                ("voffset", C.c_float), ("uscale", C.c_float), ("vscale", C.c_float), ("reserved", C.c_uint32),
+                ("pixels", C.POINTER(C.c_float))]
 
 
 class b2_render_params(C.Structure):
@@ -59,7 +67,7 @@ class b2_stats(C.Structure):
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
            "b2_scene_set_camera", "b2_scene_set_thinlens", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
+           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -177,8 +185,18 @@ class Scene:
         flat, ids = desc.flat_bsdfs()
         self.flat_bsdfs = flat
         self.material_ids = ids
+        self.flat_textures = desc.flat_textures()
+        for d in self.flat_textures:  # bitmap textures first: materials refer to them by id
+            t = b2_texture_desc()
+            t.width, t.height, t.channels, t.filter_type = d["width"], d["height"], d["channels"], d["filterType"]
+            t.wrap_u, t.wrap_v, t.max_anisotropy = d["wrapU"], d["wrapV"], d["maxAnisotropy"]
+            t.uoffset, t.voffset, t.uscale, t.vscale = d["uoffset"], d["voffset"], d["uscale"], d["vscale"]
+            t.pixels = d["pixels"].ctypes.data_as(C.POINTER(C.c_float))
+            if self.L.b2_scene_add_texture(self.h, C.byref(t)) < 0:
+                raise B2Error(ctx.err())
         for d in flat:
             m = b2_material_desc()
+            m.reflectance_texture = d.get("texture", -1) + 1
             m.type, m.distr, m.sample_visible, m.nested = d["type"], d["distr"], d["sampleVisible"], d["nested"]
             m.alpha_u, m.alpha_v, m.eta, m.thickness = d["alphaU"], d["alphaV"], d["eta"], d["thickness"]
             for k, src in (("reflectance", "reflectance"), ("transmittance", "transmittance"), ("eta_c", "etaC"), ("k_c", "kC"), ("sigma_a", "sigmaA"),
@@ -329,6 +347,33 @@ class Scene:
         self._ck(self.L.b2_medium_probe(self.h, C.c_int(medium), C.c_int(w[0]), C.c_uint64(len(data)), _p(data), C.c_uint64(seed),
                                         C.c_int(int(parity)), _p(out)))
         return out[:, 0] if w[2] == 1 else out
+
+    def texture_eval(self, tex, uv, partials=None, parity=True):
+        """Texture2D::eval (b2_texture_eval): uv (n,2); partials (n,4) = dudx, dudy, dvdx, dvdy or None (no ray differentials)."""
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        pt = np.ascontiguousarray(partials, np.float32).reshape(-1, 4) if partials is not None else None
+        out = np.zeros((len(uv), 3), np.float32)
+        self._ck(self.L.b2_texture_eval(self.h, C.c_int(tex), C.c_uint64(len(uv)), _p(uv), _p(pt), C.c_int(int(parity)), _p(out)))
+        return out
+
+    def texture_partials(self, pos, hits, spp, parity=True):
+        """uv + uv partials of camera-ray hits (b2_texture_partials): pos (n,2) film positions, hits = (t, u, v, prim) arrays of trace()."""
+        t, u, v, prim = hits
+        rec = np.zeros((len(t), 6), np.float32)
+        rec[:, 0:2] = np.asarray(pos, np.float32).reshape(-1, 2)
+        rec[:, 2], rec[:, 3], rec[:, 4] = t, u, v
+        rec[:, 5] = np.asarray(prim, np.uint32).view(np.float32)
+        out = np.zeros((len(t), 6), np.float32)
+        self._ck(self.L.b2_texture_partials(self.h, C.c_uint64(len(t)), _p(rec), C.c_int(spp), C.c_int(int(parity)), _p(out)))
+        return out
+
+    def texture_level(self, tex, level):
+        """One level of the MIP pyramid commit built (b2_texture_level) as (h, w, channels)."""
+        n, w, h = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.b2_texture_level(self.h, C.c_int(tex), C.c_int(level), C.byref(n), C.byref(w), C.byref(h), None))
+        out = np.zeros((h.value, w.value, self.flat_textures[tex]["channels"]), np.float32)
+        self._ck(self.L.b2_texture_level(self.h, C.c_int(tex), C.c_int(level), C.byref(n), C.byref(w), C.byref(h), _p(out)))
+        return out, n.value
 
     def sampler_stream(self, kind, seed, spp, px, py, sample_idx, ndim):
         out = np.zeros(ndim, np.float32)

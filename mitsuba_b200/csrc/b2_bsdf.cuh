@@ -220,6 +220,10 @@ struct BRec {
     V3 wi, wo;
     float eta;
     uint32_t sampledType;
+    // value of the bitmap texture bound to the diffuse reflectance of the leaf BSDF this record will reach (`m_reflectance->eval(bRec.its)`,
+    // diffuse.cpp:115,148), looked up once per intersection by the caller; hasTex is a compile-time false in the kernels for untextured scenes
+    bool hasTex = false;
+    V3 texR;
 };
 
 B2_DEV V3 ld3(const float *p) { return V3(p[0], p[1], p[2]); }
@@ -228,7 +232,7 @@ B2_DEV V3 ld3(const float *p) { return V3(p[0], p[1], p[2]); }
 // leaf BSDFs (types 0..2)
 // ---------------------------------------------------------------------------------------------
 template <int HINT> B2_DEV Spectrum leafEval(const DMaterial &d, const BRec &r, bool discrete) {
-    const V3 R = ld3(d.reflectance);
+    const V3 R = (r.hasTex && d.type == 0) ? r.texR : ld3(d.reflectance);
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
     if (type == 4) return Spectrum(discrete ? 1.0f : 0.0f); // null.cpp:45-47 (index-matched boundary)
     if (type == 6) { // dielectric.cpp:229-255
@@ -363,7 +367,7 @@ template <int HINT> B2_DEV float leafPdf(const DMaterial &d, const BRec &r, bool
 }
 
 template <int HINT> B2_DEV Spectrum leafSample(const DMaterial &d, BRec &r, float &pdfOut, float sx, float sy, PathSampler &smp) {
-    const V3 R = ld3(d.reflectance);
+    const V3 R = (r.hasTex && d.type == 0) ? r.texR : ld3(d.reflectance);
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
     if (type == 4) { // null.cpp:65-76
         r.wo = -r.wi; r.sampledType = ENull; r.eta = 1.0f; pdfOut = 1.0f;

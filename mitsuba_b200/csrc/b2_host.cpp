@@ -4,6 +4,7 @@
 #include "b2_types.h"
 #include "b2_launch.h"
 #include "bvh_builder.h"
+#include "../host/mipmap.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -120,6 +121,8 @@ struct b2_scene {
     std::vector<HostInstance> instances;
     int nGroups = 0;
     std::vector<HostMedium> media;
+    struct HostTexture { b2_texture_desc desc; std::vector<float> pixels; b2host::MipPyramid mip; };
+    std::vector<HostTexture> textures;
     // camera
     float camToWorld[16];
     float sampleToCamera[16];
@@ -140,6 +143,10 @@ struct b2_scene {
     DevBuf<DInstance> dInstances;
     DevBuf<int2> dPrimMedia;
     std::vector<std::unique_ptr<DevBuf<float>>> dDensity;
+    DevBuf<DTexture> dTextures;
+    std::vector<std::unique_ptr<DevBuf<float>>> dTexData;
+    DevBuf<float4> dTexc;
+    DevBuf<float> dEwaLut;
     bool hasNullBsdf = false;
     std::vector<float4> hTriAccelPrimOrder; // for b2_get_triaccel
     LaunchCfg cfgParity, cfgFast;
@@ -373,9 +380,30 @@ extern "C" int b2_scene_add_material(b2_scene *s, const b2_material_desc *m) {
         fail(s->ctx, B2_ERR_INVALID, "The interior and exterior indices of refraction must be positive and differ!"); // roughdielectric.cpp:196-198
         return -1;
     }
+    if (m->reflectance_texture != 0) {
+        if (m->type != B2_BSDF_DIFFUSE) { fail(s->ctx, B2_ERR_INVALID, "bitmap textures are supported on the 'reflectance' of a diffuse BSDF only"); return -1; }
+        if (m->reflectance_texture < 0 || m->reflectance_texture > (int) s->textures.size()) { fail(s->ctx, B2_ERR_INVALID, "invalid texture id"); return -1; }
+    }
     s->materials.push_back(*m);
     s->committed = false;
     return (int) s->materials.size() - 1;
+}
+// Texture plugin instance -> id (>= 0) or -1
+extern "C" int b2_scene_add_texture(b2_scene *s, const b2_texture_desc *t) {
+    if (!s || !t || !t->pixels) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_texture: null argument"); return -1; }
+    if (t->width <= 0 || t->height <= 0 || (t->channels != 1 && t->channels != 3)) { fail(s->ctx, B2_ERR_INVALID, "The input image has an unsupported pixel format!"); return -1; } // bitmap.cpp:276-278
+    if (t->filter_type < B2_TEX_NEAREST || t->filter_type > B2_TEX_EWA) { fail(s->ctx, B2_ERR_INVALID, "Invalid filter type, must be 'ewa', 'trilinear', or 'nearest'!"); return -1; } // bitmap.cpp:228-230
+    for (int w : {t->wrap_u, t->wrap_v})
+        if (w < B2_WRAP_REPEAT || w > B2_WRAP_ONE) { fail(s->ctx, B2_ERR_INVALID, "Invalid wrap mode, must be 'repeat', 'clamp', 'black', or 'white'!"); return -1; } // bitmap.cpp:335-337
+    if ((uint64_t) t->width * (uint64_t) t->height > (1ull << 28)) { fail(s->ctx, B2_ERR_INVALID, "texture too large"); return -1; }
+    b2_scene::HostTexture ht;
+    ht.desc = *t;
+    ht.pixels.assign(t->pixels, t->pixels + (size_t) t->width * t->height * t->channels);
+    ht.desc.pixels = nullptr;
+    if (ht.desc.filter_type != B2_TEX_EWA) ht.desc.max_anisotropy = 1.0f; // bitmap.cpp:234-235
+    s->textures.push_back(std::move(ht));
+    s->committed = false;
+    return (int) s->textures.size() - 1;
 }
 extern "C" int b2_scene_add_area_emitter(b2_scene *s, const float radiance[3], float sampling_weight) {
     if (!s || !radiance) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_area_emitter: null argument"); return -1; }
@@ -524,7 +552,8 @@ static uint32_t materialFlags(const std::vector<b2_material_desc> &mats, int id)
     const uint32_t EDiffuseReflection = 0x2, EGlossyReflection = 0x8, EGlossyTransmission = 0x10, EDeltaReflection = 0x20, EAnisotropic = 0x1000,
                    ENonSymmetric = 0x4000, EFrontSide = 0x8000, EBackSide = 0x10000, EUsesSampler = 0x20000;
     switch (d.type) {
-        case 0: return (std::max(std::max(d.reflectance[0], d.reflectance[1]), d.reflectance[2]) > 0) ? (EDiffuseReflection | EFrontSide) : 0; // diffuse.cpp:98-103
+        case 0: if (d.reflectance_texture > 0) return EDiffuseReflection | EFrontSide | 0x2000u /* ESpatiallyVarying */;
+                return (std::max(std::max(d.reflectance[0], d.reflectance[1]), d.reflectance[2]) > 0) ? (EDiffuseReflection | EFrontSide) : 0; // diffuse.cpp:98-103
         case 1: return EGlossyReflection | EFrontSide | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
         case 2: return EGlossyReflection | EGlossyTransmission | EFrontSide | EBackSide | EUsesSampler | ENonSymmetric | (d.alpha_u != d.alpha_v ? EAnisotropic : 0);
         case 4: return 0x1u /* ENull */ | EFrontSide | EBackSide; // null.cpp:38-43
@@ -550,7 +579,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     s->nPrims = (uint32_t) nPrims;
     bool anyNorm = false;
     for (auto &m : s->meshes) anyNorm |= !m.N.empty() || !m.UV.empty();
-    std::vector<float4> verts(3 * nPrims), norms(anyNorm ? 3 * nPrims : 0), triAccel(3 * nPrims);
+    const bool anyTex = !s->textures.empty();
+    std::vector<float4> verts(3 * nPrims), norms(anyNorm ? 3 * nPrims : 0), triAccel(3 * nPrims), texc(anyTex && anyNorm ? 3 * nPrims : 0);
     // candidate primitives per acceleration structure: bucket 0 = world, bucket g + 1 = shapegroup g
     const bool instanced = !s->instances.empty();
     std::vector<std::vector<PrimBox>> bBoxes(1 + (size_t) s->nGroups);
@@ -574,7 +604,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
             verts[3 * p + 1] = make_float4(p1[0], p1[1], p1[2], w1);
             verts[3 * p + 2] = make_float4(p2[0], p2[1], p2[2], w2);
             if (anyNorm) {
-                float n[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, dpdu[3] = {0, 0, 0};
+                float n[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, dpdu[3] = {0, 0, 0}, dpdv[3] = {0, 0, 0};
                 if (!m.N.empty()) {
                     memcpy(n[0], &m.N[3 * i0], 12); memcpy(n[1], &m.N[3 * i1], 12); memcpy(n[2], &m.N[3 * i2], 12);
                 }
@@ -599,17 +629,26 @@ extern "C" int b2_scene_commit(b2_scene *s) {
                             }
                             H3 b = cross3(c, a);
                             dpdu[0] = b.x; dpdu[1] = b.y; dpdu[2] = b.z;
+                            dpdv[0] = c.x; dpdv[1] = c.y; dpdv[2] = c.z;
                         } else {
                             float invDet = 1.0f / determinant;
                             dpdu[0] = (dv2 * dP1.x - dv1 * dP2.x) * invDet;
                             dpdu[1] = (dv2 * dP1.y - dv1 * dP2.y) * invDet;
                             dpdu[2] = (dv2 * dP1.z - dv1 * dP2.z) * invDet;
+                            dpdv[0] = (-du2 * dP1.x + du1 * dP2.x) * invDet;
+                            dpdv[1] = (-du2 * dP1.y + du1 * dP2.y) * invDet;
+                            dpdv[2] = (-du2 * dP1.z + du1 * dP2.z) * invDet;
                         }
                     }
                 }
                 norms[3 * p] = make_float4(n[0][0], n[0][1], n[0][2], dpdu[0]);
                 norms[3 * p + 1] = make_float4(n[1][0], n[1][1], n[1][2], dpdu[1]);
                 norms[3 * p + 2] = make_float4(n[2][0], n[2][1], n[2][2], dpdu[2]);
+                if (!texc.empty() && !m.UV.empty()) { // texture coordinates of the three vertices + dpdv of computeUVTangents
+                    texc[3 * p] = make_float4(m.UV[2 * i0], m.UV[2 * i0 + 1], dpdv[0], 0.0f);
+                    texc[3 * p + 1] = make_float4(m.UV[2 * i1], m.UV[2 * i1 + 1], dpdv[1], 0.0f);
+                    texc[3 * p + 2] = make_float4(m.UV[2 * i2], m.UV[2 * i2 + 1], dpdv[2], 0.0f);
+                }
             }
             uint32_t wds[12];
             triAccelLoad(p0, p1, p2, wds);
@@ -824,6 +863,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         memcpy(d.reflectance, m.reflectance, 12); memcpy(d.transmittance, m.transmittance, 12);
         memcpy(d.etaC, m.eta_c, 12); memcpy(d.kC, m.k_c, 12); memcpy(d.sigmaA, m.sigma_a, 12);
         d.flags = materialFlags(s->materials, (int) i);
+        d.tex = m.reflectance_texture > 0 ? m.reflectance_texture - 1 : -1;
         d.nested2 = m.nested2; d.nonlinear = m.nonlinear; d.fdrInt = m.fdr_int;
         memcpy(d.diffuseReflectance, m.diffuse_reflectance, 12);
         if (m.type == B2_BSDF_PLASTIC) d.specSamplingWeight = m.spec_sampling_weight;
@@ -842,6 +882,40 @@ extern "C" int b2_scene_commit(b2_scene *s) {
             if (t == B2_BSDF_NULL && m.emitter >= 0)
                 return fail(ctx, B2_ERR_INVALID, "Shape has an index-matched BSDF and an emitter attachment. This is not allowed!"); // shape.cpp:76-78
         } else s->classPresent[t] = true;
+    }
+    // ---- bitmap textures: MIP pyramids (host, as the reference builds them at load time) -> one device array per texture ----
+    std::vector<DTexture> dtex(s->textures.size());
+    s->dTexData.clear();
+    for (size_t i = 0; i < s->textures.size(); ++i) {
+        b2_scene::HostTexture &ht = s->textures[i];
+        const b2_texture_desc &t = ht.desc;
+        b2host::buildMipPyramid(ht.pixels.data(), t.width, t.height, t.channels, t.wrap_u, t.wrap_v, t.filter_type >= B2_TEX_TRILINEAR, ht.mip);
+        if ((int) ht.mip.level.size() > B2_TEX_MAX_LEVELS) return fail(ctx, B2_ERR_INVALID, "texture has too many MIP levels");
+        DTexture &d = dtex[i];
+        memset(&d, 0, sizeof(d));
+        d.levels = (int) ht.mip.level.size(); d.channels = t.channels; d.filter = t.filter_type; d.wrapU = t.wrap_u; d.wrapV = t.wrap_v;
+        d.maxAnisotropy = t.max_anisotropy; d.uoffset = t.uoffset; d.voffset = t.voffset; d.uscale = t.uscale; d.vscale = t.vscale;
+        d.bsdfScale = ht.mip.maximum > 1.0f ? 0.99f * (1.0f / ht.mip.maximum) : 1.0f; // bsdf.cpp:93-107
+        const int stride = t.channels == 3 ? 4 : 1; // RGB texels are padded to float4 (one 16-byte load per texel)
+        std::vector<float> packed;
+        for (int l = 0; l < d.levels; ++l) {
+            d.lw[l] = ht.mip.w[l]; d.lh[l] = ht.mip.h[l];
+            d.off[l] = (uint32_t) (packed.size() / stride);
+            const std::vector<float> &src = ht.mip.level[l];
+            const size_t nTexel = (size_t) d.lw[l] * d.lh[l];
+            if (stride == 1) packed.insert(packed.end(), src.begin(), src.end());
+            else for (size_t k = 0; k < nTexel; ++k) { packed.push_back(src[3 * k]); packed.push_back(src[3 * k + 1]); packed.push_back(src[3 * k + 2]); packed.push_back(0.0f); }
+        }
+        s->dTexData.emplace_back(new DevBuf<float>());
+        CK(ctx, s->dTexData.back()->upload(packed));
+        d.data = s->dTexData.back()->p;
+    }
+    CK(ctx, s->dTextures.upload(dtex));
+    CK(ctx, s->dTexc.upload(texc));
+    if (anyTex) {
+        std::vector<float> lut(64);
+        b2host::ewaWeightTable(lut.data());
+        CK(ctx, s->dEwaLut.upload(lut));
     }
     // ---- media (volpath) ----
     std::vector<DMedium> dmed(s->media.size());
@@ -963,6 +1037,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     }
     ds.verts = s->dVerts.p; ds.norms = s->dNorms.p; ds.nPrims = (uint32_t) nPrims;
     ds.materials = s->dMaterials.p; ds.nMaterials = (uint32_t) dm.size();
+    ds.textures = s->dTextures.p; ds.nTextures = (uint32_t) dtex.size(); ds.texc = s->dTexc.p; ds.ewaLut = s->dEwaLut.p;
     ds.emitters = s->dEmitters.p; ds.nEmitters = (uint32_t) de.size();
     ds.emitterCdf = s->dEmitterCdf.p; ds.emitterNormalization = emNorm; ds.triCdf = s->dTriCdf.p;
     memcpy(ds.cam.camToWorld, s->camToWorld, 64);
@@ -972,6 +1047,18 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.cam.origin[0] = s->camToWorld[3]; ds.cam.origin[1] = s->camToWorld[7]; ds.cam.origin[2] = s->camToWorld[11];
     ds.cam.W = s->W; ds.cam.H = s->H;
     ds.cam.apertureRadius = s->apertureRadius; ds.cam.focusDistance = s->focusDistance;
+    { // m_dx, m_dy (perspective.cpp:160-163): sampleToCamera(Point(invRes.x, 0, 0)) - sampleToCamera(Point(0)), likewise y
+        auto s2c = [&](float px, float py, float out[3]) { // Transform::operator()(Point), transform.h:108-125
+            const float *M = s->sampleToCamera;
+            const float x = M[0] * px + M[1] * py + M[2] * 0.0f + M[3], y = M[4] * px + M[5] * py + M[6] * 0.0f + M[7],
+                        z = M[8] * px + M[9] * py + M[10] * 0.0f + M[11], w = M[12] * px + M[13] * py + M[14] * 0.0f + M[15];
+            if (w != 1.0f) { const float r = 1.0f / w; out[0] = x * r; out[1] = y * r; out[2] = z * r; }
+            else { out[0] = x; out[1] = y; out[2] = z; }
+        };
+        float z0[3], ax[3], ay[3];
+        s2c(0.0f, 0.0f, z0); s2c(ds.cam.invResX, 0.0f, ax); s2c(0.0f, ds.cam.invResY, ay);
+        for (int k = 0; k < 3; ++k) { ds.cam.dx[k] = ax[k] - z0[k]; ds.cam.dy[k] = ay[k] - z0[k]; }
+    }
     ds.sobolM32 = ctx->dM32; ds.sobolVdc = ctx->dVdc; ds.sobolInv = ctx->dInv; ds.sobolNib = ctx->dNib;
     // shared-memory staging budget: up to 256 nodes (16 KB) and 256 triangles (12 KB) per CTA
     ds.stageNodes = std::min<uint32_t>(ds.nNodes, 256u);
@@ -1058,7 +1145,9 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     r.sampleLo = p->sample_lo; r.sampleHi = p->sample_hi > 0 ? p->sample_hi : p->spp;
     if (p->integrator != B2_INTEGRATOR_PATH && p->integrator != B2_INTEGRATOR_VOLPATH) return fail(ctx, B2_ERR_INVALID, "unknown integrator");
     if (p->integrator == B2_INTEGRATOR_VOLPATH && s->ds.nItems) return fail(ctx, B2_ERR_INVALID, "volpath with instanced geometry is not supported");
+    if (p->integrator == B2_INTEGRATOR_VOLPATH && s->ds.nTextures) return fail(ctx, B2_ERR_INVALID, "volpath with bitmap textures is not supported");
     r.integrator = p->integrator;
+    r.diffScale = 1.0f / std::sqrt((float) p->spp); // integrator.cpp:144-145
     if (r.sampleLo < 0 || r.sampleHi > p->spp || r.sampleLo >= r.sampleHi) return fail(ctx, B2_ERR_INVALID, "invalid sample range");
     if (p->sampler == B2_SAMPLER_SOBOL) {
         r.scramble = p->seed ? teaHost((uint32_t) p->seed, (uint32_t) (p->seed >> 32)) : 0; // sobol.cpp:96-102
@@ -1174,7 +1263,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         if (s->classPresent[c]) { ++nClasses; onlyClass = c; }
     bool sorted = nClasses > 1;
     if (p->flags & 2) sorted = false;
-    if (s->hasNullBsdf) { sorted = false; nClasses = 2; } // index-matched boundaries: generic shading kernel
+    if (s->hasNullBsdf || !s->textures.empty()) { sorted = false; nClasses = 2; } // index-matched boundaries, f-3 BSDFs, textures: generic shading kernel
     // Optional (flags bit4) for shared-memory resident scenes: rays cast inline by k_generate / k_shade (no k_extend /
     // k_occluded launches, no ray / shadow records through HBM).  Measured on Cornell it is ~4 % SLOWER than the separate
     // stages (1407 vs 1463 Msamples/s): the triangle tests then run inside the divergent, low-occupancy shade kernel
@@ -1503,6 +1592,56 @@ extern "C" int b2_medium_probe(b2_scene *s, int medium, int what, uint64_t n, co
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpy(out, dO, (size_t) outW[what] * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+// Texture probes (parity tests)
+extern "C" int b2_texture_eval(b2_scene *s, int texture_id, uint64_t n, const float *uv, const float *partials, int parity_mode, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (texture_id < 0 || texture_id >= (int) s->textures.size()) return fail(ctx, B2_ERR_INVALID, "invalid texture id");
+    if (!uv || !out) return fail(ctx, B2_ERR_INVALID, "b2_texture_eval: null argument");
+    std::vector<float> in(6 * n, 0.0f);
+    for (uint64_t i = 0; i < n; ++i) {
+        in[6 * i] = uv[2 * i]; in[6 * i + 1] = uv[2 * i + 1];
+        if (partials) for (int k = 0; k < 4; ++k) in[6 * i + 2 + k] = partials[4 * i + k];
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dI = tmp.upload(in.data(), 6 * n), *dO = tmp.alloc<float>(3 * n);
+    if (parity_mode) parity::launch_texture_probe(s->cfgParity, s->ds, 0, texture_id, partials ? 1 : 0, 1.0f, n, dI, dO, ctx->stream);
+    else fast::launch_texture_probe(s->cfgFast, s->ds, 0, texture_id, partials ? 1 : 0, 1.0f, n, dI, dO, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, dO, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+extern "C" int b2_texture_partials(b2_scene *s, uint64_t n, const float *pos_hit, int spp, int parity_mode, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (!pos_hit || !out || spp <= 0) return fail(ctx, B2_ERR_INVALID, "b2_texture_partials: invalid argument");
+    if (s->ds.nItems) return fail(ctx, B2_ERR_INVALID, "b2_texture_partials: instanced scenes are not supported by this probe");
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    float *dI = tmp.upload(pos_hit, 6 * n), *dO = tmp.alloc<float>(6 * n);
+    const float diffScale = 1.0f / std::sqrt((float) spp);
+    if (parity_mode) parity::launch_texture_probe(s->cfgParity, s->ds, 1, 0, 0, diffScale, n, dI, dO, ctx->stream);
+    else fast::launch_texture_probe(s->cfgFast, s->ds, 1, 0, 0, diffScale, n, dI, dO, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, dO, 6 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+// One level of the MIP pyramid b2_scene_commit built (host data; RGB or luminance as given).  `out` may be NULL to query the size.
+extern "C" int b2_texture_level(b2_scene *s, int texture_id, int level, int *levels, int *width, int *height, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (texture_id < 0 || texture_id >= (int) s->textures.size()) return fail(ctx, B2_ERR_INVALID, "invalid texture id");
+    const b2host::MipPyramid &mp = s->textures[texture_id].mip;
+    if (level < 0 || level >= (int) mp.level.size()) return fail(ctx, B2_ERR_INVALID, "invalid MIP level");
+    if (levels) *levels = (int) mp.level.size();
+    if (width) *width = mp.w[level];
+    if (height) *height = mp.h[level];
+    if (out) memcpy(out, mp.level[level].data(), mp.level[level].size() * sizeof(float));
     return B2_OK;
 }
 extern "C" int b2_camera_rays(b2_scene *s, uint64_t n, const float *pos, int parity_mode, float *rays) {

@@ -16,6 +16,7 @@
 #include "b2_bsdf.cuh"
 #include "b2_trace.cuh"
 #include "b2_medium.cuh"
+#include "b2_texture.cuh"
 #include "b2_launch.h"
 
 namespace b2 {
@@ -252,6 +253,36 @@ B2_DEV void cameraRay(const DCamera &cam, float sx, float sy, V3 &o, V3 &d, floa
     o = V3(cam.origin[0], cam.origin[1], cam.origin[2]);
     mint = cam.nearClip * invZ;
     maxt = cam.farClip * invZ;
+}
+
+// Sensor::sampleRayDifferential + RayDifferential::scaleDifferential(scale): the ray of cameraRay() plus the directions of the two
+// offset rays through the neighbouring pixels (their origin is the ray origin for both sensors)
+B2_DEV void cameraRayDifferential(const DCamera &cam, float spx, float spy, float apx, float apy, float scale, V3 &o, V3 &d, V3 &rxD, V3 &ryD) {
+    float mint, maxt;
+    cameraRay(cam, spx, spy, o, d, mint, maxt, apx, apy);
+    const float *M = cam.sampleToCamera;
+    const float px = spx * cam.invResX, py = spy * cam.invResY, pz = 0.0f;
+    const float w = M[12] * px + M[13] * py + M[14] * pz + M[15];
+    V3 nearP(M[0] * px + M[1] * py + M[2] * pz + M[3], M[4] * px + M[5] * py + M[6] * pz + M[7], M[8] * px + M[9] * py + M[10] * pz + M[11]);
+    if (w != 1.0f) nearP = nearP / w;
+    const V3 dx(cam.dx[0], cam.dx[1], cam.dx[2]), dy(cam.dy[0], cam.dy[1], cam.dy[2]);
+    V3 lx, ly;
+    if (cam.apertureRadius > 0) { // thinlens.cpp:326-357
+        float tx, ty;
+        squareToUniformDiskConcentric(apx, apy, tx, ty);
+        const V3 apertureP(tx * cam.apertureRadius, ty * cam.apertureRadius, 0.0f);
+        const float fDist = cam.focusDistance / nearP.z;
+        lx = normalize((nearP + dx) * fDist - apertureP);
+        ly = normalize((nearP + dy) * fDist - apertureP);
+    } else { // perspective.cpp:293-294
+        lx = normalize(nearP + dx);
+        ly = normalize(nearP + dy);
+    }
+    const float *T = cam.camToWorld;
+    const V3 wx(T[0] * lx.x + T[1] * lx.y + T[2] * lx.z, T[4] * lx.x + T[5] * lx.y + T[6] * lx.z, T[8] * lx.x + T[9] * lx.y + T[10] * lx.z);
+    const V3 wy(T[0] * ly.x + T[1] * ly.y + T[2] * ly.z, T[4] * ly.x + T[5] * ly.y + T[6] * ly.z, T[8] * ly.x + T[9] * ly.y + T[10] * ly.z);
+    rxD = d + (wx - d) * scale; // ray.h:163-168
+    ryD = d + (wy - d) * scale;
 }
 
 // sampler set-up for (pixel, sample): sobol.cpp:204-216 / counter stream
@@ -551,6 +582,48 @@ B2_DEV void fillIntersectionInst(const DScene &sc, const V3 &rayO, const V3 &ray
     its.wi = its.sh.toLocal(-rayD);
 }
 
+// Texture look-up of one intersection (`m_reflectance->eval(its)` of the diffuse leaf, diffuse.cpp:115,148): uv from the per-prim texture
+// coordinates (skdtree.h:398-405), and for a camera ray the uv partials of Intersection::computePartials from the sensor's ray
+// differentials (perspective.cpp:271-298 / thinlens.cpp:324-361, scaled by 1/sqrt(spp): integrator.cpp:144-145,181), which this
+// recomputes from the film position instead of carrying them in the pool.  `in`: the instance that was hit or null.
+B2_DEV TexCoord surfaceTexCoord(const DScene &sc, float diffScale, uint32_t prim, float bu, float bv, const DInstance *in, const V3 &p, const V3 &geoN,
+                                bool fresh, float2 pos, PathSampler smp) {
+    const size_t p3 = 3 * (size_t) prim;
+    const float4 a0 = __ldg(&sc.verts[p3]), a1 = __ldg(&sc.verts[p3 + 1]), a2 = __ldg(&sc.verts[p3 + 2]);
+    const uint32_t tflags = __float_as_uint(a2.w);
+    TexCoord tc;
+    tc.hasUVPartials = false;
+    tc.dudx = tc.dudy = tc.dvdx = tc.dvdy = 0.0f;
+    V3 dpdu, dpdv;
+    if (tflags & 2u) { // the mesh has texture coordinates: interpolated uv, tangents of TriMesh::computeUVTangents
+        const float4 t0 = __ldg(&sc.texc[p3]), t1 = __ldg(&sc.texc[p3 + 1]), t2 = __ldg(&sc.texc[p3 + 2]);
+        const float b0 = 1 - bu - bv;
+        tc.u = t0.x * b0 + t1.x * bu + t2.x * bv;
+        tc.v = t0.y * b0 + t1.y * bu + t2.y * bv;
+        dpdu = V3(__ldg(&sc.norms[p3].w), __ldg(&sc.norms[p3 + 1].w), __ldg(&sc.norms[p3 + 2].w));
+        dpdv = V3(t0.z, t1.z, t2.z);
+    } else { // skdtree.h:377-379,403-404
+        tc.u = bu; tc.v = bv;
+        const V3 p0(a0.x, a0.y, a0.z);
+        dpdu = V3(a1.x, a1.y, a1.z) - p0;
+        dpdv = V3(a2.x, a2.y, a2.z) - p0;
+    }
+    if (fresh) {
+        if (in) { dpdu = xfVector(in->M, dpdu); dpdv = xfVector(in->M, dpdv); } // instance.cpp:158-159
+        float apx = 0.5f, apy = 0.5f;
+        if (sc.cam.apertureRadius > 0) { smp.dim = 2; smp.next2D(apx, apy); } // the aperture sample of this path (dimensions 2, 3)
+        V3 o, d, rxD, ryD;
+        cameraRayDifferential(sc.cam, pos.x, pos.y, apx, apy, diffScale, o, d, rxD, ryD);
+        computeUVPartials(p, geoN, dpdu, dpdv, o, rxD, ryD, tc);
+    }
+    return tc;
+}
+static __device__ __noinline__ Spectrum shadeTexture(const DScene &sc, const DRender &rp, int tex, uint32_t prim, float bu, float bv, const DInstance *in,
+                                                   const Isect &its, bool fresh, float2 pos, PathSampler smp) {
+    const TexCoord tc = surfaceTexCoord(sc, rp.diffScale, prim, bu, bv, in, its.p, its.geoN, fresh, pos, smp);
+    return texEval(sc.textures[tex], sc.ewaLut, tc);
+}
+
 B2_DEV float miWeight(float pdfA, float pdfB) { // path.cpp:296-300
     pdfA *= pdfA;
     pdfB *= pdfB;
@@ -673,7 +746,7 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
 #endif
 // FLAT: the shadow ray and the next ray are cast inline against the shared-memory resident triangle list (tiny scenes):
 // no shadow queue, no k_extend / k_occluded launches, no ray / shadow records through HBM.
-template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MINBLOCKS) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
+template <int CLS, bool FLAT, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MINBLOCKS) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
                                                                              const unsigned long long *queueCount) {
     extern __shared__ __align__(128) unsigned char smem[];
     TraceMem tm;
@@ -800,6 +873,22 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
                 if (!done) {
                     V3 refN(0.0f);
                     if ((btype & (ETransmission | EBackSide)) == 0) refN = its.sh.n; // records.inl:160-164
+                    // textured scenes: resolve the diffuse leaf this intersection will evaluate (twosided picks a side by wi, coating wraps
+                    // its child) and look its bitmap texture up once
+                    bool hasTex = false;
+                    V3 texR(0.0f);
+                    if (TEX) {
+                        int leaf = mat;
+                        if (mats[leaf].type == 5) leaf = cosTheta(its.wi) > 0 ? mats[leaf].nested : mats[leaf].nested2;
+                        if (mats[leaf].type == 3) leaf = mats[leaf].nested;
+                        const int tex = mats[leaf].tex;
+                        if (mats[leaf].type == 0 && tex >= 0) {
+                            const uint32_t item = sc.nItems ? pool.inst[i] : 0xFFFFFFFFu;
+                            const DInstance *in = (item != 0xFFFFFFFFu && !sc.items[item].identity) ? &sc.items[item] : nullptr;
+                            hasTex = true;
+                            texR = shadeTexture(sc, rp, tex, prim, hit.y, hit.z, in, its, fresh, fresh ? pool.pos[i] : make_float2(0.0f, 0.0f), smp);
+                        }
+                    }
                     // ---- direct illumination: path.cpp:172-200 ----
                     if (btype & ESmooth) {
                         float sx, sy;
@@ -808,6 +897,7 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
                         if (sc.nEmitters > 0 && sampleEmitterDirect(sc, its.p, refN, sx, sy, ds)) {
                             ++nShadowRef; // the reference traces (and counts, skdtree.cpp:210) the shadow ray before BSDF::eval
                             BRec bRec;
+                            if (TEX) { bRec.hasTex = hasTex; bRec.texR = texR; }
                             bRec.wi = its.wi;
                             bRec.wo = its.sh.toLocal(ds.d);
                             const Spectrum bsdfVal = bsdfEval<CLS>(mats, mat, bRec);
@@ -826,6 +916,7 @@ template <int CLS, bool FLAT> __global__ void __launch_bounds__(B2_SHADE_BLOCK, 
                     // ---- BSDF sampling: path.cpp:206-226 ----
                     float bsdfPdfNew;
                     BRec bRec;
+                    if (TEX) { bRec.hasTex = hasTex; bRec.texR = texR; }
                     bRec.wi = its.wi;
                     float sx, sy;
                     smp.next2D(sx, sy);
@@ -1723,6 +1814,33 @@ __global__ void k_emitter_direct(DScene sc, uint64_t n, const float *ref, const 
         o[5] = ds.value.x; o[6] = ds.value.y; o[7] = ds.value.z; o[8] = ok ? 1.0f : 0.0f; o[9] = ds.p.x; o[10] = ds.p.y; o[11] = ds.p.z;
     }
 }
+// Texture probes (parity tests).  what = 0: Texture2D::eval of texture `tex` (in n x 6: u, v, dudx, dudy, dvdx, dvdy; hasPartials selects the
+// filtered look-up) -> out n x 3.  what = 1: uv and uv partials of camera-ray hits (in n x 6: film position, t, barycentric u, v, prim bits;
+// world triangles only) -> out n x 6: u, v, dudx, dudy, dvdx, dvdy
+__global__ void k_texture_probe(DScene sc, int what, int tex, int hasPartials, float diffScale, uint64_t n, const float *in, float *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const float *r = in + 6 * i;
+        if (what == 0) {
+            TexCoord tc;
+            tc.u = r[0]; tc.v = r[1]; tc.hasUVPartials = hasPartials != 0;
+            tc.dudx = r[2]; tc.dudy = r[3]; tc.dvdx = r[4]; tc.dvdy = r[5];
+            const Spectrum v = texEval(sc.textures[tex], sc.ewaLut, tc);
+            out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+        } else {
+            V3 o, d;
+            float mint, maxt;
+            cameraRay(sc.cam, r[0], r[1], o, d, mint, maxt);
+            Isect its;
+            const uint32_t prim = __float_as_uint(r[5]);
+            fillIntersection(sc, d, prim, r[3], r[4], its);
+            PathSampler smp;
+            smp.kind = 2; smp.index = 0; smp.dim = 0; smp.scramble32 = 0; smp.overflow = false; smp.cacheDim = 0xFFFFFFFFu;
+            const TexCoord tc = surfaceTexCoord(sc, diffScale, prim, r[3], r[4], nullptr, its.p, its.geoN, true, make_float2(r[0], r[1]), smp);
+            float *q = out + 6 * i;
+            q[0] = tc.u; q[1] = tc.v; q[2] = tc.dudx; q[3] = tc.dudy; q[4] = tc.dvdx; q[5] = tc.dvdy;
+        }
+    }
+}
 __global__ void k_camera_rays(DScene sc, uint64_t n, const float *pos, float *rays) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         V3 o, d;
@@ -1802,6 +1920,7 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridShade[2] = occupancyGrid(k_shade<2, false>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShade[3] = occupancyGrid(k_shade<3, false>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShade[4] = occupancyGrid(k_shade<-1, false>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShadeTex[0] = occupancyGrid(k_shade<-1, false, true>, B2_SHADE_BLOCK, 0, numSMs);
     if (sc.rootCount) { // fused variants for shared-memory resident scenes
         cfg.gridGenerateFlat = occupancyGrid(k_generate<true>, 256, cfg.flatSmem, numSMs);
         cfg.gridShadeFlat[0] = occupancyGrid(k_shade<0, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
@@ -1809,6 +1928,7 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
         cfg.gridShadeFlat[2] = occupancyGrid(k_shade<2, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
         cfg.gridShadeFlat[3] = occupancyGrid(k_shade<3, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
         cfg.gridShadeFlat[4] = occupancyGrid(k_shade<-1, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
+        cfg.gridShadeTex[1] = occupancyGrid(k_shade<-1, true, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
     }
 }
 
@@ -1831,7 +1951,10 @@ void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, con
             case 1: k_shade<1, true><<<cfg.gridShadeFlat[1], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
             case 2: k_shade<2, true><<<cfg.gridShadeFlat[2], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
             case 3: k_shade<3, true><<<cfg.gridShadeFlat[3], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
-            default: k_shade<-1, true><<<cfg.gridShadeFlat[4], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, nullptr, nullptr); break;
+            default:
+                if (sc.nTextures) k_shade<-1, true, true><<<cfg.gridShadeTex[1], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, nullptr, nullptr);
+                else k_shade<-1, true><<<cfg.gridShadeFlat[4], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, nullptr, nullptr);
+                break;
         }
         return;
     }
@@ -1840,7 +1963,10 @@ void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, con
         case 1: k_shade<1, false><<<cfg.gridShade[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         case 2: k_shade<2, false><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         case 3: k_shade<3, false><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        default: k_shade<-1, false><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr); break;
+        default:
+            if (sc.nTextures) k_shade<-1, false, true><<<cfg.gridShadeTex[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
+            else k_shade<-1, false><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
+            break;
     }
 }
 void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {
@@ -1876,6 +2002,10 @@ void launch_bsdf_sample(const LaunchCfg &cfg, const DScene &sc, int mat, uint64_
 }
 void launch_emitter_direct(const LaunchCfg &cfg, const DScene &sc, uint64_t n, const float *ref, const float *samples, float *out, cudaStream_t st) {
     k_emitter_direct<<<cfg.numSMs * 2, 128, 0, st>>>(sc, n, ref, samples, out);
+}
+void launch_texture_probe(const LaunchCfg &cfg, const DScene &sc, int what, int tex, int hasPartials, float diffScale, uint64_t n, const float *in, float *out,
+                          cudaStream_t st) {
+    k_texture_probe<<<cfg.numSMs * 4, 128, 0, st>>>(sc, what, tex, hasPartials, diffScale, n, in, out);
 }
 void launch_camera_rays(const LaunchCfg &cfg, const DScene &sc, uint64_t n, const float *pos, float *rays, cudaStream_t st) {
     k_camera_rays<<<cfg.numSMs * 2, 128, 0, st>>>(sc, n, pos, rays);

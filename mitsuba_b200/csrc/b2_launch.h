@@ -18,6 +18,7 @@ struct LaunchCfg {
     size_t flatSmem = 0;
     int gridGenerateFlat = 0;
     int gridShadeFlat[5] = {0, 0, 0, 0, 0};
+    int gridShadeTex[2] = {0, 0}; // k_shade<-1, FLAT, TEX = true> (textured scenes): [0] BVH, [1] flat leaf
 };
 
 #define B2_DECLARE_LAUNCHERS(NS)                                                                                               \
@@ -42,6 +43,8 @@ struct LaunchCfg {
     void launch_emitter_direct(const LaunchCfg &, const DScene &, uint64_t n, const float *ref, const float *samples,          \
                                float *out, cudaStream_t);                                                                      \
     void launch_camera_rays(const LaunchCfg &, const DScene &, uint64_t n, const float *pos, float *rays, cudaStream_t);       \
+    void launch_texture_probe(const LaunchCfg &, const DScene &, int what, int tex, int hasPartials, float diffScale, uint64_t n, const float *in,   \
+                              float *out, cudaStream_t);                                                                    \
     void launch_sampler_stream(const DScene &, const DRender &, int px, int py, int sampleIdx, int ndim, float *out,           \
                                cudaStream_t);                                                                                  \
     void launch_splat(const LaunchCfg &, const DFilter &, int W, int H, uint64_t n, const float *pos, const float *val,        \

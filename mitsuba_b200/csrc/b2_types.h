@@ -20,6 +20,22 @@ struct DMaterial {
     int32_t nonlinear;     // plastic.cpp:161
     float diffuseReflectance[3]; // plastic
     float fdrInt;          // plastic.cpp:194 (fdrExt is only used by getDiffuseReflectance)
+    int32_t tex;           // diffuse: index into DScene::textures of the `bitmap` texture bound to `reflectance`, -1 = constant
+};
+
+// One `bitmap` texture (src/textures/bitmap.cpp + include/mitsuba/render/mipmap.h): the MIP pyramid built by the host at commit
+// (Lanczos-2 resampling as the reference does), texels as float4 (RGB, channels == 3) or float (luminance, channels == 1)
+#define B2_TEX_MAX_LEVELS 16
+struct DTexture {
+    int32_t levels, channels;
+    int32_t filter;            // 0 nearest, 1 bilinear, 2 trilinear, 3 ewa (bitmap.cpp:213-230)
+    int32_t wrapU, wrapV;      // 0 repeat, 1 clamp, 2 mirror, 3 zero, 4 one (bitmap.cpp:324-338)
+    float maxAnisotropy;       // bitmap.cpp:232-235
+    float uoffset, voffset, uscale, vscale; // texture.cpp:82-95
+    float bsdfScale;           // BSDF::ensureEnergyConservation (bsdf.cpp:88-111): 0.99 / max when the image exceeds 1
+    int32_t lw[B2_TEX_MAX_LEVELS], lh[B2_TEX_MAX_LEVELS];
+    uint32_t off[B2_TEX_MAX_LEVELS]; // first texel of each level inside `data`
+    const void *data;
 };
 
 // One participating medium + its phase function (device copy of b2_medium_desc)
@@ -76,6 +92,7 @@ struct DCamera {
     float origin[3];
     int32_t W, H;
     float apertureRadius, focusDistance; // > 0: `thinlens` sensor (src/sensors/thinlens.cpp); 0: pinhole
+    float dx[3], dy[3];        // m_dx, m_dy (perspective.cpp:160-163): camera-space offset of one pixel on the near plane
 };
 
 // Scene resident in HBM
@@ -113,6 +130,11 @@ struct DScene {
     uint32_t nPrims;
     const DMaterial *materials;
     uint32_t nMaterials;
+    // bitmap textures (null / 0 without): table, per-prim texc[3*p+k] = (u_k, v_k, dpdv component k, 0), EWA weight table (64 entries)
+    const DTexture *textures;
+    uint32_t nTextures;
+    const float4 *texc;
+    const float *ewaLut;
     const DEmitter *emitters;
     uint32_t nEmitters;
     const float *emitterCdf;   // nEmitters + 1
@@ -193,6 +215,7 @@ struct DRender {
     int32_t maxDepth, rrDepth, strictNormals, hideEmitters;
     int32_t sampleLo, sampleHi;
     int32_t integrator;      // 0 path, 1 volpath
+    float diffScale;         // 1/sqrt(sampleCount): RayDifferential::scaleDifferential factor (integrator.cpp:144-145,181)
     uint32_t logRes;         // sobol m_logResolution
     float resolution;        // sobol m_resolution
     uint64_t totalWork;      // W*H*(hi-lo)

@@ -136,7 +136,7 @@ struct Parser {
             return;
         }
         static const char *objects[] = {"scene", "integrator", "sensor", "sampler", "film", "rfilter", "bsdf", "shape", "emitter", "ref", "transform",
-                                        "medium", "volume", "phase"};
+                                        "medium", "volume", "phase", "texture"};
         bool isObject = std::find_if(std::begin(objects), std::end(objects), [&](const char *o) { return tag == o; }) != std::end(objects);
         if (isObject) {
             auto n = std::make_unique<Node>();
@@ -340,6 +340,12 @@ struct Loader {
         if (n->type == "diffuse") {
             m.type = B2_BSDF_DIFFUSE;
             p.spec(p.has("reflectance") ? "reflectance" : "diffuseReflectance", half, m.reflectance); // diffuse.cpp:75-77
+            for (auto &c : n->children) { // diffuse.cpp:191-200 addChild: a Texture named reflectance / diffuseReflectance
+                const bool isTex = c->tag == "texture" || (c->tag == "ref" && textureIds.count(c->id));
+                if (!isTex) continue;
+                if (c->name != "reflectance" && c->name != "diffuseReflectance") throw Err("diffuse: texture child must be named 'reflectance' or 'diffuseReflectance'");
+                m.reflectance_texture = 1 + (c->tag == "texture" ? addTexture(c.get()) : textureIds[c->id]);
+            }
         } else if (n->type == "roughconductor") {
             m.type = B2_BSDF_ROUGHCONDUCTOR;
             p.spec("specularReflectance", one, m.reflectance);
@@ -422,6 +428,89 @@ struct Loader {
         if (!n->id.empty()) bsdfIds[n->id] = id;
         return id;
     }
+    // ---- bitmap textures ----
+    std::map<std::string, int> textureIds;
+    // Bitmap::readPFM (bitmap.cpp:3764-3814) and Bitmap::readPPM (:3857-3895, 8-bit P6), then Bitmap::convert(.., EFloat32, gamma 1)
+    // as TMIPMap's constructor applies it (mipmap.h:225-226; fmtconv.cpp:1092-1101,1136-1147): linear float, top row first
+    static void loadImage(const std::string &path, double gammaOverride, int &w, int &h, int &ch, std::vector<float> &px) {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Err("bitmap: cannot open \"" + path + "\"");
+        auto token = [&]() { std::string t; char c; while (f.get(c)) { if (c == ' ' || c == '\t' || c == '\n' || c == '\r') { if (!t.empty()) break; } else t += c; } return t; };
+        const std::string magic = token();
+        double gamma; // bitmap gamma: -1 = sRGB curve
+        if (magic == "PF" || magic == "Pf") {
+            ch = magic == "PF" ? 3 : 1;
+            w = atoi(token().c_str()); h = atoi(token().c_str());
+            const double scaleAndOrder = strtod(token().c_str(), nullptr);
+            if (w <= 0 || h <= 0 || scaleAndOrder == 0) throw Err("readPFM(): Invalid header!");
+            px.resize((size_t) w * h * ch);
+            f.read((char *) px.data(), (std::streamsize) (px.size() * 4));
+            if (!f) throw Err("readPFM(): file is truncated");
+            if (scaleAndOrder > 0) // big endian
+                for (float &v : px) { unsigned char *b = (unsigned char *) &v; std::swap(b[0], b[3]); std::swap(b[1], b[2]); }
+            const float scale = (float) std::fabs(scaleAndOrder);
+            if (scale != 1) for (float &v : px) v *= scale;
+            for (int y = 0; y < h / 2; ++y) // flipVertically: PFM stores the bottom row first
+                std::swap_ranges(px.begin() + (size_t) y * w * ch, px.begin() + (size_t) (y + 1) * w * ch, px.begin() + (size_t) (h - 1 - y) * w * ch);
+            gamma = 1.0;
+        } else if (magic == "P6") {
+            ch = 3;
+            w = atoi(token().c_str()); h = atoi(token().c_str());
+            const int maxVal = atoi(token().c_str());
+            if (w <= 0 || h <= 0 || maxVal <= 0) throw Err("readPPM(): unable to parse the file header!");
+            if (maxVal > 0xFF) throw Err("readPPM(): 16-bit PPM files are not supported");
+            std::vector<unsigned char> raw((size_t) w * h * 3);
+            f.read((char *) raw.data(), (std::streamsize) raw.size());
+            if (!f) throw Err("readPPM(): file is truncated");
+            px.resize(raw.size());
+            for (size_t i = 0; i < raw.size(); ++i) px[i] = (float) raw[i] * (1.0f / 255.0f);
+            gamma = -1.0;
+        } else throw Err("bitmap: unsupported image format in \"" + path + "\" (supported: PFM, 8-bit binary PPM)");
+        if (gammaOverride != 0) gamma = gammaOverride; // bitmap.cpp:251-252
+        if (gamma == -1.0) {
+            for (float &v : px) v = v <= 0.04045f ? v * (float) (1.0 / 12.92) : std::pow((float) ((v + 0.055f) * (float) (1.0 / 1.055)), 2.4f);
+        } else if (gamma != 1.0) {
+            for (float &v : px) v = std::pow(v, (float) gamma);
+        }
+    }
+    int addTexture(Node *n) {
+        if (n->type != "bitmap") throw Err("unsupported texture plugin \"" + n->type + "\" (supported: bitmap)");
+        Props p(n);
+        std::string fn = p.s("filename", "");
+        if (fn.empty()) throw Err("bitmap: 'filename' is required");
+        if (fn[0] != '/') fn = baseDir + "/" + fn;
+        if (!p.s("channel", "").empty()) throw Err("bitmap: the 'channel' parameter is not supported");
+        b2_texture_desc t;
+        memset(&t, 0, sizeof(t));
+        auto lowerOf = [](std::string v) { std::transform(v.begin(), v.end(), v.begin(), ::tolower); return v; };
+        const std::string ft = lowerOf(p.s("filterType", "ewa")); // bitmap.cpp:213-230
+        if (ft == "ewa") t.filter_type = B2_TEX_EWA; else if (ft == "bilinear") t.filter_type = B2_TEX_BILINEAR;
+        else if (ft == "trilinear") t.filter_type = B2_TEX_TRILINEAR; else if (ft == "nearest") t.filter_type = B2_TEX_NEAREST;
+        else throw Err("Invalid filter type '" + ft + "', must be 'ewa', 'trilinear', or 'nearest'!");
+        auto wrapOf = [](const std::string &m) { // bitmap.cpp:324-338
+            if (m == "repeat") return (int) B2_WRAP_REPEAT; if (m == "clamp") return (int) B2_WRAP_CLAMP; if (m == "mirror") return (int) B2_WRAP_MIRROR;
+            if (m == "zero" || m == "black") return (int) B2_WRAP_ZERO; if (m == "one" || m == "white") return (int) B2_WRAP_ONE;
+            throw Err("Invalid wrap mode '" + m + "', must be 'repeat', 'clamp', 'black', or 'white'!");
+        };
+        const std::string wm = p.s("wrapMode", "repeat");
+        t.wrap_u = wrapOf(p.s("wrapModeU", wm)); t.wrap_v = wrapOf(p.s("wrapModeV", wm));
+        t.max_anisotropy = (float) p.f("maxAnisotropy", 20);
+        const double gamma = p.f("gamma", 0);
+        p.b("cache", false); // MIP map cache files are not written
+        if (p.s("coordinates", "uv") != "uv") throw Err("Only UV coordinates are supported at the moment!"); // texture.cpp:81,95
+        t.uoffset = (float) p.f("uoffset", 0); t.voffset = (float) p.f("voffset", 0);
+        const double uvscale = p.f("uvscale", 1);
+        t.uscale = (float) p.f("uscale", uvscale); t.vscale = (float) p.f("vscale", uvscale);
+        p.checkAllUsed();
+        std::vector<float> px;
+        loadImage(fn, gamma, t.width, t.height, t.channels, px);
+        t.pixels = px.data();
+        const int id = b2_scene_add_texture(scene, &t);
+        if (id < 0) throw Err(b2_last_error(nullptr));
+        if (!n->id.empty()) textureIds[n->id] = id;
+        return id;
+    }
+
     int resolveRef(Node *r) {
         auto it = bsdfIds.find(r->id);
         if (it == bsdfIds.end()) throw Err("Referenced object \"" + r->id + "\" not found (BSDF and medium references are supported)");
@@ -579,7 +668,7 @@ struct Loader {
 
     struct MeshData { std::vector<float> P, N, UV; std::vector<uint32_t> idx; };
 
-    void loadObj(const std::string &path, MeshData &md) {
+    void loadObj(const std::string &path, MeshData &md, bool flipTexCoords = true) {
         std::ifstream f(path);
         if (!f) throw Err("OBJ file \"" + path + "\" could not be found!");
         std::vector<double> v, vn, vt;
@@ -594,7 +683,7 @@ struct Loader {
             if (!(ss >> k)) continue;
             if (k == "v") { double x, y, z; ss >> x >> y >> z; v.insert(v.end(), {x, y, z}); }
             else if (k == "vn") { double x, y, z; ss >> x >> y >> z; vn.insert(vn.end(), {x, y, z}); }
-            else if (k == "vt") { double x = 0, y = 0; ss >> x >> y; vt.insert(vt.end(), {x, y}); }
+            else if (k == "vt") { float x = 0, y = 0; ss >> x >> y; if (flipTexCoords) y = 1 - y; vt.insert(vt.end(), {x, y}); } // obj.cpp:305-308
             else if (k == "f") {
                 std::vector<Corner> face;
                 std::string tok;
@@ -877,7 +966,7 @@ struct Loader {
             if (fn.empty()) throw Err(n->type + ": missing 'filename'");
             if (fn[0] != '/') fn = baseDir + "/" + fn;
             bool fileFaceNormals = false;
-            if (n->type == "obj") { loadObj(fn, md); p.b("flipTexCoords", true); p.b("collapse", false); }
+            if (n->type == "obj") { loadObj(fn, md, p.b("flipTexCoords", true)); p.b("collapse", false); }
             else if (n->type == "ply") { loadPly(fn, md); p.b("srgb", true); }
             else loadSerialized(fn, (int) p.i("shapeIndex", 0), md, fileFaceNormals);
             bool faceN = p.b("faceNormals", false) || fileFaceNormals;
@@ -985,11 +1074,12 @@ struct Loader {
         rp->spp = 4; rp->sampler = B2_SAMPLER_INDEPENDENT; rp->max_depth = -1; rp->rr_depth = 5; // independent is Mitsuba's default sampler
         rp->rfilter = B2_RFILTER_GAUSSIAN; rp->rfilter_param = 0.5f;
         bool haveSensor = false;
+        for (auto &c : root->children) if (c->tag == "texture") addTexture(c.get());
         for (auto &c : root->children) if (c->tag == "bsdf") addBsdf(c.get());
         for (auto &c : root->children) if (c->tag == "medium") addMedium(c.get());
         for (auto &cu : root->children) {
             Node *c = cu.get();
-            if (c->tag == "bsdf" || c->tag == "medium") continue;
+            if (c->tag == "bsdf" || c->tag == "medium" || c->tag == "texture") continue;
             if (c->tag == "integrator") {
                 if (c->type == "volpath") rp->integrator = B2_INTEGRATOR_VOLPATH;
                 else if (c->type != "path") throw Err("unsupported integrator \"" + c->type + "\": this library implements the `path` and `volpath` plugins");

@@ -31,7 +31,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from mitsuba_b200 import api
-    assert ctypes.sizeof(api.b2_material_desc) == 4 * 4 + 4 * 4 + 15 * 4 + 8 * 4 and api.b2_material_desc.nested2.offset == 92
+    assert ctypes.sizeof(api.b2_material_desc) == 4 * 4 + 4 * 4 + 15 * 4 + 9 * 4 and api.b2_material_desc.nested2.offset == 92
+    assert api.b2_material_desc.reflectance_texture.offset == 124
+    assert ctypes.sizeof(api.b2_texture_desc) == 56 and api.b2_texture_desc.pixels.offset == 48
     assert ctypes.sizeof(api.b2_render_params) == 72
     assert api.b2_render_params.seed.offset == 8 and api.b2_render_params.flags.offset == 60 and api.b2_render_params.integrator.offset == 64
     # b2_medium_desc: 37 four-byte fields (148 B), padding, one pointer

@@ -1,0 +1,215 @@
+"""`bitmap` textures on the device against the oracle, through the C-ABI: component probes (look-up, uv partials,
+pyramid) and rendered images."""
+import dataclasses
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from mitsuba_b200 import api
+from mitsuba_b200.scene import Bsdf, RenderParams, Texture, checker_image, stress_scene, textured_scene
+from oracle import oracle_api as O
+from test_oracle_texture import WRAPS, one_texture_scene
+
+pytestmark = pytest.mark.gpu
+REL_L2_TOL = 1e-3  # BASELINE.json north_star
+
+
+def rel_l2(a, b):
+    return float(np.sqrt(((a.astype(np.float64) - b) ** 2).sum() / (b.astype(np.float64) ** 2).sum()))
+
+
+def pair(ctx, d):
+    g = api.Scene(ctx, d)
+    return g, O.OracleScene(d, sample_to_camera=g.sample_to_camera())
+
+
+def lookups(rng, n):
+    """uv in [-1.5, 2.5]^2 and a mix of footprints: sub-texel, isotropic, anisotropic (some beyond maxAnisotropy), degenerate."""
+    uv = (rng.random((n, 2)) * 4 - 1.5).astype(np.float32)
+    mag = np.float32(10.0) ** rng.uniform(-4, -0.7, (n, 1)).astype(np.float32)
+    pt = (rng.normal(size=(n, 4)).astype(np.float32) * mag).astype(np.float32)
+    aniso = rng.random(n) < 0.3
+    pt[aniso, 1] *= 0.02; pt[aniso, 3] *= 0.02   # thin in y
+    pt[rng.random(n) < 0.05] = 0.0               # no footprint at all (F = 0 -> trilinear branch with Epsilon)
+    return uv, pt
+
+
+@pytest.mark.parametrize("filter_type", ["nearest", "bilinear", "trilinear", "ewa"])
+def test_texture_lookup_matches_oracle(b2ctx, filter_type):
+    rng = np.random.default_rng(17)
+    for k, (wu, wv) in enumerate([("repeat", "repeat"), ("clamp", "mirror"), ("zero", "one"), ("mirror", "clamp")]):
+        img = checker_image(61, 40, 5, 30 + k, rgb=(k % 2 == 0))
+        tex = Texture(img, filter_type=filter_type, wrap_u=wu, wrap_v=wv, uscale=1.5, voffset=0.2, max_anisotropy=8.0)
+        g, o = pair(b2ctx, one_texture_scene(tex))
+        uv, pt = lookups(rng, 4000)
+        ref_u, ref_f = o.texture_eval(0, uv), o.texture_eval(0, uv, pt)
+        got_u, got_f = g.texture_eval(0, uv, parity=True), g.texture_eval(0, uv, pt, parity=True)
+        assert np.abs(got_u - ref_u).max() < 1e-6
+        # filtered look-ups: the MIP level / tap set comes out of log, sqrt and atan of the footprint; a last-bit difference between the host
+        # and the device libm can move one tap across the ellipse boundary, so a handful of look-ups may differ visibly
+        err = np.abs(got_f - ref_f).max(axis=1)
+        assert np.mean(err > 1e-5) < 2e-3, (filter_type, wu, wv, np.sort(err)[-5:])
+        assert err.max() < 0.05
+        fast_f = g.texture_eval(0, uv, pt, parity=False)
+        assert np.mean(np.abs(fast_f - ref_f).max(axis=1) > 1e-3) < 5e-3
+
+
+def test_device_pyramid_is_the_host_pyramid(b2ctx):
+    img = checker_image(50, 37, 4, 8)
+    g, o = pair(b2ctx, one_texture_scene(Texture(img, filter_type="ewa", wrap_u="mirror", wrap_v="repeat")))
+    info = o.texture_info(0)
+    for l in range(info["levels"]):
+        lvl, n = g.texture_level(0, l)
+        assert n == info["levels"]
+        assert np.array_equal(lvl, o.texture_level(0, l))
+
+
+def test_uv_partials_match_oracle(b2ctx):
+    d = textured_scene(96, 96)
+    g, o = pair(b2ctx, d)
+    rng = np.random.default_rng(23)
+    pos = rng.uniform(1, 95, (3000, 2)).astype(np.float32)
+    spp = 16
+    ref = o.primary_partials(pos, spp)
+    rays = g.camera_rays(pos, parity=True)
+    t, u, v, prim = g.trace(rays, parity=True)
+    hit = prim != 0xFFFFFFFF
+    assert np.array_equal(hit, ref[:, 0] == 1)
+    got = g.texture_partials(pos[hit], (t[hit], u[hit], v[hit], prim[hit]), spp, parity=True)
+    r = ref[hit]
+    assert np.abs(got[:, 0:2] - r[:, 1:3]).max() < 2e-6                       # uv
+    scale = np.abs(r[:, 3:7]).max(axis=1, keepdims=True) + 1e-9
+    rel = np.abs(got[:, 2:6] - r[:, 3:7]) / scale
+    assert np.percentile(rel, 99) < 1e-4 and rel.max() < 1e-2                 # dudx dudy dvdx dvdy (differences of nearly equal numbers)
+
+
+@pytest.mark.parametrize("filter_type", ["ewa", "trilinear", "bilinear", "nearest"])
+def test_textured_scene_image_parity(b2ctx, filter_type):
+    d = textured_scene(96, 96, filter_type=filter_type, tex_res=128)
+    g, o = pair(b2ctx, d)
+    for smp, filt in (("sobol", "box"), ("independent", "gaussian")):
+        rp = RenderParams(spp=16, sampler=smp, rfilter=filt)
+        fo, so = o.render(rp)
+        fg, sg = g.render(rp, parity=True)
+        assert rel_l2(api.develop(fg), O.develop(fo)) <= 3e-4, (filter_type, smp)
+        assert abs(sg["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+    rp = RenderParams(spp=64, sampler="sobol", rfilter="box")
+    fo, _ = o.render(rp)
+    ff, _ = g.render(rp, parity=False)
+    assert rel_l2(api.develop(ff), O.develop(fo)) <= REL_L2_TOL
+
+
+def test_textured_twosided_thinlens_and_energy_scale(b2ctx):
+    """twosided(diffuse(bitmap)) seen through a thin lens (aperture sample re-drawn for the differentials), image values above 1
+    (ensureEnergyConservation scale)."""
+    d = textured_scene(64, 64, two_sided=True, tex_res=64)
+    d.camera = dataclasses.replace(d.camera, aperture_radius=0.05, focus_distance=5.0)
+    ball = d.meshes[1].bsdf.reflectance
+    ball.pixels = (ball.pixels * np.float32(1.7)).astype(np.float32)
+    g, o = pair(b2ctx, d)
+    assert o.texture_info(1)["bsdf_scale"] < 0.99
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="box")
+    fo, so = o.render(rp)
+    fg, sg = g.render(rp, parity=True)
+    assert rel_l2(api.develop(fg), O.develop(fo)) <= 3e-4
+    assert abs(sg["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+
+
+def test_textured_instances(b2ctx):
+    """A textured shapegroup: dpdu / dpdv go through the instance transform before computePartials (instance.cpp:158-159)."""
+    d = stress_scene(5, 24, 24, 64, 64, instanced=True)
+    proto = d.meshes[0]
+    n = len(proto.P)
+    rng = np.random.default_rng(1)
+    proto.UV = rng.random((n, 2)).astype(np.float32)
+    proto.bsdf = Bsdf("diffuse", reflectance=Texture(checker_image(64, 64, 8, 3), filter_type="ewa"))
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="box")
+    fo, so = o.render(rp)
+    fg, sg = g.render(rp, parity=True)
+    assert rel_l2(api.develop(fg), O.develop(fo)) <= 5e-4
+    assert abs(sg["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+
+
+def test_texture_errors(b2ctx):
+    d = one_texture_scene(Texture(checker_image(8, 8), filter_type="ewa"))
+    g = api.Scene(b2ctx, d)
+    with pytest.raises(api.B2Error, match="volpath with bitmap textures"):
+        g.render(RenderParams(spp=1, integrator="volpath"))
+    d = one_texture_scene((0.5, 0.5, 0.5))
+    d.meshes[0].bsdf = Bsdf("roughconductor")
+    d.meshes[0].bsdf.reflectance = Texture(checker_image(8, 8))  # only `diffuse` takes a texture; flat() ignores it elsewhere
+    api.Scene(b2ctx, d)
+    with pytest.raises(api.B2Error, match="invalid texture id"):
+        g.texture_eval(3, np.zeros((1, 2), np.float32))
+
+
+def _write_pfm(path, img):
+    h, w = img.shape[:2]
+    with open(path, "wb") as f:
+        f.write(b"PF\n" if img.ndim == 3 else b"Pf\n")
+        f.write(f"{w} {h}\n-1.0\n".encode())
+        f.write(np.ascontiguousarray(img[::-1], "<f4").tobytes())  # bottom row first
+
+
+def _write_ppm(path, img8):
+    h, w = img8.shape[:2]
+    with open(path, "wb") as f:
+        f.write(f"P6\n{w} {h}\n255\n".encode())
+        f.write(np.ascontiguousarray(img8, np.uint8).tobytes())
+
+
+XML = """<scene version="0.5.0">
+<integrator type="path"/>
+<sensor type="perspective"><float name="fov" value="40"/><float name="nearClip" value="0.1"/><float name="farClip" value="100"/>
+<transform name="toWorld"><lookat origin="0.5, 0.5, 2" target="0.5, 0.5, 0" up="0, 1, 0"/></transform>
+<sampler type="sobol"><integer name="sampleCount" value="16"/></sampler>
+<film type="hdrfilm"><integer name="width" value="32"/><integer name="height" value="32"/><rfilter type="box"/></film></sensor>
+%s
+<shape type="obj"><string name="filename" value="quad.obj"/>
+<bsdf type="diffuse">%s</bsdf></shape>
+<shape type="obj"><string name="filename" value="light.obj"/><emitter type="area"><rgb name="radiance" value="5"/></emitter>
+<bsdf type="diffuse"><rgb name="reflectance" value="0"/></bsdf></shape>
+</scene>"""
+
+
+def test_bitmap_texture_through_xml(b2ctx, tmp_path):
+    (tmp_path / "quad.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nf 1/1 2/2 3/3\nf 1/1 3/3 4/4\n")
+    (tmp_path / "light.obj").write_text("v 0 0 3\nv 1 0 3\nv 1 1 3\nv 0 1 3\nf 1 3 2\nf 1 4 3\n")
+    img = checker_image(24, 16, 4, 12)
+    _write_pfm(tmp_path / "tex.pfm", img)
+    img8 = np.clip(np.round(checker_image(20, 12, 4, 13) * 255), 0, 255).astype(np.uint8)
+    _write_ppm(tmp_path / "tex.ppm", img8)
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="box")
+    # 1. PFM (linear), nested <texture>, non-default parameters
+    xml = XML % ("", '<texture type="bitmap" name="reflectance"><string name="filename" value="tex.pfm"/><string name="filterType" value="trilinear"/>'
+                     '<string name="wrapModeU" value="mirror"/><float name="uvscale" value="2"/><float name="voffset" value="0.25"/></texture>')
+    (tmp_path / "a.xml").write_text(xml)
+    sc, rpx = b2ctx.load_xml(str(tmp_path / "a.xml"))
+    f1, _ = sc.render(rpx, parity=True)
+    # obj loader: flipTexCoords (obj.cpp) turns v into 1 - v
+    ref = one_texture_scene(Texture(img, filter_type="trilinear", wrap_u="mirror", uscale=2.0, vscale=2.0, voffset=0.25))
+    ref.meshes[0].UV = np.array([(0, 1), (1, 1), (1, 0), (0, 0)], np.float32)
+    f2, _ = api.Scene(b2ctx, ref).render(rp, parity=True)
+    assert rel_l2(api.develop(f1), api.develop(f2)) < 1e-5
+    # 2. 8-bit PPM (sRGB -> linear, fmtconv.cpp:1092-1101), top-level <texture id> + <ref>
+    xml = XML % ('<texture type="bitmap" id="t"><string name="filename" value="tex.ppm"/></texture>', '<ref name="reflectance" id="t"/>')
+    (tmp_path / "b.xml").write_text(xml)
+    sc, rpx = b2ctx.load_xml(str(tmp_path / "b.xml"))
+    f1, _ = sc.render(rpx, parity=True)
+    v = img8.astype(np.float32) * np.float32(1.0 / 255.0)
+    lin = np.where(v <= 0.04045, v * np.float32(1.0 / 12.92), ((v + np.float32(0.055)) * np.float32(1.0 / 1.055)) ** np.float32(2.4)).astype(np.float32)
+    ref = one_texture_scene(Texture(lin, filter_type="ewa"))
+    ref.meshes[0].UV = np.array([(0, 1), (1, 1), (1, 0), (0, 0)], np.float32)
+    f2, _ = api.Scene(b2ctx, ref).render(rp, parity=True)
+    assert rel_l2(api.develop(f1), api.develop(f2)) < 1e-4
+    # 3. errors
+    for body, msg in (('<texture type="checkerboard" name="reflectance"/>', "unsupported texture plugin"),
+                      ('<texture type="bitmap" name="reflectance"><string name="filename" value="nope.pfm"/></texture>', "cannot open"),
+                      ('<texture type="bitmap" name="reflectance"><string name="filename" value="tex.pfm"/><string name="filterType" value="cubic"/></texture>', "Invalid filter type"),
+                      ('<texture type="bitmap" name="reflectance"><string name="filename" value="tex.pfm"/><string name="wrapMode" value="tile"/></texture>', "Invalid wrap mode")):
+        (tmp_path / "e.xml").write_text(XML % ("", body))
+        with pytest.raises(api.B2Error, match=msg):
+            b2ctx.load_xml(str(tmp_path / "e.xml"))
