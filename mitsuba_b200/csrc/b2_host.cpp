@@ -1319,9 +1319,9 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graphExec = nullptr;
     if (!useEvents) {
-        if (volpath) {
-            // k_volstep has a deep local-memory frame: its first launch may have to grow the context's local-memory pool, which
-            // is not allowed inside a stream capture.  The first iteration therefore runs as plain launches.
+        if (volpath || s->ds.nTextures) {
+            // k_volstep (and the textured k_shade) have a deep local-memory frame: their first launch may have to grow the context's
+            // local-memory pool, which is not allowed inside a stream capture.  The first iteration therefore runs as plain launches.
             enqueueIteration();
             launches += launchesPerIter;
             ++iter;
