@@ -8,6 +8,10 @@ Outputs (committed, so the GPU box and CI never read /root/reference):
   sfmt_kat.json   the 64-bit known-answer words (192) of src/tests/test_random.cpp:436-507 (Random(4321).nextULong())
   sobol_ref.npz   outputs of the REFERENCE's own sobol::sampleSingle / sobol::look_up
                   (src/samplers/sobolseq.h:45-60,104-133, compiled into oracle/_ref) on seeded inputs
+  resample_ref.npz  MIP pyramids (every level) of seeded images, computed with the REFERENCE's own Resampler<float>
+                  (include/mitsuba/core/rfilter.h:107-449) and LanczosSincFilter (src/rfilters/lanczos.cpp), compiled into
+                  oracle/_ref/librfilterref.so, applied the way Bitmap::resample + TMIPMap's constructor apply them
+                  (src/libcore/bitmap.cpp:2258-2327 x pass then y pass with clamping to [0, 1]; mipmap.h:246-277 level chain)
 """
 import ctypes as C, json, os, re
 import numpy as np
@@ -50,7 +54,52 @@ def sobol_ref():
     print("sobol_ref.npz:", n, "samples +", n, "look_ups")
 
 
+REF_BC = {"clamp": 0, "repeat": 1, "mirror": 2, "zero": 3, "one": 4}  # ReconstructionFilter::EBoundaryCondition, rfilter.h:40-53
+
+
+def reference_pyramid(img, wrap_u, wrap_v, lib=None):
+    """All MIP levels below level 0 of `img` (H, W, C) float32, non-negative, through the reference's compiled Resampler."""
+    L = lib or C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "librfilterref.so"))
+    fptr = lambda a, off=0: C.cast(a.ctypes.data + off, C.POINTER(C.c_float))
+    levels, cur = [], np.ascontiguousarray(img, np.float32)
+    while cur.shape[0] > 1 or cur.shape[1] > 1:
+        h, w, ch = cur.shape
+        nw, nh = max(1, (w + 1) // 2), max(1, (h + 1) // 2)   # mipmap.h:187-189
+        src = cur
+        if w != nw:  # bitmap.cpp:2258-2293: every row
+            tmp = np.zeros((h, nw, ch), np.float32)
+            for y in range(h):
+                L.rfref_resample(REF_BC[wrap_u], 2, w, nw, fptr(src, y * w * ch * 4), 1, fptr(tmp, y * nw * ch * 4), 1, ch, 1)
+            src = tmp
+        if h != nh:  # bitmap.cpp:2296-2327: every column (stride = row length)
+            out = np.zeros((nh, nw, ch), np.float32)
+            for x in range(nw):
+                L.rfref_resample(REF_BC[wrap_v], 2, h, nh, fptr(src, x * ch * 4), nw, fptr(out, x * ch * 4), nw, ch, 1)
+            src = out
+        cur = src
+        levels.append(cur)
+    return levels
+
+
+def resample_ref():
+    rng = np.random.default_rng(2024)
+    out = {}
+    k = 0
+    for shape in ((32, 32, 3), (37, 50, 3), (21, 13, 1), (1, 9, 1), (16, 1, 3), (5, 64, 1)):
+        for wu, wv in (("repeat", "repeat"), ("clamp", "mirror"), ("zero", "one"), ("mirror", "clamp"), ("one", "repeat")):
+            img = np.maximum((rng.random(shape) * 1.3 - 0.1).astype(np.float32), 0)  # values above 1 exercise the clamp
+            out[f"img{k}"] = img
+            out[f"wrap{k}"] = np.array([wu, wv])
+            for l, lvl in enumerate(reference_pyramid(img, wu, wv)):
+                out[f"lvl{k}_{l + 1}"] = lvl
+            k += 1
+    out["count"] = np.array(k)
+    np.savez_compressed(os.path.join(OUT, "resample_ref.npz"), **out)
+    print("resample_ref.npz:", k, "pyramids")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     sfmt_kat()
     sobol_ref()
+    resample_ref()

@@ -5,6 +5,7 @@ unity, known-answer weights from an independent float64 derivation, analytic uv 
 independently written implementation (the host-side pyramid builder that feeds the device)."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -245,3 +246,45 @@ def test_host_pyramid_equals_oracle_pyramid(wrap):
             out = np.zeros((h.value, w.value, ft["channels"]), np.float32)
             assert L.b2_mipmap_level(C.byref(t), l, C.byref(n), C.byref(w), C.byref(h), out.ctypes.data_as(C.POINTER(C.c_float))) == 0
             assert np.array_equal(out, sc.texture_level(0, l)), (shape, l)
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resample_ref.npz")
+
+
+def test_pyramids_match_the_reference_resampler():
+    """tests/golden/resample_ref.npz: every MIP level of 30 seeded images as the REFERENCE's own Resampler<float> + LanczosSincFilter
+    produce them (compiled from /root/reference into oracle/_ref/librfilterref.so; fixture written by tests/gen_golden.py).
+    Both the oracle's restatement and the product's host-side builder must reproduce them bit for bit."""
+    g = np.load(GOLDEN)
+    L = api.lib()
+    for k in range(int(g["count"])):
+        img = g[f"img{k}"]
+        wu, wv = (str(x) for x in g[f"wrap{k}"])
+        tex = Texture(img if img.shape[2] == 3 else img[:, :, 0], filter_type="ewa", wrap_u=wu, wrap_v=wv)
+        sc = O.OracleScene(one_texture_scene(tex))
+        info = sc.texture_info(0)
+        t = _desc(tex.flat())
+        n, w, h = C.c_int(), C.c_int(), C.c_int()
+        for l in range(1, info["levels"]):
+            ref = g[f"lvl{k}_{l}"]
+            assert np.array_equal(sc.texture_level(0, l), ref), (k, l, "oracle")
+            out = np.zeros(ref.shape, np.float32)
+            assert L.b2_mipmap_level(C.byref(t), l, C.byref(n), C.byref(w), C.byref(h), out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+            assert np.array_equal(out, ref), (k, l, "host builder")
+        assert f"lvl{k}_{info['levels']}" not in g.files  # same number of levels
+
+
+def test_live_reference_resampler_when_present():
+    """Same comparison against the freshly compiled reference code (only where oracle/_ref/librfilterref.so exists)."""
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "librfilterref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/librfilterref.so not built (the reference tree is not on this machine)")
+    from gen_golden import reference_pyramid
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(77)
+    for shape, wu, wv in (((48, 40, 3), "mirror", "repeat"), ((9, 31, 1), "zero", "clamp"), ((64, 3, 3), "one", "mirror")):
+        img = np.maximum((rng.random(shape) * 1.2 - 0.05).astype(np.float32), 0)
+        tex = Texture(img if shape[2] == 3 else img[:, :, 0], filter_type="trilinear", wrap_u=wu, wrap_v=wv)
+        sc = O.OracleScene(one_texture_scene(tex))
+        for l, ref in enumerate(reference_pyramid(img, wu, wv, lib)):
+            assert np.array_equal(sc.texture_level(0, l + 1), ref)
