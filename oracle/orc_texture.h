@@ -9,10 +9,14 @@
  *   texel / box / bilinear / EWA      include/mitsuba/render/mipmap.h:499-571, :586-608, :638-721, :767-838
  *   uv transform + filter choice      src/librender/texture.cpp:124-133 (Texture2D::eval), src/textures/bitmap.cpp:400-421,:452-465
  *   energy conservation of the BSDF   src/librender/bsdf.cpp:88-111 (scale texture 0.99 / max)
- * Pinning: the pyramid construction is checked bit for bit against the reference's own Resampler<float> + LanczosSincFilter, compiled
- * from /root/reference into oracle/_ref/librfilterref.so (rfilter_ref_shim.cpp; fixture tests/golden/resample_ref.npz).  mipmap.h itself
- * (the look-ups) needs Bitmap / boost::filesystem / the plugin manager and cannot be compiled here: evalBilinear / evalEWA / eval are
- * pinned by closed-form known answers only (tests/test_oracle_texture.py).
+ * Pinning: both halves are checked bit for bit against the reference's own code, compiled from /root/reference into oracle/_ref
+ * behind stand-in headers for the rest of libcore (oracle/Makefile):
+ *   librfilterref.so  Resampler<float> (rfilter.h) + LanczosSincFilter (src/rfilters/lanczos.cpp)  -> tests/golden/resample_ref.npz
+ *   libmipmapref.so   TMIPMap<Color3, Color3>::eval / evalBilinear / evalBox / evalEWA (mipmap.h with the real barray.h, spectrum.h,
+ *                     math.h, src/libcore/math.cpp)                                                 -> tests/golden/mipmap_ref.npz
+ * (tests/gen_golden.py writes the fixtures, tests/test_oracle_texture.py compares).  Texture2D's uv transform, the partials of
+ * Intersection::computePartials and the sensors' ray differentials sit in files that need all of librender; they are pinned by
+ * closed forms (finite differences of neighbouring pixels, uv scale / offset identities).
  * Image file decoding (PNG/JPEG/EXR) is not part of the path: pixels arrive as linear float, 1 or 3 channels, row-major, top row
  * first (the layout Bitmap::convert(..., EFloat, gamma 1) hands to the MIP map).
  */

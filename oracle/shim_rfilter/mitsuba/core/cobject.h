@@ -27,6 +27,9 @@
 #ifndef SINGLE_PRECISION
 #define SINGLE_PRECISION 1
 #endif
+#if defined(__linux) && !defined(__LINUX__)
+#define __LINUX__ /* include/mitsuba/core/platform.h:68-69 -- selects the double-precision fastexp / fastlog of math.h:175-199 */
+#endif
 #define Epsilon 1e-4f /* include/mitsuba/core/constants.h:28 (single precision) */
 
 namespace mitsuba { typedef float Float; }

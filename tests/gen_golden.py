@@ -12,6 +12,10 @@ Outputs (committed, so the GPU box and CI never read /root/reference):
                   (include/mitsuba/core/rfilter.h:107-449) and LanczosSincFilter (src/rfilters/lanczos.cpp), compiled into
                   oracle/_ref/librfilterref.so, applied the way Bitmap::resample + TMIPMap's constructor apply them
                   (src/libcore/bitmap.cpp:2258-2327 x pass then y pass with clamping to [0, 1]; mipmap.h:246-277 level chain)
+  mipmap_ref.npz  texture look-ups of the REFERENCE's own TMIPMap<Color3, Color3>::eval / evalBilinear / evalBox
+                  (include/mitsuba/render/mipmap.h:499-838 with the real barray.h / spectrum.h / math.{h,cpp}, compiled into
+                  oracle/_ref/libmipmapref.so) over pyramids built by the reference resampler above: seeded uv and footprints
+                  (sub-texel, isotropic, needle-shaped beyond maxAnisotropy, zero) for every filter type and wrap mode
 """
 import ctypes as C, json, os, re
 import numpy as np
@@ -98,8 +102,73 @@ def resample_ref():
     print("resample_ref.npz:", k, "pyramids")
 
 
+FILTERS = {"nearest": 0, "bilinear": 1, "trilinear": 2, "ewa": 3}  # EMIPFilterType, mipmap.h:52-61
+
+
+def texture_lookups(rng, n):
+    """uv in [-1.5, 2.5]^2; partials (dudx, dudy, dvdx, dvdy): sub-texel to many texels, 30 % needle-shaped, 5 % exactly zero."""
+    uv = (rng.random((n, 2)) * 4 - 1.5).astype(np.float32)
+    mag = np.float32(10.0) ** rng.uniform(-4, -0.7, (n, 1)).astype(np.float32)
+    pt = (rng.normal(size=(n, 4)).astype(np.float32) * mag).astype(np.float32)
+    needle = rng.random(n) < 0.3
+    pt[needle, 1] *= 0.02; pt[needle, 3] *= 0.02
+    pt[rng.random(n) < 0.05] = 0.0
+    return uv, pt
+
+
+class ReferenceMipmap:
+    """The reference's TMIPMap<Color3, Color3> over given RGB levels (list of (h, w, 3) float32), via oracle/_ref/libmipmapref.so."""
+
+    def __init__(self, levels, wrap_u, wrap_v, filter_type, max_anisotropy, lib=None):
+        self.L = lib or C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libmipmapref.so"))
+        self.L.mipref_create.restype = C.c_void_p
+        self.levels = [np.ascontiguousarray(l, np.float32) for l in levels]
+        sizes = np.array([[l.shape[1], l.shape[0]] for l in self.levels], np.int32)
+        ptrs = (C.POINTER(C.c_float) * len(self.levels))(*[l.ctypes.data_as(C.POINTER(C.c_float)) for l in self.levels])
+        aniso = max_anisotropy if filter_type == "ewa" else 1.0  # bitmap.cpp:232-235
+        self.h = C.c_void_p(self.L.mipref_create(len(self.levels), sizes.ctypes.data_as(C.POINTER(C.c_int)), ptrs, REF_BC[wrap_u], REF_BC[wrap_v],
+                                                 FILTERS[filter_type], C.c_float(aniso)))
+        self.filter_type = filter_type
+
+    def eval(self, uv, partials=None):
+        """BitmapTexture::eval(uv, d0, d1) (bitmap.cpp:452-465) or, without partials, eval(uv) (bitmap.cpp:400-421)."""
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros((len(uv), 3), np.float32)
+        if partials is None:
+            (self.L.mipref_eval_box if self.filter_type == "nearest" else self.L.mipref_eval_bilinear)(self.h, 0, len(uv), fp(uv), fp(out))
+        else:
+            d0d1 = np.ascontiguousarray(np.asarray(partials, np.float32)[:, [0, 2, 1, 3]])  # d0 = (dudx, dvdx), d1 = (dudy, dvdy): texture.cpp:127-130
+            self.L.mipref_eval(self.h, len(uv), fp(uv), fp(d0d1), fp(out))
+        return out
+
+
+def mipmap_ref():
+    rng = np.random.default_rng(4242)
+    out, k = {}, 0
+    setups = ((("repeat", "repeat"), (40, 61, 3), 20.0), (("clamp", "mirror"), (33, 32, 3), 8.0), (("zero", "one"), (16, 50, 3), 2.0),
+              (("mirror", "clamp"), (48, 48, 3), 20.0))
+    images = [rng.random(shape).astype(np.float32) for _, shape, _ in setups]
+    for j, img in enumerate(images):
+        out[f"img{j}"] = img
+    for ft in ("nearest", "bilinear", "trilinear", "ewa"):
+        for j, ((wu, wv), shape, aniso) in enumerate(setups):
+            img = images[j]
+            levels = [img] + (reference_pyramid(img, wu, wv) if ft in ("trilinear", "ewa") else [])
+            m = ReferenceMipmap(levels, wu, wv, ft, aniso)
+            uv, pt = texture_lookups(rng, 600)
+            out[f"cfg{k}"] = np.array([ft, wu, wv, str(aniso), str(j)])
+            out[f"uv{k}"] = uv; out[f"pt{k}"] = pt
+            out[f"filtered{k}"] = m.eval(uv, pt); out[f"unfiltered{k}"] = m.eval(uv)
+            k += 1
+    out["count"] = np.array(k)
+    np.savez_compressed(os.path.join(OUT, "mipmap_ref.npz"), **out)
+    print("mipmap_ref.npz:", k, "configurations x 600 look-ups")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     sfmt_kat()
     sobol_ref()
     resample_ref()
+    mipmap_ref()

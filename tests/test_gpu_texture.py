@@ -10,7 +10,7 @@ import pytest
 from mitsuba_b200 import api
 from mitsuba_b200.scene import Bsdf, RenderParams, Texture, checker_image, stress_scene, textured_scene
 from oracle import oracle_api as O
-from test_oracle_texture import WRAPS, one_texture_scene
+from test_oracle_texture import WRAPS, golden_lookup_cases, one_texture_scene
 
 pytestmark = pytest.mark.gpu
 REL_L2_TOL = 1e-3  # BASELINE.json north_star
@@ -71,6 +71,21 @@ def test_texture_lookup_matches_oracle(b2ctx, filter_type):
         # The bound that matters for this build is the image tolerance (test_textured_scene_image_parity).
         assert np.median(fast_err) < 1e-5
         assert np.mean(fast_err > 1e-3) < 0.05, (filter_type, wu, wv, float(np.mean(fast_err > 1e-3)))
+
+
+def test_texture_lookup_matches_reference_golden(b2ctx):
+    """The device look-ups against tests/golden/mipmap_ref.npz: outputs of the reference's own TMIPMap (mipmap.h compiled from
+    /root/reference, see tests/gen_golden.py), pyramids included -- no oracle in between."""
+    n = 0
+    for k, tex, uv, pt, filtered, unfiltered in golden_lookup_cases():
+        g = api.Scene(b2ctx, one_texture_scene(tex))
+        assert np.abs(g.texture_eval(0, uv, parity=True) - unfiltered).max() < 1e-6, k
+        err = np.abs(g.texture_eval(0, uv, pt, parity=True) - filtered).max(axis=1)
+        _diag(dict(golden_case=k, filter=tex.filter_type, parity_frac_gt_1e5=float(np.mean(err > 1e-5)), parity_max=float(err.max())))
+        assert np.mean(err > 1e-5) < 5e-3 and np.median(err) < 1e-6, (k, tex.filter_type, np.sort(err)[-5:])
+        g.close()
+        n += 1
+    assert n == 16
 
 
 def test_device_pyramid_is_the_host_pyramid(b2ctx):

@@ -288,3 +288,40 @@ def test_live_reference_resampler_when_present():
         sc = O.OracleScene(one_texture_scene(tex))
         for l, ref in enumerate(reference_pyramid(img, wu, wv, lib)):
             assert np.array_equal(sc.texture_level(0, l + 1), ref)
+
+
+def golden_lookup_cases():
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "mipmap_ref.npz"))
+    for k in range(int(g["count"])):
+        ft, wu, wv, aniso, j = (str(x) for x in g[f"cfg{k}"])
+        tex = Texture(g[f"img{j}"], filter_type=ft, wrap_u=wu, wrap_v=wv, max_anisotropy=float(aniso))
+        yield k, tex, g[f"uv{k}"], g[f"pt{k}"], g[f"filtered{k}"], g[f"unfiltered{k}"]
+
+
+def test_lookups_match_the_reference_mipmap():
+    """tests/golden/mipmap_ref.npz: look-ups of the REFERENCE's own TMIPMap<Color3, Color3> (mipmap.h compiled from /root/reference into
+    oracle/_ref/libmipmapref.so, over pyramids from the reference resampler; fixture written by tests/gen_golden.py) for every filter
+    type, four wrap-mode pairs and three anisotropy limits.  The oracle reproduces them bit for bit."""
+    n = 0
+    for k, tex, uv, pt, filtered, unfiltered in golden_lookup_cases():
+        sc = O.OracleScene(one_texture_scene(tex))
+        assert np.array_equal(sc.texture_eval(0, uv, pt), filtered), (k, tex.filter_type)
+        assert np.array_equal(sc.texture_eval(0, uv), unfiltered), (k, tex.filter_type)
+        n += 1
+    assert n == 16
+
+
+def test_live_reference_mipmap_when_present():
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "libmipmapref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libmipmapref.so not built (the reference tree is not on this machine)")
+    from gen_golden import ReferenceMipmap, reference_pyramid, texture_lookups
+    rng = np.random.default_rng(99)
+    img = checker_image(70, 45, 6, 1)
+    for ft, wu, wv, aniso in (("ewa", "repeat", "mirror", 12.0), ("trilinear", "clamp", "zero", 1.0), ("ewa", "one", "clamp", 3.0)):
+        tex = Texture(img, filter_type=ft, wrap_u=wu, wrap_v=wv, max_anisotropy=aniso)
+        sc = O.OracleScene(one_texture_scene(tex))
+        ref = ReferenceMipmap([img] + reference_pyramid(img, wu, wv), wu, wv, ft, aniso)
+        uv, pt = texture_lookups(rng, 20000)
+        assert np.array_equal(sc.texture_eval(0, uv, pt), ref.eval(uv, pt))
+        assert np.array_equal(sc.texture_eval(0, uv), ref.eval(uv))
