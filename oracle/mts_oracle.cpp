@@ -1358,6 +1358,95 @@ void orc_microfacet_eval(int type, float alphaU, float alphaV, int sampleVisible
         out[3 * i] = d.eval(mm); out[3 * i + 1] = d.pdf(w, mm); out[3 * i + 2] = d.smithG1(w, mm);
     }
 }
+/* ---- component hooks with the argument layout of oracle/core_ref_shim.cpp (the same functions of the reference, compiled from
+ * /root/reference): tests/test_oracle_reference_pins.py compares the two one to one ---- */
+void orc_triaccel_load(int n, const float *tris, uint32_t *records, int *status) {
+    for (int i = 0; i < n; ++i) {
+        const float *t = tris + 9 * i;
+        TriAccel a; memset(&a, 0, sizeof(a));
+        status[i] = a.load(V3(t[0], t[1], t[2]), V3(t[3], t[4], t[5]), V3(t[6], t[7], t[8]));
+        a.shapeIndex = 0; a.primIndex = 0;
+        memcpy(records + 12 * i, &a, 48);
+    }
+}
+void orc_triaccel_intersect(int n, const float *tris, const float *rays, float *out) {
+    for (int i = 0; i < n; ++i) {
+        const float *t = tris + 9 * i, *r = rays + 8 * i;
+        TriAccel a; float *o = out + 4 * i; o[0] = o[1] = o[2] = o[3] = 0;
+        if (a.load(V3(t[0], t[1], t[2]), V3(t[3], t[4], t[5]), V3(t[6], t[7], t[8])) != 0) continue;
+        Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7]);
+        float u, v, tt;
+        if (a.rayIntersect(ray, r[3], r[7], u, v, tt)) { o[0] = 1; o[1] = tt; o[2] = u; o[3] = v; }
+    }
+}
+void orc_aabb_intersect(int n, const float *boxes, const float *rays, float *out) {
+    for (int i = 0; i < n; ++i) {
+        const float *b = boxes + 6 * i, *r = rays + 8 * i;
+        AABB box; box.min = V3(b[0], b[1], b[2]); box.max = V3(b[3], b[4], b[5]);
+        Ray ray(V3(r[0], r[1], r[2]), V3(r[4], r[5], r[6]), r[3], r[7]);
+        float nearT = 0, farT = 0;
+        const bool hit = box.rayIntersect(ray, nearT, farT);
+        out[3 * i] = hit ? 1.0f : 0.0f; out[3 * i + 1] = nearT; out[3 * i + 2] = farT;
+    }
+}
+void orc_warp(int what, int n, const float *samples, float *out) {
+    for (int i = 0; i < n; ++i) {
+        const float sx = samples[2 * i], sy = samples[2 * i + 1]; float *o = out + 3 * i;
+        if (what == 0) { const V3 v = squareToCosineHemisphere(sx, sy); o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+        else if (what == 1) { const V3 v = squareToUniformSphere(sx, sy); o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+        else if (what == 2) { squareToUniformDiskConcentric(sx, sy, o[0], o[1]); o[2] = 0; }
+        else { squareToUniformTriangle(sx, sy, o[0], o[1]); o[2] = 0; }
+    }
+}
+void orc_fresnel_dielectric_ext(int n, const float *cosThetaI, float eta, float *out) {
+    for (int i = 0; i < n; ++i) { float ct; out[2 * i] = fresnelDielectricExt(cosThetaI[i], ct, eta); out[2 * i + 1] = ct; }
+}
+void orc_fresnel_conductor_exact_rgb(int n, const float *cosThetaI, const float *eta, const float *k, float *out) {
+    const Spectrum e(eta[0], eta[1], eta[2]), kk(k[0], k[1], k[2]);
+    for (int i = 0; i < n; ++i) { const Spectrum r = fresnelConductorExact(cosThetaI[i], e, kk); out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z; }
+}
+void orc_reflect(int n, const float *wi, const float *nrm, float *out) {
+    for (int i = 0; i < n; ++i) { const V3 r = reflect(V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2])); out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z; }
+}
+void orc_refract(int n, const float *wi, const float *nrm, float eta, const float *cosThetaT, float *out) {
+    for (int i = 0; i < n; ++i) { const V3 r = refract(V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]), eta, cosThetaT[i]); out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z; }
+}
+void orc_coordinate_system(int n, const float *a, float *out) {
+    for (int i = 0; i < n; ++i) { V3 b, c; coordinateSystem(V3(a[3 * i], a[3 * i + 1], a[3 * i + 2]), b, c); float *o = out + 6 * i; o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = c.x; o[4] = c.y; o[5] = c.z; }
+}
+void orc_shading_frame(int n, const float *nrm, const float *dpdu, float *out) {
+    for (int i = 0; i < n; ++i) {
+        Frame f;
+        computeShadingFrame(V3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]), V3(dpdu[3 * i], dpdu[3 * i + 1], dpdu[3 * i + 2]), f);
+        float *o = out + 9 * i;
+        o[0] = f.s.x; o[1] = f.s.y; o[2] = f.s.z; o[3] = f.t.x; o[4] = f.t.y; o[5] = f.t.z; o[6] = f.n.x; o[7] = f.n.y; o[8] = f.n.z;
+    }
+}
+float orc_pmf(int m, const float *weights, int n, const float *samples, uint32_t *index, uint32_t *indexReuse, float *reused, float *cdf) {
+    Discrete d;
+    for (int i = 0; i < m; ++i) d.append(weights[i]);
+    const float total = d.normalize();
+    for (int i = 0; i < n; ++i) {
+        index[i] = (uint32_t) d.sample(samples[i]);
+        float s = samples[i];
+        indexReuse[i] = (uint32_t) d.sampleReuse(s);
+        reused[i] = s;
+    }
+    for (int i = 0; i < m; ++i) cdf[i] = d[i];
+    return total;
+}
+/* Triangle::sample (triangle.cpp:24-62) as TriMesh::samplePosition uses it: barycentric warp of the 2-D sample */
+void orc_triangle_sample(int n, const float *tris, const float *samples, float *out) {
+    for (int i = 0; i < n; ++i) {
+        const float *t = tris + 9 * i;
+        const V3 p0(t[0], t[1], t[2]), p1(t[3], t[4], t[5]), p2(t[6], t[7], t[8]);
+        float bx, by; squareToUniformTriangle(samples[2 * i], samples[2 * i + 1], bx, by);
+        const V3 sideA = p1 - p0, sideB = p2 - p0;
+        const V3 p = p0 + (sideA * bx) + (sideB * by);
+        out[3 * i] = p.x; out[3 * i + 1] = p.y; out[3 * i + 2] = p.z;
+    }
+}
+
 /* emitter direct sampling from reference points (n x 6: ref, refN) with 2D samples -> n x 12:
  * d(3) dist pdf value(3) visible p(3) */
 void orc_sample_emitter_direct(void *s, uint64_t n, const float *ref, const float *samples, float *out) {

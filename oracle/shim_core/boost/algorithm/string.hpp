@@ -1,0 +1,6 @@
+/* Stand-in header (test infrastructure only, see oracle/shim_core/README): scaffolding that lets the reference's own sources and
+ * headers compile where they lie under /root/reference, without boost or the rest of libcore.  No algorithm lives here. */
+#pragma once
+#include <algorithm>
+#include <string>
+namespace boost { inline std::string to_lower_copy(std::string s) { std::transform(s.begin(), s.end(), s.begin(), ::tolower); return s; } inline void to_lower(std::string &s) { std::transform(s.begin(), s.end(), s.begin(), ::tolower); } }

@@ -1,0 +1,14 @@
+/* Stand-in header (test infrastructure only, see oracle/shim_core/README): scaffolding that lets the reference's own sources and
+ * headers compile where they lie under /root/reference, without boost or the rest of libcore.  No algorithm lives here. */
+#pragma once
+#include <fstream>
+#include <string>
+namespace boost { namespace filesystem {
+class path { public: path() {} path(const char *s) : m_s(s) {} path(const std::string &s) : m_s(s) {} bool empty() const { return m_s.empty(); } const std::string &string() const { return m_s; }
+  path filename() const { return *this; } path extension() const { return path(); } path parent_path() const { return path(); } path operator/(const path &o) const { return path(m_s + "/" + o.m_s); } bool is_absolute() const { return false; }
+  private: std::string m_s; };
+inline bool exists(const path &) { return false; }
+inline size_t file_size(const path &) { return 0; }
+class ifstream : public std::ifstream { public: ifstream() {} ifstream(const path &p) : std::ifstream(p.string().c_str()) {} };
+class ofstream : public std::ofstream { public: ofstream() {} ofstream(const path &p) : std::ofstream(p.string().c_str()) {} };
+} }

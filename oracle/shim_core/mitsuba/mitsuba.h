@@ -1,0 +1,30 @@
+/* Stand-in header (test infrastructure only, see oracle/shim_core/README): scaffolding that lets the reference's own sources and
+ * headers compile where they lie under /root/reference, without boost or the rest of libcore.  No algorithm lives here. */
+#pragma once
+#include <mitsuba/core/platform.h>
+#include <sstream>
+#include <string>
+#include <map>
+#include <iostream>
+#include <vector>
+#include <cmath>
+#include <algorithm>
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdexcept>
+#include <limits>
+#include <assert.h>
+using std::cout; using std::cerr; using std::endl;
+#include <mitsuba/core/constants.h>
+#include <mitsuba/core/fwd.h>
+#include <mitsuba/render/fwd.h>
+#include <mitsuba/core/math.h>
+#include <mitsuba/core/object.h>
+#include <mitsuba/core/ref.h>
+#include <mitsuba/core/logger.h>
+#include <mitsuba/core/vector.h>
+#include <mitsuba/core/point.h>
+#include <mitsuba/core/normal.h>
+#include <mitsuba/core/spectrum.h>
+#include <mitsuba/core/util.h>

@@ -16,8 +16,12 @@ Outputs (committed, so the GPU box and CI never read /root/reference):
                   (include/mitsuba/render/mipmap.h:499-838 with the real barray.h / spectrum.h / math.{h,cpp}, compiled into
                   oracle/_ref/libmipmapref.so) over pyramids built by the reference resampler above: seeded uv and footprints
                   (sub-texel, isotropic, needle-shaped beyond maxAnisotropy, zero) for every filter type and wrap mode
+  core_ref.npz    outputs of the REFERENCE's own core math on seeded inputs (tests/ref_pins.py): MicrofacetDistribution (src/bsdfs/
+                  microfacet.h), TriAccel (triaccel.h), AABB::rayIntersect (aabb.h), warp.cpp, util.cpp (fresnel*, reflect, refract,
+                  coordinateSystem, computeShadingFrame), Triangle::sample (triangle.cpp), DiscreteDistribution (pmf.h), sampleTEA
+                  (qmc.h) -- compiled into oracle/_ref/libcoreref.so by oracle/Makefile from oracle/core_ref_shim.cpp
 """
-import ctypes as C, json, os, re
+import ctypes as C, json, os, re, sys
 import numpy as np
 
 REF = os.environ.get("MTS_REFERENCE", "/root/reference")
@@ -166,8 +170,18 @@ def mipmap_ref():
     print("mipmap_ref.npz:", k, "configurations x 600 look-ups")
 
 
+def core_ref():
+    sys.path.insert(0, HERE)
+    import ref_pins
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libcoreref.so"))
+    out = ref_pins.run(lib, "coreref_", ref_pins.inputs())
+    np.savez_compressed(os.path.join(OUT, "core_ref.npz"), **out)
+    print("core_ref.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    core_ref()
     sfmt_kat()
     sobol_ref()
     resample_ref()
