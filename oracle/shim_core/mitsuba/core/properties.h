@@ -1,18 +1,45 @@
 /* Stand-in header (test infrastructure only, see oracle/shim_core/README): scaffolding that lets the reference's own sources and
- * headers compile where they lie under /root/reference, without boost or the rest of libcore.  No algorithm lives here. */
+ * headers compile where they lie under /root/reference, without boost or the rest of libcore.  No algorithm lives here.
+ * A Properties that holds floats, booleans, strings and spectra -- what the BSDF plugin constructors query. */
 #pragma once
 #include <mitsuba/mitsuba.h>
 namespace mitsuba {
 class Properties {
 public:
-    std::map<std::string, std::string> s; std::map<std::string, float> f; std::map<std::string, bool> b;
-    std::string id; const std::string &getID() const { return id; } void setID(const std::string &v) { id = v; }
-    bool hasProperty(const std::string &k) const { return s.count(k) || f.count(k) || b.count(k); }
+    enum EPropertyType { EBoolean = 0, EInteger, EFloat, EPoint, ETransform, EAnimatedTransform, ESpectrum, EString, EData };
+    Properties() {}
+    Properties(const std::string &pluginName) : m_pluginName(pluginName) {}
+    const std::string &getPluginName() const { return m_pluginName; }
+    void setPluginName(const std::string &n) { m_pluginName = n; }
+    const std::string &getID() const { return m_id; }
+    void setID(const std::string &v) { m_id = v; }
+    bool hasProperty(const std::string &k) const { return s.count(k) || f.count(k) || b.count(k) || sp.count(k) || i.count(k); }
+    EPropertyType getType(const std::string &k) const { return f.count(k) ? EFloat : (s.count(k) ? EString : (b.count(k) ? EBoolean : (i.count(k) ? EInteger : ESpectrum))); }
     std::string getString(const std::string &k) const { return s.at(k); }
     std::string getString(const std::string &k, const std::string &d) const { return s.count(k) ? s.at(k) : d; }
+    std::string getAsString(const std::string &k) const { return getString(k, ""); }
+    std::string getAsString(const std::string &k, const std::string &d) const { return getString(k, d); }
     Float getFloat(const std::string &k) const { return f.at(k); }
     Float getFloat(const std::string &k, Float d) const { return f.count(k) ? f.at(k) : d; }
+    int getInteger(const std::string &k) const { return i.at(k); }
+    int getInteger(const std::string &k, int d) const { return i.count(k) ? i.at(k) : d; }
     bool getBoolean(const std::string &k) const { return b.at(k); }
     bool getBoolean(const std::string &k, bool d) const { return b.count(k) ? b.at(k) : d; }
+    Spectrum getSpectrum(const std::string &k) const { return sp.at(k); }
+    Spectrum getSpectrum(const std::string &k, const Spectrum &d) const { return sp.count(k) ? sp.at(k) : d; }
+    void setString(const std::string &k, const std::string &v, bool = true) { s[k] = v; }
+    void setFloat(const std::string &k, Float v, bool = true) { f[k] = v; }
+    void setInteger(const std::string &k, int v, bool = true) { i[k] = v; }
+    void setBoolean(const std::string &k, bool v, bool = true) { b[k] = v; }
+    void setSpectrum(const std::string &k, const Spectrum &v, bool = true) { sp[k] = v; }
+    void markQueried(const std::string &) const {}
+    std::string toString() const { return m_pluginName; }
+private:
+    std::string m_pluginName, m_id;
+    std::map<std::string, std::string> s;
+    std::map<std::string, Float> f;
+    std::map<std::string, int> i;
+    std::map<std::string, bool> b;
+    std::map<std::string, Spectrum> sp;
 };
 }
