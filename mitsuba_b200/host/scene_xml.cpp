@@ -328,6 +328,10 @@ struct Loader {
         }
         m.sample_visible = p.b("sampleVisible", true) ? 1 : 0;
         if (m.distr == B2_DISTR_PHONG) m.sample_visible = 0;
+        // the plugins read the roughness as `m_alphaU->eval(its).average()` of a constant texture (roughconductor.cpp:273-274):
+        // TSpectrum::average() = (a + a + a) * (1.0f / 3) in float (spectrum.h:481-486), which is not always a itself
+        auto avg3 = [](float a) { volatile float r = 0.0f; r = r + a; r = r + a; r = r + a; return (float) (r * (1.0f / 3)); };
+        m.alpha_u = avg3(m.alpha_u); m.alpha_v = avg3(m.alpha_v);
     }
 
     int addBsdf(Node *n) {
@@ -358,7 +362,8 @@ struct Loader {
             float fe[3], fk[3];
             p.spec("eta", eta, fe); p.spec("k", k, fk);
             float ext = (float) namedIOR(p, "extEta", "air");
-            for (int c = 0; c < 3; ++c) { m.eta_c[c] = fe[c] / ext; m.k_c[c] = fk[c] / ext; } // roughconductor.cpp:189-190
+            const float recip = 1.0f / ext; // Spectrum / Float multiplies by the reciprocal (spectrum.h:415-425)
+            for (int c = 0; c < 3; ++c) { m.eta_c[c] = fe[c] * recip; m.k_c[c] = fk[c] * recip; } // roughconductor.cpp:189-190
             microfacet(p, m);
         } else if (n->type == "roughdielectric") {
             m.type = B2_BSDF_ROUGHDIELECTRIC;
@@ -409,7 +414,8 @@ struct Loader {
             float fe[3], fk[3];
             p.spec("eta", eta, fe); p.spec("k", k, fk);
             float ext = (float) namedIOR(p, "extEta", "air");
-            for (int c = 0; c < 3; ++c) { m.eta_c[c] = fe[c] / ext; m.k_c[c] = fk[c] / ext; }
+            const float recip = 1.0f / ext; // Spectrum / Float multiplies by the reciprocal (spectrum.h:415-425)
+            for (int c = 0; c < 3; ++c) { m.eta_c[c] = fe[c] * recip; m.k_c[c] = fk[c] * recip; }
         } else if (n->type == "plastic") { // plastic.cpp:145-204
             m.type = B2_BSDF_PLASTIC;
             float intI = (float) namedIOR(p, "intIOR", "polypropylene"), extI = (float) namedIOR(p, "extIOR", "air");

@@ -124,8 +124,11 @@ class Bsdf:
         t = BSDF_TYPES[self.type]
         distr = DISTRIBUTIONS[self.distribution.lower()]
         sv = bool(self.sample_visible) and distr != 2           # microfacet.h:145-148
+        # the plugins read the roughness as `m_alphaU->eval(its).average()` of a constant texture (roughconductor.cpp:273-274,
+        # roughdielectric.cpp): TSpectrum::average() = (a + a + a) * (1.0f / 3) in float (spectrum.h:481-486), not always a itself
+        avg3 = lambda a: float((np.float32(0.0) + np.float32(a) + np.float32(a) + np.float32(a)) * (np.float32(1.0) / np.float32(3)))
         d = dict(type=t, distr=distr, sampleVisible=int(sv), nested=-1,
-                 alphaU=float(self.alpha_u), alphaV=float(self.alpha_v), eta=1.0,
+                 alphaU=avg3(self.alpha_u), alphaV=avg3(self.alpha_v), eta=1.0,
                  thickness=float(self.thickness), reflectance=(0.0, 0.0, 0.0),
                  transmittance=tuple(float(x) for x in self.specular_transmittance),
                  etaC=(0.0, 0.0, 0.0), kC=(1.0, 1.0, 1.0), sigmaA=tuple(float(x) for x in self.sigma_a),
@@ -140,8 +143,9 @@ class Bsdf:
             d["reflectance"] = tuple(float(x) for x in self.specular_reflectance)
         if t in (1, 7):  # roughconductor.cpp:187-190, conductor.cpp:172-175
             ext = np.float32(lookup_ior(self.ext_eta, "air"))
-            d["etaC"] = tuple(float(np.float32(x) / ext) for x in self.eta)  # roughconductor.cpp:189-190
-            d["kC"] = tuple(float(np.float32(x) / ext) for x in self.k)
+            recip = np.float32(1.0) / ext  # Spectrum / Float multiplies by the reciprocal (spectrum.h:415-425)
+            d["etaC"] = tuple(float(np.float32(x) * recip) for x in self.eta)  # roughconductor.cpp:189-190
+            d["kC"] = tuple(float(np.float32(x) * recip) for x in self.k)
         if t in (2, 3, 6):
             d["eta"] = float(np.float32(lookup_ior(self.int_ior, "bk7")) / np.float32(lookup_ior(self.ext_ior, "air")))
         if t == 8:  # plastic.cpp:145-161,186-204

@@ -16,6 +16,8 @@
 #include <limits>
 #include <assert.h>
 using std::cout; using std::cerr; using std::endl;
+#define BOOST_VERSION 105000 /* selects `namespace fs = boost::filesystem` in fwd.h:180-186 */
+#include <boost/filesystem.hpp> /* stand-in */
 #include <mitsuba/core/constants.h>
 #include <mitsuba/core/fwd.h>
 #include <mitsuba/render/fwd.h>
@@ -23,6 +25,7 @@ using std::cout; using std::cerr; using std::endl;
 #include <mitsuba/core/object.h>
 #include <mitsuba/core/ref.h>
 #include <mitsuba/core/logger.h>
+#include <mitsuba/core/thread.h>
 #include <mitsuba/core/vector.h>
 #include <mitsuba/core/point.h>
 #include <mitsuba/core/normal.h>

@@ -20,6 +20,10 @@ Outputs (committed, so the GPU box and CI never read /root/reference):
                   microfacet.h), TriAccel (triaccel.h), AABB::rayIntersect (aabb.h), warp.cpp, util.cpp (fresnel*, reflect, refract,
                   coordinateSystem, computeShadingFrame), Triangle::sample (triangle.cpp), DiscreteDistribution (pmf.h), sampleTEA
                   (qmc.h) -- compiled into oracle/_ref/libcoreref.so by oracle/Makefile from oracle/core_ref_shim.cpp
+  bsdf_ref.npz    eval / pdf / sample (solid-angle and discrete measures) of the REFERENCE's own BSDF plugins -- src/bsdfs/{diffuse,
+                  roughconductor,roughdielectric,coating,dielectric,conductor,plastic,twosided}.cpp, instantiated from Properties and
+                  called through the real BSDF interface (oracle/bsdf_ref_shim.cpp -> oracle/_ref/libbsdfref.so) -- for the 18
+                  configurations of tests/bsdf_configs.py on the seeded directions of tests/ref_pins.py
 """
 import ctypes as C, json, os, re, sys
 import numpy as np
@@ -179,9 +183,25 @@ def core_ref():
     print("core_ref.npz:", len(out), "arrays")
 
 
+def bsdf_ref():
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import ref_pins
+    from bsdf_configs import configs
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libbsdfref.so"))
+    x = ref_pins.bsdf_inputs()
+    out = {}
+    for name, b in configs().items():
+        for k, v in ref_pins.run_bsdf_reference(lib, b, x).items():
+            out[f"{name}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "bsdf_ref.npz"), **out)
+    print("bsdf_ref.npz:", len(configs()), "BSDF configurations x", ref_pins.NB, "directions")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     core_ref()
+    bsdf_ref()
     sfmt_kat()
     sobol_ref()
     resample_ref()

@@ -121,3 +121,107 @@ def run(lib, prefix, x):
     f.restype = C.c_uint64
     out["tea"] = np.array([[f(C.c_uint32(int(a)), C.c_uint32(int(b)), r) for r in (4, 8)] for a, b in x["tea"]], np.uint64)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# BSDF plugins: the reference's own src/bsdfs/*.cpp (oracle/bsdf_ref_shim.cpp -> oracle/_ref/libbsdfref.so) vs the oracle
+# ---------------------------------------------------------------------------------------------------------------------------
+PLUGIN_IDS = {"diffuse": 0, "roughconductor": 1, "roughdielectric": 2, "coating": 3, "null": 4, "twosided": 5, "dielectric": 6, "conductor": 7, "plastic": 8}
+NB = 200
+
+
+def reference_bsdf(lib, b):
+    """Instantiate the reference plugin for a mitsuba_b200.scene.Bsdf through its Properties, children first."""
+    from mitsuba_b200.scene import lookup_ior
+    lib.bsdfref_create.restype = C.c_void_p
+    f, s, bl, sp = {}, {}, {}, {}
+    t = b.type
+    if t == "diffuse":
+        sp["reflectance"] = b.reflectance
+    if t in ("roughconductor", "roughdielectric"):
+        s["distribution"] = b.distribution
+        f["alphaU"], f["alphaV"] = b.alpha_u, b.alpha_v
+        bl["sampleVisible"] = b.sample_visible
+    if t in ("roughconductor", "conductor"):
+        s["material"] = "none"
+        sp["eta"], sp["k"] = b.eta, b.k
+        f["extEta"] = lookup_ior(b.ext_eta, "air")
+        sp["specularReflectance"] = b.specular_reflectance
+    if t in ("roughdielectric", "dielectric", "coating", "plastic"):
+        f["intIOR"] = lookup_ior(b.int_ior if not (t == "plastic" and b.int_ior == "bk7") else "polypropylene", "bk7")
+        f["extIOR"] = lookup_ior(b.ext_ior, "air")
+        sp["specularReflectance"] = b.specular_reflectance
+    if t in ("roughdielectric", "dielectric"):
+        sp["specularTransmittance"] = b.specular_transmittance
+    if t == "coating":
+        f["thickness"] = b.thickness
+        sp["sigmaA"] = b.sigma_a
+    if t == "plastic":
+        sp["diffuseReflectance"] = b.diffuse_reflectance
+        bl["nonlinear"] = b.nonlinear
+    kids = []
+    if t in ("coating", "twosided"):
+        kids.append(reference_bsdf(lib, b.nested))
+        if t == "twosided" and b.nested_back is not None:
+            kids.append(reference_bsdf(lib, b.nested_back))
+    arr = lambda keys: (C.c_char_p * max(1, len(keys)))(*[k.encode() for k in keys])
+    fv = (C.c_float * max(1, len(f)))(*[float(v) for v in f.values()])
+    sv = arr([str(v) for v in s.values()])
+    bv = (C.c_int * max(1, len(bl)))(*[int(bool(v)) for v in bl.values()])
+    spv = (C.c_float * max(3, 3 * len(sp)))(*[float(x) for v in sp.values() for x in v])
+    h = lib.bsdfref_create(PLUGIN_IDS[t], len(f), arr(list(f)), fv, len(s), arr(list(s)), sv, len(bl), arr(list(bl)), bv, len(sp), arr(list(sp)), spv,
+                           kids[0] if kids else None, kids[1] if len(kids) > 1 else None)
+    assert h, t
+    return C.c_void_p(h)
+
+
+def bsdf_inputs(seed=777):
+    rng = np.random.default_rng(seed)
+    x = {"wi": _dirs(rng, NB), "wo": _dirs(rng, NB), "samples": rng.random((NB, 3)).astype(np.float32)}
+    x["wi"][: NB // 2, 2] = np.abs(x["wi"][: NB // 2, 2])  # half of them from the front side
+    x["wi"][:6, 2] = np.float32(2e-3)  # grazing
+    x["wi"][:6] /= np.linalg.norm(x["wi"][:6], axis=1, keepdims=True)
+    # mirror / refracted directions for the discrete measure are produced by sample(); eval(EDiscrete) is fed with them below
+    return x
+
+
+def run_bsdf_reference(lib, b, x):
+    h = reference_bsdf(lib, b)
+    lib.bsdfref_type.restype = C.c_uint
+    out = {"type": np.uint32(lib.bsdfref_type(h))}
+    rgb, pdf = np.zeros((NB, 3), np.float32), np.zeros(NB, np.float32)
+    lib.bsdfref_eval(h, NB, _f(x["wi"]), _f(x["wo"]), 0, _f(rgb), _f(pdf))
+    out["eval"], out["pdf"] = rgb, pdf
+    smp = np.zeros((NB, 10), np.float32)
+    lib.bsdfref_sample(h, NB, _f(x["wi"]), _f(x["samples"]), _f(smp))
+    smp[np.all(smp[:, 3:6] == 0, axis=1), 6] = 0
+    out["sample"] = smp
+    wo2 = np.ascontiguousarray(smp[:, 0:3])
+    rgb2, pdf2 = np.zeros((NB, 3), np.float32), np.zeros(NB, np.float32)
+    lib.bsdfref_eval(h, NB, _f(x["wi"]), _f(wo2), 1, _f(rgb2), _f(pdf2))  # EDiscrete at the sampled directions
+    out["eval_discrete"], out["pdf_discrete"] = rgb2, pdf2
+    rgb3, pdf3 = np.zeros((NB, 3), np.float32), np.zeros(NB, np.float32)
+    lib.bsdfref_eval(h, NB, _f(x["wi"]), _f(wo2), 0, _f(rgb3), _f(pdf3))  # ESolidAngle at the sampled directions
+    out["eval_at_sample"], out["pdf_at_sample"] = rgb3, pdf3
+    return out
+
+
+def run_bsdf_oracle(b, x):
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from bsdf_configs import flatten
+    from oracle import oracle_api as O
+    flat, bid = flatten(b)
+    out = {"type": np.uint32(O.bsdf_type(flat, bid))}
+    out["eval"], out["pdf"] = O.bsdf_eval(flat, bid, x["wi"], x["wo"])
+    arr = O.make_bsdf_array(flat)
+    smp = np.zeros((NB, 10), np.float32)
+    O.lib().orc_bsdf_sample(arr, C.c_int(len(flat)), C.c_int(bid), C.c_uint64(NB), _f(x["wi"]), _f(x["samples"]), _f(smp))
+    zero = np.all(smp[:, 3:6] == 0, axis=1)
+    smp[zero, 0:3] = 0; smp[zero, 6] = 0; smp[zero, 7] = 0; smp[zero, 8] = 0  # wo / pdf / type / eta are unspecified after a failed sample
+    smp[:, 9] = 0
+    out["sample"] = smp
+    wo2 = np.ascontiguousarray(smp[:, 0:3])
+    out["eval_discrete"], out["pdf_discrete"] = O.bsdf_eval(flat, bid, x["wi"], wo2, discrete=True)
+    out["eval_at_sample"], out["pdf_at_sample"] = O.bsdf_eval(flat, bid, x["wi"], wo2)
+    return out
