@@ -1249,6 +1249,13 @@ void orc_filter_table(int kind, float param, float *values32, float *radius, int
     RFilter f(kind, param); memcpy(values32, f.values, 128); *radius = f.radius; *border = f.borderSize;
 }
 /* splat n samples (pos 2, value 4: rgb+alpha) into a W x H film through 32x32 ImageBlocks */
+/* one ImageBlock (layout of oracle/render_ref_shim.cpp::renderref_block_put): data (w + 2 border) x (h + 2 border) x 5 */
+void orc_block_put(int ox, int oy, int w, int h, int kind, float param, int n, const float *pos, const float *val, float *data, int *ok) {
+    RFilter filter(kind, param);
+    ImageBlock blk(ox, oy, w, h, &filter);
+    for (int i = 0; i < n; ++i) ok[i] = blk.put(pos[2 * i], pos[2 * i + 1], V3(val[4 * i], val[4 * i + 1], val[4 * i + 2]), val[4 * i + 3]) ? 1 : 0;
+    memcpy(data, blk.data.data(), blk.data.size() * sizeof(float));
+}
 void orc_splat(int W, int H, int kind, float param, uint64_t n, const float *pos, const float *val, float *film) {
     RFilter filter(kind, param);
     const int bs = 32, nbx = (W + bs - 1) / bs, nby = (H + bs - 1) / bs;
@@ -1434,6 +1441,21 @@ float orc_pmf(int m, const float *weights, int n, const float *samples, uint32_t
     }
     for (int i = 0; i < m; ++i) cdf[i] = d[i];
     return total;
+}
+/* rec 27n: p, geoFrame.n, dpdu, dpdv, ray.o, rxOrigin, ryOrigin, rxDirection, ryDirection -> out 4n: dudx dudy dvdx dvdy
+   (layout of oracle/render_ref_shim.cpp::renderref_compute_partials) */
+void orc_compute_partials(int n, const float *rec, float *out) {
+    for (int i = 0; i < n; ++i) {
+        const float *r = rec + 27 * i;
+        Intersection its;
+        its.p = V3(r[0], r[1], r[2]); its.geoFrame.n = V3(r[3], r[4], r[5]);
+        its.dpdu = V3(r[6], r[7], r[8]); its.dpdv = V3(r[9], r[10], r[11]);
+        RayDiff rd; rd.has = true;
+        rd.rxO = V3(r[15], r[16], r[17]); rd.ryO = V3(r[18], r[19], r[20]); rd.rxD = V3(r[21], r[22], r[23]); rd.ryD = V3(r[24], r[25], r[26]);
+        Ray ray(V3(r[12], r[13], r[14]), V3(0, 0, 1));
+        Scene::computePartials(its, ray, rd);
+        out[4 * i] = its.tex.dudx; out[4 * i + 1] = its.tex.dudy; out[4 * i + 2] = its.tex.dvdx; out[4 * i + 3] = its.tex.dvdy;
+    }
 }
 /* Triangle::sample (triangle.cpp:24-62) as TriMesh::samplePosition uses it: barycentric warp of the 2-D sample */
 void orc_triangle_sample(int n, const float *tris, const float *samples, float *out) {

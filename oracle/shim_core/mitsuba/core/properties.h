@@ -21,6 +21,8 @@ public:
     std::string getAsString(const std::string &k, const std::string &d) const { return getString(k, d); }
     Float getFloat(const std::string &k) const { return f.at(k); }
     Float getFloat(const std::string &k, Float d) const { return f.count(k) ? f.at(k) : d; }
+    size_t getSize(const std::string &k) const { return (size_t) i.at(k); }
+    size_t getSize(const std::string &k, size_t d) const { return i.count(k) ? (size_t) i.at(k) : d; }
     int getInteger(const std::string &k) const { return i.at(k); }
     int getInteger(const std::string &k, int d) const { return i.count(k) ? i.at(k) : d; }
     bool getBoolean(const std::string &k) const { return b.at(k); }

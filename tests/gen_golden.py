@@ -24,6 +24,9 @@ Outputs (committed, so the GPU box and CI never read /root/reference):
                   roughconductor,roughdielectric,coating,dielectric,conductor,plastic,twosided}.cpp, instantiated from Properties and
                   called through the real BSDF interface (oracle/bsdf_ref_shim.cpp -> oracle/_ref/libbsdfref.so) -- for the 18
                   configurations of tests/bsdf_configs.py on the seeded directions of tests/ref_pins.py
+  render_ref.npz  Intersection::computePartials (src/librender/intersection.cpp), the box / gaussian filter tables of
+                  ReconstructionFilter::configure (src/libcore/rfilter.cpp + src/rfilters/*.cpp), ImageBlock::put (imageblock.h) and
+                  the SobolSampler plugin's stream (src/samplers/sobol.cpp) -- oracle/render_ref_shim.cpp -> oracle/_ref/librenderref.so
 """
 import ctypes as C, json, os, re, sys
 import numpy as np
@@ -198,8 +201,18 @@ def bsdf_ref():
     print("bsdf_ref.npz:", len(configs()), "BSDF configurations x", ref_pins.NB, "directions")
 
 
+def render_ref():
+    sys.path.insert(0, HERE)
+    import ref_pins
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "librenderref.so"))
+    out = ref_pins.run_render(lib, "renderref_", ref_pins.render_inputs())
+    np.savez_compressed(os.path.join(OUT, "render_ref.npz"), **out)
+    print("render_ref.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    render_ref()
     core_ref()
     bsdf_ref()
     sfmt_kat()

@@ -225,3 +225,65 @@ def run_bsdf_oracle(b, x):
     out["eval_discrete"], out["pdf_discrete"] = O.bsdf_eval(flat, bid, x["wi"], wo2, discrete=True)
     out["eval_at_sample"], out["pdf_at_sample"] = O.bsdf_eval(flat, bid, x["wi"], wo2)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# uv partials, reconstruction filters, ImageBlock::put, the Sobol' sampler plugin (oracle/render_ref_shim.cpp -> librenderref.so)
+# ---------------------------------------------------------------------------------------------------------------------------
+NR = 300
+SOBOL_CASES = [(0, 64, 64, 16, 5, 7, 3), (0, 100, 60, 64, 99, 59, 63), (12345, 256, 256, 4, 17, 200, 2), (7, 33, 1024, 1024, 0, 1000, 777), (1, 8, 8, 1, 3, 3, 0)]
+
+
+def render_inputs(seed=2718):
+    rng = np.random.default_rng(seed)
+    x = {}
+    rec = np.zeros((NR, 27), np.float32)
+    n = _dirs(rng, NR)
+    rec[:, 0:3] = rng.uniform(-2, 2, (NR, 3))
+    rec[:, 3:6] = n
+    rec[:, 6:9] = rng.normal(size=(NR, 3)) * 2
+    rec[:, 9:12] = rng.normal(size=(NR, 3)) * 2
+    o = rec[:, 0:3] + n * 3 + rng.normal(size=(NR, 3)).astype(np.float32)
+    rec[:, 12:15] = rec[:, 15:18] = rec[:, 18:21] = o
+    d = rec[:, 0:3] - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rec[:, 21:24] = d + rng.normal(size=(NR, 3)) * 0.01
+    rec[:, 24:27] = d + rng.normal(size=(NR, 3)) * 0.01
+    rec[:5, 6:12] = 0.0                      # dpdu = dpdv = 0
+    rec[5:10, 9:12] = rec[5:10, 6:9]         # singular system
+    rec[10:14, 21:24] = np.cross(n[10:14], rng.normal(size=(4, 3)))  # offset ray parallel to the surface: prx == 0 up to rounding
+    x["partials"] = np.ascontiguousarray(rec, np.float32)
+    pos = np.stack([rng.uniform(10 - 3, 10 + 16 + 3, NR), rng.uniform(20 - 3, 20 + 12 + 3, NR)], -1).astype(np.float32)
+    val = rng.random((NR, 4)).astype(np.float32)
+    val[:4, 0] = 0.0
+    x["put_pos"], x["put_val"] = pos, val
+    return x
+
+
+def run_render(lib, prefix, x, oracle_scene=None):
+    fn = lambda name: getattr(lib, prefix + name)
+    out = {}
+    a = np.zeros((NR, 4), np.float32)
+    fn("compute_partials")(NR, _f(x["partials"]), _f(a))
+    out["partials"] = a
+    for kind in (0, 1):
+        v, r, b = np.zeros(32, np.float32), C.c_float(), C.c_int()
+        if prefix == "orc_":
+            fn("filter_table")(kind, C.c_float(0.5), _f(v), C.byref(r), C.byref(b))  # gaussian.cpp:35-38 default stddev
+        else:
+            fn("filter_table")(kind, _f(v), C.byref(r), C.byref(b))
+        out[f"filter{kind}_values"], out[f"filter{kind}_radius"], out[f"filter{kind}_border"] = v, np.float32(r.value), np.int32(b.value)
+        border = b.value
+        data = np.zeros((12 + 2 * border, 16 + 2 * border, 5), np.float32)
+        ok = np.zeros(NR, np.int32)
+        args = [10, 20, 16, 12, kind] + ([C.c_float(0.5)] if prefix == "orc_" else []) + [NR, _f(x["put_pos"]), _f(x["put_val"]), _f(data), ok.ctypes.data_as(C.POINTER(C.c_int))]
+        fn("block_put")(*args)
+        out[f"put{kind}_data"], out[f"put{kind}_ok"] = data, ok
+    for i, (scr, W, H, spp, px, py, idx) in enumerate(SOBOL_CASES):
+        s = np.zeros(24, np.float32)
+        if prefix == "orc_":
+            s = oracle_scene(W, H).sampler_stream("sobol", scr, spp, px, py, idx, 24)
+        else:
+            fn("sobol_stream")(C.c_uint64(scr), W, H, spp, px, py, idx, 24, _f(s))
+        out[f"sobol{i}"] = np.asarray(s, np.float32)
+    return out

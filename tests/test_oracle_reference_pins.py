@@ -106,3 +106,37 @@ def test_oracle_bsdfs_match_live_reference_plugins_when_present():
         ref = ref_pins.run_bsdf_reference(lib, b, x)
         got = ref_pins.run_bsdf_oracle(b, x)
         assert _bsdf_close(name, ref, got) is None, (name, _bsdf_close(name, ref, got))
+
+
+def _oracle_scene(W, H):
+    from mitsuba_b200.scene import cornell_box
+    return O.OracleScene(cornell_box(W, H))
+
+
+def test_oracle_partials_filters_splat_and_sobol_match_reference_golden():
+    """tests/golden/render_ref.npz (see tests/gen_golden.py): Intersection::computePartials incl. its degenerate branches, the
+    discretised box / gaussian filters, 300 ImageBlock::put splats per filter (block borders, clamping), and the SobolSampler plugin's
+    first 24 dimensions for five (scramble, resolution, spp, pixel, sample) settings -- all bit for bit."""
+    g = np.load(os.path.join(HERE, "golden", "render_ref.npz"))
+    got = ref_pins.run_render(O.lib(), "orc_", ref_pins.render_inputs(), _oracle_scene)
+    assert len(g.files) == len(got) == 16
+    assert not [k for k in g.files if not same(g[k], got[k])]
+    assert g["put1_ok"].all() and g["put1_data"][..., 4].sum() > 100
+    # rejected samples (imageblock.h:136-139: negative / non-finite values): closed form, no contribution
+    L = O.lib()
+    pos = np.array([[15.0, 25.0]] * 4, np.float32)
+    val = np.array([[-1, 0, 0, 1], [np.nan, 0, 0, 1], [np.inf, 0, 0, 1], [0, 0, 0, -0.5]], np.float32)
+    data, ok = np.zeros((16, 20, 5), np.float32), np.ones(4, np.int32)
+    L.orc_block_put(10, 20, 16, 12, 1, C.c_float(0.5), 4, ref_pins._f(pos), ref_pins._f(val), ref_pins._f(data), ok.ctypes.data_as(C.POINTER(C.c_int)))
+    assert not ok.any() and not data.any()
+
+
+def test_oracle_partials_filters_splat_and_sobol_match_live_reference_when_present():
+    so = os.path.join(HERE, "..", "oracle", "_ref", "librenderref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/librenderref.so not built (the reference tree is not on this machine)")
+    lib = C.CDLL(so)
+    x = ref_pins.render_inputs(seed=55)
+    ref = ref_pins.run_render(lib, "renderref_", x)
+    got = ref_pins.run_render(O.lib(), "orc_", x, _oracle_scene)
+    assert not [k for k in ref if not same(ref[k], got[k])]
