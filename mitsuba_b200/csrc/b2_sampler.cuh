@@ -130,6 +130,9 @@ struct PathSampler {
         }
     }
     B2_DEV void next2D(float &a, float &b) {
+        // sobol.cpp:231-232: with no sample arrays requested m_arrayStartDim == m_arrayEndDim == 5, and a 2-D request at dimension 4
+        // ("dim + 1 >= start && dim < end") jumps to dimension 5 -- Sobol' dimension 4 is never used by consecutive next2D() calls
+        if (kind == 0 && dim == 4u) dim = 5u;
         if (kind == 0 && dim + 1 >= 1024u) { overflow = true; dim = 1022u; }
         a = next1D();
         b = next1D();

@@ -146,8 +146,11 @@ struct Sampler {
     virtual bool exhausted() const { return false; }
 };
 
-/* src/samplers/sobol.cpp:147-158,167-216,218-252.  No sample arrays are requested by `path`,
- * so m_arrayStartDim == m_arrayEndDim == 5 and the skip tests at :220-221,:231-232 never fire. */
+/* src/samplers/sobol.cpp:147-158,167-216,218-252.  No sample arrays are requested by `path`, so m_arrayStartDim ==
+ * m_arrayEndDim == 5 (:105,:170-172).  next1D's skip test (:220-221, `dim >= start && dim < end`) then never fires, but next2D's
+ * (:231-232, `dim + 1 >= start && dim < end`) does for dim == 4: a 2-D request that would straddle the (empty) array range jumps to
+ * dimension 5, i.e. Sobol' dimension 4 is never used by a sequence of next2D() calls.  Found by rendering with the reference's own
+ * sampler + integrator sources (oracle/path_ref_shim.cpp); restated here and in the device sampler. */
 struct SobolSampler : Sampler {
     const SobolTables *T;
     uint64_t scramble = 0;      /* after the TEA step of sobol.cpp:96-102 */
@@ -180,6 +183,7 @@ struct SobolSampler : Sampler {
         return sobolSample(*T, sobolIndex, dimension++, (uint32_t) scramble);
     }
     void next2D(float &a, float &b) override {
+        if (dimension + 1 >= 5 && dimension < 5) dimension = 5; /* sobol.cpp:231-232 with m_arrayStartDim == m_arrayEndDim == 5 */
         if (dimension + 1 >= kSobolDims) { dimOverflow = sampleOverflow = true; dimension = kSobolDims - 2; }
         if (dimension == 0 && sobolIndex != sampleIndex) {
             a = sobolSample(*T, sobolIndex, dimension++, (uint32_t) scramble) * resolution - px;

@@ -1,0 +1,364 @@
+/* A minimal Mitsuba 0.6 `path` renderer assembled from the REFERENCE's own sources, compiled where they lie under /root/reference
+ * (never copied) into oracle/_ref/libpathref.so by oracle/Makefile, behind the stand-in headers of oracle/shim_core/:
+ *   src/integrators/path/path.cpp (MIPathTracer::Li) + src/librender/integrator.cpp (SamplingIntegrator::renderBlock)
+ *   src/librender/{scene,skdtree,trimesh,shape,emitter,sensor,film,bsdf,texture,medium,phase,subsurface,sampler,intersection,
+ *                  imageblock,shader}.cpp with gkdtree.h / sahkdtree3.h / triaccel.h / records.inl
+ *   src/sensors/perspective.cpp, src/emitters/area.cpp, src/samplers/{sobol,independent}.cpp + sobolseq.cpp,
+ *   src/rfilters/{gaussian,box}.cpp, the nine BSDF plugins of src/bsdfs/, src/libcore/{util,warp,math,quad,qmc,triangle,transform,
+ *   aabb,rfilter,random,spectrum,timer}.cpp
+ * The scene graph is built the way the XML loader would build it (plugins through their own CreateInstance + Properties, addChild,
+ * configure, Scene::initialize builds the SAH kd-tree) and rendered block by block with SamplingIntegrator::renderBlock.
+ *
+ * Scaffolding (not the reference): everything listed under "scaffolding" below -- the threading / scheduling / serialization /
+ * plugin-manager / OpenGL layers are reduced to no-ops, Bitmap is a plain float buffer, the film is a stand-in that only carries
+ * the resolution and the reconstruction filter; blocks are accumulated into the output in block order by this file.
+ * Used only to pin the oracle at image level (tests/gen_golden.py -> tests/golden/path_ref.npz). */
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/renderproc.h>
+#include <mitsuba/render/renderqueue.h>
+#include <mitsuba/core/plugin.h>
+#include <mitsuba/core/sched.h>
+#include <mitsuba/core/statistics.h>
+#include <mitsuba/core/bitmap.h>
+#include <mitsuba/hw/basicshader.h>
+#include <mitsuba/hw/renderer.h>
+#include <mitsuba/core/zstream.h>
+#include <mitsuba/core/lock.h>
+#include <mitsuba/core/tls.h>
+
+namespace mitsuba {
+/* ---------------------------------------------- scaffolding ---------------------------------------------- */
+ConfigurableObject::ConfigurableObject(Stream *, InstanceManager *) {}
+void ConfigurableObject::setParent(ConfigurableObject *) {}
+void ConfigurableObject::addChild(const std::string &, ConfigurableObject *) {}
+void ConfigurableObject::configure() {}
+void ConfigurableObject::serialize(Stream *, InstanceManager *) const {}
+MTS_IMPLEMENT_CLASS(ConfigurableObject, true, SerializableObject)
+SerializableObject::SerializableObject(Stream *, InstanceManager *) {}
+MTS_IMPLEMENT_CLASS(SerializableObject, true, Object)
+void NetworkedObject::bindUsedResources(ParallelProcess *) const {}
+void NetworkedObject::wakeup(ConfigurableObject *, std::map<std::string, SerializableObject *> &) {}
+void NetworkedObject::serialize(Stream *, InstanceManager *) const {}
+MTS_IMPLEMENT_CLASS(NetworkedObject, true, ConfigurableObject)
+MTS_IMPLEMENT_CLASS(WorkResult, true, Object)
+SerializableObject *InstanceManager::getInstance(Stream *) { return NULL; }
+void InstanceManager::serialize(Stream *, const SerializableObject *) {}
+ref<PluginManager> PluginManager::m_instance;
+ConfigurableObject *PluginManager::createObject(const Class *, const Properties &) { return NULL; }
+ref<Scheduler> Scheduler::m_scheduler;
+SerializableObject *Scheduler::getResource(int, int) { return NULL; }
+int Scheduler::registerResource(SerializableObject *) { return 0; }
+bool Scheduler::unregisterResource(int) { return true; }
+bool Scheduler::wait(const ParallelProcess *) { return true; }
+bool Scheduler::cancel(ParallelProcess *, bool) { return true; }
+bool Scheduler::schedule(ParallelProcess *) { return true; }
+size_t Scheduler::getCoreCount() const { return 1; }
+Float RenderQueue::getRenderTime(const RenderJob *) const { return 0; }
+/* single-threaded: locks and condition variables do nothing, "thread-local" storage is one object */
+struct Mutex::MutexPrivate {};
+Mutex::Mutex() {}
+Mutex::~Mutex() {}
+MTS_IMPLEMENT_CLASS(Mutex, false, Object)
+void Mutex::lock() {}
+void Mutex::unlock() {}
+struct ConditionVariable::ConditionVariablePrivate {};
+ConditionVariable::ConditionVariable(Mutex *) {}
+ConditionVariable::~ConditionVariable() {}
+MTS_IMPLEMENT_CLASS(ConditionVariable, false, Object)
+void ConditionVariable::wait() {}
+void ConditionVariable::signal() {}
+void ConditionVariable::broadcast() {}
+namespace detail {
+struct ThreadLocalBase::ThreadLocalPrivate { ConstructFunctor construct; void *value; };
+ThreadLocalBase::ThreadLocalBase(const ConstructFunctor &c, const DestructFunctor &) : d(new ThreadLocalPrivate()) { d->construct = c; d->value = NULL; }
+ThreadLocalBase::~ThreadLocalBase() {}
+void *ThreadLocalBase::get(bool &existed) { existed = d->value != NULL; if (!existed) d->value = d->construct(); return d->value; }
+}
+StatsCounter::StatsCounter(const std::string &, const std::string &, EStatsType, uint64_t, uint64_t) {}
+StatsCounter::~StatsCounter() {}
+Shader *Renderer::registerShaderForResource(const HWResource *) { return NULL; }
+void Renderer::unregisterShaderForResource(const HWResource *) {}
+ConstantSpectrumTexture::ConstantSpectrumTexture(Stream *stream, InstanceManager *manager) : Texture(stream, manager) {}
+Shader *ConstantSpectrumTexture::createShader(Renderer *) const { return NULL; }
+ref<Bitmap> ConstantSpectrumTexture::getBitmap(const Vector2i &) const { return NULL; }
+void ConstantSpectrumTexture::serialize(Stream *, InstanceManager *) const {}
+MTS_IMPLEMENT_CLASS(ConstantSpectrumTexture, false, Texture)
+ConstantFloatTexture::ConstantFloatTexture(Stream *stream, InstanceManager *manager) : Texture(stream, manager) {}
+Shader *ConstantFloatTexture::createShader(Renderer *) const { return NULL; }
+ref<Bitmap> ConstantFloatTexture::getBitmap(const Vector2i &) const { return NULL; }
+void ConstantFloatTexture::serialize(Stream *, InstanceManager *) const {}
+MTS_IMPLEMENT_CLASS(ConstantFloatTexture, false, Texture)
+/* a static transform only (src/libcore/track.cpp needs Eigen) */
+AnimatedTransform::AnimatedTransform(Stream *) {}
+void AnimatedTransform::TransformFunctor::operator()(const Float &, Transform &) const {}
+AABB AnimatedTransform::getTranslationBounds() const { AABB b; b.expandBy(m_transform(Point(0.0f))); return b; }
+void AnimatedTransform::serialize(Stream *) const {}
+std::string AnimatedTransform::toString() const { return "AnimatedTransform"; }
+AnimatedTransform::~AnimatedTransform() {}
+MTS_IMPLEMENT_CLASS(AnimatedTransform, false, Object)
+ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k, const Transform &d) const { return new AnimatedTransform(getTransform(k, d)); }
+ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k, const AnimatedTransform *d) const { return hasProperty(k) || !d ? new AnimatedTransform(getTransform(k, Transform())) : d; }
+ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k) const { return new AnimatedTransform(getTransform(k)); }
+std::ostream &operator<<(std::ostream &os, const ETransportMode &m) { return os << (int) m; }
+/* Bitmap: a zeroed float buffer (src/libcore/bitmap.cpp needs OpenEXR / libpng / libjpeg) */
+Bitmap::Bitmap(EPixelFormat pFmt, EComponentFormat cFmt, const Vector2i &size, uint8_t channelCount, uint8_t *)
+    : m_pixelFormat(pFmt), m_componentFormat(cFmt), m_size(size), m_data(NULL), m_gamma(1.0f), m_channelCount(channelCount), m_ownsData(true) {
+    if (pFmt == ESpectrumAlphaWeight) m_channelCount = SPECTRUM_SAMPLES + 2;
+    m_data = (uint8_t *) calloc((size_t) size.x * size.y * m_channelCount, sizeof(float));
+}
+Bitmap::~Bitmap() { if (m_data && m_ownsData) free(m_data); }
+void Bitmap::clear() { memset(m_data, 0, (size_t) m_size.x * m_size.y * m_channelCount * sizeof(float)); }
+std::string Bitmap::toString() const { return "Bitmap"; }
+MTS_IMPLEMENT_CLASS(Bitmap, false, Object)
+/* Stream: nothing is (de)serialised */
+float Stream::readSingle() { return 0; } double Stream::readDouble() { return 0; } void Stream::writeSingle(float) {} void Stream::writeDouble(double) {}
+int Stream::readInt() { return 0; } void Stream::writeInt(int) {} float Stream::readFloat() { return 0; } void Stream::writeFloat(float) {}
+void Stream::readFloatArray(float *, size_t) {} void Stream::writeFloatArray(const float *, size_t) {}
+std::string Stream::readString() { return ""; } void Stream::writeString(const std::string &) {} void Stream::read(void *, size_t) {} void Stream::write(const void *, size_t) {}
+void Stream::readSingleArray(float *, size_t) {} void Stream::writeSingleArray(const float *, size_t) {}
+void Stream::readUIntArray(unsigned int *, size_t) {} void Stream::writeUIntArray(const unsigned int *, size_t) {}
+void Stream::readDoubleArray(double *, size_t) {} void Stream::writeDoubleArray(const double *, size_t) {}
+void Stream::seek(size_t) {} void Stream::setByteOrder(int) {} void Stream::copyTo(Stream *, long long) {}
+void Stream::readULongArray(uint64_t *, size_t) {} void Stream::writeULongArray(const uint64_t *, size_t) {}
+unsigned int Stream::readUInt() { return 0; } void Stream::writeUInt(unsigned int) {} size_t Stream::readSize() { return 0; } void Stream::writeSize(size_t) {}
+bool Stream::readBool() { return false; } void Stream::writeBool(bool) {} short Stream::readShort() { return 0; } void Stream::writeShort(short) {}
+long long Stream::readLong() { return 0; } void Stream::writeLong(long long) {} unsigned long long Stream::readULong() { return 0; } void Stream::writeULong(unsigned long long) {}
+void Stream::skip(size_t) {} void Stream::flush() {}
+size_t Stream::getPos() const { return 0; }
+size_t Stream::getSize() const { return 0; }
+template <typename T> void Stream::readArray(T *, size_t) {}
+template <typename T> void Stream::writeArray(const T *, size_t) {}
+template <typename T> T Stream::readElement() { return T(); }
+template <typename T> void Stream::writeElement(T) {}
+template void Stream::readArray<float>(float *, size_t); template void Stream::writeArray<float>(const float *, size_t);
+template void Stream::readArray<int>(int *, size_t); template void Stream::writeArray<int>(const int *, size_t);
+template void Stream::readArray<unsigned int>(unsigned int *, size_t); template void Stream::writeArray<unsigned int>(const unsigned int *, size_t);
+template void Stream::readArray<unsigned long>(unsigned long *, size_t); template void Stream::writeArray<unsigned long>(const unsigned long *, size_t);
+template void Stream::readArray<double>(double *, size_t); template void Stream::writeArray<double>(const double *, size_t);
+template int Stream::readElement<int>(); template void Stream::writeElement<int>(int);
+template float Stream::readElement<float>(); template void Stream::writeElement<float>(float);
+ZStream::ZStream(Stream *child, EStreamType, int) : m_childStream(child) {}
+ZStream::~ZStream() {}
+std::string ZStream::toString() const { return "ZStream"; }
+MTS_IMPLEMENT_CLASS(ZStream, false, Stream)
+}
+
+/* SamplingIntegrator::render() (integrator.cpp:96-128, never called here: the blocks are rendered directly) constructs a
+   BlockedRenderProcess; its constructor symbol is satisfied without dragging in the scheduler classes */
+extern "C" void _ZN7mitsuba20BlockedRenderProcessC1EPKNS_9RenderJobEPNS_11RenderQueueEi() { abort(); }
+
+using namespace mitsuba;
+
+#define DECL(name) extern "C" void *CreateInstance_##name(const Properties &props);
+DECL(diffuse) DECL(roughconductor) DECL(roughdielectric) DECL(coating) DECL(dielectric) DECL(conductor) DECL(plastic) DECL(twosided) DECL(null)
+DECL(gaussian) DECL(box) DECL(sobol) DECL(independent) DECL(path) DECL(perspective) DECL(area)
+
+/* carries resolution + reconstruction filter to the sensor / integrator (hdrfilm.cpp needs the Bitmap file writers) */
+class StandinFilm : public Film {
+public:
+    StandinFilm(const Properties &props) : Film(props) {}
+    void clear() {}
+    void put(const ImageBlock *) {}
+    void setBitmap(const Bitmap *, Float) {}
+    void addBitmap(const Bitmap *, Float) {}
+    void setDestinationFile(const fs::path &, uint32_t) {}
+    void develop(const Scene *, Float) {}
+    bool develop(const Point2i &, const Vector2i &, const Point2i &, Bitmap *) const { return false; }
+    bool destinationExists(const fs::path &) const { return false; }
+    bool hasAlpha() const { return true; } /* the `rgba` film: RadianceQueryRecord::EOpacity stays set (integrator.cpp:160-161) */
+    std::string toString() const { return "StandinFilm"; }
+    const Class *getClass() const { return Film::m_theClass; }
+};
+
+struct PathRef {
+    ref<Scene> scene;
+    ref<Sensor> sensor;
+    ref<Sampler> sampler;
+    ref<Integrator> integrator;
+    ref<Film> film;
+    int W, H;
+    std::vector<Object *> keep;
+};
+
+extern "C" {
+void *pathref_new() {
+    PathRef *p = new PathRef();
+    p->scene = new Scene(Properties("scene"));
+    return p;
+}
+/* same layout as bsdfref_create (oracle/bsdf_ref_shim.cpp) */
+void *pathref_bsdf(int plugin, int nf, const char **fk, const float *fv, int ns, const char **sk, const char **sv, int nb, const char **bk, const int *bv,
+                   int nsp, const char **spk, const float *spv, void *child, void *child2) {
+    Properties props;
+    for (int i = 0; i < nf; ++i) props.setFloat(fk[i], fv[i]);
+    for (int i = 0; i < ns; ++i) props.setString(sk[i], sv[i]);
+    for (int i = 0; i < nb; ++i) props.setBoolean(bk[i], bv[i] != 0);
+    for (int i = 0; i < nsp; ++i) { Spectrum s; s[0] = spv[3 * i]; s[1] = spv[3 * i + 1]; s[2] = spv[3 * i + 2]; props.setSpectrum(spk[i], s); }
+    BSDF *b = NULL;
+    switch (plugin) {
+        case 0: b = (BSDF *) CreateInstance_diffuse(props); break;
+        case 1: b = (BSDF *) CreateInstance_roughconductor(props); break;
+        case 2: b = (BSDF *) CreateInstance_roughdielectric(props); break;
+        case 3: b = (BSDF *) CreateInstance_coating(props); break;
+        case 4: b = (BSDF *) CreateInstance_null(props); break;
+        case 5: b = (BSDF *) CreateInstance_twosided(props); break;
+        case 6: b = (BSDF *) CreateInstance_dielectric(props); break;
+        case 7: b = (BSDF *) CreateInstance_conductor(props); break;
+        case 8: b = (BSDF *) CreateInstance_plastic(props); break;
+    }
+    if (!b) return NULL;
+    if (child) b->addChild("", (ConfigurableObject *) (BSDF *) child);
+    if (child2) b->addChild("", (ConfigurableObject *) (BSDF *) child2);
+    b->configure();
+    return b;
+}
+/* a TriMesh as the loaders leave it (positions, optional normals / texcoords, triangles), its BSDF, optionally an area emitter */
+void pathref_add_mesh(void *h, const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf, const float *radiance, float samplingWeight) {
+    PathRef *p = (PathRef *) h;
+    ref<TriMesh> mesh = new TriMesh("mesh", (size_t) nT, (size_t) nV, N != NULL, UV != NULL, false, false, N == NULL /* face normals, skdtree.h:383-399 */);
+    memcpy(mesh->getVertexPositions(), P, sizeof(float) * 3 * nV);
+    if (N) memcpy(mesh->getVertexNormals(), N, sizeof(float) * 3 * nV);
+    if (UV) memcpy(mesh->getVertexTexcoords(), UV, sizeof(float) * 2 * nV);
+    memcpy(mesh->getTriangles(), idx, sizeof(uint32_t) * 3 * nT);
+    mesh->addChild("", (ConfigurableObject *) (BSDF *) bsdf);
+    if (radiance) {
+        Properties ep("area");
+        Spectrum s; s[0] = radiance[0]; s[1] = radiance[1]; s[2] = radiance[2];
+        ep.setSpectrum("radiance", s);
+        ep.setFloat("samplingWeight", samplingWeight);
+        Emitter *em = (Emitter *) CreateInstance_area(ep);
+        mesh->addChild("", em);
+        em->setParent(mesh);      /* the scene loader calls setParent() after addChild() (scenehandler.cpp); AreaLight keeps the shape */
+        em->configure();
+    }
+    mesh->configure();
+    p->scene->addChild("", mesh);
+    p->keep.push_back(mesh);
+}
+/* perspective sensor + film + sampler + path integrator; rfilter 0 box / 1 gaussian; sampler 0 sobol / 1 independent */
+void pathref_setup(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
+                   int maxDepth, int rrDepth, int strictNormals, int hideEmitters) {
+    PathRef *p = (PathRef *) h;
+    p->W = W; p->H = H;
+    Properties fp("hdrfilm");
+    fp.setInteger("width", W); fp.setInteger("height", H);
+    p->film = new StandinFilm(fp);
+    Properties rp;
+    ReconstructionFilter *rf = (ReconstructionFilter *) (rfilter == 0 ? CreateInstance_box(rp) : CreateInstance_gaussian(rp));
+    rf->configure();
+    p->film->addChild("", rf);
+    p->film->configure();
+    Properties sp;
+    sp.setInteger("sampleCount", spp);
+    sp.setInteger("scramble", (int) scramble);
+    p->sampler = (Sampler *) (samplerKind == 0 ? CreateInstance_sobol(sp) : CreateInstance_independent(sp));
+    p->sampler->configure();
+    Properties cp("perspective");
+    Matrix4x4 M;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M.m[r][c] = toWorld[4 * r + c];
+    cp.setTransform("toWorld", Transform(M));
+    cp.setFloat("fov", fov); cp.setFloat("nearClip", nearClip); cp.setFloat("farClip", farClip);
+    p->sensor = (Sensor *) CreateInstance_perspective(cp);
+    p->sensor->addChild("", p->film);
+    p->sensor->addChild("", p->sampler);
+    p->sensor->configure();
+    Properties ip("path");
+    ip.setInteger("maxDepth", maxDepth); ip.setInteger("rrDepth", rrDepth);
+    ip.setBoolean("strictNormals", strictNormals != 0); ip.setBoolean("hideEmitters", hideEmitters != 0);
+    p->integrator = (Integrator *) CreateInstance_path(ip);
+    p->integrator->configure();
+    p->scene->addChild("", p->sensor);
+    p->scene->addChild("", p->integrator);
+    p->scene->configure();
+    p->scene->getKDTree()->setParallelBuild(false);
+    p->scene->initialize();
+    p->integrator->configureSampler(p->scene, p->sampler);
+}
+/* m_sampleToCamera as PerspectiveCameraImpl::configure derives it (perspective.cpp:146-153; the member itself is private to the plugin):
+ * the same chain of the reference's own Transform operations, no crop window.  Row-major 4 x 4. */
+void pathref_sample_to_camera(void *h, float *out16) {
+    PathRef *p = (PathRef *) h;
+    const PerspectiveCamera *cam = static_cast<const PerspectiveCamera *>(p->sensor.get());
+    const Float aspect = cam->getAspect();
+    const Transform cameraToSample =
+          Transform::scale(Vector(1.0f / 1.0f, 1.0f / 1.0f, 1.0f))
+        * Transform::translate(Vector(-0.0f, -0.0f, 0.0f))
+        * Transform::scale(Vector(-0.5f, -0.5f * aspect, 1.0f))
+        * Transform::translate(Vector(-1.0f, -1.0f / aspect, 0.0f))
+        * Transform::perspective(cam->getXFov(), cam->getNearClip(), cam->getFarClip());
+    const Transform sampleToCamera = cameraToSample.inverse();
+    const Matrix4x4 &M = sampleToCamera.getMatrix();
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out16[4 * r + c] = M.m[r][c];
+}
+/* Sensor::sampleRay for film positions: pos 2n -> rays 8n (o, mint, d, maxt) */
+void pathref_camera_rays(void *h, int n, const float *pos, float *rays) {
+    PathRef *p = (PathRef *) h;
+    for (int i = 0; i < n; ++i) {
+        Ray ray;
+        p->sensor->sampleRay(ray, Point2(pos[2 * i], pos[2 * i + 1]), Point2(0.5f), 0.5f);
+        float *o = rays + 8 * i;
+        o[0] = ray.o.x; o[1] = ray.o.y; o[2] = ray.o.z; o[3] = ray.mint; o[4] = ray.d.x; o[5] = ray.d.y; o[6] = ray.d.z; o[7] = ray.maxt;
+    }
+}
+/* Scene::rayIntersect(ray, its) (kd-tree traversal + ShapeKDTree::fillIntersectionRecord): rays 8n (o, mint, d, maxt) -> out 24n:
+ * p geoN shN s t wi (3 each), t, -, primIndex, valid, pad 2 (layout of the oracle's orc_intersect_full; the mesh index is not comparable) */
+void pathref_intersect(void *h, int n, const float *rays, float *out) {
+    PathRef *p = (PathRef *) h;
+    for (int i = 0; i < n; ++i) {
+        const float *r = rays + 8 * i;
+        Ray ray(Point(r[0], r[1], r[2]), Vector(r[4], r[5], r[6]), r[3], r[7], 0.0f);
+        Intersection its;
+        float *o = out + 24 * i;
+        memset(o, 0, 96);
+        if (p->scene->rayIntersect(ray, its)) {
+            const Vector vs[6] = {Vector(its.p), Vector(its.geoFrame.n), Vector(its.shFrame.n), its.shFrame.s, its.shFrame.t, its.wi};
+            for (int k = 0; k < 6; ++k) { o[3 * k] = vs[k].x; o[3 * k + 1] = vs[k].y; o[3 * k + 2] = vs[k].z; }
+            o[18] = its.t; o[20] = (float) its.primIndex; o[21] = 1.0f;
+        }
+    }
+}
+/* Scene::sampleEmitterDirect(dRec, sample, testVisibility = true): ref 6n (ref, refN), samples 2n -> out 12n: d(3) dist pdf value(3) ok p(3)
+ * (layout of the oracle's orc_sample_emitter_direct) */
+void pathref_sample_emitter_direct(void *h, int n, const float *ref, const float *samples, float *out) {
+    PathRef *p = (PathRef *) h;
+    for (int i = 0; i < n; ++i) {
+        DirectSamplingRecord dRec(Point(ref[6 * i], ref[6 * i + 1], ref[6 * i + 2]), 0.0f);
+        dRec.refN = Normal(ref[6 * i + 3], ref[6 * i + 4], ref[6 * i + 5]);
+        const Spectrum value = p->scene->sampleEmitterDirect(dRec, Point2(samples[2 * i], samples[2 * i + 1]), true);
+        float *o = out + 12 * i;
+        o[0] = dRec.d.x; o[1] = dRec.d.y; o[2] = dRec.d.z; o[3] = dRec.dist; o[4] = dRec.pdf;
+        o[5] = value[0]; o[6] = value[1]; o[7] = value[2]; o[8] = value.isZero() ? 0.0f : 1.0f; o[9] = dRec.p.x; o[10] = dRec.p.y; o[11] = dRec.p.z;
+    }
+}
+/* film out: H x W x 5 (rgb, alpha, weight), blocks of 32 x 32 rendered by SamplingIntegrator::renderBlock with the pixels of a block in
+ * scanline order and accumulated here in block order (the reference's scheduler hands out Hilbert-ordered pixels and merges blocks in
+ * completion order: float summation order only) */
+void pathref_render(void *h, float *out) {
+    PathRef *p = (PathRef *) h;
+    SamplingIntegrator *integrator = static_cast<SamplingIntegrator *>(p->integrator.get());
+    const ReconstructionFilter *rf = p->film->getReconstructionFilter();
+    const int bs = 32, border = rf->getBorderSize(), W = p->W, H = p->H;
+    memset(out, 0, sizeof(float) * 5 * (size_t) W * H);
+    bool stop = false;
+    for (int oy = 0; oy < H; oy += bs)
+        for (int ox = 0; ox < W; ox += bs) {
+            const int sx = std::min(bs, W - ox), sy = std::min(bs, H - oy);
+            ref<ImageBlock> block = new ImageBlock(Bitmap::ESpectrumAlphaWeight, Vector2i(sx, sy), rf);
+            block->setOffset(Point2i(ox, oy));
+            std::vector<TPoint2<uint8_t> > points;
+            for (int y = 0; y < sy; ++y) for (int x = 0; x < sx; ++x) points.push_back(TPoint2<uint8_t>((uint8_t) x, (uint8_t) y));
+            integrator->renderBlock(p->scene, p->sensor, p->sampler, block, stop, points);
+            const float *data = block->getBitmap()->getFloat32Data();
+            const int bw = sx + 2 * border, bh = sy + 2 * border;
+            for (int y = 0; y < bh; ++y) {
+                const int fy = oy - border + y;
+                if (fy < 0 || fy >= H) continue;
+                for (int x = 0; x < bw; ++x) {
+                    const int fx = ox - border + x;
+                    if (fx < 0 || fx >= W) continue;
+                    for (int k = 0; k < 5; ++k) out[((size_t) fy * W + fx) * 5 + k] += data[((size_t) y * bw + x) * 5 + k];
+                }
+            }
+        }
+}
+}

@@ -4,3 +4,4 @@
 #include <algorithm>
 #include <string>
 namespace boost { inline std::string to_lower_copy(std::string s) { std::transform(s.begin(), s.end(), s.begin(), ::tolower); return s; } inline void to_lower(std::string &s) { std::transform(s.begin(), s.end(), s.begin(), ::tolower); } }
+namespace boost { inline bool ends_with(const std::string &s, const std::string &e) { return s.size() >= e.size() && s.compare(s.size() - e.size(), e.size(), e) == 0; } inline bool starts_with(const std::string &s, const std::string &e) { return s.compare(0, e.size(), e) == 0; } }

@@ -10,5 +10,5 @@ class path { public: path() {} path(const char *s) : m_s(s) {} path(const std::s
 inline bool exists(const path &) { return false; }
 inline size_t file_size(const path &) { return 0; }
 class ifstream : public std::ifstream { public: ifstream() {} ifstream(const path &p) : std::ifstream(p.string().c_str()) {} };
-class ofstream : public std::ofstream { public: ofstream() {} ofstream(const path &p) : std::ofstream(p.string().c_str()) {} };
+class ofstream : public std::ofstream { public: ofstream() {} ofstream(const path &p, std::ios_base::openmode m = std::ios_base::out) : std::ofstream(p.string().c_str(), m) {} };
 } }

@@ -3,10 +3,12 @@
  * A Properties that holds floats, booleans, strings and spectra -- what the BSDF plugin constructors query. */
 #pragma once
 #include <mitsuba/mitsuba.h>
+#include <mitsuba/core/transform.h>
 namespace mitsuba {
+class AnimatedTransform;
 class Properties {
 public:
-    enum EPropertyType { EBoolean = 0, EInteger, EFloat, EPoint, ETransform, EAnimatedTransform, ESpectrum, EString, EData };
+    enum EPropertyType { EBoolean = 0, EInteger, EFloat, EPoint, EVector, ETransform, EAnimatedTransform, ESpectrum, EString, EData };
     Properties() {}
     Properties(const std::string &pluginName) : m_pluginName(pluginName) {}
     const std::string &getPluginName() const { return m_pluginName; }
@@ -34,6 +36,21 @@ public:
     void setInteger(const std::string &k, int v, bool = true) { i[k] = v; }
     void setBoolean(const std::string &k, bool v, bool = true) { b[k] = v; }
     void setSpectrum(const std::string &k, const Spectrum &v, bool = true) { sp[k] = v; }
+    Transform getTransform(const std::string &k) const { return tr.at(k); }
+    Transform getTransform(const std::string &k, const Transform &d) const { return tr.count(k) ? tr.at(k) : d; }
+    void setTransform(const std::string &k, const Transform &v, bool = true) { tr[k] = v; }
+    ref<const AnimatedTransform> getAnimatedTransform(const std::string &k) const;                       /* defined by the shim that needs it */
+    ref<const AnimatedTransform> getAnimatedTransform(const std::string &k, const AnimatedTransform *d) const;
+    ref<const AnimatedTransform> getAnimatedTransform(const std::string &k, const Transform &d) const;
+    void setAnimatedTransform(const std::string &k, const AnimatedTransform *, bool = true) {}
+    Point getPoint(const std::string &k) const { return pt.at(k); }
+    Point getPoint(const std::string &k, const Point &d) const { return pt.count(k) ? pt.at(k) : d; }
+    Vector getVector(const std::string &k) const { return Vector(pt.at(k)); }
+    Vector getVector(const std::string &k, const Vector &d) const { return pt.count(k) ? Vector(pt.at(k)) : d; }
+    void setPoint(const std::string &k, const Point &v, bool = true) { pt[k] = v; }
+    bool removeProperty(const std::string &k) { return f.erase(k) + s.erase(k) + b.erase(k) + i.erase(k) + sp.erase(k) + tr.erase(k) > 0; }
+    void putPropertyNames(std::vector<std::string> &) const {}
+    std::vector<std::string> getUnqueried() const { return std::vector<std::string>(); }
     void markQueried(const std::string &) const {}
     std::string toString() const { return m_pluginName; }
 private:
@@ -43,5 +60,7 @@ private:
     std::map<std::string, int> i;
     std::map<std::string, bool> b;
     std::map<std::string, Spectrum> sp;
+    std::map<std::string, Transform> tr;
+    std::map<std::string, Point> pt;
 };
 }

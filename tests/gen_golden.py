@@ -27,6 +27,11 @@ Outputs (committed, so the GPU box and CI never read /root/reference):
   render_ref.npz  Intersection::computePartials (src/librender/intersection.cpp), the box / gaussian filter tables of
                   ReconstructionFilter::configure (src/libcore/rfilter.cpp + src/rfilters/*.cpp), ImageBlock::put (imageblock.h) and
                   the SobolSampler plugin's stream (src/samplers/sobol.cpp) -- oracle/render_ref_shim.cpp -> oracle/_ref/librenderref.so
+  path_ref.npz    IMAGES rendered by the reference's own code: oracle/path_ref_shim.cpp assembles MIPathTracer (path.cpp),
+                  SamplingIntegrator::renderBlock, Scene, ShapeKDTree, TriMesh, the perspective sensor, the area emitter, the Sobol'
+                  sampler, the reconstruction filters, ImageBlock and the BSDF plugins from /root/reference into
+                  oracle/_ref/libpathref.so.  Cornell box and material-ball scenes (tests/ref_pins.py::image_cases), film (H, W, 5)
+                  + the sampleToCamera matrix the reference's sensor derives
 """
 import ctypes as C, json, os, re, sys
 import numpy as np
@@ -210,8 +215,22 @@ def render_ref():
     print("render_ref.npz:", len(out), "arrays")
 
 
+def path_ref():
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import ref_pins
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so"))
+    out = {}
+    for name, desc, rp in ref_pins.image_cases():
+        film, s2c = ref_pins.reference_render(lib, desc, rp, want_camera=True)
+        out[name + "/film"], out[name + "/s2c"] = film, s2c
+    np.savez_compressed(os.path.join(OUT, "path_ref.npz"), **out)
+    print("path_ref.npz:", len(out) // 2, "images")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    path_ref()
     render_ref()
     core_ref()
     bsdf_ref()

@@ -287,3 +287,57 @@ def run_render(lib, prefix, x, oracle_scene=None):
             fn("sobol_stream")(C.c_uint64(scr), W, H, spp, px, py, idx, 24, _f(s))
         out[f"sobol{i}"] = np.asarray(s, np.float32)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# whole images: a minimal `path` renderer assembled from the reference's own sources (oracle/path_ref_shim.cpp -> libpathref.so)
+# ---------------------------------------------------------------------------------------------------------------------------
+def reference_render(lib, desc, rp, want_camera=False):
+    """Render a mitsuba_b200.scene.SceneDesc with the reference's MIPathTracer / Scene / ShapeKDTree / plugins.  Returns (H, W, 5)
+    (and, with want_camera, the reference's sampleToCamera matrix: camera set-up is host work, both sides should start from it)."""
+    from mitsuba_b200.scene import Bsdf
+    lib.pathref_new.restype = C.c_void_p
+    lib.pathref_bsdf.restype = C.c_void_p
+    h = C.c_void_p(lib.pathref_new())
+
+    class _L:  # reference_bsdf() talks to `bsdfref_create`; here the same function is called pathref_bsdf
+        bsdfref_create = lib.pathref_bsdf
+    memo = {}
+    for m in desc.meshes:
+        b = m.bsdf if m.bsdf is not None else Bsdf("diffuse", reflectance=(0.0,) * 3 if m.radiance is not None else (0.5,) * 3)
+        if id(b) not in memo:
+            memo[id(b)] = reference_bsdf(_L, b)
+        P = np.ascontiguousarray(m.P, np.float32)
+        N = np.ascontiguousarray(m.N, np.float32) if m.N is not None else None
+        UV = np.ascontiguousarray(m.UV, np.float32) if m.UV is not None else None
+        I = np.ascontiguousarray(m.idx, np.uint32)
+        rad = np.asarray(m.radiance, np.float32) if m.radiance is not None else None
+        lib.pathref_add_mesh(h, _f(P), _f(N) if N is not None else None, _f(UV) if UV is not None else None, len(P),
+                             I.ctypes.data_as(C.POINTER(C.c_uint32)), len(I), memo[id(b)], _f(rad) if rad is not None else None, C.c_float(m.sampling_weight))
+    cam = desc.camera
+    tw = np.ascontiguousarray(cam.to_world, np.float32)
+    lib.pathref_setup(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
+                      {"box": 0, "gaussian": 1}[rp.rfilter], {"sobol": 0, "independent": 1}[rp.sampler], rp.spp, C.c_uint64(rp.seed),
+                      rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters))
+    film = np.zeros((cam.height, cam.width, 5), np.float32)
+    lib.pathref_render(h, _f(film))
+    if want_camera:
+        s2c = np.zeros((4, 4), np.float32)
+        lib.pathref_sample_to_camera(h, _f(s2c))
+        return film, s2c
+    return film
+
+
+def image_cases():
+    """(name, SceneDesc, RenderParams) of the image-level pins: `path`, Sobol' sampler."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from bsdf_configs import configs
+    from mitsuba_b200.scene import RenderParams, cornell_box, material_ball
+    cf = configs()
+    yield "cbox_box_8spp", cornell_box(48, 48), RenderParams(spp=8, sampler="sobol", rfilter="box")
+    yield "cbox_gaussian_16spp", cornell_box(40, 32), RenderParams(spp=16, sampler="sobol", rfilter="gaussian")
+    yield "cbox_depth3_scramble", cornell_box(32, 32), RenderParams(spp=4, sampler="sobol", rfilter="gaussian", max_depth=3, rr_depth=2, seed=7)
+    yield "cbox_strict_hidden", cornell_box(32, 32), RenderParams(spp=4, sampler="sobol", rfilter="box", strict_normals=True, hide_emitters=True)
+    for name in ("roughconductor_ggx", "roughdielectric_beckmann", "coating_diffuse", "dielectric", "conductor", "roughconductor_as", "twosided_two", "plastic"):
+        yield "ball_" + name, material_ball(cf[name], 40, 40, n_theta=20, n_phi=40), RenderParams(spp=8, sampler="sobol", rfilter="gaussian")

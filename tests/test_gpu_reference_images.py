@@ -1,0 +1,34 @@
+"""The device renderer against images rendered by the REFERENCE's own code (tests/golden/path_ref.npz: MIPathTracer::Li, renderBlock,
+Scene, ShapeKDTree, sensor, emitter, Sobol' sampler, filters, ImageBlock and the BSDF plugins compiled from /root/reference into
+oracle/_ref/libpathref.so -- see tests/gen_golden.py).  No oracle in between: this is the reference's output."""
+import os
+
+import numpy as np
+import pytest
+
+import ref_pins
+from mitsuba_b200 import api
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rel_l2(a, b):
+    return float(np.sqrt(((a.astype(np.float64) - b) ** 2).sum() / (b.astype(np.float64) ** 2).sum()))
+
+
+def test_device_images_match_the_reference_renderer(b2ctx):
+    g = np.load(os.path.join(HERE, "golden", "path_ref.npz"))
+    n = 0
+    for name, desc, rp in ref_pins.image_cases():
+        ref = g[name + "/film"]
+        sc = api.Scene(b2ctx, desc)
+        film, st = sc.render(rp, parity=True)
+        film = np.asarray(film).reshape(ref.shape)
+        # identical sample sets and splats; what is left is libm (device sin/cos/exp vs glibc) and the last bit of the camera matrix
+        assert np.allclose(film[..., 4], ref[..., 4], rtol=1e-5, atol=1e-6), name            # weights
+        assert np.allclose(film[..., 3], ref[..., 3], rtol=1e-4, atol=1e-4), name            # alpha
+        assert rel_l2(film[..., :3], ref[..., :3]) <= 3e-4, (name, rel_l2(film[..., :3], ref[..., :3]))
+        sc.close()
+        n += 1
+    assert n == 12
