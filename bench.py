@@ -82,7 +82,57 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+REF_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libpathref.so")
+_REF = {}
+
+
+def _ref_worker_init(width, height, spp):
+    """One scene per worker process: the reference's own Scene / ShapeKDTree / MIPathTracer (oracle/path_ref_shim.cpp)."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    import ref_pins
+    from mitsuba_b200.scene import RenderParams, cornell_box
+    lib = C.CDLL(REF_LIB)
+    d = cornell_box(width, height)
+    rp = RenderParams(spp=spp, sampler="sobol", rfilter="box")
+    _REF["lib"], _REF["handle"], _REF["shape"] = lib, ref_pins.reference_scene(lib, d, rp), (height, width, 5)
+
+
+def _ref_worker_render(args):
+    import ctypes as C
+    first, step = args
+    film = np.zeros(_REF["shape"], np.float32)
+    _REF["lib"].pathref_render_blocks(_REF["handle"], first, step, film.ctypes.data_as(C.POINTER(C.c_float)))
+    return float(film[..., 4].sum())
+
+
 def cpu_reference_run(steps, warmup, sample_spp=None, threads=0):
+    """The reference on the host cores, on a bounded sample of the SAME workload (`sample_spp` samples of every pixel of the
+    1024 x 1024 image).  kind "reference": the reference's own sources (path.cpp, scene.cpp, skdtree.cpp, the plugins ...) compiled into
+    oracle/_ref/libpathref.so, one process per core, each rendering every cores-th 32 x 32 block with SamplingIntegrator::renderBlock
+    (the reference's scheduler is not part of that build).  Falls back to the oracle port (kind "port") where that library is absent."""
+    if os.path.exists(REF_LIB) and not os.environ.get("B2_BENCH_ORACLE_PORT"):
+        import multiprocessing as mp
+        cores = threads or os.cpu_count()
+        sample_spp = sample_spp or 16
+        with mp.get_context("fork").Pool(cores, initializer=_ref_worker_init, initargs=(WORKLOAD["width"], WORKLOAD["height"], sample_spp)) as pool:
+            shares = [(i, cores) for i in range(cores)]
+            for _ in range(max(warmup, 1)):
+                pool.map(_ref_worker_render, shares)
+            t0 = time.time()
+            for _ in range(steps):
+                w = pool.map(_ref_worker_render, shares)
+            dt = (time.time() - t0) / max(steps, 1)
+        n = WORKLOAD["width"] * WORKLOAD["height"] * sample_spp
+        assert abs(sum(w) - n) < 1e-3 * n, "the shares do not add up to the whole image"
+        return dict(value=n / dt / 1e6, unit="Msamples/s", cores=cores, kind="reference",
+                    sample=f"{sample_spp} spp (Sobol', box filter) of every pixel of the 1024x1024 Cornell workload ({n / 1e6:.1f} Msamples per step), "
+                           "reference sources compiled into oracle/_ref/libpathref.so, one process per core",
+                    ms_per_step=dt * 1e3, mean_path_length=None)
+    return cpu_port_run(steps, warmup, sample_spp, threads)
+
+
+def cpu_port_run(steps, warmup, sample_spp=None, threads=0):
     """The CPU restatement of the reference (oracle, kind "port") on the host cores: a bounded sample of the SAME workload
     (the first `sample_spp` sample indices of every pixel of the 1024 x 1024 image)."""
     from mitsuba_b200.scene import RenderParams, cornell_box
@@ -219,7 +269,9 @@ def run_reference(args):
             "config": {"workload": "Cornell box (S1) 1024x1024, path/sobol/box, bounded sample on the host cores", **WORKLOAD},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "Mitsuba-0.6-equivalent CPU restatement (oracle/), not the Mitsuba binary: the reference cannot be built offline (DESIGN.md)"}
+            "note": ("the reference's own sources (MIPathTracer::Li, renderBlock, Scene, ShapeKDTree, plugins) compiled into oracle/_ref/libpathref.so; "
+                     "the Mitsuba binary itself (SCons, Boost, Xerces, OpenEXR) cannot be built offline (DESIGN.md)") if r["kind"] == "reference" else
+                    "Mitsuba-0.6-equivalent CPU restatement (oracle/), not the Mitsuba binary: the reference cannot be built offline (DESIGN.md)"}
     print(json.dumps(line))
     return 0
 

@@ -333,8 +333,12 @@ void pathref_sample_emitter_direct(void *h, int n, const float *ref, const float
 /* film out: H x W x 5 (rgb, alpha, weight), blocks of 32 x 32 rendered by SamplingIntegrator::renderBlock with the pixels of a block in
  * scanline order and accumulated here in block order (the reference's scheduler hands out Hilbert-ordered pixels and merges blocks in
  * completion order: float summation order only) */
-void pathref_render(void *h, float *out) {
+void pathref_render_blocks(void *h, int first, int step, float *out);
+void pathref_render(void *h, float *out) { pathref_render_blocks(h, 0, 1, out); }
+/* the blocks with index == first (mod step): lets several processes share one image (bench.py --impl reference) */
+void pathref_render_blocks(void *h, int first, int step, float *out) {
     PathRef *p = (PathRef *) h;
+    int blockIndex = 0;
     SamplingIntegrator *integrator = static_cast<SamplingIntegrator *>(p->integrator.get());
     const ReconstructionFilter *rf = p->film->getReconstructionFilter();
     const int bs = 32, border = rf->getBorderSize(), W = p->W, H = p->H;
@@ -342,6 +346,7 @@ void pathref_render(void *h, float *out) {
     bool stop = false;
     for (int oy = 0; oy < H; oy += bs)
         for (int ox = 0; ox < W; ox += bs) {
+            if ((blockIndex++ % step) != first) continue;
             const int sx = std::min(bs, W - ox), sy = std::min(bs, H - oy);
             ref<ImageBlock> block = new ImageBlock(Bitmap::ESpectrumAlphaWeight, Vector2i(sx, sy), rf);
             block->setOffset(Point2i(ox, oy));

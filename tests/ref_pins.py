@@ -292,9 +292,8 @@ def run_render(lib, prefix, x, oracle_scene=None):
 # ---------------------------------------------------------------------------------------------------------------------------
 # whole images: a minimal `path` renderer assembled from the reference's own sources (oracle/path_ref_shim.cpp -> libpathref.so)
 # ---------------------------------------------------------------------------------------------------------------------------
-def reference_render(lib, desc, rp, want_camera=False):
-    """Render a mitsuba_b200.scene.SceneDesc with the reference's MIPathTracer / Scene / ShapeKDTree / plugins.  Returns (H, W, 5)
-    (and, with want_camera, the reference's sampleToCamera matrix: camera set-up is host work, both sides should start from it)."""
+def reference_scene(lib, desc, rp):
+    """Build a mitsuba_b200.scene.SceneDesc as a reference Scene (the reference's own classes, oracle/path_ref_shim.cpp) -> handle."""
     from mitsuba_b200.scene import Bsdf
     lib.pathref_new.restype = C.c_void_p
     lib.pathref_bsdf.restype = C.c_void_p
@@ -319,6 +318,14 @@ def reference_render(lib, desc, rp, want_camera=False):
     lib.pathref_setup(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
                       {"box": 0, "gaussian": 1}[rp.rfilter], {"sobol": 0, "independent": 1}[rp.sampler], rp.spp, C.c_uint64(rp.seed),
                       rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters))
+    return h
+
+
+def reference_render(lib, desc, rp, want_camera=False):
+    """Render a mitsuba_b200.scene.SceneDesc with the reference's MIPathTracer / Scene / ShapeKDTree / plugins.  Returns (H, W, 5)
+    (and, with want_camera, the reference's sampleToCamera matrix: camera set-up is host work, both sides should start from it)."""
+    h = reference_scene(lib, desc, rp)
+    cam = desc.camera
     film = np.zeros((cam.height, cam.width, 5), np.float32)
     lib.pathref_render(h, _f(film))
     if want_camera:
