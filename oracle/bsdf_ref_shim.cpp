@@ -100,6 +100,15 @@ void Stream::writeBool(bool) {}
 void Stream::writeUInt(unsigned int) {}
 size_t Stream::readSize() { return 0; }
 void Stream::writeSize(size_t) {}
+void Stream::read(void *, size_t) {}
+void Stream::write(const void *, size_t) {}
+size_t Stream::getPos() const { return 0; }
+size_t Stream::getSize() const { return 0; }
+void Stream::seek(size_t) {}
+void Stream::flush() {}
+void Stream::truncate(size_t) {}
+bool Stream::canRead() const { return false; }
+bool Stream::canWrite() const { return false; }
 template <> void Stream::writeArray<float>(const float *, size_t) {}
 }
 

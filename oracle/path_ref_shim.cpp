@@ -25,6 +25,10 @@
 #include <mitsuba/core/zstream.h>
 #include <mitsuba/core/lock.h>
 #include <mitsuba/core/tls.h>
+#include <mitsuba/render/medium.h>
+#include <mitsuba/render/phase.h>
+#include <mitsuba/render/volume.h>
+#include "orc_sampler.h" /* orc::CounterSampler: this repository's counter-based `independent` stream, served to the reference integrator */
 
 namespace mitsuba {
 /* ---------------------------------------------- scaffolding ---------------------------------------------- */
@@ -111,8 +115,8 @@ void Bitmap::clear() { memset(m_data, 0, (size_t) m_size.x * m_size.y * m_channe
 std::string Bitmap::toString() const { return "Bitmap"; }
 MTS_IMPLEMENT_CLASS(Bitmap, false, Object)
 /* Stream: nothing is (de)serialised */
-float Stream::readSingle() { return 0; } double Stream::readDouble() { return 0; } void Stream::writeSingle(float) {} void Stream::writeDouble(double) {}
-int Stream::readInt() { return 0; } void Stream::writeInt(int) {} float Stream::readFloat() { return 0; } void Stream::writeFloat(float) {}
+float Stream::readSingle() { float v = 0; read(&v, sizeof(v)); return v; } /* little-endian host = the .vol byte order */ double Stream::readDouble() { return 0; } void Stream::writeSingle(float) {} void Stream::writeDouble(double) {}
+int Stream::readInt() { int v = 0; read(&v, sizeof(v)); return v; } void Stream::writeInt(int) {} float Stream::readFloat() { float v = 0; read(&v, sizeof(v)); return v; } void Stream::writeFloat(float) {}
 void Stream::readFloatArray(float *, size_t) {} void Stream::writeFloatArray(const float *, size_t) {}
 std::string Stream::readString() { return ""; } void Stream::writeString(const std::string &) {} void Stream::read(void *, size_t) {} void Stream::write(const void *, size_t) {}
 void Stream::readSingleArray(float *, size_t) {} void Stream::writeSingleArray(const float *, size_t) {}
@@ -123,7 +127,7 @@ void Stream::readULongArray(uint64_t *, size_t) {} void Stream::writeULongArray(
 unsigned int Stream::readUInt() { return 0; } void Stream::writeUInt(unsigned int) {} size_t Stream::readSize() { return 0; } void Stream::writeSize(size_t) {}
 bool Stream::readBool() { return false; } void Stream::writeBool(bool) {} short Stream::readShort() { return 0; } void Stream::writeShort(short) {}
 long long Stream::readLong() { return 0; } void Stream::writeLong(long long) {} unsigned long long Stream::readULong() { return 0; } void Stream::writeULong(unsigned long long) {}
-void Stream::skip(size_t) {} void Stream::flush() {}
+void Stream::skip(size_t n) { seek(getPos() + n); } void Stream::flush() {} void Stream::truncate(size_t) {} bool Stream::canRead() const { return true; } bool Stream::canWrite() const { return false; }
 size_t Stream::getPos() const { return 0; }
 size_t Stream::getSize() const { return 0; }
 template <typename T> void Stream::readArray(T *, size_t) {}
@@ -140,6 +144,8 @@ template float Stream::readElement<float>(); template void Stream::writeElement<
 ZStream::ZStream(Stream *child, EStreamType, int) : m_childStream(child) {}
 ZStream::~ZStream() {}
 std::string ZStream::toString() const { return "ZStream"; }
+void ZStream::read(void *, size_t) {} void ZStream::write(const void *, size_t) {} void ZStream::seek(size_t) {} size_t ZStream::getPos() const { return 0; }
+size_t ZStream::getSize() const { return 0; } void ZStream::truncate(size_t) {} void ZStream::flush() {} bool ZStream::canWrite() const { return false; } bool ZStream::canRead() const { return false; }
 MTS_IMPLEMENT_CLASS(ZStream, false, Stream)
 }
 
@@ -152,6 +158,24 @@ using namespace mitsuba;
 #define DECL(name) extern "C" void *CreateInstance_##name(const Properties &props);
 DECL(diffuse) DECL(roughconductor) DECL(roughdielectric) DECL(coating) DECL(dielectric) DECL(conductor) DECL(plastic) DECL(twosided) DECL(null)
 DECL(gaussian) DECL(box) DECL(sobol) DECL(independent) DECL(path) DECL(perspective) DECL(area)
+DECL(volpath) DECL(heterogeneous) DECL(homogeneous) DECL(gridvolume) DECL(constvolume) DECL(isotropic) DECL(hg)
+
+/* The `independent` sampler of this repository is a counter-based stream, not the reference's SFMT: to compare volpath
+ * images sample for sample the reference integrator is handed that stream through the real Sampler interface. */
+class CounterSamplerPlugin : public Sampler {
+public:
+    CounterSamplerPlugin(int W, size_t spp, uint64_t seed) : Sampler(Properties()), m_impl(W, (uint32_t) spp, seed) { m_sampleCount = spp; }
+    void generate(const Point2i &pos) { m_impl.generate(pos.x, pos.y); m_sampleIndex = 0; }
+    void advance() { m_impl.advance(); ++m_sampleIndex; }
+    Float next1D() { return m_impl.next1D(); }
+    Point2 next2D() { float a, b; m_impl.next2D(a, b); return Point2(a, b); }
+    ref<Sampler> clone() { return this; }
+    void setSampleIndex(size_t) {}
+    std::string toString() const { return "CounterSampler"; }
+    const Class *getClass() const { return Sampler::m_theClass; }
+private:
+    orc::CounterSampler m_impl;
+};
 
 /* carries resolution + reconstruction filter to the sensor / integrator (hdrfilm.cpp needs the Bitmap file writers) */
 class StandinFilm : public Film {
@@ -212,15 +236,71 @@ void *pathref_bsdf(int plugin, int nf, const char **fk, const float *fv, int ns,
     b->configure();
     return b;
 }
+/* phase 0 isotropic / 1 hg(g) */
+static PhaseFunction *makePhase(int phase, float g) {
+    Properties pp;
+    if (phase == 1) pp.setFloat("g", g);
+    PhaseFunction *ph = (PhaseFunction *) (phase == 1 ? CreateInstance_hg(pp) : CreateInstance_isotropic(pp));
+    ph->configure();
+    return ph;
+}
+/* `homogeneous` medium (src/medium/homogeneous.cpp): sigmaA / sigmaS RGB; strategy "balance" | "single" | "manual" */
+void *pathref_medium_homogeneous(const float *sigmaA, const float *sigmaS, const char *strategy, float samplingDensity, float mediumSamplingWeight, int phase, float g) {
+    Properties mp("homogeneous");
+    Spectrum a, sc;
+    for (int i = 0; i < 3; ++i) { a[i] = sigmaA[i]; sc[i] = sigmaS[i]; }
+    mp.setSpectrum("sigmaA", a); mp.setSpectrum("sigmaS", sc);
+    mp.setString("strategy", strategy);
+    if (samplingDensity > 0) mp.setFloat("samplingDensity", samplingDensity);
+    if (mediumSamplingWeight >= 0) mp.setFloat("mediumSamplingWeight", mediumSamplingWeight);
+    Medium *m = (Medium *) CreateInstance_homogeneous(mp);
+    m->addChild("", makePhase(phase, g));
+    m->configure();
+    return m;
+}
+/* `heterogeneous` medium, method woodcock (src/medium/heterogeneous.cpp): density = `gridvolume` read from a .vol file with an
+ * optional toWorld (row-major 4 x 4, NULL = identity), albedo = `constvolume`; scale */
+void *pathref_medium_heterogeneous(const char *volFile, const float *toWorld, const float *albedo, float scale, int phase, float g) {
+    Properties gp("gridvolume");
+    gp.setString("filename", volFile);
+    if (toWorld) { Matrix4x4 M; for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M.m[r][c] = toWorld[4 * r + c]; gp.setTransform("toWorld", Transform(M)); }
+    VolumeDataSource *density = (VolumeDataSource *) CreateInstance_gridvolume(gp);
+    density->configure();
+    Properties cp("constvolume");
+    Spectrum al; for (int i = 0; i < 3; ++i) al[i] = albedo[i];
+    cp.setSpectrum("value", al);
+    VolumeDataSource *alb = (VolumeDataSource *) CreateInstance_constvolume(cp);
+    alb->configure();
+    Properties mp("heterogeneous");
+    mp.setString("method", "woodcock");
+    mp.setFloat("scale", scale);
+    Medium *m = (Medium *) CreateInstance_heterogeneous(mp);
+    m->addChild("density", density);
+    m->addChild("albedo", alb);
+    m->addChild("", makePhase(phase, g));
+    m->configure();
+    return m;
+}
 /* a TriMesh as the loaders leave it (positions, optional normals / texcoords, triangles), its BSDF, optionally an area emitter */
+void pathref_add_mesh_media(void *h, const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf, const float *radiance, float samplingWeight,
+                            void *interior, void *exterior);
 void pathref_add_mesh(void *h, const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf, const float *radiance, float samplingWeight) {
+    pathref_add_mesh_media(h, P, N, UV, nV, idx, nT, bsdf, radiance, samplingWeight, NULL, NULL);
+}
+/* bsdf may be NULL for an index-matched medium boundary: Shape::configure then creates the `null` BSDF itself (shape.cpp:64-68) through
+   the plugin manager, which this build does not have -- so the `null` plugin is attached here */
+void pathref_add_mesh_media(void *h, const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf, const float *radiance, float samplingWeight,
+                            void *interior, void *exterior) {
     PathRef *p = (PathRef *) h;
     ref<TriMesh> mesh = new TriMesh("mesh", (size_t) nT, (size_t) nV, N != NULL, UV != NULL, false, false, N == NULL /* face normals, skdtree.h:383-399 */);
     memcpy(mesh->getVertexPositions(), P, sizeof(float) * 3 * nV);
     if (N) memcpy(mesh->getVertexNormals(), N, sizeof(float) * 3 * nV);
     if (UV) memcpy(mesh->getVertexTexcoords(), UV, sizeof(float) * 2 * nV);
     memcpy(mesh->getTriangles(), idx, sizeof(uint32_t) * 3 * nT);
+    if (!bsdf) { Properties np("null"); BSDF *nb = (BSDF *) CreateInstance_null(np); nb->configure(); bsdf = nb; }
     mesh->addChild("", (ConfigurableObject *) (BSDF *) bsdf);
+    if (interior) mesh->addChild("interior", (ConfigurableObject *) (Medium *) interior);
+    if (exterior) mesh->addChild("exterior", (ConfigurableObject *) (Medium *) exterior);
     if (radiance) {
         Properties ep("area");
         Spectrum s; s[0] = radiance[0]; s[1] = radiance[1]; s[2] = radiance[2];
@@ -236,8 +316,15 @@ void pathref_add_mesh(void *h, const float *P, const float *N, const float *UV, 
     p->keep.push_back(mesh);
 }
 /* perspective sensor + film + sampler + path integrator; rfilter 0 box / 1 gaussian; sampler 0 sobol / 1 independent */
+void pathref_setup2(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
+                    int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind);
 void pathref_setup(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
                    int maxDepth, int rrDepth, int strictNormals, int hideEmitters) {
+    pathref_setup2(h, toWorld, fov, nearClip, farClip, W, H, rfilter, samplerKind, spp, scramble, maxDepth, rrDepth, strictNormals, hideEmitters, 0);
+}
+/* samplerKind 0 sobol, 1 independent (SFMT), 2 this repository's counter stream; integratorKind 0 path, 1 volpath */
+void pathref_setup2(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
+                    int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind) {
     PathRef *p = (PathRef *) h;
     p->W = W; p->H = H;
     Properties fp("hdrfilm");
@@ -251,7 +338,8 @@ void pathref_setup(void *h, const float *toWorld, float fov, float nearClip, flo
     Properties sp;
     sp.setInteger("sampleCount", spp);
     sp.setInteger("scramble", (int) scramble);
-    p->sampler = (Sampler *) (samplerKind == 0 ? CreateInstance_sobol(sp) : CreateInstance_independent(sp));
+    if (samplerKind == 2) p->sampler = new CounterSamplerPlugin(W, (size_t) spp, scramble);
+    else p->sampler = (Sampler *) (samplerKind == 0 ? CreateInstance_sobol(sp) : CreateInstance_independent(sp));
     p->sampler->configure();
     Properties cp("perspective");
     Matrix4x4 M;
@@ -265,7 +353,7 @@ void pathref_setup(void *h, const float *toWorld, float fov, float nearClip, flo
     Properties ip("path");
     ip.setInteger("maxDepth", maxDepth); ip.setInteger("rrDepth", rrDepth);
     ip.setBoolean("strictNormals", strictNormals != 0); ip.setBoolean("hideEmitters", hideEmitters != 0);
-    p->integrator = (Integrator *) CreateInstance_path(ip);
+    p->integrator = (Integrator *) (integratorKind == 1 ? CreateInstance_volpath(ip) : CreateInstance_path(ip));
     p->integrator->configure();
     p->scene->addChild("", p->sensor);
     p->scene->addChild("", p->integrator);

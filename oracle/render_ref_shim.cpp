@@ -31,6 +31,15 @@ void Stream::readFloatArray(Float *, size_t) {}
 void Stream::writeFloatArray(const Float *, size_t) {}
 size_t Stream::readSize() { return 0; }
 void Stream::writeSize(size_t) {}
+void Stream::read(void *, size_t) {}
+void Stream::write(const void *, size_t) {}
+size_t Stream::getPos() const { return 0; }
+size_t Stream::getSize() const { return 0; }
+void Stream::seek(size_t) {}
+void Stream::flush() {}
+void Stream::truncate(size_t) {}
+bool Stream::canRead() const { return false; }
+bool Stream::canWrite() const { return false; }
 int Stream::readInt() { return 0; }
 void Stream::writeInt(int) {}
 unsigned int Stream::readUInt() { return 0; }

@@ -3,12 +3,16 @@
 #pragma once
 #include <fstream>
 #include <string>
+#include <cstdio>
+#include <unistd.h>
 namespace boost { namespace filesystem {
 class path { public: path() {} path(const char *s) : m_s(s) {} path(const std::string &s) : m_s(s) {} bool empty() const { return m_s.empty(); } const std::string &string() const { return m_s; }
   path filename() const { return *this; } path extension() const { return path(); } path parent_path() const { return path(); } path operator/(const path &o) const { return path(m_s + "/" + o.m_s); } bool is_absolute() const { return false; }
   private: std::string m_s; };
-inline bool exists(const path &) { return false; }
-inline size_t file_size(const path &) { return 0; }
+inline bool exists(const path &p) { return ::access(p.string().c_str(), F_OK) == 0; }
+inline size_t file_size(const path &p) { std::ifstream f(p.string().c_str(), std::ios::binary | std::ios::ate); return f ? (size_t) f.tellg() : 0; }
+inline bool remove(const path &p) { return ::remove(p.string().c_str()) == 0; }
+inline void resize_file(const path &p, size_t n) { if (::truncate(p.string().c_str(), (off_t) n)) {} }
 class ifstream : public std::ifstream { public: ifstream() {} ifstream(const path &p) : std::ifstream(p.string().c_str()) {} };
 class ofstream : public std::ofstream { public: ofstream() {} ofstream(const path &p, std::ios_base::openmode m = std::ios_base::out) : std::ofstream(p.string().c_str(), m) {} };
 } }

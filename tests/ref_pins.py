@@ -301,23 +301,51 @@ def reference_scene(lib, desc, rp):
 
     class _L:  # reference_bsdf() talks to `bsdfref_create`; here the same function is called pathref_bsdf
         bsdfref_create = lib.pathref_bsdf
-    memo = {}
+    memo, mmemo, keep = {}, {}, []
+    lib.pathref_medium_homogeneous.restype = C.c_void_p
+    lib.pathref_medium_heterogeneous.restype = C.c_void_p
+
+    def medium(md):
+        if md is None:
+            return None
+        if id(md) not in mmemo:
+            ph = {"isotropic": 0, "hg": 1}[md.phase]
+            if md.type == "homogeneous":
+                sa, ss = np.asarray(md.sigma_a, np.float32), np.asarray(md.sigma_s, np.float32)
+                mmemo[id(md)] = C.c_void_p(lib.pathref_medium_homogeneous(_f(sa), _f(ss), md.strategy.encode(), C.c_float(md.sampling_density),
+                                                                             C.c_float(md.medium_sampling_weight), ph, C.c_float(md.g)))
+            else:
+                import tempfile
+                dens = np.ascontiguousarray(md.density, np.float32)
+                nz, ny, nx = dens.shape
+                f = tempfile.NamedTemporaryFile(suffix=".vol", delete=False)
+                f.write(b"VOL\x03" + np.array([1, nx, ny, nz, 1], "<i4").tobytes() + np.array(list(md.aabb_min) + list(md.aabb_max), "<f4").tobytes() + dens.tobytes())
+                f.close()
+                keep.append(f.name)
+                tw = np.ascontiguousarray(md.to_world, np.float32) if md.to_world is not None else None
+                al = np.asarray(md.albedo, np.float32)
+                mmemo[id(md)] = C.c_void_p(lib.pathref_medium_heterogeneous(f.name.encode(), _f(tw) if tw is not None else None, _f(al), C.c_float(md.scale), ph, C.c_float(md.g)))
+        return mmemo[id(md)]
     for m in desc.meshes:
-        b = m.bsdf if m.bsdf is not None else Bsdf("diffuse", reflectance=(0.0,) * 3 if m.radiance is not None else (0.5,) * 3)
-        if id(b) not in memo:
+        b = m.bsdf
+        if b is None and m.interior is None and m.exterior is None:
+            b = Bsdf("diffuse", reflectance=(0.0,) * 3 if m.radiance is not None else (0.5,) * 3)
+        if b is not None and id(b) not in memo:
             memo[id(b)] = reference_bsdf(_L, b)
         P = np.ascontiguousarray(m.P, np.float32)
         N = np.ascontiguousarray(m.N, np.float32) if m.N is not None else None
         UV = np.ascontiguousarray(m.UV, np.float32) if m.UV is not None else None
         I = np.ascontiguousarray(m.idx, np.uint32)
         rad = np.asarray(m.radiance, np.float32) if m.radiance is not None else None
-        lib.pathref_add_mesh(h, _f(P), _f(N) if N is not None else None, _f(UV) if UV is not None else None, len(P),
-                             I.ctypes.data_as(C.POINTER(C.c_uint32)), len(I), memo[id(b)], _f(rad) if rad is not None else None, C.c_float(m.sampling_weight))
+        lib.pathref_add_mesh_media(h, _f(P), _f(N) if N is not None else None, _f(UV) if UV is not None else None, len(P),
+                                   I.ctypes.data_as(C.POINTER(C.c_uint32)), len(I), memo[id(b)] if b is not None else None, _f(rad) if rad is not None else None,
+                                   C.c_float(m.sampling_weight), medium(m.interior), medium(m.exterior))
     cam = desc.camera
     tw = np.ascontiguousarray(cam.to_world, np.float32)
-    lib.pathref_setup(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
-                      {"box": 0, "gaussian": 1}[rp.rfilter], {"sobol": 0, "independent": 1}[rp.sampler], rp.spp, C.c_uint64(rp.seed),
-                      rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters))
+    # `independent` here is this repository's counter-based stream (kind 2), handed to the reference integrator through the Sampler interface
+    lib.pathref_setup2(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
+                       {"box": 0, "gaussian": 1}[rp.rfilter], {"sobol": 0, "independent": 2}[rp.sampler], rp.spp, C.c_uint64(rp.seed),
+                       rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters), {"path": 0, "volpath": 1}[rp.integrator])
     return h
 
 
@@ -348,3 +376,15 @@ def image_cases():
     yield "cbox_strict_hidden", cornell_box(32, 32), RenderParams(spp=4, sampler="sobol", rfilter="box", strict_normals=True, hide_emitters=True)
     for name in ("roughconductor_ggx", "roughdielectric_beckmann", "coating_diffuse", "dielectric", "conductor", "roughconductor_as", "twosided_two", "plastic"):
         yield "ball_" + name, material_ball(cf[name], 40, 40, n_theta=20, n_phi=40), RenderParams(spp=8, sampler="sobol", rfilter="gaussian")
+    # volpath (src/integrators/path/volpath.cpp) with the reference's medium / volume / phase plugins; `independent` = this repository's
+    # counter stream served to the reference integrator through the Sampler interface
+    from mitsuba_b200.scene import Medium, smoke_scene
+    yield "vol_cbox_sobol", cornell_box(32, 32), RenderParams(spp=4, sampler="sobol", rfilter="box", integrator="volpath")
+    yield "path_cbox_counter", cornell_box(32, 32), RenderParams(spp=4, sampler="independent", rfilter="gaussian")
+    for strat in ("balance", "single"):
+        d = smoke_scene(40, 40, res=8)
+        d.meshes[2].interior = Medium("homogeneous", sigma_a=(0.5, 0.6, 0.7), sigma_s=(2.0, 2.5, 3.0), strategy=strat, phase="hg", g=0.3)
+        yield "vol_homogeneous_" + strat, d, RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
+    yield "vol_heterogeneous_iso", smoke_scene(40, 40, res=8, scale=6.0), RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
+    yield "vol_heterogeneous_hg", smoke_scene(40, 40, res=16, scale=12.0, phase="hg", g=0.5), RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
+    yield "vol_heterogeneous_sobol", smoke_scene(32, 32, res=8, scale=4.0), RenderParams(spp=4, sampler="sobol", rfilter="box", integrator="volpath", max_depth=4)

@@ -28,7 +28,9 @@ def test_device_images_match_the_reference_renderer(b2ctx):
         # identical sample sets and splats; what is left is libm (device sin/cos/exp vs glibc) and the last bit of the camera matrix
         assert np.allclose(film[..., 4], ref[..., 4], rtol=1e-5, atol=1e-6), name            # weights
         assert np.allclose(film[..., 3], ref[..., 3], rtol=1e-4, atol=1e-4), name            # alpha
-        assert rel_l2(film[..., :3], ref[..., :3]) <= 3e-4, (name, rel_l2(film[..., :3], ref[..., :3]))
+        # volpath: a Woodcock walk compares density / max against a random number, so device libm rounding flips an occasional collision
+        tol = 2e-3 if name.startswith("vol_h") else 3e-4
+        assert rel_l2(film[..., :3], ref[..., :3]) <= tol, (name, rel_l2(film[..., :3], ref[..., :3]))
         sc.close()
         n += 1
-    assert n == 12
+    assert n == 19
