@@ -86,16 +86,38 @@ REF_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_r
 _REF = {}
 
 
-def _ref_worker_init(width, height, spp):
-    """One scene per worker process: the reference's own Scene / ShapeKDTree / MIPathTracer (oracle/path_ref_shim.cpp)."""
+def _ref_worker_init(width, height, spp, scene="cornell"):
+    """One scene per worker process: the reference's own Scene / ShapeKDTree / MIPathTracer or VolumetricPathTracer (oracle/path_ref_shim.cpp)."""
     import ctypes as C
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
     import ref_pins
-    from mitsuba_b200.scene import RenderParams, cornell_box
+    from mitsuba_b200.scene import RenderParams, cornell_box, smoke_scene
     lib = C.CDLL(REF_LIB)
-    d = cornell_box(width, height)
-    rp = RenderParams(spp=spp, sampler="sobol", rfilter="box")
+    if scene == "smoke":  # BASELINE configs[3]: 128^3 heterogeneous medium, volpath, this repository's counter stream as the sampler
+        d, rp = smoke_scene(width, height, res=128), RenderParams(spp=spp, sampler="independent", rfilter="gaussian", integrator="volpath")
+    else:
+        d, rp = cornell_box(width, height), RenderParams(spp=spp, sampler="sobol", rfilter="box")
     _REF["lib"], _REF["handle"], _REF["shape"] = lib, ref_pins.reference_scene(lib, d, rp), (height, width, 5)
+
+
+def reference_cpu_rate(scene, width, height, spp, steps=1, warmup=1, cores=0):
+    """Msamples/s of the reference's own code (oracle/_ref/libpathref.so) on `cores` processes, or None where the library is absent."""
+    if not os.path.exists(REF_LIB) or os.environ.get("B2_BENCH_ORACLE_PORT"):
+        return None
+    import multiprocessing as mp
+    cores = cores or os.cpu_count()
+    with mp.get_context("fork").Pool(cores, initializer=_ref_worker_init, initargs=(width, height, spp, scene)) as pool:
+        shares = [(i, cores) for i in range(cores)]
+        for _ in range(warmup):
+            pool.map(_ref_worker_render, shares)
+        t0 = time.time()
+        for _ in range(steps):
+            w = pool.map(_ref_worker_render, shares)
+        dt = (time.time() - t0) / max(steps, 1)
+    n = width * height * spp
+    if abs(sum(w) - n) > 2e-2 * n:  # film weights (gaussian: the border pixels lose a little)
+        raise RuntimeError("the shares of the reference render do not add up to the whole image")
+    return dict(value=n / dt / 1e6, unit="Msamples/s", cores=cores, kind="reference", ms_per_step=dt * 1e3)
 
 
 def _ref_worker_render(args):
@@ -111,24 +133,13 @@ def cpu_reference_run(steps, warmup, sample_spp=None, threads=0):
     1024 x 1024 image).  kind "reference": the reference's own sources (path.cpp, scene.cpp, skdtree.cpp, the plugins ...) compiled into
     oracle/_ref/libpathref.so, one process per core, each rendering every cores-th 32 x 32 block with SamplingIntegrator::renderBlock
     (the reference's scheduler is not part of that build).  Falls back to the oracle port (kind "port") where that library is absent."""
-    if os.path.exists(REF_LIB) and not os.environ.get("B2_BENCH_ORACLE_PORT"):
-        import multiprocessing as mp
-        cores = threads or os.cpu_count()
-        sample_spp = sample_spp or 16
-        with mp.get_context("fork").Pool(cores, initializer=_ref_worker_init, initargs=(WORKLOAD["width"], WORKLOAD["height"], sample_spp)) as pool:
-            shares = [(i, cores) for i in range(cores)]
-            for _ in range(max(warmup, 1)):
-                pool.map(_ref_worker_render, shares)
-            t0 = time.time()
-            for _ in range(steps):
-                w = pool.map(_ref_worker_render, shares)
-            dt = (time.time() - t0) / max(steps, 1)
+    sample_spp = sample_spp or 16
+    r = reference_cpu_rate("cornell", WORKLOAD["width"], WORKLOAD["height"], sample_spp, steps, max(warmup, 1), threads)
+    if r is not None:
         n = WORKLOAD["width"] * WORKLOAD["height"] * sample_spp
-        assert abs(sum(w) - n) < 1e-3 * n, "the shares do not add up to the whole image"
-        return dict(value=n / dt / 1e6, unit="Msamples/s", cores=cores, kind="reference",
-                    sample=f"{sample_spp} spp (Sobol', box filter) of every pixel of the 1024x1024 Cornell workload ({n / 1e6:.1f} Msamples per step), "
-                           "reference sources compiled into oracle/_ref/libpathref.so, one process per core",
-                    ms_per_step=dt * 1e3, mean_path_length=None)
+        r.update(sample=f"{sample_spp} spp (Sobol', box filter) of every pixel of the 1024x1024 Cornell workload ({n / 1e6:.1f} Msamples per step), "
+                        "reference sources compiled into oracle/_ref/libpathref.so, one process per core", mean_path_length=None)
+        return r
     return cpu_port_run(steps, warmup, sample_spp, threads)
 
 
@@ -199,7 +210,7 @@ def traversal_metric(ctx, hbm_gbs, n_inst=10, n_rays=1 << 22):
     return res
 
 
-def volpath_metric(ctx, with_cpu=True):
+def volpath_metric(ctx, with_cpu=True, cpu_ref=None):
     """BASELINE configs[3], reported next to the headline: the S4 smoke scene -- a 128^3 density grid in the unit cube,
     `heterogeneous` Woodcock medium, isotropic phase, `volpath`, 512x512 @ 256 spp -- on this rank's GPU, plus the oracle's rate for
     the same scene on the host cores (bounded sample)."""
@@ -219,7 +230,10 @@ def volpath_metric(ctx, with_cpu=True):
            "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"], "kernel": "k_volstep", "kernel_ms": best["ms_shade"],
            "mean_path_length": best["path_length_sum"] / best["samples"], "rays_per_sample": (best["rays"] + best["shadow_rays"]) / best["samples"]}
     sc.close()
-    if with_cpu:
+    if cpu_ref is not None:
+        res["cpu_baseline"] = {**{k: cpu_ref[k] for k in ("value", "unit", "cores", "kind")},
+                               "sample": "8 spp of every pixel of the same scene; the reference's volpath.cpp / heterogeneous.cpp / gridvolume.cpp compiled into oracle/_ref/libpathref.so, one process per core"}
+    elif with_cpu:
         from oracle import oracle_api as O
         o = O.OracleScene(smoke_scene(512, 512, res=128))
         rp2 = RenderParams(spp=8, rfilter="gaussian", sampler="independent", integrator="volpath")
@@ -302,6 +316,12 @@ def main():
         except Exception as e:
             print(f"[bench] reference CPU arm failed ({e}); falling back to the oracle port", file=sys.stderr)
             cpu_base = cpu_port_run(1, 0)
+    vol_cpu = None
+    if not args.no_cpu_baseline and not args.no_volpath and args.gpus == 1 and int(os.environ.get("RANK", "0")) == 0:
+        try:
+            vol_cpu = reference_cpu_rate("smoke", 512, 512, 8)
+        except Exception as e:
+            print(f"[bench] reference CPU arm (volpath) failed ({e}); the oracle port is timed instead", file=sys.stderr)
 
     import torch
     import torch.distributed as dist
@@ -459,7 +479,7 @@ def main():
         if not args.no_traversal:
             line["traversal"] = traversal_metric(ctx, peaks.get("hbm_gbs", 6650.0))
         if not args.no_volpath:
-            line["volpath"] = volpath_metric(ctx, with_cpu=not args.no_cpu_baseline)
+            line["volpath"] = volpath_metric(ctx, with_cpu=not args.no_cpu_baseline, cpu_ref=vol_cpu)
             try:
                 line["textured"] = textured_metric(ctx, with_cpu=not args.no_cpu_baseline)
             except Exception as e:  # a side measurement must not take the headline line down with it

@@ -315,16 +315,20 @@ def reference_scene(lib, desc, rp):
                 mmemo[id(md)] = C.c_void_p(lib.pathref_medium_homogeneous(_f(sa), _f(ss), md.strategy.encode(), C.c_float(md.sampling_density),
                                                                              C.c_float(md.medium_sampling_weight), ph, C.c_float(md.g)))
             else:
-                import tempfile
+                import hashlib, os, tempfile
                 dens = np.ascontiguousarray(md.density, np.float32)
                 nz, ny, nx = dens.shape
-                f = tempfile.NamedTemporaryFile(suffix=".vol", delete=False)
-                f.write(b"VOL\x03" + np.array([1, nx, ny, nz, 1], "<i4").tobytes() + np.array(list(md.aabb_min) + list(md.aabb_max), "<f4").tobytes() + dens.tobytes())
-                f.close()
-                keep.append(f.name)
+                blob = b"VOL\x03" + np.array([1, nx, ny, nz, 1], "<i4").tobytes() + np.array(list(md.aabb_min) + list(md.aabb_max), "<f4").tobytes() + dens.tobytes()
+                # gridvolume reads a file: one copy per content in the temp directory, shared by every process that needs it
+                fname = os.path.join(tempfile.gettempdir(), "b2ref_" + hashlib.sha1(blob).hexdigest()[:16] + ".vol")
+                if not os.path.exists(fname):
+                    tmp = fname + f".{os.getpid()}"
+                    with open(tmp, "wb") as f:
+                        f.write(blob)
+                    os.replace(tmp, fname)
                 tw = np.ascontiguousarray(md.to_world, np.float32) if md.to_world is not None else None
                 al = np.asarray(md.albedo, np.float32)
-                mmemo[id(md)] = C.c_void_p(lib.pathref_medium_heterogeneous(f.name.encode(), _f(tw) if tw is not None else None, _f(al), C.c_float(md.scale), ph, C.c_float(md.g)))
+                mmemo[id(md)] = C.c_void_p(lib.pathref_medium_heterogeneous(fname.encode(), _f(tw) if tw is not None else None, _f(al), C.c_float(md.scale), ph, C.c_float(md.g)))
         return mmemo[id(md)]
     for m in desc.meshes:
         b = m.bsdf
