@@ -572,6 +572,13 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     CK(ctx, cudaSetDevice(ctx->device));
     for (size_t e = 0; e < s->emitters.size(); ++e)
         if (s->emitters[e].mesh < 0 && !s->emitters[e].env) return fail(ctx, B2_ERR_INVALID, "area emitter without a parent shape");
+    // ---- emitter order of Scene::m_emitters: emitters that are direct children of the scene (`constant`) are appended by
+    // Scene::addChild (scene.cpp:510-516); the area emitters of shapes only join in Scene::initialize -> addShape (scene.cpp:322-335,
+    // :570-571), i.e. behind them and in shape order, whatever the document order.  emOrder: device index -> id, emIndex: the inverse ----
+    std::vector<int> emOrder, emIndex(s->emitters.size(), -1);
+    for (size_t e = 0; e < s->emitters.size(); ++e) if (s->emitters[e].env) emOrder.push_back((int) e);
+    for (auto &m : s->meshes) if (m.emitter >= 0) emOrder.push_back(m.emitter);
+    for (size_t k = 0; k < emOrder.size(); ++k) emIndex[emOrder[k]] = (int) k;
     // ---- flatten meshes: prim order = mesh order, triangle order (skdtree.cpp:68-72 m_shapeMap) ----
     size_t nPrims = 0;
     for (auto &m : s->meshes) { m.primOffset = (uint32_t) nPrims; nPrims += m.idx.size() / 3; }
@@ -597,7 +604,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
             const uint32_t i0 = m.idx[3 * j], i1 = m.idx[3 * j + 1], i2 = m.idx[3 * j + 2];
             const float *p0 = &m.P[3 * i0], *p1 = &m.P[3 * i1], *p2 = &m.P[3 * i2];
             uint32_t tflags = (m.N.empty() ? 0u : 1u) | (m.UV.empty() ? 0u : 2u);
-            int matBits = m.material, emBits = m.emitter;
+            int matBits = m.material, emBits = m.emitter >= 0 ? emIndex[m.emitter] : -1;
             float w0, w1, w2;
             memcpy(&w0, &matBits, 4); memcpy(&w1, &emBits, 4); memcpy(&w2, &tflags, 4);
             verts[3 * p] = make_float4(p0[0], p0[1], p0[2], w0);
@@ -947,7 +954,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     std::vector<float> emCdf(1, 0.0f), triCdf;
     float emNorm = 0.0f;
     for (size_t e = 0; e < s->emitters.size(); ++e) {
-        const HostEmitter &he = s->emitters[e];
+        const HostEmitter &he = s->emitters[emOrder[e]];
         DEmitter &d = de[e];
         memcpy(d.radiance, he.radiance, 12);
         d.samplingWeight = he.samplingWeight;
@@ -1006,7 +1013,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.triAccel = s->dTriAccel.p; ds.triPlane = s->dTriPlane.p; ds.leafPrim = s->dLeafPrim.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
     // environment emitter: index + constant.cpp:67-70 bounding sphere of (acceleration-structure box U sensor position) (scene.cpp:386-399)
     ds.envEmitter = -1;
-    for (size_t e = 0; e < s->emitters.size(); ++e) if (s->emitters[e].env) ds.envEmitter = (int) e;
+    for (size_t e = 0; e < s->emitters.size(); ++e) if (s->emitters[e].env) ds.envEmitter = emIndex[e];
     {
         float bl[3], bh[3];
         for (int a = 0; a < 3; ++a) {

@@ -1164,7 +1164,8 @@ struct Loader {
                 ep.spec("radiance", one, rad); // constant.cpp:47-50
                 const float w = (float) ep.f("samplingWeight", 1.0);
                 ep.checkAllUsed();
-                // emitters keep their document order (it is the order of Scene::m_emitters and therefore of the emitter-selection CDF)
+                // position in Scene::m_emitters (= in the emitter-selection CDF): b2_scene_commit puts scene-level emitters ahead of
+                // the shapes' area emitters whatever the document order, as Scene::addChild / Scene::initialize do (scene.cpp:510-516, :322-335)
                 if (b2_scene_add_constant_emitter(scene, rad, w) < 0) throw Err(b2_last_error(nullptr));
             }
             else throw Err("unsupported top-level element <" + c->tag + ">");

@@ -321,7 +321,7 @@ class SceneDesc:
     meshes: List[Mesh] = field(default_factory=list)
     camera: Optional[Camera] = None
     instances: List["Instance"] = field(default_factory=list)
-    env_radiance: Optional[Sequence[float]] = None   # <emitter type="constant"> (src/emitters/constant.cpp:47-52), after all area emitters
+    env_radiance: Optional[Sequence[float]] = None   # <emitter type="constant"> (src/emitters/constant.cpp:47-52); in Scene::m_emitters it precedes the area emitters (scene.cpp:510-516 vs :322-335)
     env_sampling_weight: float = 1.0
 
     def flat_bsdfs(self):

@@ -203,6 +203,17 @@ struct Scene {
             b.max = b.max + ((b.max - b.min) * eps + V3(eps));
             topAABB = b;
         }
+        /* order of Scene::m_emitters: emitters that are direct children of the scene (`constant`) are appended by Scene::addChild
+           (scene.cpp:510-516); the area emitters of shapes only join in Scene::initialize -> addShape (scene.cpp:322-335, :570-571),
+           i.e. behind them and in shape order, whatever the document order (pinned by tests/golden/path_ref_ext.npz) */
+        {
+            std::vector<int> remap(emitters.size(), -1);
+            std::vector<Emitter> sorted;
+            for (size_t e = 0; e < emitters.size(); ++e) if (emitters[e].mesh < 0) { remap[e] = (int) sorted.size(); sorted.push_back(emitters[e]); }
+            for (auto &m : meshes) if (m.emitter >= 0) { remap[m.emitter] = (int) sorted.size(); sorted.push_back(emitters[m.emitter]); }
+            for (auto &m : meshes) if (m.emitter >= 0) m.emitter = remap[m.emitter];
+            emitters.swap(sorted);
+        }
         /* scene.cpp:375-380 */
         emitterPDF = Discrete();
         for (auto &e : emitters) emitterPDF.append(e.samplingWeight);
@@ -223,8 +234,11 @@ struct Scene {
 
     /* skdtree.h:343-428 fillIntersectionRecord<true> for triangle meshes */
     /* transform.h:108-124 (affine: w == 1), :175-183, :203-211 */
-    static V3 xfPoint(const float *M, const V3 &p) {
-        return V3(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]);
+    static V3 xfPoint(const float *M, const V3 &p) { /* transform.h:108-124: homogeneous, divides unless w == 1 exactly -- which happens with
+        the reference's own float Gauss-Jordan inverse of an affine matrix (its last row can come out as (0, 3e-8, 0, 0.99999994)) */
+        const V3 r(M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3], M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7], M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11]);
+        const float w = M[12] * p.x + M[13] * p.y + M[14] * p.z + M[15];
+        return w == 1.0f ? r : r / w;
     }
     static V3 xfVector(const float *M, const V3 &v) {
         return V3(M[0] * v.x + M[1] * v.y + M[2] * v.z, M[4] * v.x + M[5] * v.y + M[6] * v.z, M[8] * v.x + M[9] * v.y + M[10] * v.z);

@@ -158,7 +158,9 @@ def make_params(rp, threads=0, sampler=None):
 class OracleScene:
     """Oracle-side scene built from a mitsuba_b200.scene.SceneDesc (plain data only)."""
 
-    def __init__(self, desc, use_tree=True, sample_to_camera=None):
+    def __init__(self, desc, use_tree=True, sample_to_camera=None, instance_inverses=None):
+        """sample_to_camera / instance_inverses: host-side matrix set-up handed in from elsewhere (the image-level pins pass the
+        reference's own Transform::inverse() results so that both renderers start from the same numbers)."""
         L = lib()
         self.L = L
         self.h = C.c_void_p(L.orc_scene_new())
@@ -187,8 +189,10 @@ class OracleScene:
                 if m.radiance is not None:
                     raise ValueError("Instancing of emitters is not supported")  # shapegroup.cpp:115-116
                 L.orc_set_mesh_group(self.h, C.c_int(mid), C.c_int(m.group))
-        for inst in getattr(desc, "instances", []):
+        for k, inst in enumerate(getattr(desc, "instances", [])):
             M, Minv = instance_matrices(inst.to_world)
+            if instance_inverses is not None:
+                Minv = np.ascontiguousarray(instance_inverses[k], np.float32)
             L.orc_add_instance(self.h, C.c_int(inst.group), _p(M), _p(Minv))
         if getattr(desc, "env_radiance", None) is not None:
             rad = np.asarray(desc.env_radiance, np.float32)

@@ -6,6 +6,8 @@
  *   src/sensors/perspective.cpp, src/emitters/area.cpp, src/samplers/{sobol,independent}.cpp + sobolseq.cpp,
  *   src/rfilters/{gaussian,box}.cpp, the nine BSDF plugins of src/bsdfs/, src/libcore/{util,warp,math,quad,qmc,triangle,transform,
  *   aabb,rfilter,random,spectrum,timer}.cpp
+ *   src/integrators/path/volpath.cpp, src/medium/{heterogeneous,homogeneous}.cpp, src/volume/{gridvolume,constvolume}.cpp,
+ *   src/phase/{isotropic,hg}.cpp, src/sensors/thinlens.cpp, src/emitters/constant.cpp, src/shapes/{shapegroup,instance}.cpp
  * The scene graph is built the way the XML loader would build it (plugins through their own CreateInstance + Properties, addChild,
  * configure, Scene::initialize builds the SAH kd-tree) and rendered block by block with SamplingIntegrator::renderBlock.
  *
@@ -48,7 +50,23 @@ MTS_IMPLEMENT_CLASS(WorkResult, true, Object)
 SerializableObject *InstanceManager::getInstance(Stream *) { return NULL; }
 void InstanceManager::serialize(Stream *, const SerializableObject *) {}
 ref<PluginManager> PluginManager::m_instance;
-ConfigurableObject *PluginManager::createObject(const Class *, const Properties &) { return NULL; }
+/* the only plugin-manager requests on this path: ThinLens::createShape (thinlens.cpp:522-534) asks for a `disk` and
+   ConstantBackgroundEmitter::createShape (constant.cpp:67-92) for a `sphere`, both called by Scene::initializeBidirectional to represent
+   the aperture / the environment to the bidirectional integrators (Scene::rayIntersectAll); the path tracer never intersects these
+   "special shapes", so an empty stand-in shape is handed back (the bounding-sphere set-up in constant.cpp's createShape is the
+   reference's own code and runs) */
+class StandinApertureShape : public Shape {
+public:
+    StandinApertureShape(const Properties &p) : Shape(p) {}
+    void configure() {}
+    AABB getAABB() const { return AABB(); }
+    size_t getPrimitiveCount() const { return 0; }
+    size_t getEffectivePrimitiveCount() const { return 0; }
+    const Class *getClass() const { return Shape::m_theClass; }
+};
+ConfigurableObject *PluginManager::createObject(const Class *, const Properties &props) {
+    return props.getPluginName() == "disk" || props.getPluginName() == "sphere" ? new StandinApertureShape(props) : NULL;
+}
 ref<Scheduler> Scheduler::m_scheduler;
 SerializableObject *Scheduler::getResource(int, int) { return NULL; }
 int Scheduler::registerResource(SerializableObject *) { return 0; }
@@ -94,11 +112,16 @@ void ConstantFloatTexture::serialize(Stream *, InstanceManager *) const {}
 MTS_IMPLEMENT_CLASS(ConstantFloatTexture, false, Texture)
 /* a static transform only (src/libcore/track.cpp needs Eigen) */
 AnimatedTransform::AnimatedTransform(Stream *) {}
+AnimatedTransform::AnimatedTransform(const AnimatedTransform *trafo) : m_transform(trafo->m_transform) {} /* track.cpp:8-16 without tracks */
 void AnimatedTransform::TransformFunctor::operator()(const Float &, Transform &) const {}
 AABB AnimatedTransform::getTranslationBounds() const { AABB b; b.expandBy(m_transform(Point(0.0f))); return b; }
 void AnimatedTransform::serialize(Stream *) const {}
 std::string AnimatedTransform::toString() const { return "AnimatedTransform"; }
 AnimatedTransform::~AnimatedTransform() {}
+/* static transforms only (no animation tracks): the no-track branches of track.cpp:123-129 and :254-264 */
+AABB AnimatedTransform::getSpatialBounds(const AABB &aabb) const { AABB r; for (int j = 0; j < 8; ++j) r.expandBy(m_transform(aabb.getCorner(j))); return r; }
+void AnimatedTransform::prependScale(const Vector &scale) { m_transform = m_transform * Transform::scale(scale); } /* track.cpp:222-223; only ThinLens::createShape (bidirectional set-up, never called here) uses it */
+void AnimatedTransform::collectKeyframes(std::set<Float> &result) const { result.insert((Float) 0); }
 MTS_IMPLEMENT_CLASS(AnimatedTransform, false, Object)
 ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k, const Transform &d) const { return new AnimatedTransform(getTransform(k, d)); }
 ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k, const AnimatedTransform *d) const { return hasProperty(k) || !d ? new AnimatedTransform(getTransform(k, Transform())) : d; }
@@ -158,6 +181,7 @@ using namespace mitsuba;
 #define DECL(name) extern "C" void *CreateInstance_##name(const Properties &props);
 DECL(diffuse) DECL(roughconductor) DECL(roughdielectric) DECL(coating) DECL(dielectric) DECL(conductor) DECL(plastic) DECL(twosided) DECL(null)
 DECL(gaussian) DECL(box) DECL(sobol) DECL(independent) DECL(path) DECL(perspective) DECL(area)
+DECL(thinlens) DECL(constant) DECL(shapegroup) DECL(instance)
 DECL(volpath) DECL(heterogeneous) DECL(homogeneous) DECL(gridvolume) DECL(constvolume) DECL(isotropic) DECL(hg)
 
 /* The `independent` sampler of this repository is a counter-based stream, not the reference's SFMT: to compare volpath
@@ -289,10 +313,9 @@ void pathref_add_mesh(void *h, const float *P, const float *N, const float *UV, 
 }
 /* bsdf may be NULL for an index-matched medium boundary: Shape::configure then creates the `null` BSDF itself (shape.cpp:64-68) through
    the plugin manager, which this build does not have -- so the `null` plugin is attached here */
-void pathref_add_mesh_media(void *h, const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf, const float *radiance, float samplingWeight,
-                            void *interior, void *exterior) {
-    PathRef *p = (PathRef *) h;
-    ref<TriMesh> mesh = new TriMesh("mesh", (size_t) nT, (size_t) nV, N != NULL, UV != NULL, false, false, N == NULL /* face normals, skdtree.h:383-399 */);
+static TriMesh *makeMesh(const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf, const float *radiance, float samplingWeight,
+                         void *interior, void *exterior) {
+    TriMesh *mesh = new TriMesh("mesh", (size_t) nT, (size_t) nV, N != NULL, UV != NULL, false, false, N == NULL /* face normals, skdtree.h:383-399 */);
     memcpy(mesh->getVertexPositions(), P, sizeof(float) * 3 * nV);
     if (N) memcpy(mesh->getVertexNormals(), N, sizeof(float) * 3 * nV);
     if (UV) memcpy(mesh->getVertexTexcoords(), UV, sizeof(float) * 2 * nV);
@@ -312,8 +335,64 @@ void pathref_add_mesh_media(void *h, const float *P, const float *N, const float
         em->configure();
     }
     mesh->configure();
+    return mesh;
+}
+void pathref_add_mesh_media(void *h, const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf, const float *radiance, float samplingWeight,
+                            void *interior, void *exterior) {
+    PathRef *p = (PathRef *) h;
+    ref<TriMesh> mesh = makeMesh(P, N, UV, nV, idx, nT, bsdf, radiance, samplingWeight, interior, exterior);
     p->scene->addChild("", mesh);
     p->keep.push_back(mesh);
+}
+/* <shape type="shapegroup"> (src/shapes/shapegroup.cpp): the member meshes (object space) are added with ShapeGroup::addChild and
+ * ShapeGroup::configure builds the group's own SAH kd-tree; the group itself is a compound of nothing (Scene::addChild would add no
+ * element), so it is only kept alive here */
+void *pathref_shapegroup_new(void *h) {
+    PathRef *p = (PathRef *) h;
+    Shape *g = (Shape *) CreateInstance_shapegroup(Properties("shapegroup"));
+    g->incRef();
+    p->keep.push_back(g);
+    return g;
+}
+void pathref_shapegroup_add_mesh(void *group, const float *P, const float *N, const float *UV, int nV, const uint32_t *idx, int nT, void *bsdf) {
+    Shape *g = (Shape *) group;
+    TriMesh *mesh = makeMesh(P, N, UV, nV, idx, nT, bsdf, NULL, 1.0f, NULL, NULL);
+    mesh->incRef();
+    g->addChild("", mesh);
+}
+void pathref_shapegroup_configure(void *group) { ((Shape *) group)->configure(); }
+/* <shape type="instance"> (src/shapes/instance.cpp) with a `toWorld` (row-major 4 x 4) referencing a configured shapegroup */
+void pathref_add_instance(void *h, void *group, const float *toWorld) {
+    PathRef *p = (PathRef *) h;
+    Properties ip("instance");
+    Matrix4x4 M;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M.m[r][c] = toWorld[4 * r + c];
+    ip.setTransform("toWorld", Transform(M));
+    ref<Shape> inst = (Shape *) CreateInstance_instance(ip);
+    inst->addChild("", (ConfigurableObject *) (Shape *) group);
+    inst->configure();
+    p->scene->addChild("", inst);
+    p->keep.push_back(inst);
+}
+/* the inverse the reference derives for a `toWorld` (Transform::Transform(const Matrix4x4 &) -> Matrix4x4::invert, transform.h / matrix.h):
+ * matrix set-up is host work, the oracle is handed the same numbers (row-major 4 x 4) */
+void pathref_transform_inverse(const float *toWorld, float *out16) {
+    Matrix4x4 M;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M.m[r][c] = toWorld[4 * r + c];
+    const Matrix4x4 &I = Transform(M).getInverseMatrix();
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out16[4 * r + c] = I.m[r][c];
+}
+/* <emitter type="constant"> (src/emitters/constant.cpp) */
+void pathref_add_constant_emitter(void *h, const float *radiance, float samplingWeight) {
+    PathRef *p = (PathRef *) h;
+    Properties ep("constant");
+    Spectrum s; s[0] = radiance[0]; s[1] = radiance[1]; s[2] = radiance[2];
+    ep.setSpectrum("radiance", s);
+    ep.setFloat("samplingWeight", samplingWeight);
+    ref<Emitter> em = (Emitter *) CreateInstance_constant(ep);
+    em->configure();
+    p->scene->addChild("", em);
+    p->keep.push_back(em);
 }
 /* perspective sensor + film + sampler + path integrator; rfilter 0 box / 1 gaussian; sampler 0 sobol / 1 independent */
 void pathref_setup2(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
@@ -323,8 +402,15 @@ void pathref_setup(void *h, const float *toWorld, float fov, float nearClip, flo
     pathref_setup2(h, toWorld, fov, nearClip, farClip, W, H, rfilter, samplerKind, spp, scramble, maxDepth, rrDepth, strictNormals, hideEmitters, 0);
 }
 /* samplerKind 0 sobol, 1 independent (SFMT), 2 this repository's counter stream; integratorKind 0 path, 1 volpath */
+void pathref_setup3(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
+                    int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind, float apertureRadius, float focusDistance);
 void pathref_setup2(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
                     int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind) {
+    pathref_setup3(h, toWorld, fov, nearClip, farClip, W, H, rfilter, samplerKind, spp, scramble, maxDepth, rrDepth, strictNormals, hideEmitters, integratorKind, 0.0f, 0.0f);
+}
+/* apertureRadius > 0: the `thinlens` sensor (src/sensors/thinlens.cpp) with that aperture and focusDistance (<= 0: the plugin's default) */
+void pathref_setup3(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
+                    int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind, float apertureRadius, float focusDistance) {
     PathRef *p = (PathRef *) h;
     p->W = W; p->H = H;
     Properties fp("hdrfilm");
@@ -346,7 +432,12 @@ void pathref_setup2(void *h, const float *toWorld, float fov, float nearClip, fl
     for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M.m[r][c] = toWorld[4 * r + c];
     cp.setTransform("toWorld", Transform(M));
     cp.setFloat("fov", fov); cp.setFloat("nearClip", nearClip); cp.setFloat("farClip", farClip);
-    p->sensor = (Sensor *) CreateInstance_perspective(cp);
+    if (apertureRadius > 0) {
+        cp.setFloat("apertureRadius", apertureRadius);
+        if (focusDistance > 0) cp.setFloat("focusDistance", focusDistance);
+        p->sensor = (Sensor *) CreateInstance_thinlens(cp);
+    } else
+        p->sensor = (Sensor *) CreateInstance_perspective(cp);
     p->sensor->addChild("", p->film);
     p->sensor->addChild("", p->sampler);
     p->sensor->configure();

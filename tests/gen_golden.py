@@ -228,9 +228,33 @@ def path_ref():
     print("path_ref.npz:", len(out) // 2, "images")
 
 
+def path_ref_ext():
+    """thinlens sensor, constant emitter, shapegroup / instance through the same assembled reference renderer (ref_pins.image_cases_ext);
+    per image: the film, the reference's sampleToCamera and its Transform::inverse() of every instance matrix."""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import ref_pins
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so"))
+    out = {}
+    n = 0
+    for name, desc, rp in ref_pins.image_cases_ext():
+        film, s2c = ref_pins.reference_render(lib, desc, rp, want_camera=True)
+        out[name + "/film"], out[name + "/s2c"] = film, s2c
+        inv = ref_pins.reference_instance_inverses(lib, desc)
+        if inv:
+            out[name + "/instance_inverses"] = np.stack(inv)
+        n += 1
+    np.savez_compressed(os.path.join(OUT, "path_ref_ext.npz"), **out)
+    print("path_ref_ext.npz:", n, "images")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--ext-only" in sys.argv:
+        path_ref_ext()
+        sys.exit(0)
     path_ref()
+    path_ref_ext()
     render_ref()
     core_ref()
     bsdf_ref()

@@ -330,6 +330,8 @@ def reference_scene(lib, desc, rp):
                 al = np.asarray(md.albedo, np.float32)
                 mmemo[id(md)] = C.c_void_p(lib.pathref_medium_heterogeneous(fname.encode(), _f(tw) if tw is not None else None, _f(al), C.c_float(md.scale), ph, C.c_float(md.g)))
         return mmemo[id(md)]
+    lib.pathref_shapegroup_new.restype = C.c_void_p
+    groups = {}
     for m in desc.meshes:
         b = m.bsdf
         if b is None and m.interior is None and m.exterior is None:
@@ -341,15 +343,29 @@ def reference_scene(lib, desc, rp):
         UV = np.ascontiguousarray(m.UV, np.float32) if m.UV is not None else None
         I = np.ascontiguousarray(m.idx, np.uint32)
         rad = np.asarray(m.radiance, np.float32) if m.radiance is not None else None
+        if m.group >= 0:  # member of a <shape type="shapegroup"> (object space); instances reference the group below
+            if m.group not in groups:
+                groups[m.group] = C.c_void_p(lib.pathref_shapegroup_new(h))
+            lib.pathref_shapegroup_add_mesh(groups[m.group], _f(P), _f(N) if N is not None else None, _f(UV) if UV is not None else None, len(P),
+                                            I.ctypes.data_as(C.POINTER(C.c_uint32)), len(I), memo[id(b)])
+            continue
         lib.pathref_add_mesh_media(h, _f(P), _f(N) if N is not None else None, _f(UV) if UV is not None else None, len(P),
                                    I.ctypes.data_as(C.POINTER(C.c_uint32)), len(I), memo[id(b)] if b is not None else None, _f(rad) if rad is not None else None,
                                    C.c_float(m.sampling_weight), medium(m.interior), medium(m.exterior))
+    for g in groups.values():
+        lib.pathref_shapegroup_configure(g)   # builds the group's kd-tree (shapegroup.cpp ShapeGroup::configure)
+    for inst in desc.instances:
+        lib.pathref_add_instance(h, groups[inst.group], _f(np.ascontiguousarray(inst.to_world, np.float32)))
+    if desc.env_radiance is not None:          # <emitter type="constant">: added last here, yet first in Scene::m_emitters (scene.cpp:510-516 vs :322-335)
+        lib.pathref_add_constant_emitter(h, _f(np.asarray(desc.env_radiance, np.float32)), C.c_float(desc.env_sampling_weight))
     cam = desc.camera
+    assert cam.fov_axis == "x"
     tw = np.ascontiguousarray(cam.to_world, np.float32)
     # `independent` here is this repository's counter-based stream (kind 2), handed to the reference integrator through the Sampler interface
-    lib.pathref_setup2(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
+    lib.pathref_setup3(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
                        {"box": 0, "gaussian": 1}[rp.rfilter], {"sobol": 0, "independent": 2}[rp.sampler], rp.spp, C.c_uint64(rp.seed),
-                       rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters), {"path": 0, "volpath": 1}[rp.integrator])
+                       rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters), {"path": 0, "volpath": 1}[rp.integrator],
+                       C.c_float(cam.aperture_radius), C.c_float(cam.focus_distance))
     return h
 
 
@@ -365,6 +381,16 @@ def reference_render(lib, desc, rp, want_camera=False):
         lib.pathref_sample_to_camera(h, _f(s2c))
         return film, s2c
     return film
+
+
+def reference_instance_inverses(lib, desc):
+    """Transform(toWorld).inverse() of every instance, computed by the reference's own Matrix4x4::invert."""
+    out = []
+    for inst in desc.instances:
+        inv = np.zeros((4, 4), np.float32)
+        lib.pathref_transform_inverse(_f(np.ascontiguousarray(inst.to_world, np.float32)), _f(inv))
+        out.append(inv)
+    return out
 
 
 def image_cases():
@@ -392,3 +418,45 @@ def image_cases():
     yield "vol_heterogeneous_iso", smoke_scene(40, 40, res=8, scale=6.0), RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
     yield "vol_heterogeneous_hg", smoke_scene(40, 40, res=16, scale=12.0, phase="hg", g=0.5), RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
     yield "vol_heterogeneous_sobol", smoke_scene(32, 32, res=8, scale=4.0), RenderParams(spp=4, sampler="sobol", rfilter="box", integrator="volpath", max_depth=4)
+
+
+def image_cases_ext():
+    """Image-level pins of the plugins that joined the assembled reference renderer later: the `thinlens` sensor
+    (src/sensors/thinlens.cpp), the `constant` environment emitter (src/emitters/constant.cpp), `shapegroup` / `instance`
+    (src/shapes/{shapegroup,instance}.cpp).  Fixture: tests/golden/path_ref_ext.npz."""
+    import dataclasses
+    from mitsuba_b200.scene import Bsdf, Instance, Mesh, RenderParams, cornell_box, cube_mesh, material_ball, smoke_scene, stress_scene, uv_sphere
+    d = cornell_box(40, 40)
+    d.camera = dataclasses.replace(d.camera, aperture_radius=25.0, focus_distance=1100.0)
+    yield "thinlens_cbox_sobol", d, RenderParams(spp=8, sampler="sobol", rfilter="gaussian")
+    d = cornell_box(32, 32)
+    d.camera = dataclasses.replace(d.camera, aperture_radius=60.0, focus_distance=900.0)
+    yield "thinlens_cbox_counter", d, RenderParams(spp=8, sampler="independent", rfilter="box", max_depth=4)
+    # constant emitter: alone (every miss is radiance), next to an area light (emitter selection + MIS both ways), hidden, under volpath
+    d = material_ball(Bsdf("roughconductor", distribution="ggx", alpha_u=0.2, alpha_v=0.2, eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421)), 40, 40, n_theta=16, n_phi=32)
+    d.meshes = [m for m in d.meshes if m.radiance is None]
+    d.env_radiance = (0.7, 0.8, 0.9)
+    yield "env_only_ball", d, RenderParams(spp=8, sampler="sobol", rfilter="gaussian")
+    d = cornell_box(36, 36)
+    d.meshes = [m for i, m in enumerate(d.meshes) if i != 1]   # open the box: drop one wall so that the environment is seen
+    d.env_radiance = (0.4, 0.6, 1.0); d.env_sampling_weight = 2.0
+    yield "env_plus_area_cbox", d, RenderParams(spp=8, sampler="sobol", rfilter="box")
+    yield "env_hidden_cbox", d, RenderParams(spp=4, sampler="independent", rfilter="gaussian", hide_emitters=True, max_depth=5)
+    d = smoke_scene(36, 36, res=8, scale=5.0)
+    d.env_radiance = (0.3, 0.4, 0.6)
+    yield "env_volpath_smoke", d, RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
+    # instancing: one group of spheres placed five times (stress scene), a second group with UV tangent frames under rotation + non-uniform
+    # scale + shear; flattened copy of the same geometry for the equivalence check lives in the tests
+    d = stress_scene(5, 12, 12, 40, 40, instanced=True)
+    P, N, UV, I = uv_sphere((0, 0, 0), 0.6, 10, 20, with_uv=True)
+    aniso = Bsdf("roughconductor", distribution="beckmann", alpha_u=0.15, alpha_v=0.4, eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421))
+    d.meshes.append(Mesh(P, I, N=N, UV=UV, bsdf=aniso, group=1))
+    Pc, Ic = cube_mesh((-0.4, -0.9, -0.4), (0.4, -0.6, 0.4))
+    d.meshes.append(Mesh(Pc, Ic, bsdf=Bsdf("diffuse", reflectance=(0.2, 0.6, 0.3)), group=1))
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    M = np.eye(4); M[:3, :3] = np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]]) @ np.diag([1.3, 0.8, 1.0]); M[0, 1] = 0.2; M[:3, 3] = (0.5, 2.6, -1.0)
+    d.instances.append(Instance(1, M.astype(np.float32)))
+    M2 = np.eye(4); M2[:3, :3] *= 0.7; M2[:3, 3] = (-2.0, 2.2, 0.5)
+    d.instances.append(Instance(1, M2.astype(np.float32)))
+    yield "instances_sobol", d, RenderParams(spp=8, sampler="sobol", rfilter="box")
+    yield "instances_counter_depth3", d, RenderParams(spp=8, sampler="independent", rfilter="gaussian", max_depth=3)
