@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 
 #include "b2mts.h"
@@ -87,7 +88,36 @@ void resampleAxis(const AxisKernel &k, int mode, int srcRes, int trgRes, const f
 
 } // namespace
 
+// The reference's bitmap texture keeps its pyramid in half precision (bitmap.cpp:177-180: TMIPMap<Color3, Color3h>): each level is
+// resampled in float from the previous float level and rounded to half -- to nearest even, overflow to infinity (half.h:431-487,
+// half.cpp:78-200) -- when it is stored (mipmap.h:226-230, :262-264).  The device arrays stay float (the values are half-representable).
+static inline float roundToHalf(float f) {
+    uint32_t x; memcpy(&x, &f, 4);
+    const uint32_t sign = x & 0x80000000u;
+    uint32_t a = x & 0x7fffffffu;
+    if (a >= 0x7f800000u) return f;
+    if (a < 0x38800000u) { // half denormals: spacing 2^-24, the float spacing in [0.5, 1)
+        float m; memcpy(&m, &a, 4);
+        volatile float t = m + 0.5f;
+        m = t - 0.5f;
+        memcpy(&a, &m, 4);
+    } else {
+        a += 0x00000fffu + ((a >> 13) & 1u);
+        a &= 0xffffe000u;
+        if (a >= 0x47800000u) a = 0x7f800000u;
+    }
+    a |= sign;
+    float r; memcpy(&r, &a, 4);
+    return r;
+}
+
+static void buildMipPyramidFloat(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out);
 void buildMipPyramid(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out) {
+    buildMipPyramidFloat(pixels, width, height, channels, wrapU, wrapV, pyramid, out);
+    for (auto &lvl : out.level) for (float &v : lvl) v = roundToHalf(v);
+}
+
+static void buildMipPyramidFloat(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out) {
     out = MipPyramid();
     out.channels = channels;
     std::vector<float> base(pixels, pixels + (size_t) width * height * channels);

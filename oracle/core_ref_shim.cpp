@@ -30,7 +30,12 @@ size_t Random::nextSize(size_t) { return 0; }
 
 using namespace mitsuba;
 
+#include <mitsuba/core/half.h>
 extern "C" {
+/* float -> half -> float through the reference's own half class (include/mitsuba/core/half.h:431-487, src/libcore/half.cpp:78-200): the
+   storage format of BitmapTexture's MIP pyramid (bitmap.cpp:177-180, TMIPMap<Color3, Color3h>) */
+void coreref_half_round(int n, const float *in, float *out) { for (int i = 0; i < n; ++i) out[i] = (float) half(in[i]); }
+
 
 /* ---- microfacet.h: type 0 beckmann, 1 ggx, 2 phong; wi (3n), samples (2n) -> out 6n: m(3), pdf from sample(), pdf(wi, m), eval(m) */
 void coreref_microfacet_sample(int type, float alphaU, float alphaV, int sampleVisible, int n, const float *wi, const float *samples, float *out) {

@@ -1133,6 +1133,8 @@ void orc_texture_info(void *s, int tex, int32_t *out, float *maximum, float *bsd
     for (int l = 0; l < t.levels; ++l) { out[1 + 2 * l] = t.lw[l]; out[2 + 2 * l] = t.lh[l]; }
     *maximum = t.maximum; *bsdfScale = t.bsdfScale;
 }
+/* probe of roundToHalf (orc_texture.h): the storage rounding of the MIP pyramid */
+void orc_half_round(uint64_t n, const float *in, float *out) { for (uint64_t i = 0; i < n; ++i) out[i] = roundToHalf(in[i]); }
 void orc_texture_level(void *s, int tex, int level, float *out) {
     const Texture &t = ((Scene *) s)->textures[tex];
     memcpy(out, t.pyramid[level].data(), t.pyramid[level].size() * sizeof(float));

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "orc_math.h"
@@ -104,6 +105,30 @@ struct Resampler {
     }
 };
 
+/* float -> half -> float, round to nearest even, overflow to infinity (half.h:431-487 fast path, half.cpp:78-200 denormals / overflow):
+ * BitmapTexture stores its pyramid as TMIPMap<Color3, Color3h> (bitmap.cpp:177-180); every level is resampled in float from the previous
+ * *float* level and only rounded when it is stored (mipmap.h:226-230, :262-264, barray.h:88-92).  Pinned against the reference's half
+ * class in oracle/_ref/libcoreref.so (tests/golden/half_ref.npz). */
+static inline float roundToHalf(float f) {
+    uint32_t x; memcpy(&x, &f, 4);
+    const uint32_t sign = x & 0x80000000u;
+    uint32_t a = x & 0x7fffffffu;
+    if (a >= 0x7f800000u) return f;                              /* infinities, NaNs */
+    if (a < 0x38800000u) {                                       /* below 2^-14: half denormals, spacing 2^-24 = the float spacing in [0.5, 1) */
+        float m; memcpy(&m, &a, 4);
+        volatile float t = m + 0.5f;                             /* rounds to nearest even at 2^-24 */
+        m = t - 0.5f;
+        memcpy(&a, &m, 4);
+    } else {
+        a += 0x00000fffu + ((a >> 13) & 1u);                     /* round the significand to 10 bits, carry into the exponent */
+        a &= 0xffffe000u;
+        if (a >= 0x47800000u) a = 0x7f800000u;                   /* 65520 and above: infinity */
+    }
+    a |= sign;
+    float r; memcpy(&r, &a, 4);
+    return r;
+}
+
 struct Texture {
     OrcTextureDesc d;
     int levels = 0;
@@ -149,6 +174,7 @@ struct Texture {
             }
         }
         levels = (int) pyramid.size();
+        for (auto &lvl : pyramid) for (float &v : lvl) v = roundToHalf(v); /* stored as half (see roundToHalf); the chain above ran on floats */
         for (int i = 0; i < kMipLutSize; ++i) { /* mipmap.h:296-302 */
             float r2 = (float) i / (float) (kMipLutSize - 1);
             weightLut[i] = fastexp(-2.0f * r2) - fastexp(-2.0f);

@@ -132,13 +132,44 @@ def texture_lookups(rng, n):
     return uv, pt
 
 
+def half_inputs(seed=0, n=20000):
+    """floats for the float -> half -> float pin: random bit patterns, [0, 2), ties, the denormal range, the overflow edge."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    x = x[np.isfinite(x)]
+    extra = np.concatenate([rng.random(n).astype(np.float32) * 2, np.arange(0, 70000, 7.25).astype(np.float32), np.float32(2.0) ** np.arange(-30, 17).astype(np.float32),
+                            (np.arange(0, 4096) * np.float32(2 ** -25)).astype(np.float32), (1 + np.arange(0, 4096) * np.float32(2 ** -12)).astype(np.float32),
+                            np.array([65504, 65519.99, 65520, 65536, 1e30, 0.0, 6.1e-5, 5.96e-8, 2.98e-8, 2.9802322e-08, 8.9e-8], np.float32)])
+    return np.concatenate([x, extra, -extra]).astype(np.float32)
+
+
+def half_store(a):
+    """A float array as BitmapTexture's pyramid stores it: TMIPMap<Color3, Color3h> (bitmap.cpp:177-180) rounds every texel to half when a
+    level is stored (mipmap.h:226-230, :262-264; half.h:431-487 / half.cpp:78-200 = round to nearest even, overflow to infinity).  That is
+    numpy's float16 conversion -- equality with the reference's own half class is pinned by tests/golden/half_ref.npz and, live, on two
+    million values (tests/test_oracle_texture.py)."""
+    with np.errstate(over="ignore"):
+        return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+def half_ref():
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libcoreref.so"))
+    x = half_inputs()
+    out = np.zeros_like(x)
+    lib.coreref_half_round(len(x), x.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_float)))
+    np.savez_compressed(os.path.join(OUT, "half_ref.npz"), x=x, y=out)
+    print("half_ref.npz:", len(x), "values")
+
+
 class ReferenceMipmap:
-    """The reference's TMIPMap<Color3, Color3> over given RGB levels (list of (h, w, 3) float32), via oracle/_ref/libmipmapref.so."""
+    """The reference's TMIPMap over given RGB levels (list of (h, w, 3) float32), via oracle/_ref/libmipmapref.so.  The levels are rounded
+    to half first (half_store): BitmapTexture instantiates TMIPMap<Color3, Color3h>, the library TMIPMap<Color3, Color3> -- over
+    half-representable texels the two are the same function."""
 
     def __init__(self, levels, wrap_u, wrap_v, filter_type, max_anisotropy, lib=None):
         self.L = lib or C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libmipmapref.so"))
         self.L.mipref_create.restype = C.c_void_p
-        self.levels = [np.ascontiguousarray(l, np.float32) for l in levels]
+        self.levels = [np.ascontiguousarray(half_store(l), np.float32) for l in levels]
         sizes = np.array([[l.shape[1], l.shape[0]] for l in self.levels], np.int32)
         ptrs = (C.POINTER(C.c_float) * len(self.levels))(*[l.ctypes.data_as(C.POINTER(C.c_float)) for l in self.levels])
         aniso = max_anisotropy if filter_type == "ewa" else 1.0  # bitmap.cpp:232-235
@@ -253,6 +284,10 @@ if __name__ == "__main__":
     if "--ext-only" in sys.argv:
         path_ref_ext()
         sys.exit(0)
+    if "--texture-only" in sys.argv:
+        half_ref()
+        mipmap_ref()
+        sys.exit(0)
     path_ref()
     path_ref_ext()
     render_ref()
@@ -261,4 +296,5 @@ if __name__ == "__main__":
     sfmt_kat()
     sobol_ref()
     resample_ref()
+    half_ref()
     mipmap_ref()
