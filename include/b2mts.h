@@ -158,7 +158,9 @@ int b2_scene_add_material(b2_scene *, const b2_material_desc *);
 /* AreaLight (src/emitters/area.cpp:64-70): radiance, samplingWeight -> id (>=0) or -1 */
 int b2_scene_add_area_emitter(b2_scene *, const float radiance[3], float sampling_weight);
 /* ConstantBackgroundEmitter (src/emitters/constant.cpp:47-52): radiance, samplingWeight -> emitter id (>=0) or -1.  At most one
- * environment emitter per scene (scene.cpp:510-514); `path` only. */
+ * environment emitter per scene (scene.cpp:510-514).  In the emitter-selection CDF it precedes the shapes' area emitters whatever the
+ * call order, as in Scene::m_emitters (Scene::addChild appends it at once, scene.cpp:510-516; area emitters join in Scene::initialize,
+ * scene.cpp:322-335): b2_scene_commit applies that order. */
 int b2_scene_add_constant_emitter(b2_scene *, const float radiance[3], float sampling_weight);
 /* TriMesh after configure(): positions, optional normals / texcoords (NULL = none -> face normals,
  * skdtree.h:383-399), triangles, material and emitter ids (-1 = no emitter).  An emitter id may be
