@@ -442,6 +442,13 @@ def image_cases_ext():
     d.env_radiance = (0.4, 0.6, 1.0); d.env_sampling_weight = 2.0
     yield "env_plus_area_cbox", d, RenderParams(spp=8, sampler="sobol", rfilter="box")
     yield "env_hidden_cbox", d, RenderParams(spp=4, sampler="independent", rfilter="gaussian", hide_emitters=True, max_depth=5)
+    # three emitters: constant (weight 0.5) + two area lights (weights 1 and 3): the emitter-selection CDF and sampleReuse over more than two entries
+    d = cornell_box(32, 32)
+    by = {m.name: m for m in d.meshes}
+    by["short"].radiance = (2.0, 4.0, 1.0); by["short"].sampling_weight = 3.0
+    d.meshes = [m for m in d.meshes if m.name != "right"]
+    d.env_radiance = (0.1, 0.2, 0.3); d.env_sampling_weight = 0.5
+    yield "env_two_area_lights", d, RenderParams(spp=8, sampler="independent", rfilter="box")
     d = smoke_scene(36, 36, res=8, scale=5.0)
     d.env_radiance = (0.3, 0.4, 0.6)
     yield "env_volpath_smoke", d, RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
