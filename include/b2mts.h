@@ -116,7 +116,8 @@ typedef struct b2_render_params {
     int32_t film_on_device;  /* 1: `film` of b2_render is a device pointer on the context's device */
     int32_t flags;           /* bit1: force unsorted shading (default: material-sorted when > 1 BSDF class);
                                 bit2: per-launch device time stamps (fills b2_stats.ms_*); bit3: plain launches + CUDA events
-                                instead of the CUDA graph; bit4: fuse the ray casts into generate/shade for tiny scenes (experiment, slower) */
+                                instead of the CUDA graph; bit4: fuse the ray casts into generate/shade for tiny scenes (experiment, slower);
+                                bit5: collect per-pixel path diagnostics (b2_get_pixel_stats) */
     int32_t integrator;      /* B2_INTEGRATOR_* (<integrator type="path"|"volpath">) */
     int32_t reserved;        /* must be 0 */
 } b2_render_params;
@@ -148,6 +149,11 @@ void b2_scene_destroy(b2_scene *);
  * major), x field of view in degrees, clip planes, film size.  m_sampleToCamera is derived inside. */
 int b2_scene_set_camera(b2_scene *, const float to_world[16], float xfov_deg, float near_clip, float far_clip,
                         int width, int height);
+/* Film crop window (src/librender/film.cpp:36-47: cropOffsetX/Y, cropWidth/Height; "Invalid crop window specification!" when it
+ * leaves the film).  Call after b2_scene_set_camera.  As in the reference the crop window becomes the film every later call sees
+ * (Film::getCropSize): b2_scene_film_size, sample positions, the Sobol' resolution and the b2_render output are crop_width x
+ * crop_height; the sensor's sampleToCamera takes the relative size / offset (src/sensors/perspective.cpp:133-153). */
+int b2_scene_set_crop(b2_scene *, int crop_offset_x, int crop_offset_y, int crop_width, int crop_height);
 /* ThinLens (src/sensors/thinlens.cpp:132-142,327-350): aperture radius and focus distance of the camera set before; 0 = pinhole.
  * The aperture sample takes Sobol' dimensions 2 and 3 (integrator.cpp:173-174). */
 int b2_scene_set_thinlens(b2_scene *, float aperture_radius, float focus_distance);
@@ -195,6 +201,10 @@ int b2_cancel(b2_scene *);
 /* Film::develop normalisation (src/libcore/fmtconv.cpp:979-990): rgb = spec * (w != 0 ? 1/w : w). host buffers */
 int b2_film_develop(const float *film, int width, int height, float *rgb);
 int b2_get_stats(b2_scene *, b2_stats *);
+/* Per-pixel path diagnostics of the last b2_render with flags bit5: out[y * W + x] = (sum of squared path lengths << 32) | sum of
+ * path lengths over the pixel's samples (the per-pixel form of the reference's "average path length" statistic, path.cpp:24,290).
+ * Comparing two builds word by word gives the fraction of pixels in which a path changed length. */
+int b2_get_pixel_stats(b2_scene *, uint64_t *out);
 
 /* ---- component entry points (the reference exposes the same pieces through its Python bindings
  *      and test plugins: ShapeKDTree::rayIntersect src/libpython/render.cpp:352-369, BSDF

@@ -66,8 +66,8 @@ class b2_stats(C.Structure):
 
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
-           "b2_scene_set_camera", "b2_scene_set_thinlens", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_trace",
+           "b2_scene_set_camera", "b2_scene_set_crop", "b2_scene_set_thinlens", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
+           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_get_pixel_stats", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -176,10 +176,12 @@ class Scene:
         self.h = C.c_void_p()
         self._ck(self.L.b2_scene_create(ctx.h, C.byref(self.h)))
         cam = desc.camera
-        self.W, self.H = cam.width, cam.height
+        self.W, self.H = cam.film_size()
         c2w = np.ascontiguousarray(cam.to_world, np.float32)
         self._ck(self.L.b2_scene_set_camera(self.h, _p(c2w), C.c_float(cam.xfov()), C.c_float(cam.near), C.c_float(cam.far),
                                             C.c_int(cam.width), C.c_int(cam.height)))
+        if getattr(cam, "crop", None):
+            self._ck(self.L.b2_scene_set_crop(self.h, *[C.c_int(int(v)) for v in cam.crop]))
         if getattr(cam, "aperture_radius", 0.0) > 0:
             self._ck(self.L.b2_scene_set_thinlens(self.h, C.c_float(cam.aperture_radius), C.c_float(cam.focus_distance if cam.focus_distance > 0 else cam.far)))
         flat, ids = desc.flat_bsdfs()
@@ -279,6 +281,12 @@ class Scene:
         st = b2_stats()
         self.L.b2_get_stats(self.h, C.byref(st))
         return st.as_dict()
+
+    def pixel_stats(self):
+        """(H, W) uint64 of the last render(flags=32): (sum of squared path lengths << 32) | sum of path lengths per pixel."""
+        out = np.zeros((self.H, self.W), np.uint64)
+        self._ck(self.L.b2_get_pixel_stats(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
 
     def triaccel(self):
         n = self.stats()["n_triangles"]

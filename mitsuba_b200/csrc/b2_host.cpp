@@ -108,6 +108,7 @@ struct RenderStore {
     DevBuf<float> dFilmW, dFilmOut;
     unsigned long long *hRing = nullptr, *dRing = nullptr; // mapped pinned progress ring written by k_publish
     DevBuf<unsigned long long> dStampStart, dStampEnd;      // per-launch %globaltimer stamps (flags bit2)
+    DevBuf<unsigned long long> dPixStats;                   // per-pixel path-length sums (flags bit5)
     ~RenderStore() { if (hRing) cudaFreeHost(hRing); }
 };
 
@@ -128,7 +129,8 @@ struct b2_scene {
     float sampleToCamera[16];
     float xfov = 0, nearClip = 1e-2f, farClip = 1e4f;
     float apertureRadius = 0, focusDistance = 0;
-    int W = 0, H = 0;
+    int W = 0, H = 0;                 // the film the integrator sees = the crop window (Film::getCropSize)
+    int filmW = 0, filmH = 0, cropX = 0, cropY = 0; // full film and crop offset (film.cpp:36-47)
     bool hasCamera = false, committed = false;
     // device scene
     DScene ds{};
@@ -311,6 +313,28 @@ static bool mat4inv(const double *m, double *inv) {
     return true;
 }
 
+// perspective.cpp:133-153 evaluated in double, rounded once: cameraToSample = scale(1/relSize) * translate(-relOffset) *
+// scale(-0.5, -0.5*aspect, 1) * translate(-1, -1/aspect, 0) * perspective(xfov, near, far), aspect from the FULL film
+static bool deriveSampleToCamera(b2_scene *s) {
+    const double aspect = (double) s->filmW / (double) s->filmH;
+    const double recip = 1.0 / ((double) s->farClip - (double) s->nearClip);
+    const double cot = 1.0 / std::tan(((double) s->xfov / 2.0) * (M_PI / 180.0));
+    const double relSX = (double) s->W / s->filmW, relSY = (double) s->H / s->filmH, relOX = (double) s->cropX / s->filmW, relOY = (double) s->cropY / s->filmH;
+    double persp[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, s->farClip * recip, -(double) s->nearClip * s->farClip * recip, 0, 0, 1, 0};
+    double tr[16] = {1, 0, 0, -1, 0, 1, 0, -1.0 / aspect, 0, 0, 1, 0, 0, 0, 0, 1};
+    double sc[16] = {-0.5, 0, 0, 0, 0, -0.5 * aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double ctr[16] = {1, 0, 0, -relOX, 0, 1, 0, -relOY, 0, 0, 1, 0, 0, 0, 0, 1};
+    double csc[16] = {1.0 / relSX, 0, 0, 0, 0, 1.0 / relSY, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double t1[16], t2[16], t3[16], c2s[16], s2c[16];
+    mat4mul(tr, persp, t1);
+    mat4mul(sc, t1, t2);
+    mat4mul(ctr, t2, t3);
+    mat4mul(csc, t3, c2s);
+    if (!mat4inv(c2s, s2c)) return false;
+    for (int i = 0; i < 16; ++i) s->sampleToCamera[i] = (float) s2c[i];
+    return true;
+}
+
 extern "C" int b2_scene_set_camera(b2_scene *s, const float to_world[16], float xfov_deg, float near_clip, float far_clip, int width,
                                    int height) {
     if (!s || !to_world) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_set_camera: null argument");
@@ -318,20 +342,26 @@ extern "C" int b2_scene_set_camera(b2_scene *s, const float to_world[16], float 
     if (near_clip <= 0) return fail(s->ctx, B2_ERR_INVALID, "The 'nearClip' parameter must be greater than zero!");   // sensor.cpp:164-165
     if (near_clip >= far_clip) return fail(s->ctx, B2_ERR_INVALID, "The 'nearClip' parameter must be smaller than 'farClip'."); // :166-167
     memcpy(s->camToWorld, to_world, 64);
-    s->xfov = xfov_deg; s->nearClip = near_clip; s->farClip = far_clip; s->W = width; s->H = height;
-    // perspective.cpp:146-153 (no crop window) evaluated in double, rounded once
-    const double aspect = (double) width / (double) height;
-    const double recip = 1.0 / ((double) far_clip - (double) near_clip);
-    const double cot = 1.0 / std::tan(((double) xfov_deg / 2.0) * (M_PI / 180.0));
-    double persp[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, far_clip * recip, -(double) near_clip * far_clip * recip, 0, 0, 1, 0};
-    double tr[16] = {1, 0, 0, -1, 0, 1, 0, -1.0 / aspect, 0, 0, 1, 0, 0, 0, 0, 1};
-    double sc[16] = {-0.5, 0, 0, 0, 0, -0.5 * aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    double t1[16], c2s[16], s2c[16];
-    mat4mul(tr, persp, t1);
-    mat4mul(sc, t1, c2s);
-    if (!mat4inv(c2s, s2c)) return fail(s->ctx, B2_ERR_INVALID, "singular camera matrix");
-    for (int i = 0; i < 16; ++i) s->sampleToCamera[i] = (float) s2c[i];
+    s->xfov = xfov_deg; s->nearClip = near_clip; s->farClip = far_clip;
+    s->filmW = width; s->filmH = height;
+    s->cropX = 0; s->cropY = 0; s->W = width; s->H = height;
+    if (!deriveSampleToCamera(s)) return fail(s->ctx, B2_ERR_INVALID, "singular camera matrix");
     s->hasCamera = true;
+    s->committed = false;
+    return B2_OK;
+}
+// Film crop window (film.cpp:36-47): the render covers crop_width x crop_height pixels whose upper left corner sits at
+// (crop_offset_x, crop_offset_y) of the full film given to b2_scene_set_camera.  As in the reference the cropped film IS the film the
+// integrator sees from then on (Film::getCropSize: sample positions, the Sobol' resolution, blocks and the output buffer are relative
+// to the crop window); only the sensor's sampleToCamera changes (perspective.cpp:133-153, relSize / relOffset).
+extern "C" int b2_scene_set_crop(b2_scene *s, int crop_offset_x, int crop_offset_y, int crop_width, int crop_height) {
+    if (!s) return fail(nullptr, B2_ERR_INVALID, "b2_scene_set_crop: null scene");
+    if (!s->hasCamera) return fail(s->ctx, B2_ERR_INVALID, "b2_scene_set_crop: set the camera first");
+    if (crop_offset_x < 0 || crop_offset_y < 0 || crop_width <= 0 || crop_height <= 0 || crop_offset_x + crop_width > s->filmW ||
+        crop_offset_y + crop_height > s->filmH)
+        return fail(s->ctx, B2_ERR_INVALID, "Invalid crop window specification!"); // film.cpp:44-48
+    s->cropX = crop_offset_x; s->cropY = crop_offset_y; s->W = crop_width; s->H = crop_height;
+    if (!deriveSampleToCamera(s)) return fail(s->ctx, B2_ERR_INVALID, "singular camera matrix");
     s->committed = false;
     return B2_OK;
 }
@@ -1073,6 +1103,11 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.refill = 16; // measured sweep 8..32 on the material-ball and 1M-triangle scenes
     if (const char *e = getenv("B2_REFILL")) ds.refill = (uint32_t) std::max(1, std::min(32, atoi(e)));
     ds.leafVote = 8;
+    // rays that leave the scene are binned into the first BSDF class that has a shading kernel launched for it (a scene without a
+    // diffuse mesh launches no class-0 kernel: its escaped paths must still be retired)
+    ds.missClass = 0;
+    for (int c = 3; c >= 0; --c)
+        if (s->classPresent[c]) ds.missClass = (uint32_t) c;
     if (const char *e = getenv("B2_LEAFVOTE")) ds.leafVote = (uint32_t) std::max(1, std::min(32, atoi(e)));
     parity::KernelSet_init(s->cfgParity, ds, ctx->numSMs);
     fast::KernelSet_init(s->cfgFast, ds, ctx->numSMs);
@@ -1166,8 +1201,11 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     } else {
         r.scramble = p->seed;
     }
-    r.tilesX = (uint32_t) (s->W + 7) / 8; r.tilesY = (uint32_t) (s->H + 7) / 8;
-    r.totalWork = (uint64_t) r.tilesX * r.tilesY * 64ull * (uint64_t) (r.sampleHi - r.sampleLo);
+    // work items = exactly the W*H*(hi-lo) (pixel, sample) pairs: whole 8x8 tiles first (tile-major, then sample, then pixel), then
+    // the pixels of the right / bottom strips that no whole tile covers (sample-major).  No item is ever invalid, so a pool slot is
+    // never consumed by a pixel outside the film (workItemPixel in b2_kernels.inl).
+    r.tilesX = (uint32_t) s->W / 8; r.tilesY = (uint32_t) s->H / 8;
+    r.totalWork = (uint64_t) s->W * (uint64_t) s->H * (uint64_t) (r.sampleHi - r.sampleLo);
     // nibble tables of sobol::look_up for this m (sobolseq.h:104-133) and the nibble counts that cover the indices
     auto bitsOf = [](uint64_t v) { uint32_t b = 0; while (v) { ++b; v >>= 1; } return b; };
     const uint32_t frameBits = std::max(1u, bitsOf((uint64_t) r.sampleHi - 1));
@@ -1260,6 +1298,11 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         CK(ctx, cudaMemsetAsync(R.dStampStart.p, 0xFF, (size_t) B2_MAX_STAMPS * 4 * 8, st));
         CK(ctx, cudaMemsetAsync(R.dStampEnd.p, 0, (size_t) B2_MAX_STAMPS * 4 * 8, st));
         r.stampStart = R.dStampStart.p; r.stampEnd = R.dStampEnd.p;
+    }
+    if (p->flags & 32) { // per-pixel path diagnostics: sum of path lengths (low word) and of their squares (high word)
+        CK(ctx, R.dPixStats.alloc(nPix));
+        CK(ctx, cudaMemsetAsync(R.dPixStats.p, 0, nPix * sizeof(unsigned long long), st));
+        r.pixStats = R.dPixStats.p;
     }
     CK(ctx, cudaMemsetAsync(R.dFilmRGBA.p, 0, nPix * sizeof(float4), st));
     CK(ctx, cudaMemsetAsync(R.dFilmW.p, 0, nPix * sizeof(float), st));
@@ -1435,6 +1478,20 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     return status;
 }
 
+// Per-pixel path diagnostics of the last b2_render that ran with flags bit5: out[y * W + x] = (sum of squared path lengths << 32) |
+// sum of path lengths over the samples of that pixel (both modulo 2^32).  Two renders of the same scene and sampler that differ in
+// one path of a pixel differ in that pixel's word: the fraction of differing words bounds the fraction of flipped paths from below.
+extern "C" int b2_get_pixel_stats(b2_scene *s, uint64_t *out) {
+    if (!s || !out) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_get_pixel_stats: null argument");
+    b2_ctx *ctx = s->ctx;
+    RenderStore &R = *ctx->store;
+    std::lock_guard<std::mutex> renderLock(R.renderMutex);
+    const size_t nPix = (size_t) s->W * s->H;
+    if (R.dPixStats.n != nPix) return fail(ctx, B2_ERR_INVALID, "b2_get_pixel_stats: the last render did not collect pixel statistics (flags bit5)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpy(out, R.dPixStats.p, nPix * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
 extern "C" int b2_cancel(b2_scene *s) {
     if (!s) return B2_ERR_INVALID;
     s->cancel.store(1);

@@ -312,6 +312,31 @@ B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uin
     }
 }
 
+// Work item -> (pixel, sample).  Items [0, tilesX*tilesY*64*nS) walk the whole 8x8 tiles of the film: tile-major, then the
+// sample index, then the pixel inside the tile (64 consecutive items = one sample of one tile: coherent camera rays and one
+// compact film footprint).  The remaining items cover the right strip (W - 8*tilesX columns beside the tiles) and the bottom
+// strip (H - 8*tilesY full rows) pixel by pixel, sample-major.  Every item is a pixel of the film, so no slot is ever wasted.
+B2_DEV void workItemPixel(const DRender &rp, int W, int H, unsigned long long w, int &px, int &py, uint32_t &s) {
+    const uint32_t nS = (uint32_t) (rp.sampleHi - rp.sampleLo);
+    const uint32_t perTile = 64u * nS;
+    const unsigned long long tiled = (unsigned long long) rp.tilesX * rp.tilesY * perTile;
+    if (w < tiled) {
+        const uint32_t tile = (uint32_t) (w / perTile), r = (uint32_t) (w % perTile);
+        s = (uint32_t) rp.sampleLo + r / 64u;
+        const uint32_t p = r & 63u;
+        px = (int) ((tile % rp.tilesX) * 8u + (p & 7u));
+        py = (int) ((tile / rp.tilesX) * 8u + (p >> 3));
+        return;
+    }
+    const unsigned long long e = w - tiled;
+    const uint32_t Wi = rp.tilesX * 8u, Hi = rp.tilesY * 8u, rw = (uint32_t) W - Wi;
+    const uint32_t nEdge = (uint32_t) W * (uint32_t) H - Wi * Hi;
+    s = (uint32_t) rp.sampleLo + (uint32_t) (e / nEdge);
+    uint32_t q = (uint32_t) (e % nEdge);
+    if (q < rw * Hi) { px = (int) (Wi + q % rw); py = (int) (q / rw); }
+    else { q -= rw * Hi; px = (int) (q % (uint32_t) W); py = (int) (Hi + q / (uint32_t) W); }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_generate: drains the finished-path queue of the previous iteration with full warps: splat (ImageBlock::put),
 // then refill the slot with the next (pixel, sample) work item.  FIRST: every slot is empty, no queue yet.
@@ -334,8 +359,6 @@ template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc
     // work items are handed out without atomics: entry j of the drained queue takes item base + j; k_publish advances
     // CTR_NEXT by the queue length after this kernel
     const unsigned long long workBase = pool.counters[CTR_NEXT];
-    const uint32_t nS = (uint32_t) (rp.sampleHi - rp.sampleLo);
-    const uint32_t perTile = 64u * nS;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
         const bool inRange = j < n;
@@ -348,21 +371,16 @@ template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc
             if (!filmPut(filt, rp.filmRGBA, rp.filmW, sc.cam.W, sc.cam.H, sp.x, sp.y, (int) (pixel & 0xFFFFu), (int) (pixel >> 16), V3(li.x, li.y, li.z), alpha))
                 ++nBad;
             ++nSamples;
-            pathLen += (fl >> 8) & 0xFFFu;
+            const uint32_t len = (fl >> 8) & 0xFFFu;
+            pathLen += len;
+            if (rp.pixStats) atomicAdd(rp.pixStats + (size_t) (pixel >> 16) * sc.cam.W + (pixel & 0xFFFFu), ((unsigned long long) (len * len) << 32) | len);
         }
         const unsigned long long w = workBase + j;
         if (inRange) {
-            bool valid = w < rp.totalWork;
+            const bool valid = w < rp.totalWork;
             int px = 0, py = 0;
             uint32_t s = 0;
-            if (valid) {
-                const uint32_t tile = (uint32_t) (w / perTile), r = (uint32_t) (w % perTile);
-                s = (uint32_t) rp.sampleLo + r / 64u;
-                const uint32_t p = r & 63u;
-                px = (int) ((tile % rp.tilesX) * 8u + (p & 7u));
-                py = (int) ((tile / rp.tilesX) * 8u + (p >> 3));
-                valid = px < sc.cam.W && py < sc.cam.H;
-            }
+            if (valid) workItemPixel(rp, sc.cam.W, sc.cam.H, w, px, py, s);
             if (valid) {
                 PathSampler smp;
                 float ax, ay;
@@ -459,7 +477,7 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
         auto commit = [&](uint32_t i, bool found, const HitRec &h) {
             pool.hit[i] = found ? make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)) : make_float4(B2_INF, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
             if (SORT) {
-                int cls = 0;
+                int cls = (int) sc.missClass;
                 if (found) cls = sc.materials[__float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w))].type;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -494,7 +512,7 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
             pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
             ++nRays;
             if (SORT) {
-                cls = 0;
+                cls = (int) sc.missClass;
                 if (h.prim != 0xFFFFFFFFu) {
                     const int mat = __float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w));
                     cls = sc.materials[mat].type;

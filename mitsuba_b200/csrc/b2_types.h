@@ -149,6 +149,7 @@ struct DScene {
     // staging limits for shared memory (number of leading BVH nodes / TriAccel records copied by TMA)
     uint32_t stageNodes, stageTris;
     uint32_t leafVote;         // persistent traversal: run the leaf code once this many lanes wait at a leaf (B2_LEAFVOTE, default 8)
+    uint32_t missClass;        // material-sorted dispatch: the class queue that takes rays which left the scene (first class present)
     uint32_t refill;           // persistent traversal: refill a warp when at least this many lanes are idle (B2_REFILL, default 16)
 };
 
@@ -219,13 +220,14 @@ struct DRender {
     uint32_t logRes;         // sobol m_logResolution
     float resolution;        // sobol m_resolution
     uint64_t totalWork;      // W*H*(hi-lo)
-    uint32_t tilesX, tilesY;
+    uint32_t tilesX, tilesY; // whole 8x8 tiles of the film (W / 8, H / 8); the remaining strips are enumerated pixel by pixel
     float4 *filmRGBA;        // H*W float4 (r,g,b,alpha) accumulators
     float *filmW;            // H*W weight accumulators
     const uint64_t *lookupNib; // [2][13][16] nibble tables of sobol look_up for this render's m: [0] vdc (delta), [1] inv
     uint32_t indexNibbles;   // nibbles needed to cover the largest Sobol' index of this render (<= 13)
     uint32_t frameNibbles, bNibbles; // nibbles of the sample index / of the 2m-bit pixel code in look_up
     unsigned long long *ring;       // device pointer of the mapped host progress ring (B2_RING x 4 words)
+    unsigned long long *pixStats;   // null unless per-pixel path diagnostics were requested (flags bit5): [pixel] += (len^2 << 32) | len
     unsigned long long *stampStart; // null unless per-launch timing was requested (b2_render_params.flags bit2)
     unsigned long long *stampEnd;
 };

@@ -1097,10 +1097,13 @@ struct Loader {
                 if (c->type != "perspective" && c->type != "thinlens") throw Err("unsupported sensor \"" + c->type + "\" (supported: perspective, thinlens)");
                 Props p(c);
                 int W = 768, H = 576; // film.cpp:30-33
+                int cropX = 0, cropY = 0, cropW = -1, cropH = -1; // film.cpp:36-43
                 for (auto &ch : c->children) {
                     if (ch->tag == "film") {
                         Props fp(ch.get());
                         W = (int) fp.i("width", 768); H = (int) fp.i("height", 576);
+                        cropX = (int) fp.i("cropOffsetX", 0); cropY = (int) fp.i("cropOffsetY", 0);
+                        cropW = (int) fp.i("cropWidth", W); cropH = (int) fp.i("cropHeight", H);
                         fp.s("pixelFormat", "rgb"); fp.s("fileFormat", "openexr"); fp.s("componentFormat", "float16"); fp.b("banner", true);
                         fp.b("attachLog", true); fp.b("highQualityEdges", false);
                         fp.checkAllUsed();
@@ -1153,6 +1156,8 @@ struct Loader {
                 }
                 p.checkAllUsed();
                 if (b2_scene_set_camera(scene, twf, (float) fov, nearC, farC, W, H)) throw Err(b2_last_error(nullptr));
+                if (cropW < 0) { cropW = W; cropH = H; }
+                if ((cropX != 0 || cropY != 0 || cropW != W || cropH != H) && b2_scene_set_crop(scene, cropX, cropY, cropW, cropH)) throw Err(b2_last_error(nullptr));
                 if (aperture > 0 && b2_scene_set_thinlens(scene, aperture, focusD)) throw Err(b2_last_error(nullptr));
                 haveSensor = true;
             } else if (c->tag == "shape") addShape(c);

@@ -267,6 +267,11 @@ class Camera:
     height: int = 576
     aperture_radius: float = 0.0        # > 0: `thinlens` sensor (src/sensors/thinlens.cpp:132-142)
     focus_distance: float = 0.0         # sensor.cpp:162 (default: farClip)
+    crop: tuple | None = None           # (cropOffsetX, cropOffsetY, cropWidth, cropHeight), film.cpp:36-47; None = the whole film
+
+    def film_size(self):
+        """(width, height) of the film the integrator sees: the crop window if there is one (Film::getCropSize)."""
+        return (self.crop[2], self.crop[3]) if self.crop else (self.width, self.height)
 
     def xfov(self) -> float:
         """src/librender/sensor.cpp:243-263,293-316."""
@@ -287,7 +292,7 @@ class Camera:
         raise ValueError("fovAxis must be one of smaller, larger, diagonal, x, y")
 
     def sample_to_camera(self) -> np.ndarray:
-        """Inverse of m_cameraToSample, src/sensors/perspective.cpp:146-153 (no crop window)."""
+        """Inverse of m_cameraToSample, src/sensors/perspective.cpp:133-153 (crop window: relSize / relOffset)."""
         aspect = self.width / self.height
         recip = 1.0 / (self.far - self.near)
         cot = 1.0 / math.tan(math.radians(self.xfov() / 2.0))
@@ -296,6 +301,11 @@ class Camera:
         tr = np.eye(4); tr[0, 3] = -1.0; tr[1, 3] = -1.0 / aspect
         sc = np.diag([-0.5, -0.5 * aspect, 1.0, 1.0])
         cam_to_sample = sc @ tr @ persp
+        if self.crop:
+            ox, oy, cw, ch = self.crop
+            ctr = np.eye(4); ctr[0, 3] = -ox / self.width; ctr[1, 3] = -oy / self.height
+            csc = np.diag([self.width / cw, self.height / ch, 1.0, 1.0])
+            cam_to_sample = csc @ ctr @ cam_to_sample
         return np.linalg.inv(cam_to_sample).astype(np.float32)
 
 
@@ -506,6 +516,20 @@ def material_ball(bsdf: Bsdf, width=1024, height=1024, n_theta=200, n_phi=200) -
     cam = Camera(look_at((0, 2.2, -5.0), (0, 0.9, 0), (0, 1, 0)), fov=35.0, near=0.1, far=100.0,
                  width=width, height=height)
     return SceneDesc(meshes, cam)
+
+
+def config3_scene(width=1024, height=1024, n_theta=200, n_phi=200) -> SceneDesc:
+    """BASELINE.json configs[2]: "material ball roughconductor + roughdielectric (GGX)" -- the S2 set-up with two balls, a GGX rough
+    conductor (copper-like eta / k, alpha 0.1) and a GGX rough dielectric (bk7 in air, alpha 0.1), ~160k triangles at 200 x 200."""
+    d = material_ball(Bsdf("roughconductor", distribution="ggx", alpha_u=0.1, alpha_v=0.1, eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421)),
+                      width, height, n_theta, n_phi)
+    ball = d.meshes[1]
+    ball.P = (ball.P + np.array([-1.1, 0, 0], np.float32)).astype(np.float32)
+    ball.name = "ball_conductor"
+    P, N, UV, I = uv_sphere((1.1, 1.0, 0), 1.0, n_theta, n_phi, smooth=True)
+    d.meshes.insert(2, Mesh(P, I, N=N, bsdf=Bsdf("roughdielectric", distribution="ggx", alpha_u=0.1, alpha_v=0.1, int_ior="bk7", ext_ior="air"),
+                            name="ball_dielectric"))
+    return d
 
 
 def checker_image(w=256, h=256, cells=8, seed=5, rgb=True) -> np.ndarray:

@@ -205,12 +205,12 @@ class OracleScene:
             if mi >= 0 or me >= 0:
                 L.orc_set_mesh_media(self.h, C.c_int(i), C.c_int(mi), C.c_int(me))
         cam = desc.camera
-        self.W, self.H = cam.width, cam.height
+        self.W, self.H = cam.film_size()   # the crop window is the film the integrator sees (Film::getCropSize)
         c2w = np.ascontiguousarray(cam.to_world, np.float32)
         # the camera matrix may be handed over from the implementation under test so both sides start from
         # identical float32 inputs (its derivation is host-side set-up, perspective.cpp:146-153, not the hot path)
         s2c = np.ascontiguousarray(cam.sample_to_camera() if sample_to_camera is None else sample_to_camera, np.float32)
-        L.orc_set_camera(self.h, _p(c2w), _p(s2c), C.c_float(cam.near), C.c_float(cam.far), C.c_int(cam.width), C.c_int(cam.height))
+        L.orc_set_camera(self.h, _p(c2w), _p(s2c), C.c_float(cam.near), C.c_float(cam.far), C.c_int(self.W), C.c_int(self.H))
         if getattr(cam, "aperture_radius", 0.0) > 0:
             L.orc_set_thinlens(self.h, C.c_float(cam.aperture_radius), C.c_float(cam.focus_distance if cam.focus_distance > 0 else cam.far))
         L.orc_commit(self.h, C.c_int(1 if use_tree else 0))

@@ -408,13 +408,27 @@ void pathref_setup2(void *h, const float *toWorld, float fov, float nearClip, fl
                     int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind) {
     pathref_setup3(h, toWorld, fov, nearClip, farClip, W, H, rfilter, samplerKind, spp, scramble, maxDepth, rrDepth, strictNormals, hideEmitters, integratorKind, 0.0f, 0.0f);
 }
+void pathref_setup4(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
+                    int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind, float apertureRadius, float focusDistance,
+                    int cropX, int cropY, int cropW, int cropH);
 /* apertureRadius > 0: the `thinlens` sensor (src/sensors/thinlens.cpp) with that aperture and focusDistance (<= 0: the plugin's default) */
 void pathref_setup3(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
                     int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind, float apertureRadius, float focusDistance) {
+    pathref_setup4(h, toWorld, fov, nearClip, farClip, W, H, rfilter, samplerKind, spp, scramble, maxDepth, rrDepth, strictNormals, hideEmitters, integratorKind,
+                   apertureRadius, focusDistance, 0, 0, W, H);
+}
+/* film crop window (film.cpp:36-47): W x H is the full film; the render (blocks, sample positions, output buffer) covers cropW x cropH */
+void pathref_setup4(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,
+                    int maxDepth, int rrDepth, int strictNormals, int hideEmitters, int integratorKind, float apertureRadius, float focusDistance,
+                    int cropX, int cropY, int cropW, int cropH) {
     PathRef *p = (PathRef *) h;
-    p->W = W; p->H = H;
+    p->W = cropW; p->H = cropH;
     Properties fp("hdrfilm");
     fp.setInteger("width", W); fp.setInteger("height", H);
+    if (cropX != 0 || cropY != 0 || cropW != W || cropH != H) {
+        fp.setInteger("cropOffsetX", cropX); fp.setInteger("cropOffsetY", cropY);
+        fp.setInteger("cropWidth", cropW); fp.setInteger("cropHeight", cropH);
+    }
     p->film = new StandinFilm(fp);
     Properties rp;
     ReconstructionFilter *rf = (ReconstructionFilter *) (rfilter == 0 ? CreateInstance_box(rp) : CreateInstance_gaussian(rp));
@@ -424,7 +438,7 @@ void pathref_setup3(void *h, const float *toWorld, float fov, float nearClip, fl
     Properties sp;
     sp.setInteger("sampleCount", spp);
     sp.setInteger("scramble", (int) scramble);
-    if (samplerKind == 2) p->sampler = new CounterSamplerPlugin(W, (size_t) spp, scramble);
+    if (samplerKind == 2) p->sampler = new CounterSamplerPlugin(cropW, (size_t) spp, scramble);
     else p->sampler = (Sampler *) (samplerKind == 0 ? CreateInstance_sobol(sp) : CreateInstance_independent(sp));
     p->sampler->configure();
     Properties cp("perspective");
@@ -454,14 +468,18 @@ void pathref_setup3(void *h, const float *toWorld, float fov, float nearClip, fl
     p->integrator->configureSampler(p->scene, p->sampler);
 }
 /* m_sampleToCamera as PerspectiveCameraImpl::configure derives it (perspective.cpp:146-153; the member itself is private to the plugin):
- * the same chain of the reference's own Transform operations, no crop window.  Row-major 4 x 4. */
+ * the same chain of the reference's own Transform operations, incl. the crop window.  Row-major 4 x 4. */
 void pathref_sample_to_camera(void *h, float *out16) {
     PathRef *p = (PathRef *) h;
     const PerspectiveCamera *cam = static_cast<const PerspectiveCamera *>(p->sensor.get());
     const Float aspect = cam->getAspect();
+    const Vector2i &filmSize = p->film->getSize(), &cropSize = p->film->getCropSize();
+    const Point2i &cropOffset = p->film->getCropOffset();
+    const Vector2 relSize((Float) cropSize.x / (Float) filmSize.x, (Float) cropSize.y / (Float) filmSize.y);
+    const Point2 relOffset((Float) cropOffset.x / (Float) filmSize.x, (Float) cropOffset.y / (Float) filmSize.y);
     const Transform cameraToSample =
-          Transform::scale(Vector(1.0f / 1.0f, 1.0f / 1.0f, 1.0f))
-        * Transform::translate(Vector(-0.0f, -0.0f, 0.0f))
+          Transform::scale(Vector(1.0f / relSize.x, 1.0f / relSize.y, 1.0f))
+        * Transform::translate(Vector(-relOffset.x, -relOffset.y, 0.0f))
         * Transform::scale(Vector(-0.5f, -0.5f * aspect, 1.0f))
         * Transform::translate(Vector(-1.0f, -1.0f / aspect, 0.0f))
         * Transform::perspective(cam->getXFov(), cam->getNearClip(), cam->getFarClip());

@@ -362,10 +362,11 @@ def reference_scene(lib, desc, rp):
     assert cam.fov_axis == "x"
     tw = np.ascontiguousarray(cam.to_world, np.float32)
     # `independent` here is this repository's counter-based stream (kind 2), handed to the reference integrator through the Sampler interface
-    lib.pathref_setup3(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
+    crop = cam.crop or (0, 0, cam.width, cam.height)
+    lib.pathref_setup4(h, _f(tw), C.c_float(cam.fov), C.c_float(cam.near), C.c_float(cam.far), cam.width, cam.height,
                        {"box": 0, "gaussian": 1}[rp.rfilter], {"sobol": 0, "independent": 2}[rp.sampler], rp.spp, C.c_uint64(rp.seed),
                        rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters), {"path": 0, "volpath": 1}[rp.integrator],
-                       C.c_float(cam.aperture_radius), C.c_float(cam.focus_distance))
+                       C.c_float(cam.aperture_radius), C.c_float(cam.focus_distance), *[int(v) for v in crop])
     return h
 
 
@@ -374,7 +375,8 @@ def reference_render(lib, desc, rp, want_camera=False):
     (and, with want_camera, the reference's sampleToCamera matrix: camera set-up is host work, both sides should start from it)."""
     h = reference_scene(lib, desc, rp)
     cam = desc.camera
-    film = np.zeros((cam.height, cam.width, 5), np.float32)
+    fw, fh = cam.film_size()
+    film = np.zeros((fh, fw, 5), np.float32)
     lib.pathref_render(h, _f(film))
     if want_camera:
         s2c = np.zeros((4, 4), np.float32)
@@ -467,3 +469,11 @@ def image_cases_ext():
     d.instances.append(Instance(1, M2.astype(np.float32)))
     yield "instances_sobol", d, RenderParams(spp=8, sampler="sobol", rfilter="box")
     yield "instances_counter_depth3", d, RenderParams(spp=8, sampler="independent", rfilter="gaussian", max_depth=3)
+    # film crop window (film.cpp:36-47, perspective.cpp:133-153): the crop is the film the integrator sees (blocks, Sobol' resolution,
+    # sample positions relative to it); sizes that are multiples of neither the 8x8 work tiles nor the 32x32 blocks
+    d = cornell_box(96, 64)
+    d.camera = dataclasses.replace(d.camera, crop=(17, 9, 43, 33))
+    yield "crop_cbox_sobol", d, RenderParams(spp=8, sampler="sobol", rfilter="gaussian")
+    d = cornell_box(80, 80)
+    d.camera = dataclasses.replace(d.camera, crop=(40, 0, 40, 37), aperture_radius=20.0, focus_distance=1000.0)
+    yield "crop_thinlens_counter", d, RenderParams(spp=4, sampler="independent", rfilter="box", max_depth=5)

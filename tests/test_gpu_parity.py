@@ -63,9 +63,15 @@ def test_closest_hit_and_occlusion_exact(cbox):
     assert np.array_equal(p0, p1) and np.array_equal(t0, t1) and np.array_equal(u0, u1) and np.array_equal(v0, v1)
     rays[:, 7] = np.random.default_rng(3).uniform(20, 700, len(rays))
     assert np.array_equal(o.trace(rays, 1)[3], g.trace(rays, 1, parity=True)[3])
-    # FMA build: same primitive, t within a few ulp
-    t2, _, _, p2 = g.trace(rays[:, :], 0, parity=False)
+    # FMA build (plane-form triangle test, paired flat-leaf records): same primitive, t within a few ulp -- except rays that graze an
+    # edge shared by two triangles, where either neighbour is a correct answer
     rays[:, 7] = np.inf
+    t2, u2, v2, p2 = g.trace(rays, 0, parity=False)
+    same = p2 == p0
+    assert same.mean() > 0.9995, same.mean()
+    hit = same & (p0 != 0xFFFFFFFF)
+    assert np.allclose(t2[hit], t0[hit], rtol=2e-5, atol=0) and np.allclose(u2[hit], u0[hit], atol=2e-4) and np.allclose(v2[hit], v0[hit], atol=2e-4)
+    assert np.array_equal(p2 == 0xFFFFFFFF, p0 == 0xFFFFFFFF) or (np.not_equal(p2 == 0xFFFFFFFF, p0 == 0xFFFFFFFF)).mean() < 2e-4
 
 
 def test_traversal_large_mesh_exact(b2ctx):
@@ -400,6 +406,57 @@ def test_fused_and_unfused_pipelines_agree(cbox):
         assert np.allclose(a, b, rtol=2e-5, atol=2e-5)
         for k in ("samples", "rays", "shadow_rays", "path_length_sum", "unoccluded_shadow_rays"):
             assert sa[k] == sb[k], k
+
+
+def test_ragged_film_small_pool_high_spp_terminates(b2ctx):
+    """Film sizes that are not multiples of the 8x8 work tiles must not consume pool slots for pixels outside the film: with a 1024-slot
+    pool, 20x12 pixels and 64 spp the old tile enumeration (3x2 tiles = 384 items per sample for 240 pixels) ran out of slots."""
+    d = cornell_box(20, 12)
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=64, sampler="sobol", rfilter="box")
+    fg, sg = g.render(rp, parity=True, pool_size=1024)
+    fo, so = o.render(rp)
+    assert sg["samples"] == 20 * 12 * 64 == so["samples"]
+    assert np.allclose(fg[..., 4], fo[..., 4], rtol=1e-5, atol=1e-5)
+    assert rel_l2(api.develop(fg), O.develop(fo)) < 5e-4
+    # 100x100 @ 8 spp through a 4096-slot pool: 13x13 tiles used to waste 6900 of 16900 items per sample
+    d = cornell_box(100, 100)
+    g = api.Scene(b2ctx, d)
+    f, st = g.render(RenderParams(spp=8, sampler="sobol", rfilter="box"), parity=False, pool_size=4096)
+    assert st["samples"] == 100 * 100 * 8 and np.rint(f[..., 4]).min() >= 8
+
+
+def test_open_scene_without_a_diffuse_class(b2ctx):
+    """Material-sorted dispatch on a scene with two BSDF classes but no diffuse mesh, open to a constant environment: rays that leave the
+    scene must still be retired (they are binned into the first class that has a shading kernel)."""
+    d = material_ball(MATERIALS["roughdielectric_ggx"], 48, 48, 24, 48)
+    d.meshes = [m for m in d.meshes if m.name in ("ground", "ball")]
+    d.meshes[0].bsdf = MATERIALS["roughconductor_ggx"]
+    d.env_radiance = (0.5, 0.6, 0.8)
+    g, o = pair(b2ctx, d)
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="box")
+    fo, so = o.render(rp)
+    for flags in (0, 2):
+        fg, sg = g.render(rp, parity=True, flags=flags)
+        assert sg["samples"] == so["samples"]
+        assert rel_l2(api.develop(fg), O.develop(fo)) <= REL_L2_TOL
+
+
+def test_crop_window_parity(b2ctx):
+    """Film crop window (film.cpp:36-47): the crop is the film the integrator sees; device vs oracle on the same camera matrix."""
+    d = cornell_box(96, 64)
+    d.camera = dataclasses.replace(d.camera, crop=(17, 9, 43, 33))
+    g, o = pair(b2ctx, d)
+    assert (g.W, g.H) == (43, 33)
+    assert np.allclose(g.sample_to_camera(), d.camera.sample_to_camera(), rtol=1e-6, atol=1e-6)
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="gaussian")
+    fo, so = o.render(rp); fg, sg = g.render(rp, parity=True)
+    assert fg.shape == (33, 43, 5) and sg["samples"] == 43 * 33 * 16
+    assert rel_l2(api.develop(fg), O.develop(fo)) < 5e-4
+    with pytest.raises(api.B2Error, match="Invalid crop window"):
+        bad = cornell_box(32, 32)
+        bad.camera = dataclasses.replace(bad.camera, crop=(10, 10, 30, 8))
+        api.Scene(b2ctx, bad)
 
 
 def test_ragged_film_and_non_square(b2ctx):

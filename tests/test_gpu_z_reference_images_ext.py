@@ -38,7 +38,7 @@ def test_device_images_of_thinlens_constant_emitter_and_instances_match_the_refe
         assert rel_l2(film[..., :3], ref[..., :3]) <= tol, (name, rel_l2(film[..., :3], ref[..., :3]))
         sc.close()
         n += 1
-    assert n == 9
+    assert n == 11
 
 
 def test_device_emitter_selection_puts_the_constant_emitter_first(b2ctx):

@@ -204,7 +204,7 @@ def test_oracle_images_of_thinlens_constant_emitter_and_instances_match_the_refe
             assert np.array_equal(own[..., 3:], ref[..., 3:])   # same splats: alpha and weight channels
             assert np.sqrt(((own - ref) ** 2).sum() / (ref ** 2).sum()) < 1e-3
         n += 1
-    assert n == 9
+    assert n == 11
 
 
 def test_emitter_order_and_instanced_records_match_the_live_reference_when_present():
