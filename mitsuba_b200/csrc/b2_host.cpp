@@ -98,7 +98,7 @@ template <typename T> struct DevBuf {
 struct RenderStore {
     std::mutex renderMutex;
     uint32_t capacity = 0;
-    DevBuf<float4> pRay, pSt, pHit, pShD, pShC;
+    DevBuf<float4> pRay, pSt, pHit, pShO, pShD, pShC;
     DevBuf<uint2> pSmp, pVol;
     DevBuf<uint32_t> pInst;
     DevBuf<float2> pPos;
@@ -860,33 +860,51 @@ extern "C" int b2_scene_commit(b2_scene *s) {
                 kind[i] = para ? 1 : 2;
             }
         }
+        // records per class, each as rows of float4: parallelogram / single = 3 rows (plane, U, V), coplanar pair = 5 rows (plane, U, V, U', V')
+        std::vector<std::vector<float4>> recs[3];
+        std::vector<std::pair<uint32_t, uint32_t>> recIdx[3];
         for (int pass = 1; pass <= 3; ++pass)
             for (uint32_t i = 0; i < n; ++i) {
                 if (pass < 3) {
                     if (mate[i] < (int) i || kind[i] != pass) continue; // each pair once, from its lower index
                     const uint32_t j = (uint32_t) mate[i];
-                    float4 rows[3];
+                    std::vector<float4> rows;
                     if (pass == 1) {
                         const int ka = cornerA[i];
-                        planeRows(V(i, ka), V(i, (ka + 1) % 3), V(i, (ka + 2) % 3), rows);
-                        flatRec.insert(flatRec.end(), rows, rows + 3);
-                        ++flatP;
+                        rows.resize(3);
+                        planeRows(V(i, ka), V(i, (ka + 1) % 3), V(i, (ka + 2) % 3), rows.data());
                     } else {
-                        flatRec.insert(flatRec.end(), &leafPlane[3 * i], &leafPlane[3 * i] + 3);
-                        flatRec.insert(flatRec.end(), &leafPlane[3 * j + 1], &leafPlane[3 * j + 1] + 2);
-                        ++flatC;
+                        rows.assign(&leafPlane[3 * i], &leafPlane[3 * i] + 3);
+                        rows.insert(rows.end(), &leafPlane[3 * j + 1], &leafPlane[3 * j + 1] + 2);
                     }
-                    flatIdx.push_back(i); flatIdx.push_back(j);
+                    recs[pass - 1].push_back(rows); recIdx[pass - 1].emplace_back(i, j);
                 } else {
                     if (mate[i] >= 0) continue;
-                    flatRec.insert(flatRec.end(), &leafPlane[3 * i], &leafPlane[3 * i] + 3);
-                    flatIdx.push_back(i); flatIdx.push_back(i);
-                    ++flatS;
+                    recs[2].push_back(std::vector<float4>(&leafPlane[3 * i], &leafPlane[3 * i] + 3));
+                    recIdx[2].emplace_back(i, i);
                 }
             }
+        // Two records wide (b2_trace.cuh traverseFlat: one packed FFMA2 evaluates both): row r of records 2j and 2j + 1 becomes the two
+        // float4 (x, x', y, y') (z, z', w, w'); an odd count is padded with a plane that is never hit (N = 0, d0 = -1 -> t = -inf)
+        for (int c = 0; c < 3; ++c) {
+            const size_t rowsPer = c == 1 ? 5 : 3;
+            if (recs[c].size() & 1) {
+                std::vector<float4> pad(rowsPer, make_float4(0, 0, 0, 0));
+                pad[0].w = -1.0f;
+                recs[c].push_back(pad); recIdx[c].emplace_back(0u, 0u);
+            }
+            for (size_t j = 0; j + 1 < recs[c].size(); j += 2)
+                for (size_t r = 0; r < rowsPer; ++r) {
+                    const float4 &a = recs[c][j][r], &b = recs[c][j + 1][r];
+                    flatRec.push_back(make_float4(a.x, b.x, a.y, b.y));
+                    flatRec.push_back(make_float4(a.z, b.z, a.w, b.w));
+                }
+            for (auto &ij : recIdx[c]) { flatIdx.push_back(ij.first); flatIdx.push_back(ij.second); }
+            (c == 0 ? flatP : c == 1 ? flatC : flatS) = (uint32_t) (recs[c].size() / 2); // packed steps
+        }
     }
     if (getenv("B2_VERBOSE"))
-        fprintf(stderr, "[b2mts] commit: %zu triangles, flat leaf %u (parallelograms %u, coplanar pairs %u, singles %u), bvh nodes %zu depth %d\n", nPrims, rootCount,
+        fprintf(stderr, "[b2mts] commit: %zu triangles, flat leaf %u (two-wide steps: parallelograms %u, coplanar pairs %u, singles %u), bvh nodes %zu depth %d\n", nPrims, rootCount,
                 flatP, flatC, flatS, bvh.nodes.size(), bvh.depth);
     // ---- materials ----
     std::vector<DMaterial> dm(s->materials.size());
@@ -1100,6 +1118,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     // shared-memory staging budget: up to 256 nodes (16 KB) and 256 triangles (12 KB) per CTA
     ds.stageNodes = std::min<uint32_t>(ds.nNodes, 256u);
     ds.stageTris = rootCount ? rootCount : 0u; // a BVH's leaf-ordered head is arbitrary: only the flat leaf is worth staging
+    ds.stageTriBytes = std::max(ds.stageTris * 48u, (ds.flatBytes + 15u) & ~15u);
     ds.refill = 16; // measured sweep 8..32 on the material-ball and 1M-triangle scenes
     if (const char *e = getenv("B2_REFILL")) ds.refill = (uint32_t) std::max(1, std::min(32, atoi(e)));
     ds.leafVote = 8;
@@ -1238,7 +1257,7 @@ static int ensurePool(b2_scene *s, uint32_t Q, bool vol) {
     RenderStore &R = *ctx->store;
     if (R.capacity != Q) {
         CK(ctx, R.pRay.alloc((size_t) 2 * Q)); CK(ctx, R.pSt.alloc((size_t) 2 * Q)); CK(ctx, R.pHit.alloc(Q));
-        CK(ctx, R.pShD.alloc(Q)); CK(ctx, R.pShC.alloc(Q)); CK(ctx, R.pSmp.alloc(Q)); CK(ctx, R.pPos.alloc(Q));
+        CK(ctx, R.pShO.alloc(Q)); CK(ctx, R.pShD.alloc(Q)); CK(ctx, R.pShC.alloc(Q)); CK(ctx, R.pSmp.alloc(Q)); CK(ctx, R.pPos.alloc(Q));
         CK(ctx, R.pPix.alloc(Q)); CK(ctx, R.pFlags.alloc(Q));
         CK(ctx, R.pMatQueue.alloc((size_t) 4 * Q)); CK(ctx, R.pDoneQueue.alloc((size_t) 2 * Q));
         R.pVol.release(); R.pInst.release();
@@ -1249,7 +1268,7 @@ static int ensurePool(b2_scene *s, uint32_t Q, bool vol) {
     DPool &p = s->pool;
     p.capacity = Q;
     p.ray = R.pRay.p; p.st = R.pSt.p; p.hit = R.pHit.p; p.smp = R.pSmp.p; p.pos = R.pPos.p; p.pix = R.pPix.p; p.flags = R.pFlags.p;
-    p.shD = R.pShD.p; p.shC = R.pShC.p; p.matQueue = R.pMatQueue.p;
+    p.shO = R.pShO.p; p.shD = R.pShD.p; p.shC = R.pShC.p; p.matQueue = R.pMatQueue.p;
     p.doneQueue = R.pDoneQueue.p;
     p.counters = s->dCounters.p;
     p.vol = R.pVol.p;
@@ -1314,12 +1333,6 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     bool sorted = nClasses > 1;
     if (p->flags & 2) sorted = false;
     if (s->hasNullBsdf || !s->textures.empty()) { sorted = false; nClasses = 2; } // index-matched boundaries, f-3 BSDFs, textures: generic shading kernel
-    // Optional (flags bit4) for shared-memory resident scenes: rays cast inline by k_generate / k_shade (no k_extend /
-    // k_occluded launches, no ray / shadow records through HBM).  Measured on Cornell it is ~4 % SLOWER than the separate
-    // stages (1407 vs 1463 Msamples/s): the triangle tests then run inside the divergent, low-occupancy shade kernel
-    // instead of the lockstep traversal kernels, so the default keeps the stages separate.
-    const bool fused = s->ds.rootCount > 0 && (p->flags & 16) && !volpath;
-    if (fused) sorted = false;
     s->cancel.store(0);
     cudaEvent_t evStart, evStop;
     CK(ctx, cudaEventCreate(&evStart));
@@ -1343,23 +1356,23 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         launchesPerIter = 0;
 #define ITER(ns)                                                                                               \
         do {                                                                                                   \
-            tick(0); ns::launch_generate(cfg, s->ds, s->pool, r, filt, fused, st); tick(-1);                   \
+            tick(0); ns::launch_generate(cfg, s->ds, s->pool, r, filt, st); tick(-1);                   \
             if (volpath) { /* volpath: every ray of an iteration is cast inline by k_volstep */                 \
                 tick(2); ns::launch_volstep(cfg, s->ds, s->pool, r, st); tick(-1);                             \
                 launchesPerIter = 3;                                                                           \
                 break;                                                                                         \
             }                                                                                                  \
-            if (!fused) { tick(1); ns::launch_extend(cfg, s->ds, s->pool, r, sorted, st); tick(-1); ++launchesPerIter; } \
+            tick(1); ns::launch_extend(cfg, s->ds, s->pool, r, sorted, st); tick(-1); ++launchesPerIter;        \
             tick(2);                                                                                           \
             if (sorted) {                                                                                      \
                 for (int c = 0; c < 4; ++c)                                                                    \
-                    if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, fused, st); ++launchesPerIter; } \
+                    if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, st); ++launchesPerIter; } \
             } else {                                                                                           \
-                ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, fused, st);    \
+                ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);           \
                 ++launchesPerIter;                                                                             \
             }                                                                                                  \
             tick(-1);                                                                                          \
-            if (!fused) { tick(3); ns::launch_occluded(cfg, s->ds, s->pool, r, st); tick(-1); ++launchesPerIter; } \
+            tick(3); ns::launch_occluded(cfg, s->ds, s->pool, r, st); tick(-1); ++launchesPerIter;              \
             launchesPerIter += 2;                                                                              \
         } while (0)
         if (parityMode) ITER(parity);

@@ -75,7 +75,7 @@ B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem) {
     float4 *sNodes = (float4 *) (smem + off);
     off += (size_t) sc.stageNodes * 64;
     float4 *sTris = (float4 *) (smem + off);
-    off += (size_t) sc.stageTris * 48;
+    off += (size_t) sc.stageTriBytes;
     off = (off + 15) & ~(size_t) 15;
     uint64_t *bar = (uint64_t *) (smem + off);
     stageScene(sc, sNodes, sTris, bar);
@@ -95,40 +95,24 @@ B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem) {
     return tm;
 }
 
-// Tiny scenes: only the triangle list is staged (no node array, no traversal stack); used by the kernels that cast their
-// rays inline (k_generate<true>, k_shade<CLS, true>)
-B2_DEV TraceMem setupFlatMem(const DScene &sc, unsigned char *smem) {
-    float4 *sTris = (float4 *) smem;
-    size_t off = ((size_t) sc.stageTris * 48 + 15) & ~(size_t) 15;
-    uint64_t *bar = (uint64_t *) (smem + off);
-    stageScene(sc, sTris, sTris, bar);
-    TraceMem tm;
-    tm.gNodes = nullptr; tm.sNodes = nullptr; tm.stageNodes = 0;
-    tm.sTris = sTris; tm.stageTris = sc.stageTris; tm.stack = nullptr; tm.stride = 0;
-#ifdef B2_FAST_TRI
-    tm.gTris = sc.triPlane;
-#else
-    tm.gTris = sc.triAccel;
-#endif
-    return tm;
+// ------------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) staging of per-slot records: the thread that will work on a slot in the NEXT loop iteration issues the copies
+// of that slot's pool records into its own shared-memory cells now and waits for them one iteration later, so the HBM latency of
+// the scattered / streamed 16-byte records overlaps with the arithmetic of the current item instead of stalling the warp
+// (ncu, round 1: k_shade and k_generate were long-scoreboard bound at 28-32 % of the DRAM peak).  Every thread reads back only
+// what it copied itself, so cp.async.wait_group is the only synchronisation needed.
+// ------------------------------------------------------------------------------------------------
+B2_DEV void cpAsync16(void *smemDst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(smemDst)), "l"(gsrc) : "memory");
 }
-// closest hit / occlusion of one ray against the staged flat leaf, with the reference's clip + adaptive epsilon
-B2_DEV void castClosestFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float rayMint, float rayMaxt, HitRec &h) {
-    h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
-    const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    float mint, maxt;
-    uint32_t pt = 0;
-    if (clipRay<false>(sc, o, d, dRcp, rayMint, rayMaxt, mint, maxt))
-        if (!traverseFlat<false, false>(sc, tm, o, d, mint, maxt, h, pt)) { h.t = B2_INF; h.prim = 0xFFFFFFFFu; }
+B2_DEV void cpAsync8(void *smemDst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(smemDst)), "l"(gsrc) : "memory");
 }
-B2_DEV bool castOccludedFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float rayMaxt) {
-    const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    float mint, maxt;
-    uint32_t pt = 0;
-    HitRec h;
-    if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, rayMaxt, mint, maxt)) return traverseFlat<true, false>(sc, tm, o, d, mint, maxt, h, pt);
-    return false;
+B2_DEV void cpAsync4(void *smemDst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smemAddr(smemDst)), "l"(gsrc) : "memory");
 }
+B2_DEV void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> B2_DEV void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 B2_DEV unsigned long long globalTimer() {
     unsigned long long t;
@@ -160,6 +144,12 @@ B2_DEV unsigned long long warpAppend64(bool want, unsigned long long *counter) {
     if (lane == leader) base = atomicAdd(counter, (unsigned long long) __popc(mask));
     base = __shfl_sync(mask, base, leader);
     return base + (unsigned long long) __popc(mask & ((1u << lane) - 1u));
+}
+// 64-bit atomic add whose (low word of the) result is consumed later: nothing between the issue and the first use waits for it
+B2_DEV uint32_t atomAddPending(unsigned long long *counter, uint32_t v) {
+    unsigned long long r;
+    asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(r) : "l"(counter), "l"((unsigned long long) v) : "memory");
+    return (uint32_t) r;
 }
 B2_DEV uint32_t warpAppend(bool want, unsigned long long *counter) { return (uint32_t) warpAppend64(want, counter); }
 // two independent appends whose atomics are issued back to back (their latencies overlap); all 32 lanes must call
@@ -340,18 +330,24 @@ B2_DEV void workItemPixel(const DRender &rp, int W, int H, unsigned long long w,
 // ------------------------------------------------------------------------------------------------
 // k_generate: drains the finished-path queue of the previous iteration with full warps: splat (ImageBlock::put),
 // then refill the slot with the next (pixel, sample) work item.  FIRST: every slot is empty, no queue yet.
+// The four records of a finished slot (flags, pixel, Li, sample position) are gathered through the queue index, which is fetched one
+// loop iteration ahead.  B2_STAGE_GEN (A/B switch, off): also stage the records themselves one iteration ahead with cp.async --
+// measured neutral on B200 (507 vs 504 ms per 5 steps): what the DRAM wait loses, the LDGSTS issue cost (MIO throttle) takes back.
 // ------------------------------------------------------------------------------------------------
-// FLAT (tiny scenes, DScene::rootCount > 0): the camera ray is cast inline against the shared-memory resident triangle
-// list -- the kernel is memory-latency bound, the extra arithmetic hides behind it and the k_extend launch disappears.
-template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
-    extern __shared__ __align__(128) unsigned char smem[];
+#define B2_GEN_BLOCK 256
+#ifndef B2_GEN_MINBLOCKS
+#define B2_GEN_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(B2_GEN_BLOCK, B2_GEN_MINBLOCKS) k_generate(DScene sc, DPool pool, DRender rp, DFilter filt) {
+#ifdef B2_STAGE_GEN
+    __shared__ __align__(16) float4 sLi[2][B2_GEN_BLOCK];
+    __shared__ __align__(8) float2 sPos[2][B2_GEN_BLOCK];
+    __shared__ uint32_t sFlags[2][B2_GEN_BLOCK], sPix[2][B2_GEN_BLOCK];
+#endif
     const uint32_t Q = pool.capacity;
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER];
     const bool FIRST = it == 0;
     stampBegin(rp, it, STAGE_GENERATE);
-    TraceMem tm;
-    if (FLAT) tm = setupFlatMem(sc, smem);
-    uint32_t nRays = 0;
     const uint32_t *queue = pool.doneQueue + (size_t) ((it + 1u) & 1u) * Q; // written by k_shade of iteration it - 1
     const uint32_t n = FIRST ? Q : (uint32_t) pool.counters[((it + 1u) & 1u) ? CTR_DONE1 : CTR_DONE0];
     uint32_t nSamples = 0, nBad = 0, nNew = 0;
@@ -359,14 +355,44 @@ template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc
     // work items are handed out without atomics: entry j of the drained queue takes item base + j; k_publish advances
     // CTR_NEXT by the queue length after this kernel
     const unsigned long long workBase = pool.counters[CTR_NEXT];
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t j = base + threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x, tid = threadIdx.x;
+    auto slotOf = [&](uint32_t j) -> uint32_t { return j < n ? (FIRST ? j : __ldg(queue + j)) : 0u; };
+    uint32_t j = blockIdx.x * blockDim.x + tid;
+    uint32_t iCur = slotOf(j), iNext = slotOf(j + stride); // the queue entry of the next iteration is fetched one iteration ahead
+#ifdef B2_STAGE_GEN
+    auto stage = [&](int buf, uint32_t j, uint32_t i) {
+        if (!FIRST && j < n) {
+            cpAsync16(&sLi[buf][tid], &pool.st[2 * (size_t) i + 1]);
+            cpAsync8(&sPos[buf][tid], &pool.pos[i]);
+            cpAsync4(&sFlags[buf][tid], &pool.flags[i]);
+            cpAsync4(&sPix[buf][tid], &pool.pix[i]);
+        }
+        cpAsyncCommit();
+    };
+    stage(0, j, iCur);
+    int buf = 0;
+#endif
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride, j += stride) {
         const bool inRange = j < n;
-        const uint32_t i = inRange ? (FIRST ? j : queue[j]) : 0u;
+        const uint32_t i = iCur;
+#ifdef B2_STAGE_GEN
+        stage(buf ^ 1, j + stride, iNext);
+#endif
+        iCur = iNext;
+        iNext = slotOf(j + 2 * stride);
+#ifdef B2_STAGE_GEN
+        cpAsyncWait<1>();
+#endif
         if (inRange && !FIRST) {
+#ifdef B2_STAGE_GEN
+            const uint32_t fl = sFlags[buf][tid], pixel = sPix[buf][tid];
+            const float4 li = sLi[buf][tid];
+            const float2 sp = sPos[buf][tid];
+#else
             const uint32_t fl = pool.flags[i], pixel = pool.pix[i];
             const float4 li = pool.st[2 * (size_t) i + 1];
             const float2 sp = pool.pos[i];
+#endif
             const float alpha = (fl & PF_ALPHA) ? 1.0f : 0.0f;
             if (!filmPut(filt, rp.filmRGBA, rp.filmW, sc.cam.W, sc.cam.H, sp.x, sp.y, (int) (pixel & 0xFFFFu), (int) (pixel >> 16), V3(li.x, li.y, li.z), alpha))
                 ++nBad;
@@ -391,14 +417,7 @@ template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc
                 float apx = 0.5f, apy = 0.5f;
                 if (sc.cam.apertureRadius > 0) smp.next2D(apx, apy); // needsApertureSample, integrator.cpp:173-174
                 cameraRay(sc.cam, spx, spy, o, d, mint, maxt, apx, apy);
-                if (FLAT) {
-                    HitRec h;
-                    castClosestFlat(sc, tm, o, d, mint, maxt, h);
-                    pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-                    ++nRays;
-                } else {
-                    pool.ray[2 * (size_t) i] = make_float4(o.x, o.y, o.z, mint);
-                }
+                pool.ray[2 * (size_t) i] = make_float4(o.x, o.y, o.z, mint);
                 pool.ray[2 * (size_t) i + 1] = make_float4(d.x, d.y, d.z, maxt);
                 pool.st[2 * (size_t) i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
                 pool.st[2 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -408,10 +427,16 @@ template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc
                 pool.flags[i] = (PF_ALIVE | PF_FRESH) | (1u << 8) | (smp.dim << 20); // depth = 1 (integrator.h:221-227)
                 ++nNew;
             } else {
-                pool.flags[i] = 0;
+                pool.flags[i] = 0; // no work left: the slot stays empty for the rest of the render
             }
         }
+#ifdef B2_STAGE_GEN
+        buf ^= 1;
+#endif
     }
+#ifdef B2_STAGE_GEN
+    cpAsyncWait<0>();
+#endif
     nNew = warpSum(nNew);
     nSamples = warpSum(nSamples);
     nBad = warpSum(nBad);
@@ -421,10 +446,6 @@ template <bool FLAT> __global__ void __launch_bounds__(256) k_generate(DScene sc
         if (nSamples) atomicAdd(pool.counters + CTR_SAMPLES, (unsigned long long) nSamples);
         if (nBad) atomicAdd(pool.counters + CTR_BAD, (unsigned long long) nBad);
         if (pathLen) atomicAdd(pool.counters + CTR_PATHLEN, (unsigned long long) pathLen);
-    }
-    if (FLAT) {
-        nRays = warpSum(nRays);
-        if ((threadIdx.x & 31) == 0 && nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
     }
     stampEnd(rp, it, STAGE_GENERATE);
 }
@@ -530,6 +551,114 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
     nRays = warpSum(nRays);
     if ((threadIdx.x & 31) == 0 && nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
     stampEnd(rp, it, STAGE_EXTEND);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flat-leaf variants (DScene::rootCount > 0: the whole scene is one shared-memory resident leaf, e.g. the Cornell box): own kernels so
+// that the register allocation is not the maximum over the BVH / instanced code paths (72 -> ~56 registers: 4 instead of 3 CTAs per
+// SM), no traversal stack in shared memory, and the records of the NEXT item of the grid-stride loop are loaded into registers before
+// the current ray is tested (ncu, round 2: a quarter of these kernels' stall samples sat on the first use of the freshly loaded ray).
+// ------------------------------------------------------------------------------------------------
+B2_DEV TraceMem setupFlatLeaf(const DScene &sc, unsigned char *smem) {
+    float4 *sTris = (float4 *) smem;
+    const size_t off = ((size_t) sc.stageTriBytes + 15) & ~(size_t) 15;
+    uint64_t *bar = (uint64_t *) (smem + off);
+    DScene tmp = sc;
+    tmp.stageNodes = 0; // the flat leaf has no node array
+    stageScene(tmp, sTris, sTris, bar);
+    TraceMem tm;
+    tm.gNodes = nullptr; tm.sNodes = nullptr; tm.stageNodes = 0;
+    tm.sTris = sTris; tm.stageTris = sc.stageTris; tm.stack = nullptr; tm.stride = 0;
+#ifdef B2_FAST_TRI
+    tm.gTris = sc.triPlane;
+#else
+    tm.gTris = sc.triAccel;
+#endif
+    return tm;
+}
+
+template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK, 4) k_extend_flat(DScene sc, DPool pool, DRender rp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
+    stampBegin(rp, it, STAGE_EXTEND);
+    const TraceMem tm = setupFlatLeaf(sc, smem);
+    const uint32_t Q = pool.capacity;
+    uint32_t nRays = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t flN = 0;
+    float4 roN = make_float4(0, 0, 0, 0), rdN = roN;
+    if (i < Q) { flN = pool.flags[i]; roN = pool.ray[2 * (size_t) i]; rdN = pool.ray[2 * (size_t) i + 1]; }
+    for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += stride, i += stride) {
+        const uint32_t fl = flN;
+        const float4 ro = roN;
+        float4 rd = rdN;
+        const uint32_t iN = i + stride;
+        if (iN < Q) { flN = pool.flags[iN]; roN = pool.ray[2 * (size_t) iN]; rdN = pool.ray[2 * (size_t) iN + 1]; } else flN = 0;
+        const bool live = i < Q && (fl & PF_ALIVE) != 0;
+        int cls = -1;
+        if (live) {
+            if (!(fl & PF_FRESH)) rd.w = B2_INF; // w carries the pending BSDF pdf for non-camera rays; their maxt is +inf (ray.h:66-68)
+            const V3 o(ro.x, ro.y, ro.z), d(rd.x, rd.y, rd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // ray.h:83-84
+            HitRec h;
+            h.t = B2_INF; h.u = 0; h.v = 0; h.prim = 0xFFFFFFFFu;
+            float mint, maxt;
+            uint32_t pt = 0;
+            if (clipRay<false>(sc, o, d, dRcp, (fl & PF_FRESH) ? ro.w : B2_EPSILON, rd.w, mint, maxt))
+                if (!traverseFlat<false, false>(sc, tm, o, d, mint, maxt, h, pt)) { h.t = B2_INF; h.prim = 0xFFFFFFFFu; }
+            pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            ++nRays;
+            if (SORT) {
+                cls = (int) sc.missClass;
+                if (h.prim != 0xFFFFFFFFu) cls = sc.materials[__float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w))].type;
+            }
+        }
+        if (SORT) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t at = warpAppend(cls == c, pool.counters + CTR_CLASS0 + c);
+                if (cls == c) pool.matQueue[(size_t) c * Q + at] = i;
+            }
+        }
+    }
+    nRays = warpSum(nRays);
+    if ((threadIdx.x & 31) == 0 && nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
+    stampEnd(rp, it, STAGE_EXTEND);
+}
+
+__global__ void __launch_bounds__(B2_TRACE_BLOCK, 4) k_occluded_flat(DScene sc, DPool pool, DRender rp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
+    stampBegin(rp, it, STAGE_OCCLUDED);
+    const TraceMem tm = setupFlatLeaf(sc, smem);
+    const uint32_t n = (uint32_t) pool.counters[CTR_SHADOW];
+    uint32_t nClear = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 roN = make_float4(0, 0, 0, 0), sdN = roN, scN = roN;
+    if (j < n) { roN = pool.shO[j]; sdN = pool.shD[j]; scN = pool.shC[j]; }
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride, j += stride) {
+        const float4 ro = roN, sd = sdN, scn = scN;
+        const uint32_t jN = j + stride;
+        if (jN < n) { roN = pool.shO[jN]; sdN = pool.shD[jN]; scN = pool.shC[jN]; }
+        if (j < n) {
+            const V3 o(ro.x, ro.y, ro.z), d(sd.x, sd.y, sd.z);
+            const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            float mint, maxt;
+            bool occluded = false;
+            HitRec h;
+            uint32_t pt = 0;
+            if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt)) occluded = traverseFlat<true, false>(sc, tm, o, d, mint, maxt, h, pt);
+            if (!occluded) { // Li += value * bsdfVal * weight (path.cpp:197): reduction at L2, no read of the slot
+                redAddV4(&pool.st[2 * (size_t) __float_as_uint(scn.w) + 1], scn.x, scn.y, scn.z, 0.0f);
+                ++nClear;
+            }
+        }
+    }
+    nClear = warpSum(nClear);
+    if ((threadIdx.x & 31) == 0 && nClear) atomicAdd(pool.counters + CTR_UNOCCLUDED, (unsigned long long) nClear);
+    stampEnd(rp, it, STAGE_OCCLUDED);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -758,32 +887,82 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
 // ------------------------------------------------------------------------------------------------
 // k_shade
 // ------------------------------------------------------------------------------------------------
-// resident CTAs per SM the register allocator must leave room for (6 x 128 threads -> <= 85 registers; measured best)
+// resident CTAs per SM the register allocator must leave room for.  Measured on B200 (round 2, Cornell 1024^2 @ 1024 spp, ms of k_shade
+// per step): 4 -> 303, 5 -> 277, 6 -> 289, 8 -> 328.  5 x 128 threads leaves 102 registers: no spills, 20 warps per SM.
 #ifndef B2_SHADE_MINBLOCKS
-#define B2_SHADE_MINBLOCKS 6
+#define B2_SHADE_MINBLOCKS 5
 #endif
-// FLAT: the shadow ray and the next ray are cast inline against the shared-memory resident triangle list (tiny scenes):
-// no shadow queue, no k_extend / k_occluded launches, no ray / shadow records through HBM.
-template <int CLS, bool FLAT, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MINBLOCKS) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
+// B2_STAGE_SHADE (A/B switch, off): stage the five records every item needs (flags, hit, ray direction + pdf, throughput + eta, sampler
+// state: 60 bytes) one loop iteration ahead with cp.async.  Measured on B200 (Cornell 1024^2 @ 1024 spp): 8 % SLOWER -- the kernel is
+// bound by the dependent chain of the shading body at 6 warps per scheduler, not by these loads; an LDGSTS costs 8 issue cycles.
+template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_BLOCK, B2_SHADE_MINBLOCKS) k_shade(DScene sc, DPool pool, DRender rp, const uint32_t *queue,
                                                                              const unsigned long long *queueCount) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    TraceMem tm;
-    if (FLAT) tm = setupFlatMem(sc, smem);
-    uint32_t nRays = 0, nClear = 0;
+#ifdef B2_STAGE_SHADE
+    __shared__ __align__(16) float4 sHit[2][B2_SHADE_BLOCK], sRd[2][B2_SHADE_BLOCK], sThr[2][B2_SHADE_BLOCK];
+    __shared__ __align__(8) uint2 sSmp[2][B2_SHADE_BLOCK];
+    __shared__ uint32_t sState[2][B2_SHADE_BLOCK];
+#endif
     const uint32_t Q = pool.capacity;
     const uint32_t n = queue ? (uint32_t) *queueCount : Q;
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
     stampBegin(rp, it, STAGE_SHADE);
     uint32_t nDimOvf = 0, nShadowRef = 0, nDone = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t stride = gridDim.x * blockDim.x, tid = threadIdx.x;
+    // queue appends in flight (see the end of the loop body): ballots of the lanes that append, queue bases (lane 0), parked records
+    __shared__ __align__(16) float4 sShO[B2_SHADE_BLOCK], sShD[B2_SHADE_BLOCK], sShC[B2_SHADE_BLOCK];
+    __shared__ uint32_t sDoneSlot[B2_SHADE_BLOCK];
+    uint32_t pendA = 0, pendB = 0, baseA = 0, baseB = 0;
+    auto flushPending = [&]() {
+        if ((pendA | pendB) == 0) return; // warp-uniform
+        const uint32_t lane = tid & 31u, below = (1u << lane) - 1u;
+        const uint32_t bA = __shfl_sync(0xffffffffu, baseA, 0), bB = __shfl_sync(0xffffffffu, baseB, 0);
+        if ((pendA >> lane) & 1u) pool.doneQueue[(size_t) (it & 1u) * Q + bA + __popc(pendA & below)] = sDoneSlot[tid];
+        if ((pendB >> lane) & 1u) {
+            const uint32_t at = bB + __popc(pendB & below);
+            pool.shO[at] = sShO[tid]; pool.shD[at] = sShD[tid]; pool.shC[at] = sShC[tid];
+        }
+        pendA = pendB = 0;
+    };
+#ifdef B2_STAGE_SHADE
+    auto slotOf = [&](uint32_t j) -> uint32_t { return j < n ? (queue ? __ldg(queue + j) : j) : 0u; };
+    auto stage = [&](int buf, uint32_t j, uint32_t i) {
+        if (j < n) {
+            cpAsync4(&sState[buf][tid], &pool.flags[i]);
+            cpAsync16(&sHit[buf][tid], &pool.hit[i]);
+            cpAsync16(&sRd[buf][tid], &pool.ray[2 * (size_t) i + 1]);
+            cpAsync16(&sThr[buf][tid], &pool.st[2 * (size_t) i]);
+            cpAsync8(&sSmp[buf][tid], &pool.smp[i]);
+        }
+        cpAsyncCommit();
+    };
+    uint32_t iCur = slotOf(blockIdx.x * blockDim.x + tid), iNext = slotOf(blockIdx.x * blockDim.x + tid + stride);
+    stage(0, blockIdx.x * blockDim.x + tid, iCur);
+    int buf = 0;
+#endif
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
         const uint32_t j = base + threadIdx.x;
-        uint32_t i = 0;
         bool live = j < n;
-        if (live) i = queue ? queue[j] : j;
-        // all loads of the slot are issued together (memory-level parallelism); Li is fetched only when it changes
         uint32_t state = 0;
         float4 hit = make_float4(0, 0, 0, 0), rd4 = hit, thr4 = hit;
         uint2 sm2 = make_uint2(0, 0);
+#ifdef B2_STAGE_SHADE
+        const uint32_t i = iCur;
+        stage(buf ^ 1, j + stride, iNext);
+        iCur = iNext;
+        iNext = slotOf(j + 2 * stride);
+        cpAsyncWait<1>();
+        if (live) {
+            state = sState[buf][tid];
+            hit = sHit[buf][tid];
+            rd4 = sRd[buf][tid];
+            thr4 = sThr[buf][tid];
+            sm2 = sSmp[buf][tid];
+        }
+        buf ^= 1;
+#else
+        uint32_t i = 0;
+        if (live) i = queue ? queue[j] : j;
+        // all loads of the slot are issued together (memory-level parallelism); Li is never read here (it is updated by reductions)
         if (live) {
             state = pool.flags[i];
             hit = pool.hit[i];
@@ -791,18 +970,19 @@ template <int CLS, bool FLAT, bool TEX = false> __global__ void __launch_bounds_
             thr4 = pool.st[2 * (size_t) i];
             sm2 = pool.smp[i];
         }
+#endif
         uint32_t flags = state & 0xFFu;
         if (!queue) live = live && (flags & PF_ALIVE);
         // shadow-ray output of this lane
         bool emitShadow = false;
-        V3 shD(0.0f);
+        V3 shD(0.0f), shO(0.0f);
         float shMaxt = 0;
         Spectrum shC(0.0f);
         if (live) {
             int depth = (int) ((state >> 8) & 0xFFFu);
             const V3 rayD(rd4.x, rd4.y, rd4.z);
-            Spectrum T(thr4.x, thr4.y, thr4.z), LiAdd(0.0f), LiNee(0.0f); // radiance added by this invocation: emitter hit, then (FLAT) NEE
-            bool liTouched = false, neeTouched = false;
+            Spectrum T(thr4.x, thr4.y, thr4.z), LiAdd(0.0f); // radiance added by this invocation (emitter / environment hit)
+            bool liTouched = false;
             float eta = thr4.w;
             const float bsdfPdfPrev = rd4.w;
             float bsdfPdfOut = 0.0f;
@@ -925,9 +1105,8 @@ template <int CLS, bool FLAT, bool TEX = false> __global__ void __launch_bounds_
                                 shC = T * ds.value * bsdfVal * weight;
                                 shD = ds.d;
                                 shMaxt = ds.dist * (1 - B2_SHADOW_EPSILON);
-                                if (FLAT) { // visibility test of Scene::sampleEmitterDirect (scene.cpp:838-843), inline
-                                    if (!castOccludedFlat(sc, tm, its.p, shD, shMaxt)) { LiNee = shC; neeTouched = true; ++nClear; }
-                                } else emitShadow = true;
+                                shO = its.p;
+                                emitShadow = true; // the visibility test of Scene::sampleEmitterDirect (scene.cpp:838-843) is k_occluded's
                             }
                         }
                     }
@@ -949,23 +1128,12 @@ template <int CLS, bool FLAT, bool TEX = false> __global__ void __launch_bounds_
                         else {
                             if (bRec.sampledType & EDelta) flags |= PF_DELTA;
                             if (dot(wo, refN) >= 0) flags |= PF_REFN_OK;
-                            if (FLAT) { // scene->rayIntersect(ray, its) of path.cpp:226, inline
-                                HitRec h;
-                                castClosestFlat(sc, tm, its.p, wo, B2_EPSILON, B2_INF, h);
-                                pool.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-                                ++nRays;
-                            } else {
-                                pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, isZero(refN) ? 2.0f : dot(wo, refN));
-                            }
+                            pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, isZero(refN) ? 2.0f : dot(wo, refN));
                             pool.ray[2 * (size_t) i + 1] = make_float4(wo.x, wo.y, wo.z, bsdfPdfNew); // w: pdf of this sample (maxt = inf)
                             T = T * bsdfWeight; // :252-253 (applied early: only read again if the next ray hits)
                             eta *= bRec.eta;
                             bsdfPdfOut = bsdfPdfNew;
                         }
-                    }
-                    if (done && emitShadow) {
-                        // the path ends here but its shadow ray still has to be resolved: k_occluded reads the origin from rayO
-                        pool.ray[2 * (size_t) i] = make_float4(its.p.x, its.p.y, its.p.z, B2_EPSILON);
                     }
                 }
             }
@@ -974,40 +1142,37 @@ template <int CLS, bool FLAT, bool TEX = false> __global__ void __launch_bounds_
             if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
             (void) bsdfPdfOut;
             pool.st[2 * (size_t) i] = make_float4(T.x, T.y, T.z, eta);
-            if (liTouched || neeTouched) { // Li += ... (path.cpp:150,197,263), same order as the reference
-                float4 li4 = pool.st[2 * (size_t) i + 1];
-                if (liTouched) { li4.x += LiAdd.x; li4.y += LiAdd.y; li4.z += LiAdd.z; }
-                if (neeTouched) { li4.x += LiNee.x; li4.y += LiNee.y; li4.z += LiNee.z; }
-                pool.st[2 * (size_t) i + 1] = li4;
-            }
+            // Li += ... (path.cpp:150,263): a fire-and-forget reduction at L2 instead of a load / add / store round trip; k_occluded adds
+            // this vertex's direct illumination (path.cpp:197) with the same instruction afterwards, i.e. in the reference's order
+            if (liTouched) redAddV4(&pool.st[2 * (size_t) i + 1], LiAdd.x, LiAdd.y, LiAdd.z, 0.0f);
             state = flags | ((uint32_t) depth << 8) | (smp.dim << 20);
             pool.flags[i] = state;
         }
-        // finished paths: queue the slot for the next k_generate (splat + refill); shadow-ray compaction.
-        // Warp ballot, one atomic per warp and queue, both in flight together.
+        // finished paths: queue the slot for the next k_generate (splat + refill); shadow-ray compaction.  Warp ballot, one atomic per
+        // warp and queue.  The atomics' results are NOT consumed here: the records are parked in shared memory and written out at the
+        // end of the next loop iteration, when the queue positions have long arrived (ncu, round 2: 20 % of this kernel's stall samples
+        // sat on the two shuffles that broadcast the freshly returned atomic).
         const bool fin = live && (state & PF_DONE);
-        uint32_t dq, at;
-        warpAppend2(fin, pool.counters + ((it & 1u) ? CTR_DONE1 : CTR_DONE0), emitShadow, pool.counters + CTR_SHADOW, dq, at);
-        if (fin) {
-            pool.doneQueue[(size_t) (it & 1u) * Q + dq] = i;
-            ++nDone;
+        flushPending();
+        pendA = __ballot_sync(0xffffffffu, fin); pendB = __ballot_sync(0xffffffffu, emitShadow);
+        if ((tid & 31) == 0) { // (inline PTX: nvcc turns atomicAdd into elect + ATOMG + SHFL, and that shuffle would wait for the result here)
+            if (pendA) baseA = atomAddPending(pool.counters + ((it & 1u) ? CTR_DONE1 : CTR_DONE0), (uint32_t) __popc(pendA));
+            if (pendB) baseB = atomAddPending(pool.counters + CTR_SHADOW, (uint32_t) __popc(pendB));
         }
-        if (emitShadow) {
-            pool.shD[at] = make_float4(shD.x, shD.y, shD.z, shMaxt);
-            pool.shC[at] = make_float4(shC.x, shC.y, shC.z, __uint_as_float(i));
+        if (fin) { sDoneSlot[tid] = i; ++nDone; }
+        if (emitShadow) { // 48-byte shadow record: origin, direction + maxt, contribution + slot (k_occluded touches nothing else)
+            sShO[tid] = make_float4(shO.x, shO.y, shO.z, 0.0f);
+            sShD[tid] = make_float4(shD.x, shD.y, shD.z, shMaxt);
+            sShC[tid] = make_float4(shC.x, shC.y, shC.z, __uint_as_float(i));
         }
     }
+    flushPending();
+#ifdef B2_STAGE_SHADE
+    cpAsyncWait<0>();
+#endif
     nDimOvf = warpSum(nDimOvf);
     nShadowRef = warpSum(nShadowRef);
     nDone = warpSum(nDone);
-    if (FLAT) {
-        nRays = warpSum(nRays);
-        nClear = warpSum(nClear);
-        if ((threadIdx.x & 31) == 0) {
-            if (nRays) atomicAdd(pool.counters + CTR_RAYS, (unsigned long long) nRays);
-            if (nClear) atomicAdd(pool.counters + CTR_UNOCCLUDED, (unsigned long long) nClear);
-        }
-    }
     if ((threadIdx.x & 31) == 0) {
         if (nDone) atomicAdd(pool.counters + CTR_ACTIVE, ~(unsigned long long) nDone + 1ull); // -= nDone
         if (nDimOvf) atomicAdd(pool.counters + CTR_DIMOVF, (unsigned long long) nDimOvf);
@@ -1030,19 +1195,15 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
         uint32_t nv = 0, pt = 0;
         float4 cur = make_float4(0, 0, 0, 0); // contribution + slot of the ray this lane is tracing
         auto fetch = [&](uint32_t j, V3 &o, V3 &d, float &mint, float &maxt) -> int {
-            const float4 sd = pool.shD[j];
+            const float4 ro = pool.shO[j], sd = pool.shD[j];
             cur = pool.shC[j];
-            const float4 ro = pool.ray[2 * (size_t) __float_as_uint(cur.w)];
             o = V3(ro.x, ro.y, ro.z); d = V3(sd.x, sd.y, sd.z);
             const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             return clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt) ? 2 : 1;
         };
         auto commit = [&](uint32_t, bool found, const HitRec &) {
-            if (!found) {
-                const uint32_t slot = __float_as_uint(cur.w);
-                float4 li = pool.st[2 * (size_t) slot + 1];
-                li.x += cur.x; li.y += cur.y; li.z += cur.z;
-                pool.st[2 * (size_t) slot + 1] = li;
+            if (!found) { // Li += value * bsdfVal * weight (path.cpp:197): reduction at L2, no read of the slot
+                redAddV4(&pool.st[2 * (size_t) __float_as_uint(cur.w) + 1], cur.x, cur.y, cur.z, 0.0f);
                 ++nClear;
             }
         };
@@ -1051,9 +1212,8 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
         if (j < n) {
-            const float4 sd = pool.shD[j], scn = pool.shC[j];
+            const float4 ro = pool.shO[j], sd = pool.shD[j], scn = pool.shC[j];
             const uint32_t slot = __float_as_uint(scn.w);
-            const float4 ro = pool.ray[2 * (size_t) slot];
             const V3 o(ro.x, ro.y, ro.z), d(sd.x, sd.y, sd.z);
             const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             float mint, maxt;
@@ -1064,9 +1224,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
             if (clipRay<true>(sc, o, d, dRcp, B2_EPSILON, sd.w, mint, maxt))
                 occluded = sc.nItems ? traverseTop<true, false>(sc, tm, o, d, mint, maxt, h, item, nv, pt) : traverse<true, false>(sc, tm, o, d, mint, maxt, h, nv, pt);
             if (!occluded) {
-                float4 li = pool.st[2 * (size_t) slot + 1];
-                li.x += scn.x; li.y += scn.y; li.z += scn.z;
-                pool.st[2 * (size_t) slot + 1] = li;
+                redAddV4(&pool.st[2 * (size_t) slot + 1], scn.x, scn.y, scn.z, 0.0f);
                 ++nClear;
             }
         }
@@ -1892,7 +2050,7 @@ __global__ void k_splat(DFilter f, int W, int H, uint64_t n, const float *pos, c
 static size_t traceSmemBytes(const DScene &sc, int block) {
     size_t off = (size_t) B2_STACK_DEPTH * block * sizeof(uint32_t);
     off = (off + 127) & ~(size_t) 127;
-    off += (size_t) sc.stageNodes * 64 + (size_t) sc.stageTris * 48;
+    off += (size_t) sc.stageNodes * 64 + (size_t) sc.stageTriBytes;
     off = (off + 15) & ~(size_t) 15;
     return off + 16;
 }
@@ -1922,6 +2080,12 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     setSmemAttr((const void *) k_trace_rays<true, false>, cfg.traceSmem);
     setSmemAttr((const void *) k_trace_rays<false, true>, cfg.traceSmem);
     setSmemAttr((const void *) k_trace_rays<true, true>, cfg.traceSmem);
+    cfg.flatSmem = (((size_t) sc.stageTriBytes + 15) & ~(size_t) 15) + 16;
+    if (sc.rootCount) {
+        cfg.gridExtendFlat = occupancyGrid(k_extend_flat<false>, B2_TRACE_BLOCK, cfg.flatSmem, numSMs);
+        cfg.gridExtendFlatSort = occupancyGrid(k_extend_flat<true>, B2_TRACE_BLOCK, cfg.flatSmem, numSMs);
+        cfg.gridOccludedFlat = occupancyGrid(k_occluded_flat, B2_TRACE_BLOCK, cfg.flatSmem, numSMs);
+    }
     cfg.gridExtend = occupancyGrid(k_extend<false>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridExtendSort = occupancyGrid(k_extend<true>, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.gridOccluded = occupancyGrid(k_occluded, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
@@ -1931,64 +2095,45 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     setSmemAttr((const void *) k_volstep_lockstep, cfg.traceSmem);
     cfg.gridVolLockstep = occupancyGrid(k_volstep_lockstep, B2_TRACE_BLOCK, cfg.traceSmem, numSMs);
     cfg.volLockstep = getenv("B2_VOL_LOCKSTEP") ? atoi(getenv("B2_VOL_LOCKSTEP")) : 1; // measured: 127 vs 95 Msamples/s (smoke 128^3, 512^2 @ 256 spp)
-    cfg.flatSmem = (((size_t) sc.stageTris * 48 + 15) & ~(size_t) 15) + 16;
-    cfg.gridGenerate = occupancyGrid(k_generate<false>, 256, 0, numSMs);
-    cfg.gridShade[0] = occupancyGrid(k_shade<0, false>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[1] = occupancyGrid(k_shade<1, false>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[2] = occupancyGrid(k_shade<2, false>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[3] = occupancyGrid(k_shade<3, false>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShade[4] = occupancyGrid(k_shade<-1, false>, B2_SHADE_BLOCK, 0, numSMs);
-    cfg.gridShadeTex[0] = occupancyGrid(k_shade<-1, false, true>, B2_SHADE_BLOCK, 0, numSMs);
-    if (sc.rootCount) { // fused variants for shared-memory resident scenes
-        cfg.gridGenerateFlat = occupancyGrid(k_generate<true>, 256, cfg.flatSmem, numSMs);
-        cfg.gridShadeFlat[0] = occupancyGrid(k_shade<0, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
-        cfg.gridShadeFlat[1] = occupancyGrid(k_shade<1, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
-        cfg.gridShadeFlat[2] = occupancyGrid(k_shade<2, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
-        cfg.gridShadeFlat[3] = occupancyGrid(k_shade<3, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
-        cfg.gridShadeFlat[4] = occupancyGrid(k_shade<-1, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
-        cfg.gridShadeTex[1] = occupancyGrid(k_shade<-1, true, true>, B2_SHADE_BLOCK, cfg.flatSmem, numSMs);
-    }
+    cfg.gridGenerate = occupancyGrid(k_generate, B2_GEN_BLOCK, 0, numSMs);
+    cfg.gridShade[0] = occupancyGrid(k_shade<0>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[1] = occupancyGrid(k_shade<1>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[2] = occupancyGrid(k_shade<2>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[3] = occupancyGrid(k_shade<3>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShade[4] = occupancyGrid(k_shade<-1>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShadeTex = occupancyGrid(k_shade<-1, true>, B2_SHADE_BLOCK, 0, numSMs);
 }
 
-void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, bool flat, cudaStream_t st) {
-    if (flat) k_generate<true><<<cfg.gridGenerateFlat, 256, cfg.flatSmem, st>>>(sc, pool, rp, f);
-    else k_generate<false><<<cfg.gridGenerate, 256, 0, st>>>(sc, pool, rp, f);
+void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, cudaStream_t st) {
+    k_generate<<<cfg.gridGenerate, B2_GEN_BLOCK, 0, st>>>(sc, pool, rp, f);
     k_publish<<<1, 32, 0, st>>>(pool, rp);
 }
 void launch_extend(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, bool sort, cudaStream_t st) {
+    if (sc.rootCount) {
+        if (sort) k_extend_flat<true><<<cfg.gridExtendFlatSort, B2_TRACE_BLOCK, cfg.flatSmem, st>>>(sc, pool, rp);
+        else k_extend_flat<false><<<cfg.gridExtendFlat, B2_TRACE_BLOCK, cfg.flatSmem, st>>>(sc, pool, rp);
+        return;
+    }
     if (sort) k_extend<true><<<cfg.gridExtendSort, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
     else k_extend<false><<<cfg.gridExtend, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
-void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, int cls, bool queued, bool flat, cudaStream_t st) {
+void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, int cls, bool queued, cudaStream_t st) {
     const uint32_t *q = queued ? pool.matQueue + (size_t) cls * pool.capacity : nullptr;
     const unsigned long long *qc = queued ? pool.counters + CTR_CLASS0 + cls : nullptr;
-    if (flat) {
-        const size_t sm = cfg.flatSmem;
-        switch (cls) {
-            case 0: k_shade<0, true><<<cfg.gridShadeFlat[0], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
-            case 1: k_shade<1, true><<<cfg.gridShadeFlat[1], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
-            case 2: k_shade<2, true><<<cfg.gridShadeFlat[2], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
-            case 3: k_shade<3, true><<<cfg.gridShadeFlat[3], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, q, qc); break;
-            default:
-                if (sc.nTextures) k_shade<-1, true, true><<<cfg.gridShadeTex[1], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, nullptr, nullptr);
-                else k_shade<-1, true><<<cfg.gridShadeFlat[4], B2_SHADE_BLOCK, sm, st>>>(sc, pool, rp, nullptr, nullptr);
-                break;
-        }
-        return;
-    }
     switch (cls) {
-        case 0: k_shade<0, false><<<cfg.gridShade[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        case 1: k_shade<1, false><<<cfg.gridShade[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        case 2: k_shade<2, false><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
-        case 3: k_shade<3, false><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 0: k_shade<0><<<cfg.gridShade[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 1: k_shade<1><<<cfg.gridShade[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 2: k_shade<2><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        case 3: k_shade<3><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         default:
-            if (sc.nTextures) k_shade<-1, false, true><<<cfg.gridShadeTex[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
-            else k_shade<-1, false><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
+            if (sc.nTextures) k_shade<-1, true><<<cfg.gridShadeTex, B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
+            else k_shade<-1><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
             break;
     }
 }
 void launch_occluded(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {
-    k_occluded<<<cfg.gridOccluded, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
+    if (sc.rootCount) k_occluded_flat<<<cfg.gridOccludedFlat, B2_TRACE_BLOCK, cfg.flatSmem, st>>>(sc, pool, rp);
+    else k_occluded<<<cfg.gridOccluded, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
 void launch_volstep(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, cudaStream_t st) {
     if (cfg.volLockstep) k_volstep_lockstep<<<cfg.gridVolLockstep, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);

@@ -14,21 +14,18 @@ struct LaunchCfg {
     int gridExtend = 0, gridExtendSort = 0, gridOccluded = 0, gridTrace = 0, gridGenerate = 0, gridVolstep = 0, gridVolLockstep = 0;
     int volLockstep = 1; // B2_VOL_LOCKSTEP=0: the ticketed k_volstep instead of k_volstep_lockstep
     int gridShade[5] = {0, 0, 0, 0, 0};
-    // fused variants for shared-memory resident scenes (rays cast inline by k_generate / k_shade)
+    int gridShadeTex = 0; // k_shade<-1, TEX = true> (textured scenes)
+    // flat-leaf variants (shared-memory resident scenes): k_extend_flat / k_occluded_flat
     size_t flatSmem = 0;
-    int gridGenerateFlat = 0;
-    int gridShadeFlat[5] = {0, 0, 0, 0, 0};
-    int gridShadeTex[2] = {0, 0}; // k_shade<-1, FLAT, TEX = true> (textured scenes): [0] BVH, [1] flat leaf
+    int gridExtendFlat = 0, gridExtendFlatSort = 0, gridOccludedFlat = 0;
 };
 
 #define B2_DECLARE_LAUNCHERS(NS)                                                                                               \
     namespace NS {                                                                                                             \
     void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs);                                                         \
-    void launch_generate(const LaunchCfg &, const DScene &, const DPool &, const DRender &, const DFilter &, bool flat,        \
-                         cudaStream_t);                                                                                        \
+    void launch_generate(const LaunchCfg &, const DScene &, const DPool &, const DRender &, const DFilter &, cudaStream_t);    \
     void launch_extend(const LaunchCfg &, const DScene &, const DPool &, const DRender &, bool sort, cudaStream_t);            \
-    void launch_shade(const LaunchCfg &, const DScene &, const DPool &, const DRender &, int cls, bool queued, bool flat,      \
-                      cudaStream_t);                                                                                           \
+    void launch_shade(const LaunchCfg &, const DScene &, const DPool &, const DRender &, int cls, bool queued, cudaStream_t);  \
     void launch_occluded(const LaunchCfg &, const DScene &, const DPool &, const DRender &, cudaStream_t);                     \
     void launch_volstep(const LaunchCfg &, const DScene &, const DPool &, const DRender &, cudaStream_t);                      \
     void launch_medium_probe(const LaunchCfg &, const DScene &, int medium, int what, uint64_t n, const float *in,             \

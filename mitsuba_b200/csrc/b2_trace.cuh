@@ -132,61 +132,116 @@ B2_DEV bool boxHit(float bx0, float by0, float bz0, float bx1, float by1, float 
 #ifdef B2_FAST_TRI
 // Throughput build: the list holds paired records (b2_host.cpp "flat leaf of the throughput build"): a coplanar pair of
 // triangles costs one plane test + one hit point; a parallelogram additionally shares (u, v).
+//
+// Blackwell: a scalar FFMA issues every second cycle per scheduler, the packed FFMA2 (PTX fma.rn.f32x2, one instruction = two
+// FP32 FMAs on a 64-bit register pair) is what reaches the full FP32 rate.  The kernels that run this loop are FP32-issue bound
+// (ncu: 70-77 % issue active), so the leaf is stored TWO RECORDS WIDE: element k of record 2j sits next to element k of record
+// 2j + 1, one packed instruction evaluates both, and the ray is kept duplicated in register pairs.  Odd counts are padded with a
+// record that can never be hit (N = 0, d0 = -1: t = -inf).
+struct F2 { float x, y; };
+B2_DEV unsigned long long f2bits(const F2 &a) { return ((unsigned long long) __float_as_uint(a.y) << 32) | __float_as_uint(a.x); }
+B2_DEV F2 f2from(unsigned long long v) { F2 r; r.x = __uint_as_float((uint32_t) v); r.y = __uint_as_float((uint32_t) (v >> 32)); return r; }
+B2_DEV F2 fma2(const F2 &a, const F2 &b, const F2 &c) {
+    unsigned long long r;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2bits(a)), "l"(f2bits(b)), "l"(f2bits(c)));
+    return f2from(r);
+}
+B2_DEV F2 mul2(const F2 &a, const F2 &b) {
+    unsigned long long r;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2bits(a)), "l"(f2bits(b)));
+    return f2from(r);
+}
+B2_DEV F2 sub2(const F2 &a, const F2 &b) {
+    unsigned long long r;
+    asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2bits(a)), "l"(f2bits(b)));
+    return f2from(r);
+}
+B2_DEV F2 lo2(const float4 &v) { F2 r; r.x = v.x; r.y = v.y; return r; }
+B2_DEV F2 hi2(const float4 &v) { F2 r; r.x = v.z; r.y = v.w; return r; }
+B2_DEV F2 dup2(float v) { F2 r; r.x = v; r.y = v; return r; }
+
+struct FlatRay2 { F2 ox, oy, oz, dx, dy, dz; };
+// plane test of two records: rows r0 = (Nx, Nx', Ny, Ny'), r1 = (Nz, Nz', d0, d0') -> t of both, hit point of both
+B2_DEV void flatPlane2(const FlatRay2 &r, const float4 &r0, const float4 &r1, F2 &t, F2 &px, F2 &py, F2 &pz) {
+    F2 den = mul2(lo2(r0), r.dx); den = fma2(hi2(r0), r.dy, den); den = fma2(lo2(r1), r.dz, den);
+    F2 nd = mul2(lo2(r0), r.ox); nd = fma2(hi2(r0), r.oy, nd); nd = fma2(lo2(r1), r.oz, nd);
+    const F2 num = sub2(hi2(r1), nd);
+    t.x = __fdividef(num.x, den.x); t.y = __fdividef(num.y, den.y);
+    px = fma2(t, r.dx, r.ox); py = fma2(t, r.dy, r.oy); pz = fma2(t, r.dz, r.oz);
+}
+// one barycentric of two records: rows a = (Ux, Ux', Uy, Uy'), b = (Uz, Uz', du, du')
+B2_DEV F2 flatCoord2(const float4 &a, const float4 &b, const F2 &px, const F2 &py, const F2 &pz) {
+    F2 u = fma2(lo2(a), px, hi2(b)); u = fma2(hi2(a), py, u); u = fma2(lo2(b), pz, u);
+    return u;
+}
+
 template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, const TraceMem &tm, const V3 &o, const V3 &d, float mint, float maxt,
                                                              HitRec &hit, uint32_t &primTests) {
-    const uint32_t nP = sc.flatP, nC = sc.flatC, nS = sc.flatS;
+    // record numbering (index into flatIdx): parallelograms [0, 2 nP2), coplanar pairs [2 nP2, 2 nP2 + 2 nC2), singles behind them
+    const uint32_t nP2 = sc.flatP, nC2 = sc.flatC, nS2 = sc.flatS; // packed steps (two records each)
     int best = -1;
     bool second = false;
+    FlatRay2 r;
+    r.ox = dup2(o.x); r.oy = dup2(o.y); r.oz = dup2(o.z); r.dx = dup2(d.x); r.dy = dup2(d.y); r.dz = dup2(d.z);
     const float4 *p = tm.sTris;
-#pragma unroll 4
-    for (uint32_t i = 0; i < nP; ++i, p += 3) {
-        const float4 q0 = p[0], q1 = p[1], q2 = p[2];
-        const float den = q0.x * d.x + q0.y * d.y + q0.z * d.z;
-        const float num = q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z);
-        const float t = __fdividef(num, den);
-        const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
-        const float u = q1.x * px + q1.y * py + q1.z * pz + q1.w;
-        const float v = q2.x * px + q2.y * py + q2.z * pz + q2.w;
-        if ((t >= mint) & (t <= maxt) & (u >= 0.0f) & (v >= 0.0f) & (u <= 1.0f) & (v <= 1.0f)) {
+#pragma unroll 2
+    for (uint32_t i = 0; i < nP2; ++i, p += 6) {
+        F2 t, px, py, pz;
+        flatPlane2(r, p[0], p[1], t, px, py, pz);
+        const F2 u = flatCoord2(p[2], p[3], px, py, pz), v = flatCoord2(p[4], p[5], px, py, pz);
+        if ((t.x >= mint) & (t.x <= maxt) & (u.x >= 0.0f) & (v.x >= 0.0f) & (u.x <= 1.0f) & (v.x <= 1.0f)) {
             if (SHADOW) return true;
-            hit.t = t; hit.u = u; hit.v = v; best = (int) i;
-            maxt = t;
+            hit.t = t.x; hit.u = u.x; hit.v = v.x; best = (int) (2 * i);
+            maxt = t.x;
+        }
+        if ((t.y >= mint) & (t.y <= maxt) & (u.y >= 0.0f) & (v.y >= 0.0f) & (u.y <= 1.0f) & (v.y <= 1.0f)) {
+            if (SHADOW) return true;
+            hit.t = t.y; hit.u = u.y; hit.v = v.y; best = (int) (2 * i + 1);
+            maxt = t.y;
         }
     }
-#pragma unroll 2
-    for (uint32_t i = 0; i < nC; ++i, p += 5) {
-        const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4];
-        const float den = q0.x * d.x + q0.y * d.y + q0.z * d.z;
-        const float num = q0.w - (q0.x * o.x + q0.y * o.y + q0.z * o.z);
-        const float t = __fdividef(num, den);
-        const float px = o.x + t * d.x, py = o.y + t * d.y, pz = o.z + t * d.z;
-        const float uA = q1.x * px + q1.y * py + q1.z * pz + q1.w;
-        const float vA = q2.x * px + q2.y * py + q2.z * pz + q2.w;
-        const float uB = q3.x * px + q3.y * py + q3.z * pz + q3.w;
-        const float vB = q4.x * px + q4.y * py + q4.z * pz + q4.w;
-        const bool hA = (uA >= 0.0f) & (vA >= 0.0f) & (uA + vA <= 1.0f);
-        const bool hB = (uB >= 0.0f) & (vB >= 0.0f) & (uB + vB <= 1.0f);
-        if ((t >= mint) & (t <= maxt) & (hA | hB)) {
-            if (SHADOW) return true;
-            hit.t = t; hit.u = hB ? uB : uA; hit.v = hB ? vB : vA; best = (int) (nP + i); second = hB;
-            maxt = t;
+    for (uint32_t i = 0; i < nC2; ++i, p += 10) {
+        F2 t, px, py, pz;
+        flatPlane2(r, p[0], p[1], t, px, py, pz);
+        const F2 uA = flatCoord2(p[2], p[3], px, py, pz), vA = flatCoord2(p[4], p[5], px, py, pz);
+        const F2 uB = flatCoord2(p[6], p[7], px, py, pz), vB = flatCoord2(p[8], p[9], px, py, pz);
+        {
+            const bool hA = (uA.x >= 0.0f) & (vA.x >= 0.0f) & (uA.x + vA.x <= 1.0f), hB = (uB.x >= 0.0f) & (vB.x >= 0.0f) & (uB.x + vB.x <= 1.0f);
+            if ((t.x >= mint) & (t.x <= maxt) & (hA | hB)) {
+                if (SHADOW) return true;
+                hit.t = t.x; hit.u = hB ? uB.x : uA.x; hit.v = hB ? vB.x : vA.x; best = (int) (2 * (nP2 + i)); second = hB;
+                maxt = t.x;
+            }
+        }
+        {
+            const bool hA = (uA.y >= 0.0f) & (vA.y >= 0.0f) & (uA.y + vA.y <= 1.0f), hB = (uB.y >= 0.0f) & (vB.y >= 0.0f) & (uB.y + vB.y <= 1.0f);
+            if ((t.y >= mint) & (t.y <= maxt) & (hA | hB)) {
+                if (SHADOW) return true;
+                hit.t = t.y; hit.u = hB ? uB.y : uA.y; hit.v = hB ? vB.y : vA.y; best = (int) (2 * (nP2 + i) + 1); second = hB;
+                maxt = t.y;
+            }
         }
     }
-#pragma unroll 2
-    for (uint32_t i = 0; i < nS; ++i, p += 3) {
-        const float4 q0 = p[0], q1 = p[1], q2 = p[2];
-        float tu, tv, tt;
-        if (triPlaneIntersect(q0, q1, q2, o, d, mint, maxt, tu, tv, tt)) {
+    for (uint32_t i = 0; i < nS2; ++i, p += 6) {
+        F2 t, px, py, pz;
+        flatPlane2(r, p[0], p[1], t, px, py, pz);
+        const F2 u = flatCoord2(p[2], p[3], px, py, pz), v = flatCoord2(p[4], p[5], px, py, pz);
+        if ((t.x >= mint) & (t.x <= maxt) & (u.x >= 0.0f) & (v.x >= 0.0f) & (u.x + v.x <= 1.0f)) {
             if (SHADOW) return true;
-            hit.t = tt; hit.u = tu; hit.v = tv; best = (int) (nP + nC + i); second = false;
-            maxt = tt;
+            hit.t = t.x; hit.u = u.x; hit.v = v.x; best = (int) (2 * (nP2 + nC2 + i)); second = false;
+            maxt = t.x;
+        }
+        if ((t.y >= mint) & (t.y <= maxt) & (u.y >= 0.0f) & (v.y >= 0.0f) & (u.y + v.y <= 1.0f)) {
+            if (SHADOW) return true;
+            hit.t = t.y; hit.u = u.y; hit.v = v.y; best = (int) (2 * (nP2 + nC2 + i) + 1); second = false;
+            maxt = t.y;
         }
     }
     if (COUNT) primTests += sc.rootCount;
     if (best < 0) return false;
     const uint2 id = __ldg(sc.flatIdx + best);
     uint32_t leaf = id.x;
-    if ((uint32_t) best < nP) {
+    if ((uint32_t) best < 2 * nP2) {
         // the record's frame starts at the unshared corner of the first triangle: pick the half, then evaluate that
         // triangle's own barycentrics at the hit point
         if (hit.u + hit.v > 1.0f) leaf = id.y;

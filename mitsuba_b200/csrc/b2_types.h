@@ -103,8 +103,9 @@ struct DScene {
     // (t = (d0 - N.o) / N.d, u = U.P + du, v = V.P + dv); leafPrim maps the leaf-ordered index to the prim id
     const float4 *triPlane;
     const uint32_t *leafPrim;
-    // throughput build, flat leaf only: flatP parallelogram records (3 rows), flatC coplanar pairs (5 rows), flatS single
-    // triangles (3 rows), in this order; flatIdx[r] = leaf indices of the record's first / second triangle
+    // throughput build, flat leaf only: paired records stored TWO WIDE for the packed FP32 instructions (b2_trace.cuh traverseFlat):
+    // flatP steps of two parallelograms (6 rows), flatC steps of two coplanar pairs (10 rows), flatS steps of two single triangles
+    // (6 rows), in this order; flatIdx[r] = leaf indices of record r's first / second triangle
     const float4 *flatRec;
     const uint2 *flatIdx;
     uint32_t flatP, flatC, flatS, flatBytes;
@@ -148,6 +149,7 @@ struct DScene {
     const uint32_t *sobolNib;  // [1024][13][16]: XOR of the 4 columns of nibble p selected by v (b2_host.cpp: buildSobolNibbles)
     // staging limits for shared memory (number of leading BVH nodes / TriAccel records copied by TMA)
     uint32_t stageNodes, stageTris;
+    uint32_t stageTriBytes;    // shared memory reserved for the staged triangles: max(stageTris * 48, flatBytes) (the two-wide flat leaf pads odd counts)
     uint32_t leafVote;         // persistent traversal: run the leaf code once this many lanes wait at a leaf (B2_LEAFVOTE, default 8)
     uint32_t missClass;        // material-sorted dispatch: the class queue that takes rays which left the scene (first class present)
     uint32_t refill;           // persistent traversal: refill a warp when at least this many lanes are idle (B2_REFILL, default 16)
@@ -183,7 +185,8 @@ struct DPool {
     uint32_t *flags;   // PF_* | depth << 8 | sampler dimension << 20
     uint32_t *inst;    // instanced scenes only: item index of the hit (0xFFFFFFFF = none)
     uint2 *vol;        // volpath only: (current medium id or -1, sampler dimension); null for `path`
-    // shadow queue (compacted by warp ballot)
+    // shadow queue (compacted by warp ballot): 48-byte records, everything k_occluded needs
+    float4 *shO;       // o.xyz, -
     float4 *shD;       // d.xyz, maxt
     float4 *shC;       // contribution rgb, slot (bits)
     // material-class queues
