@@ -111,13 +111,16 @@ typedef struct b2_render_params {
     int32_t sample_lo, sample_hi; /* this call renders sample indices [lo,hi) of every pixel; hi<=0 -> spp.
                                      Shards the work across GPUs (replaces BlockedImageProcess work units,
                                      src/librender/imageproc.cpp:43-78) */
-    int32_t parity_mode;     /* 1: kernels compiled with -fmad=false (tight float parity); 0: FMA contraction on */
+    int32_t parity_mode;     /* 1: kernels compiled with -fmad=false (tight float parity); 0: throughput kernels (FMA contraction, fast math),
+                                except where flags bit8 explains */
     int32_t pool_size;       /* in-flight paths (0 = default) */
     int32_t film_on_device;  /* 1: `film` of b2_render is a device pointer on the context's device */
     int32_t flags;           /* bit1: force unsorted shading (default: material-sorted when > 1 BSDF class);
                                 bit2: per-launch device time stamps (fills b2_stats.ms_*); bit3: plain launches + CUDA events
                                 instead of the CUDA graph; bit4: fuse the ray casts into generate/shade for tiny scenes (experiment, slower);
-                                bit5: collect per-pixel path diagnostics (b2_get_pixel_stats) */
+                                bit5: collect per-pixel path diagnostics (b2_get_pixel_stats); bit6: per-sample event traces (b2_get_path_traces);
+                                bit8: force the throughput kernels (parity_mode 0 renders `path` scenes that contain a transmissive BSDF with the
+                                IEEE kernels: such scenes amplify ulp-level differences chaotically, DESIGN.md "parity") */
     int32_t integrator;      /* B2_INTEGRATOR_* (<integrator type="path"|"volpath">) */
     int32_t reserved;        /* must be 0 */
 } b2_render_params;
@@ -205,6 +208,9 @@ int b2_get_stats(b2_scene *, b2_stats *);
  * path lengths over the pixel's samples (the per-pixel form of the reference's "average path length" statistic, path.cpp:24,290).
  * Comparing two builds word by word gives the fraction of pixels in which a path changed length. */
 int b2_get_pixel_stats(b2_scene *, uint64_t *out);
+/* Per-sample event traces of the last b2_render with flags bit6 (diagnostics; sobol sampler): out[(y * W + x) * n_samples + s], one event
+ * byte per bounce (material hit, shadow ray emitted, how the vertex ended, reflected / transmitted lobe), see b2_host.cpp. */
+int b2_get_path_traces(b2_scene *, uint64_t n_words, uint64_t *out);
 
 /* ---- component entry points (the reference exposes the same pieces through its Python bindings
  *      and test plugins: ShapeKDTree::rayIntersect src/libpython/render.cpp:352-369, BSDF

@@ -67,7 +67,7 @@ class b2_stats(C.Structure):
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
            "b2_scene_set_camera", "b2_scene_set_crop", "b2_scene_set_thinlens", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_get_pixel_stats", "b2_trace",
+           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_get_pixel_stats", "b2_get_path_traces", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -286,6 +286,12 @@ class Scene:
         """(H, W) uint64 of the last render(flags=32): (sum of squared path lengths << 32) | sum of path lengths per pixel."""
         out = np.zeros((self.H, self.W), np.uint64)
         self._ck(self.L.b2_get_pixel_stats(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def path_traces(self, n_samples):
+        """(H, W, n_samples) uint64 event traces of the last render(flags=64), one byte per bounce (include/b2mts.h)."""
+        out = np.zeros((self.H, self.W, n_samples), np.uint64)
+        self._ck(self.L.b2_get_path_traces(self.h, C.c_uint64(out.size), out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out
 
     def triaccel(self):

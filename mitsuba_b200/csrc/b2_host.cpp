@@ -109,6 +109,7 @@ struct RenderStore {
     unsigned long long *hRing = nullptr, *dRing = nullptr; // mapped pinned progress ring written by k_publish
     DevBuf<unsigned long long> dStampStart, dStampEnd;      // per-launch %globaltimer stamps (flags bit2)
     DevBuf<unsigned long long> dPixStats;                   // per-pixel path-length sums (flags bit5)
+    DevBuf<unsigned long long> dPathTrace;                  // per-sample event traces (flags bit6)
     ~RenderStore() { if (hRing) cudaFreeHost(hRing); }
 };
 
@@ -150,6 +151,7 @@ struct b2_scene {
     DevBuf<float4> dTexc;
     DevBuf<float> dEwaLut;
     bool hasNullBsdf = false;
+    bool hasTransmission = false;  // some BSDF transmits (ETransmission): `path` renders of such scenes use the IEEE kernels (b2_render)
     std::vector<float4> hTriAccelPrimOrder; // for b2_get_triaccel
     LaunchCfg cfgParity, cfgFast;
     bool classPresent[4] = {false, false, false, false};
@@ -930,6 +932,9 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         }
     }
     s->hasNullBsdf = false;
+    s->hasTransmission = false;
+    for (size_t i = 0; i < s->materials.size(); ++i)
+        if (materialFlags(s->materials, (int) i) & 0x55u /* ETransmission incl. ENull */) s->hasTransmission = true;
     for (auto &m : s->meshes) {
         const int t = s->materials[m.material].type;
         if (t >= B2_BSDF_NULL) {
@@ -1290,7 +1295,16 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     DFilter filt;
     rc = makeFilter(ctx, p->rfilter, p->rfilter_param, filt);
     if (rc) return rc;
-    const bool parityMode = p->parity_mode != 0;
+    // Which kernel set renders?  parity_mode 1: the IEEE build (-fmad=false, accurate division / sqrt / sincos, TriAccel).  parity_mode 0: the
+    // throughput build -- EXCEPT for `path` renders of scenes with a transmissive BSDF.  A path that bounces inside a glass ball amplifies
+    // ulp-level differences chaotically: under FMA contraction alone 3e-5 of such paths leave the reference's path (profiles/
+    // r02_flip_trace.json: different hit, other lobe, other ending -- not fast-math, not the plane-form triangle test), each an unrelated
+    // sample of a heavy-tailed estimator, i.e. 1.2e-3 relative L2 at 1024^2 @ 512 spp whatever else the kernels do.  Shading such scenes
+    // with the IEEE kernels and keeping only the traversal fast ("hybrid", tried: exact TriAccel (t,u,v) of the winning triangle) removes
+    // a third of the flips -- the fast traversal still picks the neighbouring triangle at shared edges -- so those scenes get the IEEE
+    // build as a whole; it costs 7 % on BASELINE config 3 (BVH traversal dominates there).  flags bit8 forces the throughput kernels.
+    const bool autoIeee = s->hasTransmission && p->integrator == B2_INTEGRATOR_PATH && !(p->flags & 256);
+    const bool parityMode = p->parity_mode != 0 || autoIeee;
     const LaunchCfg &cfg = parityMode ? s->cfgParity : s->cfgFast;
     uint32_t Q = p->pool_size > 0 ? (uint32_t) p->pool_size : (1u << 22); // 4M paths: measured sweet spot on B200
     Q = std::max<uint32_t>(Q, 1024u);
@@ -1323,6 +1337,13 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         CK(ctx, cudaMemsetAsync(R.dPixStats.p, 0, nPix * sizeof(unsigned long long), st));
         r.pixStats = R.dPixStats.p;
     }
+    if (p->flags & 64) { // per-sample event traces (diagnostics; Sobol' sampler, film resolution > 2): one byte per bounce, eight bounces
+        if (p->sampler != B2_SAMPLER_SOBOL || r.logRes <= 1) return fail(ctx, B2_ERR_INVALID, "path traces (flags bit6) need the sobol sampler and a film larger than 2 pixels");
+        const size_t nTr = nPix * (size_t) (r.sampleHi - r.sampleLo);
+        CK(ctx, R.dPathTrace.alloc(nTr));
+        CK(ctx, cudaMemsetAsync(R.dPathTrace.p, 0, nTr * sizeof(unsigned long long), st));
+        r.pathTrace = R.dPathTrace.p;
+    }
     CK(ctx, cudaMemsetAsync(R.dFilmRGBA.p, 0, nPix * sizeof(float4), st));
     CK(ctx, cudaMemsetAsync(R.dFilmW.p, 0, nPix * sizeof(float), st));
     CK(ctx, cudaMemsetAsync(s->dCounters.p, 0, CTR_COUNT * sizeof(unsigned long long), st));
@@ -1354,29 +1375,29 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     // one iteration = generate (+publish) -> extend -> shade (per material class) -> occluded
     auto enqueueIteration = [&]() {
         launchesPerIter = 0;
-#define ITER(ns)                                                                                               \
+#define ITER(nsS, cfgS, nsT, cfgT) /* nsS: generate + shade (+ volpath); nsT: the ray queries */                                            \
         do {                                                                                                   \
-            tick(0); ns::launch_generate(cfg, s->ds, s->pool, r, filt, st); tick(-1);                   \
+            tick(0); nsS::launch_generate(cfgS, s->ds, s->pool, r, filt, st); tick(-1);                        \
             if (volpath) { /* volpath: every ray of an iteration is cast inline by k_volstep */                 \
-                tick(2); ns::launch_volstep(cfg, s->ds, s->pool, r, st); tick(-1);                             \
+                tick(2); nsS::launch_volstep(cfgS, s->ds, s->pool, r, st); tick(-1);                           \
                 launchesPerIter = 3;                                                                           \
                 break;                                                                                         \
             }                                                                                                  \
-            tick(1); ns::launch_extend(cfg, s->ds, s->pool, r, sorted, st); tick(-1); ++launchesPerIter;        \
+            tick(1); nsT::launch_extend(cfgT, s->ds, s->pool, r, sorted, st); tick(-1); ++launchesPerIter;     \
             tick(2);                                                                                           \
             if (sorted) {                                                                                      \
                 for (int c = 0; c < 4; ++c)                                                                    \
-                    if (s->classPresent[c]) { ns::launch_shade(cfg, s->ds, s->pool, r, c, true, st); ++launchesPerIter; } \
+                    if (s->classPresent[c]) { nsS::launch_shade(cfgS, s->ds, s->pool, r, c, true, st); ++launchesPerIter; } \
             } else {                                                                                           \
-                ns::launch_shade(cfg, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);           \
+                nsS::launch_shade(cfgS, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);         \
                 ++launchesPerIter;                                                                             \
             }                                                                                                  \
             tick(-1);                                                                                          \
-            tick(3); ns::launch_occluded(cfg, s->ds, s->pool, r, st); tick(-1); ++launchesPerIter;              \
+            tick(3); nsT::launch_occluded(cfgT, s->ds, s->pool, r, st); tick(-1); ++launchesPerIter;           \
             launchesPerIter += 2;                                                                              \
         } while (0)
-        if (parityMode) ITER(parity);
-        else ITER(fast);
+        if (parityMode) ITER(parity, s->cfgParity, parity, s->cfgParity);
+        else ITER(fast, s->cfgFast, fast, s->cfgFast);
 #undef ITER
     };
     cudaGraph_t graph = nullptr;
@@ -1503,6 +1524,20 @@ extern "C" int b2_get_pixel_stats(b2_scene *s, uint64_t *out) {
     if (R.dPixStats.n != nPix) return fail(ctx, B2_ERR_INVALID, "b2_get_pixel_stats: the last render did not collect pixel statistics (flags bit5)");
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaMemcpy(out, R.dPixStats.p, nPix * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+// Per-sample event traces of the last b2_render that ran with flags bit6 (diagnostics): out[(y * W + x) * n_samples + s] holds one event
+// byte per bounce k (bits 8k .. 8k+7, k < 8): bits 0-2 material id of the hit (7 = the ray left the scene), bit 3 a shadow ray was emitted,
+// bits 4-5 how the vertex ended (0 continues, 1 Russian roulette, 2 zero BSDF sample / strict normals, 3 depth limit or miss),
+// bit 6 the sampled lobe transmits, bit 7 always set.  Two builds that disagree on a path disagree in its word.
+extern "C" int b2_get_path_traces(b2_scene *s, uint64_t n_words, uint64_t *out) {
+    if (!s || !out) return fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_get_path_traces: null argument");
+    b2_ctx *ctx = s->ctx;
+    RenderStore &R = *ctx->store;
+    std::lock_guard<std::mutex> renderLock(R.renderMutex);
+    if (R.dPathTrace.n != n_words || !n_words) return fail(ctx, B2_ERR_INVALID, "b2_get_path_traces: size does not match the last traced render (flags bit6)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpy(out, R.dPathTrace.p, n_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 extern "C" int b2_cancel(b2_scene *s) {

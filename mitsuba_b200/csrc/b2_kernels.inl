@@ -980,6 +980,9 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
         Spectrum shC(0.0f);
         if (live) {
             int depth = (int) ((state >> 8) & 0xFFFu);
+            const int vertex = (state & PF_FRESH) ? 1 : depth + 1; // (diagnostics) the path vertex this invocation shades
+            uint32_t endKind = 0;
+            bool transmitted = false;
             const V3 rayD(rd4.x, rd4.y, rd4.z);
             Spectrum T(thr4.x, thr4.y, thr4.z), LiAdd(0.0f); // radiance added by this invocation (emitter / environment hit)
             bool liTouched = false;
@@ -1042,7 +1045,7 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
                     // rRec.type = ERadianceNoEmission; Russian roulette :276-286
                     if (depth++ >= rp.rrDepth) {
                         float q = fminf(maxComp(T) * eta * eta, 0.95f);
-                        if (smp.next1D() >= q) done = true;
+                        if (smp.next1D() >= q) { done = true; endKind = 1; }
                         else T = T / q;
                     }
                 }
@@ -1118,13 +1121,14 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
                     float sx, sy;
                     smp.next2D(sx, sy);
                     const Spectrum bsdfWeight = bsdfSample<CLS>(mats, mat, bRec, bsdfPdfNew, sx, sy, smp);
-                    if (isZero(bsdfWeight)) done = true;
+                    if (isZero(bsdfWeight)) { done = true; endKind = 2; }
                     else {
+                        transmitted = (bRec.sampledType & ETransmission) != 0;
                         flags &= ~(PF_DELTA | PF_REFN_OK | PF_FRESH);
                         if (bRec.sampledType != ENull) flags |= PF_SCATTERED;
                         const V3 wo = its.sh.toWorld(bRec.wo);
                         const float woDotGeoN = dot(its.geoN, wo);
-                        if (rp.strictNormals && woDotGeoN * cosTheta(bRec.wo) <= 0) done = true;
+                        if (rp.strictNormals && woDotGeoN * cosTheta(bRec.wo) <= 0) { done = true; endKind = 2; }
                         else {
                             if (bRec.sampledType & EDelta) flags |= PF_DELTA;
                             if (dot(wo, refN) >= 0) flags |= PF_REFN_OK;
@@ -1138,6 +1142,14 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
                 }
             }
             if (smp.overflow) ++nDimOvf;
+            if (done && endKind == 0) endKind = 3;
+            if (rp.pathTrace && vertex >= 1 && vertex <= 8) { // diagnostics: one event byte per bounce (include/b2mts.h)
+                const uint32_t pixel = pool.pix[i];
+                const uint32_t sIdx = (uint32_t) (smp.index >> (2u * rp.logRes)) - (uint32_t) rp.sampleLo; // sobol look_up: index = (sample << 2m) | ...
+                const size_t key = ((size_t) (pixel >> 16) * sc.cam.W + (pixel & 0xFFFFu)) * (size_t) (rp.sampleHi - rp.sampleLo) + sIdx;
+                const uint32_t ev = 0x80u | (valid ? ((uint32_t) its.material & 7u) : 7u) | (emitShadow ? 8u : 0u) | (endKind << 4) | (transmitted ? 0x40u : 0u);
+                rp.pathTrace[key] |= (unsigned long long) ev << (8 * (vertex - 1));
+            }
             flags &= ~PF_FRESH;
             if (done) flags = (flags & ~PF_ALIVE) | PF_DONE;
             (void) bsdfPdfOut;

@@ -27,6 +27,7 @@ struct TraceMem {
 struct HitRec {
     float t, u, v;
     uint32_t prim;
+    uint32_t leaf;   // leaf-ordered index of the triangle (into triAccel / triPlane); valid when prim is
 };
 
 // triaccel.h:96-158
@@ -250,6 +251,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, co
         hit.u = r1.x * px + r1.y * py + r1.z * pz + r1.w;
         hit.v = r2.x * px + r2.y * py + r2.z * pz + r2.w;
     } else if (second) leaf = id.y;
+    hit.leaf = leaf;
     hit.prim = __ldg(sc.leafPrim + leaf);
     return true;
 }
@@ -272,7 +274,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverseFlat(const DScene &sc, co
         }
     }
     if (COUNT) primTests += n;
-    if (found) hit.prim = __ldg(sc.leafPrim + best);
+    if (found) { hit.leaf = best; hit.prim = __ldg(sc.leafPrim + best); }
     return found;
 }
 #endif
@@ -340,7 +342,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverse(const DScene &sc, const 
         --sp;
         ref = (int) tm.stack[sp * stride];
     }
-    if (found) hit.prim = __ldg(sc.leafPrim + best);
+    if (found) { hit.leaf = best; hit.prim = __ldg(sc.leafPrim + best); }
     return found;
 }
 
@@ -438,7 +440,7 @@ template <bool SHADOW, bool COUNT> B2_DEV bool traverseTop(const DScene &sc, con
         --sp;
         ref = (int) tm.stack[sp * stride];
     }
-    if (found) hit.prim = __ldg(sc.leafPrim + best);
+    if (found) { hit.leaf = best; hit.prim = __ldg(sc.leafPrim + best); }
     return found;
 }
 
@@ -472,7 +474,7 @@ B2_DEV void traverseQueue(const DScene &sc, const TraceMem &tm, uint32_t n, unsi
         const unsigned idle = __ballot_sync(FULL, !active);
         if (idle == FULL || (!exhausted && __popc(idle) >= refill)) {
             if (pending) {
-                if (found) hit.prim = __ldg(sc.leafPrim + best);
+                if (found) { hit.leaf = best; hit.prim = __ldg(sc.leafPrim + best); }
                 commit(idx, found, hit);
                 pending = false;
             }

@@ -231,6 +231,7 @@ struct DRender {
     uint32_t frameNibbles, bNibbles; // nibbles of the sample index / of the 2m-bit pixel code in look_up
     unsigned long long *ring;       // device pointer of the mapped host progress ring (B2_RING x 4 words)
     unsigned long long *pixStats;   // null unless per-pixel path diagnostics were requested (flags bit5): [pixel] += (len^2 << 32) | len
+    unsigned long long *pathTrace;  // null unless per-sample event traces were requested (flags bit6): [pixel * nS + s] gets one event byte per bounce
     unsigned long long *stampStart; // null unless per-launch timing was requested (b2_render_params.flags bit2)
     unsigned long long *stampEnd;
 };

@@ -224,14 +224,19 @@ def test_material_ball_image_parity(b2ctx, name, sorted_shading):
     # conductor, 3e-6 diffuse: profiles/r02_parity_probe.json); a flipped path is an unrelated sample of a heavy-tailed estimator, so the
     # image error behaves like 3.7 * sqrt(f / spp): 2.7e-3 at 32 spp whatever the kernel does, 4.5e-4 at 2048 spp.  The 1e-3 bar is
     # therefore tested where it is resolvable, together with the diagnostic itself (fraction of pixels whose path lengths changed).
+    # (flags 256 forces the throughput kernels: by default a `path` render of a scene with a transmissive BSDF is dispatched to the IEEE
+    # kernels for exactly this reason, which the last assertion checks)
     rp_hi = RenderParams(spp=2048, sampler="sobol", rfilter="gaussian")
     fo_hi, so_hi = o.render(rp_hi)
-    fg_hi, sg_hi = g.render(rp_hi, parity=False)
+    fg_hi, sg_hi = g.render(rp_hi, parity=False, flags=256)
     assert rel_l2(api.develop(fg_hi), O.develop(fo_hi)) <= REL_L2_TOL, name
     assert abs(sg_hi["path_length_sum"] - so_hi["pathLengthSum"]) <= 2e-4 * so_hi["pathLengthSum"]
     g.render(rp, parity=True, flags=32); pp = g.pixel_stats()
-    g.render(rp, parity=False, flags=32); pf = g.pixel_stats()
+    g.render(rp, parity=False, flags=32 | 256); pf = g.pixel_stats()
     assert (pp != pf).sum() <= 2e-4 * 64 * 64 * 32, (name, int((pp != pf).sum()))   # <= 2e-4 of the paths change length (measured <= 5e-5)
+    if "dielectric" in name:
+        g.render(rp, parity=False, flags=32)
+        assert np.array_equal(g.pixel_stats(), pp)   # default dispatch of a transmissive scene = the IEEE kernels
 
 
 MATERIALS_F3 = {   # SURVEY.md 8f-3 plugins (generic shading kernel)
