@@ -137,6 +137,7 @@ typedef struct b2_stats {
     uint64_t bytes_uploaded;                /* host->device bytes of the last b2_scene_commit */
     uint64_t pool_size;                     /* in-flight paths of the last b2_render */
     uint64_t unoccluded_shadow_rays;        /* shadow rays that reached the emitter (their contribution was added) */
+    uint64_t bvh_node_bytes;                /* size of one node of the tree the ray queries walk (80: 8-wide compressed, 64: binary) */
 } b2_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

@@ -59,7 +59,7 @@ class b2_stats(C.Structure):
                                           "node_visits", "prim_tests", "iterations", "kernel_launches")] + \
                [(n, C.c_float) for n in ("ms_total", "ms_generate", "ms_extend", "ms_shade", "ms_occluded", "ms_film")] + \
                [(n, C.c_uint64) for n in ("n_triangles", "n_bvh_nodes", "n_generate", "n_extend", "n_shade", "n_occluded",
-                                          "bytes_uploaded", "pool_size", "unoccluded_shadow_rays")]
+                                          "bytes_uploaded", "pool_size", "unoccluded_shadow_rays", "bvh_node_bytes")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

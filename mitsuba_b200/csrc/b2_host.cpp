@@ -139,6 +139,7 @@ struct b2_scene {
     DevBuf<uint32_t> dLeafPrim, dFlatIdx;
     DevBuf<float4> dFlatRec;
     DevBuf<BVHNode> dNodes;
+    DevBuf<BVH8Node> dNodes8;
     DevBuf<DMaterial> dMaterials;
     DevBuf<DEmitter> dEmitters;
     DevBuf<float> dEmitterCdf, dTriCdf;
@@ -241,15 +242,20 @@ extern "C" int b2_context_create(int device, b2_ctx **out) {
                         if ((v >> k) & 1) x ^= m32[(size_t) d * 52 + 4 * p + k];
                     nib[((size_t) d * 13 + p) * 16 + v] = x;
                 }
-        cudaMalloc((void **) &ctx->dNib, nib.size() * 4);
-        cudaMemcpy(ctx->dNib, nib.data(), nib.size() * 4, cudaMemcpyHostToDevice);
+        if (cudaMalloc((void **) &ctx->dNib, nib.size() * 4) != cudaSuccess ||
+            cudaMemcpy(ctx->dNib, nib.data(), nib.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            b2_context_destroy(ctx);
+            return fail(nullptr, B2_ERR_CUDA, "b2_context_create: upload of the Sobol' nibble tables failed");
+        }
     }
-    cudaMalloc((void **) &ctx->dM32, m32.size() * 4);
-    cudaMalloc((void **) &ctx->dVdc, vdc.size() * 8);
-    cudaMalloc((void **) &ctx->dInv, inv.size() * 8);
-    cudaMemcpy(ctx->dM32, m32.data(), m32.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(ctx->dVdc, vdc.data(), vdc.size() * 8, cudaMemcpyHostToDevice);
-    cudaMemcpy(ctx->dInv, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice);
+    if (cudaMalloc((void **) &ctx->dM32, m32.size() * 4) != cudaSuccess || cudaMalloc((void **) &ctx->dVdc, vdc.size() * 8) != cudaSuccess ||
+        cudaMalloc((void **) &ctx->dInv, inv.size() * 8) != cudaSuccess ||
+        cudaMemcpy(ctx->dM32, m32.data(), m32.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ctx->dVdc, vdc.data(), vdc.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ctx->dInv, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        b2_context_destroy(ctx);
+        return fail(nullptr, B2_ERR_CUDA, "b2_context_create: upload of the Sobol' tables failed");
+    }
     ctx->tablesLoaded = true;
     *out = ctx;
     return B2_OK;
@@ -718,7 +724,11 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         bvh.depth = 1;
         rootCount = (uint32_t) ids.size();
     } else {
-        buildBVH(boxes, ids, 4, instanced ? 19 : B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh);
+        // non-instanced scenes also get the 8-wide compressed tree over the same leaves: that is what the ray-query kernels walk (the binary
+        // tree stays for volpath's inline queries)
+        const bool wide = !instanced && !getenv("B2_NO_WIDE");
+        buildBVH(boxes, ids, 4, instanced ? 19 : B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh, wide);
+        if (bvh.depth8 > B2_STACK8_DEPTH - 1) bvh.nodes8.clear(); // deeper than the wide traversal's stack: binary tree only
     }
     // ---- instancing: one BVH per shapegroup appended to the node / leaf arrays, then a top-level BVH over the items
     //      (item 0 = the world triangles, item k = instance k - 1); stack budget: 9 (top) + 3 (leaf items) + 19 (bottom) < 32 ----
@@ -1054,6 +1064,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     CK(ctx, s->dVerts.upload(verts));
     CK(ctx, s->dNorms.upload(norms));
     CK(ctx, s->dNodes.upload(bvh.nodes));
+    CK(ctx, s->dNodes8.upload(bvh.nodes8));
     CK(ctx, s->dMaterials.upload(dm));
     CK(ctx, s->dEmitters.upload(de));
     CK(ctx, s->dEmitterCdf.upload(emCdf));
@@ -1084,6 +1095,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     }
     ds.items = s->dInstances.p; ds.nItems = (uint32_t) items.size(); ds.tlasRoot = tlasRoot;
     ds.media = s->dMedia.p; ds.primMedia = anyMedia ? s->dPrimMedia.p : nullptr; ds.nMedia = (uint32_t) dmed.size();
+    ds.nodes8 = bvh.nodes8.empty() ? nullptr : s->dNodes8.p; ds.nNodes8 = (uint32_t) bvh.nodes8.size();
     ds.nodes = s->dNodes.p; ds.nNodes = (uint32_t) bvh.nodes.size(); ds.rootRef = bvh.rootRef; ds.rootCount = rootCount;
     ds.flatRec = s->dFlatRec.p; ds.flatIdx = (const uint2 *) s->dFlatIdx.p; ds.flatP = flatP; ds.flatC = flatC; ds.flatS = flatS;
     ds.flatBytes = (uint32_t) (flatRec.size() * 16);
@@ -1122,6 +1134,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.sobolM32 = ctx->dM32; ds.sobolVdc = ctx->dVdc; ds.sobolInv = ctx->dInv; ds.sobolNib = ctx->dNib;
     // shared-memory staging budget: up to 256 nodes (16 KB) and 256 triangles (12 KB) per CTA
     ds.stageNodes = std::min<uint32_t>(ds.nNodes, 256u);
+    ds.stageNodes8 = std::min<uint32_t>(ds.nNodes8, 192u); // 15 KB: the root, its children and most of the third level
     ds.stageTris = rootCount ? rootCount : 0u; // a BVH's leaf-ordered head is arbitrary: only the flat leaf is worth staging
     ds.stageTriBytes = std::max(ds.stageTris * 48u, (ds.flatBytes + 15u) & ~15u);
     ds.refill = 16; // measured sweep 8..32 on the material-ball and 1M-triangle scenes
@@ -1139,7 +1152,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     CK(ctx, s->dCounters.alloc(CTR_COUNT));
     memset(&s->stats, 0, sizeof(s->stats));
     s->stats.n_triangles = nPrims;
-    s->stats.n_bvh_nodes = bvh.nodes.size();
+    s->stats.n_bvh_nodes = bvh.nodes8.empty() ? bvh.nodes.size() : bvh.nodes8.size();
+    s->stats.bvh_node_bytes = bvh.nodes8.empty() ? sizeof(BVHNode) : sizeof(BVH8Node);
     s->stats.bytes_uploaded = leafTri.size() * 16 + leafPlane.size() * 16 + bvh.leafPrims.size() * 4 + verts.size() * 16 + norms.size() * 16 + bvh.nodes.size() * sizeof(BVHNode) +
                               dm.size() * sizeof(DMaterial) + de.size() * sizeof(DEmitter) + (emCdf.size() + triCdf.size()) * 4;
     s->committed = true;
@@ -1229,6 +1243,17 @@ static int fillRender(b2_scene *s, const b2_render_params *p, DRender &r) {
     // the pixels of the right / bottom strips that no whole tile covers (sample-major).  No item is ever invalid, so a pool slot is
     // never consumed by a pixel outside the film (workItemPixel in b2_kernels.inl).
     r.tilesX = (uint32_t) s->W / 8; r.tilesY = (uint32_t) s->H / 8;
+    { // samples per tile visit: the largest divisor of the sample count that does not exceed B2_ROUND_SPP (0 = all samples at once).
+      // Measured on B200, Cornell 1024^2 @ 256 spp, Msamples/s: box filter 1646 / 1633 / 1619 / 1585 and gaussian 1229 / 1387 / 1455 /
+      // 1464 for all / 64 / 16 / 4 samples per round: a 5 x 5 splat wants the in-flight paths spread over many pixels, a 1-pixel one does not.
+        const uint32_t nS = (uint32_t) (r.sampleHi - r.sampleLo);
+        uint32_t want = p->rfilter == B2_RFILTER_GAUSSIAN ? 8 : 0;
+        if (const char *e = getenv("B2_ROUND_SPP")) want = (uint32_t) atoi(e);
+        r.roundSpp = nS;
+        if (want > 0 && want < nS)
+            for (uint32_t d = want; d >= 1; --d)
+                if (nS % d == 0) { r.roundSpp = d; break; }
+    }
     r.totalWork = (uint64_t) s->W * (uint64_t) s->H * (uint64_t) (r.sampleHi - r.sampleLo);
     // nibble tables of sobol::look_up for this m (sobolseq.h:104-133) and the nibble counts that cover the indices
     auto bitsOf = [](uint64_t v) { uint32_t b = 0; while (v) { ++b; v >>= 1; } return b; };
@@ -1355,9 +1380,25 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     if (p->flags & 2) sorted = false;
     if (s->hasNullBsdf || !s->textures.empty()) { sorted = false; nClasses = 2; } // index-matched boundaries, f-3 BSDFs, textures: generic shading kernel
     s->cancel.store(0);
+    // every early return below leaves the stream idle and releases the events / the captured graph
+    struct RenderGuard {
+        cudaStream_t st;
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaGraph_t *graph = nullptr;
+        cudaGraphExec_t *exec = nullptr;
+        ~RenderGuard() {
+            cudaStreamSynchronize(st);
+            if (exec && *exec) cudaGraphExecDestroy(*exec);
+            if (graph && *graph) cudaGraphDestroy(*graph);
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } guard{st};
     cudaEvent_t evStart, evStop;
     CK(ctx, cudaEventCreate(&evStart));
+    guard.a = evStart;
     CK(ctx, cudaEventCreate(&evStop));
+    guard.b = evStop;
     CK(ctx, cudaEventRecord(evStart, st));
     uint64_t iter = 0, checked = 0, launches = 0;
     bool finished = false;
@@ -1402,6 +1443,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     };
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graphExec = nullptr;
+    guard.graph = &graph; guard.exec = &graphExec;
     if (!useEvents) {
         if (volpath || s->ds.nTextures) {
             // k_volstep (and the textured k_shade) have a deep local-memory frame: their first launch may have to grow the context's
@@ -1454,9 +1496,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         ++iter;
         if (iter > 100000000ull) { status = fail(ctx, B2_ERR_CUDA, "render loop did not terminate"); break; }
     }
-    if (graphExec) cudaGraphExecDestroy(graphExec);
-    if (graph) cudaGraphDestroy(graph);
-    // pack + copy out
+    // pack + copy out (the guard destroys the graph and the events when this function returns)
     CK(ctx, cudaEventRecord(evStop, st));
     if (status == B2_OK) {
         float *dOut = film;
@@ -1474,8 +1514,6 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     CK(ctx, cudaMemcpy(ctr.data(), s->dCounters.p, CTR_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     float ms = 0;
     cudaEventElapsedTime(&ms, evStart, evStop);
-    cudaEventDestroy(evStart);
-    cudaEventDestroy(evStop);
     b2_stats &t = s->stats;
     t.ms_generate = t.ms_extend = t.ms_shade = t.ms_occluded = 0;
     t.n_generate = t.n_extend = t.n_shade = t.n_occluded = 0;
@@ -1584,22 +1622,36 @@ extern "C" int b2_trace_device(b2_scene *s, uint64_t n, const float *d_rays, int
     b2_ctx *ctx = s->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
     const bool count = (mode & 2) != 0;
     const bool shadow = (mode & 1) != 0;
     if (n > 0xFFFFFFFFull) return fail(ctx, B2_ERR_INVALID, "b2_trace: at most 2^32-1 rays per call");
+    struct EventPair { cudaEvent_t a = nullptr, b = nullptr; ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } ev;
+    CK(ctx, cudaEventCreate(&ev.a));
+    CK(ctx, cudaEventCreate(&ev.b));
+    cudaEvent_t a = ev.a, b = ev.b;
     if (count) cudaMemsetAsync(s->dCounters.p + CTR_NODEVIS, 0, 16, st);
     cudaMemsetAsync(s->dCounters.p + CTR_TICKET_EXT, 0, 8, st);
+    // B2_BIN=1 (experiment): tickets binned by (entry cell, direction cell) first -- inside the timed region
+    TmpDev tmp;
+    uint32_t *order = nullptr;
+    const bool bin = s->ds.nodes8 && !s->ds.rootCount && !s->ds.nItems && n >= (1u << 16) && getenv("B2_BIN"); // A/B switch: measured 12 % slower
+    uint32_t *keys = nullptr, *hist = nullptr;
+    if (bin) {
+        keys = tmp.alloc<uint32_t>(n); hist = tmp.alloc<uint32_t>(B2_NBINS + 1); order = tmp.alloc<uint32_t>(n);
+        if (!keys || !hist || !order) return fail(ctx, B2_ERR_CUDA, "b2_trace: device allocation failed");
+    }
     cudaEventRecord(a, st);
-    if (parity_mode) parity::launch_trace(s->cfgParity, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, st);
-    else fast::launch_trace(s->cfgFast, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, st);
+    if (bin) {
+        if (parity_mode) parity::launch_bin(s->cfgParity, s->ds, s->pool, (const float4 *) d_rays, (uint32_t) n, keys, hist, order, st);
+        else fast::launch_bin(s->cfgFast, s->ds, s->pool, (const float4 *) d_rays, (uint32_t) n, keys, hist, order, st);
+    }
+    if (parity_mode) parity::launch_trace(s->cfgParity, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, order, st);
+    else fast::launch_trace(s->cfgFast, s->ds, (const float4 *) d_rays, (float4 *) d_tuvp, n, shadow, count, s->dCounters.p, order, st);
     cudaEventRecord(b, st);
     CK(ctx, cudaStreamSynchronize(st));
     CK(ctx, cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a); cudaEventDestroy(b);
     if (ms_kernel) *ms_kernel = ms;
     if (count) {
         unsigned long long c[2];

@@ -27,8 +27,9 @@ namespace B2_KNS {
 // ------------------------------------------------------------------------------------------------
 B2_DEV uint32_t smemAddr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
-B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t *bar) {
-    const uint32_t nb = sc.stageNodes * 64u;
+B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t *bar, bool wide = false) {
+    const uint32_t nb = wide ? sc.stageNodes8 * 80u : sc.stageNodes * 64u;
+    const void *nodeSrc = wide ? (const void *) sc.nodes8 : (const void *) sc.nodes;
     const uint32_t barA = smemAddr(bar);
 #ifdef B2_FAST_TRI
     // flat leaf: the paired records (never larger than the triangle list they replace); BVH: head of the plane array
@@ -47,7 +48,7 @@ B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barA), "r"(nb + tb) : "memory");
         if (nb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(sNodes)),
-                         "l"(sc.nodes), "r"(nb), "r"(barA)
+                         "l"(nodeSrc), "r"(nb), "r"(barA)
                          : "memory");
         if (tb)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(sTris)),
@@ -68,18 +69,24 @@ B2_DEV void stageScene(const DScene &sc, float4 *sNodes, float4 *sTris, uint64_t
 }
 
 // dynamic shared memory carve-up for the traversal kernels
-B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem) {
+// (wide: the 8-ary tree -- uint2 stack entries, 80-byte nodes staged -- for the kernels that walk it: k_extend / k_occluded / k_trace_rays
+// on non-instanced BVH scenes)
+B2_DEV TraceMem setupTraceMem(const DScene &sc, unsigned char *smem, bool wide = false) {
     uint32_t *stack = (uint32_t *) smem;
-    size_t off = (size_t) B2_STACK_DEPTH * blockDim.x * sizeof(uint32_t);
+    size_t off = wide ? (size_t) B2_STACK8_DEPTH * blockDim.x * sizeof(uint2) : (size_t) B2_STACK_DEPTH * blockDim.x * sizeof(uint32_t);
     off = (off + 127) & ~(size_t) 127;
     float4 *sNodes = (float4 *) (smem + off);
-    off += (size_t) sc.stageNodes * 64;
+    off += wide ? (size_t) sc.stageNodes8 * 80 : (size_t) sc.stageNodes * 64;
     float4 *sTris = (float4 *) (smem + off);
     off += (size_t) sc.stageTriBytes;
     off = (off + 15) & ~(size_t) 15;
     uint64_t *bar = (uint64_t *) (smem + off);
-    stageScene(sc, sNodes, sTris, bar);
+    stageScene(sc, sNodes, sTris, bar, wide);
     TraceMem tm;
+    tm.gNodes8 = (const float4 *) sc.nodes8;
+    tm.sNodes8 = sNodes;
+    tm.stageNodes8 = wide ? sc.stageNodes8 : 0u;
+    tm.stack8 = (uint2 *) smem + threadIdx.x;
     tm.gNodes = (const float4 *) sc.nodes;
 #ifdef B2_FAST_TRI
     tm.gTris = sc.triPlane;
@@ -202,8 +209,10 @@ B2_DEV bool filmPut(const DFilter &f, float4 *filmRGBA, float *filmW, int W, int
             if (fx < 0 || fx >= W) continue;
             const float w = evalDiscretized(f, (float) x - px) * wy;
             const size_t o = (size_t) fy * W + fx;
-            redAddV4(filmRGBA + o, w * value[0], w * value[1], w * value[2], w * value[3]);
-            atomicAdd(filmW + o, w * value[4]);
+            // one 16-byte reduction per pixel: (r, g, b, weight * alpha); the rest of the weight, w (1 - alpha), goes to a second plane and
+            // is zero -- no second atomic -- whenever the camera ray hit something (k_film_pack: weight = both parts, no cancellation)
+            redAddV4(filmRGBA + o, w * value[0], w * value[1], w * value[2], w * (value[4] * value[3]));
+            if (value[3] != 1.0f) atomicAdd(filmW + o, w * (value[4] * (1.0f - value[3])));
         }
     }
     return true;
@@ -302,17 +311,24 @@ B2_DEV void samplerInit(const DScene &sc, const DRender &rp, int px, int py, uin
     }
 }
 
-// Work item -> (pixel, sample).  Items [0, tilesX*tilesY*64*nS) walk the whole 8x8 tiles of the film: tile-major, then the
-// sample index, then the pixel inside the tile (64 consecutive items = one sample of one tile: coherent camera rays and one
-// compact film footprint).  The remaining items cover the right strip (W - 8*tilesX columns beside the tiles) and the bottom
+// Work item -> (pixel, sample).  Items [0, tilesX*tilesY*64*nS) walk the whole 8x8 tiles of the film in rounds of roundSpp samples:
+// round-major, then tile, then the sample index inside the round, then the pixel inside the tile (64 consecutive items = one sample of
+// one tile: coherent camera rays and one compact film footprint).  The remaining items cover the right strip (W - 8*tilesX columns beside the tiles) and the bottom
 // strip (H - 8*tilesY full rows) pixel by pixel, sample-major.  Every item is a pixel of the film, so no slot is ever wasted.
 B2_DEV void workItemPixel(const DRender &rp, int W, int H, unsigned long long w, int &px, int &py, uint32_t &s) {
     const uint32_t nS = (uint32_t) (rp.sampleHi - rp.sampleLo);
     const uint32_t perTile = 64u * nS;
     const unsigned long long tiled = (unsigned long long) rp.tilesX * rp.tilesY * perTile;
     if (w < tiled) {
-        const uint32_t tile = (uint32_t) (w / perTile), r = (uint32_t) (w % perTile);
-        s = (uint32_t) rp.sampleLo + r / 64u;
+        // rounds of rp.roundSpp samples: every tile receives roundSpp samples, then the next round starts.  The pool then holds paths of
+        // pool / (64 * roundSpp) tiles instead of pool / (64 * nS): fewer film atomics land on the same pixel at the same time (the L2
+        // serialises atomics per address), while 64 consecutive items are still one sample of one tile (coherent camera rays).
+        const uint32_t S = rp.roundSpp, perVisit = 64u * S;
+        const unsigned long long perRound = (unsigned long long) rp.tilesX * rp.tilesY * perVisit;
+        const uint32_t round = (uint32_t) (w / perRound);
+        const unsigned long long rem = w % perRound;
+        const uint32_t tile = (uint32_t) (rem / perVisit), r = (uint32_t) (rem % perVisit);
+        s = (uint32_t) rp.sampleLo + round * S + r / 64u;
         const uint32_t p = r & 63u;
         px = (int) ((tile % rp.tilesX) * 8u + (p & 7u));
         py = (int) ((tile / rp.tilesX) * 8u + (p >> 3));
@@ -477,7 +493,8 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u; // k_publish already advanced the counter
     stampBegin(rp, it, STAGE_EXTEND);
-    const TraceMem tm = setupTraceMem(sc, smem);
+    const bool wide = sc.nodes8 != nullptr && !sc.rootCount && !sc.nItems;
+    const TraceMem tm = setupTraceMem(sc, smem, wide);
     const uint32_t Q = pool.capacity;
     uint32_t nRays = 0;
     if (!sc.rootCount && !sc.nItems) {
@@ -507,7 +524,8 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
                 }
             }
         };
-        traverseQueue<false, false>(sc, tm, Q, pool.counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
+        if (wide) traverseQueue8<false, false>(sc, tm, Q, pool.counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
+        else traverseQueue<false, false>(sc, tm, Q, pool.counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
     } else
     for (uint32_t base = blockIdx.x * blockDim.x; base < Q; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
@@ -1200,7 +1218,8 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
     stampBegin(rp, it, STAGE_OCCLUDED);
-    const TraceMem tm = setupTraceMem(sc, smem);
+    const bool wide = sc.nodes8 != nullptr && !sc.rootCount && !sc.nItems;
+    const TraceMem tm = setupTraceMem(sc, smem, wide);
     const uint32_t n = (uint32_t) pool.counters[CTR_SHADOW];
     uint32_t nClear = 0;
     if (!sc.rootCount && !sc.nItems) {
@@ -1219,7 +1238,8 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_occluded(DScene sc, DPool po
                 ++nClear;
             }
         };
-        traverseQueue<true, false>(sc, tm, n, pool.counters + CTR_TICKET_OCC, fetch, commit, nv, pt);
+        if (wide) traverseQueue8<true, false>(sc, tm, n, pool.counters + CTR_TICKET_OCC, fetch, commit, nv, pt);
+        else traverseQueue<true, false>(sc, tm, n, pool.counters + CTR_TICKET_OCC, fetch, commit, nv, pt);
     } else
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t j = base + threadIdx.x;
@@ -1907,12 +1927,77 @@ __global__ void k_medium_probe(DScene sc, int medium, int what, uint64_t n, cons
     }
 }
 
-// film pack: (float4 rgba, float w) planes -> interleaved H*W*5 (hdrfilm.cpp:351-356 ESpectrumAlphaWeight)
+// film pack: (float4 (r, g, b, weight * alpha), float weight * (1 - alpha)) planes -> interleaved H*W*5 (hdrfilm.cpp:351-356 ESpectrumAlphaWeight)
 __global__ void k_film_pack(const float4 *rgba, const float *w, float *out, size_t n) {
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-        const float4 v = rgba[i];
+        const float4 v = rgba[i]; // (r, g, b, sum of weight * alpha); w[i] = sum of weight * (1 - alpha)
         float *o = out + 5 * i;
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; o[4] = w[i];
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; o[4] = v.w + w[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray binning (counting sort) in front of the wide-tree traversal: rays that enter the scene box in the same cell of an 8 x 8 x 8
+// grid AND point into the same cell of a 16 x 16 octahedral direction map get consecutive tickets, so the lanes of a warp walk
+// similar nodes (fewer idle lanes, the node and triangle lines they share are fetched once).  Three hand-written passes: key +
+// histogram (one global atomic per ray over 131 072 bins), exclusive scan (one CTA), scatter (one atomic per ray).  The order inside a
+// bin is arbitrary; hits do not depend on it.
+// ------------------------------------------------------------------------------------------------
+B2_DEV uint32_t spread3(uint32_t v) { // 3 bits -> every third bit
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4);
+}
+B2_DEV uint32_t rayBinKey(const DScene &sc, const V3 &o, const V3 &d) {
+    const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float t0, t1;
+    V3 p = o;
+    if (sceneBoxIntersect(sc, o, d, dRcp, t0, t1) && t0 > 0) p = o + d * t0; // entry point of a ray that starts outside the scene box
+    const float ex = sc.aabbMax[0] - sc.aabbMin[0], ey = sc.aabbMax[1] - sc.aabbMin[1], ez = sc.aabbMax[2] - sc.aabbMin[2];
+    const uint32_t cx = (uint32_t) fminf(fmaxf((p.x - sc.aabbMin[0]) / ex * 8.0f, 0.0f), 7.0f);
+    const uint32_t cy = (uint32_t) fminf(fmaxf((p.y - sc.aabbMin[1]) / ey * 8.0f, 0.0f), 7.0f);
+    const uint32_t cz = (uint32_t) fminf(fmaxf((p.z - sc.aabbMin[2]) / ez * 8.0f, 0.0f), 7.0f);
+    // octahedral map of the direction
+    const float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+    float u = d.x * inv, v = d.y * inv;
+    if (d.z < 0) { const float uu = (1.0f - fabsf(v)) * (u >= 0 ? 1.0f : -1.0f), vv = (1.0f - fabsf(u)) * (v >= 0 ? 1.0f : -1.0f); u = uu; v = vv; }
+    const uint32_t du = (uint32_t) fminf(fmaxf((u * 0.5f + 0.5f) * 16.0f, 0.0f), 15.0f), dv = (uint32_t) fminf(fmaxf((v * 0.5f + 0.5f) * 16.0f, 0.0f), 15.0f);
+    return ((spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2)) << 8) | (du << 4) | dv;
+}
+// rays: the ray array of b2_trace_device, or null = the path pool (live slots only: a dead slot gets no ticket)
+__global__ void k_bin_count(DScene sc, DPool pool, const float4 *rays, uint32_t n, uint32_t *keys, uint32_t *hist) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 ro, rd;
+        if (rays) { ro = rays[2 * (size_t) i]; rd = rays[2 * (size_t) i + 1]; }
+        else {
+            if (!(pool.flags[i] & PF_ALIVE)) { keys[i] = 0xFFFFFFFFu; continue; }
+            ro = pool.ray[2 * (size_t) i]; rd = pool.ray[2 * (size_t) i + 1];
+        }
+        const uint32_t k = rayBinKey(sc, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z));
+        keys[i] = k;
+        atomicAdd(hist + k, 1u);
+    }
+}
+// one CTA of 1024 threads: exclusive prefix sum over the B2_NBINS counters in place; hist[B2_NBINS] = total
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *hist) {
+    __shared__ uint32_t sSum[1024];
+    const uint32_t per = B2_NBINS / 1024u, base = threadIdx.x * per;
+    uint32_t acc = 0;
+    for (uint32_t k = 0; k < per; ++k) acc += hist[base + k];
+    sSum[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) { // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t v = threadIdx.x >= off ? sSum[threadIdx.x - off] : 0u;
+        __syncthreads();
+        sSum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? sSum[threadIdx.x - 1] : 0u;
+    for (uint32_t k = 0; k < per; ++k) { const uint32_t c = hist[base + k]; hist[base + k] = run; run += c; }
+    if (threadIdx.x == 1023) hist[B2_NBINS] = run;
+}
+__global__ void k_bin_scatter(uint32_t n, const uint32_t *keys, uint32_t *cursor, uint32_t *order) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        if (k != 0xFFFFFFFFu) order[atomicAdd(cursor + k, 1u)] = i;
     }
 }
 
@@ -1920,22 +2005,26 @@ __global__ void k_film_pack(const float4 *rgba, const float *w, float *out, size
 // component kernels (b2_trace / b2_bsdf_* / b2_sample_emitter_direct / b2_camera_rays / b2_sampler_stream / b2_splat)
 // ------------------------------------------------------------------------------------------------
 template <bool SHADOW, bool COUNT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_trace_rays(DScene sc, const float4 *rays, float4 *out, uint64_t n,
-                                                                                                   unsigned long long *counters) {
+                                                                                                   unsigned long long *counters, const uint32_t *order) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const TraceMem tm = setupTraceMem(sc, smem);
+    const bool wide = sc.nodes8 != nullptr && !sc.rootCount && !sc.nItems;
+    const TraceMem tm = setupTraceMem(sc, smem, wide);
     uint32_t nv = 0, pt = 0;
     if (!sc.rootCount && !sc.nItems) {
-        auto fetch = [&](uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) -> int {
+        auto fetch = [&](uint32_t t, V3 &o, V3 &d, float &mint, float &maxt) -> int {
+            const uint32_t i = order ? order[t] : t; // binned tickets (k_bin_*): neighbouring lanes get similar rays
             const float4 ro = rays[2 * (size_t) i], rd = rays[2 * (size_t) i + 1];
             o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z);
             const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
             return clipRay<SHADOW>(sc, o, d, dRcp, ro.w, rd.w, mint, maxt) ? 2 : 1;
         };
-        auto commit = [&](uint32_t i, bool found, const HitRec &h) {
+        auto commit = [&](uint32_t t, bool found, const HitRec &h) {
+            const uint32_t i = order ? order[t] : t;
             if (SHADOW) out[i] = make_float4(0, 0, 0, __uint_as_float(found ? 1u : 0u));
             else out[i] = found ? make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)) : make_float4(B2_INF, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
         };
-        traverseQueue<SHADOW, COUNT>(sc, tm, (uint32_t) n, counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
+        if (wide) traverseQueue8<SHADOW, COUNT>(sc, tm, (uint32_t) n, counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
+        else traverseQueue<SHADOW, COUNT>(sc, tm, (uint32_t) n, counters + CTR_TICKET_EXT, fetch, commit, nv, pt);
     } else
     for (uint64_t base = blockIdx.x * (uint64_t) blockDim.x; base < n; base += (uint64_t) gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
@@ -2059,12 +2148,19 @@ __global__ void k_splat(DFilter f, int W, int H, uint64_t n, const float *pos, c
 // ------------------------------------------------------------------------------------------------
 // launchers (host side of this translation unit)
 // ------------------------------------------------------------------------------------------------
-static size_t traceSmemBytes(const DScene &sc, int block) {
+static size_t traceSmemBytes(const DScene &sc, int block) { // the larger of the two carve-ups of setupTraceMem
     size_t off = (size_t) B2_STACK_DEPTH * block * sizeof(uint32_t);
     off = (off + 127) & ~(size_t) 127;
     off += (size_t) sc.stageNodes * 64 + (size_t) sc.stageTriBytes;
     off = (off + 15) & ~(size_t) 15;
-    return off + 16;
+    size_t off8 = 0;
+    if (sc.nodes8) {
+        off8 = (size_t) B2_STACK8_DEPTH * block * sizeof(uint2);
+        off8 = (off8 + 127) & ~(size_t) 127;
+        off8 += (size_t) sc.stageNodes8 * 80 + (size_t) sc.stageTriBytes;
+        off8 = (off8 + 15) & ~(size_t) 15;
+    }
+    return (off > off8 ? off : off8) + 16;
 }
 
 template <typename K> static int occupancyGrid(K kernel, int block, size_t smem, int numSMs) {
@@ -2159,15 +2255,23 @@ void launch_film_pack(const LaunchCfg &cfg, const float4 *rgba, const float *w, 
     k_film_pack<<<cfg.numSMs * 4, 256, 0, st>>>(rgba, w, out, n);
 }
 void launch_trace(const LaunchCfg &cfg, const DScene &sc, const float4 *rays, float4 *out, uint64_t n, bool shadow, bool count,
-                  unsigned long long *counters, cudaStream_t st) {
+                  unsigned long long *counters, const uint32_t *order, cudaStream_t st) {
     const int g = cfg.gridTrace;
     if (shadow) {
-        if (count) k_trace_rays<true, true><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
-        else k_trace_rays<true, false><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
+        if (count) k_trace_rays<true, true><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters, order);
+        else k_trace_rays<true, false><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters, order);
     } else {
-        if (count) k_trace_rays<false, true><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
-        else k_trace_rays<false, false><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters);
+        if (count) k_trace_rays<false, true><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters, order);
+        else k_trace_rays<false, false><<<g, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, rays, out, n, counters, order);
     }
+}
+// counting sort of ray tickets by (entry cell, direction cell): keys n, hist B2_NBINS + 1 (left holding the bin END offsets), order n
+void launch_bin(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const float4 *rays, uint32_t n, uint32_t *keys, uint32_t *hist,
+                uint32_t *order, cudaStream_t st) {
+    cudaMemsetAsync(hist, 0, (B2_NBINS + 1) * sizeof(uint32_t), st);
+    k_bin_count<<<cfg.numSMs * 8, 256, 0, st>>>(sc, pool, rays, n, keys, hist);
+    k_bin_scan<<<1, 1024, 0, st>>>(hist);
+    k_bin_scatter<<<cfg.numSMs * 8, 256, 0, st>>>(n, keys, hist, order);
 }
 void launch_bsdf_eval(const LaunchCfg &cfg, const DScene &sc, int mat, uint64_t n, const float *wi, const float *wo, float *rgb, float *pdf, cudaStream_t st) {
     k_bsdf_eval<<<cfg.numSMs * 2, 128, 0, st>>>(sc, mat, n, wi, wo, rgb, pdf);

@@ -5,6 +5,8 @@
 
 #define B2_TRACE_BLOCK 256
 #define B2_SHADE_BLOCK 128
+#define B2_BIN_BITS 17
+#define B2_NBINS (1u << B2_BIN_BITS)
 
 namespace b2 {
 
@@ -32,7 +34,9 @@ struct LaunchCfg {
                              uint64_t seed, float *out, cudaStream_t);                                                         \
     void launch_film_pack(const LaunchCfg &, const float4 *rgba, const float *w, float *out, size_t n, cudaStream_t);          \
     void launch_trace(const LaunchCfg &, const DScene &, const float4 *rays, float4 *out, uint64_t n, bool shadow, bool count, \
-                      unsigned long long *counters, cudaStream_t);                                                             \
+                      unsigned long long *counters, const uint32_t *order, cudaStream_t);                                      \
+    void launch_bin(const LaunchCfg &, const DScene &, const DPool &, const float4 *rays, uint32_t n, uint32_t *keys,          \
+                    uint32_t *hist, uint32_t *order, cudaStream_t);                                                            \
     void launch_bsdf_eval(const LaunchCfg &, const DScene &, int mat, uint64_t n, const float *wi, const float *wo,            \
                           float *rgb, float *pdf, cudaStream_t);                                                               \
     void launch_bsdf_sample(const LaunchCfg &, const DScene &, int mat, uint64_t n, const float *wi, const float *samples,     \

@@ -84,6 +84,23 @@ struct BVHNode {
 };
 static_assert(sizeof(BVHNode) == 64, "BVHNode must be 64 bytes");
 
+// 80-byte node of the 8-wide tree (after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide
+// BVHs", HPG 2017, restated): the eight child boxes are 8-bit offsets from `p` in units of 2^e per axis (conservative: lo rounded down,
+// hi rounded up), internal children are consecutive nodes starting at childBase (in slot order), the <= 3 triangles of each leaf child
+// sit at triBase + offset in the leaf-ordered triangle array.  Slot s holds the child that lies towards (s&1 ? +x : -x, s&2 ? +y : -y,
+// s&4 ? +z : -z) of the node centre, so a ray with direction octant o visits the hit children in the order of decreasing s ^ (7 ^ o).
+struct BVH8Node {
+    float p[3];
+    int8_t e[3];
+    uint8_t imask;        // bit s: child s is an internal node
+    uint32_t childBase;   // first internal child
+    uint32_t triBase;     // first triangle of this node's leaf children
+    uint8_t meta[8];      // leaf child: (triangle count 1..3) << 5 | offset (0..23) from triBase; 0: empty slot or internal child
+    uint8_t qlo[3][8], qhi[3][8];
+};
+static_assert(sizeof(BVH8Node) == 80, "BVH8Node must be 80 bytes");
+#define B2_STACK8_DEPTH 28   // uint2 entries per lane of the wide traversal (one pending child group per level)
+
 struct DCamera {
     float camToWorld[16];
     float sampleToCamera[16];
@@ -121,6 +138,8 @@ struct DScene {
     uint32_t nMedia;
     const BVHNode *nodes;
     uint32_t nNodes;
+    const BVH8Node *nodes8;    // wide tree of non-instanced BVH scenes (null otherwise): what k_extend / k_occluded / b2_trace walk
+    uint32_t nNodes8, stageNodes8;
     int32_t rootRef;           // root child reference (leaf-only scenes: a leaf ref)
     uint32_t rootCount;        // > 0: the whole scene is one flat leaf of rootCount triangles (tiny scenes, tested in lockstep)
     float aabbMin[3], aabbMax[3]; // enlarged scene box (gkdtree.h:1213-1220)
@@ -223,9 +242,10 @@ struct DRender {
     uint32_t logRes;         // sobol m_logResolution
     float resolution;        // sobol m_resolution
     uint64_t totalWork;      // W*H*(hi-lo)
+    uint32_t roundSpp;       // samples every tile receives per round of the work enumeration (divides hi - lo; workItemPixel)
     uint32_t tilesX, tilesY; // whole 8x8 tiles of the film (W / 8, H / 8); the remaining strips are enumerated pixel by pixel
-    float4 *filmRGBA;        // H*W float4 (r,g,b,alpha) accumulators
-    float *filmW;            // H*W weight accumulators
+    float4 *filmRGBA;        // H*W float4 accumulators (r, g, b, weight * alpha)
+    float *filmW;            // H*W accumulators of weight * (1 - alpha): touched only by samples whose camera ray missed
     const uint64_t *lookupNib; // [2][13][16] nibble tables of sobol look_up for this render's m: [0] vdc (delta), [1] inv
     uint32_t indexNibbles;   // nibbles needed to cover the largest Sobol' index of this render (<= 13)
     uint32_t frameNibbles, bNibbles; // nibbles of the sample index / of the 2m-bit pixel code in look_up

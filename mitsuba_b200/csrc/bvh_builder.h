@@ -17,9 +17,14 @@ struct BVHResult {
     std::vector<uint32_t> leafPrims; // leaf-ordered prim ids
     int32_t rootRef = -1;
     int depth = 0;
+    // wide tree over the same leaves (only when requested): 8-wide nodes with quantised child boxes, BFS order (the internal children of a
+    // node are consecutive); its leaves index the SAME leaf-ordered triangle array (leafPrims is then emitted in the wide tree's order)
+    std::vector<BVH8Node> nodes8;
+    int depth8 = 0;
 };
 
-// boxes: one per candidate prim (ids[i] is its global prim id).  maxLeaf <= 7, maxDepth <= B2_STACK_DEPTH.
-void buildBVH(const std::vector<PrimBox> &boxes, const std::vector<uint32_t> &ids, int maxLeaf, int maxDepth, int threads, BVHResult &out);
+// boxes: one per candidate prim (ids[i] is its global prim id).  maxLeaf <= 7 (<= 3 with `wide`), maxDepth <= B2_STACK_DEPTH.
+// wide: also collapse the binary tree into the 8-wide compressed tree (BVHResult::nodes8).
+void buildBVH(const std::vector<PrimBox> &boxes, const std::vector<uint32_t> &ids, int maxLeaf, int maxDepth, int threads, BVHResult &out, bool wide = false);
 
 } // namespace b2

@@ -571,17 +571,21 @@ struct Loader {
         }
         if (n->type == "homogeneous") { // medium.cpp:27-37 + materials.h:90-190 (no preset table) + homogeneous.cpp:156-222
             m.type = B2_MEDIUM_HOMOGENEOUS;
-            if (p.has("material")) throw Err("homogeneous: material presets are not supported, give sigmaS/sigmaA or sigmaT/albedo");
+            // materials.h:90-160 lookupMaterial: the coefficients START from a preset -- "Skin1" unless `material` names another one -- in
+            // mm^-1, times 100; whatever the scene gives overrides its half of the pair (a scene that only sets sigmaS keeps Skin1's sigmaA)
+            if (p.has("material") && p.s("material", "Skin1") != "Skin1" && p.s("material", "Skin1") != "skin1")
+                throw Err("homogeneous: of the measured material presets only the default \"Skin1\" is known here; give sigmaS/sigmaA or sigmaT/albedo");
             const bool hasAS = p.has("sigmaS") || p.has("sigmaA"), hasTA = p.has("sigmaT") || p.has("albedo");
             if (hasAS && hasTA) throw Err("You can either specify sigmaS & sigmaA *or* sigmaT & albedo, but no other combinations!");
-            if (!hasAS && !hasTA) throw Err("homogeneous: give sigmaS/sigmaA or sigmaT/albedo (material presets are not supported)");
-            const double zero[3] = {0, 0, 0};
+            const double skinS[3] = {0.74 * 100, 0.88 * 100, 1.01 * 100}, skinA[3] = {0.032 * 100, 0.17 * 100, 0.48 * 100}; // materials.h:44
             float sS[3], sA[3];
-            if (hasAS) { p.spec("sigmaS", zero, sS); p.spec("sigmaA", zero, sA); }
-            else {
+            p.spec("sigmaS", skinS, sS); p.spec("sigmaA", skinA, sA);
+            if (!hasAS) for (int c = 0; c < 3; ++c) { sS[c] = (float) skinS[c]; sA[c] = (float) skinA[c]; }
+            if (hasTA) { // sigmaT defaults to sigmaA + sigmaS, albedo to sigmaS / (sigmaS + sigmaA) of the preset (materials.h:150-156)
+                const double dT[3] = {sA[0] + sS[0], sA[1] + sS[1], sA[2] + sS[2]};
+                const double dAl[3] = {sS[0] / dT[0], sS[1] / dT[1], sS[2] / dT[2]};
                 float sT[3], al[3];
-                if (!p.has("sigmaT") || !p.has("albedo")) throw Err("homogeneous: sigmaT and albedo must be given together");
-                p.spec("sigmaT", zero, sT); p.spec("albedo", zero, al);
+                p.spec("sigmaT", dT, sT); p.spec("albedo", dAl, al);
                 for (int c = 0; c < 3; ++c) { sS[c] = al[c] * sT[c]; sA[c] = sT[c] - sS[c]; }
             }
             if (p.has("g")) g = p.f("g", 0);
@@ -1083,10 +1087,12 @@ struct Loader {
         for (auto &c : root->children) if (c->tag == "texture") addTexture(c.get());
         for (auto &c : root->children) if (c->tag == "bsdf") addBsdf(c.get());
         for (auto &c : root->children) if (c->tag == "medium") addMedium(c.get());
+        bool haveIntegrator = false;
         for (auto &cu : root->children) {
             Node *c = cu.get();
             if (c->tag == "bsdf" || c->tag == "medium" || c->tag == "texture") continue;
             if (c->tag == "integrator") {
+                haveIntegrator = true;
                 if (c->type == "volpath") rp->integrator = B2_INTEGRATOR_VOLPATH;
                 else if (c->type != "path") throw Err("unsupported integrator \"" + c->type + "\": this library implements the `path` and `volpath` plugins");
                 Props p(c);
@@ -1176,6 +1182,8 @@ struct Loader {
             else throw Err("unsupported top-level element <" + c->tag + ">");
         }
         if (!haveSensor) throw Err("scene has no <sensor>");
+        // the reference gives a scene without an <integrator> the `direct` plugin (scene.cpp:274-276), which is not on this library's path
+        if (!haveIntegrator) throw Err("scene has no <integrator>: Mitsuba would render it with `direct`; this library implements `path` and `volpath`");
     }
 };
 

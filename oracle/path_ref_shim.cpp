@@ -76,6 +76,7 @@ bool Scheduler::cancel(ParallelProcess *, bool) { return true; }
 bool Scheduler::schedule(ParallelProcess *) { return true; }
 size_t Scheduler::getCoreCount() const { return 1; }
 Float RenderQueue::getRenderTime(const RenderJob *) const { return 0; }
+void RenderQueue::signalRefresh(const RenderJob *) {} /* GUI notification after Film::setBitmap: no listeners here */
 /* single-threaded: locks and condition variables do nothing, "thread-local" storage is one object */
 struct Mutex::MutexPrivate {};
 Mutex::Mutex() {}
@@ -207,7 +208,8 @@ public:
     StandinFilm(const Properties &props) : Film(props) {}
     void clear() {}
     void put(const ImageBlock *) {}
-    void setBitmap(const Bitmap *, Float) {}
+    void setBitmap(const Bitmap *bitmap, Float) { m_last = const_cast<Bitmap *>(bitmap); } /* an integrator that renders the whole film (b200path) hands it over here */
+    ref<Bitmap> m_last;
     void addBitmap(const Bitmap *, Float) {}
     void setDestinationFile(const fs::path &, uint32_t) {}
     void develop(const Scene *, Float) {}
@@ -237,7 +239,8 @@ void *pathref_new() {
 /* same layout as bsdfref_create (oracle/bsdf_ref_shim.cpp) */
 void *pathref_bsdf(int plugin, int nf, const char **fk, const float *fv, int ns, const char **sk, const char **sv, int nb, const char **bk, const int *bv,
                    int nsp, const char **spk, const float *spv, void *child, void *child2) {
-    Properties props;
+    static const char *const pluginNames[] = {"diffuse", "roughconductor", "roughdielectric", "coating", "null", "twosided", "dielectric", "conductor", "plastic"};
+    Properties props(plugin >= 0 && plugin < 9 ? pluginNames[plugin] : ""); /* the XML loader names the plugin in the Properties (scenehandler.cpp) */
     for (int i = 0; i < nf; ++i) props.setFloat(fk[i], fv[i]);
     for (int i = 0; i < ns; ++i) props.setString(sk[i], sv[i]);
     for (int i = 0; i < nb; ++i) props.setBoolean(bk[i], bv[i] != 0);
@@ -262,7 +265,7 @@ void *pathref_bsdf(int plugin, int nf, const char **fk, const float *fv, int ns,
 }
 /* phase 0 isotropic / 1 hg(g) */
 static PhaseFunction *makePhase(int phase, float g) {
-    Properties pp;
+    Properties pp(phase == 1 ? "hg" : "isotropic");
     if (phase == 1) pp.setFloat("g", g);
     PhaseFunction *ph = (PhaseFunction *) (phase == 1 ? CreateInstance_hg(pp) : CreateInstance_isotropic(pp));
     ph->configure();
@@ -430,18 +433,18 @@ void pathref_setup4(void *h, const float *toWorld, float fov, float nearClip, fl
         fp.setInteger("cropWidth", cropW); fp.setInteger("cropHeight", cropH);
     }
     p->film = new StandinFilm(fp);
-    Properties rp;
+    Properties rp(rfilter == 0 ? "box" : "gaussian");
     ReconstructionFilter *rf = (ReconstructionFilter *) (rfilter == 0 ? CreateInstance_box(rp) : CreateInstance_gaussian(rp));
     rf->configure();
     p->film->addChild("", rf);
     p->film->configure();
-    Properties sp;
+    Properties sp(samplerKind == 0 ? "sobol" : "independent");
     sp.setInteger("sampleCount", spp);
     sp.setInteger("scramble", (int) scramble);
     if (samplerKind == 2) p->sampler = new CounterSamplerPlugin(cropW, (size_t) spp, scramble);
     else p->sampler = (Sampler *) (samplerKind == 0 ? CreateInstance_sobol(sp) : CreateInstance_independent(sp));
     p->sampler->configure();
-    Properties cp("perspective");
+    Properties cp(apertureRadius > 0 ? "thinlens" : "perspective");
     Matrix4x4 M;
     for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M.m[r][c] = toWorld[4 * r + c];
     cp.setTransform("toWorld", Transform(M));
@@ -527,6 +530,32 @@ void pathref_sample_emitter_direct(void *h, int n, const float *ref, const float
         o[5] = value[0]; o[6] = value[1]; o[7] = value[2]; o[8] = value.isZero() ? 0.0f : 1.0f; o[9] = dRec.p.x; o[10] = dRec.p.y; o[11] = dRec.p.z;
     }
 }
+#ifdef WITH_B200_SHIM
+/* The same Scene object rendered through the Mitsuba-side plugin of this repository (mitsuba_b200/host/b200_integrator.cpp, class
+ * B200PathTracer: Integrator::render -> C-ABI of libb2mts.so -> film through Film::setBitmap) instead of MIPathTracer + renderBlock.
+ * Returns 0 and fills out (H x W x 5), or 1 with the exception text in err. */
+extern "C" void *CreateInstance_b200path(const Properties &props);
+int pathref_render_b200(void *h, int device, int parity, float *out, char *err, int errLen) {
+    PathRef *p = (PathRef *) h;
+    try {
+        const Properties &op = p->integrator->getProperties();
+        Properties ip("b200path");
+        ip.setInteger("maxDepth", op.getInteger("maxDepth", -1)); ip.setInteger("rrDepth", op.getInteger("rrDepth", 5));
+        ip.setBoolean("strictNormals", op.getBoolean("strictNormals", false)); ip.setBoolean("hideEmitters", op.getBoolean("hideEmitters", false));
+        ip.setInteger("device", device); ip.setBoolean("parity", parity != 0);
+        ref<Integrator> integ = (Integrator *) CreateInstance_b200path(ip);
+        integ->configure();
+        if (!integ->render(p->scene, NULL, NULL, 0, 0, 0)) throw std::runtime_error("render() was cancelled");
+        StandinFilm *film = static_cast<StandinFilm *>(p->film.get());
+        if (!film->m_last) throw std::runtime_error("the integrator did not hand a bitmap to the film");
+        memcpy(out, film->m_last->getFloat32Data(), sizeof(float) * 5 * (size_t) p->W * p->H);
+        return 0;
+    } catch (const std::exception &e) {
+        if (err && errLen > 0) { strncpy(err, e.what(), (size_t) errLen - 1); err[errLen - 1] = 0; }
+        return 1;
+    }
+}
+#endif
 /* film out: H x W x 5 (rgb, alpha, weight), blocks of 32 x 32 rendered by SamplingIntegrator::renderBlock with the pixels of a block in
  * scanline order and accumulated here in block order (the reference's scheduler hands out Hilbert-ordered pixels and merges blocks in
  * completion order: float summation order only) */

@@ -72,3 +72,13 @@ def test_product_does_not_import_the_oracle():
                 if re.search(r"oracle/|oracle_api|libmtsoracle|import oracle|from oracle|\borc_", txt):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_wide_bvh_builder_selftest():
+    """Host-side check of the 8-wide compressed tree (no device): every leaf position referenced exactly once by both trees, and a walk with
+    the device's arithmetic reaches every primitive whose own box a ray hits (conservative quantisation), incl. axis-parallel rays."""
+    import ctypes as C
+    from mitsuba_b200 import api
+    L = api.lib()
+    for n, seed, rays in ((1, 1, 10), (3, 2, 10), (4, 3, 50), (17, 4, 300), (1000, 5, 400), (30000, 6, 150)):
+        assert L.b2_bvh_selftest(C.c_uint32(n), C.c_uint32(seed), C.c_uint32(rays)) == 0, n
