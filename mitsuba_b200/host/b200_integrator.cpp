@@ -131,8 +131,8 @@ public:
             d.nonlinear = p.getBoolean("nonlinear", false) ? 1 : 0;
             /* plastic.cpp:186-202 (configure): the diffuse Fresnel reflectances and the sampling weight */
             d.fdr_int = (float) fresnelDiffuseReflectance(1 / d.eta, false); d.fdr_ext = (float) fresnelDiffuseReflectance(d.eta, false);
-            const float dAvg = (d.diffuse_reflectance[0] + d.diffuse_reflectance[1] + d.diffuse_reflectance[2]) / 3, sAvg = (d.reflectance[0] + d.reflectance[1] + d.reflectance[2]) / 3;
-            d.spec_sampling_weight = sAvg / (dAvg + sAvg);
+            const Float dAvg = p.getSpectrum("diffuseReflectance", Spectrum(0.5f)).getLuminance(), sAvg = p.getSpectrum("specularReflectance", Spectrum(1.0f)).getLuminance();
+            d.spec_sampling_weight = (float) (sAvg / (dAvg + sAvg));
         } else if (type == "coating" || type == "twosided" || type == "roughcoating" || type == "mask" || type == "mixturebsdf" || type == "blendbsdf" || type == "bumpmap") {
             Log(EError, "b200path: BSDF \"%s\" wraps another BSDF, which Mitsuba 0.6 keeps in a private member (INTEGRATION.md 1.2)", type.c_str());
         } else if (type == "null") {
@@ -159,7 +159,8 @@ public:
         if (sensorType != "perspective" && sensorType != "thinlens") Log(EError, "b200path: unsupported sensor \"%s\"", sensorType.c_str());
         const PerspectiveCamera *cam = static_cast<const PerspectiveCamera *>(sensor);
         const Film *film = scene->getFilm();
-        const Matrix4x4 &m = cam->getWorldTransform((Float) 0).getMatrix();
+        const Transform camToWorld = cam->getWorldTransform((Float) 0); /* (returned by value: keep it alive while the matrix is read) */
+        const Matrix4x4 &m = camToWorld.getMatrix();
         float toWorld[16];
         for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) toWorld[4 * i + j] = (float) m.m[i][j];
         const Vector2i full = film->getSize(), crop = film->getCropSize();

@@ -537,6 +537,7 @@ void pathref_sample_emitter_direct(void *h, int n, const float *ref, const float
 extern "C" void *CreateInstance_b200path(const Properties &props);
 int pathref_render_b200(void *h, int device, int parity, float *out, char *err, int errLen) {
     PathRef *p = (PathRef *) h;
+    struct ThrowScope { ThrowScope() { standinLogThrows() = true; } ~ThrowScope() { standinLogThrows() = false; } } scope; /* Log(EError) throws in here */
     try {
         const Properties &op = p->integrator->getProperties();
         Properties ip("b200path");

@@ -6,9 +6,12 @@
 #include <stdexcept>
 namespace mitsuba {
 enum ELogLevel { ETrace = 0, EDebug = 100, EInfo = 200, EWarn = 300, EError = 400 };
-/* like Logger::log (src/libcore/logger.cpp:100-147): messages below EError are dropped here, EError throws std::runtime_error */
+/* Logger::log (src/libcore/logger.cpp:100-147) throws std::runtime_error for EError.  Here messages are dropped, and EError only throws
+   while standinLogThrows() is set (the harness of the b200path plugin sets it around Integrator::render): the scene-building entry points
+   are extern "C" functions called from Python, which an exception must not cross */
+inline bool &standinLogThrows() { static bool flag = false; return flag; }
 inline void standinLog(ELogLevel level, const char *fmt, ...) {
-    if (level < EError) return;
+    if (level < EError || !standinLogThrows()) return;
     char buf[1024];
     va_list ap;
     va_start(ap, fmt);

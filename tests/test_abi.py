@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -82,3 +83,26 @@ def test_wide_bvh_builder_selftest():
     L = api.lib()
     for n, seed, rays in ((1, 1, 10), (3, 2, 10), (4, 3, 50), (17, 4, 300), (1000, 5, 400), (30000, 6, 150)):
         assert L.b2_bvh_selftest(C.c_uint32(n), C.c_uint32(seed), C.c_uint32(rays)) == 0, n
+
+
+def test_mitsuba_side_plugin_propagates_library_errors_as_mitsuba_exceptions():
+    """The compiled Mitsuba-side plugin (class B200PathTracer, oracle/_ref/libb200shim.so): on a machine without a CUDA device the C-ABI's
+    B2_ERR_NO_DEVICE comes back through Log(EError) -> std::runtime_error, the way every Mitsuba plugin reports an error."""
+    import ctypes as C
+    import sys
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "libb200shim.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libb200shim.so not built (the reference tree is not on this machine)")
+    from mitsuba_b200 import api
+    if api.lib().b2_device_count() > 0:
+        pytest.skip("a CUDA device is present: tests/test_gpu_shim.py renders through the plugin")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_pins
+    lib = C.CDLL(so)
+    desc, rp = next((d, r) for n, d, r in ref_pins.image_cases() if n == "cbox_box_8spp")
+    h = ref_pins.reference_scene(lib, desc, rp)
+    out = np.zeros((desc.camera.height, desc.camera.width, 5), np.float32)
+    err = C.create_string_buffer(1024)
+    lib.pathref_render_b200.restype = C.c_int
+    rc = lib.pathref_render_b200(h, 0, 1, out.ctypes.data_as(C.POINTER(C.c_float)), err, 1024)
+    assert rc == 1 and b"no CUDA device" in err.value
