@@ -193,6 +193,10 @@ static std::string dataDir() {
     }
     return "data";
 }
+extern "C" const char *b2_data_dir_(void) { // the data directory, for the scene-file front end (conductor presets)
+    static std::string dir = dataDir();
+    return dir.c_str();
+}
 template <typename T> static bool readFile(const std::string &path, std::vector<T> &out, size_t expect) {
     std::ifstream f(path, std::ios::binary);
     if (!f) return false;

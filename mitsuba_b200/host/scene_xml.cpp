@@ -19,6 +19,7 @@
 #include <map>
 #include <memory>
 #include <sstream>
+extern "C" const char *b2_data_dir_(void); // b2_host.cpp: <dir of libb2mts.so>/data or $B2MTS_DATA
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -311,6 +312,24 @@ struct Loader {
     std::map<std::string, int> bsdfIds; // id -> material id
     std::string baseDir;
 
+    // material="<name>" of the conductor plugins (roughconductor.cpp:174-190): the RGB (eta, k) the reference derives from
+    // data/ior/<name>.{eta,k}.spd, read from the table mitsuba_b200/data/conductor_presets.txt (generated with the reference's own
+    // spectrum code by tools/extract_conductor_presets.py; hex floats)
+    static bool conductorPreset(const std::string &material, double eta[3], double k[3]) {
+        const char *dir = b2_data_dir_();
+        std::ifstream f(std::string(dir ? dir : "data") + "/conductor_presets.txt");
+        std::string line;
+        while (std::getline(f, line)) {
+            if (line.empty() || line[0] == '#') continue;
+            std::istringstream is(line);
+            std::string name, tok[6];
+            is >> name >> tok[0] >> tok[1] >> tok[2] >> tok[3] >> tok[4] >> tok[5];
+            if (name != material || !is) continue;
+            for (int i = 0; i < 3; ++i) { eta[i] = strtod(tok[i].c_str(), nullptr); k[i] = strtod(tok[3 + i].c_str(), nullptr); }
+            return true;
+        }
+        return false;
+    }
     static void microfacet(Props &p, b2_material_desc &m) { // microfacet.h:95-148
         m.distr = B2_DISTR_BECKMANN; m.alpha_u = m.alpha_v = 0.1f;
         if (p.has("distribution")) {
@@ -357,8 +376,8 @@ struct Loader {
             std::string lower = material;
             std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
             double eta[3] = {0, 0, 0}, k[3] = {1, 1, 1};
-            if (lower != "none" && !(p.has("eta") && p.has("k")))
-                throw Err("roughconductor: material=\"" + material + "\" needs the data/ior .spd tables (not supported); pass RGB 'eta' and 'k'");
+            if (lower != "none" && !conductorPreset(material, eta, k) && !(p.has("eta") && p.has("k")))
+                throw Err("roughconductor: unknown material preset \"" + material + "\" (data/ior/" + material + ".eta.spd); pass RGB 'eta' and 'k'");
             float fe[3], fk[3];
             p.spec("eta", eta, fe); p.spec("k", k, fk);
             float ext = (float) namedIOR(p, "extEta", "air");
@@ -409,8 +428,8 @@ struct Loader {
             std::string lower = material;
             std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
             double eta[3] = {0, 0, 0}, k[3] = {1, 1, 1};
-            if (lower != "none" && !(p.has("eta") && p.has("k")))
-                throw Err("conductor: material=\"" + material + "\" needs the data/ior .spd tables (not supported); pass RGB 'eta' and 'k'");
+            if (lower != "none" && !conductorPreset(material, eta, k) && !(p.has("eta") && p.has("k")))
+                throw Err("conductor: unknown material preset \"" + material + "\" (data/ior/" + material + ".eta.spd); pass RGB 'eta' and 'k'");
             float fe[3], fk[3];
             p.spec("eta", eta, fe); p.spec("k", k, fk);
             float ext = (float) namedIOR(p, "extEta", "air");

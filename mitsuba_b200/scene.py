@@ -54,6 +54,19 @@ def _fresnel_dielectric_ext(cos_i, eta):
     return np.where(tir, 1.0, 0.5 * (rs * rs + rp * rp))
 
 
+def conductor_preset(material: str):
+    """RGB (eta, k) of a data/ior material preset as the reference derives it (table mitsuba_b200/data/conductor_presets.txt, generated with
+    the reference's own spectrum code by tools/extract_conductor_presets.py)."""
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "conductor_presets.txt")) as f:
+        for line in f:
+            t = line.split()
+            if t and t[0] == material:
+                v = [float.fromhex(x) for x in t[1:7]]
+                return tuple(v[:3]), tuple(v[3:])
+    raise ValueError(f"unknown conductor material preset {material!r}")
+
+
 def fresnel_diffuse_reflectance(eta: float) -> float:
     """util.cpp:807-859 fresnelDiffuseReflectance(eta, fast=false): integral of F(sqrt(xi), eta) over xi in [0, 1]
     (composite Simpson in float64 instead of the reference's adaptive Gauss-Lobatto with 1e-5 tolerance)."""
@@ -110,6 +123,7 @@ class Bsdf:
     sample_visible: bool = True                                # microfacet.h:138
     eta: Sequence[float] = (0.0, 0.0, 0.0)                     # roughconductor eta (RGB), material="none"
     k: Sequence[float] = (1.0, 1.0, 1.0)
+    material: str = "none"                                     # conductors: a data/ior preset ("Cu", "Au", ...) overrides eta / k (roughconductor.cpp:174-190)
     ext_eta: object = "air"                                    # roughconductor.cpp:187
     int_ior: object = "bk7"                                    # roughdielectric.cpp:190 / coating.cpp:112
     ext_ior: object = "air"
@@ -144,8 +158,9 @@ class Bsdf:
         if t in (1, 7):  # roughconductor.cpp:187-190, conductor.cpp:172-175
             ext = np.float32(lookup_ior(self.ext_eta, "air"))
             recip = np.float32(1.0) / ext  # Spectrum / Float multiplies by the reciprocal (spectrum.h:415-425)
-            d["etaC"] = tuple(float(np.float32(x) * recip) for x in self.eta)  # roughconductor.cpp:189-190
-            d["kC"] = tuple(float(np.float32(x) * recip) for x in self.k)
+            eta, k = (self.eta, self.k) if self.material.lower() == "none" else conductor_preset(self.material)
+            d["etaC"] = tuple(float(np.float32(x) * recip) for x in eta)  # roughconductor.cpp:189-190
+            d["kC"] = tuple(float(np.float32(x) * recip) for x in k)
         if t in (2, 3, 6):
             d["eta"] = float(np.float32(lookup_ior(self.int_ior, "bk7")) / np.float32(lookup_ior(self.ext_ior, "air")))
         if t == 8:  # plastic.cpp:145-161,186-204

@@ -530,6 +530,19 @@ void pathref_sample_emitter_direct(void *h, int n, const float *ref, const float
         o[5] = value[0]; o[6] = value[1]; o[7] = value[2]; o[8] = value.isZero() ? 0.0f : 1.0f; o[9] = dRec.p.x; o[10] = dRec.p.y; o[11] = dRec.p.z;
     }
 }
+/* The RGB (eta, k) a conductor plugin derives from material="<name>" (roughconductor.cpp:174-190, conductor.cpp:160-176): the reference's own
+ * InterpolatedSpectrum file reader + Spectrum::fromContinuousSpectrum (src/libcore/spectrum.cpp) on <dataDir>/ior/<name>.{eta,k}.spd.
+ * Used by tools/extract_conductor_presets.py to generate mitsuba_b200/data/conductor_presets.txt and by the test that pins that table. */
+int pathref_conductor_preset(const char *dataDir, const char *material, float *eta3, float *k3) {
+    try {
+        const std::string base = std::string(dataDir) + "/ior/" + material;
+        Spectrum eta, k;
+        eta.fromContinuousSpectrum(InterpolatedSpectrum(fs::path(base + ".eta.spd")));
+        k.fromContinuousSpectrum(InterpolatedSpectrum(fs::path(base + ".k.spd")));
+        for (int i = 0; i < 3; ++i) { eta3[i] = eta[i]; k3[i] = k[i]; }
+        return 0;
+    } catch (...) { return 1; }
+}
 #ifdef WITH_B200_SHIM
 /* The same Scene object rendered through the Mitsuba-side plugin of this repository (mitsuba_b200/host/b200_integrator.cpp, class
  * B200PathTracer: Integrator::render -> C-ABI of libb2mts.so -> film through Film::setBitmap) instead of MIPathTracer + renderBlock.

@@ -225,3 +225,39 @@ def test_instances_xml_matches_python_scene(b2ctx):
     assert st["n_triangles"] == s2["n_triangles"]
     assert rel_l2(api.develop(film), api.develop(f2)) < 1e-3
     assert abs(st["rays"] - s2["rays"]) <= 1e-3 * s2["rays"]
+
+
+def test_conductor_material_presets_and_crop_window_through_the_scene_file(b2ctx, tmp_path):
+    """<bsdf type="roughconductor"> with its DEFAULT material (the plugin's material="Cu": data/ior/Cu.{eta,k}.spd -> RGB, roughconductor.cpp:174-190)
+    and a named preset render like the same scene with explicit RGB eta / k; <film> cropOffsetX/Y + cropWidth/Height (film.cpp:36-47)."""
+    from mitsuba_b200.scene import conductor_preset
+    tmpl = '''<scene version="0.5.0"><integrator type="path"/>
+      <sensor type="perspective"><float name="fov" value="40"/>
+        <transform name="toWorld"><lookat origin="0, 1.5, -4" target="0, 0.5, 0" up="0, 1, 0"/></transform>
+        <sampler type="sobol"><integer name="sampleCount" value="16"/></sampler>
+        <film type="hdrfilm"><integer name="width" value="64"/><integer name="height" value="48"/>%s<rfilter type="box"/></film></sensor>
+      <bsdf type="roughconductor" id="metal"><float name="alpha" value="0.2"/><string name="distribution" value="ggx"/>%s</bsdf>
+      <shape type="obj"><string name="filename" value="%s"/><ref id="metal"/></shape>
+      <shape type="obj"><string name="filename" value="%s"/><bsdf type="diffuse"/><emitter type="area"><rgb name="radiance" value="12, 12, 12"/></emitter></shape>
+    </scene>'''
+    ball, light = tmp_path / "ball.obj", tmp_path / "light.obj"
+    ball.write_text("v -1 0 -1\nv 1 0 -1\nv 1 0 1\nv -1 0 1\nv 0 1.4 0\nf 1 2 3\nf 1 3 4\nf 1 5 2\nf 2 5 3\nf 3 5 4\nf 4 5 1\n")
+    light.write_text("v -1 3 -1\nv 1 3 -1\nv 1 3 1\nv -1 3 1\nf 1 3 2\nf 1 4 3\n")
+
+    def render(film_extra, bsdf_extra):
+        p = tmp_path / "s.xml"
+        p.write_text(tmpl % (film_extra, bsdf_extra, ball, light))
+        sc, rp = b2ctx.load_xml(str(p))
+        return sc.render(rp, parity=True)[0], sc
+
+    for material, explicit in (("", conductor_preset("Cu")), ('<string name="material" value="Au"/>', conductor_preset("Au"))):
+        a, _ = render("", material)
+        eta, k = explicit
+        b, _ = render("", '<string name="material" value="none"/><rgb name="eta" value="%r, %r, %r"/><rgb name="k" value="%r, %r, %r"/>' % (*eta, *k))
+        assert a[..., :3].max() > 0.05 and rel_l2(api.develop(a), api.develop(b)) < 1e-5
+    with pytest.raises(api.B2Error, match="unknown material preset"):
+        render("", '<string name="material" value="Unobtainium"/>')
+    crop, sc = render('<integer name="cropOffsetX" value="8"/><integer name="cropOffsetY" value="16"/><integer name="cropWidth" value="40"/><integer name="cropHeight" value="24"/>', "")
+    assert crop.shape == (24, 40, 5) and (sc.W, sc.H) == (40, 24)
+    with pytest.raises(api.B2Error, match="Invalid crop window"):
+        render('<integer name="cropOffsetX" value="60"/><integer name="cropWidth" value="40"/>', "")

@@ -248,3 +248,29 @@ def test_emitter_order_and_instanced_records_match_the_live_reference_when_prese
     assert np.array_equal(a[:, 21], b[:, 21]) and (a[:, 21] == 1).sum() > 1000
     hit = a[:, 21] == 1
     assert np.array_equal(a[hit][:, :19], b[hit][:, :19]) and np.array_equal(a[hit, 20], b[hit, 20])
+
+
+def test_conductor_material_presets_match_the_reference_spectrum_code():
+    """material="Cu" etc. of the conductor plugins (roughconductor.cpp:174-190): the committed table (mitsuba_b200/data/conductor_presets.txt)
+    against the live reference -- InterpolatedSpectrum + Spectrum::fromContinuousSpectrum on data/ior/*.spd -- where it is present, and against
+    the values the reference's documentation quotes for copper everywhere."""
+    from mitsuba_b200.scene import Bsdf, conductor_preset
+    eta, k = conductor_preset("Cu")
+    assert np.allclose(eta, (0.2004, 0.9240, 1.1022), atol=1e-4) and np.allclose(k, (3.9129, 2.4528, 2.1421), atol=1e-4)
+    d = Bsdf("roughconductor", material="Au").flat()
+    from mitsuba_b200.scene import lookup_ior
+    assert np.allclose(d["etaC"], np.float32(conductor_preset("Au")[0]) / np.float32(lookup_ior("air", "air")), rtol=1e-6)   # / extEta (air)
+    so = os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so")
+    if not os.path.exists(so) or not os.path.exists("/root/reference/data/ior"):
+        return
+    lib = C.CDLL(so)
+    n = 0
+    for line in open(os.path.join(HERE, "..", "mitsuba_b200", "data", "conductor_presets.txt")):
+        t = line.split()
+        if not t or t[0].startswith("#"):
+            continue
+        e, kk = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        assert lib.pathref_conductor_preset(b"/root/reference/data", t[0].encode(), ref_pins._f(e), ref_pins._f(kk)) == 0
+        assert np.array_equal(np.float32([float.fromhex(x) for x in t[1:7]]), np.concatenate([e, kk])), t[0]
+        n += 1
+    assert n >= 60
