@@ -1629,7 +1629,10 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
 // assigned statically, so every lane of a warp enters the same Woodcock loop at the same time (ncu: k_volstep ran 2.3 of 32 lanes per
 // instruction).  Same draws in the same order per path as k_volstep and the oracle.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(B2_TRACE_BLOCK, 4) k_volstep_lockstep(DScene sc, DPool pool, DRender rp) {
+#ifndef B2_VOLLS_MINBLOCKS
+#define B2_VOLLS_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOLLS_MINBLOCKS) k_volstep_lockstep(DScene sc, DPool pool, DRender rp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t it = (uint32_t) pool.counters[CTR_ITER] - 1u;
     stampBegin(rp, it, STAGE_SHADE);

@@ -600,6 +600,7 @@ B2_DEV void traverseQueue8(const DScene &sc, const TraceMem &tm, uint32_t n, uns
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t stride = tm.stride;
+
     bool active = false, pending = false, exhausted = false, found = false;
     uint32_t idx = 0, best = 0;
     V3 o(0.0f), d(0.0f), idir(0.0f), ood(0.0f);
@@ -658,6 +659,8 @@ B2_DEV void traverseQueue8(const DScene &sc, const TraceMem &tm, uint32_t n, uns
                 continue;
             }
         }
+        // per-lane results of the node visit: hit internal children (visiting order), triangles of the hit leaf children
+        uint32_t hmask = 0, tmask = 0, triBase = 0, imaskN = 0, childBaseN = 0;
         if (active) {
             // ---- node: eight quantised child boxes ----
             float4 n0, n1, n2, n3, n4;
@@ -684,7 +687,6 @@ B2_DEV void traverseQueue8(const DScene &sc, const TraceMem &tm, uint32_t n, uns
             const uint32_t nz0 = __float_as_uint(pz ? n3.x : n4.z), nz1 = __float_as_uint(pz ? n3.y : n4.w);
             const uint32_t fz0 = __float_as_uint(pz ? n4.z : n3.x), fz1 = __float_as_uint(pz ? n4.w : n3.y);
             const uint32_t meta0 = __float_as_uint(n1.z), meta1 = __float_as_uint(n1.w);
-            uint32_t hmask = 0, tmask = 0;
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
                 const int k = s & 3;
@@ -699,11 +701,14 @@ B2_DEV void traverseQueue8(const DScene &sc, const TraceMem &tm, uint32_t n, uns
                     else tmask |= ((1u << (m >> 5)) - 1u) << (m & 31u); // an empty slot has m == 0: no bits
                 }
             }
+            triBase = __float_as_uint(n1.y); imaskN = imask; childBaseN = __float_as_uint(n1.x);
             // ---- the triangles of the leaf children that were hit ----
-            // Tried on B200 (10 M triangles, 4 Mi incoherent rays; this loop: 1.60 Grays/s): requesting the next triangle's rows before the
-            // current one is tested + prefetching the hit children into the L2: 1.51; postponing the triangles until 8 lanes of the warp wait
-            // (one triangle pass for many lanes): 1.51; binning the tickets by entry cell x direction cell first (B2_BIN=1): 1.41.
-            const uint32_t triBase = __float_as_uint(n1.y);
+            // ncu (round 2, 10 M triangles, 1.60 Grays/s): this per-lane loop runs at 3 of 32 lanes (10 M warp-level passes against 2.1 M
+            // node passes at 23 lanes) and 37 % of the stall samples sit on the first use of a freshly loaded triangle.  Four remedies were
+            // implemented and measured on the same workload; all were SLOWER and are not kept: next-triangle prefetch + prefetch.global.L2
+            // of the hit children 1.51; postponing the triangles until 8 lanes of the warp wait 1.51; binning the tickets by entry cell x
+            // direction cell (B2_BIN=1) 1.41; a warp-cooperative pass (prefix-sum numbered (lane, triangle) pairs, every lane tests one pair
+            // with the owner's ray fetched by shuffles, closest hit by a 64-bit shared-memory atomicMin) 1.21.
             while (tmask) {
                 const uint32_t ti = triBase + (uint32_t) (__ffs((int) tmask) - 1);
                 tmask &= tmask - 1u;
@@ -723,7 +728,7 @@ B2_DEV void traverseQueue8(const DScene &sc, const TraceMem &tm, uint32_t n, uns
             else {
                 if (hmask) {
                     if (grpBits >> 24) { tm.stack8[sp * stride] = make_uint2(grpBase, grpBits); ++sp; }
-                    grpBase = __float_as_uint(n1.x); grpBits = hmask | imask;
+                    grpBase = childBaseN; grpBits = hmask | imaskN;
                 }
                 if (!(grpBits >> 24)) {
                     if (sp == 0) { active = false; pending = true; }

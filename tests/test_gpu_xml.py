@@ -242,7 +242,7 @@ def test_conductor_material_presets_and_crop_window_through_the_scene_file(b2ctx
     </scene>'''
     ball, light = tmp_path / "ball.obj", tmp_path / "light.obj"
     ball.write_text("v -1 0 -1\nv 1 0 -1\nv 1 0 1\nv -1 0 1\nv 0 1.4 0\nf 1 2 3\nf 1 3 4\nf 1 5 2\nf 2 5 3\nf 3 5 4\nf 4 5 1\n")
-    light.write_text("v -1 3 -1\nv 1 3 -1\nv 1 3 1\nv -1 3 1\nf 1 3 2\nf 1 4 3\n")
+    light.write_text("v -1 3 -1\nv 1 3 -1\nv 1 3 1\nv -1 3 1\nf 1 2 3\nf 1 3 4\n")   # facing down
 
     def render(film_extra, bsdf_extra):
         p = tmp_path / "s.xml"
