@@ -22,6 +22,9 @@
 #include <mitsuba/core/sched.h>
 #include <mitsuba/core/statistics.h>
 #include <mitsuba/core/bitmap.h>
+#include <mitsuba/core/fstream.h>
+#include <mitsuba/render/mipmap.h>
+#include <mitsuba/hw/gputexture.h>
 #include <mitsuba/hw/basicshader.h>
 #include <mitsuba/hw/renderer.h>
 #include <mitsuba/core/zstream.h>
@@ -128,6 +131,14 @@ ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string 
 ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k, const AnimatedTransform *d) const { return hasProperty(k) || !d ? new AnimatedTransform(getTransform(k, Transform())) : d; }
 ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k) const { return new AnimatedTransform(getTransform(k)); }
 std::ostream &operator<<(std::ostream &os, const ETransportMode &m) { return os << (int) m; }
+/* envmap.cpp's image-file path (constructor else-branch, serialize) and its OpenGL shader: never reached through the cache-file route */
+FileStream::FileStream(const fs::path &, EFileMode) { throw std::runtime_error("FileStream: image files are not readable here"); }
+size_t FileStream::getSize() const { return 0; }
+void GPUTexture::initAndRelease() {}
+ref<Bitmap> Bitmap::expand() { throw std::runtime_error("Bitmap::expand: not available"); }
+ref<Bitmap> Bitmap::convert(EPixelFormat, EComponentFormat, Float, Float, Spectrum::EConversionIntent) { throw std::runtime_error("Bitmap::convert: not available"); }
+ref<Bitmap> Bitmap::resample(const ReconstructionFilter *, ReconstructionFilter::EBoundaryCondition, ReconstructionFilter::EBoundaryCondition, const Vector2i &, Float, Float) const { throw std::runtime_error("Bitmap::resample: not available"); }
+void Bitmap::write(EFileFormat, Stream *, int) const { throw std::runtime_error("Bitmap::write: not available"); }
 /* Bitmap: a zeroed float buffer (src/libcore/bitmap.cpp needs OpenEXR / libpng / libjpeg) */
 Bitmap::Bitmap(EPixelFormat pFmt, EComponentFormat cFmt, const Vector2i &size, uint8_t channelCount, uint8_t *)
     : m_pixelFormat(pFmt), m_componentFormat(cFmt), m_size(size), m_data(NULL), m_gamma(1.0f), m_channelCount(channelCount), m_ownsData(true) {
@@ -182,7 +193,7 @@ using namespace mitsuba;
 #define DECL(name) extern "C" void *CreateInstance_##name(const Properties &props);
 DECL(diffuse) DECL(roughconductor) DECL(roughdielectric) DECL(coating) DECL(dielectric) DECL(conductor) DECL(plastic) DECL(twosided) DECL(null)
 DECL(gaussian) DECL(box) DECL(sobol) DECL(independent) DECL(path) DECL(perspective) DECL(area)
-DECL(thinlens) DECL(constant) DECL(shapegroup) DECL(instance)
+DECL(thinlens) DECL(constant) DECL(shapegroup) DECL(instance) DECL(envmap)
 DECL(volpath) DECL(heterogeneous) DECL(homogeneous) DECL(gridvolume) DECL(constvolume) DECL(isotropic) DECL(hg)
 
 /* The `independent` sampler of this repository is a counter-based stream, not the reference's SFMT: to compare volpath
@@ -396,6 +407,91 @@ void pathref_add_constant_emitter(void *h, const float *radiance, float sampling
     em->configure();
     p->scene->addChild("", em);
     p->keep.push_back(em);
+}
+/* <emitter type="envmap"> (src/emitters/envmap.cpp).  The image file readers (OpenEXR, RGBE, ...) are not here, so the pyramid enters the
+ * real class the way a second Mitsuba run reads it: through its MIP map cache file (envmap.cpp:143-147 -> mipmap.h:320-380).  The caller
+ * hands in the pyramid levels (float RGB, row-major, level l of size sizes[2l] x sizes[2l+1]); they are written next to a placeholder image
+ * `<stem>.img` as `<stem>.mip` with the header validateCacheFile (mipmap.h:405-446) expects and the reference's own BlockedArray layout and
+ * float -> half conversion (TSpectrum<half>, src/libcore/half.cpp).  CDF tables, look-ups and sampling are then all the reference's. */
+namespace {
+typedef TMIPMap<Spectrum, TSpectrum<half, SPECTRUM_SAMPLES> > EnvMIP;
+struct EnvCacheWriter : public EnvMIP { typedef EnvMIP::MIPMapHeader Header; typedef EnvMIP::Array2DType Array; };
+}
+int pathref_add_envmap(void *h, const char *stem, int nLevels, const int *sizes, const float *const *levels, const float *toWorld, float scale, float samplingWeight) {
+    PathRef *p = (PathRef *) h;
+    const std::string img = std::string(stem) + ".img", mip = std::string(stem) + ".mip";
+    { FILE *f = fopen(img.c_str(), "wb"); if (!f) return -1; fputs("placeholder for the decoded image handed in as a MIP map cache\n", f); fclose(f); }
+    boost::system::error_code ec;
+    const uint64_t timestamp = (uint64_t) fs::last_write_time(fs::path(img), ec);
+    size_t padding = sizeof(EnvCacheWriter::Header) % MTS_MIPMAP_CACHE_ALIGNMENT;
+    if (padding) padding = MTS_MIPMAP_CACHE_ALIGNMENT - padding;
+    size_t total = sizeof(EnvCacheWriter::Header) + padding;
+    for (int l = 0; l < nLevels; ++l) total += EnvCacheWriter::Array::bufferSize(Vector2i(sizes[2 * l], sizes[2 * l + 1]));
+    uint8_t *buf = (uint8_t *) allocAligned(total);
+    memset(buf, 0, total);
+    EnvCacheWriter::Header header;
+    memset(&header, 0, sizeof(header));
+    memcpy(header.identifier, "MIP", 3);
+    header.version = MTS_MIPMAP_CACHE_VERSION;
+    header.pixelFormat = (uint8_t) Bitmap::ERGB;
+    header.levels = (uint8_t) nLevels;
+    header.bcu = (uint8_t) ReconstructionFilter::ERepeat; header.bcv = (uint8_t) ReconstructionFilter::EClamp;
+    header.filterType = (uint8_t) EEWA;
+    header.gamma = 1.0f;
+    header.width = sizes[0]; header.height = sizes[1];
+    header.timestamp = timestamp;
+    memcpy(buf, &header, sizeof(header));
+    uint8_t *ptr = buf + sizeof(EnvCacheWriter::Header) + padding;
+    for (int l = 0; l < nLevels; ++l) {
+        EnvCacheWriter::Array a;
+        a.map(ptr, Vector2i(sizes[2 * l], sizes[2 * l + 1]));
+        a.init((const Spectrum *) levels[l]);
+        ptr += a.getBufferSize();
+    }
+    { FILE *f = fopen(mip.c_str(), "wb"); if (!f) { freeAligned(buf); return -1; } fwrite(buf, 1, total, f); fclose(f); }
+    freeAligned(buf);
+    Properties ep("envmap");
+    ep.setString("filename", img);
+    ep.setFloat("scale", scale);
+    ep.setFloat("samplingWeight", samplingWeight);
+    if (toWorld) {
+        Matrix4x4 M;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M.m[r][c] = toWorld[4 * r + c];
+        ep.setTransform("toWorld", Transform(M));
+    }
+    ref<Emitter> em = (Emitter *) CreateInstance_envmap(ep);
+    em->configure();
+    p->scene->addChild("", em);
+    p->keep.push_back(em);
+    return 0;
+}
+/* Scene::evalEnvironment for n rays: rays 6n (o, d) without differentials, or 18n (o, d, rxO, rxD, ryO, ryD) with them -> out 3n */
+void pathref_eval_environment(void *h, int n, int withDifferentials, const float *rays, float *out) {
+    PathRef *p = (PathRef *) h;
+    const int stride = withDifferentials ? 18 : 6;
+    for (int i = 0; i < n; ++i) {
+        const float *r = rays + (size_t) stride * i;
+        RayDifferential ray(Point(r[0], r[1], r[2]), Vector(r[3], r[4], r[5]), 0.0f);
+        if (withDifferentials) {
+            ray.rxOrigin = Point(r[6], r[7], r[8]); ray.rxDirection = Vector(r[9], r[10], r[11]);
+            ray.ryOrigin = Point(r[12], r[13], r[14]); ray.ryDirection = Vector(r[15], r[16], r[17]);
+            ray.hasDifferentials = true;
+        }
+        const Spectrum v = p->scene->evalEnvironment(ray);
+        out[3 * i] = v[0]; out[3 * i + 1] = v[1]; out[3 * i + 2] = v[2];
+    }
+}
+/* Scene::pdfEmitterDirect for the environment emitter: ref 6n (ref, refN), d 3n -> out n (solid-angle density incl. the emitter choice) */
+void pathref_pdf_environment_direct(void *h, int n, const float *ref, const float *d, float *out) {
+    PathRef *p = (PathRef *) h;
+    for (int i = 0; i < n; ++i) {
+        DirectSamplingRecord dRec(Point(ref[6 * i], ref[6 * i + 1], ref[6 * i + 2]), 0.0f);
+        dRec.refN = Normal(ref[6 * i + 3], ref[6 * i + 4], ref[6 * i + 5]);
+        dRec.d = Vector(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        dRec.measure = ESolidAngle;
+        dRec.object = p->scene->getEnvironmentEmitter();
+        out[i] = p->scene->getEnvironmentEmitter() ? p->scene->pdfEmitterDirect(dRec) : 0.0f;
+    }
 }
 /* perspective sensor + film + sampler + path integrator; rfilter 0 box / 1 gaussian; sampler 0 sobol / 1 independent */
 void pathref_setup2(void *h, const float *toWorld, float fov, float nearClip, float farClip, int W, int H, int rfilter, int samplerKind, int spp, uint64_t scramble,

@@ -9,6 +9,8 @@ class AnimatedTransform;
 class Properties {
 public:
     enum EPropertyType { EBoolean = 0, EInteger, EFloat, EPoint, EVector, ETransform, EAnimatedTransform, ESpectrum, EString, EData };
+    struct Data { uint8_t *ptr; size_t size; };                                                   /* properties.h:73-84 */
+    Data getData(const std::string &) const { Data d; d.ptr = NULL; d.size = 0; return d; }      /* never set here: hasProperty() says no */
     Properties() {}
     Properties(const std::string &pluginName) : m_pluginName(pluginName) {}
     const std::string &getPluginName() const { return m_pluginName; }
