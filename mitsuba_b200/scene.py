@@ -272,6 +272,24 @@ class Instance:
 
 
 @dataclass
+class EnvMap:
+    """<emitter type="envmap"> (src/emitters/envmap.cpp:106-181): a latitude-longitude radiance map around the scene.
+
+    `pixels` is the decoded image as linear float RGB, (H, W, 3), top row first (the reference's Bitmap after convert(..., EFloat));
+    `to_world` orients it (default: +Y up, the image centre looks down -Z); `scale` multiplies the radiance."""
+    pixels: np.ndarray = None
+    scale: float = 1.0
+    to_world: Optional[np.ndarray] = None
+    sampling_weight: float = 1.0
+    to_local: Optional[np.ndarray] = None   # inverse of to_world; derived when absent (tests hand in the reference's own float inverse)
+
+    def matrices(self):
+        M64 = np.eye(4) if self.to_world is None else np.asarray(self.to_world, np.float64)
+        inv = np.linalg.inv(M64) if self.to_local is None else np.asarray(self.to_local, np.float64)
+        return np.ascontiguousarray(M64, np.float32), np.ascontiguousarray(inv, np.float32)
+
+
+@dataclass
 class Camera:
     to_world: np.ndarray                # 4x4 camera-to-world (row major)
     fov: float = 39.3077                # degrees along `fov_axis`
@@ -348,6 +366,7 @@ class SceneDesc:
     instances: List["Instance"] = field(default_factory=list)
     env_radiance: Optional[Sequence[float]] = None   # <emitter type="constant"> (src/emitters/constant.cpp:47-52); in Scene::m_emitters it precedes the area emitters (scene.cpp:510-516 vs :322-335)
     env_sampling_weight: float = 1.0
+    envmap: Optional["EnvMap"] = None              # <emitter type="envmap">; a scene holds at most one environment emitter (scene.cpp:510-514)
 
     def flat_bsdfs(self):
         """Flatten the BSDF tree to an array (nested referenced by index); returns (list, per-mesh id)."""

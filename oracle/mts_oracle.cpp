@@ -20,6 +20,7 @@
 #include "orc_accel.h"
 #include "orc_bsdf.h"
 #include "orc_medium.h"
+#include "orc_envmap.h"
 #include <thread>
 #include <atomic>
 #include <mutex>
@@ -96,7 +97,8 @@ struct Discrete {
     }
 };
 
-struct Emitter { V3 radiance; float samplingWeight; int mesh; /* -1: `constant` environment emitter (src/emitters/constant.cpp) */ };
+struct Emitter { V3 radiance; float samplingWeight; int mesh; /* -1: environment emitter: `constant` (src/emitters/constant.cpp) ... */
+                 int envmap = -1; /* ... or, when >= 0, `envmap` (src/emitters/envmap.cpp, orc_envmap.h): index into Scene::envmaps */ };
 
 struct Intersection { /* include/mitsuba/render/shape.h:131-171 (fields `path` reads) */
     float t = kInf; V3 p; Frame geoFrame, shFrame; V3 wi; V3 dpdu, dpdv; int mesh = -1; uint32_t prim = 0; int instance = -1;
@@ -114,6 +116,7 @@ struct Scene {
     std::vector<Texture> textures; /* `bitmap` textures (orc_texture.h) referenced by OrcBsdf::texture */
     std::vector<Mesh> meshes;
     std::vector<Emitter> emitters;
+    std::vector<EnvMap> envmaps;
     std::vector<OrcMedium> media;
     /* instancing: src/shapes/{shapegroup,instance}.cpp */
     struct Instance { int group; float M[16], Minv[16]; };
@@ -350,6 +353,28 @@ struct Scene {
         float emPdf;
         size_t index = emitterPDF.sampleReuse(sx, emPdf);
         const Emitter &em = emitters[index];
+        if (em.mesh < 0 && em.envmap >= 0) { /* envmap.cpp:516-543 sampleDirect, then scene.cpp:838-851 */
+            const EnvMap &env = envmaps[em.envmap];
+            V3 value, d; float pdf;
+            env.sampleDirection(sx, sy, d, value, pdf);
+            const V3 dw = EnvMap::xfVector(env.toWorld, d);
+            float nearT, farT;
+            dRec.pdf = 0.0f;
+            if (value.isZero() || pdf == 0 || !bsphereIntersect(dRec.ref, dw, nearT, farT) || nearT >= 0 || farT <= 0) return Spectrum(0.0f);
+            dRec.pdf = pdf;
+            dRec.p = dRec.ref + dw * farT;
+            dRec.n = normalize(bsCenter - dRec.p);
+            dRec.dist = farT; dRec.d = dw; dRec.solidAngle = true;
+            value = value / pdf;
+            if (!testVisibility) { dRec.emitter = (int) index; if (emPdfOut) *emPdfOut = emPdf; return value; }
+            Ray ray(dRec.ref, dRec.d, kEpsilon, dRec.dist * (1 - kShadowEpsilon));
+            ++st.shadowRays;
+            if (instances.empty() ? accel.rayOccluded(ray, &st.nodeVisits, &st.primTests) : topOccluded(ray, st)) return Spectrum(0.0f);
+            dRec.emitter = (int) index;
+            dRec.pdf *= emPdf;
+            value /= emPdf;
+            return value;
+        }
         if (em.mesh < 0) { /* constant.cpp:171-208 sampleDirect */
             V3 d; float pdf;
             if (!dRec.refN.isZero()) {
@@ -420,6 +445,12 @@ struct Scene {
         }
         return Spectrum(0.0f);
     }
+    /* Scene::evalEnvironment (scene.h:727-730): constant.cpp:151-153 or envmap.cpp:380-410 (filtered when the ray carries differentials) */
+    Spectrum evalEnvironment(const Ray &ray, const RayDiff *rd = nullptr) const {
+        const Emitter &em = emitters[envEmitter];
+        if (em.envmap < 0) return em.radiance;
+        return envmaps[em.envmap].evalEnvironment(ray.d, rd && rd->has ? &rd->rxD : nullptr, rd && rd->has ? &rd->ryD : nullptr);
+    }
     /* scene.cpp:949-952; scene.h:848-850; area.cpp:175-183; shape.cpp:117-126; trimesh.cpp:358-360 */
     /* bsphere.h:88-95 + util.cpp:447-485 */
     bool bsphereIntersect(const V3 &ro, const V3 &rd, float &x0, float &x1) const {
@@ -436,6 +467,10 @@ struct Scene {
     }
     float pdfEmitterDirect(const DRec &dRec) const {
         const Emitter &em = emitters[dRec.emitter];
+        if (em.mesh < 0 && em.envmap >= 0) { /* envmap.cpp:545-556, measure == ESolidAngle */
+            const EnvMap &env = envmaps[em.envmap];
+            return env.pdfDirection(EnvMap::xfVector(env.toLocal, dRec.d)) * (em.samplingWeight * emitterPDF.normalization);
+        }
         if (em.mesh < 0) { /* constant.cpp:210-224, measure == ESolidAngle */
             float pdfSA = !dRec.refN.isZero() ? kInvPi * std::max(0.0f, dot(dRec.d, dRec.refN)) : kInvFourPi;
             return pdfSA * (em.samplingWeight * emitterPDF.normalization);
@@ -515,7 +550,7 @@ struct Scene {
         const int maxDepth = rp.maxDepth, rrDepth = rp.rrDepth;
         while (depth <= maxDepth || maxDepth < 0) {
             if (!its.isValid()) { /* path.cpp:136-143 */
-                if (envEmitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered)) Li += throughput * emitters[envEmitter].radiance;
+                if (envEmitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered)) Li += throughput * evalEnvironment(ray, &rayDiff);
                 break;
             }
             const Mesh &mesh = meshes[its.mesh];
@@ -572,7 +607,7 @@ struct Scene {
             } else { /* path.cpp:239-252 */
                 if (envEmitter < 0) break;
                 if (rp.hideEmitters && !scattered) break;
-                value = emitters[envEmitter].radiance;
+                value = evalEnvironment(ray);
                 /* fillDirectSamplingRecord (constant.cpp:239-253): the ray starts inside the bounding sphere */
                 float nearT, farT;
                 if (!bsphereIntersect(ray.o, ray.d, nearT, farT) || nearT > 0 || farT < 0) break;
@@ -699,14 +734,16 @@ struct Scene {
             if (bsphereIntersect(ray.o, ray.d, nearT, farT) && !(nearT > 0) && !(farT < 0)) {
                 dRec.p = ray(farT); dRec.n = normalize(bsCenter - dRec.p); dRec.solidAngle = true; dRec.emitter = envEmitter;
                 dRec.d = ray.d; dRec.dist = farT;
-                value = transmittance * emitters[envEmitter].radiance;
+                value = transmittance * evalEnvironment(ray);
             }
         }
     }
-    Spectrum LiVol(const Ray &r, Sampler *sampler, const OrcRenderParams &rp, float &alpha, OrcStats &st) const {
+    Spectrum LiVol(const Ray &r, Sampler *sampler, const OrcRenderParams &rp, float &alpha, OrcStats &st, const RayDiff *sensorDiff = nullptr) const {
         BsdfSet bs{bsdfs.data(), (int) bsdfs.size()};
         Intersection its;
         Ray ray(r);
+        RayDiff rayDiff; /* RayDifferential ray(r), volpath.cpp:89: only the sensor ray carries differentials (they reach envmap's filtered look-up) */
+        if (sensorDiff) rayDiff = *sensorDiff;
         Spectrum Li(0.0f);
         float eta = 1.0f;
         int depth = 1;
@@ -749,6 +786,7 @@ struct Scene {
                 if (phaseVal == 0) break;
                 throughput *= phaseVal;
                 ray = Ray(mRec.p, wo, 0, kInf);
+                rayDiff.has = false;
                 Spectrum value(0.0f);
                 rayIntersectAndLookForEmitter(sampler, medium, maxDepth - depth - 1, ray, its, dRec, value, st);
                 if (!value.isZero()) {
@@ -760,7 +798,7 @@ struct Scene {
                 if (medium >= 0) throughput *= mRec.transmittance / mRec.pdfFailure;
                 if (!its.isValid()) { /* volpath.cpp:190-202 */
                     if (envEmitter >= 0 && emittedRadiance && (!rp.hideEmitters || scattered)) {
-                        Spectrum value = throughput * emitters[envEmitter].radiance;
+                        Spectrum value = throughput * evalEnvironment(ray, &rayDiff);
                         if (medium >= 0) value *= MediumEval(media[medium]).evalTransmittance(ray, sampler);
                         Li += value;
                     }
@@ -808,6 +846,7 @@ struct Scene {
                 float woDotGeoN = dot(its.geoFrame.n, wo);
                 if (woDotGeoN * Frame::cosTheta(bRec.wo) <= 0 && rp.strictNormals) break;
                 ray = Ray(its.p, wo);
+                rayDiff.has = false;
                 throughput *= bsdfWeight;
                 eta *= bRec.eta;
                 if (mesh.isMediumTransition()) medium = targetMedium(mesh, its.geoFrame.n, ray.d);
@@ -1050,6 +1089,56 @@ int orc_add_constant_emitter(void *s, const float *radiance, float samplingWeigh
     sc->emitters.push_back(e);
     return (int) sc->emitters.size() - 1;
 }
+/* <emitter type="envmap">: linear float RGB pixels (row-major, top row first), scale, toWorld and its inverse, samplingWeight
+   (envmap.cpp:106-181).  Returns the emitter index, or -1 when the map is black / not finite (envmap.cpp:311-315) */
+int orc_add_envmap_emitter(void *s, int width, int height, const float *pixels, float scale, const float *toWorld, const float *toLocal, float samplingWeight) {
+    Scene *sc = (Scene *) s;
+    sc->envmaps.emplace_back();
+    if (!sc->envmaps.back().build(width, height, pixels, scale, toWorld, toLocal)) { sc->envmaps.pop_back(); return -1; }
+    Emitter e; e.radiance = V3(0.0f); e.samplingWeight = samplingWeight; e.mesh = -1; e.envmap = (int) sc->envmaps.size() - 1;
+    sc->emitters.push_back(e);
+    return (int) sc->emitters.size() - 1;
+}
+/* the pyramid and the tables of environment map `env`: info = levels, then (w, h) per level */
+void orc_envmap_info(void *s, int env, int32_t *info, float *normalization) {
+    const EnvMap &e = ((Scene *) s)->envmaps[env];
+    info[0] = e.mip.levels;
+    for (int l = 0; l < e.mip.levels; ++l) { info[1 + 2 * l] = e.mip.lw[l]; info[2 + 2 * l] = e.mip.lh[l]; }
+    *normalization = e.normalization;
+}
+void orc_envmap_level(void *s, int env, int level, float *out) {
+    const EnvMap &e = ((Scene *) s)->envmaps[env];
+    memcpy(out, e.mip.pyramid[level].data(), e.mip.pyramid[level].size() * sizeof(float));
+}
+void orc_envmap_tables(void *s, int env, float *cdfRows, float *cdfCols, float *rowWeights) {
+    const EnvMap &e = ((Scene *) s)->envmaps[env];
+    memcpy(cdfRows, e.cdfRows.data(), e.cdfRows.size() * sizeof(float));
+    memcpy(cdfCols, e.cdfCols.data(), e.cdfCols.size() * sizeof(float));
+    memcpy(rowWeights, e.rowWeights.data(), e.rowWeights.size() * sizeof(float));
+}
+/* Scene::evalEnvironment for n rays after commit: rays 6n (o, d), or 18n (o, d, rxO, rxD, ryO, ryD) with differentials -> out 3n */
+void orc_eval_environment(void *s, uint64_t n, int withDifferentials, const float *rays, float *out) {
+    Scene *sc = (Scene *) s;
+    const int stride = withDifferentials ? 18 : 6;
+    for (uint64_t i = 0; i < n; ++i) {
+        const float *r = rays + (size_t) stride * i;
+        Ray ray(V3(r[0], r[1], r[2]), V3(r[3], r[4], r[5]));
+        RayDiff rd;
+        if (withDifferentials) { rd.has = true; rd.rxO = V3(r[6], r[7], r[8]); rd.rxD = V3(r[9], r[10], r[11]); rd.ryO = V3(r[12], r[13], r[14]); rd.ryD = V3(r[15], r[16], r[17]); }
+        const Spectrum v = sc->envEmitter >= 0 ? sc->evalEnvironment(ray, &rd) : Spectrum(0.0f);
+        out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+    }
+}
+/* Scene::pdfEmitterDirect for the environment emitter: ref 6n (ref, refN), d 3n -> out n */
+void orc_pdf_environment_direct(void *s, uint64_t n, const float *ref, const float *d, float *out) {
+    Scene *sc = (Scene *) s;
+    for (uint64_t i = 0; i < n; ++i) {
+        DRec dRec;
+        dRec.ref = V3(ref[6 * i], ref[6 * i + 1], ref[6 * i + 2]); dRec.refN = V3(ref[6 * i + 3], ref[6 * i + 4], ref[6 * i + 5]);
+        dRec.d = V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]); dRec.emitter = sc->envEmitter; dRec.solidAngle = true;
+        out[i] = sc->envEmitter >= 0 ? sc->pdfEmitterDirect(dRec) : 0.0f;
+    }
+}
 /* <shape type="shapegroup"> / <shape type="instance">: meshes added with orc_set_mesh_group live in the group's object space */
 int orc_add_shapegroup(void *s) { Scene *sc = (Scene *) s; sc->groups.emplace_back(); return (int) sc->groups.size() - 1; }
 void orc_set_mesh_group(void *s, int mesh, int group) { ((Scene *) s)->meshes[mesh].group = group; }
@@ -1177,7 +1266,7 @@ static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcSt
     std::vector<std::unique_ptr<ImageBlock>> blocks(nBlocks);
     std::atomic<int> next(0);
     std::vector<OrcStats> tstats(nThreads);
-    const bool useDiff = !sc->textures.empty();
+    const bool useDiff = !sc->textures.empty() || !sc->envmaps.empty(); /* who reads them: bitmap textures (computePartials) and envmap::evalEnvironment */
     const float diffScaleFactor = 1.0f / std::sqrt((float) rp->spp); /* integrator.cpp:144-145 */
     auto worker = [&](int tid) {
         OrcStats st{};
@@ -1205,7 +1294,7 @@ static void render_impl(Scene *sc, const OrcRenderParams *rp, float *film, OrcSt
                         RayDiff rd;
                         Ray ray = sc->sampleRay(spx, spy, apx, apy, useDiff ? &rd : nullptr, diffScaleFactor);
                         float alpha;
-                        Spectrum spec = rp->integrator == 1 ? sc->LiVol(ray, sampler.get(), *rp, alpha, st) : sc->Li(ray, sampler.get(), *rp, alpha, st, useDiff ? &rd : nullptr); /* sensor weight = 1 */
+                        Spectrum spec = rp->integrator == 1 ? sc->LiVol(ray, sampler.get(), *rp, alpha, st, useDiff ? &rd : nullptr) : sc->Li(ray, sampler.get(), *rp, alpha, st, useDiff ? &rd : nullptr); /* sensor weight = 1 */
                         if (!blk->put(spx, spy, spec, alpha)) ++st.badSamples;
                         if (perSample) {
                             float *o = perSample + (((size_t) y * W + x) * (size_t) (hi - lo) + (size_t) (j - lo)) * 4;

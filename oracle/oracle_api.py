@@ -197,6 +197,15 @@ class OracleScene:
         if getattr(desc, "env_radiance", None) is not None:
             rad = np.asarray(desc.env_radiance, np.float32)
             L.orc_add_constant_emitter(self.h, _p(rad), C.c_float(desc.env_sampling_weight))
+        if getattr(desc, "envmap", None) is not None:
+            if getattr(desc, "env_radiance", None) is not None:
+                raise ValueError("The scene may only contain one environment emitter")  # scene.cpp:510-514
+            em = desc.envmap
+            px = np.ascontiguousarray(em.pixels, np.float32)
+            M, Minv = em.matrices()
+            L.orc_add_envmap_emitter.restype = C.c_int
+            if L.orc_add_envmap_emitter(self.h, C.c_int(px.shape[1]), C.c_int(px.shape[0]), _p(px), C.c_float(em.scale), _p(M), _p(Minv), C.c_float(em.sampling_weight)) < 0:
+                raise ValueError("The environment map is completely black or holds a non-finite value")  # envmap.cpp:311-315
         media, mids = desc.flat_media()
         self.flat_media = [md.flat() for md in media]
         for d in self.flat_media:

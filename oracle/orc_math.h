@@ -76,6 +76,7 @@ inline V3 safeSqrtSpec(const V3 &v) {
 inline float fastexp(float v) { return (float) ::exp((double) v); }
 inline float fastlog(float v) { return (float) ::log((double) v); }
 inline float safe_sqrt(float v) { return std::sqrt(std::max(0.0f, v)); }
+inline float safe_acos(float v) { return std::acos(std::min(1.0f, std::max(-1.0f, v))); } /* math.h:250-252 */
 inline float signum(float v) { return copysignf(1.0f, v); }
 inline void sincos(float t, float *s, float *c) { ::sincosf(t, s, c); }
 

@@ -139,7 +139,8 @@ struct Texture {
     float maximum = 0;   /* component-wise maximum of level 0 (mipmap.h:229-241) */
     float bsdfScale = 1; /* bsdf.cpp:88-111 */
 
-    void build(const OrcTextureDesc &desc, const float *pixels) {
+    /* maxValue: the upper clamp of the resampling passes (mipmap.h:156-157, :262: 1 for `bitmap` textures, infinity for `envmap`) */
+    void build(const OrcTextureDesc &desc, const float *pixels, float maxValue = 1.0f) {
         d = desc;
         if (d.filterType != TexEWA) d.maxAnisotropy = 1.0f;
         const int ch = d.channels;
@@ -161,12 +162,12 @@ struct Texture {
                     Resampler r(d.wrapU, w, nw);
                     std::vector<float> &dst = (h == nh) ? next : temp;
                     if (h != nh) temp.resize((size_t) nw * h * ch);
-                    for (int y = 0; y < h; ++y) r.resampleAndClamp(src->data() + (size_t) y * w * ch, 1, dst.data() + (size_t) y * nw * ch, 1, ch, 0.0f, 1.0f);
+                    for (int y = 0; y < h; ++y) r.resampleAndClamp(src->data() + (size_t) y * w * ch, 1, dst.data() + (size_t) y * nw * ch, 1, ch, 0.0f, maxValue);
                     src = &dst;
                 }
                 if (h != nh) { /* y pass, :2296-2327 */
                     Resampler r(d.wrapV, h, nh);
-                    for (int x = 0; x < nw; ++x) r.resampleAndClamp(src->data() + (size_t) x * ch, nw, next.data() + (size_t) x * ch, nw, ch, 0.0f, 1.0f);
+                    for (int x = 0; x < nw; ++x) r.resampleAndClamp(src->data() + (size_t) x * ch, nw, next.data() + (size_t) x * ch, nw, ch, 0.0f, maxValue);
                 }
                 w = nw; h = nh;
                 pyramid.push_back(next); lw.push_back(w); lh.push_back(h);

@@ -131,10 +131,12 @@ ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string 
 ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k, const AnimatedTransform *d) const { return hasProperty(k) || !d ? new AnimatedTransform(getTransform(k, Transform())) : d; }
 ref<const AnimatedTransform> Properties::getAnimatedTransform(const std::string &k) const { return new AnimatedTransform(getTransform(k)); }
 std::ostream &operator<<(std::ostream &os, const ETransportMode &m) { return os << (int) m; }
-/* envmap.cpp's image-file path (constructor else-branch, serialize) and its OpenGL shader: never reached through the cache-file route */
-FileStream::FileStream(const fs::path &, EFileMode) { throw std::runtime_error("FileStream: image files are not readable here"); }
-size_t FileStream::getSize() const { return 0; }
+/* envmap.cpp's image-file path (constructor else-branch, serialize) and its OpenGL shader: never reached through the cache-file route
+   (FileStream itself is the reference's own src/libcore/fstream.cpp) */
 void GPUTexture::initAndRelease() {}
+std::ostream &operator<<(std::ostream &os, const Bitmap::EPixelFormat &v) { return os << (int) v; } /* TMIPMap::toString only */
+std::ostream &operator<<(std::ostream &os, const Bitmap::EComponentFormat &v) { return os << (int) v; }
+Bitmap::Bitmap(EFileFormat, Stream *, const std::string &) { throw std::runtime_error("Bitmap: image files are not readable here"); }
 ref<Bitmap> Bitmap::expand() { throw std::runtime_error("Bitmap::expand: not available"); }
 ref<Bitmap> Bitmap::convert(EPixelFormat, EComponentFormat, Float, Float, Spectrum::EConversionIntent) { throw std::runtime_error("Bitmap::convert: not available"); }
 ref<Bitmap> Bitmap::resample(const ReconstructionFilter *, ReconstructionFilter::EBoundaryCondition, ReconstructionFilter::EBoundaryCondition, const Vector2i &, Float, Float) const { throw std::runtime_error("Bitmap::resample: not available"); }

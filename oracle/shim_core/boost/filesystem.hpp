@@ -8,7 +8,7 @@
 #include <sys/stat.h>
 #include <ctime>
 namespace boost { namespace filesystem {
-class path { public: path() {} path(const char *s) : m_s(s) {} path(const std::string &s) : m_s(s) {} bool empty() const { return m_s.empty(); } const std::string &string() const { return m_s; }
+class path { public: path() {} path(const char *s) : m_s(s) {} path(const std::string &s) : m_s(s) {} bool empty() const { return m_s.empty(); } const std::string &string() const { return m_s; } const char *c_str() const { return m_s.c_str(); }
   path filename() const { return *this; } path extension() const { return path(); } path parent_path() const { return path(); } path operator/(const path &o) const { return path(m_s + "/" + o.m_s); } bool is_absolute() const { return false; }
   path &replace_extension(const path &e) { size_t dot = m_s.find_last_of('.'), sl = m_s.find_last_of('/'); if (dot != std::string::npos && (sl == std::string::npos || dot > sl)) m_s.erase(dot); m_s += e.m_s; return *this; }
   private: std::string m_s; };

@@ -279,8 +279,31 @@ def path_ref_ext():
     print("path_ref_ext.npz:", n, "images")
 
 
+def path_ref_env():
+    """envmap emitter through the same assembled reference renderer (ref_pins.image_cases_env); per image: the film, the reference's
+    sampleToCamera and its Transform::inverse() of the map's toWorld."""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import ref_pins
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so"))
+    out = {}
+    n = 0
+    for name, desc, rp in ref_pins.image_cases_env():
+        film, s2c = ref_pins.reference_render(lib, desc, rp, want_camera=True)
+        out[name + "/film"], out[name + "/s2c"] = film, s2c
+        inv = ref_pins.reference_envmap_inverse(lib, desc)
+        if inv is not None:
+            out[name + "/env_to_local"] = inv
+        n += 1
+    np.savez_compressed(os.path.join(OUT, "path_ref_env.npz"), **out)
+    print("path_ref_env.npz:", n, "images")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--env-only" in sys.argv:
+        path_ref_env()
+        sys.exit(0)
     if "--ext-only" in sys.argv:
         path_ref_ext()
         sys.exit(0)
@@ -290,6 +313,7 @@ if __name__ == "__main__":
         sys.exit(0)
     path_ref()
     path_ref_ext()
+    path_ref_env()
     render_ref()
     core_ref()
     bsdf_ref()

@@ -358,6 +358,9 @@ def reference_scene(lib, desc, rp):
         lib.pathref_add_instance(h, groups[inst.group], _f(np.ascontiguousarray(inst.to_world, np.float32)))
     if desc.env_radiance is not None:          # <emitter type="constant">: added last here, yet first in Scene::m_emitters (scene.cpp:510-516 vs :322-335)
         lib.pathref_add_constant_emitter(h, _f(np.asarray(desc.env_radiance, np.float32)), C.c_float(desc.env_sampling_weight))
+    if getattr(desc, "envmap", None) is not None:   # <emitter type="envmap">: the pyramid is this repository's (oracle) resampling of the image,
+        # handed to the reference's EnvironmentMap as a MIP map cache file (path_ref_shim.cpp pathref_add_envmap); tables / look-ups / sampling are its own
+        add_reference_envmap(lib, h, desc.envmap)
     cam = desc.camera
     assert cam.fov_axis == "x"
     tw = np.ascontiguousarray(cam.to_world, np.float32)
@@ -368,6 +371,45 @@ def reference_scene(lib, desc, rp):
                        rp.max_depth, rp.rr_depth, int(rp.strict_normals), int(rp.hide_emitters), {"path": 0, "volpath": 1}[rp.integrator],
                        C.c_float(cam.aperture_radius), C.c_float(cam.focus_distance), *[int(v) for v in crop])
     return h
+
+
+def envmap_pyramid(em):
+    """The MIP pyramid (float32 RGB levels, already rounded to half precision) the oracle derives from the decoded image."""
+    from oracle.oracle_api import lib as olib, _p
+    L = olib()
+    px = np.ascontiguousarray(em.pixels, np.float32)
+    M, Minv = em.matrices()
+    L.orc_scene_new.restype = C.c_void_p
+    s = C.c_void_p(L.orc_scene_new())
+    L.orc_add_envmap_emitter.restype = C.c_int
+    assert L.orc_add_envmap_emitter(s, px.shape[1], px.shape[0], _p(px), C.c_float(em.scale), _p(M), _p(Minv), C.c_float(em.sampling_weight)) >= 0
+    info = (C.c_int32 * 64)(); nrm = C.c_float()
+    L.orc_envmap_info(s, 0, info, C.byref(nrm))
+    levels = []
+    for l in range(info[0]):
+        a = np.empty((info[2 + 2 * l], info[1 + 2 * l], 3), np.float32)
+        L.orc_envmap_level(s, 0, l, _p(a))
+        levels.append(a)
+    L.orc_scene_free(s)
+    return levels
+
+
+def add_reference_envmap(lib, h, em):
+    import hashlib, os, tempfile
+    levels = envmap_pyramid(em)
+    sizes = np.array([[a.shape[1], a.shape[0]] for a in levels], np.int32)
+    ptrs = (C.POINTER(C.c_float) * len(levels))(*[_f(a) for a in levels])
+    tw = np.ascontiguousarray(em.to_world, np.float32) if em.to_world is not None else None
+    stem = os.path.join(tempfile.gettempdir(), f"b2ref_env_{os.getpid()}_" + hashlib.sha1(levels[0].tobytes()).hexdigest()[:12])
+    lib.pathref_add_envmap.restype = C.c_int
+    rc = lib.pathref_add_envmap(h, stem.encode(), len(levels), sizes.ctypes.data_as(C.POINTER(C.c_int)), ptrs, _f(tw) if tw is not None else None,
+                                C.c_float(em.scale), C.c_float(em.sampling_weight))
+    for ext in (".img", ".mip"):       # the class has mapped the cache by now (MemoryMappedFile keeps its own handle)
+        try:
+            os.unlink(stem + ext)
+        except OSError:
+            pass
+    assert rc == 0
 
 
 def reference_render(lib, desc, rp, want_camera=False):
@@ -477,3 +519,51 @@ def image_cases_ext():
     d = cornell_box(80, 80)
     d.camera = dataclasses.replace(d.camera, crop=(40, 0, 40, 37), aperture_radius=20.0, focus_distance=1000.0)
     yield "crop_thinlens_counter", d, RenderParams(spp=4, sampler="independent", rfilter="box", max_depth=5)
+
+
+def sky_image(w=64, h=32, seed=4, sun=40.0):
+    """A synthetic latitude-longitude radiance map: cubed noise, a small very bright patch (sampling must find it), a darker lower half."""
+    rng = np.random.default_rng(seed)
+    img = (rng.random((h, w, 3)) ** 3).astype(np.float32) * 0.8
+    img[h // 6:h // 6 + max(1, h // 10), w // 3:w // 3 + max(1, w // 16)] += np.float32(sun)
+    img[h // 2:, :] *= np.float32(0.2)
+    return img
+
+
+def envmap_rotation():
+    c, s = np.cos(0.6), np.sin(0.6)
+    M = np.eye(4, dtype=np.float32)
+    M[:3, :3] = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32) @ np.array([[1, 0, 0], [0, np.cos(0.3), -np.sin(0.3)], [0, np.sin(0.3), np.cos(0.3)]], np.float32)
+    return M
+
+
+def image_cases_env():
+    """Image-level pins of the `envmap` emitter (src/emitters/envmap.cpp) through the assembled reference renderer: seen directly (the
+    filtered look-up with the sensor's ray differentials), as the only light, next to an area light (emitter selection + MIS both ways),
+    hidden, under volpath, and with a map whose sizes are not powers of two.  Fixture: tests/golden/path_ref_env.npz."""
+    from mitsuba_b200.scene import Bsdf, EnvMap, RenderParams, cornell_box, material_ball, smoke_scene
+    gold = Bsdf("roughconductor", distribution="ggx", alpha_u=0.2, alpha_v=0.2, eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421))
+    d = material_ball(gold, 40, 40, n_theta=16, n_phi=32)
+    d.meshes = [m for m in d.meshes if m.radiance is None]
+    d.envmap = EnvMap(pixels=sky_image(), scale=1.5, to_world=envmap_rotation())
+    yield "envmap_only_ball", d, RenderParams(spp=8, sampler="sobol", rfilter="gaussian")
+    d = cornell_box(36, 36)
+    d.meshes = [m for i, m in enumerate(d.meshes) if i != 1]
+    d.envmap = EnvMap(pixels=sky_image(50, 25, seed=9, sun=15.0), scale=0.5, sampling_weight=2.0)   # identity toWorld, odd sizes (7 levels)
+    yield "envmap_plus_area_cbox", d, RenderParams(spp=8, sampler="independent", rfilter="box")
+    yield "envmap_hidden_cbox", d, RenderParams(spp=4, sampler="sobol", rfilter="gaussian", hide_emitters=True, max_depth=5)
+    d = material_ball(Bsdf("roughdielectric", distribution="beckmann", alpha_u=0.1, alpha_v=0.1, int_ior=1.5, ext_ior=1.0), 32, 32, n_theta=12, n_phi=24)
+    d.envmap = EnvMap(pixels=sky_image(32, 16, seed=2), to_world=envmap_rotation(), sampling_weight=0.5)  # the area light stays: two emitters
+    yield "envmap_glass_ball", d, RenderParams(spp=8, sampler="sobol", rfilter="box")
+    d = smoke_scene(36, 36, res=8, scale=5.0)
+    d.envmap = EnvMap(pixels=sky_image(16, 8, seed=3, sun=5.0), scale=0.7)
+    yield "envmap_volpath_smoke", d, RenderParams(spp=8, sampler="independent", rfilter="gaussian", integrator="volpath")
+
+
+def reference_envmap_inverse(lib, desc):
+    """Transform::inverse() of the map's toWorld as the reference computes it (float Gauss-Jordan) -- matrix set-up is host work."""
+    if desc.envmap is None or desc.envmap.to_world is None:
+        return None
+    inv = np.zeros((4, 4), np.float32)
+    lib.pathref_transform_inverse(_f(np.ascontiguousarray(desc.envmap.to_world, np.float32)), _f(inv))
+    return inv

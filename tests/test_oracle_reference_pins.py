@@ -250,6 +250,79 @@ def test_emitter_order_and_instanced_records_match_the_live_reference_when_prese
     assert np.array_equal(a[hit][:, :19], b[hit][:, :19]) and np.array_equal(a[hit, 20], b[hit, 20])
 
 
+def _env_desc(desc, g, name):
+    import dataclasses
+    if (name + "/env_to_local") in g.files:
+        desc.envmap = dataclasses.replace(desc.envmap, to_local=g[name + "/env_to_local"])
+    return desc
+
+
+def test_oracle_images_with_an_environment_map_match_the_reference_renderer_golden():
+    """tests/golden/path_ref_env.npz: the reference's EnvironmentMap (src/emitters/envmap.cpp) inside the assembled reference renderer --
+    seen directly by the camera (EWA look-up driven by the sensor's ray differentials, envmap.cpp:392-406), as the only light, next to an
+    area light with samplingWeight 2 / 0.5, hidden, under volpath, power-of-two and odd map sizes -- reproduced BIT FOR BIT by the oracle
+    (orc_envmap.h).  The pyramid the reference class reads is the oracle's resampling of the image (handed over as a MIP map cache file,
+    the way a second Mitsuba run reads it); the CDF tables, look-ups, direction sampling and densities are the reference's own."""
+    g = np.load(os.path.join(HERE, "golden", "path_ref_env.npz"))
+    n = 0
+    for name, desc, rp in ref_pins.image_cases_env():
+        ref = g[name + "/film"]
+        film = np.asarray(O.OracleScene(_env_desc(desc, g, name), sample_to_camera=g[name + "/s2c"]).render(rp)[0]).reshape(ref.shape)
+        assert np.array_equal(film, ref), (name, float(np.abs(film - ref).max()))
+        assert ref[..., :3].max() > 0.1 and ref[..., 4].min() > 0
+        n += 1
+    assert n == 5
+
+
+def test_environment_map_lookups_sampling_and_densities_match_the_live_reference_when_present():
+    """Component probes behind the images above, on inputs the fixture does not hold: Scene::evalEnvironment without and with ray
+    differentials, Scene::pdfEmitterDirect and Scene::sampleEmitterDirect for the environment map -- bit for bit."""
+    so = os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libpathref.so not built (the reference tree is not on this machine)")
+    import dataclasses
+    lib = C.CDLL(so)
+    cases = {name: (desc, rp) for name, desc, rp in ref_pins.image_cases_env()}
+    rng = np.random.default_rng(5)
+    L = O.lib()
+    for name in ("envmap_only_ball", "envmap_plus_area_cbox"):
+        desc, rp = cases[name]
+        inv = ref_pins.reference_envmap_inverse(lib, desc)
+        if inv is not None:
+            desc.envmap = dataclasses.replace(desc.envmap, to_local=inv)
+        h = ref_pins.reference_scene(lib, desc, rp)
+        o = O.OracleScene(desc)
+        n = 3000
+        rays = np.zeros((n, 6), np.float32); rays[:, 3:] = ref_pins._dirs(rng, n)
+        rays[:3, 3:] = [(0, 1, 0), (0, -1, 0), (0, 0, 1)]                        # poles and the seam of the parameterisation
+        a = np.zeros((n, 3), np.float32); b = np.zeros((n, 3), np.float32)
+        lib.pathref_eval_environment(h, n, 0, ref_pins._f(rays), ref_pins._f(a))
+        L.orc_eval_environment(o.h, C.c_uint64(n), 0, O._p(rays), O._p(b))
+        assert np.array_equal(a, b) and a.max() > 1
+        rd = np.zeros((n, 18), np.float32); rd[:, :6] = rays
+        for k, sc in ((9, 0.02), (15, 0.3)):                                       # from a fraction of a texel to strongly anisotropic footprints
+            v = rays[:, 3:] + sc * rng.standard_normal((n, 3)).astype(np.float32) * rng.random((n, 1)).astype(np.float32) ** 2
+            rd[:, k:k + 3] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        lib.pathref_eval_environment(h, n, 1, ref_pins._f(rd), ref_pins._f(a))
+        L.orc_eval_environment(o.h, C.c_uint64(n), 1, O._p(rd), O._p(b))
+        assert np.array_equal(a, b) and a.max() > 1
+        refp = np.zeros((n, 6), np.float32)
+        refp[:, 0:3] = rng.uniform(-1, 1, (n, 3)) if name == "envmap_only_ball" else rng.uniform(50, 500, (n, 3))
+        refp[:, 3:6] = ref_pins._dirs(rng, n)
+        dd = ref_pins._dirs(rng, n).astype(np.float32)
+        pa = np.zeros(n, np.float32); pb = np.zeros(n, np.float32)
+        lib.pathref_pdf_environment_direct(h, n, ref_pins._f(refp), ref_pins._f(dd), ref_pins._f(pa))
+        L.orc_pdf_environment_direct(o.h, C.c_uint64(n), O._p(refp), O._p(dd), O._p(pb))
+        assert np.array_equal(pa, pb) and pa.max() > 0.5
+        smp = rng.random((n, 2)).astype(np.float32)
+        sa = np.zeros((n, 12), np.float32)
+        lib.pathref_sample_emitter_direct(h, n, ref_pins._f(refp), ref_pins._f(smp), ref_pins._f(sa))
+        sb = o.sample_emitter_direct(refp, smp)
+        ok = sa[:, 8] == 1
+        assert np.array_equal(sa[:, 8], sb[:, 8]) and ok.sum() > 100
+        assert np.array_equal(sa[ok], sb[ok])
+
+
 def test_conductor_material_presets_match_the_reference_spectrum_code():
     """material="Cu" etc. of the conductor plugins (roughconductor.cpp:174-190): the committed table (mitsuba_b200/data/conductor_presets.txt)
     against the live reference -- InterpolatedSpectrum + Spectrum::fromContinuousSpectrum on data/ior/*.spd -- where it is present, and against
