@@ -172,6 +172,17 @@ int b2_scene_add_area_emitter(b2_scene *, const float radiance[3], float samplin
  * call order, as in Scene::m_emitters (Scene::addChild appends it at once, scene.cpp:510-516; area emitters join in Scene::initialize,
  * scene.cpp:322-335): b2_scene_commit applies that order. */
 int b2_scene_add_constant_emitter(b2_scene *, const float radiance[3], float sampling_weight);
+/* EnvironmentMap (src/emitters/envmap.cpp:106-181): a latitude-longitude radiance map around the scene -> emitter id (>=0) or -1.
+ * `pixels` is the decoded image (what Bitmap::convert(ERGB, EFloat) hands to the MIP map, envmap.cpp:172-175): width x height x 3 linear
+ * floats, row-major, top row first; decoding image files is the caller's side of the boundary.  scale = the plugin's `scale`;
+ * to_world / to_local = the plugin's toWorld and its inverse as row-major 4x4 (both NULL: identity); sampling_weight = `samplingWeight`.
+ * b2_scene_commit builds what the plugin builds when it is loaded and configured: the half-precision MIP pyramid (2-lobe Lanczos, repeat /
+ * clamp boundaries, no upper clamp) and the marginal / conditional CDF tables over luminance x sin(theta) (envmap.cpp:260-329).  The
+ * kernels then implement evalEnvironment (:380-410, EWA-filtered with the sensor ray's differentials for directly visible background),
+ * sampleDirect / pdfDirect (:516-560) and fillDirectSamplingRecord (:359-374).  Shares the one-environment-emitter rule and the
+ * emitter order of b2_scene_add_constant_emitter.  Errors as the plugin raises them: a black map, a non-finite pixel, a side > 65535. */
+int b2_scene_add_envmap_emitter(b2_scene *, int width, int height, const float *pixels, float scale, const float *to_world, const float *to_local,
+                                float sampling_weight);
 /* TriMesh after configure(): positions, optional normals / texcoords (NULL = none -> face normals,
  * skdtree.h:383-399), triangles, material and emitter ids (-1 = no emitter).  An emitter id may be
  * attached to exactly one mesh (area.cpp:185-199).  Returns mesh id or -1. */
@@ -241,6 +252,10 @@ int b2_texture_eval(b2_scene *, int texture_id, uint64_t n, const float *uv, con
 /* uv and uv partials of camera-ray hits (sampleRayDifferential + scaleDifferential(1/sqrt(spp)) + Intersection::computePartials):
  * pos_hit n x 6 = film position (2), then t, u, v, prim as b2_trace returns them -> out n x 6: u v dudx dudy dvdx dvdy */
 int b2_texture_partials(b2_scene *, uint64_t n, const float *pos_hit, int spp, int parity_mode, float *out);
+/* Probes of the committed environment map: what 0 = Scene::evalEnvironment for n world directions (in n x 3 -> out n x 3); 1 = the same
+ * for sensor rays with differentials (in n x 9: d, rxDirection, ryDirection -> out n x 3); 2 = Scene::pdfEmitterDirect of the map for n
+ * directions, solid-angle measure including the emitter-selection probability (in n x 3 -> out n) */
+int b2_envmap_probe(b2_scene *, int what, uint64_t n, const float *in, int parity_mode, float *out);
 /* One level of the MIP pyramid built at commit (TMIPMap constructor, mipmap.h:155-303); out may be NULL to query the size */
 int b2_texture_level(b2_scene *, int texture_id, int level, int *levels, int *width, int *height, float *out);
 /* The same without a scene or a device: host-side pyramid construction for the given description */

@@ -67,7 +67,7 @@ class b2_stats(C.Structure):
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
            "b2_scene_set_camera", "b2_scene_set_crop", "b2_scene_set_thinlens", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_get_pixel_stats", "b2_get_path_traces", "b2_trace",
+           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_envmap_emitter", "b2_envmap_probe", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_get_pixel_stats", "b2_get_path_traces", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -82,7 +82,7 @@ def lib():
         L.b2_last_error.restype = C.c_char_p
         L.b2_last_error.argtypes = [C.c_void_p]
         L.b2_version.restype = C.c_char_p
-        for name in ("b2_scene_add_material", "b2_scene_add_area_emitter", "b2_scene_add_mesh", "b2_scene_add_medium", "b2_scene_add_constant_emitter"):
+        for name in ("b2_scene_add_material", "b2_scene_add_area_emitter", "b2_scene_add_mesh", "b2_scene_add_medium", "b2_scene_add_constant_emitter", "b2_scene_add_envmap_emitter"):
             getattr(L, name).restype = C.c_int
         _LIB = L
     return _LIB
@@ -252,6 +252,16 @@ class Scene:
             rad = np.asarray(desc.env_radiance, np.float32)
             if self.L.b2_scene_add_constant_emitter(self.h, _p(rad), C.c_float(desc.env_sampling_weight)) < 0:
                 raise B2Error(ctx.err())
+        if getattr(desc, "envmap", None) is not None:
+            em = desc.envmap
+            px = np.ascontiguousarray(em.pixels, np.float32)
+            if px.ndim != 3 or px.shape[2] != 3:
+                raise B2Error("envmap pixels must be (H, W, 3) linear float RGB")
+            M, Minv = em.matrices()
+            ident = em.to_world is None
+            if self.L.b2_scene_add_envmap_emitter(self.h, C.c_int(px.shape[1]), C.c_int(px.shape[0]), _p(px), C.c_float(em.scale),
+                                                  None if ident else _p(M), None if ident else _p(Minv), C.c_float(em.sampling_weight)) < 0:
+                raise B2Error(ctx.err())
         for i, (mi, me) in enumerate(media_ids):
             if mi >= 0 or me >= 0:
                 self._ck(self.L.b2_scene_set_mesh_media(self.h, C.c_int(i), C.c_int(mi), C.c_int(me)))
@@ -352,6 +362,14 @@ class Scene:
         out = np.zeros((len(ref), 12), np.float32)
         self._ck(self.L.b2_sample_emitter_direct(self.h, C.c_uint64(len(ref)), _p(ref), _p(samples), C.c_int(int(parity)), _p(out)))
         return out
+
+    def envmap_probe(self, what, data, parity=True):
+        """what: 'eval' (n,3 directions) | 'eval_diff' (n,9: d, rxDirection, ryDirection) | 'pdf' (n,3 directions) (b2_envmap_probe)."""
+        w = {"eval": (0, 3, 3), "eval_diff": (1, 9, 3), "pdf": (2, 3, 1)}[what]
+        data = np.ascontiguousarray(data, np.float32).reshape(-1, w[1])
+        out = np.zeros((len(data), w[2]), np.float32)
+        self._ck(self.L.b2_envmap_probe(self.h, C.c_int(w[0]), C.c_uint64(len(data)), _p(data), C.c_int(int(parity)), _p(out)))
+        return out[:, 0] if w[2] == 1 else out
 
     def medium_probe(self, medium, what, data, seed=0, parity=True):
         """what: 'transmittance' | 'sample_distance' | 'density' | 'phase' (b2_medium_probe)."""

@@ -33,7 +33,7 @@ UNITS = [
     (os.path.join(HOST, "mipmap.cpp"), []),
 ]
 HEADERS = [os.path.join(CSRC, f) for f in ("b2_math.cuh", "b2_types.h", "b2_sampler.cuh", "b2_bsdf.cuh", "b2_trace.cuh",
-                                           "b2_kernels.inl", "b2_launch.h", "bvh_builder.h", "b2_medium.cuh", "b2_texture.cuh")] + \
+                                           "b2_kernels.inl", "b2_launch.h", "bvh_builder.h", "b2_medium.cuh", "b2_texture.cuh", "b2_envmap.cuh")] + \
           [os.path.join(HOST, "mipmap.h")] + \
           [os.path.join(HERE, "..", "include", "b2mts.h")]
 

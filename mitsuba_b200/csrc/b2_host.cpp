@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -125,6 +126,11 @@ struct b2_scene {
     std::vector<HostMedium> media;
     struct HostTexture { b2_texture_desc desc; std::vector<float> pixels; b2host::MipPyramid mip; };
     std::vector<HostTexture> textures;
+    // <emitter type="envmap">: the decoded image and its placement; pyramid + sampling tables are derived at commit
+    struct HostEnvMap { int w = 0, h = 0; std::vector<float> pixels; float scale = 1; float toWorld[16], toLocal[16]; b2host::MipPyramid mip; };
+    std::unique_ptr<HostEnvMap> envmap;
+    DevBuf<float> dEnvTexels, dEnvCdfRows, dEnvCdfCols, dEnvRowWeights;
+    DevBuf<DEnvMap> dEnvMap;
     // camera
     float camToWorld[16];
     float sampleToCamera[16];
@@ -463,6 +469,33 @@ extern "C" int b2_scene_add_constant_emitter(b2_scene *s, const float radiance[3
         if (e.env) { fail(s->ctx, B2_ERR_INVALID, "The scene may only contain one environment emitter"); return -1; }
     HostEmitter e;
     memcpy(e.radiance, radiance, 12);
+    e.samplingWeight = sampling_weight;
+    e.env = true;
+    s->emitters.push_back(e);
+    s->committed = false;
+    return (int) s->emitters.size() - 1;
+}
+// <emitter type="envmap"> (src/emitters/envmap.cpp:106-181): `pixels` = the decoded image, linear float RGB, row-major, top row first
+extern "C" int b2_scene_add_envmap_emitter(b2_scene *s, int width, int height, const float *pixels, float scale, const float *to_world, const float *to_local,
+                                           float sampling_weight) {
+    if (!s || !pixels) { fail(s ? s->ctx : nullptr, B2_ERR_INVALID, "b2_scene_add_envmap_emitter: null argument"); return -1; }
+    if ((to_world == nullptr) != (to_local == nullptr)) { fail(s->ctx, B2_ERR_INVALID, "b2_scene_add_envmap_emitter: to_world and to_local go together"); return -1; }
+    for (auto &e : s->emitters)
+        if (e.env) { fail(s->ctx, B2_ERR_INVALID, "The scene may only contain one environment emitter"); return -1; } // scene.cpp:510-514
+    if (width <= 0 || height <= 0) { fail(s->ctx, B2_ERR_INVALID, "b2_scene_add_envmap_emitter: empty image"); return -1; }
+    if (std::max(width, height) > 0xFFFF) { fail(s->ctx, B2_ERR_INVALID, "Environment maps images must be smaller than 65536  pixels in width and height"); return -1; } // envmap.cpp:160-162
+    std::unique_ptr<b2_scene::HostEnvMap> em(new b2_scene::HostEnvMap());
+    em->w = width; em->h = height; em->scale = scale;
+    em->pixels.assign(pixels, pixels + (size_t) width * height * 3);
+    static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    memcpy(em->toWorld, to_world ? to_world : I, 64); memcpy(em->toLocal, to_local ? to_local : I, 64);
+    // the checks of configure() (envmap.cpp:311-315) need the luminance sum; a cheap pass over the image tells the same
+    double sum = 0;
+    for (float v : em->pixels) { if (!std::isfinite(v)) { fail(s->ctx, B2_ERR_INVALID, "The environment map contains an invalid floating point value (nan/inf) -- giving up."); return -1; } sum += std::max(v, 0.0f); }
+    if (sum == 0) { fail(s->ctx, B2_ERR_INVALID, "The environment map is completely black -- this is not allowed."); return -1; }
+    s->envmap = std::move(em);
+    HostEmitter e;
+    e.radiance[0] = e.radiance[1] = e.radiance[2] = 0.0f;
     e.samplingWeight = sampling_weight;
     e.env = true;
     s->emitters.push_back(e);
@@ -986,7 +1019,64 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     }
     CK(ctx, s->dTextures.upload(dtex));
     CK(ctx, s->dTexc.upload(texc));
-    if (anyTex) {
+    // ---- environment map: pyramid (half-rounded floats, RGB padded to float4) + the tables of EnvironmentMap::configure (envmap.cpp:260-329) ----
+    if (s->envmap) {
+        b2_scene::HostEnvMap &he = *s->envmap;
+        b2host::buildMipPyramid(he.pixels.data(), he.w, he.h, 3, B2_WRAP_REPEAT, B2_WRAP_CLAMP, true, he.mip, std::numeric_limits<float>::infinity());
+        if ((int) he.mip.level.size() > B2_TEX_MAX_LEVELS) return fail(ctx, B2_ERR_INVALID, "environment map has too many MIP levels");
+        DEnvMap de;
+        memset(&de, 0, sizeof(de));
+        DTexture &d = de.tex;
+        d.levels = (int) he.mip.level.size(); d.channels = 3; d.filter = B2_TEX_EWA; d.wrapU = B2_WRAP_REPEAT; d.wrapV = B2_WRAP_CLAMP;
+        d.maxAnisotropy = 10.0f; d.uscale = d.vscale = 1.0f; d.bsdfScale = 1.0f; // envmap.cpp:139-142
+        std::vector<float> packed;
+        for (int l = 0; l < d.levels; ++l) {
+            d.lw[l] = he.mip.w[l]; d.lh[l] = he.mip.h[l];
+            d.off[l] = (uint32_t) (packed.size() / 4);
+            const std::vector<float> &src = he.mip.level[l];
+            const size_t nTexel = (size_t) d.lw[l] * d.lh[l];
+            packed.reserve(packed.size() + 4 * nTexel);
+            for (size_t k = 0; k < nTexel; ++k) { packed.push_back(src[3 * k]); packed.push_back(src[3 * k + 1]); packed.push_back(src[3 * k + 2]); packed.push_back(0.0f); }
+        }
+        const int w = he.w, h = he.h;
+        std::vector<float> cdfCols((size_t) (w + 1) * h), cdfRows((size_t) h + 1), rowWeights((size_t) h);
+        size_t colPos = 0, rowPos = 0;
+        float rowSum = 0.0f;
+        const float kPi = 3.14159265358979323846f;
+        const std::vector<float> &base = he.mip.level[0];
+        cdfRows[rowPos++] = 0;
+        for (int y = 0; y < h; ++y) {
+            float colSum = 0;
+            cdfCols[colPos++] = 0;
+            for (int x = 0; x < w; ++x) {
+                const float *px = &base[3 * ((size_t) y * w + x)];
+                colSum += px[0] * 0.212671f + px[1] * 0.715160f + px[2] * 0.072169f; // spectrum.h:725-727
+                cdfCols[colPos++] = colSum;
+            }
+            const float normalization = 1.0f / colSum;
+            for (int x = 1; x < w; ++x) cdfCols[colPos - x - 1] *= normalization;
+            cdfCols[colPos - 1] = 1.0f;
+            const float weight = std::sin((y + 0.5f) * kPi / h);
+            rowWeights[y] = weight;
+            rowSum += colSum * weight;
+            cdfRows[rowPos++] = rowSum;
+        }
+        const float normalization = 1.0f / rowSum;
+        for (int y = 1; y < h; ++y) cdfRows[rowPos - y - 1] *= normalization;
+        cdfRows[rowPos - 1] = 1.0f;
+        if (rowSum == 0) return fail(ctx, B2_ERR_INVALID, "The environment map is completely black -- this is not allowed.");
+        if (!std::isfinite(rowSum)) return fail(ctx, B2_ERR_INVALID, "The environment map contains an invalid floating point value (nan/inf) -- giving up.");
+        de.normalization = 1.0f / (rowSum * (2 * kPi / w) * (kPi / h));
+        de.pixelSizeX = 2 * kPi / w; de.pixelSizeY = kPi / h;
+        de.scale = he.scale; de.w = w; de.h = h;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { de.toWorld[3 * r + c] = he.toWorld[4 * r + c]; de.toLocal[3 * r + c] = he.toLocal[4 * r + c]; }
+        CK(ctx, s->dEnvTexels.upload(packed));
+        CK(ctx, s->dEnvCdfRows.upload(cdfRows)); CK(ctx, s->dEnvCdfCols.upload(cdfCols)); CK(ctx, s->dEnvRowWeights.upload(rowWeights));
+        d.data = s->dEnvTexels.p;
+        de.cdfRows = s->dEnvCdfRows.p; de.cdfCols = s->dEnvCdfCols.p; de.rowWeights = s->dEnvRowWeights.p;
+        CK(ctx, s->dEnvMap.upload(std::vector<DEnvMap>(1, de)));
+    }
+    if (anyTex || s->envmap) {
         std::vector<float> lut(64);
         b2host::ewaWeightTable(lut.data());
         CK(ctx, s->dEwaLut.upload(lut));
@@ -1081,6 +1171,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     ds.triAccel = s->dTriAccel.p; ds.triPlane = s->dTriPlane.p; ds.leafPrim = s->dLeafPrim.p; ds.nLeafTris = (uint32_t) bvh.leafPrims.size();
     // environment emitter: index + constant.cpp:67-70 bounding sphere of (acceleration-structure box U sensor position) (scene.cpp:386-399)
     ds.envEmitter = -1;
+    ds.envmap = s->envmap ? s->dEnvMap.p : nullptr;
     for (size_t e = 0; e < s->emitters.size(); ++e) if (s->emitters[e].env) ds.envEmitter = emIndex[e];
     {
         float bl[3], bh[3];
@@ -1382,7 +1473,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
         if (s->classPresent[c]) { ++nClasses; onlyClass = c; }
     bool sorted = nClasses > 1;
     if (p->flags & 2) sorted = false;
-    if (s->hasNullBsdf || !s->textures.empty()) { sorted = false; nClasses = 2; } // index-matched boundaries, f-3 BSDFs, textures: generic shading kernel
+    if (s->hasNullBsdf || !s->textures.empty() || s->envmap) { sorted = false; nClasses = 2; } // index-matched boundaries, f-3 BSDFs, textures, environment map: generic shading kernel
     s->cancel.store(0);
     // every early return below leaves the stream idle and releases the events / the captured graph
     struct RenderGuard {
@@ -1449,7 +1540,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     cudaGraphExec_t graphExec = nullptr;
     guard.graph = &graph; guard.exec = &graphExec;
     if (!useEvents) {
-        if (volpath || s->ds.nTextures) {
+        if (volpath || s->ds.nTextures || s->ds.envmap) {
             // k_volstep (and the textured k_shade) have a deep local-memory frame: their first launch may have to grow the context's
             // local-memory pool, which is not allowed inside a stream capture.  The first iteration therefore runs as plain launches.
             enqueueIteration();
@@ -1781,6 +1872,24 @@ extern "C" int b2_texture_eval(b2_scene *s, int texture_id, uint64_t n, const fl
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpy(out, dO, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+// Probes of the committed environment map (tests): what 0 = Scene::evalEnvironment for n directions (in 3n -> out 3n), 1 = the same for sensor
+// rays with differential directions (in 9n: d, rxD, ryD -> out 3n), 2 = Scene::pdfEmitterDirect of the map for n directions (in 3n -> out n)
+extern "C" int b2_envmap_probe(b2_scene *s, int what, uint64_t n, const float *in, int parity_mode, float *out) {
+    NEED_COMMIT(s);
+    b2_ctx *ctx = s->ctx;
+    if (!s->envmap) return fail(ctx, B2_ERR_INVALID, "b2_envmap_probe: the scene has no environment map");
+    if (!in || !out || what < 0 || what > 2) return fail(ctx, B2_ERR_INVALID, "b2_envmap_probe: invalid argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    TmpDev tmp;
+    const size_t nin = (what == 1 ? 9 : 3) * n, nout = (what == 2 ? 1 : 3) * n;
+    float *dI = tmp.upload(in, nin), *dO = tmp.alloc<float>(nout);
+    if (parity_mode) parity::launch_envmap_probe(s->cfgParity, s->ds, what, n, dI, dO, ctx->stream);
+    else fast::launch_envmap_probe(s->cfgFast, s->ds, what, n, dI, dO, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, dO, nout * sizeof(float), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 extern "C" int b2_texture_partials(b2_scene *s, uint64_t n, const float *pos_hit, int spp, int parity_mode, float *out) {

@@ -17,6 +17,7 @@
 #include "b2_trace.cuh"
 #include "b2_medium.cuh"
 #include "b2_texture.cuh"
+#include "b2_envmap.cuh"
 #include "b2_launch.h"
 
 namespace b2 {
@@ -789,6 +790,16 @@ static __device__ __noinline__ Spectrum shadeTexture(const DScene &sc, const DRe
     return texEval(sc.textures[tex], sc.ewaLut, tc);
 }
 
+// Scene::evalEnvironment for a sensor ray that left the scene (path.cpp:136-143, volpath.cpp:190-202): the filtered look-up of
+// envmap.cpp:392-406 with the sensor's ray differentials, recomputed from the film position like the texture partials above
+static __device__ __noinline__ Spectrum envEvalCamera(const DScene &sc, float diffScale, float2 pos, PathSampler smp) {
+    float apx = 0.5f, apy = 0.5f;
+    if (sc.cam.apertureRadius > 0) { smp.dim = 2; smp.next2D(apx, apy); }
+    V3 o, d, rxD, ryD;
+    cameraRayDifferential(sc.cam, pos.x, pos.y, apx, apy, diffScale, o, d, rxD, ryD);
+    return envEval(*sc.envmap, sc.ewaLut, d, true, rxD, ryD);
+}
+
 B2_DEV float miWeight(float pdfA, float pdfB) { // path.cpp:296-300
     pdfA *= pdfA;
     pdfB *= pdfB;
@@ -819,16 +830,25 @@ struct DirectSample {
 // Scene::sampleEmitterDirect (scene.cpp:828-852) up to, not including, the visibility ray:
 // emitter pick (pmf.h sampleReuse), AreaLight::sampleDirect (area.cpp:158-173), Shape::sampleDirect
 // (shape.cpp:102-115), TriMesh::samplePosition (trimesh.cpp:412-424), Triangle::sample (triangle.cpp:24-62)
-B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN, float sx, float sy, DirectSample &ds, float *emPdfOut = nullptr) {
+// withMap: compile-time switch of the call site -- the untextured k_shade instances leave the environment-map code out (scenes with a
+// map are shaded by the textured instance, see launch_shade), so their registers and stack stay what they were without it
+B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN, float sx, float sy, DirectSample &ds, float *emPdfOut = nullptr,
+                                const bool withMap = true) {
     const uint32_t ei = cdfSample(sc.emitterCdf, sc.nEmitters, sx);
     const float c0 = __ldg(sc.emitterCdf + ei), c1 = __ldg(sc.emitterCdf + ei + 1);
     const float emPdf = c1 - c0;
     sx = (sx - c0) / (c1 - c0);
     const DEmitter &em = sc.emitters[ei];
-    if (em.nTri == 0) { // `constant` environment emitter: constant.cpp:171-208
+    if (em.nTri == 0) { // environment emitter: `constant` (constant.cpp:171-208) or `envmap` (envmap.cpp:516-543)
         V3 d;
         float pdf;
-        if (!isZero(refN)) {
+        Spectrum rad(em.radiance[0], em.radiance[1], em.radiance[2]);
+        const bool isMap = withMap && sc.envmap != nullptr;
+        if (isMap) {
+            V3 dl;
+            envSampleDirection(*sc.envmap, sx, sy, dl, rad, pdf);
+            d = envToWorld(*sc.envmap, dl);
+        } else if (!isZero(refN)) {
             d = squareToCosineHemisphere(sx, sy);
             pdf = squareToCosineHemispherePdf(d);
             Frame f;
@@ -843,6 +863,7 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
             pdf = 0.07957747154594766788f;
         }
         ds.pdf = 0.0f; ds.value = Spectrum(0.0f); ds.emitter = (int) ei;
+        if (isMap && (isZero(rad) || pdf == 0)) return false;
         // bsphere.h:88-95 + util.cpp:447-485
         const V3 c(sc.bsCenter[0], sc.bsCenter[1], sc.bsCenter[2]);
         const V3 o = ref - c;
@@ -856,8 +877,8 @@ B2_DEV bool sampleEmitterDirect(const DScene &sc, const V3 &ref, const V3 &refN,
         ds.p = ref + d * x1;
         ds.n = normalize(c - ds.p);
         ds.d = d; ds.dist = x1;
-        if (!isZero(refN) && dot(d, refN) <= 0) return false; // roundoff moved the sample to the back side: value 0
-        ds.value = V3(em.radiance[0], em.radiance[1], em.radiance[2]) / pdf;
+        if (!isMap && !isZero(refN) && dot(d, refN) <= 0) return false; // constant.cpp: roundoff moved the sample to the back side: value 0
+        ds.value = rad / pdf;
         if (emPdfOut) { ds.pdf = pdf; *emPdfOut = emPdf; return true; }
         ds.pdf = pdf * emPdf;
         ds.value = ds.value / emPdf;
@@ -1035,12 +1056,17 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
                     if (sc.envEmitter >= 0 && !(rp.hideEmitters && !(flags & PF_SCATTERED))) {
                         const DEmitter &em = sc.emitters[sc.envEmitter];
                         float lumPdf = 0.0f;
-                        if (!(flags & PF_DELTA)) { // constant.cpp:210-224 (ESolidAngle) x emitter pick probability
-                            const float c = pool.ray[2 * (size_t) i].w; // dot(wo, refN) of the vertex that sampled this ray; 2 = refN is zero
-                            const float pdfSA = c == 2.0f ? 0.07957747154594766788f : B2_INV_PI * fmaxf(0.0f, c);
+                        if (!(flags & PF_DELTA)) { // constant.cpp:210-224 / envmap.cpp:545-556 (ESolidAngle) x emitter pick probability
+                            float pdfSA;
+                            if (TEX && sc.envmap) pdfSA = envPdfDirection(*sc.envmap, envToLocal(*sc.envmap, rayD));
+                            else {
+                                const float c = pool.ray[2 * (size_t) i].w; // dot(wo, refN) of the vertex that sampled this ray; 2 = refN is zero
+                                pdfSA = c == 2.0f ? 0.07957747154594766788f : B2_INV_PI * fmaxf(0.0f, c);
+                            }
                             lumPdf = pdfSA * (em.samplingWeight * sc.emitterNormalization);
                         }
-                        LiAdd = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]) * miWeight(bsdfPdfPrev, lumPdf);
+                        const Spectrum le = (TEX && sc.envmap) ? envEval(*sc.envmap, sc.ewaLut, rayD, false, V3(0.0f), V3(0.0f)) : V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                        LiAdd = T * le * miWeight(bsdfPdfPrev, lumPdf);
                         liTouched = true;
                     }
                     done = true;
@@ -1073,7 +1099,7 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
             if (!done && !valid) { // camera ray missed (:136-143): environment radiance unless hidden
                 if (sc.envEmitter >= 0 && !rp.hideEmitters) {
                     const DEmitter &em = sc.emitters[sc.envEmitter];
-                    LiAdd = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                    LiAdd = T * ((TEX && sc.envmap) ? envEvalCamera(sc, rp.diffScale, pool.pos[i], smp) : V3(em.radiance[0], em.radiance[1], em.radiance[2]));
                     liTouched = true;
                 }
                 done = true;
@@ -1113,7 +1139,7 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
                         float sx, sy;
                         smp.next2D(sx, sy);
                         DirectSample ds;
-                        if (sc.nEmitters > 0 && sampleEmitterDirect(sc, its.p, refN, sx, sy, ds)) {
+                        if (sc.nEmitters > 0 && sampleEmitterDirect(sc, its.p, refN, sx, sy, ds, nullptr, TEX)) {
                             ++nShadowRef; // the reference traces (and counts, skdtree.cpp:210) the shadow ray before BSDF::eval
                             BRec bRec;
                             if (TEX) { bRec.hasTex = hasTex; bRec.texR = texR; }
@@ -1395,14 +1421,15 @@ B2_DEV void volIntersectAndLookForEmitter(VolEnv &env, PathSampler &smp, int med
     } else if (sc.envEmitter >= 0) { // volpath.cpp:418-424: the ray left the scene -> environment emitter (constant.cpp:239-253)
         const DEmitter &e = sc.emitters[sc.envEmitter];
         eq.d = d; eq.n = V3(0.0f); eq.dist = 0.0f; eq.emitter = sc.envEmitter; // the solid-angle density needs d only
-        value = transmittance * V3(e.radiance[0], e.radiance[1], e.radiance[2]);
+        value = transmittance * (sc.envmap ? envEval(*sc.envmap, sc.ewaLut, d, false, V3(0.0f), V3(0.0f)) : V3(e.radiance[0], e.radiance[1], e.radiance[2]));
     }
 }
 // scene.cpp:949-952; area.cpp:175-183; shape.cpp:117-126; constant.cpp:210-224
 B2_DEV float volPdfEmitterDirect(const DScene &sc, const EmitterQuery &eq, const V3 &refN) {
     const DEmitter &em = sc.emitters[eq.emitter];
     if (em.nTri == 0) {
-        const float pdfSA = !isZero(refN) ? B2_INV_PI * fmaxf(0.0f, dot(eq.d, refN)) : 0.07957747154594766788f;
+        const float pdfSA = sc.envmap ? envPdfDirection(*sc.envmap, envToLocal(*sc.envmap, eq.d)) // envmap.cpp:545-556
+                                      : !isZero(refN) ? B2_INV_PI * fmaxf(0.0f, dot(eq.d, refN)) : 0.07957747154594766788f;
         return pdfSA * (em.samplingWeight * sc.emitterNormalization);
     }
     float pdfDirect = 0.0f;
@@ -1457,7 +1484,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
                 medium = -1; // sensor medium: vacuum (a camera inside a medium is out of scope)
                 env.closest(rayO, rayD, ro4.w, rd4.w, hit); // rRec.rayIntersect(ray), volpath.cpp:97
                 if (hit.prim != 0xFFFFFFFFu) flags |= PF_ALPHA;
-                flags &= ~PF_FRESH;
+                flags = (flags & ~PF_FRESH) | PF_CAMRAY;
             } else {
                 const uint2 v = pool.vol[i];
                 medium = (int) v.x; smp.dim = v.y;
@@ -1496,7 +1523,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
                     const float phaseVal = phaseSample(med, -rayD, wo, phasePdf, smp);
                     if (phaseVal == 0) { done = true; break; }
                     T = T * phaseVal;
-                    rayO = mRec.p; rayD = wo; rayMintCur = 0.0f; rayMaxtCur = B2_INF;
+                    rayO = mRec.p; rayD = wo; rayMintCur = 0.0f; rayMaxtCur = B2_INF; flags &= ~PF_CAMRAY;
                     Spectrum value(0.0f);
                     EmitterQuery eq;
                     volIntersectAndLookForEmitter(env, smp, medium, rp.maxDepth - depth - 1, rayO, rayD, 0.0f, hit, eq, value);
@@ -1506,7 +1533,9 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
                     if (hit.prim == 0xFFFFFFFFu) { // volpath.cpp:190-202
                         if (sc.envEmitter >= 0 && !scattered && !rp.hideEmitters) {
                             const DEmitter &em = sc.emitters[sc.envEmitter];
-                            Spectrum value = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                            Spectrum value = T * (!sc.envmap ? V3(em.radiance[0], em.radiance[1], em.radiance[2])
+                                                             : (flags & PF_CAMRAY) ? envEvalCamera(sc, rp.diffScale, pool.pos[i], smp)
+                                                                                   : envEval(*sc.envmap, sc.ewaLut, rayD, false, V3(0.0f), V3(0.0f)));
                             if (medium >= 0) value = value * mediumTransmittance(sc.media[medium], rayO, rayD, rayMintCur, rayMaxtCur, smp);
                             Li = Li + value;
                         }
@@ -1561,7 +1590,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOL_MINBLOCKS) k_volstep(DS
                     if (isZero(bsdfWeight)) { done = true; break; }
                     const V3 wo = its.sh.toWorld(bRec.wo);
                     if (dot(its.geoN, wo) * cosTheta(bRec.wo) <= 0 && rp.strictNormals) { done = true; break; }
-                    rayO = its.p; rayD = wo; rayMintCur = B2_EPSILON; rayMaxtCur = B2_INF;
+                    rayO = its.p; rayD = wo; rayMintCur = B2_EPSILON; rayMaxtCur = B2_INF; flags &= ~PF_CAMRAY;
                     T = T * bsdfWeight;
                     eta *= bRec.eta;
                     if (transition) medium = targetMedium(media, its.geoN, rayD);
@@ -1705,7 +1734,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOLLS_MINBLOCKS) k_volstep_
         if (fresh) {
             env.closest(rayO, rayD, rayMintCur, rayMaxtCur, hit);
             if (hit.prim != 0xFFFFFFFFu) flags |= PF_ALPHA;
-            flags &= ~PF_FRESH;
+            flags = (flags & ~PF_FRESH) | PF_CAMRAY;
         }
         // One pass per launch: a lane that crosses an index-matched boundary (the reference `continue`s, volpath.cpp:302-311) keeps its
         // state and takes the repeated loop iteration in the NEXT launch -- repeating it here would leave the rest of the warp waiting.
@@ -1738,7 +1767,9 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOLLS_MINBLOCKS) k_volstep_
                     if (hit.prim == 0xFFFFFFFFu) { // volpath.cpp:190-202
                         if (sc.envEmitter >= 0 && !scattered && !rp.hideEmitters) {
                             const DEmitter &em = sc.emitters[sc.envEmitter];
-                            Spectrum value = T * V3(em.radiance[0], em.radiance[1], em.radiance[2]);
+                            Spectrum value = T * (!sc.envmap ? V3(em.radiance[0], em.radiance[1], em.radiance[2])
+                                                             : (flags & PF_CAMRAY) ? envEvalCamera(sc, rp.diffScale, pool.pos[i], smp)
+                                                                                   : envEval(*sc.envmap, sc.ewaLut, rayD, false, V3(0.0f), V3(0.0f)));
                             if (medium >= 0) value = value * mediumTransmittance(sc.media[medium], rayO, rayD, rayMintCur, rayMaxtCur, smp);
                             Li = Li + value;
                         }
@@ -1805,7 +1836,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOLLS_MINBLOCKS) k_volstep_
                     if (phaseVal == 0) { done = true; busy = false; run = false; }
                     else {
                         T = T * phaseVal;
-                        rayO = mRec.p; rayD = wo; rayMintCur = 0.0f; rayMaxtCur = B2_INF;
+                        rayO = mRec.p; rayD = wo; rayMintCur = 0.0f; rayMaxtCur = B2_INF; flags &= ~PF_CAMRAY;
                         refN = V3(0.0f);
                     }
                 } else {
@@ -1817,7 +1848,7 @@ __global__ void __launch_bounds__(B2_TRACE_BLOCK, B2_VOLLS_MINBLOCKS) k_volstep_
                     const V3 wo = its.sh.toWorld(bRec.wo);
                     if (isZero(bsdfWeight) || (dot(its.geoN, wo) * cosTheta(bRec.wo) <= 0 && rp.strictNormals)) { done = true; busy = false; run = false; }
                     else {
-                        rayO = its.p; rayD = wo; rayMintCur = B2_EPSILON; rayMaxtCur = B2_INF;
+                        rayO = its.p; rayD = wo; rayMintCur = B2_EPSILON; rayMaxtCur = B2_INF; flags &= ~PF_CAMRAY;
                         T = T * bsdfWeight;
                         eta *= bRec.eta;
                         if (transition) medium = targetMedium(media, its.geoN, rayD);
@@ -2121,6 +2152,23 @@ __global__ void k_texture_probe(DScene sc, int what, int tex, int hasPartials, f
         }
     }
 }
+// probes of the environment map: what 0 = evalEnvironment(d) (in 3n -> out 3n), 1 = evalEnvironment with differential directions
+// (in 9n: d, rxD, ryD -> out 3n), 2 = pdfEmitterDirect for direction d (in 3n -> out n)
+__global__ void k_envmap_probe(DScene sc, int what, uint64_t n, const float *in, float *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const DEnvMap &e = *sc.envmap;
+        if (what == 2) {
+            const float *r = in + 3 * i;
+            const DEmitter &em = sc.emitters[sc.envEmitter];
+            out[i] = envPdfDirection(e, envToLocal(e, V3(r[0], r[1], r[2]))) * (em.samplingWeight * sc.emitterNormalization);
+        } else {
+            const float *r = in + (what == 1 ? 9 : 3) * i;
+            const Spectrum v = what == 1 ? envEval(e, sc.ewaLut, V3(r[0], r[1], r[2]), true, V3(r[3], r[4], r[5]), V3(r[6], r[7], r[8]))
+                                         : envEval(e, sc.ewaLut, V3(r[0], r[1], r[2]), false, V3(0.0f), V3(0.0f));
+            out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+        }
+    }
+}
 __global__ void k_camera_rays(DScene sc, uint64_t n, const float *pos, float *rays) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         V3 o, d;
@@ -2237,7 +2285,7 @@ void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, con
         case 2: k_shade<2><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         case 3: k_shade<3><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         default:
-            if (sc.nTextures) k_shade<-1, true><<<cfg.gridShadeTex, B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
+            if (sc.nTextures || sc.envmap) k_shade<-1, true><<<cfg.gridShadeTex, B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
             else k_shade<-1><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
             break;
     }
@@ -2288,6 +2336,9 @@ void launch_emitter_direct(const LaunchCfg &cfg, const DScene &sc, uint64_t n, c
 void launch_texture_probe(const LaunchCfg &cfg, const DScene &sc, int what, int tex, int hasPartials, float diffScale, uint64_t n, const float *in, float *out,
                           cudaStream_t st) {
     k_texture_probe<<<cfg.numSMs * 4, 128, 0, st>>>(sc, what, tex, hasPartials, diffScale, n, in, out);
+}
+void launch_envmap_probe(const LaunchCfg &cfg, const DScene &sc, int what, uint64_t n, const float *in, float *out, cudaStream_t st) {
+    k_envmap_probe<<<cfg.numSMs * 4, 128, 0, st>>>(sc, what, n, in, out);
 }
 void launch_camera_rays(const LaunchCfg &cfg, const DScene &sc, uint64_t n, const float *pos, float *rays, cudaStream_t st) {
     k_camera_rays<<<cfg.numSMs * 2, 128, 0, st>>>(sc, n, pos, rays);

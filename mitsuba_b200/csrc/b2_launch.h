@@ -46,6 +46,7 @@ struct LaunchCfg {
     void launch_camera_rays(const LaunchCfg &, const DScene &, uint64_t n, const float *pos, float *rays, cudaStream_t);       \
     void launch_texture_probe(const LaunchCfg &, const DScene &, int what, int tex, int hasPartials, float diffScale, uint64_t n, const float *in,   \
                               float *out, cudaStream_t);                                                                    \
+    void launch_envmap_probe(const LaunchCfg &, const DScene &, int what, uint64_t n, const float *in, float *out, cudaStream_t); \
     void launch_sampler_stream(const DScene &, const DRender &, int px, int py, int sampleIdx, int ndim, float *out,           \
                                cudaStream_t);                                                                                  \
     void launch_splat(const LaunchCfg &, const DFilter &, int W, int H, uint64_t n, const float *pos, const float *val,        \

@@ -25,7 +25,7 @@ struct DMaterial {
 
 // One `bitmap` texture (src/textures/bitmap.cpp + include/mitsuba/render/mipmap.h): the MIP pyramid built by the host at commit
 // (Lanczos-2 resampling as the reference does), texels as float4 (RGB, channels == 3) or float (luminance, channels == 1)
-#define B2_TEX_MAX_LEVELS 16
+#define B2_TEX_MAX_LEVELS 17   // 65535 texels on a side (the largest environment map, envmap.cpp:160-162) -> 17 levels
 struct DTexture {
     int32_t levels, channels;
     int32_t filter;            // 0 nearest, 1 bilinear, 2 trilinear, 3 ewa (bitmap.cpp:213-230)
@@ -36,6 +36,18 @@ struct DTexture {
     int32_t lw[B2_TEX_MAX_LEVELS], lh[B2_TEX_MAX_LEVELS];
     uint32_t off[B2_TEX_MAX_LEVELS]; // first texel of each level inside `data`
     const void *data;
+};
+
+// `envmap` emitter (src/emitters/envmap.cpp): the pyramid as a texture (repeat / clamp, EWA, maxAnisotropy 10, RGB texels padded to
+// float4, values half-representable), the sampling tables of configure() (envmap.cpp:260-329) and the 3x3 parts of toWorld / its inverse
+struct DEnvMap {
+    DTexture tex;
+    const float *cdfRows;      // h + 1
+    const float *cdfCols;      // h rows of w + 1
+    const float *rowWeights;   // h: sin(theta) of the row centres
+    float normalization, scale, pixelSizeX, pixelSizeY;
+    float toWorld[9], toLocal[9];
+    int32_t w, h;
 };
 
 // One participating medium + its phase function (device copy of b2_medium_desc)
@@ -71,7 +83,7 @@ struct DEmitter {
     float samplingWeight;
     float invSurfaceArea;
     uint32_t cdfOffset;    // into triCdf (nTri + 1 floats, cdf[0] = 0)
-    uint32_t nTri;         // 0: `constant` environment emitter (src/emitters/constant.cpp), no mesh
+    uint32_t nTri;         // 0: environment emitter, no mesh: `constant` (src/emitters/constant.cpp) or, when DScene::envmap is set, `envmap`
     uint32_t primOffset;   // global prim index of the mesh's first triangle
 };
 
@@ -131,6 +143,7 @@ struct DScene {
     uint32_t nItems;
     int32_t tlasRoot;          // root reference of the top-level BVH (leaf refs there index `items`)
     int32_t envEmitter;        // index of the environment emitter or -1 (Scene::getEnvironmentEmitter)
+    const DEnvMap *envmap;     // non-null: that emitter is an `envmap` (else `constant`)
     float bsCenter[3], bsRadius; // constant.cpp:67-70 m_sceneBSphere: sphere of the scene box (incl. the sensor position), radius x 1.5
     // participating media (volpath): media table and per-prim (interior, exterior) ids, -1 = vacuum; null without media
     const DMedium *media;
@@ -189,6 +202,7 @@ enum : uint32_t {
     PF_DELTA = 1u << 4,       // last sampled lobe was EDelta (path.cpp:261)
     PF_REFN_OK = 1u << 5,     // dot(wo, refN) >= 0 for the pending emitter-hit MIS test (area.cpp:178)
     PF_ALPHA = 1u << 6,       // camera ray hit something
+    PF_CAMRAY = 1u << 7,      // volpath: the current segment is still the sensor ray (it carries ray differentials, volpath.cpp:89 / ray.h:150-157)
 };
 
 // Wavefront pool: structure of arrays, one entry per in-flight path ("slot"), 16-byte records

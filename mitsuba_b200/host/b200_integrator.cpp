@@ -179,7 +179,27 @@ public:
             const Emitter *e = emitters[i].get();
             if (e->getShape() != NULL && !e->isEnvironmentEmitter()) continue; /* area lights are marshalled with their mesh */
             const Properties &ep = e->getProperties();
-            if (ep.getPluginName() != "constant") Log(EError, "b200path: unsupported emitter \"%s\" (supported: area, constant)", ep.getPluginName().c_str());
+            if (ep.getPluginName() == "envmap") { /* EnvironmentMap: src/emitters/envmap.cpp */
+                /* the image as the plugin holds it: level 0 of its half-precision pyramid (Emitter::getBitmap -> TMIPMap::toBitmap,
+                   envmap.cpp:632-634, mipmap.h:486-497).  b2_scene_commit rebuilds the coarser levels from it (from the rounded, not the
+                   original float image: only the EWA look-up of directly visible background reads them) and the sampling tables */
+                ref<Bitmap> bm = e->getBitmap(Vector2i(0));
+                if (bm == NULL || bm->getPixelFormat() != Bitmap::ERGB || bm->getComponentFormat() != Bitmap::EFloat16)
+                    Log(EError, "b200path: the environment map is not an RGB half-precision image (spectral builds are not supported)");
+                const Vector2i size = bm->getSize();
+                const half *src = (const half *) bm->getData();
+                std::vector<float> px((size_t) size.x * size.y * 3);
+                for (size_t k = 0; k < px.size(); ++k) px[k] = (float) src[k];
+                const Transform envToWorld = e->getWorldTransform()->eval(0);
+                float a[16], b[16];
+                for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
+                    a[4 * r + c] = (float) envToWorld.getMatrix().m[r][c]; b[4 * r + c] = (float) envToWorld.getInverseMatrix().m[r][c];
+                }
+                if (b2_scene_add_envmap_emitter(sc, size.x, size.y, px.data(), (float) ep.getFloat("scale", 1.0f), a, b, (float) ep.getFloat("samplingWeight", 1.0f)) < 0)
+                    Log(EError, "%s", b2_last_error(ctx));
+                continue;
+            }
+            if (ep.getPluginName() != "constant") Log(EError, "b200path: unsupported emitter \"%s\" (supported: area, constant, envmap)", ep.getPluginName().c_str());
             float rad[3];
             rgbOf(ep.getSpectrum("radiance", Spectrum(1.0f)), rad);
             if (b2_scene_add_constant_emitter(sc, rad, (float) ep.getFloat("samplingWeight", 1.0f)) < 0) Log(EError, "%s", b2_last_error(ctx));

@@ -67,7 +67,7 @@ struct AxisKernel {
 
 // resample `count` lines along one axis: element (line, i, ch) sits at src[line * lineStride + i * elemStride + ch]
 void resampleAxis(const AxisKernel &k, int mode, int srcRes, int trgRes, const float *src, float *dst, int count, size_t srcLineStride, size_t srcElemStride,
-                  size_t dstLineStride, size_t dstElemStride, int channels) {
+                  size_t dstLineStride, size_t dstElemStride, int channels, float maxValue) {
     for (int line = 0; line < count; ++line) {
         const float *s = src + line * srcLineStride;
         float *d = dst + line * dstLineStride;
@@ -80,7 +80,7 @@ void resampleAxis(const AxisKernel &k, int mode, int srcRes, int trgRes, const f
                     const int pos = wrapIndex(mode, k.first[i] + j, srcRes, c, isC);
                     result += (isC ? c : s[pos * srcElemStride + ch]) * wt[j];
                 }
-                d[i * dstElemStride + ch] = std::min(1.0f, std::max(0.0f, result));
+                d[i * dstElemStride + ch] = std::min(maxValue, std::max(0.0f, result));
             }
         }
     }
@@ -111,13 +111,13 @@ static inline float roundToHalf(float f) {
     return r;
 }
 
-static void buildMipPyramidFloat(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out);
-void buildMipPyramid(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out) {
-    buildMipPyramidFloat(pixels, width, height, channels, wrapU, wrapV, pyramid, out);
+static void buildMipPyramidFloat(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out, float maxValue);
+void buildMipPyramid(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out, float maxValue) {
+    buildMipPyramidFloat(pixels, width, height, channels, wrapU, wrapV, pyramid, out, maxValue);
     for (auto &lvl : out.level) for (float &v : lvl) v = roundToHalf(v);
 }
 
-static void buildMipPyramidFloat(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out) {
+static void buildMipPyramidFloat(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out, float maxValue) {
     out = MipPyramid();
     out.channels = channels;
     std::vector<float> base(pixels, pixels + (size_t) width * height * channels);
@@ -136,11 +136,11 @@ static void buildMipPyramidFloat(const float *pixels, int width, int height, int
         if (w != nw) { // rows first
             float *dst = next.data();
             if (h != nh) { tmp.resize((size_t) nw * h * channels); dst = tmp.data(); }
-            resampleAxis(AxisKernel(w, nw), wrapU, w, nw, src, dst, h, (size_t) w * channels, channels, (size_t) nw * channels, channels, channels);
+            resampleAxis(AxisKernel(w, nw), wrapU, w, nw, src, dst, h, (size_t) w * channels, channels, (size_t) nw * channels, channels, channels, maxValue);
             src = dst;
         }
         if (h != nh) // then columns
-            resampleAxis(AxisKernel(h, nh), wrapV, h, nh, src, next.data(), nw, channels, (size_t) nw * channels, channels, (size_t) nw * channels, channels);
+            resampleAxis(AxisKernel(h, nh), wrapV, h, nh, src, next.data(), nw, channels, (size_t) nw * channels, channels, (size_t) nw * channels, channels, maxValue);
         w = nw; h = nh;
         out.w.push_back(w); out.h.push_back(h);
         out.level.push_back(std::move(next));

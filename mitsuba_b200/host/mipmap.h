@@ -16,7 +16,8 @@ struct MipPyramid {
 };
 
 // wrap modes: 0 repeat, 1 clamp, 2 mirror, 3 zero, 4 one.  `pyramid` false: level 0 only (filter types nearest / bilinear, mipmap.h:185,246)
-void buildMipPyramid(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out);
+// maxValue: upper clamp of the resampled levels (mipmap.h:156-157, :262): 1 for `bitmap` textures, infinity for `envmap` (envmap.cpp:172-175)
+void buildMipPyramid(const float *pixels, int width, int height, int channels, int wrapU, int wrapV, bool pyramid, MipPyramid &out, float maxValue = 1.0f);
 
 // EWA filter weights (mipmap.h:296-302)
 void ewaWeightTable(float *lut64);

@@ -490,13 +490,110 @@ struct Loader {
             px.resize(raw.size());
             for (size_t i = 0; i < raw.size(); ++i) px[i] = (float) raw[i] * (1.0f / 255.0f);
             gamma = -1.0;
-        } else throw Err("bitmap: unsupported image format in \"" + path + "\" (supported: PFM, 8-bit binary PPM)");
+        } else if (magic.size() >= 2 && magic[0] == '#' && magic[1] == '?') {
+            // Radiance RGBE (.hdr / .pic), Bitmap::readRGBE (bitmap.cpp:3590-3689): text header up to the "-Y h +X w" line, then either flat
+            // 4-byte pixels or per-scanline run-length coding of the four byte planes; value = mantissa * 2^(e - 136) (:3522-3530)
+            f.seekg(0);
+            std::vector<unsigned char> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            size_t pos = 0;
+            auto line = [&]() { std::string t; while (pos < file.size() && file[pos] != '\n') t += (char) file[pos++]; ++pos; return t; };
+            line();
+            bool knownFormat = false;
+            w = h = 0;
+            while (pos < file.size()) {
+                const std::string l = line();
+                if (l.compare(0, 22, "FORMAT=32-bit_rle_rgbe") == 0) knownFormat = true;
+                if (l.compare(0, 3, "-Y ") == 0) {
+                    if (sscanf(l.c_str(), "-Y %i +X %i", &h, &w) < 2) throw Err("readRGBE(): parser error!");
+                    break;
+                }
+            }
+            if (!knownFormat) throw Err("readRGBE(): invalid format!");
+            if (w <= 0 || h <= 0) throw Err("readRGBE(): parser error!");
+            ch = 3;
+            px.assign((size_t) w * h * 3, 0.0f);
+            auto need = [&](size_t n) { if (pos + n > file.size()) throw Err("readRGBE(): file is truncated"); };
+            auto decode = [](const unsigned char *q, float *o) {
+                if (q[3]) { const float m = std::ldexp(1.0f, (int) q[3] - 136); o[0] = q[0] * m; o[1] = q[1] * m; o[2] = q[2] * m; }
+                else o[0] = o[1] = o[2] = 0.0f;
+            };
+            auto flat = [&](size_t firstPixel) { // the rest of the file is uncompressed
+                const size_t n = (size_t) w * h - firstPixel;
+                need(4 * n);
+                for (size_t k = 0; k < n; ++k, pos += 4) decode(&file[pos], &px[3 * (firstPixel + k)]);
+            };
+            if (w < 8 || w > 0x7fff) flat(0);
+            else {
+                std::vector<unsigned char> planes((size_t) 4 * w);
+                for (int y = 0; y < h; ++y) {
+                    need(4);
+                    const unsigned char *hd = &file[pos];
+                    if (hd[0] != 2 || hd[1] != 2 || (hd[2] & 0x80)) { // no scanline marker: the file is flat from here on (only legal in row 0)
+                        flat((size_t) y * w);
+                        break;
+                    }
+                    if ((((int) hd[2]) << 8 | hd[3]) != w) throw Err("readRGBE(): wrong scanline width!");
+                    pos += 4;
+                    for (int c = 0; c < 4; ++c) {
+                        unsigned char *out = &planes[(size_t) c * w], *end = out + w;
+                        while (out < end) {
+                            need(2);
+                            int count = file[pos];
+                            if (count > 128) { // run
+                                count -= 128;
+                                if (count > end - out) throw Err("readRGBE(): bad scanline data!");
+                                std::fill(out, out + count, file[pos + 1]);
+                                pos += 2;
+                            } else { // literal bytes
+                                if (count == 0 || count > end - out) throw Err("readRGBE(): bad scanline data!");
+                                need(1 + (size_t) count);
+                                std::copy(&file[pos + 1], &file[pos + 1] + count, out);
+                                pos += 1 + (size_t) count;
+                            }
+                            out += count;
+                        }
+                    }
+                    for (int x = 0; x < w; ++x) {
+                        const unsigned char q[4] = {planes[x], planes[(size_t) w + x], planes[(size_t) 2 * w + x], planes[(size_t) 3 * w + x]};
+                        decode(q, &px[3 * ((size_t) y * w + x)]);
+                    }
+                }
+            }
+            gamma = 1.0;
+        } else throw Err("bitmap: unsupported image format in \"" + path + "\" (supported: PFM, Radiance RGBE, 8-bit binary PPM)");
         if (gammaOverride != 0) gamma = gammaOverride; // bitmap.cpp:251-252
         if (gamma == -1.0) {
             for (float &v : px) v = v <= 0.04045f ? v * (float) (1.0 / 12.92) : std::pow((float) ((v + 0.055f) * (float) (1.0 / 1.055)), 2.4f);
         } else if (gamma != 1.0) {
             for (float &v : px) v = std::pow(v, (float) gamma);
         }
+    }
+    // <emitter type="envmap"> (src/emitters/envmap.cpp:106-181): filename, scale, toWorld, gamma, samplingWeight; `cache` is accepted and
+    // ignored (MIP map cache files are neither read nor written: the pyramid is rebuilt at commit)
+    void addEnvMap(Node *n) {
+        Props p(n);
+        std::string fn = p.s("filename", "");
+        if (fn.empty()) throw Err("envmap: 'filename' is required");
+        if (fn[0] != '/') fn = baseDir + "/" + fn;
+        if (p.has("intensityScale")) throw Err("The 'intensityScale' parameter has been deprecated and is now called scale."); // envmap.cpp:177-178
+        const double gamma = p.f("gamma", 0);
+        const float scale = (float) p.f("scale", 1.0);
+        const float weight = (float) p.f("samplingWeight", 1.0);
+        p.b("cache", false);
+        M4 tw = p.xf("toWorld"), inv;
+        if (!tw.inverse(inv)) throw Err("envmap: singular toWorld transform");
+        p.checkAllUsed();
+        int w, h, ch;
+        std::vector<float> px;
+        loadImage(fn, gamma, w, h, ch, px);
+        if (ch == 1) { // luminance image -> RGB (Bitmap::convert to ERGB)
+            std::vector<float> rgb((size_t) w * h * 3);
+            for (size_t k = 0; k < (size_t) w * h; ++k) rgb[3 * k] = rgb[3 * k + 1] = rgb[3 * k + 2] = px[k];
+            px.swap(rgb);
+        }
+        float a[16], b[16];
+        for (int i = 0; i < 16; ++i) { a[i] = (float) tw.m[i]; b[i] = (float) inv.m[i]; }
+        if (b2_scene_add_envmap_emitter(scene, w, h, px.data(), scale, a, b, weight) < 0) throw Err(b2_last_error(nullptr));
     }
     int addTexture(Node *n) {
         if (n->type != "bitmap") throw Err("unsupported texture plugin \"" + n->type + "\" (supported: bitmap)");
@@ -1187,7 +1284,8 @@ struct Loader {
                 haveSensor = true;
             } else if (c->tag == "shape") addShape(c);
             else if (c->tag == "emitter") {
-                if (c->type != "constant") throw Err("unsupported top-level emitter \"" + c->type + "\" (supported: constant; area emitters are attached to shapes)");
+                if (c->type == "envmap") { addEnvMap(c); continue; }
+                if (c->type != "constant") throw Err("unsupported top-level emitter \"" + c->type + "\" (supported: constant, envmap; area emitters are attached to shapes)");
                 Props ep(c);
                 const double one[3] = {1, 1, 1};
                 float rad[3];

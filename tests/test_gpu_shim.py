@@ -18,7 +18,8 @@ SHIM = os.path.join(HERE, "..", "oracle", "_ref", "libb200shim.so")
 # cases the 0.6 object API lets the plugin marshal: `path`, Sobol' sampler, BSDFs without children, no media, no instances
 SUPPORTED = ["cbox_box_8spp", "cbox_gaussian_16spp", "cbox_depth3_scramble", "cbox_strict_hidden", "ball_roughconductor_ggx",
              "ball_roughdielectric_beckmann", "ball_dielectric", "ball_conductor", "ball_roughconductor_as", "ball_plastic",
-             "thinlens_cbox_sobol", "env_only_ball", "env_plus_area_cbox", "crop_cbox_sobol"]
+             "thinlens_cbox_sobol", "env_only_ball", "env_plus_area_cbox", "crop_cbox_sobol",
+             "envmap_only_ball", "envmap_hidden_cbox", "envmap_glass_ball"]   # EnvironmentMap: image, scale, toWorld read back through the Emitter interface
 
 
 def rel_l2(a, b):
@@ -44,8 +45,9 @@ def render_through_plugin(lib, desc, rp, parity=True):
 
 
 def test_reference_scenes_render_through_the_mitsuba_side_plugin(shim):
-    g = {**np.load(os.path.join(HERE, "golden", "path_ref.npz")), **np.load(os.path.join(HERE, "golden", "path_ref_ext.npz"))}
-    cases = {name: (desc, rp) for name, desc, rp in list(ref_pins.image_cases()) + list(ref_pins.image_cases_ext())}
+    g = {**np.load(os.path.join(HERE, "golden", "path_ref.npz")), **np.load(os.path.join(HERE, "golden", "path_ref_ext.npz")),
+         **np.load(os.path.join(HERE, "golden", "path_ref_env.npz"))}
+    cases = {name: (desc, rp) for name, desc, rp in list(ref_pins.image_cases()) + list(ref_pins.image_cases_ext()) + list(ref_pins.image_cases_env())}
     for name in SUPPORTED:
         desc, rp = cases[name]
         ref = g[name + "/film"]
@@ -54,7 +56,7 @@ def test_reference_scenes_render_through_the_mitsuba_side_plugin(shim):
         film = film.reshape(ref.shape)
         assert np.allclose(film[..., 4], ref[..., 4], rtol=1e-5, atol=1e-6), name       # weights: identical sample positions and splats
         assert np.allclose(film[..., 3], ref[..., 3], rtol=1e-4, atol=1e-4), name       # alpha
-        tol = 1e-3 if name.startswith("crop") else 3e-4                                   # as tests/test_gpu_z_reference_images_ext.py
+        tol = 1e-3 if name.startswith(("crop", "envmap")) else 3e-4                       # as tests/test_gpu_z_reference_images_ext.py, test_gpu_envmap.py
         assert rel_l2(film[..., :3], ref[..., :3]) <= tol, (name, rel_l2(film[..., :3], ref[..., :3]))
 
 

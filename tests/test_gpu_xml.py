@@ -261,3 +261,70 @@ def test_conductor_material_presets_and_crop_window_through_the_scene_file(b2ctx
     assert crop.shape == (24, 40, 5) and (sc.W, sc.H) == (40, 24)
     with pytest.raises(api.B2Error, match="Invalid crop window"):
         render('<integer name="cropOffsetX" value="60"/><integer name="cropWidth" value="40"/>', "")
+
+
+def _rgbe_bytes(img, rle):
+    """Radiance .hdr encoding of a float RGB image; returns (file bytes, the image a reader decodes from them)."""
+    h, w, _ = img.shape
+    m = img.max(axis=2)
+    e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, 0).astype(np.int32)
+    scale = np.where(m > 1e-32, np.ldexp(1.0, 8 - e), 0.0)
+    mant = np.clip(np.floor(img * scale[..., None]), 0, 255).astype(np.uint8)
+    ebyte = np.where(m > 1e-32, e + 128, 0).astype(np.uint8)
+    rgbe = np.concatenate([mant, ebyte[..., None]], axis=2)
+    decoded = np.where(ebyte[..., None] > 0, mant.astype(np.float32) * np.ldexp(np.float32(1.0), ebyte.astype(np.int32) - 136)[..., None], 0).astype(np.float32)
+    out = bytearray(b"#?RADIANCE\n# written by tests/test_gpu_xml.py\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n" + f"-Y {h} +X {w}\n".encode())
+    if not rle:
+        out += rgbe.tobytes()
+        return bytes(out), decoded
+    for y in range(h):
+        out += bytes([2, 2, w >> 8, w & 255])
+        for c in range(4):
+            row = rgbe[y, :, c]
+            x = 0
+            while x < w:
+                run = 1
+                while x + run < w and run < 127 and row[x + run] == row[x]:
+                    run += 1
+                if run >= 3:
+                    out += bytes([128 + run, int(row[x])]); x += run
+                else:
+                    lit = min(w - x, 5)   # short literal packets
+                    out += bytes([lit]) + row[x:x + lit].tobytes(); x += lit
+    return bytes(out), decoded
+
+
+@pytest.mark.parametrize("encoding", ["rle", "flat", "pfm"])
+def test_envmap_emitter_through_the_scene_file(b2ctx, tmp_path, encoding):
+    """<emitter type="envmap"> with a Radiance .hdr (run-length coded and flat) or PFM image, scale, toWorld and samplingWeight: the film of
+    the loaded scene equals the film of the same scene handed over through the C-ABI, and the reference-pinned oracle's film."""
+    import shutil
+    import ref_pins
+    from mitsuba_b200.scene import EnvMap
+    shutil.copytree(os.path.join(ROOT, "scenes", "meshes"), tmp_path / "meshes")
+    img = ref_pins.sky_image(32, 16, seed=21, sun=20.0)
+    img[:, 8:14] = img[:, 8:9]                      # a few constant stretches so that the scanline coder emits runs
+    if encoding == "pfm":
+        fname, decoded = "sky.pfm", img
+        with open(tmp_path / fname, "wb") as f:
+            f.write(b"PF\n32 16\n-1.0\n" + img[::-1].astype("<f4").tobytes())
+    else:
+        fname = "sky.hdr"
+        data, decoded = _rgbe_bytes(img, encoding == "rle")
+        (tmp_path / fname).write_bytes(data)
+    emitter = (f'\t<emitter type="envmap"><string name="filename" value="{fname}"/><float name="scale" value="0.8"/><float name="samplingWeight" value="2"/>'
+               '<transform name="toWorld"><rotate y="1" angle="35"/></transform></emitter>\n')
+    p = tmp_path / "sky.xml"
+    p.write_text(open(os.path.join(ROOT, "scenes", "cbox.xml")).read().replace("</scene>", emitter + "</scene>"))
+    sc, rp = b2ctx.load_xml(str(p), ["spp=16", "res=48"])
+    film, _ = sc.render(rp, parity=True, width=48, height=48)
+    a = np.deg2rad(35.0)
+    M = np.eye(4); M[0, 0] = M[2, 2] = np.cos(a); M[0, 2] = np.sin(a); M[2, 0] = -np.sin(a)
+    d = cornell_box(48, 48)
+    d.envmap = EnvMap(pixels=decoded, scale=0.8, to_world=M.astype(np.float32), sampling_weight=2.0)
+    sc2 = api.Scene(b2ctx, d)
+    film2, _ = sc2.render(RenderParams(spp=16, sampler="sobol", rfilter="box"), parity=True)
+    assert rel_l2(api.develop(film), api.develop(film2)) < 1e-5
+    fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert rel_l2(api.develop(film), O.develop(fo)) < 1e-3
+    sc.close(); sc2.close()
