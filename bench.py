@@ -121,7 +121,9 @@ _REF = {}
 
 def bench_scene(name, width, height):
     """Scene description + render parameters of the named BASELINE config (spp filled in by the caller)."""
-    from mitsuba_b200.scene import RenderParams, config3_scene, cornell_box, smoke_scene, stress_scene
+    from mitsuba_b200.scene import RenderParams, config3_scene, cornell_box, envmap_scene, smoke_scene, stress_scene
+    if name == "env":
+        return envmap_scene(width, height), dict(sampler="sobol", rfilter="gaussian")
     if name == "c2":
         return cornell_box(width, height), dict(sampler="sobol", rfilter="box")
     if name == "c3":
@@ -347,6 +349,34 @@ def textured_metric(ctx, with_cpu=True):
     res = {"workload": "S2 material ball, 3 bitmap textures (1024^2, ewa, maxAnisotropy 20), ~80k triangles, path, sobol, gaussian filter, 1024x1024 @ 64 spp, 1 GPU",
            "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"], "kernel": "k_shade<-1, TEX>", "kernel_ms": best["ms_shade"],
            "mean_path_length": best["path_length_sum"] / best["samples"]}
+    sc.close()
+    return res
+
+
+def envmap_metric(ctx, with_parity=True):
+    """SURVEY.md 8f-3, reported next to the headline: the config-3 material balls lit by a 1024 x 512 environment map only (seen directly with
+    the EWA look-up, reflected, refracted, and sampled through its CDF tables), `path`, 1024x1024 @ 64 spp on this rank's GPU; and the film of
+    that run against the reference's own EnvironmentMap + MIPathTracer on every 16th block."""
+    from mitsuba_b200 import api
+    from mitsuba_b200.scene import RenderParams
+    d, kw = bench_scene("env", 1024, 1024)
+    sc = api.Scene(ctx, d)
+    rp = RenderParams(spp=64, **kw)
+    sc.render(RenderParams(spp=4, **kw))
+    best, film = None, None
+    for _ in range(2):
+        f, st = sc.render(rp, flags=4)
+        if best is None or st["ms_total"] < best["ms_total"]:
+            best, film = st, f
+    n = 1024 * 1024 * 64
+    res = {"workload": "config-3 material balls (GGX conductor + rough dielectric, ~160k triangles) lit by a 1024x512 envmap only (ewa, maxAnisotropy 10), path, sobol, "
+                       "gaussian filter, 1024x1024 @ 64 spp, 1 GPU", "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"],
+           "kernel": "k_shade<-1, TEX>", "kernel_ms": best["ms_shade"], "mean_path_length": best["path_length_sum"] / best["samples"]}
+    if with_parity:
+        ref = reference_parity_film("env", 1024, 1024, 64)
+        if ref is not None:
+            res["parity"] = parity_entry(ref, np.asarray(film).reshape(1024, 1024, 5), 64, "the film of the timed run")
+            res["parity"]["build"] = "IEEE kernels (a transmissive BSDF is in the scene: DESIGN.md section 5)"
     sc.close()
     return res
 
@@ -624,6 +654,11 @@ def main():
                 line["textured"] = textured_metric(ctx)
             except Exception as e:
                 line["textured"] = {"error": str(e)}
+        if not args.no_configs and args.config == "c2" and full_size and world == 1:
+            try:
+                line["envmap"] = envmap_metric(ctx, with_parity=not args.no_parity)
+            except Exception as e:
+                line["envmap"] = {"error": str(e)}
         if cpu_base is not None:
             line["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core", "compiler_flags", "cpu_info", "strict_build") if k in cpu_base}
         print(json.dumps(line))

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -640,11 +641,24 @@ static uint32_t materialFlags(const std::vector<b2_material_desc> &mats, int id)
     }
 }
 
+// B2_COMMIT_TIMING=1: host-side phase times of b2_scene_commit on stderr (where the seconds of a multi-million-triangle commit go)
+struct CommitClock {
+    bool on = getenv("B2_COMMIT_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b2 commit] %-28s %8.1f ms (total %8.1f ms)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
 extern "C" int b2_scene_commit(b2_scene *s) {
     if (!s) return fail(nullptr, B2_ERR_INVALID, "b2_scene_commit: null scene");
     b2_ctx *ctx = s->ctx;
     if (!s->hasCamera) return fail(ctx, B2_ERR_INVALID, "scene has no sensor");
     CK(ctx, cudaSetDevice(ctx->device));
+    CommitClock clk;
     for (size_t e = 0; e < s->emitters.size(); ++e)
         if (s->emitters[e].mesh < 0 && !s->emitters[e].env) return fail(ctx, B2_ERR_INVALID, "area emitter without a parent shape");
     // ---- emitter order of Scene::m_emitters: emitters that are direct children of the scene (`constant`) are appended by
@@ -747,6 +761,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         }
     }
     s->hTriAccelPrimOrder = triAccel;
+    clk.mark("flatten + TriAccel");
     // ---- BVH ----
     BVHResult bvh;
     int threads = (int) std::thread::hardware_concurrency();
@@ -767,6 +782,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         buildBVH(boxes, ids, 4, instanced ? 19 : B2_STACK_DEPTH - 2, threads > 0 ? threads : 1, bvh, wide);
         if (bvh.depth8 > B2_STACK8_DEPTH - 1) bvh.nodes8.clear(); // deeper than the wide traversal's stack: binary tree only
     }
+    clk.mark("BVH (world)");
     // ---- instancing: one BVH per shapegroup appended to the node / leaf arrays, then a top-level BVH over the items
     //      (item 0 = the world triangles, item k = instance k - 1); stack budget: 9 (top) + 3 (leaf items) + 19 (bottom) < 32 ----
     std::vector<DInstance> items;
@@ -866,6 +882,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         memcpy(&leafTri[3 * i], &triAccel[3 * p], 48);
         planeRows(verts[3 * p], verts[3 * p + 1], verts[3 * p + 2], &leafPlane[3 * i]);
     }
+    clk.mark("instancing / leaf order");
     // ---- flat leaf of the throughput build: coplanar triangle pairs share the plane test ----
     // Two triangles with a common edge that lie in one plane are stored as ONE record: a parallelogram (3 rows: the
     // lockstep test is 0 <= u,v <= 1 in the frame of the unshared corner) or a general coplanar pair (5 rows: one t and
@@ -955,6 +972,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     if (getenv("B2_VERBOSE"))
         fprintf(stderr, "[b2mts] commit: %zu triangles, flat leaf %u (two-wide steps: parallelograms %u, coplanar pairs %u, singles %u), bvh nodes %zu depth %d\n", nPrims, rootCount,
                 flatP, flatC, flatS, bvh.nodes.size(), bvh.depth);
+    clk.mark("leaf records");
     // ---- materials ----
     std::vector<DMaterial> dm(s->materials.size());
     for (int c = 0; c < 4; ++c) s->classPresent[c] = false;
@@ -1106,6 +1124,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         for (auto &m : s->meshes)
             for (size_t j = 0; j < m.idx.size() / 3; ++j) primMedia[m.primOffset + j] = make_int2(m.interior, m.exterior);
     }
+    clk.mark("materials / textures / media");
     // ---- emitters: scene.cpp:375-380, trimesh.cpp:388-403, pmf.h ----
     std::vector<DEmitter> de(s->emitters.size());
     std::vector<float> emCdf(1, 0.0f), triCdf;
@@ -1149,6 +1168,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
             emCdf.back() = 1.0f;
         }
     }
+    clk.mark("emitters");
     // ---- upload ----
     CK(ctx, s->dTriAccel.upload(leafTri));
     CK(ctx, s->dTriPlane.upload(leafPlane));
@@ -1251,6 +1271,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     s->stats.bvh_node_bytes = bvh.nodes8.empty() ? sizeof(BVHNode) : sizeof(BVH8Node);
     s->stats.bytes_uploaded = leafTri.size() * 16 + leafPlane.size() * 16 + bvh.leafPrims.size() * 4 + verts.size() * 16 + norms.size() * 16 + bvh.nodes.size() * sizeof(BVHNode) +
                               dm.size() * sizeof(DMaterial) + de.size() * sizeof(DEmitter) + (emCdf.size() + triCdf.size()) * 4;
+    clk.mark("upload");
     s->committed = true;
     return B2_OK;
 }

@@ -3,9 +3,12 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <limits>
+#include <chrono>
 #include <queue>
 #include <thread>
 
@@ -37,50 +40,110 @@ struct TmpNode {
     int depth = 0;
 };
 
-struct Builder {
-    const std::vector<PrimBox> &boxes;
-    std::vector<uint32_t> order; // permutation of [0, n) partitioned in place
-    std::vector<float> cx, cy, cz;
-    int maxLeaf, maxDepth;
-    std::atomic<int> threadsLeft;
-
-    Builder(const std::vector<PrimBox> &b, int ml, int md, int threads) : boxes(b), maxLeaf(ml), maxDepth(md), threadsLeft(threads - 1) {
-        size_t n = b.size();
-        order.resize(n);
-        cx.resize(n); cy.resize(n); cz.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            order[i] = (uint32_t) i;
-            cx[i] = 0.5f * (b[i].lo[0] + b[i].hi[0]);
-            cy[i] = 0.5f * (b[i].lo[1] + b[i].hi[1]);
-            cz[i] = 0.5f * (b[i].lo[2] + b[i].hi[2]);
+// Worker threads the top of the tree can borrow: a node with many primitives splits its reductions (bounds, bins) and its partition over
+// them; further down whole subtrees go to their own thread.  All reductions are min / max / integer counts and the partition is stable,
+// so the tree does not depend on the number of threads (b2_bvh_selftest compares 1 against many).
+struct Workers {
+    std::atomic<int> idle;
+    explicit Workers(int threads) : idle(threads - 1) {}
+    int borrow(int want) { // up to `want` extra threads
+        int got = 0;
+        while (got < want) {
+            int cur = idle.load();
+            if (cur <= 0) break;
+            if (idle.compare_exchange_weak(cur, cur - 1)) ++got;
         }
+        return got;
     }
-    float centroid(uint32_t p, int axis) const { return axis == 0 ? cx[p] : (axis == 1 ? cy[p] : cz[p]); }
+    void giveBack(int n) { idle.fetch_add(n); }
+};
+
+// run f(chunkIndex, begin, end) over [0, count) cut into `parts` contiguous chunks, parts - 1 of them on new threads
+template <typename F> void forChunks(uint32_t count, int parts, F f) {
+    if (parts <= 1) { f(0, 0u, count); return; }
+    std::vector<std::thread> th;
+    th.reserve(parts > 1 ? parts - 1 : 0);
+    for (int c = 1; c < parts; ++c)
+        th.emplace_back([=]() { f(c, (uint32_t) ((uint64_t) count * c / parts), (uint32_t) ((uint64_t) count * (c + 1) / parts)); });
+    f(0, 0u, (uint32_t) ((uint64_t) count / parts));
+    for (auto &t : th) t.join();
+}
+
+struct Builder {
+    // the primitives travel with the permutation (box + id, 28 bytes): every pass over a node streams its range instead of gathering
+    // boxes through an index (the gathers were DRAM-latency bound: 57 ns per primitive and level on 2.5 M triangles)
+    struct Ref { float lo[3], hi[3]; uint32_t id; };
+    const std::vector<PrimBox> &boxes;
+    std::vector<Ref> refs;      // partitioned in place
+    std::vector<Ref> scratch;   // the right-hand side of a partition, same index range as the node (disjoint between subtrees)
+    std::vector<uint32_t> order; // refs[i].id after the build: permutation of [0, n)
+    int maxLeaf, maxDepth;
+    Workers workers;
+    int totalThreads;
+    static const uint32_t kParallelNode = 1u << 17; // nodes with at least this many primitives are worth splitting over threads
+    static const int NB = 16;
+
+    Builder(const std::vector<PrimBox> &b, int ml, int md, int threads) : boxes(b), maxLeaf(ml), maxDepth(md), workers(threads), totalThreads(threads) {
+        const size_t n = b.size();
+        refs.resize(n); scratch.resize(n);
+        const int parts = n >= kParallelNode ? 1 + workers.borrow(std::min<int>(threads - 1, (int) (n / kParallelNode))) : 1;
+        forChunks((uint32_t) n, parts, [&](int, uint32_t lo, uint32_t hi) {
+            for (uint32_t i = lo; i < hi; ++i) {
+                memcpy(refs[i].lo, b[i].lo, 12); memcpy(refs[i].hi, b[i].hi, 12);
+                refs[i].id = i;
+            }
+        });
+        workers.giveBack(parts - 1);
+    }
+    static float centroid(const Ref &r, int axis) { return 0.5f * (r.lo[axis] + r.hi[axis]); }
+    void finish() { // the permutation the callers read
+        order.resize(refs.size());
+        for (size_t i = 0; i < refs.size(); ++i) order[i] = refs[i].id;
+        std::vector<Ref>().swap(scratch);
+    }
+    static int binOf(float c, float lo, float scale) { return std::min(std::max((int) ((c - lo) * scale), 0), NB - 1); }
+
+    struct Bins { Box bb[3][NB]; uint32_t bc[3][NB]; };
 
     // builds the subtree over order[start, start+count) into `nodes` (local vector), returns local root index
     int build(std::vector<TmpNode> &nodes, uint32_t start, uint32_t count, int depth) {
         int me = (int) nodes.size();
         nodes.emplace_back();
+        // threads for the passes over this node's primitives
+        int parts = 1;
+        if (count >= kParallelNode) parts += workers.borrow((int) (((uint64_t) totalThreads * count + boxes.size() - 1) / boxes.size()) - 1); // a share in proportion to the node's size
         Box box, cbox;
         box.reset(); cbox.reset();
-        for (uint32_t i = start; i < start + count; ++i) {
-            uint32_t p = order[i];
-            box.grow(boxes[p].lo, boxes[p].hi);
-            float c[3] = {cx[p], cy[p], cz[p]};
-            cbox.growPt(c);
+        {
+            Box pb1[2];
+            std::vector<Box> pbN;
+            if (parts > 1) pbN.resize(2 * (size_t) parts);
+            Box *pb = parts > 1 ? pbN.data() : pb1, *pc = pb + parts; // no heap traffic for the millions of small nodes
+            forChunks(count, parts, [&](int c, uint32_t lo, uint32_t hi) {
+                Box b1, c1;
+                b1.reset(); c1.reset();
+                for (uint32_t i = start + lo; i < start + hi; ++i) {
+                    const Ref &p = refs[i];
+                    b1.grow(p.lo, p.hi);
+                    const float c3[3] = {centroid(p, 0), centroid(p, 1), centroid(p, 2)};
+                    c1.growPt(c3);
+                }
+                pb[c] = b1; pc[c] = c1;
+            });
+            for (int c = 0; c < parts; ++c) { box.grow(pb[c].lo, pb[c].hi); cbox.grow(pc[c].lo, pc[c].hi); }
         }
         nodes[me].box = box;
         nodes[me].depth = depth;
         nodes[me].start = start;
         nodes[me].count = count;
-        if (count == 1) return me;
+        if (count == 1) { workers.giveBack(parts - 1); return me; }
         const bool canLeaf = (int) count <= maxLeaf;
         // depth cap: if the remaining levels can only just hold a balanced tree, split at the object median
         int remaining = maxDepth - depth;
         int need = 0;
         { uint32_t leaves = (count + (uint32_t) maxLeaf - 1) / (uint32_t) maxLeaf; while ((1u << need) < leaves) ++need; }
         bool forceMedian = need + 1 >= remaining;
-        if (canLeaf && (forceMedian || remaining <= 1)) return me;
+        if (canLeaf && (forceMedian || remaining <= 1)) { workers.giveBack(parts - 1); return me; }
         int axis = 0;
         float ext[3] = {cbox.hi[0] - cbox.lo[0], cbox.hi[1] - cbox.lo[1], cbox.hi[2] - cbox.lo[2]};
         if (ext[1] > ext[axis]) axis = 1;
@@ -88,22 +151,38 @@ struct Builder {
         uint32_t mid = start + count / 2;
         bool done = false;
         if (!forceMedian && ext[axis] > 0) {
-            const int NB = 16;
             float bestCost = std::numeric_limits<float>::infinity();
             int bestAxis = -1, bestBin = -1;
+            float scale[3];
+            for (int a = 0; a < 3; ++a) scale[a] = ext[a] > 0 ? NB / ext[a] : 0.0f;
+            // one pass fills the bins of all three axes; chunks keep their own bins, merged afterwards (min / max / counts: exact)
+            Bins bins1;
+            std::vector<Bins> binsN;
+            if (parts > 1) binsN.resize(parts);
+            Bins *pbins = parts > 1 ? binsN.data() : &bins1;
+            forChunks(count, parts, [&](int c, uint32_t lo, uint32_t hi) {
+                Bins &bn = pbins[c];
+                for (int a = 0; a < 3; ++a) for (int k = 0; k < NB; ++k) { bn.bb[a][k].reset(); bn.bc[a][k] = 0; }
+                for (uint32_t i = start + lo; i < start + hi; ++i) {
+                    const Ref &p = refs[i];
+                    for (int a = 0; a < 3; ++a) {
+                        if (!(ext[a] > 0)) continue;
+                        const int k = binOf(centroid(p, a), cbox.lo[a], scale[a]);
+                        bn.bb[a][k].grow(p.lo, p.hi);
+                        bn.bc[a][k]++;
+                    }
+                }
+            });
+            Bins &bins = pbins[0];
+            for (int c = 1; c < parts; ++c)
+                for (int a = 0; a < 3; ++a) for (int k = 0; k < NB; ++k) {
+                    if (pbins[c].bc[a][k]) bins.bb[a][k].grow(pbins[c].bb[a][k].lo, pbins[c].bb[a][k].hi);
+                    bins.bc[a][k] += pbins[c].bc[a][k];
+                }
             for (int a = 0; a < 3; ++a) {
                 if (!(ext[a] > 0)) continue;
-                Box bb[NB];
-                uint32_t bc[NB];
-                for (int k = 0; k < NB; ++k) { bb[k].reset(); bc[k] = 0; }
-                float scale = NB / ext[a];
-                for (uint32_t i = start; i < start + count; ++i) {
-                    uint32_t p = order[i];
-                    int k = (int) ((centroid(p, a) - cbox.lo[a]) * scale);
-                    k = std::min(std::max(k, 0), NB - 1);
-                    bb[k].grow(boxes[p].lo, boxes[p].hi);
-                    bc[k]++;
-                }
+                const Box *bb = bins.bb[a];
+                const uint32_t *bc = bins.bc[a];
                 float rightArea[NB];
                 uint32_t rightCount[NB];
                 Box acc;
@@ -129,40 +208,73 @@ struct Builder {
                 float leafCost = box.area() * count;
                 float splitCost = 1.0f * box.area() + bestCost; // traversal cost 1, intersection cost 1
                 if (splitCost < leafCost || !canLeaf) {
-                    float scale = NB / ext[bestAxis];
-                    auto it = std::partition(order.begin() + start, order.begin() + start + count, [&](uint32_t p) {
-                        int k = (int) ((centroid(p, bestAxis) - cbox.lo[bestAxis]) * scale);
-                        k = std::min(std::max(k, 0), NB - 1);
-                        return k <= bestBin;
-                    });
-                    mid = (uint32_t) (it - order.begin());
+                    const float sc = scale[bestAxis], clo = cbox.lo[bestAxis];
+                    auto goesLeft = [&](const Ref &p) { return binOf(centroid(p, bestAxis), clo, sc) <= bestBin; };
+                    // stable partition: left-hand primitives keep their order in place, right-hand ones pass through `scratch`
+                    uint32_t totalLeft = 0;
+                    if (parts == 1) {
+                        uint32_t l = start, r = 0;
+                        for (uint32_t i = start; i < start + count; ++i) {
+                            const Ref p = refs[i];
+                            if (goesLeft(p)) refs[l++] = p; else scratch[start + r++] = p;
+                        }
+                        memcpy(refs.data() + l, scratch.data() + start, (size_t) r * sizeof(Ref));
+                        totalLeft = l - start;
+                    } else {
+                        std::vector<uint32_t> nLeft(parts);
+                        forChunks(count, parts, [&](int c, uint32_t lo, uint32_t hi) {
+                            uint32_t n = 0;
+                            for (uint32_t i = start + lo; i < start + hi; ++i) n += goesLeft(refs[i]) ? 1u : 0u;
+                            nLeft[c] = n;
+                        });
+                        for (int c = 0; c < parts; ++c) totalLeft += nLeft[c];
+                        // chunk c writes its left-hand elements at leftBase[c] and its right-hand ones at totalLeft + rightBase[c] of `scratch`
+                        std::vector<uint32_t> leftBase(parts), rightBase(parts);
+                        uint32_t lb = 0, rb = 0;
+                        for (int c = 0; c < parts; ++c) {
+                            leftBase[c] = lb; rightBase[c] = rb;
+                            const uint32_t lo = (uint32_t) ((uint64_t) count * c / parts), hi = (uint32_t) ((uint64_t) count * (c + 1) / parts);
+                            lb += nLeft[c]; rb += (hi - lo) - nLeft[c];
+                        }
+                        forChunks(count, parts, [&](int c, uint32_t lo, uint32_t hi) {
+                            uint32_t l = start + leftBase[c], r = start + totalLeft + rightBase[c];
+                            for (uint32_t i = start + lo; i < start + hi; ++i) {
+                                const Ref &p = refs[i];
+                                if (goesLeft(p)) scratch[l++] = p; else scratch[r++] = p;
+                            }
+                        });
+                        forChunks(count, parts, [&](int, uint32_t lo, uint32_t hi) {
+                            memcpy(refs.data() + start + lo, scratch.data() + start + lo, (size_t) (hi - lo) * sizeof(Ref));
+                        });
+                    }
+                    mid = start + totalLeft;
                     done = mid > start && mid < start + count;
                 }
             }
         }
+        workers.giveBack(parts - 1);
         if (!done && canLeaf) return me;
         if (!done) {
-            std::nth_element(order.begin() + start, order.begin() + start + count / 2, order.begin() + start + count,
-                             [&](uint32_t a, uint32_t b) { return centroid(a, axis) < centroid(b, axis); });
+            std::nth_element(refs.begin() + start, refs.begin() + start + count / 2, refs.begin() + start + count,
+                             [&](const Ref &a, const Ref &b) { const float ca = centroid(a, axis), cb = centroid(b, axis); return ca < cb || (ca == cb && a.id < b.id); });
             mid = start + count / 2;
         }
         uint32_t lc = mid - start, rc = count - lc;
         // large subtrees: build the left child on another thread
         int l, r;
-        if (lc > 200000 && threadsLeft.fetch_sub(1) > 0) {
+        if (lc > 50000 && rc > 50000 && workers.borrow(1) == 1) {
             std::vector<TmpNode> sub;
-            auto fut = std::async(std::launch::async, [&]() { return build(sub, start, lc, depth + 1); });
+            std::thread th([&]() { l = build(sub, start, lc, depth + 1); });
             r = build(nodes, mid, rc, depth + 1);
-            int subRoot = fut.get();
-            threadsLeft.fetch_add(1);
+            th.join();
+            workers.giveBack(1);
             int offset = (int) nodes.size();
             for (auto &t : sub) {
                 if (t.left >= 0) { t.left += offset; t.right += offset; }
                 nodes.push_back(t);
             }
-            l = subRoot + offset;
+            l += offset;
         } else {
-            if (lc > 200000) threadsLeft.fetch_add(1);
             l = build(nodes, start, lc, depth + 1);
             r = build(nodes, mid, rc, depth + 1);
         }
@@ -196,10 +308,17 @@ struct WideBuild {
 
     WideBuild(const std::vector<TmpNode> &t, float tn) : tmp(t), tiny(tn), leafStart(t.size(), 0xFFFFFFFFu) {}
 
-    void run(int root) {
+    // what the structural pass decides per wide node; the quantisation pass fills the node from it
+    struct Plan { int child[8]; uint32_t childBase, triBase; }; // child[s]: TmpNode in slot s or -1
+
+    // Pass 1 (serial, breadth first: it assigns the consecutive child indices and the triangle order): collapse, slot assignment, numbering.
+    // Pass 2 (parallel over the nodes): node box, quantisation grid, quantised child boxes, flags.
+    void run(int root, int threads = 1) {
         struct Item { int tnode; uint32_t index; int depth; };
         std::queue<Item> q;
-        nodes.emplace_back();
+        std::vector<Plan> plans;
+        plans.emplace_back();
+        newOrder.reserve(tmp.size());
         q.push({root, 0u, 1});
         while (!q.empty()) {
             const Item it = q.front(); q.pop();
@@ -215,22 +334,8 @@ struct WideBuild {
                 const int t = ch[best];
                 ch[best] = tmp[t].left; ch[n++] = tmp[t].right;
             }
-            // padded node box and quantisation grid
             Box nb; nb.reset();
-            float clo[8][3], chi[8][3];
-            for (int k = 0; k < n; ++k) { padBox(tmp[ch[k]].box, tiny, clo[k], chi[k]); nb.grow(clo[k], chi[k]); }
-            BVH8Node nd;
-            memset(&nd, 0, sizeof(nd));
-            double scale[3];
-            for (int a = 0; a < 3; ++a) {
-                nd.p[a] = nb.lo[a];
-                const double ext = (double) nb.hi[a] - (double) nb.lo[a];
-                int e = ext > 0 ? (int) std::ceil(std::log2(ext / 255.0)) : -100;
-                e = std::max(-100, std::min(100, e));
-                while (std::ldexp(255.0, e) < ext && e < 100) ++e;
-                nd.e[a] = (int8_t) e;
-                scale[a] = std::ldexp(1.0, e);
-            }
+            for (int k = 0; k < n; ++k) { float clo[3], chi[3]; padBox(tmp[ch[k]].box, tiny, clo, chi); nb.grow(clo, chi); }
             // slot assignment: greedy on dot(child centre - node centre, octant direction of the slot)
             int slotOf[8], used = 0;
             bool done[8] = {false, false, false, false, false, false, false, false};
@@ -254,43 +359,83 @@ struct WideBuild {
                 }
                 done[bk] = true; used |= 1 << bs; slotOf[bk] = bs;
             }
-            int childAt[8];
-            for (int s = 0; s < 8; ++s) childAt[s] = -1;
-            for (int k = 0; k < n; ++k) childAt[slotOf[k]] = k;
-            nd.childBase = (uint32_t) nodes.size();
-            nd.triBase = (uint32_t) newOrder.size();
-            uint32_t triOff = 0;
+            Plan pl;
+            for (int s = 0; s < 8; ++s) pl.child[s] = -1;
+            for (int k = 0; k < n; ++k) pl.child[slotOf[k]] = ch[k];
+            pl.childBase = (uint32_t) plans.size();
+            pl.triBase = (uint32_t) newOrder.size();
             for (int s = 0; s < 8; ++s) {
-                const int k = childAt[s];
-                if (k < 0) continue; // empty slot: qlo = qhi = 0 and no flag -- its test result is masked out
-                const TmpNode &c = tmp[ch[k]];
-                for (int a = 0; a < 3; ++a) {
-                    int lo = (int) std::floor(((double) clo[k][a] - (double) nd.p[a]) / scale[a]);
-                    int hi = (int) std::ceil(((double) chi[k][a] - (double) nd.p[a]) / scale[a]);
-                    lo = std::max(0, std::min(255, lo)); hi = std::max(0, std::min(255, hi));
-                    // the device decodes p + q * 2^e in float: keep the decoded box around the padded child box
-                    while (lo > 0 && (float) ((double) nd.p[a] + lo * scale[a]) > clo[k][a]) --lo;
-                    while (hi < 255 && (float) ((double) nd.p[a] + hi * scale[a]) < chi[k][a]) ++hi;
-                    nd.qlo[a][s] = (uint8_t) lo; nd.qhi[a][s] = (uint8_t) hi;
-                }
+                if (pl.child[s] < 0) continue;
+                const TmpNode &c = tmp[pl.child[s]];
                 if (c.left >= 0) {
-                    nd.imask |= (uint8_t) (1u << s);
-                    const uint32_t idx = (uint32_t) nodes.size();
-                    nodes.emplace_back();
-                    q.push({ch[k], idx, it.depth + 1});
+                    const uint32_t idx = (uint32_t) plans.size();
+                    plans.emplace_back();
+                    q.push({pl.child[s], idx, it.depth + 1});
                 } else {
-                    nd.meta[s] = (uint8_t) ((c.count << 5) | triOff);
-                    leafStart[ch[k]] = (uint32_t) newOrder.size();
+                    leafStart[pl.child[s]] = (uint32_t) newOrder.size();
                     for (uint32_t i = 0; i < c.count; ++i) newOrder.push_back(c.start + i);
-                    triOff += c.count;
                 }
             }
-            nodes[it.index] = nd;
+            plans[it.index] = pl;
         }
+        nodes.resize(plans.size());
+        const int parts = plans.size() >= 4096 ? std::max(1, threads) : 1;
+        forChunks((uint32_t) plans.size(), parts, [&](int, uint32_t lo, uint32_t hi) { for (uint32_t i = lo; i < hi; ++i) quantise(plans[i], nodes[i]); });
+    }
+
+    void quantise(const Plan &pl, BVH8Node &out) const {
+        Box nb; nb.reset();
+        float clo[8][3], chi[8][3];
+        for (int s = 0; s < 8; ++s) if (pl.child[s] >= 0) { padBox(tmp[pl.child[s]].box, tiny, clo[s], chi[s]); nb.grow(clo[s], chi[s]); }
+        BVH8Node nd;
+        memset(&nd, 0, sizeof(nd));
+        double scale[3];
+        for (int a = 0; a < 3; ++a) {
+            nd.p[a] = nb.lo[a];
+            const double ext = (double) nb.hi[a] - (double) nb.lo[a];
+            int e = ext > 0 ? (int) std::ceil(std::log2(ext / 255.0)) : -100;
+            e = std::max(-100, std::min(100, e));
+            while (std::ldexp(255.0, e) < ext && e < 100) ++e;
+            nd.e[a] = (int8_t) e;
+            scale[a] = std::ldexp(1.0, e);
+        }
+        nd.childBase = pl.childBase;
+        nd.triBase = pl.triBase;
+        uint32_t triOff = 0;
+        for (int s = 0; s < 8; ++s) {
+            if (pl.child[s] < 0) continue; // empty slot: qlo = qhi = 0 and no flag -- its test result is masked out
+            const TmpNode &c = tmp[pl.child[s]];
+            for (int a = 0; a < 3; ++a) {
+                int lo = (int) std::floor(((double) clo[s][a] - (double) nd.p[a]) / scale[a]);
+                int hi = (int) std::ceil(((double) chi[s][a] - (double) nd.p[a]) / scale[a]);
+                lo = std::max(0, std::min(255, lo)); hi = std::max(0, std::min(255, hi));
+                // the device decodes p + q * 2^e in float: keep the decoded box around the padded child box
+                while (lo > 0 && (float) ((double) nd.p[a] + lo * scale[a]) > clo[s][a]) --lo;
+                while (hi < 255 && (float) ((double) nd.p[a] + hi * scale[a]) < chi[s][a]) ++hi;
+                nd.qlo[a][s] = (uint8_t) lo; nd.qhi[a][s] = (uint8_t) hi;
+            }
+            if (c.left >= 0) nd.imask |= (uint8_t) (1u << s);
+            else { nd.meta[s] = (uint8_t) ((c.count << 5) | triOff); triOff += c.count; }
+        }
+        out = nd;
     }
 };
 
+namespace {
+// B2_COMMIT_TIMING=1: phase times of the build on stderr (see b2_scene_commit)
+struct BuildClock {
+    bool on = getenv("B2_COMMIT_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b2 commit]   bvh: %-22s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    }
+};
+}
 void buildBVH(const std::vector<PrimBox> &boxes, const std::vector<uint32_t> &ids, int maxLeaf, int maxDepth, int threads, BVHResult &out, bool wide) {
+    BuildClock clk;
     out.nodes.clear();
     out.leafPrims.clear();
     out.nodes8.clear();
@@ -301,7 +446,10 @@ void buildBVH(const std::vector<PrimBox> &boxes, const std::vector<uint32_t> &id
     Builder B(boxes, maxLeaf, maxDepth, std::max(1, threads));
     std::vector<TmpNode> tmp;
     tmp.reserve(2 * (size_t) n / std::max(1, maxLeaf) + 16);
+    clk.mark("centroids");
     int root = B.build(tmp, 0, n, 0);
+    B.finish();
+    clk.mark("binned SAH (binary)");
     // scene scale for the padding
     float diag = 0;
     for (int i = 0; i < 3; ++i) diag = std::max(diag, tmp[root].box.hi[i] - tmp[root].box.lo[i]);
@@ -311,11 +459,12 @@ void buildBVH(const std::vector<PrimBox> &boxes, const std::vector<uint32_t> &id
     std::vector<uint32_t> leafStart;
     if (wide && tmp[root].left >= 0) {
         WideBuild W(tmp, tiny);
-        W.run(root);
+        W.run(root, std::max(1, threads));
         out.nodes8.swap(W.nodes);
         out.depth8 = W.depth;
         leafStart.swap(W.leafStart);
         for (uint32_t i = 0; i < n; ++i) out.leafPrims[i] = ids[B.order[W.newOrder[i]]];
+        clk.mark("8-wide collapse");
     } else {
         for (uint32_t i = 0; i < n; ++i) out.leafPrims[i] = ids[B.order[i]];
     }
@@ -341,19 +490,22 @@ void buildBVH(const std::vector<PrimBox> &boxes, const std::vector<uint32_t> &id
     }
     out.nodes.resize(bfs.size());
     int maxd = 0;
-    for (size_t k = 0; k < bfs.size(); ++k) {
-        const TmpNode &t = tmp[bfs[k]];
-        const TmpNode &L = tmp[t.left], &R = tmp[t.right];
-        BVHNode &nd = out.nodes[k];
-        padBox(L.box, tiny, nd.lmin, nd.lmax);
-        padBox(R.box, tiny, nd.rmin, nd.rmax);
-        nd.left = L.left >= 0 ? innerIndex[t.left] : leafRef(L);
-        nd.right = R.left >= 0 ? innerIndex[t.right] : leafRef(R);
-        nd.pad0 = nd.pad1 = 0;
-        maxd = std::max(maxd, t.depth + 2);
-    }
+    for (size_t k = 0; k < bfs.size(); ++k) maxd = std::max(maxd, tmp[bfs[k]].depth + 2);
+    forChunks((uint32_t) bfs.size(), bfs.size() >= 4096 ? std::max(1, threads) : 1, [&](int, uint32_t klo, uint32_t khi) {
+        for (uint32_t k = klo; k < khi; ++k) {
+            const TmpNode &t = tmp[bfs[k]];
+            const TmpNode &L = tmp[t.left], &R = tmp[t.right];
+            BVHNode &nd = out.nodes[k];
+            padBox(L.box, tiny, nd.lmin, nd.lmax);
+            padBox(R.box, tiny, nd.rmin, nd.rmax);
+            nd.left = L.left >= 0 ? innerIndex[t.left] : leafRef(L);
+            nd.right = R.left >= 0 ? innerIndex[t.right] : leafRef(R);
+            nd.pad0 = nd.pad1 = 0;
+        }
+    });
     out.rootRef = 0;
     out.depth = maxd;
+    clk.mark("binary relayout");
 }
 
 } // namespace b2
@@ -438,5 +590,46 @@ extern "C" int b2_bvh_selftest(uint32_t n, uint32_t seed, uint32_t nRays) {
             if (hit && !reached[i]) return 8;
         }
     }
+    return 0;
+}
+
+// Host-only timing entry (no device): builds the trees over n boxes (lo xyz, hi xyz per primitive) with `threads` threads; returns the
+// number of binary inner nodes, *wideNodes = the number of 8-wide nodes.  Used by scripts/bvh_build_bench.py.
+extern "C" int b2_bvh_build_only(const float *boxes6, uint32_t n, int threads, int wide, uint32_t *wideNodes) {
+    using namespace b2;
+    std::vector<PrimBox> boxes(n);
+    std::vector<uint32_t> ids(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int a = 0; a < 3; ++a) { boxes[i].lo[a] = boxes6[6 * (size_t) i + a]; boxes[i].hi[a] = boxes6[6 * (size_t) i + 3 + a]; }
+        ids[i] = i;
+    }
+    BVHResult res;
+    buildBVH(boxes, ids, 4, 26, threads, res, wide != 0);
+    if (wideNodes) *wideNodes = (uint32_t) res.nodes8.size();
+    return (int) res.nodes.size();
+}
+
+// Host-only check that the build does not depend on the number of threads: the same n pseudo-random boxes built with threadsA and threadsB
+// must give byte-identical binary nodes, wide nodes and leaf order.  0 = identical.
+extern "C" int b2_bvh_thread_invariance(uint32_t n, uint32_t seed, int threadsA, int threadsB) {
+    using namespace b2;
+    std::vector<PrimBox> boxes(n);
+    std::vector<uint32_t> ids(n);
+    uint32_t st = seed * 747796405u + 2891336453u;
+    auto rnd = [&]() { st = st * 747796405u + 2891336453u; uint32_t w = ((st >> ((st >> 28u) + 4u)) ^ st) * 277803737u; return (float) (((w >> 22u) ^ w) >> 8) * (1.0f / 16777216.0f); };
+    for (uint32_t i = 0; i < n; ++i) {
+        ids[i] = i;
+        // clustered sizes and a sprinkling of exact duplicates (ties in every comparison the builder makes)
+        float c[3] = {rnd() * 100 - 50, rnd() * 100 - 50, rnd() * 10 - 5}, r = 0.01f + 0.3f * rnd() * rnd();
+        if (i > 0 && (i % 97) == 0) { boxes[i] = boxes[i - 1]; continue; }
+        for (int a = 0; a < 3; ++a) { boxes[i].lo[a] = c[a] - r * rnd(); boxes[i].hi[a] = c[a] + r * rnd(); }
+    }
+    BVHResult a, b;
+    buildBVH(boxes, ids, 4, B2_STACK_DEPTH - 2, threadsA, a, true);
+    buildBVH(boxes, ids, 4, B2_STACK_DEPTH - 2, threadsB, b, true);
+    if (a.nodes.size() != b.nodes.size() || a.nodes8.size() != b.nodes8.size() || a.leafPrims != b.leafPrims) return 1;
+    if (a.rootRef != b.rootRef || a.depth != b.depth || a.depth8 != b.depth8) return 2;
+    if (!a.nodes.empty() && memcmp(a.nodes.data(), b.nodes.data(), a.nodes.size() * sizeof(BVHNode))) return 3;
+    if (!a.nodes8.empty() && memcmp(a.nodes8.data(), b.nodes8.data(), a.nodes8.size() * sizeof(BVH8Node))) return 4;
     return 0;
 }

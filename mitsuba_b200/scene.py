@@ -566,6 +566,40 @@ def config3_scene(width=1024, height=1024, n_theta=200, n_phi=200) -> SceneDesc:
     return d
 
 
+def synthetic_sky(w=1024, h=512, seed=4, sun=400.0) -> np.ndarray:
+    """A latitude-longitude radiance map for tests and the bench: blue gradient above the horizon, a small sun (`sun` times brighter
+    than the sky, a few texels wide: direct sampling has to find it), a dim ground half, and texel-scale noise (the filtered look-up of
+    directly visible background has something to filter).  (h, w, 3) float32, top row first."""
+    rng = np.random.default_rng(seed)
+    v = (np.arange(h, dtype=np.float64)[:, None] + 0.5) / h           # 0 = zenith, 1 = nadir
+    u = (np.arange(w, dtype=np.float64)[None, :] + 0.5) / w
+    up = np.clip(1.0 - 2.0 * v, 0.0, 1.0)
+    img = np.empty((h, w, 3))
+    img[..., 0] = 0.25 + 0.35 * (1 - up) ** 3
+    img[..., 1] = 0.40 + 0.35 * (1 - up) ** 3
+    img[..., 2] = 0.75 + 0.15 * (1 - up) ** 3
+    img[v[:, 0] > 0.5] = (0.12, 0.10, 0.08)
+    img *= 0.7 + 0.6 * rng.random((h, w, 1))
+    su, sv, r = 0.30, 0.22, 1.5 / h
+    d2 = ((np.minimum(np.abs(u - su), 1 - np.abs(u - su)) * 2.0) ** 2 + (v - sv) ** 2) / (r * r)
+    img += sun * np.exp(-d2)[..., None] * np.array([1.0, 0.9, 0.7])
+    return img.astype(np.float32)
+
+
+def envmap_scene(width=1024, height=1024, map_width=1024, n_theta=200, n_phi=200) -> SceneDesc:
+    """The config-3 material balls without their area light, lit by `synthetic_sky` only (rotated a little so that the sun is not on a
+    symmetry axis): the environment is seen directly, by reflection, through the glass ball and by direct sampling."""
+    d = config3_scene(width, height, n_theta, n_phi)
+    d.meshes = [m for m in d.meshes if m.radiance is None]
+    a, b = 0.6, 0.2
+    ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    M = np.eye(4)
+    M[:3, :3] = ry @ rx
+    d.envmap = EnvMap(pixels=synthetic_sky(map_width, map_width // 2), scale=1.0, to_world=M.astype(np.float32))
+    return d
+
+
 def checker_image(w=256, h=256, cells=8, seed=5, rgb=True) -> np.ndarray:
     """Procedural test image: coloured checkerboard + fine noise (so that filtering matters), linear float32 in [0, 1]."""
     rng = np.random.default_rng(seed)

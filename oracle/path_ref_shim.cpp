@@ -144,7 +144,17 @@ void Bitmap::write(EFileFormat, Stream *, int) const { throw std::runtime_error(
 /* Bitmap: a zeroed float buffer (src/libcore/bitmap.cpp needs OpenEXR / libpng / libjpeg) */
 Bitmap::Bitmap(EPixelFormat pFmt, EComponentFormat cFmt, const Vector2i &size, uint8_t channelCount, uint8_t *)
     : m_pixelFormat(pFmt), m_componentFormat(cFmt), m_size(size), m_data(NULL), m_gamma(1.0f), m_channelCount(channelCount), m_ownsData(true) {
-    if (pFmt == ESpectrumAlphaWeight) m_channelCount = SPECTRUM_SAMPLES + 2;
+    /* Bitmap::updateChannelCount (bitmap.cpp): the formats that occur here */
+    switch (pFmt) {
+        case ELuminance: m_channelCount = 1; break;
+        case ELuminanceAlpha: m_channelCount = 2; break;
+        case ERGB: case EXYZ: m_channelCount = 3; break;
+        case ERGBA: case EXYZA: m_channelCount = 4; break;
+        case ESpectrum: m_channelCount = SPECTRUM_SAMPLES; break;
+        case ESpectrumAlpha: m_channelCount = SPECTRUM_SAMPLES + 1; break;
+        case ESpectrumAlphaWeight: m_channelCount = SPECTRUM_SAMPLES + 2; break;
+        default: break; /* EMultiChannel: as passed */
+    }
     m_data = (uint8_t *) calloc((size_t) size.x * size.y * m_channelCount, sizeof(float));
 }
 Bitmap::~Bitmap() { if (m_data && m_ownsData) free(m_data); }
@@ -465,6 +475,18 @@ int pathref_add_envmap(void *h, const char *stem, int nLevels, const int *sizes,
     em->configure();
     p->scene->addChild("", em);
     p->keep.push_back(em);
+    return 0;
+}
+/* Emitter::getBitmap of the environment emitter (EnvironmentMap: level 0 of its half-precision pyramid, envmap.cpp:632-634): size in wh,
+ * RGB floats in out (may be NULL to query the size).  What the b200path plugin marshals. */
+int pathref_environment_bitmap(void *h, int *wh, float *out) {
+    PathRef *p = (PathRef *) h;
+    const Emitter *e = p->scene->getEnvironmentEmitter();
+    if (!e) return -1;
+    ref<Bitmap> bm = e->getBitmap(Vector2i(0));
+    if (bm == NULL || bm->getPixelFormat() != Bitmap::ERGB || bm->getComponentFormat() != Bitmap::EFloat16) return -2;
+    wh[0] = bm->getSize().x; wh[1] = bm->getSize().y;
+    if (out) { const half *src = (const half *) bm->getData(); for (size_t k = 0; k < (size_t) wh[0] * wh[1] * 3; ++k) out[k] = (float) src[k]; }
     return 0;
 }
 /* Scene::evalEnvironment for n rays: rays 6n (o, d) without differentials, or 18n (o, d, rxO, rxD, ryO, ryD) with them -> out 3n */

@@ -106,3 +106,14 @@ def test_mitsuba_side_plugin_propagates_library_errors_as_mitsuba_exceptions():
     lib.pathref_render_b200.restype = C.c_int
     rc = lib.pathref_render_b200(h, 0, 1, out.ctypes.data_as(C.POINTER(C.c_float)), err, 1024)
     assert rc == 1 and b"no CUDA device" in err.value
+
+
+def test_bvh_build_does_not_depend_on_the_thread_count():
+    """The host builder splits big nodes over threads (bounds, bins, stable partition) and hands subtrees to threads: min / max / counts
+    and a stable partition are order-free, so 1 thread and many must give byte-identical trees (binary nodes, 8-wide nodes, leaf order)."""
+    import ctypes as C
+    from mitsuba_b200 import api
+    L = api.lib()
+    L.b2_bvh_thread_invariance.restype = C.c_int
+    for n, ta, tb in ((300000, 1, 8), (500000, 3, 16)):
+        assert L.b2_bvh_thread_invariance(C.c_uint32(n), C.c_uint32(n + 1), ta, tb) == 0, (n, ta, tb)
