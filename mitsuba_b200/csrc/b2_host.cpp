@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -162,7 +163,7 @@ struct b2_scene {
     bool hasTransmission = false;  // some BSDF transmits (ETransmission): `path` renders of such scenes use the IEEE kernels (b2_render)
     std::vector<float4> hTriAccelPrimOrder; // for b2_get_triaccel
     LaunchCfg cfgParity, cfgFast;
-    bool classPresent[4] = {false, false, false, false};
+    bool classPresent[B2_NCLASS] = {false, false, false, false, false}; // [4]: BSDF types without a specialised shading kernel
     // pool
     DPool pool{};
     DevBuf<uint64_t> dLookupNib;
@@ -641,6 +642,23 @@ static uint32_t materialFlags(const std::vector<b2_material_desc> &mats, int id)
     }
 }
 
+// Threads the host-side build may use: hardware threads, capped by the scheduler affinity and the cgroup CPU quota (a 128-thread box
+// leased with a 16-CPU quota runs 128 workers slower than 16)
+static int usableThreads() {
+    int n = (int) std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n > 0 ? n : CPU_COUNT(&set), CPU_COUNT(&set));
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char quota[64]; long long period = 0;
+        if (fscanf(f, "%63s %lld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) {
+            const long long q = atoll(quota);
+            if (q > 0) n = std::min<long long>(n, std::max<long long>(1, (q + period - 1) / period));
+        }
+        fclose(f);
+    }
+    if (const char *e = getenv("B2_BUILD_THREADS")) n = atoi(e);
+    return std::max(1, n);
+}
 // B2_COMMIT_TIMING=1: host-side phase times of b2_scene_commit on stderr (where the seconds of a multi-million-triangle commit go)
 struct CommitClock {
     bool on = getenv("B2_COMMIT_TIMING") != nullptr;
@@ -764,7 +782,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     clk.mark("flatten + TriAccel");
     // ---- BVH ----
     BVHResult bvh;
-    int threads = (int) std::thread::hardware_concurrency();
+    int threads = usableThreads();
     // Tiny scenes skip the tree: the whole triangle list is one leaf, staged in shared memory and tested by all lanes
     // in lockstep (no divergence).  Break-even against the BVH2 walk measured on the Cornell scene, see DESIGN.md.
     uint32_t flatLimit = 64;
@@ -975,7 +993,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     clk.mark("leaf records");
     // ---- materials ----
     std::vector<DMaterial> dm(s->materials.size());
-    for (int c = 0; c < 4; ++c) s->classPresent[c] = false;
+    for (int c = 0; c < B2_NCLASS; ++c) s->classPresent[c] = false;
     for (size_t i = 0; i < s->materials.size(); ++i) {
         const b2_material_desc &m = s->materials[i];
         DMaterial &d = dm[i];
@@ -1003,7 +1021,8 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     for (auto &m : s->meshes) {
         const int t = s->materials[m.material].type;
         if (t >= B2_BSDF_NULL) {
-            s->hasNullBsdf = true; // types without a specialised kernel are shaded by the generic one (no per-class queue)
+            s->hasNullBsdf = true; // types without a specialised kernel are shaded by the generic one (class queue 4)
+            s->classPresent[B2_NCLASS - 1] = true;
             if (t == B2_BSDF_NULL && m.emitter >= 0)
                 return fail(ctx, B2_ERR_INVALID, "Shape has an index-matched BSDF and an emitter attachment. This is not allowed!"); // shape.cpp:76-78
         } else s->classPresent[t] = true;
@@ -1258,7 +1277,7 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     // rays that leave the scene are binned into the first BSDF class that has a shading kernel launched for it (a scene without a
     // diffuse mesh launches no class-0 kernel: its escaped paths must still be retired)
     ds.missClass = 0;
-    for (int c = 3; c >= 0; --c)
+    for (int c = B2_NCLASS - 1; c >= 0; --c)
         if (s->classPresent[c]) ds.missClass = (uint32_t) c;
     if (const char *e = getenv("B2_LEAFVOTE")) ds.leafVote = (uint32_t) std::max(1, std::min(32, atoi(e)));
     parity::KernelSet_init(s->cfgParity, ds, ctx->numSMs);
@@ -1405,7 +1424,7 @@ static int ensurePool(b2_scene *s, uint32_t Q, bool vol) {
         CK(ctx, R.pRay.alloc((size_t) 2 * Q)); CK(ctx, R.pSt.alloc((size_t) 2 * Q)); CK(ctx, R.pHit.alloc(Q));
         CK(ctx, R.pShO.alloc(Q)); CK(ctx, R.pShD.alloc(Q)); CK(ctx, R.pShC.alloc(Q)); CK(ctx, R.pSmp.alloc(Q)); CK(ctx, R.pPos.alloc(Q));
         CK(ctx, R.pPix.alloc(Q)); CK(ctx, R.pFlags.alloc(Q));
-        CK(ctx, R.pMatQueue.alloc((size_t) 4 * Q)); CK(ctx, R.pDoneQueue.alloc((size_t) 2 * Q));
+        CK(ctx, R.pMatQueue.alloc((size_t) B2_NCLASS * Q)); CK(ctx, R.pDoneQueue.alloc((size_t) 2 * Q));
         R.pVol.release(); R.pInst.release();
         R.capacity = Q;
     }
@@ -1490,11 +1509,13 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
     CK(ctx, cudaMemsetAsync(s->dCounters.p, 0, CTR_COUNT * sizeof(unsigned long long), st));
     CK(ctx, cudaMemsetAsync(R.pFlags.p, 0, (size_t) Q * sizeof(uint32_t), st));
     int nClasses = 0, onlyClass = -1;
-    for (int c = 0; c < 4; ++c)
-        if (s->classPresent[c]) { ++nClasses; onlyClass = c; }
+    for (int c = 0; c < B2_NCLASS; ++c)
+        if (s->classPresent[c]) { ++nClasses; onlyClass = c == B2_NCLASS - 1 ? -1 : c; }
+    // more than one class: k_extend bins the hits by BSDF class and every class gets its own shading launch over its queue -- the four
+    // specialised instances, and the generic instance for the rest (null, twosided, dielectric, conductor, plastic); scenes with bitmap
+    // textures or an environment map use the TEX instances of the same classes (launch_shade)
     bool sorted = nClasses > 1;
     if (p->flags & 2) sorted = false;
-    if (s->hasNullBsdf || !s->textures.empty() || s->envmap) { sorted = false; nClasses = 2; } // index-matched boundaries, f-3 BSDFs, textures, environment map: generic shading kernel
     s->cancel.store(0);
     // every early return below leaves the stream idle and releases the events / the captured graph
     struct RenderGuard {
@@ -1543,7 +1564,7 @@ extern "C" int b2_render(b2_scene *s, const b2_render_params *p, float *film) {
             tick(1); nsT::launch_extend(cfgT, s->ds, s->pool, r, sorted, st); tick(-1); ++launchesPerIter;     \
             tick(2);                                                                                           \
             if (sorted) {                                                                                      \
-                for (int c = 0; c < 4; ++c)                                                                    \
+                for (int c = 0; c < B2_NCLASS; ++c)                                                            \
                     if (s->classPresent[c]) { nsS::launch_shade(cfgS, s->ds, s->pool, r, c, true, st); ++launchesPerIter; } \
             } else {                                                                                           \
                 nsS::launch_shade(cfgS, s->ds, s->pool, r, nClasses == 1 ? onlyClass : -1, false, st);         \

@@ -467,6 +467,9 @@ __global__ void __launch_bounds__(B2_GEN_BLOCK, B2_GEN_MINBLOCKS) k_generate(DSc
     stampEnd(rp, it, STAGE_GENERATE);
 }
 
+// counter of class queue c (the fifth one lives outside the sliding window of CTR_CLASS0..3)
+B2_DEV int classCounter(int c) { return c < 4 ? CTR_CLASS0 + c : CTR_CLASSG; }
+
 // One thread, between k_generate and k_extend: publishes progress to the host ring, clears the per-iteration queue
 // counters and advances the iteration.  Keeping the iteration on the device lets ONE CUDA graph serve every iteration.
 __global__ void k_publish(DPool pool, DRender rp) {
@@ -480,7 +483,7 @@ __global__ void k_publish(DPool pool, DRender rp) {
     slot[0] = it + 1;
     c[CTR_TICKET_EXT] = 0; c[CTR_TICKET_OCC] = 0;
     c[CTR_SHADOW] = 0;
-    c[CTR_CLASS0] = 0; c[CTR_CLASS0 + 1] = 0; c[CTR_CLASS0 + 2] = 0; c[CTR_CLASS0 + 3] = 0;
+    c[CTR_CLASS0] = 0; c[CTR_CLASS0 + 1] = 0; c[CTR_CLASS0 + 2] = 0; c[CTR_CLASS0 + 3] = 0; c[CTR_CLASSG] = 0;
     const int dq = ((it + 1) & 1) ? CTR_DONE1 : CTR_DONE0;
     c[CTR_NEXT] += it == 0 ? (unsigned long long) pool.capacity : c[dq]; // work items k_generate just handed out
     c[dq] = 0; // drained by this iteration's k_generate, refilled by k_shade of it + 1
@@ -517,10 +520,10 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
             pool.hit[i] = found ? make_float4(h.t, h.u, h.v, __uint_as_float(h.prim)) : make_float4(B2_INF, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
             if (SORT) {
                 int cls = (int) sc.missClass;
-                if (found) cls = sc.materials[__float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w))].type;
+                if (found) cls = min((int) sc.materials[__float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w))].type, B2_NCLASS - 1);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t at = warpAppend(cls == c, pool.counters + CTR_CLASS0 + c);
+                for (int c = 0; c < B2_NCLASS; ++c) {
+                    const uint32_t at = warpAppend(cls == c, pool.counters + classCounter(c));
                     if (cls == c) pool.matQueue[(size_t) c * Q + at] = i;
                 }
             }
@@ -555,14 +558,14 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK) k_extend(
                 cls = (int) sc.missClass;
                 if (h.prim != 0xFFFFFFFFu) {
                     const int mat = __float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w));
-                    cls = sc.materials[mat].type;
+                    cls = min((int) sc.materials[mat].type, B2_NCLASS - 1);
                 }
             }
         }
         if (SORT) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t at = warpAppend(cls == c, pool.counters + CTR_CLASS0 + c);
+            for (int c = 0; c < B2_NCLASS; ++c) {
+                const uint32_t at = warpAppend(cls == c, pool.counters + classCounter(c));
                 if (cls == c) pool.matQueue[(size_t) c * Q + at] = i;
             }
         }
@@ -630,13 +633,13 @@ template <bool SORT> __global__ void __launch_bounds__(B2_TRACE_BLOCK, 4) k_exte
             ++nRays;
             if (SORT) {
                 cls = (int) sc.missClass;
-                if (h.prim != 0xFFFFFFFFu) cls = sc.materials[__float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w))].type;
+                if (h.prim != 0xFFFFFFFFu) cls = min((int) sc.materials[__float_as_int(__ldg(&sc.verts[3 * (size_t) h.prim].w))].type, B2_NCLASS - 1);
             }
         }
         if (SORT) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t at = warpAppend(cls == c, pool.counters + CTR_CLASS0 + c);
+            for (int c = 0; c < B2_NCLASS; ++c) {
+                const uint32_t at = warpAppend(cls == c, pool.counters + classCounter(c));
                 if (cls == c) pool.matQueue[(size_t) c * Q + at] = i;
             }
         }
@@ -2261,6 +2264,10 @@ void KernelSet_init(LaunchCfg &cfg, const DScene &sc, int numSMs) {
     cfg.gridShade[3] = occupancyGrid(k_shade<3>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShade[4] = occupancyGrid(k_shade<-1>, B2_SHADE_BLOCK, 0, numSMs);
     cfg.gridShadeTex = occupancyGrid(k_shade<-1, true>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShadeTexCls[0] = occupancyGrid(k_shade<0, true>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShadeTexCls[1] = occupancyGrid(k_shade<1, true>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShadeTexCls[2] = occupancyGrid(k_shade<2, true>, B2_SHADE_BLOCK, 0, numSMs);
+    cfg.gridShadeTexCls[3] = occupancyGrid(k_shade<3, true>, B2_SHADE_BLOCK, 0, numSMs);
 }
 
 void launch_generate(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, const DFilter &f, cudaStream_t st) {
@@ -2277,16 +2284,28 @@ void launch_extend(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, co
     else k_extend<false><<<cfg.gridExtend, B2_TRACE_BLOCK, cfg.traceSmem, st>>>(sc, pool, rp);
 }
 void launch_shade(const LaunchCfg &cfg, const DScene &sc, const DPool &pool, const DRender &rp, int cls, bool queued, cudaStream_t st) {
+    // cls 0..3: a specialised instance; cls 4 (queued) or -1 (unqueued): the generic instance
     const uint32_t *q = queued ? pool.matQueue + (size_t) cls * pool.capacity : nullptr;
-    const unsigned long long *qc = queued ? pool.counters + CTR_CLASS0 + cls : nullptr;
+    const unsigned long long *qc = queued ? pool.counters + (cls < 4 ? CTR_CLASS0 + cls : CTR_CLASSG) : nullptr;
+    // scenes with bitmap textures or an environment map: the instances that carry the look-up code (one per BSDF class, so that the
+    // class-sorted queues keep a warp on one BSDF: the unsorted generic instance ran 4 of 32 lanes per instruction on mixed materials)
+    if (sc.nTextures || sc.envmap) {
+        switch (cls) {
+            case 0: k_shade<0, true><<<cfg.gridShadeTexCls[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+            case 1: k_shade<1, true><<<cfg.gridShadeTexCls[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+            case 2: k_shade<2, true><<<cfg.gridShadeTexCls[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+            case 3: k_shade<3, true><<<cfg.gridShadeTexCls[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+            default: k_shade<-1, true><<<cfg.gridShadeTex, B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
+        }
+        return;
+    }
     switch (cls) {
         case 0: k_shade<0><<<cfg.gridShade[0], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         case 1: k_shade<1><<<cfg.gridShade[1], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         case 2: k_shade<2><<<cfg.gridShade[2], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         case 3: k_shade<3><<<cfg.gridShade[3], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc); break;
         default:
-            if (sc.nTextures || sc.envmap) k_shade<-1, true><<<cfg.gridShadeTex, B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
-            else k_shade<-1><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, nullptr, nullptr);
+            k_shade<-1><<<cfg.gridShade[4], B2_SHADE_BLOCK, 0, st>>>(sc, pool, rp, q, qc);
             break;
     }
 }

@@ -17,6 +17,7 @@ struct LaunchCfg {
     int volLockstep = 1; // B2_VOL_LOCKSTEP=0: the ticketed k_volstep instead of k_volstep_lockstep
     int gridShade[5] = {0, 0, 0, 0, 0};
     int gridShadeTex = 0; // k_shade<-1, TEX = true> (textured scenes)
+    int gridShadeTexCls[4] = {0, 0, 0, 0}; // k_shade<c, TEX = true>: class-sorted dispatch of textured / environment-mapped scenes
     // flat-leaf variants (shared-memory resident scenes): k_extend_flat / k_occluded_flat
     size_t flatSmem = 0;
     int gridExtendFlat = 0, gridExtendFlatSort = 0, gridOccludedFlat = 0;

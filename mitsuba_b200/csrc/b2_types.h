@@ -111,6 +111,7 @@ struct BVH8Node {
     uint8_t qlo[3][8], qhi[3][8];
 };
 static_assert(sizeof(BVH8Node) == 80, "BVH8Node must be 80 bytes");
+#define B2_NCLASS 5          // class queues of the material-sorted dispatch: diffuse, roughconductor, roughdielectric, coating, everything else
 #define B2_STACK8_DEPTH 28   // uint2 entries per lane of the wide traversal (one pending child group per level)
 
 struct DCamera {
@@ -223,7 +224,7 @@ struct DPool {
     float4 *shD;       // d.xyz, maxt
     float4 *shC;       // contribution rgb, slot (bits)
     // material-class queues
-    uint32_t *matQueue;   // [nClasses][capacity]
+    uint32_t *matQueue;   // [B2_NCLASS][capacity]: four specialised BSDF classes + the generic one
     // finished-path queues, double buffered: k_shade of iteration k appends to doneQueue[k & 1], k_generate of
     // iteration k + 1 drains it (splat + refill) with full warps
     uint32_t *doneQueue;  // [2][capacity]
@@ -238,6 +239,7 @@ enum { CTR_DONE0 = 0, CTR_SHADOW = 1, CTR_CLASS0 = 2, /* 2..5 */ CTR_DONE1 = 6, 
        CTR_ITER = 17,   // host-loop iteration, advanced on the device by k_publish (one graph serves every iteration)
        CTR_UNOCCLUDED = 18,
        CTR_TICKET_EXT = 19, CTR_TICKET_OCC = 20, // work tickets of the persistent traversal loops (zeroed by k_publish)
+       CTR_CLASSG = 21,  // fifth class queue: hits on BSDFs without a specialised shading kernel (null, twosided, dielectric, conductor, plastic)
        CTR_COUNT = 22 };
 
 // progress ring in mapped pinned host memory, written by k_publish: {sequence = iteration + 1, live paths, next work item, -}

@@ -23,6 +23,12 @@ elif name == "envmap":      # config-3 balls under the synthetic sky only
     d = envmap_scene(res, res)
 elif name == "envconst":    # the same geometry under a constant environment (what the map costs on top)
     d = envmap_scene(res, res); d.envmap = None; d.env_radiance = (0.5, 0.6, 0.8)
+elif name == "f3mix":       # config 3 with a twosided ground and a plastic third ball: BSDFs with and without a specialised shading instance
+    from mitsuba_b200.scene import Bsdf, Mesh, uv_sphere
+    d = config3_scene(res, res)
+    d.meshes[0].bsdf = Bsdf("twosided", nested=Bsdf("diffuse", reflectance=(0.5, 0.5, 0.5)))
+    P, N, UV, I = uv_sphere((0.0, 0.6, -1.6), 0.6, 120, 120, smooth=True)
+    d.meshes.insert(3, Mesh(P, I, N=N, bsdf=Bsdf("plastic", int_ior=1.49, diffuse_reflectance=(0.1, 0.27, 0.36)), name="ball_plastic"))
 elif name == "textured":
     d = textured_scene(res, res, filter_type="ewa", tex_res=1024, n_theta=200, n_phi=200)
 else:
