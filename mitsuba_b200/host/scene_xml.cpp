@@ -457,9 +457,147 @@ struct Loader {
     std::map<std::string, int> textureIds;
     // Bitmap::readPFM (bitmap.cpp:3764-3814) and Bitmap::readPPM (:3857-3895, 8-bit P6), then Bitmap::convert(.., EFloat32, gamma 1)
     // as TMIPMap's constructor applies it (mipmap.h:225-226; fmtconv.cpp:1092-1101,1136-1147): linear float, top row first
+    // OpenEXR scan-line images (Bitmap::readOpenEXR, bitmap.cpp, goes through the OpenEXR library; this is a reader of the published file
+    // layout): single-part, flat, not tiled; channels R, G, B (others ignored) or a lone Y / single channel; HALF, FLOAT or UINT samples;
+    // compression NONE, RLE, ZIPS or ZIP (what Mitsuba's own hdrfilm writes).  PIZ / PXR24 / B44 / DWA files are refused by name.
+    static float halfBitsToFloat(uint16_t hb) {
+        const uint32_t sign = (uint32_t) (hb & 0x8000u) << 16, exp = (hb >> 10) & 0x1Fu, man = hb & 0x3FFu;
+        uint32_t bits;
+        if (exp == 0) {
+            if (man == 0) bits = sign;
+            else { // denormal: normalise
+                int e = -1; uint32_t m = man;
+                do { ++e; m <<= 1; } while (!(m & 0x400u));
+                bits = sign | ((uint32_t) (127 - 15 - e) << 23) | ((m & 0x3FFu) << 13);
+            }
+        } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+        else bits = sign | ((exp + 112u) << 23) | (man << 13);
+        float r; memcpy(&r, &bits, 4);
+        return r;
+    }
+    static void loadOpenEXR(const std::string &path, int &w, int &h, int &ch, std::vector<float> &px) {
+        std::ifstream f(path, std::ios::binary);
+        std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        size_t pos = 8;
+        auto need = [&](size_t n) { if (pos + n > d.size()) throw Err("readOpenEXR(): \"" + path + "\" is truncated"); };
+        auto i32 = [&](size_t at) { int32_t v; memcpy(&v, &d[at], 4); return v; };
+        if (d.size() < 8) throw Err("readOpenEXR(): \"" + path + "\" is truncated");
+        const uint32_t version = (uint32_t) i32(4);
+        if ((version & 0xFFu) != 2) throw Err("readOpenEXR(): unsupported file version");
+        if (version & 0x200u) throw Err("readOpenEXR(): tiled images are not supported (\"" + path + "\")");
+        if (version & 0x1800u) throw Err("readOpenEXR(): deep / multi-part images are not supported (\"" + path + "\")");
+        struct Chan { std::string name; int type; size_t offset; }; // offset of the channel's samples inside one scan line
+        std::vector<Chan> chans;
+        int compression = -1, xMin = 0, yMin = 0, xMax = -1, yMax = -1;
+        auto cstr = [&]() { std::string t; while (true) { need(1); const char c = (char) d[pos++]; if (!c) break; t += c; } return t; };
+        while (true) { // attributes: name\0 type\0 size value
+            const std::string name = cstr();
+            if (name.empty()) break;
+            const std::string type = cstr();
+            need(4);
+            const int32_t size = i32(pos); pos += 4;
+            if (size < 0) throw Err("readOpenEXR(): corrupt header");
+            need((size_t) size);
+            const size_t end = pos + (size_t) size;
+            if (name == "channels") {
+                while (pos < end && d[pos]) {
+                    Chan c; c.name = cstr();
+                    need(16);
+                    c.type = i32(pos);
+                    if (i32(pos + 8) != 1 || i32(pos + 12) != 1) throw Err("readOpenEXR(): sub-sampled channels are not supported");
+                    if (c.type < 0 || c.type > 2) throw Err("readOpenEXR(): unknown pixel type");
+                    pos += 16;
+                    c.offset = 0;
+                    chans.push_back(c);
+                }
+            } else if (name == "compression" && size >= 1) compression = d[pos];
+            else if (name == "dataWindow" && size >= 16) { xMin = i32(pos); yMin = i32(pos + 4); xMax = i32(pos + 8); yMax = i32(pos + 12); }
+            pos = end;
+        }
+        w = xMax - xMin + 1; h = yMax - yMin + 1;
+        if (w <= 0 || h <= 0 || chans.empty() || compression < 0) throw Err("readOpenEXR(): incomplete header in \"" + path + "\"");
+        static const char *cname[] = {"NONE", "RLE", "ZIPS", "ZIP", "PIZ", "PXR24", "B44", "B44A", "DWAA", "DWAB"};
+        if (compression > 3) throw Err(std::string("readOpenEXR(): ") + (compression < 10 ? cname[compression] : "this") + " compression is not supported (supported: NONE, RLE, ZIPS, ZIP); re-save \"" + path + "\" with ZIP compression");
+        const int linesPerBlock = compression == 3 ? 16 : 1;
+        size_t lineBytes = 0;
+        for (Chan &c : chans) { c.offset = lineBytes; lineBytes += (size_t) w * (c.type == 1 ? 2 : 4); } // the list is stored in alphabetical order = file order
+        int src[3] = {-1, -1, -1};
+        for (size_t k = 0; k < chans.size(); ++k) {
+            if (chans[k].name == "R") src[0] = (int) k; else if (chans[k].name == "G") src[1] = (int) k; else if (chans[k].name == "B") src[2] = (int) k;
+        }
+        if (src[0] >= 0 && src[1] >= 0 && src[2] >= 0) ch = 3;
+        else {
+            ch = 1; src[0] = -1;
+            for (size_t k = 0; k < chans.size(); ++k) if (chans[k].name == "Y") src[0] = (int) k;
+            if (src[0] < 0 && chans.size() == 1) src[0] = 0;
+            if (src[0] < 0) throw Err("readOpenEXR(): \"" + path + "\" has neither R, G, B nor a luminance channel");
+        }
+        px.assign((size_t) w * h * ch, 0.0f);
+        const int nBlocks = (h + linesPerBlock - 1) / linesPerBlock;
+        need((size_t) nBlocks * 8);
+        const size_t table = pos;
+        std::vector<unsigned char> raw, tmp;
+        for (int b = 0; b < nBlocks; ++b) {
+            uint64_t off; memcpy(&off, &d[table + (size_t) b * 8], 8);
+            if (off + 8 > d.size()) throw Err("readOpenEXR(): \"" + path + "\" is truncated");
+            const int y0 = i32((size_t) off) - yMin, dataSize = i32((size_t) off + 4);
+            if (y0 < 0 || y0 >= h || dataSize < 0 || off + 8 + (uint64_t) dataSize > d.size()) throw Err("readOpenEXR(): corrupt chunk in \"" + path + "\"");
+            const int lines = std::min(linesPerBlock, h - y0);
+            const size_t expect = lineBytes * (size_t) lines;
+            const unsigned char *in = &d[(size_t) off + 8];
+            raw.resize(expect);
+            if ((size_t) dataSize == expect || compression == 0) { // stored as is (also what the compressors fall back to when they do not shrink the block)
+                if ((size_t) dataSize != expect) throw Err("readOpenEXR(): chunk size mismatch");
+                memcpy(raw.data(), in, expect);
+            } else {
+                tmp.resize(expect);
+                if (compression == 1) { // run-length: n >= 0: the next byte n + 1 times; n < 0: -n literal bytes
+                    size_t o = 0, i = 0;
+                    while (i < (size_t) dataSize) {
+                        const int n = (signed char) in[i++];
+                        if (n < 0) { const size_t c = (size_t) -n; if (i + c > (size_t) dataSize || o + c > expect) throw Err("readOpenEXR(): corrupt RLE data"); memcpy(&tmp[o], in + i, c); i += c; o += c; }
+                        else { const size_t c = (size_t) n + 1; if (i >= (size_t) dataSize || o + c > expect) throw Err("readOpenEXR(): corrupt RLE data"); memset(&tmp[o], in[i++], c); o += c; }
+                    }
+                    if (o != expect) throw Err("readOpenEXR(): corrupt RLE data");
+                } else {
+                    uLongf got = (uLongf) expect;
+                    if (uncompress(tmp.data(), &got, in, (uLong) dataSize) != Z_OK || got != expect) throw Err("readOpenEXR(): corrupt zlib data in \"" + path + "\"");
+                }
+                for (size_t i = 1; i < expect; ++i) tmp[i] = (unsigned char) (tmp[i - 1] + tmp[i] - 128); // byte-delta predictor
+                const size_t half = (expect + 1) / 2;                                                     // then the two interleaved halves
+                for (size_t i = 0; i < half; ++i) { raw[2 * i] = tmp[i]; if (2 * i + 1 < expect) raw[2 * i + 1] = tmp[half + i]; }
+            }
+            for (int l = 0; l < lines; ++l)
+                for (int c = 0; c < ch; ++c) {
+                    const Chan &cn = chans[src[c]];
+                    const unsigned char *row = raw.data() + (size_t) l * lineBytes + cn.offset;
+                    float *out = &px[((size_t) (y0 + l) * w) * ch + c];
+                    for (int x = 0; x < w; ++x) {
+                        float v;
+                        if (cn.type == 1) { uint16_t hb; memcpy(&hb, row + 2 * (size_t) x, 2); v = halfBitsToFloat(hb); }
+                        else if (cn.type == 2) memcpy(&v, row + 4 * (size_t) x, 4);
+                        else { uint32_t u; memcpy(&u, row + 4 * (size_t) x, 4); v = (float) u; }
+                        out[(size_t) x * ch] = v;
+                    }
+                }
+        }
+    }
     static void loadImage(const std::string &path, double gammaOverride, int &w, int &h, int &ch, std::vector<float> &px) {
         std::ifstream f(path, std::ios::binary);
         if (!f) throw Err("bitmap: cannot open \"" + path + "\"");
+        {
+            unsigned char m4[4] = {0, 0, 0, 0};
+            f.read((char *) m4, 4);
+            if (f.gcount() == 4 && m4[0] == 0x76 && m4[1] == 0x2f && m4[2] == 0x31 && m4[3] == 0x01) { // OpenEXR magic 20000630
+                f.close();
+                loadOpenEXR(path, w, h, ch, px);
+                const double g = gammaOverride != 0 ? gammaOverride : 1.0; // the file is linear; a `gamma` property overrides that (bitmap.cpp:251-252)
+                if (g == -1.0) { for (float &v : px) v = v <= 0.04045f ? v * (float) (1.0 / 12.92) : std::pow((float) ((v + 0.055f) * (float) (1.0 / 1.055)), 2.4f); }
+                else if (g != 1.0) for (float &v : px) v = std::pow(v, (float) g);
+                return;
+            }
+            f.clear(); f.seekg(0);
+        }
         auto token = [&]() { std::string t; char c; while (f.get(c)) { if (c == ' ' || c == '\t' || c == '\n' || c == '\r') { if (!t.empty()) break; } else t += c; } return t; };
         const std::string magic = token();
         double gamma; // bitmap gamma: -1 = sRGB curve
@@ -560,7 +698,7 @@ struct Loader {
                 }
             }
             gamma = 1.0;
-        } else throw Err("bitmap: unsupported image format in \"" + path + "\" (supported: PFM, Radiance RGBE, 8-bit binary PPM)");
+        } else throw Err("bitmap: unsupported image format in \"" + path + "\" (supported: OpenEXR scan-line NONE / RLE / ZIP, PFM, Radiance RGBE, 8-bit binary PPM)");
         if (gammaOverride != 0) gamma = gammaOverride; // bitmap.cpp:251-252
         if (gamma == -1.0) {
             for (float &v : px) v = v <= 0.04045f ? v * (float) (1.0 / 12.92) : std::pow((float) ((v + 0.055f) * (float) (1.0 / 1.055)), 2.4f);
@@ -1308,6 +1446,23 @@ struct Loader {
 
 extern "C" int b2_set_error_(b2_ctx *, int, const char *);
 
+// Host-only: decode an image file the way the scene-file front end does for `bitmap` textures and `envmap` emitters (linear float, top row
+// first).  out may be NULL to query the size; returns 0, or -1 with the message in err.
+extern "C" int b2_load_image(const char *path, float gamma, int *width, int *height, int *channels, float *out, char *err, int errLen) {
+    try {
+        int w, h, ch;
+        std::vector<float> px;
+        Loader::loadImage(path ? path : "", gamma, w, h, ch, px);
+        if (width) *width = w;
+        if (height) *height = h;
+        if (channels) *channels = ch;
+        if (out) memcpy(out, px.data(), px.size() * sizeof(float));
+        return 0;
+    } catch (const std::exception &e) {
+        if (err && errLen > 0) { strncpy(err, e.what(), (size_t) errLen - 1); err[errLen - 1] = 0; }
+        return -1;
+    }
+}
 extern "C" int b2_load_xml(b2_ctx *ctx, const char *path, const char *const *defines, int n_defines, b2_scene **out, b2_render_params *params) {
     if (!ctx || !path || !out || !params) return b2_set_error_(ctx, B2_ERR_INVALID, "b2_load_xml: null argument");
     *out = nullptr;

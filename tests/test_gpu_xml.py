@@ -294,7 +294,7 @@ def _rgbe_bytes(img, rle):
     return bytes(out), decoded
 
 
-@pytest.mark.parametrize("encoding", ["rle", "flat", "pfm"])
+@pytest.mark.parametrize("encoding", ["rle", "flat", "pfm", "exr"])
 def test_envmap_emitter_through_the_scene_file(b2ctx, tmp_path, encoding):
     """<emitter type="envmap"> with a Radiance .hdr (run-length coded and flat) or PFM image, scale, toWorld and samplingWeight: the film of
     the loaded scene equals the film of the same scene handed over through the C-ABI, and the reference-pinned oracle's film."""
@@ -304,7 +304,11 @@ def test_envmap_emitter_through_the_scene_file(b2ctx, tmp_path, encoding):
     shutil.copytree(os.path.join(ROOT, "scenes", "meshes"), tmp_path / "meshes")
     img = ref_pins.sky_image(32, 16, seed=21, sun=20.0)
     img[:, 8:14] = img[:, 8:9]                      # a few constant stretches so that the scanline coder emits runs
-    if encoding == "pfm":
+    if encoding == "exr":   # a file written by the OpenEXR library (ZIP, half), 32 x 16 texels: tests/golden/images
+        fname = "sky.exr"
+        shutil.copy(os.path.join(ROOT, "tests", "golden", "images", "sky_zip_half.exr"), tmp_path / fname)
+        decoded = np.load(os.path.join(ROOT, "tests", "golden", "images", "expected.npz"))["sky_zip_half.exr"]
+    elif encoding == "pfm":
         fname, decoded = "sky.pfm", img
         with open(tmp_path / fname, "wb") as f:
             f.write(b"PF\n32 16\n-1.0\n" + img[::-1].astype("<f4").tobytes())
