@@ -659,6 +659,15 @@ static int usableThreads() {
     if (const char *e = getenv("B2_BUILD_THREADS")) n = atoi(e);
     return std::max(1, n);
 }
+// f(begin, end) over [0, n) in contiguous chunks, one per thread (per-element work that is independent and writes to its own slots)
+template <typename F> static void parallelFor(size_t n, int threads, F f) {
+    const int parts = (int) std::min<size_t>((size_t) std::max(1, threads), std::max<size_t>(1, n / 65536));
+    if (parts <= 1) { f((size_t) 0, n); return; }
+    std::vector<std::thread> th;
+    for (int c = 1; c < parts; ++c) th.emplace_back([=]() { f(n * c / parts, n * (c + 1) / parts); });
+    f((size_t) 0, n / parts);
+    for (auto &t : th) t.join();
+}
 // B2_COMMIT_TIMING=1: host-side phase times of b2_scene_commit on stderr (where the seconds of a multi-million-triangle commit go)
 struct CommitClock {
     bool on = getenv("B2_COMMIT_TIMING") != nullptr;
@@ -703,10 +712,14 @@ extern "C" int b2_scene_commit(b2_scene *s) {
     std::vector<uint32_t> &ids = bIds[0];
     boxes.reserve(nPrims); ids.reserve(nPrims);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const int hostThreads = usableThreads();
+    std::vector<PrimBox> primBox(nPrims);          // per-prim boxes in prim order; compacted into the buckets (minus degenerates) below
+    std::vector<uint8_t> primDegenerate(nPrims, 0);
     for (size_t mi = 0; mi < s->meshes.size(); ++mi) {
         const HostMesh &m = s->meshes[mi];
         const size_t nT = m.idx.size() / 3;
-        for (size_t j = 0; j < nT; ++j) {
+        parallelFor(nT, hostThreads, [&](size_t jlo, size_t jhi) {
+        for (size_t j = jlo; j < jhi; ++j) {
             const size_t p = m.primOffset + j;
             const uint32_t i0 = m.idx[3 * j], i1 = m.idx[3 * j + 1], i2 = m.idx[3 * j + 2];
             const float *p0 = &m.P[3 * i0], *p1 = &m.P[3 * i1], *p2 = &m.P[3 * i2];
@@ -773,11 +786,21 @@ extern "C" int b2_scene_commit(b2_scene *s) {
             for (int a = 0; a < 3; ++a) {
                 pb.lo[a] = std::min(std::min(p0[a], p1[a]), p2[a]);
                 pb.hi[a] = std::max(std::max(p0[a], p1[a]), p2[a]);
-                if (m.group < 0) { lo[a] = std::min(lo[a], pb.lo[a]); hi[a] = std::max(hi[a], pb.hi[a]); }
             }
-            if (wds[0] != 3) { bBoxes[m.group + 1].push_back(pb); bIds[m.group + 1].push_back((uint32_t) p); } // k == 3: degenerate, never hit (triaccel.h:75-78)
+            primBox[p] = pb;
+            primDegenerate[p] = wds[0] == 3; // k == 3: degenerate, never hit (triaccel.h:75-78): not a candidate of any tree
+        }
+        });
+        std::vector<PrimBox> &bb = bBoxes[m.group + 1];
+        std::vector<uint32_t> &bi = bIds[m.group + 1];
+        for (size_t j = 0; j < nT; ++j) {
+            const size_t p = m.primOffset + j;
+            const PrimBox &pb = primBox[p];
+            if (m.group < 0) for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], pb.lo[a]); hi[a] = std::max(hi[a], pb.hi[a]); }
+            if (!primDegenerate[p]) { bb.push_back(pb); bi.push_back((uint32_t) p); }
         }
     }
+    std::vector<PrimBox>().swap(primBox);
     s->hTriAccelPrimOrder = triAccel;
     clk.mark("flatten + TriAccel");
     // ---- BVH ----
@@ -895,11 +918,13 @@ extern "C" int b2_scene_commit(b2_scene *s) {
         out[1] = make_float4((float) U[0], (float) U[1], (float) U[2], (float) -(U[0] * p0[0] + U[1] * p0[1] + U[2] * p0[2]));
         out[2] = make_float4((float) V[0], (float) V[1], (float) V[2], (float) -(V[0] * p0[0] + V[1] * p0[1] + V[2] * p0[2]));
     };
-    for (size_t i = 0; i < bvh.leafPrims.size(); ++i) {
-        const size_t p = bvh.leafPrims[i];
-        memcpy(&leafTri[3 * i], &triAccel[3 * p], 48);
-        planeRows(verts[3 * p], verts[3 * p + 1], verts[3 * p + 2], &leafPlane[3 * i]);
-    }
+    parallelFor(bvh.leafPrims.size(), usableThreads(), [&](size_t ilo, size_t ihi) {
+        for (size_t i = ilo; i < ihi; ++i) {
+            const size_t p = bvh.leafPrims[i];
+            memcpy(&leafTri[3 * i], &triAccel[3 * p], 48);
+            planeRows(verts[3 * p], verts[3 * p + 1], verts[3 * p + 2], &leafPlane[3 * i]);
+        }
+    });
     clk.mark("instancing / leaf order");
     // ---- flat leaf of the throughput build: coplanar triangle pairs share the plane test ----
     // Two triangles with a common edge that lie in one plane are stored as ONE record: a parallelogram (3 rows: the

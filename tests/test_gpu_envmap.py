@@ -125,3 +125,23 @@ def test_envmap_errors_follow_the_plugin(b2ctx):
     d.env_radiance = (1.0, 1.0, 1.0)
     with pytest.raises(api.B2Error, match="only contain one environment emitter"):
         api.Scene(b2ctx, d)
+
+
+def test_environment_map_with_instances_and_a_thin_lens_matches_the_oracle(b2ctx):
+    """The map next to the other widenings it has to live with: a two-level scene (shapegroup / instance) seen through a thin lens -- the
+    filtered look-up of directly visible background then needs the aperture sample of the path -- against the oracle, which reproduces
+    the reference for each of these features on its own (tests/test_oracle_reference_pins.py)."""
+    import dataclasses
+    from mitsuba_b200.scene import EnvMap, RenderParams, stress_scene
+    d = stress_scene(5, 12, 12, 48, 48, instanced=True)
+    d.meshes = [m for m in d.meshes if m.radiance is None]
+    d.camera = dataclasses.replace(d.camera, aperture_radius=0.05, focus_distance=8.0)
+    d.envmap = EnvMap(pixels=ref_pins.sky_image(48, 24, seed=13, sun=25.0), scale=1.2, to_world=ref_pins.envmap_rotation())
+    rp = RenderParams(spp=16, sampler="sobol", rfilter="gaussian")
+    sc = api.Scene(b2ctx, d)
+    want = np.asarray(O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(rp)[0])
+    for parity in (True, False):
+        film = np.asarray(sc.render(rp, parity=parity)[0]).reshape(want.shape)
+        assert np.allclose(film[..., 4], want[..., 4], rtol=1e-5, atol=1e-6)
+        assert rel_l2(api.develop(film), O.develop(want)) <= (3e-3 if parity else 2e-2), (parity, rel_l2(api.develop(film), O.develop(want)))
+    sc.close()
