@@ -260,7 +260,7 @@ template <int HINT> B2_DEV Spectrum leafEval(const DMaterial &d, const BRec &r, 
             return Spectrum(0.0f);
         }
         const float Fo = fresnelDielectricExt(cosTheta(r.wo), d.eta);
-        Spectrum diff = ld3(d.diffuseReflectance);
+        Spectrum diff = r.hasTex ? r.texR : ld3(d.diffuseReflectance); // the caller resolves the bitmap texture of plastic's diffuseReflectance
         if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
         else diff = diff / (1 - d.fdrInt);
         const float invEta2 = 1 / (d.eta * d.eta);
@@ -415,7 +415,7 @@ template <int HINT> B2_DEV Spectrum leafSample(const DMaterial &d, BRec &r, floa
         r.sampledType = EDiffuseReflection;
         r.wo = squareToCosineHemisphere((sx - probSpecular) / (1 - probSpecular), sy);
         const float Fo = fresnelDielectricExt(cosTheta(r.wo), d.eta);
-        Spectrum diff = ld3(d.diffuseReflectance);
+        Spectrum diff = r.hasTex ? r.texR : ld3(d.diffuseReflectance); // the caller resolves the bitmap texture of plastic's diffuseReflectance
         if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
         else diff = diff / (1 - d.fdrInt);
         pdfOut = (1 - probSpecular) * squareToCosineHemispherePdf(r.wo);

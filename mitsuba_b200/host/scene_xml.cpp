@@ -444,7 +444,16 @@ struct Loader {
             m.nonlinear = p.b("nonlinear", false) ? 1 : 0;
             m.fdr_int = (float) fresnelDiffuseReflectance(1.0 / m.eta); m.fdr_ext = (float) fresnelDiffuseReflectance(m.eta);
             auto lum = [](const float *c) { return c[0] * 0.212671f + c[1] * 0.715160f + c[2] * 0.072169f; }; // spectrum.h:725-727
-            const float dAvg = lum(m.diffuse_reflectance), sAvg = lum(m.reflectance);
+            float dAvg = lum(m.diffuse_reflectance);
+            for (auto &c : n->children) { // plastic.cpp:217-230 addChild: a Texture named diffuseReflectance
+                const bool isTex = c->tag == "texture" || (c->tag == "ref" && textureIds.count(c->id));
+                if (!isTex) continue;
+                if (c->name != "diffuseReflectance") throw Err("plastic: bitmap textures are supported on 'diffuseReflectance' only");
+                const int tid = c->tag == "texture" ? addTexture(c.get()) : textureIds[c->id];
+                m.reflectance_texture = 1 + tid;
+                dAvg = textureAvgLum[tid]; // m_diffuseReflectance->getAverage().getLuminance(), plastic.cpp:199
+            }
+            const float sAvg = lum(m.reflectance);
             m.spec_sampling_weight = sAvg / (dAvg + sAvg);
         } else throw Err("unsupported BSDF plugin \"" + n->type + "\" (supported: diffuse, roughconductor, roughdielectric, coating, twosided, dielectric, conductor, plastic)");
         p.checkAllUsed();
@@ -455,6 +464,7 @@ struct Loader {
     }
     // ---- bitmap textures ----
     std::map<std::string, int> textureIds;
+    std::vector<float> textureAvgLum; // per texture id: luminance of its average (what plastic's specular sampling weight reads)
     // Bitmap::readPFM (bitmap.cpp:3764-3814) and Bitmap::readPPM (:3857-3895, 8-bit P6), then Bitmap::convert(.., EFloat32, gamma 1)
     // as TMIPMap's constructor applies it (mipmap.h:225-226; fmtconv.cpp:1092-1101,1136-1147): linear float, top row first
     // OpenEXR scan-line images (Bitmap::readOpenEXR, bitmap.cpp, goes through the OpenEXR library; this is a reader of the published file
@@ -767,6 +777,18 @@ struct Loader {
         t.pixels = px.data();
         const int id = b2_scene_add_texture(scene, &t);
         if (id < 0) throw Err(b2_last_error(nullptr));
+        { // Texture::getAverage().getLuminance() as the BSDF constructors read it: float running sums of level 0 (after clampNegative) in
+          // raster order over the texel count (barray.h:102-124), times the energy-conservation scale for images that exceed 1 (bsdf.cpp:88-111)
+            const size_t nTexel = (size_t) t.width * t.height;
+            float sum[3] = {0, 0, 0}, mx = 0;
+            for (size_t k = 0; k < nTexel; ++k)
+                for (int c = 0; c < t.channels; ++c) { const float v = std::max(px[k * t.channels + c], 0.0f); sum[c] += v; mx = std::max(mx, v); }
+            const float scale = mx > 1.0f ? 0.99f * (1.0f / mx) : 1.0f;
+            float avg[3];
+            for (int c = 0; c < 3; ++c) avg[c] = sum[t.channels == 3 ? c : 0] / (float) nTexel * scale;
+            if ((int) textureAvgLum.size() <= id) textureAvgLum.resize((size_t) id + 1, 0.0f);
+            textureAvgLum[id] = avg[0] * 0.212671f + avg[1] * 0.715160f + avg[2] * 0.072169f;
+        }
         if (!n->id.empty()) textureIds[n->id] = id;
         return id;
     }

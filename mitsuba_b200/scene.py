@@ -98,6 +98,22 @@ class Texture:
     uscale: float = 1.0
     vscale: float = 1.0
 
+    def average_luminance(self) -> float:
+        """Luminance of Texture::getAverage() as a BSDF constructor reads it (bitmap.cpp:501-511 -> mipmap.h getAverage: the float
+        running sum of level 0 after clampNegative, in raster order, over the texel count: barray.h:102-124), times the energy-conservation
+        scale the BSDF wraps around a texture whose maximum exceeds 1 (bsdf.cpp:88-111)."""
+        px = np.maximum(np.ascontiguousarray(self.pixels, np.float32), np.float32(0))
+        if px.ndim == 3 and px.shape[2] == 1:
+            px = px[:, :, 0]
+        n = np.float32(px.shape[0] * px.shape[1])
+        mx = float(px.max())
+        scale = np.float32(0.99) * (np.float32(1.0) / np.float32(mx)) if mx > 1.0 else np.float32(1.0)
+        if px.ndim == 2:
+            v = np.cumsum(px.reshape(-1), dtype=np.float32)[-1] / n * scale
+            return float(v * np.float32(0.212671) + v * np.float32(0.715160) + v * np.float32(0.072169))   # Spectrum(v).getLuminance()
+        avg = [np.cumsum(px[:, :, c].reshape(-1), dtype=np.float32)[-1] / n * scale for c in range(3)]
+        return float(avg[0] * np.float32(0.212671) + avg[1] * np.float32(0.715160) + avg[2] * np.float32(0.072169))
+
     def flat(self) -> dict:
         px = np.ascontiguousarray(self.pixels, np.float32)
         if px.ndim == 3 and px.shape[2] == 1:
@@ -146,7 +162,7 @@ class Bsdf:
                  thickness=float(self.thickness), reflectance=(0.0, 0.0, 0.0),
                  transmittance=tuple(float(x) for x in self.specular_transmittance),
                  etaC=(0.0, 0.0, 0.0), kC=(1.0, 1.0, 1.0), sigmaA=tuple(float(x) for x in self.sigma_a),
-                 nested2=-1, diffuseReflectance=tuple(float(x) for x in self.diffuse_reflectance), fdrInt=0.0, fdrExt=0.0,
+                 nested2=-1, diffuseReflectance=(0.5, 0.5, 0.5) if isinstance(self.diffuse_reflectance, Texture) else tuple(float(x) for x in self.diffuse_reflectance), fdrInt=0.0, fdrExt=0.0,
                  specSamplingWeight=0.0, nonlinear=int(self.nonlinear), texture=-1)
         if t == 0 and isinstance(self.reflectance, Texture):
             d["texture_obj"] = self.reflectance   # resolved to an index by SceneDesc.flat_bsdfs()
@@ -170,7 +186,13 @@ class Bsdf:
             d["fdrInt"] = fresnel_diffuse_reflectance(1.0 / float(eta))
             d["fdrExt"] = fresnel_diffuse_reflectance(float(eta))
             lum = lambda c: float(c[0]) * 0.212671 + float(c[1]) * 0.715160 + float(c[2]) * 0.072169  # spectrum.h:725-727
-            d_avg, s_avg = lum(self.diffuse_reflectance), lum(self.specular_reflectance)
+            if isinstance(self.diffuse_reflectance, Texture):   # <texture name="diffuseReflectance" type="bitmap">
+                d["texture_obj"] = self.diffuse_reflectance
+                d["diffuseReflectance"] = (0.5, 0.5, 0.5)
+                d_avg = self.diffuse_reflectance.average_luminance()
+            else:
+                d_avg = lum(self.diffuse_reflectance)
+            s_avg = lum(self.specular_reflectance)
             d["specSamplingWeight"] = float(np.float32(s_avg / (d_avg + s_avg)))
         return d
 

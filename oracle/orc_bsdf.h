@@ -29,7 +29,7 @@ typedef struct OrcBsdf {
     float fdrInt, fdrExt;  /* plastic.cpp:194-195 fresnelDiffuseReflectance(1/eta), (eta), integrated on the host */
     float specSamplingWeight;    /* plastic.cpp:199-202 */
     int32_t nonlinear;     /* plastic.cpp:161 */
-    int32_t texture;       /* diffuse: index of a `bitmap` texture that replaces `reflectance` (src/textures/bitmap.cpp), -1 = constant */
+    int32_t texture;       /* index of a `bitmap` texture (src/textures/bitmap.cpp) bound to `reflectance` of diffuse or `diffuseReflectance` of plastic, -1 = constant */
 } OrcBsdf;
 }
 
@@ -271,10 +271,18 @@ struct BsdfSet {
         }
         return V3(d.reflectance[0], d.reflectance[1], d.reflectance[2]);
     }
-    /* BSDF::usesRayDifferentials(): diffuse.cpp:101, twosided.cpp:91-92; the other plugins take constants here */
+    /* m_diffuseReflectance->eval(bRec.its) of plastic (plastic.cpp:271,304,415): constant or the bitmap texture */
+    static V3 diffuseReflectance(const OrcBsdf &d, const BRec &r) {
+        if (d.type == 8 && d.texture >= 0 && r.its) {
+            const TexCtx &t = *r.its;
+            return t.textures[d.texture].eval(t.u, t.v, t.hasUVPartials, t.dudx, t.dudy, t.dvdx, t.dvdy);
+        }
+        return V3(d.diffuseReflectance[0], d.diffuseReflectance[1], d.diffuseReflectance[2]);
+    }
+    /* BSDF::usesRayDifferentials(): diffuse.cpp:101, plastic.cpp:196-197, twosided.cpp:91-92; the other plugins take constants here */
     bool usesRayDifferentials(int id) const {
         const OrcBsdf &d = b[id];
-        if (d.type == 0) return d.texture >= 0;
+        if (d.type == 0 || d.type == 8) return d.texture >= 0;
         if (d.type == 5) return usesRayDifferentials(d.nested) || usesRayDifferentials(d.nested2);
         if (d.type == 3) return usesRayDifferentials(d.nested); /* coating.cpp:172-174 */
         return false;
@@ -356,7 +364,7 @@ struct BsdfSet {
                 return Spectrum(0.0f);
             }
             float Fo = fresnelDielectricExt(Frame::cosTheta(r.wo), d.eta);
-            Spectrum diff(d.diffuseReflectance[0], d.diffuseReflectance[1], d.diffuseReflectance[2]);
+            Spectrum diff = diffuseReflectance(d, r);
             if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
             else diff /= 1 - d.fdrInt;
             const float invEta2 = 1 / (d.eta * d.eta);
@@ -618,7 +626,7 @@ struct BsdfSet {
                 r.sampledType = EDiffuseReflection;
                 r.wo = squareToCosineHemisphere((sx - probSpecular) / (1 - probSpecular), sy);
                 float Fo = fresnelDielectricExt(Frame::cosTheta(r.wo), d.eta);
-                Spectrum diff(d.diffuseReflectance[0], d.diffuseReflectance[1], d.diffuseReflectance[2]);
+                Spectrum diff = diffuseReflectance(d, r);
                 if (d.nonlinear) diff = diff / (Spectrum(1.0f) - diff * d.fdrInt);
                 else diff /= 1 - d.fdrInt;
                 pdfOut = (1 - probSpecular) * squareToCosineHemispherePdf(r.wo);

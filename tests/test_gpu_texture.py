@@ -245,3 +245,55 @@ def test_bitmap_texture_through_xml(b2ctx, tmp_path):
         (tmp_path / "e.xml").write_text(XML % ("", body))
         with pytest.raises(api.B2Error, match=msg):
             b2ctx.load_xml(str(tmp_path / "e.xml"))
+
+
+def test_textured_plastic_image_parity_and_scene_file_route(b2ctx, tmp_path):
+    """`plastic` with a bitmap on diffuseReflectance (nonlinear on the ball, linear behind `twosided` on the ground): device against the oracle,
+    and the same material through the scene file (texture child + the sampling weight from the texture's average)."""
+    d = textured_scene(96, 96, tex_res=128)
+    ball = d.meshes[1]
+    ball.bsdf = Bsdf("plastic", diffuse_reflectance=ball.bsdf.reflectance, nonlinear=True, int_ior=1.49)
+    ground = d.meshes[0]
+    ground.bsdf = Bsdf("twosided", nested=Bsdf("plastic", diffuse_reflectance=ground.bsdf.reflectance, specular_reflectance=(0.8, 0.9, 1.0)))
+    g, o = pair(b2ctx, d)
+    for smp, filt in (("sobol", "box"), ("independent", "gaussian")):
+        rp = RenderParams(spp=16, sampler=smp, rfilter=filt)
+        fo, so = o.render(rp)
+        fg, sg = g.render(rp, parity=True)
+        assert rel_l2(api.develop(fg), O.develop(fo)) <= 3e-4, smp
+        assert abs(sg["rays"] - so["rays"]) <= 1e-3 * so["rays"]
+    rp = RenderParams(spp=64, sampler="sobol", rfilter="box")
+    fo, _ = o.render(rp)
+    ff, _ = g.render(rp, parity=False)
+    assert rel_l2(api.develop(ff), O.develop(fo)) <= REL_L2_TOL
+    # scene file: a quad with <bsdf type="plastic"><texture name="diffuseReflectance" type="bitmap"/></bsdf>
+    img = checker_image(32, 16, 4, 9)
+    with open(tmp_path / "t.pfm", "wb") as f:
+        f.write(b"PF\n32 16\n-1.0\n" + img[::-1].astype("<f4").tobytes())
+    (tmp_path / "quad.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nf 1/1 2/2 3/3\nf 1/1 3/3 4/4\n"
+                                       "")
+    (tmp_path / "light.obj").write_text("v 0 0 3\nv 1 0 3\nv 1 1 3\nv 0 1 3\nf 1 3 2\nf 1 4 3\n")
+    xml = """<scene version="0.6.0">
+  <integrator type="path"/>
+  <sensor type="perspective"><float name="fov" value="40"/><float name="nearClip" value="0.1"/><float name="farClip" value="100"/>
+    <transform name="toWorld"><lookat origin="0.5, 0.5, 2" target="0.5, 0.5, 0" up="0, 1, 0"/></transform>
+    <sampler type="sobol"><integer name="sampleCount" value="16"/></sampler>
+    <film type="hdrfilm"><integer name="width" value="48"/><integer name="height" value="48"/><rfilter type="box"/></film></sensor>
+  <shape type="obj"><string name="filename" value="quad.obj"/>
+    <bsdf type="plastic"><float name="intIOR" value="1.49"/><texture name="diffuseReflectance" type="bitmap"><string name="filename" value="t.pfm"/></texture></bsdf></shape>
+  <shape type="obj"><string name="filename" value="light.obj"/><bsdf type="diffuse"><rgb name="reflectance" value="0 0 0"/></bsdf>
+    <emitter type="area"><rgb name="radiance" value="5 5 5"/></emitter></shape>
+</scene>"""
+    (tmp_path / "scene.xml").write_text(xml)
+    sc, rp = b2ctx.load_xml(str(tmp_path / "scene.xml"), [])
+    film, _ = sc.render(rp, parity=True, width=48, height=48)
+    from mitsuba_b200.scene import Camera, Mesh, SceneDesc, look_at
+    P = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)], np.float32)
+    I = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    UV = np.array([(0, 0), (1, 0), (1, 1), (0, 1)], np.float32)
+    quad = Mesh(P, I, UV=UV, bsdf=Bsdf("plastic", int_ior=1.49, diffuse_reflectance=Texture(img)), name="quad")
+    light = Mesh(P + np.array([0, 0, 3], np.float32), I[:, ::-1].copy(), bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(5.0, 5.0, 5.0), name="light")
+    d2 = SceneDesc([quad, light], Camera(look_at((0.5, 0.5, 2.0), (0.5, 0.5, 0), (0, 1, 0)), fov=40.0, near=0.1, far=100.0, width=48, height=48))
+    fo, _ = O.OracleScene(d2, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert rel_l2(api.develop(film), O.develop(fo)) <= 3e-4
+    sc.close()

@@ -373,3 +373,26 @@ def test_stored_texels_are_half_representable_and_the_maximum_is_not():
     scale = np.float32(0.99) * (np.float32(1) / img.max())
     got = sc.texture_eval(0, uv)[0]
     assert np.allclose(got, half_store(img[7, 10]) * scale, rtol=2e-6) or np.allclose(got, half_store(img[7, 10]), rtol=2e-6)
+
+
+def test_constant_texture_on_plastic_renders_like_the_constant_and_sets_the_sampling_weight():
+    """plastic.diffuseReflectance bound to a bitmap (plastic.cpp:158-159,199-202,271,304,415): a one-colour image must render like the constant
+    (texels are stored as half), and the specular sampling weight is derived from the texture's average the way the constructor does."""
+    from gen_golden import half_store
+    col = np.array([0.6, 0.4, 0.3], np.float32)
+    img = np.full((8, 8, 3), 1.0, np.float32) * col
+    rp = RenderParams(spp=8, sampler="sobol", rfilter="box")
+    d1 = one_texture_scene(None)
+    d1.meshes[0].bsdf = Bsdf("plastic", diffuse_reflectance=Texture(img, filter_type="ewa"))
+    d2 = one_texture_scene(None)
+    d2.meshes[0].bsdf = Bsdf("plastic", diffuse_reflectance=tuple(float(v) for v in half_store(col)))
+    w1, w2 = d1.meshes[0].bsdf.flat()["specSamplingWeight"], d2.meshes[0].bsdf.flat()["specSamplingWeight"]
+    assert abs(w1 - w2) < 2e-4 and 0.6 < w1 < 0.75            # 1 / (1 + lum(0.6, 0.4, 0.3)); the texture's average is of the unrounded floats
+    d2.meshes[0].bsdf.flat = lambda f=d2.meshes[0].bsdf.flat: dict(f(), specSamplingWeight=w1)   # same weight: same lobe choices
+    f1, s1 = O.OracleScene(d1).render(rp)
+    f2, s2 = O.OracleScene(d2).render(rp)
+    assert s1["rays"] == s2["rays"]
+    assert np.abs(O.develop(f1) - O.develop(f2)).max() < 1e-5
+    # an image above 1 is scaled for energy conservation (bsdf.cpp:88-111), and so is the average the weight is computed from
+    t = Texture((img * np.float32(2.0)).astype(np.float32))
+    assert abs(t.average_luminance() - 0.99 / 1.2 * (0.6 * 2 * 0.212671 + 0.4 * 2 * 0.715160 + 0.3 * 2 * 0.072169)) < 1e-5
