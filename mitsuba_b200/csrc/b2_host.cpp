@@ -661,7 +661,7 @@ static int usableThreads() {
 }
 // f(begin, end) over [0, n) in contiguous chunks, one per thread (per-element work that is independent and writes to its own slots)
 template <typename F> static void parallelFor(size_t n, int threads, F f) {
-    const int parts = (int) std::min<size_t>((size_t) std::max(1, threads), std::max<size_t>(1, n / 65536));
+    const int parts = (int) std::min<size_t>((size_t) std::max(1, threads), std::max<size_t>(1, n / 8192));
     if (parts <= 1) { f((size_t) 0, n); return; }
     std::vector<std::thread> th;
     for (int c = 1; c < parts; ++c) th.emplace_back([=]() { f(n * c / parts, n * (c + 1) / parts); });

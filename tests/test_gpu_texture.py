@@ -290,7 +290,7 @@ def test_textured_plastic_image_parity_and_scene_file_route(b2ctx, tmp_path):
     from mitsuba_b200.scene import Camera, Mesh, SceneDesc, look_at
     P = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)], np.float32)
     I = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
-    UV = np.array([(0, 0), (1, 0), (1, 1), (0, 1)], np.float32)
+    UV = np.array([(0, 1), (1, 1), (1, 0), (0, 0)], np.float32)   # the obj plugin flips v by default (flipTexCoords, obj.cpp)
     quad = Mesh(P, I, UV=UV, bsdf=Bsdf("plastic", int_ior=1.49, diffuse_reflectance=Texture(img)), name="quad")
     light = Mesh(P + np.array([0, 0, 3], np.float32), I[:, ::-1].copy(), bsdf=Bsdf("diffuse", reflectance=(0, 0, 0)), radiance=(5.0, 5.0, 5.0), name="light")
     d2 = SceneDesc([quad, light], Camera(look_at((0.5, 0.5, 2.0), (0.5, 0.5, 0), (0, 1, 0)), fov=40.0, near=0.1, far=100.0, width=48, height=48))
