@@ -347,7 +347,7 @@ def textured_metric(ctx, with_cpu=True):
             best = st
     n = 1024 * 1024 * 64
     res = {"workload": "S2 material ball, 3 bitmap textures (1024^2, ewa, maxAnisotropy 20), ~80k triangles, path, sobol, gaussian filter, 1024x1024 @ 64 spp, 1 GPU",
-           "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"], "kernel": "k_shade<-1, TEX>", "kernel_ms": best["ms_shade"],
+           "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"], "kernel": "k_shade<class, TEX> (one launch per BSDF class queue)", "kernel_ms": best["ms_shade"],
            "mean_path_length": best["path_length_sum"] / best["samples"]}
     sc.close()
     return res
@@ -371,7 +371,7 @@ def envmap_metric(ctx, with_parity=True):
     n = 1024 * 1024 * 64
     res = {"workload": "config-3 material balls (GGX conductor + rough dielectric, ~160k triangles) lit by a 1024x512 envmap only (ewa, maxAnisotropy 10), path, sobol, "
                        "gaussian filter, 1024x1024 @ 64 spp, 1 GPU", "value": n / best["ms_total"] / 1e3, "unit": "Msamples/s", "ms": best["ms_total"],
-           "kernel": "k_shade<-1, TEX>", "kernel_ms": best["ms_shade"], "mean_path_length": best["path_length_sum"] / best["samples"]}
+           "kernel": "k_shade<class, TEX> (one launch per BSDF class queue)", "kernel_ms": best["ms_shade"], "mean_path_length": best["path_length_sum"] / best["samples"]}
     if with_parity:
         ref = reference_parity_film("env", 1024, 1024, 64)
         if ref is not None:

@@ -53,8 +53,9 @@ typedef struct b2_material_desc {
     float fdr_int, fdr_ext;  /* plastic.cpp:194-195: fresnelDiffuseReflectance(1/eta), (eta) */
     float spec_sampling_weight; /* plastic.cpp:199-202 */
     int32_t nonlinear;       /* plastic.cpp:161 */
-    int32_t reflectance_texture; /* diffuse and plastic: 0 = the constant above; k > 0 = the bitmap texture with id k - 1 (b2_scene_add_texture)
-                                    is bound to `reflectance` of diffuse (diffuse.cpp:75-77,115,148) or `diffuseReflectance` of plastic
+    int32_t reflectance_texture; /* diffuse, roughconductor, conductor, plastic: 0 = the constant above; k > 0 = the bitmap texture with id k - 1
+                                    (b2_scene_add_texture) is bound to `reflectance` of diffuse (diffuse.cpp:75-77,115,148), `specularReflectance`
+                                    of roughconductor / conductor (roughconductor.cpp:285,369,415; conductor.cpp:221-256) or `diffuseReflectance` of plastic
                                     (plastic.cpp:158-159,271,304,415; spec_sampling_weight then takes the texture's average, :199-202) */
 } b2_material_desc;
 

@@ -232,7 +232,7 @@ B2_DEV V3 ld3(const float *p) { return V3(p[0], p[1], p[2]); }
 // leaf BSDFs (types 0..2)
 // ---------------------------------------------------------------------------------------------
 template <int HINT> B2_DEV Spectrum leafEval(const DMaterial &d, const BRec &r, bool discrete) {
-    const V3 R = (r.hasTex && d.type == 0) ? r.texR : ld3(d.reflectance);
+    const V3 R = (r.hasTex && (d.type == 0 || d.type == 1 || d.type == 7)) ? r.texR : ld3(d.reflectance); // diffuse reflectance, (rough)conductor specularReflectance
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
     if (type == 4) return Spectrum(discrete ? 1.0f : 0.0f); // null.cpp:45-47 (index-matched boundary)
     if (type == 6) { // dielectric.cpp:229-255
@@ -367,7 +367,7 @@ template <int HINT> B2_DEV float leafPdf(const DMaterial &d, const BRec &r, bool
 }
 
 template <int HINT> B2_DEV Spectrum leafSample(const DMaterial &d, BRec &r, float &pdfOut, float sx, float sy, PathSampler &smp) {
-    const V3 R = (r.hasTex && d.type == 0) ? r.texR : ld3(d.reflectance);
+    const V3 R = (r.hasTex && (d.type == 0 || d.type == 1 || d.type == 7)) ? r.texR : ld3(d.reflectance); // diffuse reflectance, (rough)conductor specularReflectance
     const int type = (HINT >= 0 && HINT < 3) ? HINT : d.type;
     if (type == 4) { // null.cpp:65-76
         r.wo = -r.wi; r.sampledType = ENull; r.eta = 1.0f; pdfOut = 1.0f;

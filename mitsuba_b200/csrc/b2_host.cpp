@@ -431,7 +431,7 @@ extern "C" int b2_scene_add_material(b2_scene *s, const b2_material_desc *m) {
         return -1;
     }
     if (m->reflectance_texture != 0) {
-        if (m->type != B2_BSDF_DIFFUSE && m->type != B2_BSDF_PLASTIC) { fail(s->ctx, B2_ERR_INVALID, "bitmap textures are supported on the 'reflectance' of a diffuse BSDF and the 'diffuseReflectance' of a plastic BSDF only"); return -1; }
+        if (m->type != B2_BSDF_DIFFUSE && m->type != B2_BSDF_PLASTIC && m->type != B2_BSDF_ROUGHCONDUCTOR && m->type != B2_BSDF_CONDUCTOR) { fail(s->ctx, B2_ERR_INVALID, "bitmap textures are supported on the 'reflectance' of diffuse, the 'specularReflectance' of roughconductor / conductor and the 'diffuseReflectance' of plastic only"); return -1; }
         if (m->reflectance_texture < 0 || m->reflectance_texture > (int) s->textures.size()) { fail(s->ctx, B2_ERR_INVALID, "invalid texture id"); return -1; }
     }
     s->materials.push_back(*m);

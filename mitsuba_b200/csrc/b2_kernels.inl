@@ -1130,7 +1130,7 @@ template <int CLS, bool TEX = false> __global__ void __launch_bounds__(B2_SHADE_
                         if (mats[leaf].type == 5) leaf = cosTheta(its.wi) > 0 ? mats[leaf].nested : mats[leaf].nested2;
                         if (mats[leaf].type == 3) leaf = mats[leaf].nested;
                         const int tex = mats[leaf].tex;
-                        if ((mats[leaf].type == 0 || mats[leaf].type == 8) && tex >= 0) { // diffuse `reflectance`, plastic `diffuseReflectance`
+                        if (tex >= 0) { // diffuse `reflectance`, (rough)conductor `specularReflectance`, plastic `diffuseReflectance` (the host binds nothing else)
                             const uint32_t item = sc.nItems ? pool.inst[i] : 0xFFFFFFFFu;
                             const DInstance *in = (item != 0xFFFFFFFFu && !sc.items[item].identity) ? &sc.items[item] : nullptr;
                             hasTex = true;

@@ -372,6 +372,7 @@ struct Loader {
         } else if (n->type == "roughconductor") {
             m.type = B2_BSDF_ROUGHCONDUCTOR;
             p.spec("specularReflectance", one, m.reflectance);
+            m.reflectance_texture = textureChild(n, "specularReflectance", "roughconductor");
             std::string material = p.s("material", "Cu");
             std::string lower = material;
             std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
@@ -424,6 +425,7 @@ struct Loader {
         } else if (n->type == "conductor") { // conductor.cpp:153-176
             m.type = B2_BSDF_CONDUCTOR;
             p.spec("specularReflectance", one, m.reflectance);
+            m.reflectance_texture = textureChild(n, "specularReflectance", "conductor");
             std::string material = p.s("material", "Cu");
             std::string lower = material;
             std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
@@ -742,6 +744,17 @@ struct Loader {
         float a[16], b[16];
         for (int i = 0; i < 16; ++i) { a[i] = (float) tw.m[i]; b[i] = (float) inv.m[i]; }
         if (b2_scene_add_envmap_emitter(scene, w, h, px.data(), scale, a, b, weight) < 0) throw Err(b2_last_error(nullptr));
+    }
+    // a Texture child (or reference) named `name` of BSDF node n -> reflectance_texture binding (0 = none)
+    int textureChild(Node *n, const char *name, const char *plugin) {
+        int bound = 0;
+        for (auto &c : n->children) {
+            const bool isTex = c->tag == "texture" || (c->tag == "ref" && textureIds.count(c->id));
+            if (!isTex) continue;
+            if (c->name != name) throw Err(std::string(plugin) + ": bitmap textures are supported on '" + name + "' only");
+            bound = 1 + (c->tag == "texture" ? addTexture(c.get()) : textureIds[c->id]);
+        }
+        return bound;
     }
     int addTexture(Node *n) {
         if (n->type != "bitmap") throw Err("unsupported texture plugin \"" + n->type + "\" (supported: bitmap)");

@@ -169,6 +169,9 @@ class Bsdf:
             d["reflectance"] = (0.5, 0.5, 0.5)
         elif t == 0:
             d["reflectance"] = tuple(float(x) for x in self.reflectance)
+        elif t in (1, 7) and isinstance(self.specular_reflectance, Texture):   # <texture name="specularReflectance" type="bitmap">
+            d["texture_obj"] = self.specular_reflectance
+            d["reflectance"] = (1.0, 1.0, 1.0)
         else:
             d["reflectance"] = tuple(float(x) for x in self.specular_reflectance)
         if t in (1, 7):  # roughconductor.cpp:187-190, conductor.cpp:172-175

@@ -29,7 +29,7 @@ typedef struct OrcBsdf {
     float fdrInt, fdrExt;  /* plastic.cpp:194-195 fresnelDiffuseReflectance(1/eta), (eta), integrated on the host */
     float specSamplingWeight;    /* plastic.cpp:199-202 */
     int32_t nonlinear;     /* plastic.cpp:161 */
-    int32_t texture;       /* index of a `bitmap` texture (src/textures/bitmap.cpp) bound to `reflectance` of diffuse or `diffuseReflectance` of plastic, -1 = constant */
+    int32_t texture;       /* index of a `bitmap` texture (src/textures/bitmap.cpp) bound to `reflectance` of diffuse, `specularReflectance` of roughconductor / conductor or `diffuseReflectance` of plastic, -1 = constant */
 } OrcBsdf;
 }
 
@@ -263,9 +263,10 @@ struct BsdfSet {
         }
     }
 
-    /* m_reflectance->eval(bRec.its): constant, or the bitmap texture at the intersection (diffuse.cpp:115,148) */
+    /* m_reflectance->eval(bRec.its) (diffuse.cpp:115,148) / m_specularReflectance->eval(bRec.its) (roughconductor.cpp:285,369,415; conductor.cpp:221-256):
+       constant, or the bitmap texture at the intersection */
     static V3 reflectance(const OrcBsdf &d, const BRec &r) {
-        if (d.type == 0 && d.texture >= 0 && r.its) {
+        if ((d.type == 0 || d.type == 1 || d.type == 7) && d.texture >= 0 && r.its) { /* diffuse `reflectance`; roughconductor / conductor `specularReflectance` */
             const TexCtx &t = *r.its;
             return t.textures[d.texture].eval(t.u, t.v, t.hasUVPartials, t.dudx, t.dudy, t.dvdx, t.dvdy);
         }
@@ -282,7 +283,7 @@ struct BsdfSet {
     /* BSDF::usesRayDifferentials(): diffuse.cpp:101, plastic.cpp:196-197, twosided.cpp:91-92; the other plugins take constants here */
     bool usesRayDifferentials(int id) const {
         const OrcBsdf &d = b[id];
-        if (d.type == 0 || d.type == 8) return d.texture >= 0;
+        if (d.type == 0 || d.type == 8 || d.type == 1 || d.type == 7) return d.texture >= 0; /* roughconductor.cpp:223-227, conductor.cpp:178-179 */
         if (d.type == 5) return usesRayDifferentials(d.nested) || usesRayDifferentials(d.nested2);
         if (d.type == 3) return usesRayDifferentials(d.nested); /* coating.cpp:172-174 */
         return false;

@@ -255,6 +255,10 @@ def test_textured_plastic_image_parity_and_scene_file_route(b2ctx, tmp_path):
     ball.bsdf = Bsdf("plastic", diffuse_reflectance=ball.bsdf.reflectance, nonlinear=True, int_ior=1.49)
     ground = d.meshes[0]
     ground.bsdf = Bsdf("twosided", nested=Bsdf("plastic", diffuse_reflectance=ground.bsdf.reflectance, specular_reflectance=(0.8, 0.9, 1.0)))
+    # and the luminance-textured backdrop becomes a rough conductor whose specularReflectance is that texture
+    back = d.meshes[3]
+    back.bsdf = Bsdf("roughconductor", distribution="ggx", alpha_u=0.3, alpha_v=0.3, eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421),
+                     specular_reflectance=back.bsdf.reflectance)
     g, o = pair(b2ctx, d)
     for smp, filt in (("sobol", "box"), ("independent", "gaussian")):
         rp = RenderParams(spp=16, sampler=smp, rfilter=filt)
@@ -272,7 +276,7 @@ def test_textured_plastic_image_parity_and_scene_file_route(b2ctx, tmp_path):
         f.write(b"PF\n32 16\n-1.0\n" + img[::-1].astype("<f4").tobytes())
     (tmp_path / "quad.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nf 1/1 2/2 3/3\nf 1/1 3/3 4/4\n"
                                        "")
-    (tmp_path / "light.obj").write_text("v 0 0 3\nv 1 0 3\nv 1 1 3\nv 0 1 3\nf 1 3 2\nf 1 4 3\n")
+    (tmp_path / "light.obj").write_text("v 0 0 3\nv 1 0 3\nv 1 1 3\nv 0 1 3\nf 3 2 1\nf 4 3 1\n"   # same vertex order as I[:, ::-1] below: the emitter is sampled by barycentrics)
     xml = """<scene version="0.6.0">
   <integrator type="path"/>
   <sensor type="perspective"><float name="fov" value="40"/><float name="nearClip" value="0.1"/><float name="farClip" value="100"/>

@@ -396,3 +396,22 @@ def test_constant_texture_on_plastic_renders_like_the_constant_and_sets_the_samp
     # an image above 1 is scaled for energy conservation (bsdf.cpp:88-111), and so is the average the weight is computed from
     t = Texture((img * np.float32(2.0)).astype(np.float32))
     assert abs(t.average_luminance() - 0.99 / 1.2 * (0.6 * 2 * 0.212671 + 0.4 * 2 * 0.715160 + 0.3 * 2 * 0.072169)) < 1e-5
+
+
+@pytest.mark.parametrize("plugin", ["roughconductor", "conductor"])
+def test_constant_texture_on_specular_reflectance_renders_like_the_constant(plugin):
+    """specularReflectance of roughconductor / conductor bound to a bitmap (roughconductor.cpp:285,369,415; conductor.cpp:221-256)."""
+    from gen_golden import half_store
+    col = np.array([0.9, 0.6, 0.3], np.float32)
+    img = np.full((4, 4, 3), 1.0, np.float32) * col
+    rp = RenderParams(spp=8, sampler="sobol", rfilter="box")
+    kw = dict(eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421))
+    if plugin == "roughconductor":
+        kw.update(distribution="ggx", alpha_u=0.3, alpha_v=0.3)
+    d1, d2 = one_texture_scene(None), one_texture_scene(None)
+    d1.meshes[0].bsdf = Bsdf(plugin, specular_reflectance=Texture(img), **kw)
+    d2.meshes[0].bsdf = Bsdf(plugin, specular_reflectance=tuple(float(v) for v in half_store(col)), **kw)
+    f1, s1 = O.OracleScene(d1).render(rp)
+    f2, s2 = O.OracleScene(d2).render(rp)
+    assert s1["rays"] == s2["rays"]
+    assert np.abs(O.develop(f1) - O.develop(f2)).max() < 1e-5 and O.develop(f1).max() > 1e-3
