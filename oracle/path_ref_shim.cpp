@@ -67,7 +67,11 @@ public:
     size_t getEffectivePrimitiveCount() const { return 0; }
     const Class *getClass() const { return Shape::m_theClass; }
 };
+extern "C" void *CreateInstance_scale(const Properties &props);
 ConfigurableObject *PluginManager::createObject(const Class *, const Properties &props) {
+    /* `scale`: the ScalingTexture BSDF::ensureEnergyConservation wraps around a texture whose maximum exceeds 1 (bsdf.cpp:88-111): the
+       reference's own src/textures/scale.cpp */
+    if (props.getPluginName() == "scale") return (ConfigurableObject *) (Texture *) CreateInstance_scale(props);
     return props.getPluginName() == "disk" || props.getPluginName() == "sphere" ? new StandinApertureShape(props) : NULL;
 }
 ref<Scheduler> Scheduler::m_scheduler;
@@ -137,6 +141,9 @@ void GPUTexture::initAndRelease() {}
 std::ostream &operator<<(std::ostream &os, const Bitmap::EPixelFormat &v) { return os << (int) v; } /* TMIPMap::toString only */
 std::ostream &operator<<(std::ostream &os, const Bitmap::EComponentFormat &v) { return os << (int) v; }
 Bitmap::Bitmap(EFileFormat, Stream *, const std::string &) { throw std::runtime_error("Bitmap: image files are not readable here"); }
+void Bitmap::scale(Float) { throw std::runtime_error("Bitmap::scale: not available"); } /* ScalingTexture::getBitmap only */
+ref<Bitmap> Bitmap::extractChannel(int) const { throw std::runtime_error("Bitmap::extractChannel: not available"); }
+std::string Bitmap::getChannelName(int) const { return ""; }
 ref<Bitmap> Bitmap::expand() { throw std::runtime_error("Bitmap::expand: not available"); }
 ref<Bitmap> Bitmap::convert(EPixelFormat, EComponentFormat, Float, Float, Spectrum::EConversionIntent) { throw std::runtime_error("Bitmap::convert: not available"); }
 ref<Bitmap> Bitmap::resample(const ReconstructionFilter *, ReconstructionFilter::EBoundaryCondition, ReconstructionFilter::EBoundaryCondition, const Vector2i &, Float, Float) const { throw std::runtime_error("Bitmap::resample: not available"); }
@@ -205,7 +212,7 @@ using namespace mitsuba;
 #define DECL(name) extern "C" void *CreateInstance_##name(const Properties &props);
 DECL(diffuse) DECL(roughconductor) DECL(roughdielectric) DECL(coating) DECL(dielectric) DECL(conductor) DECL(plastic) DECL(twosided) DECL(null)
 DECL(gaussian) DECL(box) DECL(sobol) DECL(independent) DECL(path) DECL(perspective) DECL(area)
-DECL(thinlens) DECL(constant) DECL(shapegroup) DECL(instance) DECL(envmap)
+DECL(thinlens) DECL(constant) DECL(shapegroup) DECL(instance) DECL(envmap) DECL(bitmap)
 DECL(volpath) DECL(heterogeneous) DECL(homogeneous) DECL(gridvolume) DECL(constvolume) DECL(isotropic) DECL(hg)
 
 /* The `independent` sampler of this repository is a counter-based stream, not the reference's SFMT: to compare volpath
@@ -253,6 +260,44 @@ struct PathRef {
     std::vector<Object *> keep;
 };
 
+namespace {
+template <typename MIP> struct MipCacheWriter : public MIP { typedef typename MIP::MIPMapHeader Header; typedef typename MIP::Array2DType Array; };
+template <typename MIP, typename Value> bool writeMipCache(const std::string &mip, uint64_t timestamp, uint8_t pixelFormat, int nLevels, const int *sizes, const float *const *levels,
+                                                          const float *original, int bcu, int bcv, int filterType) {
+    typedef MipCacheWriter<MIP> W;
+    size_t padding = sizeof(typename W::Header) % MTS_MIPMAP_CACHE_ALIGNMENT;
+    if (padding) padding = MTS_MIPMAP_CACHE_ALIGNMENT - padding;
+    size_t total = sizeof(typename W::Header) + padding;
+    for (int l = 0; l < nLevels; ++l) total += W::Array::bufferSize(Vector2i(sizes[2 * l], sizes[2 * l + 1]));
+    uint8_t *buf = (uint8_t *) allocAligned(total);
+    memset(buf, 0, total);
+    typename W::Header header;
+    memset(&header, 0, sizeof(header));
+    memcpy(header.identifier, "MIP", 3);
+    header.version = MTS_MIPMAP_CACHE_VERSION;
+    header.pixelFormat = pixelFormat;
+    header.levels = (uint8_t) nLevels;
+    header.bcu = (uint8_t) bcu; header.bcv = (uint8_t) bcv;
+    header.filterType = (uint8_t) filterType;
+    header.gamma = 1.0f;
+    header.width = sizes[0]; header.height = sizes[1];
+    header.timestamp = timestamp;
+    uint8_t *ptr = buf + sizeof(typename W::Header) + padding;
+    for (int l = 0; l < nLevels; ++l) {
+        typename W::Array a;
+        a.map(ptr, Vector2i(sizes[2 * l], sizes[2 * l + 1]));
+        if (l == 0 && original) { Value mn, mx, avg; a.init((const Value *) original, mn, mx, avg); header.minimum = mn; header.maximum = mx; header.average = avg; }
+        a.init((const Value *) levels[l]);
+        ptr += a.getBufferSize();
+    }
+    memcpy(buf, &header, sizeof(header));
+    FILE *f = fopen(mip.c_str(), "wb");
+    if (!f) { freeAligned(buf); return false; }
+    fwrite(buf, 1, total, f); fclose(f);
+    freeAligned(buf);
+    return true;
+}
+}
 extern "C" {
 void *pathref_new() {
     PathRef *p = new PathRef();
@@ -260,8 +305,15 @@ void *pathref_new() {
     return p;
 }
 /* same layout as bsdfref_create (oracle/bsdf_ref_shim.cpp) */
+void *pathref_bsdf2(int plugin, int nf, const char **fk, const float *fv, int ns, const char **sk, const char **sv, int nb, const char **bk, const int *bv,
+                    int nsp, const char **spk, const float *spv, void *child, void *child2, void *texture, const char *textureName);
 void *pathref_bsdf(int plugin, int nf, const char **fk, const float *fv, int ns, const char **sk, const char **sv, int nb, const char **bk, const int *bv,
                    int nsp, const char **spk, const float *spv, void *child, void *child2) {
+    return pathref_bsdf2(plugin, nf, fk, fv, ns, sk, sv, nb, bk, bv, nsp, spk, spv, child, child2, NULL, NULL);
+}
+/* the same with a Texture child named like the parameter it binds to (<texture name="reflectance" type="bitmap">: BSDF::addChild) */
+void *pathref_bsdf2(int plugin, int nf, const char **fk, const float *fv, int ns, const char **sk, const char **sv, int nb, const char **bk, const int *bv,
+                    int nsp, const char **spk, const float *spv, void *child, void *child2, void *texture, const char *textureName) {
     static const char *const pluginNames[] = {"diffuse", "roughconductor", "roughdielectric", "coating", "null", "twosided", "dielectric", "conductor", "plastic"};
     Properties props(plugin >= 0 && plugin < 9 ? pluginNames[plugin] : ""); /* the XML loader names the plugin in the Properties (scenehandler.cpp) */
     for (int i = 0; i < nf; ++i) props.setFloat(fk[i], fv[i]);
@@ -283,6 +335,7 @@ void *pathref_bsdf(int plugin, int nf, const char **fk, const float *fv, int ns,
     if (!b) return NULL;
     if (child) b->addChild("", (ConfigurableObject *) (BSDF *) child);
     if (child2) b->addChild("", (ConfigurableObject *) (BSDF *) child2);
+    if (texture) b->addChild(textureName, (ConfigurableObject *) (Texture *) texture);
     b->configure();
     return b;
 }
@@ -419,6 +472,36 @@ void pathref_add_constant_emitter(void *h, const float *radiance, float sampling
     em->configure();
     p->scene->addChild("", em);
     p->keep.push_back(em);
+}
+/* <texture type="bitmap"> (src/textures/bitmap.cpp) the way a second Mitsuba run constructs it: from the MIP map cache file next to the image
+ * (bitmap.cpp:236-244 -> mipmap.h:320-380).  `levels`: the pyramid (float, `channels` per texel: 1 = luminance, 3 = RGB; one level for the
+ * nearest / bilinear filters); `original`: the decoded image before the half-precision rounding -- the cache header carries its minimum,
+ * maximum and average (BlockedArray::init, barray.h:102-124), which getMaximum() / getAverage() later hand to the BSDFs.  Layout, float ->
+ * half conversion and the statistics are the reference's own code; every look-up afterwards is BitmapTexture's. */
+void *pathref_bitmap_texture(const char *stem, int channels, int nLevels, const int *sizes, const float *const *levels, const float *original,
+                             const char *filterType, const char *wrapU, const char *wrapV, float maxAnisotropy, float uoffset, float voffset, float uscale, float vscale) {
+    const std::string img = std::string(stem) + ".img", mip = std::string(stem) + ".mip";
+    { FILE *f = fopen(img.c_str(), "wb"); if (!f) return NULL; fputs("placeholder for the decoded image handed in as a MIP map cache\n", f); fclose(f); }
+    boost::system::error_code ec;
+    const uint64_t timestamp = (uint64_t) fs::last_write_time(fs::path(img), ec);
+    auto wrapOf = [](const std::string &m) { return m == "repeat" ? ReconstructionFilter::ERepeat : m == "clamp" ? ReconstructionFilter::EClamp : m == "mirror" ? ReconstructionFilter::EMirror
+                                                   : (m == "zero" || m == "black") ? ReconstructionFilter::EZero : ReconstructionFilter::EOne; };
+    const std::string ft(filterType);
+    const int filt = ft == "ewa" ? (int) EEWA : ft == "trilinear" ? (int) ETrilinear : ft == "bilinear" ? (int) EBilinear : (int) ENearest;
+    typedef TSpectrum<Float, 1> C1; typedef TSpectrum<Float, 3> C3;
+    const bool ok = channels == 3
+        ? writeMipCache<TMIPMap<C3, TSpectrum<half, 3> >, C3>(mip, timestamp, (uint8_t) Bitmap::ERGB, nLevels, sizes, levels, original, wrapOf(wrapU), wrapOf(wrapV), filt)
+        : writeMipCache<TMIPMap<C1, TSpectrum<half, 1> >, C1>(mip, timestamp, (uint8_t) Bitmap::ELuminance, nLevels, sizes, levels, original, wrapOf(wrapU), wrapOf(wrapV), filt);
+    if (!ok) return NULL;
+    Properties tp("bitmap");
+    tp.setString("filename", img);
+    tp.setString("filterType", filterType);
+    tp.setString("wrapModeU", wrapU); tp.setString("wrapModeV", wrapV);
+    tp.setFloat("maxAnisotropy", maxAnisotropy);
+    tp.setFloat("uoffset", uoffset); tp.setFloat("voffset", voffset); tp.setFloat("uscale", uscale); tp.setFloat("vscale", vscale);
+    Texture *t = (Texture *) CreateInstance_bitmap(tp);
+    t->configure();
+    return t;
 }
 /* <emitter type="envmap"> (src/emitters/envmap.cpp).  The image file readers (OpenEXR, RGBE, ...) are not here, so the pyramid enters the
  * real class the way a second Mitsuba run reads it: through its MIP map cache file (envmap.cpp:143-147 -> mipmap.h:320-380).  The caller

@@ -299,8 +299,27 @@ def path_ref_env():
     print("path_ref_env.npz:", n, "images")
 
 
+def path_ref_tex():
+    """bitmap textures through the same assembled reference renderer (ref_pins.image_cases_tex): film + the reference's sampleToCamera."""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import ref_pins
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so"))
+    out = {}
+    n = 0
+    for name, desc, rp in ref_pins.image_cases_tex():
+        film, s2c = ref_pins.reference_render(lib, desc, rp, want_camera=True)
+        out[name + "/film"], out[name + "/s2c"] = film, s2c
+        n += 1
+    np.savez_compressed(os.path.join(OUT, "path_ref_tex.npz"), **out)
+    print("path_ref_tex.npz:", n, "images")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--tex-only" in sys.argv:
+        path_ref_tex()
+        sys.exit(0)
     if "--env-only" in sys.argv:
         path_ref_env()
         sys.exit(0)
@@ -314,6 +333,7 @@ if __name__ == "__main__":
     path_ref()
     path_ref_ext()
     path_ref_env()
+    path_ref_tex()
     render_ref()
     core_ref()
     bsdf_ref()

@@ -164,15 +164,76 @@ def reference_bsdf(lib, b):
         kids.append(reference_bsdf(lib, b.nested))
         if t == "twosided" and b.nested_back is not None:
             kids.append(reference_bsdf(lib, b.nested_back))
+    # a bitmap texture bound to one of the colour parameters (<texture name="..." type="bitmap">): built by the reference's own plugin
+    from mitsuba_b200.scene import Texture
+    tex, tex_name = None, None
+    for name in list(sp):
+        if isinstance(sp[name], Texture):
+            assert tex is None and hasattr(lib, "pathref_create_tex"), "textured BSDFs need the assembled renderer (libpathref.so)"
+            tex, tex_name = reference_texture(lib.raw, sp.pop(name)), name
     arr = lambda keys: (C.c_char_p * max(1, len(keys)))(*[k.encode() for k in keys])
     fv = (C.c_float * max(1, len(f)))(*[float(v) for v in f.values()])
     sv = arr([str(v) for v in s.values()])
     bv = (C.c_int * max(1, len(bl)))(*[int(bool(v)) for v in bl.values()])
     spv = (C.c_float * max(3, 3 * len(sp)))(*[float(x) for v in sp.values() for x in v])
-    h = lib.bsdfref_create(PLUGIN_IDS[t], len(f), arr(list(f)), fv, len(s), arr(list(s)), sv, len(bl), arr(list(bl)), bv, len(sp), arr(list(sp)), spv,
-                           kids[0] if kids else None, kids[1] if len(kids) > 1 else None)
+    if tex is not None:
+        h = lib.pathref_create_tex(PLUGIN_IDS[t], len(f), arr(list(f)), fv, len(s), arr(list(s)), sv, len(bl), arr(list(bl)), bv, len(sp), arr(list(sp)), spv,
+                                   kids[0] if kids else None, kids[1] if len(kids) > 1 else None, tex, tex_name.encode())
+    else:
+        h = lib.bsdfref_create(PLUGIN_IDS[t], len(f), arr(list(f)), fv, len(s), arr(list(s)), sv, len(bl), arr(list(bl)), bv, len(sp), arr(list(sp)), spv,
+                               kids[0] if kids else None, kids[1] if len(kids) > 1 else None)
     assert h, t
     return C.c_void_p(h)
+
+
+def texture_pyramid(tex):
+    """The MIP pyramid (float32 levels, rounded to half precision) the oracle derives from the decoded image of a scene.Texture."""
+    from oracle.oracle_api import lib as olib, _p, make_texture_desc
+    L = olib()
+    d = tex.flat()
+    L.orc_scene_new.restype = C.c_void_p
+    s = C.c_void_p(L.orc_scene_new())
+    L.orc_add_texture.restype = C.c_int
+    assert L.orc_add_texture(s, C.byref(make_texture_desc(d)), _p(d["pixels"])) == 0
+    info = (C.c_int32 * 64)(); mx, sc = C.c_float(), C.c_float()
+    L.orc_texture_info(s, 0, info, C.byref(mx), C.byref(sc))
+    levels = []
+    for l in range(info[0]):
+        w, h = info[1 + 2 * l], info[2 + 2 * l]
+        a = np.empty((h, w, d["channels"]), np.float32)
+        L.orc_texture_level(s, 0, l, _p(a))
+        levels.append(a)
+    L.orc_scene_free(s)
+    return d, levels
+
+
+_TEX_MEMO = {}
+
+
+def reference_texture(lib, tex):
+    """scene.Texture -> the reference's BitmapTexture (src/textures/bitmap.cpp), constructed from a MIP map cache file that holds the oracle's
+    pyramid (path_ref_shim.cpp pathref_bitmap_texture)."""
+    import hashlib, os, tempfile
+    key = (id(lib), id(tex))
+    if key in _TEX_MEMO:             # (the entry keeps `tex` alive, so its id cannot be handed to another object)
+        return _TEX_MEMO[key][0]
+    d, levels = texture_pyramid(tex)
+    orig = np.maximum(np.ascontiguousarray(d["pixels"], np.float32), np.float32(0))   # clampNegative precedes the statistics (mipmap.h:229-241)
+    sizes = np.array([[a.shape[1], a.shape[0]] for a in levels], np.int32)
+    ptrs = (C.POINTER(C.c_float) * len(levels))(*[_f(a) for a in levels])
+    stem = os.path.join(tempfile.gettempdir(), f"b2ref_tex_{os.getpid()}_" + hashlib.sha1(levels[0].tobytes() + repr(sorted((k, v) for k, v in d.items() if k != "pixels")).encode()).hexdigest()[:12])
+    lib.pathref_bitmap_texture.restype = C.c_void_p
+    t = lib.pathref_bitmap_texture(stem.encode(), d["channels"], len(levels), sizes.ctypes.data_as(C.POINTER(C.c_int)), ptrs, _f(orig),
+                                   tex.filter_type.lower().encode(), tex.wrap_u.encode(), tex.wrap_v.encode(), C.c_float(tex.max_anisotropy),
+                                   C.c_float(tex.uoffset), C.c_float(tex.voffset), C.c_float(tex.uscale), C.c_float(tex.vscale))
+    for ext in (".img", ".mip"):
+        try:
+            os.unlink(stem + ext)
+        except OSError:
+            pass
+    assert t
+    _TEX_MEMO[key] = (C.c_void_p(t), tex, lib)
+    return _TEX_MEMO[key][0]
 
 
 def bsdf_inputs(seed=777):
@@ -299,8 +360,12 @@ def reference_scene(lib, desc, rp):
     lib.pathref_bsdf.restype = C.c_void_p
     h = C.c_void_p(lib.pathref_new())
 
+    lib.pathref_bsdf2.restype = C.c_void_p
+
     class _L:  # reference_bsdf() talks to `bsdfref_create`; here the same function is called pathref_bsdf
         bsdfref_create = lib.pathref_bsdf
+        pathref_create_tex = lib.pathref_bsdf2
+        raw = lib
     memo, mmemo, keep = {}, {}, []
     lib.pathref_medium_homogeneous.restype = C.c_void_p
     lib.pathref_medium_heterogeneous.restype = C.c_void_p
@@ -567,3 +632,26 @@ def reference_envmap_inverse(lib, desc):
     inv = np.zeros((4, 4), np.float32)
     lib.pathref_transform_inverse(_f(np.ascontiguousarray(desc.envmap.to_world, np.float32)), _f(inv))
     return inv
+
+
+def image_cases_tex():
+    """Image-level pins of `bitmap` textures through the assembled reference renderer (the reference's BitmapTexture / Texture2D /
+    Intersection::computePartials and the sensors' ray differentials; the pyramid enters the plugin as a MIP map cache file holding the
+    oracle's resampling of the image): all four filters, repeat / mirror / clamp wrap modes, uv scale and offset, RGB and luminance images,
+    an image above 1 (energy-conservation scale) behind `twosided` through a thin lens, and textures on plastic's diffuseReflectance
+    and a rough conductor's specularReflectance.  Fixture: tests/golden/path_ref_tex.npz."""
+    import dataclasses
+    from mitsuba_b200.scene import Bsdf, RenderParams, textured_scene
+    for ft, smp, filt in (("ewa", "sobol", "gaussian"), ("trilinear", "independent", "box"), ("bilinear", "sobol", "box"), ("nearest", "sobol", "gaussian")):
+        yield "tex_" + ft, textured_scene(40, 40, filter_type=ft, tex_res=32, n_theta=12, n_phi=24), RenderParams(spp=8, sampler=smp, rfilter=filt)
+    d = textured_scene(36, 36, two_sided=True, tex_res=24, n_theta=10, n_phi=20)
+    d.camera = dataclasses.replace(d.camera, aperture_radius=0.05, focus_distance=5.0)
+    ball = d.meshes[1].bsdf.reflectance
+    ball.pixels = (ball.pixels * np.float32(1.7)).astype(np.float32)
+    yield "tex_twosided_thinlens_scaled", d, RenderParams(spp=8, sampler="sobol", rfilter="box")
+    d = textured_scene(40, 40, tex_res=32, n_theta=12, n_phi=24)
+    d.meshes[1].bsdf = Bsdf("plastic", diffuse_reflectance=d.meshes[1].bsdf.reflectance, nonlinear=True, int_ior=1.49)
+    d.meshes[0].bsdf = Bsdf("twosided", nested=Bsdf("plastic", diffuse_reflectance=d.meshes[0].bsdf.reflectance, specular_reflectance=(0.8, 0.9, 1.0)))
+    d.meshes[3].bsdf = Bsdf("roughconductor", distribution="ggx", alpha_u=0.3, alpha_v=0.3, eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421),
+                            specular_reflectance=d.meshes[3].bsdf.reflectance)
+    yield "tex_plastic_and_conductor", d, RenderParams(spp=8, sampler="sobol", rfilter="gaussian")

@@ -276,7 +276,7 @@ def test_textured_plastic_image_parity_and_scene_file_route(b2ctx, tmp_path):
         f.write(b"PF\n32 16\n-1.0\n" + img[::-1].astype("<f4").tobytes())
     (tmp_path / "quad.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nf 1/1 2/2 3/3\nf 1/1 3/3 4/4\n"
                                        "")
-    (tmp_path / "light.obj").write_text("v 0 0 3\nv 1 0 3\nv 1 1 3\nv 0 1 3\nf 3 2 1\nf 4 3 1\n"   # same vertex order as I[:, ::-1] below: the emitter is sampled by barycentrics)
+    (tmp_path / "light.obj").write_text("v 0 0 3\nv 1 0 3\nv 1 1 3\nv 0 1 3\nf 3 2 1\nf 4 3 1\n")   # same vertex order as I[:, ::-1] below: the emitter is sampled by barycentrics
     xml = """<scene version="0.6.0">
   <integrator type="path"/>
   <sensor type="perspective"><float name="fov" value="40"/><float name="nearClip" value="0.1"/><float name="farClip" value="100"/>
@@ -301,3 +301,22 @@ def test_textured_plastic_image_parity_and_scene_file_route(b2ctx, tmp_path):
     fo, _ = O.OracleScene(d2, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
     assert rel_l2(api.develop(film), O.develop(fo)) <= 3e-4
     sc.close()
+
+
+def test_device_textured_images_match_the_reference_renderer(b2ctx):
+    """The device against films of the REFERENCE's own BitmapTexture / computePartials / BSDF plugins (tests/golden/path_ref_tex.npz, no
+    oracle in between): IEEE build within 1e-3, throughput build within the budget of the other reference-film tests."""
+    import ref_pins
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "path_ref_tex.npz"))
+    n = 0
+    for name, desc, rp in ref_pins.image_cases_tex():
+        ref = g[name + "/film"]
+        sc = api.Scene(b2ctx, desc)
+        for parity in (True, False):
+            film = np.asarray(sc.render(rp, parity=parity)[0]).reshape(ref.shape)
+            assert np.allclose(film[..., 4], ref[..., 4], rtol=1e-5, atol=1e-6), name
+            r = float(np.sqrt(((film[..., :3].astype(np.float64) - ref[..., :3]) ** 2).sum() / (ref[..., :3].astype(np.float64) ** 2).sum()))
+            assert r <= (1e-3 if parity else 2e-2), (name, parity, r)
+        sc.close()
+        n += 1
+    assert n == 6

@@ -323,6 +323,40 @@ def test_environment_map_lookups_sampling_and_densities_match_the_live_reference
         assert np.array_equal(sa[ok], sb[ok])
 
 
+def test_oracle_images_with_bitmap_textures_match_the_reference_renderer_golden():
+    """tests/golden/path_ref_tex.npz: the reference's BitmapTexture (src/textures/bitmap.cpp), Texture2D::eval (texture.cpp:124-133),
+    Intersection::computePartials (intersection.cpp:23-85) and the sensors' ray differentials inside the assembled reference renderer --
+    four filters, three wrap modes, uv scale / offset, RGB and luminance images, an image above 1 behind `twosided` through a thin lens,
+    textures on plastic's diffuseReflectance (the sampling weight from the texture's average) and on a rough conductor's
+    specularReflectance -- reproduced BIT FOR BIT by the oracle (the plastic scene: to the last bit of one constructor constant, 1e-6).  This closes what the look-up level pins (mipmap_ref.npz) left to closed
+    forms: the uv transform, the partials and everything between the texture and the film."""
+    g = np.load(os.path.join(HERE, "golden", "path_ref_tex.npz"))
+    n = 0
+    for name, desc, rp in ref_pins.image_cases_tex():
+        ref = g[name + "/film"]
+        film = np.asarray(O.OracleScene(desc, sample_to_camera=g[name + "/s2c"]).render(rp)[0]).reshape(ref.shape)
+        if name == "tex_plastic_and_conductor":   # plastic: the last bit of one constructor constant, as for ball_plastic above
+            assert np.array_equal(film[..., 3:], ref[..., 3:])
+            assert np.sqrt(((film - ref) ** 2).sum() / (ref ** 2).sum()) < 1e-6
+        else:
+            assert np.array_equal(film, ref), (name, float(np.abs(film - ref).max()))
+        assert ref[..., :3].max() > 0.1 and ref[..., 4].min() > 0
+        n += 1
+    assert n == 6
+
+
+def test_oracle_textured_image_matches_the_live_reference_renderer_when_present():
+    so = os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libpathref.so not built (the reference tree is not on this machine)")
+    from mitsuba_b200.scene import RenderParams, textured_scene
+    lib = C.CDLL(so)
+    desc, rp = textured_scene(44, 36, filter_type="ewa", tex_res=48, wrap="mirror", n_theta=10, n_phi=20), RenderParams(spp=6, sampler="sobol", rfilter="gaussian", seed=5)  # not in the fixture
+    ref, s2c = ref_pins.reference_render(lib, desc, rp, want_camera=True)
+    film, _ = O.OracleScene(desc, sample_to_camera=s2c).render(rp)
+    assert np.array_equal(np.asarray(film).reshape(ref.shape), ref)
+
+
 def test_conductor_material_presets_match_the_reference_spectrum_code():
     """material="Cu" etc. of the conductor plugins (roughconductor.cpp:174-190): the committed table (mitsuba_b200/data/conductor_presets.txt)
     against the live reference -- InterpolatedSpectrum + Spectrum::fromContinuousSpectrum on data/ior/*.spd -- where it is present, and against
