@@ -259,6 +259,10 @@ int b2_texture_partials(b2_scene *, uint64_t n, const float *pos_hit, int spp, i
  * linear floats, row-major, top row first (what Bitmap::convert(.., EFloat32, gamma 1) hands to the MIP map).  gamma 0 = the file's own
  * (EXR / RGBE / PFM linear, PPM sRGB), -1 = sRGB, > 0 = that exponent (bitmap.cpp:251-252).  out NULL: size query.  0 or -1 + message. */
 int b2_load_image(const char *path, float gamma, int *width, int *height, int *channels, float *out, char *err, int err_len);
+/* Host-only: (wavelength nm, value) samples in increasing wavelength -> ITU-R BT.709 linear RGB, what the scene file's <spectrum filename="x.spd">
+ * and <spectrum value="l0:v0, l1:v1, ..."> become (scenehandler.cpp:557-611: InterpolatedSpectrum, zeroExtend, fromContinuousSpectrum against the
+ * CIE 1931 observer, clampNegative).  The integrals are evaluated exactly; the reference's adaptive quadrature agrees to 1e-4.  0 or -1 + message. */
+int b2_spectrum_to_rgb(const float *wavelengths, const float *values, int n, int zero_extend, float rgb[3], char *err, int err_len);
 /* Probes of the committed environment map: what 0 = Scene::evalEnvironment for n world directions (in n x 3 -> out n x 3); 1 = the same
  * for sensor rays with differentials (in n x 9: d, rxDirection, ryDirection -> out n x 3); 2 = Scene::pdfEmitterDirect of the map for n
  * directions, solid-angle measure including the emitter-selection probability (in n x 3 -> out n) */

@@ -67,7 +67,7 @@ class b2_stats(C.Structure):
 
 EXPORTS = ["b2_context_create", "b2_context_destroy", "b2_last_error", "b2_scene_create", "b2_scene_destroy",
            "b2_scene_set_camera", "b2_scene_set_crop", "b2_scene_set_thinlens", "b2_scene_get_sample_to_camera", "b2_scene_film_size", "b2_scene_add_material", "b2_scene_add_area_emitter",
-           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_envmap_emitter", "b2_envmap_probe", "b2_load_image", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_get_pixel_stats", "b2_get_path_traces", "b2_trace",
+           "b2_scene_add_mesh", "b2_scene_add_shapegroup", "b2_scene_set_mesh_group", "b2_scene_add_instance", "b2_scene_add_constant_emitter", "b2_scene_add_envmap_emitter", "b2_envmap_probe", "b2_load_image", "b2_spectrum_to_rgb", "b2_scene_add_medium", "b2_scene_set_mesh_media", "b2_medium_probe", "b2_scene_add_texture", "b2_texture_eval", "b2_texture_partials", "b2_texture_level", "b2_mipmap_level", "b2_scene_commit", "b2_render", "b2_cancel", "b2_film_develop", "b2_get_stats", "b2_get_pixel_stats", "b2_get_path_traces", "b2_trace",
            "b2_trace_device", "b2_bsdf_eval", "b2_bsdf_sample", "b2_sample_emitter_direct", "b2_sampler_stream",
            "b2_camera_rays", "b2_splat", "b2_get_triaccel", "b2_load_xml", "b2_version", "b2_device_count"]
 
@@ -86,6 +86,18 @@ def lib():
             getattr(L, name).restype = C.c_int
         _LIB = L
     return _LIB
+
+
+def spectrum_to_rgb(wavelengths, values, zero_extend=True):
+    """(wavelength nm, value) samples -> linear RGB as the scene file's <spectrum> tags are converted (b2_spectrum_to_rgb; host-only)."""
+    L = lib()
+    w = np.ascontiguousarray(wavelengths, np.float32); v = np.ascontiguousarray(values, np.float32)
+    rgb = np.zeros(3, np.float32)
+    err = C.create_string_buffer(1024)
+    if L.b2_spectrum_to_rgb(w.ctypes.data_as(C.POINTER(C.c_float)), v.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(len(w)), C.c_int(int(zero_extend)),
+                            rgb.ctypes.data_as(C.POINTER(C.c_float)), err, 1024):
+        raise B2Error(err.value.decode(errors="replace"))
+    return rgb
 
 
 def load_image(path, gamma=0.0):

@@ -31,10 +31,11 @@ UNITS = [
     (os.path.join(CSRC, "bvh_builder.cpp"), []),
     (os.path.join(HOST, "scene_xml.cpp"), []),
     (os.path.join(HOST, "mipmap.cpp"), []),
+    (os.path.join(HOST, "spectrum.cpp"), []),
 ]
 HEADERS = [os.path.join(CSRC, f) for f in ("b2_math.cuh", "b2_types.h", "b2_sampler.cuh", "b2_bsdf.cuh", "b2_trace.cuh",
                                            "b2_kernels.inl", "b2_launch.h", "bvh_builder.h", "b2_medium.cuh", "b2_texture.cuh", "b2_envmap.cuh")] + \
-          [os.path.join(HOST, "mipmap.h")] + \
+          [os.path.join(HOST, "mipmap.h"), os.path.join(HOST, "spectrum.h")] + \
           [os.path.join(HERE, "..", "include", "b2mts.h")]
 
 

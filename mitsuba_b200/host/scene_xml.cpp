@@ -10,6 +10,7 @@
 #include "../../include/b2mts.h"
 #include <expat.h>
 #include <zlib.h>
+#include "spectrum.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -215,13 +216,39 @@ struct Parser {
         } else if (tag == "string") { v.kind = Value::String; v.s = need("value"); }
         else if (tag == "rgb" || tag == "srgb" || tag == "spectrum") {
             v.kind = Value::Spectrum;
-            if (tag == "spectrum" && a.count("filename")) throw Err("<spectrum filename=...>: .spd spectra are not supported (use RGB values)");
+            if (tag == "spectrum" && a.count("filename")) { // scenehandler.cpp:557-568: InterpolatedSpectrum(path), zeroExtend, fromContinuousSpectrum, clampNegative
+                if (a.count("value")) throw Err("<spectrum>: please provide one of 'value' or 'filename'");
+                if (a.count("intent")) throw Err("<spectrum>: 'intent' and 'filename' cannot be specified at the same time!");
+                std::string fn = a.at("filename");
+                if (!fn.empty() && fn[0] != '/') fn = baseDir + "/" + fn;
+                std::vector<double> wl, val;
+                std::string err;
+                float rgb[3];
+                if (!b2host::readSpd(fn, wl, val, err) || !b2host::spectrumToRGB(wl, val, true, rgb, err)) throw Err(err);
+                for (int i = 0; i < 3; ++i) v.v[i] = rgb[i];
+                cur->props[pname] = v;
+                return;
+            }
             auto t = tokenize(need("value"));
+            if (tag == "spectrum" && !t.empty() && t[0].find(':') != std::string::npos) { // wavelength:value pairs, scenehandler.cpp:594-611
+                if (a.count("intent")) throw Err("<spectrum>: 'intent' can only be specified when given a single-valued argument.");
+                std::vector<double> wl, val;
+                for (const std::string &tok : t) {
+                    auto pr = tokenize(tok, ":");
+                    if (pr.size() != 2) throw Err("Invalid spectrum->value mapping specified");
+                    wl.push_back(toF(pr[0], "spectrum")); val.push_back(toF(pr[1], "spectrum"));
+                }
+                std::string err;
+                float rgb[3];
+                if (!b2host::spectrumToRGB(wl, val, true, rgb, err)) throw Err(err);
+                for (int i = 0; i < 3; ++i) v.v[i] = rgb[i];
+                cur->props[pname] = v;
+                return;
+            }
             if (t.size() == 1 && t[0].size() == 7 && t[0][0] == '#' && tag != "spectrum") {
                 long enc = strtol(t[0].c_str() + 1, nullptr, 16);
                 v.v[0] = ((enc >> 16) & 0xFF) / 255.0; v.v[1] = ((enc >> 8) & 0xFF) / 255.0; v.v[2] = (enc & 0xFF) / 255.0;
             } else if (t.size() == 1) {
-                if (t[0].find(':') != std::string::npos) throw Err("<spectrum>: wavelength:value lists are not supported (use RGB values)");
                 v.v[0] = v.v[1] = v.v[2] = toF(t[0], "spectrum"); // reflectance: flat; illuminant: D65 == white in the RGB build
             } else if (t.size() == 3) { for (int i = 0; i < 3; ++i) v.v[i] = toF(t[i], "spectrum"); }
             else throw Err("Invalid spectrum value specified (length does not match the current spectral discretization!)");
@@ -1511,6 +1538,7 @@ extern "C" int b2_load_xml(b2_ctx *ctx, const char *path, const char *const *def
     std::string p = path;
     size_t slash = p.find_last_of('/');
     std::string baseDir = slash == std::string::npos ? "." : p.substr(0, slash);
+    P.baseDir = baseDir; // <spectrum filename="..."> is resolved while parsing
     std::ifstream f(path, std::ios::binary);
     if (!f) return b2_set_error_(ctx, B2_ERR_IO, (std::string("cannot open scene file ") + path).c_str());
     std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());

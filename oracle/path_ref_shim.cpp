@@ -298,6 +298,7 @@ template <typename MIP, typename Value> bool writeMipCache(const std::string &mi
     return true;
 }
 }
+namespace mitsuba { extern const Float CIE_wavelengths[471]; extern const Float CIE_X_entries[471]; extern const Float CIE_Y_entries[471]; extern const Float CIE_Z_entries[471]; }
 extern "C" {
 void *pathref_new() {
     PathRef *p = new PathRef();
@@ -732,6 +733,28 @@ void pathref_sample_emitter_direct(void *h, int n, const float *ref, const float
         o[0] = dRec.d.x; o[1] = dRec.d.y; o[2] = dRec.d.z; o[3] = dRec.dist; o[4] = dRec.pdf;
         o[5] = value[0]; o[6] = value[1]; o[7] = value[2]; o[8] = value.isZero() ? 0.0f : 1.0f; o[9] = dRec.p.x; o[10] = dRec.p.y; o[11] = dRec.p.z;
     }
+}
+/* The CIE 1931 2-degree observer table the reference integrates against (src/libcore/spectrum.cpp:29-34,743-1141: 471 entries, 360..830 nm,
+ * 1 nm): out 471 x 4 = wavelength, xbar, ybar, zbar.  Used by tools/extract_cie_table.py to write mitsuba_b200/data/cie1931_xyz_1nm.txt
+ * (public standard data, stored like the Sobol' tables) and by the test that pins that file. */
+int pathref_cie_tables(float *out) {
+    for (int i = 0; i < 471; ++i) { out[4 * i] = CIE_wavelengths[i]; out[4 * i + 1] = CIE_X_entries[i]; out[4 * i + 2] = CIE_Y_entries[i]; out[4 * i + 3] = CIE_Z_entries[i]; }
+    return 471;
+}
+/* <spectrum value="l0:v0, l1:v1, ..."> / <spectrum filename="x.spd"> as the scene loader turns them into a property (scenehandler.cpp:557-611):
+ * InterpolatedSpectrum, zeroExtend(), Spectrum::fromContinuousSpectrum (spectrum.cpp:172-186: adaptive Gauss-Lobatto quadrature of the product
+ * with the matching functions), clampNegative. */
+int pathref_spectrum_to_rgb(int n, const float *wavelengths, const float *values, int zeroExtend, float *rgb) {
+    try {
+        InterpolatedSpectrum interp((size_t) n);
+        for (int i = 0; i < n; ++i) interp.append(wavelengths[i], values[i]);
+        if (zeroExtend) interp.zeroExtend();
+        Spectrum discrete;
+        discrete.fromContinuousSpectrum(interp);
+        discrete.clampNegative();
+        for (int i = 0; i < 3; ++i) rgb[i] = discrete[i];
+        return 0;
+    } catch (...) { return 1; }
 }
 /* The RGB (eta, k) a conductor plugin derives from material="<name>" (roughconductor.cpp:174-190, conductor.cpp:160-176): the reference's own
  * InterpolatedSpectrum file reader + Spectrum::fromContinuousSpectrum (src/libcore/spectrum.cpp) on <dataDir>/ior/<name>.{eta,k}.spd.

@@ -299,6 +299,39 @@ def path_ref_env():
     print("path_ref_env.npz:", n, "images")
 
 
+def spectrum_inputs(seed=0, n=200):
+    """Random piecewise-linear spectra: 2..60 knots somewhere in 300..900 nm, smooth and spiky, with and without zero extension."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < n:
+        k = len(cases)
+        m = int(rng.integers(2, 60)); lo = rng.uniform(300, 500); hi = rng.uniform(550, 900)
+        w = np.unique(np.round(np.sort(rng.uniform(lo, hi, m)), 2)).astype(np.float32)
+        if len(w) < 2:
+            continue
+        v = (rng.random(len(w)) ** 2 * rng.uniform(0.1, 5)).astype(np.float32)
+        if k % 5 == 0:
+            v[rng.integers(len(w))] += np.float32(50)
+        cases.append((w, v, int(k % 2)))
+    return cases
+
+
+def spectrum_ref():
+    """What the reference's scene loader makes of <spectrum> samples (InterpolatedSpectrum + zeroExtend + Spectrum::fromContinuousSpectrum +
+    clampNegative of src/libcore/spectrum.cpp, through oracle/_ref/libpathref.so) for spectrum_inputs(), plus its CIE observer table."""
+    lib = C.CDLL(os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so"))
+    f = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    out = []
+    for w, v, ze in spectrum_inputs():
+        rgb = np.zeros(3, np.float32)
+        assert lib.pathref_spectrum_to_rgb(len(w), f(w), f(v), ze, f(rgb)) == 0
+        out.append(rgb)
+    t = np.zeros((471, 4), np.float32)
+    lib.pathref_cie_tables(f(t))
+    np.savez_compressed(os.path.join(OUT, "spectrum_ref.npz"), rgb=np.stack(out), cie=t)
+    print("spectrum_ref.npz:", len(out), "spectra")
+
+
 def path_ref_tex():
     """bitmap textures through the same assembled reference renderer (ref_pins.image_cases_tex): film + the reference's sampleToCamera."""
     sys.path.insert(0, HERE)
@@ -320,6 +353,9 @@ if __name__ == "__main__":
     if "--tex-only" in sys.argv:
         path_ref_tex()
         sys.exit(0)
+    if "--spectrum-only" in sys.argv:
+        spectrum_ref()
+        sys.exit(0)
     if "--env-only" in sys.argv:
         path_ref_env()
         sys.exit(0)
@@ -334,6 +370,7 @@ if __name__ == "__main__":
     path_ref_ext()
     path_ref_env()
     path_ref_tex()
+    spectrum_ref()
     render_ref()
     core_ref()
     bsdf_ref()

@@ -332,3 +332,29 @@ def test_envmap_emitter_through_the_scene_file(b2ctx, tmp_path, encoding):
     fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
     assert rel_l2(api.develop(film), O.develop(fo)) < 1e-3
     sc.close(); sc2.close()
+
+
+def test_spectra_from_spd_files_and_wavelength_lists_through_the_scene_file(b2ctx, tmp_path):
+    """<spectrum filename="x.spd"> and <spectrum value="l:v, ..."> (scenehandler.cpp:557-611): the loaded scene renders like the same scene with the
+    RGB colours the host-only conversion (tests/test_spectrum.py: held to the reference's converter) gives for those samples."""
+    import shutil
+    shutil.copytree(os.path.join(ROOT, "scenes", "meshes"), tmp_path / "meshes")
+    wl = np.array([380, 450, 520, 590, 660, 730], np.float32)
+    green = np.array([0.05, 0.1, 0.6, 0.35, 0.1, 0.05], np.float32)
+    red = np.array([0.04, 0.05, 0.06, 0.3, 0.7, 0.75], np.float32)
+    (tmp_path / "red.spd").write_text("# wavelength (nm)  reflectance\n" + "".join(f"{w:g} {v:g}\n" for w, v in zip(wl, red)))
+    xml = open(os.path.join(ROOT, "scenes", "cbox.xml")).read()
+    xml = xml.replace('<rgb name="reflectance" value="0.14 0.45 0.091"/>', '<spectrum name="reflectance" value="' + ", ".join(f"{w:g}:{v:g}" for w, v in zip(wl, green)) + '"/>')
+    xml = xml.replace('<rgb name="reflectance" value="0.63 0.065 0.05"/>', '<spectrum name="reflectance" filename="red.spd"/>')
+    p = tmp_path / "spectral.xml"
+    p.write_text(xml)
+    sc, rp = b2ctx.load_xml(str(p), ["spp=16", "res=48"])
+    film, _ = sc.render(rp, parity=True, width=48, height=48)
+    d = cornell_box(48, 48)
+    by = {m.name: m for m in d.meshes}
+    by["right"].bsdf.reflectance = tuple(float(v) for v in api.spectrum_to_rgb(wl, green))
+    by["left"].bsdf.reflectance = tuple(float(v) for v in api.spectrum_to_rgb(wl, red))
+    assert by["right"].bsdf.reflectance[1] > by["right"].bsdf.reflectance[0] and by["left"].bsdf.reflectance[0] > by["left"].bsdf.reflectance[1]
+    fo, _ = O.OracleScene(d, sample_to_camera=sc.sample_to_camera()).render(RenderParams(spp=16, sampler="sobol", rfilter="box"))
+    assert rel_l2(api.develop(film), O.develop(fo)) < 3e-4
+    sc.close()
