@@ -255,9 +255,9 @@ int b2_texture_eval(b2_scene *, int texture_id, uint64_t n, const float *uv, con
  * pos_hit n x 6 = film position (2), then t, u, v, prim as b2_trace returns them -> out n x 6: u v dudx dudy dvdx dvdy */
 int b2_texture_partials(b2_scene *, uint64_t n, const float *pos_hit, int spp, int parity_mode, float *out);
 /* Host-only (no device): decode an image file the way b2_load_xml does for `bitmap` textures and `envmap` emitters -- OpenEXR scan-line
- * files (NONE / RLE / ZIPS / ZIP; HALF / FLOAT / UINT; R,G,B or a luminance channel), Radiance RGBE (.hdr), PFM, 8-bit binary PPM -- into
+ * files (NONE / RLE / ZIPS / ZIP; HALF / FLOAT / UINT; R,G,B or a luminance channel), PNG (non-interlaced), Radiance RGBE (.hdr), PFM, 8-bit binary PPM -- into
  * linear floats, row-major, top row first (what Bitmap::convert(.., EFloat32, gamma 1) hands to the MIP map).  gamma 0 = the file's own
- * (EXR / RGBE / PFM linear, PPM sRGB), -1 = sRGB, > 0 = that exponent (bitmap.cpp:251-252).  out NULL: size query.  0 or -1 + message. */
+ * (EXR / RGBE / PFM linear, PPM sRGB, PNG sRGB or its gAMA), -1 = sRGB, > 0 = that exponent (bitmap.cpp:251-252).  out NULL: size query.  0 or -1 + message. */
 int b2_load_image(const char *path, float gamma, int *width, int *height, int *channels, float *out, char *err, int err_len);
 /* Host-only: (wavelength nm, value) samples in increasing wavelength -> ITU-R BT.709 linear RGB, what the scene file's <spectrum filename="x.spd">
  * and <spectrum value="l0:v0, l1:v1, ..."> become (scenehandler.cpp:557-611: InterpolatedSpectrum, zeroExtend, fromContinuousSpectrum against the

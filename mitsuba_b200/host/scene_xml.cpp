@@ -621,6 +621,84 @@ struct Loader {
                 }
         }
     }
+    // PNG (Bitmap::readPNG, bitmap.cpp:2465-2555, goes through libpng; this is a reader of the published format on top of zlib): non-interlaced,
+    // 8- or 16-bit grey / grey+alpha / RGB / RGBA, 2-, 4- and 8-bit palettes and 2- / 4-bit grey expanded to 8 bits; alpha is dropped (bitmap.cpp:
+    // 270-275); the file's gamma is the sRGB curve unless a gAMA chunk (without an sRGB chunk) says otherwise (:2534-2541).  Returns that gamma.
+    static double loadPNG(const std::string &path, int &w, int &h, int &ch, std::vector<float> &px) {
+        std::ifstream f(path, std::ios::binary);
+        std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        auto be32 = [&](size_t at) { return ((uint32_t) d[at] << 24) | ((uint32_t) d[at + 1] << 16) | ((uint32_t) d[at + 2] << 8) | (uint32_t) d[at + 3]; };
+        size_t pos = 8;
+        int depth = 0, ctype = -1, interlace = 0;
+        bool haveSRGB = false, haveGamma = false;
+        double fileGamma = 0;
+        std::vector<unsigned char> idat, palette;
+        w = h = 0;
+        while (pos + 12 <= d.size()) {
+            const uint32_t len = be32(pos);
+            const std::string type((const char *) &d[pos + 4], 4);
+            const size_t body = pos + 8;
+            if (body + (size_t) len + 4 > d.size()) throw Err("readPNG(): \"" + path + "\" is truncated");
+            if (type == "IHDR" && len >= 13) {
+                w = (int) be32(body); h = (int) be32(body + 4); depth = d[body + 8]; ctype = d[body + 9]; interlace = d[body + 12];
+                if (d[body + 10] != 0 || d[body + 11] != 0) throw Err("readPNG(): unknown compression / filter method");
+            } else if (type == "PLTE") palette.assign(d.begin() + (long) body, d.begin() + (long) (body + len));
+            else if (type == "IDAT") idat.insert(idat.end(), d.begin() + (long) body, d.begin() + (long) (body + len));
+            else if (type == "sRGB") haveSRGB = true;
+            else if (type == "gAMA" && len >= 4) { haveGamma = true; fileGamma = be32(body) / 100000.0; }
+            else if (type == "IEND") break;
+            pos = body + len + 4;
+        }
+        if (w <= 0 || h <= 0 || idat.empty()) throw Err("readPNG(): \"" + path + "\" holds no image");
+        if (interlace != 0) throw Err("readPNG(): interlaced files are not supported (\"" + path + "\")");
+        int nch;
+        switch (ctype) { case 0: nch = 1; break; case 2: nch = 3; break; case 3: nch = 1; break; case 4: nch = 2; break; case 6: nch = 4; break; default: throw Err("readPNG(): Unknown color type"); }
+        const bool okDepth = ctype == 3 ? (depth == 2 || depth == 4 || depth == 8) : ctype == 0 ? (depth == 2 || depth == 4 || depth == 8 || depth == 16) : (depth == 8 || depth == 16);
+        if (!okDepth) throw Err("readPNG(): Unsupported bit depth: " + std::to_string(depth));
+        if (ctype == 3 && palette.size() < 3) throw Err("readPNG(): palette image without a palette");
+        const size_t rowBytes = ((size_t) w * nch * depth + 7) / 8, bpp = std::max<size_t>(1, (size_t) nch * depth / 8);
+        std::vector<unsigned char> raw((rowBytes + 1) * (size_t) h);
+        uLongf got = (uLongf) raw.size();
+        if (uncompress(raw.data(), &got, idat.data(), (uLong) idat.size()) != Z_OK || got != raw.size()) throw Err("readPNG(): corrupt image data in \"" + path + "\"");
+        std::vector<unsigned char> prev(rowBytes, 0), cur(rowBytes);
+        ch = (ctype == 0 || ctype == 4) ? 1 : 3;
+        px.assign((size_t) w * h * ch, 0.0f);
+        const float s8 = 1.0f / 255.0f, s16 = 1.0f / 65535.0f; // fmtconv: unsigned integer samples -> [0, 1]
+        for (int y = 0; y < h; ++y) {
+            const unsigned char *in = &raw[(size_t) y * (rowBytes + 1)];
+            const int filter = in[0];
+            for (size_t i = 0; i < rowBytes; ++i) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+                int pred = 0;
+                switch (filter) {
+                    case 0: pred = 0; break;
+                    case 1: pred = a; break;
+                    case 2: pred = b; break;
+                    case 3: pred = (a + b) >> 1; break;
+                    case 4: { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                    default: throw Err("readPNG(): corrupt image data in \"" + path + "\"");
+                }
+                cur[i] = (unsigned char) (in[1 + i] + pred);
+            }
+            float *out = &px[(size_t) y * w * ch];
+            for (int x = 0; x < w; ++x) {
+                if (ctype == 3 || (ctype == 0 && depth < 8)) { // packed indices / packed grey
+                    const int perByte = 8 / depth, shift = (perByte - 1 - x % perByte) * depth, v = depth == 8 ? cur[x] : (cur[x / perByte] >> shift) & ((1 << depth) - 1);
+                    if (ctype == 3) {
+                        if ((size_t) v * 3 + 2 >= palette.size()) throw Err("readPNG(): palette index out of range");
+                        for (int c = 0; c < 3; ++c) out[3 * x + c] = (float) palette[(size_t) v * 3 + c] * s8;
+                    } else out[x] = (float) (v * (255 / ((1 << depth) - 1))) * s8; // png_set_expand_gray_1_2_4_to_8
+                } else if (depth == 8) {
+                    for (int c = 0; c < ch; ++c) out[(size_t) x * ch + c] = (float) cur[(size_t) x * nch + c] * s8;
+                } else {
+                    for (int c = 0; c < ch; ++c) { const size_t at = ((size_t) x * nch + c) * 2; out[(size_t) x * ch + c] = (float) (((unsigned) cur[at] << 8) | cur[at + 1]) * s16; }
+                }
+            }
+            prev.swap(cur);
+        }
+        if (haveSRGB || !haveGamma) return -1.0;
+        return (double) (1.0f / (float) fileGamma);
+    }
     static void loadImage(const std::string &path, double gammaOverride, int &w, int &h, int &ch, std::vector<float> &px) {
         std::ifstream f(path, std::ios::binary);
         if (!f) throw Err("bitmap: cannot open \"" + path + "\"");
@@ -631,6 +709,18 @@ struct Loader {
                 f.close();
                 loadOpenEXR(path, w, h, ch, px);
                 const double g = gammaOverride != 0 ? gammaOverride : 1.0; // the file is linear; a `gamma` property overrides that (bitmap.cpp:251-252)
+                if (g == -1.0) { for (float &v : px) v = v <= 0.04045f ? v * (float) (1.0 / 12.92) : std::pow((float) ((v + 0.055f) * (float) (1.0 / 1.055)), 2.4f); }
+                else if (g != 1.0) for (float &v : px) v = std::pow(v, (float) g);
+                return;
+            }
+            unsigned char m8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            f.clear(); f.seekg(0);
+            f.read((char *) m8, 8);
+            static const unsigned char pngMagic[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+            if (f.gcount() == 8 && memcmp(m8, pngMagic, 8) == 0) {
+                f.close();
+                double g = loadPNG(path, w, h, ch, px);
+                if (gammaOverride != 0) g = gammaOverride; // bitmap.cpp:251-252
                 if (g == -1.0) { for (float &v : px) v = v <= 0.04045f ? v * (float) (1.0 / 12.92) : std::pow((float) ((v + 0.055f) * (float) (1.0 / 1.055)), 2.4f); }
                 else if (g != 1.0) for (float &v : px) v = std::pow(v, (float) g);
                 return;
@@ -737,7 +827,7 @@ struct Loader {
                 }
             }
             gamma = 1.0;
-        } else throw Err("bitmap: unsupported image format in \"" + path + "\" (supported: OpenEXR scan-line NONE / RLE / ZIP, PFM, Radiance RGBE, 8-bit binary PPM)");
+        } else throw Err("bitmap: unsupported image format in \"" + path + "\" (supported: OpenEXR scan-line NONE / RLE / ZIP, PNG, PFM, Radiance RGBE, 8-bit binary PPM)");
         if (gammaOverride != 0) gamma = gammaOverride; // bitmap.cpp:251-252
         if (gamma == -1.0) {
             for (float &v : px) v = v <= 0.04045f ? v * (float) (1.0 / 12.92) : std::pow((float) ((v + 0.055f) * (float) (1.0 / 1.055)), 2.4f);

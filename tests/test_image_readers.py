@@ -33,3 +33,45 @@ def test_unsupported_files_are_refused_by_name(tmp_path):
         api.load_image(str(p))
     with pytest.raises(api.B2Error, match="cannot open"):
         api.load_image(str(tmp_path / "missing.exr"))
+
+
+def _srgb_to_linear(v):
+    v = v.astype(np.float32)
+    return np.where(v <= np.float32(0.04045), v * np.float32(1 / 12.92), np.power((v + np.float32(0.055)) * np.float32(1 / 1.055), np.float32(2.4))).astype(np.float32)
+
+
+def test_png_files_decode_like_libpng_and_become_linear_like_the_reference_bitmap():
+    """PNG (bitmap.cpp:2465-2555 through libpng; here an own reader on zlib): files written by libpng (8 / 16 bit, grey / RGB / RGBA, one that
+    uses every scan-line filter) and hand-assembled ones (4-bit palette, 2-bit grey, a gAMA chunk; filter types 0-4 in turn) decode to the same
+    integer samples; samples / 255 (65535) go through the sRGB curve -- or through the exponent 1 / gAMA -- as Bitmap::convert does
+    (fmtconv.cpp:1092-1101); alpha is dropped (bitmap.cpp:270-275)."""
+    want = np.load(os.path.join(IMAGES, "png_expected.npz"))
+    assert len(want.files) == 9
+    for name in want.files:
+        ints = want[name]
+        v = ints.astype(np.float32) * (np.float32(1 / 65535) if ints.dtype == np.uint16 else np.float32(1 / 255))
+        lin = np.power(v, np.float32(np.float32(1.0) / np.float32(0.45455))) if name == "rgb8_gama.png" else _srgb_to_linear(v)
+        got = api.load_image(os.path.join(IMAGES, name))
+        assert got.shape == lin.shape, (name, got.shape, lin.shape)
+        assert np.allclose(got, lin, rtol=2e-6, atol=1e-7), (name, float(np.abs(got - lin).max()))
+        raw = api.load_image(os.path.join(IMAGES, name), gamma=1.0)                     # a `gamma` property of 1: the samples themselves
+        assert np.array_equal(raw, v), name
+
+
+def test_pfm_and_ppm_files(tmp_path):
+    """The two formats the loader read first (Bitmap::readPFM / readPPM, bitmap.cpp:3764-3814, :3857-3895): PFM is linear and stored bottom row
+    first, little- or big-endian by the sign of its scale; binary 8-bit PPM goes through the sRGB curve."""
+    rng = np.random.default_rng(2)
+    img = rng.random((5, 7, 3)).astype(np.float32)
+    (tmp_path / "le.pfm").write_bytes(b"PF\n7 5\n-1.0\n" + img[::-1].astype("<f4").tobytes())
+    (tmp_path / "be.pfm").write_bytes(b"PF\n7 5\n2.0\n" + img[::-1].astype(">f4").tobytes())
+    (tmp_path / "grey.pfm").write_bytes(b"Pf\n7 5\n-1.0\n" + img[::-1, :, 0].astype("<f4").tobytes())
+    assert np.array_equal(api.load_image(tmp_path / "le.pfm"), img)
+    assert np.array_equal(api.load_image(tmp_path / "be.pfm"), img * np.float32(2.0))
+    assert np.array_equal(api.load_image(tmp_path / "grey.pfm")[..., 0], img[..., 0])
+    raw = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    (tmp_path / "a.ppm").write_bytes(b"P6\n7 5\n255\n" + raw.tobytes())
+    assert np.allclose(api.load_image(tmp_path / "a.ppm"), _srgb_to_linear(raw.astype(np.float32) * np.float32(1 / 255)), rtol=2e-6, atol=1e-7)
+    (tmp_path / "x.bin").write_bytes(b"GIF89a....")
+    with pytest.raises(api.B2Error, match="unsupported image format"):
+        api.load_image(tmp_path / "x.bin")
