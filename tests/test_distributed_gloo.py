@@ -33,6 +33,9 @@ def test_shard_ranges_tile_the_sample_range():
 def _case(kind):
     if kind == "volpath":   # the medium does not change the partitioning (independent (pixel, sample) units)
         return smoke_scene(24, 24, res=12), RenderParams(spp=6, rfilter="gaussian", sampler="independent", integrator="volpath")
+    if kind == "envmap":    # an environment map is scene data replicated on every rank, like the geometry
+        from mitsuba_b200.scene import envmap_scene
+        return envmap_scene(24, 24, map_width=32, n_theta=8, n_phi=16), RenderParams(spp=6, rfilter="gaussian")
     return cornell_box(32, 32), RenderParams(spp=6, rfilter="gaussian")
 
 
@@ -58,7 +61,7 @@ def _worker(rank, world, port, out_path, kind="path"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["path", "volpath"])
+@pytest.mark.parametrize("kind", ["path", "volpath", "envmap"])
 def test_two_rank_gloo_reduce_equals_single_process(tmp_path, kind):
     out = str(tmp_path / "film.npy")
     port = 29500 + (os.getpid() + (7 if kind == "volpath" else 0)) % 2000

@@ -357,6 +357,25 @@ def test_oracle_textured_image_matches_the_live_reference_renderer_when_present(
     assert np.array_equal(np.asarray(film).reshape(ref.shape), ref)
 
 
+def test_environment_map_image_the_plugin_marshals_is_the_stored_level_zero_when_present():
+    """What the Mitsuba-side plugin reads back from an EnvironmentMap instance (Emitter::getBitmap -> TMIPMap::toBitmap, envmap.cpp:632-634):
+    the half-precision level 0 of its pyramid -- bit for bit the oracle's level 0 -- so the pyramid b2_scene_commit rebuilds from it starts from
+    the same texels the reference samples."""
+    so = os.path.join(HERE, "..", "oracle", "_ref", "libb200shim.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libb200shim.so not built (the reference tree is not on this machine)")
+    lib = C.CDLL(so)
+    cases = {name: (desc, rp) for name, desc, rp in ref_pins.image_cases_env()}
+    for name in ("envmap_only_ball", "envmap_plus_area_cbox"):
+        desc, rp = cases[name]
+        h = ref_pins.reference_scene(lib, desc, rp)
+        wh = (C.c_int * 2)()
+        assert lib.pathref_environment_bitmap(h, wh, None) == 0
+        out = np.zeros((wh[1], wh[0], 3), np.float32)
+        assert lib.pathref_environment_bitmap(h, wh, ref_pins._f(out)) == 0
+        assert np.array_equal(out, ref_pins.envmap_pyramid(desc.envmap)[0])
+
+
 def test_conductor_material_presets_match_the_reference_spectrum_code():
     """material="Cu" etc. of the conductor plugins (roughconductor.cpp:174-190): the committed table (mitsuba_b200/data/conductor_presets.txt)
     against the live reference -- InterpolatedSpectrum + Spectrum::fromContinuousSpectrum on data/ior/*.spd -- where it is present, and against
