@@ -361,9 +361,9 @@ def test_environment_map_image_the_plugin_marshals_is_the_stored_level_zero_when
     """What the Mitsuba-side plugin reads back from an EnvironmentMap instance (Emitter::getBitmap -> TMIPMap::toBitmap, envmap.cpp:632-634):
     the half-precision level 0 of its pyramid -- bit for bit the oracle's level 0 -- so the pyramid b2_scene_commit rebuilds from it starts from
     the same texels the reference samples."""
-    so = os.path.join(HERE, "..", "oracle", "_ref", "libb200shim.so")
+    so = os.path.join(HERE, "..", "oracle", "_ref", "libpathref.so")   # the same translation units the plugin's library links (libb200shim.so)
     if not os.path.exists(so):
-        pytest.skip("oracle/_ref/libb200shim.so not built (the reference tree is not on this machine)")
+        pytest.skip("oracle/_ref/libpathref.so not built (the reference tree is not on this machine)")
     lib = C.CDLL(so)
     cases = {name: (desc, rp) for name, desc, rp in ref_pins.image_cases_env()}
     for name in ("envmap_only_ball", "envmap_plus_area_cbox"):
